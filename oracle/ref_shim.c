@@ -1,0 +1,202 @@
+/* oracle/ref_shim.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A flat C interface (ctypes-friendly: plain pointers and sizes) over the
+ * UNMODIFIED reference C library (HMMER 3.4 + Easel, compiled from
+ * /root/reference/vendor by oracle/Makefile).  Nothing in pyhmmer_b200/ may
+ * link or load this; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs do.
+ *
+ * The call sequences mirror what pyhmmer itself does around each reference
+ * function (cited inline), so that the values returned here are the values a
+ * pyhmmer user would observe.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include "p7_config.h"
+#include "easel.h"
+#include "esl_alphabet.h"
+#include "esl_sq.h"
+#include "esl_hmm.h"
+#include "esl_random.h"
+#include "esl_randomseq.h"
+#include "esl_gumbel.h"
+#include "esl_exponential.h"
+#include "esl_vectorops.h"
+#include "hmmer.h"
+
+typedef struct {
+  ESL_ALPHABET *abc;
+  P7_BG        *bg;
+  P7_HMM       *hmm;
+  P7_PROFILE   *gm;
+  P7_OPROFILE  *om;
+  P7_OMX       *ox;    /* scratch for single-comparison calls */
+  P7_OMX       *oxb;
+} REFM;
+
+static int g_inited = 0;
+static void ref_init(void) {
+  if (!g_inited) { p7_FLogsumInit(); g_inited = 1; }   /* as `import pyhmmer.plan7` does (plan7.pyx:9968-9986); impl_Init() is NOT called */
+}
+
+/* Read the idx-th (0-based) HMM of an HMMER3 ASCII/binary file and configure it the way
+ * Pipeline.search_hmm does for an HMM query: Profile.configure(hmm, bg, L) =
+ * p7_ProfileConfig(hmm,bg,gm,L,p7_LOCAL) (plan7.pyx:8082), then OptimizedProfile.convert =
+ * p7_oprofile_Convert (plan7.pyx:4961). */
+REFM *refm_read(const char *path, int idx, int L)
+{
+  P7_HMMFILE *hfp = NULL;
+  REFM *m = calloc(1, sizeof(REFM));
+  int i, status;
+  ref_init();
+  if (p7_hmmfile_Open(path, NULL, &hfp, NULL) != eslOK) { free(m); return NULL; }
+  for (i = 0; i <= idx; i++) {
+    if (m->hmm) { p7_hmm_Destroy(m->hmm); m->hmm = NULL; }
+    status = p7_hmmfile_Read(hfp, &m->abc, &m->hmm);
+    if (status != eslOK) { p7_hmmfile_Close(hfp); free(m); return NULL; }
+  }
+  p7_hmmfile_Close(hfp);
+  m->bg = p7_bg_Create(m->abc);
+  m->gm = p7_profile_Create(m->hmm->M, m->abc);
+  m->om = p7_oprofile_Create(m->hmm->M, m->abc);
+  p7_ProfileConfig(m->hmm, m->bg, m->gm, L, p7_LOCAL);
+  p7_oprofile_Convert(m->gm, m->om);
+  m->ox  = p7_omx_Create(m->hmm->M, 0, 400);
+  m->oxb = p7_omx_Create(m->hmm->M, 0, 400);
+  return m;
+}
+
+void refm_free(REFM *m)
+{
+  if (!m) return;
+  p7_omx_Destroy(m->ox); p7_omx_Destroy(m->oxb);
+  p7_oprofile_Destroy(m->om); p7_profile_Destroy(m->gm);
+  p7_bg_Destroy(m->bg); p7_hmm_Destroy(m->hmm); esl_alphabet_Destroy(m->abc);
+  free(m);
+}
+
+int  refm_M(const REFM *m)   { return m->om->M; }
+int  refm_K(const REFM *m)   { return m->abc->K; }
+int  refm_Kp(const REFM *m)  { return m->abc->Kp; }
+int  refm_abc_type(const REFM *m) { return m->abc->type; }
+const char *refm_name(const REFM *m) { return m->hmm->name; }
+const char *refm_acc(const REFM *m)  { return m->hmm->acc; }
+const char *refm_desc(const REFM *m) { return m->hmm->desc; }
+int  refm_max_length(const REFM *m) { return m->om->max_length; }
+void refm_evparam(const REFM *m, float *out6) { memcpy(out6, m->om->evparam, 6*sizeof(float)); }
+void refm_cutoff(const REFM *m, float *out6)  { memcpy(out6, m->om->cutoff, 6*sizeof(float)); }
+void refm_compo(const REFM *m, float *out20)  { memcpy(out20, m->om->compo, p7_MAXABET*sizeof(float)); }
+void refm_bg_f(const REFM *m, float *out)     { memcpy(out, m->bg->f, m->abc->K*sizeof(float)); }
+
+/* raw HMM parameters: t[(M+1)*7], mat[(M+1)*K], ins[(M+1)*K] */
+void refm_hmm_params(const REFM *m, float *t, float *mat, float *ins)
+{
+  int M = m->hmm->M, K = m->abc->K, k;
+  for (k = 0; k <= M; k++) {
+    memcpy(t   + k*7, m->hmm->t[k],   7*sizeof(float));
+    memcpy(mat + k*K, m->hmm->mat[k], K*sizeof(float));
+    memcpy(ins + k*K, m->hmm->ins[k], K*sizeof(float));
+  }
+}
+/* generic profile: tsc[(M+1)*8], rsc[Kp*(M+1)*2], xsc[4*2] */
+void refm_gm_params(const REFM *m, float *tsc, float *rsc, float *xsc)
+{
+  int M = m->gm->M, Kp = m->abc->Kp, x;
+  memcpy(tsc, m->gm->tsc, (size_t)(M+1)*p7P_NTRANS*sizeof(float));
+  for (x = 0; x < Kp; x++) memcpy(rsc + (size_t)x*(M+1)*2, m->gm->rsc[x], (size_t)(M+1)*2*sizeof(float));
+  memcpy(xsc, m->gm->xsc, 8*sizeof(float));
+}
+
+/* optimized-profile scalars: out[0..] = tbm_b tec_b tjb_b base_b bias_b | base_w ddbound_w | xw[4][2] */
+void refm_om_ints(const REFM *m, int *out)
+{
+  const P7_OPROFILE *om = m->om; int i, j, n = 0;
+  out[n++] = om->tbm_b; out[n++] = om->tec_b; out[n++] = om->tjb_b; out[n++] = om->base_b; out[n++] = om->bias_b;
+  out[n++] = om->base_w; out[n++] = om->ddbound_w;
+  for (i = 0; i < 4; i++) for (j = 0; j < 2; j++) out[n++] = om->xw[i][j];
+  out[n++] = om->L; out[n++] = om->mode;
+}
+/* out = scale_b scale_w ncj_roundoff nj | xf[4][2] */
+void refm_om_floats(const REFM *m, float *out)
+{
+  const P7_OPROFILE *om = m->om; int i, j, n = 0;
+  out[n++] = om->scale_b; out[n++] = om->scale_w; out[n++] = om->ncj_roundoff; out[n++] = om->nj;
+  for (i = 0; i < 4; i++) for (j = 0; j < 2; j++) out[n++] = om->xf[i][j];
+}
+/* Striped tables, copied out as stored by the reference (impl_sse.h:75-100).
+ * sizes: rbv Kp*Q16*16 u8 ; sbv Kp*(Q16+p7O_EXTRA_SB)*16 u8 ; rwv Kp*Q8*8 i16 ; twv 8*Q8*8 i16 ;
+ *        rfv Kp*Q4*4 f32 ; tfv 8*Q4*4 f32 */
+int refm_Q16(const REFM *m) { return p7O_NQB(m->om->M); }
+int refm_Q8 (const REFM *m) { return p7O_NQW(m->om->M); }
+int refm_Q4 (const REFM *m) { return p7O_NQF(m->om->M); }
+int refm_extra_sb(void)     { return p7O_EXTRA_SB; }
+void refm_om_tables(const REFM *m, uint8_t *rbv, uint8_t *sbv, int16_t *rwv, int16_t *twv, float *rfv, float *tfv)
+{
+  const P7_OPROFILE *om = m->om;
+  int Kp = m->abc->Kp, x;
+  int Q16 = p7O_NQB(om->M), Q8 = p7O_NQW(om->M), Q4 = p7O_NQF(om->M);
+  for (x = 0; x < Kp; x++) {
+    if (rbv) memcpy(rbv + (size_t)x*Q16*16, om->rbv[x], (size_t)Q16*16);
+    if (sbv) memcpy(sbv + (size_t)x*(Q16+p7O_EXTRA_SB)*16, om->sbv[x], (size_t)(Q16+p7O_EXTRA_SB)*16);
+    if (rwv) memcpy(rwv + (size_t)x*Q8*8, om->rwv[x], (size_t)Q8*16);
+    if (rfv) memcpy(rfv + (size_t)x*Q4*4, om->rfv[x], (size_t)Q4*16);
+  }
+  if (twv) memcpy(twv, om->twv, (size_t)8*Q8*16);
+  if (tfv) memcpy(tfv, om->tfv, (size_t)8*Q4*16);
+}
+
+/* length / mode reconfiguration, exactly the calls the search loop makes (plan7.pyx:6431-6436) */
+void refm_set_length(REFM *m, int L) { p7_bg_SetLength(m->bg, L); p7_oprofile_ReconfigLength(m->om, L); }
+void refm_set_multihit(REFM *m, int L, int multihit)
+{ if (multihit) p7_oprofile_ReconfigMultihit(m->om, L); else p7_oprofile_ReconfigUnihit(m->om, L); }
+
+/* ---- single-comparison filters; dsq is 1..L with sentinels at 0 and L+1 (esl_sq.h:100-102) ---- */
+static void grow(REFM *m, int L) { p7_omx_GrowTo(m->ox, m->om->M, 0, L); p7_omx_GrowTo(m->oxb, m->om->M, 0, L); }
+
+int ref_ssv(REFM *m, const uint8_t *dsq, int L, float *sc) { refm_set_length(m, L); return p7_SSVFilter(dsq, L, m->om, sc); }
+int ref_msv(REFM *m, const uint8_t *dsq, int L, float *sc) { grow(m, L); refm_set_length(m, L); return p7_MSVFilter(dsq, L, m->om, m->ox, sc); }
+int ref_vit(REFM *m, const uint8_t *dsq, int L, float *sc) { grow(m, L); refm_set_length(m, L); return p7_ViterbiFilter(dsq, L, m->om, m->ox, sc); }
+int ref_fwd(REFM *m, const uint8_t *dsq, int L, float *sc) { grow(m, L); refm_set_length(m, L); return p7_ForwardParser(dsq, L, m->om, m->ox, sc); }
+/* Forward then Backward parser; optionally returns the xmx specials (each (L+1)*p7X_NXCELLS floats) */
+int ref_fwdbck(REFM *m, const uint8_t *dsq, int L, float *fsc, float *bsc, float *fx, float *bx)
+{
+  int st;
+  grow(m, L); refm_set_length(m, L);
+  st = p7_ForwardParser(dsq, L, m->om, m->ox, fsc);            if (st != eslOK) return st;
+  st = p7_BackwardParser(dsq, L, m->om, m->ox, m->oxb, bsc);   if (st != eslOK) return st;
+  if (fx) memcpy(fx, m->ox->xmx,  (size_t)(L+1)*p7X_NXCELLS*sizeof(float));
+  if (bx) memcpy(bx, m->oxb->xmx, (size_t)(L+1)*p7X_NXCELLS*sizeof(float));
+  return eslOK;
+}
+int ref_nxcells(void) { return p7X_NXCELLS; }
+
+/* null1 (p7_bg.c:357) and bias-filter (p7_bg.c:471) scores, set up as p7_pli_NewModel + the search loop do */
+float ref_null1(REFM *m, const uint8_t *dsq, int L)
+{ float sc; p7_bg_SetLength(m->bg, L); p7_bg_NullOne(m->bg, dsq, L, &sc); return sc; }
+float ref_bias(REFM *m, const uint8_t *dsq, int L)
+{
+  float sc;
+  p7_bg_SetFilter(m->bg, m->om->M, m->om->compo);   /* p7_pli_NewModel, p7_pipeline.c:504 */
+  p7_bg_SetLength(m->bg, L);                        /* per sequence, plan7.pyx:6431 */
+  p7_bg_FilterScore(m->bg, dsq, L, &sc);
+  return sc;
+}
+
+/* generic (unstriped, log-space) reference DP on the P7_PROFILE; needs length config on gm */
+int ref_generic(REFM *m, const uint8_t *dsq, int L, float *gmsv, float *gvit, float *gfwd, float *gbck)
+{
+  P7_GMX *gx = p7_gmx_Create(m->gm->M, L);
+  p7_ReconfigLength(m->gm, L);
+  if (gmsv) p7_GMSV    (dsq, L, m->gm, gx, 2.0, gmsv);
+  if (gvit) p7_GViterbi(dsq, L, m->gm, gx, gvit);
+  if (gfwd) p7_GForward(dsq, L, m->gm, gx, gfwd);
+  if (gbck) p7_GBackward(dsq, L, m->gm, gx, gbck);
+  p7_gmx_Destroy(gx);
+  return eslOK;
+}
+
+double ref_gumbel_surv(double x, double mu, double lambda) { return esl_gumbel_surv(x, mu, lambda); }
+double ref_exp_surv(double x, double mu, double lambda)    { return esl_exp_surv(x, mu, lambda); }
