@@ -1,0 +1,172 @@
+/* b2h.h -- C ABI of libb2h.so, the B200-native profile-HMM comparison engine.
+ *
+ * This is the drop-in boundary for pyhmmer's search path.  Every entry point is
+ * `extern "C"`, takes plain pointers and sizes, returns an Easel-compatible int
+ * status (easel.h:100-128 in the reference) and never throws across the ABI.
+ * INTEGRATION.md shows the Cython stub a pyhmmer maintainer would add to bind
+ * each of them.  Reference interfaces replaced (paths relative to the reference
+ * checkout):
+ *
+ *   b2h_profile_config        p7_ProfileConfig            vendor/hmmer/src/modelconfig.c:48
+ *   b2h_oprofile_convert      p7_oprofile_Convert         vendor/hmmer/src/impl_sse/p7_oprofile.c:1014
+ *   b2h_profile_upload*       P7_OPROFILE tables          vendor/hmmer/src/impl_sse/impl_sse.h:75-142
+ *   b2h_seqdb_create          ESL_SQ** of a DigitalSequenceBlock   src/pyhmmer/easel.pxd:313-321
+ *   b2h_ssv_filter            p7_SSVFilter                vendor/hmmer/src/impl_sse/ssvfilter.c:876
+ *   b2h_msv_filter            p7_MSVFilter                vendor/hmmer/src/impl_sse/msvfilter.c:74
+ *   b2h_viterbi_filter        p7_ViterbiFilter            vendor/hmmer/src/impl_sse/vitfilter.c:83
+ *   b2h_forward_parser        p7_ForwardParser            vendor/hmmer/src/impl_sse/fwdback.c:132
+ *   b2h_backward_parser       p7_BackwardParser           vendor/hmmer/src/impl_sse/fwdback.c:236
+ *   b2h_null_scores           p7_bg_NullOne, p7_bg_FilterScore   vendor/hmmer/src/p7_bg.c:357,471
+ *   b2h_search / b2h_scan     Pipeline._search_loop / _scan_loop (= p7_Pipeline per target)
+ *                             src/pyhmmer/plan7.pyx:6394-6453, 6625-6677; vendor/hmmer/src/p7_pipeline.c:697-936
+ *
+ * All DP runs in hand-written sm_100a kernels; there is NO CPU fallback: on a box
+ * without a CUDA device b2h_ctx_create() fails with B2H_ECUDA.
+ */
+#ifndef B2H_H_INCLUDED
+#define B2H_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes: the Easel values the reference's callers already switch on */
+#define B2H_OK          0
+#define B2H_EMEM        5
+#define B2H_EINVAL     11
+#define B2H_ERANGE     16
+#define B2H_ENORESULT  19
+#define B2H_ECUDA     100   /* CUDA runtime / device failure (no Easel equivalent) */
+
+#define B2H_NEVPARAM    6   /* MMU MLAMBDA VMU VLAMBDA FTAU FLAMBDA (hmmer.h p7_evparams_e) */
+#define B2H_NCUTOFFS    6   /* GA1 GA2 TC1 TC2 NC1 NC2 */
+#define B2H_MAXABET    20
+#define B2H_MAXCODE    29
+
+typedef struct b2h_ctx     b2h_ctx;      /* one per (process, GPU): device, stream, workspaces */
+typedef struct b2h_seqdb   b2h_seqdb;    /* device-resident target sequence arena              */
+typedef struct b2h_profile b2h_profile;  /* device-resident optimized profile                  */
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side, un-striped ("node-major") optimized profile.  Node k (1..M) lives at index k-1.
+ * Transition rows follow p7o_tsc_e order BM MM IM DM MD MI II DD with the reference's
+ * rotation already undone:  BM[k]: B->M_k   MM/IM/DM[k]: {M,I,D}_{k-1}->M_k
+ *                           MD[k]: M_k->D_{k+1}   MI[k]: M_k->I_k   II[k]: I_k->I_k   DD[k]: D_k->D_{k+1}
+ * (this is exactly de-striping rbv/rwv/twv/rfv/tfv with k = q + z*Q + 1, p7_oprofile.c:800,856,949).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t  M, K, Kp;
+  int32_t  L;                 /* length the L-dependent scalars below are configured for */
+  int32_t  mode_multihit;     /* 1: multihit local (nj=1), 0: unihit local (nj=0)         */
+  int32_t  max_length;
+  /* MSV / SSV (uint8) */
+  const uint8_t *msv_cost;    /* [Kp][M] biased match costs (rbv de-striped); 255 = -inf  */
+  uint8_t  tbm_b, tec_b, tjb_b, base_b, bias_b;
+  float    scale_b;
+  /* ViterbiFilter (int16) */
+  const int16_t *vit_rsc;     /* [Kp][M]  */
+  const int16_t *vit_tsc;     /* [8][M]   */
+  int16_t  xw[4][2];          /* [E N J C][MOVE LOOP] */
+  int16_t  base_w, ddbound_w;
+  float    scale_w;
+  /* Forward / Backward (fp32 odds ratios) */
+  const float *fwd_rsc;       /* [Kp][M]  */
+  const float *fwd_tsc;       /* [8][M]   */
+  float    xf[4][2];
+  /* statistics, cutoffs, composition */
+  float    evparam[B2H_NEVPARAM];
+  float    cutoff[B2H_NCUTOFFS];
+  float    compo[B2H_MAXABET];
+  float    bgf[B2H_MAXABET];  /* null-model residue frequencies (P7_BG.f) */
+  const uint8_t *degen;       /* [Kp][K] alphabet degeneracy matrix (ESL_ALPHABET.degen), for the bias filter */
+} b2h_oprofile_desc;
+
+/* ---- host math that must agree bit-for-bit with the reference's libm call sites ---- */
+
+/* HMM file value decoding: out[i] = (in[i] is '*' i.e. +inf) ? 0 : expf(-in[i])   (p7_hmmfile.c:1486-1547) */
+int b2h_hmm_decode_probs(const double *neglog, float *out, size_t n);
+
+/* p7_ProfileConfig (local modes only): HMM probabilities -> log-odds generic profile.
+ *   t   [(M+1)*7]  MM MI MD IM II DM DD     mat [(M+1)*K]    bgf[K]
+ *   degen [Kp*K]   alphabet degeneracy matrix (esl_alphabet.h: degen[x][y])
+ * outputs: tsc [M*8] (nodes 0..M-1) MM IM DM BM MD DD MI II (p7p_tsc_e), msc [Kp*(M+1)] match log-odds,
+ *          xsc [4*2] E N J C x LOOP MOVE (p7p_xtransitions_e: LOOP=0, MOVE=1). */
+int b2h_profile_config(int M, int K, int Kp, const uint8_t *degen,
+                       const float *t, const float *mat, const float *bgf,
+                       int L, int multihit,
+                       float *tsc, float *msc, float *xsc);
+
+/* p7_oprofile_Convert: generic profile -> the three score systems, node-major layout.
+ * Caller allocates: msv_cost[Kp*M] vit_rsc[Kp*M] vit_tsc[8*M] fwd_rsc[Kp*M] fwd_tsc[8*M];
+ * scalars are written into *desc (the table pointers in *desc are left untouched). */
+int b2h_oprofile_convert(int M, int K, int Kp, int L, int multihit,
+                         const float *tsc, const float *msc, const float *xsc,
+                         uint8_t *msv_cost, int16_t *vit_rsc, int16_t *vit_tsc,
+                         float *fwd_rsc, float *fwd_tsc, b2h_oprofile_desc *desc);
+
+/* De-stripe a reference P7_OPROFILE's SSE tables (what a Cython binding holding a P7_OPROFILE* passes):
+ * rbv [Kp][Q16][16], rwv [Kp][Q8][8], twv [8*Q8][8] (7 interleaved per q, then DD), rfv [Kp][Q4][4], tfv likewise. */
+int b2h_destripe_oprofile(int M, int Kp,
+                          const uint8_t *rbv, const int16_t *rwv, const int16_t *twv,
+                          const float *rfv, const float *tfv,
+                          uint8_t *msv_cost, int16_t *vit_rsc, int16_t *vit_tsc,
+                          float *fwd_rsc, float *fwd_tsc);
+
+/* Length-dependent scalars for one target length, as p7_oprofile_ReconfigLength / p7_bg_SetLength
+ * compute them (p7_oprofile.c:1095-1136, p7_bg.c:189,357).  nj = 1 (multihit) or 0 (unihit). */
+typedef struct {
+  uint8_t tjb_b;          /* unbiased_byteify(logf(3/(L+3)))            */
+  int16_t xw_move;        /* wordify(logf(pmove))                       */
+  float   pmove, ploop;   /* (2+nj)/(L+2+nj), 1-pmove                   */
+  float   null1;          /* L*log(p1)+log(1-p1), p1=L/(L+1)            */
+  float   p1;
+  float   flt_len_a;      /* (float)L*logf(p1)      (bias filter tail)  */
+  float   flt_len_b;      /* logf(1.-p1)                                */
+} b2h_len_params;
+int b2h_length_params(int L, float nj, b2h_len_params *out);
+
+/* ------------------------------- device objects ------------------------------------------ */
+
+int         b2h_ctx_create(int device, b2h_ctx **out);
+void        b2h_ctx_destroy(b2h_ctx *ctx);
+/* Run all subsequent work of this context on an existing CUDA stream (cudaStream_t cast to void*);
+ * NULL restores the context's own stream. */
+int         b2h_ctx_set_stream(b2h_ctx *ctx, void *cuda_stream);
+int         b2h_ctx_synchronize(b2h_ctx *ctx);
+const char *b2h_ctx_last_error(const b2h_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t    b2h_ctx_launch_count(const b2h_ctx *ctx);
+
+/* Upload n digital sequences.  dsq[i] points at an Easel digital sequence: residues at
+ * dsq[i][1..len[i]], sentinel bytes at [0] and [len+1] (esl_sq.h:100-102), i.e. ESL_SQ.dsq / ESL_SQ.n. */
+int  b2h_seqdb_create(b2h_ctx *ctx, const uint8_t *const *dsq, const int64_t *len, size_t n, b2h_seqdb **out);
+/* Same, from one concatenated residue buffer (no sentinels) + offsets[n+1]. */
+int  b2h_seqdb_create_packed(b2h_ctx *ctx, const uint8_t *residues, const int64_t *offsets, size_t n, b2h_seqdb **out);
+void b2h_seqdb_destroy(b2h_seqdb *db);
+size_t  b2h_seqdb_nseq(const b2h_seqdb *db);
+int64_t b2h_seqdb_nres(const b2h_seqdb *db);
+
+int  b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *desc, b2h_profile **out);
+void b2h_profile_destroy(b2h_profile *p);
+
+/* ------------------------- per-stage entry points (dense outputs) ------------------------ *
+ * One profile against every sequence of the database, in database order.  sc[n] and status[n]
+ * are HOST buffers; status[i] is the Easel code the reference function would have returned
+ * for that comparison (eslOK / eslERANGE / eslENORESULT), sc[i] the value it would have stored.
+ * Each comparison is configured for its own target length first, exactly as the search loop
+ * does (p7_bg_SetLength + p7_oprofile_ReconfigLength, plan7.pyx:6431-6436).                 */
+int b2h_ssv_filter     (b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *sc, int32_t *status);
+int b2h_msv_filter     (b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *sc, int32_t *status);
+int b2h_viterbi_filter (b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *sc, int32_t *status);
+int b2h_forward_parser (b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *sc, int32_t *status);
+int b2h_backward_parser(b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *sc, int32_t *status);
+/* null1[n] = p7_bg_NullOne; filtersc[n] = p7_bg_FilterScore after p7_bg_SetFilter(M, compo) (may be NULL) */
+int b2h_null_scores    (b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *null1, float *filtersc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2H_H_INCLUDED */

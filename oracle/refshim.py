@@ -1,0 +1,167 @@
+"""ctypes wrapper over oracle/_ref/libhmmer_ref.so (the UNMODIFIED reference C library + ref_shim.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never by pyhmmer_b200/.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libhmmer_ref.so")
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libhmmer_ref.so missing: run `make -C oracle` where /root/reference exists")
+        L = ctypes.CDLL(LIB)
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        L.refm_read.restype = vp
+        L.refm_read.argtypes = [ctypes.c_char_p, ci, ci]
+        L.refm_free.argtypes = [vp]
+        for f in ("refm_M", "refm_K", "refm_Kp", "refm_abc_type", "refm_max_length", "refm_Q16", "refm_Q8", "refm_Q4"):
+            getattr(L, f).restype = ci
+            getattr(L, f).argtypes = [vp]
+        for f in ("refm_name", "refm_acc", "refm_desc"):
+            getattr(L, f).restype = ctypes.c_char_p
+            getattr(L, f).argtypes = [vp]
+        for f in ("refm_evparam", "refm_cutoff", "refm_compo", "refm_bg_f", "refm_om_ints", "refm_om_floats"):
+            getattr(L, f).argtypes = [vp, vp]
+        L.refm_hmm_params.argtypes = [vp, vp, vp, vp]
+        L.refm_gm_params.argtypes = [vp, vp, vp, vp]
+        L.refm_om_tables.argtypes = [vp] * 7
+        L.refm_set_length.argtypes = [vp, ci]
+        L.refm_set_multihit.argtypes = [vp, ci, ci]
+        for f in ("ref_ssv", "ref_msv", "ref_vit", "ref_fwd"):
+            getattr(L, f).restype = ci
+            getattr(L, f).argtypes = [vp, vp, ci, ctypes.POINTER(cf)]
+        L.ref_fwdbck.restype = ci
+        L.ref_fwdbck.argtypes = [vp, vp, ci, ctypes.POINTER(cf), ctypes.POINTER(cf), vp, vp]
+        L.ref_null1.restype = cf
+        L.ref_null1.argtypes = [vp, vp, ci]
+        L.ref_bias.restype = cf
+        L.ref_bias.argtypes = [vp, vp, ci]
+        L.ref_generic.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+        L.ref_gumbel_surv.restype = ctypes.c_double
+        L.ref_gumbel_surv.argtypes = [ctypes.c_double] * 3
+        L.ref_exp_surv.restype = ctypes.c_double
+        L.ref_exp_surv.argtypes = [ctypes.c_double] * 3
+        L.ref_nxcells.restype = ci
+        _lib = L
+    return _lib
+
+
+def dsq_of(codes):
+    """Residue codes -> Easel digital sequence with sentinels (esl_sq.h:100-102)."""
+    codes = np.asarray(codes, dtype=np.uint8)
+    d = np.full(codes.size + 2, 255, dtype=np.uint8)
+    d[1:-1] = codes
+    return d
+
+
+class RefModel:
+    """One HMM of a file, configured as Pipeline.search_hmm configures an HMM query."""
+
+    def __init__(self, path, index=0, L=400):
+        self.L = lib()
+        self.h = self.L.refm_read(os.fsencode(path), index, L)
+        if not self.h:
+            raise ValueError("cannot read HMM %d of %s" % (index, path))
+        self.M, self.K, self.Kp = self.L.refm_M(self.h), self.L.refm_K(self.h), self.L.refm_Kp(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.refm_free(self.h)
+        except Exception:
+            pass
+
+    def _vec(self, fn, n, dtype=np.float32):
+        out = np.zeros(n, dtype=dtype)
+        getattr(self.L, fn)(self.h, out.ctypes.data)
+        return out
+
+    evparam = property(lambda s: s._vec("refm_evparam", 6))
+    cutoff = property(lambda s: s._vec("refm_cutoff", 6))
+    compo = property(lambda s: s._vec("refm_compo", 20))
+    bg_f = property(lambda s: s._vec("refm_bg_f", s.K))
+    name = property(lambda s: s.L.refm_name(s.h))
+    max_length = property(lambda s: s.L.refm_max_length(s.h))
+
+    def hmm_params(self):
+        M, K = self.M, self.K
+        t = np.zeros((M + 1, 7), np.float32); mat = np.zeros((M + 1, K), np.float32); ins = np.zeros((M + 1, K), np.float32)
+        self.L.refm_hmm_params(self.h, t.ctypes.data, mat.ctypes.data, ins.ctypes.data)
+        return t, mat, ins
+
+    def gm_params(self):
+        M, Kp = self.M, self.Kp
+        tsc = np.zeros((M + 1, 8), np.float32); rsc = np.zeros((Kp, M + 1, 2), np.float32); xsc = np.zeros((4, 2), np.float32)
+        self.L.refm_gm_params(self.h, tsc.ctypes.data, rsc.ctypes.data, xsc.ctypes.data)
+        return tsc, rsc, xsc
+
+    def om_scalars(self):
+        i = self._vec("refm_om_ints", 17, np.int32)
+        f = self._vec("refm_om_floats", 12)
+        return dict(tbm_b=i[0], tec_b=i[1], tjb_b=i[2], base_b=i[3], bias_b=i[4], base_w=i[5], ddbound_w=i[6],
+                    xw=i[7:15].reshape(4, 2), L=i[15], mode=i[16],
+                    scale_b=f[0], scale_w=f[1], nj=f[3], xf=f[4:12].reshape(4, 2))
+
+    def om_tables_striped(self):
+        M, Kp = self.M, self.Kp
+        Q16, Q8, Q4 = self.L.refm_Q16(self.h), self.L.refm_Q8(self.h), self.L.refm_Q4(self.h)
+        rbv = np.zeros((Kp, Q16, 16), np.uint8)
+        rwv = np.zeros((Kp, Q8, 8), np.int16); twv = np.zeros((8 * Q8, 8), np.int16)
+        rfv = np.zeros((Kp, Q4, 4), np.float32); tfv = np.zeros((8 * Q4, 4), np.float32)
+        self.L.refm_om_tables(self.h, rbv.ctypes.data, None, rwv.ctypes.data, twv.ctypes.data, rfv.ctypes.data, tfv.ctypes.data)
+        return rbv, rwv, twv, rfv, tfv
+
+    def om_tables(self):
+        """De-striped (node-major) tables: k = q + z*Q + 1 (p7_oprofile.c:800,856,949)."""
+        M, Kp = self.M, self.Kp
+        rbv, rwv, twv, rfv, tfv = self.om_tables_striped()
+
+        def destripe(v):            # (Q, W) -> [k-1] for k = q + z*Q + 1
+            return v.T.reshape(-1)[:M]
+
+        msv = np.stack([destripe(rbv[x]) for x in range(Kp)])
+        vr = np.stack([destripe(rwv[x]) for x in range(Kp)])
+        fr = np.stack([destripe(rfv[x]) for x in range(Kp)])
+        Q8, Q4 = rwv.shape[1], rfv.shape[1]
+        vt = np.stack([destripe(twv[t:7 * Q8:7]) for t in range(7)] + [destripe(twv[7 * Q8:])])
+        ft = np.stack([destripe(tfv[t:7 * Q4:7]) for t in range(7)] + [destripe(tfv[7 * Q4:])])
+        return msv, vr, vt, fr, ft
+
+    def _score(self, fn, codes):
+        d = dsq_of(codes)
+        sc = ctypes.c_float()
+        st = getattr(self.L, fn)(self.h, d.ctypes.data, d.size - 2, ctypes.byref(sc))
+        return sc.value, st
+
+    def ssv(self, codes): return self._score("ref_ssv", codes)
+    def msv(self, codes): return self._score("ref_msv", codes)
+    def vit(self, codes): return self._score("ref_vit", codes)
+    def fwd(self, codes): return self._score("ref_fwd", codes)
+
+    def fwdbck(self, codes, want_x=False):
+        d = dsq_of(codes); n = d.size - 2
+        f, b = ctypes.c_float(), ctypes.c_float()
+        nx = self.L.ref_nxcells()
+        fx = np.zeros((n + 1, nx), np.float32); bx = np.zeros((n + 1, nx), np.float32)
+        st = self.L.ref_fwdbck(self.h, d.ctypes.data, n, ctypes.byref(f), ctypes.byref(b), fx.ctypes.data, bx.ctypes.data)
+        return (f.value, b.value, st, fx, bx) if want_x else (f.value, b.value, st)
+
+    def null1(self, codes):
+        d = dsq_of(codes); return self.L.ref_null1(self.h, d.ctypes.data, d.size - 2)
+
+    def bias(self, codes):
+        d = dsq_of(codes); return self.L.ref_bias(self.h, d.ctypes.data, d.size - 2)

@@ -1,0 +1,159 @@
+"""ctypes binding of ``libb2h.so`` (the C ABI declared in ``include/b2h.h``).
+
+There is deliberately no fallback: if the CUDA library has not been built this module raises,
+and if no CUDA device is present :func:`context` raises -- nothing in this package computes a
+score on the CPU.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2h.so")
+
+B2H_OK, B2H_EMEM, B2H_EINVAL, B2H_ERANGE, B2H_ENORESULT, B2H_ECUDA = 0, 5, 11, 16, 19, 100
+
+c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+c_u8, c_i16, c_i32, c_i64, c_u64 = ctypes.c_uint8, ctypes.c_int16, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
+P = ctypes.POINTER
+
+
+class OProfileDesc(ctypes.Structure):
+    """``b2h_oprofile_desc`` (include/b2h.h)."""
+    _fields_ = [
+        ("M", c_i32), ("K", c_i32), ("Kp", c_i32), ("L", c_i32), ("mode_multihit", c_i32), ("max_length", c_i32),
+        ("msv_cost", c_void_p),
+        ("tbm_b", c_u8), ("tec_b", c_u8), ("tjb_b", c_u8), ("base_b", c_u8), ("bias_b", c_u8),
+        ("scale_b", c_float),
+        ("vit_rsc", c_void_p), ("vit_tsc", c_void_p),
+        ("xw", (c_i16 * 2) * 4), ("base_w", c_i16), ("ddbound_w", c_i16), ("scale_w", c_float),
+        ("fwd_rsc", c_void_p), ("fwd_tsc", c_void_p),
+        ("xf", (c_float * 2) * 4),
+        ("evparam", c_float * 6), ("cutoff", c_float * 6), ("compo", c_float * 20), ("bgf", c_float * 20),
+        ("degen", c_void_p),
+    ]
+
+
+class LenParams(ctypes.Structure):
+    """``b2h_len_params`` (include/b2h.h)."""
+    _fields_ = [("tjb_b", c_u8), ("xw_move", c_i16), ("pmove", c_float), ("ploop", c_float),
+                ("null1", c_float), ("p1", c_float), ("flt_len_a", c_float), ("flt_len_b", c_float)]
+
+
+class B2HError(RuntimeError):
+    def __init__(self, status, fn, detail=""):
+        self.status = status
+        super().__init__("%s failed with status %d%s" % (fn, status, (": " + detail) if detail else ""))
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "pyhmmer_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+
+    def sig(name, restype, *argtypes):
+        f = getattr(lib, name)
+        f.restype = restype
+        f.argtypes = list(argtypes)
+        return f
+
+    sig("b2h_hmm_decode_probs", c_int, c_void_p, c_void_p, c_size_t)
+    sig("b2h_profile_config", c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+        c_int, c_int, c_void_p, c_void_p, c_void_p)
+    sig("b2h_oprofile_convert", c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(OProfileDesc))
+    sig("b2h_destripe_oprofile", c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
+    sig("b2h_length_params", c_int, c_int, c_float, P(LenParams))
+    sig("b2h_ctx_create", c_int, c_int, P(c_void_p))
+    sig("b2h_ctx_destroy", None, c_void_p)
+    sig("b2h_ctx_set_stream", c_int, c_void_p, c_void_p)
+    sig("b2h_ctx_synchronize", c_int, c_void_p)
+    sig("b2h_ctx_last_error", ctypes.c_char_p, c_void_p)
+    sig("b2h_ctx_launch_count", c_u64, c_void_p)
+    sig("b2h_seqdb_create", c_int, c_void_p, c_void_p, c_void_p, c_size_t, P(c_void_p))
+    sig("b2h_seqdb_create_packed", c_int, c_void_p, c_void_p, c_void_p, c_size_t, P(c_void_p))
+    sig("b2h_seqdb_destroy", None, c_void_p)
+    sig("b2h_seqdb_nseq", c_size_t, c_void_p)
+    sig("b2h_seqdb_nres", c_i64, c_void_p)
+    sig("b2h_profile_upload", c_int, c_void_p, P(OProfileDesc), P(c_void_p))
+    sig("b2h_profile_destroy", None, c_void_p)
+    for name in ("b2h_ssv_filter", "b2h_msv_filter", "b2h_viterbi_filter", "b2h_forward_parser",
+                 "b2h_backward_parser"):
+        if hasattr(lib, name):
+            sig(name, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
+    if hasattr(lib, "b2h_null_scores"):
+        sig("b2h_null_scores", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
+    return lib
+
+
+lib = _load()
+
+
+def ptr(a):
+    """Raw data pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def check(status, fn, ctx=None):
+    if status != B2H_OK:
+        detail = ""
+        if ctx is not None:
+            detail = (lib.b2h_ctx_last_error(ctx) or b"").decode()
+        raise B2HError(status, fn, detail)
+
+
+class Context:
+    """One ``b2h_ctx`` = one GPU of this process."""
+
+    def __init__(self, device=0):
+        h = c_void_p()
+        st = lib.b2h_ctx_create(device, ctypes.byref(h))
+        if st != B2H_OK:
+            raise B2HError(st, "b2h_ctx_create",
+                           "no usable CUDA device %d (sm_100a required; this package has no CPU path)" % device)
+        self.handle = h
+        self.device = device
+
+    def set_stream(self, cuda_stream):
+        check(lib.b2h_ctx_set_stream(self.handle, c_void_p(cuda_stream or 0)), "b2h_ctx_set_stream", self.handle)
+
+    def synchronize(self):
+        check(lib.b2h_ctx_synchronize(self.handle), "b2h_ctx_synchronize", self.handle)
+
+    @property
+    def launch_count(self):
+        return int(lib.b2h_ctx_launch_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            lib.b2h_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_contexts = {}
+_lock = threading.Lock()
+
+
+def context(device=None):
+    """The process-wide :class:`Context` for ``device`` (default: ``LOCAL_RANK`` or 0)."""
+    if device is None:
+        device = int(os.environ.get("B2H_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _lock:
+        ctx = _contexts.get(device)
+        if ctx is None:
+            ctx = _contexts[device] = Context(device)
+        return ctx

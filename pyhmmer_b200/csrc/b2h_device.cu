@@ -1,0 +1,273 @@
+// b2h_device.cu -- context, sequence arena and profile upload for libb2h.so.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include "b2h_internal.h"
+
+extern "C" {
+
+int b2h_ctx_create(int device, b2h_ctx **out)
+{
+  if (!out) return B2H_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+    return B2H_ECUDA;                       // no CPU fallback, by design
+  b2h_ctx *ctx = new b2h_ctx();
+  ctx->device = device;
+  B2H_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B2H_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { delete ctx; return B2H_ECUDA; }   // sm_100a cubins only
+  ctx->sm_count = prop.multiProcessorCount;
+  B2H_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  B2H_CUDA(cudaMalloc(&ctx->d_counters, 64 * sizeof(int)));
+  *out = ctx;
+  return B2H_OK;
+}
+
+void b2h_ctx_destroy(b2h_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int b2h_ctx_set_stream(b2h_ctx *ctx, void *s)
+{
+  if (!ctx) return B2H_EINVAL;
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return B2H_OK;
+}
+
+int b2h_ctx_synchronize(b2h_ctx *ctx)
+{
+  if (!ctx) return B2H_EINVAL;
+  B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+  return B2H_OK;
+}
+
+const char *b2h_ctx_last_error(const b2h_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t    b2h_ctx_launch_count(const b2h_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------
+// sequence arena
+// ------------------------------------------------------------------------------------------
+static int seqdb_finish(b2h_ctx *ctx, b2h_seqdb *db, const std::vector<uint8_t> &arena)
+{
+  const size_t n = db->n;
+  std::vector<int32_t> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return db->h_len[a] > db->h_len[b]; });
+
+  std::vector<uint8_t> tjb(n); std::vector<int16_t> xwm(n);
+  std::vector<float> pmove(n), null1(n), p1(n), flta(n), fltb(n);
+  // L-dependent scalars depend on L only: memoise (databases have few distinct lengths)
+  std::vector<int> cacheL; std::vector<b2h_len_params> cacheP;
+  {
+    std::vector<int32_t> lens(db->h_len);
+    std::sort(lens.begin(), lens.end());
+    lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
+    cacheL.assign(lens.begin(), lens.end());
+    cacheP.resize(cacheL.size());
+    for (size_t i = 0; i < cacheL.size(); i++) b2h_length_params(cacheL[i], 1.0f, &cacheP[i]);
+  }
+  for (size_t s = 0; s < n; s++) {
+    size_t i = std::lower_bound(cacheL.begin(), cacheL.end(), db->h_len[s]) - cacheL.begin();
+    const b2h_len_params &q = cacheP[i];
+    tjb[s] = q.tjb_b; xwm[s] = q.xw_move; pmove[s] = q.pmove; null1[s] = q.null1; p1[s] = q.p1;
+    flta[s] = q.flt_len_a; fltb[s] = q.flt_len_b;
+  }
+  db->arena_bytes = arena.size();
+  B2H_CUDA(cudaSetDevice(ctx->device));
+  B2H_CUDA(cudaMalloc(&db->d_res, std::max<size_t>(arena.size(), 16)));
+  B2H_CUDA(cudaMalloc(&db->d_off, (n + 1) * sizeof(int64_t)));
+  B2H_CUDA(cudaMalloc(&db->d_len, std::max<size_t>(n, 1) * sizeof(int32_t)));
+  B2H_CUDA(cudaMalloc(&db->d_order, std::max<size_t>(n, 1) * sizeof(int32_t)));
+  B2H_CUDA(cudaMalloc(&db->d_tjb, std::max<size_t>(n, 1)));
+  B2H_CUDA(cudaMalloc(&db->d_xwmove, std::max<size_t>(n, 1) * sizeof(int16_t)));
+  B2H_CUDA(cudaMalloc(&db->d_pmove, std::max<size_t>(n, 1) * sizeof(float)));
+  B2H_CUDA(cudaMalloc(&db->d_null1, std::max<size_t>(n, 1) * sizeof(float)));
+  B2H_CUDA(cudaMalloc(&db->d_p1, std::max<size_t>(n, 1) * sizeof(float)));
+  B2H_CUDA(cudaMalloc(&db->d_flta, std::max<size_t>(n, 1) * sizeof(float)));
+  B2H_CUDA(cudaMalloc(&db->d_fltb, std::max<size_t>(n, 1) * sizeof(float)));
+  cudaStream_t st = ctx->stream;
+  if (!arena.empty()) B2H_CUDA(cudaMemcpyAsync(db->d_res, arena.data(), arena.size(), cudaMemcpyHostToDevice, st));
+  B2H_CUDA(cudaMemcpyAsync(db->d_off, db->h_off.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (n) {
+    B2H_CUDA(cudaMemcpyAsync(db->d_len, db->h_len.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    B2H_CUDA(cudaMemcpyAsync(db->d_order, order.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    B2H_CUDA(cudaMemcpyAsync(db->d_tjb, tjb.data(), n, cudaMemcpyHostToDevice, st));
+    B2H_CUDA(cudaMemcpyAsync(db->d_xwmove, xwm.data(), n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    B2H_CUDA(cudaMemcpyAsync(db->d_pmove, pmove.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+    B2H_CUDA(cudaMemcpyAsync(db->d_null1, null1.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+    B2H_CUDA(cudaMemcpyAsync(db->d_p1, p1.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+    B2H_CUDA(cudaMemcpyAsync(db->d_flta, flta.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+    B2H_CUDA(cudaMemcpyAsync(db->d_fltb, fltb.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  B2H_CUDA(cudaStreamSynchronize(st));     // host staging vectors die here
+  return B2H_OK;
+}
+
+static int seqdb_build(b2h_ctx *ctx, size_t n, const int64_t *len,
+                       const uint8_t *const *dsq, const uint8_t *packed, const int64_t *poff, b2h_seqdb **out)
+{
+  if (!ctx || !out || (n && !len && !poff)) return B2H_EINVAL;
+  *out = nullptr;
+  b2h_seqdb *db = new b2h_seqdb();
+  db->ctx = ctx; db->n = n;
+  db->h_len.resize(n); db->h_off.resize(n + 1);
+  size_t total = 0;
+  for (size_t s = 0; s < n; s++) {
+    int64_t L = poff ? poff[s+1] - poff[s] : len[s];
+    if (L < 0 || L > 100000000) { delete db; return B2H_EINVAL; }
+    db->h_len[s] = (int32_t)L; db->h_off[s] = (int64_t)total;
+    db->nres += L; db->maxL = std::max(db->maxL, (int)L);
+    total += ((size_t)L + 15) & ~(size_t)15;
+    if (L % 16 == 0) total += 16;           // always at least one pad byte after the last residue
+  }
+  db->h_off[n] = (int64_t)total;
+  std::vector<uint8_t> arena(total, (uint8_t)B2H_PAD_CODE);
+  for (size_t s = 0; s < n; s++) {
+    const uint8_t *src = poff ? packed + poff[s] : dsq[s] + 1;      // Easel dsq is 1-based
+    uint8_t *dst = arena.data() + db->h_off[s];
+    for (int32_t i = 0; i < db->h_len[s]; i++) dst[i] = src[i] < B2H_NCODE ? src[i] : (uint8_t)B2H_PAD_CODE;
+  }
+  int st = seqdb_finish(ctx, db, arena);
+  if (st != B2H_OK) { b2h_seqdb_destroy(db); return st; }
+  *out = db;
+  return B2H_OK;
+}
+
+int b2h_seqdb_create(b2h_ctx *ctx, const uint8_t *const *dsq, const int64_t *len, size_t n, b2h_seqdb **out)
+{ return seqdb_build(ctx, n, len, dsq, nullptr, nullptr, out); }
+
+int b2h_seqdb_create_packed(b2h_ctx *ctx, const uint8_t *residues, const int64_t *offsets, size_t n, b2h_seqdb **out)
+{ return seqdb_build(ctx, n, nullptr, nullptr, residues, offsets, out); }
+
+void b2h_seqdb_destroy(b2h_seqdb *db)
+{
+  if (!db) return;
+  if (db->ctx) cudaSetDevice(db->ctx->device);
+  void *ptrs[] = { db->d_res, db->d_off, db->d_len, db->d_order, db->d_tjb, db->d_xwmove, db->d_pmove,
+                   db->d_null1, db->d_p1, db->d_flta, db->d_fltb };
+  for (void *p : ptrs) if (p) cudaFree(p);
+  delete db;
+}
+size_t  b2h_seqdb_nseq(const b2h_seqdb *db) { return db ? db->n : 0; }
+int64_t b2h_seqdb_nres(const b2h_seqdb *db) { return db ? db->nres : 0; }
+
+// ------------------------------------------------------------------------------------------
+// profile upload
+// ------------------------------------------------------------------------------------------
+// Lane-striped 16-bit table for the SSV/MSV kernels: word (x, j, lane) packs the values of the two
+// cells (lane, c=j) and (lane, c=j+NR); cell (lane,c) is model node k = lane*2*NR + c + 1.
+// Words are ordered [x][j/4][lane][j%4] for the full groups of four registers (one LDS.128 per
+// lane, conflict-free), followed by the NR%4 leftover registers as [x][lane][j%4 .. ].
+static size_t striped_word_index(int NR, int x, int j, int lane)
+{
+  const int full = NR / 4, rem = NR % 4;
+  size_t base = (size_t)x * NR * 32;
+  if (j < full * 4) return base + ((size_t)(j / 4) * 32 + lane) * 4 + (j % 4);
+  return base + (size_t)full * 128 + (size_t)lane * rem + (j - full * 4);
+}
+
+int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **out)
+{
+  if (!ctx || !d || !out || d->M < 1 || d->Kp > B2H_NCODE - 1 || d->K > B2H_MAXABET) return B2H_EINVAL;
+  *out = nullptr;
+  const int M = d->M, Kp = d->Kp;
+  const int NR = b2h_nr_for_M(M);
+  if (NR < 0) { ctx->err = "model too long for the register-tiled MSV kernel (M > 3071)"; return B2H_EINVAL; }
+  b2h_profile *p = new b2h_profile();
+  p->ctx = ctx; p->M = M; p->K = d->K; p->Kp = Kp; p->max_length = d->max_length; p->multihit = d->mode_multihit;
+  p->NR = NR; p->tbm_b = d->tbm_b; p->tec_b = d->tec_b; p->base_b = d->base_b; p->bias_b = d->bias_b; p->scale_b = d->scale_b;
+  memcpy(p->xw, d->xw, sizeof p->xw); p->base_w = d->base_w; p->ddbound_w = d->ddbound_w; p->scale_w = d->scale_w;
+  memcpy(p->xf, d->xf, sizeof p->xf);
+  memcpy(p->evparam, d->evparam, sizeof p->evparam); memcpy(p->cutoff, d->cutoff, sizeof p->cutoff);
+  memcpy(p->compo, d->compo, sizeof p->compo); memcpy(p->bgf, d->bgf, sizeof p->bgf);
+  p->Mpad = (M + 31) & ~31;
+
+  // --- SSV signed scores / MSV costs, lane-striped ---
+  const size_t nwords = (size_t)B2H_NCODE * NR * 32;
+  std::vector<uint32_t> ssv(nwords), msv(nwords);
+  auto cost_of = [&](int x, int k) -> int {          // k is 1-based; anything off the model is the -inf cost
+    return (x < Kp && k <= M) ? (int)d->msv_cost[(size_t)x * M + (k-1)] : 255;
+  };
+  for (int x = 0; x < B2H_NCODE; x++)
+    for (int lane = 0; lane < 32; lane++)
+      for (int j = 0; j < NR; j++) {
+        int klo = lane * 2 * NR + j + 1, khi = klo + NR;
+        int clo = cost_of(x, klo), chi = cost_of(x, khi);
+        // SSV subtracts sbv = clamp(cost - bias, .., 127) as a signed byte (p7_oprofile.c:721-761): add its negation
+        int slo = -std::min(clo - (int)d->bias_b, 127), shi = -std::min(chi - (int)d->bias_b, 127);
+        size_t w = striped_word_index(NR, x, j, lane);
+        ssv[w] = ((uint32_t)(uint16_t)(int16_t)shi << 16) | (uint32_t)(uint16_t)(int16_t)slo;
+        msv[w] = ((uint32_t)chi << 16) | (uint32_t)clo;
+      }
+
+  // --- Viterbi / Forward tables, padded ---
+  const int Mp = p->Mpad;
+  std::vector<int16_t> vr((size_t)B2H_NCODE * Mp, (int16_t)-32768), vt((size_t)8 * Mp, (int16_t)-32768);
+  std::vector<float>   fr((size_t)B2H_NCODE * Mp, 0.0f),            ft((size_t)8 * Mp, 0.0f);
+  for (int x = 0; x < Kp; x++)
+    for (int k = 0; k < M; k++) {
+      vr[(size_t)x * Mp + k] = d->vit_rsc[(size_t)x * M + k];
+      fr[(size_t)x * Mp + k] = d->fwd_rsc[(size_t)x * M + k];
+    }
+  for (int t = 0; t < 8; t++)
+    for (int k = 0; k < M; k++) {
+      vt[(size_t)t * Mp + k] = d->vit_tsc[(size_t)t * M + k];
+      ft[(size_t)t * Mp + k] = d->fwd_tsc[(size_t)t * M + k];
+    }
+
+  // --- bias-filter 2-state HMM (p7_bg_SetFilter p7_bg.c:429, esl_hmm_Configure esl_hmm.c:118) ---
+  std::vector<float> eo((size_t)B2H_NCODE * 2, 1.0f);
+  {
+    const int K = d->K;
+    for (int x = 0; x < K; x++) { eo[x*2+0] = d->bgf[x] / d->bgf[x]; eo[x*2+1] = d->compo[x] / d->bgf[x]; }
+    for (int x = K + 1; x <= Kp - 3; x++)
+      for (int s = 0; s < 2; s++) {
+        float num = 0.0f, denom = 0.0f;
+        for (int y = 0; y < K; y++)
+          if (d->degen && d->degen[(size_t)x * K + y]) { num += (s == 0 ? d->bgf[y] : d->compo[y]); denom += d->bgf[y]; }
+        eo[x*2+s] = (denom > 0.0f) ? num / denom : 0.0f;
+      }
+    float L1 = (float)((double)(float)M / 8.0);
+    p->bias_t10 = 1.0f / (L1 + 1.0f);
+    p->bias_t11 = L1 / (L1 + 1.0f);
+  }
+
+  int st = B2H_OK;
+  do {
+    cudaError_t e;
+#define UP(dst, vec, T) \
+    if ((e = cudaMalloc(&dst, vec.size() * sizeof(T))) != cudaSuccess || \
+        (e = cudaMemcpyAsync(dst, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) \
+      { ctx->err = cudaGetErrorString(e); st = B2H_ECUDA; break; }
+    cudaSetDevice(ctx->device);
+    UP(p->d_ssv_emis, ssv, uint32_t); UP(p->d_msv_cost, msv, uint32_t);
+    UP(p->d_vit_rsc, vr, int16_t);    UP(p->d_vit_tsc, vt, int16_t);
+    UP(p->d_fwd_rsc, fr, float);      UP(p->d_fwd_tsc, ft, float);
+    UP(p->d_bias_eo, eo, float);
+#undef UP
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); st = B2H_ECUDA; }
+  } while (0);
+  if (st != B2H_OK) { b2h_profile_destroy(p); return st; }
+  *out = p;
+  return B2H_OK;
+}
+
+void b2h_profile_destroy(b2h_profile *p)
+{
+  if (!p) return;
+  if (p->ctx) cudaSetDevice(p->ctx->device);
+  void *ptrs[] = { p->d_ssv_emis, p->d_msv_cost, p->d_vit_rsc, p->d_vit_tsc, p->d_fwd_rsc, p->d_fwd_tsc, p->d_bias_eo };
+  for (void *q : ptrs) if (q) cudaFree(q);
+  delete p;
+}
+
+} // extern "C"

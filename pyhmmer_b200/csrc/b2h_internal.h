@@ -1,0 +1,103 @@
+// b2h_internal.h -- shared declarations for libb2h.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "b2h.h"
+
+// ---------------------------------------------------------------------------------------------
+// Data layout in HBM
+//
+//  sequence arena   one uint8 buffer; sequence s occupies res[off[s] .. off[s]+len[s]) with
+//                   off[s] % 16 == 0 and the tail up to the next multiple of 16 filled with
+//                   B2H_PAD_CODE, so kernels may read whole 4/16-byte words.  Per-sequence
+//                   side arrays (len, L-dependent scalars) are SoA.  `order[]` lists sequence
+//                   indices by decreasing length: persistent CTAs pull work in that order so
+//                   the longest comparisons start first.
+//  profile tables   node-major (k-1 indexed) copies of the three score systems, plus a
+//                   pre-swizzled 16-bit "lane-striped" emission table per integer filter laid
+//                   out exactly as the kernels' LDS.128 reads want it (see b2h_msv.cu).
+// ---------------------------------------------------------------------------------------------
+
+#define B2H_PAD_CODE   31     // residue code used for arena padding; tables have 32 residue rows
+#define B2H_NCODE      32
+#define B2H_MAX_NR     48     // SSV/MSV register tiles: 64*NR cells per warp => M <= 3071
+
+struct b2h_ctx {
+  int           device = 0;
+  int           sm_count = 0;
+  cudaStream_t  own_stream = nullptr;
+  cudaStream_t  stream = nullptr;
+  std::string   err;
+  uint64_t      launches = 0;
+  int          *d_counters = nullptr;   // small pool of work counters
+};
+
+struct b2h_seqdb {
+  b2h_ctx  *ctx = nullptr;
+  size_t    n = 0;
+  int64_t   nres = 0;
+  int       maxL = 0;
+  size_t    arena_bytes = 0;
+  std::vector<int32_t> h_len;
+  std::vector<int64_t> h_off;
+  uint8_t  *d_res = nullptr;
+  int64_t  *d_off = nullptr;
+  int32_t  *d_len = nullptr;
+  int32_t  *d_order = nullptr;
+  // L-dependent scalars, multihit (nj=1) configuration -- what the search loop uses
+  uint8_t  *d_tjb = nullptr;
+  int16_t  *d_xwmove = nullptr;
+  float    *d_pmove = nullptr;     // ploop = 1 - pmove is recomputed (same float op)
+  float    *d_null1 = nullptr;
+  float    *d_p1 = nullptr;
+  float    *d_flta = nullptr, *d_fltb = nullptr;
+};
+
+struct b2h_profile {
+  b2h_ctx *ctx = nullptr;
+  int M = 0, K = 0, Kp = 0, max_length = 0, multihit = 1;
+  // MSV
+  int NR = 0;                     // 32-bit cell registers per lane in the SSV/MSV kernels
+  uint8_t tbm_b = 0, tec_b = 0, base_b = 0, bias_b = 0;
+  float scale_b = 0;
+  uint32_t *d_ssv_emis = nullptr; // [32][NR][32 lanes] packed s16x2 signed scores (SSV)
+  uint32_t *d_msv_cost = nullptr; // same layout, packed u8 costs widened to 16 bit (full MSV)
+  // Viterbi
+  int16_t *d_vit_rsc = nullptr;   // [32][Mpad]
+  int16_t *d_vit_tsc = nullptr;   // [8][Mpad]
+  int16_t xw[4][2] = {{0}};
+  int16_t base_w = 0, ddbound_w = 0;
+  float scale_w = 0;
+  // Forward/Backward
+  float *d_fwd_rsc = nullptr;     // [32][Mpad]
+  float *d_fwd_tsc = nullptr;     // [8][Mpad]
+  float xf[4][2] = {{0}};
+  int Mpad = 0;                   // M rounded up to a multiple of 32
+  float evparam[B2H_NEVPARAM];
+  float cutoff[B2H_NCUTOFFS];
+  float compo[B2H_MAXABET];
+  float bgf[B2H_MAXABET];
+  float *d_bias_eo = nullptr;     // [32][2] bias-filter emission odds (esl_hmm_Configure)
+  float bias_t10 = 0, bias_t11 = 0;   // fhmm->t[1][0], t[1][1]
+};
+
+#define B2H_CUDA(call)                                                                   \
+  do { cudaError_t e_ = (call);                                                          \
+       if (e_ != cudaSuccess) {                                                          \
+         if (ctx) { char b_[256]; snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); ctx->err = b_; } \
+         return B2H_ECUDA; } } while (0)
+
+static inline int b2h_nr_for_M(int M) {
+  // need 64*NR >= M+1 so that the last cell of lane 31 is always padding (see b2h_msv.cu)
+  int nr = (M + 1 + 63) / 64;
+  static const int allowed[] = {1,2,3,4,5,6,8,10,12,16,20,24,32,40,48};
+  for (int a : allowed) if (a >= nr) return a;
+  return -1;
+}
+
+// kernel launchers (b2h_msv.cu)
+int b2h_launch_ssv_dense(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, int with_msv_fallback,
+                         float *d_sc, int32_t *d_status);
