@@ -101,3 +101,59 @@ static inline int b2h_nr_for_M(int M) {
 // kernel launchers (b2h_msv.cu)
 int b2h_launch_ssv_dense(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, int with_msv_fallback,
                          float *d_sc, int32_t *d_status);
+
+// ---------------------------------------------------------------------------------------------
+// Device-side views (passed to kernels by value or through small device arrays)
+// ---------------------------------------------------------------------------------------------
+struct SeqDev {
+  const uint8_t *res; const int64_t *off; const int32_t *len;
+  const uint8_t *tjb; const int16_t *xwmove; const float *pmove, *null1, *p1, *flta, *fltb;
+  const int32_t *order; int n;
+};
+static inline SeqDev b2h_seqdev(const b2h_seqdb *db) {
+  SeqDev s; s.res = db->d_res; s.off = db->d_off; s.len = db->d_len; s.tjb = db->d_tjb; s.xwmove = db->d_xwmove;
+  s.pmove = db->d_pmove; s.null1 = db->d_null1; s.p1 = db->d_p1; s.flta = db->d_flta; s.fltb = db->d_fltb;
+  s.order = db->d_order; s.n = (int)db->n; return s;
+}
+
+struct ProfDev {
+  const uint32_t *ssv_emis, *msv_cost;
+  const int16_t *vit_rsc, *vit_tsc;
+  const float *fwd_rsc, *fwd_tsc, *bias_eo;
+  int M, Mpad, NR;
+  int tbm, tec, base, bias; float scale_b;
+  int xw_E_move, xw_E_loop, base_w, ddbound_w; float scale_w;
+  float xf_E_move, xf_E_loop;
+  float evparam[B2H_NEVPARAM];
+  float bias_t10, bias_t11;
+};
+static inline ProfDev b2h_profdev(const b2h_profile *p) {
+  ProfDev d; d.ssv_emis = p->d_ssv_emis; d.msv_cost = p->d_msv_cost; d.vit_rsc = p->d_vit_rsc; d.vit_tsc = p->d_vit_tsc;
+  d.fwd_rsc = p->d_fwd_rsc; d.fwd_tsc = p->d_fwd_tsc; d.bias_eo = p->d_bias_eo;
+  d.M = p->M; d.Mpad = p->Mpad; d.NR = p->NR; d.tbm = p->tbm_b; d.tec = p->tec_b; d.base = p->base_b; d.bias = p->bias_b; d.scale_b = p->scale_b;
+  d.xw_E_move = p->xw[0][0]; d.xw_E_loop = p->xw[0][1]; d.base_w = p->base_w; d.ddbound_w = p->ddbound_w; d.scale_w = p->scale_w;
+  d.xf_E_move = p->xf[0][0]; d.xf_E_loop = p->xf[0][1];
+  for (int i = 0; i < B2H_NEVPARAM; i++) d.evparam[i] = p->evparam[i];
+  d.bias_t10 = p->bias_t10; d.bias_t11 = p->bias_t11; return d;
+}
+
+// A stage's work: comparisons (entries) grouped by profile.  Entry e of profile p lives at
+// ent_s[poff[p] .. poff[p+1]); CTAs pull "items" = chunks of B2H_ITEM_ENTRIES consecutive entries of
+// one profile from *counter; itemoff[p] is the first item id of profile p, itemoff[P] the item count.
+#define B2H_ITEM_ENTRIES 16
+struct WorkList {
+  const ProfDev *profs;      // [P]
+  const int32_t *ent_s;      // sequence index of each entry
+  const int32_t *poff;       // [P+1]
+  const int32_t *itemoff;    // [P+1]
+  int            P;
+  int           *counter;
+};
+
+// per-entry outputs of a DP stage
+struct StageOut { float *sc; int32_t *status; float *fwd_xmx, *bck_xmx; const int64_t *xoff; };
+
+int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out);
+int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out);
+int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out);
+int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc);

@@ -21,6 +21,7 @@ SOURCES = [
     "b2h_device.cu",
     "b2h_api.cu",
     "b2h_msv.cu",
+    "b2h_dp.cu",
 ]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
