@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- hmmsearch GCUPS / sequences-per-second on B200 (BASELINE.json's metric and configs[1]).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                       # this repo's CUDA engine
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1       # the reference's CPU pipeline, all host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU, target DB sharded
+
+Workload (N=1): 100 Pfam-like synthetic profile HMMs (M ~ lognormal, mean ~200, [30,800]) calibrated on the
+GPU, against 50 000 synthetic proteins (iid background residues, L ~ N(350,100) in [50,1500]); 1 % of the
+targets carry a domain emitted from one of the profiles so that the survivor tail (Forward/Backward, domain
+definition, alignment) is exercised.  With N GPUs every rank gets its own 50 000-sequence shard of a
+N x 50 000 database (weak scaling, target-sharded as the reference's parallel="targets" mode).
+
+A "step" is one complete hmmsearch of the 100 queries against the database: the whole p7_Pipeline cascade
+(SSV/MSV, bias, Viterbi, Forward, Backward, domain definition, hit assembly).  Nothing is skipped.
+`value` is measured with the database and the profiles already resident in HBM; `e2e` repeats the step
+through the public Python API with host buffers (packing, H2D upload of sequences and profile tables, D2H
+of the results all inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PROFILES = 100
+N_SEQS = 50000
+PLANT_FRAC = 0.01
+
+
+def build_inputs(rank, world, n_profiles=N_PROFILES, n_seqs=N_SEQS):
+    """Seeded synthetic inputs.  Profiles are identical on every rank; each rank gets its own target shard."""
+    from pyhmmer_b200 import easel, synth
+    abc = easel.Alphabet.amino()
+    prng = np.random.default_rng(20240901)
+    Ms = np.clip(np.rint(np.exp(prng.normal(np.log(180.0), 0.55, n_profiles))), 30, 800).astype(int)
+    hmms = [synth.random_hmm(abc, int(M), prng, name="synPF%05d" % i) for i, M in enumerate(Ms)]
+    srng = np.random.default_rng(777 + rank)
+    seqs = synth.random_sequences(abc, n_seqs, srng, prefix="r%d_" % rank)
+    nplant = int(n_seqs * PLANT_FRAC)
+    where = srng.choice(n_seqs, nplant, replace=False)
+    for j, t in enumerate(where):
+        dom = synth.emit_sequence(hmms[j % n_profiles], srng)
+        s = seqs[int(t)]
+        cut = int(srng.integers(0, len(s) + 1))
+        s.sequence = np.concatenate([s.sequence[:cut], dom, s.sequence[cut:]])[:1500]
+    seqs._cache = {}
+    return abc, hmms, seqs
+
+
+STATS_FILE = os.path.join(ROOT, "tests", "golden", "bench_stats.json")
+
+
+def apply_stats(hmms):
+    """Committed E-value statistics of the seeded synthetic profiles (fitted once on a B200 by synth.calibrate and
+    kept under tests/golden/ so that this arm and `--impl reference` score identical models in any order)."""
+    try:
+        st = json.load(open(STATS_FILE))
+    except Exception:
+        return False
+    if len(st.get("evparam", [])) < len(hmms):
+        return False
+    for h, ev in zip(hmms, st["evparam"]):
+        h._evparam[:] = np.array(ev, dtype=np.float32)
+    return True
+
+
+def write_hmm_file(hmms, path):
+    with open(path, "wb") as f:
+        for h in hmms:
+            h.write(f)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def reference_arm(args, rank, world_size):
+    """The reference's own CPU implementation of the path (oracle/_ref = HMMER 3.4 compiled from the reference's
+    sources), all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import refshim
+    import psutil
+    abc, hmms, seqs = build_inputs(0, 1)
+    from pyhmmer_b200 import synth
+    calibrated = apply_stats(hmms)
+    cores = psutil.cpu_count(logical=True) or os.cpu_count() or 1
+    ncore = max(1, min(cores, 64))
+    sample_p, sample_s = args.ref_profiles, args.ref_seqs
+    sub = seqs[:sample_s]
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "q.hmm")
+        write_hmm_file(hmms[:sample_p], path)
+        models = [refshim.RefModel(path, i, 400) for i in range(sample_p)]
+        codes = [s.sequence for s in sub]
+        cells = float(sum(h.M for h in hmms[:sample_p])) * float(sum(len(s) for s in sub))
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            nh, ctr = refshim.search_mt(models, codes, ncore)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    tot = sum(times)
+    gcups = cells * len(times) / tot / 1e9
+    sample = "%d profiles x %d of the %d sequences per step (same generator, seed, planted homologs); %s" % (
+        sample_p, sample_s, N_SEQS, "committed GPU-fitted statistics" if calibrated else "placeholder statistics")
+    line = {
+        "impl": "reference", "metric": "hmmsearch GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "seqs_per_s": sample_s * sample_p * len(times) / tot,
+        "config": {"workload": "hmmsearch: 100 Pfam-like profiles (M~200) vs 50k synthetic proteins (BASELINE configs[1]); reference CPU pipeline on a bounded sample",
+                   "profiles": sample_p, "sequences": sample_s, "hits": int(nh), "pipeline_counters": ctr},
+        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": ncore, "kind": "reference", "sample": sample},
+        "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b2h", choices=["b2h", "reference"])
+    ap.add_argument("--ref-profiles", type=int, default=100)
+    ap.add_argument("--ref-seqs", type=int, default=10000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b2h":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pyhmmer_b200 import _lib, plan7, synth, parallel
+
+    ctx = _lib.context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    abc, hmms, seqs = build_inputs(rank, world)
+    if not apply_stats(hmms):
+        synth.calibrate(hmms, ctx)                                # GPU calibration (same seed => same numbers on every rank)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        if rank == 0:
+            json.dump({"evparam": [[float(v) for v in h._evparam] for h in hmms]},
+                      open(os.path.join(ROOT, "gpurun_out", "bench_stats.json"), "w"))
+    # round-trip the models through the ASCII format so that both arms score the very same numbers
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "q.hmm")
+        write_hmm_file(hmms, p)
+        with plan7.HMMFile(p) as f:
+            hmms = list(f)
+    pli = plan7.Pipeline(abc)
+    oms = [pli._optimized(h, len(seqs[0])) for h in hmms]
+    db = plan7.SequenceDatabase.of(ctx, seqs)                      # resident in HBM
+    for om in oms:
+        om._device(ctx)
+    cells_local = float(sum(h.M for h in hmms)) * float(seqs.total_residues)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step_resident():
+        hits, doms, text, counters = pli._run(oms, seqs)
+        if world > 1:                                              # the single exchange of the path: all-gather of the hit records
+            w = parallel.World.current()
+            parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, counters, 0), w)
+        return hits, counters
+
+    def one_step_e2e():
+        seqs._cache = {}                                           # re-pack and re-upload the sequences
+        for om in oms:
+            om._dev = {}                                           # re-upload the profile tables
+        hits, doms, text, counters = pli._run(oms, seqs)
+        if world > 1:
+            w = parallel.World.current()
+            parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, counters, 0), w)
+        return pli._assemble(oms, oms, seqs, hits, doms, text, counters)   # thresholded TopHits, one per query
+
+    sampler = ClockSampler(local)
+    times, stage_acc = [], {}
+    launches0 = 0
+    hits = counters = None
+    for it in range(args.warmup + args.steps):
+        flush.fill_(it & 0xff)
+        barrier()
+        if it == args.warmup:
+            sampler.start()
+            ctx.set_profiling(True)
+            ctx.stage_ms(reset=True)
+            launches0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        hits, counters = one_step_resident()
+        e1.record(stream)
+        barrier()
+        if it >= args.warmup:
+            times.append(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    stage_ms = ctx.stage_ms(reset=True)
+    ctx.set_profiling(False)
+    launches = ctx.launch_count - launches0
+    tot_ms = sum(times)
+    t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+    c = torch.tensor([cells_local, float(len(seqs)) * len(hmms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    tot_ms = float(t.item())
+    cells_all, comps_all = float(c[0].item()), float(c[1].item())
+    K = len(times)
+    gcups = cells_all * K / (tot_ms * 1e-3) / 1e9
+
+    # end-to-end through the public API with host buffers
+    e2e_times = []
+    for it in range(2 + max(2, K // 2)):
+        flush.fill_(it & 0xff)
+        barrier()
+        t0 = time.perf_counter()
+        res = one_step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if it >= 2:
+            e2e_times.append(dt)
+    te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_gcups = cells_all * len(e2e_times) / float(te.item()) / 1e9
+    h2d = int(seqs.total_residues + 16 * len(seqs) + 46 * len(seqs)) + int(sum(32 * 128 * ((h.M + 64) // 64) + 32 * (80 + 160 + 1) * ((h.M + 31) // 32 * 32) for h in hmms))
+    nh = sum(len(r) for r in res)
+    d2h = int(nh * 96 + sum(len(h.domains) * 88 + sum(4 * (len(d.alignment) + 1) for d in h.domains) for r in res for h in r))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # roofline of the dominant kernel (SSV): algorithmic bytes of SURVEY 8(d) / its measured device time
+    pk, pk_kind = peaks()
+    msv_tab_bytes = sum(29 * h.M for h in hmms)
+    n_past_msv = int(counters[:, 0].sum()) if counters is not None else 0
+    b_alg = float(seqs.total_residues + 2 * len(seqs)) + msv_tab_bytes + 16.0 * n_past_msv      # per step, this rank
+    ssv_ms = stage_ms["ssv"] / K
+    achieved = b_alg / (ssv_ms * 1e-3) / 1e9 if ssv_ms > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ssv_traffic.json")))["dram_bytes_per_step"]
+    except Exception:
+        pass
+    line = {
+        "metric": "hmmsearch GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "seqs_per_s": comps_all * K / (tot_ms * 1e-3),
+        "config": {"workload": "hmmsearch: 100 Pfam-like profiles (M~200) vs 50k synthetic proteins on 1xB200 (BASELINE configs[1]); "
+                               "per-rank shard of 50k targets at N>1",
+                   "profiles": len(hmms), "sequences_per_rank": len(seqs), "sum_M": int(sum(h.M for h in hmms)),
+                   "residues_per_rank": int(seqs.total_residues), "planted_homolog_fraction": PLANT_FRAC,
+                   "l2": "flushed (256 MiB write) between steps", "sharding": "targets by rank, one all-gather of hit records",
+                   "hits_rank0": len(hits), "pipeline_counters_rank0": counters.sum(0).tolist(),
+                   "stage_ms_per_step": {k: v / K for k, v in stage_ms.items()},
+                   "ssv_kernel_gcups": (cells_local / (ssv_ms * 1e-3) / 1e9) if ssv_ms > 0 else None},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                     "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_kind": pk_kind,
+                     "kernel": "ssv_kernel<NR> (all launches of a step)", "algorithmic_bytes_per_step": b_alg,
+                     "note": "compute-bound DP: compulsory HBM traffic is ~6e-5 B/cell (SURVEY 8d), so the HBM fraction is tiny by construction; "
+                             "ssv_kernel_gcups vs the DPX issue ceiling is the informative figure (DESIGN.md)"},
+        "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * float(te.item()) / len(e2e_times)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            from oracle import refshim
+            import psutil
+            cores = max(1, min(psutil.cpu_count(logical=True) or 1, 64))
+            sp, ss = 100, 10000
+            with tempfile.TemporaryDirectory() as td:
+                p = os.path.join(td, "q.hmm")
+                write_hmm_file(hmms[:sp], p)
+                models = [refshim.RefModel(p, i, 400) for i in range(sp)]
+                codes = [s.sequence for s in seqs[:ss]]
+                t0 = time.perf_counter()
+                nhr, ctr = refshim.search_mt(models, codes, cores)
+                dt = time.perf_counter() - t0
+            cb_cells = float(sum(h.M for h in hmms[:sp])) * float(sum(len(c_) for c_ in codes))
+            line["cpu_baseline"] = {"value": cb_cells / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                                    "sample": "%d profiles x first %d of the 50k sequences, %.1f s wall on %d threads; oracle/_ref = HMMER 3.4 SSE2 built from the reference sources" % (sp, ss, dt, cores),
+                                    "pipeline_counters": ctr, "hits": int(nhr)}
+        except Exception as exc:                      # the checker is optional for the measurement itself
+            line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (exc,)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,11 @@ void        b2h_ctx_destroy(b2h_ctx *ctx);
 int         b2h_ctx_set_stream(b2h_ctx *ctx, void *cuda_stream);
 int         b2h_ctx_synchronize(b2h_ctx *ctx);
 const char *b2h_ctx_last_error(const b2h_ctx *ctx);
+/* Per-stage device timing for bench.py's roofline line: when enabled, b2h_search brackets each stage's
+ * launches with CUDA events on the context's stream.  b2h_ctx_stage_ms() returns the accumulated
+ * milliseconds {SSV, MSV, bias, Viterbi, Forward, survivor Fwd+Bck, grouping, reserved} and optionally resets. */
+int         b2h_ctx_set_profiling(b2h_ctx *ctx, int on);
+int         b2h_ctx_stage_ms(b2h_ctx *ctx, double *ms8, int reset);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t    b2h_ctx_launch_count(const b2h_ctx *ctx);
 
@@ -165,6 +170,68 @@ int b2h_forward_parser (b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *s
 int b2h_backward_parser(b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *sc, int32_t *status);
 /* null1[n] = p7_bg_NullOne; filtersc[n] = p7_bg_FilterScore after p7_bg_SetFilter(M, compo) (may be NULL) */
 int b2h_null_scores    (b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *null1, float *filtersc);
+
+/* --------------------------- the fused search path (p7_Pipeline per target) ----------------- *
+ * b2h_search() is what Pipeline._search_loop / _scan_loop (plan7.pyx:6394-6453, 6625-6677) do for
+ * P profiles x every sequence of the database: the whole acceleration-filter cascade runs on the
+ * GPU with on-device survivor compaction (SSV/MSV -> bias -> Viterbi -> Forward -> Backward);
+ * only comparisons that pass F3 come back to the host, where domain definition
+ * (p7_domaindef_ByPosteriorHeuristics, p7_domaindef.c:384) finishes them into hits.
+ * Reporting / inclusion thresholds (E, T, Z, domZ, bit cutoffs) are NOT applied here: every
+ * comparison that p7_Pipeline would have scored to completion is returned, and the caller
+ * applies p7_pli_TargetReportable with the running Z exactly as the sequential loop would. */
+typedef struct {
+  double   F1, F2, F3;        /* P-value thresholds of the three filters (0.02, 1e-3, 1e-5)          */
+  int32_t  do_biasfilter;     /* pli->do_biasfilter                                                  */
+  int32_t  do_null2;          /* pli->do_null2                                                       */
+  uint32_t seed;              /* RNG seed for stochastic traceback clustering (42)                   */
+  int32_t  host_threads;      /* worker threads for the host-side domain definition (0 = all cores) */
+} b2h_search_params;
+
+typedef struct {              /* mirrors P7_HIT (hmmer.h:711-743) without strings */
+  int32_t  profile;           /* index into the profiles[] argument                */
+  int32_t  seq;               /* index into the sequence database                  */
+  float    score, pre_score, sum_score;     /* bits */
+  double   lnP, pre_lnP, sum_lnP;
+  float    nexpected;
+  int32_t  nregions, nclustered, noverlaps, nenvelopes, ndom;
+  int32_t  best_domain;
+  int64_t  dom_offset;        /* first domain of this hit in the domains array     */
+} b2h_hit;
+
+typedef struct {              /* mirrors P7_DOMAIN + P7_ALIDISPLAY coordinates (hmmer.h:614-628, 580-607) */
+  int32_t  ienv, jenv, iali, jali;
+  float    envsc, domcorrection, dombias, oasc, bitscore;
+  double   lnP;
+  int32_t  hmmfrom, hmmto, sqfrom, sqto;
+  int32_t  N;                 /* alignment display length                          */
+  int64_t  text_offset;       /* model | mline | aseq | ppline [| rfline] [| csline], each N+1 bytes, NUL-terminated */
+  int32_t  has_rf, has_cs;
+} b2h_domain;
+
+typedef struct b2h_results b2h_results;
+
+int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const b2h_seqdb *db,
+               const b2h_search_params *params, b2h_results **out);
+size_t            b2h_results_nhits   (const b2h_results *r);
+const b2h_hit    *b2h_results_hits    (const b2h_results *r);
+size_t            b2h_results_ndomains(const b2h_results *r);
+const b2h_domain *b2h_results_domains (const b2h_results *r);
+const char       *b2h_results_text    (const b2h_results *r, size_t *nbytes);
+/* [P][4] = n_past_msv, n_past_bias, n_past_vit, n_past_fwd per profile (P7_PIPELINE counters, hmmer.h:1228-1241) */
+const int64_t    *b2h_results_counters(const b2h_results *r);
+void              b2h_results_destroy (b2h_results *r);
+
+/* Diagnostic (used by the CPU-only tests of the host-side domain definition): build a profile object
+ * without any device state, and run the post-Backward part of p7_Pipeline for ONE comparison from given
+ * Forward/Backward parser specials ((L+1) rows of {E,N,J,B,C,SCALE}).  dsq[0..L-1] are the residues. */
+int b2h_profile_create_host(const b2h_oprofile_desc *desc, b2h_profile **out);
+int b2h_debug_domaindef(const b2h_profile *p, const uint8_t *dsq, int L, const float *fwd_xmx, const float *bck_xmx,
+                        float fwdsc, const b2h_search_params *params, b2h_results **out);
+
+/* Annotation lines needed to render alignments (P7_OPROFILE.consensus / rf / cs, 1..M); any may be NULL. */
+int b2h_profile_set_annotation(b2h_profile *p, const char *consensus, const char *rf, const char *cs,
+                               const char *alphabet_symbols /* ESL_ALPHABET.sym, Kp chars */);
 
 #ifdef __cplusplus
 }

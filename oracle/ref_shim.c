@@ -200,3 +200,181 @@ int ref_generic(REFM *m, const uint8_t *dsq, int L, float *gmsv, float *gvit, fl
 
 double ref_gumbel_surv(double x, double mu, double lambda) { return esl_gumbel_surv(x, mu, lambda); }
 double ref_exp_surv(double x, double mu, double lambda)    { return esl_exp_surv(x, mu, lambda); }
+
+/* =====================================================================================
+ * The search loop, exactly as pyhmmer runs it (Pipeline._search_loop, plan7.pyx:6394-6453):
+ *   p7_pli_NewModel; for each target: p7_pli_NewSeq, p7_bg_SetLength, p7_oprofile_ReconfigLength,
+ *   p7_Pipeline, p7_pipeline_Reuse.
+ * Reporting thresholds are opened wide (E = 1e300) so that every comparison p7_Pipeline scores to
+ * completion comes back; the caller applies thresholds itself.
+ * ===================================================================================== */
+#include <pthread.h>
+#include "esl_getopts.h"
+
+typedef struct {
+  int   seq;
+  float score, pre_score, sum_score, nexpected;
+  double lnP, pre_lnP, sum_lnP;
+  int   nregions, nclustered, noverlaps, nenvelopes, ndom, best_domain;
+  long  dom_offset;
+} REF_HIT;
+
+typedef struct {
+  int   ienv, jenv, iali, jali;
+  float envsc, domcorrection, dombias, oasc, bitscore;
+  double lnP;
+  int   hmmfrom, hmmto, sqfrom, sqto, N;
+  long  text_offset;          /* model | mline | aseq | ppline, each N+1 bytes */
+} REF_DOM;
+
+typedef struct {
+  long nhits, ndoms, ntext;
+  REF_HIT *hits; REF_DOM *doms; char *text;
+  long counters[4];           /* n_past_msv, n_past_bias, n_past_vit, n_past_fwd */
+  double seconds;
+} REF_RESULT;
+
+static P7_PIPELINE *make_pipeline(const REFM *m, double F1, double F2, double F3, int do_bias, int do_null2, unsigned seed)
+{
+  P7_PIPELINE *pli = p7_pipeline_Create(NULL, m->om->M, 400, FALSE, p7_SEARCH_SEQS);
+  pli->F1 = F1; pli->F2 = F2; pli->F3 = F3;
+  pli->do_biasfilter = do_bias; pli->do_null2 = do_null2;
+  pli->E = 1e300; pli->domE = 1e300; pli->incE = 1e300; pli->incdomE = 1e300;
+  if (seed != 42) { esl_randomness_Init(pli->r, seed); pli->do_reseeding = pli->ddef->do_reseeding = (seed != 0); }
+  return pli;
+}
+
+static void collect(P7_TOPHITS *th, const int *seqidx_of_hit, REF_RESULT *r)
+{
+  long h, d, ndoms = 0, ntext = 0;
+  for (h = 0; h < (long)th->N; h++) for (d = 0; d < th->unsrt[h].ndom; d++) { ndoms++; ntext += 4 * (th->unsrt[h].dcl[d].ad->N + 1); }
+  r->nhits = th->N; r->ndoms = ndoms; r->ntext = ntext;
+  r->hits = calloc(th->N + 1, sizeof(REF_HIT)); r->doms = calloc(ndoms + 1, sizeof(REF_DOM)); r->text = calloc(ntext + 1, 1);
+  ndoms = 0; ntext = 0;
+  for (h = 0; h < (long)th->N; h++) {
+    P7_HIT *hit = &th->unsrt[h]; REF_HIT *o = &r->hits[h];
+    o->seq = seqidx_of_hit[h];
+    o->score = hit->score; o->pre_score = hit->pre_score; o->sum_score = hit->sum_score; o->nexpected = hit->nexpected;
+    o->lnP = hit->lnP; o->pre_lnP = hit->pre_lnP; o->sum_lnP = hit->sum_lnP;
+    o->nregions = hit->nregions; o->nclustered = hit->nclustered; o->noverlaps = hit->noverlaps; o->nenvelopes = hit->nenvelopes;
+    o->ndom = hit->ndom; o->best_domain = hit->best_domain; o->dom_offset = ndoms;
+    for (d = 0; d < hit->ndom; d++) {
+      P7_DOMAIN *dom = &hit->dcl[d]; REF_DOM *q = &r->doms[ndoms++]; P7_ALIDISPLAY *ad = dom->ad;
+      q->ienv = dom->ienv; q->jenv = dom->jenv; q->iali = dom->iali; q->jali = dom->jali;
+      q->envsc = dom->envsc; q->domcorrection = dom->domcorrection; q->dombias = dom->dombias; q->oasc = dom->oasc;
+      q->bitscore = dom->bitscore; q->lnP = dom->lnP;
+      q->hmmfrom = ad->hmmfrom; q->hmmto = ad->hmmto; q->sqfrom = ad->sqfrom; q->sqto = ad->sqto; q->N = ad->N;
+      q->text_offset = ntext;
+      memcpy(r->text + ntext, ad->model, ad->N + 1);  ntext += ad->N + 1;
+      memcpy(r->text + ntext, ad->mline, ad->N + 1);  ntext += ad->N + 1;
+      memcpy(r->text + ntext, ad->aseq, ad->N + 1);   ntext += ad->N + 1;
+      memcpy(r->text + ntext, ad->ppline, ad->N + 1); ntext += ad->N + 1;
+    }
+  }
+}
+
+/* single-threaded, full results */
+REF_RESULT *ref_search(REFM *m, const uint8_t *const *dsq, const int64_t *len, int n,
+                       double F1, double F2, double F3, int do_bias, int do_null2, unsigned seed)
+{
+  REF_RESULT  *r   = calloc(1, sizeof(REF_RESULT));
+  P7_PIPELINE *pli = make_pipeline(m, F1, F2, F3, do_bias, do_null2, seed);
+  P7_TOPHITS  *th  = p7_tophits_Create();
+  int *seqidx = malloc(sizeof(int) * (n + 1));
+  int t; char name[32];
+  p7_oprofile_ReconfigMultihit(m->om, 400);
+  p7_pli_NewModel(pli, m->om, m->bg);
+  for (t = 0; t < n; t++) {
+    ESL_SQ *sq;
+    uint64_t before = th->N;
+    snprintf(name, sizeof name, "seq%d", t);
+    sq = esl_sq_CreateDigitalFrom(m->abc, name, dsq[t], len[t], NULL, NULL, NULL);
+    p7_pli_NewSeq(pli, sq);
+    p7_bg_SetLength(m->bg, sq->n);
+    p7_oprofile_ReconfigLength(m->om, sq->n);
+    p7_Pipeline(pli, m->om, m->bg, sq, NULL, th);
+    p7_pipeline_Reuse(pli);
+    if (th->N > before) seqidx[before] = t;
+    esl_sq_Destroy(sq);
+  }
+  collect(th, seqidx, r);
+  r->counters[0] = pli->n_past_msv; r->counters[1] = pli->n_past_bias; r->counters[2] = pli->n_past_vit; r->counters[3] = pli->n_past_fwd;
+  free(seqidx); p7_tophits_Destroy(th); p7_pipeline_Destroy(pli);
+  return r;
+}
+void ref_result_free(REF_RESULT *r) { if (r) { free(r->hits); free(r->doms); free(r->text); free(r); } }
+long ref_result_nhits(const REF_RESULT *r) { return r->nhits; }
+long ref_result_ndoms(const REF_RESULT *r) { return r->ndoms; }
+const REF_HIT *ref_result_hits(const REF_RESULT *r) { return r->hits; }
+const REF_DOM *ref_result_doms(const REF_RESULT *r) { return r->doms; }
+const char *ref_result_text(const REF_RESULT *r) { return r->text; }
+const long *ref_result_counters(const REF_RESULT *r) { return r->counters; }
+
+/* ---- multi-threaded timing run (bench.py --impl reference / cpu_baseline): the target database is split
+ * into <nthreads> contiguous slices balanced by residues, as pyhmmer's target-parallel dispatcher does
+ * (_hmmsearch.py:153-171); every thread owns a pipeline, a background and a clone of each query profile. */
+typedef struct {
+  REFM **models; int nmodels;
+  const uint8_t *const *dsq; const int64_t *len; int t0, t1;
+  double F1, F2, F3; int do_bias, do_null2;
+  long nhits; long counters[4];
+} MT_JOB;
+
+static void *mt_worker(void *arg)
+{
+  MT_JOB *job = (MT_JOB *)arg;
+  int q, t, c;
+  job->nhits = 0; for (c = 0; c < 4; c++) job->counters[c] = 0;
+  for (q = 0; q < job->nmodels; q++) {
+    REFM *m = job->models[q];
+    P7_OPROFILE *om = p7_oprofile_Clone(m->om);
+    P7_BG *bg = p7_bg_Clone(m->bg);
+    P7_PIPELINE *pli = p7_pipeline_Create(NULL, om->M, 400, FALSE, p7_SEARCH_SEQS);
+    P7_TOPHITS *th = p7_tophits_Create();
+    ESL_SQ *sq = esl_sq_CreateDigital(m->abc);
+    pli->F1 = job->F1; pli->F2 = job->F2; pli->F3 = job->F3; pli->do_biasfilter = job->do_bias; pli->do_null2 = job->do_null2;
+    p7_pli_NewModel(pli, om, bg);
+    for (t = job->t0; t < job->t1; t++) {
+      esl_sq_GrowTo(sq, job->len[t]);
+      memcpy(sq->dsq, job->dsq[t], job->len[t] + 2);
+      sq->n = job->len[t];
+      esl_sq_SetName(sq, "s");
+      p7_pli_NewSeq(pli, sq);
+      p7_bg_SetLength(bg, sq->n);
+      p7_oprofile_ReconfigLength(om, sq->n);
+      p7_Pipeline(pli, om, bg, sq, NULL, th);
+      p7_pipeline_Reuse(pli);
+      esl_sq_Reuse(sq);
+    }
+    job->nhits += th->N;
+    job->counters[0] += pli->n_past_msv; job->counters[1] += pli->n_past_bias; job->counters[2] += pli->n_past_vit; job->counters[3] += pli->n_past_fwd;
+    esl_sq_Destroy(sq); p7_tophits_Destroy(th); p7_pipeline_Destroy(pli); p7_bg_Destroy(bg); p7_oprofile_Destroy(om);
+  }
+  return NULL;
+}
+
+/* returns the number of hits; counters4 receives the summed pipeline counters */
+long ref_search_mt(REFM **models, int nmodels, const uint8_t *const *dsq, const int64_t *len, int n, int nthreads,
+                   double F1, double F2, double F3, int do_bias, int do_null2, long *counters4)
+{
+  pthread_t *th = malloc(sizeof(pthread_t) * nthreads);
+  MT_JOB *jobs = calloc(nthreads, sizeof(MT_JOB));
+  int64_t total = 0, acc = 0; int t, j = 0, c; long nhits = 0;
+  for (t = 0; t < n; t++) total += len[t];
+  for (t = 0; t < nthreads; t++) { jobs[t].t0 = jobs[t].t1 = n; }
+  jobs[0].t0 = 0;
+  for (t = 0; t < n; t++) {                       /* contiguous slices balanced by residues */
+    acc += len[t];
+    if (j < nthreads - 1 && acc >= (total * (j + 1)) / nthreads) { jobs[j].t1 = t + 1; j++; jobs[j].t0 = t + 1; }
+  }
+  jobs[j].t1 = n;
+  for (t = 0; t < nthreads; t++) {
+    jobs[t].models = models; jobs[t].nmodels = nmodels; jobs[t].dsq = dsq; jobs[t].len = len;
+    jobs[t].F1 = F1; jobs[t].F2 = F2; jobs[t].F3 = F3; jobs[t].do_bias = do_bias; jobs[t].do_null2 = do_null2;
+    pthread_create(&th[t], NULL, mt_worker, &jobs[t]);
+  }
+  for (c = 0; c < 4; c++) counters4[c] = 0;
+  for (t = 0; t < nthreads; t++) { pthread_join(th[t], NULL); nhits += jobs[t].nhits; for (c = 0; c < 4; c++) counters4[c] += jobs[t].counters[c]; }
+  free(th); free(jobs);
+  return nhits;
+}

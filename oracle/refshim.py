@@ -14,6 +14,21 @@ LIB = os.path.join(HERE, "_ref", "libhmmer_ref.so")
 _lib = None
 
 
+class RefHit(ctypes.Structure):
+    _fields_ = [("seq", ctypes.c_int), ("score", ctypes.c_float), ("pre_score", ctypes.c_float), ("sum_score", ctypes.c_float),
+                ("nexpected", ctypes.c_float), ("lnP", ctypes.c_double), ("pre_lnP", ctypes.c_double), ("sum_lnP", ctypes.c_double),
+                ("nregions", ctypes.c_int), ("nclustered", ctypes.c_int), ("noverlaps", ctypes.c_int), ("nenvelopes", ctypes.c_int),
+                ("ndom", ctypes.c_int), ("best_domain", ctypes.c_int), ("dom_offset", ctypes.c_long)]
+
+
+class RefDom(ctypes.Structure):
+    _fields_ = [("ienv", ctypes.c_int), ("jenv", ctypes.c_int), ("iali", ctypes.c_int), ("jali", ctypes.c_int),
+                ("envsc", ctypes.c_float), ("domcorrection", ctypes.c_float), ("dombias", ctypes.c_float), ("oasc", ctypes.c_float),
+                ("bitscore", ctypes.c_float), ("lnP", ctypes.c_double),
+                ("hmmfrom", ctypes.c_int), ("hmmto", ctypes.c_int), ("sqfrom", ctypes.c_int), ("sqto", ctypes.c_int), ("N", ctypes.c_int),
+                ("text_offset", ctypes.c_long)]
+
+
 def available():
     return os.path.exists(LIB)
 
@@ -56,6 +71,18 @@ def lib():
         L.ref_exp_surv.restype = ctypes.c_double
         L.ref_exp_surv.argtypes = [ctypes.c_double] * 3
         L.ref_nxcells.restype = ci
+        L.ref_search.restype = vp
+        L.ref_search.argtypes = [vp, vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ctypes.c_uint]
+        L.ref_result_free.argtypes = [vp]
+        for f in ("ref_result_nhits", "ref_result_ndoms"):
+            getattr(L, f).restype = ctypes.c_long
+            getattr(L, f).argtypes = [vp]
+        L.ref_result_hits.restype = ctypes.POINTER(RefHit); L.ref_result_hits.argtypes = [vp]
+        L.ref_result_doms.restype = ctypes.POINTER(RefDom); L.ref_result_doms.argtypes = [vp]
+        L.ref_result_text.restype = vp; L.ref_result_text.argtypes = [vp]
+        L.ref_result_counters.restype = ctypes.POINTER(ctypes.c_long); L.ref_result_counters.argtypes = [vp]
+        L.ref_search_mt.restype = ctypes.c_long
+        L.ref_search_mt.argtypes = [vp, ci, vp, vp, ci, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, vp]
         _lib = L
     return _lib
 
@@ -165,3 +192,37 @@ class RefModel:
 
     def bias(self, codes):
         d = dsq_of(codes); return self.L.ref_bias(self.h, d.ctypes.data, d.size - 2)
+
+
+    def search(self, seqs, F1=0.02, F2=1e-3, F3=1e-5, bias_filter=True, null2=True, seed=42):
+        """The reference search loop over <seqs> (list of residue-code arrays); returns (hits, doms, text, counters)."""
+        dsqs = [dsq_of(c) for c in seqs]
+        n = len(dsqs)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[d.ctypes.data for d in dsqs])
+        lens = np.array([d.size - 2 for d in dsqs], dtype=np.int64)
+        r = self.L.ref_search(self.h, ptrs, lens.ctypes.data, n, F1, F2, F3, int(bias_filter), int(null2), seed)
+        try:
+            nh, nd = self.L.ref_result_nhits(r), self.L.ref_result_ndoms(r)
+            hp, dp = self.L.ref_result_hits(r), self.L.ref_result_doms(r)
+            hits = [RefHit.from_buffer_copy(hp[i]) for i in range(nh)]
+            doms = [RefDom.from_buffer_copy(dp[i]) for i in range(nd)]
+            ntext = sum(4 * (d.N + 1) for d in doms)
+            text = ctypes.string_at(self.L.ref_result_text(r), ntext) if ntext else b""
+            cp = self.L.ref_result_counters(r)
+            counters = [cp[i] for i in range(4)]
+        finally:
+            self.L.ref_result_free(r)
+        return hits, doms, text, counters
+
+
+def search_mt(models, seqs, nthreads, F1=0.02, F2=1e-3, F3=1e-5, bias_filter=True, null2=True):
+    """Timing run: every model against <seqs> with <nthreads> threads; returns (nhits, counters)."""
+    L = lib()
+    dsqs = [dsq_of(c) for c in seqs]
+    n = len(dsqs)
+    ptrs = (ctypes.c_void_p * max(n, 1))(*[d.ctypes.data for d in dsqs])
+    lens = np.array([d.size - 2 for d in dsqs], dtype=np.int64)
+    mp = (ctypes.c_void_p * len(models))(*[m.h for m in models])
+    ctr = (ctypes.c_long * 4)()
+    nh = L.ref_search_mt(mp, len(models), ptrs, lens.ctypes.data, n, nthreads, F1, F2, F3, int(bias_filter), int(null2), ctr)
+    return nh, list(ctr)

@@ -42,6 +42,28 @@ class LenParams(ctypes.Structure):
                 ("null1", c_float), ("p1", c_float), ("flt_len_a", c_float), ("flt_len_b", c_float)]
 
 
+class SearchParams(ctypes.Structure):
+    """``b2h_search_params`` (include/b2h.h)."""
+    _fields_ = [("F1", ctypes.c_double), ("F2", ctypes.c_double), ("F3", ctypes.c_double),
+                ("do_biasfilter", c_i32), ("do_null2", c_i32), ("seed", ctypes.c_uint32), ("host_threads", c_i32)]
+
+
+class HitRec(ctypes.Structure):
+    """``b2h_hit`` (include/b2h.h)."""
+    _fields_ = [("profile", c_i32), ("seq", c_i32), ("score", c_float), ("pre_score", c_float), ("sum_score", c_float),
+                ("lnP", ctypes.c_double), ("pre_lnP", ctypes.c_double), ("sum_lnP", ctypes.c_double),
+                ("nexpected", c_float), ("nregions", c_i32), ("nclustered", c_i32), ("noverlaps", c_i32),
+                ("nenvelopes", c_i32), ("ndom", c_i32), ("best_domain", c_i32), ("dom_offset", c_i64)]
+
+
+class DomainRec(ctypes.Structure):
+    """``b2h_domain`` (include/b2h.h)."""
+    _fields_ = [("ienv", c_i32), ("jenv", c_i32), ("iali", c_i32), ("jali", c_i32),
+                ("envsc", c_float), ("domcorrection", c_float), ("dombias", c_float), ("oasc", c_float), ("bitscore", c_float),
+                ("lnP", ctypes.c_double), ("hmmfrom", c_i32), ("hmmto", c_i32), ("sqfrom", c_i32), ("sqto", c_i32),
+                ("N", c_i32), ("text_offset", c_i64), ("has_rf", c_i32), ("has_cs", c_i32)]
+
+
 class B2HError(RuntimeError):
     def __init__(self, status, fn, detail=""):
         self.status = status
@@ -75,6 +97,8 @@ def _load():
     sig("b2h_ctx_synchronize", c_int, c_void_p)
     sig("b2h_ctx_last_error", ctypes.c_char_p, c_void_p)
     sig("b2h_ctx_launch_count", c_u64, c_void_p)
+    sig("b2h_ctx_set_profiling", c_int, c_void_p, c_int)
+    sig("b2h_ctx_stage_ms", c_int, c_void_p, c_void_p, c_int)
     sig("b2h_seqdb_create", c_int, c_void_p, c_void_p, c_void_p, c_size_t, P(c_void_p))
     sig("b2h_seqdb_create_packed", c_int, c_void_p, c_void_p, c_void_p, c_size_t, P(c_void_p))
     sig("b2h_seqdb_destroy", None, c_void_p)
@@ -86,12 +110,37 @@ def _load():
                  "b2h_backward_parser"):
         if hasattr(lib, name):
             sig(name, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
+    sig("b2h_search", c_int, c_void_p, c_void_p, c_size_t, c_void_p, P(SearchParams), P(c_void_p))
+    sig("b2h_results_nhits", c_size_t, c_void_p)
+    sig("b2h_results_hits", P(HitRec), c_void_p)
+    sig("b2h_results_ndomains", c_size_t, c_void_p)
+    sig("b2h_results_domains", P(DomainRec), c_void_p)
+    sig("b2h_results_text", c_void_p, c_void_p, P(c_size_t))
+    sig("b2h_results_counters", P(c_i64), c_void_p)
+    sig("b2h_results_destroy", None, c_void_p)
+    sig("b2h_profile_set_annotation", c_int, c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p)
+    sig("b2h_profile_create_host", c_int, P(OProfileDesc), P(c_void_p))
+    sig("b2h_debug_domaindef", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, P(SearchParams), P(c_void_p))
     if hasattr(lib, "b2h_null_scores"):
         sig("b2h_null_scores", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
     return lib
 
 
 lib = _load()
+
+
+def read_results(handle):
+    """Copy a ``b2h_results`` into python objects: (hits, domains, text, counters_flat)."""
+    nh = lib.b2h_results_nhits(handle)
+    nd = lib.b2h_results_ndomains(handle)
+    hp = lib.b2h_results_hits(handle)
+    dp = lib.b2h_results_domains(handle)
+    hits = [HitRec.from_buffer_copy(hp[i]) for i in range(nh)]
+    doms = [DomainRec.from_buffer_copy(dp[i]) for i in range(nd)]
+    nb = c_size_t()
+    tp = lib.b2h_results_text(handle, ctypes.byref(nb))
+    text = ctypes.string_at(tp, nb.value) if nb.value else b""
+    return hits, doms, text
 
 
 def ptr(a):
@@ -127,6 +176,15 @@ class Context:
 
     def synchronize(self):
         check(lib.b2h_ctx_synchronize(self.handle), "b2h_ctx_synchronize", self.handle)
+
+    def set_profiling(self, on):
+        check(lib.b2h_ctx_set_profiling(self.handle, int(on)), "b2h_ctx_set_profiling", self.handle)
+
+    def stage_ms(self, reset=True):
+        """{stage: milliseconds} accumulated by b2h_search since the last reset (needs set_profiling(True))."""
+        a = np.zeros(8, dtype=np.float64)
+        check(lib.b2h_ctx_stage_ms(self.handle, ptr(a), int(reset)), "b2h_ctx_stage_ms", self.handle)
+        return dict(zip(("ssv", "msv", "bias", "viterbi", "forward", "fwdbck_survivors", "grouping", "reserved"), a.tolist()))
 
     @property
     def launch_count(self):

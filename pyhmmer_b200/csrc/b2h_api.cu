@@ -29,17 +29,19 @@ bool args_ok(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db) {
 
 // One profile against every sequence: the trivial work list (entries in the length-sorted order).
 struct DenseList {
-  b2h_ctx *ctx; ProfDev *d_prof = nullptr; int32_t *d_poff = nullptr, *d_itemoff = nullptr;
+  b2h_ctx *ctx; ProfDev *d_prof = nullptr; int32_t *d_poff = nullptr, *d_itemoff = nullptr, *d_cls = nullptr;
   WorkList wl; int nitems = 0;
   DenseList(b2h_ctx *c) : ctx(c) {}
   int build(const b2h_profile *p, const b2h_seqdb *db) {
     ProfDev h = b2h_profdev(p);
     const int n = (int)db->n;
     nitems = (n + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES;
-    int32_t poff[2] = {0, n}, itemoff[2] = {0, nitems};
+    int32_t poff[2] = {0, n}, itemoff[2] = {0, nitems}, cls0 = 0;
     B2H_CUDA(cudaMallocAsync(&d_prof, sizeof(ProfDev), ctx->stream));
     B2H_CUDA(cudaMallocAsync(&d_poff, sizeof poff, ctx->stream));
     B2H_CUDA(cudaMallocAsync(&d_itemoff, sizeof itemoff, ctx->stream));
+    B2H_CUDA(cudaMallocAsync(&d_cls, sizeof cls0, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(d_cls, &cls0, sizeof cls0, cudaMemcpyHostToDevice, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(d_prof, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(d_poff, poff, sizeof poff, cudaMemcpyHostToDevice, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(d_itemoff, itemoff, sizeof itemoff, cudaMemcpyHostToDevice, ctx->stream));
@@ -47,7 +49,7 @@ struct DenseList {
     wl.profs = d_prof; wl.ent_s = db->d_order; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = 1; wl.counter = ctx->d_counters + 8;
     return B2H_OK;
   }
-  ~DenseList() { if (d_prof) cudaFreeAsync(d_prof, ctx->stream); if (d_poff) cudaFreeAsync(d_poff, ctx->stream); if (d_itemoff) cudaFreeAsync(d_itemoff, ctx->stream); }
+  ~DenseList() { if (d_prof) cudaFreeAsync(d_prof, ctx->stream); if (d_poff) cudaFreeAsync(d_poff, ctx->stream); if (d_itemoff) cudaFreeAsync(d_itemoff, ctx->stream); if (d_cls) cudaFreeAsync(d_cls, ctx->stream); }
 };
 
 // scatter entry-ordered results back to database order
@@ -105,23 +107,44 @@ int dense_dp(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, dp_launche
 
 extern "C" {
 
-int b2h_ssv_filter(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, float *sc, int32_t *status)
+// SSV (mode 0) or MSV = SSV + full-MSV fallback (mode 1) for one profile against the whole database
+static int dense_msv(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, int mode, float *sc, int32_t *status)
 {
   if (!args_ok(ctx, p, db)) return B2H_EINVAL;
-  DenseOut o(ctx, db->n);
+  const size_t n = db->n;
+  if (n == 0) return B2H_OK;
+  DenseOut o(ctx, n);
   int st = o.alloc();                                       if (st != B2H_OK) return st;
-  st = b2h_launch_ssv_dense(ctx, p, db, 0, o.d_sc, o.d_status);   if (st != B2H_OK) return st;
-  return o.fetch(sc, status);
+  DenseList dl(ctx);
+  if ((st = dl.build(p, db)) != B2H_OK) return st;
+  // redo list R + its grouping
+  int32_t *buf = nullptr; int *ctr = nullptr;
+  B2H_CUDA(cudaMallocAsync(&buf, (4 * n + 8) * sizeof(int32_t), ctx->stream));
+  B2H_CUDA(cudaMallocAsync(&ctr, 8 * sizeof(int), ctx->stream));
+  B2H_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(int), ctx->stream));
+  SurvList R; R.p = buf; R.s = buf + n; R.a = nullptr; R.b = nullptr; R.n = ctr; R.cnt = ctr + 1; R.cap = (int)n;
+  Grouped G; G.p = buf + 2 * n; G.s = buf + 3 * n; G.a = nullptr; G.b = nullptr; G.poff = buf + 4 * n; G.itemoff = buf + 4 * n + 2; G.fill = ctr + 2;
+  SsvArgs a;
+  a.profs = dl.d_prof; a.cls = dl.d_cls; a.ncls = 1; a.sd = b2h_seqdev(db);
+  a.chunks = (int)((n + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK); a.counter = ctx->d_counters; a.zero = 0u;
+  a.mode = mode; a.out_sc = o.d_sc; a.out_status = o.d_status; a.R = R; a.A = R; a.F1 = 1.0;
+  st = b2h_launch_ssv(ctx, p->NR, a);
+  if (st == B2H_OK && mode == 1) {
+    st = b2h_launch_group(ctx, R, 1, G);
+    if (st == B2H_OK) {
+      WorkList wl = dl.wl; wl.ent_s = G.s; wl.poff = G.poff; wl.itemoff = G.itemoff;
+      st = b2h_launch_msv(ctx, wl, a.sd, p->Mpad, 0, 1, o.d_sc, o.d_status, R, 1.0);
+    }
+  }
+  if (st == B2H_OK) st = o.fetch(sc, status);
+  cudaFreeAsync(buf, ctx->stream); cudaFreeAsync(ctr, ctx->stream);
+  return st;
 }
 
+int b2h_ssv_filter(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, float *sc, int32_t *status)
+{ return dense_msv(ctx, p, db, 0, sc, status); }
 int b2h_msv_filter(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, float *sc, int32_t *status)
-{
-  if (!args_ok(ctx, p, db)) return B2H_EINVAL;
-  DenseOut o(ctx, db->n);
-  int st = o.alloc();                                       if (st != B2H_OK) return st;
-  st = b2h_launch_ssv_dense(ctx, p, db, 1, o.d_sc, o.d_status);   if (st != B2H_OK) return st;
-  return o.fetch(sc, status);
-}
+{ return dense_msv(ctx, p, db, 1, sc, status); }
 
 int b2h_viterbi_filter(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, float *sc, int32_t *status)
 { return dense_dp(ctx, p, db, b2h_launch_viterbi, false, sc, status); }

@@ -32,6 +32,7 @@ void b2h_ctx_destroy(b2h_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -50,6 +51,13 @@ int b2h_ctx_synchronize(b2h_ctx *ctx)
   return B2H_OK;
 }
 
+int b2h_ctx_set_profiling(b2h_ctx *ctx, int on) { if (!ctx) return B2H_EINVAL; ctx->profiling = on; return B2H_OK; }
+int b2h_ctx_stage_ms(b2h_ctx *ctx, double *ms8, int reset)
+{
+  if (!ctx || !ms8) return B2H_EINVAL;
+  for (int i = 0; i < 8; i++) { ms8[i] = ctx->stage_ms[i]; if (reset) ctx->stage_ms[i] = 0; }
+  return B2H_OK;
+}
 const char *b2h_ctx_last_error(const b2h_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t    b2h_ctx_launch_count(const b2h_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
@@ -137,6 +145,7 @@ static int seqdb_build(b2h_ctx *ctx, size_t n, const int64_t *len,
     for (int32_t i = 0; i < db->h_len[s]; i++) dst[i] = src[i] < B2H_NCODE ? src[i] : (uint8_t)B2H_PAD_CODE;
   }
   int st = seqdb_finish(ctx, db, arena);
+  db->h_res.swap(arena);
   if (st != B2H_OK) { b2h_seqdb_destroy(db); return st; }
   *out = db;
   return B2H_OK;
@@ -175,13 +184,16 @@ static size_t striped_word_index(int NR, int x, int j, int lane)
   return base + (size_t)full * 128 + (size_t)lane * rem + (j - full * 4);
 }
 
+int b2h_profile_create_host(const b2h_oprofile_desc *d, b2h_profile **out)
+{ return b2h_profile_upload(nullptr, d, out); }
+
 int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **out)
 {
-  if (!ctx || !d || !out || d->M < 1 || d->Kp > B2H_NCODE - 1 || d->K > B2H_MAXABET) return B2H_EINVAL;
+  if (!d || !out || d->M < 1 || d->Kp > B2H_NCODE - 1 || d->K > B2H_MAXABET) return B2H_EINVAL;
   *out = nullptr;
   const int M = d->M, Kp = d->Kp;
   const int NR = b2h_nr_for_M(M);
-  if (NR < 0) { ctx->err = "model too long for the register-tiled MSV kernel (M > 3071)"; return B2H_EINVAL; }
+  if (NR < 0) { if (ctx) ctx->err = "model too long for the register-tiled MSV kernel (M > 3071)"; return B2H_EINVAL; }
   b2h_profile *p = new b2h_profile();
   p->ctx = ctx; p->M = M; p->K = d->K; p->Kp = Kp; p->max_length = d->max_length; p->multihit = d->mode_multihit;
   p->NR = NR; p->tbm_b = d->tbm_b; p->tec_b = d->tec_b; p->base_b = d->base_b; p->bias_b = d->bias_b; p->scale_b = d->scale_b;
@@ -190,10 +202,14 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
   memcpy(p->evparam, d->evparam, sizeof p->evparam); memcpy(p->cutoff, d->cutoff, sizeof p->cutoff);
   memcpy(p->compo, d->compo, sizeof p->compo); memcpy(p->bgf, d->bgf, sizeof p->bgf);
   p->Mpad = (M + 31) & ~31;
+  p->h_fwd_rsc.assign(d->fwd_rsc, d->fwd_rsc + (size_t)Kp * M);
+  p->h_fwd_tsc.assign(d->fwd_tsc, d->fwd_tsc + (size_t)8 * M);
+  if (d->degen) p->h_degen.assign(d->degen, d->degen + (size_t)Kp * d->K);
+  p->symbols = (d->K == 20) ? "ACDEFGHIKLMNPQRSTVWY-BJZOUX*~" : "ACGT-RYMKSWHBVDN*~";
 
   // --- SSV signed scores / MSV costs, lane-striped ---
   const size_t nwords = (size_t)B2H_NCODE * NR * 32;
-  std::vector<uint32_t> ssv(nwords), msv(nwords);
+  std::vector<uint32_t> ssv(nwords);
   auto cost_of = [&](int x, int k) -> int {          // k is 1-based; anything off the model is the -inf cost
     return (x < Kp && k <= M) ? (int)d->msv_cost[(size_t)x * M + (k-1)] : 255;
   };
@@ -206,16 +222,17 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
         int slo = -std::min(clo - (int)d->bias_b, 127), shi = -std::min(chi - (int)d->bias_b, 127);
         size_t w = striped_word_index(NR, x, j, lane);
         ssv[w] = ((uint32_t)(uint16_t)(int16_t)shi << 16) | (uint32_t)(uint16_t)(int16_t)slo;
-        msv[w] = ((uint32_t)chi << 16) | (uint32_t)clo;
       }
 
   // --- Viterbi / Forward tables, padded ---
   const int Mp = p->Mpad;
   std::vector<int16_t> vr((size_t)B2H_NCODE * Mp, (int16_t)-32768), vt((size_t)8 * Mp, (int16_t)-32768);
   std::vector<float>   fr((size_t)B2H_NCODE * Mp, 0.0f),            ft((size_t)8 * Mp, 0.0f);
+  std::vector<uint8_t> mc((size_t)B2H_NCODE * Mp, (uint8_t)255);
   for (int x = 0; x < Kp; x++)
     for (int k = 0; k < M; k++) {
       vr[(size_t)x * Mp + k] = d->vit_rsc[(size_t)x * M + k];
+      mc[(size_t)x * Mp + k] = d->msv_cost[(size_t)x * M + k];
       fr[(size_t)x * Mp + k] = d->fwd_rsc[(size_t)x * M + k];
     }
   for (int t = 0; t < 8; t++)
@@ -242,14 +259,14 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
   }
 
   int st = B2H_OK;
-  do {
+  if (ctx) do {
     cudaError_t e;
 #define UP(dst, vec, T) \
     if ((e = cudaMalloc(&dst, vec.size() * sizeof(T))) != cudaSuccess || \
         (e = cudaMemcpyAsync(dst, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) \
       { ctx->err = cudaGetErrorString(e); st = B2H_ECUDA; break; }
     cudaSetDevice(ctx->device);
-    UP(p->d_ssv_emis, ssv, uint32_t); UP(p->d_msv_cost, msv, uint32_t);
+    UP(p->d_ssv_emis, ssv, uint32_t); UP(p->d_msv_cost8, mc, uint8_t);
     UP(p->d_vit_rsc, vr, int16_t);    UP(p->d_vit_tsc, vt, int16_t);
     UP(p->d_fwd_rsc, fr, float);      UP(p->d_fwd_tsc, ft, float);
     UP(p->d_bias_eo, eo, float);
@@ -265,9 +282,19 @@ void b2h_profile_destroy(b2h_profile *p)
 {
   if (!p) return;
   if (p->ctx) cudaSetDevice(p->ctx->device);
-  void *ptrs[] = { p->d_ssv_emis, p->d_msv_cost, p->d_vit_rsc, p->d_vit_tsc, p->d_fwd_rsc, p->d_fwd_tsc, p->d_bias_eo };
+  void *ptrs[] = { p->d_ssv_emis, p->d_msv_cost8, p->d_vit_rsc, p->d_vit_tsc, p->d_fwd_rsc, p->d_fwd_tsc, p->d_bias_eo };
   for (void *q : ptrs) if (q) cudaFree(q);
   delete p;
+}
+
+int b2h_profile_set_annotation(b2h_profile *p, const char *consensus, const char *rf, const char *cs, const char *symbols)
+{
+  if (!p) return B2H_EINVAL;
+  p->consensus = consensus ? consensus : "";
+  p->rf = rf ? rf : "";
+  p->cs = cs ? cs : "";
+  if (symbols && *symbols) p->symbols = symbols;
+  return B2H_OK;
 }
 
 } // extern "C"

@@ -1,0 +1,857 @@
+// b2h_domaindef.cpp -- host-side domain definition for the comparisons that passed the Forward filter.
+//
+// The GPU cascade hands over, per survivor, the Forward and Backward parser special-state rows.
+// This file restates (in plain node-major scalar C++, nothing striped, nothing copied) what
+// p7_Pipeline does after p7_BackwardParser (p7_pipeline.c:767-933):
+//
+//   p7_DomainDecoding (impl_sse/decoding.c:160)           -> btot / etot / mocc
+//   region finding + is_multidomain_region (p7_domaindef.c:384-493, 531)
+//   multidomain regions: multihit p7_Forward on the region, 200 stochastic tracebacks
+//     (impl_sse/stotrace.c:71) with Easel's LCG stream (esl_random.c knuth()), p7_Null2_ByTrace
+//     (impl_sse/null2.c:131), single-linkage clustering of segment pairs (p7_spensemble.c:281)
+//   every envelope: unihit p7_Forward / p7_Backward / p7_Decoding (fwdback.c, decoding.c:76),
+//     p7_OptimalAccuracy + p7_OATrace (impl_sse/optacc.c:58, 225), p7_Null2_ByExpectation (null2.c:44),
+//     alignment display (p7_alidisplay.c:92)
+//   per-sequence and per-domain scores, null2 corrections, P-values (p7_pipeline.c:776-933)
+//
+// Survivors are ~1e-5 of all comparisons; this is "row 11-12, host orchestration" of SURVEY 8(a).
+// Moving the envelope DP to the GPU is SURVEY 8(f) rank 1 (next round).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <thread>
+#include "b2h_internal.h"
+#include "b2h_domaindef.h"
+
+namespace {
+
+const float NEGINF = -std::numeric_limits<float>::infinity();
+enum { XE = 0, XN = 1, XJ = 2, XB = 3, XC = 4, XSC = 5, NX = 6 };
+enum { sM = 0, sD = 1, sI = 2 };
+enum { T_BM = 0, T_MM, T_IM, T_DM, T_MD, T_MI, T_II, T_DD };
+enum { ST_M = 1, ST_D, ST_I, ST_S, ST_N, ST_B, ST_E, ST_C, ST_T, ST_J };   // p7t_statetype_e values are irrelevant; only identity matters
+
+// p7_FLogsum's lookup table (logsum.c:58-113)
+struct Logsum {
+  float tbl[16000];
+  Logsum() { for (int i = 0; i < 16000; i++) tbl[i] = (float)log(1. + exp((double)-i / 1000.f)); }
+  float operator()(float a, float b) const {
+    const float mx = a > b ? a : b, mn = a > b ? b : a;
+    return (mn == NEGINF || (mx - mn) >= 15.7f) ? mx : mx + tbl[(int)((mx - mn) * 1000.f)];
+  }
+};
+const Logsum &flogsum() { static Logsum L; return L; }
+
+// esl_vec_FSum: Kahan summation (esl_vectorops.c)
+float kahan_sum(const float *v, int n) {
+  float sum = 0.f, c = 0.f;
+  for (int i = 0; i < n; i++) { float y = v[i] - c; float t = sum + y; c = (t - sum) - y; sum = t; }
+  return sum;
+}
+void fnorm(float *v, int n) {
+  float s = kahan_sum(v, n);
+  if (s != 0.0f) for (int i = 0; i < n; i++) v[i] /= s;
+  else           for (int i = 0; i < n; i++) v[i] = (float)(1. / (float)n);
+}
+
+// Easel's "fast" generator as the pipeline creates it (esl_randomness_CreateFast; esl_random.c knuth())
+struct FastRng {
+  uint32_t seed, x;
+  static uint32_t mix3(uint32_t a, uint32_t b, uint32_t c) {
+    a -= b; a -= c; a ^= (c >> 13); b -= c; b -= a; b ^= (a << 8);  c -= a; c -= b; c ^= (b >> 13);
+    a -= b; a -= c; a ^= (c >> 12); b -= c; b -= a; b ^= (a << 16); c -= a; c -= b; c ^= (b >> 5);
+    a -= b; a -= c; a ^= (c >> 3);  b -= c; b -= a; b ^= (a << 10); c -= a; c -= b; c ^= (b >> 15);
+    return c;
+  }
+  void init(uint32_t s) { seed = s; x = mix3(s, 87654321u, 12345678u); if (x == 0) x = 42; }
+  double next() { x *= 69069u; x += 1u; return (double)x / 4294967296.0; }
+  int fchoose(const float *p, int n) {
+    double norm = 0.0, sum = 0.0; const double roll = next();
+    for (int i = 0; i < n; i++) norm += p[i];
+    for (int i = 0; i < n; i++) { sum += (double)p[i]; if (roll < (sum / norm)) return i; }
+    return n - 1;
+  }
+};
+
+struct Model {               // host view of one profile in a given uni/multihit + length configuration
+  int M, K, Kp;
+  const float *rsc;          // [Kp][M]
+  const float *t[8];         // node-major transition rows, index k-1
+  float eM, eL;              // xf[E][MOVE], xf[E][LOOP]
+  float pmove, ploop;        // xf[N|C|J][MOVE|LOOP]
+  const uint8_t *degen;
+  float r(int x, int k) const { return (x < Kp) ? rsc[(size_t)x * M + (k - 1)] : 0.0f; }
+};
+
+void configure(Model &m, bool multihit, int L) {
+  const float nj = multihit ? 1.0f : 0.0f;
+  m.eM = multihit ? 0.5f : 1.0f; m.eL = multihit ? 0.5f : 0.0f;
+  m.pmove = (2.0f + nj) / ((float)L + 2.0f + nj);
+  m.ploop = 1.0f - m.pmove;
+}
+
+struct Mx {                  // full DP matrix: rows 0..L, nodes 0..M (node 0 unused), cells {M,D,I}; specials per row
+  int M = 0, L = 0;
+  std::vector<float> dp, x;
+  float totscale = 0.f; bool own_scales = false;
+  void resize(int M_, int L_) { M = M_; L = L_; dp.assign((size_t)(L + 1) * (M + 2) * 3, 0.0f); x.assign((size_t)(L + 1) * NX, 0.0f); }
+  float *row(int i) { return dp.data() + (size_t)i * (M + 2) * 3; }
+  const float *row(int i) const { return dp.data() + (size_t)i * (M + 2) * 3; }
+  float &X(int i, int s) { return x[(size_t)i * NX + s]; }
+  float X(int i, int s) const { return x[(size_t)i * NX + s]; }
+};
+#define C3(rowp, k, s) (rowp)[(size_t)(k) * 3 + (s)]
+
+// forward_engine, do_full (fwdback.c:256-463).  dsq[0..L-1].  Returns false on eslERANGE.
+bool forward_full(const Model &m, const uint8_t *dsq, int L, Mx &ox, float *sc)
+{
+  const int M = m.M;
+  ox.resize(M, L);
+  float xE = 0.f, xN = 1.f, xJ = 0.f, xB = m.pmove, xC = 0.f;
+  ox.X(0, XE) = 0.f; ox.X(0, XN) = 1.f; ox.X(0, XJ) = 0.f; ox.X(0, XB) = xB; ox.X(0, XC) = 0.f; ox.X(0, XSC) = 1.f;
+  ox.totscale = 0.f;
+  for (int i = 1; i <= L; i++) {
+    const float *pp = ox.row(i - 1); float *cp = ox.row(i);
+    const int x = dsq[i - 1];
+    float em = 0.f, ed = 0.f;
+    C3(cp, 1, sD) = 0.f;
+    for (int k = 1; k <= M; k++) {
+      const int c = k - 1;
+      float v = xB * m.t[T_BM][c];
+      v += C3(pp, k - 1, sM) * m.t[T_MM][c];
+      v += C3(pp, k - 1, sI) * m.t[T_IM][c];
+      v += C3(pp, k - 1, sD) * m.t[T_DM][c];
+      v *= m.r(x, k);
+      C3(cp, k, sM) = v;
+      C3(cp, k, sI) = C3(pp, k, sM) * m.t[T_MI][c] + C3(pp, k, sI) * m.t[T_II][c];
+      if (k < M) C3(cp, k + 1, sD) = v * m.t[T_MD][c] + C3(cp, k, sD) * m.t[T_DD][c];
+      em += v; ed += C3(cp, k, sD);
+    }
+    xE = em + ed;
+    xN = xN * m.ploop;
+    xC = (xC * m.ploop) + (xE * m.eM);
+    xJ = (xJ * m.ploop) + (xE * m.eL);
+    xB = (xJ * m.pmove) + (xN * m.pmove);
+    if (xE > 1.0e4f) {
+      xN = xN / xE; xC = xC / xE; xJ = xJ / xE; xB = xB / xE;
+      const float inv = 1.0f / xE;
+      for (int k = 1; k <= M; k++) { C3(cp, k, sM) *= inv; C3(cp, k, sD) *= inv; C3(cp, k, sI) *= inv; }
+      ox.X(i, XSC) = xE;
+      ox.totscale = (float)((double)ox.totscale + log((double)xE));
+      xE = 1.0f;
+    } else ox.X(i, XSC) = 1.0f;
+    ox.X(i, XE) = xE; ox.X(i, XN) = xN; ox.X(i, XJ) = xJ; ox.X(i, XB) = xB; ox.X(i, XC) = xC;
+  }
+  if (std::isnan(xC) || (L > 0 && xC == 0.0f) || std::isinf(xC)) return false;
+  if (sc) *sc = (float)((double)ox.totscale + log((double)(xC * m.pmove)));
+  return true;
+}
+
+// backward_engine, do_full (fwdback.c:468-733)
+bool backward_full(const Model &m, const uint8_t *dsq, int L, const Mx &fwd, Mx &bk, float *sc)
+{
+  const int M = m.M;
+  bk.resize(M, L);
+  bk.own_scales = false;
+  float xJ = 0.f, xB = 0.f, xN = 0.f, xC = m.pmove, xE = xC * m.eM;
+  {
+    float *cp = bk.row(L);
+    for (int k = M; k >= 1; k--) {
+      const float dn = (k < M) ? C3(cp, k + 1, sD) : 0.f;
+      C3(cp, k, sD) = xE + m.t[T_DD][k - 1] * dn;
+      C3(cp, k, sM) = xE + m.t[T_MD][k - 1] * dn;
+      C3(cp, k, sI) = 0.f;
+    }
+    const float scL = fwd.X(L, XSC);
+    if (scL > 1.0f) {
+      xE = xE / scL; xN = xN / scL; xC = xC / scL; xJ = xJ / scL; xB = xB / scL;
+      const float inv = 1.0f / scL;
+      for (int k = 1; k <= M; k++) { C3(cp, k, sM) *= inv; C3(cp, k, sD) *= inv; C3(cp, k, sI) *= inv; }
+    }
+    bk.X(L, XSC) = scL;
+    bk.totscale = (float)log((double)scL);
+    bk.X(L, XE) = xE; bk.X(L, XN) = xN; bk.X(L, XJ) = xJ; bk.X(L, XB) = xB; bk.X(L, XC) = xC;
+  }
+  for (int i = L - 1; i >= 1; i--) {
+    const float *pp = bk.row(i + 1); float *cp = bk.row(i);
+    const int x = dsq[i];                                    // x_{i+1}
+    float bsum = 0.f;
+    for (int k = 1; k <= M; k++) {
+      const int c = k - 1;
+      const float mpv = (k < M) ? C3(pp, k + 1, sM) * m.r(x, k + 1) : 0.f;
+      const float ipv = C3(pp, k, sI);
+      const float tmm = (k < M) ? m.t[T_MM][c + 1] : 0.f, tim = (k < M) ? m.t[T_IM][c + 1] : 0.f, tdm = (k < M) ? m.t[T_DM][c + 1] : 0.f;
+      C3(cp, k, sI) = (ipv * m.t[T_II][c]) + (mpv * tim);
+      C3(cp, k, sD) = mpv * tdm;
+      C3(cp, k, sM) = (ipv * m.t[T_MI][c]) + (mpv * tmm);
+      bsum += (C3(pp, k, sM) * m.r(x, k)) * m.t[T_BM][c];
+    }
+    xB = bsum;
+    xC = xC * m.ploop;
+    xJ = (xB * m.pmove) + (xJ * m.ploop);
+    xN = (xB * m.pmove) + (xN * m.ploop);
+    xE = (xC * m.eM) + (xJ * m.eL);
+    for (int k = M; k >= 1; k--) {
+      const float dn = (k < M) ? C3(cp, k + 1, sD) : 0.f;
+      C3(cp, k, sD) = (C3(cp, k, sD) + xE) + m.t[T_DD][k - 1] * dn;
+      C3(cp, k, sM) = (C3(cp, k, sM) + xE) + m.t[T_MD][k - 1] * dn;
+    }
+    if (xB > 1.0e16f) bk.own_scales = true;
+    const float scale = bk.own_scales ? ((xB > 1.0e4f) ? xB : 1.0f) : fwd.X(i, XSC);
+    bk.X(i, XSC) = scale;
+    if (scale > 1.0f) {
+      xE /= scale; xN /= scale; xJ /= scale; xB /= scale; xC /= scale;
+      const float inv = 1.0f / scale;
+      for (int k = 1; k <= M; k++) { C3(cp, k, sM) *= inv; C3(cp, k, sD) *= inv; C3(cp, k, sI) *= inv; }
+      bk.totscale = (float)((double)bk.totscale + log((double)scale));
+    }
+    bk.X(i, XE) = xE; bk.X(i, XN) = xN; bk.X(i, XJ) = xJ; bk.X(i, XB) = xB; bk.X(i, XC) = xC;
+  }
+  {
+    float bsum = 0.f;
+    if (L >= 1) { const float *pp = bk.row(1); const int x = dsq[0];
+      for (int k = 1; k <= M; k++) bsum += (C3(pp, k, sM) * m.r(x, k)) * m.t[T_BM][k - 1]; }
+    xB = bsum;
+    xN = (xB * m.pmove) + (xN * m.ploop);
+    bk.X(0, XB) = xB; bk.X(0, XC) = 0.f; bk.X(0, XJ) = 0.f; bk.X(0, XN) = xN; bk.X(0, XE) = 0.f; bk.X(0, XSC) = 1.f;
+  }
+  if (std::isnan(xN) || (L > 0 && xN == 0.0f) || std::isinf(xN)) return false;
+  if (sc) *sc = (float)((double)bk.totscale + log((double)xN));
+  return true;
+}
+
+// p7_Decoding (decoding.c:76-134): posterior probabilities; pp may alias nothing (separate matrix). Returns false on eslERANGE.
+bool decoding(const Model &m, const Mx &f, const Mx &b, Mx &pp)
+{
+  const int M = m.M, L = f.L;
+  pp.resize(M, L);
+  float scaleproduct = 1.0f / b.X(0, XN);
+  for (int i = 1; i <= L; i++) {
+    const float *fr = f.row(i), *br = b.row(i); float *pr = pp.row(i);
+    const float totr = scaleproduct * f.X(i, XSC);
+    for (int k = 1; k <= M; k++) {
+      C3(pr, k, sM) = (C3(fr, k, sM) * C3(br, k, sM)) * totr;
+      C3(pr, k, sD) = 0.f;
+      C3(pr, k, sI) = (C3(fr, k, sI) * C3(br, k, sI)) * totr;
+    }
+    pp.X(i, XE) = 0.f;
+    pp.X(i, XN) = f.X(i - 1, XN) * b.X(i, XN) * m.ploop * scaleproduct;
+    pp.X(i, XJ) = f.X(i - 1, XJ) * b.X(i, XJ) * m.ploop * scaleproduct;
+    pp.X(i, XC) = f.X(i - 1, XC) * b.X(i, XC) * m.ploop * scaleproduct;
+    pp.X(i, XB) = 0.f;
+    if (b.own_scales) scaleproduct *= f.X(i, XSC) / b.X(i, XSC);
+  }
+  return !std::isinf(scaleproduct);
+}
+
+// p7_OptimalAccuracy (optacc.c:58-176).  "impossible transition" contributes 0.0 (the AND-mask trick), not -inf.
+float optimal_accuracy(const Model &m, const Mx &pp, Mx &ox)
+{
+  const int M = m.M, L = pp.L;
+  ox.resize(M, L);
+  { float *r0 = ox.row(0); for (int k = 0; k <= M + 1; k++) { C3(r0, k, sM) = NEGINF; C3(r0, k, sD) = NEGINF; C3(r0, k, sI) = NEGINF; } }
+  ox.X(0, XE) = NEGINF; ox.X(0, XN) = 0.f; ox.X(0, XJ) = NEGINF; ox.X(0, XB) = 0.f; ox.X(0, XC) = NEGINF;
+  auto gate = [](float t, float v) -> float { return (t > 0.0f) ? v : 0.0f; };
+  for (int i = 1; i <= L; i++) {
+    const float *pr = ox.row(i - 1); float *cr = ox.row(i); const float *ppr = pp.row(i);
+    const float xB = ox.X(i - 1, XB);
+    float xE = NEGINF;
+    C3(cr, 0, sM) = C3(cr, 0, sD) = C3(cr, 0, sI) = NEGINF;
+    float dcv = NEGINF;                                          // value entering D(i,k): from M(i,k-1)
+    for (int k = 1; k <= M; k++) {
+      const int c = k - 1;
+      float sv = gate(m.t[T_BM][c], xB);
+      sv = std::max(sv, gate(m.t[T_MM][c], C3(pr, k - 1, sM)));
+      sv = std::max(sv, gate(m.t[T_IM][c], C3(pr, k - 1, sI)));
+      sv = std::max(sv, gate(m.t[T_DM][c], C3(pr, k - 1, sD)));
+      sv = sv + C3(ppr, k, sM);
+      xE = std::max(xE, sv);
+      C3(cr, k, sM) = sv;
+      // D(i,k) = max(M->D from k-1, D->D from k-1)
+      float d = dcv;
+      if (k > 1) d = std::max(d, gate(m.t[T_DD][c - 1], C3(cr, k - 1, sD)));
+      C3(cr, k, sD) = d;
+      dcv = gate(m.t[T_MD][c], sv);
+      float iv = gate(m.t[T_MI][c], C3(pr, k, sM));
+      iv = std::max(iv, gate(m.t[T_II][c], C3(pr, k, sI)));
+      C3(cr, k, sI) = iv + C3(ppr, k, sI);
+    }
+    for (int k = 1; k <= M; k++) xE = std::max(xE, C3(cr, k, sD));
+    ox.X(i, XE) = xE;
+    float t1 = (m.ploop == 0.0f) ? 0.0f : ox.X(i - 1, XJ) + pp.X(i, XJ);
+    float t2 = (m.eL == 0.0f) ? 0.0f : ox.X(i, XE);
+    ox.X(i, XJ) = std::max(t1, t2);
+    t1 = (m.ploop == 0.0f) ? 0.0f : ox.X(i - 1, XC) + pp.X(i, XC);
+    t2 = (m.eM == 0.0f) ? 0.0f : ox.X(i, XE);
+    ox.X(i, XC) = std::max(t1, t2);
+    ox.X(i, XN) = (m.ploop == 0.0f) ? 0.0f : ox.X(i - 1, XN) + pp.X(i, XN);
+    t1 = (m.pmove == 0.0f) ? 0.0f : ox.X(i, XN);
+    t2 = (m.pmove == 0.0f) ? 0.0f : ox.X(i, XJ);
+    ox.X(i, XB) = std::max(t1, t2);
+  }
+  return ox.X(L, XC);
+}
+
+struct Trace {
+  std::vector<int8_t> st; std::vector<int> k, i; std::vector<float> pp;
+  // domain index (p7_trace_Index)
+  std::vector<int> tfrom, tto, sqfrom, sqto, hmmfrom, hmmto;
+  void clear() { st.clear(); k.clear(); i.clear(); pp.clear(); tfrom.clear(); tto.clear(); sqfrom.clear(); sqto.clear(); hmmfrom.clear(); hmmto.clear(); }
+  void push(int s, int kk, int ii, float p = 0.f) {
+    // p7_trace_AppendWithPP: only emitting states keep their i, only main states their k (p7_trace.c)
+    int ki = 0, ii2 = 0;
+    switch (s) {
+      case ST_N: case ST_C: case ST_J: ii2 = (!st.empty() && st.back() == s) ? ii : 0; break;
+      case ST_M: ki = kk; ii2 = ii; break;
+      case ST_I: ki = kk; ii2 = ii; break;
+      case ST_D: ki = kk; break;
+      default: break;
+    }
+    st.push_back((int8_t)s); k.push_back(ki); i.push_back(ii2); pp.push_back((ii2 > 0) ? p : 0.f);
+  }
+  void reverse() {
+    // p7_trace_Reverse (p7_trace.c): traces built backwards hold C-,Cx,Cx; pull residues back by one before reversing
+    for (size_t z = 0; z + 1 < st.size(); z++)
+      if (st[z] == st[z + 1] && (st[z] == ST_N || st[z] == ST_C || st[z] == ST_J) && i[z] == 0 && i[z + 1] > 0) {
+        i[z] = i[z + 1]; i[z + 1] = 0; pp[z] = pp[z + 1]; pp[z + 1] = 0.f;
+      }
+    std::reverse(st.begin(), st.end()); std::reverse(k.begin(), k.end()); std::reverse(i.begin(), i.end()); std::reverse(pp.begin(), pp.end()); }
+  void index() {
+    tfrom.clear(); tto.clear(); sqfrom.clear(); sqto.clear(); hmmfrom.clear(); hmmto.clear();
+    for (size_t z = 0; z < st.size(); z++) {
+      if (st[z] == ST_B) { tfrom.push_back((int)z); sqfrom.push_back(0); hmmfrom.push_back(0); tto.push_back(0); sqto.push_back(0); hmmto.push_back(0); }
+      else if (st[z] == ST_M && !tfrom.empty()) {
+        const size_t d = tfrom.size() - 1;
+        if (sqfrom[d] == 0) sqfrom[d] = i[z];
+        if (hmmfrom[d] == 0) hmmfrom[d] = k[z];
+        sqto[d] = i[z]; hmmto[d] = k[z];
+      } else if (st[z] == ST_E && !tfrom.empty()) tto[tfrom.size() - 1] = (int)z;
+    }
+  }
+  int ndom() const { return (int)tfrom.size(); }
+};
+// NB on traceback bookkeeping: the reference appends (state, k, i) during the walk from T back to S where an
+// N/C/J state "emits on transition": p7_trace_Append stores i only for the second and later of a run in
+// traceback order; after p7_trace_Reverse the FIRST state of each run is the non-emitting one.  We build the
+// trace directly in traceback order with the same rule and then reverse, exactly as the reference does.
+
+inline int Qf(int M) { return std::max(2, (M - 1) / 4 + 1); }     // p7O_NQF
+
+// p7_OATrace (optacc.c:225-268) with its select_* helpers
+bool oa_trace(const Model &m, const Mx &pp, const Mx &ox, Trace &tr)
+{
+  const int M = m.M, L = ox.L, Q = Qf(M);
+  int i = L, k = 0;
+  tr.clear();
+  tr.push(ST_T, k, i); tr.push(ST_C, k, i);
+  int s0 = ST_C;
+  auto path = [](float t, float v) -> float { return (t == 0.0f) ? NEGINF : v; };
+  size_t guard = (size_t)(L + M + 8) * 4 + 64;
+  while (s0 != ST_S) {
+    if (guard-- == 0) return false;
+    int s1 = -1;
+    switch (s0) {
+      case ST_M: {
+        const float *pr = ox.row(i - 1); const int c = k - 1;
+        float p[4] = { path(m.t[T_MM][c], C3(pr, k - 1, sM)), path(m.t[T_IM][c], C3(pr, k - 1, sI)),
+                       path(m.t[T_DM][c], C3(pr, k - 1, sD)), path(m.t[T_BM][c], ox.X(i - 1, XB)) };
+        if (k == 1) { p[0] = path(m.t[T_MM][c], 0.0f); p[1] = path(m.t[T_IM][c], 0.0f); p[2] = path(m.t[T_DM][c], 0.0f); }   // rightshiftz: zeros shift in
+        static const int state[4] = { ST_M, ST_I, ST_D, ST_B };
+        int best = 0; for (int j = 1; j < 4; j++) if (p[j] > p[best]) best = j;
+        s1 = state[best]; k--; i--; break; }
+      case ST_D: {
+        const float *cr = ox.row(i); const int c = k - 1;
+        const float p0 = (k > 1) ? path(m.t[T_MD][c - 1], C3(cr, k - 1, sM)) : NEGINF;
+        const float p1 = (k > 1) ? path(m.t[T_DD][c - 1], C3(cr, k - 1, sD)) : NEGINF;
+        s1 = (p0 >= p1) ? ST_M : ST_D; k--; break; }
+      case ST_I: {
+        const float *pr = ox.row(i - 1); const int c = k - 1;
+        const float p0 = path(m.t[T_MI][c], C3(pr, k, sM)), p1 = path(m.t[T_II][c], C3(pr, k, sI));
+        s1 = (p0 >= p1) ? ST_M : ST_I; i--; break; }
+      case ST_N: s1 = (i == 0) ? ST_S : ST_N; break;
+      case ST_C: {
+        const float p0 = (m.ploop == 0.0f) ? NEGINF : ox.X(i - 1, XC) + pp.X(i, XC);
+        const float p1 = (m.eM == 0.0f) ? NEGINF : ox.X(i, XE);
+        s1 = (p0 > p1) ? ST_C : ST_E; break; }
+      case ST_J: {
+        const float p0 = (m.ploop == 0.0f) ? NEGINF : ox.X(i - 1, XJ) + pp.X(i, XJ);
+        const float p1 = (m.eL == 0.0f) ? NEGINF : ox.X(i, XE);
+        s1 = (p0 > p1) ? ST_J : ST_E; break; }
+      case ST_E: {
+        // the reference scans its striped row: q outer, lane r inner, M cells win ties (>=), D cells need > (optacc.c:404-421)
+        const float *cr = ox.row(i);
+        float mx = NEGINF; int smax = -1, kmax = 0;
+        for (int q = 0; q < Q; q++) {
+          for (int r = 0; r < 4; r++) { const int kk = r * Q + q + 1; if (kk <= M && C3(cr, kk, sM) >= mx) { mx = C3(cr, kk, sM); smax = ST_M; kmax = kk; } }
+          for (int r = 0; r < 4; r++) { const int kk = r * Q + q + 1; if (kk <= M && C3(cr, kk, sD) >  mx) { mx = C3(cr, kk, sD); smax = ST_D; kmax = kk; } }
+        }
+        k = kmax; s1 = smax; break; }
+      case ST_B: {
+        const float p0 = (m.pmove == 0.0f) ? NEGINF : ox.X(i, XN);
+        const float p1 = (m.pmove == 0.0f) ? NEGINF : ox.X(i, XJ);
+        s1 = (p0 > p1) ? ST_N : ST_J; break; }
+      default: return false;
+    }
+    if (s1 == -1) return false;
+    float postprob = 0.0f;
+    switch (s1) {
+      case ST_M: postprob = C3(pp.row(i), k, sM); break;
+      case ST_I: postprob = C3(pp.row(i), k, sI); break;
+      case ST_N: if (s0 == s1) postprob = pp.X(i, XN); break;
+      case ST_C: if (s0 == s1) postprob = pp.X(i, XC); break;
+      case ST_J: if (s0 == s1) postprob = pp.X(i, XJ); break;
+      default: break;
+    }
+    tr.push(s1, k, i, postprob);
+    if ((s1 == ST_N || s1 == ST_J || s1 == ST_C) && s1 == s0) i--;
+    s0 = s1;
+  }
+  tr.reverse();
+  return true;
+}
+
+// p7_StochasticTrace (stotrace.c:71-113)
+bool stochastic_trace(FastRng &rng, const Model &m, int L, const Mx &ox, Trace &tr)
+{
+  const int M = m.M, Q = Qf(M);
+  int i = L, k = 0;
+  tr.clear();
+  tr.push(ST_T, k, i); tr.push(ST_C, k, i);
+  int s0 = ST_C;
+  size_t guard = (size_t)(L + M + 8) * 8 + 64;
+  while (s0 != ST_S) {
+    if (guard-- == 0) return false;
+    int s1 = -1;
+    switch (s0) {
+      case ST_M: {
+        const float *pr = ox.row(i - 1); const int c = k - 1;
+        float p[4] = { ox.X(i - 1, XB) * m.t[T_BM][c], C3(pr, k - 1, sM) * m.t[T_MM][c], C3(pr, k - 1, sI) * m.t[T_IM][c], C3(pr, k - 1, sD) * m.t[T_DM][c] };
+        if (k == 1) { p[1] = 0.0f * m.t[T_MM][c]; p[2] = 0.0f * m.t[T_IM][c]; p[3] = 0.0f * m.t[T_DM][c]; }
+        static const int state[4] = { ST_B, ST_M, ST_I, ST_D };
+        fnorm(p, 4); s1 = state[rng.fchoose(p, 4)]; k--; i--; break; }
+      case ST_D: {
+        const float *cr = ox.row(i); const int c = k - 1;
+        float p[2] = { (k > 1) ? C3(cr, k - 1, sM) * m.t[T_MD][c - 1] : 0.0f, (k > 1) ? C3(cr, k - 1, sD) * m.t[T_DD][c - 1] : 0.0f };
+        fnorm(p, 2); s1 = (rng.fchoose(p, 2) == 0) ? ST_M : ST_D; k--; break; }
+      case ST_I: {
+        const float *pr = ox.row(i - 1); const int c = k - 1;
+        float p[2] = { C3(pr, k, sM) * m.t[T_MI][c], C3(pr, k, sI) * m.t[T_II][c] };
+        fnorm(p, 2); s1 = (rng.fchoose(p, 2) == 0) ? ST_M : ST_I; i--; break; }
+      case ST_N: s1 = (i == 0) ? ST_S : ST_N; break;
+      case ST_C: {
+        float p[2] = { ox.X(i - 1, XC) * m.ploop, ox.X(i, XE) * m.eM * ox.X(i, XSC) };
+        fnorm(p, 2); s1 = (rng.fchoose(p, 2) == 0) ? ST_C : ST_E; break; }
+      case ST_J: {
+        float p[2] = { ox.X(i - 1, XJ) * m.ploop, ox.X(i, XE) * m.eL * ox.X(i, XSC) };
+        fnorm(p, 2); s1 = (rng.fchoose(p, 2) == 0) ? ST_J : ST_E; break; }
+      case ST_E: {
+        double sum = 0.0; const double roll = rng.next();
+        const float norm = (float)(1.0 / ox.X(i, XE));
+        const float *cr = ox.row(i);
+        bool found = false;
+        for (int rep = 0; rep < 4 && !found; rep++)
+          for (int q = 0; q < Q && !found; q++) {
+            for (int r = 0; r < 4 && !found; r++) { const int kk = r * Q + q + 1; const float v = (kk <= M) ? C3(cr, kk, sM) * norm : 0.0f; sum += v; if (roll < sum) { k = kk; s1 = ST_M; found = true; } }
+            for (int r = 0; r < 4 && !found; r++) { const int kk = r * Q + q + 1; const float v = (kk <= M) ? C3(cr, kk, sD) * norm : 0.0f; sum += v; if (roll < sum) { k = kk; s1 = ST_D; found = true; } }
+          }
+        if (!found) return false;
+        break; }
+      case ST_B: {
+        float p[2] = { ox.X(i, XN) * m.pmove, ox.X(i, XJ) * m.pmove };
+        fnorm(p, 2); s1 = (rng.fchoose(p, 2) == 0) ? ST_N : ST_J; break; }
+      default: return false;
+    }
+    if (s1 == -1) return false;
+    tr.push(s1, k, i);
+    if ((s1 == ST_N || s1 == ST_J || s1 == ST_C) && s1 == s0) i--;
+    s0 = s1;
+  }
+  tr.reverse();
+  return true;
+}
+
+void avg_degenerate(const Model &m, float *null2)      // esl_abc_FAvgScVec + the three special codes
+{
+  for (int x = m.K + 1; x <= m.Kp - 3; x++) {
+    float result = 0.f; int nd = 0;
+    for (int y = 0; y < m.K; y++) if (m.degen && m.degen[(size_t)x * m.K + y]) { result += null2[y]; nd++; }
+    null2[x] = nd ? result / (float)nd : 0.0f;
+  }
+  null2[m.K] = 1.0f; null2[m.Kp - 2] = 1.0f; null2[m.Kp - 1] = 1.0f;
+}
+
+// p7_Null2_ByExpectation (null2.c:44-110)
+void null2_by_expectation(const Model &m, const Mx &pp, float *null2)
+{
+  const int M = m.M, Ld = pp.L;
+  std::vector<float> em(M + 1, 0.f), ei(M + 1, 0.f);
+  float xn = pp.X(1, XN), xc = pp.X(1, XC), xj = pp.X(1, XJ);
+  { const float *r = pp.row(1); for (int k = 1; k <= M; k++) { em[k] = C3(r, k, sM); ei[k] = C3(r, k, sI); } }
+  for (int i = 2; i <= Ld; i++) {
+    const float *r = pp.row(i);
+    for (int k = 1; k <= M; k++) { em[k] = C3(r, k, sM) + em[k]; ei[k] = C3(r, k, sI) + ei[k]; }
+    xn += pp.X(i, XN); xc += pp.X(i, XC); xj += pp.X(i, XJ);
+  }
+  const float norm = (float)(1.0 / (float)Ld);
+  for (int k = 1; k <= M; k++) { em[k] *= norm; ei[k] *= norm; }
+  xn *= norm; xc *= norm; xj *= norm;
+  const float xfactor = xn + xc + xj;
+  for (int x = 0; x < m.K; x++) {
+    float sv = 0.f;
+    for (int k = 1; k <= M; k++) { sv += em[k] * m.r(x, k); sv += ei[k]; }
+    null2[x] = sv + xfactor;
+  }
+  avg_degenerate(m, null2);
+}
+
+// p7_Null2_ByTrace (null2.c:131-205).  Reference quirk kept: I states are counted in the M slot of their node.
+void null2_by_trace(const Model &m, const Trace &tr, int zstart, int zend, float *null2)
+{
+  const int M = m.M;
+  std::vector<float> em(M + 1, 0.f);
+  float xn = 0.f, xc = 0.f, xj = 0.f; int Ld = 0;
+  for (int z = zstart; z <= zend; z++) {
+    if (tr.i[z] == 0) continue;
+    Ld++;
+    if (tr.k[z] > 0) em[tr.k[z]] += 1.0f;
+    else switch (tr.st[z]) { case ST_N: xn += 1.0f; break; case ST_C: xc += 1.0f; break; case ST_J: xj += 1.0f; break; default: break; }
+  }
+  const float norm = (float)(1.0 / (float)Ld);
+  for (int k = 1; k <= M; k++) em[k] *= norm;
+  xn *= norm; xc *= norm; xj *= norm;
+  const float xfactor = xn + xc + xj;
+  for (int x = 0; x < m.K; x++) {
+    float sv = 0.f;
+    for (int k = 1; k <= M; k++) sv += em[k] * m.r(x, k);
+    null2[x] = sv + xfactor;
+  }
+  avg_degenerate(m, null2);
+}
+
+// ---- segment-pair ensemble clustering (p7_spensemble.c) ----
+struct SegPair { int idx, i, j, k, m; float prob; };
+
+bool sp_link(const SegPair &h1, const SegPair &h2)      // link_spsamples with min_overlap 0.8, of_smaller, max_diagdiff 4
+{
+  int nov = std::min(h1.j, h2.j) - std::max(h1.i, h2.i) + 1;
+  int n = std::min(h1.j - h1.i + 1, h2.j - h2.i + 1);
+  if ((float)nov / (float)n < 0.8f) return false;
+  nov = std::min(h1.m, h2.m) - std::max(h1.k, h2.k);
+  n = std::min(h1.m - h1.k + 1, h2.m - h2.k + 1);
+  if ((float)nov / (float)n < 0.8f) return false;
+  int d1 = h1.i - h1.k, d2 = h2.i - h2.k; if (std::abs(d1 - d2) <= 4) return true;
+  d1 = h1.j - h1.m; d2 = h2.j - h2.m;     if (std::abs(d1 - d2) <= 4) return true;
+  return false;
+}
+
+void sp_cluster(const std::vector<SegPair> &sp, int nsamples, std::vector<SegPair> &sigc)
+{
+  const int n = (int)sp.size();
+  std::vector<int> a(n), b(n), assign(n, 0);
+  // esl_cluster_SingleLinkage (esl_cluster.c)
+  for (int v = 0; v < n; v++) a[v] = n - v - 1;
+  int na = n, nb = 0, nc = 0;
+  while (na > 0) {
+    int v = a[na - 1]; na--; b[nb++] = v;
+    while (nb > 0) {
+      v = b[nb - 1]; nb--; assign[v] = nc;
+      for (int i = na - 1; i >= 0; i--)
+        if (sp_link(sp[v], sp[a[i]])) { const int w = a[i]; a[i] = a[na - 1]; na--; b[nb++] = w; }
+    }
+    nc++;
+  }
+  sigc.clear();
+  std::vector<int> epc;
+  for (int c = 0; c < nc; c++) {
+    int ninc = 0, idx_of_last = -1;
+    for (int h = 0; h < n; h++) if (assign[h] == c) { if (sp[h].idx != idx_of_last) ninc++; idx_of_last = sp[h].idx; }
+    if ((float)ninc / (float)nsamples < 0.25f) continue;
+    int imin = 0, imax = 0, jmin = 0, jmax = 0, kmin = 0, kmax = 0, mmin = 0, mmax = 0;
+    for (int h = 0; h < n; h++) if (assign[h] == c) {
+      if (imin == 0) { imin = imax = sp[h].i; jmin = jmax = sp[h].j; kmin = kmax = sp[h].k; mmin = mmax = sp[h].m; }
+      else { imin = std::min(imin, sp[h].i); imax = std::max(imax, sp[h].i); jmin = std::min(jmin, sp[h].j); jmax = std::max(jmax, sp[h].j);
+             kmin = std::min(kmin, sp[h].k); kmax = std::max(kmax, sp[h].k); mmin = std::min(mmin, sp[h].m); mmax = std::max(mmax, sp[h].m); }
+    }
+    const int thr = (int)ceilf((float)ninc * 0.02f);
+    auto argmax = [&](int w) { int best = 0; for (int z = 1; z < w; z++) if (epc[z] > epc[best]) best = z; return best; };
+    auto leftmost = [&](int lo, int hi, int SegPair::*fld) {
+      epc.assign(hi - lo + 1, 0);
+      for (int h = 0; h < n; h++) if (assign[h] == c) epc[sp[h].*fld - lo]++;
+      int best; for (best = lo; best <= hi; best++) if (epc[best - lo] >= thr) break;
+      if (best > hi) best = lo + argmax(hi - lo + 1);
+      return best; };
+    auto rightmost = [&](int lo, int hi, int SegPair::*fld) {
+      epc.assign(hi - lo + 1, 0);
+      for (int h = 0; h < n; h++) if (assign[h] == c) epc[sp[h].*fld - lo]++;
+      int best; for (best = hi; best >= lo; best--) if (epc[best - lo] >= thr) break;
+      if (best < lo) best = lo + argmax(hi - lo + 1);
+      return best; };
+    const int best_i = leftmost(imin, imax, &SegPair::i), best_k = leftmost(kmin, kmax, &SegPair::k);
+    const int best_j = rightmost(jmin, jmax, &SegPair::j), best_m = rightmost(mmin, mmax, &SegPair::m);
+    if (best_i > best_j || best_k > best_m) continue;
+    SegPair s; s.i = best_i; s.j = best_j; s.k = best_k; s.m = best_m; s.idx = c; s.prob = (float)ninc / (float)nsamples;
+    sigc.push_back(s);
+  }
+  // qsort by start; qsort is not stable, but equal starts within one region are vanishingly rare
+  std::stable_sort(sigc.begin(), sigc.end(), [](const SegPair &x, const SegPair &y) { return x.i < y.i; });
+}
+
+struct DomOut { b2h_domain d; std::string text; };
+struct HitOut { bool valid = false; b2h_hit hit; std::vector<DomOut> doms; };
+
+char encode_pp(float p) { return (p + 0.05 >= 1.0) ? '*' : (char)((char)((p + 0.05) * 10.0) + '0'); }
+
+struct Worker {
+  Mx fwd, bck, pp, oa;
+  Trace tr;
+  std::vector<float> btot, etot, mocc, n2sc;
+  FastRng rng;
+};
+
+// rescore_isolated_domain (p7_domaindef.c:814-982), protein (non long-target) branch.  i..j are 1-based in the full sequence.
+bool rescore_domain(Worker &w, Model &m, const b2h_profile *prof, const uint8_t *dsq, int L, int i, int j, bool null2_is_done, DomOut &out)
+{
+  const int Ld = j - i + 1;
+  float envsc;
+  if (!forward_full(m, dsq + i - 1, Ld, w.fwd, &envsc)) envsc = std::numeric_limits<float>::infinity();   // p7_Forward's status is ignored by the caller
+  backward_full(m, dsq + i - 1, Ld, w.fwd, w.bck, nullptr);
+  if (!decoding(m, w.fwd, w.bck, w.pp)) return false;                      // eslERANGE -> domain dropped (eslFAIL)
+  const float oasc = optimal_accuracy(m, w.pp, w.oa);
+  if (!oa_trace(m, w.pp, w.oa, w.tr)) return false;
+  for (size_t z = 0; z < w.tr.st.size(); z++) if (w.tr.i[z] > 0) w.tr.i[z] += i - 1;
+
+  // alignment display (p7_alidisplay_Create, p7_alidisplay.c:92-273): first M .. last M of the (single) domain
+  int z1 = -1, z2 = -1;
+  for (size_t z = 0; z < w.tr.st.size(); z++) if (w.tr.st[z] == ST_M) { if (z1 < 0) z1 = (int)z; z2 = (int)z; }
+  if (z1 < 0) return false;
+  const int N = z2 - z1 + 1;
+  const bool has_rf = !prof->rf.empty(), has_cs = !prof->cs.empty();
+  std::string model(N, ' '), mline(N, ' '), aseq(N, ' '), ppline(N, ' '), rfline, csline;
+  if (has_rf) rfline.assign(N, ' ');
+  if (has_cs) csline.assign(N, ' ');
+  const std::string &sym = prof->symbols;
+  auto cons = [&](int k) -> char { return (k >= 1 && k <= (int)prof->consensus.size()) ? prof->consensus[k - 1] : 'x'; };
+  for (int z = z1; z <= z2; z++) {
+    const int k = w.tr.k[z], ii = w.tr.i[z], s = w.tr.st[z], a = z - z1;
+    const int x = (ii > 0) ? dsq[ii - 1] : 0;
+    if (has_rf) rfline[a] = (s == ST_I) ? '.' : prof->rf[k - 1];
+    if (has_cs) csline[a] = (s == ST_I) ? '.' : prof->cs[k - 1];
+    ppline[a] = (s == ST_D) ? '.' : encode_pp(w.tr.pp[z]);
+    if (s == ST_M) {
+      model[a] = cons(k);
+      const char cu = (char)toupper((unsigned char)cons(k));
+      const size_t cpos = sym.find(cu);
+      if (cpos != std::string::npos && (int)cpos == x) mline[a] = model[a];
+      else if (m.r(x, k) > 1.0f) mline[a] = '+';
+      else mline[a] = ' ';
+      aseq[a] = (char)toupper((unsigned char)sym[x]);
+    } else if (s == ST_I) {
+      model[a] = '.'; mline[a] = ' '; aseq[a] = (char)tolower((unsigned char)sym[x]);
+    } else {
+      model[a] = cons(k); mline[a] = ' '; aseq[a] = '-';
+    }
+  }
+  b2h_domain &d = out.d;
+  memset(&d, 0, sizeof d);
+  d.hmmfrom = w.tr.k[z1]; d.hmmto = w.tr.k[z2]; d.sqfrom = w.tr.i[z1]; d.sqto = w.tr.i[z2]; d.N = N;
+  d.has_rf = has_rf; d.has_cs = has_cs;
+  out.text.clear();
+  for (const std::string *sp : { &model, &mline, &aseq, &ppline }) { out.text += *sp; out.text.push_back('\0'); }
+  if (has_rf) { out.text += rfline; out.text.push_back('\0'); }
+  if (has_cs) { out.text += csline; out.text.push_back('\0'); }
+
+  float domcorrection = 0.0f;
+  if (!null2_is_done) {
+    float null2[B2H_NCODE];
+    null2_by_expectation(m, w.pp, null2);
+    for (int pos = i; pos <= j; pos++) w.n2sc[pos] = logf(null2[dsq[pos - 1] < m.Kp ? dsq[pos - 1] : m.Kp - 1]);
+  }
+  for (int pos = i; pos <= j; pos++) domcorrection += w.n2sc[pos];
+  d.domcorrection = domcorrection;
+  d.iali = d.sqfrom; d.jali = d.sqto; d.ienv = i; d.jenv = j; d.envsc = envsc; d.oasc = oasc;
+  return true;
+}
+
+void ddef_one(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, HitOut &out)
+{
+  out.valid = false; out.doms.clear();
+  const b2h_profile *prof = t.prof;
+  const int L = t.L;
+  Model m; m.M = prof->M; m.K = prof->K; m.Kp = prof->Kp; m.rsc = prof->h_fwd_rsc.data();
+  for (int q = 0; q < 8; q++) m.t[q] = prof->h_fwd_tsc.data() + (size_t)q * prof->M;
+  m.degen = prof->h_degen.empty() ? nullptr : prof->h_degen.data();
+  configure(m, true, L);
+  const float ploop_multi = m.ploop;
+
+  // p7_DomainDecoding (decoding.c:160-193) on the parser specials
+  auto FX = [&](int i, int s) { return t.fx[(size_t)i * NX + s]; };
+  auto BX = [&](int i, int s) { return t.bx[(size_t)i * NX + s]; };
+  w.btot.assign(L + 1, 0.f); w.etot.assign(L + 1, 0.f); w.mocc.assign(L + 1, 0.f); w.n2sc.assign(L + 1, 0.f);
+  {
+    float scaleproduct = 1.0f / BX(0, XN);
+    for (int i = 1; i <= L; i++) {
+      w.btot[i] = w.btot[i - 1] + (FX(i - 1, XB) * BX(i - 1, XB) * FX(i - 1, XSC) * scaleproduct);
+      if (t.bck_own_scales) scaleproduct *= FX(i - 1, XSC) / BX(i - 1, XSC);
+      w.etot[i] = w.etot[i - 1] + (FX(i, XE) * BX(i, XE) * FX(i, XSC) * scaleproduct);
+      float njcp = FX(i - 1, XN) * BX(i, XN) * ploop_multi * scaleproduct;
+      njcp += FX(i - 1, XJ) * BX(i, XJ) * ploop_multi * scaleproduct;
+      njcp += FX(i - 1, XC) * BX(i, XC) * ploop_multi * scaleproduct;
+      w.mocc[i] = (float)(1. - (double)njcp);
+    }
+    if (std::isinf(scaleproduct)) return;                 // eslERANGE from p7_DomainDecoding: the reference's pipeline fails here
+  }
+  const float nexpected = w.btot[L];
+  int nregions = 0, nclustered = 0, noverlaps = 0, nenvelopes = 0;
+  const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
+  const int nsamples = 200;
+
+  configure(m, false, L);                                 // p7_oprofile_ReconfigUnihit(om, saveL)
+  int i = -1; bool triggered = false;
+  for (int j = 1; j <= L; j++) {
+    if (!triggered) {
+      if (w.mocc[j] - (w.btot[j] - w.btot[j - 1]) < rt2) i = j;
+      else if (i == -1) i = j;
+      if (w.mocc[j] >= rt1) triggered = true;
+    } else if (w.mocc[j] - (w.etot[j] - w.etot[j - 1]) < rt2) {
+      nregions++;
+      // is_multidomain_region (p7_domaindef.c:531)
+      float mx = -1.0f;
+      for (int z = i; z <= j; z++) { const float en = std::min(w.etot[z] - w.etot[i - 1], w.btot[j] - w.btot[z - 1]); mx = std::max(mx, en); }
+      if (mx >= rt3) {
+        nclustered++;
+        configure(m, true, L);                            // ReconfigMultihit(om, saveL)
+        const int Lr = j - i + 1;
+        forward_full(m, t.dsq + i - 1, Lr, w.fwd, nullptr);
+        // region_trace_ensemble (p7_domaindef.c:597-678)
+        for (int pos = i; pos <= j; pos++) w.n2sc[pos] = 0.0f;
+        if (prm->seed != 0) w.rng.init(prm->seed);        // do_reseeding
+        std::vector<SegPair> sp;
+        float null2[B2H_NCODE];
+        for (int ts = 0; ts < nsamples; ts++) {
+          if (!stochastic_trace(w.rng, m, Lr, w.fwd, w.tr)) break;
+          w.tr.index();
+          int pos = 1;
+          for (int d = 0; d < w.tr.ndom(); d++) {
+            SegPair s; s.idx = ts; s.i = w.tr.sqfrom[d] + i - 1; s.j = w.tr.sqto[d] + i - 1; s.k = w.tr.hmmfrom[d]; s.m = w.tr.hmmto[d]; s.prob = 0.f;
+            sp.push_back(s);
+            null2_by_trace(m, w.tr, w.tr.tfrom[d], w.tr.tto[d], null2);
+            for (; pos <= w.tr.sqfrom[d]; pos++) w.n2sc[i + pos - 1] += 1.0f;
+            for (; pos <= w.tr.sqto[d];   pos++) { const int x = t.dsq[i + pos - 2]; w.n2sc[i + pos - 1] += null2[x < m.Kp ? x : m.Kp - 1]; }
+          }
+          for (; pos <= Lr; pos++) w.n2sc[i + pos - 1] += 1.0f;
+        }
+        for (int pos = i; pos <= j; pos++) w.n2sc[pos] = logf(w.n2sc[pos] / (float)nsamples);
+        std::vector<SegPair> sigc;
+        sp_cluster(sp, nsamples, sigc);
+        // remove dominated clusters (p7_domaindef.c:647-676)
+        std::vector<char> dominated(sigc.size(), 0);
+        for (size_t d = 0; d < sigc.size(); d++)
+          for (size_t d2 = d + 1; d2 < sigc.size(); d2++) {
+            const int nov = std::min(sigc[d].j, sigc[d2].j) - std::max(sigc[d].i, sigc[d2].i) + 1;
+            if (nov == 0) break;
+            const int n = std::min(sigc[d].j - sigc[d].i + 1, sigc[d2].j - sigc[d2].i + 1);
+            if ((float)nov / (float)n >= 0.8f) { if (sigc[d].prob > sigc[d2].prob) dominated[d2] = 1; else dominated[d] = 1; }
+          }
+        configure(m, false, L);                           // back to unihit
+        int last_j2 = 0;
+        for (size_t d = 0; d < sigc.size(); d++) {
+          if (dominated[d]) continue;
+          const int i2 = sigc[d].i, j2 = sigc[d].j;
+          if (i2 <= last_j2) noverlaps++;
+          nenvelopes++;
+          DomOut dom;
+          if (rescore_domain(w, m, prof, t.dsq, L, i2, j2, true, dom)) { out.doms.push_back(std::move(dom)); last_j2 = j2; }
+        }
+      } else {
+        nenvelopes++;
+        DomOut dom;
+        if (rescore_domain(w, m, prof, t.dsq, L, i, j, false, dom)) out.doms.push_back(std::move(dom));
+      }
+      i = -1; triggered = false;
+    }
+  }
+  if (nregions == 0 || nenvelopes == 0 || out.doms.empty()) return;
+
+  // per-sequence and per-domain scores (p7_pipeline.c:776-865)
+  b2h_len_params lp; b2h_length_params(L, 1.0f, &lp);
+  const float nullsc = lp.null1, fwdsc = t.surv.fwdsc;
+  const float omega = (float)(1. / 256.);
+  const double LOG2 = 0.69314718055994529;
+  float seqbias;
+  if (prm->do_null2) {
+    seqbias = kahan_sum(w.n2sc.data(), L + 1);
+    seqbias = flogsum()(0.0f, (float)(log((double)omega) + (double)seqbias));
+  } else seqbias = 0.0f;
+  float pre_score = (float)((double)(fwdsc - nullsc) / LOG2);
+  float seq_score = (float)((double)(fwdsc - (nullsc + seqbias)) / LOG2);
+  float sum_score = 0.0f; seqbias = 0.0f; int Ld = 0;
+  if (prm->do_null2) {
+    for (auto &dm : out.doms) if (dm.d.envsc - dm.d.domcorrection > 0.0f) { sum_score += dm.d.envsc; Ld += dm.d.jenv - dm.d.ienv + 1; seqbias += dm.d.domcorrection; }
+    seqbias = flogsum()(0.0f, (float)(log((double)omega) + (double)seqbias));
+  } else {
+    for (auto &dm : out.doms) if (dm.d.envsc > 0.0f) { sum_score += dm.d.envsc; Ld += dm.d.jenv - dm.d.ienv + 1; }
+    seqbias = 0.0f;
+  }
+  sum_score = (float)((double)sum_score + (double)(L - Ld) * log((double)((float)L / (float)(L + 3))));
+  const float pre2_score = (float)((double)(sum_score - nullsc) / LOG2);
+  sum_score = (float)((double)(sum_score - (nullsc + seqbias)) / LOG2);
+  if (Ld > 0 && sum_score > seq_score) { seq_score = sum_score; pre_score = pre2_score; }
+  const double tau = prof->evparam[4], lam = prof->evparam[5];
+  auto logsurv = [&](double x) { return (x < tau) ? 0.0 : -lam * (x - tau); };
+  b2h_hit &h = out.hit;
+  memset(&h, 0, sizeof h);
+  h.profile = t.surv.profile; h.seq = t.surv.seq;
+  h.score = seq_score; h.pre_score = pre_score; h.sum_score = sum_score;
+  h.lnP = logsurv((double)seq_score); h.pre_lnP = logsurv((double)pre_score); h.sum_lnP = logsurv((double)sum_score);
+  h.nexpected = nexpected; h.nregions = nregions; h.nclustered = nclustered; h.noverlaps = noverlaps; h.nenvelopes = nenvelopes;
+  h.ndom = (int)out.doms.size(); h.best_domain = 0;
+  for (int d = 0; d < h.ndom; d++) {
+    b2h_domain &dd = out.doms[d].d;
+    const int Ldd = dd.jenv - dd.ienv + 1;
+    float bs = (float)((double)dd.envsc + (double)(L - Ldd) * log((double)((float)L / (float)(L + 3))));
+    dd.dombias = prm->do_null2 ? flogsum()(0.0f, (float)(log((double)omega) + (double)dd.domcorrection)) : 0.0f;
+    bs = (float)((double)(bs - (nullsc + dd.dombias)) / LOG2);
+    dd.bitscore = bs;
+    dd.lnP = logsurv((double)bs);
+    if (dd.bitscore > out.doms[h.best_domain].d.bitscore) h.best_domain = d;
+  }
+  out.valid = true;
+}
+
+} // namespace
+
+b2h_ddef_pool::b2h_ddef_pool(int n)
+{
+  if (n <= 0) n = (int)std::thread::hardware_concurrency();
+  nthreads = std::max(1, std::min(n, 64));
+}
+
+int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_params *prm, b2h_results *res)
+{
+  const size_t n = tasks.size();
+  std::vector<HitOut> outs(n);
+  std::atomic<size_t> next(0);
+  auto body = [&]() {
+    Worker w; w.rng.init(prm->seed ? prm->seed : 42u);
+    for (;;) { const size_t e = next.fetch_add(1); if (e >= n) break; ddef_one(w, tasks[e], prm, outs[e]); }
+  };
+  const int nt = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(n, 1));
+  if (nt <= 1) body();
+  else { std::vector<std::thread> th; for (int i = 0; i < nt; i++) th.emplace_back(body); for (auto &x : th) x.join(); }
+  for (size_t e = 0; e < n; e++) {
+    if (!outs[e].valid) continue;
+    b2h_hit h = outs[e].hit;
+    h.dom_offset = (int64_t)res->doms.size();
+    for (auto &dm : outs[e].doms) {
+      b2h_domain d = dm.d;
+      d.text_offset = (int64_t)res->text.size();
+      res->text.insert(res->text.end(), dm.text.begin(), dm.text.end());
+      res->doms.push_back(d);
+    }
+    res->hits.push_back(h);
+  }
+  return B2H_OK;
+}

@@ -33,6 +33,10 @@ struct b2h_ctx {
   std::string   err;
   uint64_t      launches = 0;
   int          *d_counters = nullptr;   // small pool of work counters
+  int           profiling = 0;
+  double        stage_ms[8] = {0};
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_open;   // (stage, begin, end) awaiting a sync
 };
 
 struct b2h_seqdb {
@@ -42,6 +46,7 @@ struct b2h_seqdb {
   int       maxL = 0;
   size_t    arena_bytes = 0;
   std::vector<int32_t> h_len;
+  std::vector<uint8_t> h_res;      // host copy of the arena (domain definition reads residues)
   std::vector<int64_t> h_off;
   uint8_t  *d_res = nullptr;
   int64_t  *d_off = nullptr;
@@ -64,7 +69,7 @@ struct b2h_profile {
   uint8_t tbm_b = 0, tec_b = 0, base_b = 0, bias_b = 0;
   float scale_b = 0;
   uint32_t *d_ssv_emis = nullptr; // [32][NR][32 lanes] packed s16x2 signed scores (SSV)
-  uint32_t *d_msv_cost = nullptr; // same layout, packed u8 costs widened to 16 bit (full MSV)
+  uint8_t  *d_msv_cost8 = nullptr; // [32][Mpad] node-major u8 costs (255 = -inf) for the full MSV kernel
   // Viterbi
   int16_t *d_vit_rsc = nullptr;   // [32][Mpad]
   int16_t *d_vit_tsc = nullptr;   // [8][Mpad]
@@ -81,6 +86,10 @@ struct b2h_profile {
   float compo[B2H_MAXABET];
   float bgf[B2H_MAXABET];
   float *d_bias_eo = nullptr;     // [32][2] bias-filter emission odds (esl_hmm_Configure)
+  // host copies for the domain-definition stage
+  std::vector<float> h_fwd_rsc, h_fwd_tsc;   // [Kp][M], [8][M] node-major odds ratios
+  std::vector<uint8_t> h_degen;              // [Kp][K]
+  std::string consensus, rf, cs, symbols;    // 1..M annotation (index k-1), alphabet symbols
   float bias_t10 = 0, bias_t11 = 0;   // fhmm->t[1][0], t[1][1]
 };
 
@@ -90,6 +99,18 @@ struct b2h_profile {
          if (ctx) { char b_[256]; snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); ctx->err = b_; } \
          return B2H_ECUDA; } } while (0)
 
+// stage timing (only when ctx->profiling): events are resolved at the next host sync of the search
+struct StageTimer {
+  b2h_ctx *ctx; int stage; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  static cudaEvent_t get(b2h_ctx *c) { if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); } return c->ev_pool[c->ev_used++]; }
+  StageTimer(b2h_ctx *c, int st) : ctx(c), stage(st) { if (c->profiling) { e0 = get(c); e1 = get(c); cudaEventRecord(e0, c->stream); } }
+  ~StageTimer() { if (e0) { cudaEventRecord(e1, ctx->stream); ctx->ev_open.push_back({stage, {e0, e1}}); } }
+};
+static inline void b2h_resolve_timers(b2h_ctx *c) {
+  for (auto &o : c->ev_open) { float ms = 0.f; if (cudaEventElapsedTime(&ms, o.second.first, o.second.second) == cudaSuccess) c->stage_ms[o.first] += ms; }
+  c->ev_open.clear(); c->ev_used = 0;
+}
+
 static inline int b2h_nr_for_M(int M) {
   // need 64*NR >= M+1 so that the last cell of lane 31 is always padding (see b2h_msv.cu)
   int nr = (M + 1 + 63) / 64;
@@ -98,9 +119,6 @@ static inline int b2h_nr_for_M(int M) {
   return -1;
 }
 
-// kernel launchers (b2h_msv.cu)
-int b2h_launch_ssv_dense(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, int with_msv_fallback,
-                         float *d_sc, int32_t *d_status);
 
 // ---------------------------------------------------------------------------------------------
 // Device-side views (passed to kernels by value or through small device arrays)
@@ -117,7 +135,7 @@ static inline SeqDev b2h_seqdev(const b2h_seqdb *db) {
 }
 
 struct ProfDev {
-  const uint32_t *ssv_emis, *msv_cost;
+  const uint32_t *ssv_emis; const uint8_t *msv_cost8;
   const int16_t *vit_rsc, *vit_tsc;
   const float *fwd_rsc, *fwd_tsc, *bias_eo;
   int M, Mpad, NR;
@@ -128,7 +146,7 @@ struct ProfDev {
   float bias_t10, bias_t11;
 };
 static inline ProfDev b2h_profdev(const b2h_profile *p) {
-  ProfDev d; d.ssv_emis = p->d_ssv_emis; d.msv_cost = p->d_msv_cost; d.vit_rsc = p->d_vit_rsc; d.vit_tsc = p->d_vit_tsc;
+  ProfDev d; d.ssv_emis = p->d_ssv_emis; d.msv_cost8 = p->d_msv_cost8; d.vit_rsc = p->d_vit_rsc; d.vit_tsc = p->d_vit_tsc;
   d.fwd_rsc = p->d_fwd_rsc; d.fwd_tsc = p->d_fwd_tsc; d.bias_eo = p->d_bias_eo;
   d.M = p->M; d.Mpad = p->Mpad; d.NR = p->NR; d.tbm = p->tbm_b; d.tec = p->tec_b; d.base = p->base_b; d.bias = p->bias_b; d.scale_b = p->scale_b;
   d.xw_E_move = p->xw[0][0]; d.xw_E_loop = p->xw[0][1]; d.base_w = p->base_w; d.ddbound_w = p->ddbound_w; d.scale_w = p->scale_w;
@@ -157,3 +175,29 @@ int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int m
 int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out);
 int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out);
 int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc);
+
+// A compacted list of comparisons produced by a stage's epilogue (device memory).  Appends are
+// atomic (*n, and cnt[p] for the later grouping by profile); a,b carry the stage's scores.
+struct SurvList { int32_t *p, *s; float *a, *b; int *n; int *cnt; int cap; };
+
+#define B2H_SSV_CHUNK 64       // sequences per SSV work item
+struct SsvArgs {
+  const ProfDev *profs;        // all profiles of the batch
+  const int32_t *cls;          // indices of the profiles of this register-tile class (device)
+  int            ncls;
+  SeqDev         sd;
+  int            chunks;       // ceil(nseq / B2H_SSV_CHUNK)
+  int           *counter;
+  uint32_t       zero;         // always 0 (see b2h_msv.cu)
+  int            mode;         // 0: dense p7_SSVFilter  1: dense, queue eslENORESULT in R  2: cascade (P-value test, A and R)
+  float         *out_sc; int32_t *out_status;
+  SurvList       A, R;
+  double         F1;
+};
+int b2h_launch_ssv(b2h_ctx *ctx, int NR, const SsvArgs &a);
+// full MSV (with J) over a grouped work list; mode 1: dense outputs indexed by sequence, 2: cascade append to A
+int b2h_launch_msv(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, int mode,
+                   float *out_sc, int32_t *out_status, SurvList A, double F1);
+// group a SurvList by profile: poff/itemoff[P+1] and the grouped arrays (device)
+struct Grouped { int32_t *p, *s; float *a, *b; int32_t *poff, *itemoff; int *fill; };
+int b2h_launch_group(b2h_ctx *ctx, const SurvList &in, int P, Grouped out);

@@ -26,30 +26,7 @@
 namespace {
 
 constexpr int SSV_THREADS = 256;
-
-struct MsvProf {
-  const uint32_t *emis;     // SSV signed scores, lane-striped
-  const uint32_t *cost;     // MSV costs, lane-striped
-  int   M;
-  int   tbm, tec, base, bias;
-  float scale_b;
-};
-
-struct MsvArgs {
-  MsvProf        prof;
-  const uint8_t *res;
-  const int64_t *off;
-  const int32_t *len;
-  const uint8_t *tjb;
-  const int32_t *order;
-  int            nseq;
-  int           *counter;     // [0]: work cursor of the SSV pass  [1]: #entries in redo list  [2]: cursor of the MSV pass
-  int32_t       *redo;        // sequences whose SSV result was eslENORESULT
-  float         *out_sc;
-  int32_t       *out_status;
-  int            msv_fallback; // 0: report p7_SSVFilter's own status; 1: queue ENORESULT for the MSV pass
-  uint32_t       zero;         // always 0: a register ptxas cannot constant-fold (packed-zero operand of VIADDMNMX)
-};
+constexpr uint32_t FULL = 0xffffffffu;
 
 // ---- mbarrier / TMA bulk-copy helpers (PTX ISA 8.x; SASS: SYNCS + UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,12 +75,32 @@ __device__ __forceinline__ void load_row(uint32_t addr, uint32_t addr_rem, uint3
   if (REM == 2) { uint2 v = lds64(addr_rem); e[4*FULL] = v.x; e[4*FULL+1] = v.y; }
   if (REM == 3) { e[4*FULL] = lds32(addr_rem); e[4*FULL+1] = lds32(addr_rem + 4); e[4*FULL+2] = lds32(addr_rem + 8); }
 }
-// an opaque zero: keeps ptxas from re-materialising the constant operand of every VIADDMNMX
-__device__ __forceinline__ uint32_t opaque_zero() { uint32_t z; asm volatile("mov.u32 %0, 0;" : "=r"(z)); return z; }
+
+// esl_gumbel_surv (vendor/easel/esl_gumbel.c:129): same expression, double precision
+__device__ __forceinline__ double gumbel_surv(double x, double mu, double lambda)
+{
+  const double y = lambda * (x - mu);
+  const double ey = -exp(-y);
+  return (fabs(ey) < 5e-9) ? -ey : 1.0 - exp(ey);
+}
+
+__device__ __forceinline__ void surv_append(const SurvList &l, int p, int s, float a, float b)
+{
+  const int slot = atomicAdd(l.n, 1);            // *n may run past cap: the host checks and re-runs with a smaller batch
+  if (slot < l.cap) { l.p[slot] = p; l.s[slot] = s; if (l.a) l.a[slot] = a; if (l.b) l.b[slot] = b; atomicAdd(l.cnt + p, 1); }
+}
+
+// First-level filter decision of p7_Pipeline (p7_pipeline.c:721-725): P-value of the MSV score against F1.
+__device__ __forceinline__ bool msv_passes(float usc, float nullsc, const ProfDev &P, double F1)
+{
+  const float seq_score = (float)((double)(usc - nullsc) / 0.69314718055994529);
+  const double pv = gumbel_surv((double)seq_score, (double)P.evparam[0], (double)P.evparam[1]);
+  return !(pv > F1);
+}
 
 // p7_SSVFilter's post-processing (ssvfilter.c:881-923) applied to the wide-lane maximum `maxw`
 // (cells are kept relative to the constant begin score, so the reference's get_xE() == maxw + 128).
-__device__ __forceinline__ void ssv_finish(int maxw, const MsvProf &p, int tjb, float &sc, int &status)
+__device__ __forceinline__ void ssv_finish(int maxw, const ProfDev &p, int tjb, float &sc, int &status)
 {
   if (tjb + p.tbm + p.tec + p.bias >= 127) { sc = 0.f; status = B2H_ENORESULT; return; }
   if (maxw >= 127 - p.bias) {                      // xE >= 255 - bias_b
@@ -122,213 +119,272 @@ __device__ __forceinline__ void ssv_finish(int maxw, const MsvProf &p, int tjb, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// SSV pass: all sequences.
+// SSV pass over (profile x sequence) for every profile of one register-tile class.
+// Work item = (profile, chunk of B2H_SSV_CHUNK sequences in length-sorted order), profile-major, so
+// a persistent CTA re-stages the emission table only when it crosses a profile boundary.
 // ------------------------------------------------------------------------------------------------
 template <int NR>
-__global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const MsvArgs a)
+__global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
 {
   extern __shared__ __align__(128) uint32_t s_tab[];      // [32 residues][NR*32 words]
   __shared__ uint64_t s_bar;
+  __shared__ int s_item;
   constexpr uint32_t TAB_BYTES = (uint32_t)B2H_NCODE * NR * 128u;
   constexpr int ROW_WORDS = NR * 32;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_tab, a.prof.emis, TAB_BYTES, &s_bar); }
-  mbar_wait(&s_bar, 0);
+  uint32_t phase = 0;
+  int cur_pc = -1;
 
   const int src_lane = (lane + 31) & 31;                   // rotate: lane 0 reads lane 31's last cell, which is always padding (= 0)
   const uint32_t tab_lane = smem_u32(s_tab) + lane * 16;
   const uint32_t tab_rem  = smem_u32(s_tab) + (NR / 4) * 512 + lane * (NR % 4) * 4;
   const uint32_t zero = a.zero;
+  const int nitems = a.ncls * a.chunks;
 
   for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(a.counter, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= a.nseq) break;
-    const int s = a.order[item];
-    const int L = a.len[s];
-    const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.res + a.off[s]);
-    const int nwords = (L + 3) >> 2;                       // tail rows are B2H_PAD_CODE rows: every score -127, harmless
+    __syncthreads();                                       // every warp is done with the previous item (and table)
+    if (threadIdx.x == 0) s_item = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= nitems) break;
+    const int pc = item / a.chunks, chunk = item - pc * a.chunks;
+    const int pidx = a.cls[pc];
+    const ProfDev &P = a.profs[pidx];
+    if (pc != cur_pc) {
+      cur_pc = pc;
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_tab, P.ssv_emis, TAB_BYTES, &s_bar); }
+      mbar_wait(&s_bar, phase); phase ^= 1;
+    }
+    const int e_end = min(a.sd.n, (chunk + 1) * B2H_SSV_CHUNK);
+    for (int e = chunk * B2H_SSV_CHUNK + warp; e < e_end; e += nwarps) {
+      const int s = a.sd.order[e];
+      const int L = a.sd.len[s];
+      const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.sd.res + a.sd.off[s]);
+      const int nwords = (L + 3) >> 2;                     // tail rows are B2H_PAD_CODE rows: every score -127, harmless
 
-    uint32_t m[NR];
+      uint32_t m[NR];
 #pragma unroll
-    for (int j = 0; j < NR; j++) m[j] = 0u;
-    uint32_t xe = 0u;
+      for (int j = 0; j < NR; j++) m[j] = 0u;
+      uint32_t xe = 0u;
 
-    for (int w0 = 0; w0 < nwords; w0 += 32) {
-      const uint32_t myw = (w0 + lane < nwords) ? __ldg(seqw + w0 + lane) : 0x1f1f1f1fu;
-      const int nw = min(32, nwords - w0);
-      for (int wi = 0; wi < nw; wi++) {
-        const uint32_t wr = __shfl_sync(0xffffffffu, myw, wi);
+      for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const uint32_t myw = (w0 + lane < nwords) ? __ldg(seqw + w0 + lane) : 0x1f1f1f1fu;
+        const int nw = min(32, nwords - w0);
+        for (int wi = 0; wi < nw; wi++) {
+          const uint32_t wr = __shfl_sync(FULL, myw, wi);
 #pragma unroll
-        for (int rr = 0; rr < 4; rr++) {
-          const uint32_t x = __byte_perm(wr, 0u, 0x4440u + rr);
-          uint32_t e[NR];
-          load_row<NR>(tab_lane + x * (ROW_WORDS * 4), tab_rem + x * (ROW_WORDS * 4), e);
-          const uint32_t t  = __shfl_sync(0xffffffffu, m[NR-1], src_lane);
-          const uint32_t s0 = __byte_perm(t, m[NR-1], 0x5432u);     // lo <- previous lane's last cell, hi <- own cell NR-1
+          for (int rr = 0; rr < 4; rr++) {
+            const uint32_t x = __byte_perm(wr, 0u, 0x4440u + rr);
+            uint32_t ev[NR];
+            load_row<NR>(tab_lane + x * (ROW_WORDS * 4), tab_rem + x * (ROW_WORDS * 4), ev);
+            const uint32_t t  = __shfl_sync(FULL, m[NR-1], src_lane);
+            const uint32_t s0 = __byte_perm(t, m[NR-1], 0x5432u);     // lo <- previous lane's last cell, hi <- own cell NR-1
 #pragma unroll
-          for (int j = NR - 1; j >= 1; j--) m[j] = __viaddmax_s16x2(m[j-1], e[j], zero);
-          m[0] = __viaddmax_s16x2(s0, e[0], zero);
+            for (int j = NR - 1; j >= 1; j--) m[j] = __viaddmax_s16x2(m[j-1], ev[j], zero);
+            m[0] = __viaddmax_s16x2(s0, ev[0], zero);
 #pragma unroll
-          for (int j = 0; j + 1 < NR; j += 2) xe = __vimax3_s16x2(xe, m[j], m[j+1]);
-          if (NR & 1) xe = __vimax3_s16x2(xe, m[NR-1], m[NR-1]);
+            for (int j = 0; j + 1 < NR; j += 2) xe = __vimax3_s16x2(xe, m[j], m[j+1]);
+            if (NR & 1) xe = __vimax3_s16x2(xe, m[NR-1], m[NR-1]);
+          }
         }
       }
-    }
-    int v = max((int)(xe & 0xffffu), (int)(xe >> 16));
-    v = __reduce_max_sync(0xffffffffu, v);
-    if (lane == 0) {
-      float sc; int status;
-      ssv_finish(v, a.prof, (int)a.tjb[s], sc, status);
-      if (a.msv_fallback && status == B2H_ENORESULT) {
-        const int slot = atomicAdd(a.counter + 1, 1);
-        a.redo[slot] = s;
-      } else {
-        a.out_sc[s] = sc; a.out_status[s] = status;
+      int v = max((int)(xe & 0xffffu), (int)(xe >> 16));
+      v = __reduce_max_sync(FULL, v);
+      if (lane == 0) {
+        float sc; int status;
+        ssv_finish(v, P, (int)a.sd.tjb[s], sc, status);
+        if (a.mode == 0) { a.out_sc[s] = sc; a.out_status[s] = status; }
+        else if (status == B2H_ENORESULT) surv_append(a.R, pidx, s, 0.f, 0.f);
+        else if (a.mode == 1) { a.out_sc[s] = sc; a.out_status[s] = status; }
+        else if (msv_passes(sc, a.sd.null1[s], P, a.F1)) surv_append(a.A, pidx, s, sc, 0.f);
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Full MSV pass (with the J state): only the comparisons SSV could not decide.
-// Saturating uint8 arithmetic of msvfilter.c:132-207 made explicit in s16 lanes.
+// Full MSV (with the J state, msvfilter.c:106-207) for the comparisons SSV could not decide (~1 %).
+// Generic in M: one warp per comparison, lanes interleaved over nodes, the row lives in shared
+// memory as bytes; the uint8 saturating arithmetic is written out explicitly.
 // ------------------------------------------------------------------------------------------------
-template <int NR>
-__global__ void __launch_bounds__(SSV_THREADS) msv_kernel(const MsvArgs a)
+struct Item { int p, e_begin, e_end; };
+__device__ __forceinline__ bool next_item(const WorkList &wl, int *s_item, Item &it)
 {
-  extern __shared__ __align__(128) uint32_t s_tab[];
+  __syncthreads();
+  if (threadIdx.x == 0) *s_item = atomicAdd(wl.counter, 1);
+  __syncthreads();
+  const int item = *s_item;
+  if (item >= wl.itemoff[wl.P]) return false;
+  int lo = 0, hi = wl.P;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (wl.itemoff[mid] <= item) lo = mid; else hi = mid; }
+  it.p = lo;
+  it.e_begin = wl.poff[lo] + (item - wl.itemoff[lo]) * B2H_ITEM_ENTRIES;
+  it.e_end   = min(wl.poff[lo + 1], it.e_begin + B2H_ITEM_ENTRIES);
+  return true;
+}
+
+__global__ void __launch_bounds__(256) msv_kernel(const WorkList wl, const SeqDev sd, int max_Mpad, int mode,
+                                                   float *out_sc, int32_t *out_status, const SurvList A, double F1)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t s_bar;
-  constexpr uint32_t TAB_BYTES = (uint32_t)B2H_NCODE * NR * 128u;
-  constexpr int ROW_WORDS = NR * 32;
-  const int lane = threadIdx.x & 31;
-  const int nredo = a.counter[1];
-  if (nredo == 0) return;
+  __shared__ int s_item;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int S = max_Mpad + 64;
+  uint8_t *s_cost = smem;                                   // [32][Mpad]
+  uint8_t *rows = smem + (size_t)32 * max_Mpad + (size_t)warp * 2 * S;
 
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_tab, a.prof.cost, TAB_BYTES, &s_bar); }
-  mbar_wait(&s_bar, 0);
-
-  const int src_lane = (lane + 31) & 31;
-  const uint32_t tab_lane = smem_u32(s_tab) + lane * 16;
-  const uint32_t tab_rem  = smem_u32(s_tab) + (NR / 4) * 512 + lane * (NR % 4) * 4;
-  const int bias = a.prof.bias, base = a.prof.base, tec = a.prof.tec;
-  const uint32_t biasv = (uint32_t)bias * 0x00010001u;
-
-  for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(a.counter + 2, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= nredo) break;
-    const int s = a.redo[item];
-    const int L = a.len[s];
-    const uint8_t *seq = a.res + a.off[s];
-    const int tjb  = a.tjb[s];
-    const int tjbm = (tjb + a.prof.tbm) & 0xff;              // (int8)tjb + (int8)tbm splatted into bytes (msvfilter.c:116)
-
-    uint32_t m[NR];
-#pragma unroll
-    for (int j = 0; j < NR; j++) m[j] = 0u;
-    int xJ = 0;
-    int xB = max(base - tjbm, 0);
-    bool overflow = false;
-
-    for (int i = 0; i < L; i++) {
-      const uint32_t x = seq[i];
-      uint32_t c[NR];
-      load_row<NR>(tab_lane + x * (ROW_WORDS * 4), tab_rem + x * (ROW_WORDS * 4), c);
-      const uint32_t xBv = (uint32_t)xB * 0x00010001u;
-      const uint32_t t  = __shfl_sync(0xffffffffu, m[NR-1], src_lane);
-      const uint32_t s0 = __byte_perm(t, m[NR-1], 0x5432u);
-      uint32_t xev = 0u;
-#pragma unroll
-      for (int j = NR - 1; j >= 0; j--) {
-        uint32_t sv = (j == 0) ? s0 : m[j-1];
-        sv = __vmaxs2(sv, xBv);                               // max_epu8(mpv, xBv)
-        sv = __viaddmin_s16x2(sv, biasv, 0x00ff00ffu);        // adds_epu8(sv, biasv)
-        sv = __vsub2(sv, c[j]);                               // subs_epu8(sv, cost) ...
-        sv = __vimax_s16x2_relu(sv, sv);                      // ... saturating at 0
-        m[j] = sv;
-        xev = __vmaxs2(xev, sv);
-      }
-      int xE = max((int)(xev & 0xffffu), (int)(xev >> 16));
-      xE = __reduce_max_sync(0xffffffffu, xE);
-      if (xE + bias >= 255) { overflow = true; break; }       // adds_epu8(xEv, biasv) == 255
-      xE = max(xE - tec, 0);
-      xJ = max(xJ, xE);
-      xB = max(max(base, xJ) - tjbm, 0);
+  uint32_t phase = 0;
+  int cur_p = -1;
+  Item it;
+  while (next_item(wl, &s_item, it)) {
+    const ProfDev &P = wl.profs[it.p];
+    const int Mpad = P.Mpad;
+    if (it.p != cur_p) {
+      cur_p = it.p;
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, 32u * Mpad); tma_load_1d(s_cost, P.msv_cost8, 32u * Mpad, &s_bar); }
+      mbar_wait(&s_bar, phase); phase ^= 1;
     }
-    if (lane == 0) {
-      if (overflow) { a.out_sc[s] = INFINITY; a.out_status[s] = B2H_ERANGE; }
-      else {
-        float sc = ((float)(xJ - tjb) - (float)base);
-        sc /= a.prof.scale_b;
-        sc -= 3.0f;
-        a.out_sc[s] = sc; a.out_status[s] = B2H_OK;
+    const int bias = P.bias, base = P.base, tec = P.tec;
+    for (int e = it.e_begin + warp; e < it.e_end; e += nwarps) {
+      const int s = wl.ent_s[e];
+      const int L = sd.len[s];
+      const uint8_t *seq = sd.res + sd.off[s];
+      const int tjb  = sd.tjb[s];
+      const int tjbm = (tjb + P.tbm) & 0xff;               // (int8)tjb + (int8)tbm splatted into bytes (msvfilter.c:116)
+      for (int j = lane; j < 2 * S; j += 32) rows[j] = 0;
+      __syncwarp();
+      int xJ = 0, xB = max(base - tjbm, 0);
+      bool overflow = false;
+      for (int i = 1; i <= L; i++) {
+        const uint8_t *cost = s_cost + (size_t)seq[i - 1] * Mpad;
+        uint8_t *cur = rows + (i & 1) * S, *prv = rows + ((i & 1) ^ 1) * S;
+        int xEm = 0;
+        for (int k = lane + 1; k <= Mpad; k += 32) {
+          int sv = max((int)prv[k - 1], xB);               // max_epu8(mpv, xBv)
+          sv = min(sv + bias, 255);                        // adds_epu8(sv, biasv)
+          sv = max(sv - (int)cost[k - 1], 0);              // subs_epu8(sv, *rsc)
+          cur[k] = (uint8_t)sv;
+          xEm = max(xEm, sv);
+        }
+        const int xE0 = __reduce_max_sync(FULL, xEm);
+        if (xE0 + bias >= 255) { overflow = true; break; } // adds_epu8(xEv, biasv) == 255
+        const int xE = max(xE0 - tec, 0);
+        xJ = max(xJ, xE);
+        xB = max(max(base, xJ) - tjbm, 0);
+        __syncwarp();
       }
+      if (lane == 0) {
+        float sc; int status = B2H_OK;
+        if (overflow) { sc = INFINITY; status = B2H_ERANGE; }
+        else { sc = ((float)(xJ - tjb) - (float)base); sc /= P.scale_b; sc -= 3.0f; }
+        if (mode == 1) { out_sc[s] = sc; out_status[s] = status; }
+        else if (msv_passes(sc, sd.null1[s], P, F1)) surv_append(A, it.p, s, sc, 0.f);
+      }
+      __syncwarp();
     }
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Group a survivor list by profile (counting sort on the per-profile counts the epilogues kept).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) group_scan_kernel(const int *cnt, int P, int32_t *poff, int32_t *itemoff, int *fill)
+{
+  __shared__ int s_part[1024];
+  __shared__ int s_ipart[1024];
+  const int t = threadIdx.x;
+  const int per = (P + 1023) / 1024;
+  const int b = t * per, e = min(P, b + per);
+  int sum = 0, isum = 0;
+  for (int i = b; i < e; i++) { sum += cnt[i]; isum += (cnt[i] + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES; }
+  s_part[t] = sum; s_ipart[t] = isum;
+  __syncthreads();
+  if (t == 0) {
+    int a = 0, ia = 0;
+    for (int i = 0; i < 1024; i++) { const int v = s_part[i], iv = s_ipart[i]; s_part[i] = a; s_ipart[i] = ia; a += v; ia += iv; }
+    poff[P] = a; itemoff[P] = ia;
+  }
+  __syncthreads();
+  int a = s_part[t], ia = s_ipart[t];
+  for (int i = b; i < e; i++) {
+    poff[i] = a; itemoff[i] = ia; fill[i] = 0;
+    a += cnt[i]; ia += (cnt[i] + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES;
+  }
+}
+
+__global__ void group_scatter_kernel(const SurvList in, const int32_t *poff, int *fill, Grouped out)
+{
+  const int n = min(*in.n, in.cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int p = in.p[i];
+    const int pos = poff[p] + atomicAdd(fill + p, 1);
+    out.p[pos] = p; out.s[pos] = in.s[i];
+    if (out.a) out.a[pos] = in.a[i];
+    if (out.b) out.b[pos] = in.b[i];
+  }
+}
+
 template <int NR>
-int launch_nr(b2h_ctx *ctx, const MsvArgs &a, int with_msv)
+int launch_ssv_nr(b2h_ctx *ctx, const SsvArgs &a)
 {
   const size_t smem = (size_t)B2H_NCODE * NR * 128;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2H_CUDA(cudaFuncSetAttribute(ssv_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2H_CUDA(cudaFuncSetAttribute(msv_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  B2H_CUDA(cudaFuncSetAttribute(ssv_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ssv_kernel<NR>, SSV_THREADS, smem));
   if (occ < 1) occ = 1;
-  const int warps_per_cta = SSV_THREADS / 32;
   int grid = ctx->sm_count * occ;
-  int need = (a.nseq + warps_per_cta - 1) / warps_per_cta;
-  if (grid > need) grid = need > 0 ? need : 1;
+  const long long nitems = (long long)a.ncls * a.chunks;
+  if (grid > nitems) grid = (int)(nitems > 0 ? nitems : 1);
   ssv_kernel<NR><<<grid, SSV_THREADS, smem, ctx->stream>>>(a);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());
-  if (with_msv) {
-    msv_kernel<NR><<<grid, SSV_THREADS, smem, ctx->stream>>>(a);
-    ctx->launches++;
-    B2H_CUDA(cudaGetLastError());
-  }
   return B2H_OK;
 }
 
 } // namespace
 
-int b2h_launch_ssv_dense(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, int with_msv_fallback,
-                         float *d_sc, int32_t *d_status)
+int b2h_launch_ssv(b2h_ctx *ctx, int NR, const SsvArgs &a)
 {
-  MsvArgs a;
-  a.prof.emis = p->d_ssv_emis; a.prof.cost = p->d_msv_cost; a.prof.M = p->M;
-  a.prof.tbm = p->tbm_b; a.prof.tec = p->tec_b; a.prof.base = p->base_b; a.prof.bias = p->bias_b; a.prof.scale_b = p->scale_b;
-  a.res = db->d_res; a.off = db->d_off; a.len = db->d_len; a.tjb = db->d_tjb; a.order = db->d_order;
-  a.nseq = (int)db->n; a.counter = ctx->d_counters;
-  a.out_sc = d_sc; a.out_status = d_status; a.msv_fallback = with_msv_fallback;
-  a.redo = nullptr; a.zero = 0u;
-  if (db->n == 0) return B2H_OK;
-  int32_t *d_redo = nullptr;
-  B2H_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(int), ctx->stream));
-  if (with_msv_fallback) {
-    B2H_CUDA(cudaMallocAsync(&d_redo, db->n * sizeof(int32_t), ctx->stream));
-    a.redo = d_redo;
-  }
-  int st;
-  switch (p->NR) {
-#define CASE(n) case n: st = launch_nr<n>(ctx, a, with_msv_fallback); break;
+  if (a.ncls <= 0 || a.sd.n <= 0) return B2H_OK;
+  B2H_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
+  switch (NR) {
+#define CASE(n) case n: return launch_ssv_nr<n>(ctx, a);
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(10) CASE(12) CASE(16) CASE(20) CASE(24) CASE(32) CASE(40) CASE(48)
 #undef CASE
-    default: st = B2H_EINVAL;
   }
-  if (d_redo) cudaFreeAsync(d_redo, ctx->stream);
-  return st;
+  return B2H_EINVAL;
+}
+
+int b2h_launch_msv(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, int mode,
+                   float *out_sc, int32_t *out_status, SurvList A, double F1)
+{
+  const int nwarps = 8;
+  const size_t smem = (size_t)32 * max_Mpad + (size_t)nwarps * 2 * (max_Mpad + 64) + 128;
+  if (smem > 220 * 1024) { ctx->err = "model too long for the MSV kernel"; return B2H_EINVAL; }
+  B2H_CUDA(cudaFuncSetAttribute(msv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msv_kernel, nwarps * 32, smem));
+  if (occ < 1) occ = 1;
+  int grid = ctx->sm_count * occ;
+  if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
+  B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), ctx->stream));
+  msv_kernel<<<grid, nwarps * 32, smem, ctx->stream>>>(wl, sd, max_Mpad, mode, out_sc, out_status, A, F1);
+  ctx->launches++;
+  B2H_CUDA(cudaGetLastError());
+  return B2H_OK;
+}
+
+int b2h_launch_group(b2h_ctx *ctx, const SurvList &in, int P, Grouped out)
+{
+  group_scan_kernel<<<1, 1024, 0, ctx->stream>>>(in.cnt, P, out.poff, out.itemoff, out.fill);
+  ctx->launches++;
+  B2H_CUDA(cudaGetLastError());
+  group_scatter_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(in, out.poff, out.fill, out);
+  ctx->launches++;
+  B2H_CUDA(cudaGetLastError());
+  return B2H_OK;
 }

@@ -1,0 +1,341 @@
+// b2h_search.cu -- the fused filter cascade of p7_Pipeline (p7_pipeline.c:697-936) for
+// P profiles x N sequences, with on-device survivor compaction between stages.
+//
+//   SSV (all P*N comparisons) --eslENORESULT--> full MSV
+//        | P(msv) <= F1
+//   bias filter (2-state HMM) | P <= F1 --P <= F2 (skip Viterbi, p7_pipeline.c:748)-----.
+//        | P > F2                                                                       |
+//   ViterbiFilter | P(vit) <= F2 -------------------------------------------------------+
+//   ForwardParser | P(fwd) <= F3
+//   list D  --(device->host: a few bytes per survivor)-->  Forward/Backward parsers with stored
+//   specials for D only, then host-side domain definition (b2h_domaindef.cpp).
+//
+// Every list is a struct-of-arrays in HBM appended to with atomics by the stage epilogues and
+// regrouped by profile (counting sort) before the next stage, so that the next kernel can stage one
+// profile's tables per CTA.  Nothing but list D and its O(L) special-state rows crosses PCIe.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <vector>
+#include "b2h_internal.h"
+#include "b2h_domaindef.h"
+
+namespace {
+
+__device__ __forceinline__ double gumbel_surv(double x, double mu, double lambda)
+{
+  const double y = lambda * (x - mu);
+  const double ey = -exp(-y);
+  return (fabs(ey) < 5e-9) ? -ey : 1.0 - exp(ey);
+}
+__device__ __forceinline__ double exp_surv(double x, double mu, double lambda)
+{
+  return (x < mu) ? 1.0 : exp(-lambda * (x - mu));
+}
+__device__ __forceinline__ void surv_append(const SurvList &l, int p, int s, float a, float b)
+{
+  const int slot = atomicAdd(l.n, 1);
+  if (slot < l.cap) { l.p[slot] = p; l.s[slot] = s; if (l.a) l.a[slot] = a; if (l.b) l.b[slot] = b; atomicAdd(l.cnt + p, 1); }
+}
+__device__ __forceinline__ float bits(float sc, float null) { return (float)((double)(sc - null) / 0.69314718055994529); }
+
+// after the bias filter (p7_pipeline.c:728-754): entries of the grouped MSV-survivor list
+__global__ void bias_post_kernel(const ProfDev *profs, const SeqDev sd, const Grouped g, const int32_t *nent,
+                                 const float *filtersc, int do_bias, double F1, double F2, int *cnt_bias, SurvList V, SurvList F)
+{
+  const int n = *nent;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int p = g.p[e], s = g.s[e];
+    const ProfDev &P = profs[p];
+    const float usc = g.a[e];
+    const float fsc = do_bias ? filtersc[e] : sd.null1[s];
+    const double pv = gumbel_surv((double)bits(usc, fsc), (double)P.evparam[0], (double)P.evparam[1]);
+    if (do_bias && pv > F1) continue;
+    atomicAdd(cnt_bias + p, 1);
+    if (pv > F2) surv_append(V, p, s, fsc, 0.f); else surv_append(F, p, s, fsc, 0.f);
+  }
+}
+
+__global__ void vit_post_kernel(const ProfDev *profs, const Grouped g, const int32_t *nent, const float *vfsc, double F2, SurvList F)
+{
+  const int n = *nent;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int p = g.p[e];
+    const ProfDev &P = profs[p];
+    const double pv = gumbel_surv((double)bits(vfsc[e], g.a[e]), (double)P.evparam[2], (double)P.evparam[3]);
+    if (pv > F2) continue;
+    surv_append(F, p, g.s[e], g.a[e], 0.f);
+  }
+}
+
+__global__ void fwd_post_kernel(const ProfDev *profs, const Grouped g, const int32_t *nent, const float *fwdsc, const int32_t *fst,
+                                double F3, SurvList D, int *nerr)
+{
+  const int n = *nent;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int p = g.p[e];
+    const ProfDev &P = profs[p];
+    if (fst[e] != B2H_OK) { atomicAdd(nerr, 1); continue; }
+    const double pv = exp_surv((double)bits(fwdsc[e], g.a[e]), (double)P.evparam[4], (double)P.evparam[5]);
+    if (pv > F3) continue;
+    surv_append(D, p, g.s[e], fwdsc[e], g.a[e]);
+  }
+}
+
+// A pool of device buffers for one batch of the cascade
+struct Pool {
+  b2h_ctx *ctx; std::vector<void *> ptrs;
+  explicit Pool(b2h_ctx *c) : ctx(c) {}
+  template <typename T> int get(T **out, size_t n) {
+    void *p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMallocAsync: ") + cudaGetErrorString(e); return B2H_EMEM; }
+    ptrs.push_back(p); *out = (T *)p; return B2H_OK;
+  }
+  ~Pool() { for (void *p : ptrs) cudaFreeAsync(p, ctx->stream); }
+};
+
+#define TRY(x) do { int st_ = (x); if (st_ != B2H_OK) return st_; } while (0)
+
+int make_list(Pool &pool, SurvList &l, size_t cap, int P, int *ctr, int *cnt, bool with_b)
+{
+  TRY(pool.get(&l.p, cap)); TRY(pool.get(&l.s, cap)); TRY(pool.get(&l.a, cap));
+  l.b = nullptr;
+  if (with_b) TRY(pool.get(&l.b, cap));
+  l.n = ctr; l.cnt = cnt; l.cap = (int)cap;
+  return B2H_OK;
+}
+
+} // namespace
+
+// One batch of profiles [p0, p1) against the whole database: runs the cascade, returns list D on the host.
+static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p0, int p1, const b2h_seqdb *db,
+                         const b2h_search_params *prm, std::vector<b2h_survivor> &outD, int64_t *counters /*[P][4], global index*/)
+{
+  const int P = p1 - p0, N = (int)db->n;
+  const size_t cap = (size_t)P * N;
+  const SeqDev sd = b2h_seqdev(db);
+  Pool pool(ctx);
+  B2H_CUDA(cudaSetDevice(ctx->device));
+
+  // profile descriptors + register-tile classes
+  std::vector<ProfDev> hprof(P);
+  std::map<int, std::vector<int32_t>> classes;
+  int max_Mpad = 0;
+  for (int i = 0; i < P; i++) {
+    hprof[i] = b2h_profdev(profiles[p0 + i]);
+    classes[hprof[i].NR].push_back(i);
+    max_Mpad = std::max(max_Mpad, hprof[i].Mpad);
+  }
+  ProfDev *d_prof; TRY(pool.get(&d_prof, P));
+  B2H_CUDA(cudaMemcpyAsync(d_prof, hprof.data(), P * sizeof(ProfDev), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<int32_t> hcls; std::vector<std::pair<int, std::pair<int, int>>> cls_ranges;   // NR -> (offset, count)
+  for (auto &kv : classes) { cls_ranges.push_back({kv.first, {(int)hcls.size(), (int)kv.second.size()}}); hcls.insert(hcls.end(), kv.second.begin(), kv.second.end()); }
+  int32_t *d_cls; TRY(pool.get(&d_cls, hcls.size()));
+  B2H_CUDA(cudaMemcpyAsync(d_cls, hcls.data(), hcls.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+  // counters: [0..5] list sizes n(A,R,V,F,D,err), then 6 per-profile count arrays (A,R,V,F,D,bias) + fill
+  int *d_ctr; TRY(pool.get(&d_ctr, 8 + (size_t)7 * P));
+  B2H_CUDA(cudaMemsetAsync(d_ctr, 0, (8 + (size_t)7 * P) * sizeof(int), ctx->stream));
+  int *cntA = d_ctr + 8, *cntR = cntA + P, *cntV = cntR + P, *cntF = cntV + P, *cntD = cntF + P, *cntB = cntD + P, *fill = cntB + P;
+  SurvList A, R, V, F, D;
+  TRY(make_list(pool, A, cap, P, d_ctr + 0, cntA, false));
+  TRY(make_list(pool, R, cap, P, d_ctr + 1, cntR, false));
+  TRY(make_list(pool, V, cap, P, d_ctr + 2, cntV, false));
+  TRY(make_list(pool, F, cap, P, d_ctr + 3, cntF, false));
+  TRY(make_list(pool, D, cap, P, d_ctr + 4, cntD, true));
+  Grouped G;
+  TRY(pool.get(&G.p, cap)); TRY(pool.get(&G.s, cap)); TRY(pool.get(&G.a, cap)); G.b = nullptr;
+  TRY(pool.get(&G.poff, (size_t)P + 1)); TRY(pool.get(&G.itemoff, (size_t)P + 1)); G.fill = fill;
+  float *stage_sc; int32_t *stage_st; TRY(pool.get(&stage_sc, cap)); TRY(pool.get(&stage_st, cap));
+  WorkList wl; wl.profs = d_prof; wl.ent_s = G.s; wl.poff = G.poff; wl.itemoff = G.itemoff; wl.P = P; wl.counter = ctx->d_counters + 8;
+  const int32_t *nent = G.poff + P;                  // number of entries of the current grouped list (device)
+  const int pgrid = ctx->sm_count * 8;
+
+  // 1. SSV over every comparison
+  { StageTimer tm(ctx, 0);
+  for (auto &cr : cls_ranges) {
+    SsvArgs a;
+    a.profs = d_prof; a.cls = d_cls + cr.second.first; a.ncls = cr.second.second; a.sd = sd;
+    a.chunks = (N + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK; a.counter = ctx->d_counters; a.zero = 0u; a.mode = 2;
+    a.out_sc = nullptr; a.out_status = nullptr; a.A = A; a.R = R; a.F1 = prm->F1;
+    TRY(b2h_launch_ssv(ctx, cr.first, a));
+  } }
+  // 2. full MSV for the comparisons SSV could not decide
+  {
+    Grouped GR = G; GR.a = nullptr;
+    { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, R, P, GR)); }
+    StageTimer tm(ctx, 1);
+    TRY(b2h_launch_msv(ctx, wl, sd, max_Mpad, 0, 2, nullptr, nullptr, A, prm->F1));
+  }
+  // 3. bias filter on the MSV survivors
+  { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, A, P, G)); }
+  { StageTimer tm(ctx, 2);
+    if (prm->do_biasfilter) TRY(b2h_launch_bias(ctx, wl, sd, ctx->sm_count * 128 * 8, stage_sc));
+    bias_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, sd, G, nent, stage_sc, prm->do_biasfilter, prm->F1, prm->F2, cntB, V, F);
+    ctx->launches++; }
+  // 4. ViterbiFilter
+  { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, V, P, G)); }
+  { StageTimer tm(ctx, 3);
+    StageOut so; so.sc = stage_sc; so.status = stage_st; so.fwd_xmx = so.bck_xmx = nullptr; so.xoff = nullptr;
+    TRY(b2h_launch_viterbi(ctx, wl, sd, max_Mpad, 0, so));
+    vit_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, G, nent, stage_sc, prm->F2, F);
+    ctx->launches++; }
+  // 5. Forward parser
+  { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, F, P, G)); }
+  { StageTimer tm(ctx, 4);
+    StageOut so; so.sc = stage_sc; so.status = stage_st; so.fwd_xmx = so.bck_xmx = nullptr; so.xoff = nullptr;
+    TRY(b2h_launch_forward(ctx, wl, sd, max_Mpad, 0, so));
+    fwd_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, G, nent, stage_sc, stage_st, prm->F3, D, d_ctr + 5);
+    ctx->launches++; }
+  B2H_CUDA(cudaGetLastError());
+
+  // 6. list D and the counters come home
+  std::vector<int> hctr(8 + (size_t)7 * P);
+  B2H_CUDA(cudaMemcpyAsync(hctr.data(), d_ctr, hctr.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+  b2h_resolve_timers(ctx);
+  if (hctr[5] > 0) { ctx->err = "numerical overflow in the Forward parser"; return B2H_ERANGE; }
+  const int nD = hctr[4];
+  for (int i = 0; i < P; i++) {
+    int64_t *c = counters + (size_t)(p0 + i) * 4;
+    c[0] = hctr[8 + i]; c[1] = hctr[8 + 5 * P + i]; c[2] = hctr[8 + 3 * P + i]; c[3] = hctr[8 + 4 * P + i];
+  }
+  std::vector<int32_t> dp(nD), ds(nD); std::vector<float> da(nD), dbv(nD);
+  if (nD) {
+    B2H_CUDA(cudaMemcpyAsync(dp.data(), D.p, nD * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(ds.data(), D.s, nD * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(da.data(), D.a, nD * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(dbv.data(), D.b, nD * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  outD.reserve(outD.size() + nD);
+  for (int i = 0; i < nD; i++) { b2h_survivor v; v.profile = p0 + dp[i]; v.seq = ds[i]; v.fwdsc = da[i]; v.filtersc = dbv[i]; outD.push_back(v); }
+  return B2H_OK;
+}
+
+// Forward + Backward parsers with stored special-state rows for the F3 survivors (sorted by profile),
+// chunked so that the specials of one chunk stay within a fixed budget; then host domain definition.
+static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, const b2h_search_params *prm,
+                            std::vector<b2h_survivor> &surv, b2h_results *res)
+{
+  std::sort(surv.begin(), surv.end(), [](const b2h_survivor &x, const b2h_survivor &y) {
+    return x.profile != y.profile ? x.profile < y.profile : x.seq < y.seq; });
+  const SeqDev sd = b2h_seqdev(db);
+  const size_t ROW_BUDGET = (size_t)32 << 20;        // rows of 6 floats per chunk (x2 matrices = 1.5 GB)
+  size_t i0 = 0;
+  b2h_ddef_pool ddpool(prm->host_threads);
+  while (i0 < surv.size()) {
+    size_t i1 = i0, rows = 0;
+    while (i1 < surv.size() && (i1 == i0 || rows + db->h_len[surv[i1].seq] + 1 <= ROW_BUDGET)) { rows += db->h_len[surv[i1].seq] + 1; i1++; }
+    const int n = (int)(i1 - i0);
+    // work list of this chunk: profiles present, in order
+    std::vector<ProfDev> hprof; std::vector<int32_t> poff, itemoff, ent_s(n); std::vector<int64_t> xoff(n);
+    int max_Mpad = 0; int64_t acc = 0; int items = 0;
+    for (int e = 0; e < n; e++) {
+      const b2h_survivor &v = surv[i0 + e];
+      if (e == 0 || v.profile != surv[i0 + e - 1].profile) {
+        if (e) items += ((e - poff.back()) + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES;
+        hprof.push_back(b2h_profdev(profiles[v.profile])); poff.push_back(e); itemoff.push_back(items);
+        max_Mpad = std::max(max_Mpad, hprof.back().Mpad);
+      }
+      ent_s[e] = v.seq; xoff[e] = acc; acc += db->h_len[v.seq] + 1;
+    }
+    items += ((n - poff.back()) + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES;
+    poff.push_back(n); itemoff.push_back(items);
+    const int Pc = (int)hprof.size();
+    Pool pool(ctx);
+    ProfDev *d_prof; int32_t *d_poff, *d_itemoff, *d_ent; int64_t *d_xoff; float *d_fx, *d_bx, *d_fsc, *d_bsc; int32_t *d_fst, *d_bst;
+    TRY(pool.get(&d_prof, Pc)); TRY(pool.get(&d_poff, Pc + 1)); TRY(pool.get(&d_itemoff, Pc + 1)); TRY(pool.get(&d_ent, n));
+    TRY(pool.get(&d_xoff, n)); TRY(pool.get(&d_fx, (size_t)acc * 6)); TRY(pool.get(&d_bx, (size_t)acc * 6));
+    TRY(pool.get(&d_fsc, n)); TRY(pool.get(&d_bsc, n)); TRY(pool.get(&d_fst, n)); TRY(pool.get(&d_bst, n));
+    B2H_CUDA(cudaMemcpyAsync(d_prof, hprof.data(), Pc * sizeof(ProfDev), cudaMemcpyHostToDevice, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(d_poff, poff.data(), (Pc + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(d_itemoff, itemoff.data(), (Pc + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(d_ent, ent_s.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(d_xoff, xoff.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    WorkList wl; wl.profs = d_prof; wl.ent_s = d_ent; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = Pc; wl.counter = ctx->d_counters + 8;
+    StageOut sf; sf.sc = d_fsc; sf.status = d_fst; sf.fwd_xmx = d_fx; sf.bck_xmx = nullptr; sf.xoff = d_xoff;
+    StageTimer *tm = new StageTimer(ctx, 5);
+    TRY(b2h_launch_forward(ctx, wl, sd, max_Mpad, items, sf));
+    StageOut sb; sb.sc = d_bsc; sb.status = d_bst; sb.fwd_xmx = d_fx; sb.bck_xmx = d_bx; sb.xoff = d_xoff;
+    TRY(b2h_launch_backward(ctx, wl, sd, max_Mpad, items, sb));
+    delete tm;
+    std::vector<float> fx((size_t)acc * 6), bx((size_t)acc * 6); std::vector<int32_t> bst(n);
+    B2H_CUDA(cudaMemcpyAsync(fx.data(), d_fx, fx.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(bx.data(), d_bx, bx.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(bst.data(), d_bst, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+    b2h_resolve_timers(ctx);
+    // host-side domain definition, one task per survivor
+    std::vector<b2h_ddef_task> tasks(n);
+    for (int e = 0; e < n; e++) {
+      b2h_ddef_task &t = tasks[e];
+      const b2h_survivor &v = surv[i0 + e];
+      t.surv = v; t.prof = profiles[v.profile];
+      t.dsq = db->h_res.data() + db->h_off[v.seq]; t.L = db->h_len[v.seq];
+      t.fx = fx.data() + (size_t)xoff[e] * 6; t.bx = bx.data() + (size_t)xoff[e] * 6;
+      t.bck_own_scales = (bst[e] & 0x100) != 0;
+    }
+    int st = ddpool.run(tasks, prm, res);
+    if (st != B2H_OK) { ctx->err = "domain definition failed"; return st; }
+    i0 = i1;
+  }
+  return B2H_OK;
+}
+
+extern "C" {
+
+int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const b2h_seqdb *db,
+               const b2h_search_params *prm, b2h_results **out)
+{
+  if (!ctx || !profiles || !db || !prm || !out || db->ctx != ctx) return B2H_EINVAL;
+  for (size_t i = 0; i < P; i++) if (!profiles[i] || profiles[i]->ctx != ctx) return B2H_EINVAL;
+  *out = nullptr;
+  b2h_results *res = new b2h_results();
+  res->counters.assign(P * 4, 0);
+  const size_t N = db->n;
+  std::vector<b2h_survivor> surv;
+  if (N > 0 && P > 0) {
+    const size_t CAP = (size_t)1 << 25;                 // comparisons per batch: every list is sized for the worst case
+    size_t pb = std::max<size_t>(1, CAP / N);
+    for (size_t p0 = 0; p0 < P; p0 += pb) {
+      const size_t p1 = std::min(P, p0 + pb);
+      int st = cascade_batch(ctx, profiles, (int)p0, (int)p1, db, prm, surv, res->counters.data());
+      if (st != B2H_OK) { delete res; return st; }
+    }
+    int st = finish_survivors(ctx, profiles, db, prm, surv, res);
+    if (st != B2H_OK) { delete res; return st; }
+  }
+  *out = res;
+  return B2H_OK;
+}
+
+int b2h_debug_domaindef(const b2h_profile *p, const uint8_t *dsq, int L, const float *fwd_xmx, const float *bck_xmx,
+                        float fwdsc, const b2h_search_params *prm, b2h_results **out)
+{
+  if (!p || !dsq || !fwd_xmx || !bck_xmx || !prm || !out) return B2H_EINVAL;
+  b2h_results *res = new b2h_results();
+  res->counters.assign(4, 0);
+  std::vector<b2h_ddef_task> tasks(1);
+  tasks[0].surv.profile = 0; tasks[0].surv.seq = 0; tasks[0].surv.fwdsc = fwdsc; tasks[0].surv.filtersc = 0.f;
+  tasks[0].prof = p; tasks[0].dsq = dsq; tasks[0].L = L; tasks[0].fx = fwd_xmx; tasks[0].bx = bck_xmx; tasks[0].bck_own_scales = false;
+  b2h_ddef_pool pool(1);
+  int st = pool.run(tasks, prm, res);
+  if (st != B2H_OK) { delete res; return st; }
+  *out = res;
+  return B2H_OK;
+}
+
+size_t            b2h_results_nhits   (const b2h_results *r) { return r ? r->hits.size() : 0; }
+const b2h_hit    *b2h_results_hits    (const b2h_results *r) { return r ? r->hits.data() : nullptr; }
+size_t            b2h_results_ndomains(const b2h_results *r) { return r ? r->doms.size() : 0; }
+const b2h_domain *b2h_results_domains (const b2h_results *r) { return r ? r->doms.data() : nullptr; }
+const char       *b2h_results_text    (const b2h_results *r, size_t *n) { if (n) *n = r ? r->text.size() : 0; return r ? r->text.data() : nullptr; }
+const int64_t    *b2h_results_counters(const b2h_results *r) { return r ? r->counters.data() : nullptr; }
+void              b2h_results_destroy (b2h_results *r) { delete r; }
+
+} // extern "C"

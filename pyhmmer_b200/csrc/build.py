@@ -22,6 +22,8 @@ SOURCES = [
     "b2h_api.cu",
     "b2h_msv.cu",
     "b2h_dp.cu",
+    "b2h_search.cu",
+    "b2h_domaindef.cpp",
 ]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

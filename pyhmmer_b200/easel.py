@@ -114,18 +114,25 @@ class Alphabet:
         return self._outmap[np.asarray(codes, dtype=np.uint8)].tobytes().decode("ascii")
 
 
+def _text(v):
+    """Names are `str` as in pyhmmer >= 0.11; `bytes` are accepted and decoded."""
+    if v is None:
+        return ""
+    return v.decode("utf-8", "replace") if isinstance(v, (bytes, bytearray)) else str(v)
+
+
 class _Sequence:
-    def __init__(self, name=b"", description=b"", accession=b"", source=b""):
-        self.name = bytes(name or b"")
-        self.description = bytes(description or b"")
-        self.accession = bytes(accession or b"")
-        self.source = bytes(source or b"")
+    def __init__(self, name="", description="", accession="", source=""):
+        self.name = _text(name)
+        self.description = _text(description)
+        self.accession = _text(accession)
+        self.source = _text(source)
 
 
 class TextSequence(_Sequence):
     """A sequence in text mode (``pyhmmer.easel.TextSequence``)."""
 
-    def __init__(self, name=b"", description=b"", accession=b"", sequence="", source=b""):
+    def __init__(self, name="", description="", accession="", sequence="", source=""):
         super().__init__(name, description, accession, source)
         self.sequence = sequence
 
@@ -144,7 +151,7 @@ class DigitalSequence(_Sequence):
     ``sequence`` holds the residue codes 0..Kp-1 *without* Easel's two sentinel bytes.
     """
 
-    def __init__(self, alphabet, name=b"", description=b"", accession=b"", sequence=None, source=b""):
+    def __init__(self, alphabet, name="", description="", accession="", sequence=None, source=""):
         super().__init__(name, description, accession, source)
         self.alphabet = alphabet
         if sequence is None:

@@ -1,0 +1,108 @@
+"""`hmmsearch` / `hmmscan` entry points with the reference's signatures (src/pyhmmer/hmmer/_hmmsearch.py:294,
+_hmmscan.py:91), running on the B200 engine.
+
+The reference fans queries (or target slices) out over CPU threads; here one process drives one GPU and
+every query batch is ONE fused cascade launch sequence over (batch x database).  With several GPUs
+(one process per GPU under ``torch.distributed``) the *target database* is sharded by residues -- exactly the
+reference's ``parallel="targets"`` strategy (_hmmsearch.py:115-289) -- and the per-rank hits are combined by a
+single all-gather at the end (`pyhmmer_b200.parallel`).
+"""
+import collections
+import os
+
+from . import plan7
+from .easel import DigitalSequenceBlock, DigitalSequence, SequenceFile
+from .plan7 import Pipeline, HMM, Profile, OptimizedProfile, OptimizedProfileBlock
+
+__all__ = ["hmmsearch", "hmmscan"]
+
+_QUERY_BATCH = 256
+
+
+def _as_block(sequences, alphabet):
+    if isinstance(sequences, DigitalSequenceBlock):
+        return sequences
+    if isinstance(sequences, SequenceFile):
+        if not sequences.digital:
+            raise ValueError("target sequences file is not in digital mode")
+        return sequences.read_block()
+    return DigitalSequenceBlock(alphabet, sequences)
+
+
+def hmmsearch(queries, sequences, *, cpus=0, callback=None, backend="threading", parallel="queries",
+              batch_size=_QUERY_BATCH, **options):
+    """Search HMM/profile queries against a sequence database; yields one `TopHits` per query, in order.
+
+    ``cpus``, ``backend`` and ``parallel`` are accepted for signature compatibility; the work division is
+    decided by the GPU engine (``cpus`` bounds the host threads used for domain definition).
+    """
+    if isinstance(queries, (HMM, Profile, OptimizedProfile)):
+        queries = (queries,)
+    it = iter(queries)
+    first = next(it, None)
+    if first is None:
+        return
+    alphabet = first.alphabet
+    block = _as_block(sequences, alphabet)
+    options.setdefault("host_threads", cpus or 0)
+    pipeline = Pipeline(alphabet, **options)
+    from . import parallel as par
+    world = par.World.current()
+    local = par.shard_block(block, world) if world.size > 1 else None
+    batch = [first]
+    total = 0
+
+    def flush(batch):
+        nonlocal total
+        if world.size > 1:
+            results = par.search_sharded(pipeline, batch, block, local, world)
+        else:
+            results = pipeline._search_many(batch, block)
+        for q, th in zip(batch, results):
+            total += 1
+            if callback is not None:
+                callback(q, total)
+            yield th
+
+    for q in it:
+        batch.append(q)
+        if len(batch) >= batch_size:
+            yield from flush(batch)
+            batch = []
+    if batch:
+        yield from flush(batch)
+
+
+def hmmscan(queries, profiles, *, cpus=0, callback=None, backend="threading", background=None,
+            batch_size=_QUERY_BATCH, **options):
+    """Scan query sequences against a profile database; yields one `TopHits` per query sequence, in order."""
+    if isinstance(queries, DigitalSequence):
+        queries = (queries,)
+    targets = profiles if isinstance(profiles, (list, OptimizedProfileBlock)) else list(profiles)
+    if not targets:
+        for q in queries:
+            yield plan7.TopHits(q, "scan")
+        return
+    alphabet = targets[0].alphabet
+    options.setdefault("host_threads", cpus or 0)
+    pipeline = Pipeline(alphabet, background=background, **options)
+    # convert HMM / Profile targets once (the reference does the same up front, _hmmscan.py:191-215)
+    oms = OptimizedProfileBlock(alphabet, [pipeline._optimized(t, pipeline.L_HINT) for t in targets])
+    total = 0
+    batch = []
+
+    def flush(batch):
+        nonlocal total
+        for q, th in zip(batch, pipeline._scan_many(batch, oms)):
+            total += 1
+            if callback is not None:
+                callback(q, total)
+            yield th
+
+    for q in queries:
+        batch.append(q)
+        if len(batch) >= batch_size:
+            yield from flush(batch)
+            batch = []
+    if batch:
+        yield from flush(batch)

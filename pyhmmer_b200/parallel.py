@@ -1,0 +1,147 @@
+"""Multi-GPU search: shard the TARGET database across ranks, all-gather the hits once at the end.
+
+Every (profile, sequence) comparison is independent, so the path shards with no data-path collective
+(SURVEY 8(e)).  One process per GPU (``torch.distributed``, backend ``nccl``; ``gloo`` for the CPU tests of
+this host logic).  Rank r keeps the contiguous slice r of the database, balanced by residues -- the rule
+of the reference's target-parallel dispatcher (src/pyhmmer/hmmer/_hmmsearch.py:153-171) -- runs the whole
+fused cascade on its slice, and contributes its serialized hit records to ONE all-gather (sizes first, then
+padded byte buffers).  Every rank then rebuilds identical `TopHits`: hits are admitted in global target
+order with the global running Z, so the result equals the unsharded search exactly.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+from .easel import DigitalSequenceBlock
+
+__all__ = ["World", "shard_block", "search_sharded", "all_gather_bytes", "pack_records", "unpack_records"]
+
+
+class World:
+    """Rank / size of this process in the job (1 process = 1 GPU)."""
+
+    def __init__(self, rank=0, size=1, dist=None, device=None):
+        self.rank, self.size, self.dist, self.device = rank, size, dist, device
+
+    @classmethod
+    def current(cls):
+        try:
+            import torch.distributed as dist
+        except Exception:
+            return cls()
+        if dist.is_available() and dist.is_initialized():
+            backend = dist.get_backend()
+            device = None
+            if backend == "nccl":
+                import torch
+                device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+            return cls(dist.get_rank(), dist.get_world_size(), dist, device)
+        return cls()
+
+
+def shard_bounds(lengths, nshards):
+    """Contiguous slices balanced by residue count (reference rule: _hmmsearch.py:153-171)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n = len(lengths)
+    total = int(lengths.sum())
+    bounds = [0]
+    acc = 0
+    j = 0
+    for t in range(n):
+        acc += int(lengths[t])
+        if j < nshards - 1 and acc >= (total * (j + 1)) // nshards:
+            bounds.append(t + 1)
+            j += 1
+    while len(bounds) < nshards:
+        bounds.append(n)
+    bounds.append(n)
+    return bounds
+
+
+def shard_block(block, world):
+    """(offset, sub-block) of this rank."""
+    b = shard_bounds([len(s) for s in block], world.size)
+    lo, hi = b[world.rank], b[world.rank + 1]
+    return lo, DigitalSequenceBlock(block.alphabet, list.__getitem__(block, slice(lo, hi)))
+
+
+def pack_records(hits, doms, text, counters, seq_offset):
+    """Serialize one rank's results: header | HitRec[] | DomainRec[] | text | counters (int64)."""
+    nh, nd = len(hits), len(doms)
+    ha = (_lib.HitRec * max(nh, 1))(*hits)
+    for i in range(nh):
+        ha[i].seq += seq_offset
+    da = (_lib.DomainRec * max(nd, 1))(*doms)
+    cnt = np.ascontiguousarray(counters, dtype=np.int64)
+    header = np.array([nh, nd, len(text), cnt.size], dtype=np.int64).tobytes()
+    return b"".join([header, bytes(ha)[: nh * ctypes.sizeof(_lib.HitRec)], bytes(da)[: nd * ctypes.sizeof(_lib.DomainRec)],
+                     bytes(text), cnt.tobytes()])
+
+
+def unpack_records(buf):
+    nh, nd, nt, nc = (int(v) for v in np.frombuffer(buf[:32], dtype=np.int64))
+    o = 32
+    hs, ds = ctypes.sizeof(_lib.HitRec), ctypes.sizeof(_lib.DomainRec)
+    hits = list((_lib.HitRec * nh).from_buffer_copy(buf[o:o + nh * hs])) if nh else []
+    o += nh * hs
+    doms = list((_lib.DomainRec * nd).from_buffer_copy(buf[o:o + nd * ds])) if nd else []
+    o += nd * ds
+    text = bytes(buf[o:o + nt])
+    o += nt
+    counters = np.frombuffer(buf[o:o + 8 * nc], dtype=np.int64).copy()
+    return hits, doms, text, counters
+
+
+def all_gather_bytes(data, world):
+    """One variable-length all-gather: sizes, then padded uint8 buffers (NCCL over NVLink, or gloo on CPU)."""
+    if world.size == 1:
+        return [data]
+    import torch
+    dist = world.dist
+    dev = world.device or torch.device("cpu")
+    size = torch.tensor([len(data)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world.size)]
+    dist.all_gather(sizes, size)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(max(sizes), 1)
+    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    if len(data):
+        buf[: len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+    outs = [torch.empty(mx, dtype=torch.uint8, device=dev) for _ in range(world.size)]
+    dist.all_gather(outs, buf)
+    return [bytes(o[:n].cpu().numpy().tobytes()) for o, n in zip(outs, sizes)]
+
+
+def merge_rank_records(parts):
+    """Concatenate per-rank (hits, doms, text, counters); hits come out ordered by (profile, global seq)."""
+    hits, doms, text = [], [], bytearray()
+    counters = None
+    for h, d, t, c in parts:
+        dbase, tbase = len(doms), len(text)
+        for r in h:
+            r.dom_offset += dbase
+        for r in d:
+            r.text_offset += tbase
+        hits.extend(h)
+        doms.extend(d)
+        text.extend(t)
+        counters = c.copy() if counters is None else counters + c
+    hits.sort(key=lambda r: (r.profile, r.seq))
+    return hits, doms, bytes(text), counters
+
+
+def search_sharded(pipeline, queries, block, local, world):
+    """One query batch against the sharded database; every rank returns the same list of `TopHits`."""
+    lo, sub = local
+    L = len(block[0]) if len(block) else pipeline.L_HINT
+    oms = [pipeline._optimized(q, L) for q in queries]
+    if len(sub):
+        hits, doms, text, counters = pipeline._run(oms, sub)
+    else:
+        hits, doms, text, counters = [], [], b"", np.zeros((len(oms), 4), np.int64)
+    mine = pack_records(hits, doms, text, counters, lo)
+    parts = [unpack_records(b) for b in all_gather_bytes(mine, world)]
+    hits, doms, text, counters = merge_rank_records(parts)
+    return pipeline._assemble(queries, oms, block, hits, doms, text, counters.reshape(len(oms), 4))

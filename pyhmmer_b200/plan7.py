@@ -19,7 +19,8 @@ from . import _lib
 from ._lib import lib, ptr, check, OProfileDesc
 from .easel import Alphabet, DigitalSequence, DigitalSequenceBlock, AlphabetMismatch
 
-__all__ = ["HMM", "HMMFile", "Background", "Profile", "OptimizedProfile", "EvalueParameters", "Cutoffs"]
+__all__ = ["HMM", "HMMFile", "Background", "Profile", "OptimizedProfile", "OptimizedProfileBlock", "EvalueParameters", "Cutoffs",
+           "Pipeline", "TopHits", "Hit", "Domain", "Domains", "Alignment", "MissingCutoffs", "SequenceDatabase"]
 
 P7_EVPARAM_UNSET = -99999.0
 P7_CUTOFF_UNSET = -99999.0
@@ -102,10 +103,10 @@ class HMM:
     ``match_emissions`` / ``insert_emissions`` are (M+1, K); row 0 is the begin node.
     """
 
-    def __init__(self, alphabet, M, name=b""):
+    def __init__(self, alphabet, M, name=""):
         self.alphabet = alphabet
         self.M = int(M)
-        self.name = bytes(name)
+        self.name = name.decode() if isinstance(name, (bytes, bytearray)) else str(name)
         self.accession = None
         self.description = None
         K = alphabet.K
@@ -174,11 +175,11 @@ class HMM:
             return "      *" if p == 0.0 else " %8.5f" % (-math.log(p))
 
         w("HMMER3/f [3.4 | Aug 2023]\n")
-        w("NAME  %s\n" % self.name.decode())
+        w("NAME  %s\n" % self.name)
         if self.accession:
-            w("ACC   %s\n" % self.accession.decode())
+            w("ACC   %s\n" % self.accession)
         if self.description:
-            w("DESC  %s\n" % self.description.decode())
+            w("DESC  %s\n" % self.description)
         w("LENG  %d\n" % self.M)
         if self.max_length > 0:
             w("MAXL  %d\n" % self.max_length)
@@ -315,11 +316,11 @@ class HMMFile:
             raise ValueError("no NAME / LENG found for HMM")
         K = abc.K
         self._line()                                   # the "m->m m->i ..." column header
-        hmm = HMM(abc, M, hdr["NAME"].split()[0].encode())
+        hmm = HMM(abc, M, hdr["NAME"].split()[0])
         if "ACC" in hdr:
-            hmm.accession = hdr["ACC"].split()[0].encode()
+            hmm.accession = hdr["ACC"].split()[0]
         if "DESC" in hdr:
-            hmm.description = hdr["DESC"].encode()
+            hmm.description = hdr["DESC"]
         if "MAXL" in hdr:
             hmm.max_length = int(hdr["MAXL"])
         if "NSEQ" in hdr:
@@ -474,6 +475,7 @@ class OptimizedProfile:
         self._dev = {}
         self.name, self.accession, self.description = profile.name, profile.accession, profile.description
         self.consensus = profile.consensus
+        self.reference, self.consensus_structure = profile.reference, profile.consensus_structure
         self._evparam, self._cutoff, self._compo = profile._evparam, profile._cutoff, profile._compo
         self.L = profile.L
         self.multihit = profile.multihit
@@ -504,6 +506,9 @@ class OptimizedProfile:
             out = ctypes.c_void_p()
             check(lib.b2h_profile_upload(ctx.handle, ctypes.byref(self._desc), ctypes.byref(out)),
                   "b2h_profile_upload", ctx.handle)
+            enc = lambda t: t.encode("ascii") if t else None
+            lib.b2h_profile_set_annotation(out, enc(self.consensus), enc(self.reference), enc(self.consensus_structure),
+                                           self.alphabet.symbols.encode("ascii"))
             h = self._dev[ctx] = _DeviceHandle(out, lib.b2h_profile_destroy)
         return h.handle
 
@@ -523,6 +528,23 @@ class OptimizedProfile:
         """``OptimizedProfile.ssv_filter`` (plan7.pyx:5022): SSV score in nats, ``None`` if SSV cannot decide."""
         sc, st = self._filter_one(lib.b2h_ssv_filter, seq)
         return None if st == _lib.B2H_ENORESULT else sc
+
+
+class OptimizedProfileBlock(list):
+    """An ordered block of `OptimizedProfile` sharing one alphabet (``pyhmmer.plan7.OptimizedProfileBlock``)."""
+
+    def __init__(self, alphabet, iterable=()):
+        super().__init__()
+        self.alphabet = alphabet
+        for om in iterable:
+            self.append(om)
+
+    def append(self, om):
+        if not isinstance(om, OptimizedProfile):
+            raise TypeError("expected OptimizedProfile, found %s" % type(om).__name__)
+        if om.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, om.alphabet)
+        super().append(om)
 
 
 class _DeviceHandle:
@@ -559,3 +581,432 @@ class SequenceDatabase:
         if hit is None:
             hit = block._cache[("db", ctx)] = cls(ctx, block)
         return hit
+
+
+# =====================================================================================================
+# Results: TopHits / Hit / Domain / Alignment   (reference: plan7.pyx 8312-9278, 1850-2234, 1441-1687, 229-425)
+# =====================================================================================================
+class Alignment:
+    """Alignment of one domain to the model (``P7_ALIDISPLAY``)."""
+
+    def __init__(self, domain, rec, text):
+        self.domain = domain
+        n, off = rec.N, rec.text_offset
+        f = [text[off + i * (n + 1): off + i * (n + 1) + n].decode("ascii") for i in range(4 + rec.has_rf + rec.has_cs)]
+        self.hmm_sequence, self.identity_sequence, self.target_sequence, self.posterior_probabilities = f[:4]
+        self.hmm_reference = f[4] if rec.has_rf else None
+        self.hmm_consensus_structure = f[4 + rec.has_rf] if rec.has_cs else None
+        self.hmm_from, self.hmm_to = rec.hmmfrom, rec.hmmto
+        self.target_from, self.target_to = rec.sqfrom, rec.sqto
+
+    hmm_name = property(lambda self: self.domain.hit.hits.query.name)
+    hmm_accession = property(lambda self: self.domain.hit.hits.query.accession)
+    hmm_length = property(lambda self: self.domain.hit.hits.query.M)
+    target_name = property(lambda self: self.domain.hit.name)
+    target_length = property(lambda self: self.domain.hit.length)
+
+    def __len__(self):
+        return len(self.hmm_sequence)
+
+
+class Domain:
+    """One domain of a hit (``P7_DOMAIN``)."""
+
+    def __init__(self, hit, rec, text):
+        self.hit = hit
+        self._rec = rec
+        self.env_from, self.env_to = rec.ienv, rec.jenv
+        self.score = float(rec.bitscore)
+        self.bias = float(rec.dombias) * _LN2_INV_F        # dcl.dombias is kept in nats; reported in bits (plan7.pyx:1502)
+        self.correction = float(rec.domcorrection) * _LN2_INV_F
+        self.envelope_score = float(rec.envsc) * _LN2_INV_F
+        self.expected_accuracy = float(rec.oasc)
+        self.lnP = float(rec.lnP)
+        self.reported = False
+        self.included = False
+        self.alignment = Alignment(self, rec, text)
+
+    @property
+    def pvalue(self):
+        return math.exp(self.lnP)
+
+    @property
+    def c_evalue(self):
+        return math.exp(self.lnP) * self.hit.hits.domZ
+
+    @property
+    def i_evalue(self):
+        return math.exp(self.lnP) * self.hit.hits.Z
+
+
+_LN2_INV_F = 1.0 / 0.69314718055994529
+
+
+class Domains:
+    def __init__(self, hit):
+        self.hit = hit
+
+    def __len__(self):
+        return len(self.hit._domains)
+
+    def __getitem__(self, i):
+        return self.hit._domains[i]
+
+    def __iter__(self):
+        return iter(self.hit._domains)
+
+    @property
+    def reported(self):
+        return [d for d in self.hit._domains if d.reported]
+
+    @property
+    def included(self):
+        return [d for d in self.hit._domains if d.included]
+
+
+class Hit:
+    """One target (search) or model (scan) that p7_Pipeline scored to completion (``P7_HIT``)."""
+
+    def __init__(self, hits, rec, target, doms, text):
+        self.hits = hits
+        self._rec = rec
+        self.name = target.name
+        self.accession = getattr(target, "accession", None) or None
+        self.description = getattr(target, "description", None) or None
+        self.length = len(target) if not hasattr(target, "M") else target.M
+        self.score = float(rec.score)
+        self.pre_score = float(rec.pre_score)
+        self.sum_score = float(rec.sum_score)
+        self.bias = self.pre_score - self.score
+        self.lnP = float(rec.lnP)
+        self.sortkey = -self.lnP if hits._params["inc_by_E"] else self.score
+        self.reported = False
+        self.included = False
+        self.dropped = False
+        self.new = False
+        self.duplicate = False
+        self._index = rec.seq if hits.mode == "search" else rec.profile
+        self._domains = [Domain(self, doms[rec.dom_offset + d], text) for d in range(rec.ndom)]
+        self.best_domain = self._domains[rec.best_domain]
+        self.domains = Domains(self)
+
+    @property
+    def pvalue(self):
+        return math.exp(self.lnP)
+
+    @property
+    def evalue(self):
+        return math.exp(self.lnP) * self.hits.Z
+
+    def __repr__(self):
+        return "<Hit name=%r score=%.1f evalue=%.2g>" % (self.name, self.score, self.evalue)
+
+
+class TopHits:
+    """A sorted, thresholded list of hits (``P7_TOPHITS`` + the P7_PIPELINE snapshot pyhmmer keeps)."""
+
+    def __init__(self, query=None, mode="search"):
+        self.query = query
+        self.mode = mode
+        self._hits = []
+        self._params = dict(E=10.0, T=None, domE=10.0, domT=None, incE=0.01, incT=None, incdomE=0.01, incdomT=None,
+                            inc_by_E=True, by_E=True, dom_by_E=True, incdom_by_E=True, bit_cutoffs=None, Z=None, domZ=None)
+        self.Z = 0.0
+        self.domZ = 0.0
+        self.searched_models = 0
+        self.searched_nodes = 0
+        self.searched_sequences = 0
+        self.searched_residues = 0
+        self.n_past_msv = self.n_past_bias = self.n_past_vit = self.n_past_fwd = 0
+
+    # -- list protocol --
+    def __len__(self):
+        return len(self._hits)
+
+    def __getitem__(self, i):
+        return self._hits[i]
+
+    def __iter__(self):
+        return iter(self._hits)
+
+    def __bool__(self):
+        return bool(self._hits)
+
+    @property
+    def reported(self):
+        return [h for h in self._hits if h.reported]
+
+    @property
+    def included(self):
+        return [h for h in self._hits if h.included]
+
+    @property
+    def hits_reported(self):
+        return sum(1 for h in self._hits if h.reported)
+
+    @property
+    def hits_included(self):
+        return sum(1 for h in self._hits if h.included)
+
+    # -- p7_pli_*Reportable / Includable (p7_pipeline.c:407-464) --
+    def _target_reportable(self, score, lnP, Z):
+        p = self._params
+        return (math.exp(lnP) * Z <= p["E"]) if p["by_E"] else (score >= p["T"])
+
+    def _target_includable(self, score, lnP, Z):
+        p = self._params
+        return (math.exp(lnP) * Z <= p["incE"]) if p["inc_by_E"] else (score >= p["incT"])
+
+    def _domain_reportable(self, score, lnP):
+        p = self._params
+        return (math.exp(lnP) * self.domZ <= p["domE"]) if p["dom_by_E"] else (score >= p["domT"])
+
+    def _domain_includable(self, score, lnP):
+        p = self._params
+        return (math.exp(lnP) * self.domZ <= p["incdomE"]) if p["incdom_by_E"] else (score >= p["incdomT"])
+
+    def _sort_by_key(self):
+        """p7_tophits_SortBySortkey (p7_tophits.c:393; comparator hit_sorter_by_sortkey)."""
+        self._hits.sort(key=lambda h: (-h.sortkey, h.name, h._domains[0].alignment.target_from))
+
+    def _threshold(self):
+        """p7_tophits_Threshold (p7_tophits.c:1057)."""
+        if not self._params["bit_cutoffs"]:
+            for h in self._hits:
+                h.reported = h.included = False
+                if not h.duplicate and self._target_reportable(h.score, h.lnP, self.Z):
+                    h.reported = True
+                    h.included = self._target_includable(h.score, h.lnP, self.Z)
+        if self._params["domZ"] is None:
+            self.domZ = float(sum(1 for h in self._hits if h.reported))
+        if not self._params["bit_cutoffs"]:
+            for h in self._hits:
+                for d in h._domains:
+                    d.reported = d.included = False
+                if h.reported:
+                    for d in h._domains:
+                        d.reported = self._domain_reportable(d.score, d.lnP)
+                        d.included = h.included and self._domain_includable(d.score, d.lnP)
+
+    def merge(self, *others):
+        """``TopHits.merge`` (plan7.pyx:9172-9273): combine hits of target-sharded searches of one query."""
+        merged = TopHits(self.query, self.mode)
+        merged._params = dict(self._params)
+        parts = (self,) + others
+        for part in parts:
+            for h in part._hits:
+                h.hits = merged
+                merged._hits.append(h)
+            for a in ("searched_sequences", "searched_residues", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd"):
+                setattr(merged, a, getattr(merged, a) + getattr(part, a))
+        merged.searched_models, merged.searched_nodes = self.searched_models, self.searched_nodes
+        if self.mode == "scan":
+            merged.searched_models = sum(p.searched_models for p in parts)
+            merged.searched_nodes = sum(p.searched_nodes for p in parts)
+            merged.searched_sequences, merged.searched_residues = self.searched_sequences, self.searched_residues
+        if self._params["Z"] is None:       # Z_setby == NTARGETS: search spaces add up (p7_pipeline_Merge)
+            merged.Z = float(sum(p.Z for p in parts))
+        else:
+            merged.Z = self.Z
+        merged.domZ = self.domZ
+        merged._sort_by_key()
+        merged._threshold()
+        return merged
+
+
+# =====================================================================================================
+# Pipeline   (reference: plan7.pyx 5423-6906; p7_pipeline.c)
+# =====================================================================================================
+class Pipeline:
+    """The accelerated comparison pipeline, one query at a time -- B200 back-end of ``pyhmmer.plan7.Pipeline``.
+
+    Keyword arguments, defaults and meaning are those of the reference (plan7.pyx:5471-5560).
+    """
+    M_HINT = 100
+    L_HINT = 100
+
+    def __init__(self, alphabet, background=None, *, bias_filter=True, null2=True, seed=42, Z=None, domZ=None,
+                 F1=0.02, F2=1e-3, F3=1e-5, E=10.0, T=None, domE=10.0, domT=None, incE=0.01, incT=None,
+                 incdomE=0.01, incdomT=None, bit_cutoffs=None, device=None, host_threads=0):
+        self.alphabet = alphabet
+        self.background = background if background is not None else Background(alphabet)
+        self.bias_filter, self.null2, self.seed = bool(bias_filter), bool(null2), int(seed)
+        self.Z, self.domZ = Z, domZ
+        self.F1, self.F2, self.F3 = float(F1), float(F2), float(F3)
+        self.E, self.T, self.domE, self.domT = E, T, domE, domT
+        self.incE, self.incT, self.incdomE, self.incdomT = incE, incT, incdomE, incdomT
+        if bit_cutoffs not in (None, "gathering", "trusted", "noise"):
+            raise ValueError("invalid bit cutoffs: %r" % (bit_cutoffs,))
+        self.bit_cutoffs = bit_cutoffs
+        self._ctx = _lib.context(device)
+        self.host_threads = host_threads
+        self.clear()
+
+    def clear(self):
+        self._nseqs = self._nres = self._nmodels = self._nnodes = 0
+
+    # -- query preparation (plan7.pyx:5979-6013) --
+    def _optimized(self, query, L):
+        if isinstance(query, OptimizedProfile):
+            return query
+        if isinstance(query, HMM):
+            query = Profile(query.M, self.alphabet).configure(query, self.background, L)
+        if isinstance(query, Profile):
+            return query.to_optimized()
+        raise TypeError("Expected HMM, Profile or OptimizedProfile, found %s" % type(query).__name__)
+
+    def _params_struct(self):
+        return _lib.SearchParams(self.F1, self.F2, self.F3, int(self.bias_filter), int(self.null2), self.seed, int(self.host_threads))
+
+    def _cutoffs(self, om):
+        """p7_pli_NewModelThresholds (p7_pipeline.c:535): model-specific bit thresholds."""
+        if self.bit_cutoffs is None:
+            return None
+        i = {"gathering": 0, "trusted": 2, "noise": 4}[self.bit_cutoffs]
+        if om._cutoff[i] == P7_CUTOFF_UNSET:
+            raise MissingCutoffs(om.name, self.bit_cutoffs)
+        return float(om._cutoff[i]), float(om._cutoff[i + 1])
+
+    def _tophits(self, query, mode, cut):
+        th = TopHits(query, mode)
+        p = th._params
+        p.update(E=self.E, domE=self.domE, incE=self.incE, incdomE=self.incdomE, Z=self.Z, domZ=self.domZ,
+                 bit_cutoffs=self.bit_cutoffs)
+        p["by_E"], p["T"] = (self.T is None), (0.0 if self.T is None else self.T)
+        p["dom_by_E"], p["domT"] = (self.domT is None), (0.0 if self.domT is None else self.domT)
+        p["inc_by_E"], p["incT"] = (self.incT is None), (0.0 if self.incT is None else self.incT)
+        p["incdom_by_E"], p["incdomT"] = (self.incdomT is None), (0.0 if self.incdomT is None else self.incdomT)
+        if cut is not None:                                   # --cut_ga/--cut_tc/--cut_nc (p7_pipeline.c:165-190, 540-560)
+            p.update(by_E=False, dom_by_E=False, inc_by_E=False, incdom_by_E=False,
+                     T=cut[0], incT=cut[0], domT=cut[1], incdomT=cut[1])
+        return th
+
+    def _run(self, oms, block):
+        ctx = self._ctx
+        db = SequenceDatabase.of(ctx, block)
+        handles = (ctypes.c_void_p * len(oms))(*[om._device(ctx) for om in oms])
+        prm = self._params_struct()
+        out = ctypes.c_void_p()
+        st = lib.b2h_search(ctx.handle, handles, len(oms), db.handle, ctypes.byref(prm), ctypes.byref(out))
+        if st == _lib.B2H_ERANGE:
+            raise OverflowError("numerical overflow in the optimized vector implementation")
+        check(st, "b2h_search", ctx.handle)
+        try:
+            hits, doms, text = _lib.read_results(out)
+            cp = lib.b2h_results_counters(out)
+            counters = np.array([cp[i] for i in range(4 * len(oms))], dtype=np.int64).reshape(len(oms), 4)
+        finally:
+            lib.b2h_results_destroy(out)
+        return hits, doms, text, counters
+
+    def _admit(self, th, rec, target, doms, text, Z_running, cut):
+        """Hit admission as p7_Pipeline does it at the moment the comparison finishes (p7_pipeline.c:838):
+        with the *running* Z when the search space is being counted (p7_pipeline.c:580)."""
+        p = th._params
+        if p["by_E"]:
+            ok = math.exp(rec.lnP) * Z_running <= p["E"]
+        else:
+            ok = rec.score >= p["T"]
+        if not ok:
+            return
+        h = Hit(th, rec, target, doms, text)
+        if cut is not None:                                   # flags set immediately under bit cutoffs (p7_pipeline.c:905-925)
+            h.reported = h.score >= p["T"]
+            h.included = h.reported and h.score >= p["incT"]
+            for d in h._domains:
+                d.reported = d.score >= p["domT"]
+                d.included = d.reported and d.score >= p["incdomT"]
+        th._hits.append(h)
+
+    def search_hmm(self, query, sequences):
+        """Search ``sequences`` (a `DigitalSequenceBlock`) with one query; returns `TopHits` (plan7.pyx:6121-6260)."""
+        return self._search_many([query], sequences)[0]
+
+    def _search_many(self, queries, sequences):
+        if not isinstance(sequences, DigitalSequenceBlock):
+            raise TypeError("expected DigitalSequenceBlock, found %s" % type(sequences).__name__)
+        if sequences.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, sequences.alphabet)
+        for q in queries:
+            if q.alphabet != self.alphabet:
+                raise AlphabetMismatch(self.alphabet, q.alphabet)
+        if sequences and len(sequences.largest()) > 100000:
+            raise ValueError("sequence length over comparison pipeline limit (100000)")
+        L = len(sequences[0]) if len(sequences) else self.L_HINT
+        oms = [self._optimized(q, L) for q in queries]
+        if len(sequences):
+            hits, doms, text, counters = self._run(oms, sequences)
+        else:
+            hits, doms, text, counters = [], [], b"", np.zeros((len(oms), 4), np.int64)
+        return self._assemble(queries, oms, sequences, hits, doms, text, counters)
+
+    def _assemble(self, queries, oms, sequences, hits, doms, text, counters):
+        """Turn raw hit records (ordered by profile, then target) into thresholded `TopHits`, one per query."""
+        cuts = [self._cutoffs(om) for om in oms]
+        n = len(sequences)
+        nres = sequences.total_residues
+        results = []
+        by_query = [[] for _ in oms]
+        for rec in hits:
+            by_query[rec.profile].append(rec)
+        for qi, (query, om) in enumerate(zip(queries, oms)):
+            th = self._tophits(query, "search", cuts[qi])
+            self._nmodels += 1
+            self._nnodes += om.M
+            for rec in by_query[qi]:                           # already in target order
+                Z_running = self.Z if self.Z is not None else float(rec.seq + 1)
+                self._admit(th, rec, sequences[rec.seq], doms, text, Z_running, cuts[qi])
+            th.Z = float(self.Z) if self.Z is not None else float(n)
+            th.domZ = float(self.domZ) if self.domZ is not None else 0.0
+            th.searched_models, th.searched_nodes = 1, om.M
+            th.searched_sequences, th.searched_residues = n, nres
+            th.n_past_msv, th.n_past_bias, th.n_past_vit, th.n_past_fwd = (int(v) for v in counters[qi])
+            th._sort_by_key()
+            th._threshold()
+            results.append(th)
+        self._nseqs += n
+        self._nres += nres
+        return results
+
+    def scan_seq(self, query, targets):
+        """Scan one sequence against a list of profiles (``OptimizedProfileBlock``); returns `TopHits` (plan7.pyx:6534-6677)."""
+        return self._scan_many([query], targets)[0]
+
+    def _scan_many(self, queries, targets):
+        if any(q.alphabet != self.alphabet for q in queries):
+            raise AlphabetMismatch(self.alphabet, [q.alphabet for q in queries if q.alphabet != self.alphabet][0])
+        oms = [self._optimized(t, self.L_HINT) for t in targets]
+        cuts = [self._cutoffs(om) for om in oms]
+        block = DigitalSequenceBlock(self.alphabet, queries)
+        if oms and len(block):
+            hits, doms, text, counters = self._run(oms, block)
+        else:
+            hits, doms, text, counters = [], [], b"", np.zeros((len(oms), 4), np.int64)
+        results = []
+        for si, seq in enumerate(queries):
+            th = self._tophits(seq, "scan", None)
+            mine = sorted((r for r in hits if r.seq == si), key=lambda r: r.profile)
+            for rec in mine:
+                cut = cuts[rec.profile]
+                if cut is not None:
+                    th._params.update(by_E=False, dom_by_E=False, inc_by_E=False, incdom_by_E=False,
+                                      T=cut[0], incT=cut[0], domT=cut[1], incdomT=cut[1])
+                Z_running = self.Z if self.Z is not None else float(rec.profile + 1)
+                self._admit(th, rec, oms[rec.profile], doms, text, Z_running, cut)
+            th.Z = float(self.Z) if self.Z is not None else float(len(oms))
+            th.domZ = float(self.domZ) if self.domZ is not None else 0.0
+            th.searched_models, th.searched_nodes = len(oms), sum(om.M for om in oms)
+            th.searched_sequences, th.searched_residues = 1, len(seq)
+            if len(counters):
+                th.n_past_msv, th.n_past_bias, th.n_past_vit, th.n_past_fwd = (int(v) for v in counters.sum(0)) if len(queries) == 1 else (0, 0, 0, 0)
+            th._sort_by_key()
+            th._threshold()
+            results.append(th)
+        return results
+
+
+class MissingCutoffs(ValueError):
+    """Same meaning as ``pyhmmer.errors.MissingCutoffs``."""
+
+    def __init__(self, name, kind):
+        super().__init__("model %r is missing %s bit cutoffs" % (name, kind))
