@@ -46,7 +46,7 @@ struct DenseList {
     B2H_CUDA(cudaMemcpyAsync(d_poff, poff, sizeof poff, cudaMemcpyHostToDevice, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(d_itemoff, itemoff, sizeof itemoff, cudaMemcpyHostToDevice, ctx->stream));
     B2H_CUDA(cudaStreamSynchronize(ctx->stream));           // the host staging variables above are on the stack
-    wl.profs = d_prof; wl.ent_s = db->d_order; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = 1; wl.counter = ctx->d_counters + 8;
+    wl.profs = d_prof; wl.ent_s = db->d_order; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = 1; wl.counter = ctx->d_counters + 8; wl.plo = 0; wl.phi = 1;
     return B2H_OK;
   }
   ~DenseList() { if (d_prof) cudaFreeAsync(d_prof, ctx->stream); if (d_poff) cudaFreeAsync(d_poff, ctx->stream); if (d_itemoff) cudaFreeAsync(d_itemoff, ctx->stream); if (d_cls) cudaFreeAsync(d_cls, ctx->stream); }
@@ -59,7 +59,7 @@ __global__ void unpermute_kernel(const int32_t *order, int n, const float *sc_e,
   if (e < n) { const int s = order[e]; if (sc) sc[s] = sc_e[e]; if (st) st[s] = st_e ? st_e[e] : 0; }
 }
 
-typedef int (*dp_launcher)(b2h_ctx *, const WorkList &, const SeqDev &, int, int, StageOut);
+typedef int (*dp_launcher)(b2h_ctx *, const WorkList &, const SeqDev &, const std::vector<int> &, int, StageOut);
 
 int dense_dp(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, dp_launcher launch, bool backward, float *sc, int32_t *status)
 {
@@ -72,6 +72,7 @@ int dense_dp(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, dp_launche
   DenseList dl(ctx);
   if ((st = dl.build(p, db)) != B2H_OK) return st;
   SeqDev sd = b2h_seqdev(db);
+  const std::vector<int> mp(1, p->Mpad);
   StageOut so; so.sc = oe.d_sc; so.status = oe.d_status; so.fwd_xmx = nullptr; so.bck_xmx = nullptr; so.xoff = nullptr;
   float *d_fx = nullptr; int64_t *d_xoff = nullptr;
   if (backward) {
@@ -88,10 +89,10 @@ int dense_dp(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, dp_launche
     B2H_CUDA(cudaMemcpyAsync(d_xoff, xoff.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     B2H_CUDA(cudaStreamSynchronize(ctx->stream));
     StageOut sf = so; sf.sc = of.d_sc; sf.status = of.d_status; sf.fwd_xmx = d_fx; sf.xoff = d_xoff;
-    st = b2h_launch_forward(ctx, dl.wl, sd, p->Mpad, dl.nitems, sf);
-    if (st == B2H_OK) { so.fwd_xmx = d_fx; so.xoff = d_xoff; st = launch(ctx, dl.wl, sd, p->Mpad, dl.nitems, so); }
+    st = b2h_launch_forward(ctx, dl.wl, sd, mp, dl.nitems, sf);
+    if (st == B2H_OK) { so.fwd_xmx = d_fx; so.xoff = d_xoff; st = launch(ctx, dl.wl, sd, mp, dl.nitems, so); }
   } else {
-    st = launch(ctx, dl.wl, sd, p->Mpad, dl.nitems, so);
+    st = launch(ctx, dl.wl, sd, mp, dl.nitems, so);
   }
   if (st == B2H_OK) {
     unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(db->d_order, (int)n, oe.d_sc, oe.d_status, o.d_sc, o.d_status);

@@ -23,6 +23,10 @@ int b2h_ctx_create(int device, b2h_ctx **out)
   B2H_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   B2H_CUDA(cudaMalloc(&ctx->d_counters, 64 * sizeof(int)));
+  {  // keep stream-ordered allocations cached across searches instead of returning them to the driver at every sync
+    cudaMemPool_t pool; uint64_t keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   *out = ctx;
   return B2H_OK;
 }

@@ -57,9 +57,9 @@ __device__ __forceinline__ bool next_item(const WorkList &wl, int *s_item, Item 
   __syncthreads();
   if (threadIdx.x == 0) *s_item = atomicAdd(wl.counter, 1);
   __syncthreads();
-  const int item = *s_item;
-  if (item >= wl.itemoff[wl.P]) return false;
-  int lo = 0, hi = wl.P;
+  const int item = *s_item + wl.itemoff[wl.plo];
+  if (item >= wl.itemoff[wl.phi]) return false;
+  int lo = wl.plo, hi = wl.phi;
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (wl.itemoff[mid] <= item) lo = mid; else hi = mid; }
   it.p = lo;
   it.e_begin = wl.poff[lo] + (item - wl.itemoff[lo]) * B2H_ITEM_ENTRIES;
@@ -521,36 +521,48 @@ LaunchCfg pick_cfg(int max_Mpad, int elem_bytes)
   return c;
 }
 
+// Profiles of a work list are sorted by Mpad; launch once per size class so that short models get
+// small shared-memory footprints (many CTAs per SM) instead of inheriting the largest model's.
 template <typename K>
-int launch_dp(b2h_ctx *ctx, K kernel, const WorkList &wl, const SeqDev &sd, int max_Mpad, int elem_bytes, int nitems_hint, const StageOut &out)
+int launch_dp(b2h_ctx *ctx, K kernel, const WorkList &wl_in, const SeqDev &sd, const std::vector<int> &mpads, int elem_bytes, int nitems_hint, const StageOut &out)
 {
-  LaunchCfg c = pick_cfg(max_Mpad, elem_bytes);
-  if ((size_t)6 * ((size_t)max_Mpad + 34) * elem_bytes + (size_t)8 * max_Mpad * elem_bytes > 220 * 1024) {
-    ctx->err = "model too long for the shared-memory DP kernels"; return B2H_EINVAL;
+  static const int bounds[] = {128, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 1 << 30};
+  const int P = (int)mpads.size();
+  int plo = 0, cls = 0;
+  while (plo < P) {
+    int b = 0; while (mpads[plo] > bounds[b]) b++;
+    int phi = plo; int mx = 0;
+    while (phi < P && mpads[phi] <= bounds[b]) { mx = std::max(mx, mpads[phi]); phi++; }
+    LaunchCfg c = pick_cfg(mx, elem_bytes);
+    if ((size_t)6 * ((size_t)mx + 34) * elem_bytes + (size_t)8 * mx * elem_bytes > 220 * 1024) {
+      ctx->err = "model too long for the shared-memory DP kernels"; return B2H_EINVAL;
+    }
+    B2H_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    int occ = 1;
+    B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, c.nwarps * 32, c.smem));
+    if (occ < 1) occ = 1;
+    int grid = ctx->sm_count * occ;
+    if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
+    if (grid < 1) grid = 1;
+    WorkList wl = wl_in; wl.plo = plo; wl.phi = phi; wl.counter = wl_in.counter + cls;
+    B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), ctx->stream));
+    DpCfg cfg; cfg.max_Mpad = mx; cfg.rsc_in_smem = c.rsc_in_smem;
+    kernel<<<grid, c.nwarps * 32, c.smem, ctx->stream>>>(wl, sd, cfg, out);
+    ctx->launches++;
+    B2H_CUDA(cudaGetLastError());
+    plo = phi; cls++;
   }
-  B2H_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-  int occ = 1;
-  B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, c.nwarps * 32, c.smem));
-  if (occ < 1) occ = 1;
-  int grid = ctx->sm_count * occ;
-  if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
-  if (grid < 1) grid = 1;
-  B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), ctx->stream));
-  DpCfg cfg; cfg.max_Mpad = max_Mpad; cfg.rsc_in_smem = c.rsc_in_smem;
-  kernel<<<grid, c.nwarps * 32, c.smem, ctx->stream>>>(wl, sd, cfg, out);
-  ctx->launches++;
-  B2H_CUDA(cudaGetLastError());
   return B2H_OK;
 }
 
 } // namespace
 
-int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out)
-{ return launch_dp(ctx, vit_kernel, wl, sd, max_Mpad, 2, nitems_hint, out); }
-int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out)
-{ return launch_dp(ctx, fwd_kernel, wl, sd, max_Mpad, 4, nitems_hint, out); }
-int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out)
-{ return launch_dp(ctx, bck_kernel, wl, sd, max_Mpad, 4, nitems_hint, out); }
+int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out)
+{ return launch_dp(ctx, vit_kernel, wl, sd, mpads, 2, nitems_hint, out); }
+int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out)
+{ return launch_dp(ctx, fwd_kernel, wl, sd, mpads, 4, nitems_hint, out); }
+int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out)
+{ return launch_dp(ctx, bck_kernel, wl, sd, mpads, 4, nitems_hint, out); }
 
 int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc)
 {

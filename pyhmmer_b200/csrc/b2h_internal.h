@@ -166,14 +166,16 @@ struct WorkList {
   const int32_t *itemoff;    // [P+1]
   int            P;
   int           *counter;
+  int            plo, phi;   // this launch covers profiles [plo, phi) only (profiles are sorted by size; one launch per size class)
 };
 
 // per-entry outputs of a DP stage
 struct StageOut { float *sc; int32_t *status; float *fwd_xmx, *bck_xmx; const int64_t *xoff; };
 
-int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out);
-int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out);
-int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, StageOut out);
+// mpads[p] = Mpad of profile p of the work list, ascending (one launch per size class)
+int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
+int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
+int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc);
 
 // A compacted list of comparisons produced by a stage's epilogue (device memory).  Appends are

@@ -215,9 +215,9 @@ __device__ __forceinline__ bool next_item(const WorkList &wl, int *s_item, Item 
   __syncthreads();
   if (threadIdx.x == 0) *s_item = atomicAdd(wl.counter, 1);
   __syncthreads();
-  const int item = *s_item;
-  if (item >= wl.itemoff[wl.P]) return false;
-  int lo = 0, hi = wl.P;
+  const int item = *s_item + wl.itemoff[wl.plo];
+  if (item >= wl.itemoff[wl.phi]) return false;
+  int lo = wl.plo, hi = wl.phi;
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (wl.itemoff[mid] <= item) lo = mid; else hi = mid; }
   it.p = lo;
   it.e_begin = wl.poff[lo] + (item - wl.itemoff[lo]) * B2H_ITEM_ENTRIES;

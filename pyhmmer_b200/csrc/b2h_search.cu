@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -98,6 +100,8 @@ struct Pool {
   ~Pool() { for (void *p : ptrs) cudaFreeAsync(p, ctx->stream); }
 };
 
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 #define TRY(x) do { int st_ = (x); if (st_ != B2H_OK) return st_; } while (0)
 
 int make_list(Pool &pool, SurvList &l, size_t cap, int P, int *ctr, int *cnt, bool with_b)
@@ -124,9 +128,13 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
   // profile descriptors + register-tile classes
   std::vector<ProfDev> hprof(P);
   std::map<int, std::vector<int32_t>> classes;
+  std::vector<int> perm(P), mpads(P);                  // batch-local profile order: ascending model size
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return profiles[p0 + a]->Mpad < profiles[p0 + b]->Mpad; });
   int max_Mpad = 0;
   for (int i = 0; i < P; i++) {
-    hprof[i] = b2h_profdev(profiles[p0 + i]);
+    hprof[i] = b2h_profdev(profiles[p0 + perm[i]]);
+    mpads[i] = hprof[i].Mpad;
     classes[hprof[i].NR].push_back(i);
     max_Mpad = std::max(max_Mpad, hprof[i].Mpad);
   }
@@ -151,7 +159,7 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
   TRY(pool.get(&G.p, cap)); TRY(pool.get(&G.s, cap)); TRY(pool.get(&G.a, cap)); G.b = nullptr;
   TRY(pool.get(&G.poff, (size_t)P + 1)); TRY(pool.get(&G.itemoff, (size_t)P + 1)); G.fill = fill;
   float *stage_sc; int32_t *stage_st; TRY(pool.get(&stage_sc, cap)); TRY(pool.get(&stage_st, cap));
-  WorkList wl; wl.profs = d_prof; wl.ent_s = G.s; wl.poff = G.poff; wl.itemoff = G.itemoff; wl.P = P; wl.counter = ctx->d_counters + 8;
+  WorkList wl; wl.profs = d_prof; wl.ent_s = G.s; wl.poff = G.poff; wl.itemoff = G.itemoff; wl.P = P; wl.counter = ctx->d_counters + 8; wl.plo = 0; wl.phi = P;
   const int32_t *nent = G.poff + P;                  // number of entries of the current grouped list (device)
   const int pgrid = ctx->sm_count * 8;
 
@@ -181,14 +189,14 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
   { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, V, P, G)); }
   { StageTimer tm(ctx, 3);
     StageOut so; so.sc = stage_sc; so.status = stage_st; so.fwd_xmx = so.bck_xmx = nullptr; so.xoff = nullptr;
-    TRY(b2h_launch_viterbi(ctx, wl, sd, max_Mpad, 0, so));
+    TRY(b2h_launch_viterbi(ctx, wl, sd, mpads, 0, so));
     vit_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, G, nent, stage_sc, prm->F2, F);
     ctx->launches++; }
   // 5. Forward parser
   { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, F, P, G)); }
   { StageTimer tm(ctx, 4);
     StageOut so; so.sc = stage_sc; so.status = stage_st; so.fwd_xmx = so.bck_xmx = nullptr; so.xoff = nullptr;
-    TRY(b2h_launch_forward(ctx, wl, sd, max_Mpad, 0, so));
+    TRY(b2h_launch_forward(ctx, wl, sd, mpads, 0, so));
     fwd_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, G, nent, stage_sc, stage_st, prm->F3, D, d_ctr + 5);
     ctx->launches++; }
   B2H_CUDA(cudaGetLastError());
@@ -201,7 +209,7 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
   if (hctr[5] > 0) { ctx->err = "numerical overflow in the Forward parser"; return B2H_ERANGE; }
   const int nD = hctr[4];
   for (int i = 0; i < P; i++) {
-    int64_t *c = counters + (size_t)(p0 + i) * 4;
+    int64_t *c = counters + (size_t)(p0 + perm[i]) * 4;
     c[0] = hctr[8 + i]; c[1] = hctr[8 + 5 * P + i]; c[2] = hctr[8 + 3 * P + i]; c[3] = hctr[8 + 4 * P + i];
   }
   std::vector<int32_t> dp(nD), ds(nD); std::vector<float> da(nD), dbv(nD);
@@ -213,7 +221,7 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
     B2H_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   outD.reserve(outD.size() + nD);
-  for (int i = 0; i < nD; i++) { b2h_survivor v; v.profile = p0 + dp[i]; v.seq = ds[i]; v.fwdsc = da[i]; v.filtersc = dbv[i]; outD.push_back(v); }
+  for (int i = 0; i < nD; i++) { b2h_survivor v; v.profile = p0 + perm[dp[i]]; v.seq = ds[i]; v.fwdsc = da[i]; v.filtersc = dbv[i]; outD.push_back(v); }
   return B2H_OK;
 }
 
@@ -222,7 +230,9 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
 static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, const b2h_search_params *prm,
                             std::vector<b2h_survivor> &surv, b2h_results *res)
 {
-  std::sort(surv.begin(), surv.end(), [](const b2h_survivor &x, const b2h_survivor &y) {
+  std::sort(surv.begin(), surv.end(), [&](const b2h_survivor &x, const b2h_survivor &y) {
+    const int mx = profiles[x.profile]->Mpad, my = profiles[y.profile]->Mpad;
+    if (mx != my) return mx < my;
     return x.profile != y.profile ? x.profile < y.profile : x.seq < y.seq; });
   const SeqDev sd = b2h_seqdev(db);
   const size_t ROW_BUDGET = (size_t)32 << 20;        // rows of 6 floats per chunk (x2 matrices = 1.5 GB)
@@ -233,13 +243,13 @@ static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, co
     while (i1 < surv.size() && (i1 == i0 || rows + db->h_len[surv[i1].seq] + 1 <= ROW_BUDGET)) { rows += db->h_len[surv[i1].seq] + 1; i1++; }
     const int n = (int)(i1 - i0);
     // work list of this chunk: profiles present, in order
-    std::vector<ProfDev> hprof; std::vector<int32_t> poff, itemoff, ent_s(n); std::vector<int64_t> xoff(n);
+    std::vector<ProfDev> hprof; std::vector<int32_t> poff, itemoff, ent_s(n); std::vector<int64_t> xoff(n); std::vector<int> mpads;
     int max_Mpad = 0; int64_t acc = 0; int items = 0;
     for (int e = 0; e < n; e++) {
       const b2h_survivor &v = surv[i0 + e];
       if (e == 0 || v.profile != surv[i0 + e - 1].profile) {
         if (e) items += ((e - poff.back()) + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES;
-        hprof.push_back(b2h_profdev(profiles[v.profile])); poff.push_back(e); itemoff.push_back(items);
+        hprof.push_back(b2h_profdev(profiles[v.profile])); poff.push_back(e); itemoff.push_back(items); mpads.push_back(hprof.back().Mpad);
         max_Mpad = std::max(max_Mpad, hprof.back().Mpad);
       }
       ent_s[e] = v.seq; xoff[e] = acc; acc += db->h_len[v.seq] + 1;
@@ -257,12 +267,12 @@ static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, co
     B2H_CUDA(cudaMemcpyAsync(d_itemoff, itemoff.data(), (Pc + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(d_ent, ent_s.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(d_xoff, xoff.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    WorkList wl; wl.profs = d_prof; wl.ent_s = d_ent; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = Pc; wl.counter = ctx->d_counters + 8;
+    WorkList wl; wl.profs = d_prof; wl.ent_s = d_ent; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = Pc; wl.counter = ctx->d_counters + 8; wl.plo = 0; wl.phi = Pc;
     StageOut sf; sf.sc = d_fsc; sf.status = d_fst; sf.fwd_xmx = d_fx; sf.bck_xmx = nullptr; sf.xoff = d_xoff;
     StageTimer *tm = new StageTimer(ctx, 5);
-    TRY(b2h_launch_forward(ctx, wl, sd, max_Mpad, items, sf));
+    TRY(b2h_launch_forward(ctx, wl, sd, mpads, items, sf));
     StageOut sb; sb.sc = d_bsc; sb.status = d_bst; sb.fwd_xmx = d_fx; sb.bck_xmx = d_bx; sb.xoff = d_xoff;
-    TRY(b2h_launch_backward(ctx, wl, sd, max_Mpad, items, sb));
+    TRY(b2h_launch_backward(ctx, wl, sd, mpads, items, sb));
     delete tm;
     std::vector<float> fx((size_t)acc * 6), bx((size_t)acc * 6); std::vector<int32_t> bst(n);
     B2H_CUDA(cudaMemcpyAsync(fx.data(), d_fx, fx.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -280,7 +290,9 @@ static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, co
       t.fx = fx.data() + (size_t)xoff[e] * 6; t.bx = bx.data() + (size_t)xoff[e] * 6;
       t.bck_own_scales = (bst[e] & 0x100) != 0;
     }
+    const double td0 = now_ms();
     int st = ddpool.run(tasks, prm, res);
+    if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search]   chunk of %d survivors: host domain definition %.1f ms on %d threads\n", n, now_ms() - td0, ddpool.nthreads);
     if (st != B2H_OK) { ctx->err = "domain definition failed"; return st; }
     i0 = i1;
   }
@@ -300,6 +312,7 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
   const size_t N = db->n;
   std::vector<b2h_survivor> surv;
   if (N > 0 && P > 0) {
+    const double t0 = now_ms();
     const size_t CAP = (size_t)1 << 25;                 // comparisons per batch: every list is sized for the worst case
     size_t pb = std::max<size_t>(1, CAP / N);
     for (size_t p0 = 0; p0 < P; p0 += pb) {
@@ -307,8 +320,12 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
       int st = cascade_batch(ctx, profiles, (int)p0, (int)p1, db, prm, surv, res->counters.data());
       if (st != B2H_OK) { delete res; return st; }
     }
+    const double t1 = now_ms();
     int st = finish_survivors(ctx, profiles, db, prm, surv, res);
     if (st != B2H_OK) { delete res; return st; }
+    std::stable_sort(res->hits.begin(), res->hits.end(), [](const b2h_hit &x, const b2h_hit &y) {
+      return x.profile != y.profile ? x.profile < y.profile : x.seq < y.seq; });
+    if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search] cascade %.1f ms, survivors(%zu) fwd/bck + domain definition %.1f ms\n", t1 - t0, surv.size(), now_ms() - t1);
   }
   *out = res;
   return B2H_OK;
