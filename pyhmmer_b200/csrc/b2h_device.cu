@@ -245,6 +245,23 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
       ft[(size_t)t * Mp + k] = d->fwd_tsc[(size_t)t * M + k];
     }
 
+  // --- lane-grouped emission tables of the register-resident DP kernels (b2h_dpreg.cu), models up to 256 nodes ---
+  p->regC = (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 256) ? 8 : 0;
+  std::vector<int32_t> vr32; std::vector<float> frr;
+  if (p->regC) {
+    const int C = p->regC;
+    vr32.assign((size_t)B2H_NCODE * 32 * C, -32768); frr.assign((size_t)B2H_NCODE * 32 * C, 0.0f);
+    for (int x = 0; x < Kp; x++)
+      for (int lane = 0; lane < 32; lane++)
+        for (int c = 0; c < C; c++) {
+          const int k0 = lane * C + c;
+          if (k0 >= M) continue;
+          const size_t idx = (size_t)x * 32 * C + (C == 2 ? (size_t)lane * 2 + c : (size_t)(c / 4) * 128 + (size_t)lane * 4 + (c % 4));
+          vr32[idx] = d->vit_rsc[(size_t)x * M + k0];
+          frr[idx] = d->fwd_rsc[(size_t)x * M + k0];
+        }
+  }
+
   // --- bias-filter 2-state HMM (p7_bg_SetFilter p7_bg.c:429, esl_hmm_Configure esl_hmm.c:118) ---
   std::vector<float> eo((size_t)B2H_NCODE * 2, 1.0f);
   {
@@ -274,6 +291,7 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
     UP(p->d_vit_rsc, vr, int16_t);    UP(p->d_vit_tsc, vt, int16_t);
     UP(p->d_fwd_rsc, fr, float);      UP(p->d_fwd_tsc, ft, float);
     UP(p->d_bias_eo, eo, float);
+    if (p->regC) { UP(p->d_vit_rsc32, vr32, int32_t); UP(p->d_fwd_rscr, frr, float); }
 #undef UP
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); st = B2H_ECUDA; }
   } while (0);
@@ -286,7 +304,7 @@ void b2h_profile_destroy(b2h_profile *p)
 {
   if (!p) return;
   if (p->ctx) cudaSetDevice(p->ctx->device);
-  void *ptrs[] = { p->d_ssv_emis, p->d_msv_cost8, p->d_vit_rsc, p->d_vit_tsc, p->d_fwd_rsc, p->d_fwd_tsc, p->d_bias_eo };
+  void *ptrs[] = { p->d_ssv_emis, p->d_msv_cost8, p->d_vit_rsc, p->d_vit_tsc, p->d_fwd_rsc, p->d_fwd_tsc, p->d_bias_eo, p->d_vit_rsc32, p->d_fwd_rscr };
   for (void *q : ptrs) if (q) cudaFree(q);
   delete p;
 }

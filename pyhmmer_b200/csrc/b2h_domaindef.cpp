@@ -21,8 +21,14 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
+#if defined(__SSE2__)
+#include <xmmintrin.h>
+#include <pmmintrin.h>
+#endif
 #include "b2h_internal.h"
 #include "b2h_domaindef.h"
 
@@ -97,7 +103,17 @@ struct Mx {                  // full DP matrix: rows 0..L, nodes 0..M (node 0 un
   int M = 0, L = 0;
   std::vector<float> dp, x;
   float totscale = 0.f; bool own_scales = false;
-  void resize(int M_, int L_) { M = M_; L = L_; dp.assign((size_t)(L + 1) * (M + 2) * 3, 0.0f); x.assign((size_t)(L + 1) * NX, 0.0f); }
+  // grow-only; only row 0 and the two guard columns (node 0 and node M+1) of every row are cleared: every other
+  // cell that a recurrence reads has been written by the same pass before
+  void resize(int M_, int L_) {
+    M = M_; L = L_;
+    const size_t need = (size_t)(L + 1) * (M + 2) * 3, needx = (size_t)(L + 1) * NX;
+    if (dp.size() < need) dp.resize(need);
+    if (x.size() < needx) x.resize(needx);
+    std::fill(dp.begin(), dp.begin() + (size_t)(M + 2) * 3, 0.0f);
+    for (int i = 1; i <= L; i++) { float *r = row(i); r[0] = r[1] = r[2] = 0.0f; float *g = r + (size_t)(M + 1) * 3; g[0] = g[1] = g[2] = 0.0f; }
+    std::fill(x.begin(), x.begin() + needx, 0.0f);
+  }
   float *row(int i) { return dp.data() + (size_t)i * (M + 2) * 3; }
   const float *row(int i) const { return dp.data() + (size_t)i * (M + 2) * 3; }
   float &X(int i, int s) { return x[(size_t)i * NX + s]; }
@@ -823,24 +839,97 @@ void ddef_one(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, H
 
 } // namespace
 
+// Odds-space Forward/Backward rows decay into denormals away from the alignment; x86 handles those ~100x slower.
+// HMMER's own programs run with flush-to-zero (impl_Init); pyhmmer cannot set it process-wide, we can per worker.
+struct FtzScope {
+#if defined(__SSE2__)
+  unsigned int saved;
+  FtzScope() : saved(_mm_getcsr()) { _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON); _MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON); }
+  ~FtzScope() { _mm_setcsr(saved); }
+#endif
+};
+
+// A process-wide pool of persistent worker threads (created on first use, grown on demand).  Each thread keeps its
+// Worker (DP matrices, trace buffers) across searches, so steady-state searches allocate nothing.
+namespace {
+
+class ThreadPool {
+ public:
+  static ThreadPool &get() { static ThreadPool p; return p; }
+  // run fn(worker, index) for index in [0, n) on up to nthreads threads (the caller participates)
+  template <typename F> void parallel_for(size_t n, int nthreads, F fn) {
+    if (n == 0) return;
+    std::unique_lock<std::mutex> run_lock(run_mu_);                  // one parallel_for at a time
+    nthreads = (int)std::min<size_t>((size_t)std::max(1, nthreads), n);
+    grow(nthreads - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = [&](Worker &w, size_t i) { fn(w, i); };
+      n_ = n; next_.store(0); active_ = nthreads - 1; done_ = 0; generation_++;
+    }
+    cv_.notify_all();
+    drain(self_);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return done_ == active_; });
+    job_ = nullptr;
+  }
+
+ private:
+  ThreadPool() {}
+  ~ThreadPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto &t : threads_) t.join();
+  }
+  void grow(int want) {
+    while ((int)threads_.size() < want) {
+      const int id = (int)threads_.size();
+      threads_.emplace_back([this, id] { loop(id); });
+    }
+  }
+  void drain(Worker &w) { FtzScope ftz; for (;;) { const size_t i = next_.fetch_add(1); if (i >= n_) break; job_(w, i); } }
+  void loop(int id) {
+    Worker w; w.rng.init(42u);
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || (generation_ != seen && id < active_); });
+        if (stop_) return;
+        seen = generation_;
+      }
+      drain(w);
+      { std::lock_guard<std::mutex> lk(mu_); done_++; }
+      done_cv_.notify_one();
+    }
+  }
+  std::mutex run_mu_, mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> threads_;
+  std::function<void(Worker &, size_t)> job_;
+  std::atomic<size_t> next_{0};
+  size_t n_ = 0; int active_ = 0, done_ = 0; uint64_t generation_ = 0; bool stop_ = false;
+  Worker self_;
+};
+
+} // namespace
+
 b2h_ddef_pool::b2h_ddef_pool(int n)
 {
   if (n <= 0) n = (int)std::thread::hardware_concurrency();
-  nthreads = std::max(1, std::min(n, 64));
+  nthreads = std::max(1, std::min(n, 128));
 }
 
 int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_params *prm, b2h_results *res)
 {
   const size_t n = tasks.size();
   std::vector<HitOut> outs(n);
-  std::atomic<size_t> next(0);
-  auto body = [&]() {
-    Worker w; w.rng.init(prm->seed ? prm->seed : 42u);
-    for (;;) { const size_t e = next.fetch_add(1); if (e >= n) break; ddef_one(w, tasks[e], prm, outs[e]); }
-  };
-  const int nt = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(n, 1));
-  if (nt <= 1) body();
-  else { std::vector<std::thread> th; for (int i = 0; i < nt; i++) th.emplace_back(body); for (auto &x : th) x.join(); }
+  // longest-processing-time-first: the cost of a task grows with model length x sequence length
+  std::vector<uint32_t> order(n);
+  for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    return (int64_t)tasks[a].prof->M * tasks[a].L > (int64_t)tasks[b].prof->M * tasks[b].L; });
+  ThreadPool::get().parallel_for(n, nthreads, [&](Worker &w, size_t i) { const uint32_t e = order[i]; ddef_one(w, tasks[e], prm, outs[e]); });
   for (size_t e = 0; e < n; e++) {
     if (!outs[e].valid) continue;
     b2h_hit h = outs[e].hit;

@@ -521,14 +521,26 @@ LaunchCfg pick_cfg(int max_Mpad, int elem_bytes)
   return c;
 }
 
-// Profiles of a work list are sorted by Mpad; launch once per size class so that short models get
-// small shared-memory footprints (many CTAs per SM) instead of inheriting the largest model's.
+// Profiles of a work list are sorted by Mpad.  Models of up to 256 nodes go to the register-resident kernels
+// (b2h_dpreg.cu: 2 / 4 / 8 nodes per lane); longer ones to the shared-memory kernels of this file, one launch
+// per size class so that mid-sized models do not inherit the largest model's shared-memory footprint.
 template <typename K>
-int launch_dp(b2h_ctx *ctx, K kernel, const WorkList &wl_in, const SeqDev &sd, const std::vector<int> &mpads, int elem_bytes, int nitems_hint, const StageOut &out)
+int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const SeqDev &sd, const std::vector<int> &mpads, int elem_bytes, int nitems_hint, const StageOut &out)
 {
-  static const int bounds[] = {128, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 1 << 30};
+  static const int bounds[] = {384, 512, 768, 1024, 1536, 2048, 3072, 1 << 30};
   const int P = (int)mpads.size();
   int plo = 0, cls = 0;
+  static const int regb[3] = {64, 128, 256}, regc[3] = {2, 4, 8};
+  for (int rc = 0; rc < 3 && plo < P; rc++) {
+    int phi = plo;
+    while (phi < P && mpads[phi] <= regb[rc]) phi++;
+    if (phi > plo) {
+      WorkList wl = wl_in; wl.plo = plo; wl.phi = phi; wl.counter = wl_in.counter + cls;
+      int st = b2h_launch_dpreg(ctx, kind, regc[rc], wl, sd, nitems_hint, out);
+      if (st != B2H_OK) return st;
+      plo = phi; cls++;
+    }
+  }
   while (plo < P) {
     int b = 0; while (mpads[plo] > bounds[b]) b++;
     int phi = plo; int mx = 0;
@@ -558,11 +570,11 @@ int launch_dp(b2h_ctx *ctx, K kernel, const WorkList &wl_in, const SeqDev &sd, c
 } // namespace
 
 int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out)
-{ return launch_dp(ctx, vit_kernel, wl, sd, mpads, 2, nitems_hint, out); }
+{ return launch_dp(ctx, vit_kernel, 0, wl, sd, mpads, 2, nitems_hint, out); }
 int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out)
-{ return launch_dp(ctx, fwd_kernel, wl, sd, mpads, 4, nitems_hint, out); }
+{ return launch_dp(ctx, fwd_kernel, 1, wl, sd, mpads, 4, nitems_hint, out); }
 int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out)
-{ return launch_dp(ctx, bck_kernel, wl, sd, mpads, 4, nitems_hint, out); }
+{ return launch_dp(ctx, bck_kernel, 2, wl, sd, mpads, 4, nitems_hint, out); }
 
 int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc)
 {

@@ -1,0 +1,503 @@
+// b2h_dpreg.cu -- register-resident ViterbiFilter / Forward parser / Backward parser for models with
+// M <= 32*C (C = 2, 4 or 8 nodes per lane, i.e. M <= 64 / 128 / 256: three quarters of Pfam).
+//
+// Same recurrences and the same numerical semantics as the generic kernels of b2h_dp.cu (which remain
+// the path for longer models), but organised so that almost nothing is re-read per row:
+//   * lane z owns the C consecutive nodes z*C+1 .. z*C+C; its M/I/D cells AND its 8*C transition
+//     scores live in registers for the whole comparison;
+//   * the only per-row memory traffic is one conflict-free vector load of the C emission scores of
+//     the current residue from shared memory (table staged per CTA per profile by a TMA bulk copy);
+//   * the (i-1,k-1) dependency across lanes is three warp shuffles per row;
+//   * the D->D chain is closed in two levels: serially inside the lane (C steps), then one warp scan
+//     of the 32 per-lane composites (max-plus for Viterbi, affine for Forward/Backward).
+// The generic kernels execute ~88 instructions per cell and row; these execute ~0.5.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <algorithm>
+#include "b2h_internal.h"
+
+namespace {
+
+constexpr int NEG16 = -32768;
+constexpr uint32_t FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+    "{\n .reg .pred p;\n"
+    "WAIT_%=:\n"
+    " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    " @p bra DONE_%=;\n"
+    " bra WAIT_%=;\n"
+    "DONE_%=:\n}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct Item { int p, e_begin, e_end; };
+__device__ __forceinline__ bool next_item(const WorkList &wl, int *s_item, Item &it)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) *s_item = atomicAdd(wl.counter, 1);
+  __syncthreads();
+  const int item = *s_item + wl.itemoff[wl.plo];
+  if (item >= wl.itemoff[wl.phi]) return false;
+  int lo = wl.plo, hi = wl.phi;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (wl.itemoff[mid] <= item) lo = mid; else hi = mid; }
+  it.p = lo;
+  it.e_begin = wl.poff[lo] + (item - wl.itemoff[lo]) * B2H_ITEM_ENTRIES;
+  it.e_end   = min(wl.poff[lo + 1], it.e_begin + B2H_ITEM_ENTRIES);
+  return true;
+}
+
+// The C emission values of this lane for residue x.  Table layout: [32 residues][C/4 groups][32 lanes][4]
+// (C = 2: [32][32][2]), so every access is one conflict-free LDS.64 / LDS.128 per lane.
+template <int C, typename T>
+__device__ __forceinline__ void load_emis(const T *tab, int x, int lane, T (&r)[C])
+{
+  const T *row = tab + (size_t)x * 32 * C;
+  if (C == 2) { const float2 v = *reinterpret_cast<const float2 *>(row + lane * 2); r[0] = *(const T *)&v.x; r[1] = *(const T *)&v.y; }
+  else {
+#pragma unroll
+    for (int g = 0; g < C / 4; g++) {
+      const float4 v = *reinterpret_cast<const float4 *>(row + g * 128 + lane * 4);
+      r[4*g+0] = *(const T *)&v.x; r[4*g+1] = *(const T *)&v.y; r[4*g+2] = *(const T *)&v.z; r[4*g+3] = *(const T *)&v.w;
+    }
+  }
+}
+
+// residues: each lane keeps one 4-residue word of the current 128-row window (as the SSV kernel does)
+struct SeqWin {
+  const uint32_t *seqw; int nwords; uint32_t myw; int w0;
+  __device__ __forceinline__ void init(const uint8_t *seq, int L, int lane) { seqw = reinterpret_cast<const uint32_t *>(seq); nwords = (L + 3) >> 2; w0 = -32; myw = 0; (void)lane; }
+  __device__ __forceinline__ int get(int i0, int lane) {      // residue at 0-based position i0 (monotonically increasing calls)
+    const int w = i0 >> 2;
+    if (w >= w0 + 32) { w0 = w & ~31; myw = (w0 + lane < nwords) ? __ldg(seqw + w0 + lane) : 0x1f1f1f1fu; }
+    const uint32_t wr = __shfl_sync(FULL, myw, w - w0);
+    return (wr >> ((i0 & 3) * 8)) & 0xff;
+  }
+};
+
+// =================================================================================================
+// ViterbiFilter, register resident
+// =================================================================================================
+template <int C>
+__global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqDev sd, const StageOut out)
+{
+  extern __shared__ __align__(128) int s_rsc[];            // [32][32*C] int32 emission scores
+  __shared__ uint64_t s_bar;
+  __shared__ int s_item;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr uint32_t TAB_BYTES = 32u * 32u * C * 4u;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  uint32_t phase = 0;
+  int cur_p = -1;
+  int tBM[C], tMM[C], tIM[C], tDM[C], tMD[C], tMI[C], tII[C], tDD[C];
+  int tDDin = NEG16;                                        // D_{k-1}->D_k for this lane's first node (the left lane's last tDD)
+  Item it;
+  while (next_item(wl, &s_item, it)) {
+    const ProfDev &P = wl.profs[it.p];
+    if (it.p != cur_p) {
+      cur_p = it.p;
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_rsc, P.vit_rsc32, TAB_BYTES, &s_bar); }
+      const int16_t *ts = P.vit_tsc; const int Mp = P.Mpad;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const int k0 = lane * C + c;                        // 0-based node column
+        const bool in = k0 < Mp;
+        tBM[c] = in ? ts[0 * Mp + k0] : NEG16; tMM[c] = in ? ts[1 * Mp + k0] : NEG16; tIM[c] = in ? ts[2 * Mp + k0] : NEG16;
+        tDM[c] = in ? ts[3 * Mp + k0] : NEG16; tMD[c] = in ? ts[4 * Mp + k0] : NEG16; tMI[c] = in ? ts[5 * Mp + k0] : NEG16;
+        tII[c] = in ? ts[6 * Mp + k0] : NEG16; tDD[c] = in ? ts[7 * Mp + k0] : NEG16;
+      }
+      tDDin = __shfl_up_sync(FULL, tDD[C - 1], 1); if (lane == 0) tDDin = NEG16;
+      mbar_wait(&s_bar, phase); phase ^= 1;
+    }
+    const int xwEm = P.xw_E_move, xwEl = P.xw_E_loop, base_w = P.base_w, ddbound = P.ddbound_w;
+
+    for (int e = it.e_begin + warp; e < it.e_end; e += nwarps) {
+      const int s = wl.ent_s[e];
+      const int L = sd.len[s];
+      const int xw_move = sd.xwmove[s];
+      SeqWin sw; sw.init(sd.res + sd.off[s], L, lane);
+      int M[C], I[C], D[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) { M[c] = NEG16; I[c] = NEG16; D[c] = NEG16; }
+      int xN = base_w, xB = (int16_t)(xN + xw_move), xJ = NEG16, xC = NEG16;
+      bool overflow = false;
+
+      for (int i = 0; i < L; i++) {
+        const int x = sw.get(i, lane);
+        int r[C];
+        load_emis<C, int>(s_rsc, x, lane, r);
+        int mp = __shfl_up_sync(FULL, M[C - 1], 1), ip = __shfl_up_sync(FULL, I[C - 1], 1), dp = __shfl_up_sync(FULL, D[C - 1], 1);
+        if (lane == 0) { mp = NEG16; ip = NEG16; dp = NEG16; }
+        int xEm = NEG16;
+#pragma unroll
+        for (int c = C - 1; c >= 0; c--) {
+          const int pm = (c == 0) ? mp : M[c - 1], pi = (c == 0) ? ip : I[c - 1], pd = (c == 0) ? dp : D[c - 1];
+          const int inew = __vimax3_s32(M[c] + tMI[c], I[c] + tII[c], NEG16);
+          int m = __viaddmax_s32(xB, tBM[c], NEG16);
+          m = __viaddmax_s32(pm, tMM[c], m);
+          m = __viaddmax_s32(pi, tIM[c], m);
+          m = __viaddmax_s32(pd, tDM[c], m);
+          m = __viaddmax_s32(m, r[c], NEG16);
+          xEm = max(xEm, m);
+          M[c] = m; I[c] = inew;
+        }
+        const int xE = __reduce_max_sync(FULL, xEm);
+        if (xE >= 32767) { overflow = true; break; }
+        xC = (int16_t)max(xC, xE + xwEm);
+        xJ = (int16_t)max(xJ, xE + xwEl);
+        xB = (int16_t)max(xJ + xw_move, xN + xw_move);
+        // M->D partials: D[c] is the value entering node c from M of node c-1
+        int dleft = __shfl_up_sync(FULL, __viaddmax_s32(M[C - 1], tMD[C - 1], NEG16), 1);
+        if (lane == 0) dleft = NEG16;
+        int Dm = dleft;
+        D[0] = dleft;
+#pragma unroll
+        for (int c = 1; c < C; c++) { D[c] = __viaddmax_s32(M[c - 1], tMD[c - 1], NEG16); Dm = max(Dm, D[c]); }
+        const int Dmax = __reduce_max_sync(FULL, Dm);
+        if (Dmax + ddbound > xB) {
+          // close the D->D chain: serial inside the lane, then a max-plus scan over the 32 lane composites
+          int T[C];
+          T[0] = tDDin;
+#pragma unroll
+          for (int c = 1; c < C; c++) { D[c] = __viaddmax_s32(D[c - 1], tDD[c - 1], D[c]); T[c] = T[c - 1] + tDD[c - 1]; }
+          int A = D[C - 1], Tt = T[C - 1];                   // lane composite: d -> max(A, d + Tt)
+#pragma unroll
+          for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const int A2 = __shfl_up_sync(FULL, A, dlt), T2 = __shfl_up_sync(FULL, Tt, dlt);
+            if (lane >= dlt) { A = max(A, A2 + Tt); Tt = max(T2 + Tt, -(1 << 29)); }
+          }
+          int din = __shfl_up_sync(FULL, A, 1);              // D of the previous lane's last node
+          if (lane == 0) din = NEG16;
+#pragma unroll
+          for (int c = 0; c < C; c++) D[c] = max(D[c], max(din + T[c], NEG16));
+        }
+      }
+      if (lane == 0) {
+        float sc; int st = B2H_OK;
+        if (overflow) { sc = INFINITY; st = B2H_ERANGE; }
+        else if (xC > NEG16) { sc = (float)xC + (float)xw_move - (float)base_w; sc /= P.scale_w; sc -= 3.0f; }
+        else sc = -INFINITY;
+        out.sc[e] = sc;
+        if (out.status) out.status[e] = st;
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// Forward parser, register resident
+// =================================================================================================
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqDev sd, const StageOut out)
+{
+  extern __shared__ __align__(128) float s_rscf[];          // [32][32*C] fp32 emission odds
+  __shared__ uint64_t s_bar;
+  __shared__ int s_item;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr uint32_t TAB_BYTES = 32u * 32u * C * 4u;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  uint32_t phase = 0;
+  int cur_p = -1;
+  float tBM[C], tMM[C], tIM[C], tDM[C], tMD[C], tMI[C], tII[C], tDD[C];
+  float tDDin = 0.f;
+  Item it;
+  while (next_item(wl, &s_item, it)) {
+    const ProfDev &P = wl.profs[it.p];
+    if (it.p != cur_p) {
+      cur_p = it.p;
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_rscf, P.fwd_rscr, TAB_BYTES, &s_bar); }
+      const float *ts = P.fwd_tsc; const int Mp = P.Mpad;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const int k0 = lane * C + c;
+        const bool in = k0 < Mp;
+        tBM[c] = in ? ts[0 * Mp + k0] : 0.f; tMM[c] = in ? ts[1 * Mp + k0] : 0.f; tIM[c] = in ? ts[2 * Mp + k0] : 0.f;
+        tDM[c] = in ? ts[3 * Mp + k0] : 0.f; tMD[c] = in ? ts[4 * Mp + k0] : 0.f; tMI[c] = in ? ts[5 * Mp + k0] : 0.f;
+        tII[c] = in ? ts[6 * Mp + k0] : 0.f; tDD[c] = in ? ts[7 * Mp + k0] : 0.f;
+      }
+      tDDin = __shfl_up_sync(FULL, tDD[C - 1], 1); if (lane == 0) tDDin = 0.f;
+      mbar_wait(&s_bar, phase); phase ^= 1;
+    }
+    const float tEC = P.xf_E_move, tEJ = P.xf_E_loop;
+
+    for (int e = it.e_begin + warp; e < it.e_end; e += nwarps) {
+      const int s = wl.ent_s[e];
+      const int L = sd.len[s];
+      const float pmove = sd.pmove[s], ploop = 1.0f - pmove;
+      float *xout = out.fwd_xmx ? out.fwd_xmx + out.xoff[e] * 6 : nullptr;
+      SeqWin sw; sw.init(sd.res + sd.off[s], L, lane);
+      float M[C], I[C], D[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) { M[c] = 0.f; I[c] = 0.f; D[c] = 0.f; }
+      float xN = 1.0f, xJ = 0.0f, xC = 0.0f, xB = pmove, xE = 0.0f, totscale = 0.0f;
+      if (xout && lane == 0) { xout[0] = 0.f; xout[1] = 1.f; xout[2] = 0.f; xout[3] = xB; xout[4] = 0.f; xout[5] = 1.f; }
+
+      for (int i = 1; i <= L; i++) {
+        const int x = sw.get(i - 1, lane);
+        float r[C];
+        load_emis<C, float>(s_rscf, x, lane, r);
+        float mp = __shfl_up_sync(FULL, M[C - 1], 1), ip = __shfl_up_sync(FULL, I[C - 1], 1), dp = __shfl_up_sync(FULL, D[C - 1], 1);
+        if (lane == 0) { mp = 0.f; ip = 0.f; dp = 0.f; }
+        float esum = 0.f;
+#pragma unroll
+        for (int c = C - 1; c >= 0; c--) {
+          const float pm = (c == 0) ? mp : M[c - 1], pi = (c == 0) ? ip : I[c - 1], pd = (c == 0) ? dp : D[c - 1];
+          const float inew = M[c] * tMI[c] + I[c] * tII[c];
+          float m = xB * tBM[c];
+          m += pm * tMM[c];
+          m += pi * tIM[c];
+          m += pd * tDM[c];
+          m *= r[c];
+          esum += m;
+          M[c] = m; I[c] = inew;
+        }
+        // D chain: D(k) = M(k-1)*tMD(k-1) + D(k-1)*tDD(k-1); two-level affine scan
+        float aleft = __shfl_up_sync(FULL, M[C - 1] * tMD[C - 1], 1);
+        if (lane == 0) aleft = 0.f;
+        float T[C];
+        D[0] = aleft; T[0] = tDDin;
+#pragma unroll
+        for (int c = 1; c < C; c++) { D[c] = M[c - 1] * tMD[c - 1] + D[c - 1] * tDD[c - 1]; T[c] = T[c - 1] * tDD[c - 1]; }
+        float A = D[C - 1], Tt = T[C - 1];
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const float A2 = __shfl_up_sync(FULL, A, dlt), T2 = __shfl_up_sync(FULL, Tt, dlt);
+          if (lane >= dlt) { A = A + A2 * Tt; Tt = T2 * Tt; }
+        }
+        float din = __shfl_up_sync(FULL, A, 1);
+        if (lane == 0) din = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) { D[c] = D[c] + din * T[c]; esum += D[c]; }
+        xE = warp_sum(esum);
+        xN = xN * ploop;
+        xC = (xC * ploop) + (xE * tEC);
+        xJ = (xJ * ploop) + (xE * tEJ);
+        xB = (xJ * pmove) + (xN * pmove);
+        float scale = 1.0f;
+        if (xE > 1.0e4f) {
+          xN = xN / xE; xC = xC / xE; xJ = xJ / xE; xB = xB / xE;
+          const float inv = 1.0f / xE;
+#pragma unroll
+          for (int c = 0; c < C; c++) { M[c] *= inv; I[c] *= inv; D[c] *= inv; }
+          scale = xE;
+          totscale = (float)((double)totscale + log((double)xE));
+          xE = 1.0f;
+        }
+        if (xout && lane == 0) { float *q = xout + (size_t)i * 6; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; q[5] = scale; }
+      }
+      if (lane == 0) {
+        int st = B2H_OK; float sc;
+        if (isnan(xC) || (L > 0 && xC == 0.0f) || isinf(xC)) { st = B2H_ERANGE; sc = isnan(xC) ? NAN : (xC == 0.0f ? -INFINITY : INFINITY); }
+        else sc = (float)((double)totscale + log((double)(xC * pmove)));
+        out.sc[e] = sc;
+        if (out.status) out.status[e] = st;
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// Backward parser, register resident
+// =================================================================================================
+template <int C>
+__global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqDev sd, const StageOut out)
+{
+  extern __shared__ __align__(128) float s_rscf[];
+  __shared__ uint64_t s_bar;
+  __shared__ int s_item;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr uint32_t TAB_BYTES = 32u * 32u * C * 4u;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  uint32_t phase = 0;
+  int cur_p = -1;
+  // per node k (own): tBM[k], tMD[k], tMI[k], tII[k], tDD[k]; and towards k+1: tMMn = tMM[k+1], tIMn = tIM[k+1], tDMn = tDM[k+1]
+  float tBM[C], tMD[C], tMI[C], tII[C], tDD[C], tMMn[C], tIMn[C], tDMn[C];
+  Item it;
+  while (next_item(wl, &s_item, it)) {
+    const ProfDev &P = wl.profs[it.p];
+    const int M = P.M;
+    if (it.p != cur_p) {
+      cur_p = it.p;
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_rscf, P.fwd_rscr, TAB_BYTES, &s_bar); }
+      const float *ts = P.fwd_tsc; const int Mp = P.Mpad;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const int k0 = lane * C + c;
+        const bool in = k0 < M, inn = (k0 + 1) < M;
+        tBM[c] = in ? ts[0 * Mp + k0] : 0.f; tMD[c] = in ? ts[4 * Mp + k0] : 0.f; tMI[c] = in ? ts[5 * Mp + k0] : 0.f;
+        tII[c] = in ? ts[6 * Mp + k0] : 0.f; tDD[c] = in ? ts[7 * Mp + k0] : 0.f;
+        tMMn[c] = inn ? ts[1 * Mp + k0 + 1] : 0.f; tIMn[c] = inn ? ts[2 * Mp + k0 + 1] : 0.f; tDMn[c] = inn ? ts[3 * Mp + k0 + 1] : 0.f;
+      }
+      mbar_wait(&s_bar, phase); phase ^= 1;
+    }
+    const float tEC = P.xf_E_move, tEJ = P.xf_E_loop;
+
+    for (int e = it.e_begin + warp; e < it.e_end; e += nwarps) {
+      const int s = wl.ent_s[e];
+      const int L = sd.len[s];
+      const uint8_t *seq = sd.res + sd.off[s];
+      const float pmove = sd.pmove[s], ploop = 1.0f - pmove;
+      const float *fx = out.fwd_xmx + out.xoff[e] * 6;
+      float *bx = out.bck_xmx ? out.bck_xmx + out.xoff[e] * 6 : nullptr;
+      float Mv[C], Iv[C], Dv[C];
+      float xJ = 0.0f, xB = 0.0f, xN = 0.0f, xC = pmove, xE = xC * tEC;
+      bool own_scales = false;
+      float totscale;
+
+      // reverse two-level affine closure:  D(k) = a(k) + tDD(k) * D(k+1)   (a given in Dv, result in Dv)
+      auto close_dd = [&](void) {
+        float T[C];
+        T[C - 1] = tDD[C - 1];
+#pragma unroll
+        for (int c = C - 2; c >= 0; c--) { Dv[c] = Dv[c] + tDD[c] * Dv[c + 1]; T[c] = tDD[c] * T[c + 1]; }
+        // note: Dv[C-1] still lacks the contribution of the next lane's first node
+        float A = Dv[0], Tt = T[0];                        // lane composite acting on D(first node of next lane): D(first) = A + Tt * d
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const float A2 = __shfl_down_sync(FULL, A, dlt), T2 = __shfl_down_sync(FULL, Tt, dlt);
+          if (lane + dlt < 32) { A = A + Tt * A2; Tt = Tt * T2; }
+        }
+        float din = __shfl_down_sync(FULL, A, 1);          // D of the next lane's first node
+        if (lane == 31) din = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) Dv[c] = Dv[c] + T[c] * din;
+      };
+
+      // row L
+#pragma unroll
+      for (int c = 0; c < C; c++) { const bool in = (lane * C + c) < M; Dv[c] = in ? xE : 0.f; Iv[c] = 0.f; }
+      close_dd();
+      {
+        float dnext = __shfl_down_sync(FULL, Dv[0], 1); if (lane == 31) dnext = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) { const bool in = (lane * C + c) < M; const float dn = (c == C - 1) ? dnext : Dv[c + 1]; Mv[c] = in ? xE + tMD[c] * dn : 0.f; }
+        const float scL = fx[(size_t)L * 6 + 5];
+        if (scL > 1.0f) {
+          xE = xE / scL; xN = xN / scL; xC = xC / scL; xJ = xJ / scL; xB = xB / scL;
+          const float inv = 1.0f / scL;
+#pragma unroll
+          for (int c = 0; c < C; c++) { Mv[c] *= inv; Dv[c] *= inv; }
+        }
+        totscale = (float)log((double)scL);
+        if (bx && lane == 0) { float *q = bx + (size_t)L * 6; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; q[5] = scL; }
+      }
+
+      for (int i = L - 1; i >= 1; i--) {
+        const int x = seq[i];                               // x_{i+1}
+        float r[C];
+        load_emis<C, float>(s_rscf, x, lane, r);
+        // mpv(k) = M(i+1,k+1) * e(k+1): own nodes shifted down by one
+        float me[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) me[c] = Mv[c] * r[c];   // M(i+1,k) e(k)
+        float bsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) bsum += me[c] * tBM[c];
+        float menext = __shfl_down_sync(FULL, me[0], 1); if (lane == 31) menext = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const float mpv = (c == C - 1) ? menext : me[c + 1];
+          const float ipv = Iv[c];
+          Iv[c] = (ipv * tII[c]) + (mpv * tIMn[c]);
+          Dv[c] = mpv * tDMn[c];
+          Mv[c] = (ipv * tMI[c]) + (mpv * tMMn[c]);
+        }
+        xB = warp_sum(bsum);
+        xC = xC * ploop;
+        xJ = (xB * pmove) + (xJ * ploop);
+        xN = (xB * pmove) + (xN * ploop);
+        xE = (xC * tEC) + (xJ * tEJ);
+#pragma unroll
+        for (int c = 0; c < C; c++) { const bool in = (lane * C + c) < M; Dv[c] = in ? Dv[c] + xE : 0.f; }
+        close_dd();
+        float dnext = __shfl_down_sync(FULL, Dv[0], 1); if (lane == 31) dnext = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) { const bool in = (lane * C + c) < M; const float dn = (c == C - 1) ? dnext : Dv[c + 1]; Mv[c] = in ? (Mv[c] + xE) + tMD[c] * dn : 0.f; }
+        if (xB > 1.0e16f) own_scales = true;
+        const float scale = own_scales ? ((xB > 1.0e4f) ? xB : 1.0f) : fx[(size_t)i * 6 + 5];
+        if (scale > 1.0f) {
+          xE /= scale; xN /= scale; xJ /= scale; xB /= scale; xC /= scale;
+          const float inv = 1.0f / scale;
+#pragma unroll
+          for (int c = 0; c < C; c++) { Mv[c] *= inv; Dv[c] *= inv; Iv[c] *= inv; }
+          totscale = (float)((double)totscale + log((double)scale));
+        }
+        if (bx && lane == 0) { float *q = bx + (size_t)i * 6; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; q[5] = scale; }
+      }
+      {
+        float r[C];
+        load_emis<C, float>(s_rscf, (int)seq[0], lane, r);
+        float bsum = 0.f;
+        if (L >= 1) {
+#pragma unroll
+          for (int c = 0; c < C; c++) bsum += (Mv[c] * r[c]) * tBM[c];
+        }
+        xB = warp_sum(bsum);
+        xN = (xB * pmove) + (xN * ploop);
+        if (lane == 0) {
+          if (bx) { bx[0] = 0.f; bx[1] = xN; bx[2] = 0.f; bx[3] = xB; bx[4] = 0.f; bx[5] = 1.0f; }
+          int st = B2H_OK; float sc;
+          if (isnan(xN) || (L > 0 && xN == 0.0f) || isinf(xN)) { st = B2H_ERANGE; sc = isnan(xN) ? NAN : (xN == 0.0f ? -INFINITY : INFINITY); }
+          else sc = (float)((double)totscale + log((double)xN));
+          out.sc[e] = sc;
+          if (out.status) out.status[e] = own_scales ? (st | 0x100) : st;
+        }
+      }
+    }
+  }
+}
+
+template <typename K>
+int launch_reg(b2h_ctx *ctx, K kernel, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, const StageOut &out)
+{
+  const size_t smem = (size_t)32 * 32 * C * 4;
+  B2H_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem));
+  if (occ < 1) occ = 1;
+  int grid = ctx->sm_count * occ;
+  if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
+  if (grid < 1) grid = 1;
+  B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), ctx->stream));
+  kernel<<<grid, 256, smem, ctx->stream>>>(wl, sd, out);
+  ctx->launches++;
+  B2H_CUDA(cudaGetLastError());
+  return B2H_OK;
+}
+
+} // namespace
+
+// kind: 0 Viterbi, 1 Forward, 2 Backward.  C in {2,4,8}.
+int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out)
+{
+  switch (kind * 16 + C) {
+    case 0 * 16 + 2: return launch_reg(ctx, rvit_kernel<2>, 2, wl, sd, nitems_hint, out);
+    case 0 * 16 + 4: return launch_reg(ctx, rvit_kernel<4>, 4, wl, sd, nitems_hint, out);
+    case 0 * 16 + 8: return launch_reg(ctx, rvit_kernel<8>, 8, wl, sd, nitems_hint, out);
+    case 1 * 16 + 2: return launch_reg(ctx, rfwd_kernel<2>, 2, wl, sd, nitems_hint, out);
+    case 1 * 16 + 4: return launch_reg(ctx, rfwd_kernel<4>, 4, wl, sd, nitems_hint, out);
+    case 1 * 16 + 8: return launch_reg(ctx, rfwd_kernel<8>, 8, wl, sd, nitems_hint, out);
+    case 2 * 16 + 2: return launch_reg(ctx, rbck_kernel<2>, 2, wl, sd, nitems_hint, out);
+    case 2 * 16 + 4: return launch_reg(ctx, rbck_kernel<4>, 4, wl, sd, nitems_hint, out);
+    case 2 * 16 + 8: return launch_reg(ctx, rbck_kernel<8>, 8, wl, sd, nitems_hint, out);
+  }
+  return B2H_EINVAL;
+}

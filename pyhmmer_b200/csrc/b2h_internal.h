@@ -86,6 +86,9 @@ struct b2h_profile {
   float compo[B2H_MAXABET];
   float bgf[B2H_MAXABET];
   float *d_bias_eo = nullptr;     // [32][2] bias-filter emission odds (esl_hmm_Configure)
+  int regC = 0;                   // nodes per lane of the register-resident DP kernels (2/4/8; 0 = model too long)
+  int32_t *d_vit_rsc32 = nullptr; // [32][regC/4][32][4] int32 emission scores, lane-grouped (b2h_dpreg.cu)
+  float   *d_fwd_rscr = nullptr;  // same layout, fp32 odds ratios
   // host copies for the domain-definition stage
   std::vector<float> h_fwd_rsc, h_fwd_tsc;   // [Kp][M], [8][M] node-major odds ratios
   std::vector<uint8_t> h_degen;              // [Kp][K]
@@ -138,6 +141,7 @@ struct ProfDev {
   const uint32_t *ssv_emis; const uint8_t *msv_cost8;
   const int16_t *vit_rsc, *vit_tsc;
   const float *fwd_rsc, *fwd_tsc, *bias_eo;
+  const int32_t *vit_rsc32; const float *fwd_rscr;
   int M, Mpad, NR;
   int tbm, tec, base, bias; float scale_b;
   int xw_E_move, xw_E_loop, base_w, ddbound_w; float scale_w;
@@ -147,7 +151,7 @@ struct ProfDev {
 };
 static inline ProfDev b2h_profdev(const b2h_profile *p) {
   ProfDev d; d.ssv_emis = p->d_ssv_emis; d.msv_cost8 = p->d_msv_cost8; d.vit_rsc = p->d_vit_rsc; d.vit_tsc = p->d_vit_tsc;
-  d.fwd_rsc = p->d_fwd_rsc; d.fwd_tsc = p->d_fwd_tsc; d.bias_eo = p->d_bias_eo;
+  d.fwd_rsc = p->d_fwd_rsc; d.fwd_tsc = p->d_fwd_tsc; d.bias_eo = p->d_bias_eo; d.vit_rsc32 = p->d_vit_rsc32; d.fwd_rscr = p->d_fwd_rscr;
   d.M = p->M; d.Mpad = p->Mpad; d.NR = p->NR; d.tbm = p->tbm_b; d.tec = p->tec_b; d.base = p->base_b; d.bias = p->bias_b; d.scale_b = p->scale_b;
   d.xw_E_move = p->xw[0][0]; d.xw_E_loop = p->xw[0][1]; d.base_w = p->base_w; d.ddbound_w = p->ddbound_w; d.scale_w = p->scale_w;
   d.xf_E_move = p->xf[0][0]; d.xf_E_loop = p->xf[0][1];
@@ -176,6 +180,7 @@ struct StageOut { float *sc; int32_t *status; float *fwd_xmx, *bck_xmx; const in
 int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
+int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out);
 int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc);
 
 // A compacted list of comparisons produced by a stage's epilogue (device memory).  Appends are
