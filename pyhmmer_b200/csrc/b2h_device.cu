@@ -245,8 +245,8 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
       ft[(size_t)t * Mp + k] = d->fwd_tsc[(size_t)t * M + k];
     }
 
-  // --- lane-grouped emission tables of the register-resident DP kernels (b2h_dpreg.cu), models up to 256 nodes ---
-  p->regC = (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 256) ? 8 : 0;
+  // --- lane-grouped emission tables of the register-resident DP kernels (b2h_dpreg.cu), models up to 512 nodes ---
+  p->regC = (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 256) ? 8 : (M <= 384) ? 12 : (M <= 512) ? 16 : 0;
   std::vector<int32_t> vr32; std::vector<float> frr;
   if (p->regC) {
     const int C = p->regC;

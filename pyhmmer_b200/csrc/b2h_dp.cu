@@ -521,17 +521,17 @@ LaunchCfg pick_cfg(int max_Mpad, int elem_bytes)
   return c;
 }
 
-// Profiles of a work list are sorted by Mpad.  Models of up to 256 nodes go to the register-resident kernels
-// (b2h_dpreg.cu: 2 / 4 / 8 nodes per lane); longer ones to the shared-memory kernels of this file, one launch
+// Profiles of a work list are sorted by Mpad.  Models of up to 512 nodes go to the register-resident kernels
+// (b2h_dpreg.cu: 2 / 4 / 8 / 12 / 16 nodes per lane); longer ones to the shared-memory kernels of this file, one launch
 // per size class so that mid-sized models do not inherit the largest model's shared-memory footprint.
 template <typename K>
 int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const SeqDev &sd, const std::vector<int> &mpads, int elem_bytes, int nitems_hint, const StageOut &out)
 {
-  static const int bounds[] = {384, 512, 768, 1024, 1536, 2048, 3072, 1 << 30};
+  static const int bounds[] = {768, 1024, 1536, 2048, 3072, 1 << 30};
   const int P = (int)mpads.size();
   int plo = 0, cls = 0;
-  static const int regb[3] = {64, 128, 256}, regc[3] = {2, 4, 8};
-  for (int rc = 0; rc < 3 && plo < P; rc++) {
+  static const int regb[5] = {64, 128, 256, 384, 512}, regc[5] = {2, 4, 8, 12, 16};
+  for (int rc = 0; rc < 5 && plo < P; rc++) {
     int phi = plo;
     while (phi < P && mpads[phi] <= regb[rc]) phi++;
     if (phi > plo) {

@@ -1,5 +1,5 @@
 // b2h_dpreg.cu -- register-resident ViterbiFilter / Forward parser / Backward parser for models with
-// M <= 32*C (C = 2, 4 or 8 nodes per lane, i.e. M <= 64 / 128 / 256: three quarters of Pfam).
+// M <= 32*C (C = 2, 4, 8, 12 or 16 nodes per lane, i.e. M <= 64 / 128 / 256 / 384 / 512: ~95 % of Pfam).
 //
 // Same recurrences and the same numerical semantics as the generic kernels of b2h_dp.cu (which remain
 // the path for longer models), but organised so that almost nothing is re-read per row:
@@ -485,19 +485,25 @@ int launch_reg(b2h_ctx *ctx, K kernel, int C, const WorkList &wl, const SeqDev &
 
 } // namespace
 
-// kind: 0 Viterbi, 1 Forward, 2 Backward.  C in {2,4,8}.
+// kind: 0 Viterbi, 1 Forward, 2 Backward.  C in {2,4,8,12,16}.
 int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out)
 {
-  switch (kind * 16 + C) {
-    case 0 * 16 + 2: return launch_reg(ctx, rvit_kernel<2>, 2, wl, sd, nitems_hint, out);
-    case 0 * 16 + 4: return launch_reg(ctx, rvit_kernel<4>, 4, wl, sd, nitems_hint, out);
-    case 0 * 16 + 8: return launch_reg(ctx, rvit_kernel<8>, 8, wl, sd, nitems_hint, out);
-    case 1 * 16 + 2: return launch_reg(ctx, rfwd_kernel<2>, 2, wl, sd, nitems_hint, out);
-    case 1 * 16 + 4: return launch_reg(ctx, rfwd_kernel<4>, 4, wl, sd, nitems_hint, out);
-    case 1 * 16 + 8: return launch_reg(ctx, rfwd_kernel<8>, 8, wl, sd, nitems_hint, out);
-    case 2 * 16 + 2: return launch_reg(ctx, rbck_kernel<2>, 2, wl, sd, nitems_hint, out);
-    case 2 * 16 + 4: return launch_reg(ctx, rbck_kernel<4>, 4, wl, sd, nitems_hint, out);
-    case 2 * 16 + 8: return launch_reg(ctx, rbck_kernel<8>, 8, wl, sd, nitems_hint, out);
+  switch (kind * 32 + C) {
+    case 0 * 32 + 2: return launch_reg(ctx, rvit_kernel<2>, 2, wl, sd, nitems_hint, out);
+    case 0 * 32 + 4: return launch_reg(ctx, rvit_kernel<4>, 4, wl, sd, nitems_hint, out);
+    case 0 * 32 + 8: return launch_reg(ctx, rvit_kernel<8>, 8, wl, sd, nitems_hint, out);
+    case 0 * 32 + 12: return launch_reg(ctx, rvit_kernel<12>, 12, wl, sd, nitems_hint, out);
+    case 0 * 32 + 16: return launch_reg(ctx, rvit_kernel<16>, 16, wl, sd, nitems_hint, out);
+    case 1 * 32 + 2: return launch_reg(ctx, rfwd_kernel<2>, 2, wl, sd, nitems_hint, out);
+    case 1 * 32 + 4: return launch_reg(ctx, rfwd_kernel<4>, 4, wl, sd, nitems_hint, out);
+    case 1 * 32 + 8: return launch_reg(ctx, rfwd_kernel<8>, 8, wl, sd, nitems_hint, out);
+    case 1 * 32 + 12: return launch_reg(ctx, rfwd_kernel<12>, 12, wl, sd, nitems_hint, out);
+    case 1 * 32 + 16: return launch_reg(ctx, rfwd_kernel<16>, 16, wl, sd, nitems_hint, out);
+    case 2 * 32 + 2: return launch_reg(ctx, rbck_kernel<2>, 2, wl, sd, nitems_hint, out);
+    case 2 * 32 + 4: return launch_reg(ctx, rbck_kernel<4>, 4, wl, sd, nitems_hint, out);
+    case 2 * 32 + 8: return launch_reg(ctx, rbck_kernel<8>, 8, wl, sd, nitems_hint, out);
+    case 2 * 32 + 12: return launch_reg(ctx, rbck_kernel<12>, 12, wl, sd, nitems_hint, out);
+    case 2 * 32 + 16: return launch_reg(ctx, rbck_kernel<16>, 16, wl, sd, nitems_hint, out);
   }
   return B2H_EINVAL;
 }
