@@ -1,0 +1,90 @@
+"""ctypes wrapper over oracle/_ref/liboracle_port.so (hmmer_oracle.c, the scalar C restatement).
+
+TEST INFRASTRUCTURE ONLY.  Takes a pyhmmer_b200.plan7.OptimizedProfile only as a *container* of the
+node-major tables (they are validated against the reference separately); every score is computed by
+the plain C code of hmmer_oracle.c.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "liboracle_port.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise RuntimeError("oracle/_ref/liboracle_port.so missing: run `make -C oracle port`")
+        L = ctypes.CDLL(LIB)
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        for f in ("oracle_ssv", "oracle_msv", "oracle_msv_full"):
+            getattr(L, f).restype = ci
+            getattr(L, f).argtypes = [vp, ci, ci, vp, ci, ci, ci, ci, ci, cf, ctypes.POINTER(cf)]
+        L.oracle_vit.restype = ci
+        L.oracle_vit.argtypes = [vp, ci, ci, vp, vp, ci, ci, ci, ci, cf, ctypes.POINTER(cf)]
+        L.oracle_fwd.restype = ci
+        L.oracle_fwd.argtypes = [vp, ci, ci, vp, vp, cf, cf, cf, ctypes.POINTER(cf)]
+        L.oracle_null1.restype = cf
+        L.oracle_null1.argtypes = [ci]
+        L.oracle_bias.restype = cf
+        L.oracle_bias.argtypes = [vp, ci, ci, vp]
+        _lib = L
+    return _lib
+
+
+def _len_params(L):
+    """L-dependent scalars, computed with the same libm the reference uses (via ctypes libm)."""
+    libm = ctypes.CDLL("libm.so.6")
+    libm.logf.restype = ctypes.c_float
+    libm.logf.argtypes = [ctypes.c_float]
+    libm.roundf.restype = ctypes.c_float
+    libm.roundf.argtypes = [ctypes.c_float]
+    f32 = np.float32
+    scale_b = f32(3.0 / np.log(2.0))
+    scale_w = f32(500.0 / np.log(2.0))
+    v = -libm.roundf(float(scale_b * f32(libm.logf(float(f32(3.0) / f32(L + 3))))))
+    tjb = 255 if v > 255.0 else int(v)
+    pmove = f32(3.0) / (f32(L) + f32(3.0))
+    w = libm.roundf(float(scale_w * f32(libm.logf(float(pmove)))))
+    xw_move = 32767 if w >= 32767.0 else (-32768 if w <= -32768.0 else int(w))
+    return tjb, xw_move, float(pmove)
+
+
+class Port:
+    def __init__(self, om):
+        self.om = om
+        d = om._desc
+        self.M = om.M
+        self.s = dict(tbm=d.tbm_b, tec=d.tec_b, base=d.base_b, bias=d.bias_b, scale_b=d.scale_b,
+                      xwEm=d.xw[0][0], xwEl=d.xw[0][1], base_w=d.base_w, scale_w=d.scale_w, xfEm=d.xf[0][0], xfEl=d.xf[0][1])
+
+    def _run(self, fn, codes, *args):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        sc = ctypes.c_float()
+        st = fn(codes.ctypes.data, codes.size, self.M, *args, ctypes.byref(sc))
+        return sc.value, st
+
+    def ssv(self, codes):
+        tjb, _, _ = _len_params(len(codes)); s = self.s
+        return self._run(lib().oracle_ssv, codes, self.om.msv_cost.ctypes.data, s["tbm"], s["tec"], tjb, s["base"], s["bias"], s["scale_b"])
+
+    def msv(self, codes):
+        tjb, _, _ = _len_params(len(codes)); s = self.s
+        return self._run(lib().oracle_msv, codes, self.om.msv_cost.ctypes.data, s["tbm"], s["tec"], tjb, s["base"], s["bias"], s["scale_b"])
+
+    def vit(self, codes):
+        _, xw_move, _ = _len_params(len(codes)); s = self.s
+        return self._run(lib().oracle_vit, codes, self.om.vit_rsc.ctypes.data, self.om.vit_tsc.ctypes.data,
+                         s["xwEm"], s["xwEl"], xw_move, s["base_w"], s["scale_w"])
+
+    def fwd(self, codes):
+        _, _, pmove = _len_params(len(codes)); s = self.s
+        return self._run(lib().oracle_fwd, codes, self.om.fwd_rsc.ctypes.data, self.om.fwd_tsc.ctypes.data, s["xfEm"], s["xfEl"], pmove)
+
+    @staticmethod
+    def null1(L):
+        return lib().oracle_null1(int(L))

@@ -42,21 +42,22 @@ class World:
 
 
 def shard_bounds(lengths, nshards):
-    """Contiguous slices balanced by residue count (reference rule: _hmmsearch.py:153-171)."""
-    lengths = np.asarray(lengths, dtype=np.int64)
+    """Contiguous slices balanced by residue count -- the reference's rule, literally (_hmmsearch.py:153-171):
+    chunksize = ceil(total / n); walk the targets accumulating residues; start a new chunk at the sequence
+    that pushes the running size over chunksize; pad with empty chunks."""
+    lengths = [int(v) for v in lengths]
     n = len(lengths)
-    total = int(lengths.sum())
+    total = sum(lengths)
+    chunksize = (total + nshards - 1) // nshards
     bounds = [0]
-    acc = 0
-    j = 0
-    for t in range(n):
-        acc += int(lengths[t])
-        if j < nshards - 1 and acc >= (total * (j + 1)) // nshards:
-            bounds.append(t + 1)
-            j += 1
-    while len(bounds) < nshards:
+    current = 0
+    for i, L in enumerate(lengths):
+        current += L
+        if current > chunksize and len(bounds) < nshards:
+            bounds.append(i)
+            current = 0
+    while len(bounds) <= nshards:
         bounds.append(n)
-    bounds.append(n)
     return bounds
 
 

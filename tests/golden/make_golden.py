@@ -81,6 +81,7 @@ def main():
         om = prof.to_optimized()
         msv = []
         for s in seqs[:300]:
+            om.L = len(s)                      # p7_oprofile_ReconfigLength, as the search loop does per target
             v = om.msv_filter(s)
             msv.append(None if v is None else (float(v) if v == v and abs(v) != float("inf") else str(v)))
         filt[_s(hmm.name)] = dict(file=h, msv=msv)

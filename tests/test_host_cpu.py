@@ -1,0 +1,201 @@
+"""CPU: host-side logic of the product and the C ABI surface (no GPU needed).
+
+ * HMM file parsing, profile configuration and the three score-system conversions are bit-identical to the
+   reference's p7_hmmfile_Read / p7_ProfileConfig / p7_oprofile_Convert (through oracle/_ref);
+ * the host-side domain definition reproduces the reference's hits given the reference's own parser specials;
+ * libb2h.so loads and exports every symbol include/b2h.h declares;
+ * the multi-GPU plumbing (sharding rule, record (de)serialisation, one all-gather, merge) under gloo, world_size 2.
+"""
+import ctypes
+import gzip
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from pyhmmer_b200 import _lib, easel, plan7, synth, parallel
+from oracle import refshim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+needs_ref = pytest.mark.skipif(not refshim.available(), reason="oracle/_ref not built")
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "b2h.h")).read()
+    names = set(re.findall(r"\b(b2h_[a-z0-9_]+)\s*\(", header))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert len(names) >= 30
+
+
+def test_no_cpu_fallback_without_device():
+    h = ctypes.c_void_p()
+    st = _lib.lib.b2h_ctx_create(9999, ctypes.byref(h))
+    assert st == _lib.B2H_ECUDA and not h.value
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["PF02826", "Thioesterase", "KR", "LuxC", "RREFam"])
+def test_model_preparation_bit_identical(amino, name):
+    with tempfile.NamedTemporaryFile(suffix=".hmm") as tmp:
+        with gzip.open(os.path.join(GOLD, "data", name + ".hmm.gz")) as f:
+            tmp.write(f.read())
+        tmp.flush()
+        with plan7.HMMFile(tmp.name) as f:
+            hmms = list(f)
+        for idx, hmm in enumerate(hmms):
+            ref = refshim.RefModel(tmp.name, idx, 400)
+            t, mat, ins = ref.hmm_params()
+            assert np.array_equal(t, hmm.transition_probabilities)
+            assert np.array_equal(mat[1:], hmm.match_emissions[1:]) and np.array_equal(ins, hmm.insert_emissions)
+            assert np.array_equal(ref.evparam, hmm._evparam) and np.array_equal(ref.cutoff, hmm._cutoff)
+            assert np.array_equal(ref.compo, hmm._compo)
+            prof = plan7.Profile(hmm.M, amino).configure(hmm, plan7.Background(amino), 400)
+            tsc, rsc, xsc = ref.gm_params()
+            assert np.array_equal(tsc[:hmm.M], prof.tsc) and np.array_equal(rsc[:, :, 0], prof.msc) and np.array_equal(xsc, prof.xsc)
+            om = prof.to_optimized()
+            msv, vr, vt, fr, ft = ref.om_tables()
+            assert np.array_equal(msv, om.msv_cost) and np.array_equal(vr, om.vit_rsc) and np.array_equal(vt, om.vit_tsc)
+            assert np.array_equal(fr, om.fwd_rsc) and np.array_equal(ft, om.fwd_tsc)
+            s, d = ref.om_scalars(), om._desc
+            assert (s["tbm_b"], s["tec_b"], s["tjb_b"], s["base_b"], s["bias_b"]) == (d.tbm_b, d.tec_b, d.tjb_b, d.base_b, d.bias_b)
+            assert (s["base_w"], s["ddbound_w"]) == (d.base_w, d.ddbound_w)
+            assert np.array_equal(s["xw"], np.array([list(r) for r in d.xw])) and np.array_equal(s["xf"], np.array([list(r) for r in d.xf], np.float32))
+            # de-striping the reference's SSE tables through the ABI gives the same node-major tables
+            rbv, rwv, twv, rfv, tfv = ref.om_tables_striped()
+            o = [np.empty_like(om.msv_cost), np.empty_like(om.vit_rsc), np.empty_like(om.vit_tsc), np.empty_like(om.fwd_rsc), np.empty_like(om.fwd_tsc)]
+            _lib.check(_lib.lib.b2h_destripe_oprofile(hmm.M, amino.Kp, *[_lib.ptr(a) for a in (rbv, rwv, twv, rfv, tfv)], *[_lib.ptr(a) for a in o]), "destripe")
+            assert all(np.array_equal(a, b) for a, b in zip(o, (om.msv_cost, om.vit_rsc, om.vit_tsc, om.fwd_rsc, om.fwd_tsc)))
+
+
+@needs_ref
+def test_length_params(amino):
+    with tempfile.NamedTemporaryFile(suffix=".hmm") as tmp:
+        synth.random_hmm(amino, 40, np.random.default_rng(1)).write(tmp)
+        tmp.flush()
+        ref = refshim.RefModel(tmp.name, 0, 400)
+        for L in (1, 2, 3, 10, 99, 350, 1500, 35000, 100000):
+            lp = _lib.LenParams()
+            _lib.lib.b2h_length_params(L, 1.0, ctypes.byref(lp))
+            ref.L.refm_set_length(ref.h, L)
+            s = ref.om_scalars()
+            assert lp.tjb_b == s["tjb_b"] and lp.xw_move == s["xw"][1][0]
+            assert np.float32(lp.pmove) == s["xf"][1][0] and np.float32(lp.ploop) == s["xf"][1][1]
+            assert np.float32(lp.null1) == np.float32(ref.null1(np.zeros(L, np.uint8)))
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["PF02826", "KR"])
+def test_domain_definition_on_host(amino, name):
+    """b2h_debug_domaindef fed with the reference's parser specials reproduces the reference's hits exactly:
+    envelopes, alignments, null2 corrections, stochastic-traceback clustering (Easel's LCG stream)."""
+    with easel.SequenceFile(os.path.join(GOLD, "data", "proteome.faa.gz"), digital=True, alphabet=amino) as f:
+        seqs = f.read_block()
+    with tempfile.NamedTemporaryFile(suffix=".hmm") as tmp:
+        with gzip.open(os.path.join(GOLD, "data", name + ".hmm.gz")) as f:
+            tmp.write(f.read())
+        tmp.flush()
+        with plan7.HMMFile(tmp.name) as f:
+            hmm = f.read()
+        ref = refshim.RefModel(tmp.name, 0, 400)
+        rh, rd, rtext, rc = ref.search([s.sequence for s in seqs])
+        om = plan7.Profile(hmm.M, amino).configure(hmm, plan7.Background(amino), 400).to_optimized()
+        hp = ctypes.c_void_p()
+        _lib.check(_lib.lib.b2h_profile_create_host(ctypes.byref(om._desc), ctypes.byref(hp)), "create_host")
+        _lib.lib.b2h_profile_set_annotation(hp, hmm.consensus.encode(), None, None, amino.symbols.encode())
+        prm = _lib.SearchParams(0.02, 1e-3, 1e-5, 1, 1, 42, 1)
+        nclustered = 0
+        for h in rh:
+            s = seqs[h.seq]
+            f_, b_, st, fx, bx = ref.fwdbck(s.sequence, want_x=True)
+            out = ctypes.c_void_p()
+            codes = np.ascontiguousarray(s.sequence)
+            _lib.check(_lib.lib.b2h_debug_domaindef(hp, _lib.ptr(codes), len(s), _lib.ptr(fx), _lib.ptr(bx), f_, ctypes.byref(prm), ctypes.byref(out)), "ddef")
+            hits, doms, text = _lib.read_results(out)
+            _lib.lib.b2h_results_destroy(out)
+            assert len(hits) == 1
+            m = hits[0]
+            assert abs(m.score - h.score) < 1e-3 and abs(m.sum_score - h.sum_score) < 1e-3 and abs(m.pre_score - h.pre_score) < 1e-3
+            assert (m.nregions, m.nclustered, m.noverlaps, m.nenvelopes, m.ndom, m.best_domain) == (h.nregions, h.nclustered, h.noverlaps, h.nenvelopes, h.ndom, h.best_domain)
+            nclustered += h.nclustered
+            for d in range(h.ndom):
+                a, r = doms[d], rd[h.dom_offset + d]
+                assert (a.ienv, a.jenv, a.iali, a.jali, a.hmmfrom, a.hmmto, a.sqfrom, a.sqto, a.N) == (r.ienv, r.jenv, r.iali, r.jali, r.hmmfrom, r.hmmto, r.sqfrom, r.sqto, r.N)
+                assert abs(a.envsc - r.envsc) < 2e-3 and abs(a.domcorrection - r.domcorrection) < 2e-3 and abs(a.bitscore - r.bitscore) < 2e-3 and abs(a.oasc - r.oasc) < 2e-3
+                assert text[a.text_offset:a.text_offset + 4 * (a.N + 1)] == rtext[r.text_offset:r.text_offset + 4 * (r.N + 1)]
+        _lib.lib.b2h_profile_destroy(hp)
+        if name == "PF02826":
+            assert nclustered > 0            # the stochastic clustering branch was exercised
+
+
+def test_shard_bounds_follow_the_reference_rule():
+    rng = np.random.default_rng(0)
+    lens = rng.integers(50, 1500, 5000).tolist()
+    for n in (1, 2, 4, 8):
+        b = parallel.shard_bounds(lens, n)
+        assert len(b) == n + 1 and b[0] == 0 and b[-1] == len(lens) and sorted(b) == b
+        res = [sum(lens[b[i]:b[i + 1]]) for i in range(n)]
+        assert sum(res) == sum(lens) and max(res) <= 1.02 * sum(lens) / n + 1500
+    # literal reference behaviour on a small case: chunksize = 72, a cut where the running size first exceeds it
+    assert parallel.shard_bounds([10, 10, 10, 10, 100, 1, 1, 1], 2) == [0, 4, 8]
+    assert parallel.shard_bounds([5] * 3, 8)[-1] == 3 and len(parallel.shard_bounds([5] * 3, 8)) == 9
+
+
+def _fake_records(rank):
+    hits, doms = [], []
+    text = b""
+    for j in range(3 + rank):
+        h = _lib.HitRec()
+        h.profile, h.seq, h.score, h.lnP, h.ndom, h.dom_offset = j % 2, j, 10.0 * rank + j, -5.0 - j, 1, len(doms)
+        d = _lib.DomainRec()
+        d.N, d.text_offset, d.bitscore = 2, len(text), 3.0 + j
+        text += b"AB\0ab\0AB\0**\0"
+        hits.append(h)
+        doms.append(d)
+    return hits, doms, text, np.arange(8, dtype=np.int64).reshape(2, 4) + rank
+
+
+def test_pack_unpack_roundtrip():
+    hits, doms, text, ctr = _fake_records(1)
+    h2, d2, t2, c2 = parallel.unpack_records(parallel.pack_records(hits, doms, text, ctr, 100))
+    assert [h.seq for h in h2] == [h.seq + 100 for h in hits] and [h.score for h in h2] == [h.score for h in hits]
+    assert t2 == text and np.array_equal(c2.reshape(2, 4), ctr) and [d.text_offset for d in d2] == [d.text_offset for d in doms]
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch.distributed as dist
+from pyhmmer_b200 import parallel, _lib
+sys.path.insert(0, os.path.join(%r, "tests"))
+from test_host_cpu import _fake_records
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%d" %% int(sys.argv[1]), rank=int(sys.argv[2]), world_size=2)
+w = parallel.World.current()
+assert (w.rank, w.size) == (int(sys.argv[2]), 2)
+hits, doms, text, ctr = _fake_records(w.rank)
+parts = [parallel.unpack_records(b) for b in parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, ctr, 1000 * w.rank), w)]
+mh, md, mt, mc = parallel.merge_rank_records(parts)
+assert len(mh) == 3 + 4 and [ (h.profile, h.seq) for h in mh ] == sorted((h.profile, h.seq) for h in mh)
+assert np.array_equal(mc.reshape(2, 4), np.arange(8).reshape(2, 4) * 2 + 1)
+for h in mh:
+    d = md[h.dom_offset]
+    assert mt[d.text_offset:d.text_offset + 12] == b"AB\0ab\0AB\0**\0"
+dist.barrier(); dist.destroy_process_group()
+print("rank", w.rank, "ok")
+'''
+
+
+def test_all_gather_and_merge_world_size_2_gloo():
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port_ = s.getsockname()[1]; s.close()
+    code = _WORKER % (ROOT, ROOT)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(port_), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
