@@ -37,6 +37,9 @@ void b2h_ctx_destroy(b2h_ctx *ctx)
   cudaSetDevice(ctx->device);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  for (cudaStream_t q : ctx->side) cudaStreamDestroy(q);
+  for (cudaEvent_t e : ctx->side_done) cudaEventDestroy(e);
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -280,21 +283,33 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
   }
 
   int st = B2H_OK;
-  if (ctx) do {
+  if (ctx) {
+    // one device block and one H2D copy for all tables of the profile (sections 256-byte aligned)
+    std::vector<uint8_t> stage;
+    auto add = [&](const void *src, size_t bytes) -> size_t {
+      const size_t off = (stage.size() + 255) & ~(size_t)255;
+      stage.resize(off + bytes);
+      memcpy(stage.data() + off, src, bytes);
+      return off;
+    };
+    const size_t o_ssv = add(ssv.data(), ssv.size() * 4), o_mc = add(mc.data(), mc.size());
+    const size_t o_vr = add(vr.data(), vr.size() * 2), o_vt = add(vt.data(), vt.size() * 2);
+    const size_t o_fr = add(fr.data(), fr.size() * 4), o_ft = add(ft.data(), ft.size() * 4), o_eo = add(eo.data(), eo.size() * 4);
+    size_t o_vr32 = 0, o_frr = 0;
+    if (p->regC) { o_vr32 = add(vr32.data(), vr32.size() * 4); o_frr = add(frr.data(), frr.size() * 4); }
     cudaError_t e;
-#define UP(dst, vec, T) \
-    if ((e = cudaMalloc(&dst, vec.size() * sizeof(T))) != cudaSuccess || \
-        (e = cudaMemcpyAsync(dst, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) \
-      { ctx->err = cudaGetErrorString(e); st = B2H_ECUDA; break; }
     cudaSetDevice(ctx->device);
-    UP(p->d_ssv_emis, ssv, uint32_t); UP(p->d_msv_cost8, mc, uint8_t);
-    UP(p->d_vit_rsc, vr, int16_t);    UP(p->d_vit_tsc, vt, int16_t);
-    UP(p->d_fwd_rsc, fr, float);      UP(p->d_fwd_tsc, ft, float);
-    UP(p->d_bias_eo, eo, float);
-    if (p->regC) { UP(p->d_vit_rsc32, vr32, int32_t); UP(p->d_fwd_rscr, frr, float); }
-#undef UP
-    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); st = B2H_ECUDA; }
-  } while (0);
+    if ((e = cudaMalloc(&p->d_block, stage.size())) != cudaSuccess ||
+        (e = cudaMemcpyAsync(p->d_block, stage.data(), stage.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+      ctx->err = cudaGetErrorString(e); st = B2H_ECUDA;        // (pageable source: the copy is staged before the call returns)
+    } else {
+      uint8_t *b = (uint8_t *)p->d_block;
+      p->d_ssv_emis = (uint32_t *)(b + o_ssv); p->d_msv_cost8 = b + o_mc;
+      p->d_vit_rsc = (int16_t *)(b + o_vr); p->d_vit_tsc = (int16_t *)(b + o_vt);
+      p->d_fwd_rsc = (float *)(b + o_fr); p->d_fwd_tsc = (float *)(b + o_ft); p->d_bias_eo = (float *)(b + o_eo);
+      if (p->regC) { p->d_vit_rsc32 = (int32_t *)(b + o_vr32); p->d_fwd_rscr = (float *)(b + o_frr); }
+    }
+  }
   if (st != B2H_OK) { b2h_profile_destroy(p); return st; }
   *out = p;
   return B2H_OK;
@@ -304,8 +319,7 @@ void b2h_profile_destroy(b2h_profile *p)
 {
   if (!p) return;
   if (p->ctx) cudaSetDevice(p->ctx->device);
-  void *ptrs[] = { p->d_ssv_emis, p->d_msv_cost8, p->d_vit_rsc, p->d_vit_tsc, p->d_fwd_rsc, p->d_fwd_tsc, p->d_bias_eo, p->d_vit_rsc32, p->d_fwd_rscr };
-  for (void *q : ptrs) if (q) cudaFree(q);
+  if (p->d_block) cudaFree(p->d_block);
   delete p;
 }
 

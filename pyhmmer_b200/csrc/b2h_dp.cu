@@ -530,13 +530,14 @@ int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const Seq
   static const int bounds[] = {768, 1024, 1536, 2048, 3072, 1 << 30};
   const int P = (int)mpads.size();
   int plo = 0, cls = 0;
+  ForkJoin fj(ctx);
   static const int regb[5] = {64, 128, 256, 384, 512}, regc[5] = {2, 4, 8, 12, 16};
   for (int rc = 0; rc < 5 && plo < P; rc++) {
     int phi = plo;
     while (phi < P && mpads[phi] <= regb[rc]) phi++;
     if (phi > plo) {
       WorkList wl = wl_in; wl.plo = plo; wl.phi = phi; wl.counter = wl_in.counter + cls;
-      int st = b2h_launch_dpreg(ctx, kind, regc[rc], wl, sd, nitems_hint, out);
+      int st = b2h_launch_dpreg(ctx, kind, regc[rc], wl, sd, nitems_hint, out, fj.next());
       if (st != B2H_OK) return st;
       plo = phi; cls++;
     }
@@ -557,9 +558,10 @@ int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const Seq
     if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
     if (grid < 1) grid = 1;
     WorkList wl = wl_in; wl.plo = plo; wl.phi = phi; wl.counter = wl_in.counter + cls;
-    B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), ctx->stream));
+    cudaStream_t strm = fj.next();
+    B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), strm));
     DpCfg cfg; cfg.max_Mpad = mx; cfg.rsc_in_smem = c.rsc_in_smem;
-    kernel<<<grid, c.nwarps * 32, c.smem, ctx->stream>>>(wl, sd, cfg, out);
+    kernel<<<grid, c.nwarps * 32, c.smem, strm>>>(wl, sd, cfg, out);
     ctx->launches++;
     B2H_CUDA(cudaGetLastError());
     plo = phi; cls++;

@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
 }
 
 template <typename K>
-int launch_reg(b2h_ctx *ctx, K kernel, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, const StageOut &out)
+int launch_reg(b2h_ctx *ctx, K kernel, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, const StageOut &out, cudaStream_t strm)
 {
   const size_t smem = (size_t)32 * 32 * C * 4;
   B2H_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -476,8 +476,8 @@ int launch_reg(b2h_ctx *ctx, K kernel, int C, const WorkList &wl, const SeqDev &
   int grid = ctx->sm_count * occ;
   if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
   if (grid < 1) grid = 1;
-  B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), ctx->stream));
-  kernel<<<grid, 256, smem, ctx->stream>>>(wl, sd, out);
+  B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), strm));
+  kernel<<<grid, 256, smem, strm>>>(wl, sd, out);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());
   return B2H_OK;
@@ -486,24 +486,24 @@ int launch_reg(b2h_ctx *ctx, K kernel, int C, const WorkList &wl, const SeqDev &
 } // namespace
 
 // kind: 0 Viterbi, 1 Forward, 2 Backward.  C in {2,4,8,12,16}.
-int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out)
+int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm)
 {
   switch (kind * 32 + C) {
-    case 0 * 32 + 2: return launch_reg(ctx, rvit_kernel<2>, 2, wl, sd, nitems_hint, out);
-    case 0 * 32 + 4: return launch_reg(ctx, rvit_kernel<4>, 4, wl, sd, nitems_hint, out);
-    case 0 * 32 + 8: return launch_reg(ctx, rvit_kernel<8>, 8, wl, sd, nitems_hint, out);
-    case 0 * 32 + 12: return launch_reg(ctx, rvit_kernel<12>, 12, wl, sd, nitems_hint, out);
-    case 0 * 32 + 16: return launch_reg(ctx, rvit_kernel<16>, 16, wl, sd, nitems_hint, out);
-    case 1 * 32 + 2: return launch_reg(ctx, rfwd_kernel<2>, 2, wl, sd, nitems_hint, out);
-    case 1 * 32 + 4: return launch_reg(ctx, rfwd_kernel<4>, 4, wl, sd, nitems_hint, out);
-    case 1 * 32 + 8: return launch_reg(ctx, rfwd_kernel<8>, 8, wl, sd, nitems_hint, out);
-    case 1 * 32 + 12: return launch_reg(ctx, rfwd_kernel<12>, 12, wl, sd, nitems_hint, out);
-    case 1 * 32 + 16: return launch_reg(ctx, rfwd_kernel<16>, 16, wl, sd, nitems_hint, out);
-    case 2 * 32 + 2: return launch_reg(ctx, rbck_kernel<2>, 2, wl, sd, nitems_hint, out);
-    case 2 * 32 + 4: return launch_reg(ctx, rbck_kernel<4>, 4, wl, sd, nitems_hint, out);
-    case 2 * 32 + 8: return launch_reg(ctx, rbck_kernel<8>, 8, wl, sd, nitems_hint, out);
-    case 2 * 32 + 12: return launch_reg(ctx, rbck_kernel<12>, 12, wl, sd, nitems_hint, out);
-    case 2 * 32 + 16: return launch_reg(ctx, rbck_kernel<16>, 16, wl, sd, nitems_hint, out);
+    case 0 * 32 + 2: return launch_reg(ctx, rvit_kernel<2>, 2, wl, sd, nitems_hint, out, strm);
+    case 0 * 32 + 4: return launch_reg(ctx, rvit_kernel<4>, 4, wl, sd, nitems_hint, out, strm);
+    case 0 * 32 + 8: return launch_reg(ctx, rvit_kernel<8>, 8, wl, sd, nitems_hint, out, strm);
+    case 0 * 32 + 12: return launch_reg(ctx, rvit_kernel<12>, 12, wl, sd, nitems_hint, out, strm);
+    case 0 * 32 + 16: return launch_reg(ctx, rvit_kernel<16>, 16, wl, sd, nitems_hint, out, strm);
+    case 1 * 32 + 2: return launch_reg(ctx, rfwd_kernel<2>, 2, wl, sd, nitems_hint, out, strm);
+    case 1 * 32 + 4: return launch_reg(ctx, rfwd_kernel<4>, 4, wl, sd, nitems_hint, out, strm);
+    case 1 * 32 + 8: return launch_reg(ctx, rfwd_kernel<8>, 8, wl, sd, nitems_hint, out, strm);
+    case 1 * 32 + 12: return launch_reg(ctx, rfwd_kernel<12>, 12, wl, sd, nitems_hint, out, strm);
+    case 1 * 32 + 16: return launch_reg(ctx, rfwd_kernel<16>, 16, wl, sd, nitems_hint, out, strm);
+    case 2 * 32 + 2: return launch_reg(ctx, rbck_kernel<2>, 2, wl, sd, nitems_hint, out, strm);
+    case 2 * 32 + 4: return launch_reg(ctx, rbck_kernel<4>, 4, wl, sd, nitems_hint, out, strm);
+    case 2 * 32 + 8: return launch_reg(ctx, rbck_kernel<8>, 8, wl, sd, nitems_hint, out, strm);
+    case 2 * 32 + 12: return launch_reg(ctx, rbck_kernel<12>, 12, wl, sd, nitems_hint, out, strm);
+    case 2 * 32 + 16: return launch_reg(ctx, rbck_kernel<16>, 16, wl, sd, nitems_hint, out, strm);
   }
   return B2H_EINVAL;
 }

@@ -34,6 +34,8 @@ struct b2h_ctx {
   uint64_t      launches = 0;
   int          *d_counters = nullptr;   // small pool of work counters
   int           profiling = 0;
+  // side streams: independent launches of one stage (size classes) run concurrently, forked from / joined to <stream>
+  std::vector<cudaStream_t> side; std::vector<cudaEvent_t> side_done; cudaEvent_t fork_ev = nullptr; int side_used = 0;
   double        stage_ms[8] = {0};
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_open;   // (stage, begin, end) awaiting a sync
@@ -63,6 +65,7 @@ struct b2h_seqdb {
 
 struct b2h_profile {
   b2h_ctx *ctx = nullptr;
+  void *d_block = nullptr;         // the single device allocation all d_* table pointers below point into
   int M = 0, K = 0, Kp = 0, max_length = 0, multihit = 1;
   // MSV
   int NR = 0;                     // 32-bit cell registers per lane in the SSV/MSV kernels
@@ -113,6 +116,28 @@ static inline void b2h_resolve_timers(b2h_ctx *c) {
   for (auto &o : c->ev_open) { float ms = 0.f; if (cudaEventElapsedTime(&ms, o.second.first, o.second.second) == cudaSuccess) c->stage_ms[o.first] += ms; }
   c->ev_open.clear(); c->ev_used = 0;
 }
+
+// fork/join of the side streams around a group of independent launches
+struct ForkJoin {
+  b2h_ctx *ctx; int n = 0;
+  explicit ForkJoin(b2h_ctx *c) : ctx(c) {
+    if (!c->fork_ev) cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming);
+    cudaEventRecord(c->fork_ev, c->stream);
+  }
+  cudaStream_t next() {                                   // stream for the next independent launch
+    const int i = n++ % 4;
+    if ((int)ctx->side.size() <= i) {
+      cudaStream_t s; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); ctx->side.push_back(s);
+      cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); ctx->side_done.push_back(e);
+    }
+    if (n <= 4) cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0);
+    return ctx->side[i];
+  }
+  ~ForkJoin() {
+    const int used = n < 4 ? n : 4;
+    for (int i = 0; i < used; i++) { cudaEventRecord(ctx->side_done[i], ctx->side[i]); cudaStreamWaitEvent(ctx->stream, ctx->side_done[i], 0); }
+  }
+};
 
 static inline int b2h_nr_for_M(int M) {
   // need 64*NR >= M+1 so that the last cell of lane 31 is always padding (see b2h_msv.cu)
@@ -180,7 +205,7 @@ struct StageOut { float *sc; int32_t *status; float *fwd_xmx, *bck_xmx; const in
 int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
-int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out);
+int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm);
 int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc);
 
 // A compacted list of comparisons produced by a stage's epilogue (device memory).  Appends are
@@ -201,7 +226,7 @@ struct SsvArgs {
   SurvList       A, R;
   double         F1;
 };
-int b2h_launch_ssv(b2h_ctx *ctx, int NR, const SsvArgs &a);
+int b2h_launch_ssv(b2h_ctx *ctx, int NR, const SsvArgs &a, cudaStream_t strm);
 // full MSV (with J) over a grouped work list; mode 1: dense outputs indexed by sequence, 2: cascade append to A
 int b2h_launch_msv(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, int mode,
                    float *out_sc, int32_t *out_status, SurvList A, double F1);

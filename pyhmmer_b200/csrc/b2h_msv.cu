@@ -329,7 +329,7 @@ __global__ void group_scatter_kernel(const SurvList in, const int32_t *poff, int
 }
 
 template <int NR>
-int launch_ssv_nr(b2h_ctx *ctx, const SsvArgs &a)
+int launch_ssv_nr(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
 {
   const size_t smem = (size_t)B2H_NCODE * NR * 128;
   B2H_CUDA(cudaFuncSetAttribute(ssv_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -339,7 +339,7 @@ int launch_ssv_nr(b2h_ctx *ctx, const SsvArgs &a)
   int grid = ctx->sm_count * occ;
   const long long nitems = (long long)a.ncls * a.chunks;
   if (grid > nitems) grid = (int)(nitems > 0 ? nitems : 1);
-  ssv_kernel<NR><<<grid, SSV_THREADS, smem, ctx->stream>>>(a);
+  ssv_kernel<NR><<<grid, SSV_THREADS, smem, strm>>>(a);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());
   return B2H_OK;
@@ -347,12 +347,12 @@ int launch_ssv_nr(b2h_ctx *ctx, const SsvArgs &a)
 
 } // namespace
 
-int b2h_launch_ssv(b2h_ctx *ctx, int NR, const SsvArgs &a)
+int b2h_launch_ssv(b2h_ctx *ctx, int NR, const SsvArgs &a, cudaStream_t strm)
 {
   if (a.ncls <= 0 || a.sd.n <= 0) return B2H_OK;
-  B2H_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
+  B2H_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), strm));
   switch (NR) {
-#define CASE(n) case n: return launch_ssv_nr<n>(ctx, a);
+#define CASE(n) case n: return launch_ssv_nr<n>(ctx, a, strm);
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(10) CASE(12) CASE(16) CASE(20) CASE(24) CASE(32) CASE(40) CASE(48)
 #undef CASE
   }

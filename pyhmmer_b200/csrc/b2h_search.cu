@@ -165,12 +165,14 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
 
   // 1. SSV over every comparison
   { StageTimer tm(ctx, 0);
+  ForkJoin fj(ctx);
+  int ssv_cls = 0;
   for (auto &cr : cls_ranges) {
     SsvArgs a;
     a.profs = d_prof; a.cls = d_cls + cr.second.first; a.ncls = cr.second.second; a.sd = sd;
-    a.chunks = (N + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK; a.counter = ctx->d_counters; a.zero = 0u; a.mode = 2;
+    a.chunks = (N + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK; a.counter = ctx->d_counters + 32 + (ssv_cls++ % 24); a.zero = 0u; a.mode = 2;
     a.out_sc = nullptr; a.out_status = nullptr; a.A = A; a.R = R; a.F1 = prm->F1;
-    TRY(b2h_launch_ssv(ctx, cr.first, a));
+    TRY(b2h_launch_ssv(ctx, cr.first, a, fj.next()));
   } }
   // 2. full MSV for the comparisons SSV could not decide
   {
