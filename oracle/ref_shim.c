@@ -310,12 +310,16 @@ const REF_DOM *ref_result_doms(const REF_RESULT *r) { return r->doms; }
 const char *ref_result_text(const REF_RESULT *r) { return r->text; }
 const long *ref_result_counters(const REF_RESULT *r) { return r->counters; }
 
-/* ---- multi-threaded timing run (bench.py --impl reference / cpu_baseline): the target database is split
- * into <nthreads> contiguous slices balanced by residues, as pyhmmer's target-parallel dispatcher does
- * (_hmmsearch.py:153-171); every thread owns a pipeline, a background and a clone of each query profile. */
+/* ---- multi-threaded timing run (bench.py --impl reference / cpu_baseline): every thread owns a pipeline, a
+ * background and a clone of the current query profile, and pulls blocks of MT_BLOCK target sequences from a
+ * shared counter (the work-queue scheme of HMMER's own threaded hmmsearch; pyhmmer's dispatcher splits the
+ * targets the same way, _hmmsearch.py:153-171, but statically).  Dynamic blocks keep the 128 host threads
+ * busy when a few targets (true homologs) cost 1000x the others. */
+#define MT_BLOCK 128
 typedef struct {
   REFM **models; int nmodels;
-  const uint8_t *const *dsq; const int64_t *len; int t0, t1;
+  const uint8_t *const *dsq; const int64_t *len; int n;
+  int *next;                      /* next[q] = next unclaimed target of query q (atomic) */
   double F1, F2, F3; int do_bias, do_null2;
   long nhits; long counters[4];
 } MT_JOB;
@@ -325,31 +329,38 @@ static void *mt_worker(void *arg)
   MT_JOB *job = (MT_JOB *)arg;
   int q, t, c;
   job->nhits = 0; for (c = 0; c < 4; c++) job->counters[c] = 0;
+  ESL_SQ *sq = NULL;
   for (q = 0; q < job->nmodels; q++) {
     REFM *m = job->models[q];
+    int t0 = __atomic_fetch_add(&job->next[q], MT_BLOCK, __ATOMIC_RELAXED);
+    if (t0 >= job->n) continue;
     P7_OPROFILE *om = p7_oprofile_Clone(m->om);
     P7_BG *bg = p7_bg_Clone(m->bg);
     P7_PIPELINE *pli = p7_pipeline_Create(NULL, om->M, 400, FALSE, p7_SEARCH_SEQS);
     P7_TOPHITS *th = p7_tophits_Create();
-    ESL_SQ *sq = esl_sq_CreateDigital(m->abc);
+    if (!sq) sq = esl_sq_CreateDigital(m->abc);
     pli->F1 = job->F1; pli->F2 = job->F2; pli->F3 = job->F3; pli->do_biasfilter = job->do_bias; pli->do_null2 = job->do_null2;
     p7_pli_NewModel(pli, om, bg);
-    for (t = job->t0; t < job->t1; t++) {
-      esl_sq_GrowTo(sq, job->len[t]);
-      memcpy(sq->dsq, job->dsq[t], job->len[t] + 2);
-      sq->n = job->len[t];
-      esl_sq_SetName(sq, "s");
-      p7_pli_NewSeq(pli, sq);
-      p7_bg_SetLength(bg, sq->n);
-      p7_oprofile_ReconfigLength(om, sq->n);
-      p7_Pipeline(pli, om, bg, sq, NULL, th);
-      p7_pipeline_Reuse(pli);
-      esl_sq_Reuse(sq);
+    for (; t0 < job->n; t0 = __atomic_fetch_add(&job->next[q], MT_BLOCK, __ATOMIC_RELAXED)) {
+      int t1 = t0 + MT_BLOCK < job->n ? t0 + MT_BLOCK : job->n;
+      for (t = t0; t < t1; t++) {
+        esl_sq_GrowTo(sq, job->len[t]);
+        memcpy(sq->dsq, job->dsq[t], job->len[t] + 2);
+        sq->n = job->len[t];
+        esl_sq_SetName(sq, "s");
+        p7_pli_NewSeq(pli, sq);
+        p7_bg_SetLength(bg, sq->n);
+        p7_oprofile_ReconfigLength(om, sq->n);
+        p7_Pipeline(pli, om, bg, sq, NULL, th);
+        p7_pipeline_Reuse(pli);
+        esl_sq_Reuse(sq);
+      }
     }
     job->nhits += th->N;
     job->counters[0] += pli->n_past_msv; job->counters[1] += pli->n_past_bias; job->counters[2] += pli->n_past_vit; job->counters[3] += pli->n_past_fwd;
-    esl_sq_Destroy(sq); p7_tophits_Destroy(th); p7_pipeline_Destroy(pli); p7_bg_Destroy(bg); p7_oprofile_Destroy(om);
+    p7_tophits_Destroy(th); p7_pipeline_Destroy(pli); p7_bg_Destroy(bg); p7_oprofile_Destroy(om);
   }
+  if (sq) esl_sq_Destroy(sq);
   return NULL;
 }
 
@@ -359,22 +370,15 @@ long ref_search_mt(REFM **models, int nmodels, const uint8_t *const *dsq, const 
 {
   pthread_t *th = malloc(sizeof(pthread_t) * nthreads);
   MT_JOB *jobs = calloc(nthreads, sizeof(MT_JOB));
-  int64_t total = 0, acc = 0; int t, j = 0, c; long nhits = 0;
-  for (t = 0; t < n; t++) total += len[t];
-  for (t = 0; t < nthreads; t++) { jobs[t].t0 = jobs[t].t1 = n; }
-  jobs[0].t0 = 0;
-  for (t = 0; t < n; t++) {                       /* contiguous slices balanced by residues */
-    acc += len[t];
-    if (j < nthreads - 1 && acc >= (total * (j + 1)) / nthreads) { jobs[j].t1 = t + 1; j++; jobs[j].t0 = t + 1; }
-  }
-  jobs[j].t1 = n;
+  int *next = calloc(nmodels > 0 ? nmodels : 1, sizeof(int));
+  int t, c; long nhits = 0;
   for (t = 0; t < nthreads; t++) {
-    jobs[t].models = models; jobs[t].nmodels = nmodels; jobs[t].dsq = dsq; jobs[t].len = len;
+    jobs[t].models = models; jobs[t].nmodels = nmodels; jobs[t].dsq = dsq; jobs[t].len = len; jobs[t].n = n; jobs[t].next = next;
     jobs[t].F1 = F1; jobs[t].F2 = F2; jobs[t].F3 = F3; jobs[t].do_bias = do_bias; jobs[t].do_null2 = do_null2;
     pthread_create(&th[t], NULL, mt_worker, &jobs[t]);
   }
   for (c = 0; c < 4; c++) counters4[c] = 0;
   for (t = 0; t < nthreads; t++) { pthread_join(th[t], NULL); nhits += jobs[t].nhits; for (c = 0; c < 4; c++) counters4[c] += jobs[t].counters[c]; }
-  free(th); free(jobs);
+  free(th); free(jobs); free(next);
   return nhits;
 }

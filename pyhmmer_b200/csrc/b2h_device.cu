@@ -110,6 +110,7 @@ static int seqdb_finish(b2h_ctx *ctx, b2h_seqdb *db, const std::vector<uint8_t> 
   B2H_CUDA(cudaMalloc(&db->d_flta, std::max<size_t>(n, 1) * sizeof(float)));
   B2H_CUDA(cudaMalloc(&db->d_fltb, std::max<size_t>(n, 1) * sizeof(float)));
   cudaStream_t st = ctx->stream;
+  db->h2d_bytes = arena.size() + (n + 1) * sizeof(int64_t) + n * (size_t)(4 + 4 + 1 + 2 + 4 * 5);
   if (!arena.empty()) B2H_CUDA(cudaMemcpyAsync(db->d_res, arena.data(), arena.size(), cudaMemcpyHostToDevice, st));
   B2H_CUDA(cudaMemcpyAsync(db->d_off, db->h_off.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   if (n) {
@@ -249,17 +250,20 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
     }
 
   // --- lane-grouped emission tables of the register-resident DP kernels (b2h_dpreg.cu), models up to 512 nodes ---
-  p->regC = (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 256) ? 8 : (M <= 384) ? 12 : (M <= 512) ? 16 : 0;
+  p->regC = 0; p->regW = 0;
+  for (int rc = 0; rc < B2H_N_REG_CLASSES; rc++)
+    if (M <= B2H_REG_CLASSES[rc].bound) { p->regC = B2H_REG_CLASSES[rc].C; p->regW = B2H_REG_CLASSES[rc].W; break; }
   std::vector<int32_t> vr32; std::vector<float> frr;
   if (p->regC) {
-    const int C = p->regC;
-    vr32.assign((size_t)B2H_NCODE * 32 * C, -32768); frr.assign((size_t)B2H_NCODE * 32 * C, 0.0f);
+    const int C = p->regC, W = p->regW, G = (C % 4 == 0) ? 4 : 2, stride = 32 * C * W;
+    vr32.assign((size_t)B2H_NCODE * stride, -32768); frr.assign((size_t)B2H_NCODE * stride, 0.0f);
     for (int x = 0; x < Kp; x++)
-      for (int lane = 0; lane < 32; lane++)
+      for (int gl = 0; gl < 32 * W; gl++)
         for (int c = 0; c < C; c++) {
-          const int k0 = lane * C + c;
+          const int k0 = gl * C + c;
           if (k0 >= M) continue;
-          const size_t idx = (size_t)x * 32 * C + (C == 2 ? (size_t)lane * 2 + c : (size_t)(c / 4) * 128 + (size_t)lane * 4 + (c % 4));
+          const int wi = gl / 32, lane = gl % 32;
+          const size_t idx = (size_t)x * stride + (size_t)wi * 32 * C + (size_t)(c / G) * 32 * G + (size_t)lane * G + (c % G);
           vr32[idx] = d->vit_rsc[(size_t)x * M + k0];
           frr[idx] = d->fwd_rsc[(size_t)x * M + k0];
         }
@@ -298,6 +302,7 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
     size_t o_vr32 = 0, o_frr = 0;
     if (p->regC) { o_vr32 = add(vr32.data(), vr32.size() * 4); o_frr = add(frr.data(), frr.size() * 4); }
     cudaError_t e;
+    p->h2d_bytes = stage.size();
     cudaSetDevice(ctx->device);
     if ((e = cudaMalloc(&p->d_block, stage.size())) != cudaSuccess ||
         (e = cudaMemcpyAsync(p->d_block, stage.data(), stage.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
@@ -334,3 +339,6 @@ int b2h_profile_set_annotation(b2h_profile *p, const char *consensus, const char
 }
 
 } // extern "C"
+
+extern "C" size_t b2h_seqdb_h2d_bytes(const b2h_seqdb *db) { return db ? db->h2d_bytes : 0; }
+extern "C" size_t b2h_profile_h2d_bytes(const b2h_profile *p) { return p ? p->h2d_bytes : 0; }

@@ -527,17 +527,16 @@ LaunchCfg pick_cfg(int max_Mpad, int elem_bytes)
 template <typename K>
 int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const SeqDev &sd, const std::vector<int> &mpads, int elem_bytes, int nitems_hint, const StageOut &out)
 {
-  static const int bounds[] = {768, 1024, 1536, 2048, 3072, 1 << 30};
+  static const int bounds[] = {2048, 3072, 1 << 30};
   const int P = (int)mpads.size();
   int plo = 0, cls = 0;
   ForkJoin fj(ctx);
-  static const int regb[5] = {64, 128, 256, 384, 512}, regc[5] = {2, 4, 8, 12, 16};
-  for (int rc = 0; rc < 5 && plo < P; rc++) {
+  for (int rc = 0; rc < B2H_N_REG_CLASSES && plo < P; rc++) {
     int phi = plo;
-    while (phi < P && mpads[phi] <= regb[rc]) phi++;
+    while (phi < P && mpads[phi] <= B2H_REG_CLASSES[rc].bound) phi++;
     if (phi > plo) {
       WorkList wl = wl_in; wl.plo = plo; wl.phi = phi; wl.counter = wl_in.counter + cls;
-      int st = b2h_launch_dpreg(ctx, kind, regc[rc], wl, sd, nitems_hint, out, fj.next());
+      int st = b2h_launch_dpreg(ctx, kind, B2H_REG_CLASSES[rc].C, B2H_REG_CLASSES[rc].W, wl, sd, nitems_hint, out, fj.next());
       if (st != B2H_OK) return st;
       plo = phi; cls++;
     }

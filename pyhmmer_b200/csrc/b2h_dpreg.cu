@@ -1,5 +1,11 @@
 // b2h_dpreg.cu -- register-resident ViterbiFilter / Forward parser / Backward parser for models with
-// M <= 32*C (C = 2, 4, 8, 12 or 16 nodes per lane, i.e. M <= 64 / 128 / 256 / 384 / 512: ~95 % of Pfam).
+// M <= 32*C*W: C = 2, 4, 8, 10, 12 or 16 nodes per lane, W = 1, 2 or 4 warps per comparison
+// (W = 1: M <= 64 / 128 / 256 / 384 / 512, ~95 % of Pfam;  W = 2: M <= 640 / 768 / 1024;  W = 4: M <= 1536).
+// With W > 1 the W warps of a group own consecutive 32*C-node segments of the model and meet at one named
+// barrier per row (two for Backward and for Viterbi rows that need the D->D closure): the per-warp partial
+// results (xE maxima / sums, the affine or max-plus composite of the warp's D chain, the M/I/D cells of its
+// last node) are exchanged through a few words of shared memory and combined by every warp in the same
+// order, so all warps of a group take identical decisions.
 //
 // Same recurrences and the same numerical semantics as the generic kernels of b2h_dp.cu (which remain
 // the path for longer models), but organised so that almost nothing is re-read per row:
@@ -59,14 +65,20 @@ __device__ __forceinline__ bool next_item(const WorkList &wl, int *s_item, Item 
   return true;
 }
 
-// The C emission values of this lane for residue x.  Table layout: [32 residues][C/4 groups][32 lanes][4]
-// (C = 2: [32][32][2]), so every access is one conflict-free LDS.64 / LDS.128 per lane.
+// The C emission values of this lane for residue x.  Table layout: [32 residues][W warps][C/G groups][32 lanes][G]
+// with G = 4 (C % 4 == 0) or 2, so every access is one conflict-free LDS.128 / LDS.64 per lane; <tab> already
+// points at this warp's segment and <stride> = 32*C*W is the distance between residues.
 template <int C, typename T>
-__device__ __forceinline__ void load_emis(const T *tab, int x, int lane, T (&r)[C])
+__device__ __forceinline__ void load_emis(const T *tab, int stride, int x, int lane, T (&r)[C])
 {
-  const T *row = tab + (size_t)x * 32 * C;
-  if (C == 2) { const float2 v = *reinterpret_cast<const float2 *>(row + lane * 2); r[0] = *(const T *)&v.x; r[1] = *(const T *)&v.y; }
-  else {
+  const T *row = tab + (size_t)x * stride;
+  if (C % 4 != 0) {
+#pragma unroll
+    for (int g = 0; g < C / 2; g++) {
+      const float2 v = *reinterpret_cast<const float2 *>(row + g * 64 + lane * 2);
+      r[2*g+0] = *(const T *)&v.x; r[2*g+1] = *(const T *)&v.y;
+    }
+  } else {
 #pragma unroll
     for (int g = 0; g < C / 4; g++) {
       const float4 v = *reinterpret_cast<const float4 *>(row + g * 128 + lane * 4);
@@ -74,6 +86,14 @@ __device__ __forceinline__ void load_emis(const T *tab, int x, int lane, T (&r)[
     }
   }
 }
+
+// named barrier of one W-warp group (barrier 0 stays the CTA barrier of next_item)
+template <int W>
+__device__ __forceinline__ void group_sync(int grp)
+{
+  if (W > 1) asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "r"(W * 32) : "memory");
+}
+constexpr int MAXGRP = 4;            // 256 threads / (32 * W), W >= 2
 
 // residues: each lane keeps one 4-residue word of the current 128-row window (as the SSV kernel does)
 struct SeqWin {
@@ -90,14 +110,19 @@ struct SeqWin {
 // =================================================================================================
 // ViterbiFilter, register resident
 // =================================================================================================
-template <int C>
+template <int C, int W>
 __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqDev sd, const StageOut out)
 {
-  extern __shared__ __align__(128) int s_rsc[];            // [32][32*C] int32 emission scores
+  extern __shared__ __align__(128) int s_rsc[];            // [32][W][32*C] int32 emission scores
   __shared__ uint64_t s_bar;
   __shared__ int s_item;
+  __shared__ int s_x[2][MAXGRP][6][W];                      // per row parity: M, I, D, M+tMD of each warp's last node; xE, Dmax partials
+  __shared__ int s_y[MAXGRP][2][W];                         // max-plus composite (A, T) of each warp's D chain
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr uint32_t TAB_BYTES = 32u * 32u * C * 4u;
+  const int grp = warp / W, wi = warp % W, ngrp = nwarps / W;
+  const int gl = wi * 32 + lane;                            // lane index inside the group: owns nodes gl*C .. gl*C+C-1
+  constexpr int STRIDE = 32 * C * W;
+  constexpr uint32_t TAB_BYTES = 32u * STRIDE * 4u;
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   uint32_t phase = 0;
   int cur_p = -1;
@@ -112,18 +137,20 @@ __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqD
       const int16_t *ts = P.vit_tsc; const int Mp = P.Mpad;
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        const int k0 = lane * C + c;                        // 0-based node column
+        const int k0 = gl * C + c;                          // 0-based node column
         const bool in = k0 < Mp;
         tBM[c] = in ? ts[0 * Mp + k0] : NEG16; tMM[c] = in ? ts[1 * Mp + k0] : NEG16; tIM[c] = in ? ts[2 * Mp + k0] : NEG16;
         tDM[c] = in ? ts[3 * Mp + k0] : NEG16; tMD[c] = in ? ts[4 * Mp + k0] : NEG16; tMI[c] = in ? ts[5 * Mp + k0] : NEG16;
         tII[c] = in ? ts[6 * Mp + k0] : NEG16; tDD[c] = in ? ts[7 * Mp + k0] : NEG16;
       }
-      tDDin = __shfl_up_sync(FULL, tDD[C - 1], 1); if (lane == 0) tDDin = NEG16;
+      tDDin = __shfl_up_sync(FULL, tDD[C - 1], 1);
+      if (lane == 0) tDDin = (W > 1 && wi > 0 && gl * C - 1 < Mp) ? (int)ts[7 * Mp + gl * C - 1] : NEG16;
       mbar_wait(&s_bar, phase); phase ^= 1;
     }
     const int xwEm = P.xw_E_move, xwEl = P.xw_E_loop, base_w = P.base_w, ddbound = P.ddbound_w;
+    const int *my_rsc = s_rsc + wi * 32 * C;
 
-    for (int e = it.e_begin + warp; e < it.e_end; e += nwarps) {
+    for (int e = it.e_begin + grp; e < it.e_end; e += ngrp) {
       const int s = wl.ent_s[e];
       const int L = sd.len[s];
       const int xw_move = sd.xwmove[s];
@@ -132,14 +159,16 @@ __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqD
 #pragma unroll
       for (int c = 0; c < C; c++) { M[c] = NEG16; I[c] = NEG16; D[c] = NEG16; }
       int xN = base_w, xB = (int16_t)(xN + xw_move), xJ = NEG16, xC = NEG16;
+      int cM = NEG16, cI = NEG16, cD = NEG16;              // W > 1: previous row's cells of the left warp's last node
       bool overflow = false;
+      group_sync<W>(grp);                                   // the exchange buffers of the previous comparison are free
 
       for (int i = 0; i < L; i++) {
         const int x = sw.get(i, lane);
         int r[C];
-        load_emis<C, int>(s_rsc, x, lane, r);
+        load_emis<C, int>(my_rsc, STRIDE, x, lane, r);
         int mp = __shfl_up_sync(FULL, M[C - 1], 1), ip = __shfl_up_sync(FULL, I[C - 1], 1), dp = __shfl_up_sync(FULL, D[C - 1], 1);
-        if (lane == 0) { mp = NEG16; ip = NEG16; dp = NEG16; }
+        if (lane == 0) { mp = cM; ip = cI; dp = cD; }
         int xEm = NEG16;
 #pragma unroll
         for (int c = C - 1; c >= 0; c--) {
@@ -153,19 +182,33 @@ __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqD
           xEm = max(xEm, m);
           M[c] = m; I[c] = inew;
         }
-        const int xE = __reduce_max_sync(FULL, xEm);
-        if (xE >= 32767) { overflow = true; break; }
-        xC = (int16_t)max(xC, xE + xwEm);
-        xJ = (int16_t)max(xJ, xE + xwEl);
-        xB = (int16_t)max(xJ + xw_move, xN + xw_move);
+        int xE = __reduce_max_sync(FULL, xEm);
         // M->D partials: D[c] is the value entering node c from M of node c-1
-        int dleft = __shfl_up_sync(FULL, __viaddmax_s32(M[C - 1], tMD[C - 1], NEG16), 1);
+        const int mdl = __viaddmax_s32(M[C - 1], tMD[C - 1], NEG16);
+        int dleft = __shfl_up_sync(FULL, mdl, 1);
         if (lane == 0) dleft = NEG16;
         int Dm = dleft;
         D[0] = dleft;
 #pragma unroll
         for (int c = 1; c < C; c++) { D[c] = __viaddmax_s32(M[c - 1], tMD[c - 1], NEG16); Dm = max(Dm, D[c]); }
-        const int Dmax = __reduce_max_sync(FULL, Dm);
+        int Dmax = __reduce_max_sync(FULL, Dm);
+        if (W > 1) {
+          int (*X)[W] = s_x[i & 1][grp];
+          if (lane == 31) { X[0][wi] = M[C - 1]; X[1][wi] = I[C - 1]; X[2][wi] = D[C - 1]; X[3][wi] = mdl; }
+          if (lane == 0)  { X[4][wi] = xE; X[5][wi] = Dmax; }
+          group_sync<W>(grp);
+          xE = X[4][0]; Dmax = X[5][0];
+#pragma unroll
+          for (int w = 1; w < W; w++) { xE = max(xE, X[4][w]); Dmax = max(Dmax, max(X[5][w], X[3][w - 1])); }
+          if (wi > 0) {
+            cM = X[0][wi - 1]; cI = X[1][wi - 1]; cD = X[2][wi - 1];
+            if (lane == 0) D[0] = X[3][wi - 1];
+          }
+        }
+        if (xE >= 32767) { overflow = true; break; }
+        xC = (int16_t)max(xC, xE + xwEm);
+        xJ = (int16_t)max(xJ, xE + xwEl);
+        xB = (int16_t)max(xJ + xw_move, xN + xw_move);
         if (Dmax + ddbound > xB) {
           // close the D->D chain: serial inside the lane, then a max-plus scan over the 32 lane composites
           int T[C];
@@ -180,11 +223,21 @@ __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqD
           }
           int din = __shfl_up_sync(FULL, A, 1);              // D of the previous lane's last node
           if (lane == 0) din = NEG16;
+          if (W > 1) {
+            int (*Y)[W] = s_y[grp];
+            if (lane == 31) { Y[0][wi] = A; Y[1][wi] = Tt; }
+            const int Tp = __shfl_up_sync(FULL, Tt, 1);
+            group_sync<W>(grp);
+            int d = NEG16;                                   // D of the last node of the warp to the left, closed
+#pragma unroll
+            for (int w = 0; w < W - 1; w++) if (w < wi) d = max(Y[0][w], max(d + Y[1][w], NEG16));
+            if (wi > 0) { cD = d; din = (lane == 0) ? d : max(din, max(d + Tp, NEG16)); }
+          }
 #pragma unroll
           for (int c = 0; c < C; c++) D[c] = max(D[c], max(din + T[c], NEG16));
         }
       }
-      if (lane == 0) {
+      if (gl == 0) {
         float sc; int st = B2H_OK;
         if (overflow) { sc = INFINITY; st = B2H_ERANGE; }
         else if (xC > NEG16) { sc = (float)xC + (float)xw_move - (float)base_w; sc /= P.scale_w; sc -= 3.0f; }
@@ -205,14 +258,18 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <int C>
+template <int C, int W>
 __global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqDev sd, const StageOut out)
 {
-  extern __shared__ __align__(128) float s_rscf[];          // [32][32*C] fp32 emission odds
+  extern __shared__ __align__(128) float s_rscf[];          // [32][W][32*C] fp32 emission odds
   __shared__ uint64_t s_bar;
   __shared__ int s_item;
+  __shared__ float s_x[2][MAXGRP][8][W];                    // per row parity and warp: A, T, aout, tDDlast, M_last, I_last, S1, S2
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr uint32_t TAB_BYTES = 32u * 32u * C * 4u;
+  const int grp = warp / W, wi = warp % W, ngrp = nwarps / W;
+  const int gl = wi * 32 + lane;
+  constexpr int STRIDE = 32 * C * W;
+  constexpr uint32_t TAB_BYTES = 32u * STRIDE * 4u;
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   uint32_t phase = 0;
   int cur_p = -1;
@@ -227,18 +284,21 @@ __global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqD
       const float *ts = P.fwd_tsc; const int Mp = P.Mpad;
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        const int k0 = lane * C + c;
+        const int k0 = gl * C + c;
         const bool in = k0 < Mp;
         tBM[c] = in ? ts[0 * Mp + k0] : 0.f; tMM[c] = in ? ts[1 * Mp + k0] : 0.f; tIM[c] = in ? ts[2 * Mp + k0] : 0.f;
         tDM[c] = in ? ts[3 * Mp + k0] : 0.f; tMD[c] = in ? ts[4 * Mp + k0] : 0.f; tMI[c] = in ? ts[5 * Mp + k0] : 0.f;
         tII[c] = in ? ts[6 * Mp + k0] : 0.f; tDD[c] = in ? ts[7 * Mp + k0] : 0.f;
       }
-      tDDin = __shfl_up_sync(FULL, tDD[C - 1], 1); if (lane == 0) tDDin = 0.f;
+      tDDin = __shfl_up_sync(FULL, tDD[C - 1], 1);
+      // W > 1: the value entering the first node of warp wi > 0 is handed over complete (o_in below), hence factor 1
+      if (lane == 0) tDDin = (W > 1 && wi > 0) ? 1.0f : 0.f;
       mbar_wait(&s_bar, phase); phase ^= 1;
     }
     const float tEC = P.xf_E_move, tEJ = P.xf_E_loop;
+    const float *my_rsc = s_rscf + wi * 32 * C;
 
-    for (int e = it.e_begin + warp; e < it.e_end; e += nwarps) {
+    for (int e = it.e_begin + grp; e < it.e_end; e += ngrp) {
       const int s = wl.ent_s[e];
       const int L = sd.len[s];
       const float pmove = sd.pmove[s], ploop = 1.0f - pmove;
@@ -248,14 +308,16 @@ __global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqD
 #pragma unroll
       for (int c = 0; c < C; c++) { M[c] = 0.f; I[c] = 0.f; D[c] = 0.f; }
       float xN = 1.0f, xJ = 0.0f, xC = 0.0f, xB = pmove, xE = 0.0f, totscale = 0.0f;
-      if (xout && lane == 0) { xout[0] = 0.f; xout[1] = 1.f; xout[2] = 0.f; xout[3] = xB; xout[4] = 0.f; xout[5] = 1.f; }
+      float cM = 0.f, cI = 0.f, cD = 0.f;                   // W > 1: previous row's cells of the left warp's last node
+      if (xout && gl == 0) { xout[0] = 0.f; xout[1] = 1.f; xout[2] = 0.f; xout[3] = xB; xout[4] = 0.f; xout[5] = 1.f; }
+      group_sync<W>(grp);
 
       for (int i = 1; i <= L; i++) {
         const int x = sw.get(i - 1, lane);
         float r[C];
-        load_emis<C, float>(s_rscf, x, lane, r);
+        load_emis<C, float>(my_rsc, STRIDE, x, lane, r);
         float mp = __shfl_up_sync(FULL, M[C - 1], 1), ip = __shfl_up_sync(FULL, I[C - 1], 1), dp = __shfl_up_sync(FULL, D[C - 1], 1);
-        if (lane == 0) { mp = 0.f; ip = 0.f; dp = 0.f; }
+        if (lane == 0) { mp = cM; ip = cI; dp = cD; }
         float esum = 0.f;
 #pragma unroll
         for (int c = C - 1; c >= 0; c--) {
@@ -270,7 +332,8 @@ __global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqD
           M[c] = m; I[c] = inew;
         }
         // D chain: D(k) = M(k-1)*tMD(k-1) + D(k-1)*tDD(k-1); two-level affine scan
-        float aleft = __shfl_up_sync(FULL, M[C - 1] * tMD[C - 1], 1);
+        const float aout = M[C - 1] * tMD[C - 1];
+        float aleft = __shfl_up_sync(FULL, aout, 1);
         if (lane == 0) aleft = 0.f;
         float T[C];
         D[0] = aleft; T[0] = tDDin;
@@ -284,9 +347,37 @@ __global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqD
         }
         float din = __shfl_up_sync(FULL, A, 1);
         if (lane == 0) din = 0.f;
+        if (W == 1) {
 #pragma unroll
-        for (int c = 0; c < C; c++) { D[c] = D[c] + din * T[c]; esum += D[c]; }
-        xE = warp_sum(esum);
+          for (int c = 0; c < C; c++) { D[c] = D[c] + din * T[c]; esum += D[c]; }
+          xE = warp_sum(esum);
+        } else {
+          float Tp = __shfl_up_sync(FULL, Tt, 1);             // product of tDD from the warp's entry point to this lane's entry point
+          if (lane == 0) Tp = 1.0f;
+          float sT = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; c++) { D[c] = D[c] + din * T[c]; esum += D[c]; sT += T[c]; }
+          const float S1 = warp_sum(esum), S2 = warp_sum(Tp * sT);
+          float (*X)[W] = s_x[i & 1][grp];
+          if (lane == 31) { X[0][wi] = A; X[1][wi] = Tt; X[2][wi] = aout; X[3][wi] = tDD[C - 1]; X[4][wi] = M[C - 1]; X[5][wi] = I[C - 1]; }
+          if (lane == 0)  { X[6][wi] = S1; X[7][wi] = S2; }
+          group_sync<W>(grp);
+          float o = 0.f, o_in = 0.f;                          // o: D entering the first node of the next warp
+          xE = 0.f;
+#pragma unroll
+          for (int w = 0; w < W; w++) {
+            xE += X[6][w] + o * X[7][w];
+            if (w == wi) o_in = o;
+            const float Dl = X[0][w] + X[1][w] * o;           // D of warp w's last node
+            if (w == wi - 1) { cM = X[4][w]; cI = X[5][w]; cD = Dl; }
+            o = X[2][w] + Dl * X[3][w];
+          }
+          if (wi > 0) {
+            const float oi = o_in * Tp;
+#pragma unroll
+            for (int c = 0; c < C; c++) D[c] = D[c] + oi * T[c];
+          }
+        }
         xN = xN * ploop;
         xC = (xC * ploop) + (xE * tEC);
         xJ = (xJ * ploop) + (xE * tEJ);
@@ -297,13 +388,14 @@ __global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqD
           const float inv = 1.0f / xE;
 #pragma unroll
           for (int c = 0; c < C; c++) { M[c] *= inv; I[c] *= inv; D[c] *= inv; }
+          if (W > 1) { cM *= inv; cI *= inv; cD *= inv; }
           scale = xE;
           totscale = (float)((double)totscale + log((double)xE));
           xE = 1.0f;
         }
-        if (xout && lane == 0) { float *q = xout + (size_t)i * 6; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; q[5] = scale; }
+        if (xout && gl == 0) { float *q = xout + (size_t)i * 6; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; q[5] = scale; }
       }
-      if (lane == 0) {
+      if (gl == 0) {
         int st = B2H_OK; float sc;
         if (isnan(xC) || (L > 0 && xC == 0.0f) || isinf(xC)) { st = B2H_ERANGE; sc = isnan(xC) ? NAN : (xC == 0.0f ? -INFINITY : INFINITY); }
         else sc = (float)((double)totscale + log((double)(xC * pmove)));
@@ -317,14 +409,18 @@ __global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqD
 // =================================================================================================
 // Backward parser, register resident
 // =================================================================================================
-template <int C>
+template <int C, int W>
 __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqDev sd, const StageOut out)
 {
   extern __shared__ __align__(128) float s_rscf[];
   __shared__ uint64_t s_bar;
   __shared__ int s_item;
+  __shared__ float s_x[MAXGRP][4][W];                       // per warp: bsum partial, composite (A, T) of the D chain, M of its first node
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr uint32_t TAB_BYTES = 32u * 32u * C * 4u;
+  const int grp = warp / W, wi = warp % W, ngrp = nwarps / W;
+  const int gl = wi * 32 + lane;
+  constexpr int STRIDE = 32 * C * W;
+  constexpr uint32_t TAB_BYTES = 32u * STRIDE * 4u;
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   uint32_t phase = 0;
   int cur_p = -1;
@@ -340,7 +436,7 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
       const float *ts = P.fwd_tsc; const int Mp = P.Mpad;
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        const int k0 = lane * C + c;
+        const int k0 = gl * C + c;
         const bool in = k0 < M, inn = (k0 + 1) < M;
         tBM[c] = in ? ts[0 * Mp + k0] : 0.f; tMD[c] = in ? ts[4 * Mp + k0] : 0.f; tMI[c] = in ? ts[5 * Mp + k0] : 0.f;
         tII[c] = in ? ts[6 * Mp + k0] : 0.f; tDD[c] = in ? ts[7 * Mp + k0] : 0.f;
@@ -349,8 +445,10 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
       mbar_wait(&s_bar, phase); phase ^= 1;
     }
     const float tEC = P.xf_E_move, tEJ = P.xf_E_loop;
+    const float *my_rsc = s_rscf + wi * 32 * C;
+    float (*X)[W] = s_x[grp];
 
-    for (int e = it.e_begin + warp; e < it.e_end; e += nwarps) {
+    for (int e = it.e_begin + grp; e < it.e_end; e += ngrp) {
       const int s = wl.ent_s[e];
       const int L = sd.len[s];
       const uint8_t *seq = sd.res + sd.off[s];
@@ -361,6 +459,7 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
       float xJ = 0.0f, xB = 0.0f, xN = 0.0f, xC = pmove, xE = xC * tEC;
       bool own_scales = false;
       float totscale;
+      float dext = 0.f;                                     // W > 1: closed D of the first node of the warp to the right
 
       // reverse two-level affine closure:  D(k) = a(k) + tDD(k) * D(k+1)   (a given in Dv, result in Dv)
       auto close_dd = [&](void) {
@@ -377,18 +476,39 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
         }
         float din = __shfl_down_sync(FULL, A, 1);          // D of the next lane's first node
         if (lane == 31) din = 0.f;
+        if (W > 1) {
+          if (lane == 0) { X[1][wi] = A; X[2][wi] = Tt; }
+          const float Tn = __shfl_down_sync(FULL, Tt, 1);
+          group_sync<W>(grp);
+          float d = 0.f;
+#pragma unroll
+          for (int w = W - 1; w >= 1; w--) if (w > wi) d = X[1][w] + X[2][w] * d;
+          dext = d;
+          din = (lane == 31) ? d : din + Tn * d;
+        }
 #pragma unroll
         for (int c = 0; c < C; c++) Dv[c] = Dv[c] + T[c] * din;
       };
+      // sum of the warps' partials of xB (every warp adds them in the same order)
+      auto group_sum = [&](float v) -> float {
+        if (W == 1) return v;
+        if (lane == 0) X[0][wi] = v;
+        group_sync<W>(grp);
+        float t = X[0][0];
+#pragma unroll
+        for (int w = 1; w < W; w++) t += X[0][w];
+        return t;
+      };
+      group_sync<W>(grp);
 
       // row L
 #pragma unroll
-      for (int c = 0; c < C; c++) { const bool in = (lane * C + c) < M; Dv[c] = in ? xE : 0.f; Iv[c] = 0.f; }
+      for (int c = 0; c < C; c++) { const bool in = (gl * C + c) < M; Dv[c] = in ? xE : 0.f; Iv[c] = 0.f; }
       close_dd();
       {
-        float dnext = __shfl_down_sync(FULL, Dv[0], 1); if (lane == 31) dnext = 0.f;
+        float dnext = __shfl_down_sync(FULL, Dv[0], 1); if (lane == 31) dnext = (W > 1) ? dext : 0.f;
 #pragma unroll
-        for (int c = 0; c < C; c++) { const bool in = (lane * C + c) < M; const float dn = (c == C - 1) ? dnext : Dv[c + 1]; Mv[c] = in ? xE + tMD[c] * dn : 0.f; }
+        for (int c = 0; c < C; c++) { const bool in = (gl * C + c) < M; const float dn = (c == C - 1) ? dnext : Dv[c + 1]; Mv[c] = in ? xE + tMD[c] * dn : 0.f; }
         const float scL = fx[(size_t)L * 6 + 5];
         if (scL > 1.0f) {
           xE = xE / scL; xN = xN / scL; xC = xC / scL; xJ = xJ / scL; xB = xB / scL;
@@ -397,13 +517,14 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
           for (int c = 0; c < C; c++) { Mv[c] *= inv; Dv[c] *= inv; }
         }
         totscale = (float)log((double)scL);
-        if (bx && lane == 0) { float *q = bx + (size_t)L * 6; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; q[5] = scL; }
+        if (bx && gl == 0) { float *q = bx + (size_t)L * 6; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; q[5] = scL; }
+        if (W > 1 && lane == 0) X[3][wi] = Mv[0];
       }
 
       for (int i = L - 1; i >= 1; i--) {
         const int x = seq[i];                               // x_{i+1}
         float r[C];
-        load_emis<C, float>(s_rscf, x, lane, r);
+        load_emis<C, float>(my_rsc, STRIDE, x, lane, r);
         // mpv(k) = M(i+1,k+1) * e(k+1): own nodes shifted down by one
         float me[C];
 #pragma unroll
@@ -411,7 +532,9 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
         float bsum = 0.f;
 #pragma unroll
         for (int c = 0; c < C; c++) bsum += me[c] * tBM[c];
-        float menext = __shfl_down_sync(FULL, me[0], 1); if (lane == 31) menext = 0.f;
+        xB = group_sum(warp_sum(bsum));                     // (W > 1: also orders the X[3] hand-over of the previous row)
+        float menext = __shfl_down_sync(FULL, me[0], 1);
+        if (lane == 31) menext = (W > 1 && wi < W - 1) ? X[3][wi + 1] * s_rscf[(size_t)x * STRIDE + (wi + 1) * 32 * C] : 0.f;
 #pragma unroll
         for (int c = 0; c < C; c++) {
           const float mpv = (c == C - 1) ? menext : me[c + 1];
@@ -420,17 +543,16 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
           Dv[c] = mpv * tDMn[c];
           Mv[c] = (ipv * tMI[c]) + (mpv * tMMn[c]);
         }
-        xB = warp_sum(bsum);
         xC = xC * ploop;
         xJ = (xB * pmove) + (xJ * ploop);
         xN = (xB * pmove) + (xN * ploop);
         xE = (xC * tEC) + (xJ * tEJ);
 #pragma unroll
-        for (int c = 0; c < C; c++) { const bool in = (lane * C + c) < M; Dv[c] = in ? Dv[c] + xE : 0.f; }
+        for (int c = 0; c < C; c++) { const bool in = (gl * C + c) < M; Dv[c] = in ? Dv[c] + xE : 0.f; }
         close_dd();
-        float dnext = __shfl_down_sync(FULL, Dv[0], 1); if (lane == 31) dnext = 0.f;
+        float dnext = __shfl_down_sync(FULL, Dv[0], 1); if (lane == 31) dnext = (W > 1) ? dext : 0.f;
 #pragma unroll
-        for (int c = 0; c < C; c++) { const bool in = (lane * C + c) < M; const float dn = (c == C - 1) ? dnext : Dv[c + 1]; Mv[c] = in ? (Mv[c] + xE) + tMD[c] * dn : 0.f; }
+        for (int c = 0; c < C; c++) { const bool in = (gl * C + c) < M; const float dn = (c == C - 1) ? dnext : Dv[c + 1]; Mv[c] = in ? (Mv[c] + xE) + tMD[c] * dn : 0.f; }
         if (xB > 1.0e16f) own_scales = true;
         const float scale = own_scales ? ((xB > 1.0e4f) ? xB : 1.0f) : fx[(size_t)i * 6 + 5];
         if (scale > 1.0f) {
@@ -440,19 +562,20 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
           for (int c = 0; c < C; c++) { Mv[c] *= inv; Dv[c] *= inv; Iv[c] *= inv; }
           totscale = (float)((double)totscale + log((double)scale));
         }
-        if (bx && lane == 0) { float *q = bx + (size_t)i * 6; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; q[5] = scale; }
+        if (bx && gl == 0) { float *q = bx + (size_t)i * 6; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; q[5] = scale; }
+        if (W > 1 && lane == 0) X[3][wi] = Mv[0];
       }
       {
         float r[C];
-        load_emis<C, float>(s_rscf, (int)seq[0], lane, r);
+        load_emis<C, float>(my_rsc, STRIDE, (int)seq[0], lane, r);
         float bsum = 0.f;
         if (L >= 1) {
 #pragma unroll
           for (int c = 0; c < C; c++) bsum += (Mv[c] * r[c]) * tBM[c];
         }
-        xB = warp_sum(bsum);
+        xB = group_sum(warp_sum(bsum));
         xN = (xB * pmove) + (xN * ploop);
-        if (lane == 0) {
+        if (gl == 0) {
           if (bx) { bx[0] = 0.f; bx[1] = xN; bx[2] = 0.f; bx[3] = xB; bx[4] = 0.f; bx[5] = 1.0f; }
           int st = B2H_OK; float sc;
           if (isnan(xN) || (L > 0 && xN == 0.0f) || isinf(xN)) { st = B2H_ERANGE; sc = isnan(xN) ? NAN : (xN == 0.0f ? -INFINITY : INFINITY); }
@@ -466,9 +589,9 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
 }
 
 template <typename K>
-int launch_reg(b2h_ctx *ctx, K kernel, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, const StageOut &out, cudaStream_t strm)
+int launch_reg(b2h_ctx *ctx, K kernel, int C, int W, const WorkList &wl, const SeqDev &sd, int nitems_hint, const StageOut &out, cudaStream_t strm)
 {
-  const size_t smem = (size_t)32 * 32 * C * 4;
+  const size_t smem = (size_t)32 * 32 * C * W * 4;
   B2H_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem));
@@ -485,25 +608,19 @@ int launch_reg(b2h_ctx *ctx, K kernel, int C, const WorkList &wl, const SeqDev &
 
 } // namespace
 
-// kind: 0 Viterbi, 1 Forward, 2 Backward.  C in {2,4,8,12,16}.
-int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm)
+// kind: 0 Viterbi, 1 Forward, 2 Backward.  (C, W): nodes per lane, warps per comparison -- see b2h_reg_class().
+int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, int W, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm)
 {
-  switch (kind * 32 + C) {
-    case 0 * 32 + 2: return launch_reg(ctx, rvit_kernel<2>, 2, wl, sd, nitems_hint, out, strm);
-    case 0 * 32 + 4: return launch_reg(ctx, rvit_kernel<4>, 4, wl, sd, nitems_hint, out, strm);
-    case 0 * 32 + 8: return launch_reg(ctx, rvit_kernel<8>, 8, wl, sd, nitems_hint, out, strm);
-    case 0 * 32 + 12: return launch_reg(ctx, rvit_kernel<12>, 12, wl, sd, nitems_hint, out, strm);
-    case 0 * 32 + 16: return launch_reg(ctx, rvit_kernel<16>, 16, wl, sd, nitems_hint, out, strm);
-    case 1 * 32 + 2: return launch_reg(ctx, rfwd_kernel<2>, 2, wl, sd, nitems_hint, out, strm);
-    case 1 * 32 + 4: return launch_reg(ctx, rfwd_kernel<4>, 4, wl, sd, nitems_hint, out, strm);
-    case 1 * 32 + 8: return launch_reg(ctx, rfwd_kernel<8>, 8, wl, sd, nitems_hint, out, strm);
-    case 1 * 32 + 12: return launch_reg(ctx, rfwd_kernel<12>, 12, wl, sd, nitems_hint, out, strm);
-    case 1 * 32 + 16: return launch_reg(ctx, rfwd_kernel<16>, 16, wl, sd, nitems_hint, out, strm);
-    case 2 * 32 + 2: return launch_reg(ctx, rbck_kernel<2>, 2, wl, sd, nitems_hint, out, strm);
-    case 2 * 32 + 4: return launch_reg(ctx, rbck_kernel<4>, 4, wl, sd, nitems_hint, out, strm);
-    case 2 * 32 + 8: return launch_reg(ctx, rbck_kernel<8>, 8, wl, sd, nitems_hint, out, strm);
-    case 2 * 32 + 12: return launch_reg(ctx, rbck_kernel<12>, 12, wl, sd, nitems_hint, out, strm);
-    case 2 * 32 + 16: return launch_reg(ctx, rbck_kernel<16>, 16, wl, sd, nitems_hint, out, strm);
+#define B2H_REG_CASE(CC, WW) \
+    case (WW) * 64 + (CC): \
+      if (kind == 0) return launch_reg(ctx, rvit_kernel<CC, WW>, CC, WW, wl, sd, nitems_hint, out, strm); \
+      if (kind == 1) return launch_reg(ctx, rfwd_kernel<CC, WW>, CC, WW, wl, sd, nitems_hint, out, strm); \
+      if (kind == 2) return launch_reg(ctx, rbck_kernel<CC, WW>, CC, WW, wl, sd, nitems_hint, out, strm); \
+      break;
+  switch (W * 64 + C) {
+    B2H_REG_CASE(2, 1) B2H_REG_CASE(4, 1) B2H_REG_CASE(8, 1) B2H_REG_CASE(12, 1) B2H_REG_CASE(16, 1)
+    B2H_REG_CASE(10, 2) B2H_REG_CASE(12, 2) B2H_REG_CASE(16, 2) B2H_REG_CASE(12, 4)
   }
+#undef B2H_REG_CASE
   return B2H_EINVAL;
 }

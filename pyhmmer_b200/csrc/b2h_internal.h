@@ -47,6 +47,7 @@ struct b2h_seqdb {
   int64_t   nres = 0;
   int       maxL = 0;
   size_t    arena_bytes = 0;
+  size_t    h2d_bytes = 0;         // bytes copied host->device when the database was made resident
   std::vector<int32_t> h_len;
   std::vector<uint8_t> h_res;      // host copy of the arena (domain definition reads residues)
   std::vector<int64_t> h_off;
@@ -89,8 +90,9 @@ struct b2h_profile {
   float compo[B2H_MAXABET];
   float bgf[B2H_MAXABET];
   float *d_bias_eo = nullptr;     // [32][2] bias-filter emission odds (esl_hmm_Configure)
-  int regC = 0;                   // nodes per lane of the register-resident DP kernels (2/4/8; 0 = model too long)
-  int32_t *d_vit_rsc32 = nullptr; // [32][regC/4][32][4] int32 emission scores, lane-grouped (b2h_dpreg.cu)
+  size_t h2d_bytes = 0;           // size of the single device block (= bytes uploaded)
+  int regC = 0, regW = 0;         // nodes per lane / warps per comparison of the register-resident DP kernels (0 = model too long)
+  int32_t *d_vit_rsc32 = nullptr; // [32][regW][regC/G][32][G] int32 emission scores, lane-grouped (b2h_dpreg.cu)
   float   *d_fwd_rscr = nullptr;  // same layout, fp32 odds ratios
   // host copies for the domain-definition stage
   std::vector<float> h_fwd_rsc, h_fwd_tsc;   // [Kp][M], [8][M] node-major odds ratios
@@ -205,7 +207,12 @@ struct StageOut { float *sc; int32_t *status; float *fwd_xmx, *bck_xmx; const in
 int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
-int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm);
+int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, int W, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm);
+// register-resident DP size classes: nodes per lane C and warps per comparison W for a model of M nodes (0,0: too long)
+struct b2h_regclass { int bound, C, W; };
+static const b2h_regclass B2H_REG_CLASSES[] = {{64, 2, 1}, {128, 4, 1}, {256, 8, 1}, {384, 12, 1}, {512, 16, 1},
+                                               {640, 10, 2}, {768, 12, 2}, {1024, 16, 2}, {1536, 12, 4}};
+static const int B2H_N_REG_CLASSES = 9;
 int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc);
 
 // A compacted list of comparisons produced by a stage's epilogue (device memory).  Appends are

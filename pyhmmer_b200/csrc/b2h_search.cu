@@ -20,7 +20,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <numeric>
+#include <thread>
 #include <vector>
 #include "b2h_internal.h"
 #include "b2h_domaindef.h"
@@ -229,8 +231,36 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
 
 // Forward + Backward parsers with stored special-state rows for the F3 survivors (sorted by profile),
 // chunked so that the specials of one chunk stay within a fixed budget; then host domain definition.
+// One chunk of survivors whose parser specials are on the host: the domain definition runs on the host thread pool
+// from a helper thread while the calling thread goes on feeding the GPU with the next wave of profiles.
+struct DdefJob {
+  std::vector<float> fx, bx; std::vector<int32_t> bst; std::vector<b2h_ddef_task> tasks;
+  std::thread th; int status = B2H_OK; double ms = 0.0;
+};
+struct DdefAsync {
+  b2h_ddef_pool &pool; const b2h_search_params *prm; b2h_results *res; std::unique_ptr<DdefJob> cur; double total_ms = 0.0;
+  DdefAsync(b2h_ddef_pool &p, const b2h_search_params *pr, b2h_results *r) : pool(p), prm(pr), res(r) {}
+  int join() {
+    if (!cur) return B2H_OK;
+    cur->th.join();
+    const int st = cur->status; total_ms += cur->ms;
+    if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search]   chunk of %zu survivors: host domain definition %.1f ms on %d threads\n", cur->tasks.size(), cur->ms, pool.nthreads);
+    cur.reset();
+    return st;
+  }
+  int launch(std::unique_ptr<DdefJob> job) {                 // at most one job in flight: the pool is not re-entrant
+    const int st = join();
+    if (st != B2H_OK) return st;
+    cur = std::move(job);
+    DdefJob *j = cur.get();
+    j->th = std::thread([this, j]() { const double t0 = now_ms(); j->status = pool.run(j->tasks, prm, res); j->ms = now_ms() - t0; });
+    return B2H_OK;
+  }
+  ~DdefAsync() { if (cur) cur->th.join(); }
+};
+
 static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, const b2h_search_params *prm,
-                            std::vector<b2h_survivor> &surv, b2h_results *res)
+                            std::vector<b2h_survivor> &surv, DdefAsync &ddef)
 {
   std::sort(surv.begin(), surv.end(), [&](const b2h_survivor &x, const b2h_survivor &y) {
     const int mx = profiles[x.profile]->Mpad, my = profiles[y.profile]->Mpad;
@@ -239,7 +269,6 @@ static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, co
   const SeqDev sd = b2h_seqdev(db);
   const size_t ROW_BUDGET = (size_t)32 << 20;        // rows of 6 floats per chunk (x2 matrices = 1.5 GB)
   size_t i0 = 0;
-  b2h_ddef_pool ddpool(prm->host_threads);
   while (i0 < surv.size()) {
     size_t i1 = i0, rows = 0;
     while (i1 < surv.size() && (i1 == i0 || rows + db->h_len[surv[i1].seq] + 1 <= ROW_BUDGET)) { rows += db->h_len[surv[i1].seq] + 1; i1++; }
@@ -276,14 +305,17 @@ static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, co
     StageOut sb; sb.sc = d_bsc; sb.status = d_bst; sb.fwd_xmx = d_fx; sb.bck_xmx = d_bx; sb.xoff = d_xoff;
     TRY(b2h_launch_backward(ctx, wl, sd, mpads, items, sb));
     delete tm;
-    std::vector<float> fx((size_t)acc * 6), bx((size_t)acc * 6); std::vector<int32_t> bst(n);
+    std::unique_ptr<DdefJob> job(new DdefJob());
+    std::vector<float> &fx = job->fx, &bx = job->bx; std::vector<int32_t> &bst = job->bst;
+    fx.resize((size_t)acc * 6); bx.resize((size_t)acc * 6); bst.resize(n);
     B2H_CUDA(cudaMemcpyAsync(fx.data(), d_fx, fx.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(bx.data(), d_bx, bx.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(bst.data(), d_bst, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     B2H_CUDA(cudaStreamSynchronize(ctx->stream));
     b2h_resolve_timers(ctx);
     // host-side domain definition, one task per survivor
-    std::vector<b2h_ddef_task> tasks(n);
+    std::vector<b2h_ddef_task> &tasks = job->tasks;
+    tasks.resize(n);
     for (int e = 0; e < n; e++) {
       b2h_ddef_task &t = tasks[e];
       const b2h_survivor &v = surv[i0 + e];
@@ -292,9 +324,7 @@ static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, co
       t.fx = fx.data() + (size_t)xoff[e] * 6; t.bx = bx.data() + (size_t)xoff[e] * 6;
       t.bck_own_scales = (bst[e] & 0x100) != 0;
     }
-    const double td0 = now_ms();
-    int st = ddpool.run(tasks, prm, res);
-    if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search]   chunk of %d survivors: host domain definition %.1f ms on %d threads\n", n, now_ms() - td0, ddpool.nthreads);
+    const int st = ddef.launch(std::move(job));
     if (st != B2H_OK) { ctx->err = "domain definition failed"; return st; }
     i0 = i1;
   }
@@ -312,22 +342,51 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
   b2h_results *res = new b2h_results();
   res->counters.assign(P * 4, 0);
   const size_t N = db->n;
-  std::vector<b2h_survivor> surv;
   if (N > 0 && P > 0) {
     const double t0 = now_ms();
+    // Profiles are processed longest first, in waves of about equal DP volume: while the host threads define the
+    // domains of one wave's survivors the GPU already runs the cascade of the next wave, and the wave whose host
+    // work cannot be hidden (the last) holds the shortest models.  Hits are re-sorted by (profile, target) at the end.
+    std::vector<int> order(P);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return profiles[a]->M > profiles[b]->M; });
+    std::vector<const b2h_profile *> sp(P);
+    double cells = 0.0;
+    for (size_t i = 0; i < P; i++) { sp[i] = profiles[order[i]]; cells += sp[i]->M; }
     const size_t CAP = (size_t)1 << 25;                 // comparisons per batch: every list is sized for the worst case
-    size_t pb = std::max<size_t>(1, CAP / N);
-    for (size_t p0 = 0; p0 < P; p0 += pb) {
-      const size_t p1 = std::min(P, p0 + pb);
-      int st = cascade_batch(ctx, profiles, (int)p0, (int)p1, db, prm, surv, res->counters.data());
-      if (st != B2H_OK) { delete res; return st; }
+    const size_t pb = std::max<size_t>(1, CAP / N);
+    int nwaves = (P >= 32) ? 4 : (P >= 8) ? 2 : 1;
+    if (const char *ev = getenv("B2H_WAVES")) nwaves = std::max(1, atoi(ev));
+    std::vector<size_t> bounds{0};                       // wave boundaries in sorted order
+    { double acc = 0.0; size_t start = 0; int slot = 1;
+      for (size_t i = 0; i < P; i++) {
+        acc += sp[i]->M;
+        if (i + 1 == P || i + 1 - start >= pb || acc >= cells * slot / nwaves) {
+          bounds.push_back(i + 1); start = i + 1;
+          while (slot < nwaves && acc >= cells * slot / nwaves) slot++;
+        }
+      } }
+    std::vector<int64_t> scnt(P * 4, 0);
+    b2h_ddef_pool ddpool(prm->host_threads);
+    DdefAsync ddef(ddpool, prm, res);
+    size_t nsurv = 0; double tg = 0.0;
+    for (size_t w = 0; w + 1 < bounds.size(); w++) {
+      std::vector<b2h_survivor> surv;
+      const double tw = now_ms();
+      int st = cascade_batch(ctx, sp.data(), (int)bounds[w], (int)bounds[w + 1], db, prm, surv, scnt.data());
+      if (st == B2H_OK) st = finish_survivors(ctx, sp.data(), db, prm, surv, ddef);
+      if (st != B2H_OK) { ddef.join(); delete res; return st; }
+      nsurv += surv.size(); tg += now_ms() - tw;
     }
     const double t1 = now_ms();
-    int st = finish_survivors(ctx, profiles, db, prm, surv, res);
-    if (st != B2H_OK) { delete res; return st; }
+    int st = ddef.join();
+    if (st != B2H_OK) { ctx->err = "domain definition failed"; delete res; return st; }
+    for (b2h_hit &h : res->hits) h.profile = order[h.profile];
+    for (size_t i = 0; i < P; i++) for (int c = 0; c < 4; c++) res->counters[(size_t)order[i] * 4 + c] = scnt[i * 4 + c];
     std::stable_sort(res->hits.begin(), res->hits.end(), [](const b2h_hit &x, const b2h_hit &y) {
       return x.profile != y.profile ? x.profile < y.profile : x.seq < y.seq; });
-    if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search] cascade %.1f ms, survivors(%zu) fwd/bck + domain definition %.1f ms\n", t1 - t0, surv.size(), now_ms() - t1);
+    if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search] %zu waves: GPU cascade + survivor parsers %.1f ms, %zu survivors, host domain definition %.1f ms in total (%.1f ms not hidden), all %.1f ms\n",
+                                     bounds.size() - 1, tg, nsurv, ddef.total_ms, now_ms() - t1, now_ms() - t0);
   }
   *out = res;
   return B2H_OK;

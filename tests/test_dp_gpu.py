@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 FB_TOL = 1e-4      # nats; north_star's bound, and HMMER's own Fwd==Bck contract (fwdback.c:925-927)
 
 
-@pytest.mark.parametrize("M", [1, 2, 7, 8, 9, 31, 32, 33, 64, 100, 200, 257, 500, 900])
+@pytest.mark.parametrize("M", [1, 2, 7, 8, 9, 31, 32, 33, 64, 100, 200, 257, 500, 513, 640, 641, 768, 900, 1024, 1025, 1300, 1536, 1600])
 def test_viterbi_bit_exact(ctx, amino, make_pair, M):
     rng = np.random.default_rng(2000 + M)
     pair = make_pair(synth.random_hmm(amino, M, rng))
@@ -26,7 +26,7 @@ def test_viterbi_bit_exact(ctx, amino, make_pair, M):
     print("M=%d: %d comparisons, %d overflowed" % (M, len(block), n_inf))
 
 
-@pytest.mark.parametrize("M", [1, 2, 9, 33, 64, 100, 200, 257, 500, 900])
+@pytest.mark.parametrize("M", [1, 2, 9, 33, 64, 100, 200, 257, 500, 513, 640, 641, 768, 900, 1024, 1025, 1300, 1536, 1600])
 def test_forward_backward_parsers(ctx, amino, make_pair, M):
     rng = np.random.default_rng(3000 + M)
     pair = make_pair(synth.random_hmm(amino, M, rng))
