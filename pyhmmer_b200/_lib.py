@@ -137,8 +137,9 @@ def read_results(handle):
     nd = lib.b2h_results_ndomains(handle)
     hp = lib.b2h_results_hits(handle)
     dp = lib.b2h_results_domains(handle)
-    hits = [HitRec.from_buffer_copy(hp[i]) for i in range(nh)]
-    doms = [DomainRec.from_buffer_copy(dp[i]) for i in range(nd)]
+    # one copy per record array; the list elements are views into those copies
+    hits = list((HitRec * nh).from_buffer_copy(ctypes.string_at(hp, nh * ctypes.sizeof(HitRec)))) if nh else []
+    doms = list((DomainRec * nd).from_buffer_copy(ctypes.string_at(dp, nd * ctypes.sizeof(DomainRec)))) if nd else []
     nb = c_size_t()
     tp = lib.b2h_results_text(handle, ctypes.byref(nb))
     text = ctypes.string_at(tp, nb.value) if nb.value else b""

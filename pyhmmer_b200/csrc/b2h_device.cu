@@ -1,7 +1,10 @@
 // b2h_device.cu -- context, sequence arena and profile upload for libb2h.so.
+#include <cuda_fp16.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include "b2h_internal.h"
 
 extern "C" {
@@ -22,6 +25,7 @@ int b2h_ctx_create(int device, b2h_ctx **out)
   ctx->sm_count = prop.multiProcessorCount;
   B2H_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
+  if (const char *ev = getenv("B2H_SSV_INT16")) ctx->ssv_fp16 = (atoi(ev) == 0);
   B2H_CUDA(cudaMalloc(&ctx->d_counters, 64 * sizeof(int)));
   {  // keep stream-ordered allocations cached across searches instead of returning them to the driver at every sync
     cudaMemPool_t pool; uint64_t keep = ~0ull;
@@ -36,6 +40,7 @@ void b2h_ctx_destroy(b2h_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  for (auto &pf : ctx->pinned_free) cudaFreeHost(pf.first);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   for (cudaStream_t q : ctx->side) cudaStreamDestroy(q);
   for (cudaEvent_t e : ctx->side_done) cudaEventDestroy(e);
@@ -71,61 +76,22 @@ uint64_t    b2h_ctx_launch_count(const b2h_ctx *ctx) { return ctx ? ctx->launche
 // ------------------------------------------------------------------------------------------
 // sequence arena
 // ------------------------------------------------------------------------------------------
-static int seqdb_finish(b2h_ctx *ctx, b2h_seqdb *db, const std::vector<uint8_t> &arena)
+static void *pinned_get(b2h_ctx *ctx, size_t bytes, size_t *cap)
 {
-  const size_t n = db->n;
-  std::vector<int32_t> order(n);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return db->h_len[a] > db->h_len[b]; });
-
-  std::vector<uint8_t> tjb(n); std::vector<int16_t> xwm(n);
-  std::vector<float> pmove(n), null1(n), p1(n), flta(n), fltb(n);
-  // L-dependent scalars depend on L only: memoise (databases have few distinct lengths)
-  std::vector<int> cacheL; std::vector<b2h_len_params> cacheP;
-  {
-    std::vector<int32_t> lens(db->h_len);
-    std::sort(lens.begin(), lens.end());
-    lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
-    cacheL.assign(lens.begin(), lens.end());
-    cacheP.resize(cacheL.size());
-    for (size_t i = 0; i < cacheL.size(); i++) b2h_length_params(cacheL[i], 1.0f, &cacheP[i]);
+  size_t best = (size_t)-1;
+  for (size_t i = 0; i < ctx->pinned_free.size(); i++)
+    if (ctx->pinned_free[i].second >= bytes && (best == (size_t)-1 || ctx->pinned_free[i].second < ctx->pinned_free[best].second)) best = i;
+  if (best != (size_t)-1) {
+    void *p = ctx->pinned_free[best].first; *cap = ctx->pinned_free[best].second;
+    ctx->pinned_free.erase(ctx->pinned_free.begin() + best);
+    return p;
   }
-  for (size_t s = 0; s < n; s++) {
-    size_t i = std::lower_bound(cacheL.begin(), cacheL.end(), db->h_len[s]) - cacheL.begin();
-    const b2h_len_params &q = cacheP[i];
-    tjb[s] = q.tjb_b; xwm[s] = q.xw_move; pmove[s] = q.pmove; null1[s] = q.null1; p1[s] = q.p1;
-    flta[s] = q.flt_len_a; fltb[s] = q.flt_len_b;
-  }
-  db->arena_bytes = arena.size();
-  B2H_CUDA(cudaSetDevice(ctx->device));
-  B2H_CUDA(cudaMalloc(&db->d_res, std::max<size_t>(arena.size(), 16)));
-  B2H_CUDA(cudaMalloc(&db->d_off, (n + 1) * sizeof(int64_t)));
-  B2H_CUDA(cudaMalloc(&db->d_len, std::max<size_t>(n, 1) * sizeof(int32_t)));
-  B2H_CUDA(cudaMalloc(&db->d_order, std::max<size_t>(n, 1) * sizeof(int32_t)));
-  B2H_CUDA(cudaMalloc(&db->d_tjb, std::max<size_t>(n, 1)));
-  B2H_CUDA(cudaMalloc(&db->d_xwmove, std::max<size_t>(n, 1) * sizeof(int16_t)));
-  B2H_CUDA(cudaMalloc(&db->d_pmove, std::max<size_t>(n, 1) * sizeof(float)));
-  B2H_CUDA(cudaMalloc(&db->d_null1, std::max<size_t>(n, 1) * sizeof(float)));
-  B2H_CUDA(cudaMalloc(&db->d_p1, std::max<size_t>(n, 1) * sizeof(float)));
-  B2H_CUDA(cudaMalloc(&db->d_flta, std::max<size_t>(n, 1) * sizeof(float)));
-  B2H_CUDA(cudaMalloc(&db->d_fltb, std::max<size_t>(n, 1) * sizeof(float)));
-  cudaStream_t st = ctx->stream;
-  db->h2d_bytes = arena.size() + (n + 1) * sizeof(int64_t) + n * (size_t)(4 + 4 + 1 + 2 + 4 * 5);
-  if (!arena.empty()) B2H_CUDA(cudaMemcpyAsync(db->d_res, arena.data(), arena.size(), cudaMemcpyHostToDevice, st));
-  B2H_CUDA(cudaMemcpyAsync(db->d_off, db->h_off.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  if (n) {
-    B2H_CUDA(cudaMemcpyAsync(db->d_len, db->h_len.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    B2H_CUDA(cudaMemcpyAsync(db->d_order, order.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    B2H_CUDA(cudaMemcpyAsync(db->d_tjb, tjb.data(), n, cudaMemcpyHostToDevice, st));
-    B2H_CUDA(cudaMemcpyAsync(db->d_xwmove, xwm.data(), n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-    B2H_CUDA(cudaMemcpyAsync(db->d_pmove, pmove.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
-    B2H_CUDA(cudaMemcpyAsync(db->d_null1, null1.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
-    B2H_CUDA(cudaMemcpyAsync(db->d_p1, p1.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
-    B2H_CUDA(cudaMemcpyAsync(db->d_flta, flta.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
-    B2H_CUDA(cudaMemcpyAsync(db->d_fltb, fltb.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
-  }
-  B2H_CUDA(cudaStreamSynchronize(st));     // host staging vectors die here
-  return B2H_OK;
+  for (auto &pf : ctx->pinned_free) cudaFreeHost(pf.first);      // too small for this database: do not hoard them
+  ctx->pinned_free.clear();
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  *cap = bytes;
+  return p;
 }
 
 static int seqdb_build(b2h_ctx *ctx, size_t n, const int64_t *len,
@@ -146,15 +112,100 @@ static int seqdb_build(b2h_ctx *ctx, size_t n, const int64_t *len,
     if (L % 16 == 0) total += 16;           // always at least one pad byte after the last residue
   }
   db->h_off[n] = (int64_t)total;
-  std::vector<uint8_t> arena(total, (uint8_t)B2H_PAD_CODE);
-  for (size_t s = 0; s < n; s++) {
-    const uint8_t *src = poff ? packed + poff[s] : dsq[s] + 1;      // Easel dsq is 1-based
-    uint8_t *dst = arena.data() + db->h_off[s];
-    for (int32_t i = 0; i < db->h_len[s]; i++) dst[i] = src[i] < B2H_NCODE ? src[i] : (uint8_t)B2H_PAD_CODE;
+  db->arena_bytes = total;
+
+  // block layout
+  const size_t n1 = std::max<size_t>(n, 1);
+  size_t o = 0;
+  auto sect = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
+  const size_t o_res = sect(std::max<size_t>(total, 16)), o_off = sect((n + 1) * sizeof(int64_t)), o_len = sect(n1 * 4), o_ord = sect(n1 * 4),
+               o_tjb = sect(n1), o_xwm = sect(n1 * 2), o_pmv = sect(n1 * 4), o_nl1 = sect(n1 * 4), o_p1 = sect(n1 * 4),
+               o_fa = sect(n1 * 4), o_fb = sect(n1 * 4);
+  db->block_bytes = o;
+  B2H_CUDA(cudaSetDevice(ctx->device));
+  db->h_block = (uint8_t *)pinned_get(ctx, o, &db->h_block_cap);
+  if (!db->h_block) { delete db; ctx->err = "cudaHostAlloc failed"; return B2H_EMEM; }
+  uint8_t *hb = db->h_block;
+  db->h_res = hb + o_res;
+
+  // residues: clamp codes to the 32-row tables, pad each sequence to its 16-byte boundary
+  {
+    auto fill = [&](size_t s0, size_t s1) {
+      for (size_t s = s0; s < s1; s++) {
+        const uint8_t *src = poff ? packed + poff[s] : dsq[s] + 1;      // Easel dsq is 1-based
+        uint8_t *dst = hb + o_res + db->h_off[s];
+        const int32_t L = db->h_len[s];
+        for (int32_t i = 0; i < L; i++) dst[i] = src[i] < B2H_NCODE ? src[i] : (uint8_t)B2H_PAD_CODE;
+        const int64_t end = db->h_off[s + 1] - db->h_off[s];
+        for (int64_t i = L; i < end; i++) dst[i] = (uint8_t)B2H_PAD_CODE;
+      }
+    };
+    const int T = (total > ((size_t)4 << 20)) ? (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (T <= 1) fill(0, n);
+    else {
+      std::vector<std::thread> th;
+      size_t s0 = 0;
+      for (int t = 0; t < T; t++) {                                     // contiguous ranges of about equal bytes
+        size_t s1 = s0;
+        const int64_t want = (int64_t)(total * (size_t)(t + 1) / T);
+        if (t == T - 1) s1 = n; else { s1 = std::upper_bound(db->h_off.begin() + s0, db->h_off.begin() + n, want) - db->h_off.begin(); s1 = std::min(std::max(s1, s0), n); }
+        th.emplace_back(fill, s0, s1);
+        s0 = s1;
+      }
+      for (auto &t : th) t.join();
+    }
+    if (total < 16) memset(hb + o_res + total, B2H_PAD_CODE, 16 - total);
   }
-  int st = seqdb_finish(ctx, db, arena);
-  db->h_res.swap(arena);
-  if (st != B2H_OK) { b2h_seqdb_destroy(db); return st; }
+  memcpy(hb + o_off, db->h_off.data(), (n + 1) * sizeof(int64_t));
+  if (n) memcpy(hb + o_len, db->h_len.data(), n * 4);
+
+  // order[]: sequence indices by decreasing length (stable) -- counting sort when the length range is small
+  {
+    int32_t *order = (int32_t *)(hb + o_ord);
+    if ((size_t)db->maxL <= 8 * n + 4096) {
+      std::vector<int32_t> start((size_t)db->maxL + 2, 0);
+      for (size_t s = 0; s < n; s++) start[db->maxL - db->h_len[s] + 1]++;
+      for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
+      for (size_t s = 0; s < n; s++) order[start[db->maxL - db->h_len[s]]++] = (int32_t)s;
+    } else {
+      std::iota(order, order + n, 0);
+      std::stable_sort(order, order + n, [&](int a, int b) { return db->h_len[a] > db->h_len[b]; });
+    }
+  }
+  // L-dependent scalars depend on L only: memoise (databases have few distinct lengths)
+  {
+    uint8_t *tjb = hb + o_tjb; int16_t *xwm = (int16_t *)(hb + o_xwm);
+    float *pmove = (float *)(hb + o_pmv), *null1 = (float *)(hb + o_nl1), *p1 = (float *)(hb + o_p1), *flta = (float *)(hb + o_fa), *fltb = (float *)(hb + o_fb);
+    std::vector<int32_t> lens(db->h_len);
+    std::vector<int32_t> slot;
+    std::vector<b2h_len_params> cacheP;
+    const bool direct = (size_t)db->maxL <= 8 * n + 4096;
+    if (direct) slot.assign((size_t)db->maxL + 1, -1);
+    else { std::sort(lens.begin(), lens.end()); lens.erase(std::unique(lens.begin(), lens.end()), lens.end()); cacheP.resize(lens.size()); for (size_t i = 0; i < lens.size(); i++) b2h_length_params(lens[i], 1.0f, &cacheP[i]); }
+    for (size_t s = 0; s < n; s++) {
+      const int32_t L = db->h_len[s];
+      size_t i;
+      if (direct) { if (slot[L] < 0) { slot[L] = (int32_t)cacheP.size(); cacheP.emplace_back(); b2h_length_params(L, 1.0f, &cacheP.back()); } i = slot[L]; }
+      else i = std::lower_bound(lens.begin(), lens.end(), L) - lens.begin();
+      const b2h_len_params &q = cacheP[i];
+      tjb[s] = q.tjb_b; xwm[s] = q.xw_move; pmove[s] = q.pmove; null1[s] = q.null1; p1[s] = q.p1;
+      flta[s] = q.flt_len_a; fltb[s] = q.flt_len_b;
+    }
+  }
+
+  // one stream-ordered allocation, one H2D copy (the pinned source lives as long as the database)
+  cudaError_t e;
+  if ((e = cudaMallocAsync((void **)&db->d_block, db->block_bytes, ctx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(db->d_block, hb, db->block_bytes, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+    ctx->err = std::string("sequence database upload: ") + cudaGetErrorString(e);
+    b2h_seqdb_destroy(db);
+    return B2H_ECUDA;
+  }
+  db->h2d_bytes = db->block_bytes;
+  uint8_t *b = db->d_block;
+  db->d_res = b + o_res; db->d_off = (int64_t *)(b + o_off); db->d_len = (int32_t *)(b + o_len); db->d_order = (int32_t *)(b + o_ord);
+  db->d_tjb = b + o_tjb; db->d_xwmove = (int16_t *)(b + o_xwm); db->d_pmove = (float *)(b + o_pmv); db->d_null1 = (float *)(b + o_nl1);
+  db->d_p1 = (float *)(b + o_p1); db->d_flta = (float *)(b + o_fa); db->d_fltb = (float *)(b + o_fb);
   *out = db;
   return B2H_OK;
 }
@@ -168,10 +219,15 @@ int b2h_seqdb_create_packed(b2h_ctx *ctx, const uint8_t *residues, const int64_t
 void b2h_seqdb_destroy(b2h_seqdb *db)
 {
   if (!db) return;
-  if (db->ctx) cudaSetDevice(db->ctx->device);
-  void *ptrs[] = { db->d_res, db->d_off, db->d_len, db->d_order, db->d_tjb, db->d_xwmove, db->d_pmove,
-                   db->d_null1, db->d_p1, db->d_flta, db->d_fltb };
-  for (void *p : ptrs) if (p) cudaFree(p);
+  b2h_ctx *ctx = db->ctx;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (db->d_block) { if (ctx) cudaFreeAsync(db->d_block, ctx->stream); else cudaFree(db->d_block); }
+  if (db->h_block) {
+    if (ctx) {
+      cudaStreamSynchronize(ctx->stream);             // the H2D copy of this block may still be in flight
+      ctx->pinned_free.emplace_back((void *)db->h_block, db->h_block_cap);
+    } else cudaFreeHost(db->h_block);
+  }
   delete db;
 }
 size_t  b2h_seqdb_nseq(const b2h_seqdb *db) { return db ? db->n : 0; }
@@ -229,7 +285,10 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
         // SSV subtracts sbv = clamp(cost - bias, .., 127) as a signed byte (p7_oprofile.c:721-761): add its negation
         int slo = -std::min(clo - (int)d->bias_b, 127), shi = -std::min(chi - (int)d->bias_b, 127);
         size_t w = striped_word_index(NR, x, j, lane);
-        ssv[w] = ((uint32_t)(uint16_t)(int16_t)shi << 16) | (uint32_t)(uint16_t)(int16_t)slo;
+        if (ctx && ctx->ssv_fp16)   // the same integers as fp16 bit patterns (exact: |score| <= 127)
+          ssv[w] = ((uint32_t)__half_as_ushort(__float2half_rn((float)shi)) << 16) | (uint32_t)__half_as_ushort(__float2half_rn((float)slo));
+        else
+          ssv[w] = ((uint32_t)(uint16_t)(int16_t)shi << 16) | (uint32_t)(uint16_t)(int16_t)slo;
       }
 
   // --- Viterbi / Forward tables, padded ---
@@ -304,7 +363,7 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
     cudaError_t e;
     p->h2d_bytes = stage.size();
     cudaSetDevice(ctx->device);
-    if ((e = cudaMalloc(&p->d_block, stage.size())) != cudaSuccess ||
+    if ((e = cudaMallocAsync((void **)&p->d_block, stage.size(), ctx->stream)) != cudaSuccess ||
         (e = cudaMemcpyAsync(p->d_block, stage.data(), stage.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
       ctx->err = cudaGetErrorString(e); st = B2H_ECUDA;        // (pageable source: the copy is staged before the call returns)
     } else {
@@ -324,7 +383,7 @@ void b2h_profile_destroy(b2h_profile *p)
 {
   if (!p) return;
   if (p->ctx) cudaSetDevice(p->ctx->device);
-  if (p->d_block) cudaFree(p->d_block);
+  if (p->d_block) { if (p->ctx) cudaFreeAsync(p->d_block, p->ctx->stream); else cudaFree(p->d_block); }
   delete p;
 }
 

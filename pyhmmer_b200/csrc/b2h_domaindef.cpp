@@ -916,7 +916,7 @@ class ThreadPool {
 
 b2h_ddef_pool::b2h_ddef_pool(int n)
 {
-  if (n <= 0) n = (int)std::thread::hardware_concurrency();
+  if (n <= 0) n = (int)std::thread::hardware_concurrency() - 2;   // leave room for the thread that feeds the GPU
   nthreads = std::max(1, std::min(n, 128));
 }
 

@@ -34,11 +34,14 @@ struct b2h_ctx {
   uint64_t      launches = 0;
   int          *d_counters = nullptr;   // small pool of work counters
   int           profiling = 0;
+  int           ssv_fp16 = 1;          // SSV cells as fp16x2 (HFMA2.RELU) instead of s16x2 (VIADDMNMX); B2H_SSV_INT16=1 selects the latter
   // side streams: independent launches of one stage (size classes) run concurrently, forked from / joined to <stream>
   std::vector<cudaStream_t> side; std::vector<cudaEvent_t> side_done; cudaEvent_t fork_ev = nullptr; int side_used = 0;
   double        stage_ms[8] = {0};
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_open;   // (stage, begin, end) awaiting a sync
+  // page-locked host buffers of destroyed sequence databases, kept for the next one (pinning costs ~0.3 ms/MB)
+  std::vector<std::pair<void *, size_t>> pinned_free;
 };
 
 struct b2h_seqdb {
@@ -49,8 +52,12 @@ struct b2h_seqdb {
   size_t    arena_bytes = 0;
   size_t    h2d_bytes = 0;         // bytes copied host->device when the database was made resident
   std::vector<int32_t> h_len;
-  std::vector<uint8_t> h_res;      // host copy of the arena (domain definition reads residues)
   std::vector<int64_t> h_off;
+  // One page-locked host block and one device block with the same layout: arena | off | len | order | tjb | xwmove |
+  // pmove | null1 | p1 | flta | fltb (sections 256-byte aligned), moved by a single H2D copy.
+  uint8_t  *h_block = nullptr; size_t h_block_cap = 0;
+  uint8_t  *d_block = nullptr; size_t block_bytes = 0;
+  const uint8_t *h_res = nullptr;  // host copy of the arena inside h_block (domain definition reads residues)
   uint8_t  *d_res = nullptr;
   int64_t  *d_off = nullptr;
   int32_t  *d_len = nullptr;

@@ -20,6 +20,7 @@
 // otherwise (eslENORESULT) the comparison is redone by the full MSV recurrence with saturating
 // uint8 arithmetic; overflow returns +inf/eslERANGE.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cmath>
 #include "b2h_internal.h"
 
@@ -123,7 +124,19 @@ __device__ __forceinline__ void ssv_finish(int maxw, const ProfDev &p, int tjb, 
 // Work item = (profile, chunk of B2H_SSV_CHUNK sequences in length-sorted order), profile-major, so
 // a persistent CTA re-stages the emission table only when it crosses a profile boundary.
 // ------------------------------------------------------------------------------------------------
-template <int NR>
+// H = true: cells are packed fp16x2 instead of s16x2.  Every value of the recurrence is an integer of magnitude
+// < 2048 until a comparison has overflowed anyway, so fp16 arithmetic is exact, and the update
+// max(m + e, 0) becomes ONE HFMA2.RELU on the FMA pipe (128 lanes/clk/SM) instead of one VIADDMNMX on the ALU pipe
+// (64 lanes/clk/SM), which is the pipe this kernel saturates.  Non-negative fp16 values order like their bit
+// patterns, so the running maximum stays an integer VIMNMX3 over the same registers.
+__device__ __forceinline__ uint32_t hfma2_relu_add(uint32_t m, uint32_t e)
+{
+  uint32_t r;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(m), "r"(0x3c003c00u), "r"(e));
+  return r;
+}
+
+template <int NR, bool H>
 __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
 {
   extern __shared__ __align__(128) uint32_t s_tab[];      // [32 residues][NR*32 words]
@@ -182,8 +195,8 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
             const uint32_t t  = __shfl_sync(FULL, m[NR-1], src_lane);
             const uint32_t s0 = __byte_perm(t, m[NR-1], 0x5432u);     // lo <- previous lane's last cell, hi <- own cell NR-1
 #pragma unroll
-            for (int j = NR - 1; j >= 1; j--) m[j] = __viaddmax_s16x2(m[j-1], ev[j], zero);
-            m[0] = __viaddmax_s16x2(s0, ev[0], zero);
+            for (int j = NR - 1; j >= 1; j--) m[j] = H ? hfma2_relu_add(m[j-1], ev[j]) : __viaddmax_s16x2(m[j-1], ev[j], zero);
+            m[0] = H ? hfma2_relu_add(s0, ev[0]) : __viaddmax_s16x2(s0, ev[0], zero);
 #pragma unroll
             for (int j = 0; j + 1 < NR; j += 2) xe = __vimax3_s16x2(xe, m[j], m[j+1]);
             if (NR & 1) xe = __vimax3_s16x2(xe, m[NR-1], m[NR-1]);
@@ -192,6 +205,10 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
       }
       int v = max((int)(xe & 0xffffu), (int)(xe >> 16));
       v = __reduce_max_sync(FULL, v);
+      if (H) {                                               // fp16 bit pattern (>= +0) -> integer value; inf -> "overflowed"
+        const float f = __half2float(__ushort_as_half((unsigned short)v));
+        v = (f > 30000.0f) ? 30000 : (int)f;
+      }
       if (lane == 0) {
         float sc; int status;
         ssv_finish(v, P, (int)a.sd.tjb[s], sc, status);
@@ -328,18 +345,18 @@ __global__ void group_scatter_kernel(const SurvList in, const int32_t *poff, int
   }
 }
 
-template <int NR>
+template <int NR, bool H>
 int launch_ssv_nr(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
 {
   const size_t smem = (size_t)B2H_NCODE * NR * 128;
-  B2H_CUDA(cudaFuncSetAttribute(ssv_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2H_CUDA(cudaFuncSetAttribute(ssv_kernel<NR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
-  B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ssv_kernel<NR>, SSV_THREADS, smem));
+  B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ssv_kernel<NR, H>, SSV_THREADS, smem));
   if (occ < 1) occ = 1;
   int grid = ctx->sm_count * occ;
   const long long nitems = (long long)a.ncls * a.chunks;
   if (grid > nitems) grid = (int)(nitems > 0 ? nitems : 1);
-  ssv_kernel<NR><<<grid, SSV_THREADS, smem, strm>>>(a);
+  ssv_kernel<NR, H><<<grid, SSV_THREADS, smem, strm>>>(a);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());
   return B2H_OK;
@@ -352,7 +369,7 @@ int b2h_launch_ssv(b2h_ctx *ctx, int NR, const SsvArgs &a, cudaStream_t strm)
   if (a.ncls <= 0 || a.sd.n <= 0) return B2H_OK;
   B2H_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), strm));
   switch (NR) {
-#define CASE(n) case n: return launch_ssv_nr<n>(ctx, a, strm);
+#define CASE(n) case n: return ctx->ssv_fp16 ? launch_ssv_nr<n, true>(ctx, a, strm) : launch_ssv_nr<n, false>(ctx, a, strm);
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(10) CASE(12) CASE(16) CASE(20) CASE(24) CASE(32) CASE(40) CASE(48)
 #undef CASE
   }

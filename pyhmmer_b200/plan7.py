@@ -587,17 +587,29 @@ class SequenceDatabase:
 # Results: TopHits / Hit / Domain / Alignment   (reference: plan7.pyx 8312-9278, 1850-2234, 1441-1687, 229-425)
 # =====================================================================================================
 class Alignment:
-    """Alignment of one domain to the model (``P7_ALIDISPLAY``)."""
+    """Alignment of one domain to the model (``P7_ALIDISPLAY``).  The text lines are decoded on first access."""
 
     def __init__(self, domain, rec, text):
         self.domain = domain
-        n, off = rec.N, rec.text_offset
-        f = [text[off + i * (n + 1): off + i * (n + 1) + n].decode("ascii") for i in range(4 + rec.has_rf + rec.has_cs)]
-        self.hmm_sequence, self.identity_sequence, self.target_sequence, self.posterior_probabilities = f[:4]
-        self.hmm_reference = f[4] if rec.has_rf else None
-        self.hmm_consensus_structure = f[4 + rec.has_rf] if rec.has_cs else None
+        self._rec, self._text, self._lines = rec, text, None
         self.hmm_from, self.hmm_to = rec.hmmfrom, rec.hmmto
         self.target_from, self.target_to = rec.sqfrom, rec.sqto
+
+    def _line(self, i):
+        f = self._lines
+        if f is None:
+            rec, text = self._rec, self._text
+            n, off = rec.N, rec.text_offset
+            f = self._lines = [text[off + j * (n + 1): off + j * (n + 1) + n].decode("ascii")
+                               for j in range(4 + rec.has_rf + rec.has_cs)]
+        return f[i]
+
+    hmm_sequence = property(lambda self: self._line(0))
+    identity_sequence = property(lambda self: self._line(1))
+    target_sequence = property(lambda self: self._line(2))
+    posterior_probabilities = property(lambda self: self._line(3))
+    hmm_reference = property(lambda self: self._line(4) if self._rec.has_rf else None)
+    hmm_consensus_structure = property(lambda self: self._line(4 + self._rec.has_rf) if self._rec.has_cs else None)
 
     hmm_name = property(lambda self: self.domain.hit.hits.query.name)
     hmm_accession = property(lambda self: self.domain.hit.hits.query.accession)
@@ -606,7 +618,7 @@ class Alignment:
     target_length = property(lambda self: self.domain.hit.length)
 
     def __len__(self):
-        return len(self.hmm_sequence)
+        return self._rec.N
 
 
 class Domain:
