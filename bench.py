@@ -244,7 +244,7 @@ def main():
     e2e_phases = []
 
     def one_step_e2e():
-        seqs._cache = {k: v for k, v in seqs._cache.items() if k == "packed"}   # host buffers stay; drop the device copy: re-upload
+        seqs._cache = {k: v for k, v in seqs._cache.items() if k in ("packed", "nres")}   # host buffers stay; drop the device copy: re-upload
         for om in oms:
             om._dev = {}                                           # re-upload the profile tables
         t0 = time.perf_counter()
@@ -265,6 +265,7 @@ def main():
 
     sampler = ClockSampler(local)
     times, stage_acc = [], {}
+    host_split = []
     launches0 = 0
     hits = counters = None
     for it in range(args.warmup + args.steps):
@@ -277,11 +278,14 @@ def main():
             launches0 = ctx.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        tw0 = time.perf_counter()
         hits, counters = one_step_resident()
+        tw1 = time.perf_counter()
         e1.record(stream)
         barrier()
         if it >= args.warmup:
             times.append(e0.elapsed_time(e1))
+            host_split.append((tw1 - tw0,) + tuple(pli._last_run_s))
     clocks = sampler.stop()
     stage_ms = ctx.stage_ms(reset=True)
     ctx.set_profiling(False)
@@ -309,6 +313,9 @@ def main():
         if it >= 2:
             e2e_times.append(dt)
     if rank == 0:
+        hs = np.array(host_split) * 1e3
+        print("[bench] resident step, host wall ms (whole step, handles, b2h_search, reading results): mean %s; device-event ms %s"
+              % (np.round(hs.mean(0), 2).tolist(), np.round(times, 1).tolist()), file=sys.stderr)
         ph = np.array(e2e_phases[2:]) * 1e3
         print("[bench] e2e phases ms (seqdb upload, profile upload, search+D2H, TopHits assembly): mean %s, per step %s"
               % (np.round(ph.mean(0), 1).tolist(), np.round(ph.sum(1), 1).tolist()), file=sys.stderr)

@@ -229,7 +229,10 @@ class DigitalSequenceBlock(list):
 
     @property
     def total_residues(self):
-        return sum(len(s) for s in self)
+        n = self._cache.get("nres")
+        if n is None:
+            n = self._cache["nres"] = sum(len(s) for s in self)
+        return n
 
     def _packed(self):
         hit = self._cache.get("packed")

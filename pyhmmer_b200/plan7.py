@@ -11,6 +11,7 @@ Profile 7767-8310, OptimizedProfile 4392-5070, Pipeline 5423-6906, TopHits 8312-
 """
 import ctypes
 import math
+import time
 import os
 
 import numpy as np
@@ -895,20 +896,24 @@ class Pipeline:
 
     def _run(self, oms, block):
         ctx = self._ctx
+        t0 = time.perf_counter()
         db = SequenceDatabase.of(ctx, block)
         handles = (ctypes.c_void_p * len(oms))(*[om._device(ctx) for om in oms])
         prm = self._params_struct()
         out = ctypes.c_void_p()
+        t1 = time.perf_counter()
         st = lib.b2h_search(ctx.handle, handles, len(oms), db.handle, ctypes.byref(prm), ctypes.byref(out))
+        t2 = time.perf_counter()
         if st == _lib.B2H_ERANGE:
             raise OverflowError("numerical overflow in the optimized vector implementation")
         check(st, "b2h_search", ctx.handle)
         try:
             hits, doms, text = _lib.read_results(out)
             cp = lib.b2h_results_counters(out)
-            counters = np.array([cp[i] for i in range(4 * len(oms))], dtype=np.int64).reshape(len(oms), 4)
+            counters = np.ctypeslib.as_array(cp, shape=(len(oms), 4)).copy()
         finally:
             lib.b2h_results_destroy(out)
+        self._last_run_s = (t1 - t0, t2 - t1, time.perf_counter() - t2)    # (uploads / handles, b2h_search, reading the results)
         return hits, doms, text, counters
 
     def _admit(self, th, rec, target, doms, text, Z_running, cut):
