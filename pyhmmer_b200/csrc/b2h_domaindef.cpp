@@ -18,7 +18,9 @@
 // Moving the envelope DP to the GPU is SURVEY 8(f) rank 1 (next round).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <condition_variable>
@@ -86,10 +88,13 @@ struct Model {               // host view of one profile in a given uni/multihit
   int M, K, Kp;
   const float *rsc;          // [Kp][M]
   const float *t[8];         // node-major transition rows, index k-1
+  const float *zrow;         // M zeros: the emission row of residue codes outside the table
+  const float *pf_up, *pf_dn;// blocked prefix products of tDD for the D->D chains (index n = node, see chain_up / chain_down)
   float eM, eL;              // xf[E][MOVE], xf[E][LOOP]
   float pmove, ploop;        // xf[N|C|J][MOVE|LOOP]
   const uint8_t *degen;
   float r(int x, int k) const { return (x < Kp) ? rsc[(size_t)x * M + (k - 1)] : 0.0f; }
+  const float *rrow(int x) const { return (x < Kp) ? rsc + (size_t)x * M : zrow; }      // index k-1
 };
 
 void configure(Model &m, bool multihit, int L) {
@@ -99,53 +104,112 @@ void configure(Model &m, bool multihit, int L) {
   m.ploop = 1.0f - m.pmove;
 }
 
-struct Mx {                  // full DP matrix: rows 0..L, nodes 0..M (node 0 unused), cells {M,D,I}; specials per row
-  int M = 0, L = 0;
-  std::vector<float> dp, x;
+// Full DP matrix: rows 0..L; every row is three planes {M, D, I} of S floats (node k at index k, node 0 and node M+1
+// are guards), so that the recurrences are unit-stride loops the compiler vectorises.  Specials per row in x.
+struct Mx {
+  int M = 0, L = 0; size_t S = 0;
+  std::vector<float> dp, x, rs;          // rs: per-row factor of a posterior matrix (see backward_decode)
   float totscale = 0.f; bool own_scales = false;
   // grow-only; only row 0 and the two guard columns (node 0 and node M+1) of every row are cleared: every other
   // cell that a recurrence reads has been written by the same pass before
-  void resize(int M_, int L_) {
-    M = M_; L = L_;
-    const size_t need = (size_t)(L + 1) * (M + 2) * 3, needx = (size_t)(L + 1) * NX;
+  void resize(int M_, int L_, bool with_cells = true) {
+    M = M_; L = L_; S = ((size_t)M + 2 + 15) & ~(size_t)15;
+    const size_t need = with_cells ? (size_t)(L + 1) * S * 3 : 0, needx = (size_t)(L + 1) * NX;
     if (dp.size() < need) dp.resize(need);
     if (x.size() < needx) x.resize(needx);
-    std::fill(dp.begin(), dp.begin() + (size_t)(M + 2) * 3, 0.0f);
-    for (int i = 1; i <= L; i++) { float *r = row(i); r[0] = r[1] = r[2] = 0.0f; float *g = r + (size_t)(M + 1) * 3; g[0] = g[1] = g[2] = 0.0f; }
+    if (with_cells) {
+      std::fill(dp.begin(), dp.begin() + S * 3, 0.0f);
+      for (int i = 1; i <= L; i++) { float *r = row(i); for (int s = 0; s < 3; s++) { r[s * S] = 0.0f; r[s * S + M + 1] = 0.0f; } }
+    }
     std::fill(x.begin(), x.begin() + needx, 0.0f);
   }
-  float *row(int i) { return dp.data() + (size_t)i * (M + 2) * 3; }
-  const float *row(int i) const { return dp.data() + (size_t)i * (M + 2) * 3; }
+  float *row(int i) { return dp.data() + (size_t)i * S * 3; }
+  const float *row(int i) const { return dp.data() + (size_t)i * S * 3; }
   float &X(int i, int s) { return x[(size_t)i * NX + s]; }
   float X(int i, int s) const { return x[(size_t)i * NX + s]; }
 };
-#define C3(rowp, k, s) (rowp)[(size_t)(k) * 3 + (s)]
+#define C3(rowp, k, s) (rowp)[(size_t)(s) * SS + (size_t)(k)]     /* SS = the matrix' plane stride, in scope */
+
+// ---- D->D chains.  y[n+1] += t[n] * y[n] is a serial mul+add chain (8 cycles per node); cut into blocks of CB
+// nodes it becomes (1) independent local chains per block, which the core overlaps, and (2) one vectorisable pass
+// adding the block's incoming value times the prefix products of t (precomputed per model). ----
+constexpr int CB = 16;
+void chain_prefix(const float *tDD /* index k-1 */, int M, std::vector<float> &up, std::vector<float> &dn)
+{
+  up.assign(M + 2, 0.f); dn.assign(M + 2, 0.f);
+  for (int n0 = 1; n0 <= M - 1; n0 += CB) {                       // forward: n = 1..M-1, t[n] = tDD[n-1]
+    float p = 1.0f;
+    for (int n = n0; n <= std::min(M - 1, n0 + CB - 1); n++) { p *= tDD[n - 1]; up[n] = p; }
+  }
+  for (int k0 = M; k0 >= 1; k0 -= CB) {                           // backward: k = M..1, t[k] = tDD[k-1]
+    float p = 1.0f;
+    for (int k = k0; k >= std::max(1, k0 - CB + 1); k--) { p *= tDD[k - 1]; dn[k] = p; }
+  }
+}
+// y[n+1] = y[n+1] + t[n]*y[n], n = 1..N ascending (y[1] final on entry); t[n] = tDD[n-1]
+inline void chain_up(float *__restrict__ y, const float *__restrict__ tDD, const float *__restrict__ pf, int N)
+{
+  for (int n0 = 1; n0 <= N; n0 += CB) {
+    const int n1 = std::min(N, n0 + CB - 1);
+    for (int n = n0 + 1; n <= n1; n++) y[n + 1] += tDD[n - 1] * y[n];
+  }
+  for (int n0 = 1; n0 <= N; n0 += CB) {
+    const int n1 = std::min(N, n0 + CB - 1);
+    const float yin = y[n0];
+    if (yin == 0.0f) continue;
+#pragma omp simd
+    for (int n = n0; n <= n1; n++) y[n + 1] += pf[n] * yin;
+  }
+}
+// y[k] = y[k] + t[k]*y[k+1], k = N..1 descending (y[N+1] final on entry); t[k] = tDD[k-1]
+inline void chain_down(float *__restrict__ y, const float *__restrict__ tDD, const float *__restrict__ pf, int N)
+{
+  for (int k0 = N; k0 >= 1; k0 -= CB) {
+    const int k1 = std::max(1, k0 - CB + 1);
+    for (int k = k0 - 1; k >= k1; k--) y[k] += tDD[k - 1] * y[k + 1];
+  }
+  for (int k0 = N; k0 >= 1; k0 -= CB) {
+    const int k1 = std::max(1, k0 - CB + 1);
+    const float yin = y[k0 + 1];
+    if (yin == 0.0f) continue;
+#pragma omp simd
+    for (int k = k1; k <= k0; k++) y[k] += pf[k] * yin;
+  }
+}
 
 // forward_engine, do_full (fwdback.c:256-463).  dsq[0..L-1].  Returns false on eslERANGE.
 bool forward_full(const Model &m, const uint8_t *dsq, int L, Mx &ox, float *sc)
 {
   const int M = m.M;
   ox.resize(M, L);
+  const size_t SS = ox.S;
+  const float *__restrict__ tBM = m.t[T_BM], *__restrict__ tMM = m.t[T_MM], *__restrict__ tIM = m.t[T_IM], *__restrict__ tDM = m.t[T_DM],
+              *__restrict__ tMD = m.t[T_MD], *__restrict__ tMI = m.t[T_MI], *__restrict__ tII = m.t[T_II];
   float xE = 0.f, xN = 1.f, xJ = 0.f, xB = m.pmove, xC = 0.f;
   ox.X(0, XE) = 0.f; ox.X(0, XN) = 1.f; ox.X(0, XJ) = 0.f; ox.X(0, XB) = xB; ox.X(0, XC) = 0.f; ox.X(0, XSC) = 1.f;
   ox.totscale = 0.f;
   for (int i = 1; i <= L; i++) {
     const float *pp = ox.row(i - 1); float *cp = ox.row(i);
-    const int x = dsq[i - 1];
-    float em = 0.f, ed = 0.f;
-    C3(cp, 1, sD) = 0.f;
-    for (int k = 1; k <= M; k++) {
-      const int c = k - 1;
-      float v = xB * m.t[T_BM][c];
-      v += C3(pp, k - 1, sM) * m.t[T_MM][c];
-      v += C3(pp, k - 1, sI) * m.t[T_IM][c];
-      v += C3(pp, k - 1, sD) * m.t[T_DM][c];
-      v *= m.r(x, k);
-      C3(cp, k, sM) = v;
-      C3(cp, k, sI) = C3(pp, k, sM) * m.t[T_MI][c] + C3(pp, k, sI) * m.t[T_II][c];
-      if (k < M) C3(cp, k + 1, sD) = v * m.t[T_MD][c] + C3(cp, k, sD) * m.t[T_DD][c];
-      em += v; ed += C3(cp, k, sD);
+    const float *__restrict__ pM = pp + sM * SS, *__restrict__ pD = pp + sD * SS, *__restrict__ pI = pp + sI * SS;
+    float *__restrict__ cM = cp + sM * SS, *__restrict__ cD = cp + sD * SS, *__restrict__ cI = cp + sI * SS;
+    const float *__restrict__ rs = m.rrow(dsq[i - 1]);
+    cD[1] = 0.f;
+#pragma omp simd
+    for (int c = 0; c < M; c++) {                              // node k = c + 1
+      float v = xB * tBM[c];
+      v += pM[c] * tMM[c];
+      v += pI[c] * tIM[c];
+      v += pD[c] * tDM[c];
+      v *= rs[c];
+      cM[c + 1] = v;
+      cI[c + 1] = pM[c + 1] * tMI[c] + pI[c + 1] * tII[c];
+      cD[c + 2] = v * tMD[c];                                  // M(k) -> D(k+1); the D->D term is added by chain_up
     }
+    cD[M + 1] = 0.f;                                           // guard column
+    chain_up(cD, m.t[T_DD], m.pf_up, M - 1);
+    float em = 0.f, ed = 0.f;
+#pragma omp simd reduction(+:em,ed)
+    for (int k = 1; k <= M; k++) { em += cM[k]; ed += cD[k]; }
     xE = em + ed;
     xN = xN * m.ploop;
     xC = (xC * m.ploop) + (xE * m.eM);
@@ -154,7 +218,8 @@ bool forward_full(const Model &m, const uint8_t *dsq, int L, Mx &ox, float *sc)
     if (xE > 1.0e4f) {
       xN = xN / xE; xC = xC / xE; xJ = xJ / xE; xB = xB / xE;
       const float inv = 1.0f / xE;
-      for (int k = 1; k <= M; k++) { C3(cp, k, sM) *= inv; C3(cp, k, sD) *= inv; C3(cp, k, sI) *= inv; }
+#pragma omp simd
+      for (int k = 1; k <= M; k++) { cM[k] *= inv; cD[k] *= inv; cI[k] *= inv; }
       ox.X(i, XSC) = xE;
       ox.totscale = (float)((double)ox.totscale + log((double)xE));
       xE = 1.0f;
@@ -166,136 +231,179 @@ bool forward_full(const Model &m, const uint8_t *dsq, int L, Mx &ox, float *sc)
   return true;
 }
 
-// backward_engine, do_full (fwdback.c:468-733)
-bool backward_full(const Model &m, const uint8_t *dsq, int L, const Mx &fwd, Mx &bk, float *sc)
+// backward_engine, do_full (fwdback.c:468-733) fused with p7_Decoding (decoding.c:76-134): the Backward rows are
+// consumed as they are produced (two rolling rows in <brow>), and what is stored is the posterior matrix
+//   pp(i,k) = f(i,k) * b(i,k) * rs[i],   rs[i] = scaleproduct(i) * fwd scale(i)
+// with the per-row factor kept apart (it is only known once Backward has reached row 0).  bk receives the Backward
+// specials.  Returns false on eslERANGE from either routine.
+bool backward_decode(const Model &m, const uint8_t *dsq, int L, const Mx &fwd, Mx &bk, Mx &pp, std::vector<float> &brow)
 {
   const int M = m.M;
-  bk.resize(M, L);
+  bk.resize(M, L, false);
+  pp.resize(M, L);
+  const size_t SS = fwd.S;
+  if (brow.size() < 6 * SS) brow.resize(6 * SS);
+  std::fill(brow.begin(), brow.begin() + 6 * SS, 0.0f);
+  const float *__restrict__ tBM = m.t[T_BM], *__restrict__ tMM = m.t[T_MM], *__restrict__ tIM = m.t[T_IM], *__restrict__ tDM = m.t[T_DM],
+              *__restrict__ tMD = m.t[T_MD], *__restrict__ tMI = m.t[T_MI], *__restrict__ tII = m.t[T_II], *__restrict__ tDD = m.t[T_DD];
   bk.own_scales = false;
   float xJ = 0.f, xB = 0.f, xN = 0.f, xC = m.pmove, xE = xC * m.eM;
+  auto emit_pp = [&](int i, const float *__restrict__ bM, const float *__restrict__ bI) {
+    const float *fr = fwd.row(i); float *pr = pp.row(i);
+    const float *__restrict__ fM = fr + sM * SS, *__restrict__ fI = fr + sI * SS;
+    float *__restrict__ qM = pr + sM * SS, *__restrict__ qI = pr + sI * SS;
+#pragma omp simd
+    for (int k = 1; k <= M; k++) { qM[k] = fM[k] * bM[k]; qI[k] = fI[k] * bI[k]; }
+  };
   {
-    float *cp = bk.row(L);
-    for (int k = M; k >= 1; k--) {
-      const float dn = (k < M) ? C3(cp, k + 1, sD) : 0.f;
-      C3(cp, k, sD) = xE + m.t[T_DD][k - 1] * dn;
-      C3(cp, k, sM) = xE + m.t[T_MD][k - 1] * dn;
-      C3(cp, k, sI) = 0.f;
-    }
+    float *cp = brow.data() + (size_t)(L & 1) * 3 * SS;
+    float *__restrict__ cM = cp + sM * SS, *__restrict__ cD = cp + sD * SS, *__restrict__ cI = cp + sI * SS;
+    cD[M + 1] = 0.f;
+#pragma omp simd
+    for (int k = 1; k <= M; k++) { cD[k] = xE; cI[k] = 0.f; }
+    chain_down(cD, tDD, m.pf_dn, M);
+#pragma omp simd
+    for (int k = 1; k <= M; k++) cM[k] = xE + tMD[k - 1] * cD[k + 1];
     const float scL = fwd.X(L, XSC);
     if (scL > 1.0f) {
       xE = xE / scL; xN = xN / scL; xC = xC / scL; xJ = xJ / scL; xB = xB / scL;
       const float inv = 1.0f / scL;
-      for (int k = 1; k <= M; k++) { C3(cp, k, sM) *= inv; C3(cp, k, sD) *= inv; C3(cp, k, sI) *= inv; }
+#pragma omp simd
+      for (int k = 1; k <= M; k++) { cM[k] *= inv; cD[k] *= inv; cI[k] *= inv; }
     }
     bk.X(L, XSC) = scL;
     bk.totscale = (float)log((double)scL);
     bk.X(L, XE) = xE; bk.X(L, XN) = xN; bk.X(L, XJ) = xJ; bk.X(L, XB) = xB; bk.X(L, XC) = xC;
+    if (L >= 1) emit_pp(L, cM, cI);
   }
   for (int i = L - 1; i >= 1; i--) {
-    const float *pp = bk.row(i + 1); float *cp = bk.row(i);
-    const int x = dsq[i];                                    // x_{i+1}
+    const float *pr = brow.data() + (size_t)((i + 1) & 1) * 3 * SS; float *cp = brow.data() + (size_t)(i & 1) * 3 * SS;
+    const float *__restrict__ pM = pr + sM * SS, *__restrict__ pI = pr + sI * SS;
+    float *__restrict__ cM = cp + sM * SS, *__restrict__ cD = cp + sD * SS, *__restrict__ cI = cp + sI * SS;
+    const float *__restrict__ rs = m.rrow(dsq[i]);             // x_{i+1}, index k-1
     float bsum = 0.f;
-    for (int k = 1; k <= M; k++) {
-      const int c = k - 1;
-      const float mpv = (k < M) ? C3(pp, k + 1, sM) * m.r(x, k + 1) : 0.f;
-      const float ipv = C3(pp, k, sI);
-      const float tmm = (k < M) ? m.t[T_MM][c + 1] : 0.f, tim = (k < M) ? m.t[T_IM][c + 1] : 0.f, tdm = (k < M) ? m.t[T_DM][c + 1] : 0.f;
-      C3(cp, k, sI) = (ipv * m.t[T_II][c]) + (mpv * tim);
-      C3(cp, k, sD) = mpv * tdm;
-      C3(cp, k, sM) = (ipv * m.t[T_MI][c]) + (mpv * tmm);
-      bsum += (C3(pp, k, sM) * m.r(x, k)) * m.t[T_BM][c];
+    // mpv(k) = M(i+1,k+1) * e(k+1) (0 for k = M): node k+1 is index c+1 of the transition rows
+#pragma omp simd reduction(+:bsum)
+    for (int k = 1; k < M; k++) {
+      const float mpv = pM[k + 1] * rs[k];
+      const float ipv = pI[k];
+      cI[k] = (ipv * tII[k - 1]) + (mpv * tIM[k]);
+      cD[k] = mpv * tDM[k];
+      cM[k] = (ipv * tMI[k - 1]) + (mpv * tMM[k]);
+      bsum += (pM[k] * rs[k - 1]) * tBM[k - 1];
     }
+    { const float ipv = pI[M];                                 // k = M: mpv = 0, and the transitions towards M+1 count as 0
+      cI[M] = (ipv * tII[M - 1]) + (0.f * 0.f);
+      cD[M] = 0.f * 0.f;
+      cM[M] = (ipv * tMI[M - 1]) + (0.f * 0.f);
+      bsum += (pM[M] * rs[M - 1]) * tBM[M - 1]; }
     xB = bsum;
     xC = xC * m.ploop;
     xJ = (xB * m.pmove) + (xJ * m.ploop);
     xN = (xB * m.pmove) + (xN * m.ploop);
     xE = (xC * m.eM) + (xJ * m.eL);
-    for (int k = M; k >= 1; k--) {
-      const float dn = (k < M) ? C3(cp, k + 1, sD) : 0.f;
-      C3(cp, k, sD) = (C3(cp, k, sD) + xE) + m.t[T_DD][k - 1] * dn;
-      C3(cp, k, sM) = (C3(cp, k, sM) + xE) + m.t[T_MD][k - 1] * dn;
-    }
+    cD[M + 1] = 0.f;
+#pragma omp simd
+    for (int k = 1; k <= M; k++) cD[k] = cD[k] + xE;
+    chain_down(cD, tDD, m.pf_dn, M);
+#pragma omp simd
+    for (int k = 1; k <= M; k++) cM[k] = (cM[k] + xE) + tMD[k - 1] * cD[k + 1];
     if (xB > 1.0e16f) bk.own_scales = true;
     const float scale = bk.own_scales ? ((xB > 1.0e4f) ? xB : 1.0f) : fwd.X(i, XSC);
     bk.X(i, XSC) = scale;
     if (scale > 1.0f) {
       xE /= scale; xN /= scale; xJ /= scale; xB /= scale; xC /= scale;
       const float inv = 1.0f / scale;
-      for (int k = 1; k <= M; k++) { C3(cp, k, sM) *= inv; C3(cp, k, sD) *= inv; C3(cp, k, sI) *= inv; }
+#pragma omp simd
+      for (int k = 1; k <= M; k++) { cM[k] *= inv; cD[k] *= inv; cI[k] *= inv; }
       bk.totscale = (float)((double)bk.totscale + log((double)scale));
     }
     bk.X(i, XE) = xE; bk.X(i, XN) = xN; bk.X(i, XJ) = xJ; bk.X(i, XB) = xB; bk.X(i, XC) = xC;
+    emit_pp(i, cM, cI);
   }
   {
     float bsum = 0.f;
-    if (L >= 1) { const float *pp = bk.row(1); const int x = dsq[0];
-      for (int k = 1; k <= M; k++) bsum += (C3(pp, k, sM) * m.r(x, k)) * m.t[T_BM][k - 1]; }
+    if (L >= 1) {
+      const float *pr = brow.data() + (size_t)(1 & 1) * 3 * SS; const float *__restrict__ pM = pr + sM * SS;
+      const float *__restrict__ rs = m.rrow(dsq[0]);
+#pragma omp simd reduction(+:bsum)
+      for (int k = 1; k <= M; k++) bsum += (pM[k] * rs[k - 1]) * tBM[k - 1];
+    }
     xB = bsum;
     xN = (xB * m.pmove) + (xN * m.ploop);
     bk.X(0, XB) = xB; bk.X(0, XC) = 0.f; bk.X(0, XJ) = 0.f; bk.X(0, XN) = xN; bk.X(0, XE) = 0.f; bk.X(0, XSC) = 1.f;
   }
-  if (std::isnan(xN) || (L > 0 && xN == 0.0f) || std::isinf(xN)) return false;
-  if (sc) *sc = (float)((double)bk.totscale + log((double)xN));
-  return true;
-}
-
-// p7_Decoding (decoding.c:76-134): posterior probabilities; pp may alias nothing (separate matrix). Returns false on eslERANGE.
-bool decoding(const Model &m, const Mx &f, const Mx &b, Mx &pp)
-{
-  const int M = m.M, L = f.L;
-  pp.resize(M, L);
-  float scaleproduct = 1.0f / b.X(0, XN);
+  if (std::isnan(xN) || (L > 0 && xN == 0.0f) || std::isinf(xN)) { /* p7_Backward's status is ignored by the caller too */ }
+  // p7_Decoding's row factors and special-state posteriors
+  if (pp.rs.size() < (size_t)L + 1) pp.rs.resize((size_t)L + 1);
+  float scaleproduct = 1.0f / bk.X(0, XN);
+  pp.rs[0] = 0.f;
   for (int i = 1; i <= L; i++) {
-    const float *fr = f.row(i), *br = b.row(i); float *pr = pp.row(i);
-    const float totr = scaleproduct * f.X(i, XSC);
-    for (int k = 1; k <= M; k++) {
-      C3(pr, k, sM) = (C3(fr, k, sM) * C3(br, k, sM)) * totr;
-      C3(pr, k, sD) = 0.f;
-      C3(pr, k, sI) = (C3(fr, k, sI) * C3(br, k, sI)) * totr;
-    }
+    pp.rs[i] = scaleproduct * fwd.X(i, XSC);
     pp.X(i, XE) = 0.f;
-    pp.X(i, XN) = f.X(i - 1, XN) * b.X(i, XN) * m.ploop * scaleproduct;
-    pp.X(i, XJ) = f.X(i - 1, XJ) * b.X(i, XJ) * m.ploop * scaleproduct;
-    pp.X(i, XC) = f.X(i - 1, XC) * b.X(i, XC) * m.ploop * scaleproduct;
+    pp.X(i, XN) = fwd.X(i - 1, XN) * bk.X(i, XN) * m.ploop * scaleproduct;
+    pp.X(i, XJ) = fwd.X(i - 1, XJ) * bk.X(i, XJ) * m.ploop * scaleproduct;
+    pp.X(i, XC) = fwd.X(i - 1, XC) * bk.X(i, XC) * m.ploop * scaleproduct;
     pp.X(i, XB) = 0.f;
-    if (b.own_scales) scaleproduct *= f.X(i, XSC) / b.X(i, XSC);
+    if (bk.own_scales) scaleproduct *= fwd.X(i, XSC) / bk.X(i, XSC);
   }
   return !std::isinf(scaleproduct);
 }
 
 // p7_OptimalAccuracy (optacc.c:58-176).  "impossible transition" contributes 0.0 (the AND-mask trick), not -inf.
-float optimal_accuracy(const Model &m, const Mx &pp, Mx &ox)
+// The D(k) <- D(k-1) dependency is a max/mask chain: exact under any re-association, so it is blocked like the
+// Forward chain (local chains per block, then the incoming value gated by the block's running AND of the masks).
+float optimal_accuracy(const Model &m, const Mx &pp, Mx &ox, std::vector<float> &pmask)
 {
   const int M = m.M, L = pp.L;
   ox.resize(M, L);
+  const size_t SS = ox.S;
+  const float *__restrict__ tBM = m.t[T_BM], *__restrict__ tMM = m.t[T_MM], *__restrict__ tIM = m.t[T_IM], *__restrict__ tDM = m.t[T_DM],
+              *__restrict__ tMD = m.t[T_MD], *__restrict__ tMI = m.t[T_MI], *__restrict__ tII = m.t[T_II], *__restrict__ tDD = m.t[T_DD];
+  // pm[k] = 1 if every D(j-1)->D(j) transition from the start of k's block up to k is possible (k = 2..M; tDD[j-2])
+  if (pmask.size() < (size_t)M + 2) pmask.resize((size_t)M + 2);
+  float *__restrict__ pm = pmask.data();
+  for (int k0 = 2; k0 <= M; k0 += CB) { bool ok = true; for (int k = k0; k <= std::min(M, k0 + CB - 1); k++) { ok = ok && (tDD[k - 2] > 0.0f); pm[k] = ok ? 1.0f : 0.0f; } }
   { float *r0 = ox.row(0); for (int k = 0; k <= M + 1; k++) { C3(r0, k, sM) = NEGINF; C3(r0, k, sD) = NEGINF; C3(r0, k, sI) = NEGINF; } }
   ox.X(0, XE) = NEGINF; ox.X(0, XN) = 0.f; ox.X(0, XJ) = NEGINF; ox.X(0, XB) = 0.f; ox.X(0, XC) = NEGINF;
-  auto gate = [](float t, float v) -> float { return (t > 0.0f) ? v : 0.0f; };
   for (int i = 1; i <= L; i++) {
     const float *pr = ox.row(i - 1); float *cr = ox.row(i); const float *ppr = pp.row(i);
-    const float xB = ox.X(i - 1, XB);
+    const float *__restrict__ pM = pr + sM * SS, *__restrict__ pD = pr + sD * SS, *__restrict__ pI = pr + sI * SS;
+    float *__restrict__ cM = cr + sM * SS, *__restrict__ cD = cr + sD * SS, *__restrict__ cI = cr + sI * SS;
+    const float *__restrict__ qM = ppr + sM * SS, *__restrict__ qI = ppr + sI * SS;
+    const float xB = ox.X(i - 1, XB), ps = pp.rs[i];
+    cM[0] = cD[0] = cI[0] = NEGINF;
+    cD[1] = NEGINF;
     float xE = NEGINF;
-    C3(cr, 0, sM) = C3(cr, 0, sD) = C3(cr, 0, sI) = NEGINF;
-    float dcv = NEGINF;                                          // value entering D(i,k): from M(i,k-1)
-    for (int k = 1; k <= M; k++) {
-      const int c = k - 1;
-      float sv = gate(m.t[T_BM][c], xB);
-      sv = std::max(sv, gate(m.t[T_MM][c], C3(pr, k - 1, sM)));
-      sv = std::max(sv, gate(m.t[T_IM][c], C3(pr, k - 1, sI)));
-      sv = std::max(sv, gate(m.t[T_DM][c], C3(pr, k - 1, sD)));
-      sv = sv + C3(ppr, k, sM);
+#pragma omp simd reduction(max:xE)
+    for (int c = 0; c < M; c++) {                              // node k = c + 1
+      float sv = (tBM[c] > 0.0f) ? xB : 0.0f;
+      sv = std::max(sv, (tMM[c] > 0.0f) ? pM[c] : 0.0f);
+      sv = std::max(sv, (tIM[c] > 0.0f) ? pI[c] : 0.0f);
+      sv = std::max(sv, (tDM[c] > 0.0f) ? pD[c] : 0.0f);
+      sv = sv + qM[c + 1] * ps;
       xE = std::max(xE, sv);
-      C3(cr, k, sM) = sv;
-      // D(i,k) = max(M->D from k-1, D->D from k-1)
-      float d = dcv;
-      if (k > 1) d = std::max(d, gate(m.t[T_DD][c - 1], C3(cr, k - 1, sD)));
-      C3(cr, k, sD) = d;
-      dcv = gate(m.t[T_MD][c], sv);
-      float iv = gate(m.t[T_MI][c], C3(pr, k, sM));
-      iv = std::max(iv, gate(m.t[T_II][c], C3(pr, k, sI)));
-      C3(cr, k, sI) = iv + C3(ppr, k, sI);
+      cM[c + 1] = sv;
+      cD[c + 2] = (tMD[c] > 0.0f) ? sv : 0.0f;                 // value entering D(k+1) from M(k)
+      float iv = (tMI[c] > 0.0f) ? pM[c + 1] : 0.0f;
+      iv = std::max(iv, (tII[c] > 0.0f) ? pI[c + 1] : 0.0f);
+      cI[c + 1] = iv + qI[c + 1] * ps;
     }
-    for (int k = 1; k <= M; k++) xE = std::max(xE, C3(cr, k, sD));
+    // D(k) = max(D(k), gate(tDD[k-2], D(k-1))), k = 2..M
+    for (int k0 = 2; k0 <= M; k0 += CB) {
+      const int k1 = std::min(M, k0 + CB - 1);
+      if (!(tDD[k0 - 2] > 0.0f)) cD[k0] = std::max(cD[k0], 0.0f);
+      for (int k = k0 + 1; k <= k1; k++) cD[k] = std::max(cD[k], (tDD[k - 2] > 0.0f) ? cD[k - 1] : 0.0f);
+    }
+    for (int k0 = 2; k0 <= M; k0 += CB) {
+      const int k1 = std::min(M, k0 + CB - 1);
+      const float yin = cD[k0 - 1];
+#pragma omp simd
+      for (int k = k0; k <= k1; k++) cD[k] = std::max(cD[k], (pm[k] > 0.0f) ? yin : cD[k]);
+    }
+    cD[M + 1] = 0.f;
+#pragma omp simd reduction(max:xE)
+    for (int k = 1; k <= M; k++) xE = std::max(xE, cD[k]);
     ox.X(i, XE) = xE;
     float t1 = (m.ploop == 0.0f) ? 0.0f : ox.X(i - 1, XJ) + pp.X(i, XJ);
     float t2 = (m.eL == 0.0f) ? 0.0f : ox.X(i, XE);
@@ -360,6 +468,7 @@ inline int Qf(int M) { return std::max(2, (M - 1) / 4 + 1); }     // p7O_NQF
 bool oa_trace(const Model &m, const Mx &pp, const Mx &ox, Trace &tr)
 {
   const int M = m.M, L = ox.L, Q = Qf(M);
+  const size_t SS = ox.S;
   int i = L, k = 0;
   tr.clear();
   tr.push(ST_T, k, i); tr.push(ST_C, k, i);
@@ -414,8 +523,8 @@ bool oa_trace(const Model &m, const Mx &pp, const Mx &ox, Trace &tr)
     if (s1 == -1) return false;
     float postprob = 0.0f;
     switch (s1) {
-      case ST_M: postprob = C3(pp.row(i), k, sM); break;
-      case ST_I: postprob = C3(pp.row(i), k, sI); break;
+      case ST_M: postprob = C3(pp.row(i), k, sM) * pp.rs[i]; break;
+      case ST_I: postprob = C3(pp.row(i), k, sI) * pp.rs[i]; break;
       case ST_N: if (s0 == s1) postprob = pp.X(i, XN); break;
       case ST_C: if (s0 == s1) postprob = pp.X(i, XC); break;
       case ST_J: if (s0 == s1) postprob = pp.X(i, XJ); break;
@@ -433,6 +542,7 @@ bool oa_trace(const Model &m, const Mx &pp, const Mx &ox, Trace &tr)
 bool stochastic_trace(FastRng &rng, const Model &m, int L, const Mx &ox, Trace &tr)
 {
   const int M = m.M, Q = Qf(M);
+  const size_t SS = ox.S;
   int i = L, k = 0;
   tr.clear();
   tr.push(ST_T, k, i); tr.push(ST_C, k, i);
@@ -503,12 +613,16 @@ void avg_degenerate(const Model &m, float *null2)      // esl_abc_FAvgScVec + th
 void null2_by_expectation(const Model &m, const Mx &pp, float *null2)
 {
   const int M = m.M, Ld = pp.L;
+  const size_t SS = pp.S;
   std::vector<float> em(M + 1, 0.f), ei(M + 1, 0.f);
   float xn = pp.X(1, XN), xc = pp.X(1, XC), xj = pp.X(1, XJ);
-  { const float *r = pp.row(1); for (int k = 1; k <= M; k++) { em[k] = C3(r, k, sM); ei[k] = C3(r, k, sI); } }
+  { const float *r = pp.row(1); const float ps = pp.rs[1]; for (int k = 1; k <= M; k++) { em[k] = C3(r, k, sM) * ps; ei[k] = C3(r, k, sI) * ps; } }
   for (int i = 2; i <= Ld; i++) {
-    const float *r = pp.row(i);
-    for (int k = 1; k <= M; k++) { em[k] = C3(r, k, sM) + em[k]; ei[k] = C3(r, k, sI) + ei[k]; }
+    const float *r = pp.row(i); const float ps = pp.rs[i];
+    const float *__restrict__ qM = r + sM * SS, *__restrict__ qI = r + sI * SS;
+    float *__restrict__ am = em.data(), *__restrict__ ai = ei.data();
+#pragma omp simd
+    for (int k = 1; k <= M; k++) { am[k] = qM[k] * ps + am[k]; ai[k] = qI[k] * ps + ai[k]; }
     xn += pp.X(i, XN); xc += pp.X(i, XC); xj += pp.X(i, XJ);
   }
   const float norm = (float)(1.0 / (float)Ld);
@@ -620,10 +734,19 @@ struct HitOut { bool valid = false; b2h_hit hit; std::vector<DomOut> doms; };
 
 char encode_pp(float p) { return (p + 0.05 >= 1.0) ? '*' : (char)((char)((p + 0.05) * 10.0) + '0'); }
 
+#ifdef B2H_DDEF_PROF
+static double g_T[10]; static const char *g_N[10] = {"fwd(env)","bck+dec","OA","oatrace","alidisp+null2","fwd(region)","stotrace+null2bytrace","cluster","ddecoding","other"};
+struct ProfT { int i; std::chrono::steady_clock::time_point t0; ProfT(int i_) : i(i_), t0(std::chrono::steady_clock::now()) {} ~ProfT() { g_T[i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } };
+struct ProfDump { ~ProfDump() { for (int i = 0; i < 10; i++) fprintf(stderr, "[ddef prof] %-24s %8.2f ms\n", g_N[i], g_T[i]); } } g_dump;
+#define PROF(i) ProfT prof_##i(i)
+#else
+#define PROF(i)
+#endif
 struct Worker {
   Mx fwd, bck, pp, oa;
   Trace tr;
   std::vector<float> btot, etot, mocc, n2sc;
+  std::vector<float> brow, pmask, pf_up, pf_dn, zrow;     // rolling Backward rows, D-chain tables of the current model
   FastRng rng;
 };
 
@@ -632,11 +755,13 @@ bool rescore_domain(Worker &w, Model &m, const b2h_profile *prof, const uint8_t 
 {
   const int Ld = j - i + 1;
   float envsc;
+  { PROF(0);
   if (!forward_full(m, dsq + i - 1, Ld, w.fwd, &envsc)) envsc = std::numeric_limits<float>::infinity();   // p7_Forward's status is ignored by the caller
-  backward_full(m, dsq + i - 1, Ld, w.fwd, w.bck, nullptr);
-  if (!decoding(m, w.fwd, w.bck, w.pp)) return false;                      // eslERANGE -> domain dropped (eslFAIL)
-  const float oasc = optimal_accuracy(m, w.pp, w.oa);
-  if (!oa_trace(m, w.pp, w.oa, w.tr)) return false;
+  }
+  { PROF(1); if (!backward_decode(m, dsq + i - 1, Ld, w.fwd, w.bck, w.pp, w.brow)) return false; }   // eslERANGE from p7_Decoding -> domain dropped (eslFAIL)
+  float oasc; { PROF(2); oasc = optimal_accuracy(m, w.pp, w.oa, w.pmask); }
+  { PROF(3); if (!oa_trace(m, w.pp, w.oa, w.tr)) return false; }
+  PROF(4);
   for (size_t z = 0; z < w.tr.st.size(); z++) if (w.tr.i[z] > 0) w.tr.i[z] += i - 1;
 
   // alignment display (p7_alidisplay_Create, p7_alidisplay.c:92-273): first M .. last M of the (single) domain
@@ -699,6 +824,9 @@ void ddef_one(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, H
   Model m; m.M = prof->M; m.K = prof->K; m.Kp = prof->Kp; m.rsc = prof->h_fwd_rsc.data();
   for (int q = 0; q < 8; q++) m.t[q] = prof->h_fwd_tsc.data() + (size_t)q * prof->M;
   m.degen = prof->h_degen.empty() ? nullptr : prof->h_degen.data();
+  chain_prefix(m.t[T_DD], m.M, w.pf_up, w.pf_dn);
+  if (w.zrow.size() < (size_t)m.M) w.zrow.assign((size_t)m.M, 0.0f);
+  m.pf_up = w.pf_up.data(); m.pf_dn = w.pf_dn.data(); m.zrow = w.zrow.data();
   configure(m, true, L);
   const float ploop_multi = m.ploop;
 
@@ -740,7 +868,7 @@ void ddef_one(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, H
         nclustered++;
         configure(m, true, L);                            // ReconfigMultihit(om, saveL)
         const int Lr = j - i + 1;
-        forward_full(m, t.dsq + i - 1, Lr, w.fwd, nullptr);
+        { PROF(5); forward_full(m, t.dsq + i - 1, Lr, w.fwd, nullptr); }
         // region_trace_ensemble (p7_domaindef.c:597-678)
         for (int pos = i; pos <= j; pos++) w.n2sc[pos] = 0.0f;
         if (prm->seed != 0) w.rng.init(prm->seed);        // do_reseeding
@@ -916,7 +1044,14 @@ class ThreadPool {
 
 b2h_ddef_pool::b2h_ddef_pool(int n)
 {
-  if (n <= 0) n = (int)std::thread::hardware_concurrency() - 2;   // leave room for the thread that feeds the GPU
+  if (n <= 0) {
+    // all hardware threads but two (the thread that feeds the GPU needs a core), shared fairly between the ranks
+    // of a one-process-per-GPU job on this node (torchrun exports LOCAL_WORLD_SIZE)
+    n = (int)std::thread::hardware_concurrency();
+    int ranks = 1;
+    if (const char *ev = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(ev));
+    n = std::max(1, n / ranks - 2);
+  }
   nthreads = std::max(1, std::min(n, 128));
 }
 
