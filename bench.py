@@ -180,6 +180,8 @@ def reference_arm(args, rank, world_size):
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -338,6 +340,14 @@ def main():
     b_alg = float(seqs.total_residues + 2 * len(seqs)) + msv_tab_bytes + 16.0 * n_past_msv      # per step, this rank
     ssv_ms = stage_ms["ssv"] / K
     achieved = b_alg / (ssv_ms * 1e-3) / 1e9 if ssv_ms > 0 else None
+    # the resource the SSV kernel actually saturates: the shared-memory data pipe (128 B/clk/SM).  Per DP row a warp
+    # reads NR*128 B of emission scores (LDS) and moves 1.25 shuffles (one wavefront each).
+    nr_classes = [1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32, 40, 48]
+    rows = float(sum(((len(q) + 3) // 4) * 4 for q in seqs))
+    smem_bytes = sum(rows * (min(n for n in nr_classes if 64 * n >= h.M + 1) + 1.25) * 128.0 for h in hmms)
+    sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    smem_peak = 128.0 * torch.cuda.get_device_properties(local).multi_processor_count * sm_clock / 1e9
+    smem_ach = smem_bytes / (ssv_ms * 1e-3) / 1e9 if ssv_ms > 0 else None
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ssv_traffic.json")))["dram_bytes_per_step"]
@@ -359,8 +369,11 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
                      "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_kind": pk_kind,
                      "kernel": "ssv_kernel<NR> (all launches of a step)", "algorithmic_bytes_per_step": b_alg,
-                     "note": "compute-bound DP: compulsory HBM traffic is ~6e-5 B/cell (SURVEY 8d), so the HBM fraction is tiny by construction; "
-                             "ssv_kernel_gcups vs the DPX issue ceiling is the informative figure (DESIGN.md)"},
+                     "on_chip": {"bound": "shared-memory data pipe (LDS + SHFL wavefronts)", "achieved": smem_ach, "peak": smem_peak,
+                                 "unit": "GB/s", "frac": (smem_ach / smem_peak) if smem_ach else None,
+                                 "bytes_per_step": smem_bytes},
+                     "note": "DP filter with ~6e-5 compulsory HBM bytes per cell (SURVEY 8d): the HBM fraction is tiny by construction. "
+                             "The kernel is bound by the shared-memory pipe: 2 B of emission scores per cell; see on_chip and profiles/"},
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * float(te.item()) / len(e2e_times)},
         "gpu_launches": int(launches), "clocks": clocks,
