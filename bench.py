@@ -252,8 +252,7 @@ def main():
         t0 = time.perf_counter()
         plan7.SequenceDatabase.of(ctx, seqs)                       # H2D of the packed residues (+ per-target scalars)
         t1 = time.perf_counter()
-        for om in oms:
-            om._device(ctx)                                        # H2D of every profile's tables
+        plan7.OptimizedProfile._device_many(ctx, oms)              # H2D of every profile's tables
         t2 = time.perf_counter()
         hits, doms, text, counters = pli._run(oms, seqs)           # b2h_search + D2H of the hit records
         t3 = time.perf_counter()

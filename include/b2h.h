@@ -155,6 +155,9 @@ size_t  b2h_seqdb_nseq(const b2h_seqdb *db);
 int64_t b2h_seqdb_nres(const b2h_seqdb *db);
 
 int  b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *desc, b2h_profile **out);
+/* The same for n profiles: the host-side table building runs on several threads, the copies are issued in order.
+ * out[0..n) receives the handles; on failure nothing is left allocated. (An OptimizedProfileBlock in one call.) */
+int  b2h_profile_upload_many(b2h_ctx *ctx, const b2h_oprofile_desc *const *descs, size_t n, b2h_profile **out);
 void b2h_profile_destroy(b2h_profile *p);
 
 /* ------------------------- per-stage entry points (dense outputs) ------------------------ *

@@ -106,6 +106,7 @@ def _load():
     sig("b2h_seqdb_nres", c_i64, c_void_p)
     sig("b2h_profile_upload", c_int, c_void_p, P(OProfileDesc), P(c_void_p))
     sig("b2h_profile_destroy", None, c_void_p)
+    sig("b2h_profile_upload_many", c_int, c_void_p, c_void_p, c_size_t, c_void_p)
     for name in ("b2h_ssv_filter", "b2h_msv_filter", "b2h_viterbi_filter", "b2h_forward_parser",
                  "b2h_backward_parser"):
         if hasattr(lib, name):

@@ -251,7 +251,10 @@ static size_t striped_word_index(int NR, int x, int j, int lane)
 int b2h_profile_create_host(const b2h_oprofile_desc *d, b2h_profile **out)
 { return b2h_profile_upload(nullptr, d, out); }
 
-int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **out)
+// Host half of an upload: the profile object and, when a context is given, the staged image of its device block
+// (sections 256-byte aligned; offsets in <offs>).  Pure CPU work, safe to run for many profiles in parallel.
+struct ProfStage { std::vector<uint8_t> bytes; size_t offs[9] = {0}; };
+static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **out, ProfStage *stg)
 {
   if (!d || !out || d->M < 1 || d->Kp > B2H_NCODE - 1 || d->K > B2H_MAXABET) return B2H_EINVAL;
   *out = nullptr;
@@ -345,38 +348,68 @@ int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **o
     p->bias_t11 = L1 / (L1 + 1.0f);
   }
 
-  int st = B2H_OK;
-  if (ctx) {
-    // one device block and one H2D copy for all tables of the profile (sections 256-byte aligned)
-    std::vector<uint8_t> stage;
+  if (ctx && stg) {
+    std::vector<uint8_t> &stage = stg->bytes;
     auto add = [&](const void *src, size_t bytes) -> size_t {
       const size_t off = (stage.size() + 255) & ~(size_t)255;
       stage.resize(off + bytes);
       memcpy(stage.data() + off, src, bytes);
       return off;
     };
-    const size_t o_ssv = add(ssv.data(), ssv.size() * 4), o_mc = add(mc.data(), mc.size());
-    const size_t o_vr = add(vr.data(), vr.size() * 2), o_vt = add(vt.data(), vt.size() * 2);
-    const size_t o_fr = add(fr.data(), fr.size() * 4), o_ft = add(ft.data(), ft.size() * 4), o_eo = add(eo.data(), eo.size() * 4);
-    size_t o_vr32 = 0, o_frr = 0;
-    if (p->regC) { o_vr32 = add(vr32.data(), vr32.size() * 4); o_frr = add(frr.data(), frr.size() * 4); }
-    cudaError_t e;
+    stg->offs[0] = add(ssv.data(), ssv.size() * 4); stg->offs[1] = add(mc.data(), mc.size());
+    stg->offs[2] = add(vr.data(), vr.size() * 2);   stg->offs[3] = add(vt.data(), vt.size() * 2);
+    stg->offs[4] = add(fr.data(), fr.size() * 4);   stg->offs[5] = add(ft.data(), ft.size() * 4);
+    stg->offs[6] = add(eo.data(), eo.size() * 4);
+    if (p->regC) { stg->offs[7] = add(vr32.data(), vr32.size() * 4); stg->offs[8] = add(frr.data(), frr.size() * 4); }
     p->h2d_bytes = stage.size();
-    cudaSetDevice(ctx->device);
-    if ((e = cudaMallocAsync((void **)&p->d_block, stage.size(), ctx->stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(p->d_block, stage.data(), stage.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
-      ctx->err = cudaGetErrorString(e); st = B2H_ECUDA;        // (pageable source: the copy is staged before the call returns)
-    } else {
-      uint8_t *b = (uint8_t *)p->d_block;
-      p->d_ssv_emis = (uint32_t *)(b + o_ssv); p->d_msv_cost8 = b + o_mc;
-      p->d_vit_rsc = (int16_t *)(b + o_vr); p->d_vit_tsc = (int16_t *)(b + o_vt);
-      p->d_fwd_rsc = (float *)(b + o_fr); p->d_fwd_tsc = (float *)(b + o_ft); p->d_bias_eo = (float *)(b + o_eo);
-      if (p->regC) { p->d_vit_rsc32 = (int32_t *)(b + o_vr32); p->d_fwd_rscr = (float *)(b + o_frr); }
-    }
   }
-  if (st != B2H_OK) { b2h_profile_destroy(p); return st; }
   *out = p;
   return B2H_OK;
+}
+
+// Device half: one stream-ordered allocation and one H2D copy for all tables of the profile.
+static int profile_commit(b2h_ctx *ctx, b2h_profile *p, const ProfStage &stg)
+{
+  cudaError_t e;
+  cudaSetDevice(ctx->device);
+  if ((e = cudaMallocAsync((void **)&p->d_block, stg.bytes.size(), ctx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(p->d_block, stg.bytes.data(), stg.bytes.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+    ctx->err = cudaGetErrorString(e); return B2H_ECUDA;        // (pageable source: the copy is staged before the call returns)
+  }
+  uint8_t *b = (uint8_t *)p->d_block;
+  p->d_ssv_emis = (uint32_t *)(b + stg.offs[0]); p->d_msv_cost8 = b + stg.offs[1];
+  p->d_vit_rsc = (int16_t *)(b + stg.offs[2]); p->d_vit_tsc = (int16_t *)(b + stg.offs[3]);
+  p->d_fwd_rsc = (float *)(b + stg.offs[4]); p->d_fwd_tsc = (float *)(b + stg.offs[5]); p->d_bias_eo = (float *)(b + stg.offs[6]);
+  if (p->regC) { p->d_vit_rsc32 = (int32_t *)(b + stg.offs[7]); p->d_fwd_rscr = (float *)(b + stg.offs[8]); }
+  return B2H_OK;
+}
+
+int b2h_profile_upload(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **out)
+{
+  ProfStage stg;
+  b2h_profile *p = nullptr;
+  if (out) *out = nullptr;
+  int st = profile_build(ctx, d, &p, ctx ? &stg : nullptr);
+  if (st != B2H_OK) return st;
+  if (ctx && (st = profile_commit(ctx, p, stg)) != B2H_OK) { b2h_profile_destroy(p); return st; }
+  *out = p;
+  return B2H_OK;
+}
+
+int b2h_profile_upload_many(b2h_ctx *ctx, const b2h_oprofile_desc *const *descs, size_t n, b2h_profile **out)
+{
+  if (!ctx || !descs || !out) return B2H_EINVAL;
+  for (size_t i = 0; i < n; i++) out[i] = nullptr;
+  std::vector<ProfStage> stg(n);
+  std::vector<int> status(n, B2H_OK);
+  const int T = (int)std::min<size_t>(std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())), n);
+  auto work = [&](int t) { for (size_t i = t; i < n; i += T) status[i] = profile_build(ctx, descs[i], &out[i], &stg[i]); };
+  if (T <= 1) work(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
+  int st = B2H_OK;
+  for (size_t i = 0; i < n && st == B2H_OK; i++) { st = status[i]; if (st == B2H_OK) st = profile_commit(ctx, out[i], stg[i]); }
+  if (st != B2H_OK) { for (size_t i = 0; i < n; i++) { b2h_profile_destroy(out[i]); out[i] = nullptr; } }
+  return st;
 }
 
 void b2h_profile_destroy(b2h_profile *p)

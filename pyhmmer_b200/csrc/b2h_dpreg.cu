@@ -173,15 +173,17 @@ __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqD
 #pragma unroll
         for (int c = C - 1; c >= 0; c--) {
           const int pm = (c == 0) ? mp : M[c - 1], pi = (c == 0) ? ip : I[c - 1], pd = (c == 0) ? dp : D[c - 1];
-          const int inew = __vimax3_s32(M[c] + tMI[c], I[c] + tII[c], NEG16);
+          const int inew = __viaddmax_s32(M[c], tMI[c], __viaddmax_s32(I[c], tII[c], NEG16));
           int m = __viaddmax_s32(xB, tBM[c], NEG16);
           m = __viaddmax_s32(pm, tMM[c], m);
           m = __viaddmax_s32(pi, tIM[c], m);
           m = __viaddmax_s32(pd, tDM[c], m);
           m = __viaddmax_s32(m, r[c], NEG16);
-          xEm = max(xEm, m);
           M[c] = m; I[c] = inew;
         }
+#pragma unroll
+        for (int c = 0; c + 1 < C; c += 2) xEm = __vimax3_s32(xEm, M[c], M[c + 1]);      // one VIMNMX3 per two cells
+        if (C & 1) xEm = max(xEm, M[C - 1]);
         int xE = __reduce_max_sync(FULL, xEm);
         // M->D partials: D[c] is the value entering node c from M of node c-1
         const int mdl = __viaddmax_s32(M[C - 1], tMD[C - 1], NEG16);
@@ -190,7 +192,10 @@ __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqD
         int Dm = dleft;
         D[0] = dleft;
 #pragma unroll
-        for (int c = 1; c < C; c++) { D[c] = __viaddmax_s32(M[c - 1], tMD[c - 1], NEG16); Dm = max(Dm, D[c]); }
+        for (int c = 1; c < C; c++) D[c] = __viaddmax_s32(M[c - 1], tMD[c - 1], NEG16);
+#pragma unroll
+        for (int c = 1; c + 1 < C; c += 2) Dm = __vimax3_s32(Dm, D[c], D[c + 1]);
+        if (!(C & 1)) Dm = max(Dm, D[C - 1]);
         int Dmax = __reduce_max_sync(FULL, Dm);
         if (W > 1) {
           int (*X)[W] = s_x[i & 1][grp];

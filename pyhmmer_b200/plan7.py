@@ -513,6 +513,21 @@ class OptimizedProfile:
             h = self._dev[ctx] = _DeviceHandle(out, lib.b2h_profile_destroy)
         return h.handle
 
+    @staticmethod
+    def _device_many(ctx, oms):
+        """Device handles for a list of profiles; the ones not yet resident are uploaded in one call."""
+        todo = [om for om in oms if om._dev.get(ctx) is None]
+        if len(todo) > 1:
+            descs = (ctypes.c_void_p * len(todo))(*[ctypes.addressof(om._desc) for om in todo])
+            outs = (ctypes.c_void_p * len(todo))()
+            check(lib.b2h_profile_upload_many(ctx.handle, descs, len(todo), outs), "b2h_profile_upload_many", ctx.handle)
+            enc = lambda t: t.encode("ascii") if t else None
+            for om, h in zip(todo, outs):
+                lib.b2h_profile_set_annotation(h, enc(om.consensus), enc(om.reference), enc(om.consensus_structure),
+                                               om.alphabet.symbols.encode("ascii"))
+                om._dev[ctx] = _DeviceHandle(ctypes.c_void_p(h), lib.b2h_profile_destroy)
+        return [om._device(ctx) for om in oms]
+
     def _filter_one(self, fn, seq):
         ctx = _lib.context()
         db = SequenceDatabase(ctx, DigitalSequenceBlock(self.alphabet, [seq]))
@@ -898,7 +913,7 @@ class Pipeline:
         ctx = self._ctx
         t0 = time.perf_counter()
         db = SequenceDatabase.of(ctx, block)
-        handles = (ctypes.c_void_p * len(oms))(*[om._device(ctx) for om in oms])
+        handles = (ctypes.c_void_p * len(oms))(*OptimizedProfile._device_many(ctx, oms))
         prm = self._params_struct()
         out = ctypes.c_void_p()
         t1 = time.perf_counter()
