@@ -18,7 +18,6 @@
 // Moving the envelope DP to the GPU is SURVEY 8(f) rank 1 (next round).
 #include <algorithm>
 #include <atomic>
-#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -734,14 +733,6 @@ struct HitOut { bool valid = false; b2h_hit hit; std::vector<DomOut> doms; };
 
 char encode_pp(float p) { return (p + 0.05 >= 1.0) ? '*' : (char)((char)((p + 0.05) * 10.0) + '0'); }
 
-#ifdef B2H_DDEF_PROF
-static double g_T[10]; static const char *g_N[10] = {"fwd(env)","bck+dec","OA","oatrace","alidisp+null2","fwd(region)","stotrace+null2bytrace","cluster","ddecoding","other"};
-struct ProfT { int i; std::chrono::steady_clock::time_point t0; ProfT(int i_) : i(i_), t0(std::chrono::steady_clock::now()) {} ~ProfT() { g_T[i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } };
-struct ProfDump { ~ProfDump() { for (int i = 0; i < 10; i++) fprintf(stderr, "[ddef prof] %-24s %8.2f ms\n", g_N[i], g_T[i]); } } g_dump;
-#define PROF(i) ProfT prof_##i(i)
-#else
-#define PROF(i)
-#endif
 struct Worker {
   Mx fwd, bck, pp, oa;
   Trace tr;
@@ -750,23 +741,42 @@ struct Worker {
   FastRng rng;
 };
 
-// rescore_isolated_domain (p7_domaindef.c:814-982), protein (non long-target) branch.  i..j are 1-based in the full sequence.
-bool rescore_domain(Worker &w, Model &m, const b2h_profile *prof, const uint8_t *dsq, int L, int i, int j, bool null2_is_done, DomOut &out)
-{
-  const int Ld = j - i + 1;
-  float envsc;
-  { PROF(0);
-  if (!forward_full(m, dsq + i - 1, Ld, w.fwd, &envsc)) envsc = std::numeric_limits<float>::infinity();   // p7_Forward's status is ignored by the caller
-  }
-  { PROF(1); if (!backward_decode(m, dsq + i - 1, Ld, w.fwd, w.bck, w.pp, w.brow)) return false; }   // eslERANGE from p7_Decoding -> domain dropped (eslFAIL)
-  float oasc; { PROF(2); oasc = optimal_accuracy(m, w.pp, w.oa, w.pmask); }
-  { PROF(3); if (!oa_trace(m, w.pp, w.oa, w.tr)) return false; }
-  PROF(4);
-  for (size_t z = 0; z < w.tr.st.size(); z++) if (w.tr.i[z] > 0) w.tr.i[z] += i - 1;
+// One envelope of one survivor.  Phase A (regions) fills i, j, null2_done; phase B (the O(M*Ld) numeric part of
+// rescore_isolated_domain: Forward, Backward/Decoding, OptimalAccuracy + trace, Null2_ByExpectation) fills the rest,
+// on the host (rescore_numeric) or on the GPU (b2h_envelope.cu); phase C renders the alignment and the scores.
+struct EnvRec {
+  int i = 0, j = 0;                // envelope, 1-based in the full sequence
+  bool null2_done = false;         // the region's null2 odds were already set by the trace ensemble
+  bool ok = false;                 // phase B succeeded (false = the reference's eslFAIL / eslERANGE: domain dropped)
+  float envsc = 0.f, oasc = 0.f;
+  float null2[B2H_NCODE];          // only when !null2_done
+  Trace tr;                        // optimal-accuracy trace; i coordinates relative to the envelope (1..Ld)
+};
 
-  // alignment display (p7_alidisplay_Create, p7_alidisplay.c:92-273): first M .. last M of the (single) domain
+// rescore_isolated_domain (p7_domaindef.c:814-982), protein (non long-target) branch: the numeric part.
+bool rescore_numeric(Worker &w, Model &m, const uint8_t *dsq, EnvRec &e)
+{
+  const int i = e.i, Ld = e.j - e.i + 1;
+  e.ok = false;
+  if (!forward_full(m, dsq + i - 1, Ld, w.fwd, &e.envsc)) e.envsc = std::numeric_limits<float>::infinity();   // p7_Forward's status is ignored by the caller
+  if (!backward_decode(m, dsq + i - 1, Ld, w.fwd, w.bck, w.pp, w.brow)) return false;   // eslERANGE from p7_Decoding -> domain dropped (eslFAIL)
+  e.oasc = optimal_accuracy(m, w.pp, w.oa, w.pmask);
+  if (!oa_trace(m, w.pp, w.oa, e.tr)) return false;
+  if (!e.null2_done) null2_by_expectation(m, w.pp, e.null2);
+  e.ok = true;
+  return true;
+}
+
+// the rest of rescore_isolated_domain: alignment display (p7_alidisplay_Create, p7_alidisplay.c:92-273) from first M to
+// last M of the (single) domain, null2 correction of the envelope.  n2sc is the survivor's per-residue null2 score vector.
+bool render_domain(const Model &m, const b2h_profile *prof, const uint8_t *dsq, EnvRec &e, std::vector<float> &n2sc, DomOut &out)
+{
+  if (!e.ok) return false;
+  const int i = e.i, j = e.j;
+  Trace &tr = e.tr;
+  for (size_t z = 0; z < tr.st.size(); z++) if (tr.i[z] > 0) tr.i[z] += i - 1;
   int z1 = -1, z2 = -1;
-  for (size_t z = 0; z < w.tr.st.size(); z++) if (w.tr.st[z] == ST_M) { if (z1 < 0) z1 = (int)z; z2 = (int)z; }
+  for (size_t z = 0; z < tr.st.size(); z++) if (tr.st[z] == ST_M) { if (z1 < 0) z1 = (int)z; z2 = (int)z; }
   if (z1 < 0) return false;
   const int N = z2 - z1 + 1;
   const bool has_rf = !prof->rf.empty(), has_cs = !prof->cs.empty();
@@ -776,11 +786,11 @@ bool rescore_domain(Worker &w, Model &m, const b2h_profile *prof, const uint8_t 
   const std::string &sym = prof->symbols;
   auto cons = [&](int k) -> char { return (k >= 1 && k <= (int)prof->consensus.size()) ? prof->consensus[k - 1] : 'x'; };
   for (int z = z1; z <= z2; z++) {
-    const int k = w.tr.k[z], ii = w.tr.i[z], s = w.tr.st[z], a = z - z1;
+    const int k = tr.k[z], ii = tr.i[z], s = tr.st[z], a = z - z1;
     const int x = (ii > 0) ? dsq[ii - 1] : 0;
     if (has_rf) rfline[a] = (s == ST_I) ? '.' : prof->rf[k - 1];
     if (has_cs) csline[a] = (s == ST_I) ? '.' : prof->cs[k - 1];
-    ppline[a] = (s == ST_D) ? '.' : encode_pp(w.tr.pp[z]);
+    ppline[a] = (s == ST_D) ? '.' : encode_pp(tr.pp[z]);
     if (s == ST_M) {
       model[a] = cons(k);
       const char cu = (char)toupper((unsigned char)cons(k));
@@ -797,7 +807,7 @@ bool rescore_domain(Worker &w, Model &m, const b2h_profile *prof, const uint8_t 
   }
   b2h_domain &d = out.d;
   memset(&d, 0, sizeof d);
-  d.hmmfrom = w.tr.k[z1]; d.hmmto = w.tr.k[z2]; d.sqfrom = w.tr.i[z1]; d.sqto = w.tr.i[z2]; d.N = N;
+  d.hmmfrom = tr.k[z1]; d.hmmto = tr.k[z2]; d.sqfrom = tr.i[z1]; d.sqto = tr.i[z2]; d.N = N;
   d.has_rf = has_rf; d.has_cs = has_cs;
   out.text.clear();
   for (const std::string *sp : { &model, &mline, &aseq, &ppline }) { out.text += *sp; out.text.push_back('\0'); }
@@ -805,35 +815,49 @@ bool rescore_domain(Worker &w, Model &m, const b2h_profile *prof, const uint8_t 
   if (has_cs) { out.text += csline; out.text.push_back('\0'); }
 
   float domcorrection = 0.0f;
-  if (!null2_is_done) {
-    float null2[B2H_NCODE];
-    null2_by_expectation(m, w.pp, null2);
-    for (int pos = i; pos <= j; pos++) w.n2sc[pos] = logf(null2[dsq[pos - 1] < m.Kp ? dsq[pos - 1] : m.Kp - 1]);
-  }
-  for (int pos = i; pos <= j; pos++) domcorrection += w.n2sc[pos];
+  if (!e.null2_done)
+    for (int pos = i; pos <= j; pos++) n2sc[pos] = logf(e.null2[dsq[pos - 1] < m.Kp ? dsq[pos - 1] : m.Kp - 1]);
+  for (int pos = i; pos <= j; pos++) domcorrection += n2sc[pos];
   d.domcorrection = domcorrection;
-  d.iali = d.sqfrom; d.jali = d.sqto; d.ienv = i; d.jenv = j; d.envsc = envsc; d.oasc = oasc;
+  d.iali = d.sqfrom; d.jali = d.sqto; d.ienv = i; d.jenv = j; d.envsc = e.envsc; d.oasc = e.oasc;
   return true;
 }
 
-void ddef_one(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, HitOut &out)
+// What phase A leaves behind for one survivor.
+struct TaskState {
+  bool dead = true;                // p7_DomainDecoding failed (eslERANGE): no hit
+  std::vector<float> n2sc;         // per-residue null2 scores, 0..L
+  float nexpected = 0.f;
+  int nregions = 0, nclustered = 0;
+  std::vector<EnvRec> envs;        // in sequence order
+  std::vector<int> region_of;      // region id of each envelope (overlap bookkeeping is per clustered region)
+};
+
+void model_of(Worker &w, const b2h_profile *prof, Model &m)
 {
-  out.valid = false; out.doms.clear();
-  const b2h_profile *prof = t.prof;
-  const int L = t.L;
-  Model m; m.M = prof->M; m.K = prof->K; m.Kp = prof->Kp; m.rsc = prof->h_fwd_rsc.data();
+  m.M = prof->M; m.K = prof->K; m.Kp = prof->Kp; m.rsc = prof->h_fwd_rsc.data();
   for (int q = 0; q < 8; q++) m.t[q] = prof->h_fwd_tsc.data() + (size_t)q * prof->M;
   m.degen = prof->h_degen.empty() ? nullptr : prof->h_degen.data();
   chain_prefix(m.t[T_DD], m.M, w.pf_up, w.pf_dn);
   if (w.zrow.size() < (size_t)m.M) w.zrow.assign((size_t)m.M, 0.0f);
   m.pf_up = w.pf_up.data(); m.pf_dn = w.pf_dn.data(); m.zrow = w.zrow.data();
+}
+
+// Phase A: p7_DomainDecoding on the parser specials, region finding, trace-ensemble clustering of multidomain
+// regions (p7_domaindef.c:384-493, 531, 597-678) -> the list of envelopes to rescore.
+void ddef_regions(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, TaskState &ts)
+{
+  ts.dead = true; ts.envs.clear(); ts.region_of.clear(); ts.nregions = ts.nclustered = 0;
+  const b2h_profile *prof = t.prof;
+  const int L = t.L;
+  Model m; model_of(w, prof, m);
   configure(m, true, L);
   const float ploop_multi = m.ploop;
 
   // p7_DomainDecoding (decoding.c:160-193) on the parser specials
   auto FX = [&](int i, int s) { return t.fx[(size_t)i * NX + s]; };
   auto BX = [&](int i, int s) { return t.bx[(size_t)i * NX + s]; };
-  w.btot.assign(L + 1, 0.f); w.etot.assign(L + 1, 0.f); w.mocc.assign(L + 1, 0.f); w.n2sc.assign(L + 1, 0.f);
+  w.btot.assign(L + 1, 0.f); w.etot.assign(L + 1, 0.f); w.mocc.assign(L + 1, 0.f); ts.n2sc.assign(L + 1, 0.f);
   {
     float scaleproduct = 1.0f / BX(0, XN);
     for (int i = 1; i <= L; i++) {
@@ -847,8 +871,9 @@ void ddef_one(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, H
     }
     if (std::isinf(scaleproduct)) return;                 // eslERANGE from p7_DomainDecoding: the reference's pipeline fails here
   }
-  const float nexpected = w.btot[L];
-  int nregions = 0, nclustered = 0, noverlaps = 0, nenvelopes = 0;
+  ts.nexpected = w.btot[L];
+  ts.dead = false;
+  int &nregions = ts.nregions, &nclustered = ts.nclustered;
   const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
   const int nsamples = 200;
 
@@ -868,26 +893,26 @@ void ddef_one(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, H
         nclustered++;
         configure(m, true, L);                            // ReconfigMultihit(om, saveL)
         const int Lr = j - i + 1;
-        { PROF(5); forward_full(m, t.dsq + i - 1, Lr, w.fwd, nullptr); }
+        forward_full(m, t.dsq + i - 1, Lr, w.fwd, nullptr);
         // region_trace_ensemble (p7_domaindef.c:597-678)
-        for (int pos = i; pos <= j; pos++) w.n2sc[pos] = 0.0f;
+        for (int pos = i; pos <= j; pos++) ts.n2sc[pos] = 0.0f;
         if (prm->seed != 0) w.rng.init(prm->seed);        // do_reseeding
         std::vector<SegPair> sp;
         float null2[B2H_NCODE];
-        for (int ts = 0; ts < nsamples; ts++) {
+        for (int smp = 0; smp < nsamples; smp++) {
           if (!stochastic_trace(w.rng, m, Lr, w.fwd, w.tr)) break;
           w.tr.index();
           int pos = 1;
           for (int d = 0; d < w.tr.ndom(); d++) {
-            SegPair s; s.idx = ts; s.i = w.tr.sqfrom[d] + i - 1; s.j = w.tr.sqto[d] + i - 1; s.k = w.tr.hmmfrom[d]; s.m = w.tr.hmmto[d]; s.prob = 0.f;
+            SegPair s; s.idx = smp; s.i = w.tr.sqfrom[d] + i - 1; s.j = w.tr.sqto[d] + i - 1; s.k = w.tr.hmmfrom[d]; s.m = w.tr.hmmto[d]; s.prob = 0.f;
             sp.push_back(s);
             null2_by_trace(m, w.tr, w.tr.tfrom[d], w.tr.tto[d], null2);
-            for (; pos <= w.tr.sqfrom[d]; pos++) w.n2sc[i + pos - 1] += 1.0f;
-            for (; pos <= w.tr.sqto[d];   pos++) { const int x = t.dsq[i + pos - 2]; w.n2sc[i + pos - 1] += null2[x < m.Kp ? x : m.Kp - 1]; }
+            for (; pos <= w.tr.sqfrom[d]; pos++) ts.n2sc[i + pos - 1] += 1.0f;
+            for (; pos <= w.tr.sqto[d];   pos++) { const int x = t.dsq[i + pos - 2]; ts.n2sc[i + pos - 1] += null2[x < m.Kp ? x : m.Kp - 1]; }
           }
-          for (; pos <= Lr; pos++) w.n2sc[i + pos - 1] += 1.0f;
+          for (; pos <= Lr; pos++) ts.n2sc[i + pos - 1] += 1.0f;
         }
-        for (int pos = i; pos <= j; pos++) w.n2sc[pos] = logf(w.n2sc[pos] / (float)nsamples);
+        for (int pos = i; pos <= j; pos++) ts.n2sc[pos] = logf(ts.n2sc[pos] / (float)nsamples);
         std::vector<SegPair> sigc;
         sp_cluster(sp, nsamples, sigc);
         // remove dominated clusters (p7_domaindef.c:647-676)
@@ -899,22 +924,42 @@ void ddef_one(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, H
             const int n = std::min(sigc[d].j - sigc[d].i + 1, sigc[d2].j - sigc[d2].i + 1);
             if ((float)nov / (float)n >= 0.8f) { if (sigc[d].prob > sigc[d2].prob) dominated[d2] = 1; else dominated[d] = 1; }
           }
-        configure(m, false, L);                           // back to unihit
-        int last_j2 = 0;
         for (size_t d = 0; d < sigc.size(); d++) {
           if (dominated[d]) continue;
-          const int i2 = sigc[d].i, j2 = sigc[d].j;
-          if (i2 <= last_j2) noverlaps++;
-          nenvelopes++;
-          DomOut dom;
-          if (rescore_domain(w, m, prof, t.dsq, L, i2, j2, true, dom)) { out.doms.push_back(std::move(dom)); last_j2 = j2; }
+          EnvRec e; e.i = sigc[d].i; e.j = sigc[d].j; e.null2_done = true;
+          ts.envs.push_back(std::move(e)); ts.region_of.push_back(nregions);
         }
       } else {
-        nenvelopes++;
-        DomOut dom;
-        if (rescore_domain(w, m, prof, t.dsq, L, i, j, false, dom)) out.doms.push_back(std::move(dom));
+        EnvRec e; e.i = i; e.j = j; e.null2_done = false;
+        ts.envs.push_back(std::move(e)); ts.region_of.push_back(nregions);
       }
       i = -1; triggered = false;
+    }
+  }
+}
+
+// Phase C: alignments, overlap bookkeeping, per-sequence and per-domain scores (p7_pipeline.c:776-865).
+void ddef_finish(const b2h_ddef_task &t, const b2h_search_params *prm, TaskState &ts, HitOut &out)
+{
+  out.valid = false; out.doms.clear();
+  if (ts.dead) return;
+  const b2h_profile *prof = t.prof;
+  const int L = t.L;
+  Model m; m.M = prof->M; m.K = prof->K; m.Kp = prof->Kp; m.rsc = prof->h_fwd_rsc.data();
+  for (int q = 0; q < 8; q++) m.t[q] = prof->h_fwd_tsc.data() + (size_t)q * prof->M;
+  m.degen = nullptr; m.zrow = nullptr; m.pf_up = m.pf_dn = nullptr;
+  const float nexpected = ts.nexpected;
+  const int nregions = ts.nregions, nclustered = ts.nclustered;
+  int noverlaps = 0, nenvelopes = 0;
+  {
+    int last_j2 = 0, cur_region = -1;
+    for (size_t d = 0; d < ts.envs.size(); d++) {
+      EnvRec &e = ts.envs[d];
+      if (ts.region_of[d] != cur_region) { cur_region = ts.region_of[d]; last_j2 = 0; }
+      if (e.null2_done && e.i <= last_j2) noverlaps++;
+      nenvelopes++;
+      DomOut dom;
+      if (render_domain(m, prof, t.dsq, e, ts.n2sc, dom)) { out.doms.push_back(std::move(dom)); if (e.null2_done) last_j2 = e.j; }
     }
   }
   if (nregions == 0 || nenvelopes == 0 || out.doms.empty()) return;
@@ -926,7 +971,7 @@ void ddef_one(Worker &w, const b2h_ddef_task &t, const b2h_search_params *prm, H
   const double LOG2 = 0.69314718055994529;
   float seqbias;
   if (prm->do_null2) {
-    seqbias = kahan_sum(w.n2sc.data(), L + 1);
+    seqbias = kahan_sum(ts.n2sc.data(), L + 1);
     seqbias = flogsum()(0.0f, (float)(log((double)omega) + (double)seqbias));
   } else seqbias = 0.0f;
   float pre_score = (float)((double)(fwdsc - nullsc) / LOG2);
@@ -1059,12 +1104,28 @@ int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_param
 {
   const size_t n = tasks.size();
   std::vector<HitOut> outs(n);
+  std::vector<TaskState> states(n);
   // longest-processing-time-first: the cost of a task grows with model length x sequence length
   std::vector<uint32_t> order(n);
   for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
   std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
     return (int64_t)tasks[a].prof->M * tasks[a].L > (int64_t)tasks[b].prof->M * tasks[b].L; });
-  ThreadPool::get().parallel_for(n, nthreads, [&](Worker &w, size_t i) { const uint32_t e = order[i]; ddef_one(w, tasks[e], prm, outs[e]); });
+  // phase A: regions and envelopes
+  ThreadPool::get().parallel_for(n, nthreads, [&](Worker &w, size_t i) { const uint32_t e = order[i]; ddef_regions(w, tasks[e], prm, states[e]); });
+  // phase B: the O(M*Ld) numeric rescoring of every envelope, largest first
+  std::vector<std::pair<uint32_t, uint32_t>> envs;
+  for (size_t e = 0; e < n; e++) for (size_t d = 0; d < states[e].envs.size(); d++) envs.emplace_back((uint32_t)e, (uint32_t)d);
+  std::sort(envs.begin(), envs.end(), [&](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) {
+    const EnvRec &x = states[a.first].envs[a.second], &y = states[b.first].envs[b.second];
+    return (int64_t)tasks[a.first].prof->M * (x.j - x.i + 1) > (int64_t)tasks[b.first].prof->M * (y.j - y.i + 1); });
+  ThreadPool::get().parallel_for(envs.size(), nthreads, [&](Worker &w, size_t i) {
+    const b2h_ddef_task &t = tasks[envs[i].first];
+    Model m; model_of(w, t.prof, m);
+    configure(m, false, t.L);                               // p7_oprofile_ReconfigUnihit(om, saveL)
+    rescore_numeric(w, m, t.dsq, states[envs[i].first].envs[envs[i].second]);
+  });
+  // phase C: alignments and scores
+  ThreadPool::get().parallel_for(n, nthreads, [&](Worker &, size_t i) { ddef_finish(tasks[i], prm, states[i], outs[i]); });
   for (size_t e = 0; e < n; e++) {
     if (!outs[e].valid) continue;
     b2h_hit h = outs[e].hit;
