@@ -27,6 +27,8 @@ int b2h_ctx_create(int device, b2h_ctx **out)
   ctx->stream = ctx->own_stream;
   if (const char *ev = getenv("B2H_SSV_INT16")) ctx->ssv_fp16 = (atoi(ev) == 0);
   B2H_CUDA(cudaMalloc(&ctx->d_counters, 64 * sizeof(int)));
+  B2H_CUDA(cudaMalloc(&ctx->d_env_counter, 16 * sizeof(int)));
+  B2H_CUDA(cudaStreamCreateWithFlags(&ctx->env_stream, cudaStreamNonBlocking));
   {  // keep stream-ordered allocations cached across searches instead of returning them to the driver at every sync
     cudaMemPool_t pool; uint64_t keep = ~0ull;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
@@ -40,6 +42,8 @@ void b2h_ctx_destroy(b2h_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_env_counter) cudaFree(ctx->d_env_counter);
+  if (ctx->env_stream) cudaStreamDestroy(ctx->env_stream);
   for (auto &pf : ctx->pinned_free) cudaFreeHost(pf.first);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   for (cudaStream_t q : ctx->side) cudaStreamDestroy(q);
@@ -71,7 +75,7 @@ int b2h_ctx_stage_ms(b2h_ctx *ctx, double *ms8, int reset)
   return B2H_OK;
 }
 const char *b2h_ctx_last_error(const b2h_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-uint64_t    b2h_ctx_launch_count(const b2h_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t    b2h_ctx_launch_count(const b2h_ctx *ctx) { return ctx ? ctx->launches.load() : (uint64_t)0; }
 
 // ------------------------------------------------------------------------------------------
 // sequence arena

@@ -823,6 +823,35 @@ bool render_domain(const Model &m, const b2h_profile *prof, const uint8_t *dsq, 
   return true;
 }
 
+// p7_Null2_ByExpectation's second half from the column sums of the posterior matrix (the GPU returns those)
+void null2_from_sums(const Model &m, int Ld, const float *em_in, const float *ei_in, float xn, float xc, float xj, float *null2)
+{
+  const int M = m.M;
+  const float norm = (float)(1.0 / (float)Ld);
+  xn *= norm; xc *= norm; xj *= norm;
+  const float xfactor = xn + xc + xj;
+  for (int x = 0; x < m.K; x++) {
+    float sv = 0.f;
+    for (int k = 1; k <= M; k++) { sv += (em_in[k - 1] * norm) * m.r(x, k); sv += ei_in[k - 1] * norm; }
+    null2[x] = sv + xfactor;
+  }
+  avg_degenerate(m, null2);
+}
+
+// rebuild the Trace from the records of a traceback done elsewhere (same push/reverse rules as oa_trace)
+bool trace_from_records(const std::vector<int32_t> &rec, int Ld, Trace &tr)
+{
+  tr.clear();
+  tr.push(ST_T, 0, Ld); tr.push(ST_C, 0, Ld);
+  for (size_t z = 0; z + 3 < rec.size(); z += 4) {
+    float p; memcpy(&p, &rec[z + 3], 4);
+    tr.push(rec[z], rec[z + 1], rec[z + 2], p);
+  }
+  if (tr.st.empty() || tr.st.back() != ST_S) return false;
+  tr.reverse();
+  return true;
+}
+
 // What phase A leaves behind for one survivor.
 struct TaskState {
   bool dead = true;                // p7_DomainDecoding failed (eslERANGE): no hit
@@ -1100,7 +1129,7 @@ b2h_ddef_pool::b2h_ddef_pool(int n)
   nthreads = std::max(1, std::min(n, 128));
 }
 
-int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_params *prm, b2h_results *res)
+int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_params *prm, b2h_results *res, b2h_env_backend *backend)
 {
   const size_t n = tasks.size();
   std::vector<HitOut> outs(n);
@@ -1118,7 +1147,33 @@ int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_param
   std::sort(envs.begin(), envs.end(), [&](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) {
     const EnvRec &x = states[a.first].envs[a.second], &y = states[b.first].envs[b.second];
     return (int64_t)tasks[a.first].prof->M * (x.j - x.i + 1) > (int64_t)tasks[b.first].prof->M * (y.j - y.i + 1); });
+  std::vector<char> on_host(envs.size(), 1);
+  if (backend && !envs.empty()) {
+    std::vector<b2h_env_job> jobs(envs.size());
+    for (size_t q = 0; q < envs.size(); q++) {
+      const EnvRec &e = states[envs[q].first].envs[envs[q].second];
+      jobs[q].task = (int)envs[q].first; jobs[q].i = e.i; jobs[q].j = e.j;
+    }
+    const int st = backend->run(tasks, jobs);
+    if (st != B2H_OK) return st;
+    ThreadPool::get().parallel_for(envs.size(), nthreads, [&](Worker &, size_t q) {
+      const b2h_env_job &jb = jobs[q];
+      if (jb.status != 0) return;                            // left to the host below
+      const b2h_ddef_task &t = tasks[envs[q].first];
+      EnvRec &e = states[envs[q].first].envs[envs[q].second];
+      const int Ld = e.j - e.i + 1;
+      e.envsc = jb.envsc; e.oasc = jb.oasc;
+      e.ok = trace_from_records(jb.trace, Ld, e.tr);
+      if (e.ok && !e.null2_done) {
+        Model m; m.M = t.prof->M; m.K = t.prof->K; m.Kp = t.prof->Kp; m.rsc = t.prof->h_fwd_rsc.data();
+        m.degen = t.prof->h_degen.empty() ? nullptr : t.prof->h_degen.data();
+        null2_from_sums(m, Ld, jb.em.data(), jb.ei.data(), jb.xn, jb.xc, jb.xj, e.null2);
+      }
+      on_host[q] = 0;
+    });
+  }
   ThreadPool::get().parallel_for(envs.size(), nthreads, [&](Worker &w, size_t i) {
+    if (!on_host[i]) return;
     const b2h_ddef_task &t = tasks[envs[i].first];
     Model m; model_of(w, t.prof, m);
     configure(m, false, t.L);                               // p7_oprofile_ReconfigUnihit(om, saveL)

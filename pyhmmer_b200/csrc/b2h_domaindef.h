@@ -25,9 +25,26 @@ struct b2h_ddef_task {
   bool               bck_own_scales;
 };
 
+// One envelope handed to a rescoring backend, and what comes back (b2h_envelope.cu fills these on the GPU).
+struct b2h_env_job {
+  int task = 0;                    // index into the task list
+  int i = 0, j = 0;                // envelope in the target, 1-based
+  // results
+  int   status = -1;               // 0 = done; anything else: rescore this envelope on the host
+  float envsc = 0.f, oasc = 0.f;
+  float xn = 0.f, xc = 0.f, xj = 0.f;          // summed posteriors of N, C, J over the envelope (null2)
+  std::vector<float> em, ei;       // summed posteriors of M / I per node, index k-1 (null2)
+  std::vector<int32_t> trace;      // optimal-accuracy trace in traceback order: records {state, k, i, bits(postprob)}
+};
+struct b2h_env_backend {
+  virtual ~b2h_env_backend() {}
+  virtual int run(const std::vector<b2h_ddef_task> &tasks, std::vector<b2h_env_job> &jobs) = 0;
+};
+
 struct b2h_ddef_pool {
   int nthreads;
   explicit b2h_ddef_pool(int n);
-  // runs every task (in parallel), appends the resulting hits to <res> in task order
-  int run(std::vector<b2h_ddef_task> &tasks, const b2h_search_params *prm, b2h_results *res);
+  // runs every task (in parallel), appends the resulting hits to <res> in task order.  With a backend the numeric
+  // rescoring of the envelopes runs there (GPU); without (host-only profiles, tests) on the pool's threads.
+  int run(std::vector<b2h_ddef_task> &tasks, const b2h_search_params *prm, b2h_results *res, b2h_env_backend *backend = nullptr);
 };

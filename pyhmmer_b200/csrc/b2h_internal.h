@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <atomic>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -31,7 +32,7 @@ struct b2h_ctx {
   cudaStream_t  own_stream = nullptr;
   cudaStream_t  stream = nullptr;
   std::string   err;
-  uint64_t      launches = 0;
+  std::atomic<uint64_t> launches{0};   // (the envelope kernels are launched from the domain-definition thread)
   int          *d_counters = nullptr;   // small pool of work counters
   int           profiling = 0;
   int           ssv_fp16 = 1;          // SSV cells as fp16x2 (HFMA2.RELU) instead of s16x2 (VIADDMNMX); B2H_SSV_INT16=1 selects the latter
@@ -40,6 +41,8 @@ struct b2h_ctx {
   double        stage_ms[8] = {0};
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_open;   // (stage, begin, end) awaiting a sync
+  cudaStream_t  env_stream = nullptr;  // stream of the envelope kernels (they overlap the next wave's cascade)
+  int          *d_env_counter = nullptr;
   // page-locked host buffers of destroyed sequence databases, kept for the next one (pinning costs ~0.3 ms/MB)
   std::vector<std::pair<void *, size_t>> pinned_free;
 };
@@ -206,6 +209,21 @@ struct WorkList {
   int           *counter;
   int            plo, phi;   // this launch covers profiles [plo, phi) only (profiles are sorted by size; one launch per size class)
 };
+
+// A batch of envelopes for the kernels of b2h_envelope.cu: entries [e_lo, e_hi) of one (C, W) size class, largest first.
+// Matrices of envelope e: F (3 planes), PP (2 planes), OA (3 planes) of (Ld+1) rows x Mp floats, at plane offset moff[e];
+// special-state rows (6 floats) at row offset xoff[e]; trace records at toff[e] (capacity tcap[e]).
+struct EnvDev {
+  const ProfDev *profs; const int32_t *prof, *seq, *i0, *Ld; const float *pmove;
+  const int64_t *moff, *moff_n, *xoff, *toff; const int32_t *tcap;
+  float *F, *PP, *OA, *fx, *bx, *ox;
+  float *envsc, *oasc, *em, *ei, *xnull; int32_t *status, *tlen; int4 *trace;
+  int *counter; int e_lo, e_hi;
+};
+int b2h_launch_envelope(b2h_ctx *ctx, int kind, int C, int W, const EnvDev &ev, const SeqDev &sd, cudaStream_t strm);
+struct b2h_envclass { int bound, C, W; };
+static const b2h_envclass B2H_ENV_CLASSES[] = {{128, 4, 1}, {256, 8, 1}, {384, 12, 1}, {768, 12, 2}, {1536, 12, 4}, {3072, 12, 8}};
+static const int B2H_N_ENV_CLASSES = 6;
 
 // per-entry outputs of a DP stage
 struct StageOut { float *sc; int32_t *status; float *fwd_xmx, *bck_xmx; const int64_t *xoff; };

@@ -231,6 +231,125 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
 
 // Forward + Backward parsers with stored special-state rows for the F3 survivors (sorted by profile),
 // chunked so that the specials of one chunk stay within a fixed budget; then host domain definition.
+// The GPU backend of the domain definition's phase B: every envelope of a chunk of survivors through
+// efwd/ebck/eoa kernels (b2h_envelope.cu) on the context's envelope stream, results back as b2h_env_job fields.
+// Called from the domain-definition thread while the main thread feeds the cascade of the next wave.
+struct EnvGpu : b2h_env_backend {
+  b2h_ctx *ctx; const b2h_seqdb *db; double ms = 0.0; size_t nenv = 0;
+  EnvGpu(b2h_ctx *c, const b2h_seqdb *d) : ctx(c), db(d) {}
+  template <typename T> int dalloc(std::vector<void *> &keep, T **out, size_t n) {
+    void *p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), ctx->env_stream);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMallocAsync (envelopes): ") + cudaGetErrorString(e); return B2H_EMEM; }
+    keep.push_back(p); *out = (T *)p; return B2H_OK;
+  }
+  int run(const std::vector<b2h_ddef_task> &tasks, std::vector<b2h_env_job> &jobs) override {
+    const double t0 = now_ms();
+    B2H_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->env_stream;
+    const SeqDev sd = b2h_seqdev(db);
+    // order: by size class, inside a class as given (largest first)
+    const size_t n = jobs.size();
+    std::vector<int> cls(n), perm;
+    for (size_t q = 0; q < n; q++) {
+      const int M = tasks[jobs[q].task].prof->M; int c = 0;
+      while (c < B2H_N_ENV_CLASSES && M > B2H_ENV_CLASSES[c].bound) c++;
+      cls[q] = c;                                            // == B2H_N_ENV_CLASSES: longer than any class (cannot happen: SSV tiles stop at 3071)
+    }
+    const size_t BUDGET = (size_t)6 << 30;                   // bytes of matrix scratch per pass
+    std::vector<char> done(n, 0);
+    for (;;) {
+      // take envelopes class by class until the scratch budget is full
+      perm.clear();
+      std::vector<int> cls_lo(B2H_N_ENV_CLASSES + 1, 0);
+      size_t bytes = 0; bool full = false;
+      for (int c = 0; c < B2H_N_ENV_CLASSES && !full; c++) {
+        cls_lo[c] = (int)perm.size();
+        const size_t Mp = (size_t)32 * B2H_ENV_CLASSES[c].C * B2H_ENV_CLASSES[c].W;
+        for (size_t q = 0; q < n; q++) {
+          if (done[q] || cls[q] != c) continue;
+          const size_t need = (size_t)(jobs[q].j - jobs[q].i + 2) * Mp * 8 * sizeof(float);
+          if (!perm.empty() && bytes + need > BUDGET) { full = true; break; }
+          bytes += need; perm.push_back((int)q); done[q] = 1;
+        }
+        cls_lo[c + 1] = (int)perm.size();
+      }
+      for (int c = 0; c < B2H_N_ENV_CLASSES; c++) cls_lo[c + 1] = std::max(cls_lo[c + 1], cls_lo[c]);
+      const int m = (int)perm.size();
+      if (m == 0) break;
+      // per-envelope arrays
+      std::vector<ProfDev> hprof; std::vector<const b2h_profile *> seen;
+      std::vector<int32_t> h_prof(m), h_seq(m), h_i0(m), h_Ld(m), h_tcap(m);
+      std::vector<float> h_pmove(m);
+      std::vector<int64_t> h_moff(m), h_moffn(m), h_xoff(m), h_toff(m);
+      int64_t moff = 0, moffn = 0, xoff = 0, toff = 0;
+      for (int z = 0; z < m; z++) {
+        const b2h_env_job &jb = jobs[perm[z]];
+        const b2h_ddef_task &t = tasks[jb.task];
+        size_t pi = 0; while (pi < seen.size() && seen[pi] != t.prof) pi++;
+        if (pi == seen.size()) { seen.push_back(t.prof); hprof.push_back(b2h_profdev(t.prof)); }
+        const int c = cls[perm[z]];
+        const int64_t Mp = (int64_t)32 * B2H_ENV_CLASSES[c].C * B2H_ENV_CLASSES[c].W;
+        const int Ld = jb.j - jb.i + 1;
+        h_prof[z] = (int32_t)pi; h_seq[z] = t.surv.seq; h_i0[z] = jb.i; h_Ld[z] = Ld;
+        h_pmove[z] = (2.0f + 0.0f) / ((float)t.L + 2.0f + 0.0f);     // configure(m, false, L)
+        h_tcap[z] = Ld + t.prof->M + 16;
+        h_moff[z] = moff; h_moffn[z] = moffn; h_xoff[z] = xoff; h_toff[z] = toff;
+        moff += (int64_t)(Ld + 1) * Mp; moffn += Mp; xoff += Ld + 1; toff += h_tcap[z];
+      }
+      std::vector<void *> keep;
+      EnvDev ev;
+      ProfDev *d_prof; int32_t *d_pi, *d_seq, *d_i0, *d_Ld, *d_tcap; float *d_pmove; int64_t *d_moff, *d_moffn, *d_xoff, *d_toff;
+      int rc = B2H_OK;
+      auto A = [&](int r) { if (rc == B2H_OK) rc = r; };
+      A(dalloc(keep, &d_prof, hprof.size())); A(dalloc(keep, &d_pi, m)); A(dalloc(keep, &d_seq, m)); A(dalloc(keep, &d_i0, m)); A(dalloc(keep, &d_Ld, m));
+      A(dalloc(keep, &d_tcap, m)); A(dalloc(keep, &d_pmove, m)); A(dalloc(keep, &d_moff, m)); A(dalloc(keep, &d_moffn, m)); A(dalloc(keep, &d_xoff, m)); A(dalloc(keep, &d_toff, m));
+      A(dalloc(keep, &ev.F, (size_t)moff * 3)); A(dalloc(keep, &ev.PP, (size_t)moff * 2)); A(dalloc(keep, &ev.OA, (size_t)moff * 3));
+      A(dalloc(keep, &ev.fx, (size_t)xoff * 6)); A(dalloc(keep, &ev.bx, (size_t)xoff * 6)); A(dalloc(keep, &ev.ox, (size_t)xoff * 6));
+      A(dalloc(keep, &ev.envsc, m)); A(dalloc(keep, &ev.oasc, m)); A(dalloc(keep, &ev.em, (size_t)moffn)); A(dalloc(keep, &ev.ei, (size_t)moffn));
+      A(dalloc(keep, &ev.xnull, (size_t)m * 4)); A(dalloc(keep, &ev.status, m)); A(dalloc(keep, &ev.tlen, m)); A(dalloc(keep, &ev.trace, (size_t)toff));
+      auto release = [&]() { for (void *p : keep) cudaFreeAsync(p, st); };
+      if (rc != B2H_OK) { release(); return rc; }
+#define H2D(dst, src) cudaMemcpyAsync(dst, (src).data(), (src).size() * sizeof((src)[0]), cudaMemcpyHostToDevice, st)
+      H2D(d_prof, hprof); H2D(d_pi, h_prof); H2D(d_seq, h_seq); H2D(d_i0, h_i0); H2D(d_Ld, h_Ld); H2D(d_tcap, h_tcap); H2D(d_pmove, h_pmove);
+      H2D(d_moff, h_moff); H2D(d_moffn, h_moffn); H2D(d_xoff, h_xoff); H2D(d_toff, h_toff);
+#undef H2D
+      cudaMemsetAsync(ev.tlen, 0xff, (size_t)m * sizeof(int32_t), st);
+      ev.profs = d_prof; ev.prof = d_pi; ev.seq = d_seq; ev.i0 = d_i0; ev.Ld = d_Ld; ev.pmove = d_pmove;
+      ev.moff = d_moff; ev.moff_n = d_moffn; ev.xoff = d_xoff; ev.toff = d_toff; ev.tcap = d_tcap; ev.counter = ctx->d_env_counter;
+      for (int c = 0; c < B2H_N_ENV_CLASSES && rc == B2H_OK; c++) {
+        if (cls_lo[c + 1] <= cls_lo[c]) continue;
+        ev.e_lo = cls_lo[c]; ev.e_hi = cls_lo[c + 1];
+        for (int kind = 0; kind < 3 && rc == B2H_OK; kind++) rc = b2h_launch_envelope(ctx, kind, B2H_ENV_CLASSES[c].C, B2H_ENV_CLASSES[c].W, ev, sd, st);
+      }
+      if (rc != B2H_OK) { release(); return rc; }
+      std::vector<float> r_envsc(m), r_oasc(m), r_xnull((size_t)m * 4), r_em((size_t)moffn), r_ei((size_t)moffn);
+      std::vector<int32_t> r_status(m), r_tlen(m), r_trace((size_t)toff * 4);
+#define D2H(dst, src) cudaMemcpyAsync((dst).data(), src, (dst).size() * sizeof((dst)[0]), cudaMemcpyDeviceToHost, st)
+      D2H(r_envsc, ev.envsc); D2H(r_oasc, ev.oasc); D2H(r_xnull, ev.xnull); D2H(r_em, ev.em); D2H(r_ei, ev.ei);
+      D2H(r_status, ev.status); D2H(r_tlen, ev.tlen); D2H(r_trace, ev.trace);
+#undef D2H
+      cudaError_t ce = cudaStreamSynchronize(st);
+      release();
+      if (ce != cudaSuccess) { ctx->err = std::string("envelope kernels: ") + cudaGetErrorString(ce); return B2H_ECUDA; }
+      for (int z = 0; z < m; z++) {
+        b2h_env_job &jb = jobs[perm[z]];
+        const int M = tasks[jb.task].prof->M;
+        const int base = r_status[z] & 0xff;                                             // a Forward range error only makes envsc = inf
+        if ((base != B2H_OK && base != B2H_ERANGE) || (r_status[z] & 0x300) || r_tlen[z] < 0) { jb.status = 1; continue; }
+        jb.status = 0; jb.envsc = r_envsc[z]; jb.oasc = r_oasc[z];
+        jb.xn = r_xnull[(size_t)z * 4 + 0]; jb.xc = r_xnull[(size_t)z * 4 + 1]; jb.xj = r_xnull[(size_t)z * 4 + 2];
+        jb.em.assign(r_em.begin() + h_moffn[z], r_em.begin() + h_moffn[z] + M);
+        jb.ei.assign(r_ei.begin() + h_moffn[z], r_ei.begin() + h_moffn[z] + M);
+        jb.trace.assign(r_trace.begin() + h_toff[z] * 4, r_trace.begin() + (h_toff[z] + r_tlen[z]) * 4);
+      }
+      nenv += (size_t)m;
+    }
+    ms += now_ms() - t0;
+    return B2H_OK;
+  }
+};
+
 // One chunk of survivors whose parser specials are on the host: the domain definition runs on the host thread pool
 // from a helper thread while the calling thread goes on feeding the GPU with the next wave of profiles.
 struct DdefJob {
@@ -238,8 +357,8 @@ struct DdefJob {
   std::thread th; int status = B2H_OK; double ms = 0.0;
 };
 struct DdefAsync {
-  b2h_ddef_pool &pool; const b2h_search_params *prm; b2h_results *res; std::unique_ptr<DdefJob> cur; double total_ms = 0.0;
-  DdefAsync(b2h_ddef_pool &p, const b2h_search_params *pr, b2h_results *r) : pool(p), prm(pr), res(r) {}
+  b2h_ddef_pool &pool; const b2h_search_params *prm; b2h_results *res; b2h_env_backend *backend; std::unique_ptr<DdefJob> cur; double total_ms = 0.0;
+  DdefAsync(b2h_ddef_pool &p, const b2h_search_params *pr, b2h_results *r, b2h_env_backend *be) : pool(p), prm(pr), res(r), backend(be) {}
   int join() {
     if (!cur) return B2H_OK;
     cur->th.join();
@@ -253,7 +372,7 @@ struct DdefAsync {
     if (st != B2H_OK) return st;
     cur = std::move(job);
     DdefJob *j = cur.get();
-    j->th = std::thread([this, j]() { const double t0 = now_ms(); j->status = pool.run(j->tasks, prm, res); j->ms = now_ms() - t0; });
+    j->th = std::thread([this, j]() { const double t0 = now_ms(); j->status = pool.run(j->tasks, prm, res, backend); j->ms = now_ms() - t0; });
     return B2H_OK;
   }
   ~DdefAsync() { if (cur) cur->th.join(); }
@@ -368,7 +487,9 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
       } }
     std::vector<int64_t> scnt(P * 4, 0);
     b2h_ddef_pool ddpool(prm->host_threads);
-    DdefAsync ddef(ddpool, prm, res);
+    EnvGpu envgpu(ctx, db);
+    const bool host_env = getenv("B2H_ENVELOPES_ON_HOST") != nullptr;     // debugging aid: rescore envelopes with the host code
+    DdefAsync ddef(ddpool, prm, res, host_env ? nullptr : &envgpu);
     size_t nsurv = 0; double tg = 0.0;
     for (size_t w = 0; w + 1 < bounds.size(); w++) {
       std::vector<b2h_survivor> surv;
@@ -385,8 +506,8 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     for (size_t i = 0; i < P; i++) for (int c = 0; c < 4; c++) res->counters[(size_t)order[i] * 4 + c] = scnt[i * 4 + c];
     std::stable_sort(res->hits.begin(), res->hits.end(), [](const b2h_hit &x, const b2h_hit &y) {
       return x.profile != y.profile ? x.profile < y.profile : x.seq < y.seq; });
-    if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search] %zu waves: GPU cascade + survivor parsers %.1f ms, %zu survivors, host domain definition %.1f ms in total (%.1f ms not hidden), all %.1f ms\n",
-                                     bounds.size() - 1, tg, nsurv, ddef.total_ms, now_ms() - t1, now_ms() - t0);
+    if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search] %zu waves: GPU cascade + survivor parsers %.1f ms, %zu survivors, host domain definition %.1f ms in total (%.1f ms not hidden; %zu envelopes on the GPU, %.1f ms), all %.1f ms\n",
+                                     bounds.size() - 1, tg, nsurv, ddef.total_ms, now_ms() - t1, envgpu.nenv, envgpu.ms, now_ms() - t0);
   }
   *out = res;
   return B2H_OK;

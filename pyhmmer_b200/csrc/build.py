@@ -23,6 +23,7 @@ SOURCES = [
     "b2h_msv.cu",
     "b2h_dp.cu",
     "b2h_dpreg.cu",
+    "b2h_envelope.cu",
     "b2h_search.cu",
     "b2h_domaindef.cpp",
 ]
