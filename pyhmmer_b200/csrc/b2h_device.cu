@@ -29,6 +29,8 @@ int b2h_ctx_create(int device, b2h_ctx **out)
   B2H_CUDA(cudaMalloc(&ctx->d_counters, 64 * sizeof(int)));
   B2H_CUDA(cudaMalloc(&ctx->d_env_counter, 16 * sizeof(int)));
   B2H_CUDA(cudaStreamCreateWithFlags(&ctx->env_stream, cudaStreamNonBlocking));
+  B2H_CUDA(cudaEventCreateWithFlags(&ctx->env_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 8; i++) { B2H_CUDA(cudaStreamCreateWithFlags(&ctx->env_side[i], cudaStreamNonBlocking)); B2H_CUDA(cudaEventCreateWithFlags(&ctx->env_join[i], cudaEventDisableTiming)); }
   {  // keep stream-ordered allocations cached across searches instead of returning them to the driver at every sync
     cudaMemPool_t pool; uint64_t keep = ~0ull;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
@@ -44,6 +46,8 @@ void b2h_ctx_destroy(b2h_ctx *ctx)
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_env_counter) cudaFree(ctx->d_env_counter);
   if (ctx->env_stream) cudaStreamDestroy(ctx->env_stream);
+  if (ctx->env_fork) cudaEventDestroy(ctx->env_fork);
+  for (int i = 0; i < 8; i++) { if (ctx->env_side[i]) cudaStreamDestroy(ctx->env_side[i]); if (ctx->env_join[i]) cudaEventDestroy(ctx->env_join[i]); }
   for (auto &pf : ctx->pinned_free) cudaFreeHost(pf.first);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   for (cudaStream_t q : ctx->side) cudaStreamDestroy(q);

@@ -302,10 +302,10 @@ __global__ void __launch_bounds__(256) ebck_kernel(const EnvDev ev, const SeqDev
       return t;
     };
     // posterior row i: F(i,k) * B(i,k) for M and I; column sums weighted by Forward's scale of the row
+    float fM[C], fI[C];                                          // Forward row of the posterior row being produced (loaded a row ahead)
+    auto fetch_f = [&](int i) { const float *fr = Fm + (size_t)i * 3 * Mp + k0; load_plane<C>(fr, fM); load_plane<C>(fr + 2 * Mp, fI); };
     auto emit_pp = [&](int i) {
-      const float *fr = Fm + (size_t)i * 3 * Mp + k0;
-      float fM[C], fI[C], q[C];
-      load_plane<C>(fr, fM); load_plane<C>(fr + 2 * Mp, fI);
+      float q[C];
       const float fsc = fx[(size_t)i * 6 + 5];
       float *pr = Pm + (size_t)i * 2 * Mp + k0;
 #pragma unroll
@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(256) ebck_kernel(const EnvDev ev, const SeqDev
     group_sync<W>(grp);
 
     // row L
+    if (L >= 1) fetch_f(L);
 #pragma unroll
     for (int c = 0; c < C; c++) { const bool in = (k0 + c) < M; Dv[c] = in ? xE : 0.f; Iv[c] = 0.f; }
     close_dd();
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(256) ebck_kernel(const EnvDev ev, const SeqDev
 
     for (int i = L - 1; i >= 1; i--) {
       const int x = seq[i];                               // x_{i+1}
+      fetch_f(i);
       float r[C];
       load_nodes<C>(P.fwd_rsc + (size_t)x * Mpad, k0, Mpad, r);
       float me[C];
@@ -469,24 +471,40 @@ __global__ void __launch_bounds__(256) eoa_kernel(const EnvDev ev, const SeqDev 
     float cM = NEGINF, cI = NEGINF, cD = NEGINF;                 // W > 1: previous row's cells of the left warp's last node
     group_sync<W>(grp);
 
+    uint8_t *Bp = ev.BP + ev.moff[e];                            // back-pointers: one byte per cell, (Ld+1) rows of Mp
+    float qMn[C], qIn[C];
+    if (L >= 1) { const float *pr = Pm + (size_t)1 * 2 * Mp + k0; load_plane<C>(pr, qMn); load_plane<C>(pr + Mp, qIn); }
     for (int i = 1; i <= L; i++) {
       const float rs = sp * fx[(size_t)i * 6 + 5];
-      const float *pr = Pm + (size_t)i * 2 * Mp + k0;
       float qM[C], qI[C];
-      load_plane<C>(pr, qM); load_plane<C>(pr + Mp, qI);
+#pragma unroll
+      for (int c = 0; c < C; c++) { qM[c] = qMn[c]; qI[c] = qIn[c]; }
+      if (i < L) { const float *pr = Pm + (size_t)(i + 1) * 2 * Mp + k0; load_plane<C>(pr, qMn); load_plane<C>(pr + Mp, qIn); }   // next row, one row ahead
       float mp = __shfl_up_sync(FULL, Mv[C - 1], 1), ip = __shfl_up_sync(FULL, Iv[C - 1], 1), dp = __shfl_up_sync(FULL, Dv[C - 1], 1);
       if (lane == 0) { mp = cM; ip = cI; dp = cD; }
       float xEm = NEGINF;
+      uint32_t bp[C];                                            // bits 0-1: M came from M/I/D/B; bit 2: I came from I; bit 3: D came from D
 #pragma unroll
       for (int c = C - 1; c >= 0; c--) {
-        const float pm = (c == 0) ? mp : Mv[c - 1], pi = (c == 0) ? ip : Iv[c - 1], pd = (c == 0) ? dp : Dv[c - 1];
+        float pm = (c == 0) ? mp : Mv[c - 1], pi = (c == 0) ? ip : Iv[c - 1], pd = (c == 0) ? dp : Dv[c - 1];
         const int g = gm[c];
         float iv = (g & G_MI) ? Mv[c] : 0.0f;
         iv = fmaxf(iv, (g & G_II) ? Iv[c] : 0.0f);
+        // p7_OATrace's choices at this cell, made now while the candidates are in registers (select_i / select_m, optacc.c:300-371)
+        const float i0p = (g & G_MI) ? Mv[c] : NEGINF, i1p = (g & G_II) ? Iv[c] : NEGINF;
+        uint32_t b = (i0p >= i1p) ? 0u : 4u;
         float sv = (g & G_BM) ? xB : 0.0f;
         sv = fmaxf(sv, (g & G_MM) ? pm : 0.0f);
         sv = fmaxf(sv, (g & G_IM) ? pi : 0.0f);
         sv = fmaxf(sv, (g & G_DM) ? pd : 0.0f);
+        if (k0 + c == 0) { pm = 0.0f; pi = 0.0f; pd = 0.0f; }     // node 1: zeros shift in (rightshiftz)
+        const float p0 = (g & G_MM) ? pm : NEGINF, p1 = (g & G_IM) ? pi : NEGINF, p2 = (g & G_DM) ? pd : NEGINF, p3 = (g & G_BM) ? xB : NEGINF;
+        { uint32_t best = 0u; float bv = p0;
+          if (p1 > bv) { bv = p1; best = 1u; }
+          if (p2 > bv) { bv = p2; best = 2u; }
+          if (p3 > bv) { bv = p3; best = 3u; }
+          b |= best; }
+        bp[c] = b;
         const bool in = (k0 + c) < M;
         sv = in ? sv + qM[c] * rs : NEGINF;
         xEm = fmaxf(xEm, sv);
@@ -539,6 +557,20 @@ __global__ void __launch_bounds__(256) eoa_kernel(const EnvDev ev, const SeqDev 
       }
 #pragma unroll
       for (int c = 0; c < C; c++) { const bool in = (k0 + c) < M; Dv[c] = in ? fmaxf(Dv[c], pm[c] ? din : NEGINF) : NEGINF; xEm = fmaxf(xEm, Dv[c]); }
+      {   // select_d (optacc.c:340-352): D(k) from M(k-1) unless D(k-1) is strictly better; <din> is the closed D left of this lane
+        float mleft = __shfl_up_sync(FULL, Mv[C - 1], 1);
+        if (lane == 0) mleft = (W > 1 && wi > 0) ? cM : NEGINF;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const int gp = (c == 0) ? gprev : gm[c - 1];
+          const float p0 = (gp & G_MD) ? ((c == 0) ? mleft : Mv[c - 1]) : NEGINF;
+          const float p1 = (gp & G_DD) ? ((c == 0) ? din : Dv[c - 1]) : NEGINF;
+          if (!(p0 >= p1)) bp[c] |= 8u;
+        }
+        uint32_t *brow = reinterpret_cast<uint32_t *>(Bp + (size_t)i * Mp + k0);
+#pragma unroll
+        for (int g = 0; g < C / 4; g++) brow[g] = bp[4*g] | (bp[4*g+1] << 8) | (bp[4*g+2] << 16) | (bp[4*g+3] << 24);
+      }
       xE = warp_max(xEm);
       if (W > 1) {
         float (*X)[W] = s_x[i & 1][grp];
@@ -580,32 +612,21 @@ __global__ void __launch_bounds__(256) eoa_kernel(const EnvDev ev, const SeqDev 
       int nrec = 0, i = L, k = 0, s0 = ST_C;
       bool bad = false;
       auto O = [&](int r, int kk, int pl) -> float { return Om[(size_t)r * 3 * Mp + (size_t)pl * Mp + (kk - 1)]; };   // node kk (1-based) lives at column kk-1
-      auto T_ = [&](int tr, int kk) -> float { return ts[(size_t)tr * Mpad + (kk - 1)]; };                          // transition row tr of node kk
       auto OX = [&](int r, int q) -> float { return ox[(size_t)r * 6 + q]; };
-      auto path = [](float t, float v) -> float { return (t == 0.0f) ? NEGINF : v; };
       int guard = (L + M + 8) * 4 + 64;
+      // the record of a step is stored one step later, so that the loads of its posterior probability are not on the
+      // critical path of the walk (the next back-pointer load is issued first)
+      int ps = -1, pk = 0, pi_ = 0; float pa = 0.f, pb = 0.f;     // pending record: state, k, i, postprob = pa * pb
       while (s0 != ST_S) {
         if (guard-- <= 0) { bad = true; break; }
         int s1 = -1;
+        uint32_t b = 0;
+        if (s0 == ST_M || s0 == ST_D || s0 == ST_I) b = Bp[(size_t)i * Mp + (k - 1)];
+        if (ps >= 0) { if (lane == 0) rec[nrec - 1] = make_int4(ps, pk, pi_, __float_as_int(pa * pb)); ps = -1; }
         switch (s0) {
-          case ST_M: {
-            float p0, p1, p2;
-            if (k == 1) { p0 = path(T_(1, k), 0.0f); p1 = path(T_(2, k), 0.0f); p2 = path(T_(3, k), 0.0f); }
-            else { p0 = path(T_(1, k), O(i - 1, k - 1, 0)); p1 = path(T_(2, k), O(i - 1, k - 1, 2)); p2 = path(T_(3, k), O(i - 1, k - 1, 1)); }
-            const float p3 = path(T_(0, k), OX(i - 1, 3));
-            int best = 0; float bv = p0;
-            if (p1 > bv) { bv = p1; best = 1; }
-            if (p2 > bv) { bv = p2; best = 2; }
-            if (p3 > bv) { bv = p3; best = 3; }
-            s1 = (best == 0) ? ST_M : (best == 1) ? ST_I : (best == 2) ? ST_D : ST_B;
-            k--; i--; break; }
-          case ST_D: {
-            const float p0 = (k > 1) ? path(T_(4, k - 1), O(i, k - 1, 0)) : NEGINF;
-            const float p1 = (k > 1) ? path(T_(7, k - 1), O(i, k - 1, 1)) : NEGINF;
-            s1 = (p0 >= p1) ? ST_M : ST_D; k--; break; }
-          case ST_I: {
-            const float p0 = path(T_(5, k), O(i - 1, k, 0)), p1 = path(T_(6, k), O(i - 1, k, 2));
-            s1 = (p0 >= p1) ? ST_M : ST_I; i--; break; }
+          case ST_M: { const uint32_t ch = b & 3u; s1 = (ch == 0u) ? ST_M : (ch == 1u) ? ST_I : (ch == 2u) ? ST_D : ST_B; k--; i--; break; }
+          case ST_D: s1 = (b & 8u) ? ST_D : ST_M; k--; break;
+          case ST_I: s1 = (b & 4u) ? ST_I : ST_M; i--; break;
           case ST_N: s1 = (i == 0) ? ST_S : ST_N; break;
           case ST_C: {
             const float ppC = fx[(size_t)(i - 1) * 6 + 4] * bx[(size_t)i * 6 + 4] * ploop * sp;
@@ -642,20 +663,22 @@ __global__ void __launch_bounds__(256) eoa_kernel(const EnvDev ev, const SeqDev 
           default: bad = true; break;
         }
         if (bad || s1 == -1) { bad = true; break; }
-        float postprob = 0.0f;
+        if (nrec >= cap) { bad = true; break; }
+        // posterior probability of the new state: loads issued now, consumed when the record is stored
+        pa = 0.f; pb = 0.f;
         if (s1 == ST_M || s1 == ST_I) {
-          const float rs = sp * fx[(size_t)i * 6 + 5];
-          postprob = Pm[(size_t)i * 2 * Mp + (size_t)(s1 == ST_M ? 0 : 1) * Mp + (k - 1)] * rs;
+          pb = sp * fx[(size_t)i * 6 + 5];
+          pa = Pm[(size_t)i * 2 * Mp + (size_t)(s1 == ST_M ? 0 : 1) * Mp + (k - 1)];
         } else if (s1 == s0 && (s1 == ST_N || s1 == ST_C || s1 == ST_J)) {
           const int q = (s1 == ST_N) ? 1 : (s1 == ST_J) ? 2 : 4;
-          postprob = fx[(size_t)(i - 1) * 6 + q] * bx[(size_t)i * 6 + q] * ploop * sp;
+          pa = fx[(size_t)(i - 1) * 6 + q] * bx[(size_t)i * 6 + q] * ploop; pb = sp;
         }
-        if (nrec >= cap) { bad = true; break; }
-        if (lane == 0) rec[nrec] = make_int4(s1, k, i, __float_as_int(postprob));
+        ps = s1; pk = k; pi_ = i;
         nrec++;
         if ((s1 == ST_N || s1 == ST_J || s1 == ST_C) && s1 == s0) i--;
         s0 = s1;
       }
+      if (ps >= 0 && lane == 0) rec[nrec - 1] = make_int4(ps, pk, pi_, __float_as_int(pa * pb));
       if (lane == 0) { ev.tlen[e] = bad ? -1 : nrec; }
     }
   }

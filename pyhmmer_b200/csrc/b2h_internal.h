@@ -43,6 +43,7 @@ struct b2h_ctx {
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_open;   // (stage, begin, end) awaiting a sync
   cudaStream_t  env_stream = nullptr;  // stream of the envelope kernels (they overlap the next wave's cascade)
   int          *d_env_counter = nullptr;
+  cudaStream_t  env_side[8] = {nullptr}; cudaEvent_t env_fork = nullptr, env_join[8] = {nullptr};   // one side stream per envelope size class
   // page-locked host buffers of destroyed sequence databases, kept for the next one (pinning costs ~0.3 ms/MB)
   std::vector<std::pair<void *, size_t>> pinned_free;
 };
@@ -216,7 +217,7 @@ struct WorkList {
 struct EnvDev {
   const ProfDev *profs; const int32_t *prof, *seq, *i0, *Ld; const float *pmove;
   const int64_t *moff, *moff_n, *xoff, *toff; const int32_t *tcap;
-  float *F, *PP, *OA, *fx, *bx, *ox;
+  float *F, *PP, *OA, *fx, *bx, *ox; uint8_t *BP;
   float *envsc, *oasc, *em, *ei, *xnull; int32_t *status, *tlen; int4 *trace;
   int *counter; int e_lo, e_hi;
 };

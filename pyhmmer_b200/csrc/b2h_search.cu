@@ -268,7 +268,7 @@ struct EnvGpu : b2h_env_backend {
         const size_t Mp = (size_t)32 * B2H_ENV_CLASSES[c].C * B2H_ENV_CLASSES[c].W;
         for (size_t q = 0; q < n; q++) {
           if (done[q] || cls[q] != c) continue;
-          const size_t need = (size_t)(jobs[q].j - jobs[q].i + 2) * Mp * 8 * sizeof(float);
+          const size_t need = (size_t)(jobs[q].j - jobs[q].i + 2) * Mp * (8 * sizeof(float) + 1);
           if (!perm.empty() && bytes + need > BUDGET) { full = true; break; }
           bytes += need; perm.push_back((int)q); done[q] = 1;
         }
@@ -304,7 +304,7 @@ struct EnvGpu : b2h_env_backend {
       auto A = [&](int r) { if (rc == B2H_OK) rc = r; };
       A(dalloc(keep, &d_prof, hprof.size())); A(dalloc(keep, &d_pi, m)); A(dalloc(keep, &d_seq, m)); A(dalloc(keep, &d_i0, m)); A(dalloc(keep, &d_Ld, m));
       A(dalloc(keep, &d_tcap, m)); A(dalloc(keep, &d_pmove, m)); A(dalloc(keep, &d_moff, m)); A(dalloc(keep, &d_moffn, m)); A(dalloc(keep, &d_xoff, m)); A(dalloc(keep, &d_toff, m));
-      A(dalloc(keep, &ev.F, (size_t)moff * 3)); A(dalloc(keep, &ev.PP, (size_t)moff * 2)); A(dalloc(keep, &ev.OA, (size_t)moff * 3));
+      A(dalloc(keep, &ev.F, (size_t)moff * 3)); A(dalloc(keep, &ev.PP, (size_t)moff * 2)); A(dalloc(keep, &ev.OA, (size_t)moff * 3)); A(dalloc(keep, &ev.BP, (size_t)moff));
       A(dalloc(keep, &ev.fx, (size_t)xoff * 6)); A(dalloc(keep, &ev.bx, (size_t)xoff * 6)); A(dalloc(keep, &ev.ox, (size_t)xoff * 6));
       A(dalloc(keep, &ev.envsc, m)); A(dalloc(keep, &ev.oasc, m)); A(dalloc(keep, &ev.em, (size_t)moffn)); A(dalloc(keep, &ev.ei, (size_t)moffn));
       A(dalloc(keep, &ev.xnull, (size_t)m * 4)); A(dalloc(keep, &ev.status, m)); A(dalloc(keep, &ev.tlen, m)); A(dalloc(keep, &ev.trace, (size_t)toff));
@@ -317,12 +317,19 @@ struct EnvGpu : b2h_env_backend {
       cudaMemsetAsync(ev.tlen, 0xff, (size_t)m * sizeof(int32_t), st);
       ev.profs = d_prof; ev.prof = d_pi; ev.seq = d_seq; ev.i0 = d_i0; ev.Ld = d_Ld; ev.pmove = d_pmove;
       ev.moff = d_moff; ev.moff_n = d_moffn; ev.xoff = d_xoff; ev.toff = d_toff; ev.tcap = d_tcap; ev.counter = ctx->d_env_counter;
+      // every size class on its own stream (forked from / joined to the envelope stream): a class launch is as long as
+      // its longest envelope and fills only a few SMs, so the classes overlap
+      cudaEventRecord(ctx->env_fork, st);
       for (int c = 0; c < B2H_N_ENV_CLASSES && rc == B2H_OK; c++) {
         if (cls_lo[c + 1] <= cls_lo[c]) continue;
-        ev.e_lo = cls_lo[c]; ev.e_hi = cls_lo[c + 1];
-        for (int kind = 0; kind < 3 && rc == B2H_OK; kind++) rc = b2h_launch_envelope(ctx, kind, B2H_ENV_CLASSES[c].C, B2H_ENV_CLASSES[c].W, ev, sd, st);
+        cudaStream_t sc = ctx->env_side[c];
+        cudaStreamWaitEvent(sc, ctx->env_fork, 0);
+        ev.e_lo = cls_lo[c]; ev.e_hi = cls_lo[c + 1]; ev.counter = ctx->d_env_counter + c;
+        for (int kind = 0; kind < 3 && rc == B2H_OK; kind++) rc = b2h_launch_envelope(ctx, kind, B2H_ENV_CLASSES[c].C, B2H_ENV_CLASSES[c].W, ev, sd, sc);
+        cudaEventRecord(ctx->env_join[c], sc);
+        cudaStreamWaitEvent(st, ctx->env_join[c], 0);
       }
-      if (rc != B2H_OK) { release(); return rc; }
+      if (rc != B2H_OK) { cudaStreamSynchronize(st); release(); return rc; }
       std::vector<float> r_envsc(m), r_oasc(m), r_xnull((size_t)m * 4), r_em((size_t)moffn), r_ei((size_t)moffn);
       std::vector<int32_t> r_status(m), r_tlen(m), r_trace((size_t)toff * 4);
 #define D2H(dst, src) cudaMemcpyAsync((dst).data(), src, (dst).size() * sizeof((dst)[0]), cudaMemcpyDeviceToHost, st)
