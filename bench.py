@@ -339,11 +339,18 @@ def main():
     b_alg = float(seqs.total_residues + 2 * len(seqs)) + msv_tab_bytes + 16.0 * n_past_msv      # per step, this rank
     ssv_ms = stage_ms["ssv"] / K
     achieved = b_alg / (ssv_ms * 1e-3) / 1e9 if ssv_ms > 0 else None
-    # the resource the SSV kernel actually saturates: the shared-memory data pipe (128 B/clk/SM).  Per DP row a warp
-    # reads NR*128 B of emission scores (LDS) and moves 1.25 shuffles (one wavefront each).
-    nr_classes = [1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32, 40, 48]
+    # the resource the SSV kernel actually saturates: the shared-memory data pipe (128 B/clk/SM).  Per DP row a WARP
+    # (32/G comparisons side by side) moves b2h_ssv_tile_info's wavefronts: emission scores (LDS) + 1.25 shuffles.
+    import ctypes
+
+    def ssv_row_bytes(M):
+        G, NR, wf = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        _lib.check(_lib.lib.b2h_ssv_tile_info(int(M), ctypes.byref(G), ctypes.byref(NR), ctypes.byref(wf)), "b2h_ssv_tile_info")
+        return wf.value * 128.0 * G.value / 32.0, 2.0 * G.value * NR.value      # bytes per row per comparison, cells per row incl. padding
+
     rows = float(sum(((len(q) + 3) // 4) * 4 for q in seqs))
-    smem_bytes = sum(rows * (min(n for n in nr_classes if 64 * n >= h.M + 1) + 1.25) * 128.0 for h in hmms)
+    smem_bytes = sum(rows * ssv_row_bytes(h.M)[0] for h in hmms)
+    padded_cells = sum(rows * ssv_row_bytes(h.M)[1] for h in hmms)
     sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
     smem_peak = 128.0 * torch.cuda.get_device_properties(local).multi_processor_count * sm_clock / 1e9
     smem_ach = smem_bytes / (ssv_ms * 1e-3) / 1e9 if ssv_ms > 0 else None
@@ -364,10 +371,11 @@ def main():
                    "l2": "flushed (256 MiB write) between steps", "sharding": "targets by rank, one all-gather of hit records",
                    "hits_rank0": len(hits), "pipeline_counters_rank0": counters.sum(0).tolist(),
                    "stage_ms_per_step": {k: v / K for k, v in stage_ms.items()},
-                   "ssv_kernel_gcups": (cells_local / (ssv_ms * 1e-3) / 1e9) if ssv_ms > 0 else None},
+                   "ssv_kernel_gcups": (cells_local / (ssv_ms * 1e-3) / 1e9) if ssv_ms > 0 else None,
+                   "ssv_kernel_gcups_incl_padding": (padded_cells / (ssv_ms * 1e-3) / 1e9) if ssv_ms > 0 else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
                      "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_kind": pk_kind,
-                     "kernel": "ssv_kernel<NR> (all launches of a step)", "algorithmic_bytes_per_step": b_alg,
+                     "kernel": "ssv_kernel<G,NR> (all launches of a step)", "algorithmic_bytes_per_step": b_alg,
                      "on_chip": {"bound": "shared-memory data pipe (LDS + SHFL wavefronts)", "achieved": smem_ach, "peak": smem_peak,
                                  "unit": "GB/s", "frac": (smem_ach / smem_peak) if smem_ach else None,
                                  "bytes_per_step": smem_bytes},

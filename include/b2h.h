@@ -240,6 +240,11 @@ int b2h_profile_set_annotation(b2h_profile *p, const char *consensus, const char
 size_t b2h_seqdb_h2d_bytes(const b2h_seqdb *db);
 size_t b2h_profile_h2d_bytes(const b2h_profile *p);
 
+/* Register tile the SSV kernel uses for a model of M nodes: G lanes per comparison (32/G comparisons per warp), NR packed
+ * registers (2*NR nodes) per lane, and the number of 128-byte shared-memory wavefronts one DP row of one WARP moves
+ * (emission loads + shuffles) -- the quantity bench.py's on-chip roofline is computed from.  B2H_EINVAL if M > 3071. */
+int b2h_ssv_tile_info(int M, int *G, int *NR, double *wavefronts_per_row);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,6 @@ int b2h_ctx_create(int device, b2h_ctx **out)
   ctx->sm_count = prop.multiProcessorCount;
   B2H_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
-  if (const char *ev = getenv("B2H_SSV_INT16")) ctx->ssv_fp16 = (atoi(ev) == 0);
   B2H_CUDA(cudaMalloc(&ctx->d_counters, 64 * sizeof(int)));
   B2H_CUDA(cudaMalloc(&ctx->d_env_counter, 16 * sizeof(int)));
   B2H_CUDA(cudaStreamCreateWithFlags(&ctx->env_stream, cudaStreamNonBlocking));
@@ -244,16 +243,19 @@ int64_t b2h_seqdb_nres(const b2h_seqdb *db) { return db ? db->nres : 0; }
 // ------------------------------------------------------------------------------------------
 // profile upload
 // ------------------------------------------------------------------------------------------
-// Lane-striped 16-bit table for the SSV/MSV kernels: word (x, j, lane) packs the values of the two
-// cells (lane, c=j) and (lane, c=j+NR); cell (lane,c) is model node k = lane*2*NR + c + 1.
-// Words are ordered [x][j/4][lane][j%4] for the full groups of four registers (one LDS.128 per
-// lane, conflict-free), followed by the NR%4 leftover registers as [x][lane][j%4 .. ].
-static size_t striped_word_index(int NR, int x, int j, int lane)
+// Lane-striped fp16x2 table of the SSV kernel for a (G, NR) register tile (b2h_ssv_tile): lane l of a group of G
+// lanes owns model nodes l*2*NR+1 .. (l+1)*2*NR, word j of that lane packs the scores of cells c=j (low half) and
+// c=j+NR (high half).  One residue row is
+//     [NR/4 chunks][G lanes][4 words]   one LDS.128 per lane and chunk; a group reads G*16 contiguous bytes
+//     [NR%4 words][32 physical lanes]   leftover words replicated for every group of the warp, so that the 32 lanes
+//                                       of a warp hit 32 different banks whatever rows their groups are reading
+// and every row is a multiple of 128 bytes.
+static size_t ssv_word_index(int G, int NR, int x, int j, int lane /* physical lane 0..31 */)
 {
-  const int full = NR / 4, rem = NR % 4;
-  size_t base = (size_t)x * NR * 32;
-  if (j < full * 4) return base + ((size_t)(j / 4) * 32 + lane) * 4 + (j % 4);
-  return base + (size_t)full * 128 + (size_t)lane * rem + (j - full * 4);
+  const int full = NR / 4, gl = lane % G;
+  const size_t base = (size_t)x * (b2h_ssv_row_bytes(G, NR) / 4);
+  if (j < full * 4) return base + ((size_t)(j / 4) * G + gl) * 4 + (j % 4);
+  return base + (size_t)full * G * 4 + (size_t)(j - full * 4) * 32 + lane;
 }
 
 int b2h_profile_create_host(const b2h_oprofile_desc *d, b2h_profile **out)
@@ -267,11 +269,11 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
   if (!d || !out || d->M < 1 || d->Kp > B2H_NCODE - 1 || d->K > B2H_MAXABET) return B2H_EINVAL;
   *out = nullptr;
   const int M = d->M, Kp = d->Kp;
-  const int NR = b2h_nr_for_M(M);
-  if (NR < 0) { if (ctx) ctx->err = "model too long for the register-tiled MSV kernel (M > 3071)"; return B2H_EINVAL; }
+  int G = 0, NR = 0;
+  if (!b2h_ssv_tile(M, &G, &NR)) { if (ctx) ctx->err = "model too long for the register-tiled SSV kernel (M > 3071)"; return B2H_EINVAL; }
   b2h_profile *p = new b2h_profile();
   p->ctx = ctx; p->M = M; p->K = d->K; p->Kp = Kp; p->max_length = d->max_length; p->multihit = d->mode_multihit;
-  p->NR = NR; p->tbm_b = d->tbm_b; p->tec_b = d->tec_b; p->base_b = d->base_b; p->bias_b = d->bias_b; p->scale_b = d->scale_b;
+  p->NR = NR; p->G = G; p->tbm_b = d->tbm_b; p->tec_b = d->tec_b; p->base_b = d->base_b; p->bias_b = d->bias_b; p->scale_b = d->scale_b;
   memcpy(p->xw, d->xw, sizeof p->xw); p->base_w = d->base_w; p->ddbound_w = d->ddbound_w; p->scale_w = d->scale_w;
   memcpy(p->xf, d->xf, sizeof p->xf);
   memcpy(p->evparam, d->evparam, sizeof p->evparam); memcpy(p->cutoff, d->cutoff, sizeof p->cutoff);
@@ -283,7 +285,7 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
   p->symbols = (d->K == 20) ? "ACDEFGHIKLMNPQRSTVWY-BJZOUX*~" : "ACGT-RYMKSWHBVDN*~";
 
   // --- SSV signed scores / MSV costs, lane-striped ---
-  const size_t nwords = (size_t)B2H_NCODE * NR * 32;
+  const size_t nwords = (size_t)B2H_NCODE * (b2h_ssv_row_bytes(G, NR) / 4);
   std::vector<uint32_t> ssv(nwords);
   auto cost_of = [&](int x, int k) -> int {          // k is 1-based; anything off the model is the -inf cost
     return (x < Kp && k <= M) ? (int)d->msv_cost[(size_t)x * M + (k-1)] : 255;
@@ -291,15 +293,13 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
   for (int x = 0; x < B2H_NCODE; x++)
     for (int lane = 0; lane < 32; lane++)
       for (int j = 0; j < NR; j++) {
-        int klo = lane * 2 * NR + j + 1, khi = klo + NR;
-        int clo = cost_of(x, klo), chi = cost_of(x, khi);
-        // SSV subtracts sbv = clamp(cost - bias, .., 127) as a signed byte (p7_oprofile.c:721-761): add its negation
-        int slo = -std::min(clo - (int)d->bias_b, 127), shi = -std::min(chi - (int)d->bias_b, 127);
-        size_t w = striped_word_index(NR, x, j, lane);
-        if (ctx && ctx->ssv_fp16)   // the same integers as fp16 bit patterns (exact: |score| <= 127)
-          ssv[w] = ((uint32_t)__half_as_ushort(__float2half_rn((float)shi)) << 16) | (uint32_t)__half_as_ushort(__float2half_rn((float)slo));
-        else
-          ssv[w] = ((uint32_t)(uint16_t)(int16_t)shi << 16) | (uint32_t)(uint16_t)(int16_t)slo;
+        const int klo = (lane % G) * 2 * NR + j + 1, khi = klo + NR;
+        const int clo = cost_of(x, klo), chi = cost_of(x, khi);
+        // SSV subtracts sbv = clamp(cost - bias, .., 127) as a signed byte (p7_oprofile.c:721-761): add its negation,
+        // stored as fp16 (exact: |score| <= 127)
+        const int slo = -std::min(clo - (int)d->bias_b, 127), shi = -std::min(chi - (int)d->bias_b, 127);
+        ssv[ssv_word_index(G, NR, x, j, lane)] =
+          ((uint32_t)__half_as_ushort(__float2half_rn((float)shi)) << 16) | (uint32_t)__half_as_ushort(__float2half_rn((float)slo));
       }
 
   // --- Viterbi / Forward tables, padded ---
@@ -442,3 +442,13 @@ int b2h_profile_set_annotation(b2h_profile *p, const char *consensus, const char
 
 extern "C" size_t b2h_seqdb_h2d_bytes(const b2h_seqdb *db) { return db ? db->h2d_bytes : 0; }
 extern "C" size_t b2h_profile_h2d_bytes(const b2h_profile *p) { return p ? p->h2d_bytes : 0; }
+
+extern "C" int b2h_ssv_tile_info(int M, int *G, int *NR, double *wavefronts_per_row)
+{
+  int g = 0, nr = 0;
+  if (M < 1 || !b2h_ssv_tile(M, &g, &nr)) return B2H_EINVAL;
+  if (G) *G = g;
+  if (NR) *NR = nr;
+  if (wavefronts_per_row) *wavefronts_per_row = 4.0 * (nr / 4) + (nr % 4) + 1.25;   // LDS.128 x NR/4, LDS.32 x NR%4, diagonal SHFL, residue SHFL / 4 rows
+  return B2H_OK;
+}

@@ -24,7 +24,7 @@
 
 #define B2H_PAD_CODE   31     // residue code used for arena padding; tables have 32 residue rows
 #define B2H_NCODE      32
-#define B2H_MAX_NR     48     // SSV/MSV register tiles: 64*NR cells per warp => M <= 3071
+#define B2H_MAX_NR     48     // SSV register tiles: a group of G lanes holds 2*G*NR cells; G=32, NR=48 => M <= 3071
 
 struct b2h_ctx {
   int           device = 0;
@@ -35,7 +35,6 @@ struct b2h_ctx {
   std::atomic<uint64_t> launches{0};   // (the envelope kernels are launched from the domain-definition thread)
   int          *d_counters = nullptr;   // small pool of work counters
   int           profiling = 0;
-  int           ssv_fp16 = 1;          // SSV cells as fp16x2 (HFMA2.RELU) instead of s16x2 (VIADDMNMX); B2H_SSV_INT16=1 selects the latter
   // side streams: independent launches of one stage (size classes) run concurrently, forked from / joined to <stream>
   std::vector<cudaStream_t> side; std::vector<cudaEvent_t> side_done; cudaEvent_t fork_ev = nullptr; int side_used = 0;
   double        stage_ms[8] = {0};
@@ -80,10 +79,10 @@ struct b2h_profile {
   void *d_block = nullptr;         // the single device allocation all d_* table pointers below point into
   int M = 0, K = 0, Kp = 0, max_length = 0, multihit = 1;
   // MSV
-  int NR = 0;                     // 32-bit cell registers per lane in the SSV/MSV kernels
+  int NR = 0, G = 0;              // SSV register tile: G lanes per comparison, NR packed cell registers (2*NR nodes) per lane
   uint8_t tbm_b = 0, tec_b = 0, base_b = 0, bias_b = 0;
   float scale_b = 0;
-  uint32_t *d_ssv_emis = nullptr; // [32][NR][32 lanes] packed s16x2 signed scores (SSV)
+  uint32_t *d_ssv_emis = nullptr; // [32 residues][b2h_ssv_row_bytes(G, NR)] packed fp16x2 signed scores (SSV), lane-striped
   uint8_t  *d_msv_cost8 = nullptr; // [32][Mpad] node-major u8 costs (255 = -inf) for the full MSV kernel
   // Viterbi
   int16_t *d_vit_rsc = nullptr;   // [32][Mpad]
@@ -152,13 +151,22 @@ struct ForkJoin {
   }
 };
 
-static inline int b2h_nr_for_M(int M) {
-  // need 64*NR >= M+1 so that the last cell of lane 31 is always padding (see b2h_msv.cu)
-  int nr = (M + 1 + 63) / 64;
-  static const int allowed[] = {1,2,3,4,5,6,8,10,12,16,20,24,32,40,48};
-  for (int a : allowed) if (a >= nr) return a;
-  return -1;
+// SSV register tile of a model of M nodes: a group of G lanes (8, 16 or 32: 4, 2 or 1 comparisons per warp) in which
+// every lane owns 2*NR consecutive nodes.  Needs 2*G*NR >= M+1 so that the last cell of the group's last lane is always
+// padding (see b2h_msv.cu).  The narrowest group that fits is taken: it wastes the fewest padded cells (granularity
+// 2*G nodes) and spreads the per-row shuffle over the most cells.
+static inline bool b2h_ssv_tile(int M, int *G, int *NR) {
+  const int need = M + 1;
+  if (need <= 16 * 32) { *G = 8;  *NR = (need + 15) / 16; return true; }
+  if (need <= 32 * 32) { *G = 16; *NR = (need + 31) / 32; return true; }
+  int nr = (need + 63) / 64;
+  static const int allowed[] = {18, 20, 22, 24, 26, 28, 30, 32, 40, 48};
+  for (int a : allowed) if (a >= nr) { *G = 32; *NR = a; return true; }
+  return false;
 }
+// bytes of one residue row of the lane-striped SSV table of a (G, NR) tile, and shared-memory wavefronts (128 B each)
+// one DP row of one warp moves: 4 per LDS.128, 1 per leftover LDS.32, 1 diagonal shuffle, 1/4 residue-word shuffle
+static inline size_t b2h_ssv_row_bytes(int G, int NR) { return (size_t)(NR / 4) * G * 16 + (size_t)(NR % 4) * 128; }
 
 
 // ---------------------------------------------------------------------------------------------
@@ -180,7 +188,7 @@ struct ProfDev {
   const int16_t *vit_rsc, *vit_tsc;
   const float *fwd_rsc, *fwd_tsc, *bias_eo;
   const int32_t *vit_rsc32; const float *fwd_rscr;
-  int M, Mpad, NR;
+  int M, Mpad, NR, G;
   int tbm, tec, base, bias; float scale_b;
   int xw_E_move, xw_E_loop, base_w, ddbound_w; float scale_w;
   float xf_E_move, xf_E_loop;
@@ -190,7 +198,7 @@ struct ProfDev {
 static inline ProfDev b2h_profdev(const b2h_profile *p) {
   ProfDev d; d.ssv_emis = p->d_ssv_emis; d.msv_cost8 = p->d_msv_cost8; d.vit_rsc = p->d_vit_rsc; d.vit_tsc = p->d_vit_tsc;
   d.fwd_rsc = p->d_fwd_rsc; d.fwd_tsc = p->d_fwd_tsc; d.bias_eo = p->d_bias_eo; d.vit_rsc32 = p->d_vit_rsc32; d.fwd_rscr = p->d_fwd_rscr;
-  d.M = p->M; d.Mpad = p->Mpad; d.NR = p->NR; d.tbm = p->tbm_b; d.tec = p->tec_b; d.base = p->base_b; d.bias = p->bias_b; d.scale_b = p->scale_b;
+  d.M = p->M; d.Mpad = p->Mpad; d.NR = p->NR; d.G = p->G; d.tbm = p->tbm_b; d.tec = p->tec_b; d.base = p->base_b; d.bias = p->bias_b; d.scale_b = p->scale_b;
   d.xw_E_move = p->xw[0][0]; d.xw_E_loop = p->xw[0][1]; d.base_w = p->base_w; d.ddbound_w = p->ddbound_w; d.scale_w = p->scale_w;
   d.xf_E_move = p->xf[0][0]; d.xf_E_loop = p->xf[0][1];
   for (int i = 0; i < B2H_NEVPARAM; i++) d.evparam[i] = p->evparam[i];
@@ -245,7 +253,7 @@ int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nent
 // atomic (*n, and cnt[p] for the later grouping by profile); a,b carry the stage's scores.
 struct SurvList { int32_t *p, *s; float *a, *b; int *n; int *cnt; int cap; };
 
-#define B2H_SSV_CHUNK 64       // sequences per SSV work item
+#define B2H_SSV_CHUNK 128      // sequences per SSV work item
 struct SsvArgs {
   const ProfDev *profs;        // all profiles of the batch
   const int32_t *cls;          // indices of the profiles of this register-tile class (device)
@@ -253,13 +261,12 @@ struct SsvArgs {
   SeqDev         sd;
   int            chunks;       // ceil(nseq / B2H_SSV_CHUNK)
   int           *counter;
-  uint32_t       zero;         // always 0 (see b2h_msv.cu)
   int            mode;         // 0: dense p7_SSVFilter  1: dense, queue eslENORESULT in R  2: cascade (P-value test, A and R)
   float         *out_sc; int32_t *out_status;
   SurvList       A, R;
   double         F1;
 };
-int b2h_launch_ssv(b2h_ctx *ctx, int NR, const SsvArgs &a, cudaStream_t strm);
+int b2h_launch_ssv(b2h_ctx *ctx, int G, int NR, const SsvArgs &a, cudaStream_t strm);
 // full MSV (with J) over a grouped work list; mode 1: dense outputs indexed by sequence, 2: cascade append to A
 int b2h_launch_msv(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, int mode,
                    float *out_sc, int32_t *out_status, SurvList A, double F1);

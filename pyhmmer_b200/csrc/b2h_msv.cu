@@ -3,18 +3,24 @@
 // Replaces p7_SSVFilter (impl_sse/ssvfilter.c:876-926) and p7_MSVFilter (impl_sse/msvfilter.c:74-208).
 // This is a new design, not a translation of the SSE code:
 //
-//  * one WARP per (profile x sequence) comparison; persistent CTAs pull sequences (longest first)
-//    from a global work counter;
+//  * one GROUP of G lanes (8, 16 or 32: b2h_ssv_tile picks the narrowest that holds the model) per
+//    (profile x sequence) comparison, so a warp runs 32/G comparisons side by side; persistent CTAs
+//    pull sequences (longest first) from a global work counter;
 //  * the profile's emission table is staged ONCE per CTA into shared memory with a TMA bulk copy
 //    (cp.async.bulk + mbarrier), pre-swizzled on the host so that every row step is one
-//    conflict-free LDS.128 per lane;
-//  * the DP row lives in registers as packed s16x2 cells.  Lane z owns the 2*NR consecutive model
-//    nodes z*2NR+1 .. (z+1)*2NR; register j packs nodes (j, j+NR) of that chunk, so the diagonal
-//    move M(i,k) <- M(i-1,k-1) is a pure register renaming plus ONE warp shuffle and one PRMT per row;
-//  * sm_100a has no native byte SIMD (vmaxu4/vaddus4 are emulated), but it has the DPX 16x2 ops:
-//    the SSV cell update is ONE VIADDMNMX.S16x2 for two cells, the running maximum ONE VIMNMX3.S16x2
-//    for four cells.  16-bit lanes make the uint8 saturation explicit (clamps) instead of implicit,
-//    and the results are bit-identical to the reference (derivation in DESIGN.md, "SSV in wide lanes").
+//    conflict-free LDS.128 per lane and 4 registers, whatever rows the groups of a warp are reading;
+//  * the DP row lives in registers as packed 16x2 cells.  Lane l of a group owns the 2*NR consecutive
+//    model nodes l*2NR+1 .. (l+1)*2NR; register j packs nodes (j, j+NR) of that chunk, so the diagonal
+//    move M(i,k) <- M(i-1,k-1) is a pure register renaming plus ONE warp shuffle and one PRMT per row.
+//    Narrow groups make NR large (M=200: G=8, NR=13), which is what the kernel wants: its ceiling is
+//    the shared-memory pipe (2 B of scores per cell), and the one shuffle per row is amortised over
+//    64*NR cells of the warp while only 2*G nodes of padding can be wasted per comparison;
+//  * sm_100a has no native byte SIMD (vmaxu4/vaddus4 are emulated); cells are fp16x2: every value of
+//    the recurrence is an integer of magnitude < 2048 until a comparison has overflowed anyway, so fp16
+//    arithmetic is exact and the cell update max(m + e, 0) is ONE HFMA2.RELU for two cells on the FMA
+//    pipe; non-negative fp16 values order like their bit patterns, so the running maximum is ONE integer
+//    VIMNMX3.S16x2 (DPX) for four cells on the ALU pipe.  The results are bit-identical to the reference
+//    (derivation in DESIGN.md, "SSV in wide lanes").
 //
 // Semantics reproduced exactly: SSV is authoritative when it can prove the J state was not used;
 // otherwise (eslENORESULT) the comparison is redone by the full MSV recurrence with saturating
@@ -63,18 +69,17 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
 }
-template <int NR>
+template <int G, int NR>
 __device__ __forceinline__ void load_row(uint32_t addr, uint32_t addr_rem, uint32_t (&e)[NR])
 {
-  constexpr int FULL = NR / 4, REM = NR % 4;
+  constexpr int FULLQ = NR / 4, REM = NR % 4;
 #pragma unroll
-  for (int g = 0; g < FULL; g++) {
-    uint4 v = lds128(addr + g * 512);
+  for (int g = 0; g < FULLQ; g++) {
+    uint4 v = lds128(addr + g * (G * 16));
     e[4*g+0] = v.x; e[4*g+1] = v.y; e[4*g+2] = v.z; e[4*g+3] = v.w;
   }
-  if (REM == 1) e[4*FULL] = lds32(addr_rem);
-  if (REM == 2) { uint2 v = lds64(addr_rem); e[4*FULL] = v.x; e[4*FULL+1] = v.y; }
-  if (REM == 3) { e[4*FULL] = lds32(addr_rem); e[4*FULL+1] = lds32(addr_rem + 4); e[4*FULL+2] = lds32(addr_rem + 8); }
+#pragma unroll
+  for (int r = 0; r < REM; r++) e[4*FULLQ + r] = lds32(addr_rem + r * 128);
 }
 
 // esl_gumbel_surv (vendor/easel/esl_gumbel.c:129): same expression, double precision
@@ -120,15 +125,10 @@ __device__ __forceinline__ void ssv_finish(int maxw, const ProfDev &p, int tjb, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// SSV pass over (profile x sequence) for every profile of one register-tile class.
+// SSV pass over (profile x sequence) for every profile of one register-tile class (G, NR).
 // Work item = (profile, chunk of B2H_SSV_CHUNK sequences in length-sorted order), profile-major, so
 // a persistent CTA re-stages the emission table only when it crosses a profile boundary.
 // ------------------------------------------------------------------------------------------------
-// H = true: cells are packed fp16x2 instead of s16x2.  Every value of the recurrence is an integer of magnitude
-// < 2048 until a comparison has overflowed anyway, so fp16 arithmetic is exact, and the update
-// max(m + e, 0) becomes ONE HFMA2.RELU on the FMA pipe (128 lanes/clk/SM) instead of one VIADDMNMX on the ALU pipe
-// (64 lanes/clk/SM), which is the pipe this kernel saturates.  Non-negative fp16 values order like their bit
-// patterns, so the running maximum stays an integer VIMNMX3 over the same registers.
 __device__ __forceinline__ uint32_t hfma2_relu_add(uint32_t m, uint32_t e)
 {
   uint32_t r;
@@ -136,24 +136,26 @@ __device__ __forceinline__ uint32_t hfma2_relu_add(uint32_t m, uint32_t e)
   return r;
 }
 
-template <int NR, bool H>
+template <int G, int NR>
 __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
 {
-  extern __shared__ __align__(128) uint32_t s_tab[];      // [32 residues][NR*32 words]
+  extern __shared__ __align__(128) uint32_t s_tab[];      // [32 residues][ROWB bytes]
   __shared__ uint64_t s_bar;
   __shared__ int s_item;
-  constexpr uint32_t TAB_BYTES = (uint32_t)B2H_NCODE * NR * 128u;
-  constexpr int ROW_WORDS = NR * 32;
+  constexpr int FULLQ = NR / 4, REM = NR % 4, NG = 32 / G;
+  constexpr uint32_t ROWB = (uint32_t)FULLQ * G * 16 + (uint32_t)REM * 128;
+  constexpr uint32_t TAB_BYTES = (uint32_t)B2H_NCODE * ROWB;
+  constexpr uint32_t PADW = 0x01010101u * B2H_PAD_CODE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int gl = lane & (G - 1), grp = lane / G;
 
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   uint32_t phase = 0;
   int cur_pc = -1;
 
-  const int src_lane = (lane + 31) & 31;                   // rotate: lane 0 reads lane 31's last cell, which is always padding (= 0)
-  const uint32_t tab_lane = smem_u32(s_tab) + lane * 16;
-  const uint32_t tab_rem  = smem_u32(s_tab) + (NR / 4) * 512 + lane * (NR % 4) * 4;
-  const uint32_t zero = a.zero;
+  const int src_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1));   // rotate inside the group: its lane 0 reads the last cell of its last lane, which is always padding (= 0)
+  const uint32_t tab_lane = smem_u32(s_tab) + gl * 16;
+  const uint32_t tab_rem  = smem_u32(s_tab) + FULLQ * G * 16 + lane * 4;
   const int nitems = a.ncls * a.chunks;
 
   for (;;) {
@@ -171,32 +173,37 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
       mbar_wait(&s_bar, phase); phase ^= 1;
     }
     const int e_end = min(a.sd.n, (chunk + 1) * B2H_SSV_CHUNK);
-    for (int e = chunk * B2H_SSV_CHUNK + warp; e < e_end; e += nwarps) {
-      const int s = a.sd.order[e];
-      const int L = a.sd.len[s];
+    for (int e0 = chunk * B2H_SSV_CHUNK + warp * NG; e0 < e_end; e0 += nwarps * NG) {
+      const int e = e0 + grp;                              // this group's comparison; groups past the end idle on padding rows
+      const bool valid = e < e_end;
+      const int s = valid ? a.sd.order[e] : 0;
+      const int L = valid ? a.sd.len[s] : 0;
       const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.sd.res + a.sd.off[s]);
       const int nwords = (L + 3) >> 2;                     // tail rows are B2H_PAD_CODE rows: every score -127, harmless
+      const int nwmax = (NG == 1) ? nwords : __reduce_max_sync(FULL, nwords);
 
       uint32_t m[NR];
 #pragma unroll
       for (int j = 0; j < NR; j++) m[j] = 0u;
       uint32_t xe = 0u;
 
-      for (int w0 = 0; w0 < nwords; w0 += 32) {
-        const uint32_t myw = (w0 + lane < nwords) ? __ldg(seqw + w0 + lane) : 0x1f1f1f1fu;
-        const int nw = min(32, nwords - w0);
+      uint32_t nextw = (gl < nwords) ? __ldg(seqw + gl) : PADW;
+      for (int w0 = 0; w0 < nwmax; w0 += G) {
+        const uint32_t myw = nextw;
+        nextw = (w0 + G + gl < nwords) ? __ldg(seqw + w0 + G + gl) : PADW;   // the next G words are in flight during these 4*G rows
+        const int nw = min(G, nwmax - w0);
         for (int wi = 0; wi < nw; wi++) {
-          const uint32_t wr = __shfl_sync(FULL, myw, wi);
+          const uint32_t wr = __shfl_sync(FULL, myw, wi, G);
 #pragma unroll
           for (int rr = 0; rr < 4; rr++) {
             const uint32_t x = __byte_perm(wr, 0u, 0x4440u + rr);
             uint32_t ev[NR];
-            load_row<NR>(tab_lane + x * (ROW_WORDS * 4), tab_rem + x * (ROW_WORDS * 4), ev);
+            load_row<G, NR>(tab_lane + x * ROWB, tab_rem + x * ROWB, ev);
             const uint32_t t  = __shfl_sync(FULL, m[NR-1], src_lane);
             const uint32_t s0 = __byte_perm(t, m[NR-1], 0x5432u);     // lo <- previous lane's last cell, hi <- own cell NR-1
 #pragma unroll
-            for (int j = NR - 1; j >= 1; j--) m[j] = H ? hfma2_relu_add(m[j-1], ev[j]) : __viaddmax_s16x2(m[j-1], ev[j], zero);
-            m[0] = H ? hfma2_relu_add(s0, ev[0]) : __viaddmax_s16x2(s0, ev[0], zero);
+            for (int j = NR - 1; j >= 1; j--) m[j] = hfma2_relu_add(m[j-1], ev[j]);
+            m[0] = hfma2_relu_add(s0, ev[0]);
 #pragma unroll
             for (int j = 0; j + 1 < NR; j += 2) xe = __vimax3_s16x2(xe, m[j], m[j+1]);
             if (NR & 1) xe = __vimax3_s16x2(xe, m[NR-1], m[NR-1]);
@@ -204,12 +211,16 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
         }
       }
       int v = max((int)(xe & 0xffffu), (int)(xe >> 16));
-      v = __reduce_max_sync(FULL, v);
-      if (H) {                                               // fp16 bit pattern (>= +0) -> integer value; inf -> "overflowed"
+      if (G == 32) v = __reduce_max_sync(FULL, v);
+      else {
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+      }
+      {                                                      // fp16 bit pattern (>= +0) -> integer value; inf -> "overflowed"
         const float f = __half2float(__ushort_as_half((unsigned short)v));
         v = (f > 30000.0f) ? 30000 : (int)f;
       }
-      if (lane == 0) {
+      if (gl == 0 && valid) {
         float sc; int status;
         ssv_finish(v, P, (int)a.sd.tjb[s], sc, status);
         if (a.mode == 0) { a.out_sc[s] = sc; a.out_status[s] = status; }
@@ -345,18 +356,22 @@ __global__ void group_scatter_kernel(const SurvList in, const int32_t *poff, int
   }
 }
 
-template <int NR, bool H>
-int launch_ssv_nr(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
+template <int G, int NR>
+int launch_ssv_tile(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
 {
-  const size_t smem = (size_t)B2H_NCODE * NR * 128;
-  B2H_CUDA(cudaFuncSetAttribute(ssv_kernel<NR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 1;
-  B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ssv_kernel<NR, H>, SSV_THREADS, smem));
-  if (occ < 1) occ = 1;
+  const size_t smem = (size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR);
+  static int occ_cached[8] = {0};                        // per device (the attribute and the occupancy are per device)
+  int &occ = occ_cached[ctx->device & 7];
+  if (occ == 0) {
+    B2H_CUDA(cudaFuncSetAttribute(ssv_kernel<G, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int o = 1;
+    B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ssv_kernel<G, NR>, SSV_THREADS, smem));
+    occ = o < 1 ? 1 : o;
+  }
   int grid = ctx->sm_count * occ;
   const long long nitems = (long long)a.ncls * a.chunks;
   if (grid > nitems) grid = (int)(nitems > 0 ? nitems : 1);
-  ssv_kernel<NR, H><<<grid, SSV_THREADS, smem, strm>>>(a);
+  ssv_kernel<G, NR><<<grid, SSV_THREADS, smem, strm>>>(a);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());
   return B2H_OK;
@@ -364,15 +379,20 @@ int launch_ssv_nr(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
 
 } // namespace
 
-int b2h_launch_ssv(b2h_ctx *ctx, int NR, const SsvArgs &a, cudaStream_t strm)
+int b2h_launch_ssv(b2h_ctx *ctx, int G, int NR, const SsvArgs &a, cudaStream_t strm)
 {
   if (a.ncls <= 0 || a.sd.n <= 0) return B2H_OK;
   B2H_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), strm));
-  switch (NR) {
-#define CASE(n) case n: return ctx->ssv_fp16 ? launch_ssv_nr<n, true>(ctx, a, strm) : launch_ssv_nr<n, false>(ctx, a, strm);
-    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(10) CASE(12) CASE(16) CASE(20) CASE(24) CASE(32) CASE(40) CASE(48)
+  switch (G * 64 + NR) {
+#define CASE(g, n) case (g) * 64 + (n): return launch_ssv_tile<g, n>(ctx, a, strm);
+#define CASE8(g, n) CASE(g, n) CASE(g, n + 1) CASE(g, n + 2) CASE(g, n + 3) CASE(g, n + 4) CASE(g, n + 5) CASE(g, n + 6) CASE(g, n + 7)
+    CASE8(8, 1) CASE8(8, 9) CASE8(8, 17) CASE8(8, 25)
+    CASE8(16, 17) CASE8(16, 25)
+    CASE(32, 18) CASE(32, 20) CASE(32, 22) CASE(32, 24) CASE(32, 26) CASE(32, 28) CASE(32, 30) CASE(32, 32) CASE(32, 40) CASE(32, 48)
+#undef CASE8
 #undef CASE
   }
+  ctx->err = "no SSV kernel for this register tile";
   return B2H_EINVAL;
 }
 

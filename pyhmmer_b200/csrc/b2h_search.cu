@@ -137,12 +137,12 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
   for (int i = 0; i < P; i++) {
     hprof[i] = b2h_profdev(profiles[p0 + perm[i]]);
     mpads[i] = hprof[i].Mpad;
-    classes[hprof[i].NR].push_back(i);
+    classes[hprof[i].G * 64 + hprof[i].NR].push_back(i);
     max_Mpad = std::max(max_Mpad, hprof[i].Mpad);
   }
   ProfDev *d_prof; TRY(pool.get(&d_prof, P));
   B2H_CUDA(cudaMemcpyAsync(d_prof, hprof.data(), P * sizeof(ProfDev), cudaMemcpyHostToDevice, ctx->stream));
-  std::vector<int32_t> hcls; std::vector<std::pair<int, std::pair<int, int>>> cls_ranges;   // NR -> (offset, count)
+  std::vector<int32_t> hcls; std::vector<std::pair<int, std::pair<int, int>>> cls_ranges;   // SSV tile G*64+NR -> (offset, count)
   for (auto &kv : classes) { cls_ranges.push_back({kv.first, {(int)hcls.size(), (int)kv.second.size()}}); hcls.insert(hcls.end(), kv.second.begin(), kv.second.end()); }
   int32_t *d_cls; TRY(pool.get(&d_cls, hcls.size()));
   B2H_CUDA(cudaMemcpyAsync(d_cls, hcls.data(), hcls.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -172,9 +172,9 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
   for (auto &cr : cls_ranges) {
     SsvArgs a;
     a.profs = d_prof; a.cls = d_cls + cr.second.first; a.ncls = cr.second.second; a.sd = sd;
-    a.chunks = (N + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK; a.counter = ctx->d_counters + 32 + (ssv_cls++ % 24); a.zero = 0u; a.mode = 2;
+    a.chunks = (N + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK; a.counter = ctx->d_counters + 32 + (ssv_cls++ % 24); a.mode = 2;
     a.out_sc = nullptr; a.out_status = nullptr; a.A = A; a.R = R; a.F1 = prm->F1;
-    TRY(b2h_launch_ssv(ctx, cr.first, a, fj.next()));
+    TRY(b2h_launch_ssv(ctx, cr.first / 64, cr.first % 64, a, fj.next()));
   } }
   // 2. full MSV for the comparisons SSV could not decide
   {
