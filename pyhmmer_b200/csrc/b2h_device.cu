@@ -321,11 +321,12 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
 
   // --- lane-grouped emission tables of the register-resident DP kernels (b2h_dpreg.cu), models up to 512 nodes ---
   p->regC = 0; p->regW = 0;
-  for (int rc = 0; rc < B2H_N_REG_CLASSES; rc++)
-    if (M <= B2H_REG_CLASSES[rc].bound) { p->regC = B2H_REG_CLASSES[rc].C; p->regW = B2H_REG_CLASSES[rc].W; break; }
+  const b2h_regclass *rcls; const int nrcls = b2h_reg_classes(&rcls);
+  for (int rc = 0; rc < nrcls; rc++)
+    if (M <= rcls[rc].bound) { p->regC = rcls[rc].C; p->regW = rcls[rc].W; break; }
   std::vector<int32_t> vr32; std::vector<float> frr;
   if (p->regC) {
-    const int C = p->regC, W = p->regW, G = (C % 4 == 0) ? 4 : 2, stride = 32 * C * W;
+    const int C = p->regC, W = p->regW, G = (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 1, stride = 32 * C * W;
     vr32.assign((size_t)B2H_NCODE * stride, -32768); frr.assign((size_t)B2H_NCODE * stride, 0.0f);
     for (int x = 0; x < Kp; x++)
       for (int gl = 0; gl < 32 * W; gl++)

@@ -531,12 +531,13 @@ int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const Seq
   const int P = (int)mpads.size();
   int plo = 0, cls = 0;
   ForkJoin fj(ctx);
-  for (int rc = 0; rc < B2H_N_REG_CLASSES && plo < P; rc++) {
+  const b2h_regclass *rcls; const int nrcls = b2h_reg_classes(&rcls);
+  for (int rc = 0; rc < nrcls && plo < P; rc++) {
     int phi = plo;
-    while (phi < P && mpads[phi] <= B2H_REG_CLASSES[rc].bound) phi++;
+    while (phi < P && mpads[phi] <= rcls[rc].bound) phi++;
     if (phi > plo) {
       WorkList wl = wl_in; wl.plo = plo; wl.phi = phi; wl.counter = wl_in.counter + cls;
-      int st = b2h_launch_dpreg(ctx, kind, B2H_REG_CLASSES[rc].C, B2H_REG_CLASSES[rc].W, wl, sd, nitems_hint, out, fj.next());
+      int st = b2h_launch_dpreg(ctx, kind, rcls[rc].C, rcls[rc].W, wl, sd, nitems_hint, out, fj.next());
       if (st != B2H_OK) return st;
       plo = phi; cls++;
     }

@@ -1,6 +1,7 @@
 // b2h_dpreg.cu -- register-resident ViterbiFilter / Forward parser / Backward parser for models with
-// M <= 32*C*W: C = 2, 4, 8, 10, 12 or 16 nodes per lane, W = 1, 2 or 4 warps per comparison
-// (W = 1: M <= 64 / 128 / 256 / 384 / 512, ~95 % of Pfam;  W = 2: M <= 640 / 768 / 1024;  W = 4: M <= 1536).
+// M <= 32*C*W: C = 2..16 nodes per lane, W = 1, 2 or 4 warps per comparison (B2H_REG_CLASSES: W = 1 for M <= 512 in
+// steps of 32 or 64 nodes, ~95 % of Pfam;  W = 2: M <= 1024;  W = 4: M <= 1536); a model runs in the smallest class
+// that holds it, so at most 32 (64) nodes per comparison are padding.
 // With W > 1 the W warps of a group own consecutive 32*C-node segments of the model and meet at one named
 // barrier per row (two for Backward and for Viterbi rows that need the D->D closure): the per-warp partial
 // results (xE maxima / sums, the affine or max-plus composite of the warp's D chain, the M/I/D cells of its
@@ -66,13 +67,16 @@ __device__ __forceinline__ bool next_item(const WorkList &wl, int *s_item, Item 
 }
 
 // The C emission values of this lane for residue x.  Table layout: [32 residues][W warps][C/G groups][32 lanes][G]
-// with G = 4 (C % 4 == 0) or 2, so every access is one conflict-free LDS.128 / LDS.64 per lane; <tab> already
+// with G = 4 (C % 4 == 0), 2 (C even) or 1, so every access is one conflict-free LDS.128 / LDS.64 / LDS.32 per lane; <tab> already
 // points at this warp's segment and <stride> = 32*C*W is the distance between residues.
 template <int C, typename T>
 __device__ __forceinline__ void load_emis(const T *tab, int stride, int x, int lane, T (&r)[C])
 {
   const T *row = tab + (size_t)x * stride;
-  if (C % 4 != 0) {
+  if (C % 2 != 0) {
+#pragma unroll
+    for (int g = 0; g < C; g++) r[g] = row[g * 32 + lane];
+  } else if (C % 4 != 0) {
 #pragma unroll
     for (int g = 0; g < C / 2; g++) {
       const float2 v = *reinterpret_cast<const float2 *>(row + g * 64 + lane * 2);
@@ -623,8 +627,10 @@ int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, int W, const WorkList &wl, c
       if (kind == 2) return launch_reg(ctx, rbck_kernel<CC, WW>, CC, WW, wl, sd, nitems_hint, out, strm); \
       break;
   switch (W * 64 + C) {
-    B2H_REG_CASE(2, 1) B2H_REG_CASE(4, 1) B2H_REG_CASE(8, 1) B2H_REG_CASE(12, 1) B2H_REG_CASE(16, 1)
-    B2H_REG_CASE(10, 2) B2H_REG_CASE(12, 2) B2H_REG_CASE(16, 2) B2H_REG_CASE(12, 4)
+    B2H_REG_CASE(2, 1) B2H_REG_CASE(3, 1) B2H_REG_CASE(4, 1) B2H_REG_CASE(5, 1) B2H_REG_CASE(6, 1) B2H_REG_CASE(7, 1) B2H_REG_CASE(8, 1)
+    B2H_REG_CASE(9, 1) B2H_REG_CASE(10, 1) B2H_REG_CASE(11, 1) B2H_REG_CASE(12, 1) B2H_REG_CASE(14, 1) B2H_REG_CASE(16, 1)
+    B2H_REG_CASE(9, 2) B2H_REG_CASE(10, 2) B2H_REG_CASE(11, 2) B2H_REG_CASE(12, 2) B2H_REG_CASE(14, 2) B2H_REG_CASE(16, 2)
+    B2H_REG_CASE(10, 4) B2H_REG_CASE(12, 4)
   }
 #undef B2H_REG_CASE
   return B2H_EINVAL;

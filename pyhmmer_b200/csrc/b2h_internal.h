@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "b2h.h"
@@ -129,7 +130,9 @@ static inline void b2h_resolve_timers(b2h_ctx *c) {
   c->ev_open.clear(); c->ev_used = 0;
 }
 
-// fork/join of the side streams around a group of independent launches
+// fork/join of the side streams around a group of independent launches (one per size class: a class launch of a few
+// hundred comparisons is as long as its longest comparison and fills a few SMs, so the classes must overlap)
+#define B2H_NSIDE 12
 struct ForkJoin {
   b2h_ctx *ctx; int n = 0;
   explicit ForkJoin(b2h_ctx *c) : ctx(c) {
@@ -137,16 +140,16 @@ struct ForkJoin {
     cudaEventRecord(c->fork_ev, c->stream);
   }
   cudaStream_t next() {                                   // stream for the next independent launch
-    const int i = n++ % 4;
+    const int i = n++ % B2H_NSIDE;
     if ((int)ctx->side.size() <= i) {
       cudaStream_t s; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); ctx->side.push_back(s);
       cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); ctx->side_done.push_back(e);
     }
-    if (n <= 4) cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0);
+    if (n <= B2H_NSIDE) cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0);
     return ctx->side[i];
   }
   ~ForkJoin() {
-    const int used = n < 4 ? n : 4;
+    const int used = n < B2H_NSIDE ? n : B2H_NSIDE;
     for (int i = 0; i < used; i++) { cudaEventRecord(ctx->side_done[i], ctx->side[i]); cudaStreamWaitEvent(ctx->stream, ctx->side_done[i], 0); }
   }
 };
@@ -244,9 +247,23 @@ int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, cons
 int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, int W, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm);
 // register-resident DP size classes: nodes per lane C and warps per comparison W for a model of M nodes (0,0: too long)
 struct b2h_regclass { int bound, C, W; };
-static const b2h_regclass B2H_REG_CLASSES[] = {{64, 2, 1}, {128, 4, 1}, {256, 8, 1}, {384, 12, 1}, {512, 16, 1},
-                                               {640, 10, 2}, {768, 12, 2}, {1024, 16, 2}, {1536, 12, 4}};
-static const int B2H_N_REG_CLASSES = 9;
+static const b2h_regclass B2H_REG_CLASSES_FINE[] = {
+  {64, 2, 1}, {96, 3, 1}, {128, 4, 1}, {160, 5, 1}, {192, 6, 1}, {224, 7, 1}, {256, 8, 1}, {288, 9, 1}, {320, 10, 1}, {352, 11, 1},
+  {384, 12, 1}, {448, 14, 1}, {512, 16, 1},
+  {576, 9, 2}, {640, 10, 2}, {704, 11, 2}, {768, 12, 2}, {896, 14, 2}, {1024, 16, 2}, {1280, 10, 4}, {1536, 12, 4}};
+static const b2h_regclass B2H_REG_CLASSES_EVEN[] = {
+  {64, 2, 1}, {128, 4, 1}, {192, 6, 1}, {256, 8, 1}, {320, 10, 1}, {384, 12, 1}, {448, 14, 1}, {512, 16, 1},
+  {640, 10, 2}, {768, 12, 2}, {896, 14, 2}, {1024, 16, 2}, {1280, 10, 4}, {1536, 12, 4}};
+static const b2h_regclass B2H_REG_CLASSES_COARSE[] = {{64, 2, 1}, {128, 4, 1}, {256, 8, 1}, {384, 12, 1}, {512, 16, 1},
+                                                      {640, 10, 2}, {768, 12, 2}, {1024, 16, 2}, {1536, 12, 4}};
+// B2H_REG_CLASSSET = fine | even | coarse (experiments; default below)
+static inline int b2h_reg_classes(const b2h_regclass **tab) {
+  static int which = -1;
+  if (which < 0) { const char *ev = getenv("B2H_REG_CLASSSET"); which = !ev ? 0 : (ev[0] == 'e' ? 1 : ev[0] == 'c' ? 2 : 0); }
+  if (which == 1) { *tab = B2H_REG_CLASSES_EVEN; return 14; }
+  if (which == 2) { *tab = B2H_REG_CLASSES_COARSE; return 9; }
+  *tab = B2H_REG_CLASSES_FINE; return 21;
+}
 int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc);
 
 // A compacted list of comparisons produced by a stage's epilogue (device memory).  Appends are

@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 FB_TOL = 1e-4      # nats; north_star's bound, and HMMER's own Fwd==Bck contract (fwdback.c:925-927)
 
 
-@pytest.mark.parametrize("M", [1, 2, 7, 8, 9, 31, 32, 33, 64, 100, 200, 257, 500, 513, 640, 641, 768, 900, 1024, 1025, 1300, 1536, 1600])
+# one model length (at least) per register size class of b2h_dpreg.cu, the class boundaries, and the shared-memory kernels beyond 1536
+@pytest.mark.parametrize("M", [1, 2, 7, 8, 9, 31, 32, 33, 64, 65, 80, 100, 150, 180, 200, 210, 257, 270, 300, 340, 384, 420, 500, 513, 550, 640,
+                               641, 700, 768, 850, 900, 1024, 1025, 1200, 1300, 1536, 1600])
 def test_viterbi_bit_exact(ctx, amino, make_pair, M):
     rng = np.random.default_rng(2000 + M)
     pair = make_pair(synth.random_hmm(amino, M, rng))
@@ -26,7 +28,8 @@ def test_viterbi_bit_exact(ctx, amino, make_pair, M):
     print("M=%d: %d comparisons, %d overflowed" % (M, len(block), n_inf))
 
 
-@pytest.mark.parametrize("M", [1, 2, 9, 33, 64, 100, 200, 257, 500, 513, 640, 641, 768, 900, 1024, 1025, 1300, 1536, 1600])
+@pytest.mark.parametrize("M", [1, 2, 9, 33, 64, 80, 100, 150, 180, 200, 210, 257, 270, 300, 340, 420, 500, 513, 550, 640, 641, 700, 768, 850, 900,
+                               1024, 1025, 1200, 1300, 1536, 1600])
 def test_forward_backward_parsers(ctx, amino, make_pair, M):
     rng = np.random.default_rng(3000 + M)
     pair = make_pair(synth.random_hmm(amino, M, rng))

@@ -40,7 +40,9 @@ def _run(fn, ctx, om, block):
     return sc, st
 
 
-@pytest.mark.parametrize("M", [1, 2, 7, 8, 9, 15, 16, 17, 33, 63, 64, 65, 100, 127, 128, 200, 255, 256, 300, 400, 700])
+# every SSV register tile family is hit: G=8 (M <= 511; NR = ceil((M+1)/16), leftover words 0..3), G=16 (M <= 1023), G=32 beyond
+@pytest.mark.parametrize("M", [1, 2, 7, 8, 9, 15, 16, 17, 31, 33, 47, 48, 63, 64, 65, 100, 127, 128, 143, 200, 255, 256, 300, 319, 400,
+                               463, 511, 512, 600, 700, 1023, 1024])
 def test_msv_and_ssv_bit_exact(ctx, amino, make_pair, M):
     rng = np.random.default_rng(1000 + M)
     pair = make_pair(synth.random_hmm(amino, M, rng))
@@ -64,7 +66,7 @@ def test_msv_and_ssv_bit_exact(ctx, amino, make_pair, M):
 
 def test_large_models(ctx, amino, make_pair):
     rng = np.random.default_rng(5)
-    for M in (1100, 2300):
+    for M in (1100, 1500, 2300):
         pair = make_pair(synth.random_hmm(amino, M, rng))
         block = _targets(amino, pair.hmm, rng, n_random=40, n_homolog=6)
         sc, st = _run(_lib.lib.b2h_msv_filter, ctx, pair.om, block)
