@@ -30,6 +30,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware work queue per stream (default 8): the engine keeps ~30 streams busy (size classes, the high-priority
+# survivor lane, envelope classes) and queue aliasing would serialise the high-priority kernels behind queued cascade
+# launches.  Must be set before the CUDA context exists, i.e. before torch touches the device.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_PROFILES = 100
 N_SEQS = 50000

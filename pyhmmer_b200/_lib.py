@@ -10,6 +10,11 @@ import threading
 
 import numpy as np
 
+# One hardware work queue per stream instead of the default 8: the engine keeps ~30 streams busy and queue aliasing would
+# serialise its high-priority survivor lane behind queued cascade launches.  Read by the driver when the CUDA context is
+# created, so it only takes effect if this package is imported before anything else initialises CUDA.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2h.so")
 

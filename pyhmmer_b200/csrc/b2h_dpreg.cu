@@ -601,10 +601,8 @@ template <typename K>
 int launch_reg(b2h_ctx *ctx, K kernel, int C, int W, const WorkList &wl, const SeqDev &sd, int nitems_hint, const StageOut &out, cudaStream_t strm)
 {
   const size_t smem = (size_t)32 * 32 * C * W * 4;
-  B2H_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
-  B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem));
-  if (occ < 1) occ = 1;
+  { const int st = b2h_kernel_occupancy(ctx, (const void *)kernel, 256, smem, &occ); if (st != B2H_OK) return st; }
   int grid = ctx->sm_count * occ;
   if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
   if (grid < 1) grid = 1;

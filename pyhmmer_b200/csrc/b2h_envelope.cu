@@ -688,8 +688,7 @@ template <typename K>
 int launch_env(b2h_ctx *ctx, K kernel, const EnvDev &ev, const SeqDev &sd, cudaStream_t strm)
 {
   int occ = 1;
-  B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0));
-  if (occ < 1) occ = 1;
+  { const int st = b2h_kernel_occupancy(ctx, (const void *)kernel, 256, 0, &occ); if (st != B2H_OK) return st; }
   const int n = ev.e_hi - ev.e_lo;
   int grid = std::min(ctx->sm_count * occ, std::max(1, n));
   B2H_CUDA(cudaMemsetAsync(ev.counter, 0, sizeof(int), strm));

@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <atomic>
 #include <cstdio>
+#include <mutex>
+#include <utility>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -46,7 +48,30 @@ struct b2h_ctx {
   cudaStream_t  env_side[8] = {nullptr}; cudaEvent_t env_fork = nullptr, env_join[8] = {nullptr};   // one side stream per envelope size class
   // page-locked host buffers of destroyed sequence databases, kept for the next one (pinning costs ~0.3 ms/MB)
   std::vector<std::pair<void *, size_t>> pinned_free;
+  // second launch lane (high-priority streams + its own work counters): the survivor Forward/Backward passes of wave w
+  // are issued here while the cascade of wave w+1 is already queued on <stream>; b2h_lane_switch swaps it in
+  cudaStream_t  alt_stream = nullptr; std::vector<cudaStream_t> alt_side; std::vector<cudaEvent_t> alt_side_done;
+  cudaEvent_t   alt_fork_ev = nullptr; int *alt_counters = nullptr; int prio_hi = 0;
+  // page-locked result buffers (survivor lists, parser special rows) recycled between searches
+  std::mutex    pin_mu; std::vector<std::pair<void *, size_t>> pin_pool;
 };
+
+// RAII: make the alternate lane the current one (only the thread that drives b2h_search does this)
+struct b2h_lane_switch {
+  b2h_ctx *c;
+  explicit b2h_lane_switch(b2h_ctx *ctx) : c(ctx) { swap(); }
+  ~b2h_lane_switch() { swap(); }
+  void swap() { std::swap(c->stream, c->alt_stream); std::swap(c->side, c->alt_side); std::swap(c->side_done, c->alt_side_done);
+                std::swap(c->fork_ev, c->alt_fork_ev); std::swap(c->d_counters, c->alt_counters); }
+};
+// occupancy (resident CTAs per SM) of a kernel at <threads> / <smem> dynamic bytes, raising its dynamic shared-memory
+// limit on first use; cached per (device, kernel, smem): the runtime queries cost ~10 us each and a search launches hundreds of kernels
+int b2h_kernel_occupancy(b2h_ctx *ctx, const void *kernel, int threads, size_t smem, int *occ);
+void *b2h_pin_get(b2h_ctx *ctx, size_t bytes);          // page-locked buffer of at least <bytes> (nullptr: out of memory)
+void  b2h_pin_put(b2h_ctx *ctx, void *p);
+
+// device block shared by the profiles of one batched upload; freed when the last of them is destroyed
+struct b2h_devblock { void *d = nullptr; std::atomic<int> refs{0}; };
 
 struct b2h_seqdb {
   b2h_ctx  *ctx = nullptr;
@@ -77,7 +102,8 @@ struct b2h_seqdb {
 
 struct b2h_profile {
   b2h_ctx *ctx = nullptr;
-  void *d_block = nullptr;         // the single device allocation all d_* table pointers below point into
+  void *d_block = nullptr;         // the single device allocation all d_* table pointers below point into (own upload), or
+  struct b2h_devblock *shared = nullptr;   // the allocation shared by every profile of one b2h_profile_upload_many call
   int M = 0, K = 0, Kp = 0, max_length = 0, multihit = 1;
   // MSV
   int NR = 0, G = 0;              // SSV register tile: G lanes per comparison, NR packed cell registers (2*NR nodes) per lane
@@ -125,9 +151,17 @@ struct StageTimer {
   StageTimer(b2h_ctx *c, int st) : ctx(c), stage(st) { if (c->profiling) { e0 = get(c); e1 = get(c); cudaEventRecord(e0, c->stream); } }
   ~StageTimer() { if (e0) { cudaEventRecord(e1, ctx->stream); ctx->ev_open.push_back({stage, {e0, e1}}); } }
 };
-static inline void b2h_resolve_timers(b2h_ctx *c) {
-  for (auto &o : c->ev_open) { float ms = 0.f; if (cudaEventElapsedTime(&ms, o.second.first, o.second.second) == cudaSuccess) c->stage_ms[o.first] += ms; }
-  c->ev_open.clear(); c->ev_used = 0;
+static inline void b2h_resolve_timers(b2h_ctx *c) {       // stages of a wave still running on the other lane stay open
+  size_t keep = 0;
+  for (auto &o : c->ev_open) {
+    float ms = 0.f;
+    const cudaError_t e = cudaEventElapsedTime(&ms, o.second.first, o.second.second);
+    if (e == cudaSuccess) c->stage_ms[o.first] += ms;
+    else if (e == cudaErrorNotReady) c->ev_open[keep++] = o;
+  }
+  (void)cudaGetLastError();
+  c->ev_open.resize(keep);
+  if (keep == 0) c->ev_used = 0;
 }
 
 // fork/join of the side streams around a group of independent launches (one per size class: a class launch of a few
@@ -142,7 +176,8 @@ struct ForkJoin {
   cudaStream_t next() {                                   // stream for the next independent launch
     const int i = n++ % B2H_NSIDE;
     if ((int)ctx->side.size() <= i) {
-      cudaStream_t s; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); ctx->side.push_back(s);
+      int prio = 0; cudaStreamGetPriority(ctx->stream, &prio);     // side streams inherit the priority of their lane
+      cudaStream_t s; cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio); ctx->side.push_back(s);
       cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); ctx->side_done.push_back(e);
     }
     if (n <= B2H_NSIDE) cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0);

@@ -360,14 +360,8 @@ template <int G, int NR>
 int launch_ssv_tile(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
 {
   const size_t smem = (size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR);
-  static int occ_cached[8] = {0};                        // per device (the attribute and the occupancy are per device)
-  int &occ = occ_cached[ctx->device & 7];
-  if (occ == 0) {
-    B2H_CUDA(cudaFuncSetAttribute(ssv_kernel<G, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int o = 1;
-    B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ssv_kernel<G, NR>, SSV_THREADS, smem));
-    occ = o < 1 ? 1 : o;
-  }
+  int occ = 1;
+  { const int st = b2h_kernel_occupancy(ctx, (const void *)ssv_kernel<G, NR>, SSV_THREADS, smem, &occ); if (st != B2H_OK) return st; }
   int grid = ctx->sm_count * occ;
   const long long nitems = (long long)a.ncls * a.chunks;
   if (grid > nitems) grid = (int)(nitems > 0 ? nitems : 1);
@@ -402,10 +396,8 @@ int b2h_launch_msv(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_M
   const int nwarps = 8;
   const size_t smem = (size_t)32 * max_Mpad + (size_t)nwarps * 2 * (max_Mpad + 64) + 128;
   if (smem > 220 * 1024) { ctx->err = "model too long for the MSV kernel"; return B2H_EINVAL; }
-  B2H_CUDA(cudaFuncSetAttribute(msv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
-  B2H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msv_kernel, nwarps * 32, smem));
-  if (occ < 1) occ = 1;
+  { const int st = b2h_kernel_occupancy(ctx, (const void *)msv_kernel, nwarps * 32, smem, &occ); if (st != B2H_OK) return st; }
   int grid = ctx->sm_count * occ;
   if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
   B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), ctx->stream));

@@ -90,16 +90,27 @@ __global__ void fwd_post_kernel(const ProfDev *profs, const Grouped g, const int
 }
 
 // A pool of device buffers for one batch of the cascade
-struct Pool {
-  b2h_ctx *ctx; std::vector<void *> ptrs;
-  explicit Pool(b2h_ctx *c) : ctx(c) {}
+struct Pool {                                        // allocations and frees are ordered on the lane current at construction
+  b2h_ctx *ctx; cudaStream_t stream; std::vector<void *> ptrs;
+  explicit Pool(b2h_ctx *c) : ctx(c), stream(c->stream) {}
   template <typename T> int get(T **out, size_t n) {
     void *p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), ctx->stream);
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), stream);
     if (e != cudaSuccess) { ctx->err = std::string("cudaMallocAsync: ") + cudaGetErrorString(e); return B2H_EMEM; }
     ptrs.push_back(p); *out = (T *)p; return B2H_OK;
   }
-  ~Pool() { for (void *p : ptrs) cudaFreeAsync(p, ctx->stream); }
+  ~Pool() { for (void *p : ptrs) cudaFreeAsync(p, stream); }
+};
+// page-locked host array from the context's pool
+template <typename T> struct Pinned {
+  b2h_ctx *ctx = nullptr; T *p = nullptr; size_t n = 0;
+  Pinned() {}
+  Pinned(const Pinned &) = delete; Pinned &operator=(const Pinned &) = delete;
+  int alloc(b2h_ctx *c, size_t count) { release(); ctx = c; n = count; p = (T *)b2h_pin_get(c, std::max<size_t>(count, 1) * sizeof(T)); if (!p) { c->err = "cudaHostAlloc failed"; return B2H_EMEM; } return B2H_OK; }
+  void release() { if (p) b2h_pin_put(ctx, p); p = nullptr; n = 0; }
+  ~Pinned() { release(); }
+  T *data() { return p; } const T *data() const { return p; }
+  T &operator[](size_t i) { return p[i]; } const T &operator[](size_t i) const { return p[i]; }
 };
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -117,20 +128,35 @@ int make_list(Pool &pool, SurvList &l, size_t cap, int P, int *ctr, int *cnt, bo
 
 } // namespace
 
-// One batch of profiles [p0, p1) against the whole database: runs the cascade, returns list D on the host.
-static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p0, int p1, const b2h_seqdb *db,
-                         const b2h_search_params *prm, std::vector<b2h_survivor> &outD, int64_t *counters /*[P][4], global index*/)
+// One batch (wave) of profiles [p0, p1) against the whole database.  cascade_enqueue queues the whole cascade on the
+// current lane and returns at once; cascade_collect waits for that wave only (an event), reads list D and the
+// counters.  Between the two the caller queues the NEXT wave, so the GPU never idles while the host digests a wave.
+struct CascadeWave {
+  std::unique_ptr<Pool> pool;
+  int p0 = 0, P = 0;
+  std::vector<int> perm;
+  Pinned<int> hctr; Pinned<ProfDev> hprof; Pinned<int32_t> hcls;
+  SurvList D;
+  cudaEvent_t done = nullptr;
+  ~CascadeWave() { if (done) cudaEventDestroy(done); }
+};
+
+static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int p0, int p1, const b2h_seqdb *db,
+                           const b2h_search_params *prm, CascadeWave &cw)
 {
   const int P = p1 - p0, N = (int)db->n;
   const size_t cap = (size_t)P * N;
   const SeqDev sd = b2h_seqdev(db);
-  Pool pool(ctx);
   B2H_CUDA(cudaSetDevice(ctx->device));
-
-  // profile descriptors + register-tile classes
-  std::vector<ProfDev> hprof(P);
+  cw.pool.reset(new Pool(ctx));
+  Pool &pool = *cw.pool;
+  cw.p0 = p0; cw.P = P;
+  // profile descriptors + register-tile classes (staged page-locked and kept with the wave: the uploads must be truly
+  // asynchronous, this wave is queued while the previous one is still running)
+  TRY(cw.hprof.alloc(ctx, P)); TRY(cw.hcls.alloc(ctx, P));
+  ProfDev *hprof = cw.hprof.data();
   std::map<int, std::vector<int32_t>> classes;
-  std::vector<int> perm(P), mpads(P);                  // batch-local profile order: ascending model size
+  std::vector<int> &perm = cw.perm; perm.resize(P); std::vector<int> mpads(P);                  // batch-local profile order: ascending model size
   std::iota(perm.begin(), perm.end(), 0);
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return profiles[p0 + a]->Mpad < profiles[p0 + b]->Mpad; });
   int max_Mpad = 0;
@@ -141,11 +167,12 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
     max_Mpad = std::max(max_Mpad, hprof[i].Mpad);
   }
   ProfDev *d_prof; TRY(pool.get(&d_prof, P));
-  B2H_CUDA(cudaMemcpyAsync(d_prof, hprof.data(), P * sizeof(ProfDev), cudaMemcpyHostToDevice, ctx->stream));
-  std::vector<int32_t> hcls; std::vector<std::pair<int, std::pair<int, int>>> cls_ranges;   // SSV tile G*64+NR -> (offset, count)
-  for (auto &kv : classes) { cls_ranges.push_back({kv.first, {(int)hcls.size(), (int)kv.second.size()}}); hcls.insert(hcls.end(), kv.second.begin(), kv.second.end()); }
-  int32_t *d_cls; TRY(pool.get(&d_cls, hcls.size()));
-  B2H_CUDA(cudaMemcpyAsync(d_cls, hcls.data(), hcls.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  B2H_CUDA(cudaMemcpyAsync(d_prof, hprof, P * sizeof(ProfDev), cudaMemcpyHostToDevice, ctx->stream));
+  int32_t *hcls = cw.hcls.data(); int ncls_tot = 0;
+  std::vector<std::pair<int, std::pair<int, int>>> cls_ranges;   // SSV tile G*64+NR -> (offset, count)
+  for (auto &kv : classes) { cls_ranges.push_back({kv.first, {ncls_tot, (int)kv.second.size()}}); for (int32_t v : kv.second) hcls[ncls_tot++] = v; }
+  int32_t *d_cls; TRY(pool.get(&d_cls, P));
+  B2H_CUDA(cudaMemcpyAsync(d_cls, hcls, P * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
 
   // counters: [0..5] list sizes n(A,R,V,F,D,err), then 6 per-profile count arrays (A,R,V,F,D,bias) + fill
   int *d_ctr; TRY(pool.get(&d_ctr, 8 + (size_t)7 * P));
@@ -205,27 +232,41 @@ static int cascade_batch(b2h_ctx *ctx, const b2h_profile *const *profiles, int p
     ctx->launches++; }
   B2H_CUDA(cudaGetLastError());
 
-  // 6. list D and the counters come home
-  std::vector<int> hctr(8 + (size_t)7 * P);
-  B2H_CUDA(cudaMemcpyAsync(hctr.data(), d_ctr, hctr.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+  // 6. the counters come home (page-locked: the copy must not block the host, the next wave is queued behind it)
+  TRY(cw.hctr.alloc(ctx, 8 + (size_t)7 * P));
+  B2H_CUDA(cudaMemcpyAsync(cw.hctr.data(), d_ctr, (8 + (size_t)7 * P) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  B2H_CUDA(cudaEventCreateWithFlags(&cw.done, cudaEventDisableTiming));
+  B2H_CUDA(cudaEventRecord(cw.done, ctx->stream));
+  cw.D = D;
+  return B2H_OK;
+}
+
+// Wait for the wave, then fetch list D over <copy_stream> (the wave's own lane may already hold the next wave's kernels).
+static int cascade_collect(b2h_ctx *ctx, CascadeWave &cw, cudaStream_t copy_stream, std::vector<b2h_survivor> &outD, int64_t *counters /*[P][4], global index*/)
+{
+  B2H_CUDA(cudaEventSynchronize(cw.done));
   b2h_resolve_timers(ctx);
+  const int P = cw.P, p0 = cw.p0;
+  const int *hctr = cw.hctr.data();
   if (hctr[5] > 0) { ctx->err = "numerical overflow in the Forward parser"; return B2H_ERANGE; }
   const int nD = hctr[4];
   for (int i = 0; i < P; i++) {
-    int64_t *c = counters + (size_t)(p0 + perm[i]) * 4;
+    int64_t *c = counters + (size_t)(p0 + cw.perm[i]) * 4;
     c[0] = hctr[8 + i]; c[1] = hctr[8 + 5 * P + i]; c[2] = hctr[8 + 3 * P + i]; c[3] = hctr[8 + 4 * P + i];
   }
-  std::vector<int32_t> dp(nD), ds(nD); std::vector<float> da(nD), dbv(nD);
   if (nD) {
-    B2H_CUDA(cudaMemcpyAsync(dp.data(), D.p, nD * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    B2H_CUDA(cudaMemcpyAsync(ds.data(), D.s, nD * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    B2H_CUDA(cudaMemcpyAsync(da.data(), D.a, nD * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    B2H_CUDA(cudaMemcpyAsync(dbv.data(), D.b, nD * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+    Pinned<int32_t> h; TRY(h.alloc(ctx, (size_t)4 * nD));
+    const SurvList &D = cw.D;
+    B2H_CUDA(cudaMemcpyAsync(h.data(), D.p, nD * sizeof(int32_t), cudaMemcpyDeviceToHost, copy_stream));
+    B2H_CUDA(cudaMemcpyAsync(h.data() + nD, D.s, nD * sizeof(int32_t), cudaMemcpyDeviceToHost, copy_stream));
+    B2H_CUDA(cudaMemcpyAsync(h.data() + 2 * (size_t)nD, D.a, nD * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+    B2H_CUDA(cudaMemcpyAsync(h.data() + 3 * (size_t)nD, D.b, nD * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+    B2H_CUDA(cudaStreamSynchronize(copy_stream));
+    outD.reserve(outD.size() + nD);
+    const float *fa = reinterpret_cast<const float *>(h.data() + 2 * (size_t)nD), *fb = reinterpret_cast<const float *>(h.data() + 3 * (size_t)nD);
+    for (int i = 0; i < nD; i++) { b2h_survivor v; v.profile = p0 + cw.perm[h[i]]; v.seq = h[(size_t)nD + i]; v.fwdsc = fa[i]; v.filtersc = fb[i]; outD.push_back(v); }
   }
-  outD.reserve(outD.size() + nD);
-  for (int i = 0; i < nD; i++) { b2h_survivor v; v.profile = p0 + perm[dp[i]]; v.seq = ds[i]; v.fwdsc = da[i]; v.filtersc = dbv[i]; outD.push_back(v); }
+  cw.pool.reset();                                    // stream-ordered frees on the wave's lane, after everything queued there so far
   return B2H_OK;
 }
 
@@ -360,7 +401,7 @@ struct EnvGpu : b2h_env_backend {
 // One chunk of survivors whose parser specials are on the host: the domain definition runs on the host thread pool
 // from a helper thread while the calling thread goes on feeding the GPU with the next wave of profiles.
 struct DdefJob {
-  std::vector<float> fx, bx; std::vector<int32_t> bst; std::vector<b2h_ddef_task> tasks;
+  Pinned<float> fx, bx; Pinned<int32_t> bst; std::vector<b2h_ddef_task> tasks;   // page-locked: the D2H copies run at PCIe speed
   std::thread th; int status = B2H_OK; double ms = 0.0;
 };
 struct DdefAsync {
@@ -432,10 +473,10 @@ static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, co
     TRY(b2h_launch_backward(ctx, wl, sd, mpads, items, sb));
     delete tm;
     std::unique_ptr<DdefJob> job(new DdefJob());
-    std::vector<float> &fx = job->fx, &bx = job->bx; std::vector<int32_t> &bst = job->bst;
-    fx.resize((size_t)acc * 6); bx.resize((size_t)acc * 6); bst.resize(n);
-    B2H_CUDA(cudaMemcpyAsync(fx.data(), d_fx, fx.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    B2H_CUDA(cudaMemcpyAsync(bx.data(), d_bx, bx.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    Pinned<float> &fx = job->fx, &bx = job->bx; Pinned<int32_t> &bst = job->bst;
+    TRY(fx.alloc(ctx, (size_t)acc * 6)); TRY(bx.alloc(ctx, (size_t)acc * 6)); TRY(bst.alloc(ctx, n));
+    B2H_CUDA(cudaMemcpyAsync(fx.data(), d_fx, (size_t)acc * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    B2H_CUDA(cudaMemcpyAsync(bx.data(), d_bx, (size_t)acc * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(bst.data(), d_bst, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     B2H_CUDA(cudaStreamSynchronize(ctx->stream));
     b2h_resolve_timers(ctx);
@@ -481,15 +522,22 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     for (size_t i = 0; i < P; i++) { sp[i] = profiles[order[i]]; cells += sp[i]->M; }
     const size_t CAP = (size_t)1 << 25;                 // comparisons per batch: every list is sized for the worst case
     const size_t pb = std::max<size_t>(1, CAP / N);
-    int nwaves = (P >= 8) ? 2 : 1;                       // measured on B200 + 128 host threads: 2 beats 1, 4 and 6
+    // Waves shrink geometrically: the host work of every wave but the last hides behind the next wave's cascade, so
+    // the last wave -- whose survivor passes, envelope kernels and host domain definition are exposed -- is the smallest.
+    int nwaves = (P >= 12) ? 3 : (P >= 6) ? 2 : 1;       // measured on B200 (100 profiles x 50k sequences): 3 waves at ratio 0.6 beat 2, 4, 5
+    double ratio = 0.6;
     if (const char *ev = getenv("B2H_WAVES")) nwaves = std::max(1, atoi(ev));
+    if (const char *ev = getenv("B2H_WAVE_RATIO")) ratio = std::min(1.0, std::max(0.05, atof(ev)));
+    std::vector<double> cum(nwaves + 1, 0.0);            // cumulative share of the DP cells after each wave
+    { double wsum = 0.0, wgt = 1.0; for (int i = 0; i < nwaves; i++) { wsum += wgt; cum[i + 1] = wsum; wgt *= ratio; }
+      for (int i = 0; i <= nwaves; i++) cum[i] /= wsum; }
     std::vector<size_t> bounds{0};                       // wave boundaries in sorted order
     { double acc = 0.0; size_t start = 0; int slot = 1;
       for (size_t i = 0; i < P; i++) {
         acc += sp[i]->M;
-        if (i + 1 == P || i + 1 - start >= pb || acc >= cells * slot / nwaves) {
+        if (i + 1 == P || i + 1 - start >= pb || acc >= cells * cum[slot]) {
           bounds.push_back(i + 1); start = i + 1;
-          while (slot < nwaves && acc >= cells * slot / nwaves) slot++;
+          while (slot < nwaves && acc >= cells * cum[slot]) slot++;
         }
       } }
     std::vector<int64_t> scnt(P * 4, 0);
@@ -498,16 +546,25 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     const bool host_env = getenv("B2H_ENVELOPES_ON_HOST") != nullptr;     // debugging aid: rescore envelopes with the host code
     DdefAsync ddef(ddpool, prm, res, host_env ? nullptr : &envgpu);
     size_t nsurv = 0; double tg = 0.0;
-    for (size_t w = 0; w + 1 < bounds.size(); w++) {
-      std::vector<b2h_survivor> surv;
+    // Software pipeline over the waves: the cascade of wave w+1 is queued on the main lane before the host waits for
+    // wave w; wave w's survivors then go through Forward/Backward on the high-priority lane (their kernels slip in
+    // between the next wave's SSV launches) and on to the domain-definition thread.
+    const size_t nw = bounds.size() - 1;
+    std::vector<std::unique_ptr<CascadeWave>> waves(nw);
+    int st = B2H_OK;
+    if (nw) { waves[0].reset(new CascadeWave()); st = cascade_enqueue(ctx, sp.data(), (int)bounds[0], (int)bounds[1], db, prm, *waves[0]); }
+    for (size_t w = 0; w < nw && st == B2H_OK; w++) {
       const double tw = now_ms();
-      int st = cascade_batch(ctx, sp.data(), (int)bounds[w], (int)bounds[w + 1], db, prm, surv, scnt.data());
-      if (st == B2H_OK) st = finish_survivors(ctx, sp.data(), db, prm, surv, ddef);
-      if (st != B2H_OK) { ddef.join(); delete res; return st; }
+      if (w + 1 < nw) { waves[w + 1].reset(new CascadeWave()); st = cascade_enqueue(ctx, sp.data(), (int)bounds[w + 1], (int)bounds[w + 2], db, prm, *waves[w + 1]); }
+      std::vector<b2h_survivor> surv;
+      if (st == B2H_OK) st = cascade_collect(ctx, *waves[w], ctx->alt_stream, surv, scnt.data());
+      waves[w].reset();
+      if (st == B2H_OK) { b2h_lane_switch lane(ctx); st = finish_survivors(ctx, sp.data(), db, prm, surv, ddef); }
       nsurv += surv.size(); tg += now_ms() - tw;
     }
+    if (st != B2H_OK) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->alt_stream); ddef.join(); waves.clear(); delete res; return st; }
     const double t1 = now_ms();
-    int st = ddef.join();
+    st = ddef.join();
     if (st != B2H_OK) { ctx->err = "domain definition failed"; delete res; return st; }
     for (b2h_hit &h : res->hits) h.profile = order[h.profile];
     for (size_t i = 0; i < P; i++) for (int c = 0; c < 4; c++) res->counters[(size_t)order[i] * 4 + c] = scnt[i * 4 + c];
