@@ -30,12 +30,14 @@ int b2h_ctx_create(int device, b2h_ctx **out)
   B2H_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   B2H_CUDA(cudaMalloc(&ctx->d_counters, 64 * sizeof(int)));
-  B2H_CUDA(cudaMalloc(&ctx->alt_counters, 64 * sizeof(int)));
   B2H_CUDA(cudaMalloc(&ctx->d_env_counter, 16 * sizeof(int)));
   // the survivor lane and the envelope streams outrank the cascade: their kernels are short, latency-bound and on the
   // critical path of the host-side domain definition, the cascade's persistent CTAs would otherwise starve them
   { int lo = 0, hi = 0; B2H_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi)); ctx->prio_hi = hi; }
-  B2H_CUDA(cudaStreamCreateWithPriority(&ctx->alt_stream, cudaStreamNonBlocking, ctx->prio_hi));
+  for (auto &l : ctx->lanes) {
+    B2H_CUDA(cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, ctx->prio_hi));
+    B2H_CUDA(cudaMalloc(&l.counters, 64 * sizeof(int)));
+  }
   B2H_CUDA(cudaStreamCreateWithPriority(&ctx->env_stream, cudaStreamNonBlocking, ctx->prio_hi));
   B2H_CUDA(cudaEventCreateWithFlags(&ctx->env_fork, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++) { B2H_CUDA(cudaStreamCreateWithPriority(&ctx->env_side[i], cudaStreamNonBlocking, ctx->prio_hi)); B2H_CUDA(cudaEventCreateWithFlags(&ctx->env_join[i], cudaEventDisableTiming)); }
@@ -58,11 +60,13 @@ void b2h_ctx_destroy(b2h_ctx *ctx)
   for (int i = 0; i < 8; i++) { if (ctx->env_side[i]) cudaStreamDestroy(ctx->env_side[i]); if (ctx->env_join[i]) cudaEventDestroy(ctx->env_join[i]); }
   for (auto &pf : ctx->pinned_free) cudaFreeHost(pf.first);
   for (auto &pf : ctx->pin_pool) cudaFreeHost(pf.first);
-  if (ctx->alt_counters) cudaFree(ctx->alt_counters);
-  if (ctx->alt_stream) cudaStreamDestroy(ctx->alt_stream);
-  for (cudaStream_t q : ctx->alt_side) cudaStreamDestroy(q);
-  for (cudaEvent_t e : ctx->alt_side_done) cudaEventDestroy(e);
-  if (ctx->alt_fork_ev) cudaEventDestroy(ctx->alt_fork_ev);
+  for (auto &l : ctx->lanes) {
+    if (l.counters) cudaFree(l.counters);
+    if (l.stream) cudaStreamDestroy(l.stream);
+    for (cudaStream_t q : l.side) cudaStreamDestroy(q);
+    for (cudaEvent_t e : l.side_done) cudaEventDestroy(e);
+    if (l.fork_ev) cudaEventDestroy(l.fork_ev);
+  }
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   for (cudaStream_t q : ctx->side) cudaStreamDestroy(q);
   for (cudaEvent_t e : ctx->side_done) cudaEventDestroy(e);
@@ -278,7 +282,26 @@ int b2h_profile_create_host(const b2h_oprofile_desc *d, b2h_profile **out)
 
 // Host half of an upload: the profile object and, when a context is given, the staged image of its device block
 // (sections 256-byte aligned; offsets in <offs>).  Pure CPU work, safe to run for many profiles in parallel.
-struct ProfStage { std::vector<uint8_t> bytes; size_t offs[9] = {0}; };
+struct ProfStage { std::vector<uint8_t> bytes; uint8_t *ext = nullptr; size_t size = 0; size_t offs[9] = {0}; };   // image in <bytes>, or written straight to <ext>
+// Size of the staged device image of a profile (sections 256-byte aligned, in the order profile_build adds them).
+static void profile_classes(int M, int *G, int *NR, int *regC, int *regW)
+{
+  *G = *NR = *regC = *regW = 0;
+  b2h_ssv_tile(M, G, NR);
+  const b2h_regclass *rcls; const int nrcls = b2h_reg_classes(&rcls);
+  for (int rc = 0; rc < nrcls; rc++) if (M <= rcls[rc].bound) { *regC = rcls[rc].C; *regW = rcls[rc].W; break; }
+}
+static size_t profile_stage_bytes(int M, int G, int NR, int regC, int regW)
+{
+  const size_t Mp = (size_t)((M + 31) & ~31);
+  size_t used = 0;
+  auto add = [&](size_t bytes) { used = ((used + 255) & ~(size_t)255) + bytes; };
+  add((size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR)); add(B2H_NCODE * Mp);
+  add(B2H_NCODE * Mp * 2); add(8 * Mp * 2); add(B2H_NCODE * Mp * 4); add(8 * Mp * 4); add((size_t)B2H_NCODE * 2 * 4);
+  if (regC) { add((size_t)B2H_NCODE * 32 * regC * regW * 4); add((size_t)B2H_NCODE * 32 * regC * regW * 4); }
+  return used;
+}
+
 static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile **out, ProfStage *stg)
 {
   if (!d || !out || d->M < 1 || d->Kp > B2H_NCODE - 1 || d->K > B2H_MAXABET) return B2H_EINVAL;
@@ -305,16 +328,19 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
   auto cost_of = [&](int x, int k) -> int {          // k is 1-based; anything off the model is the -inf cost
     return (x < Kp && k <= M) ? (int)d->msv_cost[(size_t)x * M + (k-1)] : 255;
   };
+  uint16_t half_of[256];                                 // fp16 bit patterns of the integers -128 .. 127 (exact)
+  for (int v = -128; v < 128; v++) half_of[v + 128] = __half_as_ushort(__float2half_rn((float)v));
   for (int x = 0; x < B2H_NCODE; x++)
-    for (int lane = 0; lane < 32; lane++)
+    for (int gl = 0; gl < G; gl++)
       for (int j = 0; j < NR; j++) {
-        const int klo = (lane % G) * 2 * NR + j + 1, khi = klo + NR;
+        const int klo = gl * 2 * NR + j + 1, khi = klo + NR;
         const int clo = cost_of(x, klo), chi = cost_of(x, khi);
         // SSV subtracts sbv = clamp(cost - bias, .., 127) as a signed byte (p7_oprofile.c:721-761): add its negation,
         // stored as fp16 (exact: |score| <= 127)
         const int slo = -std::min(clo - (int)d->bias_b, 127), shi = -std::min(chi - (int)d->bias_b, 127);
-        ssv[ssv_word_index(G, NR, x, j, lane)] =
-          ((uint32_t)__half_as_ushort(__float2half_rn((float)shi)) << 16) | (uint32_t)__half_as_ushort(__float2half_rn((float)slo));
+        const uint32_t w = ((uint32_t)half_of[shi + 128] << 16) | (uint32_t)half_of[slo + 128];
+        if (j < (NR / 4) * 4) ssv[ssv_word_index(G, NR, x, j, gl)] = w;
+        else for (int lane = gl; lane < 32; lane += G) ssv[ssv_word_index(G, NR, x, j, lane)] = w;     // leftover words: one copy per group of the warp
       }
 
   // --- Viterbi / Forward tables, padded ---
@@ -374,10 +400,13 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
 
   if (ctx && stg) {
     std::vector<uint8_t> &stage = stg->bytes;
+    if (!stg->ext) stage.resize(profile_stage_bytes(M, G, NR, p->regC, p->regW));
+    uint8_t *dst = stg->ext ? stg->ext : stage.data();
+    size_t used = 0;
     auto add = [&](const void *src, size_t bytes) -> size_t {
-      const size_t off = (stage.size() + 255) & ~(size_t)255;
-      stage.resize(off + bytes);
-      memcpy(stage.data() + off, src, bytes);
+      const size_t off = (used + 255) & ~(size_t)255;
+      memcpy(dst + off, src, bytes);
+      used = off + bytes;
       return off;
     };
     stg->offs[0] = add(ssv.data(), ssv.size() * 4); stg->offs[1] = add(mc.data(), mc.size());
@@ -385,7 +414,9 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
     stg->offs[4] = add(fr.data(), fr.size() * 4);   stg->offs[5] = add(ft.data(), ft.size() * 4);
     stg->offs[6] = add(eo.data(), eo.size() * 4);
     if (p->regC) { stg->offs[7] = add(vr32.data(), vr32.size() * 4); stg->offs[8] = add(frr.data(), frr.size() * 4); }
-    p->h2d_bytes = stage.size();
+    if (used > profile_stage_bytes(M, G, NR, p->regC, p->regW)) { delete p; return B2H_EINVAL; }   // (cannot happen: same arithmetic)
+    stg->size = used;
+    p->h2d_bytes = used;
   }
   *out = p;
   return B2H_OK;
@@ -396,8 +427,8 @@ static int profile_commit(b2h_ctx *ctx, b2h_profile *p, const ProfStage &stg)
 {
   cudaError_t e;
   cudaSetDevice(ctx->device);
-  if ((e = cudaMallocAsync((void **)&p->d_block, stg.bytes.size(), ctx->stream)) != cudaSuccess ||
-      (e = cudaMemcpyAsync(p->d_block, stg.bytes.data(), stg.bytes.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+  if ((e = cudaMallocAsync((void **)&p->d_block, stg.size, ctx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(p->d_block, stg.bytes.data(), stg.size, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
     ctx->err = cudaGetErrorString(e); return B2H_ECUDA;        // (pageable source: the copy is staged before the call returns)
   }
   uint8_t *b = (uint8_t *)p->d_block;
@@ -435,19 +466,21 @@ int b2h_profile_upload_many(b2h_ctx *ctx, const b2h_oprofile_desc *const *descs,
     if (T <= 1) work(0);
     else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
   };
-  run_parallel([&](size_t i) { status[i] = profile_build(ctx, descs[i], &out[i], &stg[i]); });
+  std::vector<size_t> base(n + 1, 0);
+  for (size_t i = 0; i < n; i++) {
+    if (!descs[i] || descs[i]->M < 1) return B2H_EINVAL;
+    int G, NR, rC, rW; profile_classes(descs[i]->M, &G, &NR, &rC, &rW);
+    if (!G) { ctx->err = "model too long for the register-tiled SSV kernel (M > 3071)"; return B2H_EINVAL; }
+    base[i + 1] = base[i] + ((profile_stage_bytes(descs[i]->M, G, NR, rC, rW) + 255) & ~(size_t)255);
+  }
+  cudaSetDevice(ctx->device);
+  uint8_t *h = (uint8_t *)b2h_pin_get(ctx, base[n]);
+  if (!h) { ctx->err = "cudaHostAlloc failed"; return B2H_EMEM; }
+  run_parallel([&](size_t i) { stg[i].ext = h + base[i]; status[i] = profile_build(ctx, descs[i], &out[i], &stg[i]); });
   int st = B2H_OK;
   for (size_t i = 0; i < n && st == B2H_OK; i++) st = status[i];
-  std::vector<size_t> base(n + 1, 0);
-  for (size_t i = 0; i < n && st == B2H_OK; i++) base[i + 1] = base[i] + ((stg[i].bytes.size() + 255) & ~(size_t)255);
-  uint8_t *h = nullptr; b2h_devblock *blk = nullptr;
+  b2h_devblock *blk = nullptr;
   if (st == B2H_OK) {
-    cudaSetDevice(ctx->device);
-    h = (uint8_t *)b2h_pin_get(ctx, base[n]);
-    if (!h) { ctx->err = "cudaHostAlloc failed"; st = B2H_EMEM; }
-  }
-  if (st == B2H_OK) {
-    run_parallel([&](size_t i) { memcpy(h + base[i], stg[i].bytes.data(), stg[i].bytes.size()); });
     blk = new b2h_devblock();
     cudaError_t e;
     if ((e = cudaMallocAsync(&blk->d, base[n], ctx->stream)) != cudaSuccess ||

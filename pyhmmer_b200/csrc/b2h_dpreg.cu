@@ -20,6 +20,7 @@
 // The generic kernels execute ~88 instructions per cell and row; these execute ~0.5.
 #include <cuda_runtime.h>
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 #include "b2h_internal.h"
 
@@ -603,6 +604,8 @@ int launch_reg(b2h_ctx *ctx, K kernel, int C, int W, const WorkList &wl, const S
   const size_t smem = (size_t)32 * 32 * C * W * 4;
   int occ = 1;
   { const int st = b2h_kernel_occupancy(ctx, (const void *)kernel, 256, smem, &occ); if (st != B2H_OK) return st; }
+  static const int occ_cap = getenv("B2H_DP_OCC") ? atoi(getenv("B2H_DP_OCC")) : 0;         // experiments: resident CTAs per SM
+  if (occ_cap > 0 && occ > occ_cap) occ = occ_cap;
   int grid = ctx->sm_count * occ;
   if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
   if (grid < 1) grid = 1;

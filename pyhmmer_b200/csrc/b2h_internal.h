@@ -48,21 +48,27 @@ struct b2h_ctx {
   cudaStream_t  env_side[8] = {nullptr}; cudaEvent_t env_fork = nullptr, env_join[8] = {nullptr};   // one side stream per envelope size class
   // page-locked host buffers of destroyed sequence databases, kept for the next one (pinning costs ~0.3 ms/MB)
   std::vector<std::pair<void *, size_t>> pinned_free;
-  // second launch lane (high-priority streams + its own work counters): the survivor Forward/Backward passes of wave w
-  // are issued here while the cascade of wave w+1 is already queued on <stream>; b2h_lane_switch swaps it in
-  cudaStream_t  alt_stream = nullptr; std::vector<cudaStream_t> alt_side; std::vector<cudaEvent_t> alt_side_done;
-  cudaEvent_t   alt_fork_ev = nullptr; int *alt_counters = nullptr; int prio_hi = 0;
+  // Extra launch lanes (a stream, its side streams and its own work counters; all high priority).  b2h_lane_switch
+  // swaps one in as the current lane:
+  //   B2H_LANE_SURV  survivor Forward/Backward passes of wave w, issued while later waves are already queued
+  //   B2H_LANE_POST  the cascade stages after SSV (MSV, bias, Viterbi, Forward) of wave w, which run NEXT TO the SSV
+  //                  launches of wave w+1 on the main lane: SSV saturates the shared-memory pipe, these the ALU pipe
+  struct Lane { cudaStream_t stream = nullptr; std::vector<cudaStream_t> side; std::vector<cudaEvent_t> side_done;
+                cudaEvent_t fork_ev = nullptr; int *counters = nullptr; };
+  Lane lanes[2]; int prio_hi = 0;
   // page-locked result buffers (survivor lists, parser special rows) recycled between searches
   std::mutex    pin_mu; std::vector<std::pair<void *, size_t>> pin_pool;
 };
 
-// RAII: make the alternate lane the current one (only the thread that drives b2h_search does this)
+// RAII: make one of the extra lanes the current one (only the thread that drives b2h_search does this)
+#define B2H_LANE_SURV 0
+#define B2H_LANE_POST 1
 struct b2h_lane_switch {
-  b2h_ctx *c;
-  explicit b2h_lane_switch(b2h_ctx *ctx) : c(ctx) { swap(); }
+  b2h_ctx *c; int i;
+  b2h_lane_switch(b2h_ctx *ctx, int lane) : c(ctx), i(lane) { swap(); }
   ~b2h_lane_switch() { swap(); }
-  void swap() { std::swap(c->stream, c->alt_stream); std::swap(c->side, c->alt_side); std::swap(c->side_done, c->alt_side_done);
-                std::swap(c->fork_ev, c->alt_fork_ev); std::swap(c->d_counters, c->alt_counters); }
+  void swap() { b2h_ctx::Lane &l = c->lanes[i]; std::swap(c->stream, l.stream); std::swap(c->side, l.side); std::swap(c->side_done, l.side_done);
+                std::swap(c->fork_ev, l.fork_ev); std::swap(c->d_counters, l.counters); }
 };
 // occupancy (resident CTAs per SM) of a kernel at <threads> / <smem> dynamic bytes, raising its dynamic shared-memory
 // limit on first use; cached per (device, kernel, smem): the runtime queries cost ~10 us each and a search launches hundreds of kernels

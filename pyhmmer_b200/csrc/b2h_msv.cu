@@ -362,6 +362,8 @@ int launch_ssv_tile(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
   const size_t smem = (size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR);
   int occ = 1;
   { const int st = b2h_kernel_occupancy(ctx, (const void *)ssv_kernel<G, NR>, SSV_THREADS, smem, &occ); if (st != B2H_OK) return st; }
+  static const int occ_cap = getenv("B2H_SSV_OCC") ? atoi(getenv("B2H_SSV_OCC")) : 0;       // experiments: resident CTAs per SM
+  if (occ_cap > 0 && occ > occ_cap) occ = occ_cap;
   int grid = ctx->sm_count * occ;
   const long long nitems = (long long)a.ncls * a.chunks;
   if (grid > nitems) grid = (int)(nitems > 0 ? nitems : 1);
