@@ -282,7 +282,7 @@ int b2h_profile_create_host(const b2h_oprofile_desc *d, b2h_profile **out)
 
 // Host half of an upload: the profile object and, when a context is given, the staged image of its device block
 // (sections 256-byte aligned; offsets in <offs>).  Pure CPU work, safe to run for many profiles in parallel.
-struct ProfStage { std::vector<uint8_t> bytes; uint8_t *ext = nullptr; size_t size = 0; size_t offs[9] = {0}; };   // image in <bytes>, or written straight to <ext>
+struct ProfStage { std::vector<uint8_t> bytes; uint8_t *ext = nullptr; size_t size = 0; size_t offs[10] = {0}; };   // image in <bytes>, or written straight to <ext>
 // Size of the staged device image of a profile (sections 256-byte aligned, in the order profile_build adds them).
 static void profile_classes(int M, int *G, int *NR, int *regC, int *regW)
 {
@@ -299,6 +299,7 @@ static size_t profile_stage_bytes(int M, int G, int NR, int regC, int regW)
   add((size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR)); add(B2H_NCODE * Mp);
   add(B2H_NCODE * Mp * 2); add(8 * Mp * 2); add(B2H_NCODE * Mp * 4); add(8 * Mp * 4); add((size_t)B2H_NCODE * 2 * 4);
   if (regC) { add((size_t)B2H_NCODE * 32 * regC * regW * 4); add((size_t)B2H_NCODE * 32 * regC * regW * 4); }
+  if (regC && regW == 1) add((size_t)B2H_NCODE * 32 * ((regC + 1) / 2) * 4);       // packed Viterbi table
   return used;
 }
 
@@ -381,6 +382,26 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
         }
   }
 
+  // --- packed s16x2 emission table of the 16-bit ViterbiFilter kernel (single-warp classes) ---
+  std::vector<uint32_t> vr2;
+  p->v2C = 0; p->v2_ok = 0; p->tbm_min = 0;
+  if (p->regC && p->regW == 1) {
+    const int C2 = (p->regC + 1) & ~1, H = C2 / 2, g = (H % 4 == 0) ? 4 : (H % 2 == 0) ? 2 : 1;
+    int rmax = -32768, tbm_min = 0;
+    for (int x = 0; x < Kp; x++) for (int k = 0; k < M; k++) rmax = std::max(rmax, (int)d->vit_rsc[(size_t)x * M + k]);
+    for (int k = 0; k < M; k++) tbm_min = std::min(tbm_min, (int)d->vit_tsc[k]);
+    p->v2C = C2; p->tbm_min = tbm_min; p->v2_ok = (rmax <= B2H_V2_RMAX);
+    auto val = [&](int x, int k0) -> uint32_t {           // clamped from below at V2_TF; off the model = -inf
+      const int v = (x < Kp && k0 < M) ? (int)d->vit_rsc[(size_t)x * M + k0] : -32768;
+      return (uint32_t)(uint16_t)(int16_t)std::max(v, B2H_V2_TF);
+    };
+    vr2.resize((size_t)B2H_NCODE * 32 * H);
+    for (int x = 0; x < B2H_NCODE; x++)
+      for (int lane = 0; lane < 32; lane++)
+        for (int j = 0; j < H; j++)
+          vr2[(size_t)x * 32 * H + (size_t)(j / g) * 32 * g + (size_t)lane * g + (j % g)] = val(x, lane * C2 + j) | (val(x, lane * C2 + j + H) << 16);
+  }
+
   // --- bias-filter 2-state HMM (p7_bg_SetFilter p7_bg.c:429, esl_hmm_Configure esl_hmm.c:118) ---
   std::vector<float> eo((size_t)B2H_NCODE * 2, 1.0f);
   {
@@ -414,6 +435,7 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
     stg->offs[4] = add(fr.data(), fr.size() * 4);   stg->offs[5] = add(ft.data(), ft.size() * 4);
     stg->offs[6] = add(eo.data(), eo.size() * 4);
     if (p->regC) { stg->offs[7] = add(vr32.data(), vr32.size() * 4); stg->offs[8] = add(frr.data(), frr.size() * 4); }
+    if (p->v2C) stg->offs[9] = add(vr2.data(), vr2.size() * 4);
     if (used > profile_stage_bytes(M, G, NR, p->regC, p->regW)) { delete p; return B2H_EINVAL; }   // (cannot happen: same arithmetic)
     stg->size = used;
     p->h2d_bytes = used;
@@ -436,6 +458,7 @@ static int profile_commit(b2h_ctx *ctx, b2h_profile *p, const ProfStage &stg)
   p->d_vit_rsc = (int16_t *)(b + stg.offs[2]); p->d_vit_tsc = (int16_t *)(b + stg.offs[3]);
   p->d_fwd_rsc = (float *)(b + stg.offs[4]); p->d_fwd_tsc = (float *)(b + stg.offs[5]); p->d_bias_eo = (float *)(b + stg.offs[6]);
   if (p->regC) { p->d_vit_rsc32 = (int32_t *)(b + stg.offs[7]); p->d_fwd_rscr = (float *)(b + stg.offs[8]); }
+  if (p->v2C) p->d_vit_rsc2 = (uint32_t *)(b + stg.offs[9]);
   return B2H_OK;
 }
 
@@ -502,6 +525,7 @@ int b2h_profile_upload_many(b2h_ctx *ctx, const b2h_oprofile_desc *const *descs,
       p->d_vit_rsc = (int16_t *)(b + sg.offs[2]); p->d_vit_tsc = (int16_t *)(b + sg.offs[3]);
       p->d_fwd_rsc = (float *)(b + sg.offs[4]); p->d_fwd_tsc = (float *)(b + sg.offs[5]); p->d_bias_eo = (float *)(b + sg.offs[6]);
       if (p->regC) { p->d_vit_rsc32 = (int32_t *)(b + sg.offs[7]); p->d_fwd_rscr = (float *)(b + sg.offs[8]); }
+      if (p->v2C) p->d_vit_rsc2 = (uint32_t *)(b + sg.offs[9]);
     }
   } else {
     for (size_t i = 0; i < n; i++) { b2h_profile_destroy(out[i]); out[i] = nullptr; }

@@ -17,6 +17,7 @@
 //     d -> max(A, d+T) for Viterbi (exact in integers, so the result is bit-identical to the
 //     reference's lazy-F evaluation), affine maps d -> A + d*T for Forward/Backward.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <cmath>
 #include <algorithm>
 #include "b2h_internal.h"
@@ -537,7 +538,18 @@ int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const Seq
     while (phi < P && mpads[phi] <= rcls[rc].bound) phi++;
     if (phi > plo) {
       WorkList wl = wl_in; wl.plo = plo; wl.phi = phi; wl.counter = wl_in.counter + cls;
-      int st = b2h_launch_dpreg(ctx, kind, rcls[rc].C, rcls[rc].W, wl, sd, nitems_hint, out, fj.next());
+      cudaStream_t strm = fj.next();
+      StageOut o = out;
+      static const bool vit32 = getenv("B2H_VIT32") != nullptr;        // debugging aid: 32-bit Viterbi kernel only
+      if (kind == 0 && rcls[rc].W == 1 && out.status && !vit32) {
+        // packed 16-bit kernel first; what it cannot decide exactly (strong hits, mostly) is redone in 32-bit lanes
+        int st2 = b2h_launch_vit2(ctx, (rcls[rc].C + 1) & ~1, wl, sd, nitems_hint, out, strm);
+        if (st2 != B2H_OK) return st2;
+        o.redo_only = 1;
+        static const bool noredo = getenv("B2H_VIT2_NOREDO") != nullptr; // debugging aid: leave B2H_REDO in the status array
+        if (noredo) { plo = phi; cls++; continue; }
+      }
+      int st = b2h_launch_dpreg(ctx, kind, rcls[rc].C, rcls[rc].W, wl, sd, nitems_hint, o, strm);
       if (st != B2H_OK) return st;
       plo = phi; cls++;
     }

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqD
     const int *my_rsc = s_rsc + wi * 32 * C;
 
     for (int e = it.e_begin + grp; e < it.e_end; e += ngrp) {
+      if (out.redo_only && out.status[e] != B2H_REDO) continue;      // second pass behind the packed kernel (uniform per group)
       const int s = wl.ent_s[e];
       const int L = sd.len[s];
       const int xw_move = sd.xwmove[s];
@@ -254,6 +255,184 @@ __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqD
         else sc = -INFINITY;
         out.sc[e] = sc;
         if (out.status) out.status[e] = st;
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// ViterbiFilter in packed 16-bit lanes (single-warp classes): two model nodes per 32-bit register, every term of the
+// recurrence ONE VIADDMNMX.S16x2 for two cells -- half the ALU work of rvit_kernel, which is ALU-pipe bound.
+//
+// Lane z owns the C consecutive nodes z*C .. z*C+C-1; register j (0 <= j < H = C/2) packs node j (low half) and node
+// j+H (high half), so "the cell of node k-1" is register j-1 for j >= 1 and one shuffle + PRMT for j = 0 (as in the SSV
+// kernel).  DPX adds do not saturate, so exactness is obtained differently from the reference's _mm_adds_epi16:
+//   * state cells hold (true value + V2_SIG) and are clamped from below at V2_FLOOR, table values at V2_TF, and the
+//     row maximum is kept below V2_HI; with these constants no 16-bit sum wraps (b2h_internal.h);
+//   * every true value >= V2_LO is computed exactly; values below V2_LO are only known to be below V2_LO.  Each M cell's
+//     four-way maximum contains the begin term xB + tBM >= V2_LO (checked per comparison), so inexact low terms never
+//     win there, and they stay low in the I and D chains because transitions are <= 0 (proof in DESIGN.md);
+//   * a comparison that leaves this regime (xE >= V2_HI: every strong hit; begin floor below V2_LO; final xC below
+//     V2_LO) is flagged B2H_REDO and decided by rvit_kernel in a second launch on the same stream (redo_only).
+// The D->D closure (rare on the random-sequence bulk) stays packed as well; only the scan of the 32 lane composites is 32-bit.
+// =================================================================================================
+__device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return ((int)v) >> 16; }
+
+template <int H>
+__device__ __forceinline__ void load_emis2(const uint32_t *tab, int x, int lane, uint32_t (&r)[H])
+{
+  const uint32_t *row = tab + (size_t)x * (32 * H);
+  if (H % 4 == 0) {
+#pragma unroll
+    for (int g = 0; g < H / 4; g++) { const uint4 v = *reinterpret_cast<const uint4 *>(row + g * 128 + lane * 4); r[4*g] = v.x; r[4*g+1] = v.y; r[4*g+2] = v.z; r[4*g+3] = v.w; }
+  } else if (H % 2 == 0) {
+#pragma unroll
+    for (int g = 0; g < H / 2; g++) { const uint2 v = *reinterpret_cast<const uint2 *>(row + g * 64 + lane * 2); r[2*g] = v.x; r[2*g+1] = v.y; }
+  } else {
+#pragma unroll
+    for (int g = 0; g < H; g++) r[g] = row[g * 32 + lane];
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256, (C <= 4) ? 4 : (C <= 8) ? 3 : (C <= 12) ? 2 : 1) rvit2_kernel(const WorkList wl, const SeqDev sd, const StageOut out)
+{
+  constexpr int H = C / 2;
+  extern __shared__ __align__(128) uint32_t s_rsc2[];       // [32][32*H] packed emission scores
+  __shared__ uint64_t s_bar;
+  __shared__ int s_item;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr uint32_t TAB_BYTES = 32u * 32u * H * 4u;
+  constexpr uint32_t FLOOR2 = ((uint32_t)(uint16_t)(int16_t)B2H_V2_FLOOR << 16) | (uint32_t)(uint16_t)(int16_t)B2H_V2_FLOOR;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  uint32_t phase = 0;
+  int cur_p = -1;
+  uint32_t tBM[H], tMM[H], tIM[H], tDM[H], tMD[H], tMI[H], tII[H], tDD[H];
+  uint32_t tlink[H], tfull[H];                             // (0, T_hi[j]) and (T[j], T[H+j]): see the D->D closure
+  int tDDin0 = B2H_V2_TF;
+  Item it;
+  while (next_item(wl, &s_item, it)) {
+    const ProfDev &P = wl.profs[it.p];
+    if (it.p != cur_p) {
+      cur_p = it.p;
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_rsc2, P.vit_rsc2, TAB_BYTES, &s_bar); }
+      const int16_t *ts = P.vit_tsc; const int Mp = P.Mpad;
+      auto tv = [&](int t, int k0) -> int { return (k0 < Mp) ? max((int)ts[t * Mp + k0], B2H_V2_TF) : B2H_V2_TF; };
+#pragma unroll
+      for (int j = 0; j < H; j++) {
+        const int ka = lane * C + j, kb = ka + H;           // 0-based node columns of the two halves
+        tBM[j] = pack2(tv(0, ka), tv(0, kb)); tMM[j] = pack2(tv(1, ka), tv(1, kb)); tIM[j] = pack2(tv(2, ka), tv(2, kb));
+        tDM[j] = pack2(tv(3, ka), tv(3, kb)); tMD[j] = pack2(tv(4, ka), tv(4, kb)); tMI[j] = pack2(tv(5, ka), tv(5, kb));
+        tII[j] = pack2(tv(6, ka), tv(6, kb)); tDD[j] = pack2(tv(7, ka), tv(7, kb));
+      }
+      tDDin0 = __shfl_up_sync(FULL, hi16(tDD[H - 1]), 1);      // D_{k-1} -> D_k for this lane's first node
+      if (lane == 0) tDDin0 = B2H_V2_TF;
+      {                                                        // prefix sums of tDD (clamped at V2_TF: anything lower only yields values below V2_LO)
+        int tlo = tDDin0, thi = 0;
+#pragma unroll
+        for (int j = 0; j < H; j++) { tlink[j] = pack2(0, thi); thi = max(thi + hi16(tDD[j]), B2H_V2_TF); }
+        int tl2[H];
+#pragma unroll
+        for (int j = 0; j < H; j++) { tl2[j] = tlo; tlo = max(tlo + lo16(tDD[j]), B2H_V2_TF); }
+        thi = tlo;                                             // tlo is now the sum up to the first node of the high half
+#pragma unroll
+        for (int j = 0; j < H; j++) { tfull[j] = pack2(tl2[j], thi); thi = max(thi + hi16(tDD[j]), B2H_V2_TF); }
+      }
+      mbar_wait(&s_bar, phase); phase ^= 1;
+    }
+    const int xwEm = P.xw_E_move, xwEl = P.xw_E_loop, base_w = P.base_w, ddbound = P.ddbound_w;
+
+    for (int e = it.e_begin + warp; e < it.e_end; e += nwarps) {
+      const int s = wl.ent_s[e];
+      const int L = sd.len[s];
+      const int xw_move = sd.xwmove[s];
+      bool redo = !P.v2_ok || (base_w + xw_move + P.tbm_min < B2H_V2_LO);
+      SeqWin sw; sw.init(sd.res + sd.off[s], L, lane);
+      uint32_t M[H], I[H], D[H];
+#pragma unroll
+      for (int j = 0; j < H; j++) { M[j] = FLOOR2; I[j] = FLOOR2; D[j] = FLOOR2; }
+      int xN = base_w, xB = (int16_t)(xN + xw_move), xJ = NEG16, xC = NEG16;        // specials in true coordinates
+
+      for (int i = 0; i < L && !redo; i++) {
+        const int x = sw.get(i, lane);
+        uint32_t r[H];
+        load_emis2<H>(s_rsc2, x, lane, r);
+        // cells of node k-1 for this lane's first halves: low <- last node of the lane to the left, high <- own node H-1
+        uint32_t mt = __shfl_up_sync(FULL, M[H - 1], 1), itt = __shfl_up_sync(FULL, I[H - 1], 1), dt = __shfl_up_sync(FULL, D[H - 1], 1);
+        if (lane == 0) { mt = FLOOR2; itt = FLOOR2; dt = FLOOR2; }
+        const uint32_t m0 = __byte_perm(mt, M[H - 1], 0x5432u), i0 = __byte_perm(itt, I[H - 1], 0x5432u), d0 = __byte_perm(dt, D[H - 1], 0x5432u);
+        const int xBs = xB + B2H_V2_SIG;
+        const uint32_t xB2 = pack2(xBs, xBs);
+#pragma unroll
+        for (int j = H - 1; j >= 0; j--) {
+          const uint32_t pm = (j == 0) ? m0 : M[j - 1], pi = (j == 0) ? i0 : I[j - 1], pd = (j == 0) ? d0 : D[j - 1];
+          const uint32_t inew = __viaddmax_s16x2(M[j], tMI[j], __viaddmax_s16x2(I[j], tII[j], FLOOR2));
+          uint32_t m = __viaddmax_s16x2(xB2, tBM[j], FLOOR2);
+          m = __viaddmax_s16x2(pm, tMM[j], m);
+          m = __viaddmax_s16x2(pi, tIM[j], m);
+          m = __viaddmax_s16x2(pd, tDM[j], m);
+          m = __viaddmax_s16x2(m, r[j], FLOOR2);
+          M[j] = m; I[j] = inew;
+        }
+        uint32_t xe2 = FLOOR2;
+#pragma unroll
+        for (int j = 0; j + 1 < H; j += 2) xe2 = __vimax3_s16x2(xe2, M[j], M[j + 1]);
+        if (H & 1) xe2 = __vimax3_s16x2(xe2, M[H - 1], M[H - 1]);
+        const int xE = __reduce_max_sync(FULL, max(lo16(xe2), hi16(xe2))) - B2H_V2_SIG;
+        // M->D partials: D of node k is what enters from M of node k-1
+        const uint32_t mdl = __viaddmax_s16x2(M[H - 1], tMD[H - 1], FLOOR2);
+        uint32_t mdt = __shfl_up_sync(FULL, mdl, 1);
+        if (lane == 0) mdt = FLOOR2;
+#pragma unroll
+        for (int j = H - 1; j >= 1; j--) D[j] = __viaddmax_s16x2(M[j - 1], tMD[j - 1], FLOOR2);
+        D[0] = __byte_perm(mdt, mdl, 0x5432u);
+        uint32_t dm2 = FLOOR2;
+#pragma unroll
+        for (int j = 0; j + 1 < H; j += 2) dm2 = __vimax3_s16x2(dm2, D[j], D[j + 1]);
+        if (H & 1) dm2 = __vimax3_s16x2(dm2, D[H - 1], D[H - 1]);
+        const int Dmax = __reduce_max_sync(FULL, max(lo16(dm2), hi16(dm2))) - B2H_V2_SIG;
+        if (xE >= B2H_V2_HI) { redo = true; break; }
+        xC = (int16_t)max(xC, xE + xwEm);
+        xJ = (int16_t)max(xJ, xE + xwEl);
+        xB = (int16_t)max(xJ + xw_move, xN + xw_move);
+        if (Dmax + ddbound > xB) {
+          // Close the D->D chain in packed form.  (1) the two half-chains of the lane side by side; (2) the end of the
+          // low half-chain enters the high one; (3) lane-to-lane: the closed D of the left lane's last node enters a lane
+          // through its first node and runs down its prefix sums of tDD.  Delete runs are short, so instead of a full
+          // 5-step scan the lanes hand their last node to the right neighbour until no first node improves any more
+          // (if no lane's first node is improved by its neighbour's current value, the closure is complete: a change
+          // would have to enter the leftmost changed lane through its first node) -- one or two rounds in practice.
+#pragma unroll
+          for (int j = 1; j < H; j++) D[j] = __viaddmax_s16x2(D[j - 1], tDD[j - 1], D[j]);
+          {
+            const int xin = max(lo16(D[H - 1]) + lo16(tDD[H - 1]), B2H_V2_FLOOR);
+            const uint32_t X2 = pack2(B2H_V2_FLOOR, xin);
+#pragma unroll
+            for (int j = 0; j < H; j++) D[j] = __viaddmax_s16x2(X2, tlink[j], D[j]);
+          }
+          for (;;) {
+            int din = __shfl_up_sync(FULL, hi16(D[H - 1]), 1);
+            if (lane == 0) din = B2H_V2_FLOOR;
+            const bool improves = din + tDDin0 > lo16(D[0]);
+            if (!__any_sync(FULL, improves)) break;
+            if (improves) {
+              const uint32_t DIN2 = pack2(din, din);
+#pragma unroll
+              for (int j = 0; j < H; j++) D[j] = __viaddmax_s16x2(DIN2, tfull[j], D[j]);
+            }
+          }
+        }
+      }
+      if (!redo && xC < B2H_V2_LO) redo = true;             // nothing exact reached E (e.g. a target of impossible residues)
+      if (lane == 0) {
+        if (redo) out.status[e] = B2H_REDO;
+        else {
+          float sc = (float)xC + (float)xw_move - (float)base_w; sc /= P.scale_w; sc -= 3.0f;
+          out.sc[e] = sc;
+          out.status[e] = B2H_OK;
+        }
       }
     }
   }
@@ -617,6 +796,31 @@ int launch_reg(b2h_ctx *ctx, K kernel, int C, int W, const WorkList &wl, const S
 }
 
 } // namespace
+
+// Packed 16-bit ViterbiFilter for a single-warp class of C nodes per lane (C2 = C rounded up to even): leaves B2H_REDO in
+// out.status for the comparisons the caller must hand to rvit_kernel (redo_only).
+int b2h_launch_vit2(b2h_ctx *ctx, int C2, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm)
+{
+  if (!out.status) return B2H_EINVAL;
+  auto go = [&](auto kernel) -> int {
+    const size_t smem = (size_t)32 * 32 * (C2 / 2) * 4;
+    int occ = 1;
+    { const int st = b2h_kernel_occupancy(ctx, (const void *)kernel, 256, smem, &occ); if (st != B2H_OK) return st; }
+    int grid = ctx->sm_count * occ;
+    if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
+    if (grid < 1) grid = 1;
+    B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), strm));
+    kernel<<<grid, 256, smem, strm>>>(wl, sd, out);
+    ctx->launches++;
+    B2H_CUDA(cudaGetLastError());
+    return B2H_OK;
+  };
+  switch (C2) {
+    case 2: return go(rvit2_kernel<2>);   case 4: return go(rvit2_kernel<4>);   case 6: return go(rvit2_kernel<6>);   case 8: return go(rvit2_kernel<8>);
+    case 10: return go(rvit2_kernel<10>); case 12: return go(rvit2_kernel<12>); case 14: return go(rvit2_kernel<14>); case 16: return go(rvit2_kernel<16>);
+  }
+  return B2H_EINVAL;
+}
 
 // kind: 0 Viterbi, 1 Forward, 2 Backward.  (C, W): nodes per lane, warps per comparison -- see b2h_reg_class().
 int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, int W, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm)

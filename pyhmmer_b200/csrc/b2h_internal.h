@@ -135,6 +135,7 @@ struct b2h_profile {
   float *d_bias_eo = nullptr;     // [32][2] bias-filter emission odds (esl_hmm_Configure)
   size_t h2d_bytes = 0;           // size of the single device block (= bytes uploaded)
   int regC = 0, regW = 0;         // nodes per lane / warps per comparison of the register-resident DP kernels (0 = model too long)
+  uint32_t *d_vit_rsc2 = nullptr; int v2C = 0, v2_ok = 0, tbm_min = 0;   // packed s16x2 emission table [32][H/g][32 lanes][g], H = v2C/2 (b2h_dpreg.cu)
   int32_t *d_vit_rsc32 = nullptr; // [32][regW][regC/G][32][G] int32 emission scores, lane-grouped (b2h_dpreg.cu)
   float   *d_fwd_rscr = nullptr;  // same layout, fp32 odds ratios
   // host copies for the domain-definition stage
@@ -232,6 +233,7 @@ struct ProfDev {
   const int16_t *vit_rsc, *vit_tsc;
   const float *fwd_rsc, *fwd_tsc, *bias_eo;
   const int32_t *vit_rsc32; const float *fwd_rscr;
+  const uint32_t *vit_rsc2; int v2C, v2_ok, tbm_min;     // packed ViterbiFilter: table, nodes per lane (even), usable, min tBM
   int M, Mpad, NR, G;
   int tbm, tec, base, bias; float scale_b;
   int xw_E_move, xw_E_loop, base_w, ddbound_w; float scale_w;
@@ -242,6 +244,7 @@ struct ProfDev {
 static inline ProfDev b2h_profdev(const b2h_profile *p) {
   ProfDev d; d.ssv_emis = p->d_ssv_emis; d.msv_cost8 = p->d_msv_cost8; d.vit_rsc = p->d_vit_rsc; d.vit_tsc = p->d_vit_tsc;
   d.fwd_rsc = p->d_fwd_rsc; d.fwd_tsc = p->d_fwd_tsc; d.bias_eo = p->d_bias_eo; d.vit_rsc32 = p->d_vit_rsc32; d.fwd_rscr = p->d_fwd_rscr;
+  d.vit_rsc2 = p->d_vit_rsc2; d.v2C = p->v2C; d.v2_ok = p->v2_ok; d.tbm_min = p->tbm_min;
   d.M = p->M; d.Mpad = p->Mpad; d.NR = p->NR; d.G = p->G; d.tbm = p->tbm_b; d.tec = p->tec_b; d.base = p->base_b; d.bias = p->bias_b; d.scale_b = p->scale_b;
   d.xw_E_move = p->xw[0][0]; d.xw_E_loop = p->xw[0][1]; d.base_w = p->base_w; d.ddbound_w = p->ddbound_w; d.scale_w = p->scale_w;
   d.xf_E_move = p->xf[0][0]; d.xf_E_loop = p->xf[0][1];
@@ -279,13 +282,27 @@ static const b2h_envclass B2H_ENV_CLASSES[] = {{128, 4, 1}, {256, 8, 1}, {384, 1
 static const int B2H_N_ENV_CLASSES = 6;
 
 // per-entry outputs of a DP stage
-struct StageOut { float *sc; int32_t *status; float *fwd_xmx, *bck_xmx; const int64_t *xoff; };
+struct StageOut { float *sc; int32_t *status; float *fwd_xmx, *bck_xmx; const int64_t *xoff;
+                  int redo_only = 0; };    // Viterbi: only entries whose status is B2H_REDO (left by the packed 16x2 kernel)
+#define B2H_REDO 0x7e00d0     // internal status: "decide this comparison with the exact 32-bit kernel"
+
+// Packed (s16x2) ViterbiFilter, b2h_dpreg.cu: state cells are stored as true value + V2_SIG in 16-bit halves and clamped from
+// below at the stored floor V2_FLOOR; table values are clamped from below at V2_TF.  With these constants no 16-bit sum can
+// wrap and every value >= V2_LO is exact ("Viterbi in packed 16-bit lanes"); comparisons that leave the safe
+// range (a cell >= V2_HI, begin floor below V2_LO, final score below V2_LO) are flagged B2H_REDO.
+#define B2H_V2_SIG    2400
+#define B2H_V2_LO    (-4401)
+#define B2H_V2_FLOOR (B2H_V2_LO + B2H_V2_SIG)      /* -2001, stored coordinates */
+#define B2H_V2_TF    (-30767)
+#define B2H_V2_HI     26366                        /* = V2_LO - V2_TF */
+#define B2H_V2_RMAX   3900                         /* largest emission score a profile may have: V2_HI + V2_SIG + RMAX <= 32767 */
 
 // mpads[p] = Mpad of profile p of the work list, ascending (one launch per size class)
 int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, int W, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm);
+int b2h_launch_vit2(b2h_ctx *ctx, int C2, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm);
 // register-resident DP size classes: nodes per lane C and warps per comparison W for a model of M nodes (0,0: too long)
 struct b2h_regclass { int bound, C, W; };
 static const b2h_regclass B2H_REG_CLASSES_FINE[] = {

@@ -524,6 +524,7 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
   if (!ctx || !profiles || !db || !prm || !out || db->ctx != ctx) return B2H_EINVAL;
   for (size_t i = 0; i < P; i++) if (!profiles[i] || profiles[i]->ctx != ctx) return B2H_EINVAL;
   *out = nullptr;
+  struct ExitTrace { double t; ~ExitTrace() { if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search] returned after %.1f ms\n", now_ms() - t); } } exit_trace{now_ms()};
   b2h_results *res = new b2h_results();
   res->counters.assign(P * 4, 0);
   const size_t N = db->n;
@@ -542,7 +543,7 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     const size_t pb = std::max<size_t>(1, CAP / N);
     // Waves shrink geometrically: the host work of every wave but the last hides behind the next wave's cascade, so
     // the last wave -- whose survivor passes, envelope kernels and host domain definition are exposed -- is the smallest.
-    int nwaves = (P >= 12) ? 3 : (P >= 6) ? 2 : 1;       // measured on B200 (100 profiles x 50k sequences): 3 waves at ratio 0.6 beat 2, 4, 5
+    int nwaves = (P >= 16) ? 4 : (P >= 6) ? 2 : 1;       // measured on B200 (100 profiles x 50k sequences, ms/step): 3 waves 44.1, 4 waves 42.6, 5 waves 45.4
     double ratio = 0.6;
     if (const char *ev = getenv("B2H_WAVES")) nwaves = std::max(1, atoi(ev));
     if (const char *ev = getenv("B2H_WAVE_RATIO")) ratio = std::min(1.0, std::max(0.05, atof(ev)));
@@ -583,9 +584,13 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
       const double tw = now_ms();
       top_up(w + ahead);
       std::vector<b2h_survivor> surv;
+      const double tq = now_ms();
       if (st == B2H_OK) st = cascade_collect(ctx, *waves[w], ctx->lanes[B2H_LANE_SURV].stream, surv, scnt.data());
       waves[w].reset();
+      const double tc = now_ms();
       if (st == B2H_OK) { b2h_lane_switch lane(ctx, B2H_LANE_SURV); st = finish_survivors(ctx, sp.data(), db, prm, surv, ddef); }
+      if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search]   wave %zu (%zu profiles): queued up to wave %zu at +%.1f ms, cascade collected at +%.1f ms, %zu survivors through Forward/Backward at +%.1f ms\n",
+                                       w, bounds[w + 1] - bounds[w], queued - 1, tq - t0, tc - t0, surv.size(), now_ms() - t0);
       nsurv += surv.size(); tg += now_ms() - tw;
     }
     if (st != B2H_OK) { cudaStreamSynchronize(ctx->stream); for (auto &l : ctx->lanes) cudaStreamSynchronize(l.stream); ddef.join(); waves.clear(); delete res; return st; }
