@@ -134,7 +134,9 @@ static int dense_msv(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, in
     st = b2h_launch_group(ctx, R, 1, G);
     if (st == B2H_OK) {
       WorkList wl = dl.wl; wl.ent_s = G.s; wl.poff = G.poff; wl.itemoff = G.itemoff;
-      st = b2h_launch_msv(ctx, wl, a.sd, p->Mpad, 0, 1, o.d_sc, o.d_status, R, 1.0);
+      static const bool smem_msv = getenv("B2H_MSV_SMEM") != nullptr;
+      if (smem_msv) st = b2h_launch_msv(ctx, wl, a.sd, p->Mpad, 0, 1, o.d_sc, o.d_status, R, 1.0);
+      else st = b2h_launch_msv_tiled(ctx, wl, a.sd, std::vector<int>(1, p->G * 64 + p->NR), 1, o.d_sc, o.d_status, R, 1.0);
     }
   }
   if (st == B2H_OK) st = o.fetch(sc, status);

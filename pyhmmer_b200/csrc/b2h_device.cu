@@ -329,17 +329,19 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
   auto cost_of = [&](int x, int k) -> int {          // k is 1-based; anything off the model is the -inf cost
     return (x < Kp && k <= M) ? (int)d->msv_cost[(size_t)x * M + (k-1)] : 255;
   };
-  uint16_t half_of[256];                                 // fp16 bit patterns of the integers -128 .. 127 (exact)
-  for (int v = -128; v < 128; v++) half_of[v + 128] = __half_as_ushort(__float2half_rn((float)v));
+  uint16_t half_of[512];                                 // fp16 bit patterns of the integers -256 .. 255 (exact)
+  for (int v = -256; v < 256; v++) half_of[v + 256] = __half_as_ushort(__float2half_rn((float)v));
   for (int x = 0; x < B2H_NCODE; x++)
     for (int gl = 0; gl < G; gl++)
       for (int j = 0; j < NR; j++) {
         const int klo = gl * 2 * NR + j + 1, khi = klo + NR;
         const int clo = cost_of(x, klo), chi = cost_of(x, khi);
-        // SSV subtracts sbv = clamp(cost - bias, .., 127) as a signed byte (p7_oprofile.c:721-761): add its negation,
-        // stored as fp16 (exact: |score| <= 127)
-        const int slo = -std::min(clo - (int)d->bias_b, 127), shi = -std::min(chi - (int)d->bias_b, 127);
-        const uint32_t w = ((uint32_t)half_of[shi + 128] << 16) | (uint32_t)half_of[slo + 128];
+        // score = bias - cost, stored as fp16 (exact: |score| <= 255).  MSV adds the bias and subtracts the cost as
+        // unsigned bytes (msvfilter.c:155-158); SSV subtracts sbv = clamp(cost - bias, .., 127) as a signed byte
+        // (p7_oprofile.c:721-761), and the clamp is immaterial there: an SSV cell is < 127 - bias until the comparison
+        // has overflowed, so any decrement >= 127 takes it to the floor either way.  One table serves both kernels.
+        const int slo = (int)d->bias_b - clo, shi = (int)d->bias_b - chi;
+        const uint32_t w = ((uint32_t)half_of[shi + 256] << 16) | (uint32_t)half_of[slo + 256];
         if (j < (NR / 4) * 4) ssv[ssv_word_index(G, NR, x, j, gl)] = w;
         else for (int lane = gl; lane < 32; lane += G) ssv[ssv_word_index(G, NR, x, j, lane)] = w;     // leftover words: one copy per group of the warp
       }

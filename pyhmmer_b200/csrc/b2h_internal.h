@@ -345,6 +345,8 @@ int b2h_launch_ssv(b2h_ctx *ctx, int G, int NR, const SsvArgs &a, cudaStream_t s
 // full MSV (with J) over a grouped work list; mode 1: dense outputs indexed by sequence, 2: cascade append to A
 int b2h_launch_msv(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, int mode,
                    float *out_sc, int32_t *out_status, SurvList A, double F1);
+int b2h_launch_msv_tiled(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &tiles, int mode,
+                         float *out_sc, int32_t *out_status, SurvList A, double F1);
 // group a SurvList by profile: poff/itemoff[P+1] and the grouped arrays (device)
 struct Grouped { int32_t *p, *s; float *a, *b; int32_t *poff, *itemoff; int *fill; };
 int b2h_launch_group(b2h_ctx *ctx, const SurvList &in, int P, Grouped out);

@@ -318,6 +318,112 @@ __global__ void __launch_bounds__(256) msv_kernel(const WorkList wl, const SeqDe
 }
 
 // ------------------------------------------------------------------------------------------------
+// Full MSV in the SSV kernel's register tiles: the same lane-striped fp16x2 table, G lanes per comparison, but with the
+// B/E/J states of msvfilter.c:106-207 -- one group-wide maximum and a handful of scalar updates per row.  The byte
+// saturations of the reference never act before its own overflow test fires (every cell and xB stay below 255 - bias
+// until then), so the unsaturated recurrence  m' = relu(max(m_diag, xB) + bias - cost)  is exact up to that point and
+// the overflow test is the reference's.
+// ------------------------------------------------------------------------------------------------
+template <int G, int NR>
+__global__ void __launch_bounds__(128) rmsv_kernel(const WorkList wl, const SeqDev sd, int mode,
+                                                    float *out_sc, int32_t *out_status, const SurvList A, double F1)
+{
+  extern __shared__ __align__(128) uint32_t s_tab[];
+  __shared__ uint64_t s_bar;
+  __shared__ int s_item;
+  constexpr int FULLQ = NR / 4, REM = NR % 4, NG = 32 / G;
+  constexpr uint32_t ROWB = (uint32_t)FULLQ * G * 16 + (uint32_t)REM * 128;
+  constexpr uint32_t TAB_BYTES = (uint32_t)B2H_NCODE * ROWB;
+  constexpr uint32_t PADW = 0x01010101u * B2H_PAD_CODE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int gl = lane & (G - 1), grp = lane / G;
+  const int src_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1));
+  const uint32_t tab_lane = smem_u32(s_tab) + gl * 16;
+  const uint32_t tab_rem  = smem_u32(s_tab) + FULLQ * G * 16 + lane * 4;
+
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  uint32_t phase = 0;
+  int cur_p = -1;
+  Item it;
+  while (next_item(wl, &s_item, it)) {
+    const ProfDev &P = wl.profs[it.p];
+    if (it.p != cur_p) {
+      cur_p = it.p;
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_tab, P.ssv_emis, TAB_BYTES, &s_bar); }
+      mbar_wait(&s_bar, phase); phase ^= 1;
+    }
+    const float bias = (float)P.bias, base = (float)P.base, tec = (float)P.tec;
+    for (int e0 = it.e_begin + warp * NG; e0 < it.e_end; e0 += nwarps * NG) {
+      const int e = e0 + grp;
+      const bool valid = e < it.e_end;
+      const int s = valid ? wl.ent_s[e] : 0;
+      const int L = valid ? sd.len[s] : 0;
+      const uint32_t *seqw = reinterpret_cast<const uint32_t *>(sd.res + sd.off[s]);
+      const int nwords = (L + 3) >> 2;                     // tail rows are B2H_PAD_CODE rows: every cell 0, xE = 0, specials unchanged
+      const int nwmax = (NG == 1) ? nwords : __reduce_max_sync(FULL, nwords);
+      const int tjb = valid ? (int)sd.tjb[s] : 0;
+      const float tjbm = (float)((tjb + P.tbm) & 0xff);    // (int8)tjb + (int8)tbm splatted into bytes (msvfilter.c:116)
+
+      uint32_t m[NR];
+#pragma unroll
+      for (int j = 0; j < NR; j++) m[j] = 0u;
+      float xJ = 0.f, xB = fmaxf(base - tjbm, 0.f);
+      bool overflow = false;
+
+      uint32_t nextw = (gl < nwords) ? __ldg(seqw + gl) : PADW;
+      for (int w0 = 0; w0 < nwmax; w0 += G) {
+        const uint32_t myw = nextw;
+        nextw = (w0 + G + gl < nwords) ? __ldg(seqw + w0 + G + gl) : PADW;
+        const int nw = min(G, nwmax - w0);
+        for (int wi = 0; wi < nw; wi++) {
+          const uint32_t wr = __shfl_sync(FULL, myw, wi, G);
+#pragma unroll
+          for (int rr = 0; rr < 4; rr++) {
+            const uint32_t x = __byte_perm(wr, 0u, 0x4440u + rr);
+            uint32_t ev[NR];
+            load_row<G, NR>(tab_lane + x * ROWB, tab_rem + x * ROWB, ev);
+            const __half2 xb2 = __float2half2_rn(xB);
+            const uint32_t xBh = *reinterpret_cast<const uint32_t *>(&xb2);
+            const uint32_t t  = __shfl_sync(FULL, m[NR-1], src_lane);
+            const uint32_t s0 = __byte_perm(t, m[NR-1], 0x5432u);
+            // max(m_diag, xB) on the bit patterns (both non-negative fp16), then + (bias - cost) and the floor at 0
+#pragma unroll
+            for (int j = NR - 1; j >= 1; j--) m[j] = hfma2_relu_add(__vimax3_s16x2(m[j-1], xBh, xBh), ev[j]);
+            m[0] = hfma2_relu_add(__vimax3_s16x2(s0, xBh, xBh), ev[0]);
+            uint32_t xe = 0u;
+#pragma unroll
+            for (int j = 0; j + 1 < NR; j += 2) xe = __vimax3_s16x2(xe, m[j], m[j+1]);
+            if (NR & 1) xe = __vimax3_s16x2(xe, m[NR-1], m[NR-1]);
+            int v = max((int)(xe & 0xffffu), (int)(xe >> 16));
+            if (G == 32) v = __reduce_max_sync(FULL, v);
+            else {
+#pragma unroll
+              for (int o = G / 2; o >= 1; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+            }
+            const float xE0 = __half2float(__ushort_as_half((unsigned short)v));
+            if (!overflow) {
+              if (xE0 + bias >= 255.f) overflow = true;      // adds_epu8(xEv, biasv) saturates (msvfilter.c:167-180)
+              else {
+                const float xE = fmaxf(xE0 - tec, 0.f);
+                xJ = fmaxf(xJ, xE);
+                xB = fmaxf(fmaxf(base, xJ) - tjbm, 0.f);
+              }
+            }
+          }
+        }
+      }
+      if (gl == 0 && valid) {
+        float sc; int status = B2H_OK;
+        if (overflow) { sc = INFINITY; status = B2H_ERANGE; }
+        else { sc = ((xJ - (float)tjb) - base); sc /= P.scale_b; sc -= 3.0f; }
+        if (mode == 1) { out_sc[s] = sc; out_status[s] = status; }
+        else if (msv_passes(sc, sd.null1[s], P, F1)) surv_append(A, it.p, s, sc, 0.f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Group a survivor list by profile (counting sort on the per-profile counts the epilogues kept).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) group_scan_kernel(const int *cnt, int P, int32_t *poff, int32_t *itemoff, int *fill)
@@ -406,6 +512,50 @@ int b2h_launch_msv(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_M
   msv_kernel<<<grid, nwarps * 32, smem, ctx->stream>>>(wl, sd, max_Mpad, mode, out_sc, out_status, A, F1);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());
+  return B2H_OK;
+}
+
+namespace {
+template <int G, int NR>
+int launch_rmsv_tile(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int mode, float *out_sc, int32_t *out_status, const SurvList &A, double F1, cudaStream_t strm)
+{
+  const size_t smem = (size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR);
+  int occ = 1;
+  { const int st = b2h_kernel_occupancy(ctx, (const void *)rmsv_kernel<G, NR>, 128, smem, &occ); if (st != B2H_OK) return st; }
+  B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), strm));
+  rmsv_kernel<G, NR><<<ctx->sm_count * occ, 128, smem, strm>>>(wl, sd, mode, out_sc, out_status, A, F1);
+  ctx->launches++;
+  B2H_CUDA(cudaGetLastError());
+  return B2H_OK;
+}
+} // namespace
+
+// Full MSV over a grouped work list whose profiles are sorted by model length: one launch per SSV register tile
+// (tiles[p] = G*64 + NR of profile p of the list), the launches side by side on the side streams.
+int b2h_launch_msv_tiled(b2h_ctx *ctx, const WorkList &wl_in, const SeqDev &sd, const std::vector<int> &tiles, int mode,
+                         float *out_sc, int32_t *out_status, SurvList A, double F1)
+{
+  const int P = (int)tiles.size();
+  ForkJoin fj(ctx);
+  int cls = 0;
+  for (int plo = 0; plo < P; cls++) {
+    int phi = plo;
+    while (phi < P && tiles[phi] == tiles[plo]) phi++;
+    WorkList wl = wl_in; wl.plo = plo; wl.phi = phi; wl.counter = ctx->d_counters + 32 + (cls % 24);
+    cudaStream_t strm = fj.next();
+    int st = B2H_EINVAL;
+    switch (tiles[plo]) {
+#define CASE(g, n) case (g) * 64 + (n): st = launch_rmsv_tile<g, n>(ctx, wl, sd, mode, out_sc, out_status, A, F1, strm); break;
+#define CASE8(g, n) CASE(g, n) CASE(g, n + 1) CASE(g, n + 2) CASE(g, n + 3) CASE(g, n + 4) CASE(g, n + 5) CASE(g, n + 6) CASE(g, n + 7)
+      CASE8(8, 1) CASE8(8, 9) CASE8(8, 17) CASE8(8, 25)
+      CASE8(16, 17) CASE8(16, 25)
+      CASE(32, 18) CASE(32, 20) CASE(32, 22) CASE(32, 24) CASE(32, 26) CASE(32, 28) CASE(32, 30) CASE(32, 32) CASE(32, 40) CASE(32, 48)
+#undef CASE8
+#undef CASE
+    }
+    if (st != B2H_OK) { if (st == B2H_EINVAL) ctx->err = "no MSV kernel for this register tile"; return st; }
+    plo = phi;
+  }
   return B2H_OK;
 }
 

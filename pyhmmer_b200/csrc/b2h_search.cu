@@ -158,7 +158,7 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
   std::map<int, std::vector<int32_t>> classes;
   std::vector<int> &perm = cw.perm; perm.resize(P); std::vector<int> mpads(P);                  // batch-local profile order: ascending model size
   std::iota(perm.begin(), perm.end(), 0);
-  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return profiles[p0 + a]->Mpad < profiles[p0 + b]->Mpad; });
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return profiles[p0 + a]->M < profiles[p0 + b]->M; });   // (Mpad and the SSV tile are monotone in M)
   int max_Mpad = 0;
   for (int i = 0; i < P; i++) {
     hprof[i] = b2h_profdev(profiles[p0 + perm[i]]);
@@ -224,7 +224,10 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
     Grouped GR = G; GR.a = nullptr;
     { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, R, P, GR)); }
     StageTimer tm(ctx, 1);
-    TRY(b2h_launch_msv(ctx, wl, sd, max_Mpad, 0, 2, nullptr, nullptr, A, prm->F1));
+    static const bool smem_msv = getenv("B2H_MSV_SMEM") != nullptr;      // debugging aid: the shared-memory MSV kernel
+    if (smem_msv) TRY(b2h_launch_msv(ctx, wl, sd, max_Mpad, 0, 2, nullptr, nullptr, A, prm->F1));
+    else { std::vector<int> tiles(P); for (int i = 0; i < P; i++) tiles[i] = hprof[i].G * 64 + hprof[i].NR;
+           TRY(b2h_launch_msv_tiled(ctx, wl, sd, tiles, 2, nullptr, nullptr, A, prm->F1)); }
   }
   // 3. bias filter on the MSV survivors
   { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, A, P, G)); }
