@@ -174,6 +174,15 @@ int b2h_backward_parser(b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *s
 /* null1[n] = p7_bg_NullOne; filtersc[n] = p7_bg_FilterScore after p7_bg_SetFilter(M, compo) (may be NULL) */
 int b2h_null_scores    (b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *null1, float *filtersc);
 
+/* The generic (unstriped, log-space) reference DP on the P7_PROFILE, one profile against the whole database:
+ * p7_GMSV (vendor/hmmer/src/generic_msv.c:56; what Profile.msv_filter calls, plan7.pyx:8212-8253), p7_GViterbi
+ * (generic_viterbi.c:64), p7_GForward and p7_GBackward (generic_fwdback.c:48,164), with p7_FLogsum's lookup table
+ * (logsum.c:105) and p7_ReconfigLength per target (modelconfig.c:221).  tsc [M*8], msc [Kp*(M+1)], xsc [4*2] are the
+ * outputs of b2h_profile_config; nj = 1 (multihit) or 0; nu = expected number of hits for GMSV (2.0).  Scores in nats,
+ * indexed by sequence; any output may be NULL.  Bit-identical to the reference evaluated on the same host. */
+int b2h_generic_scores(b2h_ctx *ctx, int M, int K, int Kp, const float *tsc, const float *msc, const float *xsc, float nj,
+                       const b2h_seqdb *db, float nu, float *gmsv, float *gviterbi, float *gforward, float *gbackward);
+
 /* --------------------------- the fused search path (p7_Pipeline per target) ----------------- *
  * b2h_search() is what Pipeline._search_loop / _scan_loop (plan7.pyx:6394-6453, 6625-6677) do for
  * P profiles x every sequence of the database: the whole acceleration-filter cascade runs on the

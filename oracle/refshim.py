@@ -65,7 +65,7 @@ def lib():
         L.ref_null1.argtypes = [vp, vp, ci]
         L.ref_bias.restype = cf
         L.ref_bias.argtypes = [vp, vp, ci]
-        L.ref_generic.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+        L.ref_generic.argtypes = [vp, vp, ci] + [ctypes.POINTER(cf)] * 4
         L.ref_gumbel_surv.restype = ctypes.c_double
         L.ref_gumbel_surv.argtypes = [ctypes.c_double] * 3
         L.ref_exp_surv.restype = ctypes.c_double
@@ -186,6 +186,13 @@ class RefModel:
         fx = np.zeros((n + 1, nx), np.float32); bx = np.zeros((n + 1, nx), np.float32)
         st = self.L.ref_fwdbck(self.h, d.ctypes.data, n, ctypes.byref(f), ctypes.byref(b), fx.ctypes.data, bx.ctypes.data)
         return (f.value, b.value, st, fx, bx) if want_x else (f.value, b.value, st)
+
+    def generic(self, codes):
+        """(p7_GMSV, p7_GViterbi, p7_GForward, p7_GBackward) of the generic profile reconfigured to the target's length."""
+        d = dsq_of(codes)
+        v = [ctypes.c_float() for _ in range(4)]
+        self.L.ref_generic(self.h, d.ctypes.data, d.size - 2, *[ctypes.byref(x) for x in v])
+        return tuple(x.value for x in v)
 
     def null1(self, codes):
         d = dsq_of(codes); return self.L.ref_null1(self.h, d.ctypes.data, d.size - 2)

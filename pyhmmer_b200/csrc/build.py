@@ -24,6 +24,7 @@ SOURCES = [
     "b2h_dp.cu",
     "b2h_dpreg.cu",
     "b2h_envelope.cu",
+    "b2h_generic.cu",
     "b2h_search.cu",
     "b2h_domaindef.cpp",
 ]
@@ -35,7 +36,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-I", os.path.join(ROOT, "include"),
 
 # the host-side domain definition is written as unit-stride loops for the compiler's vectoriser (AVX2: every x86-64
 # host a B200 sits in has it; `omp simd` only licenses the re-association of the marked float reductions)
-EXTRA = {"b2h_domaindef.cpp": ["-Xcompiler", "-mavx2,-fopenmp-simd"]}
+EXTRA = {"b2h_domaindef.cpp": ["-Xcompiler", "-mavx2,-fopenmp-simd"],
+         "b2h_generic.cu": ["-fmad=false"]}     # log-space sums must stay plain IEEE adds
 
 
 def _nvcc():

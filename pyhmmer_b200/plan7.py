@@ -430,6 +430,29 @@ class Profile:
         om.convert(self)
         return om
 
+    def _generic_scores(self, sequences, nu=2.0, which=("msv", "viterbi", "forward", "backward")):
+        """p7_GMSV / p7_GViterbi / p7_GForward / p7_GBackward (generic_msv.c:56, generic_viterbi.c:64,
+        generic_fwdback.c:48,164) of this profile against every sequence of a block, on the GPU; each target is scored
+        with the profile reconfigured to its length (p7_ReconfigLength).  Returns a dict of float32 arrays (nats)."""
+        if not self._configured:
+            raise ValueError("profile is not configured")
+        ctx = _lib.context()
+        block = sequences if isinstance(sequences, DigitalSequenceBlock) else DigitalSequenceBlock(self.alphabet, sequences)
+        db = SequenceDatabase(ctx, block)
+        n = len(block)
+        out = {k: np.empty(n, np.float32) for k in which}
+        check(lib.b2h_generic_scores(ctx.handle, self.M, self.alphabet.K, self.alphabet.Kp, ptr(self.tsc), ptr(self.msc), ptr(self.xsc),
+                                     1.0 if self.multihit else 0.0, db.handle, float(nu),
+                                     ptr(out.get("msv")), ptr(out.get("viterbi")), ptr(out.get("forward")), ptr(out.get("backward"))),
+              "b2h_generic_scores", ctx.handle)
+        return out
+
+    def msv_filter(self, seq, nu=2.0):
+        """``Profile.msv_filter`` (plan7.pyx:8212-8253): the generic MSV score (p7_GMSV) of one sequence, in nats."""
+        if seq.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, seq.alphabet)
+        return float(self._generic_scores([seq], nu=nu, which=("msv",))["msv"][0])
+
 
 class OptimizedProfile:
     """The device-ready form of a profile (``P7_OPROFILE`` re-imagined node-major).
