@@ -546,7 +546,10 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     const size_t pb = std::max<size_t>(1, CAP / N);
     // Waves shrink geometrically: the host work of every wave but the last hides behind the next wave's cascade, so
     // the last wave -- whose survivor passes, envelope kernels and host domain definition are exposed -- is the smallest.
-    int nwaves = (P >= 16) ? 4 : (P >= 6) ? 2 : 1;       // measured on B200 (100 profiles x 50k sequences, ms/step): 3 waves 44.1, 4 waves 42.6, 5 waves 45.4
+    // Waves only pay when a wave's cascade is long enough to hide the previous wave's host work behind it; a small job
+    // (hmmscan of one query: latency-bound launches of a few ms whatever their size) runs as one wave.
+    const double job_cells = cells * (double)db->nres;
+    int nwaves = (P >= 16 && job_cells >= 1.5e11) ? 4 : (P >= 6 && job_cells >= 4e10) ? 2 : 1;   // measured on B200 (100 profiles x 50k sequences, 3.7e11 cells, ms/step): 3 waves 44.1, 4 waves 42.6, 5 waves 45.4
     double ratio = 0.6;
     if (const char *ev = getenv("B2H_WAVES")) nwaves = std::max(1, atoi(ev));
     if (const char *ev = getenv("B2H_WAVE_RATIO")) ratio = std::min(1.0, std::max(0.05, atof(ev)));
