@@ -259,6 +259,16 @@ class HMMFile:
             raise StopIteration
         return hmm
 
+    def is_pressed(self):
+        """Whether the auxiliary files of a pressed database (hmmpress) sit next to this file (plan7.pyx:4009)."""
+        return self.name is not None and all(os.path.exists(self.name + e) for e in (".h3f", ".h3p"))
+
+    def optimized_profiles(self):
+        """An iterator over the optimized profiles of the pressed database (plan7.pyx:4030)."""
+        if not self.is_pressed():
+            raise ValueError("HMM file does not contain optimized profiles")
+        return HMMPressedFile(self.name)
+
     def _line(self):
         while True:
             line = self._fh.readline()
@@ -567,6 +577,172 @@ class OptimizedProfile:
         """``OptimizedProfile.ssv_filter`` (plan7.pyx:5022): SSV score in nats, ``None`` if SSV cannot decide."""
         sc, st = self._filter_one(lib.b2h_ssv_filter, seq)
         return None if st == _lib.B2H_ENORESULT else sc
+
+
+class HMMPressedFile:
+    """Iterate over the `OptimizedProfile` of a pressed HMM database (``pyhmmer.plan7.HMMPressedFile``, plan7.pyx:4051).
+
+    ``hmmpress`` writes every model's vectorised score tables to ``<db>.h3f`` (the MSV part, read by
+    p7_oprofile_ReadMSV, impl_sse/io.c:231) and ``<db>.h3p`` (everything else, p7_oprofile_ReadRest, io.c:498) in the
+    SSE build's striped layout.  Both are read in step here and de-striped to the node-major tables the device wants
+    (``b2h_destripe_oprofile``); no P7_HMM / P7_PROFILE is built and ``p7_oprofile_Convert`` never runs -- the path
+    hmmscan takes over a Pfam-sized database.  Format 3/f (HMMER 3.1b2 .. 3.4); byte order and ``off_t`` as written by
+    the x86-64 reference build.
+    """
+
+    _FMAGIC, _PMAGIC = 0xb3e6e6f3, 0xb3e6f0f3            # v3f_fmagic / v3f_pmagic, impl_sse/io.c:46-47
+    _EXTRA_SB = 17                                        # p7O_EXTRA_SB, impl_sse.h:28
+    _ABC = {3: "amino", 2: "dna", 1: "rna"}               # eslAMINO / eslDNA / eslRNA (esl_alphabet.h)
+
+    def __init__(self, file):
+        base = os.fspath(file)
+        for ext in (".h3f", ".h3p"):
+            if not os.path.exists(base + ext):
+                raise ValueError("%r is not a pressed HMM database (%s is missing)" % (base, base + ext))
+        self.name = base
+        self._f = open(base + ".h3f", "rb")
+        self._p = open(base + ".h3p", "rb")
+        self._alphabet = None
+        self._bg = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def close(self):
+        self._f.close()
+        self._p.close()
+
+    @property
+    def closed(self):
+        return self._f.closed
+
+    def rewind(self):
+        self._f.seek(0)
+        self._p.seek(0)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        om = self.read()
+        if om is None:
+            raise StopIteration
+        return om
+
+    @staticmethod
+    def _get(fh, fmt):
+        import struct
+        n = struct.calcsize(fmt)
+        b = fh.read(n)
+        if len(b) != n:
+            raise ValueError("truncated pressed HMM database")
+        v = struct.unpack(fmt, b)
+        return v[0] if len(v) == 1 else v
+
+    @staticmethod
+    def _arr(fh, dtype, count):
+        a = np.frombuffer(fh.read(np.dtype(dtype).itemsize * count), dtype=dtype)
+        if a.size != count:
+            raise ValueError("truncated pressed HMM database")
+        return a
+
+    def read(self):
+        f, p, get, arr = self._f, self._p, self._get, self._arr
+        head = f.read(4)
+        if not head:
+            return None
+        import struct
+        if struct.unpack("<I", head)[0] != self._FMAGIC:
+            raise ValueError("bad magic in %s.h3f: not a 3/f pressed database (hmmpress it again with HMMER >= 3.1)" % self.name)
+        # ---- .h3f: the MSV part (p7_oprofile_ReadMSV) ----
+        M, atype, n = get(f, "<iii")
+        name = f.read(n + 1)[:n].decode("ascii")
+        max_length = get(f, "<i")
+        tbm_b, tec_b, tjb_b = get(f, "<BBB")
+        scale_b = get(f, "<f")
+        base_b, bias_b = get(f, "<BB")
+        if atype not in self._ABC:
+            raise ValueError("unsupported alphabet type %d in %s" % (atype, self.name))
+        abc = getattr(Alphabet, self._ABC[atype])()
+        if self._alphabet is None:
+            self._alphabet, self._bg = abc, Background(abc)
+        elif abc != self._alphabet:
+            raise AlphabetMismatch(self._alphabet, abc)
+        K, Kp = abc.K, abc.Kp
+        Q16, Q8, Q4 = max(2, (M - 1) // 16 + 1), max(2, (M - 1) // 8 + 1), max(2, (M - 1) // 4 + 1)
+        f.seek(Kp * (Q16 + self._EXTRA_SB) * 16, 1)       # sbv: the SSV copy of the same scores, not needed (our table is built from rbv)
+        rbv = arr(f, np.uint8, Kp * Q16 * 16)
+        evparam = arr(f, np.float32, 6)
+        f.seek(3 * 8, 1)                                  # offs[p7_NOFFSETS] (off_t): disk offsets into the .h3m/.h3f/.h3p files
+        compo = arr(f, np.float32, 20)
+        if get(f, "<I") != self._FMAGIC:
+            raise ValueError("bad sentinel in %s.h3f: file corrupted?" % self.name)
+        # ---- .h3p: the rest (p7_oprofile_ReadRest) ----
+        if get(p, "<I") != self._PMAGIC:
+            raise ValueError("bad magic in %s.h3p" % self.name)
+        M2, atype2, n = get(p, "<iii")
+        name2 = p.read(n + 1)[:n].decode("ascii")
+        if M2 != M or atype2 != atype or name2 != name:
+            raise ValueError("%s.h3f and .h3p are out of step (%s / %s)" % (self.name, name, name2))
+        n = get(p, "<i")
+        acc = p.read(n + 1)[:n].decode("ascii") if n > 0 else None
+        n = get(p, "<i")
+        desc = p.read(n + 1)[:n].decode("ascii") if n > 0 else None
+        ann = [p.read(M + 2) for _ in range(4)]           # rf, mm, cs, consensus: 1..M, NUL at 0 when absent
+        twv = arr(p, np.int16, 8 * Q8 * 8)
+        rwv = arr(p, np.int16, Kp * Q8 * 8)
+        xw = arr(p, np.int16, 8)
+        scale_w = get(p, "<f")
+        base_w, ddbound_w = get(p, "<hh")
+        p.seek(4, 1)                                      # ncj_roundoff
+        tfv = arr(p, np.float32, 8 * Q4 * 4)
+        rfv = arr(p, np.float32, Kp * Q4 * 4)
+        xf = arr(p, np.float32, 8)
+        cutoff = arr(p, np.float32, 6)
+        nj = get(p, "<f")
+        mode, L = get(p, "<ii")
+        if get(p, "<I") != self._PMAGIC:
+            raise ValueError("bad sentinel in %s.h3p: file corrupted?" % self.name)
+
+        om = OptimizedProfile(M, abc)
+        om.msv_cost = np.empty((Kp, M), dtype=np.uint8)
+        om.vit_rsc = np.empty((Kp, M), dtype=np.int16)
+        om.vit_tsc = np.empty((8, M), dtype=np.int16)
+        om.fwd_rsc = np.empty((Kp, M), dtype=np.float32)
+        om.fwd_tsc = np.empty((8, M), dtype=np.float32)
+        check(lib.b2h_destripe_oprofile(M, Kp, ptr(np.ascontiguousarray(rbv)), ptr(np.ascontiguousarray(rwv)), ptr(np.ascontiguousarray(twv)),
+                                        ptr(np.ascontiguousarray(rfv)), ptr(np.ascontiguousarray(tfv)),
+                                        ptr(om.msv_cost), ptr(om.vit_rsc), ptr(om.vit_tsc), ptr(om.fwd_rsc), ptr(om.fwd_tsc)),
+              "b2h_destripe_oprofile")
+        d = OProfileDesc()
+        d.M, d.K, d.Kp, d.L, d.max_length = M, K, Kp, int(L), int(max_length)
+        d.mode_multihit = int(nj > 0.0)                    # p7_LOCAL (multihit) has nj = 1, p7_UNILOCAL nj = 0
+        d.msv_cost, d.vit_rsc, d.vit_tsc = ptr(om.msv_cost), ptr(om.vit_rsc), ptr(om.vit_tsc)
+        d.fwd_rsc, d.fwd_tsc = ptr(om.fwd_rsc), ptr(om.fwd_tsc)
+        d.tbm_b, d.tec_b, d.tjb_b, d.base_b, d.bias_b, d.scale_b = tbm_b, tec_b, tjb_b, base_b, bias_b, scale_b
+        for i in range(4):
+            for j in range(2):
+                d.xw[i][j] = int(xw[i * 2 + j])
+                d.xf[i][j] = float(xf[i * 2 + j])
+        d.base_w, d.ddbound_w, d.scale_w = int(base_w), int(ddbound_w), scale_w
+        bgf = self._bg.residue_frequencies
+        for i in range(6):
+            d.evparam[i] = float(evparam[i])
+            d.cutoff[i] = float(cutoff[i])
+        for i in range(20):
+            d.compo[i] = float(compo[i])
+            d.bgf[i] = float(bgf[i]) if i < K else 0.0
+        d.degen = ptr(abc.degen)
+        om._desc, om._dev = d, {}
+        text = lambda b: b[1:M + 1].decode("ascii") if b[1:2] != b"\0" else None      # absent annotation = NUL at position 1 (io.c:552-555)
+        om.name, om.accession, om.description = name, acc, desc
+        om.reference, om.model_mask, om.consensus_structure, om.consensus = (text(a) for a in ann)
+        om._evparam, om._cutoff, om._compo = evparam.copy(), cutoff.copy(), compo.copy()
+        om.L, om.multihit = int(L), bool(d.mode_multihit)
+        return om
 
 
 class OptimizedProfileBlock(list):

@@ -8,6 +8,7 @@ baseline/_ref by `pip install --no-index --target baseline/_ref /root/reference`
 Outputs (committed):
   data/*.hmm.gz, data/proteome.faa.gz   input fixtures = the reference's own test data (tests/data/hmms/txt, seqs)
   data/*.tbl, *.domtbl                   the reference's golden tables (produced by the HMMER CLI; tests/data/tables)
+  data/pressed/*.h3{f,p,m,i}             the reference's own hmmpress'ed fixture databases (tests/data/hmms/db), copied verbatim
   hmmsearch.json                         pyhmmer.hmmsearch results (every hit/domain field, full precision) for each
                                          fixture HMM against the proteome, plus pipeline pass counters
   filters.json                           per-stage scores from pyhmmer (OptimizedProfile.msv_filter / ssv_filter)
@@ -38,6 +39,10 @@ def gz_copy(src, dst):
 
 def main():
     data = os.path.join(HERE, "data")
+    os.makedirs(os.path.join(data, "pressed"), exist_ok=True)
+    for name in ("Thioesterase", "PF02826"):
+        for ext in ("h3f", "h3p", "h3m", "h3i"):
+            shutil.copy(os.path.join(REF, "hmms", "db", "%s.hmm.%s" % (name, ext)), os.path.join(data, "pressed"))
     os.makedirs(data, exist_ok=True)
     for h in HMMS:
         gz_copy(os.path.join(REF, "hmms/txt", h + ".hmm"), os.path.join(data, h + ".hmm.gz"))

@@ -199,3 +199,46 @@ def test_all_gather_and_merge_world_size_2_gloo():
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+@pytest.mark.parametrize("name", ["Thioesterase", "PF02826"])
+def test_pressed_database_matches_conversion(amino, name):
+    """HMMPressedFile (p7_oprofile_ReadMSV / ReadRest, impl_sse/io.c:231,498) on the reference's own hmmpress'ed fixtures:
+    the de-striped tables and scalars are identical to Profile.configure + to_optimized of the ASCII model -- which also
+    pins our p7_oprofile_Convert against bytes written by HMMER itself."""
+    import gzip
+    from pyhmmer_b200 import plan7
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data")
+    with plan7.HMMPressedFile(os.path.join(gold, "pressed", name + ".hmm")) as pf:
+        oms = list(pf)
+        pf.rewind()
+        assert len(list(pf)) == len(oms)
+    with gzip.open(os.path.join(gold, name + ".hmm.gz")) as f:
+        hmms = list(plan7.HMMFile(f))
+    assert len(oms) == len(hmms) >= 1
+    bg = plan7.Background(amino)
+    for om, h in zip(oms, hmms):
+        ref = plan7.Profile(h.M, amino).configure(h, bg, om.L).to_optimized()
+        assert (om.name, om.accession, om.description, om.M, om.multihit) == (h.name, h.accession, h.description, h.M, True)
+        assert om.consensus == ref.consensus and om.consensus_structure == ref.consensus_structure and om.reference == ref.reference
+        for t in ("msv_cost", "vit_rsc", "vit_tsc", "fwd_rsc", "fwd_tsc"):
+            assert np.array_equal(getattr(om, t), getattr(ref, t)), t
+        for fld in ("tbm_b", "tec_b", "base_b", "bias_b", "scale_b", "base_w", "ddbound_w", "scale_w", "max_length", "mode_multihit"):
+            assert getattr(om._desc, fld) == getattr(ref._desc, fld), fld
+        assert [list(r) for r in om._desc.xw] == [list(r) for r in ref._desc.xw]
+        assert [list(r) for r in om._desc.xf] == [list(r) for r in ref._desc.xf]
+        assert list(om._desc.evparam) == list(ref._desc.evparam) and list(om._desc.cutoff) == list(ref._desc.cutoff)
+        assert list(om._desc.compo) == list(ref._desc.compo)
+
+
+def test_pressed_database_errors(tmp_path):
+    from pyhmmer_b200 import plan7
+    with pytest.raises(ValueError):
+        plan7.HMMPressedFile(str(tmp_path / "missing.hmm"))
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data", "pressed", "PF02826.hmm")
+    for ext in (".h3f", ".h3p"):
+        data = open(gold + ext, "rb").read()
+        open(str(tmp_path / ("bad.hmm" + ext)), "wb").write(data)
+    open(str(tmp_path / "bad.hmm.h3f"), "wb").write(b"\x00" * 64)           # wrong magic
+    with pytest.raises(ValueError):
+        plan7.HMMPressedFile(str(tmp_path / "bad.hmm")).read()

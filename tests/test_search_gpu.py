@@ -190,3 +190,21 @@ def test_full_size_counters_match_reference(amino):
             raw = pli._run([oms[qi]], seqs)
             assert len(raw[0]) == sum(1 for h in hits if h.profile == qi)
             _compare_with_ref((raw[0], raw[1], raw[2], raw[3][0]), models[qi].search(codes))
+
+
+def test_hmmscan_over_pressed_database(amino):
+    """hmmscan against profiles read straight from the reference's hmmpress'ed fixtures (HMMPressedFile) gives the same
+    hits as against the ASCII models converted on our side."""
+    seqs = _proteome(amino)
+    queries = sorted(seqs, key=len)[-3:]
+    names = ("PF02826", "Thioesterase")
+    pressed = []
+    for n in names:
+        with plan7.HMMPressedFile(os.path.join(GOLD, "data", "pressed", n + ".hmm")) as pf:
+            pressed += list(pf)
+    ascii_models = [h for n in names for h in _hmms(n)]
+    for a, b in zip(hmmer.hmmscan(queries, pressed), hmmer.hmmscan(queries, ascii_models)):
+        assert [(h.name, round(h.score, 4), len(h.domains)) for h in a] == [(h.name, round(h.score, 4), len(h.domains)) for h in b]
+    # and the search orientation: PF02826 finds its 22 golden hits from the pressed profile too
+    th = plan7.Pipeline(amino).search_hmm(pressed[0], seqs)
+    assert len(th) == 22
