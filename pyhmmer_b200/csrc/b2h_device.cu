@@ -39,6 +39,7 @@ int b2h_ctx_create(int device, b2h_ctx **out)
     B2H_CUDA(cudaMalloc(&l.counters, 64 * sizeof(int)));
   }
   B2H_CUDA(cudaStreamCreateWithPriority(&ctx->env_stream, cudaStreamNonBlocking, ctx->prio_hi));
+  B2H_CUDA(cudaStreamCreateWithPriority(&ctx->bias_stream, cudaStreamNonBlocking, ctx->prio_hi));
   B2H_CUDA(cudaEventCreateWithFlags(&ctx->env_fork, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++) { B2H_CUDA(cudaStreamCreateWithPriority(&ctx->env_side[i], cudaStreamNonBlocking, ctx->prio_hi)); B2H_CUDA(cudaEventCreateWithFlags(&ctx->env_join[i], cudaEventDisableTiming)); }
   {  // keep stream-ordered allocations cached across searches instead of returning them to the driver at every sync
@@ -56,6 +57,7 @@ void b2h_ctx_destroy(b2h_ctx *ctx)
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_env_counter) cudaFree(ctx->d_env_counter);
   if (ctx->env_stream) cudaStreamDestroy(ctx->env_stream);
+  if (ctx->bias_stream) cudaStreamDestroy(ctx->bias_stream);
   if (ctx->env_fork) cudaEventDestroy(ctx->env_fork);
   for (int i = 0; i < 8; i++) { if (ctx->env_side[i]) cudaStreamDestroy(ctx->env_side[i]); if (ctx->env_join[i]) cudaEventDestroy(ctx->env_join[i]); }
   for (auto &pf : ctx->pinned_free) cudaFreeHost(pf.first);

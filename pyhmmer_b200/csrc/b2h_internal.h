@@ -56,6 +56,7 @@ struct b2h_ctx {
   struct Lane { cudaStream_t stream = nullptr; std::vector<cudaStream_t> side; std::vector<cudaEvent_t> side_done;
                 cudaEvent_t fork_ev = nullptr; int *counters = nullptr; };
   Lane lanes[2]; int prio_hi = 0;
+  cudaStream_t bias_stream = nullptr;  // the bias filter of a wave runs here, next to that wave's Viterbi launches
   // page-locked result buffers (survivor lists, parser special rows) recycled between searches
   std::mutex    pin_mu; std::vector<std::pair<void *, size_t>> pin_pool;
 };
