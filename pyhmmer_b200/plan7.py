@@ -83,9 +83,16 @@ class Cutoffs:
         a, b = float(self._v[i]), float(self._v[i + 1])
         return None if a == P7_CUTOFF_UNSET or b == P7_CUTOFF_UNSET else (a, b)
 
-    gathering = property(lambda self: self._pair(0))
-    trusted = property(lambda self: self._pair(2))
-    noise = property(lambda self: self._pair(4))
+    def _set(self, i, value):                              # (plan7.pyx:1290-1439: a pair of floats, or None to unset)
+        if value is None:
+            self._v[i] = self._v[i + 1] = P7_CUTOFF_UNSET
+        else:
+            a, b = value
+            self._v[i], self._v[i + 1] = float(a), float(b)
+
+    gathering = property(lambda self: self._pair(0), lambda self, v: self._set(0, v))
+    trusted = property(lambda self: self._pair(2), lambda self, v: self._set(2, v))
+    noise = property(lambda self: self._pair(4), lambda self, v: self._set(4, v))
 
     def gathering_available(self):
         return self._pair(0) is not None
@@ -1159,6 +1166,8 @@ class Pipeline:
         if sequences.alphabet != self.alphabet:
             raise AlphabetMismatch(self.alphabet, sequences.alphabet)
         for q in queries:
+            if not isinstance(q, (HMM, Profile, OptimizedProfile)):
+                raise TypeError("Expected HMM, Profile or OptimizedProfile, found %s" % type(q).__name__)
             if q.alphabet != self.alphabet:
                 raise AlphabetMismatch(self.alphabet, q.alphabet)
         if sequences and len(sequences.largest()) > 100000:
