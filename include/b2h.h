@@ -183,6 +183,13 @@ int b2h_null_scores    (b2h_ctx*, const b2h_profile*, const b2h_seqdb*, float *n
 int b2h_generic_scores(b2h_ctx *ctx, int M, int K, int Kp, const float *tsc, const float *msc, const float *xsc, float nj,
                        const b2h_seqdb *db, float nu, float *gmsv, float *gviterbi, float *gforward, float *gbackward);
 
+/* p7_GDecoding (generic_decoding.c:77) of ONE comparison: posterior probabilities from the full generic Forward and Backward
+ * matrices.  residues = L residue codes (no sentinels).  pp_dp [(L+1)][(M+1)][3] (M, I, D as P7_GMX.dp), pp_xmx [(L+1)][5]
+ * (E N J B C); the Forward and Backward scores are returned too.  The matrices are filled in the reference's order (bit-identical
+ * scores); the probabilities differ from the reference's only through expf (device vs glibc: a few ulp). */
+int b2h_generic_decoding(b2h_ctx *ctx, int M, int K, int Kp, const float *tsc, const float *msc, const float *xsc, float nj,
+                         const uint8_t *residues, int L, float *pp_dp, float *pp_xmx, float *fwdsc, float *bcksc);
+
 /* --------------------------- the fused search path (p7_Pipeline per target) ----------------- *
  * b2h_search() is what Pipeline._search_loop / _scan_loop (plan7.pyx:6394-6453, 6625-6677) do for
  * P profiles x every sequence of the database: the whole acceleration-filter cascade runs on the

@@ -198,6 +198,23 @@ int ref_generic(REFM *m, const uint8_t *dsq, int L, float *gmsv, float *gvit, fl
   return eslOK;
 }
 
+/* p7_GDecoding (generic_decoding.c:77) after p7_GForward / p7_GBackward: pp_dp [(L+1)][(M+1)][3] (M,I,D), pp_xmx [(L+1)][5] (E,N,J,B,C) */
+int ref_gdecoding(REFM *m, const uint8_t *dsq, int L, float *pp_dp, float *pp_xmx, float *fsc, float *bsc)
+{
+  int M = m->gm->M, i;
+  P7_GMX *fwd = p7_gmx_Create(M, L), *bck = p7_gmx_Create(M, L), *pp = p7_gmx_Create(M, L);
+  p7_ReconfigLength(m->gm, L);
+  p7_GForward (dsq, L, m->gm, fwd, fsc);
+  p7_GBackward(dsq, L, m->gm, bck, bsc);
+  p7_GDecoding(m->gm, fwd, bck, pp);
+  for (i = 0; i <= L; i++) {
+    memcpy(pp_dp  + (size_t)i * (M + 1) * p7G_NSCELLS, pp->dp[i], sizeof(float) * (M + 1) * p7G_NSCELLS);
+    memcpy(pp_xmx + (size_t)i * p7G_NXCELLS, pp->xmx + (size_t)i * p7G_NXCELLS, sizeof(float) * p7G_NXCELLS);
+  }
+  p7_gmx_Destroy(fwd); p7_gmx_Destroy(bck); p7_gmx_Destroy(pp);
+  return eslOK;
+}
+
 double ref_gumbel_surv(double x, double mu, double lambda) { return esl_gumbel_surv(x, mu, lambda); }
 double ref_exp_surv(double x, double mu, double lambda)    { return esl_exp_surv(x, mu, lambda); }
 

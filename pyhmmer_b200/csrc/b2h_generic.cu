@@ -86,16 +86,18 @@ __device__ float g_msv(const GenArgs &a, const float *tbl, const Rows &R, const 
 }
 
 // p7_GViterbi (VIT = true) and p7_GForward (VIT = false) share their shape: a "pull" over rows
-template <bool VIT>
-__device__ float g_fwd(const GenArgs &a, const float *tbl, const Rows &R, const uint8_t *seq, int L, float xloop, float xmove)
+// FULL: keep every row (row index = i) and the special states of every row in xout [(L+1)][5] = E N J B C, for decoding
+template <bool VIT, bool FULL = false>
+__device__ float g_fwd(const GenArgs &a, const float *tbl, const Rows &R, const uint8_t *seq, int L, float xloop, float xmove, float *xout = nullptr)
 {
   const int M = a.M;
   const float *tsc = a.tsc;
   auto OP = [&](float p, float q) { return VIT ? MX2(p, q) : LS(tbl, p, q); };
   float xN = 0.f, xB = xmove, xJ = -INFINITY, xC = -INFINITY;
   for (int k = 0; k <= M; k++) { R.at(0, 0, k) = -INFINITY; R.at(0, 1, k) = -INFINITY; R.at(0, 2, k) = -INFINITY; }
+  if (FULL) { xout[0] = -INFINITY; xout[1] = xN; xout[2] = xJ; xout[3] = xB; xout[4] = xC; }
   for (int i = 1; i <= L; i++) {
-    const int cur = i & 1, prv = cur ^ 1;
+    const int cur = FULL ? i : (i & 1), prv = FULL ? i - 1 : (cur ^ 1);
     const int x = seq[i - 1];
     const float *rsc = a.msc + (size_t)x * (M + 1);
     float xE = -INFINITY;
@@ -140,18 +142,21 @@ __device__ float g_fwd(const GenArgs &a, const float *tbl, const Rows &R, const 
       xN = xN + xloop;
       xB = LS(tbl, xN + xmove, xJ + xmove);
     }
+    if (FULL) { float *q = xout + (size_t)i * 5; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; }
   }
   return xC + xmove;
 }
 
-__device__ float g_bck(const GenArgs &a, const float *tbl, const Rows &R, const uint8_t *seq, int L, float xloop, float xmove)
+template <bool FULL = false>
+__device__ float g_bck(const GenArgs &a, const float *tbl, const Rows &R, const uint8_t *seq, int L, float xloop, float xmove, float *xout = nullptr)
 {
   const int M = a.M;
   const float *tsc = a.tsc;
   // row L
   float xJ = -INFINITY, xN = -INFINITY, xC = xmove, xE = xC + a.xE_move;
   {
-    const int r = L & 1;
+    const int r = FULL ? L : (L & 1);
+    if (FULL) { float *q = xout + (size_t)L * 5; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = -INFINITY; q[4] = xC; }
     R.at(r, 0, M) = xE; R.at(r, 2, M) = xE; R.at(r, 1, M) = -INFINITY;
     float dn = xE;                                                        // DMX(L,k+1)
     for (int k = M - 1; k >= 1; k--) {
@@ -163,7 +168,7 @@ __device__ float g_bck(const GenArgs &a, const float *tbl, const Rows &R, const 
     }
   }
   for (int i = L - 1; i >= 1; i--) {
-    const int cur = i & 1, nxt = cur ^ 1;
+    const int cur = FULL ? i : (i & 1), nxt = FULL ? i + 1 : (cur ^ 1);
     const int x1 = seq[i];                                               // residue x_{i+1} (0-based array)
     const float *rsc = a.msc + (size_t)x1 * (M + 1);
     float xB = R.at(nxt, 0, 1) + tsc[T_BM] + __ldg(rsc + 1);
@@ -172,6 +177,7 @@ __device__ float g_bck(const GenArgs &a, const float *tbl, const Rows &R, const 
     xC = xC + xloop;
     xE = LS(tbl, xJ + a.xE_loop, xC + a.xE_move);
     xN = LS(tbl, xN + xloop, xB + xmove);
+    if (FULL) { float *q = xout + (size_t)i * 5; q[0] = xE; q[1] = xN; q[2] = xJ; q[3] = xB; q[4] = xC; }
     R.at(cur, 0, M) = xE; R.at(cur, 2, M) = xE; R.at(cur, 1, M) = -INFINITY;
     float dn = xE;                                                        // DMX(i,k+1)
     for (int k = M - 1; k >= 1; k--) {
@@ -191,9 +197,56 @@ __device__ float g_bck(const GenArgs &a, const float *tbl, const Rows &R, const 
     float xB = R.at(1, 0, 1) + tsc[T_BM] + __ldg(rsc + 1);
     for (int k = 2; k <= M; k++) xB = LS(tbl, xB, R.at(1, 0, k) + tsc[(size_t)(k - 1) * 8 + T_BM] + __ldg(rsc + k));
     xN = LS(tbl, xN + xloop, xB + xmove);
+    if (FULL) { xout[0] = -INFINITY; xout[1] = xN; xout[2] = -INFINITY; xout[3] = xB; xout[4] = -INFINITY;
+                for (int k = 0; k <= M; k++) { R.at(0, 0, k) = -INFINITY; R.at(0, 1, k) = -INFINITY; R.at(0, 2, k) = -INFINITY; } }
   }
   return xN;
 }
+
+// p7_GDecoding (generic_decoding.c:77-140) needs the full Forward and Backward matrices of ONE comparison: one thread
+// fills them in the reference's order (the same functions as above, FULL), then one thread per row turns them into
+// posterior probabilities, accumulating the row's normaliser in the reference's order.
+struct DecArgs { GenArgs g; const uint8_t *seq; int L; float xloop, xmove; float *F, *B, *fx, *bx, *pp, *xpp, *sc; };
+
+__global__ void generic_full_kernel(const DecArgs d)
+{
+  extern __shared__ float s_tbl[];
+  for (int i = threadIdx.x; i < LOGSUM_TBL; i += blockDim.x) s_tbl[i] = d.g.tbl[i];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  Rows RF; RF.base = d.F; RF.stride = 1; RF.M1 = d.g.M + 1;
+  Rows RB; RB.base = d.B; RB.stride = 1; RB.M1 = d.g.M + 1;
+  d.sc[0] = g_fwd<false, true>(d.g, s_tbl, RF, d.seq, d.L, d.xloop, d.xmove, d.fx);
+  d.sc[1] = g_bck<true>(d.g, s_tbl, RB, d.seq, d.L, d.xloop, d.xmove, d.bx);
+}
+
+__global__ void generic_decode_kernel(const DecArgs d)
+{
+  const int M = d.g.M, L = d.L, M1 = M + 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > L) return;
+  float *pp = d.pp + (size_t)i * M1 * 3, *xp = d.xpp + (size_t)i * 5;
+  if (i == 0) { for (int k = 0; k <= M; k++) { pp[k*3] = pp[k*3+1] = pp[k*3+2] = 0.f; } for (int c = 0; c < 5; c++) xp[c] = 0.f; return; }
+  const float overall = d.fx[(size_t)L * 5 + 4] + d.xmove;                 // XMX_fwd(L,C) + xsc[C][MOVE]
+  auto F = [&](int st, int k) { return d.F[(((size_t)i * 3 + st) * M1 + k)]; };
+  auto B = [&](int st, int k) { return d.B[(((size_t)i * 3 + st) * M1 + k)]; };
+  float denom = 0.0f;
+  pp[0] = pp[1] = pp[2] = 0.f;
+  for (int k = 1; k < M; k++) {
+    const float m = expf(F(0, k) + B(0, k) - overall); denom += m;
+    const float iv = expf(F(1, k) + B(1, k) - overall); denom += iv;
+    pp[k*3] = m; pp[k*3+1] = iv; pp[k*3+2] = 0.f;
+  }
+  { const float m = expf(F(0, M) + B(0, M) - overall); denom += m; pp[M*3] = m; pp[M*3+1] = 0.f; pp[M*3+2] = 0.f; }
+  const float *fp = d.fx + (size_t)(i - 1) * 5, *bp = d.bx + (size_t)i * 5;
+  float xn = expf(fp[1] + bp[1] + d.xloop - overall), xj = expf(fp[2] + bp[2] + d.xloop - overall), xc = expf(fp[4] + bp[4] + d.xloop - overall);
+  denom += xn + xj + xc;
+  denom = (float)(1.0 / (double)denom);
+  for (int k = 1; k < M; k++) { pp[k*3] *= denom; pp[k*3+1] *= denom; }
+  pp[M*3] *= denom;
+  xp[0] = 0.f; xp[1] = xn * denom; xp[2] = xj * denom; xp[3] = 0.f; xp[4] = xc * denom;
+}
+
 
 __global__ void __launch_bounds__(128) generic_kernel(const GenArgs a)
 {
@@ -211,7 +264,7 @@ __global__ void __launch_bounds__(128) generic_kernel(const GenArgs a)
     if (a.gmsv) a.gmsv[s] = g_msv(a, s_tbl, R, seq, L, lp[0], lp[1]);
     if (a.gvit) a.gvit[s] = g_fwd<true>(a, s_tbl, R, seq, L, lp[2], lp[3]);
     if (a.gfwd) a.gfwd[s] = g_fwd<false>(a, s_tbl, R, seq, L, lp[2], lp[3]);
-    if (a.gbck) a.gbck[s] = (L >= 1) ? g_bck(a, s_tbl, R, seq, L, lp[2], lp[3]) : -INFINITY;
+    if (a.gbck) a.gbck[s] = (L >= 1) ? g_bck<false>(a, s_tbl, R, seq, L, lp[2], lp[3]) : -INFINITY;
   }
 }
 
@@ -280,5 +333,56 @@ extern "C" int b2h_generic_scores(b2h_ctx *ctx, int M, int K, int Kp, const floa
   e = cudaStreamSynchronize(st);
   release();
   if (e != cudaSuccess) { ctx->err = std::string("generic DP kernel: ") + cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+extern "C" int b2h_generic_decoding(b2h_ctx *ctx, int M, int K, int Kp, const float *tsc, const float *msc, const float *xsc, float nj,
+                                    const uint8_t *residues, int L, float *pp_dp, float *pp_xmx, float *fwdsc, float *bcksc)
+{
+  if (!ctx || !tsc || !msc || !xsc || !residues || !pp_dp || !pp_xmx || M < 1 || L < 1 || Kp < 1 || Kp > B2H_NCODE - 1 || K < 1 || K >= Kp) return B2H_EINVAL;
+  B2H_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  std::vector<float> tbl(LOGSUM_TBL);
+  for (int i = 0; i < LOGSUM_TBL; i++) tbl[i] = (float)log(1. + exp((double)-i / 1000.f));
+  const float pmove = (2.0f + nj) / ((float)L + 2.0f + nj), ploop = 1.0f - pmove;
+  DecArgs d;
+  d.g.M = M; d.g.K = K; d.g.Kp = Kp; d.g.xE_loop = xsc[0]; d.g.xE_move = xsc[1]; d.g.tbmk = d.g.tej = d.g.tec = 0.f;
+  d.g.lenp = nullptr; d.g.scratch = nullptr; d.g.gmsv = d.g.gvit = d.g.gfwd = d.g.gbck = nullptr;
+  d.L = L; d.xloop = (float)log((double)ploop); d.xmove = (float)log((double)pmove);
+  const size_t cells = (size_t)(L + 1) * 3 * (M + 1), xc = (size_t)(L + 1) * 5;
+  std::vector<void *> keep;
+  auto dalloc = [&](void **p, size_t bytes) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 4, st); if (e == cudaSuccess) keep.push_back(*p); return e; };
+  auto release = [&]() { for (void *p : keep) cudaFreeAsync(p, st); };
+  float *d_tsc, *d_msc, *d_tbl; uint8_t *d_seq;
+  cudaError_t e;
+  if ((e = dalloc((void **)&d_tsc, (size_t)M * 32)) != cudaSuccess || (e = dalloc((void **)&d_msc, (size_t)Kp * (M + 1) * 4)) != cudaSuccess ||
+      (e = dalloc((void **)&d_tbl, LOGSUM_TBL * 4)) != cudaSuccess || (e = dalloc((void **)&d_seq, (size_t)L)) != cudaSuccess ||
+      (e = dalloc((void **)&d.F, cells * 4)) != cudaSuccess || (e = dalloc((void **)&d.B, cells * 4)) != cudaSuccess ||
+      (e = dalloc((void **)&d.fx, xc * 4)) != cudaSuccess || (e = dalloc((void **)&d.bx, xc * 4)) != cudaSuccess ||
+      (e = dalloc((void **)&d.pp, cells * 4)) != cudaSuccess || (e = dalloc((void **)&d.xpp, xc * 4)) != cudaSuccess ||
+      (e = dalloc((void **)&d.sc, 8)) != cudaSuccess) {
+    ctx->err = std::string("generic decoding: ") + cudaGetErrorString(e); release(); return B2H_EMEM;
+  }
+  cudaMemcpyAsync(d_tsc, tsc, (size_t)M * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_msc, msc, (size_t)Kp * (M + 1) * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_tbl, tbl.data(), LOGSUM_TBL * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_seq, residues, (size_t)L, cudaMemcpyHostToDevice, st);
+  d.g.tsc = d_tsc; d.g.msc = d_msc; d.g.tbl = d_tbl; d.seq = d_seq;
+  const size_t smem = LOGSUM_TBL * sizeof(float);
+  int occ = 1;
+  { const int rc = b2h_kernel_occupancy(ctx, (const void *)generic_full_kernel, 128, smem, &occ); if (rc != B2H_OK) { release(); return rc; } }
+  generic_full_kernel<<<1, 128, smem, st>>>(d);
+  generic_decode_kernel<<<(L + 1 + 127) / 128, 128, 0, st>>>(d);
+  ctx->launches += 2;
+  // the reference indexes its matrices [i][k][s]; ours are [i][s][k] on the device and are transposed by the decode kernel's output layout
+  cudaMemcpyAsync(pp_dp, d.pp, cells * 4, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(pp_xmx, d.xpp, xc * 4, cudaMemcpyDeviceToHost, st);
+  float sc[2] = {0.f, 0.f};
+  cudaMemcpyAsync(sc, d.sc, 8, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  release();
+  if (e != cudaSuccess) { ctx->err = std::string("generic decoding kernels: ") + cudaGetErrorString(e); return B2H_ECUDA; }
+  if (fwdsc) *fwdsc = sc[0];
+  if (bcksc) *bcksc = sc[1];
   return B2H_OK;
 }

@@ -40,3 +40,21 @@ def test_profile_msv_filter(amino, make_pair):
     assert np.isfinite(got)
     ref = pair.ref.generic(seq.sequence)[0]
     assert abs(got - ref) < 1e-5        # p7_GMSV takes its length terms from L itself (generic_msv.c:62-63): no dependence on gm->L
+
+
+@pytest.mark.parametrize("M", [1, 5, 40, 130])
+def test_generic_decoding(amino, make_pair, M):
+    """p7_GDecoding: Forward/Backward scores bit-identical, posterior probabilities within a few ulp of expf."""
+    rng = np.random.default_rng(5000 + M)
+    pair = make_pair(synth.random_hmm(amino, M, rng))
+    dom = synth.emit_sequence(pair.hmm, rng)
+    for codes in (np.concatenate([rng.integers(0, 20, 30).astype(np.uint8), dom, rng.integers(0, 20, 25).astype(np.uint8)]),
+                  rng.integers(0, 20, 77).astype(np.uint8), rng.integers(0, 20, 1).astype(np.uint8)):
+        seq = easel.DigitalSequence(amino, name=b"t", sequence=codes)
+        pp, xpp, f, b = pair.profile._generic_decoding(seq)
+        rpp, rxpp, rf, rb = pair.ref.gdecoding(codes)
+        assert np.float32(rf) == np.float32(f) and np.float32(rb) == np.float32(b), (M, len(codes), rf, f, rb, b)
+        assert np.allclose(pp, rpp, rtol=2e-5, atol=1e-9), (M, len(codes), float(np.abs(pp - rpp).max()))
+        assert np.allclose(xpp, rxpp, rtol=2e-5, atol=1e-9)
+        rows = pp[1:, :, :2].sum((1, 2)) + xpp[1:, [1, 2, 4]].sum(1)
+        assert np.allclose(rows, 1.0, atol=1e-5)                # every residue is emitted by exactly one state
