@@ -254,12 +254,12 @@ def main():
         for om in oms:
             om._dev = {}                                           # re-upload the profile tables
         t0 = time.perf_counter()
-        plan7.SequenceDatabase.of(ctx, seqs)                       # H2D of the packed residues (+ per-target scalars)
-        t1 = time.perf_counter()
-        plan7.OptimizedProfile._device_many(ctx, oms)              # H2D of every profile's tables
-        t2 = time.perf_counter()
-        hits, doms, text, counters = pli._run(oms, seqs)           # b2h_search + D2H of the hit records
+        # the call a user's hmmsearch makes: packs + uploads the database and builds + uploads every profile's tables (side
+        # by side), then b2h_search and the D2H of the hit records
+        hits, doms, text, counters = pli._run(oms, seqs)
         t3 = time.perf_counter()
+        t1 = t0 + pli._last_run_s[0]                               # uploads / handles
+        t2 = t1
         if world > 1:
             w = parallel.World.current()
             parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, counters, 0), w)
@@ -322,7 +322,7 @@ def main():
         print("[bench] resident step, host wall ms (whole step, handles, b2h_search, reading results): mean %s; device-event ms %s"
               % (np.round(hs.mean(0), 2).tolist(), np.round(times, 1).tolist()), file=sys.stderr)
         ph = np.array(e2e_phases[2:]) * 1e3
-        print("[bench] e2e phases ms (seqdb upload, profile upload, search+D2H, TopHits assembly): mean %s, per step %s"
+        print("[bench] e2e phases ms (database + profile uploads, -, search+D2H, TopHits assembly): mean %s, per step %s"
               % (np.round(ph.mean(0), 1).tolist(), np.round(ph.sum(1), 1).tolist()), file=sys.stderr)
     te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -1132,8 +1132,21 @@ class Pipeline:
     def _run(self, oms, block):
         ctx = self._ctx
         t0 = time.perf_counter()
-        db = SequenceDatabase.of(ctx, block)
-        handles = (ctypes.c_void_p * len(oms))(*OptimizedProfile._device_many(ctx, oms))
+        if block._cache.get(("db", ctx)) is None and sum(1 for om in oms if om._dev.get(ctx) is None) > 8:
+            # neither side is resident yet: pack + upload the database on a helper thread while this one builds and
+            # uploads the profile tables (both are C calls that release the GIL and end in stream-ordered copies)
+            import threading
+            box = []
+            th = threading.Thread(target=lambda: box.append(SequenceDatabase.of(ctx, block)))
+            th.start()
+            try:
+                handles = (ctypes.c_void_p * len(oms))(*OptimizedProfile._device_many(ctx, oms))
+            finally:
+                th.join()
+            db = SequenceDatabase.of(ctx, block)
+        else:
+            db = SequenceDatabase.of(ctx, block)
+            handles = (ctypes.c_void_p * len(oms))(*OptimizedProfile._device_many(ctx, oms))
         prm = self._params_struct()
         out = ctypes.c_void_p()
         t1 = time.perf_counter()
