@@ -95,24 +95,42 @@ def unpack_records(buf):
     return hits, doms, text, counters
 
 
+_AG_CAP = [1 << 16]          # payload bytes per rank of the fixed-size exchange; grows to fit (every rank sees the same sizes)
+
+
 def all_gather_bytes(data, world):
-    """One variable-length all-gather: sizes, then padded uint8 buffers (NCCL over NVLink, or gloo on CPU)."""
+    """The one exchange of the path: a variable-length all-gather of byte strings (NCCL over NVLink, or gloo on CPU).
+
+    Common case = ONE collective and ONE device->host copy: every rank contributes an 8-byte length header plus its
+    payload in a fixed-capacity slot.  Only if some rank's payload does not fit (all ranks see that in the headers, so
+    they agree) is the capacity raised and the exchange repeated once."""
     if world.size == 1:
         return [data]
     import torch
     dist = world.dist
     dev = world.device or torch.device("cpu")
-    size = torch.tensor([len(data)], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world.size)]
-    dist.all_gather(sizes, size)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(max(sizes), 1)
-    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
-    if len(data):
-        buf[: len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
-    outs = [torch.empty(mx, dtype=torch.uint8, device=dev) for _ in range(world.size)]
-    dist.all_gather(outs, buf)
-    return [bytes(o[:n].cpu().numpy().tobytes()) for o, n in zip(outs, sizes)]
+    n = len(data)
+    payload = np.frombuffer(data, dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    while True:
+        cap = _AG_CAP[0]
+        slot = np.zeros(8 + cap, dtype=np.uint8)
+        slot[:8] = np.frombuffer(np.int64(n).tobytes(), dtype=np.uint8)
+        k = min(n, cap)
+        slot[8:8 + k] = payload[:k]
+        mine = torch.from_numpy(slot).to(dev, non_blocking=True)
+        out = torch.empty(world.size * (8 + cap), dtype=torch.uint8, device=dev)
+        try:
+            dist.all_gather_into_tensor(out, mine)
+        except (RuntimeError, AttributeError, NotImplementedError):   # a backend without the flat form: list form
+            outs = [torch.empty(8 + cap, dtype=torch.uint8, device=dev) for _ in range(world.size)]
+            dist.all_gather(outs, mine)
+            out = torch.cat(outs)
+        host = out.cpu().numpy().reshape(world.size, 8 + cap)
+        sizes = [int(np.frombuffer(host[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(world.size)]
+        if max(sizes) <= cap:
+            return [host[r, 8:8 + sizes[r]].tobytes() for r in range(world.size)]
+        while _AG_CAP[0] < max(sizes):
+            _AG_CAP[0] *= 2
 
 
 def merge_rank_records(parts):

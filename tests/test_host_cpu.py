@@ -186,6 +186,11 @@ assert np.array_equal(mc.reshape(2, 4), np.arange(8).reshape(2, 4) * 2 + 1)
 for h in mh:
     d = md[h.dom_offset]
     assert mt[d.text_offset:d.text_offset + 12] == b"AB\0ab\0AB\0**\0"
+# ragged sizes, incl. empty and larger than the exchange's initial slot (the capacity grows and the exchange repeats once)
+big = bytes(np.random.default_rng(w.rank).integers(0, 256, 200000 if w.rank == 1 else 0, dtype=np.uint8))
+got = parallel.all_gather_bytes(big, w)
+assert [len(g) for g in got] == [0, 200000] and got[w.rank] == big
+assert parallel.all_gather_bytes(b"x" * (w.rank + 1), w) == [b"x", b"xx"]
 dist.barrier(); dist.destroy_process_group()
 print("rank", w.rank, "ok")
 '''
