@@ -142,6 +142,11 @@ def _load():
 lib = _load()
 
 
+class RecList(list):
+    """A list of ctypes records that remembers the array they are views of (``raw``), for bulk (de)serialisation."""
+    raw = None
+
+
 def read_results(handle):
     """Copy a ``b2h_results`` into python objects: (hits, domains, text, counters_flat)."""
     nh = lib.b2h_results_nhits(handle)
@@ -149,8 +154,13 @@ def read_results(handle):
     hp = lib.b2h_results_hits(handle)
     dp = lib.b2h_results_domains(handle)
     # one copy per record array; the list elements are views into those copies
-    hits = list((HitRec * nh).from_buffer_copy(ctypes.string_at(hp, nh * ctypes.sizeof(HitRec)))) if nh else []
-    doms = list((DomainRec * nd).from_buffer_copy(ctypes.string_at(dp, nd * ctypes.sizeof(DomainRec)))) if nd else []
+    hits, doms = RecList(), RecList()
+    if nh:
+        hits.raw = (HitRec * nh).from_buffer_copy(ctypes.string_at(hp, nh * ctypes.sizeof(HitRec)))
+        hits.extend(hits.raw)
+    if nd:
+        doms.raw = (DomainRec * nd).from_buffer_copy(ctypes.string_at(dp, nd * ctypes.sizeof(DomainRec)))
+        doms.extend(doms.raw)
     nb = c_size_t()
     tp = lib.b2h_results_text(handle, ctypes.byref(nb))
     text = ctypes.string_at(tp, nb.value) if nb.value else b""

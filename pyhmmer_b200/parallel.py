@@ -68,17 +68,24 @@ def shard_block(block, world):
     return lo, DigitalSequenceBlock(block.alphabet, list.__getitem__(block, slice(lo, hi)))
 
 
+def _raw_bytes(recs, rectype):
+    """The records as one byte string: straight from the array they came in when the list still mirrors it."""
+    raw = getattr(recs, "raw", None)
+    if raw is not None and len(raw) == len(recs):
+        return bytes(raw)
+    n = len(recs)
+    return bytes((rectype * max(n, 1))(*recs))[: n * ctypes.sizeof(rectype)]
+
+
 def pack_records(hits, doms, text, counters, seq_offset):
     """Serialize one rank's results: header | HitRec[] | DomainRec[] | text | counters (int64)."""
     nh, nd = len(hits), len(doms)
-    ha = (_lib.HitRec * max(nh, 1))(*hits)
-    for i in range(nh):
-        ha[i].seq += seq_offset
-    da = (_lib.DomainRec * max(nd, 1))(*doms)
+    hb = bytearray(_raw_bytes(hits, _lib.HitRec))
+    if nh and seq_offset:
+        np.frombuffer(hb, dtype=np.dtype(_lib.HitRec))["seq"] += seq_offset       # local -> global target index
     cnt = np.ascontiguousarray(counters, dtype=np.int64)
     header = np.array([nh, nd, len(text), cnt.size], dtype=np.int64).tobytes()
-    return b"".join([header, bytes(ha)[: nh * ctypes.sizeof(_lib.HitRec)], bytes(da)[: nd * ctypes.sizeof(_lib.DomainRec)],
-                     bytes(text), cnt.tobytes()])
+    return b"".join([header, bytes(hb), _raw_bytes(doms, _lib.DomainRec), bytes(text), cnt.tobytes()])
 
 
 def unpack_records(buf):
