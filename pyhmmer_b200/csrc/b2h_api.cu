@@ -127,7 +127,7 @@ static int dense_msv(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, in
   Grouped G; G.p = buf + 2 * n; G.s = buf + 3 * n; G.a = nullptr; G.b = nullptr; G.poff = buf + 4 * n; G.itemoff = buf + 4 * n + 2; G.fill = ctr + 2;
   SsvArgs a;
   a.profs = dl.d_prof; a.cls = dl.d_cls; a.ncls = 1; a.sd = b2h_seqdev(db);
-  a.chunks = (int)((n + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK); a.counter = ctx->d_counters;
+  a.chunks = (int)((n + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK); a.counter = ctx->d_counters; a.items_per_cta = 0;
   a.mode = mode; a.out_sc = o.d_sc; a.out_status = o.d_status; a.R = R; a.A = R; a.F1 = 1.0;
   st = b2h_launch_ssv(ctx, p->G, p->NR, a, ctx->stream);
   if (st == B2H_OK && mode == 1) {

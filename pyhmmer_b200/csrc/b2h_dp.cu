@@ -525,8 +525,11 @@ LaunchCfg pick_cfg(int max_Mpad, int elem_bytes)
 // Profiles of a work list are sorted by Mpad.  Models of up to 512 nodes go to the register-resident kernels
 // (b2h_dpreg.cu: 2 / 4 / 8 / 12 / 16 nodes per lane); longer ones to the shared-memory kernels of this file, one launch
 // per size class so that mid-sized models do not inherit the largest model's shared-memory footprint.
-template <typename K>
-int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const SeqDev &sd, const std::vector<int> &mpads, int elem_bytes, int nitems_hint, const StageOut &out)
+// With <out2>, every size class gets a second launch (kernel2 / kind2) right behind the first ON THE SAME STREAM: the
+// Backward pass of a class starts as soon as that class's Forward is done instead of waiting for the slowest class.
+template <typename K, typename K2>
+int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const SeqDev &sd, const std::vector<int> &mpads, int elem_bytes, int nitems_hint, const StageOut &out,
+              K2 kernel2, int kind2, const StageOut *out2)
 {
   static const int bounds[] = {2048, 3072, 1 << 30};
   const int P = (int)mpads.size();
@@ -551,6 +554,7 @@ int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const Seq
       }
       int st = b2h_launch_dpreg(ctx, kind, rcls[rc].C, rcls[rc].W, wl, sd, nitems_hint, o, strm);
       if (st != B2H_OK) return st;
+      if (out2 && (st = b2h_launch_dpreg(ctx, kind2, rcls[rc].C, rcls[rc].W, wl, sd, nitems_hint, *out2, strm)) != B2H_OK) return st;
       plo = phi; cls++;
     }
   }
@@ -576,6 +580,13 @@ int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const Seq
     kernel<<<grid, c.nwarps * 32, c.smem, strm>>>(wl, sd, cfg, out);
     ctx->launches++;
     B2H_CUDA(cudaGetLastError());
+    if (out2) {
+      B2H_CUDA(cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+      B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), strm));
+      kernel2<<<grid, c.nwarps * 32, c.smem, strm>>>(wl, sd, cfg, *out2);
+      ctx->launches++;
+      B2H_CUDA(cudaGetLastError());
+    }
     plo = phi; cls++;
   }
   return B2H_OK;
@@ -584,11 +595,14 @@ int launch_dp(b2h_ctx *ctx, K kernel, int kind, const WorkList &wl_in, const Seq
 } // namespace
 
 int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out)
-{ return launch_dp(ctx, vit_kernel, 0, wl, sd, mpads, 2, nitems_hint, out); }
+{ return launch_dp(ctx, vit_kernel, 0, wl, sd, mpads, 2, nitems_hint, out, vit_kernel, 0, nullptr); }
 int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out)
-{ return launch_dp(ctx, fwd_kernel, 1, wl, sd, mpads, 4, nitems_hint, out); }
+{ return launch_dp(ctx, fwd_kernel, 1, wl, sd, mpads, 4, nitems_hint, out, fwd_kernel, 1, nullptr); }
 int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out)
-{ return launch_dp(ctx, bck_kernel, 2, wl, sd, mpads, 4, nitems_hint, out); }
+{ return launch_dp(ctx, bck_kernel, 2, wl, sd, mpads, 4, nitems_hint, out, bck_kernel, 2, nullptr); }
+// Forward (with stored specials) and Backward of the same work list, class by class on one stream each
+int b2h_launch_forward_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut fwd, StageOut bck)
+{ return launch_dp(ctx, fwd_kernel, 1, wl, sd, mpads, 4, nitems_hint, fwd, bck_kernel, 2, &bck); }
 
 int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nentries_hint, float *filtersc)
 {

@@ -55,7 +55,7 @@ struct b2h_ctx {
   //                  launches of wave w+1 on the main lane: SSV saturates the shared-memory pipe, these the ALU pipe
   struct Lane { cudaStream_t stream = nullptr; std::vector<cudaStream_t> side; std::vector<cudaEvent_t> side_done;
                 cudaEvent_t fork_ev = nullptr; int *counters = nullptr; };
-  Lane lanes[2]; int prio_hi = 0;
+  Lane lanes[3]; int prio_hi = 0;
   cudaStream_t bias_stream = nullptr;  // the bias filter of a wave runs here, next to that wave's Viterbi launches
   // page-locked result buffers (survivor lists, parser special rows) recycled between searches
   std::mutex    pin_mu; std::vector<std::pair<void *, size_t>> pin_pool;
@@ -64,6 +64,7 @@ struct b2h_ctx {
 // RAII: make one of the extra lanes the current one (only the thread that drives b2h_search does this)
 #define B2H_LANE_SURV 0
 #define B2H_LANE_POST 1
+#define B2H_LANE_SURV2 2      /* second survivor lane: the survivor passes of two consecutive waves may be in flight together */
 struct b2h_lane_switch {
   b2h_ctx *c; int i;
   b2h_lane_switch(b2h_ctx *ctx, int lane) : c(ctx), i(lane) { swap(); }
@@ -302,6 +303,7 @@ struct StageOut { float *sc; int32_t *status; float *fwd_xmx, *bck_xmx; const in
 int b2h_launch_viterbi(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_forward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
 int b2h_launch_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut out);
+int b2h_launch_forward_backward(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, const std::vector<int> &mpads, int nitems_hint, StageOut fwd, StageOut bck);
 int b2h_launch_dpreg(b2h_ctx *ctx, int kind, int C, int W, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm);
 int b2h_launch_vit2(b2h_ctx *ctx, int C2, const WorkList &wl, const SeqDev &sd, int nitems_hint, StageOut out, cudaStream_t strm);
 // register-resident DP size classes: nodes per lane C and warps per comparison W for a model of M nodes (0,0: too long)
@@ -336,6 +338,8 @@ struct SsvArgs {
   int            ncls;
   SeqDev         sd;
   int            chunks;       // ceil(nseq / B2H_SSV_CHUNK)
+  int            items_per_cta; // a CTA retires after this many work items (0: persistent): SM slots turn over every ~100 us, so the
+                               // short high-priority kernels of the survivor / envelope lanes are not kept waiting by a long SSV launch
   int           *counter;
   int            mode;         // 0: dense p7_SSVFilter  1: dense, queue eslENORESULT in R  2: cascade (P-value test, A and R)
   float         *out_sc; int32_t *out_status;

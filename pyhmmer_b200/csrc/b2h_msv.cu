@@ -27,6 +27,7 @@
 // uint8 arithmetic; overflow returns +inf/eslERANGE.
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <algorithm>
 #include <cmath>
 #include "b2h_internal.h"
 
@@ -157,9 +158,11 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
   const uint32_t tab_lane = smem_u32(s_tab) + gl * 16;
   const uint32_t tab_rem  = smem_u32(s_tab) + FULLQ * G * 16 + lane * 4;
   const int nitems = a.ncls * a.chunks;
+  int budget = a.items_per_cta > 0 ? a.items_per_cta : 0x7fffffff;
 
   for (;;) {
     __syncthreads();                                       // every warp is done with the previous item (and table)
+    if (budget-- <= 0) break;                              // (uniform) retire: the grid holds enough CTAs for every item
     if (threadIdx.x == 0) s_item = atomicAdd(a.counter, 1);
     __syncthreads();
     const int item = s_item;
@@ -473,6 +476,7 @@ int launch_ssv_tile(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
   int grid = ctx->sm_count * occ;
   const long long nitems = (long long)a.ncls * a.chunks;
   if (grid > nitems) grid = (int)(nitems > 0 ? nitems : 1);
+  if (a.items_per_cta > 0) grid = (int)std::max<long long>(grid, (nitems + a.items_per_cta - 1) / a.items_per_cta);
   ssv_kernel<G, NR><<<grid, SSV_THREADS, smem, strm>>>(a);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());

@@ -19,8 +19,11 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <thread>
 #include <vector>
@@ -222,6 +225,8 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
     SsvArgs a;
     a.profs = d_prof; a.cls = d_cls + cr.second.first; a.ncls = cr.second.second; a.sd = sd;
     a.chunks = (N + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK; a.counter = ctx->d_counters + 32 + (ssv_cls++ % 24); a.mode = 2;
+    static const int ipc = getenv("B2H_SSV_ITEMS_PER_CTA") ? atoi(getenv("B2H_SSV_ITEMS_PER_CTA")) : 2;   // measured (ms/step): persistent 42.0, 8 -> 43.2, 4 -> 41.3, 2 -> 40.4, 1 -> 40.4
+    a.items_per_cta = ipc;
     a.out_sc = nullptr; a.out_status = nullptr; a.A = A; a.R = R; a.F1 = prm->F1;
     TRY(b2h_launch_ssv(ctx, cr.first / 64, cr.first % 64, a, fj.next()));
   } }
@@ -467,37 +472,56 @@ struct EnvGpu : b2h_env_backend {
   }
 };
 
-// One chunk of survivors whose parser specials are on the host: the domain definition runs on the host thread pool
-// from a helper thread while the calling thread goes on feeding the GPU with the next wave of profiles.
+// One chunk of survivors whose parser specials are on the host.  The domain definition of the chunks runs on the host
+// thread pool, driven by ONE background thread that takes the chunks in order, while the calling thread goes on feeding
+// the GPU (it never waits for a domain definition before the very end).
 struct DdefJob {
   Pinned<float> fx, bx; Pinned<int32_t> bst; std::vector<b2h_ddef_task> tasks;   // page-locked: the D2H copies run at PCIe speed
-  std::thread th; int status = B2H_OK; double ms = 0.0;
 };
-struct DdefAsync {
-  b2h_ddef_pool &pool; const b2h_search_params *prm; b2h_results *res; b2h_env_backend *backend; std::unique_ptr<DdefJob> cur; double total_ms = 0.0;
-  DdefAsync(b2h_ddef_pool &p, const b2h_search_params *pr, b2h_results *r, b2h_env_backend *be) : pool(p), prm(pr), res(r), backend(be) {}
-  int join() {
-    if (!cur) return B2H_OK;
-    cur->th.join();
-    const int st = cur->status; total_ms += cur->ms;
-    if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search]   chunk of %zu survivors: host domain definition %.1f ms on %d threads\n", cur->tasks.size(), cur->ms, pool.nthreads);
-    cur.reset();
-    return st;
+struct DdefQueue {
+  b2h_ddef_pool &pool; const b2h_search_params *prm; b2h_results *res; b2h_env_backend *backend;
+  std::thread th; std::mutex mu; std::condition_variable cv; std::deque<std::unique_ptr<DdefJob>> q;
+  bool closing = false; int status = B2H_OK; double total_ms = 0.0;
+  DdefQueue(b2h_ddef_pool &p, const b2h_search_params *pr, b2h_results *r, b2h_env_backend *be) : pool(p), prm(pr), res(r), backend(be) {
+    th = std::thread([this]() {
+      for (;;) {
+        std::unique_ptr<DdefJob> job;
+        { std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return closing || !q.empty(); });
+          if (q.empty()) return;
+          job = std::move(q.front()); q.pop_front(); }
+        const double t0 = now_ms();
+        const int st = (status == B2H_OK) ? pool.run(job->tasks, prm, res, backend) : status;    // after a failure the rest is dropped
+        const double ms = now_ms() - t0;
+        { std::lock_guard<std::mutex> lk(mu); if (status == B2H_OK) status = st; total_ms += ms; }
+        if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search]   chunk of %zu survivors: host domain definition %.1f ms on %d threads\n", job->tasks.size(), ms, pool.nthreads);
+      }
+    });
   }
-  int launch(std::unique_ptr<DdefJob> job) {                 // at most one job in flight: the pool is not re-entrant
-    const int st = join();
-    if (st != B2H_OK) return st;
-    cur = std::move(job);
-    DdefJob *j = cur.get();
-    j->th = std::thread([this, j]() { const double t0 = now_ms(); j->status = pool.run(j->tasks, prm, res, backend); j->ms = now_ms() - t0; });
-    return B2H_OK;
+  void push(std::unique_ptr<DdefJob> job) { { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(job)); } cv.notify_one(); }
+  int finish() {                                               // drain the queue, stop the thread
+    if (th.joinable()) { { std::lock_guard<std::mutex> lk(mu); closing = true; } cv.notify_one(); th.join(); }
+    return status;
   }
-  ~DdefAsync() { if (cur) cur->th.join(); }
+  ~DdefQueue() { finish(); }
 };
 
-static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, const b2h_search_params *prm,
-                            std::vector<b2h_survivor> &surv, DdefAsync &ddef)
+// The survivors of one wave on their way through Forward (with stored special-state rows) and Backward: sorted by
+// profile, cut into chunks whose specials stay within a fixed budget, every chunk queued on the current (survivor) lane
+// with its D2H copies behind it; <done> fires when everything has arrived in the page-locked job buffers.
+struct SurvChunk {
+  std::unique_ptr<Pool> pool; std::unique_ptr<DdefJob> job;
+  std::vector<ProfDev> hprof; std::vector<int32_t> poff, itemoff, ent_s; std::vector<int64_t> xoff;   // H2D sources: alive until <done>
+  size_t i0 = 0; int n = 0;
+};
+struct SurvPending {
+  std::vector<b2h_survivor> surv; std::vector<std::unique_ptr<SurvChunk>> chunks; cudaEvent_t done = nullptr; size_t wave = 0;
+  ~SurvPending() { if (done) cudaEventDestroy(done); }
+};
+
+static int survivors_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, SurvPending &sp)
 {
+  std::vector<b2h_survivor> &surv = sp.surv;
   std::sort(surv.begin(), surv.end(), [&](const b2h_survivor &x, const b2h_survivor &y) {
     const int mx = profiles[x.profile]->Mpad, my = profiles[y.profile]->Mpad;
     if (mx != my) return mx < my;
@@ -509,22 +533,27 @@ static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, co
     size_t i1 = i0, rows = 0;
     while (i1 < surv.size() && (i1 == i0 || rows + db->h_len[surv[i1].seq] + 1 <= ROW_BUDGET)) { rows += db->h_len[surv[i1].seq] + 1; i1++; }
     const int n = (int)(i1 - i0);
+    sp.chunks.emplace_back(new SurvChunk());
+    SurvChunk &ck = *sp.chunks.back();
+    ck.i0 = i0; ck.n = n;
     // work list of this chunk: profiles present, in order
-    std::vector<ProfDev> hprof; std::vector<int32_t> poff, itemoff, ent_s(n); std::vector<int64_t> xoff(n); std::vector<int> mpads;
-    int max_Mpad = 0; int64_t acc = 0; int items = 0;
+    std::vector<ProfDev> &hprof = ck.hprof; std::vector<int32_t> &poff = ck.poff, &itemoff = ck.itemoff, &ent_s = ck.ent_s; std::vector<int64_t> &xoff = ck.xoff;
+    ent_s.resize(n); xoff.resize(n);
+    std::vector<int> mpads;
+    int64_t acc = 0; int items = 0;
     for (int e = 0; e < n; e++) {
       const b2h_survivor &v = surv[i0 + e];
       if (e == 0 || v.profile != surv[i0 + e - 1].profile) {
         if (e) items += ((e - poff.back()) + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES;
         hprof.push_back(b2h_profdev(profiles[v.profile])); poff.push_back(e); itemoff.push_back(items); mpads.push_back(hprof.back().Mpad);
-        max_Mpad = std::max(max_Mpad, hprof.back().Mpad);
       }
       ent_s[e] = v.seq; xoff[e] = acc; acc += db->h_len[v.seq] + 1;
     }
     items += ((n - poff.back()) + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES;
     poff.push_back(n); itemoff.push_back(items);
     const int Pc = (int)hprof.size();
-    Pool pool(ctx);
+    ck.pool.reset(new Pool(ctx));
+    Pool &pool = *ck.pool;
     ProfDev *d_prof; int32_t *d_poff, *d_itemoff, *d_ent; int64_t *d_xoff; float *d_fx, *d_bx, *d_fsc, *d_bsc; int32_t *d_fst, *d_bst;
     TRY(pool.get(&d_prof, Pc)); TRY(pool.get(&d_poff, Pc + 1)); TRY(pool.get(&d_itemoff, Pc + 1)); TRY(pool.get(&d_ent, n));
     TRY(pool.get(&d_xoff, n)); TRY(pool.get(&d_fx, (size_t)acc * 6)); TRY(pool.get(&d_bx, (size_t)acc * 6));
@@ -536,33 +565,39 @@ static int finish_survivors(b2h_ctx *ctx, const b2h_profile *const *profiles, co
     B2H_CUDA(cudaMemcpyAsync(d_xoff, xoff.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     WorkList wl; wl.profs = d_prof; wl.ent_s = d_ent; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = Pc; wl.counter = ctx->d_counters + 8; wl.plo = 0; wl.phi = Pc;
     StageOut sf; sf.sc = d_fsc; sf.status = d_fst; sf.fwd_xmx = d_fx; sf.bck_xmx = nullptr; sf.xoff = d_xoff;
-    StageTimer *tm = new StageTimer(ctx, 5);
-    TRY(b2h_launch_forward(ctx, wl, sd, mpads, items, sf));
     StageOut sb; sb.sc = d_bsc; sb.status = d_bst; sb.fwd_xmx = d_fx; sb.bck_xmx = d_bx; sb.xoff = d_xoff;
-    TRY(b2h_launch_backward(ctx, wl, sd, mpads, items, sb));
-    delete tm;
-    std::unique_ptr<DdefJob> job(new DdefJob());
-    Pinned<float> &fx = job->fx, &bx = job->bx; Pinned<int32_t> &bst = job->bst;
+    { StageTimer tm(ctx, 5); TRY(b2h_launch_forward_backward(ctx, wl, sd, mpads, items, sf, sb)); }
+    ck.job.reset(new DdefJob());
+    Pinned<float> &fx = ck.job->fx, &bx = ck.job->bx; Pinned<int32_t> &bst = ck.job->bst;
     TRY(fx.alloc(ctx, (size_t)acc * 6)); TRY(bx.alloc(ctx, (size_t)acc * 6)); TRY(bst.alloc(ctx, n));
     B2H_CUDA(cudaMemcpyAsync(fx.data(), d_fx, (size_t)acc * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(bx.data(), d_bx, (size_t)acc * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     B2H_CUDA(cudaMemcpyAsync(bst.data(), d_bst, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    B2H_CUDA(cudaStreamSynchronize(ctx->stream));
-    b2h_resolve_timers(ctx);
-    // host-side domain definition, one task per survivor
-    std::vector<b2h_ddef_task> &tasks = job->tasks;
-    tasks.resize(n);
-    for (int e = 0; e < n; e++) {
-      b2h_ddef_task &t = tasks[e];
-      const b2h_survivor &v = surv[i0 + e];
+    i0 = i1;
+  }
+  B2H_CUDA(cudaEventCreateWithFlags(&sp.done, cudaEventDisableTiming));
+  B2H_CUDA(cudaEventRecord(sp.done, ctx->stream));
+  return B2H_OK;
+}
+
+// <done> has fired: hand the chunks to the domain-definition thread, one task per survivor
+static int survivors_complete(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, SurvPending &sp, DdefQueue &ddef)
+{
+  b2h_resolve_timers(ctx);
+  for (auto &ckp : sp.chunks) {
+    SurvChunk &ck = *ckp;
+    DdefJob &job = *ck.job;
+    job.tasks.resize(ck.n);
+    for (int e = 0; e < ck.n; e++) {
+      b2h_ddef_task &t = job.tasks[e];
+      const b2h_survivor &v = sp.surv[ck.i0 + e];
       t.surv = v; t.prof = profiles[v.profile];
       t.dsq = db->h_res + db->h_off[v.seq]; t.L = db->h_len[v.seq];
-      t.fx = fx.data() + (size_t)xoff[e] * 6; t.bx = bx.data() + (size_t)xoff[e] * 6;
-      t.bck_own_scales = (bst[e] & 0x100) != 0;
+      t.fx = job.fx.data() + (size_t)ck.xoff[e] * 6; t.bx = job.bx.data() + (size_t)ck.xoff[e] * 6;
+      t.bck_own_scales = (job.bst[e] & 0x100) != 0;
     }
-    const int st = ddef.launch(std::move(job));
-    if (st != B2H_OK) { ctx->err = "domain definition failed"; return st; }
-    i0 = i1;
+    ck.pool.reset();                                           // stream-ordered frees on the chunk's lane
+    ddef.push(std::move(ck.job));
   }
   return B2H_OK;
 }
@@ -617,11 +652,13 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     b2h_ddef_pool ddpool(prm->host_threads);
     EnvGpu envgpu(ctx, db);
     const bool host_env = getenv("B2H_ENVELOPES_ON_HOST") != nullptr;     // debugging aid: rescore envelopes with the host code
-    DdefAsync ddef(ddpool, prm, res, host_env ? nullptr : &envgpu);
-    size_t nsurv = 0; double tg = 0.0;
-    // Software pipeline over the waves: the cascade of wave w+1 is queued on the main lane before the host waits for
-    // wave w; wave w's survivors then go through Forward/Backward on the high-priority lane (their kernels slip in
-    // between the next wave's SSV launches) and on to the domain-definition thread.
+    DdefQueue ddef(ddpool, prm, res, host_env ? nullptr : &envgpu);
+    size_t nsurv = 0;
+    // Software pipeline over the waves, driven by events.  The cascade of waves w+1, w+2 is queued on the main lane before
+    // the host looks at wave w.  When a wave's cascade has finished, its survivor list is fetched and its Forward/Backward
+    // passes are queued on one of two high-priority survivor lanes (their kernels slip in between the following wave's SSV
+    // launches, and the passes of two consecutive waves may run side by side); when those have arrived on the host, the
+    // chunk goes to the domain-definition thread.  This thread never blocks on either while the other can make progress.
     const size_t nw = bounds.size() - 1;
     std::vector<std::unique_ptr<CascadeWave>> waves(nw);
     int st = B2H_OK;
@@ -634,22 +671,42 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
         st = cascade_enqueue(ctx, sp.data(), (int)bounds[queued], (int)bounds[queued + 1], db, prm, *waves[queued]);
       }
     };
-    for (size_t w = 0; w < nw && st == B2H_OK; w++) {
-      const double tw = now_ms();
-      top_up(w + ahead);
-      std::vector<b2h_survivor> surv;
-      const double tq = now_ms();
-      if (st == B2H_OK) st = cascade_collect(ctx, *waves[w], ctx->lanes[B2H_LANE_SURV].stream, surv, scnt.data());
-      waves[w].reset();
-      const double tc = now_ms();
-      if (st == B2H_OK) { b2h_lane_switch lane(ctx, B2H_LANE_SURV); st = finish_survivors(ctx, sp.data(), db, prm, surv, ddef); }
-      if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search]   wave %zu (%zu profiles): queued up to wave %zu at +%.1f ms, cascade collected at +%.1f ms, %zu survivors through Forward/Backward at +%.1f ms\n",
-                                       w, bounds[w + 1] - bounds[w], queued - 1, tq - t0, tc - t0, surv.size(), now_ms() - t0);
-      nsurv += surv.size(); tg += now_ms() - tw;
+    auto fired = [](cudaEvent_t e) { const cudaError_t q = cudaEventQuery(e); if (q != cudaSuccess) (void)cudaGetLastError(); return q != cudaErrorNotReady; };
+    const bool trace = getenv("B2H_TRACE") != nullptr;
+    std::deque<std::unique_ptr<SurvPending>> pend;
+    size_t next_collect = 0;
+    while (st == B2H_OK && (next_collect < nw || !pend.empty())) {
+      if (next_collect < nw) top_up(next_collect + ahead);
+      if (st != B2H_OK) break;
+      if (!pend.empty() && fired(pend.front()->done)) {
+        SurvPending &p = *pend.front();
+        if (trace) fprintf(stderr, "[b2h_search]   wave %zu: %zu survivors through Forward/Backward at +%.1f ms\n", p.wave, p.surv.size(), now_ms() - t0);
+        st = survivors_complete(ctx, sp.data(), db, p, ddef);
+        nsurv += p.surv.size();
+        pend.pop_front();
+        continue;
+      }
+      if (next_collect < nw && pend.size() < 2 && fired(waves[next_collect]->done)) {
+        const size_t w = next_collect++;
+        std::unique_ptr<SurvPending> p(new SurvPending());
+        p->wave = w;
+        const int lane_id = (w & 1) ? B2H_LANE_SURV2 : B2H_LANE_SURV;
+        st = cascade_collect(ctx, *waves[w], ctx->lanes[lane_id].stream, p->surv, scnt.data());
+        waves[w].reset();
+        if (trace) fprintf(stderr, "[b2h_search]   wave %zu (%zu profiles): cascade collected at +%.1f ms (queued up to wave %zu)\n", w, bounds[w + 1] - bounds[w], now_ms() - t0, queued - 1);
+        if (st == B2H_OK) { b2h_lane_switch lane(ctx, lane_id); st = survivors_enqueue(ctx, sp.data(), db, *p); }
+        pend.push_back(std::move(p));
+        continue;
+      }
+      // nothing is ready: block on the only thing in flight, or yield briefly when there are two
+      if (pend.empty()) { if (cudaEventSynchronize(waves[next_collect]->done) != cudaSuccess) { ctx->err = "cascade failed"; st = B2H_ECUDA; } }
+      else if (next_collect >= nw || pend.size() >= 2) { if (cudaEventSynchronize(pend.front()->done) != cudaSuccess) { ctx->err = "survivor passes failed"; st = B2H_ECUDA; } }
+      else std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
-    if (st != B2H_OK) { cudaStreamSynchronize(ctx->stream); for (auto &l : ctx->lanes) cudaStreamSynchronize(l.stream); ddef.join(); waves.clear(); delete res; return st; }
+    const double tg = now_ms() - t0;
+    if (st != B2H_OK) { cudaStreamSynchronize(ctx->stream); for (auto &l : ctx->lanes) cudaStreamSynchronize(l.stream); ddef.finish(); pend.clear(); waves.clear(); delete res; return st; }
     const double t1 = now_ms();
-    st = ddef.join();
+    st = ddef.finish();
     if (st != B2H_OK) { ctx->err = "domain definition failed"; delete res; return st; }
     for (b2h_hit &h : res->hits) h.profile = order[h.profile];
     for (size_t i = 0; i < P; i++) for (int c = 0; c < 4; c++) res->counters[(size_t)order[i] * 4 + c] = scnt[i * 4 + c];
