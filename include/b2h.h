@@ -186,9 +186,11 @@ int b2h_generic_scores(b2h_ctx *ctx, int M, int K, int Kp, const float *tsc, con
 /* p7_GDecoding (generic_decoding.c:77) of ONE comparison: posterior probabilities from the full generic Forward and Backward
  * matrices.  residues = L residue codes (no sentinels).  pp_dp [(L+1)][(M+1)][3] (M, I, D as P7_GMX.dp), pp_xmx [(L+1)][5]
  * (E N J B C); the Forward and Backward scores are returned too.  The matrices are filled in the reference's order (bit-identical
- * scores); the probabilities differ from the reference's only through expf (device vs glibc: a few ulp). */
+ * scores); the probabilities differ from the reference's only through expf (device vs glibc: a few ulp).  dom_btot / dom_etot /
+ * dom_mocc [L+1] (each may be NULL): p7_GDomainDecoding (generic_decoding.c:207) from the same matrices' special rows. */
 int b2h_generic_decoding(b2h_ctx *ctx, int M, int K, int Kp, const float *tsc, const float *msc, const float *xsc, float nj,
-                         const uint8_t *residues, int L, float *pp_dp, float *pp_xmx, float *fwdsc, float *bcksc);
+                         const uint8_t *residues, int L, float *pp_dp, float *pp_xmx, float *fwdsc, float *bcksc,
+                         float *dom_btot, float *dom_etot, float *dom_mocc);
 
 /* --------------------------- the fused search path (p7_Pipeline per target) ----------------- *
  * b2h_search() is what Pipeline._search_loop / _scan_loop (plan7.pyx:6394-6453, 6625-6677) do for

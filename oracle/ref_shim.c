@@ -199,7 +199,8 @@ int ref_generic(REFM *m, const uint8_t *dsq, int L, float *gmsv, float *gvit, fl
 }
 
 /* p7_GDecoding (generic_decoding.c:77) after p7_GForward / p7_GBackward: pp_dp [(L+1)][(M+1)][3] (M,I,D), pp_xmx [(L+1)][5] (E,N,J,B,C) */
-int ref_gdecoding(REFM *m, const uint8_t *dsq, int L, float *pp_dp, float *pp_xmx, float *fsc, float *bsc)
+/* dom = NULL or [3][L+1]: btot, etot, mocc of p7_GDomainDecoding (generic_decoding.c:207) */
+int ref_gdecoding(REFM *m, const uint8_t *dsq, int L, float *pp_dp, float *pp_xmx, float *fsc, float *bsc, float *dom)
 {
   int M = m->gm->M, i;
   P7_GMX *fwd = p7_gmx_Create(M, L), *bck = p7_gmx_Create(M, L), *pp = p7_gmx_Create(M, L);
@@ -207,6 +208,14 @@ int ref_gdecoding(REFM *m, const uint8_t *dsq, int L, float *pp_dp, float *pp_xm
   p7_GForward (dsq, L, m->gm, fwd, fsc);
   p7_GBackward(dsq, L, m->gm, bck, bsc);
   p7_GDecoding(m->gm, fwd, bck, pp);
+  if (dom) {
+    P7_DOMAINDEF *dd = p7_domaindef_Create(NULL);
+    p7_domaindef_GrowTo(dd, L);
+    dd->btot[0] = dd->etot[0] = dd->mocc[0] = 0.;
+    p7_GDomainDecoding(m->gm, fwd, bck, dd);
+    memcpy(dom, dd->btot, sizeof(float) * (L + 1)); memcpy(dom + (L + 1), dd->etot, sizeof(float) * (L + 1)); memcpy(dom + 2 * (L + 1), dd->mocc, sizeof(float) * (L + 1));
+    p7_domaindef_Destroy(dd);
+  }
   for (i = 0; i <= L; i++) {
     memcpy(pp_dp  + (size_t)i * (M + 1) * p7G_NSCELLS, pp->dp[i], sizeof(float) * (M + 1) * p7G_NSCELLS);
     memcpy(pp_xmx + (size_t)i * p7G_NXCELLS, pp->xmx + (size_t)i * p7G_NXCELLS, sizeof(float) * p7G_NXCELLS);

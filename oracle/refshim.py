@@ -66,7 +66,7 @@ def lib():
         L.ref_bias.restype = cf
         L.ref_bias.argtypes = [vp, vp, ci]
         L.ref_generic.argtypes = [vp, vp, ci] + [ctypes.POINTER(cf)] * 4
-        L.ref_gdecoding.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf)]
+        L.ref_gdecoding.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), vp]
         L.ref_gumbel_surv.restype = ctypes.c_double
         L.ref_gumbel_surv.argtypes = [ctypes.c_double] * 3
         L.ref_exp_surv.restype = ctypes.c_double
@@ -200,8 +200,9 @@ class RefModel:
         d = dsq_of(codes); n = d.size - 2
         pp = np.zeros((n + 1, self.M + 1, 3), np.float32); xpp = np.zeros((n + 1, 5), np.float32)
         f, b = ctypes.c_float(), ctypes.c_float()
-        self.L.ref_gdecoding(self.h, d.ctypes.data, n, pp.ctypes.data, xpp.ctypes.data, ctypes.byref(f), ctypes.byref(b))
-        return pp, xpp, f.value, b.value
+        dom = np.zeros((3, n + 1), np.float32)
+        self.L.ref_gdecoding(self.h, d.ctypes.data, n, pp.ctypes.data, xpp.ctypes.data, ctypes.byref(f), ctypes.byref(b), dom.ctypes.data)
+        return pp, xpp, f.value, b.value, dom
 
     def null1(self, codes):
         d = dsq_of(codes); return self.L.ref_null1(self.h, d.ctypes.data, d.size - 2)

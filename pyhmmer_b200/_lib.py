@@ -131,7 +131,7 @@ def _load():
     sig("b2h_generic_scores", c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_float,
         c_void_p, c_void_p, c_void_p, c_void_p)
     sig("b2h_generic_decoding", c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
-        c_void_p, c_void_p, P(c_float), P(c_float))
+        c_void_p, c_void_p, P(c_float), P(c_float), c_void_p, c_void_p, c_void_p)
     sig("b2h_profile_create_host", c_int, P(OProfileDesc), P(c_void_p))
     sig("b2h_debug_domaindef", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, P(SearchParams), P(c_void_p))
     if hasattr(lib, "b2h_null_scores"):

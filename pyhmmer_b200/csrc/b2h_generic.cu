@@ -337,7 +337,8 @@ extern "C" int b2h_generic_scores(b2h_ctx *ctx, int M, int K, int Kp, const floa
 }
 
 extern "C" int b2h_generic_decoding(b2h_ctx *ctx, int M, int K, int Kp, const float *tsc, const float *msc, const float *xsc, float nj,
-                                    const uint8_t *residues, int L, float *pp_dp, float *pp_xmx, float *fwdsc, float *bcksc)
+                                    const uint8_t *residues, int L, float *pp_dp, float *pp_xmx, float *fwdsc, float *bcksc,
+                                    float *dom_btot, float *dom_etot, float *dom_mocc)
 {
   if (!ctx || !tsc || !msc || !xsc || !residues || !pp_dp || !pp_xmx || M < 1 || L < 1 || Kp < 1 || Kp > B2H_NCODE - 1 || K < 1 || K >= Kp) return B2H_EINVAL;
   B2H_CUDA(cudaSetDevice(ctx->device));
@@ -379,10 +380,35 @@ extern "C" int b2h_generic_decoding(b2h_ctx *ctx, int M, int K, int Kp, const fl
   cudaMemcpyAsync(pp_xmx, d.xpp, xc * 4, cudaMemcpyDeviceToHost, st);
   float sc[2] = {0.f, 0.f};
   cudaMemcpyAsync(sc, d.sc, 8, cudaMemcpyDeviceToHost, st);
+  std::vector<float> hfx, hbx;
+  if (dom_btot || dom_etot || dom_mocc) {
+    hfx.resize(xc); hbx.resize(xc);
+    cudaMemcpyAsync(hfx.data(), d.fx, xc * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(hbx.data(), d.bx, xc * 4, cudaMemcpyDeviceToHost, st);
+  }
   e = cudaStreamSynchronize(st);
   release();
   if (e != cudaSuccess) { ctx->err = std::string("generic decoding kernels: ") + cudaGetErrorString(e); return B2H_ECUDA; }
   if (fwdsc) *fwdsc = sc[0];
   if (bcksc) *bcksc = sc[1];
+  if (!hfx.empty()) {
+    // p7_GDomainDecoding (generic_decoding.c:207-230) from the special-state rows, on the host with the reference's libm calls
+    const float *fx = hfx.data(), *bx = hbx.data();
+    const float overall = fx[(size_t)L * 5 + 4] + d.xmove;
+    float bt = 0.f, et = 0.f;
+    if (dom_btot) dom_btot[0] = 0.f;
+    if (dom_etot) dom_etot[0] = 0.f;
+    if (dom_mocc) dom_mocc[0] = 0.f;
+    for (int i = 1; i <= L; i++) {
+      bt = (float)((double)bt + exp((double)(fx[(size_t)(i - 1) * 5 + 3] + bx[(size_t)(i - 1) * 5 + 3] - overall)));
+      et = (float)((double)et + exp((double)(fx[(size_t)i * 5 + 0] + bx[(size_t)i * 5 + 0] - overall)));
+      float njcp = expf(fx[(size_t)(i - 1) * 5 + 1] + bx[(size_t)i * 5 + 1] + d.xloop - overall);
+      njcp += expf(fx[(size_t)(i - 1) * 5 + 2] + bx[(size_t)i * 5 + 2] + d.xloop - overall);
+      njcp += expf(fx[(size_t)(i - 1) * 5 + 4] + bx[(size_t)i * 5 + 4] + d.xloop - overall);
+      if (dom_btot) dom_btot[i] = bt;
+      if (dom_etot) dom_etot[i] = et;
+      if (dom_mocc) dom_mocc[i] = (float)(1. - (double)njcp);
+    }
+  }
   return B2H_OK;
 }

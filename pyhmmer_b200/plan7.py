@@ -464,19 +464,22 @@ class Profile:
               "b2h_generic_scores", ctx.handle)
         return out
 
-    def _generic_decoding(self, seq):
+    def _generic_decoding(self, seq, domains=False):
         """p7_GDecoding (generic_decoding.c:77) of this profile (reconfigured to the target's length) and one sequence:
-        (pp[(L+1), (M+1), 3], xpp[(L+1), 5], forward score, backward score)."""
+        (pp[(L+1), (M+1), 3], xpp[(L+1), 5], forward score, backward score); with ``domains`` also the (btot, etot, mocc)
+        arrays of p7_GDomainDecoding (generic_decoding.c:207)."""
         ctx = _lib.context()
         codes = np.ascontiguousarray(seq.sequence, dtype=np.uint8)
         L = len(codes)
         pp = np.zeros((L + 1, self.M + 1, 3), np.float32)
         xpp = np.zeros((L + 1, 5), np.float32)
         f, b = ctypes.c_float(), ctypes.c_float()
+        dom = [np.zeros(L + 1, np.float32) for _ in range(3)] if domains else [None] * 3
         check(lib.b2h_generic_decoding(ctx.handle, self.M, self.alphabet.K, self.alphabet.Kp, ptr(self.tsc), ptr(self.msc), ptr(self.xsc),
-                                       1.0 if self.multihit else 0.0, ptr(codes), L, ptr(pp), ptr(xpp), ctypes.byref(f), ctypes.byref(b)),
+                                       1.0 if self.multihit else 0.0, ptr(codes), L, ptr(pp), ptr(xpp), ctypes.byref(f), ctypes.byref(b),
+                                       ptr(dom[0]), ptr(dom[1]), ptr(dom[2])),
               "b2h_generic_decoding", ctx.handle)
-        return pp, xpp, f.value, b.value
+        return (pp, xpp, f.value, b.value) + ((tuple(dom),) if domains else ())
 
     def msv_filter(self, seq, nu=2.0):
         """``Profile.msv_filter`` (plan7.pyx:8212-8253): the generic MSV score (p7_GMSV) of one sequence, in nats."""

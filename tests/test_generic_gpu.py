@@ -51,8 +51,10 @@ def test_generic_decoding(amino, make_pair, M):
     for codes in (np.concatenate([rng.integers(0, 20, 30).astype(np.uint8), dom, rng.integers(0, 20, 25).astype(np.uint8)]),
                   rng.integers(0, 20, 77).astype(np.uint8), rng.integers(0, 20, 1).astype(np.uint8)):
         seq = easel.DigitalSequence(amino, name=b"t", sequence=codes)
-        pp, xpp, f, b = pair.profile._generic_decoding(seq)
-        rpp, rxpp, rf, rb = pair.ref.gdecoding(codes)
+        pp, xpp, f, b, dom = pair.profile._generic_decoding(seq, domains=True)
+        rpp, rxpp, rf, rb, rdom = pair.ref.gdecoding(codes)
+        for got, ref in zip(dom, rdom):                          # p7_GDomainDecoding: host libm on bit-identical inputs
+            assert np.array_equal(got, ref)
         assert np.float32(rf) == np.float32(f) and np.float32(rb) == np.float32(b), (M, len(codes), rf, f, rb, b)
         assert np.allclose(pp, rpp, rtol=2e-5, atol=1e-9), (M, len(codes), float(np.abs(pp - rpp).max()))
         assert np.allclose(xpp, rxpp, rtol=2e-5, atol=1e-9)
