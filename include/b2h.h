@@ -258,6 +258,21 @@ int b2h_profile_set_annotation(b2h_profile *p, const char *consensus, const char
 size_t b2h_seqdb_h2d_bytes(const b2h_seqdb *db);
 size_t b2h_profile_h2d_bytes(const b2h_profile *p);
 
+/* ---- long-target (nhmmer) path, first stage ------------------------------------------------------------------------
+ * p7_SSVFilter_longtarget (vendor/hmmer/src/impl_sse/msvfilter.c:256) over every sequence of <db> (= the chunks a long
+ * target was cut into; LongTargetsPipeline, plan7.pyx:7542-7663), with the model's length parameters set for its
+ * max_length (p7_oprofile_ReconfigMSVLength), then p7_hmm_ScoreDataComputeRest + p7_pli_ExtendAndMergeWindows(.., 0)
+ * (p7_scoredata.c:313, p7_pipeline.c:323).  <raw>: the SSV diagonals {chunk, start n (1-based), model end k, length,
+ * score in nats} in scan order per chunk; <merged>: the windows handed to the next stage {chunk, start, -, length}.
+ * Both arrays are malloc'ed; release them with b2h_free.  B2H_EINVAL if the model carries no max_length (MAXL). */
+typedef struct { int32_t seq; int32_t k; int64_t n; int32_t length; float score; } b2h_window;
+int  b2h_longtarget_windows(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, double F1,
+                            b2h_window **raw, size_t *nraw, b2h_window **merged, size_t *nmerged);
+void b2h_free(void *p);
+/* The prefix / suffix length tables [M+1] of p7_hmm_ScoreDataComputeRest for a profile (host only; works on a profile made by
+ * b2h_profile_create_host). */
+int  b2h_window_lengths(const b2h_profile *p, float *prefix, float *suffix);
+
 /* Register tile the SSV kernel uses for a model of M nodes: G lanes per comparison (32/G comparisons per warp), NR packed
  * registers (2*NR nodes) per lane, and the number of 128-byte shared-memory wavefronts one DP row of one WARP moves
  * (emission loads + shuffles) -- the quantity bench.py's on-chip roofline is computed from.  B2H_EINVAL if M > 3071. */

@@ -224,6 +224,36 @@ int ref_gdecoding(REFM *m, const uint8_t *dsq, int L, float *pp_dp, float *pp_xm
   return eslOK;
 }
 
+/* nhmmer's first stage for one target chunk (p7_Pipeline_LongTarget, p7_pipeline.c:1535-1565): p7_oprofile_ReconfigMSVLength
+ * to the model's max_length, p7_SSVFilter_longtarget (impl_sse/msvfilter.c:256), then p7_hmm_ScoreDataComputeRest +
+ * p7_pli_ExtendAndMergeWindows(.., 0).  raw [cap][3] = n, k, length of every SSV diagonal (+ raw_sc), merged [cap][2] = n,
+ * length of the merged windows; also the prefix / suffix length tables [M+1] when asked for.  Returns counts via n_raw/n_merged. */
+int ref_longtarget_windows(REFM *m, const uint8_t *dsq, int L, double F1, int cap, int *n_raw, int64_t *raw, float *raw_sc,
+                           int *n_merged, int64_t *merged, float *prefix, float *suffix)
+{
+  P7_SCOREDATA *data = p7_hmm_ScoreDataCreate(m->om, NULL);
+  P7_HMM_WINDOWLIST wl;
+  int i, M = m->om->M;
+  wl.windows = NULL;
+  p7_hmmwindow_init(&wl);
+  p7_omx_GrowTo(m->ox, M, 0, m->om->max_length);
+  p7_oprofile_ReconfigMSVLength(m->om, m->om->max_length);
+  p7_SSVFilter_longtarget(dsq, L, m->om, m->ox, data, m->bg, F1, &wl);
+  *n_raw = wl.count;
+  for (i = 0; i < wl.count && i < cap; i++) {
+    raw[i*3+0] = wl.windows[i].n; raw[i*3+1] = wl.windows[i].k; raw[i*3+2] = wl.windows[i].length; raw_sc[i] = wl.windows[i].score;
+  }
+  p7_hmm_ScoreDataComputeRest(m->om, data);
+  if (prefix) memcpy(prefix, data->prefix_lengths, sizeof(float) * (M + 1));
+  if (suffix) memcpy(suffix, data->suffix_lengths, sizeof(float) * (M + 1));
+  p7_pli_ExtendAndMergeWindows(m->om, data, &wl, 0);
+  *n_merged = wl.count;
+  for (i = 0; i < wl.count && i < cap; i++) { merged[i*2+0] = wl.windows[i].n; merged[i*2+1] = wl.windows[i].length; }
+  free(wl.windows);
+  p7_hmm_ScoreDataDestroy(data);
+  return eslOK;
+}
+
 double ref_gumbel_surv(double x, double mu, double lambda) { return esl_gumbel_surv(x, mu, lambda); }
 double ref_exp_surv(double x, double mu, double lambda)    { return esl_exp_surv(x, mu, lambda); }
 

@@ -66,6 +66,7 @@ def lib():
         L.ref_bias.restype = cf
         L.ref_bias.argtypes = [vp, vp, ci]
         L.ref_generic.argtypes = [vp, vp, ci] + [ctypes.POINTER(cf)] * 4
+        L.ref_longtarget_windows.argtypes = [vp, vp, ci, ctypes.c_double, ci, vp, vp, vp, vp, vp, vp, vp]
         L.ref_gdecoding.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), vp]
         L.ref_gumbel_surv.restype = ctypes.c_double
         L.ref_gumbel_surv.argtypes = [ctypes.c_double] * 3
@@ -203,6 +204,18 @@ class RefModel:
         dom = np.zeros((3, n + 1), np.float32)
         self.L.ref_gdecoding(self.h, d.ctypes.data, n, pp.ctypes.data, xpp.ctypes.data, ctypes.byref(f), ctypes.byref(b), dom.ctypes.data)
         return pp, xpp, f.value, b.value, dom
+
+    def longtarget_windows(self, codes, F1=0.02, cap=100000):
+        """First stage of nhmmer on one chunk: (raw SSV diagonals [n,3] = start n, model end k, length; their scores;
+        merged windows [m,2] = start, length; prefix and suffix length tables)."""
+        d = dsq_of(codes); n = d.size - 2
+        nr, nm = ctypes.c_int(), ctypes.c_int()
+        raw = np.zeros((cap, 3), np.int64); rsc = np.zeros(cap, np.float32); mer = np.zeros((cap, 2), np.int64)
+        pre = np.zeros(self.M + 1, np.float32); suf = np.zeros(self.M + 1, np.float32)
+        self.L.ref_longtarget_windows(self.h, d.ctypes.data, n, F1, cap, ctypes.byref(nr), raw.ctypes.data, rsc.ctypes.data,
+                                      ctypes.byref(nm), mer.ctypes.data, pre.ctypes.data, suf.ctypes.data)
+        assert nr.value <= cap
+        return raw[:nr.value].copy(), rsc[:nr.value].copy(), mer[:nm.value].copy(), pre, suf
 
     def null1(self, codes):
         d = dsq_of(codes); return self.L.ref_null1(self.h, d.ctypes.data, d.size - 2)

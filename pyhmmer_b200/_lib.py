@@ -69,6 +69,11 @@ class DomainRec(ctypes.Structure):
                 ("N", c_i32), ("text_offset", c_i64), ("has_rf", c_i32), ("has_cs", c_i32)]
 
 
+class WindowRec(ctypes.Structure):
+    """``b2h_window`` (include/b2h.h)."""
+    _fields_ = [("seq", c_i32), ("k", c_i32), ("n", c_i64), ("length", c_i32), ("score", c_float)]
+
+
 class B2HError(RuntimeError):
     def __init__(self, status, fn, detail=""):
         self.status = status
@@ -132,6 +137,9 @@ def _load():
         c_void_p, c_void_p, c_void_p, c_void_p)
     sig("b2h_generic_decoding", c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
         c_void_p, c_void_p, P(c_float), P(c_float), c_void_p, c_void_p, c_void_p)
+    sig("b2h_longtarget_windows", c_int, c_void_p, c_void_p, c_void_p, ctypes.c_double, P(c_void_p), P(c_size_t), P(c_void_p), P(c_size_t))
+    sig("b2h_free", None, c_void_p)
+    sig("b2h_window_lengths", c_int, c_void_p, c_void_p, c_void_p)
     sig("b2h_profile_create_host", c_int, P(OProfileDesc), P(c_void_p))
     sig("b2h_debug_domaindef", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, P(SearchParams), P(c_void_p))
     if hasattr(lib, "b2h_null_scores"):

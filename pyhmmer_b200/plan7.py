@@ -769,6 +769,29 @@ class HMMPressedFile:
         return om
 
 
+def long_target_windows(om, chunks, F1=0.02):
+    """First stage of the long-target (nhmmer) pipeline on the GPU: ``p7_SSVFilter_longtarget`` over every sequence of
+    ``chunks`` (the pieces a long target was cut into), then ``p7_pli_ExtendAndMergeWindows`` (p7_pipeline.c:1535-1565).
+    Returns ``(raw, merged)`` numpy record arrays with fields seq, k, n, length, score (`_lib.WindowRec`)."""
+    ctx = _lib.context()
+    block = chunks if isinstance(chunks, DigitalSequenceBlock) else DigitalSequenceBlock(om.alphabet, chunks)
+    if block.alphabet != om.alphabet:
+        raise AlphabetMismatch(om.alphabet, block.alphabet)
+    db = SequenceDatabase.of(ctx, block)
+    raw, mer = ctypes.c_void_p(), ctypes.c_void_p()
+    nr, nm = ctypes.c_size_t(), ctypes.c_size_t()
+    check(lib.b2h_longtarget_windows(ctx.handle, om._device(ctx), db.handle, float(F1), ctypes.byref(raw), ctypes.byref(nr),
+                                     ctypes.byref(mer), ctypes.byref(nm)), "b2h_longtarget_windows", ctx.handle)
+    try:
+        dt = np.dtype(_lib.WindowRec)
+        out = tuple(np.frombuffer(ctypes.string_at(ptr_, n_.value * dt.itemsize), dtype=dt).copy() if n_.value else np.zeros(0, dt)
+                    for ptr_, n_ in ((raw, nr), (mer, nm)))
+    finally:
+        lib.b2h_free(raw)
+        lib.b2h_free(mer)
+    return out
+
+
 class OptimizedProfileBlock(list):
     """An ordered block of `OptimizedProfile` sharing one alphabet (``pyhmmer.plan7.OptimizedProfileBlock``)."""
 

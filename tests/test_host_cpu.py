@@ -247,3 +247,23 @@ def test_pressed_database_errors(tmp_path):
     open(str(tmp_path / "bad.hmm.h3f"), "wb").write(b"\x00" * 64)           # wrong magic
     with pytest.raises(ValueError):
         plan7.HMMPressedFile(str(tmp_path / "bad.hmm")).read()
+
+
+@pytest.mark.parametrize("M", [5, 120, 700])
+def test_window_prefix_suffix_lengths(M):
+    """p7_hmm_ScoreDataComputeRest (p7_scoredata.c:313): the MAXL-based prefix/suffix tables that turn SSV diagonals into
+    windows -- host code, bit-identical (entry 0 of the suffix table is never written by the reference)."""
+    dna = easel.Alphabet.dna()
+    rng = np.random.default_rng(M)
+    h = synth.random_hmm(dna, M, rng, name="lt")
+    h.max_length = 3 * M
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import ModelPair
+    pair = ModelPair(h)
+    o = ctypes.c_void_p()
+    assert _lib.lib.b2h_profile_create_host(ctypes.byref(pair.om._desc), ctypes.byref(o)) == 0
+    pre, suf = np.zeros(M + 1, np.float32), np.zeros(M + 1, np.float32)
+    assert _lib.lib.b2h_window_lengths(o, _lib.ptr(pre), _lib.ptr(suf)) == 0
+    _lib.lib.b2h_profile_destroy(o)
+    _, _, _, rpre, rsuf = pair.ref.longtarget_windows(rng.integers(0, 4, 500).astype(np.uint8))
+    assert np.array_equal(pre, rpre) and np.array_equal(suf[1:], rsuf[1:])
