@@ -308,7 +308,10 @@ def main():
 
     # end-to-end through the public API with host buffers
     e2e_times = []
+    import gc
     for it in range(2 + max(3, K)):
+        res = None
+        gc.collect()                                              # (untimed) the previous step's result objects: keep collector pauses out of the next step
         flush.fill_(it & 0xff)
         barrier()
         t0 = time.perf_counter()
