@@ -272,6 +272,9 @@ void b2h_free(void *p);
 /* The prefix / suffix length tables [M+1] of p7_hmm_ScoreDataComputeRest for a profile (host only; works on a profile made by
  * b2h_profile_create_host). */
 int  b2h_window_lengths(const b2h_profile *p, float *prefix, float *suffix);
+/* p7_pli_ExtendAndMergeWindows (p7_pipeline.c:323) on a caller-provided list, in place (host only): target_len[i] = length of the
+ * chunk window i lies in; pct_overlap = 0 after SSV, 0.5 after Viterbi.  *nout = number of windows left. */
+int  b2h_extend_merge_windows(const b2h_profile *p, b2h_window *windows, size_t n, const int64_t *target_len, float pct_overlap, size_t *nout);
 
 /* Register tile the SSV kernel uses for a model of M nodes: G lanes per comparison (32/G comparisons per warp), NR packed
  * registers (2*NR nodes) per lane, and the number of 128-byte shared-memory wavefronts one DP row of one WARP moves

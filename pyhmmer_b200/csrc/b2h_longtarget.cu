@@ -244,9 +244,45 @@ void window_lengths(const b2h_profile *p, float *pre, float *suf)
   for (int k = 2; k < M; k++) pre[k] += pre[k - 1];
 }
 
+// p7_pli_ExtendAndMergeWindows (p7_pipeline.c:323-400), in place: every diagonal {n, k, length} becomes the window the
+// model could reach around it (max_length x the prefix / suffix share of the nodes before / after it, plus 10 %), then
+// windows of the same chunk that overlap by more than <pct_overlap> of the shorter one are fused.  Returns the new count.
+size_t extend_merge(const b2h_profile *p, b2h_window *w, size_t n, const int64_t *target_len, float pct_overlap)
+{
+  const int M = p->M, maxlen = p->max_length;
+  std::vector<float> pre(M + 1, 0.f), suf(M + 2, 0.f);
+  window_lengths(p, pre.data(), suf.data());
+  size_t nm = 0;
+  for (size_t i = 0; i < n; i++) {
+    b2h_window x = w[i];
+    const long long ws = (long long)std::max<double>(1.0, (double)x.n - ((double)maxlen * (0.1 + (double)pre[x.k - x.length + 1])));
+    const long long we = (long long)std::min<double>((double)target_len[i], (double)x.n + (double)x.length + ((double)maxlen * (0.1 + (double)suf[x.k])));
+    x.n = ws; x.length = (int32_t)(we - ws + 1);
+    if (nm > 0 && w[nm - 1].seq == x.seq) {
+      b2h_window &pv = w[nm - 1];
+      const long long os = std::max<long long>(pv.n, x.n), oe = std::min<long long>(pv.n + pv.length - 1, x.n + x.length - 1), ol = oe - os + 1;
+      if ((float)ol / (float)std::min(pv.length, x.length) > pct_overlap) {
+        const long long ms = std::min<long long>(pv.n, x.n), me = std::max<long long>(pv.n + pv.length - 1, x.n + x.length - 1);
+        pv.n = ms; pv.length = (int32_t)(me - ms + 1);
+        continue;
+      }
+    }
+    w[nm++] = x;
+  }
+  return nm;
+}
+
 } // namespace
 
 extern "C" void b2h_free(void *p) { free(p); }
+
+extern "C" int b2h_extend_merge_windows(const b2h_profile *p, b2h_window *windows, size_t n, const int64_t *target_len, float pct_overlap, size_t *nout)
+{
+  if (!p || (!windows && n) || (!target_len && n) || !nout || p->max_length <= 0) return B2H_EINVAL;
+  for (size_t i = 0; i < n; i++) if (windows[i].k < 1 || windows[i].k > p->M || windows[i].length < 1 || windows[i].k - windows[i].length + 1 < 0) return B2H_EINVAL;
+  *nout = extend_merge(p, windows, n, target_len, pct_overlap);
+  return B2H_OK;
+}
 
 extern "C" int b2h_window_lengths(const b2h_profile *p, float *prefix, float *suffix)
 {
@@ -315,29 +351,9 @@ extern "C" int b2h_longtarget_windows(b2h_ctx *ctx, const b2h_profile *p, const 
   b2h_window *mer = (b2h_window *)malloc(std::max<size_t>(1, hw.size()) * sizeof(b2h_window));
   if (!raw || !mer) { free(raw); free(mer); return B2H_EMEM; }
   for (size_t i = 0; i < hw.size(); i++) { raw[i].seq = hw[i].seq; raw[i].k = hw[i].k; raw[i].n = hw[i].n; raw[i].length = hw[i].length; raw[i].score = hw[i].score; }
-  const int M = p->M;
-  std::vector<float> pre(M + 1, 0.f), suf(M + 2, 0.f);
-  window_lengths(p, pre.data(), suf.data());
-  // extend every diagonal to a window, then merge overlapping windows of the same chunk (p7_pli_ExtendAndMergeWindows, pct_overlap = 0)
-  size_t nm = 0;
-  const int maxlen = p->max_length;
-  for (size_t i = 0; i < hw.size(); i++) {
-    const b2h_window &w = raw[i];
-    const long long tlen = db->h_len[w.seq];
-    long long ws = (long long)std::max<double>(1.0, (double)w.n - ((double)maxlen * (0.1 + (double)pre[w.k - w.length + 1])));
-    long long we = (long long)std::min<double>((double)tlen, (double)w.n + (double)w.length + ((double)maxlen * (0.1 + (double)suf[w.k])));
-    b2h_window x = w; x.n = ws; x.length = (int32_t)(we - ws + 1);
-    if (nm > 0 && mer[nm - 1].seq == x.seq) {
-      b2h_window &pv = mer[nm - 1];
-      const long long os = std::max(pv.n, x.n), oe = std::min(pv.n + pv.length - 1, x.n + x.length - 1), ol = oe - os + 1;
-      if ((float)ol / (float)std::min(pv.length, x.length) > 0.0f) {
-        const long long ms = std::min(pv.n, x.n), me = std::max(pv.n + pv.length - 1, x.n + x.length - 1);
-        pv.n = ms; pv.length = (int32_t)(me - ms + 1);
-        continue;
-      }
-    }
-    mer[nm++] = x;
-  }
+  std::vector<int64_t> tlen(hw.size());
+  for (size_t i = 0; i < hw.size(); i++) { mer[i] = raw[i]; tlen[i] = db->h_len[raw[i].seq]; }
+  const size_t nm = extend_merge(p, mer, hw.size(), tlen.data(), 0.0f);
   *raw_out = raw; *nraw_out = hw.size(); *merged_out = mer; *nmerged_out = nm;
   return B2H_OK;
 }

@@ -257,6 +257,7 @@ def test_window_prefix_suffix_lengths(M):
     rng = np.random.default_rng(M)
     h = synth.random_hmm(dna, M, rng, name="lt")
     h.max_length = 3 * M
+    h._evparam[:] = np.array([-8.0 - np.log2(M) * 0.3, 0.70, -9.0, 0.70, -4.0, 0.70], np.float32)
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from conftest import ModelPair
     pair = ModelPair(h)
@@ -264,6 +265,21 @@ def test_window_prefix_suffix_lengths(M):
     assert _lib.lib.b2h_profile_create_host(ctypes.byref(pair.om._desc), ctypes.byref(o)) == 0
     pre, suf = np.zeros(M + 1, np.float32), np.zeros(M + 1, np.float32)
     assert _lib.lib.b2h_window_lengths(o, _lib.ptr(pre), _lib.ptr(suf)) == 0
-    _lib.lib.b2h_profile_destroy(o)
-    _, _, _, rpre, rsuf = pair.ref.longtarget_windows(rng.integers(0, 4, 500).astype(np.uint8))
+    # ... and p7_pli_ExtendAndMergeWindows on the reference's own diagonals of a chunk with planted homologs
+    chunk = rng.integers(0, 4, 60000).astype(np.uint8)
+    for _ in range(12):
+        dom = synth.emit_sequence(pair.hmm, rng)
+        pos = int(rng.integers(0, len(chunk) - len(dom)))
+        chunk[pos:pos + len(dom)] = dom
+    pair.hmm._evparam[:] = h._evparam
+    rraw, rsc, rmer, rpre, rsuf = pair.ref.longtarget_windows(chunk)
     assert np.array_equal(pre, rpre) and np.array_equal(suf[1:], rsuf[1:])
+    if len(rraw):
+        w = np.zeros(len(rraw), dtype=np.dtype(_lib.WindowRec))
+        w["n"], w["k"], w["length"], w["score"] = rraw[:, 0], rraw[:, 1], rraw[:, 2], rsc
+        tl = np.full(len(rraw), len(chunk), np.int64)
+        nout = ctypes.c_size_t()
+        assert _lib.lib.b2h_extend_merge_windows(o, _lib.ptr(w), len(w), _lib.ptr(tl), 0.0, ctypes.byref(nout)) == 0
+        assert nout.value == len(rmer)
+        assert np.array_equal(w["n"][:nout.value], rmer[:, 0]) and np.array_equal(w["length"][:nout.value], rmer[:, 1])
+    _lib.lib.b2h_profile_destroy(o)
