@@ -207,3 +207,66 @@ float oracle_bias(const uint8_t *dsq, int L, int M, const float *eo /* [Kp][2] *
   { float last = 0.0f; last += d0 * 1.0f; last += d1 * 1.0f; logsc += (float)log((double)last); }
   return logsc + (float)L * logf(p1) + logf((float)(1. - (double)p1));
 }
+
+/* p7_SSVFilter_longtarget (impl_sse/msvfilter.c:256-413), one chunk, scalar: the MSV recurrence at a constant begin score
+ * with the byte saturations written out; when a cell of a row reaches sc_thresh the best cell is taken with the reference's
+ * striped tie-break (Q = p7O_NQB(M) vectors of 16: scan order q outer, lane z inner, node k = q + Q*z + 1), the diagonal is
+ * walked back to the begin level and extended while it keeps improving (5 non-improving steps end it), the window
+ * {n, k, length, score} is recorded, the row is zeroed and the scan resumes behind the diagonal.
+ * dsq[0..L-1]; cost[x*M + k-1]; tjb for the model's max_length.  win [cap][3] = n (1-based), k, length.  Returns the count. */
+int oracle_ssv_longtarget(const uint8_t *dsq, int L, int M, const uint8_t *cost, int tbm, int tec, int tjb, int base, int bias,
+                          float scale_b, int sc_thresh, int cap, int64_t *win, float *win_sc)
+{
+  int *row = calloc((size_t)M + 1, sizeof(int)), *nxt = calloc((size_t)M + 1, sizeof(int));
+  const int Q = imax(2, (M - 1) / 16 + 1);
+  const int tjbm = (tjb + tbm) & 0xff;
+  const int xB = imax(base - tjbm, 0);
+  int i, k, q, z, nwin = 0;
+  (void)tec;
+  for (i = 1; i <= L; i++) {
+    const uint8_t *c = cost + (size_t)dsq[i-1] * M;
+    int hit = 0;
+    nxt[0] = 0;
+    for (k = 1; k <= M; k++) {
+      int sv = imax(row[k-1], xB);
+      sv = imin(sv + bias, 255);
+      sv = imax(sv - (int)c[k-1], 0);
+      nxt[k] = sv;
+      if (sv >= sc_thresh) hit = 1;
+    }
+    { int *t = row; row = nxt; nxt = t; }
+    if (hit) {
+      int end = -1, rem_sc = -1, start, target_start, target_end, sc, n, max_end, max_sc, pos_since_max;
+      float ret_sc;
+      for (q = 0; q < Q; q++)
+        for (z = 0; z < 16; z++) {
+          k = q + Q * z + 1;
+          if (k <= M && row[k] >= sc_thresh && row[k] > rem_sc) { end = k; rem_sc = row[k]; }
+        }
+      for (k = 0; k <= M; k++) row[k] = 0;
+      start = end; target_end = target_start = i; sc = rem_sc;
+      while (rem_sc > base - tjb - tbm) {
+        rem_sc -= bias - (int)cost[(size_t)dsq[target_start-1] * M + (start-1)];
+        --start; --target_start;
+      }
+      start++; target_start++;
+      k = end + 1; n = target_end + 1; max_end = target_end; max_sc = sc; pos_since_max = 0;
+      while (k < M && n <= L) {
+        sc += bias - (int)cost[(size_t)dsq[n-1] * M + (k-1)];
+        if (sc >= max_sc) { max_sc = sc; max_end = n; pos_since_max = 0; }
+        else if (++pos_since_max == 5) break;
+        k++; n++;
+      }
+      end += max_end - target_end;
+      target_end = max_end;
+      ret_sc = ((float)(max_sc - tjb) - (float)base);
+      ret_sc /= scale_b;
+      ret_sc -= 3.0f;
+      if (nwin < cap) { win[nwin*3+0] = target_start; win[nwin*3+1] = end; win[nwin*3+2] = end - start + 1; win_sc[nwin] = ret_sc; }
+      nwin++;
+      i = target_end;
+    }
+  }
+  free(row); free(nxt);
+  return nwin;
+}

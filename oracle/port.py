@@ -28,6 +28,8 @@ def lib():
         L.oracle_vit.argtypes = [vp, ci, ci, vp, vp, ci, ci, ci, ci, cf, ctypes.POINTER(cf)]
         L.oracle_fwd.restype = ci
         L.oracle_fwd.argtypes = [vp, ci, ci, vp, vp, cf, cf, cf, ctypes.POINTER(cf)]
+        L.oracle_ssv_longtarget.restype = ci
+        L.oracle_ssv_longtarget.argtypes = [vp, ci, ci, vp, ci, ci, ci, ci, ci, cf, ci, ci, vp, vp]
         L.oracle_null1.restype = cf
         L.oracle_null1.argtypes = [ci]
         L.oracle_bias.restype = cf
@@ -84,6 +86,27 @@ class Port:
     def fwd(self, codes):
         _, _, pmove = _len_params(len(codes)); s = self.s
         return self._run(lib().oracle_fwd, codes, self.om.fwd_rsc.ctypes.data, self.om.fwd_tsc.ctypes.data, s["xfEm"], s["xfEl"], pmove)
+
+    def ssv_longtarget(self, codes, F1=0.02, cap=100000):
+        """oracle_ssv_longtarget on one chunk: (windows [n,3] = start, model end, length; scores).  The threshold is the
+        reference's formula (msvfilter.c:289-327) with the length model of the profile's max_length."""
+        import math
+        d = self.om._desc
+        maxL = int(d.max_length)
+        tjb, _, _ = _len_params(maxL)
+        f32 = np.float32
+        p1 = f32(maxL) / (f32(maxL) + f32(1.0))
+        nullsc = f32(float(maxL) * math.log(float(p1)) + math.log(1.0 - float(p1)))            # p7_bg_NullOne (p7_bg.c:357)
+        mu, lam = float(d.evparam[0]), float(d.evparam[1])
+        invP = f32(mu - math.log(-1.0 * math.log(1.0 - F1)) / lam)                             # esl_gumbel_invsurv
+        s = self.s
+        thr = int(math.ceil((float(nullsc) + float(invP) * 0.69314718055994529 + 3.0) * float(f32(s["scale_b"])) + s["base"] + s["tec"] + tjb)) & 0xff
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        win = np.zeros((cap, 3), np.int64); wsc = np.zeros(cap, np.float32)
+        n = lib().oracle_ssv_longtarget(codes.ctypes.data, codes.size, self.M, self.om.msv_cost.ctypes.data, s["tbm"], s["tec"], tjb,
+                                        s["base"], s["bias"], s["scale_b"], thr, cap, win.ctypes.data, wsc.ctypes.data)
+        assert n <= cap
+        return win[:n].copy(), wsc[:n].copy()
 
     @staticmethod
     def null1(L):

@@ -414,7 +414,8 @@ struct EnvGpu : b2h_env_backend {
       }
       std::vector<void *> keep;
       EnvDev ev;
-      ProfDev *d_prof; int32_t *d_pi, *d_seq, *d_i0, *d_Ld, *d_tcap; float *d_pmove; int64_t *d_moff, *d_moffn, *d_xoff, *d_toff;
+      ProfDev *d_prof = nullptr; int32_t *d_pi = nullptr, *d_seq = nullptr, *d_i0 = nullptr, *d_Ld = nullptr, *d_tcap = nullptr; float *d_pmove = nullptr;
+      int64_t *d_moff = nullptr, *d_moffn = nullptr, *d_xoff = nullptr, *d_toff = nullptr;
       int rc = B2H_OK;
       auto A = [&](int r) { if (rc == B2H_OK) rc = r; };
       A(dalloc(keep, &d_prof, hprof.size())); A(dalloc(keep, &d_pi, m)); A(dalloc(keep, &d_seq, m)); A(dalloc(keep, &d_i0, m)); A(dalloc(keep, &d_Ld, m));

@@ -92,3 +92,25 @@ def test_port_matches_ref(amino, make_pair, M):
         fa, fb = po.fwd(c), pair.ref.fwd(c)
         assert fa[1] == fb[1] == 0 and abs(fa[0] - fb[0]) <= 1e-4 + 2e-7 * abs(fb[0])
         assert po.null1(len(c)) == pair.ref.null1(c)
+
+
+@pytest.mark.parametrize("M", [9, 120, 700])
+def test_port_longtarget_scan_matches_ref(make_pair, M):
+    """oracle_ssv_longtarget (the scalar restatement of p7_SSVFilter_longtarget) against the reference itself: every
+    diagonal of a chunk with planted homologs -- start, model end, length, score -- identical, in order."""
+    from pyhmmer_b200 import easel
+    dna = easel.Alphabet.dna()
+    rng = np.random.default_rng(M)
+    h = synth.random_hmm(dna, M, rng, name="lt")
+    h.max_length = 3 * M
+    h._evparam[:] = np.array([-8.0 - np.log2(M) * 0.3, 0.70, -9.0, 0.70, -4.0, 0.70], np.float32)
+    pair = make_pair(h)
+    chunk = rng.integers(0, 4, 60000).astype(np.uint8)
+    for _ in range(12):
+        dom = synth.emit_sequence(pair.hmm, rng)
+        pos = int(rng.integers(0, len(chunk) - len(dom)))
+        chunk[pos:pos + len(dom)] = dom
+    rraw, rsc, _, _, _ = pair.ref.longtarget_windows(chunk)
+    w, sc = port.Port(pair.om).ssv_longtarget(chunk)
+    assert len(rraw) >= 10
+    assert np.array_equal(w, rraw) and np.array_equal(sc, rsc)
