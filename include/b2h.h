@@ -258,6 +258,27 @@ int b2h_profile_set_annotation(b2h_profile *p, const char *consensus, const char
 size_t b2h_seqdb_h2d_bytes(const b2h_seqdb *db);
 size_t b2h_profile_h2d_bytes(const b2h_profile *p);
 
+/* ---- pressed profile databases ------------------------------------------------------------------------------------
+ * Bulk reader for <db>.h3f + <db>.h3p (hmmpress, format 3/f), standing in for p7_oprofile_ReadMSV / p7_oprofile_ReadRest
+ * (vendor/hmmer/src/impl_sse/io.c:231, 498) when a whole database goes to the GPU.  b2h_pressed_read returns up to
+ * max_models descriptors whose table pointers point into ONE malloc'ed block of node-major tables (ready for
+ * b2h_profile_upload_many; desc.bgf and desc.degen are left for the caller, who knows the alphabet), plus the models'
+ * strings in one NUL-separated text block (offsets in the model records, -1 = absent).  *nread = 0 at the end of the
+ * database.  The three arrays are released with b2h_free.  Host only: no device is touched. */
+typedef struct b2h_pressed b2h_pressed;
+typedef struct {
+  b2h_oprofile_desc desc;
+  int32_t alphabet_type;                               /* eslRNA = 1, eslDNA = 2, eslAMINO = 3 (esl_alphabet.h) */
+  int32_t reserved;
+  int64_t name, acc, descr, rf, mm, cs, consensus;     /* offsets into the text block */
+} b2h_pressed_model;
+int  b2h_pressed_open(const char *base_path, b2h_pressed **out);
+void b2h_pressed_close(b2h_pressed *h);
+int  b2h_pressed_rewind(b2h_pressed *h);
+const char *b2h_pressed_last_error(const b2h_pressed *h);
+int  b2h_pressed_read(b2h_pressed *h, size_t max_models, b2h_pressed_model **models, size_t *nread,
+                      void **block, size_t *block_bytes, char **text, size_t *text_bytes);
+
 /* ---- long-target (nhmmer) path, first stage ------------------------------------------------------------------------
  * p7_SSVFilter_longtarget (vendor/hmmer/src/impl_sse/msvfilter.c:256) over every sequence of <db> (= the chunks a long
  * target was cut into; LongTargetsPipeline, plan7.pyx:7542-7663), with the model's length parameters set for its

@@ -74,6 +74,12 @@ class WindowRec(ctypes.Structure):
     _fields_ = [("seq", c_i32), ("k", c_i32), ("n", c_i64), ("length", c_i32), ("score", c_float)]
 
 
+class PressedModel(ctypes.Structure):
+    """``b2h_pressed_model`` (include/b2h.h)."""
+    _fields_ = [("desc", OProfileDesc), ("alphabet_type", c_i32), ("reserved", c_i32),
+                ("name", c_i64), ("acc", c_i64), ("descr", c_i64), ("rf", c_i64), ("mm", c_i64), ("cs", c_i64), ("consensus", c_i64)]
+
+
 class B2HError(RuntimeError):
     def __init__(self, status, fn, detail=""):
         self.status = status
@@ -141,6 +147,11 @@ def _load():
     sig("b2h_free", None, c_void_p)
     sig("b2h_window_lengths", c_int, c_void_p, c_void_p, c_void_p)
     sig("b2h_extend_merge_windows", c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_float, P(c_size_t))
+    sig("b2h_pressed_open", c_int, ctypes.c_char_p, P(c_void_p))
+    sig("b2h_pressed_close", None, c_void_p)
+    sig("b2h_pressed_rewind", c_int, c_void_p)
+    sig("b2h_pressed_last_error", ctypes.c_char_p, c_void_p)
+    sig("b2h_pressed_read", c_int, c_void_p, c_size_t, P(c_void_p), P(c_size_t), P(c_void_p), P(c_size_t), P(c_void_p), P(c_size_t))
     sig("b2h_profile_create_host", c_int, P(OProfileDesc), P(c_void_p))
     sig("b2h_debug_domaindef", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, P(SearchParams), P(c_void_p))
     if hasattr(lib, "b2h_null_scores"):

@@ -28,6 +28,7 @@ SOURCES = [
     "b2h_longtarget.cu",
     "b2h_search.cu",
     "b2h_domaindef.cpp",
+    "b2h_pressed.cpp",
 ]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -603,8 +603,9 @@ class OptimizedProfile:
         return None if st == _lib.B2H_ENORESULT else sc
 
 
-class HMMPressedFile:
-    """Iterate over the `OptimizedProfile` of a pressed HMM database (``pyhmmer.plan7.HMMPressedFile``, plan7.pyx:4051).
+class _PyPressedFile:
+    """Pure-Python reader of a pressed HMM database: the format documentation in executable form and the cross-check of
+    the C reader behind `HMMPressedFile` (tests/test_host_cpu.py).
 
     ``hmmpress`` writes every model's vectorised score tables to ``<db>.h3f`` (the MSV part, read by
     p7_oprofile_ReadMSV, impl_sse/io.c:231) and ``<db>.h3p`` (everything else, p7_oprofile_ReadRest, io.c:498) in the
@@ -767,6 +768,140 @@ class HMMPressedFile:
         om._evparam, om._cutoff, om._compo = evparam.copy(), cutoff.copy(), compo.copy()
         om.L, om.multihit = int(L), bool(d.mode_multihit)
         return om
+
+
+class _PressedBatch:
+    """One batch of b2h_pressed_read: owns the table block the batch's OptimizedProfile arrays are views of."""
+
+    def __init__(self, models, n, block, nbytes, text, ntext):
+        self.models, self.n, self.block, self.nbytes = models, n, block, nbytes
+        self.text = ctypes.string_at(text, ntext) if ntext else b""
+        lib.b2h_free(text)
+        self.buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(block.value)
+        self.base = block.value
+
+    def view(self, addr, dtype, rows, cols):
+        return np.frombuffer(self.buf, dtype=dtype, count=rows * cols, offset=addr - self.base).reshape(rows, cols)
+
+    def __del__(self):
+        try:
+            lib.b2h_free(self.models)
+            lib.b2h_free(self.block)
+        except Exception:
+            pass
+
+
+class HMMPressedFile:
+    """Iterate over the `OptimizedProfile` of a pressed HMM database (``pyhmmer.plan7.HMMPressedFile``, plan7.pyx:4051).
+
+    ``hmmpress`` writes every model's vectorised score tables to ``<db>.h3f`` (the MSV part, read by
+    p7_oprofile_ReadMSV, impl_sse/io.c:231) and ``<db>.h3p`` (everything else, p7_oprofile_ReadRest, io.c:498) in the
+    SSE build's striped layout.  The C library reads them in batches and de-stripes them straight into node-major
+    tables (``b2h_pressed_read``); no P7_HMM / P7_PROFILE is built and ``p7_oprofile_Convert`` never runs -- the path
+    hmmscan takes over a Pfam-sized database.  Format 3/f (HMMER 3.1b2 .. 3.4).
+    """
+
+    BATCH = 512
+    _ABC = {3: "amino", 2: "dna", 1: "rna"}               # eslAMINO / eslDNA / eslRNA (esl_alphabet.h)
+
+    def __init__(self, file):
+        base = os.fspath(file)
+        for ext in (".h3f", ".h3p"):
+            if not os.path.exists(base + ext):
+                raise ValueError("%r is not a pressed HMM database (%s is missing)" % (base, base + ext))
+        self.name = base
+        h = ctypes.c_void_p()
+        check(lib.b2h_pressed_open(base.encode(), ctypes.byref(h)), "b2h_pressed_open")
+        self._h = h
+        self._queue = []
+        self._alphabet = self._bg = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def close(self):
+        if self._h is not None:
+            lib.b2h_pressed_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def closed(self):
+        return self._h is None
+
+    def rewind(self):
+        check(lib.b2h_pressed_rewind(self._h), "b2h_pressed_rewind")
+        self._queue = []
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        om = self.read()
+        if om is None:
+            raise StopIteration
+        return om
+
+    def _fill(self):
+        models, block, text = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        n, nb, nt = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        st = lib.b2h_pressed_read(self._h, self.BATCH, ctypes.byref(models), ctypes.byref(n), ctypes.byref(block), ctypes.byref(nb),
+                                  ctypes.byref(text), ctypes.byref(nt))
+        if st != _lib.B2H_OK:
+            raise ValueError("%s: %s" % (self.name, (lib.b2h_pressed_last_error(self._h) or b"").decode()))
+        if n.value == 0:
+            return
+        batch = _PressedBatch(models, n.value, block, nb.value, text, nt.value)
+        recs = (_lib.PressedModel * n.value).from_address(models.value)
+        txt = batch.text
+
+        def s(off):
+            return None if off < 0 else txt[off:txt.index(b"\0", off)].decode("ascii")
+
+        out = []
+        for i in range(n.value):
+            r = recs[i]
+            d = r.desc
+            if self._alphabet is None:
+                abc = getattr(Alphabet, self._ABC[r.alphabet_type])()
+                self._alphabet, self._bg, self._atype = abc, Background(abc), r.alphabet_type
+                self._bgf = (ctypes.c_float * 20)(*([float(v) for v in self._bg.residue_frequencies] + [0.0] * (20 - abc.K)))
+                self._degen = ptr(abc.degen)
+            elif r.alphabet_type != self._atype:
+                raise AlphabetMismatch(self._alphabet, getattr(Alphabet, self._ABC[r.alphabet_type])())
+            abc = self._alphabet
+            M, Kp = d.M, d.Kp
+            om = OptimizedProfile(M, abc)
+            om._batch = batch                              # keeps the table block alive
+            om.msv_cost = batch.view(d.msv_cost, np.uint8, Kp, M)
+            om.vit_rsc = batch.view(d.vit_rsc, np.int16, Kp, M)
+            om.vit_tsc = batch.view(d.vit_tsc, np.int16, 8, M)
+            om.fwd_rsc = batch.view(d.fwd_rsc, np.float32, Kp, M)
+            om.fwd_tsc = batch.view(d.fwd_tsc, np.float32, 8, M)
+            d.bgf = self._bgf
+            d.degen = self._degen
+            om._desc, om._dev = d, {}
+            om.name, om.accession, om.description = s(r.name), s(r.acc), s(r.descr)
+            om.reference, om.model_mask, om.consensus_structure, om.consensus = s(r.rf), s(r.mm), s(r.cs), s(r.consensus)
+            om._evparam = np.array(d.evparam[:], np.float32)
+            om._cutoff = np.array(d.cutoff[:], np.float32)
+            om._compo = np.array(d.compo[:], np.float32)
+            om.L, om.multihit = int(d.L), bool(d.mode_multihit)
+            out.append(om)
+        out.reverse()
+        self._queue = out
+
+    def read(self):
+        if self._h is None:
+            raise ValueError("I/O operation on closed file")
+        if not self._queue:
+            self._fill()
+        return self._queue.pop() if self._queue else None
 
 
 def long_target_windows(om, chunks, F1=0.02):

@@ -221,6 +221,12 @@ def test_pressed_database_matches_conversion(amino, name):
     with gzip.open(os.path.join(gold, name + ".hmm.gz")) as f:
         hmms = list(plan7.HMMFile(f))
     assert len(oms) == len(hmms) >= 1
+    with plan7._PyPressedFile(os.path.join(gold, "pressed", name + ".hmm")) as pf:      # the format, parsed in pure Python
+        for om, py in zip(oms, pf):
+            assert all(np.array_equal(getattr(om, t), getattr(py, t)) for t in ("msv_cost", "vit_rsc", "vit_tsc", "fwd_rsc", "fwd_tsc"))
+            assert (om.name, om.accession, om.description, om.consensus, om.reference, om.consensus_structure, om.model_mask) == \
+                   (py.name, py.accession, py.description, py.consensus, py.reference, py.consensus_structure, py.model_mask)
+            assert list(om._desc.bgf) == list(py._desc.bgf) and om.L == py.L
     bg = plan7.Background(amino)
     for om, h in zip(oms, hmms):
         ref = plan7.Profile(h.M, amino).configure(h, bg, om.L).to_optimized()
