@@ -805,6 +805,7 @@ class HMMPressedFile:
     _ABC = {3: "amino", 2: "dna", 1: "rna"}               # eslAMINO / eslDNA / eslRNA (esl_alphabet.h)
 
     def __init__(self, file):
+        self._h = None
         base = os.fspath(file)
         for ext in (".h3f", ".h3p"):
             if not os.path.exists(base + ext):
