@@ -279,6 +279,18 @@ const char *b2h_pressed_last_error(const b2h_pressed *h);
 int  b2h_pressed_read(b2h_pressed *h, size_t max_models, b2h_pressed_model **models, size_t *nread,
                       void **block, size_t *block_bytes, char **text, size_t *text_bytes);
 
+/* Batched p7_ProfileConfig + p7_oprofile_Convert for a block of HMM queries (what Pipeline.search_hmm does per query,
+ * src/pyhmmer/plan7.pyx:5979-6013): t [(M+1)*7] and mat [(M+1)*K] as for b2h_profile_config.  The descriptors (malloc'ed
+ * array of n) point into ONE malloc'ed block of node-major tables; both are released with b2h_free.  Host only. */
+typedef struct {
+  int32_t M, max_length;
+  const float *t, *mat;
+  float evparam[B2H_NEVPARAM], cutoff[B2H_NCUTOFFS], compo[B2H_MAXABET];
+} b2h_hmm_desc;
+int  b2h_hmm_convert_many(int K, int Kp, const uint8_t *degen, const float *bgf, int L, int multihit,
+                          const b2h_hmm_desc *hmms, size_t n, int nthreads,
+                          b2h_oprofile_desc **descs, void **block, size_t *block_bytes);
+
 /* ---- long-target (nhmmer) path, first stage ------------------------------------------------------------------------
  * p7_SSVFilter_longtarget (vendor/hmmer/src/impl_sse/msvfilter.c:256) over every sequence of <db> (= the chunks a long
  * target was cut into; LongTargetsPipeline, plan7.pyx:7542-7663), with the model's length parameters set for its

@@ -80,6 +80,12 @@ class PressedModel(ctypes.Structure):
                 ("name", c_i64), ("acc", c_i64), ("descr", c_i64), ("rf", c_i64), ("mm", c_i64), ("cs", c_i64), ("consensus", c_i64)]
 
 
+class HMMDesc(ctypes.Structure):
+    """``b2h_hmm_desc`` (include/b2h.h)."""
+    _fields_ = [("M", c_i32), ("max_length", c_i32), ("t", c_void_p), ("mat", c_void_p),
+                ("evparam", c_float * 6), ("cutoff", c_float * 6), ("compo", c_float * 20)]
+
+
 class B2HError(RuntimeError):
     def __init__(self, status, fn, detail=""):
         self.status = status
@@ -147,6 +153,8 @@ def _load():
     sig("b2h_free", None, c_void_p)
     sig("b2h_window_lengths", c_int, c_void_p, c_void_p, c_void_p)
     sig("b2h_extend_merge_windows", c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_float, P(c_size_t))
+    sig("b2h_hmm_convert_many", c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int,
+        P(c_void_p), P(c_void_p), P(c_size_t))
     sig("b2h_pressed_open", c_int, ctypes.c_char_p, P(c_void_p))
     sig("b2h_pressed_close", None, c_void_p)
     sig("b2h_pressed_rewind", c_int, c_void_p)

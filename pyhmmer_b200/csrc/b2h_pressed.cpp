@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 #include "b2h.h"
 
@@ -153,6 +154,57 @@ int b2h_pressed_read(b2h_pressed *h, size_t max_models, b2h_pressed_model **mode
   }
   memcpy(tx, text.data(), text.size());
   *models_out = mo; *nread = models.size(); *block_out = block; *block_bytes = off; *text_out = tx; *text_bytes = text.size();
+  return B2H_OK;
+}
+
+// Batched form of p7_ProfileConfig + p7_oprofile_Convert (b2h_profile_config, b2h_oprofile_convert) for a block of HMM
+// queries: the models are converted on <nthreads> host threads into ONE block of node-major tables, descriptors pointing
+// into it -- what Pipeline.search_hmm does per query (plan7.pyx:5979-6013), once per query block.
+int b2h_hmm_convert_many(int K, int Kp, const uint8_t *degen, const float *bgf, int L, int multihit,
+                         const b2h_hmm_desc *hmms, size_t n, int nthreads,
+                         b2h_oprofile_desc **descs_out, void **block_out, size_t *block_bytes)
+{
+  if (!degen || !bgf || (!hmms && n) || !descs_out || !block_out || !block_bytes || K < 1 || K > B2H_MAXABET || Kp < K + 3 || Kp > B2H_MAXCODE) return B2H_EINVAL;
+  *descs_out = nullptr; *block_out = nullptr; *block_bytes = 0;
+  if (n == 0) return B2H_OK;
+  std::vector<size_t> base(n + 1, 0);
+  for (size_t i = 0; i < n; i++) {
+    if (hmms[i].M < 1 || !hmms[i].t || !hmms[i].mat) return B2H_EINVAL;
+    const size_t M = hmms[i].M;
+    base[i + 1] = base[i] + (((size_t)Kp * M * (1 + 2 + 4) + (size_t)8 * M * (2 + 4) + 96 + 15) & ~(size_t)15);
+  }
+  uint8_t *block = (uint8_t *)malloc(base[n]);
+  b2h_oprofile_desc *descs = (b2h_oprofile_desc *)calloc(n, sizeof(b2h_oprofile_desc));
+  if (!block || !descs) { free(block); free(descs); return B2H_EMEM; }
+  std::vector<int> status(n, B2H_OK);
+  const int T = (int)std::min<size_t>((size_t)std::max(1, nthreads), n);
+  auto work = [&](int t) {
+    std::vector<float> tsc, msc; float xsc[8];
+    for (size_t i = t; i < n; i += T) {
+      const b2h_hmm_desc &h = hmms[i];
+      const int M = h.M;
+      tsc.resize((size_t)M * 8); msc.resize((size_t)Kp * (M + 1));
+      int st = b2h_profile_config(M, K, Kp, degen, h.t, h.mat, bgf, L, multihit, tsc.data(), msc.data(), xsc);
+      size_t off = base[i];
+      auto take = [&](size_t bytes) { void *p = block + off; off = (off + bytes + 15) & ~(size_t)15; return p; };
+      const size_t KM = (size_t)Kp * M, TM = (size_t)8 * M;
+      float *fr = (float *)take(KM * 4), *ft = (float *)take(TM * 4);
+      int16_t *vr = (int16_t *)take(KM * 2), *vt = (int16_t *)take(TM * 2);
+      uint8_t *mc = (uint8_t *)take(KM);
+      b2h_oprofile_desc &d = descs[i];
+      if (st == B2H_OK) st = b2h_oprofile_convert(M, K, Kp, L, multihit, tsc.data(), msc.data(), xsc, mc, vr, vt, fr, ft, &d);
+      d.msv_cost = mc; d.vit_rsc = vr; d.vit_tsc = vt; d.fwd_rsc = fr; d.fwd_tsc = ft;
+      d.max_length = h.max_length;
+      memcpy(d.evparam, h.evparam, sizeof d.evparam); memcpy(d.cutoff, h.cutoff, sizeof d.cutoff); memcpy(d.compo, h.compo, sizeof d.compo);
+      for (int x = 0; x < B2H_MAXABET; x++) d.bgf[x] = x < K ? bgf[x] : 0.0f;
+      d.degen = degen;
+      status[i] = st;
+    }
+  };
+  if (T <= 1) work(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
+  for (size_t i = 0; i < n; i++) if (status[i] != B2H_OK) { const int st = status[i]; free(block); free(descs); return st; }
+  *descs_out = descs; *block_out = block; *block_bytes = base[n];
   return B2H_OK;
 }
 

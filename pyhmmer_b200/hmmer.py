@@ -87,7 +87,7 @@ def hmmscan(queries, profiles, *, cpus=0, callback=None, backend="threading", ba
     options.setdefault("host_threads", cpus or 0)
     pipeline = Pipeline(alphabet, background=background, **options)
     # convert HMM / Profile targets once (the reference does the same up front, _hmmscan.py:191-215)
-    oms = OptimizedProfileBlock(alphabet, [pipeline._optimized(t, pipeline.L_HINT) for t in targets])
+    oms = OptimizedProfileBlock(alphabet, pipeline._optimized_many(list(targets), pipeline.L_HINT))
     total = 0
     batch = []
 

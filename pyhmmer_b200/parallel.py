@@ -162,7 +162,7 @@ def search_sharded(pipeline, queries, block, local, world):
     """One query batch against the sharded database; every rank returns the same list of `TopHits`."""
     lo, sub = local
     L = len(block[0]) if len(block) else pipeline.L_HINT
-    oms = [pipeline._optimized(q, L) for q in queries]
+    oms = pipeline._optimized_many(queries, L)
     if len(sub):
         hits, doms, text, counters = pipeline._run(oms, sub)
     else:

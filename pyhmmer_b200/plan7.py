@@ -791,6 +791,76 @@ class _PressedBatch:
             pass
 
 
+class _ConvertedBlock:
+    """The descriptors and the table block of one b2h_hmm_convert_many call; the OptimizedProfile arrays are views of it."""
+
+    def __init__(self, descs, n, block, nbytes):
+        self.descs, self.n, self.block = descs, n, block
+        self.buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(block.value)
+        self.base = block.value
+
+    view = _PressedBatch.view
+
+    def __del__(self):
+        try:
+            lib.b2h_free(self.descs)
+            lib.b2h_free(self.block)
+        except Exception:
+            pass
+
+
+def _convert_hmms(hmms, background, L, multihit=True, threads=0):
+    """`OptimizedProfile` of every HMM of a list, configured for target length ``L`` against ``background``: the
+    per-query ``Profile.configure`` + ``to_optimized`` of Pipeline.search_hmm (plan7.pyx:5979-6013) run for the whole
+    query block by the host library on its own threads (``b2h_hmm_convert_many``), tables in one block."""
+    n = len(hmms)
+    if n == 0:
+        return []
+    abc = background.alphabet
+    K, Kp = abc.K, abc.Kp
+    bgf = np.ascontiguousarray(background.residue_frequencies, dtype=np.float32)
+    keep = []
+    arr = (_lib.HMMDesc * n)()
+    for i, hmm in enumerate(hmms):
+        if hmm.alphabet != abc:
+            raise AlphabetMismatch(abc, hmm.alphabet)
+        t = np.ascontiguousarray(hmm.transition_probabilities, dtype=np.float32)
+        mat = np.ascontiguousarray(hmm.match_emissions, dtype=np.float32)
+        keep.append((t, mat))
+        h = arr[i]
+        h.M, h.max_length = hmm.M, int(hmm.max_length)
+        h.t, h.mat = t.ctypes.data, mat.ctypes.data
+        h.evparam[:] = hmm._evparam.tolist()
+        h.cutoff[:] = hmm._cutoff.tolist()
+        h.compo[:] = hmm._compo.tolist()
+    descs, block, nb = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t()
+    nthreads = int(threads) if threads else min(n, max(1, len(os.sched_getaffinity(0))))
+    check(lib.b2h_hmm_convert_many(K, Kp, ptr(abc.degen), ptr(bgf), int(L), int(bool(multihit)), arr, n, nthreads,
+                                   ctypes.byref(descs), ctypes.byref(block), ctypes.byref(nb)), "b2h_hmm_convert_many")
+    blk = _ConvertedBlock(descs, n, block, nb.value)
+    blk.keep = (bgf, abc.degen)                            # the descriptors point at these
+    recs = (OProfileDesc * n).from_address(descs.value)
+    out = []
+    for i, hmm in enumerate(hmms):
+        d = recs[i]
+        M = hmm.M
+        om = OptimizedProfile(M, abc)
+        om._batch = blk                                    # keeps the table block alive
+        om.msv_cost = blk.view(d.msv_cost, np.uint8, Kp, M)
+        om.vit_rsc = blk.view(d.vit_rsc, np.int16, Kp, M)
+        om.vit_tsc = blk.view(d.vit_tsc, np.int16, 8, M)
+        om.fwd_rsc = blk.view(d.fwd_rsc, np.float32, Kp, M)
+        om.fwd_tsc = blk.view(d.fwd_tsc, np.float32, 8, M)
+        om._desc, om._dev = d, {}
+        om.name, om.accession, om.description = hmm.name, hmm.accession, hmm.description
+        om.consensus = hmm.consensus
+        om.reference, om.consensus_structure = hmm.reference, hmm.consensus_structure
+        om._evparam, om._cutoff, om._compo = hmm._evparam.copy(), hmm._cutoff.copy(), hmm._compo.copy()
+        om.L, om.multihit = int(L), bool(multihit)
+        out.append(om)
+    return out
+
+
 class HMMPressedFile:
     """Iterate over the `OptimizedProfile` of a pressed HMM database (``pyhmmer.plan7.HMMPressedFile``, plan7.pyx:4051).
 
@@ -1265,6 +1335,14 @@ class Pipeline:
             return query.to_optimized()
         raise TypeError("Expected HMM, Profile or OptimizedProfile, found %s" % type(query).__name__)
 
+    def _optimized_many(self, queries, L):
+        """``_optimized`` for a block of queries: the HMMs among them are configured and converted in one library call."""
+        idx = [i for i, q in enumerate(queries) if isinstance(q, HMM)]
+        if len(idx) < 4:
+            return [self._optimized(q, L) for q in queries]
+        conv = dict(zip(idx, _convert_hmms([queries[i] for i in idx], self.background, L, threads=self.host_threads)))
+        return [conv[i] if i in conv else self._optimized(q, L) for i, q in enumerate(queries)]
+
     def _params_struct(self):
         return _lib.SearchParams(self.F1, self.F2, self.F3, int(self.bias_filter), int(self.null2), self.seed, int(self.host_threads))
 
@@ -1362,7 +1440,7 @@ class Pipeline:
         if sequences and len(sequences.largest()) > 100000:
             raise ValueError("sequence length over comparison pipeline limit (100000)")
         L = len(sequences[0]) if len(sequences) else self.L_HINT
-        oms = [self._optimized(q, L) for q in queries]
+        oms = self._optimized_many(queries, L)
         if len(sequences):
             hits, doms, text, counters = self._run(oms, sequences)
         else:
@@ -1404,7 +1482,7 @@ class Pipeline:
     def _scan_many(self, queries, targets):
         if any(q.alphabet != self.alphabet for q in queries):
             raise AlphabetMismatch(self.alphabet, [q.alphabet for q in queries if q.alphabet != self.alphabet][0])
-        oms = [self._optimized(t, self.L_HINT) for t in targets]
+        oms = self._optimized_many(targets, self.L_HINT)
         cuts = [self._cutoffs(om) for om in oms]
         block = DigitalSequenceBlock(self.alphabet, queries)
         if oms and len(block):

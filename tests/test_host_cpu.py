@@ -242,6 +242,45 @@ def test_pressed_database_matches_conversion(amino, name):
         assert list(om._desc.compo) == list(ref._desc.compo)
 
 
+@pytest.mark.parametrize("threads", [1, 3])
+def test_batched_conversion_matches_per_model(amino, threads):
+    """b2h_hmm_convert_many (the query-block form of Profile.configure + to_optimized, plan7.pyx:5979-6013): tables and
+    every descriptor scalar are bit-identical to the per-model path, for synthetic and for the reference's own models."""
+    import gzip
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data")
+    rng = np.random.default_rng(11)
+    hmms = [synth.random_hmm(amino, int(m), rng) for m in [1, 2, 3, 15, 16, 17, 255, 256, 700] + list(rng.integers(4, 400, 20))]
+    for name in ("Thioesterase", "PF02826", "KR"):
+        with gzip.open(os.path.join(gold, name + ".hmm.gz")) as f:
+            hmms += list(plan7.HMMFile(f))
+    bg = plan7.Background(amino)
+    for L in (400, 37):
+        many = plan7._convert_hmms(hmms, bg, L, threads=threads)
+        assert len(many) == len(hmms)
+        for h, om in zip(hmms, many):
+            ref = plan7.Profile(h.M, amino).configure(h, bg, L).to_optimized()
+            assert (om.name, om.accession, om.M, om.L, om.multihit) == (ref.name, ref.accession, ref.M, ref.L, ref.multihit)
+            assert (om.consensus, om.reference, om.consensus_structure) == (ref.consensus, ref.reference, ref.consensus_structure)
+            for t in ("msv_cost", "vit_rsc", "vit_tsc", "fwd_rsc", "fwd_tsc"):
+                a, b = getattr(om, t), getattr(ref, t)
+                assert a.shape == b.shape and a.dtype == b.dtype and a.tobytes() == b.tobytes(), t
+            for fld, _ in om._desc._fields_:
+                if fld in ("msv_cost", "vit_rsc", "vit_tsc", "fwd_rsc", "fwd_tsc", "degen"):
+                    continue
+                a, b = getattr(om._desc, fld), getattr(ref._desc, fld)
+                assert (bytes(a) == bytes(b)) if hasattr(a, "__len__") else (a == b), fld
+            assert np.array_equal(om._evparam, ref._evparam) and np.array_equal(om._cutoff, ref._cutoff)
+    # a Pipeline takes the batched path for blocks of HMM queries and leaves Profile / OptimizedProfile queries alone
+    pli = object.__new__(plan7.Pipeline)                  # no device here: only the query preparation is exercised
+    pli.alphabet, pli.background, pli.host_threads = amino, bg, threads
+    pre = plan7.Profile(hmms[3].M, amino).configure(hmms[3], bg, 99).to_optimized()
+    mixed = pli._optimized_many(hmms[:6] + [pre], 123)
+    assert mixed[-1] is pre and all(o.L == 123 for o in mixed[:6]) and [o.M for o in mixed[:6]] == [h.M for h in hmms[:6]]
+    assert plan7._convert_hmms([], bg, 400) == []
+    with pytest.raises(Exception):
+        plan7._convert_hmms([synth.random_hmm(easel.Alphabet.dna(), 10, rng)], bg, 400)
+
+
 def test_pressed_database_errors(tmp_path):
     from pyhmmer_b200 import plan7
     with pytest.raises(ValueError):
