@@ -309,6 +309,25 @@ int  b2h_window_lengths(const b2h_profile *p, float *prefix, float *suffix);
  * chunk window i lies in; pct_overlap = 0 after SSV, 0.5 after Viterbi.  *nout = number of windows left. */
 int  b2h_extend_merge_windows(const b2h_profile *p, b2h_window *windows, size_t n, const int64_t *target_len, float pct_overlap, size_t *nout);
 
+/* The Viterbi stage of the long-target pipeline (p7_pli_postSSV_LongTarget, p7_pipeline.c:1369-1412) for the SSV windows
+ * that passed the MSV and bias gates: <windows> holds one sequence per window (the window's residues); filtersc[i] = the
+ * null1 score at min(window, max_length) plus the B2-scaled bias correction, as the caller computed it; active[i] = 0 skips
+ * a window (NULL = all).  Every window is scanned by p7_ViterbiFilter_longtarget (impl_sse/vitfilter.c:292) with the profile
+ * configured for min(window, max_length) (p7_oprofile_ReconfigRestLength) and the score threshold of P-value F2.
+ * <marks>: the landmarks {seq = window, n = row i, k, length 1} in the reference's order; <out>: the windows handed to the
+ * Forward stage after p7_pli_ExtendAndMergeWindows(.., 0.5) and the 80 kb cut, {seq = window, n = start inside the window,
+ * length}.  Both malloc'ed (b2h_free).  B2H_EINVAL for models without max_length or above 1536 nodes. */
+int  b2h_longtarget_viterbi_windows(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *windows, const float *filtersc,
+                                    const uint8_t *active, double F2,
+                                    b2h_window **marks, size_t *nmarks, b2h_window **out, size_t *nout);
+/* The host half of the call above on its own (host only; works on a profile made by b2h_profile_create_host): <marks> is put
+ * into the reference's order in place, then extended / merged / cut into <out>.  window_len[w] = length of window w. */
+int  b2h_longtarget_vit_finish(const b2h_profile *p, b2h_window *marks, size_t nmarks, const int32_t *window_len, size_t nwindows,
+                               b2h_window **out, size_t *nout);
+/* The int16 score threshold and the N/C/J move score p7_ViterbiFilter_longtarget works with for a window whose profile is
+ * configured for cfg_len (vitfilter.c:330-346; host only). */
+int  b2h_longtarget_vit_threshold(const b2h_profile *p, int cfg_len, float filtersc, double F2, int32_t *thresh, int32_t *xw_move);
+
 /* Register tile the SSV kernel uses for a model of M nodes: G lanes per comparison (32/G comparisons per warp), NR packed
  * registers (2*NR nodes) per lane, and the number of 128-byte shared-memory wavefronts one DP row of one WARP moves
  * (emission loads + shuffles) -- the quantity bench.py's on-chip roofline is computed from.  B2H_EINVAL if M > 3071. */

@@ -270,3 +270,57 @@ int oracle_ssv_longtarget(const uint8_t *dsq, int L, int M, const uint8_t *cost,
   free(row); free(nxt);
   return nwin;
 }
+
+/* p7_ViterbiFilter_longtarget (impl_sse/vitfilter.c:292-497), one window, scalar.  The row recurrence of p7_ViterbiFilter
+ * without its overflow test; when the row's best match cell xE reaches sc_thresh, every node k holding xE is recorded as a
+ * landmark (i, k) in the reference's striped order (Q = p7O_NQW(M) vectors of 8: q outer, lane z inner, k = q + Q*z + 1), the
+ * three rows are reset to -32768 and the special states keep their values from the previous row (:411-425).  Otherwise the
+ * specials are updated and the D->D paths are closed only when Dmax + ddbound_w > xB (the lazy-F test, :450); when they are
+ * not, the row keeps its M->D values alone (:483-487).  dsq[0..L-1]; rsc[x*M+k-1], tsc[t*M+k-1]; xw_move for the length the
+ * caller configured (p7_oprofile_ReconfigRestLength).  hit [cap][2] = i (1-based), k.  Returns the number of landmarks. */
+int oracle_vit_longtarget(const uint8_t *dsq, int L, int M, const int16_t *rsc, const int16_t *tsc,
+                          int xw_E_move, int xw_E_loop, int xw_move, int base_w, int ddbound_w, int sc_thresh, int cap, int64_t *hit)
+{
+  const int16_t *tBM = tsc, *tMM = tsc + M, *tIM = tsc + 2*M, *tDM = tsc + 3*M, *tMD = tsc + 4*M, *tMI = tsc + 5*M, *tII = tsc + 6*M, *tDD = tsc + 7*M;
+  const int Q = imax(2, (M - 1) / 8 + 1);
+  size_t n = (size_t)M + 2;
+  int *Mp = malloc(n * sizeof(int)), *Ip = malloc(n * sizeof(int)), *Dp = malloc(n * sizeof(int));
+  int *Mc = malloc(n * sizeof(int)), *Ic = malloc(n * sizeof(int)), *Dc = malloc(n * sizeof(int));
+  int i, k, q, z, nhit = 0, xN = base_w, xB = (int16_t)(xN + xw_move), xJ = -32768, xC = -32768;
+  for (k = 0; k <= M + 1; k++) Mp[k] = Ip[k] = Dp[k] = -32768;
+  for (i = 1; i <= L; i++) {
+    const int16_t *r = rsc + (size_t)dsq[i-1] * M;
+    int xE = -32768, Dmax = -32768;
+    Mc[0] = Ic[0] = Dc[0] = -32768; Dc[1] = -32768;
+    for (k = 1; k <= M; k++) {
+      int m = sat16(xB + tBM[k-1]);
+      m = imax(m, sat16(Mp[k-1] + tMM[k-1]));
+      m = imax(m, sat16(Ip[k-1] + tIM[k-1]));
+      m = imax(m, sat16(Dp[k-1] + tDM[k-1]));
+      m = sat16(m + r[k-1]);
+      Mc[k] = m;
+      if (m > xE) xE = m;
+      Ic[k] = imax(sat16(Mp[k] + tMI[k-1]), sat16(Ip[k] + tII[k-1]));
+      Dc[k+1] = sat16(m + tMD[k-1]);
+    }
+    /* Dmaxv covers the M->D value of every striped cell, node M's (tMD = -32768 there) and the padding cells' included */
+    for (k = 2; k <= M + 1; k++) if (Dc[k] > Dmax) Dmax = Dc[k];
+    if (xE >= sc_thresh) {
+      for (q = 0; q < Q; q++)
+        for (z = 0; z < 8; z++) {
+          k = q + Q * z + 1;
+          if (k <= M && Mc[k] == xE) { if (nhit < cap) { hit[nhit*2] = i; hit[nhit*2+1] = k; } nhit++; }
+        }
+      for (k = 0; k <= M + 1; k++) Mc[k] = Ic[k] = Dc[k] = -32768;
+    } else {
+      xC = (int16_t)imax(xC, xE + xw_E_move);
+      xJ = (int16_t)imax(xJ, xE + xw_E_loop);
+      xB = (int16_t)imax(xJ + xw_move, xN + xw_move);
+      if (Dmax + ddbound_w > xB)
+        for (k = 2; k <= M; k++) Dc[k] = imax(Dc[k], sat16(Dc[k-1] + tDD[k-2]));
+    }
+    { int *t; t = Mp; Mp = Mc; Mc = t; t = Ip; Ip = Ic; Ic = t; t = Dp; Dp = Dc; Dc = t; }
+  }
+  free(Mp); free(Ip); free(Dp); free(Mc); free(Ic); free(Dc);
+  return nhit;
+}

@@ -30,6 +30,8 @@ def lib():
         L.oracle_fwd.argtypes = [vp, ci, ci, vp, vp, cf, cf, cf, ctypes.POINTER(cf)]
         L.oracle_ssv_longtarget.restype = ci
         L.oracle_ssv_longtarget.argtypes = [vp, ci, ci, vp, ci, ci, ci, ci, ci, cf, ci, ci, vp, vp]
+        L.oracle_vit_longtarget.restype = ci
+        L.oracle_vit_longtarget.argtypes = [vp, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
         L.oracle_null1.restype = cf
         L.oracle_null1.argtypes = [ci]
         L.oracle_bias.restype = cf
@@ -107,6 +109,31 @@ class Port:
                                         s["base"], s["bias"], s["scale_b"], thr, cap, win.ctypes.data, wsc.ctypes.data)
         assert n <= cap
         return win[:n].copy(), wsc[:n].copy()
+
+    def vit_longtarget_threshold(self, cfg_len, filtersc, F2=3e-3):
+        """The int16 score threshold p7_ViterbiFilter_longtarget derives from a P-value (vitfilter.c:330-346): float invP,
+        double arithmetic inside ceil(), truncation to int16."""
+        import math
+        d = self.om._desc
+        _, xw_move, _ = _len_params(cfg_len)
+        mu, lam = float(d.evparam[2]), float(d.evparam[3])                                     # p7_VMU, p7_VLAMBDA
+        log_part = (math.pow(F2, F2) - 1.0) / F2 if F2 < 5e-9 else math.log(-1.0 * math.log(1.0 - F2))   # esl_gumbel_invsurv
+        invP = float(np.float32(mu - log_part / lam))
+        s = self.s
+        inner = (float(np.float32(filtersc)) + 0.69314718055994529 * invP + 3.0) * float(np.float32(s["scale_w"]))
+        t = int(math.ceil(inner - float(s["xwEm"]) - float(xw_move) + float(s["base_w"])))
+        return ((t + 32768) & 0xffff) - 32768, xw_move
+
+    def vit_longtarget(self, codes, cfg_len, filtersc, F2=3e-3, cap=100000):
+        """oracle_vit_longtarget on one window with the length model of <cfg_len>: landmarks [n,2] = i, k."""
+        thr, xw_move = self.vit_longtarget_threshold(cfg_len, filtersc, F2)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        s = self.s
+        hit = np.zeros((cap, 2), np.int64)
+        n = lib().oracle_vit_longtarget(codes.ctypes.data, codes.size, self.M, self.om.vit_rsc.ctypes.data, self.om.vit_tsc.ctypes.data,
+                                        s["xwEm"], s["xwEl"], xw_move, s["base_w"], int(self.om._desc.ddbound_w), thr, cap, hit.ctypes.data)
+        assert n <= cap
+        return hit[:n].copy()
 
     @staticmethod
     def null1(L):

@@ -254,6 +254,183 @@ int ref_longtarget_windows(REFM *m, const uint8_t *dsq, int L, double F1, int ca
   return eslOK;
 }
 
+/* The window-level stages of nhmmer for one target chunk, restated from the reference's own (static) functions with the
+ * reference's public calls in the same order, so that every intermediate is observable:
+ *   p7_Pipeline_LongTarget (p7_pipeline.c:1496-1706): SSV scan, extend/merge, then per window null1, bias FilterScore,
+ *     p7_MSVFilter at the window's length, F1 gate;
+ *   p7_pli_postSSV_LongTarget (:1331-1436): B1-scaled bias gate, null1 at min(window, max_length), B2-scaled filter score,
+ *     p7_oprofile_ReconfigRestLength, p7_ViterbiFilter_longtarget, p7_pli_ExtendAndMergeWindows(.., 0.5), 80 kb splitting;
+ *   p7_pli_postViterbi_LongTarget (:1065-1112): null1, bias, ReconfigRestLength(window), p7_ForwardParser, B3-scaled F3 gate.
+ * ref_longtarget_pipeline (below) runs the real p7_Pipeline_LongTarget; tests check that both give the same pos_past_* counters.
+ *   msvwin  [cap][2] = n, length           msvsc [cap][3] = null1, FilterScore, MSV score     msvflag: bit0 passed F1, bit1 passed bias gate
+ *   vithit  [cap][3] = msv window, i, k    (every landmark p7_ViterbiFilter_longtarget records, in its order)
+ *   vitwin  [cap][3] = msv window, n (in the msv window's coordinates), length      vitsc [cap][3] = null1, FilterScore, Forward score
+ *   vitpass [cap]    = passed F3          counters [4] = pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd */
+int ref_longtarget_stages(REFM *m, const uint8_t *dsq, int L, double F1, double F2, double F3, int do_bias, int B1, int B2, int B3, int cap,
+                          int *n_msvwin, int64_t *msvwin, float *msvsc, int *msvflag,
+                          int *n_vithit, int64_t *vithit, int *n_vitwin, int64_t *vitwin, float *vitsc, int *vitpass, long *counters)
+{
+  P7_OPROFILE *om = m->om;
+  P7_BG *bg = m->bg;
+  P7_SCOREDATA *data = p7_hmm_ScoreDataCreate(om, NULL);
+  P7_HMM_WINDOWLIST wl, vl;
+  int w, i, nh = 0, nv = 0;
+  counters[0] = counters[1] = counters[2] = counters[3] = 0;
+  wl.windows = NULL; vl.windows = NULL;
+  p7_hmmwindow_init(&wl);
+  p7_bg_SetFilter(bg, om->M, om->compo);                 /* p7_pli_NewModel (p7_pipeline.c:514) */
+  p7_omx_GrowTo(m->ox, om->M, 0, om->max_length);
+  p7_oprofile_ReconfigMSVLength(om, om->max_length);
+  p7_SSVFilter_longtarget(dsq, L, om, m->ox, data, bg, F1, &wl);
+  *n_msvwin = 0; *n_vithit = 0; *n_vitwin = 0;
+  if (wl.count > 0) {
+    p7_hmm_ScoreDataComputeRest(om, data);
+    p7_pli_ExtendAndMergeWindows(om, data, &wl, 0);
+    p7_hmmwindow_init(&vl);
+    *n_msvwin = wl.count;
+    for (w = 0; w < wl.count; w++) {
+      P7_HMM_WINDOW *win = wl.windows + w;
+      const ESL_DSQ *subseq = dsq + win->n - 1;
+      int window_len = win->length;
+      float nullsc, bias_filtersc, usc, filtersc, seq_score;
+      double P;
+      if (w < cap) { msvwin[w*2] = win->n; msvwin[w*2+1] = win->length; msvflag[w] = 0; }
+      p7_bg_SetLength(bg, window_len);
+      p7_bg_NullOne(bg, subseq, window_len, &nullsc);
+      p7_bg_FilterScore(bg, subseq, window_len, &bias_filtersc);
+      p7_oprofile_ReconfigMSVLength(om, window_len);
+      p7_omx_GrowTo(m->ox, om->M, 0, window_len);
+      p7_MSVFilter(subseq, window_len, om, m->ox, &usc);
+      if (w < cap) { msvsc[w*3] = nullsc; msvsc[w*3+1] = bias_filtersc; msvsc[w*3+2] = usc; }
+      P = esl_gumbel_surv((usc - nullsc) / eslCONST_LOG2, om->evparam[p7_MMU], om->evparam[p7_MLAMBDA]);
+      if (P > F1) continue;
+      counters[0] += window_len;
+      if (w < cap) msvflag[w] |= 1;
+      {  /* p7_pli_postSSV_LongTarget */
+        int max_window_len = 80000;
+        int overlap_len = ESL_MIN(40000, om->max_length);
+        int F1_L = ESL_MIN(window_len, B1), F2_L = ESL_MIN(window_len, B2);
+        int loc_window_len, overlap;
+        if (do_bias) {
+          p7_bg_SetLength(bg, window_len);
+          p7_bg_FilterScore(bg, subseq, window_len, &bias_filtersc);
+          bias_filtersc -= nullsc;
+          filtersc = nullsc + (bias_filtersc * (float)((F1_L > window_len ? 1.0 : (float)F1_L / window_len)));
+          seq_score = (usc - filtersc) / eslCONST_LOG2;
+          P = esl_gumbel_surv(seq_score, om->evparam[p7_MMU], om->evparam[p7_MLAMBDA]);
+          if (P > F1) continue;
+        } else bias_filtersc = 0;
+        counters[1] += window_len;
+        if (w < cap) msvflag[w] |= 2;
+        loc_window_len = ESL_MIN(window_len, om->max_length);
+        p7_bg_SetLength(bg, loc_window_len);
+        p7_bg_NullOne(bg, subseq, loc_window_len, &nullsc);
+        filtersc = nullsc + (bias_filtersc * (F2_L > window_len ? 1.0 : (float)F2_L / window_len));
+        p7_oprofile_ReconfigRestLength(om, loc_window_len);
+        p7_omx_GrowTo(m->ox, om->M, 0, window_len);
+        p7_ViterbiFilter_longtarget((ESL_DSQ *)subseq, window_len, om, m->ox, filtersc, F2, &vl);
+        for (i = 0; i < vl.count; i++, nh++)
+          if (nh < cap) { vithit[nh*3] = w; vithit[nh*3+1] = vl.windows[i].n; vithit[nh*3+2] = vl.windows[i].k; }
+        p7_pli_ExtendAndMergeWindows(om, data, &vl, 0.5);
+        for (i = 0; i < vl.count; i++) {
+          if (vl.windows[i].length > max_window_len) {
+            uint64_t new_n = vl.windows[i].n; uint32_t new_len = vl.windows[i].length;
+            vl.windows[i].length = max_window_len;
+            do {
+              int shift = max_window_len - overlap_len;
+              new_n += shift; new_len -= shift;
+              p7_hmmwindow_new(&vl, 0, new_n, 0, 0, ESL_MIN(max_window_len, new_len), 0.0, p7_NOCOMPLEMENT, new_len);
+            } while (new_len > max_window_len);
+          }
+        }
+        overlap = 0;
+        for (i = 0; i < vl.count; i++, nv++) {
+          int vlen = vl.windows[i].length, passed = 0;
+          const ESL_DSQ *vsub = subseq + vl.windows[i].n - 1;
+          float vnull, vbias, fwdsc;
+          int F3_L = ESL_MIN(vlen, B3);
+          counters[2] += vlen;
+          if (i > 0) counters[2] -= ESL_MAX(0, vl.windows[i-1].n + vl.windows[i-1].length - vl.windows[i].n);
+          /* p7_pli_postViterbi_LongTarget up to the F3 gate */
+          p7_bg_SetLength(bg, vlen);
+          p7_bg_NullOne(bg, vsub, vlen, &vnull);
+          if (do_bias) { p7_bg_FilterScore(bg, vsub, vlen, &vbias); vbias -= vnull; } else vbias = 0;
+          p7_oprofile_ReconfigRestLength(om, vlen);
+          p7_omx_GrowTo(m->ox, om->M, 0, vlen);
+          p7_ForwardParser(vsub, vlen, om, m->ox, &fwdsc);
+          filtersc = vnull + (vbias * (F3_L > vlen ? 1.0 : (float)F3_L / vlen));
+          seq_score = (fwdsc - filtersc) / eslCONST_LOG2;
+          P = esl_exp_surv(seq_score, om->evparam[p7_FTAU], om->evparam[p7_FLAMBDA]);
+          if (P <= F3) { passed = 1; counters[3] += vlen - overlap; }
+          if (nv < cap) {
+            vitwin[nv*3] = w; vitwin[nv*3+1] = vl.windows[i].n; vitwin[nv*3+2] = vlen;
+            vitsc[nv*3] = vnull; vitsc[nv*3+1] = vbias + vnull; vitsc[nv*3+2] = fwdsc; vitpass[nv] = passed;
+          }
+          if (passed && i < vl.count - 1) overlap = ESL_MAX(0, vl.windows[i].n + vl.windows[i].length - vl.windows[i+1].n);
+          else overlap = 0;
+        }
+      }
+    }
+    free(vl.windows);
+  }
+  *n_vithit = nh; *n_vitwin = nv;
+  free(wl.windows);
+  p7_hmm_ScoreDataDestroy(data);
+  return eslOK;
+}
+
+/* p7_ViterbiFilter_longtarget (impl_sse/vitfilter.c:292) on one window, the profile's length model set for <cfg_len>
+ * (p7_oprofile_ReconfigRestLength; the pipeline passes min(window, max_length), p7_pipeline.c:1369-1385).
+ * hit [cap][2] = i, k of every landmark in the order the reference records them; *thresh = the int16 score threshold it derived. */
+int ref_vit_longtarget(REFM *m, const uint8_t *dsq, int L, int cfg_len, float filtersc, double P, int cap, int64_t *hit)
+{
+  P7_HMM_WINDOWLIST vl;
+  int i, n;
+  vl.windows = NULL;
+  p7_hmmwindow_init(&vl);
+  p7_oprofile_ReconfigRestLength(m->om, cfg_len);
+  p7_omx_GrowTo(m->ox, m->om->M, 0, L);
+  p7_ViterbiFilter_longtarget((ESL_DSQ *)dsq, L, m->om, m->ox, filtersc, P, &vl);
+  n = vl.count;
+  for (i = 0; i < n && i < cap; i++) { hit[i*2] = vl.windows[i].n; hit[i*2+1] = vl.windows[i].k; }
+  free(vl.windows);
+  return n;
+}
+
+/* The real thing: p7_Pipeline_LongTarget on one chunk with a long-target P7_PIPELINE, as LongTargetsPipeline's search loop
+ * drives it (plan7.pyx:7568-7643; top strand).  counters [5] = pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd, hits;
+ * hits [cap][8] = ienv, jenv, iali, jali, score (bits), bias (dombias), pre_score, lnP of every hit appended (unsorted). */
+int ref_longtarget_pipeline(REFM *m, const uint8_t *dsq, int L, double F1, double F2, double F3, int do_bias, int do_null2,
+                            long *counters, int cap, double *hits)
+{
+  P7_PIPELINE *pli = p7_pipeline_Create(NULL, m->om->M, 100, TRUE, p7_SEARCH_SEQS);
+  P7_TOPHITS *th = p7_tophits_Create();
+  P7_SCOREDATA *data = p7_hmm_ScoreDataCreate(m->om, NULL);
+  ESL_SQ *sq = esl_sq_CreateDigitalFrom(m->abc, "chunk", dsq, L, "", "", NULL);
+  int status;
+  long h;
+  pli->F1 = F1; pli->F2 = F2; pli->F3 = F3;
+  pli->do_biasfilter = do_bias; pli->do_null2 = do_null2;
+  pli->E = 1e300; pli->domE = 1e300; pli->incE = 1e300; pli->incdomE = 1e300;
+  esl_sq_SetSource(sq, "chunk");
+  sq->start = 1; sq->end = L; sq->C = 0; sq->W = L; sq->L = -1;
+  p7_pli_NewModel(pli, m->om, m->bg);
+  p7_pli_NewSeq(pli, sq);
+  status = p7_Pipeline_LongTarget(pli, m->om, data, m->bg, th, 0, sq, p7_NOCOMPLEMENT, NULL, NULL, NULL);
+  counters[0] = pli->pos_past_msv; counters[1] = pli->pos_past_bias; counters[2] = pli->pos_past_vit; counters[3] = pli->pos_past_fwd;
+  counters[4] = th->N;
+  for (h = 0; h < (long)th->N && h < cap; h++) {
+    P7_HIT *hit = th->unsrt + h;
+    hits[h*8+0] = hit->dcl[0].ienv; hits[h*8+1] = hit->dcl[0].jenv; hits[h*8+2] = hit->dcl[0].iali; hits[h*8+3] = hit->dcl[0].jali;
+    hits[h*8+4] = hit->score; hits[h*8+5] = hit->dcl[0].dombias; hits[h*8+6] = hit->pre_score; hits[h*8+7] = hit->lnP;
+  }
+  esl_sq_Destroy(sq);
+  p7_hmm_ScoreDataDestroy(data);
+  p7_tophits_Destroy(th);
+  p7_pipeline_Destroy(pli);
+  return status;
+}
+
 double ref_gumbel_surv(double x, double mu, double lambda) { return esl_gumbel_surv(x, mu, lambda); }
 double ref_exp_surv(double x, double mu, double lambda)    { return esl_exp_surv(x, mu, lambda); }
 

@@ -67,6 +67,9 @@ def lib():
         L.ref_bias.argtypes = [vp, vp, ci]
         L.ref_generic.argtypes = [vp, vp, ci] + [ctypes.POINTER(cf)] * 4
         L.ref_longtarget_windows.argtypes = [vp, vp, ci, ctypes.c_double, ci, vp, vp, vp, vp, vp, vp, vp]
+        L.ref_longtarget_stages.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ci, ci, ci] + [vp] * 11
+        L.ref_vit_longtarget.argtypes = [vp, vp, ci, ci, cf, ctypes.c_double, ci, vp]
+        L.ref_longtarget_pipeline.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, vp, ci, vp]
         L.ref_gdecoding.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), vp]
         L.ref_gumbel_surv.restype = ctypes.c_double
         L.ref_gumbel_surv.argtypes = [ctypes.c_double] * 3
@@ -216,6 +219,42 @@ class RefModel:
                                       ctypes.byref(nm), mer.ctypes.data, pre.ctypes.data, suf.ctypes.data)
         assert nr.value <= cap
         return raw[:nr.value].copy(), rsc[:nr.value].copy(), mer[:nm.value].copy(), pre, suf
+
+    def longtarget_stages(self, codes, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=240, B3=1000, cap=200000):
+        """The window-level stages of nhmmer on one chunk, restated with the reference's public calls (ref_longtarget_stages):
+        a dict of msvwin [n,2], msvsc [n,3] (null1, FilterScore, MSV), msvflag [n], vithit [h,3] (msv window, i, k),
+        vitwin [v,3] (msv window, n, length), vitsc [v,3] (null1, FilterScore, Forward), vitpass [v], counters [4]."""
+        d = dsq_of(codes); n = d.size - 2
+        nm, nh, nv = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        msvwin = np.zeros((cap, 2), np.int64); msvsc = np.zeros((cap, 3), np.float32); msvflag = np.zeros(cap, np.int32)
+        vithit = np.zeros((cap, 3), np.int64)
+        vitwin = np.zeros((cap, 3), np.int64); vitsc = np.zeros((cap, 3), np.float32); vitpass = np.zeros(cap, np.int32)
+        counters = np.zeros(4, np.int64)
+        a = lambda x: x.ctypes.data
+        self.L.ref_longtarget_stages(self.h, a(d), n, F1, F2, F3, int(bias_filter), B1, B2, B3, cap,
+                                     ctypes.addressof(nm), a(msvwin), a(msvsc), a(msvflag), ctypes.addressof(nh), a(vithit),
+                                     ctypes.addressof(nv), a(vitwin), a(vitsc), a(vitpass), a(counters))
+        assert max(nm.value, nh.value, nv.value) <= cap
+        return dict(msvwin=msvwin[:nm.value].copy(), msvsc=msvsc[:nm.value].copy(), msvflag=msvflag[:nm.value].copy(),
+                    vithit=vithit[:nh.value].copy(), vitwin=vitwin[:nv.value].copy(), vitsc=vitsc[:nv.value].copy(),
+                    vitpass=vitpass[:nv.value].copy(), counters=counters)
+
+    def vit_longtarget(self, codes, cfg_len, filtersc, F2=3e-3, cap=100000):
+        """p7_ViterbiFilter_longtarget on one window: landmarks [n,2] = i, k in the reference's order."""
+        d = dsq_of(codes); n = d.size - 2
+        hit = np.zeros((cap, 2), np.int64)
+        nh = self.L.ref_vit_longtarget(self.h, d.ctypes.data, n, int(cfg_len), float(filtersc), F2, cap, hit.ctypes.data)
+        assert nh <= cap
+        return hit[:nh].copy()
+
+    def longtarget_pipeline(self, codes, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True, cap=20000):
+        """p7_Pipeline_LongTarget itself on one chunk (top strand): (counters [5] = pos_past_msv, pos_past_bias, pos_past_vit,
+        pos_past_fwd, number of hits; hits [n,8] = ienv, jenv, iali, jali, score, bias, pre_score, lnP)."""
+        d = dsq_of(codes); n = d.size - 2
+        counters = np.zeros(5, np.int64); hits = np.zeros((cap, 8), np.float64)
+        st = self.L.ref_longtarget_pipeline(self.h, d.ctypes.data, n, F1, F2, F3, int(bias_filter), int(null2), counters.ctypes.data, cap, hits.ctypes.data)
+        assert st == 0, st
+        return counters, hits[:min(cap, int(counters[4]))].copy()
 
     def null1(self, codes):
         d = dsq_of(codes); return self.L.ref_null1(self.h, d.ctypes.data, d.size - 2)

@@ -153,6 +153,10 @@ def _load():
     sig("b2h_free", None, c_void_p)
     sig("b2h_window_lengths", c_int, c_void_p, c_void_p, c_void_p)
     sig("b2h_extend_merge_windows", c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_float, P(c_size_t))
+    sig("b2h_longtarget_viterbi_windows", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double,
+        P(c_void_p), P(c_size_t), P(c_void_p), P(c_size_t))
+    sig("b2h_longtarget_vit_finish", c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, P(c_void_p), P(c_size_t))
+    sig("b2h_longtarget_vit_threshold", c_int, c_void_p, c_int, c_float, ctypes.c_double, P(c_i32), P(c_i32))
     sig("b2h_hmm_convert_many", c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int,
         P(c_void_p), P(c_void_p), P(c_size_t))
     sig("b2h_pressed_open", c_int, ctypes.c_char_p, P(c_void_p))

@@ -354,4 +354,7 @@ int b2h_launch_msv_tiled(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, con
                          float *out_sc, int32_t *out_status, SurvList A, double F1);
 // group a SurvList by profile: poff/itemoff[P+1] and the grouped arrays (device)
 struct Grouped { int32_t *p, *s; float *a, *b; int32_t *poff, *itemoff; int *fill; };
-int b2h_launch_group(b2h_ctx *ctx, const SurvList &in, int P, Grouped out);
+int b2h_launch_group(b2h_ctx *ctx, const SurvList &in, int P, Grouped out);// p7_pli_ExtendAndMergeWindows on a host list, in place (b2h_longtarget.cu); returns the number of windows left
+size_t b2h_extend_merge(const b2h_profile *p, b2h_window *w, size_t n, const int64_t *target_len, float pct_overlap);
+
+

@@ -274,6 +274,9 @@ size_t extend_merge(const b2h_profile *p, b2h_window *w, size_t n, const int64_t
 
 } // namespace
 
+size_t b2h_extend_merge(const b2h_profile *p, b2h_window *w, size_t n, const int64_t *target_len, float pct_overlap)
+{ return extend_merge(p, w, n, target_len, pct_overlap); }
+
 extern "C" void b2h_free(void *p) { free(p); }
 
 extern "C" int b2h_extend_merge_windows(const b2h_profile *p, b2h_window *windows, size_t n, const int64_t *target_len, float pct_overlap, size_t *nout)

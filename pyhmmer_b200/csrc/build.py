@@ -26,6 +26,7 @@ SOURCES = [
     "b2h_envelope.cu",
     "b2h_generic.cu",
     "b2h_longtarget.cu",
+    "b2h_ltvit.cu",
     "b2h_search.cu",
     "b2h_domaindef.cpp",
     "b2h_pressed.cpp",

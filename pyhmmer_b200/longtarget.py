@@ -1,0 +1,214 @@
+"""The window-level stages of the long-target (nhmmer) pipeline, between the SSV scan and domain definition.
+
+``p7_Pipeline_LongTarget`` (vendor/hmmer/src/p7_pipeline.c:1496-1706) scans a target chunk with the SSV filter, turns the
+diagonals it finds into windows, and hands every window to ``p7_pli_postSSV_LongTarget`` (:1331-1436: bias gate, Viterbi
+scan for landmarks, second round of windows) and ``p7_pli_postViterbi_LongTarget`` (:1065-1112: Forward gate).  Here the
+windows of ALL chunks go through each stage together: the DP runs on the GPU through the C ABI (one launch per stage over
+a database whose "sequences" are the windows), and this module does what the reference does between the DP calls -- the
+P-value gates, the --B1/--B2/--B3 scaling of the bias correction, the bookkeeping of the ``pos_past_*`` counters -- in the
+reference's own precision (which operands are float, which double, is part of the result).
+
+`stages()` returns every intermediate, so the parity tests can compare stage by stage with the reference
+(``oracle/ref_shim.c: ref_longtarget_stages``).  The compute sits behind a small backend interface; the only backend
+shipped is the CUDA one (there is no CPU path in this package) -- the CPU-only tests drive the same host logic with the
+reference's functions as the backend.
+
+Not here yet: the long-target branch of domain definition and the hit bookkeeping behind the Forward gate.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, ptr
+
+LOG2 = 0.69314718055994529          # eslCONST_LOG2
+
+
+def gumbel_surv(x, mu, lam):
+    """esl_gumbel_surv (vendor/easel/esl_gumbel.c:129), double precision, libm's exp."""
+    y = lam * (x - mu)
+    ey = -math.exp(-y)
+    return -ey if abs(ey) < 5e-9 else 1.0 - math.exp(ey)
+
+
+def exp_surv(x, mu, lam):
+    """esl_exp_surv (vendor/easel/esl_exponential.c:128)."""
+    return 1.0 if x < mu else math.exp(-lam * (x - mu))
+
+
+_null1_cache = {}
+
+
+def null1(L):
+    """p7_bg_SetLength + p7_bg_NullOne for a target of length L (p7_bg.c:189, 357), through the host library."""
+    v = _null1_cache.get(L)
+    if v is None:
+        lp = _lib.LenParams()
+        check(lib.b2h_length_params(int(L), 1.0, ctypes.byref(lp)), "b2h_length_params")
+        v = _null1_cache[L] = np.float32(lp.null1)
+    return v
+
+
+def window_residues(block, seq, start, length):
+    """Concatenated residues and offsets of the windows (seq[i], 1-based start[i], length[i]) of a sequence block."""
+    res, off = block._packed()
+    length = np.asarray(length, np.int64)
+    woff = np.zeros(len(length) + 1, np.int64)
+    np.cumsum(length, out=woff[1:])
+    src0 = off[np.asarray(seq, np.int64)] + np.asarray(start, np.int64) - 1
+    idx = np.repeat(src0 - woff[:-1], length) + np.arange(woff[-1], dtype=np.int64)
+    return np.ascontiguousarray(res[idx]), woff
+
+
+class CudaBackend:
+    """The DP of every stage on the GPU, one profile against the windows of all chunks (C ABI of include/b2h.h)."""
+
+    def __init__(self, om, block):
+        from . import plan7
+        self.om, self.block = om, block
+        self.ctx = _lib.context()
+        self.prof = om._device(self.ctx)
+        self.db = plan7.SequenceDatabase.of(self.ctx, block)
+        self.max_length = int(om._desc.max_length)
+
+    def ssv_windows(self, F1):
+        from . import plan7
+        return plan7.long_target_windows(self.om, self.block, F1)[1]
+
+    class _WindowDB:
+        def __init__(self, ctx, res, off, n):
+            out = ctypes.c_void_p()
+            check(lib.b2h_seqdb_create_packed(ctx.handle, ptr(res), ptr(off), n, ctypes.byref(out)), "b2h_seqdb_create_packed", ctx.handle)
+            self.handle, self.n, self.length = out, n, np.diff(off).astype(np.int32)
+
+        def __del__(self):
+            try:
+                lib.b2h_seqdb_destroy(self.handle)
+            except Exception:
+                pass
+
+    def window_db(self, seq, start, length):
+        res, off = window_residues(self.block, seq, start, length)
+        return self._WindowDB(self.ctx, res, off, len(length))
+
+    def _scores(self, fn, name, wdb):
+        sc, st = np.empty(wdb.n, np.float32), np.empty(wdb.n, np.int32)
+        check(fn(self.ctx.handle, self.prof, wdb.handle, ptr(sc), ptr(st)), name, self.ctx.handle)
+        return sc
+
+    def null_bias(self, wdb):
+        n1, fs = np.empty(wdb.n, np.float32), np.empty(wdb.n, np.float32)
+        check(lib.b2h_null_scores(self.ctx.handle, self.prof, wdb.handle, ptr(n1), ptr(fs)), "b2h_null_scores", self.ctx.handle)
+        return n1, fs
+
+    def msv(self, wdb):
+        return self._scores(lib.b2h_msv_filter, "b2h_msv_filter", wdb)
+
+    def forward(self, wdb):
+        return self._scores(lib.b2h_forward_parser, "b2h_forward_parser", wdb)
+
+    def viterbi_windows(self, wdb, filtersc, active, F2):
+        marks, out = ctypes.c_void_p(), ctypes.c_void_p()
+        nm, no = ctypes.c_size_t(), ctypes.c_size_t()
+        act = np.ascontiguousarray(active, np.uint8)
+        fsc = np.ascontiguousarray(filtersc, np.float32)
+        check(lib.b2h_longtarget_viterbi_windows(self.ctx.handle, self.prof, wdb.handle, ptr(fsc), ptr(act), float(F2),
+                                                 ctypes.byref(marks), ctypes.byref(nm), ctypes.byref(out), ctypes.byref(no)),
+              "b2h_longtarget_viterbi_windows", self.ctx.handle)
+        return _take_windows(marks, nm.value), _take_windows(out, no.value)
+
+
+def _take_windows(p, n):
+    dt = np.dtype(_lib.WindowRec)
+    try:
+        return np.frombuffer(ctypes.string_at(p, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dt)
+    finally:
+        lib.b2h_free(p)
+
+
+def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=240, B3=1000, backend=None):
+    """SSV windows -> MSV / bias gates -> Viterbi landmarks and windows -> Forward gate, for every chunk of ``chunks``.
+
+    Returns a dict of numpy arrays:
+      ``msvwin``  record array (seq = chunk, n, length) of the merged SSV windows, ``msvsc`` [n,3] = null1, FilterScore, MSV
+      score per window, ``msvflag`` bit 0 = passed the MSV gate, bit 1 = passed the bias gate;
+      ``vitmark`` record array (seq = index into msvwin, n = row, k) of the Viterbi landmarks, ``vitwin`` (seq = index into
+      msvwin, n = start inside that window, length) the windows behind p7_pli_ExtendAndMergeWindows(.., 0.5) and the 80 kb cut,
+      ``vitsc`` [v,3] = null1, FilterScore, Forward score, ``vitpass`` = passed the Forward gate;
+      ``counters`` [nchunks,4] = pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd per chunk (P7_PIPELINE, hmmer.h).
+    """
+    be = backend if backend is not None else CudaBackend(om, chunks)
+    f32, f64 = np.float32, np.float64
+    ev = [float(v) for v in om._evparam]                 # MMU MLAMBDA VMU VLAMBDA FTAU FLAMBDA
+    max_length = int(om._desc.max_length)
+    nchunks = len(chunks)
+    counters = np.zeros((nchunks, 4), np.int64)
+    wdt = np.dtype(_lib.WindowRec)
+    out = dict(msvwin=np.zeros(0, wdt), msvsc=np.zeros((0, 3), f32), msvflag=np.zeros(0, np.int32), vitmark=np.zeros(0, wdt),
+               vitwin=np.zeros(0, wdt), vitsc=np.zeros((0, 3), f32), vitpass=np.zeros(0, np.int32), counters=counters)
+
+    mw = be.ssv_windows(F1)
+    n = len(mw)
+    out["msvwin"] = mw
+    if n == 0:
+        return out
+    wlen = mw["length"].astype(np.int64)
+    wdb = be.window_db(mw["seq"], mw["n"], wlen)
+    nul, bias = be.null_bias(wdb)                        # p7_bg_SetLength(window) + p7_bg_NullOne / p7_bg_FilterScore
+    usc = be.msv(wdb)                                    # p7_oprofile_ReconfigMSVLength(window) + p7_MSVFilter
+    out["msvsc"] = np.stack([nul, bias, usc], axis=1)
+    # p7_Pipeline_LongTarget's gate (:1637): float difference, double division
+    x = (usc - nul).astype(f32).astype(f64) / LOG2
+    pass_msv = np.array([not (gumbel_surv(v, ev[0], ev[1]) > F1) for v in x], bool)
+    flen = wlen.astype(f32)
+    if bias_filter:
+        # p7_pli_postSSV_LongTarget (:1359-1368): everything in float
+        b = (bias - nul).astype(f32)
+        filtersc = (nul + (b * (np.minimum(wlen, B1).astype(f32) / flen)).astype(f32)).astype(f32)
+        seq_score = ((usc - filtersc).astype(f32).astype(f64) / LOG2).astype(f32)
+        pass_bias = pass_msv & np.array([not (gumbel_surv(float(v), ev[0], ev[1]) > F1) for v in seq_score], bool)
+    else:
+        b = np.zeros(n, f32)
+        pass_bias = pass_msv.copy()
+    out["msvflag"] = pass_msv.astype(np.int32) + 2 * pass_bias.astype(np.int32)
+    np.add.at(counters[:, 0], mw["seq"][pass_msv], wlen[pass_msv])
+    np.add.at(counters[:, 1], mw["seq"][pass_bias], wlen[pass_bias])
+    # null1 of the possibly shorter length model, B2-scaled bias: the ternary makes this one double (:1376-1382)
+    nul_loc = np.array([null1(int(min(L, max_length))) for L in wlen], f32)
+    ratio2 = np.minimum(wlen, B2).astype(f32) / flen
+    filtersc2 = (nul_loc.astype(f64) + b.astype(f64) * ratio2.astype(f64)).astype(f32)
+    marks, vw = be.viterbi_windows(wdb, filtersc2, pass_bias, F2)
+    out["vitmark"], out["vitwin"] = marks, vw
+    nv = len(vw)
+    if nv == 0:
+        return out
+    vlen = vw["length"].astype(np.int64)
+    vchunk = mw["seq"][vw["seq"]]
+    vdb = be.window_db(vchunk, mw["n"][vw["seq"]] + vw["n"] - 1, vlen)
+    vnul, vbias = be.null_bias(vdb)
+    fwd = be.forward(vdb)                                # p7_oprofile_ReconfigRestLength(window) + p7_ForwardParser
+    out["vitsc"] = np.stack([vnul, vbias, fwd], axis=1)
+    vb = (vbias - vnul).astype(f32) if bias_filter else np.zeros(nv, f32)
+    ratio3 = np.minimum(vlen, B3).astype(f32) / vlen.astype(f32)
+    filtersc3 = (vnul.astype(f64) + vb.astype(f64) * ratio3.astype(f64)).astype(f32)
+    seq_score = ((fwd - filtersc3).astype(f32).astype(f64) / LOG2).astype(f32)
+    passed = np.array([not (exp_surv(float(v), ev[4], ev[5]) > F3) for v in seq_score], bool)
+    out["vitpass"] = passed.astype(np.int32)
+    # pos_past_vit / pos_past_fwd: lengths minus the overlap with the preceding window of the same SSV window (:1409-1430)
+    vend = vw["n"].astype(np.int64) + vlen
+    overlap = 0
+    for i in range(nv):
+        first = i == 0 or vw["seq"][i] != vw["seq"][i - 1]
+        last = i == nv - 1 or vw["seq"][i + 1] != vw["seq"][i]
+        if first:
+            overlap = 0
+        c = int(vchunk[i])
+        counters[c, 2] += vlen[i] - (0 if first else max(0, int(vend[i - 1] - vw["n"][i])))
+        if passed[i]:
+            counters[c, 3] += vlen[i] - overlap
+            overlap = 0 if last else max(0, int(vend[i] - vw["n"][i + 1]))
+        else:
+            overlap = 0
+    return out

@@ -1,0 +1,135 @@
+"""Shared pieces of the long-target (nhmmer) stage tests: the synthetic DNA workload, a backend that computes every DP
+of `pyhmmer_b200.longtarget.stages` with the REFERENCE's functions (oracle/_ref) so that the host logic can be checked
+without a GPU, and the stage-by-stage comparison with `ref_longtarget_stages`."""
+import ctypes
+
+import numpy as np
+
+from pyhmmer_b200 import _lib, easel, longtarget, synth
+
+
+def dna_model(make_pair, M, seed=0, mu_shift=0.0):
+    dna = easel.Alphabet.dna()
+    rng = np.random.default_rng(7000 + M + seed)
+    h = synth.random_hmm(dna, M, rng, name="lt%d" % M)
+    h.max_length = 2 * M + 50
+    mu = -8.0 - np.log2(M) * 0.3 + mu_shift
+    h._evparam[:] = np.array([mu, 0.70, mu - 1.0, 0.70, -4.0 + mu_shift / 2, 0.70], np.float32)
+    return make_pair(h), rng
+
+
+def dna_chunks(pair, rng, sizes, nplant):
+    dna = pair.hmm.alphabet
+    out = []
+    for ci, L in enumerate(sizes):
+        seq = rng.integers(0, dna.K, L).astype(np.uint8)
+        for _ in range(nplant):
+            dom = synth.emit_sequence(pair.hmm, rng)
+            if len(dom) < L:
+                pos = int(rng.integers(0, L - len(dom)))
+                seq[pos:pos + len(dom)] = dom
+        out.append(easel.DigitalSequence(dna, name=b"chunk%d" % ci, sequence=seq))
+    return easel.DigitalSequenceBlock(dna, out)
+
+
+class OracleBackend:
+    """`longtarget.stages` backend over the reference library: every score comes from HMMER's own functions, the windows'
+    extension / merging / cutting from the product's HOST code (b2h_longtarget_vit_finish) -- no device involved."""
+
+    class _WDB:
+        def __init__(self, res, off):
+            self.res, self.off, self.n = res, off, len(off) - 1
+            self.length = np.diff(off).astype(np.int32)
+
+        def seq(self, i):
+            return self.res[self.off[i]:self.off[i + 1]]
+
+    def __init__(self, pair, block):
+        self.pair, self.block, self.ref = pair, block, pair.ref
+        self.hprof = ctypes.c_void_p()
+        assert _lib.lib.b2h_profile_create_host(ctypes.byref(pair.om._desc), ctypes.byref(self.hprof)) == 0
+
+    def __del__(self):
+        _lib.lib.b2h_profile_destroy(self.hprof)
+
+    def ssv_windows(self, F1):
+        rows = []
+        for ci, s in enumerate(self.block):
+            if len(s) == 0:
+                continue
+            _, _, mer, _, _ = self.ref.longtarget_windows(s.sequence, F1=F1)
+            rows += [(ci, 0, int(n), int(l), 0.0) for n, l in mer]
+        return np.array(rows, dtype=np.dtype(_lib.WindowRec)) if rows else np.zeros(0, np.dtype(_lib.WindowRec))
+
+    def window_db(self, seq, start, length):
+        return self._WDB(*longtarget.window_residues(self.block, seq, start, length))
+
+    def null_bias(self, wdb):
+        return (np.array([self.ref.null1(wdb.seq(i)) for i in range(wdb.n)], np.float32),
+                np.array([self.ref.bias(wdb.seq(i)) for i in range(wdb.n)], np.float32))
+
+    def msv(self, wdb):
+        return np.array([self.ref.msv(wdb.seq(i))[0] for i in range(wdb.n)], np.float32)
+
+    def forward(self, wdb):
+        return np.array([self.ref.fwd(wdb.seq(i))[0] for i in range(wdb.n)], np.float32)
+
+    def viterbi_windows(self, wdb, filtersc, active, F2):
+        maxl = int(self.pair.om._desc.max_length)
+        rows = []
+        for i in range(wdb.n):
+            if active[i]:
+                hit = self.ref.vit_longtarget(wdb.seq(i), min(int(wdb.length[i]), maxl), float(filtersc[i]), F2)
+                rows += [(i, int(k), int(r), 1, 0.0) for r, k in hit]
+        marks = np.array(rows, dtype=np.dtype(_lib.WindowRec)) if rows else np.zeros(0, np.dtype(_lib.WindowRec))
+        rng = np.random.default_rng(len(rows))
+        shuffled = marks[rng.permutation(len(marks))]               # the device reports landmarks in no particular order
+        out, no = ctypes.c_void_p(), ctypes.c_size_t()
+        assert _lib.lib.b2h_longtarget_vit_finish(self.hprof, _lib.ptr(shuffled), len(shuffled), _lib.ptr(wdb.length), wdb.n,
+                                                  ctypes.byref(out), ctypes.byref(no)) == 0
+        assert np.array_equal(shuffled, marks)                      # ... and the host code restores the reference's order
+        return shuffled, longtarget._take_windows(out, no.value)
+
+
+def compare_with_reference(pair, block, got, exact_scores, **kw):
+    """Stage by stage against ref_longtarget_stages, chunk by chunk.  Returns totals for the caller's sanity checks."""
+    tot = dict(msvwin=0, vitmark=0, vitwin=0, passed=0)
+    mw, vm, vw = got["msvwin"], got["vitmark"], got["vitwin"]
+    for ci, s in enumerate(block):
+        if len(s) == 0:
+            assert not np.any(mw["seq"] == ci)
+            continue
+        ref = pair.ref.longtarget_stages(s.sequence, **kw)
+        sel = np.flatnonzero(mw["seq"] == ci)
+        assert len(sel) == len(ref["msvwin"]), (ci, len(sel), len(ref["msvwin"]))
+        assert np.array_equal(mw["n"][sel], ref["msvwin"][:, 0]) and np.array_equal(mw["length"][sel], ref["msvwin"][:, 1]), ci
+        sc = got["msvsc"][sel]
+        assert np.array_equal(sc[:, 0], ref["msvsc"][:, 0]) and np.array_equal(sc[:, 2], ref["msvsc"][:, 2]), ci     # null1, MSV: exact
+        if exact_scores:
+            assert np.array_equal(sc[:, 1], ref["msvsc"][:, 1]), ci
+        else:
+            assert np.all(np.abs(sc[:, 1] - ref["msvsc"][:, 1]) <= 4 * np.spacing(np.abs(ref["msvsc"][:, 1]))), ci
+        assert np.array_equal(got["msvflag"][sel], ref["msvflag"]), (ci, got["msvflag"][sel], ref["msvflag"])
+        base = sel[0] if len(sel) else 0
+        m = vm[(vm["seq"] >= base) & (vm["seq"] < base + len(sel))] if len(sel) else vm[:0]
+        assert len(m) == len(ref["vithit"]), (ci, len(m), len(ref["vithit"]))
+        assert np.array_equal(m["seq"] - base, ref["vithit"][:, 0]) and np.array_equal(m["n"], ref["vithit"][:, 1]) \
+            and np.array_equal(m["k"], ref["vithit"][:, 2]), ci
+        vsel = np.flatnonzero((vw["seq"] >= base) & (vw["seq"] < base + len(sel))) if len(sel) else np.zeros(0, np.int64)
+        assert len(vsel) == len(ref["vitwin"]), (ci, len(vsel), len(ref["vitwin"]))
+        assert np.array_equal(vw["seq"][vsel] - base, ref["vitwin"][:, 0]) and np.array_equal(vw["n"][vsel], ref["vitwin"][:, 1]) \
+            and np.array_equal(vw["length"][vsel], ref["vitwin"][:, 2]), ci
+        if len(vsel):
+            vs = got["vitsc"][vsel]
+            assert np.array_equal(vs[:, 0], ref["vitsc"][:, 0]), ci
+            if not kw.get("bias_filter", True):
+                vs = vs.copy(); vs[:, 1] = ref["vitsc"][:, 1]        # the reference does not run its bias filter here at all
+            if exact_scores:
+                assert np.array_equal(vs[:, 1:], ref["vitsc"][:, 1:]), ci
+            else:
+                assert np.all(np.abs(vs[:, 1] - ref["vitsc"][:, 1]) <= 4 * np.spacing(np.abs(ref["vitsc"][:, 1]))), ci
+                assert np.all(np.abs(vs[:, 2] - ref["vitsc"][:, 2]) <= 1e-4 + 2e-7 * np.abs(ref["vitsc"][:, 2])), ci   # Forward: 1e-4 nats
+            assert np.array_equal(got["vitpass"][vsel], ref["vitpass"]), ci
+        assert np.array_equal(got["counters"][ci], ref["counters"]), (ci, got["counters"][ci], ref["counters"])
+        tot["msvwin"] += len(sel); tot["vitmark"] += len(m); tot["vitwin"] += len(vsel); tot["passed"] += int(ref["vitpass"].sum())
+    return tot

@@ -1,0 +1,62 @@
+"""GPU parity of the long-target (nhmmer) window stages behind the SSV scan: MSV and bias gates,
+p7_ViterbiFilter_longtarget landmarks (`lt_vit_kernel`), second-round windows, Forward gate -- `pyhmmer_b200.longtarget.stages`
+on the CUDA backend against `ref_longtarget_stages` (the reference's own functions in the reference's own order), chunk by
+chunk: identical windows, identical landmarks in identical order, identical gate decisions and pos_past_* counters;
+null1 / MSV scores bit-identical, bias scores within 4 ulp, Forward within 1e-4 nats."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from pyhmmer_b200 import _lib, longtarget, plan7
+import lt_common
+
+pytestmark = pytest.mark.gpu
+KW = dict(F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=240, B3=1000)
+
+
+# register tiles of the Viterbi scan: C = 2 / 4 / 11 nodes per lane on one warp, two warps, four warps
+@pytest.mark.parametrize("M,mu_shift", [(40, -3.0), (121, -2.0), (333, -2.0), (600, -1.0), (1100, -1.0)])
+def test_window_stages(make_pair, M, mu_shift):
+    pair, rng = lt_common.dna_model(make_pair, M, mu_shift=mu_shift)
+    block = lt_common.dna_chunks(pair, rng, [60000, 0, 9, 25000, 262144 // 4], nplant=6)
+    got = longtarget.stages(pair.om, block, **KW)
+    tot = lt_common.compare_with_reference(pair, block, got, exact_scores=False, **KW)
+    assert tot["msvwin"] >= 5 and tot["vitmark"] >= 5 and tot["vitwin"] >= 3 and tot["passed"] >= 1, tot
+    print("M=%d: %d SSV windows, %d Viterbi landmarks, %d windows (%d past Forward) identical" %
+          (M, tot["msvwin"], tot["vitmark"], tot["vitwin"], tot["passed"]))
+
+
+def test_viterbi_landmarks_against_port_without_bias(make_pair):
+    """The kernel alone: every window active, thresholds from arbitrary filter scores, against the scalar port."""
+    from oracle import port
+    pair, rng = lt_common.dna_model(make_pair, 77, mu_shift=-2.0)
+    pt = port.Port(pair.om)
+    block = lt_common.dna_chunks(pair, rng, [1, 5, 31, 32, 33, 500, 4000, 20000], nplant=2)
+    be = longtarget.CudaBackend(pair.om, block)
+    lens = np.array([len(s) for s in block], np.int64)
+    wdb = be.window_db(np.arange(len(block)), np.ones(len(block), np.int64), lens)
+    for fsc in (-3.0, -9.0):
+        filtersc = np.full(len(block), fsc, np.float32)
+        marks, wins = be.viterbi_windows(wdb, filtersc, np.ones(len(block), np.uint8), 3e-3)
+        n = 0
+        for i, s in enumerate(block):
+            want = pt.vit_longtarget(s.sequence, min(len(s), pair.hmm.max_length), fsc)
+            mine = marks[marks["seq"] == i]
+            assert np.array_equal(mine["n"], want[:, 0]) and np.array_equal(mine["k"], want[:, 1]), (fsc, i, len(mine), len(want))
+            n += len(want)
+        assert n > 0
+
+
+def test_long_windows_are_cut_at_80kb(make_pair):
+    pair, rng = lt_common.dna_model(make_pair, 40, mu_shift=-3.0)
+    dom = lt_common.synth.emit_sequence(pair.hmm, rng)
+    seq = np.concatenate([dom] * (200000 // len(dom))).astype(np.uint8)
+    dna = pair.hmm.alphabet
+    block = lt_common.easel.DigitalSequenceBlock(dna, [lt_common.easel.DigitalSequence(dna, name=b"rep", sequence=seq)])
+    got = longtarget.stages(pair.om, block, **KW)
+    tot = lt_common.compare_with_reference(pair, block, got, exact_scores=False, **KW)
+    assert got["vitwin"]["length"].max() == 80000 and tot["vitwin"] >= 3
