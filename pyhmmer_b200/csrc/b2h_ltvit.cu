@@ -372,41 +372,53 @@ extern "C" int b2h_longtarget_viterbi_windows(b2h_ctx *ctx, const b2h_profile *p
     std::stable_sort(ord, ord + nwork, [&](int32_t x, int32_t y) { return windows->h_len[x] > windows->h_len[y]; });
     LtVitArgs a;
     a.P = b2h_profdev(p); a.sd = b2h_seqdev(windows); a.nwork = (int)nwork; a.counter = ctx->d_counters;
-    a.cap = (int)std::min<int64_t>((int64_t)1 << 24, std::max<int64_t>(4096, work_res / 4 + 4096));
-    int32_t *d_buf = nullptr; int *d_nm = nullptr; LtMark *d_marks = nullptr;
+    a.cap = (int)std::min<int64_t>((int64_t)1 << 26, std::max<int64_t>(4096, work_res / 8 + 4096));
+    int32_t *d_buf = nullptr; int *d_nm = nullptr;
     cudaError_t e;
     if ((e = cudaMallocAsync((void **)&d_buf, 3 * n * sizeof(int32_t), st)) != cudaSuccess ||
-        (e = cudaMallocAsync((void **)&d_nm, sizeof(int), st)) != cudaSuccess ||
-        (e = cudaMallocAsync((void **)&d_marks, (size_t)a.cap * sizeof(LtMark), st)) != cudaSuccess) {
+        (e = cudaMallocAsync((void **)&d_nm, sizeof(int), st)) != cudaSuccess) {
       ctx->err = cudaGetErrorString(e);
-      if (d_buf) cudaFreeAsync(d_buf, st); if (d_nm) cudaFreeAsync(d_nm, st);
+      if (d_buf) cudaFreeAsync(d_buf, st);
       return B2H_EMEM;
     }
     cudaMemcpyAsync(d_buf, hbuf.data(), 3 * n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
-    cudaMemsetAsync(d_nm, 0, sizeof(int), st);
-    cudaMemsetAsync(a.counter, 0, sizeof(int), st);
-    a.thresh = d_buf; a.xwmove = d_buf + n; a.order = d_buf + 2 * n; a.marks = d_marks; a.nmarks = d_nm;
-    int rc = B2H_EINVAL;
-    switch (p->regW * 64 + p->regC) {
+    a.thresh = d_buf; a.xwmove = d_buf + n; a.order = d_buf + 2 * n; a.nmarks = d_nm;
+    int rc = B2H_OK;
+    // the scan is deterministic: when the landmark list overflows, the count it reports sizes the second attempt
+    for (int attempt = 0; attempt < 2 && rc == B2H_OK; attempt++) {
+      LtMark *d_marks = nullptr;
+      if ((e = cudaMallocAsync((void **)&d_marks, (size_t)a.cap * sizeof(LtMark), st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = B2H_EMEM; break; }
+      a.marks = d_marks;
+      cudaMemsetAsync(d_nm, 0, sizeof(int), st);
+      cudaMemsetAsync(a.counter, 0, sizeof(int), st);
+      rc = B2H_EINVAL;
+      switch (p->regW * 64 + p->regC) {
 #define CASE(CC, WW) case (WW) * 64 + (CC): rc = launch_ltvit<CC, WW>(ctx, a, st); break;
-      CASE(2, 1) CASE(3, 1) CASE(4, 1) CASE(5, 1) CASE(6, 1) CASE(7, 1) CASE(8, 1)
-      CASE(9, 1) CASE(10, 1) CASE(11, 1) CASE(12, 1) CASE(14, 1) CASE(16, 1)
-      CASE(9, 2) CASE(10, 2) CASE(11, 2) CASE(12, 2) CASE(14, 2) CASE(16, 2)
-      CASE(10, 4) CASE(12, 4)
+        CASE(2, 1) CASE(3, 1) CASE(4, 1) CASE(5, 1) CASE(6, 1) CASE(7, 1) CASE(8, 1)
+        CASE(9, 1) CASE(10, 1) CASE(11, 1) CASE(12, 1) CASE(14, 1) CASE(16, 1)
+        CASE(9, 2) CASE(10, 2) CASE(11, 2) CASE(12, 2) CASE(14, 2) CASE(16, 2)
+        CASE(10, 4) CASE(12, 4)
 #undef CASE
-    }
-    int nm = 0;
-    if (rc == B2H_OK) {
-      cudaMemcpyAsync(&nm, d_nm, sizeof(int), cudaMemcpyDeviceToHost, st);
-      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { ctx->err = std::string("long-target Viterbi kernel: ") + cudaGetErrorString(e); rc = B2H_ECUDA; }
-      else if (nm > a.cap) { ctx->err = "long-target Viterbi: landmark list overflow"; rc = B2H_ERANGE; }
-      else if (nm > 0) {
-        hm.resize(nm);
-        cudaMemcpyAsync(hm.data(), d_marks, (size_t)nm * sizeof(LtMark), cudaMemcpyDeviceToHost, st);
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = B2H_ECUDA; }
       }
+      int nm = 0;
+      bool again = false;
+      if (rc == B2H_OK) {
+        cudaMemcpyAsync(&nm, d_nm, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { ctx->err = std::string("long-target Viterbi kernel: ") + cudaGetErrorString(e); rc = B2H_ECUDA; }
+        else if (nm > a.cap) {
+          if (attempt == 0) { a.cap = nm; again = true; }
+          else { ctx->err = "long-target Viterbi: landmark list overflow"; rc = B2H_ERANGE; }
+        }
+        else if (nm > 0) {
+          hm.resize(nm);
+          cudaMemcpyAsync(hm.data(), d_marks, (size_t)nm * sizeof(LtMark), cudaMemcpyDeviceToHost, st);
+          if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = B2H_ECUDA; }
+        }
+      }
+      cudaFreeAsync(d_marks, st);
+      if (!again) break;
     }
-    cudaFreeAsync(d_buf, st); cudaFreeAsync(d_nm, st); cudaFreeAsync(d_marks, st);
+    cudaFreeAsync(d_buf, st); cudaFreeAsync(d_nm, st);
     if (rc != B2H_OK) return rc;
   }
   const size_t nm = hm.size();

@@ -91,7 +91,7 @@ class OracleBackend:
         return shuffled, longtarget._take_windows(out, no.value)
 
 
-def compare_with_reference(pair, block, got, exact_scores, **kw):
+def compare_with_reference(pair, block, got, exact_scores, fwd_rel=2e-7, **kw):
     """Stage by stage against ref_longtarget_stages, chunk by chunk.  Returns totals for the caller's sanity checks."""
     tot = dict(msvwin=0, vitmark=0, vitwin=0, passed=0)
     mw, vm, vw = got["msvwin"], got["vitmark"], got["vitwin"]
@@ -128,7 +128,8 @@ def compare_with_reference(pair, block, got, exact_scores, **kw):
                 assert np.array_equal(vs[:, 1:], ref["vitsc"][:, 1:]), ci
             else:
                 assert np.all(np.abs(vs[:, 1] - ref["vitsc"][:, 1]) <= 4 * np.spacing(np.abs(ref["vitsc"][:, 1]))), ci
-                assert np.all(np.abs(vs[:, 2] - ref["vitsc"][:, 2]) <= 1e-4 + 2e-7 * np.abs(ref["vitsc"][:, 2])), ci   # Forward: 1e-4 nats
+                dev = np.abs(vs[:, 2] - ref["vitsc"][:, 2])                                                          # Forward: 1e-4 nats
+                assert np.all(dev <= 1e-4 + fwd_rel * np.abs(ref["vitsc"][:, 2])), (ci, float(dev.max()), ref["vitsc"][:, 2][np.argmax(dev)])
             assert np.array_equal(got["vitpass"][vsel], ref["vitpass"]), ci
         assert np.array_equal(got["counters"][ci], ref["counters"]), (ci, got["counters"][ci], ref["counters"])
         tot["msvwin"] += len(sel); tot["vitmark"] += len(m); tot["vitwin"] += len(vsel); tot["passed"] += int(ref["vitpass"].sum())

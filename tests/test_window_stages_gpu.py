@@ -39,7 +39,7 @@ def test_viterbi_landmarks_against_port_without_bias(make_pair):
     be = longtarget.CudaBackend(pair.om, block)
     lens = np.array([len(s) for s in block], np.int64)
     wdb = be.window_db(np.arange(len(block)), np.ones(len(block), np.int64), lens)
-    for fsc in (-3.0, -9.0):
+    for fsc in (-3.0, -9.0, -14.0):
         filtersc = np.full(len(block), fsc, np.float32)
         marks, wins = be.viterbi_windows(wdb, filtersc, np.ones(len(block), np.uint8), 3e-3)
         n = 0
@@ -58,5 +58,8 @@ def test_long_windows_are_cut_at_80kb(make_pair):
     dna = pair.hmm.alphabet
     block = lt_common.easel.DigitalSequenceBlock(dna, [lt_common.easel.DigitalSequence(dna, name=b"rep", sequence=seq)])
     got = longtarget.stages(pair.om, block, **KW)
-    tot = lt_common.compare_with_reference(pair, block, got, exact_scores=False, **KW)
+    # 80 kb of back-to-back homologs score ~1e5 nats: float32 resolves 8e-3 there and both implementations add thousands of
+    # rounded log(scale) terms, at different rows -- the Forward scores of THIS test are compared to 1e-4 relative, everything
+    # else (landmarks, windows, gates, counters) exactly as in the tests above
+    tot = lt_common.compare_with_reference(pair, block, got, exact_scores=False, fwd_rel=1e-4, **KW)
     assert got["vitwin"]["length"].max() == 80000 and tot["vitwin"] >= 3
