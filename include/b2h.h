@@ -328,6 +328,22 @@ int  b2h_longtarget_vit_finish(const b2h_profile *p, b2h_window *marks, size_t n
  * configured for cfg_len (vitfilter.c:330-346; host only). */
 int  b2h_longtarget_vit_threshold(const b2h_profile *p, int cfg_len, float filtersc, double F2, int32_t *thresh, int32_t *xw_move);
 
+/* Behind the Forward gate (p7_pli_postViterbi_LongTarget, p7_pipeline.c:1113-1280), host only: for every window that passed,
+ * given its residues and its Forward / Backward parser specials ((L+1) rows of {E,N,J,B,C,SCALE}, profile configured for the
+ * window's length), run domain definition with its long-target branches (p7_domaindef.c:814-982: envelope-length
+ * configuration, background re-estimated from the envelope, envelope trimmed to the alignment, bias = score without the
+ * re-estimation) and build one hit per domain: scores corrected to the model's max_length window, coordinates mapped to the
+ * target (window_start = position of the window in the chunk, seq_start = the chunk's first coordinate, the last one for the
+ * complement strand).  hit.profile = index of the window; hit.seq = the window's <seq>.  Works on host profiles. */
+typedef struct {
+  const uint8_t *dsq; int32_t L;
+  const float *fwd_xmx, *bck_xmx;
+  int64_t window_start, seq_start;
+  int32_t complement, seq;
+} b2h_lt_window;
+int  b2h_longtarget_domains(const b2h_profile *p, const b2h_lt_window *windows, size_t n, const b2h_search_params *params,
+                            b2h_results **out);
+
 /* Register tile the SSV kernel uses for a model of M nodes: G lanes per comparison (32/G comparisons per warp), NR packed
  * registers (2*NR nodes) per lane, and the number of 128-byte shared-memory wavefronts one DP row of one WARP moves
  * (emission loads + shuffles) -- the quantity bench.py's on-chip roofline is computed from.  B2H_EINVAL if M > 3071. */

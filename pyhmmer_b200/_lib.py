@@ -86,6 +86,12 @@ class HMMDesc(ctypes.Structure):
                 ("evparam", c_float * 6), ("cutoff", c_float * 6), ("compo", c_float * 20)]
 
 
+class LtWindow(ctypes.Structure):
+    """``b2h_lt_window`` (include/b2h.h)."""
+    _fields_ = [("dsq", c_void_p), ("L", c_i32), ("fwd_xmx", c_void_p), ("bck_xmx", c_void_p),
+                ("window_start", c_i64), ("seq_start", c_i64), ("complement", c_i32), ("seq", c_i32)]
+
+
 class B2HError(RuntimeError):
     def __init__(self, status, fn, detail=""):
         self.status = status
@@ -156,6 +162,7 @@ def _load():
     sig("b2h_longtarget_viterbi_windows", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double,
         P(c_void_p), P(c_size_t), P(c_void_p), P(c_size_t))
     sig("b2h_longtarget_vit_finish", c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, P(c_void_p), P(c_size_t))
+    sig("b2h_longtarget_domains", c_int, c_void_p, c_void_p, c_size_t, P(SearchParams), P(c_void_p))
     sig("b2h_longtarget_vit_threshold", c_int, c_void_p, c_int, c_float, ctypes.c_double, P(c_i32), P(c_i32))
     sig("b2h_hmm_convert_many", c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int,
         P(c_void_p), P(c_void_p), P(c_size_t))

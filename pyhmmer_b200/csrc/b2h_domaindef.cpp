@@ -1039,6 +1039,172 @@ void ddef_finish(const b2h_ddef_task &t, const b2h_search_params *prm, TaskState
   out.valid = true;
 }
 
+// =====================================================================================================
+// Long-target (nhmmer) branch: what p7_pli_postViterbi_LongTarget does with a window that passed the Forward gate
+// (p7_pipeline.c:1113-1280) and the long_target paths of rescore_isolated_domain (p7_domaindef.c:814-982).
+// =====================================================================================================
+
+// The 4-lane Cephes expf of the reference, one lane (esl_sse.c:182-246; same restatement as b2h_host.cpp's).
+inline float lt_cephes_expf(float x) {
+  const float p0 = 1.9875691500E-4f, p1 = 1.3981999507E-3f, p2 = 8.3334519073E-3f,
+              p3 = 4.1665795894E-2f, p4 = 1.6666665459E-1f, p5 = 5.0000001201E-1f;
+  const float c0 = 0.693359375f, c1 = -2.12194440e-4f;
+  const float maxlogf = 88.3762626647949f, minlogf = -88.3762626647949f;
+  const bool over = (x > maxlogf), under = (x <= minlogf);
+  float fx = x * 1.44269504088896341f;
+  fx = fx + 0.5f;
+  int k = (int)fx;
+  float tmp = (float)k;
+  if (tmp > fx) tmp = tmp - 1.0f;
+  fx = tmp;
+  k = (int)fx;
+  tmp = fx * c0;
+  float z = fx * c1;
+  x = x - tmp;
+  x = x - z;
+  z = x * x;
+  float y = p0;       y = y * x;
+  y = y + p1;         y = y * x;
+  y = y + p2;         y = y * x;
+  y = y + p3;         y = y * x;
+  y = y + p4;         y = y * x;
+  y = y + p5;         y = y * z;
+  y = y + x;
+  y = y + 1.0f;
+  union { float f; int32_t i; } u; u.i = (k + 127) << 23;
+  y = y * u.f;
+  if (over) y = std::numeric_limits<float>::infinity();
+  if (under) y = 0.0f;
+  return y;
+}
+
+// reparameterize_model (p7_domaindef.c:715-750) + p7_oprofile_UpdateFwdEmissionScores (impl_sse/p7_oprofile.c:438-487):
+// the background becomes a mixture of the model's own and the composition of the envelope i..i+Ld-1 of the window, and the
+// match odds are rebuilt from the emission probabilities p7_oprofile_GetFwdEmissionArray recovered (odds x background).
+// rsc [Kp][M] receives the new odds.  (Model masks -- the MM line -- are not carried by b2h_profile and are not honoured.)
+void lt_reparameterize(const b2h_profile *prof, const uint8_t *dsq, int wlen, int i, int Ld, std::vector<float> &rsc)
+{
+  const int M = prof->M, K = prof->K, Kp = prof->Kp;
+  const uint8_t *degen = prof->h_degen.data();
+  float cnt[B2H_MAXABET], bgn[B2H_MAXABET];
+  for (int x = 0; x < K; x++) cnt[x] = 0.f;
+  for (int pos = i; pos < i + Ld; pos++) {                  // esl_sq_CountResidues / esl_abc_FCount
+    const int x = dsq[pos - 1];
+    if (x < K) cnt[x] += 1.0f;
+    else if (x == K || x >= Kp - 2) continue;               // gap, nonresidue, missing data
+    else {
+      int nd = 0;
+      for (int y = 0; y < K; y++) nd += degen[(size_t)x * K + y] ? 1 : 0;
+      for (int y = 0; y < K; y++) if (degen[(size_t)x * K + y]) cnt[y] += 1.0f / (float)nd;
+    }
+  }
+  fnorm(cnt, K);
+  const float bg_smooth = (float)(25.0 / (double)std::min(100, std::max(50, wlen)));
+  for (int x = 0; x < K; x++) bgn[x] = (float)((double)(bg_smooth * prof->bgf[x]) + ((1.0 - (double)bg_smooth) * (double)cnt[x]));
+  rsc.resize((size_t)Kp * M);
+  const float *orig = prof->h_fwd_rsc.data();
+  float sc[B2H_MAXCODE];
+  for (int k = 1; k <= M; k++) {
+    for (int x = 0; x < K; x++) {
+      const float em = orig[(size_t)x * M + (k - 1)] * prof->bgf[x];      // p7_oprofile_GetFwdEmissionArray
+      sc[x] = (float)log((double)em / bgn[x]);
+    }
+    sc[K] = sc[Kp - 2] = sc[Kp - 1] = NEGINF;
+    for (int x = K + 1; x <= Kp - 3; x++) {                  // esl_abc_FExpectScVec
+      float result = 0.f, denom = 0.f;
+      for (int y = 0; y < K; y++) if (degen[(size_t)x * K + y]) { result += sc[y] * bgn[y]; denom += bgn[y]; }
+      sc[x] = result / denom;
+    }
+    for (int x = 0; x < Kp; x++) rsc[(size_t)x * M + (k - 1)] = lt_cephes_expf(sc[x]);
+  }
+}
+
+struct LtWindow {
+  const uint8_t *dsq; int L; const float *fx, *bx;
+  int64_t window_start, seq_start; int complement; int seq;
+};
+
+// One window: regions and envelopes exactly as for proteins (ddef_regions), then per envelope the long-target rescoring and
+// the hit the reference builds from it.  Hits are appended in the order of ddef->dcl.
+void lt_window(Worker &w, const b2h_profile *prof, const LtWindow &lw, const b2h_search_params *prm, std::vector<HitOut> &outs)
+{
+  b2h_ddef_task t;
+  t.surv.profile = 0; t.surv.seq = lw.seq; t.surv.fwdsc = 0.f; t.surv.filtersc = 0.f;
+  t.prof = prof; t.dsq = lw.dsq; t.L = lw.L; t.fx = lw.fx; t.bx = lw.bx; t.bck_own_scales = false;
+  TaskState ts;
+  ddef_regions(w, t, prm, ts);
+  if (ts.dead || ts.nregions == 0 || ts.envs.empty()) return;
+  const int max_env_extra = 20, maxL = prof->max_length;
+  std::vector<float> rsc, n2sc((size_t)lw.L + 1, 0.f);
+  const double LOG2 = 0.69314718055994529;
+  const double tau = prof->evparam[4], lam = prof->evparam[5];
+  auto logsurv = [&](double x) { return (x < tau) ? 0.0 : -lam * (x - tau); };
+  for (size_t d = 0; d < ts.envs.size(); d++) {
+    EnvRec &e = ts.envs[d];
+    int i = e.i, j = e.j;
+    Model m; model_of(w, prof, m);
+    DomOut dom;
+    bool ok = true;
+    for (int pass = 0; pass < 2; pass++) {
+      const int Ld = j - i + 1;
+      configure(m, false, Ld);                              // p7_oprofile_ReconfigRestLength(om, env_len), unihit
+      if (prm->do_null2) { lt_reparameterize(prof, lw.dsq, lw.L, i, Ld, rsc); m.rsc = rsc.data(); }
+      e.i = i; e.j = j; e.null2_done = true;               // (no null2 by expectation on this path)
+      if (!rescore_numeric(w, m, lw.dsq, e)) { ok = false; break; }
+      std::fill(n2sc.begin(), n2sc.end(), 0.f);
+      if (!render_domain(m, prof, lw.dsq, e, n2sc, dom)) { ok = false; break; }
+      if (pass == 0 && (i < dom.d.sqfrom - max_env_extra || j > dom.d.sqto + max_env_extra)) {
+        i = std::max(i, dom.d.sqfrom - max_env_extra);     // trim the envelope around the alignment and do it again
+        j = std::min(j, dom.d.sqto + max_env_extra);
+        continue;
+      }
+      break;
+    }
+    if (!ok) continue;
+    const int Ld = j - i + 1;
+    float envsc = e.envsc, domcorrection = envsc;
+    if (prm->do_null2) {                                    // what the score would have been without reparameterisation
+      Model mo; model_of(w, prof, mo);
+      configure(mo, false, Ld);
+      float sc = domcorrection;
+      if (forward_full(mo, lw.dsq + i - 1, Ld, w.fwd, &sc)) domcorrection = sc;
+    }
+    if (domcorrection < envsc) envsc = domcorrection;
+    b2h_domain &dd = dom.d;
+    dd.domcorrection = domcorrection - envsc;
+    dd.envsc = envsc; dd.ienv = i; dd.jenv = j;
+
+    // p7_pli_postViterbi_LongTarget (p7_pipeline.c:1150-1262): one hit per domain
+    const int env_len = dd.jenv - dd.ienv + 1, ali_len = dd.jali - dd.iali + 1;
+    if (ali_len < 8) continue;
+    float bitscore = dd.envsc;
+    bitscore = (float)((double)bitscore - 2 * log(2. / (env_len + 2)));
+    bitscore = (float)((double)bitscore + 2 * log(2. / (maxL + 2)));
+    bitscore = (float)((double)bitscore - (env_len - ali_len) * log((double)((float)env_len / (float)(env_len + 2))));
+    bitscore = (float)((double)bitscore + (std::max(maxL, env_len) - ali_len) * log((double)((float)maxL / (float)(maxL + 2))));
+    const float dom_bias = dd.domcorrection;
+    b2h_len_params lp; b2h_length_params(std::max(maxL, env_len), 1.0f, &lp);
+    const float dom_score = (float)((double)(bitscore - lp.null1) / LOG2);
+    const double dom_lnP = logsurv((double)dom_score);
+    // positions in the target: x + seq_start + window_start - 2 on the top strand, seq_start - (window_start + x) + 2 on the other
+    auto map  = [&](int x) -> int32_t { return (int32_t)((int64_t)x + lw.seq_start + lw.window_start - 2); };
+    auto mapc = [&](int x) -> int32_t { return (int32_t)(lw.seq_start - (lw.window_start + (int64_t)x) + 2); };
+    if (lw.complement) { dd.ienv = mapc(dd.ienv); dd.jenv = mapc(dd.jenv); dd.iali = mapc(dd.iali); dd.jali = mapc(dd.jali); dd.sqfrom = mapc(dd.sqfrom); dd.sqto = mapc(dd.sqto); }
+    else               { dd.ienv = map(dd.ienv);  dd.jenv = map(dd.jenv);  dd.iali = map(dd.iali);  dd.jali = map(dd.jali);  dd.sqfrom = map(dd.sqfrom);  dd.sqto = map(dd.sqto); }
+    dd.dombias = dom_bias; dd.bitscore = dom_score; dd.lnP = dom_lnP;
+    HitOut out;
+    b2h_hit &h = out.hit;
+    memset(&h, 0, sizeof h);
+    h.profile = 0; h.seq = lw.seq;
+    h.pre_score = (float)((double)bitscore / LOG2); h.pre_lnP = logsurv((double)h.pre_score);
+    h.score = h.sum_score = dom_score; h.lnP = h.sum_lnP = dom_lnP;
+    h.ndom = 1; h.best_domain = 0;
+    out.doms.push_back(std::move(dom));
+    out.valid = true;
+    outs.push_back(std::move(out));
+  }
+}
+
 } // namespace
 
 // Odds-space Forward/Backward rows decay into denormals away from the alignment; x86 handles those ~100x slower.
@@ -1193,5 +1359,34 @@ int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_param
     }
     res->hits.push_back(h);
   }
+  return B2H_OK;
+}
+
+// Hits of the Forward-surviving windows of a long target (host side; see lt_window).
+int b2h_longtarget_domains_host(const b2h_profile *p, const b2h_lt_window *wins, size_t n, const b2h_search_params *prm, int nthreads, b2h_results *res)
+{
+  std::vector<std::vector<HitOut>> outs(n);
+  std::vector<uint32_t> order(n);
+  for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return wins[a].L > wins[b].L; });
+  ThreadPool::get().parallel_for(n, std::max(1, nthreads), [&](Worker &w, size_t q) {
+    const b2h_lt_window &x = wins[order[q]];
+    LtWindow lw; lw.dsq = x.dsq; lw.L = x.L; lw.fx = x.fwd_xmx; lw.bx = x.bck_xmx;
+    lw.window_start = x.window_start; lw.seq_start = x.seq_start; lw.complement = x.complement; lw.seq = x.seq;
+    lt_window(w, p, lw, prm, outs[order[q]]);
+  });
+  for (size_t e = 0; e < n; e++)
+    for (auto &o : outs[e]) {
+      b2h_hit h = o.hit;
+      h.profile = (int32_t)e;                              // the window the hit came from
+      h.dom_offset = (int64_t)res->doms.size();
+      for (auto &dm : o.doms) {
+        b2h_domain d = dm.d;
+        d.text_offset = (int64_t)res->text.size();
+        res->text.insert(res->text.end(), dm.text.begin(), dm.text.end());
+        res->doms.push_back(d);
+      }
+      res->hits.push_back(h);
+    }
   return B2H_OK;
 }

@@ -48,3 +48,7 @@ struct b2h_ddef_pool {
   // rescoring of the envelopes runs there (GPU); without (host-only profiles, tests) on the pool's threads.
   int run(std::vector<b2h_ddef_task> &tasks, const b2h_search_params *prm, b2h_results *res, b2h_env_backend *backend = nullptr);
 };
+
+// Long-target (nhmmer) windows behind the Forward gate -> hits, one per domain (p7_pli_postViterbi_LongTarget); hit.profile
+// carries the index of the window the hit came from.
+int b2h_longtarget_domains_host(const b2h_profile *p, const b2h_lt_window *wins, size_t n, const b2h_search_params *prm, int nthreads, b2h_results *res);

@@ -736,6 +736,19 @@ int b2h_debug_domaindef(const b2h_profile *p, const uint8_t *dsq, int L, const f
   return B2H_OK;
 }
 
+int b2h_longtarget_domains(const b2h_profile *p, const b2h_lt_window *windows, size_t n, const b2h_search_params *prm, b2h_results **out)
+{
+  if (!p || (!windows && n) || !prm || !out || p->max_length <= 0) return B2H_EINVAL;
+  for (size_t i = 0; i < n; i++) if (!windows[i].dsq || windows[i].L < 1 || !windows[i].fwd_xmx || !windows[i].bck_xmx) return B2H_EINVAL;
+  b2h_results *res = new b2h_results();
+  res->counters.assign(4, 0);
+  b2h_ddef_pool pool(prm->host_threads);
+  const int st = b2h_longtarget_domains_host(p, windows, n, prm, pool.nthreads, res);
+  if (st != B2H_OK) { delete res; return st; }
+  *out = res;
+  return B2H_OK;
+}
+
 size_t            b2h_results_nhits   (const b2h_results *r) { return r ? r->hits.size() : 0; }
 const b2h_hit    *b2h_results_hits    (const b2h_results *r) { return r ? r->hits.data() : nullptr; }
 size_t            b2h_results_ndomains(const b2h_results *r) { return r ? r->doms.size() : 0; }

@@ -79,3 +79,88 @@ def test_long_windows_are_cut_at_80kb():
     got = longtarget.stages(pair.om, block, backend=lt_common.OracleBackend(pair, block), **kw)
     tot = lt_common.compare_with_reference(pair, block, got, exact_scores=True, **kw)
     assert got["vitwin"]["length"].max() == 80000 and tot["vitwin"] >= 3, (tot, got["vitwin"]["length"])
+
+
+@pytest.mark.parametrize("M,mu_shift,null2,complement,layout", [(60, -3.0, True, False, "plain"), (121, -2.0, True, True, "plain"),
+                                                                 (121, -2.0, False, False, "plain"), (333, -2.0, True, False, "plain"),
+                                                                 (60, -3.0, True, False, "tandem"), (121, -2.0, True, True, "tandem"),
+                                                                 (60, -3.0, True, False, "repeats"), (121, -2.0, True, False, "repeats"),
+                                                                 (121, -2.0, False, True, "repeats")])
+def test_hits_behind_the_forward_gate(M, mu_shift, null2, complement, layout):
+    """b2h_longtarget_domains (the long-target branches of domain definition + the hit arithmetic of
+    p7_pli_postViterbi_LongTarget) fed with the reference's parser specials for the windows that passed the Forward gate
+    reproduces the hits of the real p7_Pipeline_LongTarget: coordinates exactly, scores to 2e-3 bits."""
+    pair, rng = lt_common.dna_model(ModelPair, M, mu_shift=mu_shift)
+    block = lt_common.dna_chunks(pair, rng, [90000], nplant=10)
+    seq = block[0].sequence
+    if layout == "repeats":
+        # a homolog flanked by runs of a short piece of itself: the envelope reaches far beyond the alignment and the
+        # reference trims it to the alignment +- 20 and rescores (p7_domaindef.c:893-935)
+        seq = seq.copy()
+        pos = 500
+        for rep in range(24):
+            dom = lt_common.synth.emit_sequence(pair.hmm, rng)
+            frag, nrep = ((6, 10), (8, 8), (10, 6))[rep % 3]
+            a = int(rng.integers(5, max(6, len(dom) - frag - 5)))
+            tail = np.concatenate([dom[a:a + frag]] * nrep)
+            piece = np.concatenate([tail, dom, tail])
+            seq[pos:pos + len(piece)] = piece
+            pos += len(piece) + 3000
+        block = lt_common.easel.DigitalSequenceBlock(block.alphabet, [lt_common.easel.DigitalSequence(block.alphabet, name=b"r", sequence=seq)])
+    if layout == "tandem":
+        # back-to-back and overlapping copies (multi-domain regions -> stochastic clustering) and homologs continued by a
+        # degraded copy of themselves (envelopes far wider than the alignment -> the trimming pass)
+        seq = seq.copy()
+        pos = 500
+        for rep in range(6):
+            doms = [lt_common.synth.emit_sequence(pair.hmm, rng) for _ in range(3)]
+            weak = doms[2].copy()
+            mask = rng.random(len(weak)) < 0.45
+            weak[mask] = rng.integers(0, 4, int(mask.sum()))
+            piece = np.concatenate([doms[0], rng.integers(0, 4, rep).astype(np.uint8), doms[1], doms[2][:len(doms[2]) // 2], weak])
+            seq[pos:pos + len(piece)] = piece
+            pos += len(piece) + 3000
+        block = lt_common.easel.DigitalSequenceBlock(block.alphabet, [lt_common.easel.DigitalSequence(block.alphabet, name=b"t", sequence=seq)])
+    start = 1001
+    if complement:                                        # <seq> plays the chunk as esl_sq_ReverseComplement leaves it:
+        start = 1001 + len(seq) - 1                       # sq->start is then the chunk's LAST coordinate
+    kw = dict(F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=240, B3=1000)
+    got = longtarget.stages(pair.om, block, backend=lt_common.OracleBackend(pair, block), **kw)
+    cnt, rhits = pair.ref.longtarget_pipeline(seq, null2=null2, start=start, complement=complement)
+    assert np.array_equal(got["counters"][0], cnt[:4]) and len(rhits) >= 3
+    mw, vw = got["msvwin"], got["vitwin"]
+    keep = [], []
+    wins = (_lib.LtWindow * int(got["vitpass"].sum()))()
+    q = 0
+    for v in np.flatnonzero(got["vitpass"]):
+        n0 = int(mw["n"][vw["seq"][v]] + vw["n"][v] - 1)            # start of the window in the chunk, 1-based
+        L = int(vw["length"][v])
+        codes = np.ascontiguousarray(seq[n0 - 1:n0 - 1 + L])
+        _, _, st, fx, bx = pair.ref.fwdbck(codes, want_x=True)
+        assert st == 0
+        keep[0].append((codes, fx, bx))
+        w = wins[q]; q += 1
+        w.dsq, w.L, w.fwd_xmx, w.bck_xmx = codes.ctypes.data, L, fx.ctypes.data, bx.ctypes.data
+        w.window_start, w.seq_start, w.complement, w.seq = n0, start, int(complement), 0
+    hp = ctypes.c_void_p()
+    assert _lib.lib.b2h_profile_create_host(ctypes.byref(pair.om._desc), ctypes.byref(hp)) == 0
+    _lib.lib.b2h_profile_set_annotation(hp, (pair.hmm.consensus or "x" * M).encode(), None, None, pair.hmm.alphabet.symbols.encode())
+    prm = _lib.SearchParams(0.02, 3e-3, 3e-5, 1, int(null2), 42, 1)
+    out = ctypes.c_void_p()
+    _lib.check(_lib.lib.b2h_longtarget_domains(hp, wins, len(wins), ctypes.byref(prm), ctypes.byref(out)), "b2h_longtarget_domains")
+    hits, doms, text = _lib.read_results(out)
+    _lib.lib.b2h_results_destroy(out)
+    _lib.lib.b2h_profile_destroy(hp)
+    assert len(hits) == len(rhits), (len(hits), len(rhits))
+    nbias = 0
+    for h, r in zip(hits, rhits):
+        d = doms[h.dom_offset]
+        assert (d.ienv, d.jenv, d.iali, d.jali, d.hmmfrom, d.hmmto) == tuple(int(x) for x in (r[0], r[1], r[2], r[3], r[10], r[11])), (h.profile, r)
+        assert (d.sqfrom, d.sqto) == (d.iali, d.jali)
+        assert abs(h.score - r[4]) < 2e-3 and abs(d.dombias - r[5]) < 2e-3 and abs(h.pre_score - r[6]) < 2e-3, (h.score, r)
+        assert abs(h.lnP - r[7]) < 2e-3 and abs(d.envsc - r[8]) < 2e-3 and abs(d.oasc - r[9]) < 2e-3
+        assert h.ndom == 1 and d.bitscore == h.score and h.sum_score == h.score
+        nbias += d.dombias > 0
+    assert null2 or nbias == 0
+    if layout == "repeats":                               # the trimming pass ran: an envelope edge sits exactly 20 from the alignment
+        assert any(abs(int(r[2]) - int(r[0])) == 20 or abs(int(r[1]) - int(r[3])) == 20 for r in rhits)
