@@ -340,9 +340,17 @@ typedef struct {
   const float *fwd_xmx, *bck_xmx;
   int64_t window_start, seq_start;
   int32_t complement, seq;
+  int32_t bck_own_scales;     /* 0: bck_xmx uses Forward's scale factors, as the reference's Backward does */
+  int32_t reserved;
 } b2h_lt_window;
 int  b2h_longtarget_domains(const b2h_profile *p, const b2h_lt_window *windows, size_t n, const b2h_search_params *params,
                             b2h_results **out);
+/* The same with the parser passes on the GPU: <windows> holds the windows that passed the Forward gate (one sequence each);
+ * Forward and Backward parsers run on the device for all of them (profile configured for each window's length), their special
+ * rows come back, domain definition runs on the host threads.  window_start / seq_start / complement / seq: [n] per window. */
+int  b2h_longtarget_hits(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *windows, const int64_t *window_start,
+                         const int64_t *seq_start, const int32_t *complement, const int32_t *seq,
+                         const b2h_search_params *params, b2h_results **out);
 
 /* Register tile the SSV kernel uses for a model of M nodes: G lanes per comparison (32/G comparisons per warp), NR packed
  * registers (2*NR nodes) per lane, and the number of 128-byte shared-memory wavefronts one DP row of one WARP moves

@@ -435,6 +435,91 @@ int ref_longtarget_pipeline(REFM *m, const uint8_t *dsq, int L, double F1, doubl
   return status;
 }
 
+/* nhmmer as pyhmmer runs it: LongTargetsPipeline.search_hmm (src/pyhmmer/plan7.pyx:7258-7412) with its window loop
+ * _search_loop_longtargets (:7541-7663) restated in C over the reference's own functions: every target is cut into windows
+ * of <block_length> residues that keep max_length residues of context, each window goes through p7_Pipeline_LongTarget on
+ * the strands asked for, then p7_tophits_ComputeNhmmerEvalues, SortBySeqidxAndAlipos, RemoveDuplicates, SortBySortkey,
+ * Threshold.  (idlen_list_assign only fills the display's sequence length and is skipped.)
+ * strands: 0 both, 1 top only, 2 bottom only.  out [cap] in final (sorted) order; stats [6] = nres, nseqs, pos_past_msv,
+ * pos_past_bias, pos_past_vit, pos_past_fwd. */
+typedef struct {
+  long   seqidx, ienv, jenv, iali, jali, hmmfrom, hmmto;
+  float  score, bias, pre_score, envsc, oasc;
+  double lnP;
+  int    flags, dom_reported, dom_included, pad;
+} REF_LTHIT;
+
+long ref_nhmmer(REFM *m, int nseq, const uint8_t **dsq, const long *len, long block_length, int strands,
+                double F1, double F2, double F3, int do_bias, int do_null2, double E, double incE, long cap, REF_LTHIT *out, long *stats)
+{
+  P7_OPROFILE *om = m->om;
+  P7_PIPELINE *pli = p7_pipeline_Create(NULL, om->M, 100, TRUE, p7_SEARCH_SEQS);
+  P7_TOPHITS *th = p7_tophits_Create();
+  P7_SCOREDATA *data = p7_hmm_ScoreDataCreate(om, NULL);
+  ESL_SQ *tmpsq = esl_sq_CreateDigital(m->abc);
+  long C = om->max_length, W = block_length, i, h, nout;
+  int t;
+  pli->F1 = F1; pli->F2 = F2; pli->F3 = F3;
+  pli->do_biasfilter = do_bias; pli->do_null2 = do_null2;
+  pli->E = E; pli->incE = incE;
+  pli->strands = (strands == 1) ? p7_STRAND_TOPONLY : (strands == 2) ? p7_STRAND_BOTTOMONLY : p7_STRAND_BOTH;
+  pli->block_length = (int)W;
+  pli->nseqs = 0;
+  if (C <= 0 || W <= C) return -1;
+  p7_pli_NewModel(pli, om, m->bg);
+  for (t = 0; t < nseq; t++) {
+    char name[32];
+    snprintf(name, sizeof name, "seq%d", t);
+    tmpsq->idx = t; tmpsq->L = -1;
+    esl_sq_SetAccession(tmpsq, ""); esl_sq_SetName(tmpsq, name); esl_sq_SetDesc(tmpsq, ""); esl_sq_SetSource(tmpsq, name);
+    esl_sq_GrowTo(tmpsq, ESL_MIN(W + C, len[t]));
+    for (i = 0; i < len[t]; i += W - C) {
+      tmpsq->C = (i == 0) ? 0 : ESL_MIN(C, len[t] - i);
+      tmpsq->W = ESL_MIN(W, len[t] - i - tmpsq->C);
+      tmpsq->n = tmpsq->C + tmpsq->W;
+      tmpsq->start = i + 1;
+      tmpsq->end = i + tmpsq->n;
+      memcpy(tmpsq->dsq + 1, dsq[t] + i + 1, tmpsq->n);
+      tmpsq->dsq[0] = tmpsq->dsq[tmpsq->n + 1] = eslDSQ_SENTINEL;
+      p7_pli_NewSeq(pli, tmpsq);
+      if (pli->strands != p7_STRAND_BOTTOMONLY) {
+        pli->nres -= tmpsq->C;
+        p7_Pipeline_LongTarget(pli, om, data, m->bg, th, pli->nseqs, tmpsq, p7_NOCOMPLEMENT, NULL, NULL, NULL);
+        p7_pipeline_Reuse(pli);
+      } else pli->nres -= tmpsq->n;
+      if (pli->strands != p7_STRAND_TOPONLY) {
+        esl_sq_ReverseComplement(tmpsq);
+        p7_Pipeline_LongTarget(pli, om, data, m->bg, th, pli->nseqs, tmpsq, p7_COMPLEMENT, NULL, NULL, NULL);
+        p7_pipeline_Reuse(pli);
+        pli->nres += tmpsq->W;
+      }
+    }
+    esl_sq_Reuse(tmpsq);
+    pli->nseqs++;
+  }
+  p7_tophits_ComputeNhmmerEvalues(th, (double)pli->nres, om->max_length);
+  p7_tophits_SortBySeqidxAndAlipos(th);
+  p7_tophits_RemoveDuplicates(th, TRUE);
+  p7_tophits_SortBySortkey(th);
+  p7_tophits_Threshold(th, pli);
+  stats[0] = pli->nres; stats[1] = pli->nseqs; stats[2] = pli->pos_past_msv; stats[3] = pli->pos_past_bias;
+  stats[4] = pli->pos_past_vit; stats[5] = pli->pos_past_fwd;
+  nout = th->N;
+  for (h = 0; h < nout && h < cap; h++) {
+    P7_HIT *hit = th->hit[h];
+    REF_LTHIT *o = out + h;
+    o->seqidx = hit->seqidx; o->ienv = hit->dcl[0].ienv; o->jenv = hit->dcl[0].jenv; o->iali = hit->dcl[0].iali; o->jali = hit->dcl[0].jali;
+    o->hmmfrom = hit->dcl[0].ad->hmmfrom; o->hmmto = hit->dcl[0].ad->hmmto;
+    o->score = hit->score; o->bias = hit->dcl[0].dombias; o->pre_score = hit->pre_score; o->envsc = hit->dcl[0].envsc; o->oasc = hit->dcl[0].oasc;
+    o->lnP = hit->lnP; o->flags = hit->flags; o->dom_reported = hit->dcl[0].is_reported; o->dom_included = hit->dcl[0].is_included; o->pad = 0;
+  }
+  esl_sq_Destroy(tmpsq);
+  p7_hmm_ScoreDataDestroy(data);
+  p7_tophits_Destroy(th);
+  p7_pipeline_Destroy(pli);
+  return nout;
+}
+
 double ref_gumbel_surv(double x, double mu, double lambda) { return esl_gumbel_surv(x, mu, lambda); }
 double ref_exp_surv(double x, double mu, double lambda)    { return esl_exp_surv(x, mu, lambda); }
 

@@ -68,6 +68,9 @@ def lib():
         L.ref_generic.argtypes = [vp, vp, ci] + [ctypes.POINTER(cf)] * 4
         L.ref_longtarget_windows.argtypes = [vp, vp, ci, ctypes.c_double, ci, vp, vp, vp, vp, vp, vp, vp]
         L.ref_longtarget_stages.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ci, ci, ci] + [vp] * 11
+        L.ref_nhmmer.restype = ctypes.c_long
+        L.ref_nhmmer.argtypes = [vp, ci, vp, vp, ctypes.c_long, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci,
+                                 ctypes.c_double, ctypes.c_double, ctypes.c_long, vp, vp]
         L.ref_vit_longtarget.argtypes = [vp, vp, ci, ci, cf, ctypes.c_double, ci, vp]
         L.ref_longtarget_pipeline.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ctypes.c_long, ci, vp, ci, vp]
         L.ref_gdecoding.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), vp]
@@ -98,6 +101,12 @@ def dsq_of(codes):
     d = np.full(codes.size + 2, 255, dtype=np.uint8)
     d[1:-1] = codes
     return d
+
+
+class RefLtHit(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_long) for n in ("seqidx", "ienv", "jenv", "iali", "jali", "hmmfrom", "hmmto")] + \
+               [(n, ctypes.c_float) for n in ("score", "bias", "pre_score", "envsc", "oasc")] + \
+               [("lnP", ctypes.c_double), ("flags", ctypes.c_int), ("dom_reported", ctypes.c_int), ("dom_included", ctypes.c_int), ("pad", ctypes.c_int)]
 
 
 class RefModel:
@@ -238,6 +247,22 @@ class RefModel:
         return dict(msvwin=msvwin[:nm.value].copy(), msvsc=msvsc[:nm.value].copy(), msvflag=msvflag[:nm.value].copy(),
                     vithit=vithit[:nh.value].copy(), vitwin=vitwin[:nv.value].copy(), vitsc=vitsc[:nv.value].copy(),
                     vitpass=vitpass[:nv.value].copy(), counters=counters)
+
+    def nhmmer(self, seqs, block_length=0x40000, strand=None, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True,
+               E=10.0, incE=0.01, cap=100000):
+        """nhmmer as pyhmmer's LongTargetsPipeline.search_hmm runs it (ref_nhmmer): (hits in final order as RefLtHit records,
+        stats [6] = nres, nseqs, pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd).  flags: 1 reported, 2 included,
+        16 duplicate (p7_hitflags_e)."""
+        dsqs = [dsq_of(c) for c in seqs]
+        n = len(dsqs)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[d.ctypes.data for d in dsqs])
+        lens = (ctypes.c_long * max(n, 1))(*[d.size - 2 for d in dsqs])
+        out = (RefLtHit * cap)()
+        stats = (ctypes.c_long * 6)()
+        nh = self.L.ref_nhmmer(self.h, n, ptrs, lens, block_length, {None: 0, "watson": 1, "crick": 2}[strand], F1, F2, F3,
+                               int(bias_filter), int(null2), E, incE, cap, out, stats)
+        assert 0 <= nh <= cap, nh
+        return [out[i] for i in range(nh)], list(stats)
 
     def vit_longtarget(self, codes, cfg_len, filtersc, F2=3e-3, cap=100000):
         """p7_ViterbiFilter_longtarget on one window: landmarks [n,2] = i, k in the reference's order."""

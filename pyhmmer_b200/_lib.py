@@ -89,7 +89,8 @@ class HMMDesc(ctypes.Structure):
 class LtWindow(ctypes.Structure):
     """``b2h_lt_window`` (include/b2h.h)."""
     _fields_ = [("dsq", c_void_p), ("L", c_i32), ("fwd_xmx", c_void_p), ("bck_xmx", c_void_p),
-                ("window_start", c_i64), ("seq_start", c_i64), ("complement", c_i32), ("seq", c_i32)]
+                ("window_start", c_i64), ("seq_start", c_i64), ("complement", c_i32), ("seq", c_i32),
+                ("bck_own_scales", c_i32), ("reserved", c_i32)]
 
 
 class B2HError(RuntimeError):
@@ -163,6 +164,7 @@ def _load():
         P(c_void_p), P(c_size_t), P(c_void_p), P(c_size_t))
     sig("b2h_longtarget_vit_finish", c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, P(c_void_p), P(c_size_t))
     sig("b2h_longtarget_domains", c_int, c_void_p, c_void_p, c_size_t, P(SearchParams), P(c_void_p))
+    sig("b2h_longtarget_hits", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(SearchParams), P(c_void_p))
     sig("b2h_longtarget_vit_threshold", c_int, c_void_p, c_int, c_float, ctypes.c_double, P(c_i32), P(c_i32))
     sig("b2h_hmm_convert_many", c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int,
         P(c_void_p), P(c_void_p), P(c_size_t))

@@ -1121,7 +1121,7 @@ void lt_reparameterize(const b2h_profile *prof, const uint8_t *dsq, int wlen, in
 
 struct LtWindow {
   const uint8_t *dsq; int L; const float *fx, *bx;
-  int64_t window_start, seq_start; int complement; int seq;
+  int64_t window_start, seq_start; int complement; int seq; bool bck_own_scales;
 };
 
 // One window: regions and envelopes exactly as for proteins (ddef_regions), then per envelope the long-target rescoring and
@@ -1130,7 +1130,7 @@ void lt_window(Worker &w, const b2h_profile *prof, const LtWindow &lw, const b2h
 {
   b2h_ddef_task t;
   t.surv.profile = 0; t.surv.seq = lw.seq; t.surv.fwdsc = 0.f; t.surv.filtersc = 0.f;
-  t.prof = prof; t.dsq = lw.dsq; t.L = lw.L; t.fx = lw.fx; t.bx = lw.bx; t.bck_own_scales = false;
+  t.prof = prof; t.dsq = lw.dsq; t.L = lw.L; t.fx = lw.fx; t.bx = lw.bx; t.bck_own_scales = lw.bck_own_scales;
   TaskState ts;
   ddef_regions(w, t, prm, ts);
   if (ts.dead || ts.nregions == 0 || ts.envs.empty()) return;
@@ -1372,7 +1372,7 @@ int b2h_longtarget_domains_host(const b2h_profile *p, const b2h_lt_window *wins,
   ThreadPool::get().parallel_for(n, std::max(1, nthreads), [&](Worker &w, size_t q) {
     const b2h_lt_window &x = wins[order[q]];
     LtWindow lw; lw.dsq = x.dsq; lw.L = x.L; lw.fx = x.fwd_xmx; lw.bx = x.bck_xmx;
-    lw.window_start = x.window_start; lw.seq_start = x.seq_start; lw.complement = x.complement; lw.seq = x.seq;
+    lw.window_start = x.window_start; lw.seq_start = x.seq_start; lw.complement = x.complement; lw.seq = x.seq; lw.bck_own_scales = x.bck_own_scales != 0;
     lt_window(w, p, lw, prm, outs[order[q]]);
   });
   for (size_t e = 0; e < n; e++)

@@ -749,6 +749,73 @@ int b2h_longtarget_domains(const b2h_profile *p, const b2h_lt_window *windows, s
   return B2H_OK;
 }
 
+int b2h_longtarget_hits(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *windows, const int64_t *window_start,
+                        const int64_t *seq_start, const int32_t *complement, const int32_t *seq,
+                        const b2h_search_params *prm, b2h_results **out)
+{
+  if (!ctx || !p || !windows || p->ctx != ctx || windows->ctx != ctx || !prm || !out || p->max_length <= 0) return B2H_EINVAL;
+  const size_t n = windows->n;
+  if (n && (!window_start || !seq_start || !complement || !seq)) return B2H_EINVAL;
+  *out = nullptr;
+  b2h_results *res = new b2h_results();
+  res->counters.assign(4, 0);
+  struct Guard { b2h_results *r; ~Guard() { delete r; } } guard{res};
+  B2H_CUDA(cudaSetDevice(ctx->device));
+  b2h_ddef_pool pool(prm->host_threads);
+  const SeqDev sd = b2h_seqdev(windows);
+  const ProfDev hprof = b2h_profdev(p);
+  const std::vector<int> mpads(1, p->Mpad);
+  const size_t ROW_BUDGET = (size_t)8 << 20;           // rows of 6 floats per batch, two matrices
+  for (size_t i0 = 0; i0 < n;) {
+    size_t i1 = i0, rows = 0;
+    while (i1 < n && (i1 == i0 || rows + windows->h_len[i1] + 1 <= ROW_BUDGET)) { rows += windows->h_len[i1] + 1; i1++; }
+    const int nb = (int)(i1 - i0);
+    std::vector<int32_t> ent(nb); std::vector<int64_t> xoff(nb);
+    int64_t acc = 0;
+    for (int e = 0; e < nb; e++) { ent[e] = (int32_t)(i0 + e); xoff[e] = acc; acc += windows->h_len[i0 + e] + 1; }
+    const int items = (nb + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES;
+    const int32_t poff[2] = {0, nb}, itemoff[2] = {0, items};
+    std::vector<float> fx((size_t)acc * 6), bx((size_t)acc * 6);
+    std::vector<int32_t> bst(nb);
+    {
+      Pool dev(ctx);
+      ProfDev *d_prof; int32_t *d_poff, *d_itemoff, *d_ent; int64_t *d_xoff; float *d_fx, *d_bx, *d_fsc, *d_bsc; int32_t *d_fst, *d_bst;
+      TRY(dev.get(&d_prof, 1)); TRY(dev.get(&d_poff, 2)); TRY(dev.get(&d_itemoff, 2)); TRY(dev.get(&d_ent, nb)); TRY(dev.get(&d_xoff, nb));
+      TRY(dev.get(&d_fx, (size_t)acc * 6)); TRY(dev.get(&d_bx, (size_t)acc * 6));
+      TRY(dev.get(&d_fsc, nb)); TRY(dev.get(&d_bsc, nb)); TRY(dev.get(&d_fst, nb)); TRY(dev.get(&d_bst, nb));
+      B2H_CUDA(cudaMemcpyAsync(d_prof, &hprof, sizeof(ProfDev), cudaMemcpyHostToDevice, ctx->stream));
+      B2H_CUDA(cudaMemcpyAsync(d_poff, poff, sizeof poff, cudaMemcpyHostToDevice, ctx->stream));
+      B2H_CUDA(cudaMemcpyAsync(d_itemoff, itemoff, sizeof itemoff, cudaMemcpyHostToDevice, ctx->stream));
+      B2H_CUDA(cudaMemcpyAsync(d_ent, ent.data(), nb * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+      B2H_CUDA(cudaMemcpyAsync(d_xoff, xoff.data(), nb * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+      WorkList wl; wl.profs = d_prof; wl.ent_s = d_ent; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = 1; wl.counter = ctx->d_counters + 8; wl.plo = 0; wl.phi = 1;
+      StageOut sf; sf.sc = d_fsc; sf.status = d_fst; sf.fwd_xmx = d_fx; sf.bck_xmx = nullptr; sf.xoff = d_xoff;
+      StageOut sb; sb.sc = d_bsc; sb.status = d_bst; sb.fwd_xmx = d_fx; sb.bck_xmx = d_bx; sb.xoff = d_xoff;
+      TRY(b2h_launch_forward_backward(ctx, wl, sd, mpads, items, sf, sb));
+      B2H_CUDA(cudaMemcpyAsync(fx.data(), d_fx, (size_t)acc * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      B2H_CUDA(cudaMemcpyAsync(bx.data(), d_bx, (size_t)acc * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      B2H_CUDA(cudaMemcpyAsync(bst.data(), d_bst, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<b2h_lt_window> lw(nb);
+    for (int e = 0; e < nb; e++) {
+      const size_t w = i0 + e;
+      b2h_lt_window &x = lw[e];
+      x.dsq = windows->h_res + windows->h_off[w]; x.L = windows->h_len[w];
+      x.fwd_xmx = fx.data() + (size_t)xoff[e] * 6; x.bck_xmx = bx.data() + (size_t)xoff[e] * 6;
+      x.window_start = window_start[w]; x.seq_start = seq_start[w]; x.complement = complement[w]; x.seq = seq[w];
+      x.bck_own_scales = (bst[e] & 0x100) != 0; x.reserved = 0;
+    }
+    const size_t h0 = res->hits.size();
+    TRY(b2h_longtarget_domains_host(p, lw.data(), (size_t)nb, prm, pool.nthreads, res));
+    for (size_t h = h0; h < res->hits.size(); h++) res->hits[h].profile += (int32_t)i0;      // window index in the whole list
+    i0 = i1;
+  }
+  guard.r = nullptr;
+  *out = res;
+  return B2H_OK;
+}
+
 size_t            b2h_results_nhits   (const b2h_results *r) { return r ? r->hits.size() : 0; }
 const b2h_hit    *b2h_results_hits    (const b2h_results *r) { return r ? r->hits.data() : nullptr; }
 size_t            b2h_results_ndomains(const b2h_results *r) { return r ? r->doms.size() : 0; }

@@ -109,6 +109,19 @@ class CudaBackend:
     def forward(self, wdb):
         return self._scores(lib.b2h_forward_parser, "b2h_forward_parser", wdb)
 
+    def hits(self, wdb, window_start, seq_start, complement, target, prm):
+        """Forward / Backward parsers on the device for the windows behind the Forward gate, domain definition on the host
+        threads (b2h_longtarget_hits): (hits, domains, text); hit.profile = window, hit.seq = target."""
+        out = ctypes.c_void_p()
+        a = [np.ascontiguousarray(window_start, np.int64), np.ascontiguousarray(seq_start, np.int64),
+             np.ascontiguousarray(complement, np.int32), np.ascontiguousarray(target, np.int32)]
+        check(lib.b2h_longtarget_hits(self.ctx.handle, self.prof, wdb.handle, ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]),
+                                      ctypes.byref(prm), ctypes.byref(out)), "b2h_longtarget_hits", self.ctx.handle)
+        try:
+            return _lib.read_results(out)
+        finally:
+            lib.b2h_results_destroy(out)
+
     def viterbi_windows(self, wdb, filtersc, active, F2):
         marks, out = ctypes.c_void_p(), ctypes.c_void_p()
         nm, no = ctypes.c_size_t(), ctypes.c_size_t()
@@ -212,3 +225,115 @@ def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=2
         else:
             overlap = 0
     return out
+
+
+# =====================================================================================================
+# The whole search: windows over the targets, both strands, hits, E-values, duplicate removal
+# (LongTargetsPipeline.search_hmm and _search_loop_longtargets, src/pyhmmer/plan7.pyx:7258-7412, 7541-7663)
+# =====================================================================================================
+_DNA_COMPLEMENT = "TGCA-YRKMSWDVBHN*~"      # of ACGT-RYMKSWHBVDN*~ (esl_alphabet.c: set_complementarity)
+
+
+def reverse_complement(alphabet, codes):
+    """esl_sq_ReverseComplement on digital residues (nucleotide alphabets only)."""
+    if alphabet.K != 4:
+        raise ValueError("reverse complement needs a nucleotide alphabet")
+    table = np.array([alphabet.symbols.index(c if c in alphabet.symbols else {"T": "U"}.get(c, c)) for c in
+                      (_DNA_COMPLEMENT if "T" in alphabet.symbols else _DNA_COMPLEMENT.replace("T", "U"))], np.uint8)
+    return np.ascontiguousarray(table[codes[::-1]])
+
+
+def target_windows(lengths, W, C, strand=None):
+    """The windows _search_loop_longtargets cuts the targets into: (target, offset i, n, complement) in its order --
+    windows of W residues that keep C residues of the previous one as context; each on the strands asked for."""
+    if C <= 0 or W <= C:
+        raise ValueError("block length must be a strictly positive integer greater than the model's max_length")
+    out = []
+    for t, n in enumerate(lengths):
+        i = 0
+        while i < n:
+            c = 0 if i == 0 else min(C, n - i)
+            w = min(W, n - i - c)
+            if strand != "crick":
+                out.append((t, i, c + w, 0, w, c))
+            if strand != "watson":
+                out.append((t, i, c + w, 1, w, c))
+            i += W - C
+    return out
+
+
+def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True, B1=100, B2=240, B3=1000,
+           block_length=0x40000, strand=None, seed=42, host_threads=0, backend_factory=None):
+    """nhmmer for one profile: every target of ``sequences`` in windows, on both strands (or one), through `stages`
+    and the hit stage; then p7_tophits_ComputeNhmmerEvalues, the seqidx / position sort, p7_tophits_RemoveDuplicates
+    (p7_tophits.c:796, 426, 823).  Returns (hits, doms, text, duplicate flags, stats) with the hits in target order;
+    stats = dict(nres, nseqs, pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd).  hit.seq = target index."""
+    from . import easel
+    abc = om.alphabet
+    max_length = int(om._desc.max_length)
+    lens = [len(s) for s in sequences]
+    wins = target_windows(lens, int(block_length), max_length, strand)
+    chunks = []
+    for (t, i, n, comp, w, c) in wins:
+        codes = sequences[t].sequence[i:i + n]
+        chunks.append(easel.DigitalSequence(abc, name=b"w", sequence=reverse_complement(abc, codes) if comp else codes))
+    block = easel.DigitalSequenceBlock(abc, chunks)
+    nres = sum(w for (_, _, _, _, w, _) in wins)         # pli->nres: W per window and strand (plan7.pyx:7606-7640)
+    stats = dict(nres=int(nres), nseqs=len(lens), pos_past_msv=0, pos_past_bias=0, pos_past_vit=0, pos_past_fwd=0)
+    empty = (_lib.RecList(), _lib.RecList(), b"", [], stats)
+    if not wins:
+        return empty
+    be = (backend_factory or CudaBackend)(om, block)
+    st = stages(om, block, F1=F1, F2=F2, F3=F3, bias_filter=bias_filter, B1=B1, B2=B2, B3=B3, backend=be)
+    for k, col in (("pos_past_msv", 0), ("pos_past_bias", 1), ("pos_past_vit", 2), ("pos_past_fwd", 3)):
+        stats[k] = int(st["counters"][:, col].sum())
+    sel = np.flatnonzero(st["vitpass"])
+    if len(sel) == 0:
+        return empty
+    mw, vw = st["msvwin"], st["vitwin"]
+    chunk = mw["seq"][vw["seq"][sel]]                                   # chunk of every surviving window
+    wstart = (mw["n"][vw["seq"][sel]] + vw["n"][sel] - 1).astype(np.int64)  # its first residue in the chunk
+    wlen = vw["length"][sel].astype(np.int64)
+    # sq->start of the chunk: its first target coordinate, or -- after esl_sq_ReverseComplement -- its last
+    seq_start = np.array([(wins[c][1] + wins[c][2]) if wins[c][3] else (wins[c][1] + 1) for c in chunk], np.int64)
+    comp = np.array([wins[c][3] for c in chunk], np.int32)
+    target = np.array([wins[c][0] for c in chunk], np.int32)
+    prm = _lib.SearchParams(F1, F2, F3, int(bias_filter), int(null2), seed, int(host_threads))
+    hits, doms, text = be.hits(be.window_db(chunk, wstart, wlen), wstart, seq_start, comp, target, prm)
+    # p7_tophits_ComputeNhmmerEvalues: the search space is residues / window length
+    add = math.log(float(np.float32(stats["nres"])) / float(np.float32(max_length)))
+    for h in hits:
+        h.lnP += add
+        doms[h.dom_offset].lnP = h.lnP
+    # hit_sorter_by_seqidx_aliposition, then p7_tophits_RemoveDuplicates
+    def poskey(h):
+        d = doms[h.dom_offset]
+        s, e = (d.iali, d.jali) if d.iali < d.jali else (d.jali, d.iali)
+        return (h.seq, 0 if d.iali < d.jali else 1, s, -e)
+    order = sorted(range(len(hits)), key=lambda q: poskey(hits[q]))
+    dup = [False] * len(hits)
+    j = 0
+    for a in range(1, len(order)):
+        hi, hj, hp = hits[order[a]], hits[order[j]], hits[order[a - 1]]
+        di, dj = doms[hi.dom_offset], doms[hj.dom_offset]
+        s_j, e_j = dj.iali, dj.jali
+        dir_j = 1 if s_j < e_j else -1
+        if dir_j == -1:
+            s_j, e_j = e_j, s_j
+        s_i, e_i = di.iali, di.jali
+        dir_i = 1 if s_i < e_i else -1
+        if dir_i == -1:
+            s_i, e_i = e_i, s_i
+        len_i, len_j = e_i - s_i + 1, e_j - s_j + 1
+        ialilen = min(e_i, e_j) - max(s_i, s_j) + 1
+        ihmmlen = min(di.hmmto, dj.hmmto) - max(di.hmmfrom, dj.hmmfrom) + 1
+        if (hi.seq == hp.seq and dir_i == dir_j and ihmmlen > 0 and
+                (s_j - 3 <= s_i <= s_j + 3 or e_j - 3 <= e_i <= e_j + 3 or ialilen >= len_i * 0.95 or ialilen >= len_j * 0.95)):
+            remove = j if hi.lnP < hj.lnP else a
+            dup[order[remove]] = True
+            j = a if remove == j else j
+        else:
+            j = a
+    hits_sorted = _lib.RecList(hits[q] for q in order)
+    hits_sorted.raw = getattr(hits, "raw", None)
+    return hits_sorted, doms, text, [dup[q] for q in order], stats

@@ -91,6 +91,55 @@ class OracleBackend:
         return shuffled, longtarget._take_windows(out, no.value)
 
 
+def _oracle_hits(self, wdb, window_start, seq_start, complement, target, prm):
+    """The hit stage with the reference's parser specials: p7_ForwardParser / p7_BackwardParser per window (oracle/_ref),
+    then the product's host code (b2h_longtarget_domains)."""
+    n = wdb.n
+    wins = (_lib.LtWindow * max(n, 1))()
+    keep = []
+    for i in range(n):
+        codes = np.ascontiguousarray(wdb.seq(i))
+        _, _, st, fx, bx = self.ref.fwdbck(codes, want_x=True)
+        assert st == 0
+        keep.append((codes, fx, bx))
+        w = wins[i]
+        w.dsq, w.L, w.fwd_xmx, w.bck_xmx = codes.ctypes.data, len(codes), fx.ctypes.data, bx.ctypes.data
+        w.window_start, w.seq_start, w.complement, w.seq = int(window_start[i]), int(seq_start[i]), int(complement[i]), int(target[i])
+    _lib.lib.b2h_profile_set_annotation(self.hprof, (self.pair.hmm.consensus or "x" * self.pair.hmm.M).encode(), None, None,
+                                        self.pair.hmm.alphabet.symbols.encode())
+    out = ctypes.c_void_p()
+    _lib.check(_lib.lib.b2h_longtarget_domains(self.hprof, wins, n, ctypes.byref(prm), ctypes.byref(out)), "b2h_longtarget_domains")
+    try:
+        return _lib.read_results(out)
+    finally:
+        _lib.lib.b2h_results_destroy(out)
+
+
+OracleBackend.hits = _oracle_hits
+
+
+def compare_nhmmer(pair, seqs, got, **kw):
+    """`longtarget.search` against ref_nhmmer (pyhmmer's LongTargetsPipeline loop over the reference's functions): same hits
+    with the same coordinates, scores to 2e-3 bits, same duplicates, same residue / position counters."""
+    hits, doms, text, dup, stats = got
+    rhits, rstats = pair.ref.nhmmer(seqs, **kw)
+    assert [stats[k] for k in ("nres", "nseqs", "pos_past_msv", "pos_past_bias", "pos_past_vit", "pos_past_fwd")] == rstats, (stats, rstats)
+    assert len(hits) == len(rhits), (len(hits), len(rhits))
+    # the reference's final order: hit_sorter_by_sortkey (sortkey = -lnP, then name, strand, start)
+    mine = sorted(range(len(hits)), key=lambda q: (hits[q].lnP, "seq%d" % hits[q].seq,
+                                                    0 if doms[hits[q].dom_offset].iali < doms[hits[q].dom_offset].jali else 1,
+                                                    doms[hits[q].dom_offset].iali))
+    ndup = 0
+    for q, r in zip(mine, rhits):
+        h, d = hits[q], doms[hits[q].dom_offset]
+        assert (h.seq, d.ienv, d.jenv, d.iali, d.jali, d.hmmfrom, d.hmmto) == (r.seqidx, r.ienv, r.jenv, r.iali, r.jali, r.hmmfrom, r.hmmto), (q, r.seqidx, r.iali, r.jali)
+        assert abs(h.score - r.score) < 2e-3 and abs(d.dombias - r.bias) < 2e-3 and abs(h.pre_score - r.pre_score) < 2e-3
+        assert abs(h.lnP - r.lnP) < 2e-3 and abs(d.envsc - r.envsc) < 2e-3 and abs(d.oasc - r.oasc) < 2e-3
+        assert dup[q] == bool(r.flags & 16), (q, dup[q], r.flags)
+        ndup += dup[q]
+    return len(hits), ndup
+
+
 def compare_with_reference(pair, block, got, exact_scores, fwd_rel=2e-7, **kw):
     """Stage by stage against ref_longtarget_stages, chunk by chunk.  Returns totals for the caller's sanity checks."""
     tot = dict(msvwin=0, vitmark=0, vitwin=0, passed=0)

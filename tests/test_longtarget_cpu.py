@@ -164,3 +164,35 @@ def test_hits_behind_the_forward_gate(M, mu_shift, null2, complement, layout):
     assert null2 or nbias == 0
     if layout == "repeats":                               # the trimming pass ran: an envelope edge sits exactly 20 from the alignment
         assert any(abs(int(r[2]) - int(r[0])) == 20 or abs(int(r[1]) - int(r[3])) == 20 for r in rhits)
+
+
+@pytest.mark.parametrize("M,mu_shift,strand,block_length", [(121, -2.0, None, 65536), (60, -3.0, "watson", 20000), (60, -3.0, "crick", 0x40000),
+                                                             (333, -2.0, None, 30000)])
+def test_whole_search_against_the_reference_loop(M, mu_shift, strand, block_length):
+    """`longtarget.search` (windows with context over every target, both strands, all stages, E-values over residues / window
+    length, duplicate removal across window overlaps) with the reference's DP scores against ref_nhmmer."""
+    pair, rng = lt_common.dna_model(ModelPair, M, mu_shift=mu_shift)
+    block = lt_common.dna_chunks(pair, rng, [150000, 40000, 0, 700, 65536 + 17], nplant=8)
+    seqs = []
+    for s in block:                                       # homologs on the other strand as well
+        codes = s.sequence.copy()
+        for _ in range(4):
+            dom = longtarget.reverse_complement(s.alphabet, lt_common.synth.emit_sequence(pair.hmm, rng))
+            if len(dom) < len(codes):
+                pos = int(rng.integers(0, len(codes) - len(dom)))
+                codes[pos:pos + len(dom)] = dom
+        seqs.append(lt_common.easel.DigitalSequence(s.alphabet, name=s.name, sequence=codes))
+    # one homolog per strand inside the context the second window of the first target shares with the first window
+    C = pair.hmm.max_length
+    if block_length < len(seqs[0]):
+        codes = seqs[0].sequence
+        pos = block_length - C + 5
+        for dom in (lt_common.synth.emit_sequence(pair.hmm, rng), longtarget.reverse_complement(block.alphabet, lt_common.synth.emit_sequence(pair.hmm, rng))):
+            codes[pos:pos + len(dom)] = dom
+            pos += len(dom) + 12
+    got = longtarget.search(pair.om, seqs, block_length=block_length, strand=strand,
+                            backend_factory=lambda om, blk: lt_common.OracleBackend(pair, blk))
+    nh, ndup = lt_common.compare_nhmmer(pair, [s.sequence for s in seqs], got, block_length=block_length, strand=strand)
+    assert nh >= 10
+    if block_length < 100000:
+        assert ndup >= 1                                  # a hit in the context shared by two windows was found twice and removed once
