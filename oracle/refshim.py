@@ -251,7 +251,7 @@ class RefModel:
     def nhmmer(self, seqs, block_length=0x40000, strand=None, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True,
                E=10.0, incE=0.01, cap=100000):
         """nhmmer as pyhmmer's LongTargetsPipeline.search_hmm runs it (ref_nhmmer): (hits in final order as RefLtHit records,
-        stats [6] = nres, nseqs, pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd).  flags: 1 reported, 2 included,
+        stats [6] = nres, nseqs, pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd).  flags: 1 included, 2 reported,
         16 duplicate (p7_hitflags_e)."""
         dsqs = [dsq_of(c) for c in seqs]
         n = len(dsqs)

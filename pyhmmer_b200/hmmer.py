@@ -12,9 +12,9 @@ import os
 
 from . import plan7
 from .easel import DigitalSequenceBlock, DigitalSequence, SequenceFile
-from .plan7 import Pipeline, HMM, Profile, OptimizedProfile, OptimizedProfileBlock
+from .plan7 import Pipeline, LongTargetsPipeline, HMM, Profile, OptimizedProfile, OptimizedProfileBlock
 
-__all__ = ["hmmsearch", "hmmscan"]
+__all__ = ["hmmsearch", "hmmscan", "nhmmer"]
 
 _QUERY_BATCH = 256
 
@@ -106,3 +106,30 @@ def hmmscan(queries, profiles, *, cpus=0, callback=None, backend="threading", ba
             batch = []
     if batch:
         yield from flush(batch)
+
+
+def nhmmer(queries, sequences, *, cpus=0, callback=None, backend="threading", builder=None, **options):
+    """Search nucleotide HMM / profile queries against long nucleotide targets; yields one `TopHits` per query, in order
+    (``pyhmmer.hmmer.nhmmer``, src/pyhmmer/hmmer/_nhmmer.py).  Sequence and alignment queries need the reference's
+    `Builder` (model construction is outside this package's path) and are rejected."""
+    if isinstance(queries, (HMM, Profile, OptimizedProfile)):
+        queries = (queries,)
+    it = iter(queries)
+    first = next(it, None)
+    if first is None:
+        return
+    if not isinstance(first, (HMM, Profile, OptimizedProfile)):
+        raise TypeError("nhmmer queries must be HMM, Profile or OptimizedProfile (building models from sequences or "
+                        "alignments is not part of pyhmmer_b200), found %s" % type(first).__name__)
+    alphabet = first.alphabet
+    block = _as_block(sequences, alphabet)
+    options.setdefault("host_threads", cpus or 0)
+    pipeline = LongTargetsPipeline(alphabet, **options)
+    index = 0
+    import itertools
+    for query in itertools.chain((first,), it):
+        hits = pipeline.search_hmm(query, block)
+        if callback is not None:
+            callback(query, index + 1)
+        index += 1
+        yield hits

@@ -9,6 +9,7 @@ CUDA kernels behind the C ABI of ``include/b2h.h``; nothing here scores on the C
 Reference: src/pyhmmer/plan7.pyx (HMM 2236-3321, HMMFile 3323-3800, Background 427-560,
 Profile 7767-8310, OptimizedProfile 4392-5070, Pipeline 5423-6906, TopHits 8312-9278).
 """
+import copy
 import ctypes
 import math
 import time
@@ -1176,7 +1177,7 @@ class Hit:
 
     @property
     def evalue(self):
-        return math.exp(self.lnP) * self.hits.Z
+        return math.exp(self.lnP) * (1.0 if self.hits.long_targets else self.hits.Z)
 
     def __repr__(self):
         return "<Hit name=%r score=%.1f evalue=%.2g>" % (self.name, self.score, self.evalue)
@@ -1193,6 +1194,7 @@ class TopHits:
                             inc_by_E=True, by_E=True, dom_by_E=True, incdom_by_E=True, bit_cutoffs=None, Z=None, domZ=None)
         self.Z = 0.0
         self.domZ = 0.0
+        self.long_targets = False          # nhmmer hits: the search space is already inside lnP (p7_pipeline.c:411)
         self.searched_models = 0
         self.searched_nodes = 0
         self.searched_sequences = 0
@@ -1231,10 +1233,14 @@ class TopHits:
     # -- p7_pli_*Reportable / Includable (p7_pipeline.c:407-464) --
     def _target_reportable(self, score, lnP, Z):
         p = self._params
+        if self.long_targets:
+            Z = 1.0
         return (math.exp(lnP) * Z <= p["E"]) if p["by_E"] else (score >= p["T"])
 
     def _target_includable(self, score, lnP, Z):
         p = self._params
+        if self.long_targets:
+            Z = 1.0
         return (math.exp(lnP) * Z <= p["incE"]) if p["inc_by_E"] else (score >= p["incT"])
 
     def _domain_reportable(self, score, lnP):
@@ -1247,6 +1253,10 @@ class TopHits:
 
     def _sort_by_key(self):
         """p7_tophits_SortBySortkey (p7_tophits.c:393; comparator hit_sorter_by_sortkey)."""
+        if self.long_targets:              # ties: name, then the positive strand first, then position (p7_tophits.c:304-325)
+            self._hits.sort(key=lambda h: (-h.sortkey, h.name, 0 if h._domains[0]._rec.iali < h._domains[0]._rec.jali else 1,
+                                           h._domains[0]._rec.iali))
+            return
         self._hits.sort(key=lambda h: (-h.sortkey, h.name, h._domains[0].alignment.target_from))
 
     def _threshold(self):
@@ -1259,6 +1269,12 @@ class TopHits:
                     h.included = self._target_includable(h.score, h.lnP, self.Z)
         if self._params["domZ"] is None:
             self.domZ = float(sum(1 for h in self._hits if h.reported))
+        if self.long_targets:              # "no domains in dna search": the one domain of a hit follows the hit (p7_tophits.c:1078)
+            if not self._params["bit_cutoffs"]:
+                for h in self._hits:
+                    for d in h._domains:
+                        d.reported, d.included = h.reported, h.included
+            return
         if not self._params["bit_cutoffs"]:
             for h in self._hits:
                 for d in h._domains:
@@ -1517,3 +1533,104 @@ class MissingCutoffs(ValueError):
 
     def __init__(self, name, kind):
         super().__init__("model %r is missing %s bit cutoffs" % (name, kind))
+
+
+class LongTargetsPipeline(Pipeline):
+    """The pipeline for long (nucleotide) targets -- ``pyhmmer.plan7.LongTargetsPipeline`` (plan7.pyx:6917-7412), nhmmer.
+
+    Targets of any length are cut into windows of ``block_length`` residues that keep ``max_length`` residues of context
+    and are searched on both strands; hits are single domains in target coordinates (``env_from > env_to`` on the reverse
+    strand), their E-values count the search space in windows of the model's ``max_length``.  The stages run in
+    `pyhmmer_b200.longtarget` (windows of ALL targets and strands per kernel launch).
+
+    The model must carry its window length (``MAXL`` in the HMM file, as hmmbuild writes it) or ``window_length`` must be
+    given: ``p7_Builder_MaxLength`` is part of the builder, which is outside this package's path.
+    """
+    M_HINT = 100
+    L_HINT = 100
+
+    def __init__(self, alphabet, background=None, *, F1=0.02, F2=3e-3, F3=3e-5, strand=None, B1=100, B2=240, B3=1000,
+                 block_length=0x40000, window_length=None, window_beta=None, **kwargs):
+        if alphabet.K != 4:
+            raise ValueError("Expected nucleotide alphabet, found %r" % (alphabet,))
+        super().__init__(alphabet, background, F1=F1, F2=F2, F3=F3, **kwargs)
+        if strand not in (None, "watson", "crick"):
+            raise ValueError("invalid value for `strand`: %r" % (strand,))
+        if window_length is not None and window_length < 4:
+            raise ValueError("invalid window length: %r" % (window_length,))
+        if window_beta is not None and not (0.0 < window_beta < 1.0):
+            raise ValueError("invalid window beta: %r" % (window_beta,))
+        self.strand = strand
+        self.B1, self.B2, self.B3 = int(B1), int(B2), int(B3)
+        self.block_length = int(block_length)
+        self.window_length, self.window_beta = window_length, window_beta
+        self._backend_factory = None
+
+    def search_hmm(self, query, sequences):
+        """nhmmer: one query against a `DigitalSequenceBlock` of long targets; returns `TopHits` (plan7.pyx:7258-7412)."""
+        from . import longtarget
+        if not isinstance(sequences, DigitalSequenceBlock):
+            raise TypeError("expected DigitalSequenceBlock, found %s" % type(sequences).__name__)
+        if not isinstance(query, (HMM, Profile, OptimizedProfile)):
+            raise TypeError("Expected HMM, Profile or OptimizedProfile, found %s" % type(query).__name__)
+        if query.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, query.alphabet)
+        if sequences.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, sequences.alphabet)
+        L = len(sequences[0]) if len(sequences) else self.L_HINT
+        om = self._optimized(query, L)
+        max_length = int(om._desc.max_length)
+        if self.window_length is not None and self.window_length > 0:
+            max_length = int(self.window_length)
+        elif isinstance(query, HMM):
+            if max_length <= 0:
+                raise NotImplementedError("HMM without a window length (MAXL): p7_Builder_MaxLength is not part of this package; "
+                                          "pass window_length=...")
+        elif max_length <= 0:
+            raise TypeError("Cannot use `Profile` or `OptimizedProfile` query without `max_length` set")
+        if max_length != int(om._desc.max_length):          # the resident copy of the profile carries the window length
+            if isinstance(query, OptimizedProfile):
+                om = copy.copy(om)
+                om._desc = _lib.OProfileDesc.from_buffer_copy(om._desc)
+            om._desc.max_length = max_length
+            om._dev = {}
+        if self.block_length <= max_length:
+            raise ValueError("block length (%d) must be greater than the model's window length (%d)" % (self.block_length, max_length))
+        cut = self._cutoffs(om)
+        res = longtarget.search(om, sequences, F1=self.F1, F2=self.F2, F3=self.F3, bias_filter=self.bias_filter, null2=self.null2,
+                                B1=self.B1, B2=self.B2, B3=self.B3, block_length=self.block_length, strand=self.strand,
+                                seed=self.seed, host_threads=self.host_threads, backend_factory=self._backend_factory)
+        return self._long_target_tophits(query, om, sequences, res, cut)
+
+    def _long_target_tophits(self, query, om, sequences, res, cut):
+        """Hits of `longtarget.search` -> thresholded `TopHits` (the tail of search_hmm, plan7.pyx:7389-7412)."""
+        hits, doms, text, dup, stats = res
+        th = self._tophits(query, "search", cut)
+        th.long_targets = True
+        th._params["inc_by_E"] = True                        # sortkey = -lnP whatever the thresholds (p7_tophits.c:804)
+        for rec, is_dup in zip(hits, dup):
+            h = Hit(th, rec, sequences[rec.seq], doms, text)
+            h.sortkey = -h.lnP
+            h.duplicate = bool(is_dup)
+            if cut is not None and not is_dup:               # flags set by the pipeline under bit cutoffs (p7_pipeline.c:1230-1246)
+                p = th._params
+                h.reported = h.score >= p["T"]
+                h.included = h.reported and h.score >= p["incT"]
+                for d in h._domains:
+                    d.reported = d.score >= p["domT"]
+                    d.included = d.reported and d.score >= p["incdomT"]
+            th._hits.append(h)
+        th._params["inc_by_E"] = (self.incT is None) and cut is None
+        th.Z = float(self.Z) if self.Z is not None else 0.0
+        th.domZ = float(self.domZ) if self.domZ is not None else 0.0
+        th.searched_models, th.searched_nodes = 1, om.M
+        th.searched_sequences, th.searched_residues = stats["nseqs"], stats["nres"]
+        th.pos_past_msv, th.pos_past_bias = stats["pos_past_msv"], stats["pos_past_bias"]
+        th.pos_past_vit, th.pos_past_fwd = stats["pos_past_vit"], stats["pos_past_fwd"]
+        th._sort_by_key()
+        th._threshold()
+        self._nmodels += 1
+        self._nnodes += om.M
+        self._nseqs += stats["nseqs"]
+        self._nres += stats["nres"]
+        return th

@@ -8,6 +8,7 @@
    the reference's intermediates when every DP score is supplied by the reference's functions -- no device involved.
 """
 import ctypes
+import math
 import os
 import sys
 
@@ -196,3 +197,38 @@ def test_whole_search_against_the_reference_loop(M, mu_shift, strand, block_leng
     assert nh >= 10
     if block_length < 100000:
         assert ndup >= 1                                  # a hit in the context shared by two windows was found twice and removed once
+
+
+@pytest.mark.parametrize("strand,E", [(None, 10.0), ("watson", 1e-12)])
+def test_long_targets_pipeline_front_end(monkeypatch, strand, E):
+    """`plan7.LongTargetsPipeline.search_hmm` (the reference class of the same name, plan7.pyx:6917): hits in the reference's
+    final order with its reported / included / duplicate flags and E-values -- host logic only, DP from the reference."""
+    from pyhmmer_b200 import plan7
+    pair, rng = lt_common.dna_model(ModelPair, 121, mu_shift=-2.0)
+    block = lt_common.dna_chunks(pair, rng, [90000, 30000], nplant=10)
+    codes = block[0].sequence
+    pos = 20000 - pair.hmm.max_length + 5                 # a hit inside the context shared by the first two windows
+    dom = lt_common.synth.emit_sequence(pair.hmm, rng)
+    codes[pos:pos + len(dom)] = dom
+    monkeypatch.setattr(plan7._lib, "context", lambda device=None: None)     # no device: the backend below needs none
+    pli = plan7.LongTargetsPipeline(pair.hmm.alphabet, strand=strand, block_length=20000, E=E, incE=E / 100)
+    pli._backend_factory = lambda om, blk: lt_common.OracleBackend(pair, blk)
+    th = pli.search_hmm(pair.hmm, block)
+    rhits, rstats = pair.ref.nhmmer([s.sequence for s in block], block_length=20000, strand=strand, E=E, incE=E / 100)
+    assert th.long_targets and len(th) == len(rhits) >= 8
+    assert (th.searched_residues, th.searched_sequences) == (rstats[0], rstats[1])
+    for h, r in zip(th, rhits):
+        d = h.domains[0]
+        assert (h.name, d.env_from, d.env_to, d.alignment.target_from, d.alignment.target_to, d.alignment.hmm_from, d.alignment.hmm_to) == \
+               (block[r.seqidx].name, r.ienv, r.jenv, r.iali, r.jali, r.hmmfrom, r.hmmto)
+        assert abs(h.score - r.score) < 2e-3 and abs(math.log(h.evalue) - r.lnP) < 2e-3
+        assert (h.reported, h.included, h.duplicate) == (bool(r.flags & 2), bool(r.flags & 1), bool(r.flags & 16)), (h.name, r.flags)
+        assert (d.reported, d.included) == (bool(r.dom_reported), bool(r.dom_included))
+    assert any(h.duplicate for h in th) and any(h.reported for h in th)
+    assert E > 1 or any(not h.reported and not h.duplicate for h in th)      # the tight threshold left some hits unreported
+    with pytest.raises(ValueError):
+        plan7.LongTargetsPipeline(plan7.Alphabet.amino())
+    with pytest.raises(ValueError):
+        plan7.LongTargetsPipeline(pair.hmm.alphabet, strand="both")
+    with pytest.raises(ValueError):
+        plan7.LongTargetsPipeline(pair.hmm.alphabet, block_length=100).search_hmm(pair.hmm, block)
