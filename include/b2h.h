@@ -291,6 +291,10 @@ int  b2h_hmm_convert_many(int K, int Kp, const uint8_t *degen, const float *bgf,
                           const b2h_hmm_desc *hmms, size_t n, int nthreads,
                           b2h_oprofile_desc **descs, void **block, size_t *block_bytes);
 
+/* p7_Builder_MaxLength (vendor/hmmer/src/p7_builder.c:651): the window length (MAXL) of an HMM for the tail mass emit_thresh
+ * (nhmmer's --w_beta, default 1e-7), from its transition probabilities t [(M+1)*7] = MM MI MD IM II DM DD.  Host only. */
+int  b2h_hmm_max_length(int M, const float *t, double emit_thresh, int32_t *max_length);
+
 /* ---- long-target (nhmmer) path, first stage ------------------------------------------------------------------------
  * p7_SSVFilter_longtarget (vendor/hmmer/src/impl_sse/msvfilter.c:256) over every sequence of <db> (= the chunks a long
  * target was cut into; LongTargetsPipeline, plan7.pyx:7542-7663), with the model's length parameters set for its

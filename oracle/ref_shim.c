@@ -450,7 +450,8 @@ typedef struct {
 } REF_LTHIT;
 
 long ref_nhmmer(REFM *m, int nseq, const uint8_t **dsq, const long *len, long block_length, int strands,
-                double F1, double F2, double F3, int do_bias, int do_null2, double E, double incE, long cap, REF_LTHIT *out, long *stats)
+                double F1, double F2, double F3, int do_bias, int do_null2, double E, double incE, long evalue_window,
+                long cap, REF_LTHIT *out, long *stats)
 {
   P7_OPROFILE *om = m->om;
   P7_PIPELINE *pli = p7_pipeline_Create(NULL, om->M, 100, TRUE, p7_SEARCH_SEQS);
@@ -497,7 +498,9 @@ long ref_nhmmer(REFM *m, int nseq, const uint8_t **dsq, const long *len, long bl
     esl_sq_Reuse(tmpsq);
     pli->nseqs++;
   }
-  p7_tophits_ComputeNhmmerEvalues(th, (double)pli->nres, om->max_length);
+  /* the window the E-values count in: om->max_length for profile queries, p7_Builder_MaxLength(hmm, beta) for HMM queries
+   * (plan7.pyx:7345-7354) -- the caller says which */
+  p7_tophits_ComputeNhmmerEvalues(th, (double)pli->nres, evalue_window > 0 ? (int)evalue_window : om->max_length);
   p7_tophits_SortBySeqidxAndAlipos(th);
   p7_tophits_RemoveDuplicates(th, TRUE);
   p7_tophits_SortBySortkey(th);
@@ -518,6 +521,16 @@ long ref_nhmmer(REFM *m, int nseq, const uint8_t **dsq, const long *len, long bl
   p7_tophits_Destroy(th);
   p7_pipeline_Destroy(pli);
   return nout;
+}
+
+/* p7_Builder_MaxLength on the model's HMM (p7_builder.c:651); the HMM's own max_length is restored. */
+int ref_max_length(REFM *m, double emit_thresh)
+{
+  int saved = m->hmm->max_length, r;
+  p7_Builder_MaxLength(m->hmm, emit_thresh);
+  r = m->hmm->max_length;
+  m->hmm->max_length = saved;
+  return r;
 }
 
 double ref_gumbel_surv(double x, double mu, double lambda) { return esl_gumbel_surv(x, mu, lambda); }

@@ -70,7 +70,8 @@ def lib():
         L.ref_longtarget_stages.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ci, ci, ci] + [vp] * 11
         L.ref_nhmmer.restype = ctypes.c_long
         L.ref_nhmmer.argtypes = [vp, ci, vp, vp, ctypes.c_long, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci,
-                                 ctypes.c_double, ctypes.c_double, ctypes.c_long, vp, vp]
+                                 ctypes.c_double, ctypes.c_double, ctypes.c_long, ctypes.c_long, vp, vp]
+        L.ref_max_length.argtypes = [vp, ctypes.c_double]
         L.ref_vit_longtarget.argtypes = [vp, vp, ci, ci, cf, ctypes.c_double, ci, vp]
         L.ref_longtarget_pipeline.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ctypes.c_long, ci, vp, ci, vp]
         L.ref_gdecoding.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), vp]
@@ -249,7 +250,7 @@ class RefModel:
                     vitpass=vitpass[:nv.value].copy(), counters=counters)
 
     def nhmmer(self, seqs, block_length=0x40000, strand=None, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True,
-               E=10.0, incE=0.01, cap=100000):
+               E=10.0, incE=0.01, evalue_window=0, cap=100000):
         """nhmmer as pyhmmer's LongTargetsPipeline.search_hmm runs it (ref_nhmmer): (hits in final order as RefLtHit records,
         stats [6] = nres, nseqs, pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd).  flags: 1 included, 2 reported,
         16 duplicate (p7_hitflags_e)."""
@@ -260,9 +261,13 @@ class RefModel:
         out = (RefLtHit * cap)()
         stats = (ctypes.c_long * 6)()
         nh = self.L.ref_nhmmer(self.h, n, ptrs, lens, block_length, {None: 0, "watson": 1, "crick": 2}[strand], F1, F2, F3,
-                               int(bias_filter), int(null2), E, incE, cap, out, stats)
+                               int(bias_filter), int(null2), E, incE, int(evalue_window), cap, out, stats)
         assert 0 <= nh <= cap, nh
         return [out[i] for i in range(nh)], list(stats)
+
+    def max_length(self, beta=1e-7):
+        """p7_Builder_MaxLength of the model's HMM."""
+        return self.L.ref_max_length(self.h, beta)
 
     def vit_longtarget(self, codes, cfg_len, filtersc, F2=3e-3, cap=100000):
         """p7_ViterbiFilter_longtarget on one window: landmarks [n,2] = i, k in the reference's order."""

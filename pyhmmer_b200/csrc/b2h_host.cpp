@@ -5,6 +5,7 @@
 // therefore written in C++ against the same glibc libm (not numpy, whose SIMD log/exp differ
 // in the last ulp) and compiled with -ffp-contract=off.  Each function cites the reference
 // code whose arithmetic (operand types, evaluation order) it restates; none of it is copied.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -287,6 +288,56 @@ int b2h_length_params(int L, float nj, b2h_len_params *o)
   o->null1   = (float)((double)(float)L * log((double)o->p1) + log(1. - (double)o->p1));
   o->flt_len_a = (float)L * logf(o->p1);
   o->flt_len_b = logf((float)(1. - (double)o->p1));
+  return B2H_OK;
+}
+
+// p7_Builder_MaxLength (vendor/hmmer/src/p7_builder.c:651-755): the window length beyond which the model emits less than
+// emit_thresh of its probability mass -- a DP over (state, emitted length) in double precision on the HMM's transition
+// probabilities t [(M+1)*7] = MM MI MD IM II DM DD.  Capped at max(M, min(20 M, 100000)).
+int b2h_hmm_max_length(int M, const float *t, double emit_thresh, int32_t *max_length)
+{
+  if (M < 1 || !t || !max_length) return B2H_EINVAL;
+  enum { hMM = 0, hMI = 1, hMD = 2, hIM = 3, hII = 4, hDM = 5, hDD = 6 };
+  auto T = [&](int k, int x) -> double { return (double)t[(size_t)k * 7 + x]; };
+  const int length_bound = std::max(M, std::min(20 * M, 100000));
+  if (M == 1) { *max_length = 1; return B2H_OK; }
+  *max_length = length_bound;
+  std::vector<double> Iv((size_t)(M + 1) * 2, 0.0), Mv((size_t)(M + 1) * 2, 0.0), Dv((size_t)(M + 1) * 2, 0.0);
+  auto I = [&](int k, int c) -> double & { return Iv[(size_t)k * 2 + c]; };
+  auto Mm = [&](int k, int c) -> double & { return Mv[(size_t)k * 2 + c]; };
+  auto D = [&](int k, int c) -> double & { return Dv[(size_t)k * 2 + c]; };
+  Mm(1, 0) = 1.0;
+  I(1, 0) = D(1, 0) = Mm(2, 0) = I(2, 0) = 0;
+  D(2, 0) = T(1, hMD);
+  for (int k = 3; k <= M; k++) { Mm(k, 0) = I(k, 0) = 0; D(k, 0) = T(k - 1, hDD) * D(k - 1, 0); }
+  Mm(1, 1) = D(1, 1) = D(2, 1) = I(2, 1) = 0;
+  I(1, 1) = T(1, hMI) * Mm(1, 0);
+  Mm(2, 1) = T(1, hMM) * Mm(1, 0);
+  for (int k = 3; k <= M; k++) {
+    Mm(k, 1) = T(k - 1, hDM) * D(k - 1, 0);
+    I(k, 1) = 0;
+    D(k, 1) = T(k - 1, hMD) * Mm(k - 1, 1) + T(k - 1, hDD) * D(k - 1, 1);
+  }
+  double p_sum = Mm(M, 0) + Mm(M, 1) + D(M, 0) + D(M, 1);
+  int cp = 0;
+  for (int col = 3; col <= length_bound; col++) {
+    const int pp = 1 - cp;
+    double surv = 0.0;
+    Mm(1, cp) = D(1, cp) = 0;
+    I(1, cp) = T(1, hII) * I(1, pp);
+    surv += I(1, cp);
+    for (int k = 2; k <= M; k++) {
+      Mm(k, cp) = T(k - 1, hMM) * Mm(k - 1, pp) + T(k - 1, hDM) * D(k - 1, pp) + T(k - 1, hIM) * I(k - 1, pp);
+      I(k, cp) = T(k, hMI) * Mm(k, pp) + T(k, hII) * I(k, pp);
+      D(k, cp) = T(k - 1, hMD) * Mm(k - 1, cp) + T(k - 1, hDD) * D(k - 1, cp);
+      surv += I(k, cp) + Mm(k, cp) * (1 - T(k, hMD)) + D(k, cp) * (1 - T(k, hDD));
+    }
+    surv += Mm(M, cp) * T(M, hMD) + D(M, cp) * T(M, hDD) - I(M, cp);
+    p_sum += Mm(M, cp) + D(M, cp);
+    surv /= surv + p_sum;
+    if (surv < emit_thresh) { *max_length = col; break; }
+    cp = 1 - cp;
+  }
   return B2H_OK;
 }
 

@@ -263,7 +263,7 @@ def target_windows(lengths, W, C, strand=None):
 
 
 def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True, B1=100, B2=240, B3=1000,
-           block_length=0x40000, strand=None, seed=42, host_threads=0, backend_factory=None):
+           block_length=0x40000, strand=None, seed=42, host_threads=0, backend_factory=None, evalue_window=None):
     """nhmmer for one profile: every target of ``sequences`` in windows, on both strands (or one), through `stages`
     and the hit stage; then p7_tophits_ComputeNhmmerEvalues, the seqidx / position sort, p7_tophits_RemoveDuplicates
     (p7_tophits.c:796, 426, 823).  Returns (hits, doms, text, duplicate flags, stats) with the hits in target order;
@@ -301,7 +301,7 @@ def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=Tru
     prm = _lib.SearchParams(F1, F2, F3, int(bias_filter), int(null2), seed, int(host_threads))
     hits, doms, text = be.hits(be.window_db(chunk, wstart, wlen), wstart, seq_start, comp, target, prm)
     # p7_tophits_ComputeNhmmerEvalues: the search space is residues / window length
-    add = math.log(float(np.float32(stats["nres"])) / float(np.float32(max_length)))
+    add = math.log(float(np.float32(stats["nres"])) / float(np.float32(evalue_window or max_length)))
     for h in hits:
         h.lnP += add
         doms[h.dom_offset].lnP = h.lnP

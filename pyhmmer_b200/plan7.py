@@ -170,6 +170,14 @@ class HMM:
         compo /= compo.sum()
         self._compo[:K] = compo.astype(np.float32)
 
+    def compute_max_length(self, beta=1e-7):
+        """``p7_Builder_MaxLength`` (p7_builder.c:651): the window length beyond which the model emits less than ``beta``
+        of its probability mass -- what hmmbuild stores as MAXL and nhmmer recomputes for ``--w_beta``."""
+        t = np.ascontiguousarray(self.transition_probabilities, dtype=np.float32)
+        out = ctypes.c_int32()
+        check(lib.b2h_hmm_max_length(self.M, ptr(t), float(beta), ctypes.byref(out)), "b2h_hmm_max_length")
+        return int(out.value)
+
     def write(self, fh, binary=False):
         """Write the model in HMMER3/f ASCII format (``p7_hmmfile_WriteASCII``, p7_hmmfile.c:560-700)."""
         if binary:
@@ -1582,22 +1590,24 @@ class LongTargetsPipeline(Pipeline):
         max_length = int(om._desc.max_length)
         if self.window_length is not None and self.window_length > 0:
             max_length = int(self.window_length)
+            if max_length != int(om._desc.max_length):      # the resident copy of the profile carries the window length
+                if isinstance(query, OptimizedProfile):
+                    om = copy.copy(om)
+                    om._desc = _lib.OProfileDesc.from_buffer_copy(om._desc)
+                om._desc.max_length = max_length
+                om._dev = {}
         elif isinstance(query, HMM):
-            if max_length <= 0:
-                raise NotImplementedError("HMM without a window length (MAXL): p7_Builder_MaxLength is not part of this package; "
-                                          "pass window_length=...")
+            # the windows keep the model's own MAXL as context; the E-values count windows of p7_Builder_MaxLength(beta)
+            max_length = query.compute_max_length(self.window_beta if self.window_beta is not None else 1e-7)
         elif max_length <= 0:
             raise TypeError("Cannot use `Profile` or `OptimizedProfile` query without `max_length` set")
-        if max_length != int(om._desc.max_length):          # the resident copy of the profile carries the window length
-            if isinstance(query, OptimizedProfile):
-                om = copy.copy(om)
-                om._desc = _lib.OProfileDesc.from_buffer_copy(om._desc)
-            om._desc.max_length = max_length
-            om._dev = {}
-        if self.block_length <= max_length:
-            raise ValueError("block length (%d) must be greater than the model's window length (%d)" % (self.block_length, max_length))
+        if int(om._desc.max_length) <= 0:
+            raise ValueError("the model carries no window length (MAXL); pass window_length=...")
+        if self.block_length <= int(om._desc.max_length):
+            raise ValueError("block length (%d) must be greater than the model's window length (%d)" % (self.block_length, int(om._desc.max_length)))
         cut = self._cutoffs(om)
-        res = longtarget.search(om, sequences, F1=self.F1, F2=self.F2, F3=self.F3, bias_filter=self.bias_filter, null2=self.null2,
+        self._evalue_window = max_length
+        res = longtarget.search(om, sequences, evalue_window=max_length, F1=self.F1, F2=self.F2, F3=self.F3, bias_filter=self.bias_filter, null2=self.null2,
                                 B1=self.B1, B2=self.B2, B3=self.B3, block_length=self.block_length, strand=self.strand,
                                 seed=self.seed, host_threads=self.host_threads, backend_factory=self._backend_factory)
         return self._long_target_tophits(query, om, sequences, res, cut)

@@ -214,7 +214,8 @@ def test_long_targets_pipeline_front_end(monkeypatch, strand, E):
     pli = plan7.LongTargetsPipeline(pair.hmm.alphabet, strand=strand, block_length=20000, E=E, incE=E / 100)
     pli._backend_factory = lambda om, blk: lt_common.OracleBackend(pair, blk)
     th = pli.search_hmm(pair.hmm, block)
-    rhits, rstats = pair.ref.nhmmer([s.sequence for s in block], block_length=20000, strand=strand, E=E, incE=E / 100)
+    rhits, rstats = pair.ref.nhmmer([s.sequence for s in block], block_length=20000, strand=strand, E=E, incE=E / 100,
+                                    evalue_window=pair.ref.max_length())     # an HMM query: E-values count windows of p7_Builder_MaxLength
     assert th.long_targets and len(th) == len(rhits) >= 8
     assert (th.searched_residues, th.searched_sequences) == (rstats[0], rstats[1])
     for h, r in zip(th, rhits):
@@ -232,3 +233,26 @@ def test_long_targets_pipeline_front_end(monkeypatch, strand, E):
         plan7.LongTargetsPipeline(pair.hmm.alphabet, strand="both")
     with pytest.raises(ValueError):
         plan7.LongTargetsPipeline(pair.hmm.alphabet, block_length=100).search_hmm(pair.hmm, block)
+
+
+def test_max_length_matches_the_builder(amino):
+    """HMM.compute_max_length = p7_Builder_MaxLength (p7_builder.c:651) for synthetic and for the reference's own models,
+    whose MAXL line hmmbuild wrote with the default tail mass."""
+    import gzip
+    import tempfile
+    from pyhmmer_b200 import plan7
+    from oracle import refshim
+    for M in (1, 2, 3, 40, 333):
+        pair, rng = lt_common.dna_model(ModelPair, M)
+        for beta in (1e-7, 1e-3, 0.3):
+            assert pair.hmm.compute_max_length(beta) == pair.ref.max_length(beta), (M, beta)
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data")
+    for name in ("PF02826", "Thioesterase"):
+        with tempfile.NamedTemporaryFile(suffix=".hmm") as tmp:
+            with gzip.open(os.path.join(gold, name + ".hmm.gz")) as f:
+                tmp.write(f.read())
+            tmp.flush()
+            with plan7.HMMFile(tmp.name) as f:
+                hmm = f.read()
+            ref = refshim.RefModel(tmp.name, 0, 400)
+            assert hmm.compute_max_length() == ref.max_length() and (hmm.max_length <= 0 or hmm.compute_max_length() == hmm.max_length)

@@ -95,7 +95,7 @@ def test_long_targets_pipeline_api(make_pair):
     block = lt_common.dna_chunks(pair, rng, [90000, 30000], nplant=10)
     pli = plan7.LongTargetsPipeline(pair.hmm.alphabet, block_length=20000)
     th = pli.search_hmm(pair.hmm, block)
-    rhits, rstats = pair.ref.nhmmer([s.sequence for s in block], block_length=20000)
+    rhits, rstats = pair.ref.nhmmer([s.sequence for s in block], block_length=20000, evalue_window=pair.ref.max_length())
     assert len(th) == len(rhits) >= 8 and th.searched_residues == rstats[0]
     for h, r in zip(th, rhits):
         d = h.domains[0]
