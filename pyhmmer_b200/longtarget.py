@@ -13,7 +13,11 @@ reference's own precision (which operands are float, which double, is part of th
 shipped is the CUDA one (there is no CPU path in this package) -- the CPU-only tests drive the same host logic with the
 reference's functions as the backend.
 
-Not here yet: the long-target branch of domain definition and the hit bookkeeping behind the Forward gate.
+`search()` is the whole nhmmer loop for one profile (LongTargetsPipeline.search_hmm, src/pyhmmer/plan7.pyx:7258-7412): the
+targets cut into windows with context, both strands, `stages()`, then the hit stage -- Forward / Backward parser specials of
+the surviving windows from the GPU, the long-target branch of domain definition and the hit arithmetic of
+``p7_pli_postViterbi_LongTarget`` on the host threads (``b2h_longtarget_hits``) -- and what ``p7_tophits`` does to nhmmer
+hits: E-values over residues / window length, the position sort, duplicate removal.  `plan7.LongTargetsPipeline` wraps it.
 """
 import ctypes
 import math
