@@ -400,11 +400,12 @@ int ref_vit_longtarget(REFM *m, const uint8_t *dsq, int L, int cfg_len, float fi
 /* The real thing: p7_Pipeline_LongTarget on one chunk with a long-target P7_PIPELINE, as LongTargetsPipeline's search loop
  * drives it (plan7.pyx:7568-7643; top strand).  counters [5] = pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd, hits;
  * hits [cap][12] = ienv, jenv, iali, jali, score (bits), bias (dombias), pre_score, lnP, envsc, oasc, hmmfrom, hmmto of every
- * hit appended (unsorted); sq->start = <start> (so that the coordinate arithmetic is exercised), complement as given (the
+ * hit appended (unsorted), text = their alignment displays (model | mline | aseq | ppline, NUL-terminated, back to back)
+ * when asked for; sq->start = <start> (so that the coordinate arithmetic is exercised), complement as given (the
  * caller passes the reverse-complemented residues, as esl_sq_ReverseComplement leaves them, and start = the chunk's LAST
  * coordinate). */
 int ref_longtarget_pipeline(REFM *m, const uint8_t *dsq, int L, double F1, double F2, double F3, int do_bias, int do_null2,
-                            long start, int complement, long *counters, int cap, double *hits)
+                            long start, int complement, long *counters, int cap, double *hits, char *text, long textcap)
 {
   P7_PIPELINE *pli = p7_pipeline_Create(NULL, m->om->M, 100, TRUE, p7_SEARCH_SEQS);
   P7_TOPHITS *th = p7_tophits_Create();
@@ -422,8 +423,15 @@ int ref_longtarget_pipeline(REFM *m, const uint8_t *dsq, int L, double F1, doubl
   status = p7_Pipeline_LongTarget(pli, m->om, data, m->bg, th, 0, sq, complement ? p7_COMPLEMENT : p7_NOCOMPLEMENT, NULL, NULL, NULL);
   counters[0] = pli->pos_past_msv; counters[1] = pli->pos_past_bias; counters[2] = pli->pos_past_vit; counters[3] = pli->pos_past_fwd;
   counters[4] = th->N;
+  long tpos = 0;
   for (h = 0; h < (long)th->N && h < cap; h++) {
     P7_HIT *hit = th->unsrt + h;
+    if (text) {           /* model | mline | aseq | ppline, each N+1 bytes */
+      P7_ALIDISPLAY *ad = hit->dcl[0].ad;
+      const char *ln[4] = { ad->model, ad->mline, ad->aseq, ad->ppline };
+      int q;
+      for (q = 0; q < 4; q++) if (tpos + ad->N + 1 <= textcap) { memcpy(text + tpos, ln[q], ad->N + 1); tpos += ad->N + 1; }
+    }
     hits[h*12+0] = hit->dcl[0].ienv; hits[h*12+1] = hit->dcl[0].jenv; hits[h*12+2] = hit->dcl[0].iali; hits[h*12+3] = hit->dcl[0].jali;
     hits[h*12+4] = hit->score; hits[h*12+5] = hit->dcl[0].dombias; hits[h*12+6] = hit->pre_score; hits[h*12+7] = hit->lnP;
     hits[h*12+8] = hit->dcl[0].envsc; hits[h*12+9] = hit->dcl[0].oasc; hits[h*12+10] = hit->dcl[0].ad->hmmfrom; hits[h*12+11] = hit->dcl[0].ad->hmmto;

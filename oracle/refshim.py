@@ -73,7 +73,7 @@ def lib():
                                  ctypes.c_double, ctypes.c_double, ctypes.c_long, ctypes.c_long, vp, vp]
         L.ref_max_length.argtypes = [vp, ctypes.c_double]
         L.ref_vit_longtarget.argtypes = [vp, vp, ci, ci, cf, ctypes.c_double, ci, vp]
-        L.ref_longtarget_pipeline.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ctypes.c_long, ci, vp, ci, vp]
+        L.ref_longtarget_pipeline.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ctypes.c_long, ci, vp, ci, vp, vp, ctypes.c_long]
         L.ref_gdecoding.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), vp]
         L.ref_gumbel_surv.restype = ctypes.c_double
         L.ref_gumbel_surv.argtypes = [ctypes.c_double] * 3
@@ -277,14 +277,22 @@ class RefModel:
         assert nh <= cap
         return hit[:nh].copy()
 
-    def longtarget_pipeline(self, codes, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True, start=1, complement=False, cap=20000):
+    def longtarget_pipeline(self, codes, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True, start=1, complement=False, cap=20000,
+                            want_text=False):
         """p7_Pipeline_LongTarget itself on one chunk: (counters [5] = pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd,
         number of hits; hits [n,12] = ienv, jenv, iali, jali, score, bias, pre_score, lnP, envsc, oasc, hmmfrom, hmmto).
         <start> = sq->start; for the complement strand pass the reverse-complemented codes and the chunk's last coordinate."""
         d = dsq_of(codes); n = d.size - 2
         counters = np.zeros(5, np.int64); hits = np.zeros((cap, 12), np.float64)
+        tcap = 1 << 22
+        tbuf = ctypes.create_string_buffer(tcap) if want_text else None
         st = self.L.ref_longtarget_pipeline(self.h, d.ctypes.data, n, F1, F2, F3, int(bias_filter), int(null2), int(start), int(complement),
-                                            counters.ctypes.data, cap, hits.ctypes.data)
+                                            counters.ctypes.data, cap, hits.ctypes.data, tbuf, tcap)
+        if want_text:
+            assert st == 0, st
+            lines = tbuf.raw.split(b"\0")
+            nh = min(cap, int(counters[4]))
+            return counters, hits[:nh].copy(), [tuple(lines[4 * i:4 * i + 4]) for i in range(nh)]
         assert st == 0, st
         return counters, hits[:min(cap, int(counters[4]))].copy()
 

@@ -1044,40 +1044,6 @@ void ddef_finish(const b2h_ddef_task &t, const b2h_search_params *prm, TaskState
 // (p7_pipeline.c:1113-1280) and the long_target paths of rescore_isolated_domain (p7_domaindef.c:814-982).
 // =====================================================================================================
 
-// The 4-lane Cephes expf of the reference, one lane (esl_sse.c:182-246; same restatement as b2h_host.cpp's).
-inline float lt_cephes_expf(float x) {
-  const float p0 = 1.9875691500E-4f, p1 = 1.3981999507E-3f, p2 = 8.3334519073E-3f,
-              p3 = 4.1665795894E-2f, p4 = 1.6666665459E-1f, p5 = 5.0000001201E-1f;
-  const float c0 = 0.693359375f, c1 = -2.12194440e-4f;
-  const float maxlogf = 88.3762626647949f, minlogf = -88.3762626647949f;
-  const bool over = (x > maxlogf), under = (x <= minlogf);
-  float fx = x * 1.44269504088896341f;
-  fx = fx + 0.5f;
-  int k = (int)fx;
-  float tmp = (float)k;
-  if (tmp > fx) tmp = tmp - 1.0f;
-  fx = tmp;
-  k = (int)fx;
-  tmp = fx * c0;
-  float z = fx * c1;
-  x = x - tmp;
-  x = x - z;
-  z = x * x;
-  float y = p0;       y = y * x;
-  y = y + p1;         y = y * x;
-  y = y + p2;         y = y * x;
-  y = y + p3;         y = y * x;
-  y = y + p4;         y = y * x;
-  y = y + p5;         y = y * z;
-  y = y + x;
-  y = y + 1.0f;
-  union { float f; int32_t i; } u; u.i = (k + 127) << 23;
-  y = y * u.f;
-  if (over) y = std::numeric_limits<float>::infinity();
-  if (under) y = 0.0f;
-  return y;
-}
-
 // reparameterize_model (p7_domaindef.c:715-750) + p7_oprofile_UpdateFwdEmissionScores (impl_sse/p7_oprofile.c:438-487):
 // the background becomes a mixture of the model's own and the composition of the envelope i..i+Ld-1 of the window, and the
 // match odds are rebuilt from the emission probabilities p7_oprofile_GetFwdEmissionArray recovered (odds x background).
@@ -1115,7 +1081,7 @@ void lt_reparameterize(const b2h_profile *prof, const uint8_t *dsq, int wlen, in
       for (int y = 0; y < K; y++) if (degen[(size_t)x * K + y]) { result += sc[y] * bgn[y]; denom += bgn[y]; }
       sc[x] = result / denom;
     }
-    for (int x = 0; x < Kp; x++) rsc[(size_t)x * M + (k - 1)] = lt_cephes_expf(sc[x]);
+    for (int x = 0; x < Kp; x++) rsc[(size_t)x * M + (k - 1)] = b2h_cephes_expf(sc[x]);
   }
 }
 

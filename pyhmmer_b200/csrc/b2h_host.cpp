@@ -84,6 +84,8 @@ inline float cephes_expf(float x) {
 
 } // namespace
 
+float b2h_cephes_expf(float x) { return cephes_expf(x); }
+
 extern "C" {
 
 int b2h_hmm_decode_probs(const double *neglog, float *out, size_t n)

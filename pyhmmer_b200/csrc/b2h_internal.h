@@ -357,4 +357,7 @@ struct Grouped { int32_t *p, *s; float *a, *b; int32_t *poff, *itemoff; int *fil
 int b2h_launch_group(b2h_ctx *ctx, const SurvList &in, int P, Grouped out);// p7_pli_ExtendAndMergeWindows on a host list, in place (b2h_longtarget.cu); returns the number of windows left
 size_t b2h_extend_merge(const b2h_profile *p, b2h_window *w, size_t n, const int64_t *target_len, float pct_overlap);
 
+// one lane of the reference's 4-lane Cephes expf (esl_sse.c:182-246), as used to build Forward odds ratios (b2h_host.cpp)
+float b2h_cephes_expf(float x);
+
 

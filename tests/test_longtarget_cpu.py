@@ -127,7 +127,7 @@ def test_hits_behind_the_forward_gate(M, mu_shift, null2, complement, layout):
         start = 1001 + len(seq) - 1                       # sq->start is then the chunk's LAST coordinate
     kw = dict(F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=240, B3=1000)
     got = longtarget.stages(pair.om, block, backend=lt_common.OracleBackend(pair, block), **kw)
-    cnt, rhits = pair.ref.longtarget_pipeline(seq, null2=null2, start=start, complement=complement)
+    cnt, rhits, rtext = pair.ref.longtarget_pipeline(seq, null2=null2, start=start, complement=complement, want_text=True)
     assert np.array_equal(got["counters"][0], cnt[:4]) and len(rhits) >= 3
     mw, vw = got["msvwin"], got["vitwin"]
     keep = [], []
@@ -154,9 +154,10 @@ def test_hits_behind_the_forward_gate(M, mu_shift, null2, complement, layout):
     _lib.lib.b2h_profile_destroy(hp)
     assert len(hits) == len(rhits), (len(hits), len(rhits))
     nbias = 0
-    for h, r in zip(hits, rhits):
+    for h, r, rt in zip(hits, rhits, rtext):
         d = doms[h.dom_offset]
         assert (d.ienv, d.jenv, d.iali, d.jali, d.hmmfrom, d.hmmto) == tuple(int(x) for x in (r[0], r[1], r[2], r[3], r[10], r[11])), (h.profile, r)
+        assert tuple(text[d.text_offset:d.text_offset + 4 * (d.N + 1)].split(b"\0")[:4]) == rt       # the alignment display, character by character
         assert (d.sqfrom, d.sqto) == (d.iali, d.jali)
         assert abs(h.score - r[4]) < 2e-3 and abs(d.dombias - r[5]) < 2e-3 and abs(h.pre_score - r[6]) < 2e-3, (h.score, r)
         assert abs(h.lnP - r[7]) < 2e-3 and abs(d.envsc - r[8]) < 2e-3 and abs(d.oasc - r[9]) < 2e-3
