@@ -267,43 +267,45 @@ def target_windows(lengths, W, C, strand=None):
 
 
 def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True, B1=100, B2=240, B3=1000,
-           block_length=0x40000, strand=None, seed=42, host_threads=0, backend_factory=None, evalue_window=None):
+           block_length=0x40000, strand=None, seed=42, host_threads=0, backend_factory=None, evalue_window=None, world=None):
     """nhmmer for one profile: every target of ``sequences`` in windows, on both strands (or one), through `stages`
     and the hit stage; then p7_tophits_ComputeNhmmerEvalues, the seqidx / position sort, p7_tophits_RemoveDuplicates
     (p7_tophits.c:796, 426, 823).  Returns (hits, doms, text, duplicate flags, stats) with the hits in target order;
-    stats = dict(nres, nseqs, pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd).  hit.seq = target index."""
-    from . import easel
+    stats = dict(nres, nseqs, pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd).  hit.seq = target index.
+
+    With several GPUs (one process each, ``torch.distributed``) the windows are dealt to the ranks in contiguous runs
+    balanced by residues, every rank takes its windows through all stages, and ONE all-gather of the hit records
+    (`parallel.all_gather_bytes`) gives every rank the same hits before the E-value / duplicate pass."""
+    from . import easel, parallel
     abc = om.alphabet
     max_length = int(om._desc.max_length)
     lens = [len(s) for s in sequences]
     wins = target_windows(lens, int(block_length), max_length, strand)
-    chunks = []
-    for (t, i, n, comp, w, c) in wins:
-        codes = sequences[t].sequence[i:i + n]
-        chunks.append(easel.DigitalSequence(abc, name=b"w", sequence=reverse_complement(abc, codes) if comp else codes))
-    block = easel.DigitalSequenceBlock(abc, chunks)
     nres = sum(w for (_, _, _, _, w, _) in wins)         # pli->nres: W per window and strand (plan7.pyx:7606-7640)
     stats = dict(nres=int(nres), nseqs=len(lens), pos_past_msv=0, pos_past_bias=0, pos_past_vit=0, pos_past_fwd=0)
-    empty = (_lib.RecList(), _lib.RecList(), b"", [], stats)
-    if not wins:
-        return empty
-    be = (backend_factory or CudaBackend)(om, block)
-    st = stages(om, block, F1=F1, F2=F2, F3=F3, bias_filter=bias_filter, B1=B1, B2=B2, B3=B3, backend=be)
+    if world is None:
+        world = parallel.World.current()
+    mine = wins
+    if world.size > 1:
+        bounds = parallel.shard_bounds([w[2] for w in wins], world.size)
+        mine = wins[bounds[world.rank]:bounds[world.rank + 1]]
+    hits, doms, text, counters = _search_windows(om, sequences, mine, F1, F2, F3, bias_filter, null2, B1, B2, B3, seed, host_threads,
+                                                 backend_factory)
+    if world.size > 1:
+        parts = [parallel.unpack_records(buf) for buf in parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, counters, 0), world)]
+        hits, doms, tbuf, counters = _lib.RecList(), _lib.RecList(), bytearray(), np.zeros(4, np.int64)
+        for h, d, t, c in parts:                            # rank order = window order
+            for r in h:
+                r.dom_offset += len(doms)
+            for r in d:
+                r.text_offset += len(tbuf)
+            hits.extend(h); doms.extend(d); tbuf.extend(t)
+            counters = counters + c
+        text = bytes(tbuf)
     for k, col in (("pos_past_msv", 0), ("pos_past_bias", 1), ("pos_past_vit", 2), ("pos_past_fwd", 3)):
-        stats[k] = int(st["counters"][:, col].sum())
-    sel = np.flatnonzero(st["vitpass"])
-    if len(sel) == 0:
-        return empty
-    mw, vw = st["msvwin"], st["vitwin"]
-    chunk = mw["seq"][vw["seq"][sel]]                                   # chunk of every surviving window
-    wstart = (mw["n"][vw["seq"][sel]] + vw["n"][sel] - 1).astype(np.int64)  # its first residue in the chunk
-    wlen = vw["length"][sel].astype(np.int64)
-    # sq->start of the chunk: its first target coordinate, or -- after esl_sq_ReverseComplement -- its last
-    seq_start = np.array([(wins[c][1] + wins[c][2]) if wins[c][3] else (wins[c][1] + 1) for c in chunk], np.int64)
-    comp = np.array([wins[c][3] for c in chunk], np.int32)
-    target = np.array([wins[c][0] for c in chunk], np.int32)
-    prm = _lib.SearchParams(F1, F2, F3, int(bias_filter), int(null2), seed, int(host_threads))
-    hits, doms, text = be.hits(be.window_db(chunk, wstart, wlen), wstart, seq_start, comp, target, prm)
+        stats[k] = int(counters[col])
+    if not hits:
+        return _lib.RecList(), _lib.RecList(), b"", [], stats
     # p7_tophits_ComputeNhmmerEvalues: the search space is residues / window length
     add = math.log(float(np.float32(stats["nres"])) / float(np.float32(evalue_window or max_length)))
     for h in hits:
@@ -341,3 +343,34 @@ def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=Tru
     hits_sorted = _lib.RecList(hits[q] for q in order)
     hits_sorted.raw = getattr(hits, "raw", None)
     return hits_sorted, doms, text, [dup[q] for q in order], stats
+
+
+def _search_windows(om, sequences, wins, F1, F2, F3, bias_filter, null2, B1, B2, B3, seed, host_threads, backend_factory):
+    """All stages for a list of target windows (`target_windows` tuples): (hits, domains, text, pos_past_* [4])."""
+    from . import easel
+    abc = om.alphabet
+    none = (_lib.RecList(), _lib.RecList(), b"", np.zeros(4, np.int64))
+    if not wins:
+        return none
+    chunks = []
+    for (t, i, n, comp, w, c) in wins:
+        codes = sequences[t].sequence[i:i + n]
+        chunks.append(easel.DigitalSequence(abc, name=b"w", sequence=reverse_complement(abc, codes) if comp else codes))
+    block = easel.DigitalSequenceBlock(abc, chunks)
+    be = (backend_factory or CudaBackend)(om, block)
+    st = stages(om, block, F1=F1, F2=F2, F3=F3, bias_filter=bias_filter, B1=B1, B2=B2, B3=B3, backend=be)
+    counters = st["counters"].sum(axis=0).astype(np.int64)
+    sel = np.flatnonzero(st["vitpass"])
+    if len(sel) == 0:
+        return none[0], none[1], b"", counters
+    mw, vw = st["msvwin"], st["vitwin"]
+    chunk = mw["seq"][vw["seq"][sel]]                                   # chunk of every surviving window
+    wstart = (mw["n"][vw["seq"][sel]] + vw["n"][sel] - 1).astype(np.int64)  # its first residue in the chunk
+    wlen = vw["length"][sel].astype(np.int64)
+    # sq->start of the chunk: its first target coordinate, or -- after esl_sq_ReverseComplement -- its last
+    seq_start = np.array([(wins[c][1] + wins[c][2]) if wins[c][3] else (wins[c][1] + 1) for c in chunk], np.int64)
+    comp = np.array([wins[c][3] for c in chunk], np.int32)
+    target = np.array([wins[c][0] for c in chunk], np.int32)
+    prm = _lib.SearchParams(F1, F2, F3, int(bias_filter), int(null2), seed, int(host_threads))
+    hits, doms, text = be.hits(be.window_db(chunk, wstart, wlen), wstart, seq_start, comp, target, prm)
+    return hits, doms, text, counters

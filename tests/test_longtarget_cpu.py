@@ -257,3 +257,45 @@ def test_max_length_matches_the_builder(amino):
                 hmm = f.read()
             ref = refshim.RefModel(tmp.name, 0, 400)
             assert hmm.compute_max_length() == ref.max_length() and (hmm.max_length <= 0 or hmm.compute_max_length() == hmm.max_length)
+
+
+_LT_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np, torch.distributed as dist
+from pyhmmer_b200 import parallel, longtarget
+import lt_common
+from conftest import ModelPair
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%d" %% int(sys.argv[1]), rank=int(sys.argv[2]), world_size=2)
+w = parallel.World.current()
+pair, rng = lt_common.dna_model(ModelPair, 121, mu_shift=-2.0)
+block = lt_common.dna_chunks(pair, rng, [90000, 30000, 500], nplant=10)
+fac = lambda om, blk: lt_common.OracleBackend(pair, blk)
+kw = dict(block_length=20000, backend_factory=fac)
+sharded = longtarget.search(pair.om, block, world=w, **kw)
+single = longtarget.search(pair.om, block, world=parallel.World(), **kw)
+key = lambda res: [(h.seq, res[1][h.dom_offset].iali, res[1][h.dom_offset].jali, res[1][h.dom_offset].ienv, res[1][h.dom_offset].jenv,
+                    h.score, h.lnP, res[1][h.dom_offset].dombias, d) for h, d in zip(res[0], res[3])]
+assert len(single[0]) >= 10 and key(sharded) == key(single), (len(sharded[0]), len(single[0]))
+assert sharded[4] == single[4], (sharded[4], single[4])
+for res in (sharded, single):
+    for h in res[0]:
+        d = res[1][h.dom_offset]
+        assert len(res[2][d.text_offset:d.text_offset + 4 * (d.N + 1)].split(b"\0")[0]) == d.N
+dist.barrier(); dist.destroy_process_group()
+print("rank", w.rank, "ok", len(single[0]))
+'''
+
+
+def test_window_sharding_world_size_2_gloo():
+    """The multi-GPU form of the nhmmer search: windows dealt to two ranks, one all-gather of the hit records, then the
+    E-value / duplicate pass on every rank -- identical to the unsharded search (host logic; gloo on the CPU)."""
+    import socket
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port_ = s.getsockname()[1]; s.close()
+    code = _LT_WORKER % (root, root)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(port_), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
