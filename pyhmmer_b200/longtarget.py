@@ -21,6 +21,7 @@ hits: E-values over residues / window length, the position sort, duplicate remov
 """
 import ctypes
 import math
+import time
 
 import numpy as np
 
@@ -145,7 +146,20 @@ def _take_windows(p, n):
         lib.b2h_free(p)
 
 
-def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=240, B3=1000, backend=None):
+class _Clock:
+    """Wall-clock seconds per stage into a caller's dict (every backend call returns host results, i.e. is synchronous)."""
+
+    def __init__(self, sink):
+        self.sink, self.t = sink, time.perf_counter()
+
+    def lap(self, name):
+        now = time.perf_counter()
+        if self.sink is not None:
+            self.sink[name] = self.sink.get(name, 0.0) + (now - self.t)
+        self.t = now
+
+
+def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=240, B3=1000, backend=None, timings=None):
     """SSV windows -> MSV / bias gates -> Viterbi landmarks and windows -> Forward gate, for every chunk of ``chunks``.
 
     Returns a dict of numpy arrays:
@@ -156,7 +170,9 @@ def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=2
       ``vitsc`` [v,3] = null1, FilterScore, Forward score, ``vitpass`` = passed the Forward gate;
       ``counters`` [nchunks,4] = pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd per chunk (P7_PIPELINE, hmmer.h).
     """
+    clock = _Clock(timings)
     be = backend if backend is not None else CudaBackend(om, chunks)
+    clock.lap("upload")
     f32, f64 = np.float32, np.float64
     ev = [float(v) for v in om._evparam]                 # MMU MLAMBDA VMU VLAMBDA FTAU FLAMBDA
     max_length = int(om._desc.max_length)
@@ -167,6 +183,7 @@ def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=2
                vitwin=np.zeros(0, wdt), vitsc=np.zeros((0, 3), f32), vitpass=np.zeros(0, np.int32), counters=counters)
 
     mw = be.ssv_windows(F1)
+    clock.lap("ssv_scan")
     n = len(mw)
     out["msvwin"] = mw
     if n == 0:
@@ -175,6 +192,7 @@ def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=2
     wdb = be.window_db(mw["seq"], mw["n"], wlen)
     nul, bias = be.null_bias(wdb)                        # p7_bg_SetLength(window) + p7_bg_NullOne / p7_bg_FilterScore
     usc = be.msv(wdb)                                    # p7_oprofile_ReconfigMSVLength(window) + p7_MSVFilter
+    clock.lap("window_msv_bias")
     out["msvsc"] = np.stack([nul, bias, usc], axis=1)
     # p7_Pipeline_LongTarget's gate (:1637): float difference, double division
     x = (usc - nul).astype(f32).astype(f64) / LOG2
@@ -196,7 +214,9 @@ def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=2
     nul_loc = np.array([null1(int(min(L, max_length))) for L in wlen], f32)
     ratio2 = np.minimum(wlen, B2).astype(f32) / flen
     filtersc2 = (nul_loc.astype(f64) + b.astype(f64) * ratio2.astype(f64)).astype(f32)
+    clock.lap("host_gates")
     marks, vw = be.viterbi_windows(wdb, filtersc2, pass_bias, F2)
+    clock.lap("viterbi_scan")
     out["vitmark"], out["vitwin"] = marks, vw
     nv = len(vw)
     if nv == 0:
@@ -206,6 +226,7 @@ def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=2
     vdb = be.window_db(vchunk, mw["n"][vw["seq"]] + vw["n"] - 1, vlen)
     vnul, vbias = be.null_bias(vdb)
     fwd = be.forward(vdb)                                # p7_oprofile_ReconfigRestLength(window) + p7_ForwardParser
+    clock.lap("window_forward")
     out["vitsc"] = np.stack([vnul, vbias, fwd], axis=1)
     vb = (vbias - vnul).astype(f32) if bias_filter else np.zeros(nv, f32)
     ratio3 = np.minimum(vlen, B3).astype(f32) / vlen.astype(f32)
@@ -228,6 +249,7 @@ def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=2
             overlap = 0 if last else max(0, int(vend[i] - vw["n"][i + 1]))
         else:
             overlap = 0
+    clock.lap("host_gates")
     return out
 
 
@@ -267,7 +289,8 @@ def target_windows(lengths, W, C, strand=None):
 
 
 def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True, B1=100, B2=240, B3=1000,
-           block_length=0x40000, strand=None, seed=42, host_threads=0, backend_factory=None, evalue_window=None, world=None):
+           block_length=0x40000, strand=None, seed=42, host_threads=0, backend_factory=None, evalue_window=None, world=None,
+           timings=None):
     """nhmmer for one profile: every target of ``sequences`` in windows, on both strands (or one), through `stages`
     and the hit stage; then p7_tophits_ComputeNhmmerEvalues, the seqidx / position sort, p7_tophits_RemoveDuplicates
     (p7_tophits.c:796, 426, 823).  Returns (hits, doms, text, duplicate flags, stats) with the hits in target order;
@@ -290,7 +313,7 @@ def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=Tru
         bounds = parallel.shard_bounds([w[2] for w in wins], world.size)
         mine = wins[bounds[world.rank]:bounds[world.rank + 1]]
     hits, doms, text, counters = _search_windows(om, sequences, mine, F1, F2, F3, bias_filter, null2, B1, B2, B3, seed, host_threads,
-                                                 backend_factory)
+                                                 backend_factory, timings)
     if world.size > 1:
         parts = [parallel.unpack_records(buf) for buf in parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, counters, 0), world)]
         hits, doms, tbuf, counters = _lib.RecList(), _lib.RecList(), bytearray(), np.zeros(4, np.int64)
@@ -345,20 +368,24 @@ def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=Tru
     return hits_sorted, doms, text, [dup[q] for q in order], stats
 
 
-def _search_windows(om, sequences, wins, F1, F2, F3, bias_filter, null2, B1, B2, B3, seed, host_threads, backend_factory):
+def _search_windows(om, sequences, wins, F1, F2, F3, bias_filter, null2, B1, B2, B3, seed, host_threads, backend_factory, timings=None):
     """All stages for a list of target windows (`target_windows` tuples): (hits, domains, text, pos_past_* [4])."""
     from . import easel
     abc = om.alphabet
     none = (_lib.RecList(), _lib.RecList(), b"", np.zeros(4, np.int64))
     if not wins:
         return none
+    clock = _Clock(timings)
     chunks = []
     for (t, i, n, comp, w, c) in wins:
         codes = sequences[t].sequence[i:i + n]
         chunks.append(easel.DigitalSequence(abc, name=b"w", sequence=reverse_complement(abc, codes) if comp else codes))
     block = easel.DigitalSequenceBlock(abc, chunks)
+    clock.lap("cut_windows")
     be = (backend_factory or CudaBackend)(om, block)
-    st = stages(om, block, F1=F1, F2=F2, F3=F3, bias_filter=bias_filter, B1=B1, B2=B2, B3=B3, backend=be)
+    clock.lap("upload")
+    st = stages(om, block, F1=F1, F2=F2, F3=F3, bias_filter=bias_filter, B1=B1, B2=B2, B3=B3, backend=be, timings=timings)
+    clock.t = time.perf_counter()
     counters = st["counters"].sum(axis=0).astype(np.int64)
     sel = np.flatnonzero(st["vitpass"])
     if len(sel) == 0:
@@ -373,4 +400,5 @@ def _search_windows(om, sequences, wins, F1, F2, F3, bias_filter, null2, B1, B2,
     target = np.array([wins[c][0] for c in chunk], np.int32)
     prm = _lib.SearchParams(F1, F2, F3, int(bias_filter), int(null2), seed, int(host_threads))
     hits, doms, text = be.hits(be.window_db(chunk, wstart, wlen), wstart, seq_start, comp, target, prm)
+    clock.lap("hits")
     return hits, doms, text, counters
