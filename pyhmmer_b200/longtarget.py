@@ -269,6 +269,40 @@ def reverse_complement(alphabet, codes):
     return np.ascontiguousarray(table[codes[::-1]])
 
 
+class _Chunk:
+    def __init__(self, codes):
+        self.sequence = codes
+
+    def __len__(self):
+        return len(self.sequence)
+
+
+class _ChunkBlock:
+    """The windows of a search as one block: residue views into the targets (and their reverse complements), packed once
+    for the upload -- the part of `easel.DigitalSequenceBlock` the backends use, without one object and one copy per window."""
+
+    def __init__(self, alphabet, pieces):
+        self.alphabet, self._pieces, self._cache = alphabet, pieces, {}
+
+    def __len__(self):
+        return len(self._pieces)
+
+    def __getitem__(self, i):
+        return _Chunk(self._pieces[i])
+
+    def __iter__(self):
+        return (_Chunk(p) for p in self._pieces)
+
+    def _packed(self):
+        hit = self._cache.get("packed")
+        if hit is None:
+            off = np.zeros(len(self._pieces) + 1, np.int64)
+            np.cumsum([len(p) for p in self._pieces], out=off[1:])
+            res = np.concatenate(self._pieces) if self._pieces else np.zeros(0, np.uint8)
+            hit = self._cache["packed"] = (np.ascontiguousarray(res, dtype=np.uint8), off)
+        return hit
+
+
 def target_windows(lengths, W, C, strand=None):
     """The windows _search_loop_longtargets cuts the targets into: (target, offset i, n, complement) in its order --
     windows of W residues that keep C residues of the previous one as context; each on the strands asked for."""
@@ -299,8 +333,7 @@ def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=Tru
     With several GPUs (one process each, ``torch.distributed``) the windows are dealt to the ranks in contiguous runs
     balanced by residues, every rank takes its windows through all stages, and ONE all-gather of the hit records
     (`parallel.all_gather_bytes`) gives every rank the same hits before the E-value / duplicate pass."""
-    from . import easel, parallel
-    abc = om.alphabet
+    from . import parallel
     max_length = int(om._desc.max_length)
     lens = [len(s) for s in sequences]
     wins = target_windows(lens, int(block_length), max_length, strand)
@@ -370,17 +403,22 @@ def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=Tru
 
 def _search_windows(om, sequences, wins, F1, F2, F3, bias_filter, null2, B1, B2, B3, seed, host_threads, backend_factory, timings=None):
     """All stages for a list of target windows (`target_windows` tuples): (hits, domains, text, pos_past_* [4])."""
-    from . import easel
     abc = om.alphabet
     none = (_lib.RecList(), _lib.RecList(), b"", np.zeros(4, np.int64))
     if not wins:
         return none
     clock = _Clock(timings)
-    chunks = []
+    rc = {}                                                # reverse complement of a whole target, made once
+    pieces = []
     for (t, i, n, comp, w, c) in wins:
-        codes = sequences[t].sequence[i:i + n]
-        chunks.append(easel.DigitalSequence(abc, name=b"w", sequence=reverse_complement(abc, codes) if comp else codes))
-    block = easel.DigitalSequenceBlock(abc, chunks)
+        codes = sequences[t].sequence
+        if comp:
+            if t not in rc:
+                rc[t] = reverse_complement(abc, codes)
+            pieces.append(rc[t][len(codes) - (i + n):len(codes) - i])
+        else:
+            pieces.append(codes[i:i + n])
+    block = _ChunkBlock(abc, pieces)
     clock.lap("cut_windows")
     be = (backend_factory or CudaBackend)(om, block)
     clock.lap("upload")

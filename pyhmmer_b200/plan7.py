@@ -989,7 +989,7 @@ def long_target_windows(om, chunks, F1=0.02):
     ``chunks`` (the pieces a long target was cut into), then ``p7_pli_ExtendAndMergeWindows`` (p7_pipeline.c:1535-1565).
     Returns ``(raw, merged)`` numpy record arrays with fields seq, k, n, length, score (`_lib.WindowRec`)."""
     ctx = _lib.context()
-    block = chunks if isinstance(chunks, DigitalSequenceBlock) else DigitalSequenceBlock(om.alphabet, chunks)
+    block = chunks if hasattr(chunks, "_packed") else DigitalSequenceBlock(om.alphabet, chunks)
     if block.alphabet != om.alphabet:
         raise AlphabetMismatch(om.alphabet, block.alphabet)
     db = SequenceDatabase.of(ctx, block)
