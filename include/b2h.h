@@ -254,6 +254,10 @@ int b2h_debug_domaindef(const b2h_profile *p, const uint8_t *dsq, int L, const f
 int b2h_profile_set_annotation(b2h_profile *p, const char *consensus, const char *rf, const char *cs,
                                const char *alphabet_symbols /* ESL_ALPHABET.sym, Kp chars */);
 
+/* The model mask (P7_OPROFILE.mm, the HMM file's MM line; 'm' marks a masked node), 1..M; NULL = none.  Only the long-target
+ * path reads it: masked nodes keep a zero match score when the background is re-estimated (p7_oprofile.c:455). */
+int b2h_profile_set_model_mask(b2h_profile *p, const char *mm);
+
 /* Bytes copied host->device when the object was made resident (bench.py reports them as e2e.h2d_bytes_per_step). */
 size_t b2h_seqdb_h2d_bytes(const b2h_seqdb *db);
 size_t b2h_profile_h2d_bytes(const b2h_profile *p);

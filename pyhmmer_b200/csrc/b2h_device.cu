@@ -559,6 +559,13 @@ int b2h_profile_set_annotation(b2h_profile *p, const char *consensus, const char
   return B2H_OK;
 }
 
+int b2h_profile_set_model_mask(b2h_profile *p, const char *mm)
+{
+  if (!p) return B2H_EINVAL;
+  p->mm = mm ? mm : "";
+  return B2H_OK;
+}
+
 } // extern "C"
 
 extern "C" size_t b2h_seqdb_h2d_bytes(const b2h_seqdb *db) { return db ? db->h2d_bytes : 0; }

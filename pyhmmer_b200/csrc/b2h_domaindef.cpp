@@ -1047,7 +1047,9 @@ void ddef_finish(const b2h_ddef_task &t, const b2h_search_params *prm, TaskState
 // reparameterize_model (p7_domaindef.c:715-750) + p7_oprofile_UpdateFwdEmissionScores (impl_sse/p7_oprofile.c:438-487):
 // the background becomes a mixture of the model's own and the composition of the envelope i..i+Ld-1 of the window, and the
 // match odds are rebuilt from the emission probabilities p7_oprofile_GetFwdEmissionArray recovered (odds x background).
-// rsc [Kp][M] receives the new odds.  (Model masks -- the MM line -- are not carried by b2h_profile and are not honoured.)
+// rsc [Kp][M] receives the new odds; nodes the model mask marks ('m') keep a zero score.  (The reference also leaves them at
+// zero when it reverts to the original background, i.e. it overwrites a masked node's own odds after the first envelope; a
+// masked column emits the background in every model hmmbuild writes, so its odds are 1 to begin with and nothing changes.)
 void lt_reparameterize(const b2h_profile *prof, const uint8_t *dsq, int wlen, int i, int Ld, std::vector<float> &rsc)
 {
   const int M = prof->M, K = prof->K, Kp = prof->Kp;
@@ -1071,9 +1073,10 @@ void lt_reparameterize(const b2h_profile *prof, const uint8_t *dsq, int wlen, in
   const float *orig = prof->h_fwd_rsc.data();
   float sc[B2H_MAXCODE];
   for (int k = 1; k <= M; k++) {
+    const bool masked = (size_t)k <= prof->mm.size() && prof->mm[k - 1] == 'm';
     for (int x = 0; x < K; x++) {
       const float em = orig[(size_t)x * M + (k - 1)] * prof->bgf[x];      // p7_oprofile_GetFwdEmissionArray
-      sc[x] = (float)log((double)em / bgn[x]);
+      sc[x] = masked ? 0.0f : (float)log((double)em / bgn[x]);
     }
     sc[K] = sc[Kp - 2] = sc[Kp - 1] = NEGINF;
     for (int x = K + 1; x <= Kp - 3; x++) {                  // esl_abc_FExpectScVec

@@ -144,6 +144,7 @@ struct b2h_profile {
   std::vector<float> h_fwd_rsc, h_fwd_tsc;   // [Kp][M], [8][M] node-major odds ratios
   std::vector<uint8_t> h_degen;              // [Kp][K]
   std::string consensus, rf, cs, symbols;    // 1..M annotation (index k-1), alphabet symbols
+  std::string mm;                            // model mask (P7_OPROFILE.mm, 'm' = masked node), index k-1; empty = none
   float bias_t10 = 0, bias_t11 = 0;   // fhmm->t[1][0], t[1][1]
 };
 

@@ -543,6 +543,7 @@ class OptimizedProfile:
         self.name, self.accession, self.description = profile.name, profile.accession, profile.description
         self.consensus = profile.consensus
         self.reference, self.consensus_structure = profile.reference, profile.consensus_structure
+        self.model_mask = profile.model_mask
         self._evparam, self._cutoff, self._compo = profile._evparam, profile._cutoff, profile._compo
         self.L = profile.L
         self.multihit = profile.multihit
@@ -576,6 +577,8 @@ class OptimizedProfile:
             enc = lambda t: t.encode("ascii") if t else None
             lib.b2h_profile_set_annotation(out, enc(self.consensus), enc(self.reference), enc(self.consensus_structure),
                                            self.alphabet.symbols.encode("ascii"))
+            if getattr(self, "model_mask", None):
+                lib.b2h_profile_set_model_mask(out, enc(self.model_mask))
             h = self._dev[ctx] = _DeviceHandle(out, lib.b2h_profile_destroy)
         return h.handle
 
@@ -591,6 +594,8 @@ class OptimizedProfile:
             for om, h in zip(todo, outs):
                 lib.b2h_profile_set_annotation(h, enc(om.consensus), enc(om.reference), enc(om.consensus_structure),
                                                om.alphabet.symbols.encode("ascii"))
+                if getattr(om, "model_mask", None):
+                    lib.b2h_profile_set_model_mask(h, enc(om.model_mask))
                 om._dev[ctx] = _DeviceHandle(ctypes.c_void_p(h), lib.b2h_profile_destroy)
         return [om._device(ctx) for om in oms]
 
@@ -864,6 +869,7 @@ def _convert_hmms(hmms, background, L, multihit=True, threads=0):
         om.name, om.accession, om.description = hmm.name, hmm.accession, hmm.description
         om.consensus = hmm.consensus
         om.reference, om.consensus_structure = hmm.reference, hmm.consensus_structure
+        om.model_mask = hmm.model_mask
         om._evparam, om._cutoff, om._compo = hmm._evparam.copy(), hmm._cutoff.copy(), hmm._compo.copy()
         om.L, om.multihit = int(L), bool(multihit)
         out.append(om)

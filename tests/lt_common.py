@@ -8,10 +8,13 @@ import numpy as np
 from pyhmmer_b200 import _lib, easel, longtarget, synth
 
 
-def dna_model(make_pair, M, seed=0, mu_shift=0.0):
+def dna_model(make_pair, M, seed=0, mu_shift=0.0, mask=False):
     dna = easel.Alphabet.dna()
     rng = np.random.default_rng(7000 + M + seed)
     h = synth.random_hmm(dna, M, rng, name="lt%d" % M)
+    if mask:                                             # a model mask (MM line): nodes M/4 .. M/2 masked
+        h.model_mask = "".join("m" if M // 4 <= k < M // 2 else "." for k in range(1, M + 1))
+        h.match_emissions[M // 4:M // 2] = 0.25          # ... which emit the background, as hmmbuild leaves masked columns
     h.max_length = 2 * M + 50
     mu = -8.0 - np.log2(M) * 0.3 + mu_shift
     h._evparam[:] = np.array([mu, 0.70, mu - 1.0, 0.70, -4.0 + mu_shift / 2, 0.70], np.float32)
@@ -107,6 +110,8 @@ def _oracle_hits(self, wdb, window_start, seq_start, complement, target, prm):
         w.window_start, w.seq_start, w.complement, w.seq = int(window_start[i]), int(seq_start[i]), int(complement[i]), int(target[i])
     _lib.lib.b2h_profile_set_annotation(self.hprof, (self.pair.hmm.consensus or "x" * self.pair.hmm.M).encode(), None, None,
                                         self.pair.hmm.alphabet.symbols.encode())
+    if self.pair.hmm.model_mask:
+        _lib.lib.b2h_profile_set_model_mask(self.hprof, self.pair.hmm.model_mask.encode())
     out = ctypes.c_void_p()
     _lib.check(_lib.lib.b2h_longtarget_domains(self.hprof, wins, n, ctypes.byref(prm), ctypes.byref(out)), "b2h_longtarget_domains")
     try:

@@ -299,3 +299,18 @@ def test_window_sharding_world_size_2_gloo():
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_model_mask_in_the_reestimated_background():
+    """A model with an MM line: masked nodes keep a zero match score when the long-target domain definition re-estimates
+    the background (p7_oprofile_UpdateFwdEmissionScores, impl_sse/p7_oprofile.c:455) -- hits identical to ref_nhmmer."""
+    pair, rng = lt_common.dna_model(ModelPair, 121, mu_shift=-2.0, mask=True)
+    assert pair.hmm.model_mask and "m" in pair.hmm.model_mask and pair.om.model_mask == pair.hmm.model_mask
+    block = lt_common.dna_chunks(pair, rng, [90000, 30000], nplant=10)
+    got = longtarget.search(pair.om, block, block_length=0x40000, backend_factory=lambda om, blk: lt_common.OracleBackend(pair, blk))
+    nh, _ = lt_common.compare_nhmmer(pair, [s.sequence for s in block], got, block_length=0x40000)
+    assert nh >= 8
+    # ... and the mask matters: without it the same search gives different bias corrections
+    pair.hmm.model_mask = None
+    plain = longtarget.search(pair.om, block, block_length=0x40000, backend_factory=lambda om, blk: lt_common.OracleBackend(pair, blk))
+    assert [d.dombias for d in plain[1]] != [d.dombias for d in got[1]]
