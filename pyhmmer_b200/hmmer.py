@@ -88,12 +88,14 @@ def hmmscan(queries, profiles, *, cpus=0, callback=None, backend="threading", ba
     pipeline = Pipeline(alphabet, background=background, **options)
     # convert HMM / Profile targets once (the reference does the same up front, _hmmscan.py:191-215)
     oms = OptimizedProfileBlock(alphabet, pipeline._optimized_many(list(targets), pipeline.L_HINT))
+    from . import parallel as par
+    world = par.World.current()              # several GPUs: the profile block is sharded, one all-gather per batch
     total = 0
     batch = []
 
     def flush(batch):
         nonlocal total
-        for q, th in zip(batch, pipeline._scan_many(batch, oms)):
+        for q, th in zip(batch, pipeline._scan_many(batch, oms, world=world)):
             total += 1
             if callback is not None:
                 callback(q, total)

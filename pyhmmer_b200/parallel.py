@@ -77,12 +77,14 @@ def _raw_bytes(recs, rectype):
     return bytes((rectype * max(n, 1))(*recs))[: n * ctypes.sizeof(rectype)]
 
 
-def pack_records(hits, doms, text, counters, seq_offset):
+def pack_records(hits, doms, text, counters, seq_offset, profile_offset=0):
     """Serialize one rank's results: header | HitRec[] | DomainRec[] | text | counters (int64)."""
     nh, nd = len(hits), len(doms)
     hb = bytearray(_raw_bytes(hits, _lib.HitRec))
     if nh and seq_offset:
         np.frombuffer(hb, dtype=np.dtype(_lib.HitRec))["seq"] += seq_offset       # local -> global target index
+    if nh and profile_offset:
+        np.frombuffer(hb, dtype=np.dtype(_lib.HitRec))["profile"] += profile_offset   # local -> global profile index (scan)
     cnt = np.ascontiguousarray(counters, dtype=np.int64)
     header = np.array([nh, nd, len(text), cnt.size], dtype=np.int64).tobytes()
     return b"".join([header, bytes(hb), _raw_bytes(doms, _lib.DomainRec), bytes(text), cnt.tobytes()])

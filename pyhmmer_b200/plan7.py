@@ -1509,16 +1509,34 @@ class Pipeline:
         """Scan one sequence against a list of profiles (``OptimizedProfileBlock``); returns `TopHits` (plan7.pyx:6534-6677)."""
         return self._scan_many([query], targets)[0]
 
-    def _scan_many(self, queries, targets):
+    def _scan_many(self, queries, targets, world=None):
+        """Query sequences against a block of profiles.  With several ranks (``world``, one process per GPU) the PROFILE block
+        is sharded -- contiguous runs balanced by nodes -- every rank scans its profiles, and one all-gather of the hit
+        records gives every rank the same `TopHits` (Z = all models)."""
         if any(q.alphabet != self.alphabet for q in queries):
             raise AlphabetMismatch(self.alphabet, [q.alphabet for q in queries if q.alphabet != self.alphabet][0])
         oms = self._optimized_many(targets, self.L_HINT)
         cuts = [self._cutoffs(om) for om in oms]
         block = DigitalSequenceBlock(self.alphabet, queries)
-        if oms and len(block):
-            hits, doms, text, counters = self._run(oms, block)
+        from . import parallel
+        lo, local = 0, oms
+        if world is not None and world.size > 1:
+            b = parallel.shard_bounds([om.M for om in oms], world.size)
+            lo, local = b[world.rank], oms[b[world.rank]:b[world.rank + 1]]
+        if local and len(block):
+            hits, doms, text, counters = self._run(local, block)
         else:
-            hits, doms, text, counters = [], [], b"", np.zeros((len(oms), 4), np.int64)
+            hits, doms, text, counters = [], [], b"", np.zeros((len(local), 4), np.int64)
+        if world is not None and world.size > 1:
+            mine = parallel.pack_records(hits, doms, text, counters, 0, profile_offset=lo)
+            hits, doms, tbuf, cparts = [], [], bytearray(), []
+            for h, d, t, c in (parallel.unpack_records(buf) for buf in parallel.all_gather_bytes(mine, world)):
+                for r in h:
+                    r.dom_offset += len(doms)
+                for r in d:
+                    r.text_offset += len(tbuf)
+                hits.extend(h); doms.extend(d); tbuf.extend(t); cparts.append(c.reshape(-1, 4))
+            text, counters = bytes(tbuf), np.concatenate(cparts) if cparts else np.zeros((0, 4), np.int64)
         results = []
         for si, seq in enumerate(queries):
             th = self._tophits(seq, "scan", None)

@@ -206,6 +206,64 @@ def test_all_gather_and_merge_world_size_2_gloo():
     assert all("ok" in o for o in outs)
 
 
+_SCAN_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch.distributed as dist
+from pyhmmer_b200 import parallel, _lib, plan7, easel, synth
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%d" %% int(sys.argv[1]), rank=int(sys.argv[2]), world_size=2)
+w = parallel.World.current()
+abc = easel.Alphabet.amino()
+rng = np.random.default_rng(3)
+bg = plan7.Background(abc)
+oms = [plan7.Profile(int(m), abc).configure(synth.random_hmm(abc, int(m), rng, name="p%%d" %% i), bg, 100).to_optimized()
+       for i, m in enumerate(rng.integers(20, 300, 11))]
+for om in oms:
+    om._evparam[:] = np.array([-8.0, 0.7, -9.0, 0.7, -4.0, 0.7], np.float32)
+queries = [easel.DigitalSequence(abc, name=b"q%%d" %% i, sequence=rng.integers(0, 20, 50 + i).astype(np.uint8)) for i in range(3)]
+
+def fake_run(self, local, block):
+    """stands in for the device: a deterministic set of hits for (profile, query) pairs, keyed by the MODEL (not its index)"""
+    hits, doms, text = [], [], b""
+    for p, om in enumerate(local):
+        for s in range(len(block)):
+            if (om.M + s) %% 3 == 0:
+                h = _lib.HitRec()
+                h.profile, h.seq, h.score, h.pre_score, h.sum_score, h.lnP, h.ndom, h.dom_offset = p, s, om.M * 0.1 + s, om.M * 0.1 + s + 1, om.M * 0.1, -float(om.M %% 17) - s, 1, len(doms)
+                d = _lib.DomainRec()
+                d.N, d.text_offset, d.bitscore, d.lnP, d.ienv, d.jenv = 2, len(text), 3.0 + s, -3.0, 1, 10
+                text += b"AB\0ab\0AB\0**\0"
+                hits.append(h); doms.append(d)
+    return hits, doms, text, np.array([[om.M, 1, 2, 3] for om in local], np.int64).reshape(len(local), 4)
+
+pli = object.__new__(plan7.Pipeline)                     # no device here: the attributes the scan path reads are set by hand
+for k, v in dict(alphabet=abc, background=bg, bias_filter=True, null2=True, seed=42, Z=None, domZ=None, F1=0.02, F2=1e-3, F3=1e-5,
+                 E=10.0, T=None, domE=10.0, domT=None, incE=0.01, incT=None, incdomE=0.01, incdomT=None, bit_cutoffs=None, host_threads=1).items():
+    setattr(pli, k, v)
+pli.clear()
+plan7.Pipeline._run = fake_run
+sharded = pli._scan_many(queries, oms, world=w)
+single = pli._scan_many(queries, oms, world=None)
+sig = lambda ths: [[(h.name, h.score, h.lnP, h.reported, h.included, h.domains[0].alignment.hmm_from, len(h.domains)) for h in th] for th in ths]
+assert sig(sharded) == sig(single) and sum(len(th) for th in single) >= 8
+assert [th.Z for th in sharded] == [11.0] * 3 and [th.searched_models for th in sharded] == [11] * 3
+dist.barrier(); dist.destroy_process_group()
+print("rank", w.rank, "ok")
+'''
+
+
+def test_scan_profile_sharding_world_size_2_gloo():
+    """hmmscan over two ranks: the profile block is sharded by nodes, one all-gather of the hit records, identical `TopHits`
+    on every rank (SURVEY 8e) -- host logic with a stand-in for the device search."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port_ = s.getsockname()[1]; s.close()
+    code = _SCAN_WORKER % (ROOT,)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(port_), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
 @pytest.mark.parametrize("name", ["Thioesterase", "PF02826"])
 def test_pressed_database_matches_conversion(amino, name):
     """HMMPressedFile (p7_oprofile_ReadMSV / ReadRest, impl_sse/io.c:231,498) on the reference's own hmmpress'ed fixtures:
