@@ -459,7 +459,7 @@ typedef struct {
 
 long ref_nhmmer(REFM *m, int nseq, const uint8_t **dsq, const long *len, long block_length, int strands,
                 double F1, double F2, double F3, int do_bias, int do_null2, double E, double incE, long evalue_window,
-                long cap, REF_LTHIT *out, long *stats)
+                long cap, REF_LTHIT *out, long *stats, const char *const *names, const char *table_prefix)
 {
   P7_OPROFILE *om = m->om;
   P7_PIPELINE *pli = p7_pipeline_Create(NULL, om->M, 100, TRUE, p7_SEARCH_SEQS);
@@ -477,8 +477,8 @@ long ref_nhmmer(REFM *m, int nseq, const uint8_t **dsq, const long *len, long bl
   if (C <= 0 || W <= C) return -1;
   p7_pli_NewModel(pli, om, m->bg);
   for (t = 0; t < nseq; t++) {
-    char name[32];
-    snprintf(name, sizeof name, "seq%d", t);
+    char name[256];
+    if (names && names[t]) snprintf(name, sizeof name, "%s", names[t]); else snprintf(name, sizeof name, "seq%d", t);
     tmpsq->idx = t; tmpsq->L = -1;
     esl_sq_SetAccession(tmpsq, ""); esl_sq_SetName(tmpsq, name); esl_sq_SetDesc(tmpsq, ""); esl_sq_SetSource(tmpsq, name);
     esl_sq_GrowTo(tmpsq, ESL_MIN(W + C, len[t]));
@@ -513,6 +513,17 @@ long ref_nhmmer(REFM *m, int nseq, const uint8_t **dsq, const long *len, long bl
   p7_tophits_RemoveDuplicates(th, TRUE);
   p7_tophits_SortBySortkey(th);
   p7_tophits_Threshold(th, pli);
+  if (table_prefix) {     /* the tables pyhmmer's TopHits.write gives for these hits; idlen_list_assign (nhmmer.c) = the target's length */
+    char path[1024]; FILE *fp; int q;
+    for (h = 0; h < (long)th->N; h++) th->hit[h]->dcl[0].ad->L = len[th->hit[h]->seqidx];
+    for (q = 0; q < 2; q++) {
+      snprintf(path, sizeof path, "%s%s", table_prefix, q ? ".pfam" : ".tbl");
+      if ((fp = fopen(path, "w")) == NULL) return -2;
+      if (q == 0) p7_tophits_TabularTargets(fp, om->name, om->acc, th, pli, TRUE);
+      else        p7_tophits_TabularXfam(fp, om->name, om->acc, th, pli);
+      fclose(fp);
+    }
+  }
   stats[0] = pli->nres; stats[1] = pli->nseqs; stats[2] = pli->pos_past_msv; stats[3] = pli->pos_past_bias;
   stats[4] = pli->pos_past_vit; stats[5] = pli->pos_past_fwd;
   nout = th->N;
@@ -645,6 +656,45 @@ REF_RESULT *ref_search(REFM *m, const uint8_t *const *dsq, const int64_t *len, i
   free(seqidx); p7_tophits_Destroy(th); p7_pipeline_Destroy(pli);
   return r;
 }
+/* The reference's own tabular writers on a search with DEFAULT reporting thresholds, as TopHits.write does (plan7.pyx:9096:
+ * p7_tophits_TabularTargets / TabularDomains / TabularXfam after SortBySortkey + Threshold).  names / accs / descs: per target
+ * (acc / desc may hold NULL or "").  Files: <prefix>.tbl, <prefix>.domtbl, <prefix>.pfam.  Returns the number of hits. */
+long ref_search_tables(REFM *m, const uint8_t *const *dsq, const int64_t *len, int n, const char *const *names,
+                       const char *const *accs, const char *const *descs, const char *prefix)
+{
+  P7_PIPELINE *pli = p7_pipeline_Create(NULL, m->om->M, 400, FALSE, p7_SEARCH_SEQS);
+  P7_TOPHITS  *th  = p7_tophits_Create();
+  char path[1024];
+  const char *ext[3] = { ".tbl", ".domtbl", ".pfam" };
+  int t, q;
+  long nh;
+  p7_oprofile_ReconfigMultihit(m->om, 400);
+  p7_pli_NewModel(pli, m->om, m->bg);
+  for (t = 0; t < n; t++) {
+    ESL_SQ *sq = esl_sq_CreateDigitalFrom(m->abc, names[t], dsq[t], len[t], (descs && descs[t]) ? descs[t] : NULL, (accs && accs[t]) ? accs[t] : NULL, NULL);
+    p7_pli_NewSeq(pli, sq);
+    p7_bg_SetLength(m->bg, sq->n);
+    p7_oprofile_ReconfigLength(m->om, sq->n);
+    p7_Pipeline(pli, m->om, m->bg, sq, NULL, th);
+    p7_pipeline_Reuse(pli);
+    esl_sq_Destroy(sq);
+  }
+  p7_tophits_SortBySortkey(th);
+  p7_tophits_Threshold(th, pli);
+  for (q = 0; q < 3; q++) {
+    FILE *fp;
+    snprintf(path, sizeof path, "%s%s", prefix, ext[q]);
+    if ((fp = fopen(path, "w")) == NULL) return -1;
+    if (q == 0) p7_tophits_TabularTargets(fp, m->om->name, m->om->acc, th, pli, TRUE);
+    if (q == 1) p7_tophits_TabularDomains(fp, m->om->name, m->om->acc, th, pli, TRUE);
+    if (q == 2) p7_tophits_TabularXfam(fp, m->om->name, m->om->acc, th, pli);
+    fclose(fp);
+  }
+  nh = th->N;
+  p7_tophits_Destroy(th); p7_pipeline_Destroy(pli);
+  return nh;
+}
+
 void ref_result_free(REF_RESULT *r) { if (r) { free(r->hits); free(r->doms); free(r->text); free(r); } }
 long ref_result_nhits(const REF_RESULT *r) { return r->nhits; }
 long ref_result_ndoms(const REF_RESULT *r) { return r->ndoms; }

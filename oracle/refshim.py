@@ -70,7 +70,9 @@ def lib():
         L.ref_longtarget_stages.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ci, ci, ci] + [vp] * 11
         L.ref_nhmmer.restype = ctypes.c_long
         L.ref_nhmmer.argtypes = [vp, ci, vp, vp, ctypes.c_long, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci,
-                                 ctypes.c_double, ctypes.c_double, ctypes.c_long, ctypes.c_long, vp, vp]
+                                 ctypes.c_double, ctypes.c_double, ctypes.c_long, ctypes.c_long, vp, vp, vp, ctypes.c_char_p]
+        L.ref_search_tables.restype = ctypes.c_long
+        L.ref_search_tables.argtypes = [vp, vp, vp, ci, vp, vp, vp, ctypes.c_char_p]
         L.ref_max_length.argtypes = [vp, ctypes.c_double]
         L.ref_vit_longtarget.argtypes = [vp, vp, ci, ci, cf, ctypes.c_double, ci, vp]
         L.ref_longtarget_pipeline.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ctypes.c_long, ci, vp, ci, vp, vp, ctypes.c_long]
@@ -250,7 +252,7 @@ class RefModel:
                     vitpass=vitpass[:nv.value].copy(), counters=counters)
 
     def nhmmer(self, seqs, block_length=0x40000, strand=None, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True,
-               E=10.0, incE=0.01, evalue_window=0, cap=100000):
+               E=10.0, incE=0.01, evalue_window=0, cap=100000, names=None, table_prefix=None):
         """nhmmer as pyhmmer's LongTargetsPipeline.search_hmm runs it (ref_nhmmer): (hits in final order as RefLtHit records,
         stats [6] = nres, nseqs, pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd).  flags: 1 included, 2 reported,
         16 duplicate (p7_hitflags_e)."""
@@ -261,9 +263,22 @@ class RefModel:
         out = (RefLtHit * cap)()
         stats = (ctypes.c_long * 6)()
         nh = self.L.ref_nhmmer(self.h, n, ptrs, lens, block_length, {None: 0, "watson": 1, "crick": 2}[strand], F1, F2, F3,
-                               int(bias_filter), int(null2), E, incE, int(evalue_window), cap, out, stats)
+                               int(bias_filter), int(null2), E, incE, int(evalue_window), cap, out, stats,
+                               None if names is None else (ctypes.c_char_p * max(n, 1))(*[v if isinstance(v, bytes) else v.encode() for v in names]),
+                               None if table_prefix is None else os.fsencode(table_prefix))
         assert 0 <= nh <= cap, nh
         return [out[i] for i in range(nh)], list(stats)
+
+    def search_tables(self, seqs, names, accs, descs, prefix):
+        """The reference search with default thresholds, its hits written by the reference's own tabular writers to
+        <prefix>.tbl / .domtbl / .pfam (p7_tophits_TabularTargets / TabularDomains / TabularXfam).  Returns the hit count."""
+        dsqs = [dsq_of(c) for c in seqs]
+        n = len(dsqs)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[d.ctypes.data for d in dsqs])
+        lens = np.array([d.size - 2 for d in dsqs], dtype=np.int64)
+        enc = lambda v: None if v is None else (v if isinstance(v, bytes) else v.encode())
+        arr = lambda vals: (ctypes.c_char_p * max(n, 1))(*[enc(v) for v in vals])
+        return self.L.ref_search_tables(self.h, ptrs, lens.ctypes.data, n, arr(names), arr(accs), arr(descs), os.fsencode(prefix))
 
     def max_length(self, beta=1e-7):
         """p7_Builder_MaxLength of the model's HMM."""

@@ -1298,6 +1298,147 @@ class TopHits:
                         d.reported = self._domain_reportable(d.score, d.lnP)
                         d.included = h.included and self._domain_includable(d.score, d.lnP)
 
+    def write(self, fh, format="targets", header=True):
+        """Write the hits in tabular form to a file opened in binary mode (``TopHits.write``, plan7.pyx:9096-9168):
+        ``targets`` = hmmsearch ``--tblout`` (p7_tophits_TabularTargets, p7_tophits.c:1402), ``domains`` = ``--domtblout``
+        (p7_tophits_TabularDomains, :1500), ``pfam`` = ``--pfamtblout`` (p7_tophits_TabularXfam, :1590)."""
+        if format not in ("targets", "domains", "pfam"):
+            raise ValueError("invalid format %r (expected 'targets', 'domains' or 'pfam')" % (format,))
+        txt = lambda v: "" if v is None else (v.decode() if isinstance(v, bytes) else str(v))
+        q = self.query
+        qname = txt(getattr(q, "name", None))
+        qacc = getattr(q, "accession", None)
+        qacc = None if qacc is None else txt(qacc)
+        hits = self._hits
+        names = [txt(h.name) for h in hits]
+        accs = [None if h.accession is None else txt(h.accession) for h in hits]
+        descs = [None if h.description is None else txt(h.description) for h in hits]
+        tnamew = max([20] + [len(v) for v in names])
+        taccw = max([10] + [len(v) for v in accs if v is not None])
+        qnamew = max(20, len(qname))
+        qaccw = max(10, len(qacc)) if qacc is not None else 10
+        qacc_s = qacc if qacc else "-"
+        scan = self.mode == "scan"
+        lt = self.long_targets
+        posw = 0
+        if lt:
+            posw = max([7] + [len(str(v)) for h in hits if h._domains[0]._rec.iali > 0 for v in (h._domains[0]._rec.iali, h._domains[0]._rec.jali)])
+        LOG2R = 1.44269504088896341
+        out = []
+        w = out.append
+        rep = [(h, n, a, d) for h, n, a, d in zip(hits, names, accs, descs) if h.reported]
+        if format == "targets":
+            if header:
+                if lt:
+                    w("#%-*s %-*s %-*s %-*s %s %s %*s %*s %*s %*s %*s %6s %9s %6s %5s  %s\n" % (
+                        tnamew - 1, " target name", taccw, "accession", qnamew, "query name", qaccw, "accession", "hmmfrom", "hmm to",
+                        posw, "alifrom", posw, "ali to", posw, "envfrom", posw, "env to", posw, "modlen" if scan else "sq len",
+                        "strand", "  E-value", " score", " bias", "description of target"))
+                    w("#%*s %*s %*s %*s %s %s %*s %*s %*s %*s %*s %6s %9s %6s %5s %s\n" % (
+                        tnamew - 1, "-------------------", taccw, "----------", qnamew, "--------------------", qaccw, "----------", "-------",
+                        "-------", posw, "-------", posw, "-------", posw, "-------", posw, "-------", posw, "-------", "------", "---------",
+                        "------", "-----", "---------------------"))
+                else:
+                    w("#%*s %22s %22s %33s\n" % (tnamew + qnamew + taccw + qaccw + 2, "", "--- full sequence ----", "--- best 1 domain ----",
+                                                 "--- domain number estimation ----"))
+                    w("#%-*s %-*s %-*s %-*s %9s %6s %5s %9s %6s %5s %5s %3s %3s %3s %3s %3s %3s %3s %s\n" % (
+                        tnamew - 1, " target name", taccw, "accession", qnamew, "query name", qaccw, "accession", "  E-value", " score", " bias",
+                        "  E-value", " score", " bias", "exp", "reg", "clu", " ov", "env", "dom", "rep", "inc", "description of target"))
+                    w("#%*s %*s %*s %*s %9s %6s %5s %9s %6s %5s %5s %3s %3s %3s %3s %3s %3s %3s %s\n" % (
+                        tnamew - 1, "-------------------", taccw, "----------", qnamew, "--------------------", qaccw, "----------", "---------",
+                        "------", "-----", "---------", "------", "-----", "---", "---", "---", "---", "---", "---", "---", "---",
+                        "---------------------"))
+            for h, name, acc, desc in rep:
+                d = h.best_domain
+                r, dr = h._rec, d._rec
+                if lt:
+                    w("%-*s %-*s %-*s %-*s %7d %7d %*d %*d %*d %*d %*d %6s %9.2g %6.1f %5.1f  %s\n" % (
+                        tnamew, name, taccw, acc if acc else "-", qnamew, qname, qaccw, qacc_s, dr.hmmfrom, dr.hmmto,
+                        posw, dr.iali, posw, dr.jali, posw, dr.ienv, posw, dr.jenv, posw, h.length,
+                        "   +  " if dr.iali < dr.jali else "   -  ", math.exp(h.lnP), h.score, dr.dombias * LOG2R, desc if desc else "-"))
+                else:
+                    w("%-*s %-*s %-*s %-*s %9.2g %6.1f %5.1f %9.2g %6.1f %5.1f %5.1f %3d %3d %3d %3d %3d %3d %3d %s\n" % (
+                        tnamew, name, taccw, acc if acc else "-", qnamew, qname, qaccw, qacc_s,
+                        math.exp(h.lnP) * self.Z, h.score, h.pre_score - h.score, math.exp(d.lnP) * self.Z, dr.bitscore, dr.dombias * LOG2R,
+                        r.nexpected, r.nregions, r.nclustered, r.noverlaps, r.nenvelopes, r.ndom,
+                        sum(1 for x in h._domains if x.reported), sum(1 for x in h._domains if x.included), desc if desc else "-"))
+        elif format == "domains":
+            if header:
+                w("#%*s %22s %40s %11s %11s %11s\n" % (tnamew + qnamew - 1 + 15 + taccw + qaccw, "", "--- full sequence ---",
+                                                       "-------------- this domain -------------", "hmm coord", "ali coord", "env coord"))
+                w("#%-*s %-*s %5s %-*s %-*s %5s %9s %6s %5s %3s %3s %9s %9s %6s %5s %5s %5s %5s %5s %5s %5s %4s %s\n" % (
+                    tnamew - 1, " target name", taccw, "accession", "tlen", qnamew, "query name", qaccw, "accession", "qlen", "E-value", "score",
+                    "bias", "#", "of", "c-Evalue", "i-Evalue", "score", "bias", "from", "to", "from", "to", "from", "to", "acc",
+                    "description of target"))
+                w("#%*s %*s %5s %*s %*s %5s %9s %6s %5s %3s %3s %9s %9s %6s %5s %5s %5s %5s %5s %5s %5s %4s %s\n" % (
+                    tnamew - 1, "-------------------", taccw, "----------", "-----", qnamew, "--------------------", qaccw, "----------", "-----",
+                    "---------", "------", "-----", "---", "---", "---------", "---------", "------", "-----", "-----", "-----", "-----", "-----",
+                    "-----", "-----", "----", "---------------------"))
+            qM = int(getattr(q, "M", 0)) if not scan else 0
+            for h, name, acc, desc in rep:
+                nrep = sum(1 for x in h._domains if x.reported)
+                nd = 0
+                for d in h._domains:
+                    if not d.reported:
+                        continue
+                    nd += 1
+                    dr = d._rec
+                    # the display's M / L are model / sequence lengths; which one is the target depends on the mode
+                    tlen, qlen = (h.length, qM) if not scan else (h.length, len(q))
+                    acc_ = dr.oasc / (1.0 + abs(float(dr.jenv - dr.ienv)))
+                    w("%-*s %-*s %5d %-*s %-*s %5d %9.2g %6.1f %5.1f %3d %3d %9.2g %9.2g %6.1f %5.1f %5d %5d %5d %5d %5d %5d %4.2f %s\n" % (
+                        tnamew, name, taccw, acc if acc else "-", tlen, qnamew, qname, qaccw, qacc_s, qlen,
+                        math.exp(h.lnP) * self.Z, h.score, h.pre_score - h.score, nd, nrep, math.exp(d.lnP) * self.domZ, math.exp(d.lnP) * self.Z,
+                        dr.bitscore, dr.dombias * LOG2R, dr.hmmfrom, dr.hmmto, dr.sqfrom, dr.sqto, dr.ienv, dr.jenv, acc_, desc if desc else "-"))
+        else:
+            taccw = max([20] + [len(v) for v in accs if v is not None])
+            if lt:
+                w("# hit scores\n# ----------\n#\n")
+                w("# %-*s %-*s %-*s %6s %9s %5s  %s  %s %6s %*s %*s %*s %*s %*s   %s\n" % (
+                    tnamew - 1, "target name", taccw, "acc", qnamew, "query name", "bits", "  e-value", " bias", "hmm-st", "hmm-en", "strand",
+                    posw, "ali-st", posw, "ali-en", posw, "env-st", posw, "env-en", posw, "modlen" if scan else "sq-len", "description of target"))
+                w("# %-*s %-*s %-*s %6s %9s %5s %s %s %6s %*s %*s %*s %*s %*s   %s\n" % (
+                    tnamew - 1, "-------------------", taccw, "-------------------", qnamew, "-------------------", "------", "---------", "-----",
+                    "-------", "-------", "------", posw, "-------", posw, "-------", posw, "-------", posw, "-------", posw, "-------",
+                    "---------------------"))
+                for h, name, acc, desc in rep:
+                    dr = h._domains[0]._rec
+                    w("%-*s  %-*s %-*s %6.1f %9.2g %5.1f %7d %7d %s %*d %*d %*d %*d %*d   %s\n" % (
+                        tnamew, name, taccw, (acc if acc else "-") if scan else qacc_s, qnamew, qname, h.score, math.exp(h.lnP), dr.dombias * LOG2R,
+                        dr.hmmfrom, dr.hmmto, "   +  " if dr.iali < dr.jali else "   -  ", posw, dr.iali, posw, dr.jali, posw, dr.ienv,
+                        posw, dr.jenv, posw, h.length, desc if desc else "-"))
+            else:
+                w("# Sequence scores\n# ---------------\n#\n")
+                w("# %-*s %6s %9s %3s %5s %5s    %s\n" % (tnamew - 1, "name", " bits", "  E-value", "n", "exp", " bias", "description"))
+                w("# %*s %6s %9s %3s %5s %5s    %s\n" % (tnamew - 1, "-------------------", "------", "---------", "---", "-----", "-----",
+                                                         "---------------------"))
+                for h, name, acc, desc in rep:
+                    w("%-*s  %6.1f %9.2g %3d %5.1f %5.1f    %s\n" % (tnamew, name, h.score, math.exp(h.lnP) * self.Z, h._rec.ndom, h._rec.nexpected,
+                                                                    h.pre_score - h.score, desc if desc else "-"))
+                w("\n")
+                # one pseudo-hit per reported domain, sorted like hits (hit_sorter_by_sortkey: key, name, start)
+                pseudo = []
+                for h, name, acc, desc in rep:
+                    k = 0
+                    for d in h._domains:
+                        if d.reported:
+                            k += 1
+                            key = -d.lnP if self._params["inc_by_E"] else d._rec.bitscore
+                            pseudo.append((-key, name, d._rec.iali, k, d, desc))
+                pseudo.sort(key=lambda t: t[:3])
+                w("# Domain scores\n# -------------\n#\n")
+                w("# %-*s %6s %9s %5s %5s %6s %6s %6s %6s %6s %6s     %s\n" % (tnamew - 1, " name", "bits", "E-value", "hit", "bias", "env-st", "env-en",
+                                                                            "ali-st", "ali-en", "hmm-st", "hmm-en", "description"))
+                w("# %*s %6s %9s %5s %5s %6s %6s %6s %6s %6s %6s      %s\n" % (tnamew - 1, "-------------------", "------", "---------", "-----", "-----",
+                                                                            "------", "------", "------", "------", "------", "------",
+                                                                            "---------------------"))
+                for _, name, _, k, d, desc in pseudo:
+                    dr = d._rec
+                    w("%-*s  %6.1f %9.2g %5d %5.1f %6d %6d %6d %6d %6d %6d     %s\n" % (
+                        tnamew, name, dr.bitscore, math.exp(d.lnP) * self.Z, k, dr.dombias * LOG2R, dr.ienv, dr.jenv, dr.sqfrom, dr.sqto,
+                        dr.hmmfrom, dr.hmmto, desc if desc else "-"))
+        fh.write("".join(out).encode())
+
     def merge(self, *others):
         """``TopHits.merge`` (plan7.pyx:9172-9273): combine hits of target-sharded searches of one query."""
         merged = TopHits(self.query, self.mode)

@@ -386,3 +386,57 @@ def test_window_prefix_suffix_lengths(M):
         assert nout.value == len(rmer)
         assert np.array_equal(w["n"][:nout.value], rmer[:, 0]) and np.array_equal(w["length"][:nout.value], rmer[:, 1])
     _lib.lib.b2h_profile_destroy(o)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["PF02826", "KR"])
+def test_tophits_tables_match_the_reference_writers(amino, name, tmp_path):
+    """`TopHits.write` (targets / domains / pfam) against the reference's own p7_tophits_TabularTargets / TabularDomains /
+    TabularXfam on the same hits: the reference pipeline's raw hits (oracle/_ref) are assembled into `TopHits` by the
+    product's host code (running-Z admission, sort, thresholds) and written -- byte for byte the reference's tables."""
+    import io
+    with easel.SequenceFile(os.path.join(GOLD, "data", "proteome.faa.gz"), digital=True, alphabet=amino) as f:
+        seqs = f.read_block()
+    with tempfile.NamedTemporaryFile(suffix=".hmm") as tmp:
+        with gzip.open(os.path.join(GOLD, "data", name + ".hmm.gz")) as f:
+            tmp.write(f.read())
+        tmp.flush()
+        with plan7.HMMFile(tmp.name) as f:
+            hmm = f.read()
+        ref = refshim.RefModel(tmp.name, 0, 400)
+        prefix = str(tmp_path / "ref")
+        nref = ref.search_tables([s.sequence for s in seqs], [s.name for s in seqs], [s.accession or None for s in seqs],
+                                 [s.description or None for s in seqs], prefix)
+        rh, rd, rtext, rc = ref.search([s.sequence for s in seqs])
+    hits = (_lib.HitRec * len(rh))()
+    doms = (_lib.DomainRec * len(rd))()
+    for a, r in zip(hits, rh):
+        a.profile = 0
+        for fld in ("seq", "score", "pre_score", "sum_score", "nexpected", "lnP", "pre_lnP", "sum_lnP", "nregions", "nclustered", "noverlaps",
+                    "nenvelopes", "ndom", "best_domain", "dom_offset"):
+            setattr(a, fld, getattr(r, fld))
+    for a, r in zip(doms, rd):
+        for fld in ("ienv", "jenv", "iali", "jali", "envsc", "domcorrection", "dombias", "oasc", "bitscore", "lnP", "hmmfrom", "hmmto", "sqfrom",
+                    "sqto", "N", "text_offset"):
+            setattr(a, fld, getattr(r, fld))
+    pli = object.__new__(plan7.Pipeline)                  # no device here: the attributes the assembly reads are set by hand
+    for k, v in dict(alphabet=amino, background=plan7.Background(amino), bias_filter=True, null2=True, seed=42, Z=None, domZ=None, F1=0.02,
+                     F2=1e-3, F3=1e-5, E=10.0, T=None, domE=10.0, domT=None, incE=0.01, incT=None, incdomE=0.01, incdomT=None, bit_cutoffs=None,
+                     host_threads=1).items():
+        setattr(pli, k, v)
+    pli.clear()
+    om = plan7.Profile(hmm.M, amino).configure(hmm, pli.background, 400).to_optimized()
+    order = sorted(range(len(hits)), key=lambda i: hits[i].seq)
+    th = pli._assemble([hmm], [om], seqs, [hits[i] for i in order], list(doms), rtext, np.array([rc], np.int64).reshape(1, 4))[0]
+    assert len(th) == nref >= 1
+    for fmt, ext in (("targets", ".tbl"), ("domains", ".domtbl"), ("pfam", ".pfam")):
+        buf = io.BytesIO()
+        th.write(buf, format=fmt)
+        want = open(prefix + ext, "rb").read()
+        assert buf.getvalue() == want, (fmt, buf.getvalue()[:600], want[:600])
+        body = io.BytesIO()
+        th.write(body, format=fmt, header=False)
+        if fmt != "pfam":
+            assert body.getvalue() == b"".join(l for l in want.splitlines(True) if not l.startswith(b"#"))
+    with pytest.raises(ValueError):
+        th.write(io.BytesIO(), format="xml")

@@ -201,7 +201,7 @@ def test_whole_search_against_the_reference_loop(M, mu_shift, strand, block_leng
 
 
 @pytest.mark.parametrize("strand,E", [(None, 10.0), ("watson", 1e-12)])
-def test_long_targets_pipeline_front_end(monkeypatch, strand, E):
+def test_long_targets_pipeline_front_end(monkeypatch, tmp_path, strand, E):
     """`plan7.LongTargetsPipeline.search_hmm` (the reference class of the same name, plan7.pyx:6917): hits in the reference's
     final order with its reported / included / duplicate flags and E-values -- host logic only, DP from the reference."""
     from pyhmmer_b200 import plan7
@@ -216,7 +216,8 @@ def test_long_targets_pipeline_front_end(monkeypatch, strand, E):
     pli._backend_factory = lambda om, blk: lt_common.OracleBackend(pair, blk)
     th = pli.search_hmm(pair.hmm, block)
     rhits, rstats = pair.ref.nhmmer([s.sequence for s in block], block_length=20000, strand=strand, E=E, incE=E / 100,
-                                    evalue_window=pair.ref.max_length())     # an HMM query: E-values count windows of p7_Builder_MaxLength
+                                    evalue_window=pair.ref.max_length(),     # an HMM query: E-values count windows of p7_Builder_MaxLength
+                                    names=[s.name for s in block], table_prefix=str(tmp_path / "ref"))
     assert th.long_targets and len(th) == len(rhits) >= 8
     assert (th.searched_residues, th.searched_sequences) == (rstats[0], rstats[1])
     for h, r in zip(th, rhits):
@@ -228,6 +229,11 @@ def test_long_targets_pipeline_front_end(monkeypatch, strand, E):
         assert (d.reported, d.included) == (bool(r.dom_reported), bool(r.dom_included))
     assert any(h.duplicate for h in th) and any(h.reported for h in th)
     assert E > 1 or any(not h.reported and not h.duplicate for h in th)      # the tight threshold left some hits unreported
+    import io
+    for fmt, ext in (("targets", ".tbl"), ("pfam", ".pfam")):               # nhmmer's tables, byte for byte the reference writers'
+        buf = io.BytesIO()
+        th.write(buf, format=fmt)
+        assert buf.getvalue() == open(str(tmp_path / "ref") + ext, "rb").read(), (fmt, buf.getvalue()[:800])
     with pytest.raises(ValueError):
         plan7.LongTargetsPipeline(plan7.Alphabet.amino())
     with pytest.raises(ValueError):
