@@ -89,6 +89,14 @@ typedef struct {
 /* HMM file value decoding: out[i] = (in[i] is '*' i.e. +inf) ? 0 : expf(-in[i])   (p7_hmmfile.c:1486-1547) */
 int b2h_hmm_decode_probs(const double *neglog, float *out, size_t n);
 
+/* The node table of a HMMER3 ASCII model (read_asc30hmm, vendor/hmmer/src/p7_hmmfile.c:1411-1500): <text> = everything between
+ * the "HMM ..." column header lines and the closing "//".  Fields are "-log p" or "*" and become expf(-atof(field)), as in the
+ * reference.  mat / ins [(M+1)*K] (row 0 of mat untouched), t [(M+1)*7], compo [K] (*has_compo = the COMPO line was there),
+ * map [M+1], anno [(nanno-1)*M] = first character of the annotation fields after MAP (CONS, RF, MM, CS as the format has
+ * them), field-major.  B2H_ERANGE: a match line does not start with its node number; B2H_EINVAL: malformed. */
+int b2h_hmm_parse_body(const char *text, size_t len, int M, int K, int nanno,
+                       float *compo, int32_t *has_compo, float *mat, float *ins, float *t, int64_t *map, char *anno);
+
 /* p7_ProfileConfig (local modes only): HMM probabilities -> log-odds generic profile.
  *   t   [(M+1)*7]  MM MI MD IM II DM DD     mat [(M+1)*K]    bgf[K]
  *   degen [Kp*K]   alphabet degeneracy matrix (esl_alphabet.h: degen[x][y])

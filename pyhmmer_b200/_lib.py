@@ -167,6 +167,8 @@ def _load():
     sig("b2h_longtarget_hits", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(SearchParams), P(c_void_p))
     sig("b2h_longtarget_vit_threshold", c_int, c_void_p, c_int, c_float, ctypes.c_double, P(c_i32), P(c_i32))
     sig("b2h_profile_set_model_mask", c_int, c_void_p, ctypes.c_char_p)
+    sig("b2h_hmm_parse_body", c_int, ctypes.c_char_p, c_size_t, c_int, c_int, c_int, c_void_p, P(c_i32), c_void_p, c_void_p, c_void_p,
+        c_void_p, c_void_p)
     sig("b2h_hmm_max_length", c_int, c_int, c_void_p, ctypes.c_double, P(c_i32))
     sig("b2h_hmm_convert_many", c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int,
         P(c_void_p), P(c_void_p), P(c_size_t))

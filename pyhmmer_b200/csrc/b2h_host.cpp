@@ -95,6 +95,89 @@ int b2h_hmm_decode_probs(const double *neglog, float *out, size_t n)
   return B2H_OK;
 }
 
+// The node table of a HMMER3 ASCII model (read_asc30hmm, p7_hmmfile.c:1411-1500): <text> holds everything between the
+// "HMM ..." column header lines and the closing "//" -- an optional COMPO line, the node-0 insert and transition lines, then
+// per node a match line (k, K scores, <nanno> annotation fields: MAP [CONS] RF [MM] CS), an insert line (K) and a transition
+// line (7).  Scores are "-log p" or "*"; they become probabilities as the reference makes them, expf(-atof(tok)).
+// mat / ins [(M+1)*K] (row 0 of mat is left alone), t [(M+1)*7], compo [K] (has_compo says whether the line was there),
+// map [M+1], anno [(nanno-1)*M]: the first character of every annotation field after MAP, field-major.
+static inline bool fast_field(const char *p, const char *e, double *v)
+{
+  // "d.ddddd" with at most 15 significant digits: integer / power of ten is correctly rounded, i.e. what strtod returns
+  uint64_t num = 0; int digits = 0, frac = 0; bool dot = false;
+  if (p == e) return false;
+  for (; p < e; p++) {
+    if (*p >= '0' && *p <= '9') { num = num * 10 + (uint64_t)(*p - '0'); digits++; if (dot) frac++; }
+    else if (*p == '.' && !dot) dot = true;
+    else return false;
+  }
+  if (digits == 0 || digits > 15 || frac > 15) return false;
+  static const double p10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+  *v = (double)num / p10[frac];
+  return true;
+}
+
+int b2h_hmm_parse_body(const char *text, size_t len, int M, int K, int nanno,
+                       float *compo, int32_t *has_compo, float *mat, float *ins, float *t, int64_t *map, char *anno)
+{
+  if (!text || M < 1 || K < 1 || K > B2H_MAXABET || nanno < 1 || nanno > 8 || !mat || !ins || !t || !has_compo) return B2H_EINVAL;
+  const char *p = text, *end = text + len;
+  const char *tb = nullptr, *te = nullptr;
+  auto next = [&]() -> bool {                              // next whitespace-separated field; '#' starts a comment line
+    for (;;) {
+      while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) p++;
+      if (p >= end) return false;
+      if (*p == '#') { while (p < end && *p != '\n') p++; continue; }
+      tb = p;
+      while (p < end && !(*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) p++;
+      te = p;
+      return true;
+    }
+  };
+  auto prob = [&](float *out) -> bool {
+    if (!next()) return false;
+    if (te - tb == 1 && *tb == '*') { *out = 0.0f; return true; }
+    double v;
+    if (!fast_field(tb, te, &v)) {
+      char buf[64]; const size_t n = (size_t)(te - tb);
+      if (n >= sizeof buf) return false;
+      memcpy(buf, tb, n); buf[n] = 0;
+      char *ep = nullptr;
+      v = strtod(buf, &ep);
+      if (ep == buf || *ep) return false;
+    }
+    *out = std::isinf(v) ? 0.0f : expf((float)(-1.0 * v));
+    return true;
+  };
+  *has_compo = 0;
+  { const char *save = p;
+    if (next() && te - tb == 5 && memcmp(tb, "COMPO", 5) == 0) {
+      *has_compo = 1;
+      for (int x = 0; x < K; x++) { float v; if (!prob(&v)) return B2H_EINVAL; if (compo) compo[x] = v; }
+    } else p = save; }
+  for (int x = 0; x < K; x++) if (!prob(&ins[x])) return B2H_EINVAL;
+  for (int x = 0; x < 7; x++) if (!prob(&t[x])) return B2H_EINVAL;
+  for (int k = 1; k <= M; k++) {
+    if (!next()) return B2H_EINVAL;
+    long kk = 0;
+    for (const char *q = tb; q < te; q++) { if (*q < '0' || *q > '9') return B2H_EINVAL; kk = kk * 10 + (*q - '0'); }
+    if (kk != k) return B2H_ERANGE;                        // "expected match line to start with k"
+    for (int x = 0; x < K; x++) if (!prob(&mat[(size_t)k * K + x])) return B2H_EINVAL;
+    for (int a = 0; a < nanno; a++) {
+      if (!next()) return B2H_EINVAL;
+      if (a == 0) {
+        long v = 0; bool num = true;
+        for (const char *q = tb; q < te; q++) { if (*q < '0' || *q > '9') { num = false; break; } v = v * 10 + (*q - '0'); }
+        if (map) map[k] = num ? v : 0;
+      } else if (anno) anno[(size_t)(a - 1) * M + (k - 1)] = *tb;
+    }
+    for (int x = 0; x < K; x++) if (!prob(&ins[(size_t)k * K + x])) return B2H_EINVAL;
+    for (int x = 0; x < 7; x++) if (!prob(&t[(size_t)k * 7 + x])) return B2H_EINVAL;
+  }
+  if (next()) return B2H_EINVAL;                           // trailing fields
+  return B2H_OK;
+}
+
 // p7_ProfileConfig, local modes (modelconfig.c:48-187) + p7_hmm_CalculateOccupancy (p7_hmm.c:1338)
 int b2h_profile_config(int M, int K, int Kp, const uint8_t *degen,
                        const float *t, const float *mat, const float *bgf,

@@ -361,44 +361,47 @@ class HMMFile:
         flags = {k: hdr.get(k, "no").lower() == "yes" for k in ("RF", "MM", "CONS", "CS", "MAP")}
         hmm._evparam, hmm._cutoff = ev, cut
 
-        toks = self._line().split()
+        # The body is a regular table -- per node one match line (k, K scores, annotation columns), one insert line (K) and one
+        # transition line (7) -- so it is tokenised in one go and sliced as an array instead of line by line.
+        raw = []
+        while True:
+            line = self._fh.readline()
+            if not line:
+                raise ValueError("expected closing //")
+            if isinstance(line, str):
+                line = line.encode("ascii", "replace")
+            if line[:2] == b"//" or line.lstrip()[:2] == b"//":
+                break
+            raw.append(line)                            # (comment and blank lines are skipped by the field scanner)
+        names = ["MAP"] + (["CONS"] if fmt >= "e" else []) + ["RF"] + (["MM"] if fmt >= "f" else []) + ["CS"]
+        body = b"".join(raw)
         hmm._compo[:] = 0.0                             # p7_hmm_CreateBody zeroes compo; COMPO is optional
-        if toks[0] == "COMPO":
-            hmm._compo[:K] = _decode_probs(toks[1:1 + K])
-            toks = self._line().split()
-        rows_mat, rows_ins, rows_t = [None] * (M + 1), [None] * (M + 1), [None] * (M + 1)
-        rows_ins[0] = toks[:K]
-        rows_t[0] = self._line().split()[:7]
-        anno = {"MAP": [], "CONS": [], "RF": [], "MM": [], "CS": []}
-        for k in range(1, M + 1):
-            f = self._line().split()
-            if int(f[0]) != k:
-                raise ValueError("expected match line to start with %d; saw %s" % (k, f[0]))
-            rows_mat[k] = f[1:1 + K]
-            extra = f[1 + K:]
-            names = ["MAP"] + (["CONS"] if fmt >= "e" else []) + ["RF"] + (["MM"] if fmt >= "f" else []) + ["CS"]
-            for nme, val in zip(names, extra):
-                anno[nme].append(val)
-            rows_ins[k] = self._line().split()[:K]
-            rows_t[k] = self._line().split()[:7]
-        end = self._line()
-        if end is None or end.strip() != "//":
-            raise ValueError("expected closing //")
-        flat = _decode_probs([t for k in range(1, M + 1) for t in rows_mat[k]])
-        hmm.match_emissions[1:] = flat.reshape(M, K)
+        compo = np.zeros(K, np.float32)
+        has_compo = ctypes.c_int32()
+        amap = np.zeros(M + 1, np.int64)
+        achr = np.zeros((len(names) - 1, M), dtype="S1")
+        mat, ins, tr = hmm.match_emissions, hmm.insert_emissions, hmm.transition_probabilities
+        st = lib.b2h_hmm_parse_body(body, len(body), M, K, len(names), ptr(compo), ctypes.byref(has_compo), ptr(mat), ptr(ins), ptr(tr),
+                                    ptr(amap), ptr(achr))
+        if st == _lib.B2H_ERANGE:
+            raise ValueError("HMM body of %r: a match line does not start with its node number" % hdr["NAME"])
+        if st != _lib.B2H_OK:
+            raise ValueError("HMM body of %r: malformed node table (%d nodes expected)" % (hdr["NAME"], M))
+        if has_compo.value:
+            hmm._compo[:K] = compo
         hmm.match_emissions[0, 0] = 1.0               # p7_hmm_CreateBody convention for the unused node 0
-        hmm.insert_emissions[:] = _decode_probs([t for k in range(M + 1) for t in rows_ins[k]]).reshape(M + 1, K)
-        hmm.transition_probabilities[:] = _decode_probs([t for k in range(M + 1) for t in rows_t[k]]).reshape(M + 1, 7)
+        anno = {nme: achr[j - 1] for j, nme in enumerate(names) if j > 0}
+        text = lambda col: col.tobytes().decode("ascii")
         if flags["CONS"]:
-            hmm.consensus = "".join(anno["CONS"])
+            hmm.consensus = text(anno["CONS"])
         if flags["RF"]:
-            hmm.reference = "".join(anno["RF"])
+            hmm.reference = text(anno["RF"])
         if flags["MM"]:
-            hmm.model_mask = "".join(anno["MM"])
+            hmm.model_mask = text(anno["MM"])
         if flags["CS"]:
-            hmm.consensus_structure = "".join(anno["CS"])
+            hmm.consensus_structure = text(anno["CS"])
         if flags["MAP"]:
-            hmm.map = np.array([0] + [int(v) for v in anno["MAP"]], dtype=np.int64)
+            hmm.map = amap
         return hmm
 
 

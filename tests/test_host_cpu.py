@@ -440,3 +440,32 @@ def test_tophits_tables_match_the_reference_writers(amino, name, tmp_path):
             assert body.getvalue() == b"".join(l for l in want.splitlines(True) if not l.startswith(b"#"))
     with pytest.raises(ValueError):
         th.write(io.BytesIO(), format="xml")
+
+
+def test_hmm_body_parser_errors_and_odd_fields(amino):
+    """The C field scanner behind HMMFile (b2h_hmm_parse_body): comments and blank lines inside the node table, fields that
+    leave its fast decimal path (exponents, long mantissas) and malformed tables."""
+    import io
+    with gzip.open(os.path.join(GOLD, "data", "Thioesterase.hmm.gz")) as f:
+        data = f.read()
+    ref = plan7.HMMFile(io.BytesIO(data)).read()
+    lines = data.split(b"\n")
+    first = next(i for i, l in enumerate(lines) if l.split()[:1] == [b"1"])
+    # a comment, a blank line, and the same number spelled three ways
+    tok = lines[first].split()[1]
+    odd = list(lines)
+    odd[first] = lines[first].replace(tok, b"%.5fe0" % float(tok), 1)
+    odd[first + 1] = lines[first + 1].replace(lines[first + 1].split()[0], lines[first + 1].split()[0] + b"0000000000000", 1)
+    odd.insert(first, b"# a comment inside the table")
+    odd.insert(first, b"")
+    got = plan7.HMMFile(io.BytesIO(b"\n".join(odd))).read()
+    assert np.array_equal(got.match_emissions, ref.match_emissions) and np.array_equal(got.insert_emissions, ref.insert_emissions)
+    assert np.array_equal(got.transition_probabilities, ref.transition_probabilities) and got.consensus == ref.consensus
+    bad = list(lines); bad[first] = lines[first].replace(b"1", b"2", 1)
+    with pytest.raises(ValueError, match="node number"):
+        plan7.HMMFile(io.BytesIO(b"\n".join(bad))).read()
+    cut = list(lines); del cut[first + 4]
+    with pytest.raises(ValueError):
+        plan7.HMMFile(io.BytesIO(b"\n".join(cut))).read()
+    with pytest.raises(ValueError):
+        plan7.HMMFile(io.BytesIO(b"\n".join(lines[:first + 10]))).read()
