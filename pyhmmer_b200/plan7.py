@@ -1301,6 +1301,109 @@ class TopHits:
                         d.reported = self._domain_reportable(d.score, d.lnP)
                         d.included = h.included and self._domain_includable(d.score, d.lnP)
 
+    def sort(self, by="key"):
+        """``TopHits.sort`` (plan7.pyx:8932): ``key`` = by sort key (p7_tophits_SortBySortkey), ``seqidx`` = by target index and
+        alignment position (p7_tophits_SortBySeqidxAndAlipos, p7_tophits.c:335-360)."""
+        if by == "key":
+            self._sort_by_key()
+        elif by == "seqidx":
+            self._hits.sort(key=self._seqidx_key)
+        else:
+            raise ValueError("invalid value for `by`: %r (expected 'key' or 'seqidx')" % (by,))
+
+    @staticmethod
+    def _seqidx_key(h):
+        d = h._domains[0]._rec
+        s, e = (d.iali, d.jali) if d.iali < d.jali else (d.jali, d.iali)
+        return (h._index, 0 if d.iali < d.jali else 1, s, -e)
+
+    def is_sorted(self, by="key"):
+        """``TopHits.is_sorted`` (plan7.pyx:8951)."""
+        if by not in ("key", "seqidx"):
+            raise ValueError("invalid value for `by`: %r (expected 'key' or 'seqidx')" % (by,))
+        before = list(self._hits)
+        probe = TopHits(self.query, self.mode)
+        probe.long_targets, probe._hits = self.long_targets, list(self._hits)
+        probe.sort(by)
+        return all(a is b for a, b in zip(before, probe._hits))
+
+    def copy(self):
+        """``TopHits.copy`` (plan7.pyx:8897): an independent list over the same (immutable) hit records."""
+        import copy as _copy
+        new = TopHits(self.query, self.mode)
+        new.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_hits", "_params")})
+        new._params = dict(self._params)
+        for h in self._hits:
+            c = _copy.copy(h)
+            c.hits = new
+            c._domains = []
+            for d in h._domains:
+                dc = _copy.copy(d)
+                dc.hit = c
+                dc.alignment = _copy.copy(d.alignment)
+                dc.alignment.domain = dc
+                c._domains.append(dc)
+            c.best_domain = c._domains[h._domains.index(h.best_domain)]
+            c.domains = Domains(c)
+            new._hits.append(c)
+        return new
+
+    # thresholds and search-space figures, named as on the reference object (plan7.pyx:8560-8760)
+    E = property(lambda self: self._params["E"])
+    T = property(lambda self: None if self._params["by_E"] else self._params["T"])
+    domE = property(lambda self: self._params["domE"])
+    domT = property(lambda self: None if self._params["dom_by_E"] else self._params["domT"])
+    incE = property(lambda self: self._params["incE"])
+    incT = property(lambda self: None if self._params["inc_by_E"] else self._params["incT"])
+    incdomE = property(lambda self: self._params["incdomE"])
+    incdomT = property(lambda self: None if self._params["incdom_by_E"] else self._params["incdomT"])
+    bit_cutoffs = property(lambda self: self._params["bit_cutoffs"])
+
+    def __getstate__(self):
+        """Pickling: the hit / domain records as bytes plus what is needed to rebuild the objects (names, lengths, flags)."""
+        hits = self._hits
+        recs = b"".join(bytes(h._rec) for h in hits)
+        doms, text, meta = [], [], []
+        for h in hits:
+            off = []
+            for d in h._domains:
+                r = _lib.DomainRec.from_buffer_copy(d._rec)
+                a = d.alignment
+                lines = a._text[d._rec.text_offset:d._rec.text_offset + (4 + int(d._rec.has_rf) + int(d._rec.has_cs)) * (d._rec.N + 1)]
+                r.text_offset = sum(len(t) for t in text)
+                text.append(lines)
+                off.append((bytes(r), d.reported, d.included))
+            doms.append(off)
+            meta.append((h.name, h.accession, h.description, h.length, h.reported, h.included, h.duplicate, h.dropped, h.new, h.sortkey,
+                         h._index, h._domains.index(h.best_domain)))
+        state = {k: v for k, v in self.__dict__.items() if k != "_hits"}
+        state["_pickled"] = (recs, doms, b"".join(text), meta)
+        return state
+
+    def __setstate__(self, state):
+        recs, doms, text, meta = state.pop("_pickled")
+        self.__dict__.update(state)
+        self._hits = []
+        hs = ctypes.sizeof(_lib.HitRec)
+
+        class _T:                                          # what Hit() reads from a target
+            def __init__(self, name, acc, desc, length):
+                self.name, self.accession, self.description, self._n = name, acc, desc, length
+
+            def __len__(self):
+                return self._n
+
+        for i, (m, dl) in enumerate(zip(meta, doms)):
+            rec = _lib.HitRec.from_buffer_copy(recs[i * hs:(i + 1) * hs])
+            drecs = [_lib.DomainRec.from_buffer_copy(b) for b, _, _ in dl]
+            rec.dom_offset, rec.ndom = 0, len(drecs)
+            rec.best_domain = m[11]
+            h = Hit(self, rec, _T(m[0], m[1], m[2], m[3]), drecs, text)
+            h.reported, h.included, h.duplicate, h.dropped, h.new, h.sortkey, h._index = m[4], m[5], m[6], m[7], m[8], m[9], m[10]
+            for d, (_, rep, inc) in zip(h._domains, dl):
+                d.reported, d.included = rep, inc
+            self._hits.append(h)
+
     def write(self, fh, format="targets", header=True):
         """Write the hits in tabular form to a file opened in binary mode (``TopHits.write``, plan7.pyx:9096-9168):
         ``targets`` = hmmsearch ``--tblout`` (p7_tophits_TabularTargets, p7_tophits.c:1402), ``domains`` = ``--domtblout``

@@ -440,6 +440,23 @@ def test_tophits_tables_match_the_reference_writers(amino, name, tmp_path):
             assert body.getvalue() == b"".join(l for l in want.splitlines(True) if not l.startswith(b"#"))
     with pytest.raises(ValueError):
         th.write(io.BytesIO(), format="xml")
+    # copies and pickles write the same tables; sorting by target index and back restores the order
+    import pickle
+    tables = lambda t: [(lambda b: (t.write(b, format=f), b.getvalue())[1])(io.BytesIO()) for f in ("targets", "domains", "pfam")]
+    want = tables(th)
+    cp = th.copy()
+    rt = pickle.loads(pickle.dumps(th))
+    assert tables(cp) == want and tables(rt) == want
+    assert [h.name for h in rt] == [h.name for h in th] and (rt.Z, rt.domZ, rt.E, rt.incE, rt.T) == (th.Z, th.domZ, 10.0, 0.01, None)
+    assert rt[0].domains[0].alignment.hmm_sequence == th[0].domains[0].alignment.hmm_sequence
+    assert th.is_sorted()
+    cp.sort(by="seqidx")
+    assert [h._index for h in cp] == sorted(h._index for h in th) and cp.is_sorted(by="seqidx") and th.is_sorted(by="key")
+    assert [h.name for h in th] != [h.name for h in cp] or len(th) < 3      # ... and the copy did not disturb the original
+    cp.sort()
+    assert tables(cp) == want
+    with pytest.raises(ValueError):
+        th.sort(by="name")
 
 
 def test_hmm_body_parser_errors_and_odd_fields(amino):
