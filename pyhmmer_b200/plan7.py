@@ -563,6 +563,90 @@ class OptimizedProfile:
     scale_w = property(lambda self: self._desc.scale_w)
     ddbound_w = property(lambda self: self._desc.ddbound_w)
 
+    # -- the reference's striped views (plan7.pyx:4626-4813; impl_sse.h:75-142), rebuilt from the node-major tables:
+    #    vector q, lane z holds node k = q + z*Q + 1; cells beyond M hold the "minus infinity" of their score system --
+    @staticmethod
+    def _stripe(row, width, pad):
+        M = row.shape[-1]
+        Q = max(2, (M - 1) // width + 1)
+        out = np.full(row.shape[:-1] + (width, Q), pad, dtype=row.dtype)
+        out.reshape(row.shape[:-1] + (width * Q,))[..., :M] = row
+        return np.ascontiguousarray(np.swapaxes(out, -1, -2))      # [..., Q, width]
+
+    @staticmethod
+    def _stripe_transitions(t, width, pad):
+        v = OptimizedProfile._stripe(t, width, pad)                 # [8, Q, width]
+        Q = v.shape[1]
+        out = np.empty((8 * Q, width), dtype=t.dtype)
+        out[:7 * Q] = np.swapaxes(v[:7], 0, 1).reshape(7 * Q, width)     # per q: BM MM IM DM MD MI II
+        out[7 * Q:] = v[7]                                           # then all DD
+        return out
+
+    @property
+    def rbv(self):
+        """Match costs of the MSV filter, striped: uint8 [Kp, Q16*16] (``P7_OPROFILE.rbv``)."""
+        v = self._stripe(self.msv_cost, 16, 255)
+        return v.reshape(v.shape[0], -1)
+
+    @property
+    def rwv(self):
+        """ViterbiFilter match scores, striped: int16 [Kp, Q8*8] (``P7_OPROFILE.rwv``; the reference does not expose it)."""
+        v = self._stripe(self.vit_rsc, 8, -32768)
+        return v.reshape(v.shape[0], -1)
+
+    @property
+    def twv(self):
+        """ViterbiFilter transition scores, striped: int16 [8*Q8*8] (``P7_OPROFILE.twv``)."""
+        return self._stripe_transitions(self.vit_tsc, 8, -32768).reshape(-1)
+
+    @property
+    def rfv(self):
+        """Forward / Backward match odds, striped: float32 [Kp, Q4*4] (``P7_OPROFILE.rfv``)."""
+        v = self._stripe(self.fwd_rsc, 4, 0.0)
+        return v.reshape(v.shape[0], -1)
+
+    @property
+    def tfv(self):
+        """Forward / Backward transition odds, striped: float32 [8*Q4*4] (``P7_OPROFILE.tfv``)."""
+        return self._stripe_transitions(self.fwd_tsc, 4, 0.0).reshape(-1)
+
+    @property
+    def xf(self):
+        """Special-state odds, float32 [4, 2]: rows E N J C, columns MOVE LOOP as impl_sse orders them (``P7_OPROFILE.xf``)."""
+        return np.array([list(r) for r in self._desc.xf], np.float32)
+
+    def copy(self):
+        """``OptimizedProfile.copy`` (p7_oprofile_Copy): own tables and scalars, nothing resident yet."""
+        new = OptimizedProfile(self.M, self.alphabet)
+        new.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_dev", "_desc", "_batch")})
+        for t in ("msv_cost", "vit_rsc", "vit_tsc", "fwd_rsc", "fwd_tsc"):
+            setattr(new, t, getattr(self, t).copy())
+        new._evparam, new._cutoff, new._compo = self._evparam.copy(), self._cutoff.copy(), self._compo.copy()
+        d = OProfileDesc.from_buffer_copy(self._desc)
+        d.msv_cost, d.vit_rsc, d.vit_tsc = ptr(new.msv_cost), ptr(new.vit_rsc), ptr(new.vit_tsc)
+        d.fwd_rsc, d.fwd_tsc = ptr(new.fwd_rsc), ptr(new.fwd_tsc)
+        new._keep = (getattr(self, "_keep", None), self)            # what bgf / degen point at
+        new._desc, new._dev = d, {}
+        return new
+
+    def __eq__(self, other):
+        """``p7_oprofile_Compare`` (p7_oprofile.c:1500): tables and scalars, floats to a relative 1e-3."""
+        if not isinstance(other, OptimizedProfile):
+            return NotImplemented
+        if (self.M, self.alphabet) != (other.M, other.alphabet) or self._desc is None or other._desc is None:
+            return False
+        a, b = self._desc, other._desc
+        if any(getattr(a, f) != getattr(b, f) for f in ("tbm_b", "tec_b", "tjb_b", "base_b", "bias_b", "base_w", "ddbound_w", "mode_multihit", "L")):
+            return False
+        close = lambda x, y: np.allclose(x, y, rtol=1e-3, atol=0)
+        if not (close(a.scale_b, b.scale_b) and close(a.scale_w, b.scale_w) and [list(r) for r in a.xw] == [list(r) for r in b.xw]):
+            return False
+        return (np.array_equal(self.msv_cost, other.msv_cost) and np.array_equal(self.vit_rsc, other.vit_rsc)
+                and np.array_equal(self.vit_tsc, other.vit_tsc) and close(self.fwd_rsc, other.fwd_rsc) and close(self.fwd_tsc, other.fwd_tsc)
+                and close(self.xf, other.xf))
+
+    __hash__ = object.__hash__
+
     @property
     def evalue_parameters(self):
         return EvalueParameters(self._evparam)

@@ -67,6 +67,14 @@ def test_model_preparation_bit_identical(amino, name):
             assert (s["tbm_b"], s["tec_b"], s["tjb_b"], s["base_b"], s["bias_b"]) == (d.tbm_b, d.tec_b, d.tjb_b, d.base_b, d.bias_b)
             assert (s["base_w"], s["ddbound_w"]) == (d.base_w, d.ddbound_w)
             assert np.array_equal(s["xw"], np.array([list(r) for r in d.xw])) and np.array_equal(s["xf"], np.array([list(r) for r in d.xf], np.float32))
+            # ... and the striped views rebuilt from our tables are the reference's vectors, padding included
+            rbv, rwv, twv, rfv, tfv = ref.om_tables_striped()
+            assert np.array_equal(om.rbv, rbv.reshape(amino.Kp, -1)) and np.array_equal(om.rwv, rwv.reshape(amino.Kp, -1))
+            assert np.array_equal(om.twv, twv.reshape(-1)) and np.array_equal(om.rfv, rfv.reshape(amino.Kp, -1)) and np.array_equal(om.tfv, tfv.reshape(-1))
+            cp = om.copy()
+            assert cp == om and cp.msv_cost is not om.msv_cost and cp._desc.msv_cost != om._desc.msv_cost
+            cp.fwd_rsc[0, 0] *= 1.01
+            assert cp != om and om != prof
             # de-striping the reference's SSE tables through the ABI gives the same node-major tables
             rbv, rwv, twv, rfv, tfv = ref.om_tables_striped()
             o = [np.empty_like(om.msv_cost), np.empty_like(om.vit_rsc), np.empty_like(om.vit_tsc), np.empty_like(om.fwd_rsc), np.empty_like(om.fwd_tsc)]
