@@ -552,6 +552,41 @@ int ref_max_length(REFM *m, double emit_thresh)
   return r;
 }
 
+/* hmmpress's two profile files for every model of an HMM file, written by the reference's own p7_oprofile_Write
+ * (impl_sse/io.c:87) after the conversion hmmpress does (hmmpress.c:150-170: p7_ProfileConfig(hmm, bg, gm, 400, p7_LOCAL),
+ * p7_oprofile_Convert): <outbase>.h3f + <outbase>.h3p.  Returns the number of models, or -1. */
+int ref_press(const char *hmmpath, const char *outbase)
+{
+  P7_HMMFILE *hfp = NULL;
+  ESL_ALPHABET *abc = NULL;
+  P7_HMM *hmm = NULL;
+  P7_BG *bg = NULL;
+  FILE *ffp, *pfp;
+  char path[1024];
+  int n = 0;
+  ref_init();
+  if (p7_hmmfile_Open(hmmpath, NULL, &hfp, NULL) != eslOK) return -1;
+  snprintf(path, sizeof path, "%s.h3f", outbase); ffp = fopen(path, "wb");
+  snprintf(path, sizeof path, "%s.h3p", outbase); pfp = fopen(path, "wb");
+  if (!ffp || !pfp) return -1;
+  while (p7_hmmfile_Read(hfp, &abc, &hmm) == eslOK) {
+    P7_PROFILE *gm = p7_profile_Create(hmm->M, abc);
+    P7_OPROFILE *om = p7_oprofile_Create(hmm->M, abc);
+    if (!bg) bg = p7_bg_Create(abc);
+    p7_ProfileConfig(hmm, bg, gm, 400, p7_LOCAL);
+    p7_oprofile_Convert(gm, om);
+    om->offs[p7_MOFFSET] = 0; om->offs[p7_FOFFSET] = ftello(ffp); om->offs[p7_POFFSET] = ftello(pfp);
+    p7_oprofile_Write(ffp, pfp, om);
+    p7_oprofile_Destroy(om); p7_profile_Destroy(gm); p7_hmm_Destroy(hmm); hmm = NULL;
+    n++;
+  }
+  fclose(ffp); fclose(pfp);
+  p7_hmmfile_Close(hfp);
+  if (bg) p7_bg_Destroy(bg);
+  if (abc) esl_alphabet_Destroy(abc);
+  return n;
+}
+
 double ref_gumbel_surv(double x, double mu, double lambda) { return esl_gumbel_surv(x, mu, lambda); }
 double ref_exp_surv(double x, double mu, double lambda)    { return esl_exp_surv(x, mu, lambda); }
 

@@ -112,6 +112,16 @@ class RefLtHit(ctypes.Structure):
                [("lnP", ctypes.c_double), ("flags", ctypes.c_int), ("dom_reported", ctypes.c_int), ("dom_included", ctypes.c_int), ("pad", ctypes.c_int)]
 
 
+def press(hmmpath, outbase):
+    """hmmpress's .h3f / .h3p for an HMM file, written by the reference's p7_oprofile_Write (ref_press)."""
+    L = lib()
+    L.ref_press.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    n = L.ref_press(os.fsencode(hmmpath), os.fsencode(outbase))
+    if n < 0:
+        raise ValueError("cannot press %s" % hmmpath)
+    return n
+
+
 class RefModel:
     """One HMM of a file, configured as Pipeline.search_hmm configures an HMM query."""
 

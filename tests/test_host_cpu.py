@@ -553,3 +553,41 @@ def test_domain_definition_randomised_sweep(amino):
             nhits += 1
         _lib.lib.b2h_profile_destroy(hp)
     assert nhits >= 60 and nclu >= 10
+
+
+@needs_ref
+@pytest.mark.parametrize("alphabet", ["amino", "dna"])
+def test_pressed_databases_written_by_the_reference(alphabet, tmp_path):
+    """HMMPressedFile on databases the reference's own p7_oprofile_Write produces from synthetic models: both alphabets
+    (Kp = 29 and 18), model lengths around every striping boundary (Q = 2 minimum; 4 / 8 / 16 lanes) and a long one."""
+    abc = getattr(easel.Alphabet, alphabet)()
+    rng = np.random.default_rng(17)
+    Ms = [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 64, 65, 200, 1100]
+    hmms = []
+    for i, M in enumerate(Ms):
+        h = synth.random_hmm(abc, M, rng, name="m%d" % i)
+        h._evparam[:] = np.array([-8.0, 0.70, -9.0, 0.70, -4.0, 0.70], np.float32)
+        h.max_length = 3 * M + 10
+        h.accession, h.description = ("ACC%05d.1" % i, "model %d of the sweep" % i) if i % 2 else (None, None)
+        if i % 3 == 0:
+            h._cutoff[:] = np.array([25.0, 20.0, 30.0, 22.0, 18.0, 15.0], np.float32)
+        hmms.append(h)
+    path = str(tmp_path / "db.hmm")
+    with open(path, "wb") as f:
+        for h in hmms:
+            h.write(f)
+    assert refshim.press(path, path) == len(hmms)
+    bg = plan7.Background(abc)
+    with plan7.HMMFile(path) as f:
+        assert f.is_pressed()
+        back = list(f)
+    with plan7.HMMPressedFile(path) as pf:
+        oms = list(pf)
+    assert len(oms) == len(hmms) == len(back)
+    for om, h in zip(oms, back):
+        want = plan7.Profile(h.M, abc).configure(h, bg, 400).to_optimized()
+        assert om == want and (om.name, om.accession, om.description, om.M) == (h.name, h.accession, h.description, h.M)
+        for t in ("msv_cost", "vit_rsc", "vit_tsc", "fwd_rsc", "fwd_tsc"):
+            assert np.array_equal(getattr(om, t), getattr(want, t)), (h.M, t)
+        assert list(om._desc.evparam) == list(want._desc.evparam) and list(om._desc.cutoff) == list(want._desc.cutoff)
+        assert om._desc.max_length == h.max_length and list(om._desc.compo) == list(want._desc.compo)
