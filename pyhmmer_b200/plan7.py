@@ -181,7 +181,7 @@ class HMM:
     def write(self, fh, binary=False):
         """Write the model in HMMER3/f ASCII format (``p7_hmmfile_WriteASCII``, p7_hmmfile.c:560-700)."""
         if binary:
-            raise NotImplementedError("binary HMM output is outside the search path")
+            return self._write_binary(fh)
         abc = self.alphabet
         K = abc.K
 
@@ -206,9 +206,14 @@ class HMM:
         w("CONS  %s\n" % ("yes" if self.consensus else "no"))
         w("CS    %s\n" % ("yes" if self.consensus_structure else "no"))
         w("MAP   %s\n" % ("yes" if self.map is not None else "no"))
-        if self.nseq is not None:
+        if self.creation_time:
+            w("DATE  %s\n" % self.creation_time)
+        if self.command_line:
+            for n, cmd in enumerate(self.command_line.split("\n")):
+                w("COM   [%d] %s\n" % (n + 1, cmd))
+        if self.nseq is not None and self.nseq > 0:
             w("NSEQ  %d\n" % self.nseq)
-        if self.nseq_effective is not None:
+        if self.nseq_effective is not None and self.nseq_effective >= 0:
             w("EFFN  %f\n" % self.nseq_effective)
         for tag, i in (("GA", 0), ("TC", 2), ("NC", 4)):
             if self._cutoff[i] != P7_CUTOFF_UNSET:
@@ -234,6 +239,55 @@ class HMM:
         w("//\n")
 
 
+_BIN_MAGIC = {0xe8ededb7: "b", 0xe8ededb8: "c", 0xe8ededb9: "d", 0xe8ededb0: "e", 0xe8ededba: "f"}     # p7_hmmfile.c:47-52
+_ABC_TYPE = {"amino": 3, "dna": 2, "rna": 1}                                                           # esl_alphabet.h
+_H = dict(DESC=1 << 1, RF=1 << 2, CS=1 << 3, STATS=1 << 7, MAP=1 << 8, ACC=1 << 9, GA=1 << 10, TC=1 << 11, NC=1 << 12, CA=1 << 13,
+          COMPO=1 << 14, CHKSUM=1 << 15, CONS=1 << 16, MMASK=1 << 17)                                  # hmmer.h:109-126
+
+
+def _hmm_write_binary(self, fh):
+    """``p7_hmmfile_WriteBinary`` (p7_hmmfile.c:714-815), format 3/f."""
+    import struct
+    abc, M, K = self.alphabet, self.M, self.alphabet.K
+    flags = 0
+    for cond, bit in ((self.description, "DESC"), (self.reference, "RF"), (self.consensus_structure, "CS"),
+                      (self._evparam[0] != P7_EVPARAM_UNSET, "STATS"), (self.map is not None, "MAP"), (self.accession, "ACC"),
+                      (self._cutoff[0] != P7_CUTOFF_UNSET, "GA"), (self._cutoff[2] != P7_CUTOFF_UNSET, "TC"),
+                      (self._cutoff[4] != P7_CUTOFF_UNSET, "NC"), (self._compo[0] != P7_COMPO_UNSET, "COMPO"),
+                      (self.checksum is not None, "CHKSUM"), (self.consensus, "CONS"), (self.model_mask, "MMASK")):
+        if cond:
+            flags |= _H[bit]
+    w = fh.write
+    bstr = lambda v: struct.pack("<i", 0) if v is None else struct.pack("<i", len(v.encode()) + 1) + v.encode() + b"\0"
+    line = lambda v: b" " + v.encode() + b"\0"                               # annotation lines are 1..M with a leading blank
+    w(struct.pack("<Iiii", 0xe8ededba, flags, M, _ABC_TYPE[abc.type.lower()]))
+    w(np.ascontiguousarray(self.match_emissions[1:], np.float32).tobytes())
+    w(np.ascontiguousarray(self.insert_emissions, np.float32).tobytes())
+    w(np.ascontiguousarray(self.transition_probabilities, np.float32).tobytes())
+    w(bstr(self.name))
+    if self.accession:
+        w(bstr(self.accession))
+    if self.description:
+        w(bstr(self.description))
+    for v in (self.reference, self.model_mask, self.consensus, self.consensus_structure):
+        if v:
+            w(line(v))
+    w(bstr(self.command_line))
+    w(struct.pack("<if", int(self.nseq or 0), float(self.nseq_effective or 0.0)))
+    w(struct.pack("<i", int(self.max_length)))
+    w(bstr(self.creation_time))
+    if self.map is not None:
+        w(np.ascontiguousarray(self.map, np.int32).tobytes())
+    w(struct.pack("<I", int(self.checksum or 0)))
+    w(np.ascontiguousarray(self._evparam, np.float32).tobytes())
+    w(np.ascontiguousarray(self._cutoff, np.float32).tobytes())
+    if flags & _H["COMPO"]:
+        w(np.ascontiguousarray(self._compo[:K], np.float32).tobytes())
+
+
+HMM._write_binary = _hmm_write_binary
+
+
 def _decode_probs(tokens):
     """ASCII '-log p' fields -> float32 probabilities with the reference's expf (p7_hmmfile.c:1486)."""
     vals = np.array([math.inf if t == "*" else float(t) for t in tokens], dtype=np.float64)
@@ -255,6 +309,8 @@ class HMMFile:
             self._fh = file
             self._own = False
         self._alphabet = None
+        self._binary = None                    # format letter of a binary file (read_bin30hmm), False for ASCII, None = not looked yet
+        self._push = b""                       # bytes read while looking, handed back to the line reader
 
     def __enter__(self):
         return self
@@ -288,6 +344,8 @@ class HMMFile:
     def _line(self):
         while True:
             line = self._fh.readline()
+            if self._push:
+                line, self._push = self._push + (line if isinstance(line, bytes) else line.encode()), b""
             if not line:
                 return None
             if isinstance(line, bytes):
@@ -295,7 +353,89 @@ class HMMFile:
             if line.strip() and not line.lstrip().startswith("#"):
                 return line.rstrip("\n")
 
+    def _need(self, n, what):
+        b = self._fh.read(n)
+        if len(b) != n:
+            raise ValueError("binary HMM file: failed to read %s" % what)
+        return b
+
+    def _read_binary(self, first):
+        """One model of a HMMER3 binary file (read_bin30hmm, p7_hmmfile.c:1585-1700); formats 3/b .. 3/f."""
+        import struct
+        if not first:
+            magic = self._fh.read(4)
+            if not magic:
+                return None
+            if len(magic) != 4 or _BIN_MAGIC.get(struct.unpack("<I", magic)[0]) != self._binary:
+                raise ValueError("bad magic number at start of HMM")
+        fmt = self._binary
+        flags, M, atype = struct.unpack("<iii", self._need(12, "flags, model size, alphabet"))
+        name = {v: k for k, v in _ABC_TYPE.items()}.get(atype)
+        if name is None or M < 1:
+            raise ValueError("binary HMM file: unsupported alphabet type %d or model size %d" % (atype, M))
+        abc = getattr(Alphabet, name)()
+        if self._alphabet is not None and abc != self._alphabet:
+            raise AlphabetMismatch(self._alphabet, abc)
+        self._alphabet = abc
+        K = abc.K
+        arr = lambda dt, n, what: np.frombuffer(self._need(n * np.dtype(dt).itemsize, what), dtype=dt).copy()
+
+        def bstr(what):
+            n = struct.unpack("<i", self._need(4, what))[0]
+            return self._need(n, what).rstrip(b"\0").decode("ascii", "replace") if n > 0 else None
+
+        line = lambda what: self._need(M + 2, what)[1:M + 1].decode("ascii", "replace")
+        mat = arr(np.float32, M * K, "match emissions").reshape(M, K)
+        ins = arr(np.float32, (M + 1) * K, "insert emissions").reshape(M + 1, K)
+        tr = arr(np.float32, (M + 1) * 7, "transitions").reshape(M + 1, 7)
+        hmm = HMM(abc, M, bstr("name") or "")
+        hmm.match_emissions[1:] = mat
+        hmm.match_emissions[0, 0] = 1.0
+        hmm.insert_emissions[:] = ins
+        hmm.transition_probabilities[:] = tr
+        if flags & _H["ACC"]:
+            hmm.accession = bstr("accession")
+        if flags & _H["DESC"]:
+            hmm.description = bstr("description")
+        if flags & _H["RF"]:
+            hmm.reference = line("rf")
+        if flags & _H["MMASK"]:
+            hmm.model_mask = line("mm")
+        if flags & _H["CONS"]:
+            hmm.consensus = line("consensus")
+        if flags & _H["CS"]:
+            hmm.consensus_structure = line("cs")
+        if flags & _H["CA"]:
+            line("ca")
+        hmm.command_line = bstr("comlog")
+        hmm.nseq, hmm.nseq_effective = struct.unpack("<if", self._need(8, "nseq"))
+        if fmt >= "c":
+            hmm.max_length = struct.unpack("<i", self._need(4, "max_length"))[0]
+        hmm.creation_time = bstr("ctime")
+        if flags & _H["MAP"]:
+            hmm.map = arr(np.int32, M + 1, "map").astype(np.int64)
+        hmm.checksum = struct.unpack("<I", self._need(4, "checksum"))[0]
+        hmm._evparam[:] = arr(np.float32, 6, "statistical parameters")
+        hmm._cutoff[:] = arr(np.float32, 6, "score cutoffs")
+        hmm._compo[:] = 0.0
+        if flags & _H["COMPO"]:
+            hmm._compo[:K] = arr(np.float32, K, "composition")
+        if not flags & _H["CHKSUM"]:
+            hmm.checksum = None
+        return hmm
+
     def read(self):
+        first = self._binary is None
+        if first:
+            import struct
+            head = self._fh.read(4)
+            if isinstance(head, str):
+                head = head.encode()
+            self._binary = _BIN_MAGIC.get(struct.unpack("<I", head)[0], False) if len(head) == 4 else False
+            if not self._binary:
+                self._push = head
+        if self._binary:
+            return self._read_binary(first)
         line = self._line()
         if line is None:
             return None
@@ -329,6 +469,9 @@ class HMMFile:
                 i = {"GA": 0, "TC": 2, "NC": 4}[tag]
                 cut[i] = np.float32(float(f[0]))
                 cut[i + 1] = cut[i] if (abc is not None and abc.is_nucleotide()) else np.float32(float(f[1]))
+            elif tag == "COM":                           # "[n] command": the number is skipped, lines are joined (p7_hmmfile.c:1371-1381)
+                cmd = rest.partition(" ")[2].strip() if rest.startswith("[") else rest
+                hdr["COM"] = cmd if "COM" not in hdr else hdr["COM"] + "\n" + cmd
             else:
                 hdr[tag] = rest
         if stats not in (0, 7):
@@ -358,6 +501,8 @@ class HMMFile:
             hmm.checksum = int(hdr["CKSUM"])
         if "COM" in hdr:
             hmm.command_line = hdr["COM"]
+        if "DATE" in hdr:
+            hmm.creation_time = hdr["DATE"]
         flags = {k: hdr.get(k, "no").lower() == "yes" for k in ("RF", "MM", "CONS", "CS", "MAP")}
         hmm._evparam, hmm._cutoff = ev, cut
 

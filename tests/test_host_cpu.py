@@ -591,3 +591,53 @@ def test_pressed_databases_written_by_the_reference(alphabet, tmp_path):
             assert np.array_equal(getattr(om, t), getattr(want, t)), (h.M, t)
         assert list(om._desc.evparam) == list(want._desc.evparam) and list(om._desc.cutoff) == list(want._desc.cutoff)
         assert om._desc.max_length == h.max_length and list(om._desc.compo) == list(want._desc.compo)
+
+
+@needs_ref
+def test_binary_hmm_files(amino, tmp_path):
+    """HMMFile on HMMER3 binary files (read_bin30hmm, p7_hmmfile.c:1585): the reference's own .h3m fixtures give the models
+    its ASCII files give; HMM.write(binary=True) (p7_hmmfile_WriteBinary, :714) round-trips, and the reference library reads
+    what we write -- for both alphabets."""
+    fields = ("name", "accession", "description", "consensus", "reference", "model_mask", "consensus_structure", "max_length",
+              "nseq", "checksum", "M", "command_line", "creation_time")
+    arrays = ("transition_probabilities", "match_emissions", "insert_emissions", "_evparam", "_cutoff", "_compo")
+
+    def same(x, y):
+        K = x.alphabet.K
+        unset = lambda c: np.zeros(K, np.float32) if c[0] == plan7.P7_COMPO_UNSET else c[:K]   # without COMPO a model reads back zeroed (p7_hmm_CreateBody)
+        assert all(np.array_equal(getattr(x, f), getattr(y, f)) for f in arrays[:-1]) and np.array_equal(unset(x._compo), unset(y._compo))
+        assert [getattr(x, f) for f in fields] == [getattr(y, f) for f in fields], [(f, getattr(x, f), getattr(y, f)) for f in fields if getattr(x, f) != getattr(y, f)]
+        assert (x.map is None) == (y.map is None) and (x.map is None or np.array_equal(x.map, y.map))
+
+    for name in ("PF02826", "Thioesterase"):
+        with gzip.open(os.path.join(GOLD, "data", name + ".hmm.gz")) as f:
+            text = list(plan7.HMMFile(f))
+        binary = list(plan7.HMMFile(os.path.join(GOLD, "data", "pressed", name + ".hmm.h3m")))
+        assert len(text) == len(binary) >= 1
+        for a, b in zip(text, binary):
+            same(a, b)
+    rng = np.random.default_rng(5)
+    for abc in (amino, easel.Alphabet.dna()):
+        hmms = [synth.random_hmm(abc, M, rng, name="b%d" % M) for M in (1, 2, 33, 150)]
+        hmms[1].accession, hmms[1].description, hmms[2].max_length = "ACC1.2", "a model with a description", 99
+        hmms[3].model_mask = "".join("m" if 10 <= k < 20 else "." for k in range(1, 151))
+        hmms[3]._evparam[:] = np.array([-8.0, 0.7, -9.0, 0.7, -4.0, 0.7], np.float32)
+        path = str(tmp_path / ("db_%s.h3m" % abc.type.lower()))
+        with open(path, "wb") as f:
+            for h in hmms:
+                h.write(f, binary=True)
+        back = list(plan7.HMMFile(path))
+        assert len(back) == len(hmms)
+        for a, b in zip(hmms, back):
+            same(a, b)
+        for i, h in enumerate(hmms):                     # ... and HMMER reads the same numbers from our file
+            ref = refshim.RefModel(path, i, 400)
+            t, mat, ins = ref.hmm_params()
+            assert np.array_equal(t, h.transition_probabilities) and np.array_equal(mat[1:], h.match_emissions[1:]) and np.array_equal(ins, h.insert_emissions)
+    with pytest.raises(ValueError):
+        list(plan7.HMMFile(io_bytes(open(path, "rb").read()[:200])))
+
+
+def io_bytes(b):
+    import io
+    return io.BytesIO(b)
