@@ -215,6 +215,8 @@ class HMM:
             w("NSEQ  %d\n" % self.nseq)
         if self.nseq_effective is not None and self.nseq_effective >= 0:
             w("EFFN  %f\n" % self.nseq_effective)
+        if self.checksum is not None:
+            w("CKSUM %d\n" % self.checksum)
         for tag, i in (("GA", 0), ("TC", 2), ("NC", 4)):
             if self._cutoff[i] != P7_CUTOFF_UNSET:
                 w("%s    %.2f %.2f\n" % (tag, self._cutoff[i], self._cutoff[i + 1]))
