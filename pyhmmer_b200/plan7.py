@@ -517,7 +517,7 @@ class HMMFile:
                 raise ValueError("expected closing //")
             if isinstance(line, str):
                 line = line.encode("ascii", "replace")
-            if line[:2] == b"//" or line.lstrip()[:2] == b"//":
+            if b"//" in line and line.lstrip()[:2] == b"//":
                 break
             raw.append(line)                            # (comment and blank lines are skipped by the field scanner)
         names = ["MAP"] + (["CONS"] if fmt >= "e" else []) + ["RF"] + (["MM"] if fmt >= "f" else []) + ["CS"]
