@@ -725,6 +725,17 @@ long ref_search_tables(REFM *m, const uint8_t *const *dsq, const int64_t *len, i
     if (q == 2) p7_tophits_TabularXfam(fp, m->om->name, m->om->acc, th, pli);
     fclose(fp);
   }
+  {   /* every domain's alignment block as Alignment.__str__ prints it (plan7.pyx:249-270), in hit / domain order */
+    FILE *fp; long h; int d;
+    snprintf(path, sizeof path, "%s.ali", prefix);
+    if ((fp = fopen(path, "w")) == NULL) return -1;
+    for (h = 0; h < (long)th->N; h++)
+      for (d = 0; d < th->hit[h]->ndom; d++) {
+        fprintf(fp, ">> %s %d\n", th->hit[h]->name, d);
+        p7_nontranslated_alidisplay_Print(fp, th->hit[h]->dcl[d].ad, 0, -1, FALSE);
+      }
+    fclose(fp);
+  }
   nh = th->N;
   p7_tophits_Destroy(th); p7_pipeline_Destroy(pli);
   return nh;

@@ -1328,6 +1328,36 @@ class Alignment:
     hmm_reference = property(lambda self: self._line(4) if self._rec.has_rf else None)
     hmm_consensus_structure = property(lambda self: self._line(4 + self._rec.has_rf) if self._rec.has_cs else None)
 
+    def __str__(self):
+        """The alignment block as HMMER prints it (``Alignment.__str__`` = p7_nontranslated_alidisplay_Print with no line
+        width, p7_alidisplay.c:715-790): optional CS / RF lines, model, match, target and posterior-probability lines."""
+        txt = lambda v: "" if v is None else (v.decode() if isinstance(v, bytes) else str(v))
+        r = self._rec
+        hits = self.domain.hit.hits
+        scan = hits.mode == "scan"
+        hmmname = txt(self.domain.hit.name if scan else getattr(hits.query, "name", ""))
+        sqname = txt(getattr(hits.query, "name", "") if scan else self.domain.hit.name)
+        namew = max(len(hmmname), len(sqname))
+        coordw = max(len(str(v)) for v in (r.hmmfrom, r.hmmto, r.sqfrom, r.sqto))
+        model, mline, aseq, pp = self._line(0), self._line(1), self._line(2), self._line(3)
+        nk = sum(1 for c in model if c != ".")
+        ni = sum(1 for c in aseq if c != "-")
+        k2 = r.hmmfrom + nk - 1
+        i2 = r.sqfrom + ni - 1 if r.sqfrom < r.sqto else r.sqfrom - ni + 1
+        out = []
+        if r.has_cs:
+            out.append("  %*s %s CS\n" % (namew + coordw + 1, "", self.hmm_consensus_structure))
+        if r.has_rf:
+            out.append("  %*s %s RF\n" % (namew + coordw + 1, "", self.hmm_reference))
+        out.append("  %*s %*d %s %-*d\n" % (namew, hmmname, coordw, r.hmmfrom, model, coordw, k2))
+        out.append("  %*s %s\n" % (namew + coordw + 1, " ", mline))
+        if ni > 0:
+            out.append("  %*s %*d %s %-*d\n" % (namew, sqname, coordw, r.sqfrom, aseq, coordw, i2))
+        else:
+            out.append("  %*s %*s %s %*s\n" % (namew, sqname, coordw, "-", aseq, coordw, "-"))
+        out.append("  %*s %s PP\n" % (namew + coordw + 1, "", pp))
+        return "".join(out)
+
     hmm_name = property(lambda self: self.domain.hit.hits.query.name)
     hmm_accession = property(lambda self: self.domain.hit.hits.query.accession)
     hmm_length = property(lambda self: self.domain.hit.hits.query.M)

@@ -448,6 +448,15 @@ def test_tophits_tables_match_the_reference_writers(amino, name, tmp_path):
             assert body.getvalue() == b"".join(l for l in want.splitlines(True) if not l.startswith(b"#"))
     with pytest.raises(ValueError):
         th.write(io.BytesIO(), format="xml")
+    # every alignment prints as the reference prints it (Alignment.__str__ = p7_nontranslated_alidisplay_Print)
+    blocks = open(prefix + ".ali").read().split(">> ")[1:]
+    mine = [(h.name.decode() if isinstance(h.name, bytes) else h.name, i, str(d.alignment)) for h in th for i, d in enumerate(h.domains)]
+    assert len(blocks) == len(mine) >= 1
+    for blk, (hname, i, text_) in zip(blocks, mine):
+        head, _, body = blk.partition("\n")
+        # (the shim's hit records carry the four alignment lines every display has; the model's CS / RF lines are not in them)
+        body = "".join(l for l in body.splitlines(True) if not l.endswith((" CS\n", " RF\n")))
+        assert head == "%s %d" % (hname, i) and body == text_, (head, body, text_)
     # copies and pickles write the same tables; sorting by target index and back restores the order
     import pickle
     tables = lambda t: [(lambda b: (t.write(b, format=f), b.getvalue())[1])(io.BytesIO()) for f in ("targets", "domains", "pfam")]
