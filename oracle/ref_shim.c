@@ -741,6 +741,47 @@ long ref_search_tables(REFM *m, const uint8_t *const *dsq, const int64_t *len, i
   return nh;
 }
 
+/* TopHits.to_msa (plan7.pyx:8960-9080): the reference search with default thresholds, then p7_tophits_Alignment of the
+ * included domains, written in Pfam (one block) Stockholm format to <path>.  flags: 1 = p7_ALL_CONSENSUS_COLS, 2 = p7_TRIM.
+ * Returns the number of aligned sequences, 0 when nothing is included. */
+#include "esl_msa.h"
+#include "esl_msafile.h"
+long ref_search_msa(REFM *m, const uint8_t *const *dsq, const int64_t *len, int n, const char *const *names,
+                    const char *const *accs, const char *const *descs, int flags, const char *path)
+{
+  P7_PIPELINE *pli = p7_pipeline_Create(NULL, m->om->M, 400, FALSE, p7_SEARCH_SEQS);
+  P7_TOPHITS  *th  = p7_tophits_Create();
+  ESL_MSA *msa = NULL;
+  FILE *fp;
+  int t, status, opt = p7_DEFAULT;
+  long nseq = 0;
+  p7_oprofile_ReconfigMultihit(m->om, 400);
+  p7_pli_NewModel(pli, m->om, m->bg);
+  for (t = 0; t < n; t++) {
+    ESL_SQ *sq = esl_sq_CreateDigitalFrom(m->abc, names[t], dsq[t], len[t], (descs && descs[t]) ? descs[t] : NULL, (accs && accs[t]) ? accs[t] : NULL, NULL);
+    p7_pli_NewSeq(pli, sq);
+    p7_bg_SetLength(m->bg, sq->n);
+    p7_oprofile_ReconfigLength(m->om, sq->n);
+    p7_Pipeline(pli, m->om, m->bg, sq, NULL, th);
+    p7_pipeline_Reuse(pli);
+    esl_sq_Destroy(sq);
+  }
+  p7_tophits_SortBySortkey(th);
+  p7_tophits_Threshold(th, pli);
+  if (flags & 1) opt |= p7_ALL_CONSENSUS_COLS;
+  if (flags & 2) opt |= p7_TRIM;
+  status = p7_tophits_Alignment(th, m->abc, NULL, NULL, 0, opt, &msa);
+  if (status == eslOK) {
+    if ((fp = fopen(path, "w")) == NULL) return -1;
+    esl_msafile_Write(fp, msa, eslMSAFILE_PFAM);
+    fclose(fp);
+    nseq = msa->nseq;
+    esl_msa_Destroy(msa);
+  }
+  p7_tophits_Destroy(th); p7_pipeline_Destroy(pli);
+  return nseq;
+}
+
 void ref_result_free(REF_RESULT *r) { if (r) { free(r->hits); free(r->doms); free(r->text); free(r); } }
 long ref_result_nhits(const REF_RESULT *r) { return r->nhits; }
 long ref_result_ndoms(const REF_RESULT *r) { return r->ndoms; }

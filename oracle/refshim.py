@@ -290,6 +290,21 @@ class RefModel:
         arr = lambda vals: (ctypes.c_char_p * max(n, 1))(*[enc(v) for v in vals])
         return self.L.ref_search_tables(self.h, ptrs, lens.ctypes.data, n, arr(names), arr(accs), arr(descs), os.fsencode(prefix))
 
+    def search_msa(self, seqs, names, accs, descs, path, all_consensus_cols=False, trim=False):
+        """The reference search with default thresholds, then TopHits.to_msa = p7_tophits_Alignment of the included domains,
+        written to <path> in Pfam Stockholm format.  Returns the number of aligned sequences (0 = nothing included)."""
+        dsqs = [dsq_of(c) for c in seqs]
+        n = len(dsqs)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[d.ctypes.data for d in dsqs])
+        lens = np.array([d.size - 2 for d in dsqs], dtype=np.int64)
+        enc = lambda v: None if v is None else (v if isinstance(v, bytes) else v.encode())
+        arr = lambda vals: (ctypes.c_char_p * max(n, 1))(*[enc(v) for v in vals])
+        self.L.ref_search_msa.restype = ctypes.c_long
+        self.L.ref_search_msa.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p]
+        return self.L.ref_search_msa(self.h, ptrs, lens.ctypes.data, n, arr(names), arr(accs), arr(descs),
+                                     int(all_consensus_cols) | 2 * int(trim), os.fsencode(path))
+
     def max_length(self, beta=1e-7):
         """p7_Builder_MaxLength of the model's HMM."""
         return self.L.ref_max_length(self.h, beta)

@@ -324,3 +324,64 @@ class SequenceFile:
             n += 1
             r += len(s)
         return block
+
+
+class TextMSA:
+    """A multiple alignment in text mode: the part of ``pyhmmer.easel.TextMSA`` that `TopHits.to_msa` fills -- aligned
+    rows with names, accessions and descriptions, the reference (RF) line and posterior-probability annotation."""
+
+    def __init__(self, name=None, names=(), sequences=(), accessions=None, descriptions=None, reference=None,
+                 posterior_probabilities=None, consensus_posterior_probabilities=None):
+        self.name = name
+        self.names = list(names)
+        self.alignment = list(sequences)
+        self.accessions = list(accessions) if accessions is not None else [None] * len(self.names)
+        self.descriptions = list(descriptions) if descriptions is not None else [None] * len(self.names)
+        self.reference = reference
+        self.posterior_probabilities = list(posterior_probabilities) if posterior_probabilities is not None else None
+        self.consensus_posterior_probabilities = consensus_posterior_probabilities
+        if len({len(r) for r in self.alignment}) > 1:
+            raise ValueError("aligned sequences of different lengths")
+
+    def __len__(self):
+        return len(self.alignment[0]) if self.alignment else 0
+
+    @property
+    def sequences(self):
+        """The rows as `TextSequence` (aligned text)."""
+        return [TextSequence(name=n, description=d or b"", accession=a or b"", sequence=s)
+                for n, a, d, s in zip(self.names, self.accessions, self.descriptions, self.alignment)]
+
+    def write(self, fh, format="stockholm"):
+        """Write the alignment to a binary file handle: ``stockholm`` / ``pfam`` (one block) or ``afa`` (aligned FASTA)."""
+        txt = lambda v: v.decode() if isinstance(v, bytes) else str(v)
+        out = []
+        if format in ("stockholm", "pfam"):
+            names = [txt(n) for n in self.names]
+            w = max([len(n) for n in names] + [0])
+            gr = w + 9 if self.posterior_probabilities else 0
+            margin = max(w + 1, gr, 13 if self.consensus_posterior_probabilities else (8 if self.reference else 0))
+            out.append("# STOCKHOLM 1.0\n\n")
+            for n, a in zip(names, self.accessions):
+                if a:
+                    out.append("#=GS %-*s AC %s\n" % (w, n, txt(a)))
+            for n, d in zip(names, self.descriptions):
+                if d:
+                    out.append("#=GS %-*s DE %s\n" % (w, n, txt(d)))
+            out.append("\n")
+            for i, (n, row) in enumerate(zip(names, self.alignment)):
+                out.append("%-*s%s\n" % (margin, n, row))
+                if self.posterior_probabilities and self.posterior_probabilities[i]:
+                    out.append("%-*s%s\n" % (margin, "#=GR %-*s PP" % (w, n), self.posterior_probabilities[i]))
+            if self.consensus_posterior_probabilities:
+                out.append("%-*s%s\n" % (margin, "#=GC PP_cons", self.consensus_posterior_probabilities))
+            if self.reference:
+                out.append("%-*s%s\n" % (margin, "#=GC RF", self.reference))
+            out.append("//\n")
+        elif format == "afa":
+            for n, d, row in zip(self.names, self.descriptions, self.alignment):
+                out.append(">%s%s\n" % (txt(n), (" " + txt(d)) if d else ""))
+                out.extend(row[i:i + 60] + "\n" for i in range(0, len(row), 60))
+        else:
+            raise ValueError("invalid format %r (expected 'stockholm', 'pfam' or 'afa')" % (format,))
+        fh.write("".join(out).encode())

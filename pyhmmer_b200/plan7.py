@@ -1665,6 +1665,122 @@ class TopHits:
                 d.reported, d.included = rep, inc
             self._hits.append(h)
 
+    def to_msa(self, alphabet, sequences=None, traces=None, trim=False, digitize=False, all_consensus_cols=False):
+        """A multiple alignment of all included domains (``TopHits.to_msa``, plan7.pyx:8960-9080 = p7_tophits_Alignment,
+        p7_tophits.c:1251): every included domain becomes a row named ``target/from-to``, rebuilt from its alignment display
+        as the reference does (p7_alidisplay_Backconvert), and the rows are laid out by p7_tracealign_Seqs (tracealign.c:
+        map_new_msa, make_text_msa, annotate_rf, annotate_posterior_probability, rejustify_insertions_text) -- match columns
+        in upper case, insertions in lower case split half left / half right, ``x`` in the RF line on consensus columns.
+        Returns an `easel.TextMSA`.  Extra sequences / traces and digital alignments are not supported."""
+        from .easel import TextMSA
+        if sequences or traces:
+            raise NotImplementedError("additional sequences / traces are not supported")
+        if digitize:
+            raise NotImplementedError("digital alignments are not supported")
+        txt = lambda v: "" if v is None else (v.decode() if isinstance(v, bytes) else str(v))
+        rows = []
+        M = 0
+        for h in self._hits:
+            if not h.included:
+                continue
+            for d in h._domains:
+                if d.included:
+                    a = d.alignment
+                    rows.append((h, d, a.hmm_sequence, a.target_sequence, a.posterior_probabilities))
+                    M = M or int(getattr(self.query, "M", 0)) or a.hmm_to
+        if not rows:
+            raise ValueError("No included domains found")
+        gap = "-_."
+        # states per display column: k advances on every non-gap model character; I = insert after node k
+        paths = []
+        inscount = [0] * (M + 1)
+        matuse = [bool(all_consensus_cols)] * (M + 1)
+        matuse[0] = False
+        for h, d, model, aseq, pp in rows:
+            k = d._rec.hmmfrom - 1
+            path, insnum = [], {}
+            for z in range(len(model)):
+                if model[z] not in gap:
+                    k += 1
+                    if aseq[z] not in gap:
+                        path.append(("M", k, aseq[z], pp[z]))
+                        matuse[k] = True
+                    else:
+                        path.append(("D", k, None, None))
+                else:
+                    path.append(("I", k, aseq[z], pp[z]))
+                    insnum[k] = insnum.get(k, 0) + 1
+            for kk, v in insnum.items():
+                inscount[kk] = max(inscount[kk], v)
+            paths.append(path)
+        if trim:
+            inscount[0] = inscount[M] = 0
+        matmap = [0] * (M + 1)
+        alen = inscount[0]
+        for k in range(1, M + 1):
+            if matuse[k]:
+                matmap[k] = alen + 1
+                alen += 1 + inscount[k]
+            else:
+                matmap[k] = alen
+                alen += inscount[k]
+        # p7_alidisplay_DecodePostProb / EncodePostProb (p7_alidisplay.c:386-410): float values, double arithmetic on them
+        f32 = lambda v: float(np.float32(v))
+        decode = lambda c: 1.0 if c == "*" else (0.0 if c == "." else (f32(0.01) if c == "0" else f32((ord(c) - 48) / 10.0)))
+        encode = lambda p: "*" if f32(p) + 0.05 >= 1.0 else chr(int((f32(p) + 0.05) * 10.0) + 48)
+        totp, npp = [0.0] * alen, [0] * alen
+        arows, prows = [], []
+        for path in paths:
+            row, ppr = ["."] * alen, ["."] * alen
+            for k in range(1, M + 1):
+                if matuse[k]:
+                    row[matmap[k] - 1] = "-"
+            apos = 0
+            for st, k, c, p in path:
+                if st == "M":
+                    row[matmap[k] - 1] = c.upper()
+                    ppr[matmap[k] - 1] = encode(decode(p))
+                    totp[matmap[k] - 1] += decode(p)
+                    npp[matmap[k] - 1] += 1
+                    apos = matmap[k]
+                elif st == "D":
+                    if matuse[k]:
+                        row[matmap[k] - 1] = "-"
+                    apos = matmap[k]
+                elif not trim or (k != 0 and k != M):
+                    row[apos] = c.lower()
+                    ppr[apos] = encode(decode(p))
+                    apos += 1
+            # rejustify_insertions_text: the second half of every insertion longer than one goes to the right edge
+            for k in range(0, M):
+                if inscount[k] > 1:
+                    lo, hi = matmap[k], matmap[k + 1] - (1 if matuse[k + 1] else 0)
+                    nins = sum(1 for x in row[lo:hi] if x not in gap and x != "~")
+                    nins = 0 if k == 0 else nins // 2
+                    opos = npos = hi - 1
+                    while opos >= lo + nins:
+                        if row[opos] in gap:
+                            opos -= 1
+                        else:
+                            row[npos], ppr[npos] = row[opos], ppr[opos]
+                            npos -= 1
+                            opos -= 1
+                    while npos >= lo + nins:
+                        row[npos], ppr[npos] = ".", "."
+                        npos -= 1
+            arows.append("".join(row))
+            prows.append("".join(ppr))
+        rf = ["."] * alen
+        for k in range(1, M + 1):
+            if matuse[k]:
+                rf[matmap[k] - 1] = "x"
+        ppcons = "".join(encode(totp[i] / npp[i]) if npp[i] else "." for i in range(alen))
+        names = [("%s/%d-%d" % (txt(h.name), d._rec.sqfrom, d._rec.sqto)).encode() for h, d, _, _, _ in rows]
+        descs = [("[subseq from] %s" % (txt(h.description) if h.description else txt(h.name))).encode() for h, d, _, _, _ in rows]
+        accs = [txt(h.accession).encode() if h.accession else None for h, d, _, _, _ in rows]
+        return TextMSA(names=names, sequences=arows, accessions=accs, descriptions=descs, reference="".join(rf),
+                       posterior_probabilities=prows, consensus_posterior_probabilities=ppcons)
+
     def write(self, fh, format="targets", header=True):
         """Write the hits in tabular form to a file opened in binary mode (``TopHits.write``, plan7.pyx:9096-9168):
         ``targets`` = hmmsearch ``--tblout`` (p7_tophits_TabularTargets, p7_tophits.c:1402), ``domains`` = ``--domtblout``

@@ -650,3 +650,85 @@ def test_binary_hmm_files(amino, tmp_path):
 def io_bytes(b):
     import io
     return io.BytesIO(b)
+
+
+def _read_pfam_stockholm(path):
+    names, rows, pp, gs, gc = [], {}, {}, {}, {}
+    for line in open(path):
+        line = line.rstrip("\n")
+        if not line or line == "//" or line.startswith("# "):
+            continue
+        if line.startswith("#=GS"):
+            _, name, tag, val = line.split(None, 3)
+            gs[(name, tag)] = val
+        elif line.startswith("#=GR"):
+            _, name, tag, val = line.split(None, 3)
+            assert tag == "PP"
+            pp[name] = val
+        elif line.startswith("#=GC"):
+            _, tag, val = line.split(None, 2)
+            gc[tag] = val
+        else:
+            name, val = line.split(None, 1)
+            names.append(name)
+            rows[name] = val
+    return names, rows, pp, gs, gc
+
+
+@needs_ref
+@pytest.mark.parametrize("name,all_cols", [("PF02826", False), ("PF02826", True), ("KR", False)])
+def test_to_msa_matches_the_reference_alignment(amino, name, all_cols, tmp_path):
+    """`TopHits.to_msa` against p7_tophits_Alignment on the same hits (written by the reference as Pfam Stockholm): row names,
+    every aligned row, the PP rows, the RF line and the consensus PP line."""
+    import io
+    with easel.SequenceFile(os.path.join(GOLD, "data", "proteome.faa.gz"), digital=True, alphabet=amino) as f:
+        seqs = f.read_block()
+    with tempfile.NamedTemporaryFile(suffix=".hmm") as tmp:
+        with gzip.open(os.path.join(GOLD, "data", name + ".hmm.gz")) as f:
+            tmp.write(f.read())
+        tmp.flush()
+        with plan7.HMMFile(tmp.name) as f:
+            hmm = f.read()
+        ref = refshim.RefModel(tmp.name, 0, 400)
+        path = str(tmp_path / "ref.sto")
+        nref = ref.search_msa([s.sequence for s in seqs], [s.name for s in seqs], [s.accession or None for s in seqs],
+                              [s.description or None for s in seqs], path, all_consensus_cols=all_cols)
+        rh, rd, rtext, rc = ref.search([s.sequence for s in seqs])
+    hits = (_lib.HitRec * len(rh))()
+    doms = (_lib.DomainRec * len(rd))()
+    for a, r in zip(hits, rh):
+        a.profile = 0
+        for fld in ("seq", "score", "pre_score", "sum_score", "nexpected", "lnP", "pre_lnP", "sum_lnP", "nregions", "nclustered", "noverlaps",
+                    "nenvelopes", "ndom", "best_domain", "dom_offset"):
+            setattr(a, fld, getattr(r, fld))
+    for a, r in zip(doms, rd):
+        for fld in ("ienv", "jenv", "iali", "jali", "envsc", "domcorrection", "dombias", "oasc", "bitscore", "lnP", "hmmfrom", "hmmto", "sqfrom",
+                    "sqto", "N", "text_offset"):
+            setattr(a, fld, getattr(r, fld))
+    pli = object.__new__(plan7.Pipeline)
+    for k, v in dict(alphabet=amino, background=plan7.Background(amino), bias_filter=True, null2=True, seed=42, Z=None, domZ=None, F1=0.02,
+                     F2=1e-3, F3=1e-5, E=10.0, T=None, domE=10.0, domT=None, incE=0.01, incT=None, incdomE=0.01, incdomT=None, bit_cutoffs=None,
+                     host_threads=1).items():
+        setattr(pli, k, v)
+    pli.clear()
+    om = plan7.Profile(hmm.M, amino).configure(hmm, pli.background, 400).to_optimized()
+    order = sorted(range(len(hits)), key=lambda i: hits[i].seq)
+    th = pli._assemble([hmm], [om], seqs, [hits[i] for i in order], list(doms), rtext, np.array([rc], np.int64).reshape(1, 4))[0]
+    msa = th.to_msa(amino, all_consensus_cols=all_cols)
+    names, rows, pp, gs, gc = _read_pfam_stockholm(path)
+    assert nref == len(names) == len(msa.names) >= 2
+    assert [n.decode() for n in msa.names] == names
+    for n, row, p, d, a in zip(names, msa.alignment, msa.posterior_probabilities, msa.descriptions, msa.accessions):
+        assert row == rows[n], (n, row, rows[n])
+        assert p == pp[n], (n, p, pp[n])
+        assert d.decode() == gs[(n, "DE")] and (a is None or a.decode() == gs[(n, "AC")])
+    assert msa.reference == gc["RF"] and msa.consensus_posterior_probabilities == gc["PP_cons"]
+    assert len(msa) == len(gc["RF"]) and (not all_cols or gc["RF"].count("x") == hmm.M)
+    buf = io.BytesIO()
+    msa.write(buf, "stockholm")
+    again = tmp_path / "mine.sto"
+    again.write_bytes(buf.getvalue())
+    assert _read_pfam_stockholm(str(again))[:3] == (names, rows, pp)
+    for bad in (dict(digitize=True), dict(sequences=[1], traces=[1])):
+        with pytest.raises(NotImplementedError):
+            th.to_msa(amino, **bad)
