@@ -732,3 +732,63 @@ def test_to_msa_matches_the_reference_alignment(amino, name, all_cols, tmp_path)
     for bad in (dict(digitize=True), dict(sequences=[1], traces=[1])):
         with pytest.raises(NotImplementedError):
             th.to_msa(amino, **bad)
+
+
+@needs_ref
+def test_to_msa_on_synthetic_homologs(amino, tmp_path):
+    """The same comparison on seeded random models whose emitted homologs carry insertions and deletions of every length
+    (insertions longer than one are split left / right, columns used only by deletions collapse)."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import ModelPair
+    rng = np.random.default_rng(21)
+    checked = ins2 = 0
+    for M in (12, 45, 130, 260):
+        h = synth.random_hmm(amino, M, rng, name="msa%d" % M)
+        h._evparam[:] = np.array([-8.0 - np.log2(M) * 0.3, 0.70, -9.0, 0.70, -4.0, 0.70], np.float32)
+        pair = ModelPair(h)
+        seqs = []
+        for i in range(30):
+            L = int(rng.integers(M + 20, 4 * M + 200))
+            codes = rng.integers(0, 20, L).astype(np.uint8)
+            for _ in range(int(rng.integers(1, 3))):
+                dom = synth.emit_sequence(pair.hmm, rng)
+                if len(dom) < L:
+                    pos = int(rng.integers(0, L - len(dom)))
+                    codes[pos:pos + len(dom)] = dom
+            seqs.append(easel.DigitalSequence(amino, name=b"t%d" % i, sequence=codes))
+        block = easel.DigitalSequenceBlock(amino, seqs)
+        path = str(tmp_path / ("ref%d.sto" % M))
+        nref = pair.ref.search_msa([s.sequence for s in seqs], [s.name for s in seqs], [None] * len(seqs), [None] * len(seqs), path)
+        rh, rd, rtext, rc = pair.ref.search([s.sequence for s in seqs])
+        hits = (_lib.HitRec * len(rh))()
+        doms = (_lib.DomainRec * len(rd))()
+        for a, r in zip(hits, rh):
+            a.profile = 0
+            for fld in ("seq", "score", "pre_score", "sum_score", "nexpected", "lnP", "pre_lnP", "sum_lnP", "nregions", "nclustered",
+                        "noverlaps", "nenvelopes", "ndom", "best_domain", "dom_offset"):
+                setattr(a, fld, getattr(r, fld))
+        for a, r in zip(doms, rd):
+            for fld in ("ienv", "jenv", "iali", "jali", "envsc", "domcorrection", "dombias", "oasc", "bitscore", "lnP", "hmmfrom", "hmmto",
+                        "sqfrom", "sqto", "N", "text_offset"):
+                setattr(a, fld, getattr(r, fld))
+        pli = object.__new__(plan7.Pipeline)
+        for k, v in dict(alphabet=amino, background=pair.bg, bias_filter=True, null2=True, seed=42, Z=None, domZ=None, F1=0.02, F2=1e-3,
+                         F3=1e-5, E=10.0, T=None, domE=10.0, domT=None, incE=0.01, incT=None, incdomE=0.01, incdomT=None, bit_cutoffs=None,
+                         host_threads=1).items():
+            setattr(pli, k, v)
+        pli.clear()
+        order = sorted(range(len(hits)), key=lambda i: hits[i].seq)
+        th = pli._assemble([pair.hmm], [pair.om], block, [hits[i] for i in order], list(doms), rtext, np.array([rc], np.int64).reshape(1, 4))[0]
+        if nref == 0:                                    # nothing included: eslFAIL there, ValueError here
+            with pytest.raises(ValueError):
+                th.to_msa(amino)
+            continue
+        msa = th.to_msa(amino)
+        names, rows, pp, gs, gc = _read_pfam_stockholm(path)
+        assert nref == len(names) == len(msa.names) >= 5 and [n.decode() for n in msa.names] == names
+        for n, row, p in zip(names, msa.alignment, msa.posterior_probabilities):
+            assert row == rows[n] and p == pp[n], (M, n, row, rows[n])
+            ins2 += any(len(run) > 1 for run in "".join(c if c.islower() else " " for c in row).split())
+        assert msa.reference == gc["RF"] and msa.consensus_posterior_probabilities == gc["PP_cons"]
+        checked += len(names)
+    assert checked >= 30 and ins2 >= 3
