@@ -782,6 +782,44 @@ long ref_search_msa(REFM *m, const uint8_t *const *dsq, const int64_t *len, int 
   return nseq;
 }
 
+/* hmmscan of ONE sequence against a list of models as pyhmmer runs it (Pipeline._scan_loop, plan7.pyx:6625-6677), default
+ * thresholds, hits written by the reference's tabular writers to <prefix>.tbl / .domtbl / .pfam.  Returns the hit count. */
+long ref_scan_tables(REFM **models, int nmodels, const uint8_t *dsq, long len, const char *qname, const char *qacc, const char *qdesc,
+                     const char *prefix)
+{
+  P7_PIPELINE *pli = p7_pipeline_Create(NULL, 100, (int)len, FALSE, p7_SCAN_MODELS);
+  P7_TOPHITS  *th  = p7_tophits_Create();
+  ESL_SQ *sq = esl_sq_CreateDigitalFrom(models[0]->abc, qname, dsq, len, qdesc, qacc, NULL);
+  char path[1024];
+  const char *ext[3] = { ".tbl", ".domtbl", ".pfam" };
+  int t, q;
+  long nh;
+  p7_pli_NewSeq(pli, sq);
+  for (t = 0; t < nmodels; t++) {
+    REFM *m = models[t];
+    p7_oprofile_ReconfigMultihit(m->om, 400);
+    p7_pli_NewModel(pli, m->om, m->bg);
+    p7_bg_SetLength(m->bg, sq->n);
+    p7_oprofile_ReconfigLength(m->om, sq->n);
+    p7_Pipeline(pli, m->om, m->bg, sq, NULL, th);
+    p7_pipeline_Reuse(pli);
+  }
+  p7_tophits_SortBySortkey(th);
+  p7_tophits_Threshold(th, pli);
+  for (q = 0; q < 3; q++) {
+    FILE *fp;
+    snprintf(path, sizeof path, "%s%s", prefix, ext[q]);
+    if ((fp = fopen(path, "w")) == NULL) return -1;
+    if (q == 0) p7_tophits_TabularTargets(fp, sq->name, sq->acc, th, pli, TRUE);
+    if (q == 1) p7_tophits_TabularDomains(fp, sq->name, sq->acc, th, pli, TRUE);
+    if (q == 2) p7_tophits_TabularXfam(fp, sq->name, sq->acc, th, pli);
+    fclose(fp);
+  }
+  nh = th->N;
+  esl_sq_Destroy(sq); p7_tophits_Destroy(th); p7_pipeline_Destroy(pli);
+  return nh;
+}
+
 void ref_result_free(REF_RESULT *r) { if (r) { free(r->hits); free(r->doms); free(r->text); free(r); } }
 long ref_result_nhits(const REF_RESULT *r) { return r->nhits; }
 long ref_result_ndoms(const REF_RESULT *r) { return r->ndoms; }

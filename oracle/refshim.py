@@ -122,6 +122,19 @@ def press(hmmpath, outbase):
     return n
 
 
+def scan_tables(models, codes, qname, qacc, qdesc, prefix):
+    """hmmscan of one sequence against RefModel objects with default thresholds; the reference's tabular writers leave
+    <prefix>.tbl / .domtbl / .pfam (ref_scan_tables).  Returns the hit count."""
+    L = lib()
+    L.ref_scan_tables.restype = ctypes.c_long
+    L.ref_scan_tables.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_long, ctypes.c_char_p, ctypes.c_char_p,
+                                  ctypes.c_char_p, ctypes.c_char_p]
+    d = dsq_of(codes)
+    hs = (ctypes.c_void_p * len(models))(*[m.h for m in models])
+    enc = lambda v: None if v is None else (v if isinstance(v, bytes) else v.encode())
+    return L.ref_scan_tables(hs, len(models), d.ctypes.data, d.size - 2, enc(qname), enc(qacc) or b"", enc(qdesc) or b"", os.fsencode(prefix))
+
+
 class RefModel:
     """One HMM of a file, configured as Pipeline.search_hmm configures an HMM query."""
 

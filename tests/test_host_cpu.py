@@ -792,3 +792,57 @@ def test_to_msa_on_synthetic_homologs(amino, tmp_path):
         assert msa.reference == gc["RF"] and msa.consensus_posterior_probabilities == gc["PP_cons"]
         checked += len(names)
     assert checked >= 30 and ins2 >= 3
+
+
+@needs_ref
+def test_scan_tables_match_the_reference_writers(amino, tmp_path, monkeypatch):
+    """`TopHits.write` in scan mode (targets are models, the query is a sequence; tlen / qlen swap, Z = number of models):
+    the reference's raw hits of every (model, sequence) comparison go through the product's scan assembly and come out
+    as the reference's own tables, byte for byte."""
+    import io
+    with easel.SequenceFile(os.path.join(GOLD, "data", "proteome.faa.gz"), digital=True, alphabet=amino) as f:
+        seqs = {s.name: s for s in f.read_block()}
+    query = seqs["938293.PRJEB85.HG003691_78"]          # hit by several RREFam models
+    with tempfile.NamedTemporaryFile(suffix=".hmm") as tmp:
+        with gzip.open(os.path.join(GOLD, "data", "RREFam.hmm.gz")) as f:
+            tmp.write(f.read())
+        tmp.flush()
+        with plan7.HMMFile(tmp.name) as f:
+            hmms = list(f)
+        refs = [refshim.RefModel(tmp.name, i, 400) for i in range(len(hmms))]
+        prefix = str(tmp_path / "scan")
+        nref = refshim.scan_tables(refs, query.sequence, query.name, query.accession or None, query.description or None, prefix)
+        hits, doms, text = [], [], b""
+        for t, ref in enumerate(refs):
+            rh, rd, rtext, rc = ref.search([query.sequence])
+            for r in rh:
+                a = _lib.HitRec()
+                a.profile, a.seq = t, 0
+                for fld in ("score", "pre_score", "sum_score", "nexpected", "lnP", "pre_lnP", "sum_lnP", "nregions", "nclustered", "noverlaps",
+                            "nenvelopes", "ndom", "best_domain"):
+                    setattr(a, fld, getattr(r, fld))
+                a.dom_offset = len(doms)
+                for rdom in rd[r.dom_offset:r.dom_offset + r.ndom]:
+                    d = _lib.DomainRec()
+                    for fld in ("ienv", "jenv", "iali", "jali", "envsc", "domcorrection", "dombias", "oasc", "bitscore", "lnP", "hmmfrom", "hmmto",
+                                "sqfrom", "sqto", "N"):
+                        setattr(d, fld, getattr(rdom, fld))
+                    d.text_offset = len(text) + rdom.text_offset
+                    doms.append(d)
+                hits.append(a)
+            text += rtext
+    assert nref >= 1 and len(hits) >= nref
+    pli = object.__new__(plan7.Pipeline)
+    for k, v in dict(alphabet=amino, background=plan7.Background(amino), bias_filter=True, null2=True, seed=42, Z=None, domZ=None, F1=0.02,
+                     F2=1e-3, F3=1e-5, E=10.0, T=None, domE=10.0, domT=None, incE=0.01, incT=None, incdomE=0.01, incdomT=None, bit_cutoffs=None,
+                     host_threads=1).items():
+        setattr(pli, k, v)
+    pli.clear()
+    monkeypatch.setattr(plan7.Pipeline, "_run", lambda self, oms, block: (hits, doms, text, np.zeros((len(oms), 4), np.int64)))
+    th = pli._scan_many([query], hmms)[0]
+    assert th.mode == "scan" and th.Z == float(len(hmms)) and len(th) == nref
+    for fmt, ext in (("targets", ".tbl"), ("domains", ".domtbl"), ("pfam", ".pfam")):
+        buf = io.BytesIO()
+        th.write(buf, format=fmt)
+        want = open(prefix + ext, "rb").read()
+        assert buf.getvalue() == want, (fmt, buf.getvalue()[:900], want[:900])
