@@ -587,6 +587,41 @@ int ref_press(const char *hmmpath, const char *outbase)
   return n;
 }
 
+/* Builder.build for a single query sequence (plan7.pyx:1150-1260 -> p7_SingleBuilder, p7_builder.c:440): a builder with the
+ * given score matrix and gap probabilities, p7_SingleBuilder (p7_Seqmodel, composition, consensus, calibration with the
+ * Mersenne Twister seeded <seed>), the resulting HMM written in ASCII to <path>.  alphabet_type: eslAMINO 3, eslDNA 2, eslRNA 1. */
+int ref_single_builder(int alphabet_type, const uint8_t *dsq, int L, const char *name, const char *matrix, double popen, double pextend,
+                       unsigned seed, const char *path)
+{
+  ESL_ALPHABET *abc = esl_alphabet_Create(alphabet_type);
+  P7_BG *bg = p7_bg_Create(abc);
+  P7_BUILDER *bld = p7_builder_Create(NULL, abc);
+  ESL_SQ *sq = esl_sq_CreateDigitalFrom(abc, name, dsq, L, NULL, NULL, NULL);
+  P7_HMM *hmm = NULL;
+  FILE *fp;
+  int status;
+  ref_init();
+  if (seed != 42) { esl_randomness_Destroy(bld->r); bld->r = esl_randomness_CreateFast(seed); }   /* as p7_builder_Create makes it */
+  bld->do_reseeding = (seed != 0);
+  bld->w_len = -1; bld->w_beta = p7_DEFAULT_WINDOW_BETA;     /* what pyhmmer's Builder sets (plan7.pyx:840-849); Create(NULL, ..) leaves them unset */
+  if ((status = p7_builder_LoadScoreSystem(bld, matrix, popen, pextend, bg)) != eslOK) return status;
+  if ((status = p7_SingleBuilder(bld, sq, bg, &hmm, NULL, NULL, NULL)) != eslOK) return status;
+  if ((fp = fopen(path, "w")) == NULL) return -1;
+  p7_hmmfile_WriteASCII(fp, -1, hmm);
+  fclose(fp);
+  p7_hmm_Destroy(hmm); esl_sq_Destroy(sq); p7_builder_Destroy(bld); p7_bg_Destroy(bg); esl_alphabet_Destroy(abc);
+  return eslOK;
+}
+
+/* esl_random stream of the Mersenne Twister seeded <seed> (esl_random.c), and iid digital sequences drawn with it */
+void ref_mt_stream(unsigned seed, int n, double *out)
+{
+  ESL_RANDOMNESS *r = esl_randomness_Create(seed);
+  int i;
+  for (i = 0; i < n; i++) out[i] = esl_random(r);
+  esl_randomness_Destroy(r);
+}
+
 double ref_gumbel_surv(double x, double mu, double lambda) { return esl_gumbel_surv(x, mu, lambda); }
 double ref_exp_surv(double x, double mu, double lambda)    { return esl_exp_surv(x, mu, lambda); }
 

@@ -135,6 +135,27 @@ def scan_tables(models, codes, qname, qacc, qdesc, prefix):
     return L.ref_scan_tables(hs, len(models), d.ctypes.data, d.size - 2, enc(qname), enc(qacc) or b"", enc(qdesc) or b"", os.fsencode(prefix))
 
 
+def single_builder(alphabet_type, codes, name, path, matrix="BLOSUM62", popen=0.02, pextend=0.4, seed=42):
+    """Builder.build of one query sequence by the reference (p7_SingleBuilder), HMM written to <path> (ref_single_builder)."""
+    L = lib()
+    L.ref_single_builder.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_double,
+                                     ctypes.c_double, ctypes.c_uint, ctypes.c_char_p]
+    d = dsq_of(codes)
+    st = L.ref_single_builder(alphabet_type, d.ctypes.data, d.size - 2, name if isinstance(name, bytes) else name.encode(),
+                              matrix.encode(), popen, pextend, seed, os.fsencode(path))
+    if st != 0:
+        raise ValueError("p7_SingleBuilder failed with status %d" % st)
+
+
+def mt_stream(seed, n):
+    """The first n esl_random() values of Easel's Mersenne Twister seeded <seed>."""
+    L = lib()
+    L.ref_mt_stream.argtypes = [ctypes.c_uint, ctypes.c_int, ctypes.c_void_p]
+    out = np.zeros(n, np.float64)
+    L.ref_mt_stream(seed, n, out.ctypes.data)
+    return out
+
+
 class RefModel:
     """One HMM of a file, configured as Pipeline.search_hmm configures an HMM query."""
 

@@ -188,8 +188,8 @@ class HMM:
         def w(s):
             fh.write(s.encode() if isinstance(s, str) else s)
 
-        def prob(p):
-            return "      *" if p == 0.0 else " %8.5f" % (-math.log(p))
+        def prob(p):                                     # printprob (p7_hmmfile.c:2091): single-precision logf
+            return "      *" if p == 0.0 else (" %8.5f" % 0.0 if p == 1.0 else " %8.5f" % (-_logf(float(p))))
 
         w("HMMER3/f [3.4 | Aug 2023]\n")
         w("NAME  %s\n" % self.name)
@@ -240,6 +240,14 @@ class HMM:
             w("         " + " ".join(prob(p).strip().rjust(8) for p in self.transition_probabilities[k]) + "\n")
         w("//\n")
 
+
+def _libm_logf():
+    m = ctypes.CDLL("libm.so.6")
+    m.logf.restype, m.logf.argtypes = ctypes.c_float, [ctypes.c_float]
+    return m.logf
+
+
+_logf = _libm_logf()
 
 _BIN_MAGIC = {0xe8ededb7: "b", 0xe8ededb8: "c", 0xe8ededb9: "d", 0xe8ededb0: "e", 0xe8ededba: "f"}     # p7_hmmfile.c:47-52
 _ABC_TYPE = {"amino": 3, "dna": 2, "rna": 1}                                                           # esl_alphabet.h
