@@ -14,7 +14,7 @@ from . import plan7
 from .easel import DigitalSequenceBlock, DigitalSequence, SequenceFile
 from .plan7 import Pipeline, LongTargetsPipeline, HMM, Profile, OptimizedProfile, OptimizedProfileBlock
 
-__all__ = ["hmmsearch", "hmmscan", "nhmmer"]
+__all__ = ["hmmsearch", "hmmscan", "nhmmer", "phmmer"]
 
 _QUERY_BATCH = 256
 
@@ -112,16 +112,16 @@ def hmmscan(queries, profiles, *, cpus=0, callback=None, backend="threading", ba
 
 def nhmmer(queries, sequences, *, cpus=0, callback=None, backend="threading", builder=None, **options):
     """Search nucleotide HMM / profile queries against long nucleotide targets; yields one `TopHits` per query, in order
-    (``pyhmmer.hmmer.nhmmer``, src/pyhmmer/hmmer/_nhmmer.py).  Sequence and alignment queries need the reference's
-    `Builder` (model construction is outside this package's path) and are rejected."""
+    (``pyhmmer.hmmer.nhmmer``, src/pyhmmer/hmmer/_nhmmer.py).  `DigitalSequence` queries become single-sequence models
+    (`pyhmmer_b200.builder.Builder`); alignment queries are rejected (no alignment builder in this package)."""
     if isinstance(queries, (HMM, Profile, OptimizedProfile)):
         queries = (queries,)
     it = iter(queries)
     first = next(it, None)
     if first is None:
         return
-    if not isinstance(first, (HMM, Profile, OptimizedProfile)):
-        raise TypeError("nhmmer queries must be HMM, Profile or OptimizedProfile (building models from sequences or "
+    if not isinstance(first, (HMM, Profile, OptimizedProfile, DigitalSequence)):
+        raise TypeError("nhmmer queries must be HMM, Profile, OptimizedProfile or DigitalSequence (building models from "
                         "alignments is not part of pyhmmer_b200), found %s" % type(first).__name__)
     alphabet = first.alphabet
     block = _as_block(sequences, alphabet)
@@ -130,8 +130,38 @@ def nhmmer(queries, sequences, *, cpus=0, callback=None, backend="threading", bu
     index = 0
     import itertools
     for query in itertools.chain((first,), it):
-        hits = pipeline.search_hmm(query, block)
+        if isinstance(query, DigitalSequence):
+            hits = pipeline.search_seq(query, block, builder)
+        else:
+            hits = pipeline.search_hmm(query, block)
         if callback is not None:
             callback(query, index + 1)
         index += 1
+        yield hits
+
+
+def phmmer(queries, sequences, *, cpus=0, callback=None, backend="threading", builder=None, **options):
+    """Search protein query SEQUENCES against a sequence database; yields one `TopHits` per query, in order
+    (``pyhmmer.hmmer.phmmer``, src/pyhmmer/hmmer/_phmmer.py): every query becomes a single-sequence model
+    (`pyhmmer_b200.builder.Builder`: BLOSUM62, gap open 0.02 / extend 0.4, calibrated) and is searched like an HMM.
+    Alignment queries are rejected (no alignment builder in this package)."""
+    from .builder import Builder
+    if isinstance(queries, DigitalSequence):
+        queries = (queries,)
+    it = iter(queries)
+    first = next(it, None)
+    if first is None:
+        return
+    if not isinstance(first, DigitalSequence):
+        raise TypeError("phmmer queries must be DigitalSequence, found %s" % type(first).__name__)
+    alphabet = first.alphabet
+    block = _as_block(sequences, alphabet)
+    options.setdefault("host_threads", cpus or 0)
+    pipeline = Pipeline(alphabet, **options)
+    builder = Builder(alphabet, seed=pipeline.seed) if builder is None else builder
+    import itertools
+    for index, query in enumerate(itertools.chain((first,), it)):
+        hits = pipeline.search_seq(query, block, builder)
+        if callback is not None:
+            callback(query, index + 1)
         yield hits

@@ -2089,6 +2089,18 @@ class Pipeline:
         """Search ``sequences`` (a `DigitalSequenceBlock`) with one query; returns `TopHits` (plan7.pyx:6121-6260)."""
         return self._search_many([query], sequences)[0]
 
+    def search_seq(self, query, sequences, builder=None):
+        """Search with a query SEQUENCE (phmmer; plan7.pyx:6330-6390): a single-sequence model is built with ``builder``
+        (default: ``Builder(alphabet, seed=seed)``) and searched like any HMM; the hits remember the sequence as their query."""
+        from .builder import Builder
+        if query.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, query.alphabet)
+        builder = Builder(self.alphabet, seed=self.seed) if builder is None else builder
+        hmm, profile, opt = builder.build(query, self.background)
+        hits = self.search_hmm(opt, sequences)
+        hits.query = query
+        return hits
+
     def _search_many(self, queries, sequences):
         if not isinstance(sequences, DigitalSequenceBlock):
             raise TypeError("expected DigitalSequenceBlock, found %s" % type(sequences).__name__)
@@ -2268,6 +2280,23 @@ class LongTargetsPipeline(Pipeline):
                                 seed=self.seed, host_threads=self.host_threads, backend_factory=self._backend_factory)
         return self._long_target_tophits(query, om, sequences, res, cut)
 
+    def search_seq(self, query, sequences, builder=None):
+        """nhmmer with a query SEQUENCE (plan7.pyx:7420-7540): the model comes from a `Builder` that shares this pipeline's
+        window length / window beta."""
+        from .builder import Builder
+        if query.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, query.alphabet)
+        if builder is None:
+            builder = Builder(self.alphabet, seed=self.seed, window_length=self.window_length, window_beta=self.window_beta)
+        elif builder.window_length != self.window_length:
+            raise ValueError("builder and long targets pipeline have different window lengths")
+        elif self.window_beta is not None and builder.window_beta != self.window_beta:
+            raise ValueError("builder and long targets pipeline have different window beta")
+        hmm, profile, opt = builder.build(query, self.background)
+        hits = self.search_hmm(hmm, sequences)
+        hits.query = query
+        return hits
+
     def _long_target_tophits(self, query, om, sequences, res, cut):
         """Hits of `longtarget.search` -> thresholded `TopHits` (the tail of search_hmm, plan7.pyx:7389-7412)."""
         hits, doms, text, dup, stats = res
@@ -2300,3 +2329,10 @@ class LongTargetsPipeline(Pipeline):
         self._nseqs += stats["nseqs"]
         self._nres += stats["nres"]
         return th
+
+
+def __getattr__(name):                     # ``plan7.Builder``, as in the reference's module (defined in builder.py)
+    if name == "Builder":
+        from .builder import Builder
+        return Builder
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

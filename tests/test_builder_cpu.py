@@ -77,3 +77,58 @@ def test_generators_follow_easel():
     assert [r.random() for _ in range(5)] == list(a) and all(0.0 <= v < 1.0 for v in a)
     with pytest.raises(ValueError):
         builder.Builder(easel.Alphabet.amino(), score_matrix="PAM30")
+
+
+def test_sequence_queries_through_the_long_target_pipeline(monkeypatch, tmp_path):
+    """`LongTargetsPipeline.search_seq` / `hmmer.nhmmer` with a DigitalSequence query: the model comes from the Builder, the
+    search is the nhmmer path -- compared with the reference's nhmmer loop run on the same model (host logic; the filters of
+    the calibration and of the search come from the reference here)."""
+    import lt_common
+    from conftest import ModelPair
+    from pyhmmer_b200 import hmmer
+    dna = easel.Alphabet.dna()
+    bg = plan7.Background(dna)
+    rng = np.random.default_rng(77)
+    q = rng.integers(0, 4, 150).astype(np.uint8)
+    query = easel.DigitalSequence(dna, name="nquery", sequence=q)
+    state = {}
+
+    class RoundTripBuilder(builder.Builder):              # both sides search the model as its ASCII file holds it
+        def build(self, sequence, background):
+            inner = builder.Builder(dna, seed=self.seed, window_length=self.window_length, window_beta=self.window_beta)
+            hmm, _, _ = _build(inner, sequence, background)
+            state["pair"] = ModelPair(hmm)
+            h = state["pair"].hmm
+            prof = plan7.Profile(h.M, dna).configure(h, background, 200)
+            return h, prof, prof.to_optimized()
+
+    targets = []
+    for i, L in enumerate((50000, 20000)):
+        codes = rng.integers(0, 4, L).astype(np.uint8)
+        for _ in range(6):                                # diverged copies of the query, both strands
+            copy_ = q.copy()
+            m = rng.random(len(copy_)) < 0.15
+            copy_[m] = rng.integers(0, 4, int(m.sum()))
+            if rng.random() < 0.5:
+                copy_ = (3 - copy_[::-1]).astype(np.uint8)
+            pos = int(rng.integers(0, L - len(copy_)))
+            codes[pos:pos + len(copy_)] = copy_
+        targets.append(easel.DigitalSequence(dna, name="t%d" % i, sequence=codes))
+    block = easel.DigitalSequenceBlock(dna, targets)
+    monkeypatch.setattr(plan7._lib, "context", lambda device=None: None)
+    pli = plan7.LongTargetsPipeline(dna, block_length=20000)
+    pli._backend_factory = lambda om, blk: lt_common.OracleBackend(state["pair"], blk)
+    th = pli.search_seq(query, block, builder=RoundTripBuilder(dna))
+    pair = state["pair"]
+    rhits, rstats = pair.ref.nhmmer([s.sequence for s in block], block_length=20000, evalue_window=pair.ref.max_length(),
+                                    names=[s.name for s in block])
+    assert th.query is query and len(th) == len(rhits) >= 6
+    for h, r in zip(th, rhits):
+        d = h.domains[0]
+        assert (h.name, d.alignment.target_from, d.alignment.target_to) == (block[r.seqidx].name, r.iali, r.jali)
+        assert abs(h.score - r.score) < 2e-3 and h.reported == bool(r.flags & 2)
+    assert any(d.alignment.target_from > d.alignment.target_to for h in th for d in h.domains)      # a hit on the reverse strand
+    with pytest.raises(ValueError):
+        pli.search_seq(query, block, builder=builder.Builder(dna, window_length=500))
+    with pytest.raises(TypeError):
+        next(hmmer.phmmer([pair.hmm], block))
