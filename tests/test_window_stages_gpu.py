@@ -65,6 +65,43 @@ def test_long_windows_are_cut_at_80kb(make_pair):
     assert got["vitwin"]["length"].max() == 80000 and tot["vitwin"] >= 3
 
 
+def test_phmmer_builder_calibrates_on_the_gpu(tmp_path):
+    """`Builder.build` with its calibration filters on the device (MSV / Viterbi bit-exact, Forward to 1e-4 nats) against the
+    reference's p7_SingleBuilder: identical model lines, statistics to 5e-4; then `hmmer.phmmer` finds the planted copies.
+    (Host logic checked line for line on the CPU in tests/test_builder_cpu.py; first run on hardware at the end of round 1.)"""
+    import io
+    from oracle import refshim
+    from pyhmmer_b200 import builder, easel, hmmer
+    abc = easel.Alphabet.amino()
+    bg = plan7.Background(abc)
+    rng = np.random.default_rng(123)
+    codes = rng.integers(0, 20, 140).astype(np.uint8)
+    path = str(tmp_path / "ref.hmm")
+    refshim.single_builder(3, codes, "pq", path)
+    query = easel.DigitalSequence(abc, name="pq", sequence=codes)
+    hmm, profile, om = builder.Builder(abc).build(query, bg)
+    buf = io.BytesIO()
+    hmm.write(buf)
+    mine = [l for l in buf.getvalue().decode().splitlines() if not l.startswith("DATE")]
+    ref = [l for l in open(path).read().splitlines() if not l.startswith("DATE")]
+    stats = lambda ls: [[float(v) for v in l.split()[3:]] for l in ls if l.startswith("STATS")]
+    rest = lambda ls: [l for l in ls if not l.startswith("STATS")]
+    assert rest(mine) == rest(ref)
+    assert np.allclose(stats(mine), stats(ref), rtol=0, atol=5e-4), (stats(mine), stats(ref))
+    targets = []
+    for i in range(60):
+        t = rng.integers(0, 20, int(rng.integers(150, 600))).astype(np.uint8)
+        if i % 6 == 0:
+            c = codes.copy()
+            m = rng.random(len(c)) < 0.3
+            c[m] = rng.integers(0, 20, int(m.sum()))
+            pos = int(rng.integers(0, len(t) - len(c) + 1))
+            t[pos:pos + len(c)] = c
+        targets.append(easel.DigitalSequence(abc, name="t%d" % i, sequence=t))
+    th = next(hmmer.phmmer(query, easel.DigitalSequenceBlock(abc, targets)))
+    assert th.query is query and {h.name for h in th.included} == {"t%d" % i for i in range(0, 60, 6)}
+
+
 # The two tests below were written after the round's GPU budget was spent: their host logic is checked on the CPU
 # (tests/test_longtarget_cpu.py drives the same code with the reference's DP scores), the device call underneath
 # (b2h_longtarget_hits: Forward / Backward parser specials for the surviving windows) runs here for the first time.
@@ -105,40 +142,3 @@ def test_long_targets_pipeline_api(make_pair):
     from pyhmmer_b200 import hmmer
     again = list(hmmer.nhmmer(pair.hmm, block, block_length=20000))
     assert len(again) == 1 and [h.score for h in again[0]] == [h.score for h in th]
-
-
-def test_phmmer_builder_calibrates_on_the_gpu(tmp_path):
-    """`Builder.build` with its calibration filters on the device (MSV / Viterbi bit-exact, Forward to 1e-4 nats) against the
-    reference's p7_SingleBuilder: identical model lines, statistics to 5e-4; then `hmmer.phmmer` finds the planted copies.
-    (Host logic checked line for line on the CPU in tests/test_builder_cpu.py; first run on hardware at the end of round 1.)"""
-    import io
-    from oracle import refshim
-    from pyhmmer_b200 import builder, easel, hmmer
-    abc = easel.Alphabet.amino()
-    bg = plan7.Background(abc)
-    rng = np.random.default_rng(123)
-    codes = rng.integers(0, 20, 140).astype(np.uint8)
-    path = str(tmp_path / "ref.hmm")
-    refshim.single_builder(3, codes, "pq", path)
-    query = easel.DigitalSequence(abc, name="pq", sequence=codes)
-    hmm, profile, om = builder.Builder(abc).build(query, bg)
-    buf = io.BytesIO()
-    hmm.write(buf)
-    mine = [l for l in buf.getvalue().decode().splitlines() if not l.startswith("DATE")]
-    ref = [l for l in open(path).read().splitlines() if not l.startswith("DATE")]
-    stats = lambda ls: [[float(v) for v in l.split()[3:]] for l in ls if l.startswith("STATS")]
-    rest = lambda ls: [l for l in ls if not l.startswith("STATS")]
-    assert rest(mine) == rest(ref)
-    assert np.allclose(stats(mine), stats(ref), rtol=0, atol=5e-4), (stats(mine), stats(ref))
-    targets = []
-    for i in range(60):
-        t = rng.integers(0, 20, int(rng.integers(150, 600))).astype(np.uint8)
-        if i % 6 == 0:
-            c = codes.copy()
-            m = rng.random(len(c)) < 0.3
-            c[m] = rng.integers(0, 20, int(m.sum()))
-            pos = int(rng.integers(0, len(t) - len(c) + 1))
-            t[pos:pos + len(c)] = c
-        targets.append(easel.DigitalSequence(abc, name="t%d" % i, sequence=t))
-    th = next(hmmer.phmmer(query, easel.DigitalSequenceBlock(abc, targets)))
-    assert th.query is query and {h.name for h in th.included} == {"t%d" % i for i in range(0, 60, 6)}
