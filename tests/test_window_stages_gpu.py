@@ -51,20 +51,6 @@ def test_viterbi_landmarks_against_port_without_bias(make_pair):
         assert n > 0
 
 
-def test_long_windows_are_cut_at_80kb(make_pair):
-    pair, rng = lt_common.dna_model(make_pair, 40, mu_shift=-3.0)
-    dom = lt_common.synth.emit_sequence(pair.hmm, rng)
-    seq = np.concatenate([dom] * (200000 // len(dom))).astype(np.uint8)
-    dna = pair.hmm.alphabet
-    block = lt_common.easel.DigitalSequenceBlock(dna, [lt_common.easel.DigitalSequence(dna, name=b"rep", sequence=seq)])
-    got = longtarget.stages(pair.om, block, **KW)
-    # 80 kb of back-to-back homologs score ~1e5 nats: float32 resolves 8e-3 there and both implementations add thousands of
-    # rounded log(scale) terms, at different rows -- the Forward scores of THIS test are compared to 1e-4 relative, everything
-    # else (landmarks, windows, gates, counters) exactly as in the tests above
-    tot = lt_common.compare_with_reference(pair, block, got, exact_scores=False, fwd_rel=1e-4, **KW)
-    assert got["vitwin"]["length"].max() == 80000 and tot["vitwin"] >= 3
-
-
 def test_phmmer_builder_calibrates_on_the_gpu(tmp_path):
     """`Builder.build` with its calibration filters on the device (MSV / Viterbi bit-exact, Forward to 1e-4 nats) against the
     reference's p7_SingleBuilder: identical model lines, statistics to 5e-4; then `hmmer.phmmer` finds the planted copies.
@@ -100,6 +86,20 @@ def test_phmmer_builder_calibrates_on_the_gpu(tmp_path):
         targets.append(easel.DigitalSequence(abc, name="t%d" % i, sequence=t))
     th = next(hmmer.phmmer(query, easel.DigitalSequenceBlock(abc, targets)))
     assert th.query is query and {h.name for h in th.included} == {"t%d" % i for i in range(0, 60, 6)}
+
+
+def test_long_windows_are_cut_at_80kb(make_pair):
+    pair, rng = lt_common.dna_model(make_pair, 40, mu_shift=-3.0)
+    dom = lt_common.synth.emit_sequence(pair.hmm, rng)
+    seq = np.concatenate([dom] * (200000 // len(dom))).astype(np.uint8)
+    dna = pair.hmm.alphabet
+    block = lt_common.easel.DigitalSequenceBlock(dna, [lt_common.easel.DigitalSequence(dna, name=b"rep", sequence=seq)])
+    got = longtarget.stages(pair.om, block, **KW)
+    # 80 kb of back-to-back homologs score ~1e5 nats: float32 resolves 8e-3 there and both implementations add thousands of
+    # rounded log(scale) terms, at different rows -- the Forward scores of THIS test are compared to 1e-4 relative, everything
+    # else (landmarks, windows, gates, counters) exactly as in the tests above
+    tot = lt_common.compare_with_reference(pair, block, got, exact_scores=False, fwd_rel=1e-4, **KW)
+    assert got["vitwin"]["length"].max() == 80000 and tot["vitwin"] >= 3
 
 
 # The two tests below were written after the round's GPU budget was spent: their host logic is checked on the CPU
