@@ -132,3 +132,38 @@ def test_sequence_queries_through_the_long_target_pipeline(monkeypatch, tmp_path
         pli.search_seq(query, block, builder=builder.Builder(dna, window_length=500))
     with pytest.raises(TypeError):
         next(hmmer.phmmer([pair.hmm], block))
+
+
+def test_search_seq_glue_without_a_device(monkeypatch):
+    """`Pipeline.search_seq`: the query goes through the Builder and its OptimizedProfile reaches the search call; the hits
+    keep the SEQUENCE as their query (the device search itself is replaced by an empty result here)."""
+    abc = easel.Alphabet.amino()
+    bg = plan7.Background(abc)
+    rng = np.random.default_rng(9)
+    query = easel.DigitalSequence(abc, name="sq", sequence=rng.integers(0, 20, 60).astype(np.uint8))
+    block = easel.DigitalSequenceBlock(abc, [easel.DigitalSequence(abc, name="t", sequence=rng.integers(0, 20, 90).astype(np.uint8))])
+    seen = {}
+
+    def fake_run(self, oms, blk):
+        seen["oms"] = oms
+        return [], [], b"", np.zeros((len(oms), 4), np.int64)
+
+    monkeypatch.setattr(plan7._lib, "context", lambda device=None: None)
+    monkeypatch.setattr(plan7.Pipeline, "_run", fake_run)
+    pli = plan7.Pipeline(abc, background=bg)
+    b = builder.Builder(abc)
+    state = {}
+    b._scorer = _reference_scorer(state)
+    calibrate = b.calibrate
+
+    def hooked(hmm, background):
+        state["hmm"] = hmm
+        hmm._evparam[:] = np.array([-8, .7, -9, .7, -4, .7], np.float32)
+        return calibrate(hmm, background)
+    b.calibrate = hooked
+    th = pli.search_seq(query, block, builder=b)
+    assert th.query is query and len(th) == 0 and th.searched_sequences == 1
+    om = seen["oms"][0]
+    assert isinstance(om, plan7.OptimizedProfile) and om.M == 60 and om.name == "sq" and om._evparam[0] != plan7.P7_EVPARAM_UNSET
+    with pytest.raises(plan7.AlphabetMismatch):
+        pli.search_seq(easel.DigitalSequence(easel.Alphabet.dna(), name="d", sequence=np.zeros(5, np.uint8)), block)
