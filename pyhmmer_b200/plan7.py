@@ -1934,6 +1934,7 @@ class TopHits:
         """``TopHits.merge`` (plan7.pyx:9172-9273): combine hits of target-sharded searches of one query."""
         merged = TopHits(self.query, self.mode)
         merged._params = dict(self._params)
+        merged.long_targets = self.long_targets
         parts = (self,) + others
         for part in parts:
             for h in part._hits:
