@@ -110,7 +110,17 @@ _DNA1 = """
 SCORE_MATRICES = {"BLOSUM62": np.array(_BLOSUM62.split(), np.int64).reshape(20, 20), "DNA1": np.array(_DNA1.split(), np.int64).reshape(4, 4)}
 
 
+_Q_CACHE = {}
+
+
 def conditional_probabilities(alphabet, matrix, f):
+    key = (alphabet.type, matrix, np.asarray(f, np.float32).tobytes())
+    if key not in _Q_CACHE:
+        _Q_CACHE[key] = _conditional_probabilities(alphabet, matrix, f)
+    return _Q_CACHE[key]
+
+
+def _conditional_probabilities(alphabet, matrix, f):
     """P(b | a) for every query residue code a (degenerate ones included) from a score matrix and background f:
     esl_scorematrix_ProbifyGivenBG (lambda by Newton/Raphson from the far side, esl_scorematrix.c) followed by
     esl_scorematrix_JointToConditionalOnQuery.  Returns a [Kp, K] float64 array."""
@@ -188,18 +198,29 @@ class FastRandomness:
     def reinit(self):
         self._x = self._mix3(self.seed & 0xffffffff, 87654321, 12345678) or 42
 
+    _A = np.array([1], np.uint64)                         # a^k and (a^k - 1) / (a - 1) mod 2^32, grown by doubling:
+    _C = np.array([0], np.uint64)                         # x_k = A_k x_0 + C_k
+
+    @classmethod
+    def _tables(cls, n):
+        m32 = np.uint64(0xffffffff)
+        while len(cls._A) <= n:
+            m = len(cls._A)
+            Am = (cls._A[m - 1] * np.uint64(69069)) & m32                     # a^m
+            Cm = (cls._C[m - 1] * np.uint64(69069) + np.uint64(1)) & m32     # C_m
+            cls._A = np.concatenate([cls._A, (cls._A * Am) & m32])           # A_{m+i} = A_m A_i
+            cls._C = np.concatenate([cls._C, (cls._A[:m] * Cm + cls._C) & m32])   # C_{m+i} = A_i C_m + C_i
+        return cls._A, cls._C
+
     def random(self, n=None):
         if n is None:
             self._x = (self._x * 69069 + 1) & 0xffffffff
             return self._x / 4294967296.0
-        # x_k = a^k x_0 + (a^k - 1) / (a - 1): n steps at once through the 32-bit powers of the multiplier
-        out = np.empty(n, np.uint64)
-        x = self._x
-        for k in range(n):
-            x = (x * 69069 + 1) & 0xffffffff
-            out[k] = x
-        self._x = x
-        return out.astype(np.float64) / 4294967296.0
+        A, C = self._tables(n)
+        x = (A[1:n + 1] * np.uint64(self._x) + C[1:n + 1]) & np.uint64(0xffffffff)
+        if n:
+            self._x = int(x[-1])
+        return x.astype(np.float64) / 4294967296.0
 
     iid = Randomness.iid
 
