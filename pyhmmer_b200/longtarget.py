@@ -324,7 +324,7 @@ def target_windows(lengths, W, C, strand=None):
 
 def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True, B1=100, B2=240, B3=1000,
            block_length=0x40000, strand=None, seed=42, host_threads=0, backend_factory=None, evalue_window=None, world=None,
-           timings=None):
+           timings=None, evalue_residues=None):
     """nhmmer for one profile: every target of ``sequences`` in windows, on both strands (or one), through `stages`
     and the hit stage; then p7_tophits_ComputeNhmmerEvalues, the seqidx / position sort, p7_tophits_RemoveDuplicates
     (p7_tophits.c:796, 426, 823).  Returns (hits, doms, text, duplicate flags, stats) with the hits in target order;
@@ -363,7 +363,8 @@ def search(om, sequences, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=Tru
     if not hits:
         return _lib.RecList(), _lib.RecList(), b"", [], stats
     # p7_tophits_ComputeNhmmerEvalues: the search space is residues / window length
-    add = math.log(float(np.float32(stats["nres"])) / float(np.float32(evalue_window or max_length)))
+    # (a user-set Z replaces the residues searched by 1e6 Z per strand, plan7.pyx:7389-7396)
+    add = math.log(float(np.float32(evalue_residues if evalue_residues is not None else stats["nres"])) / float(np.float32(evalue_window or max_length)))
     for h in hits:
         h.lnP += add
         doms[h.dom_offset].lnP = h.lnP

@@ -2276,7 +2276,10 @@ class LongTargetsPipeline(Pipeline):
             raise ValueError("block length (%d) must be greater than the model's window length (%d)" % (self.block_length, int(om._desc.max_length)))
         cut = self._cutoffs(om)
         self._evalue_window = max_length
-        res = longtarget.search(om, sequences, evalue_window=max_length, F1=self.F1, F2=self.F2, F3=self.F3, bias_filter=self.bias_filter, null2=self.null2,
+        residues = None
+        if self.Z is not None:                               # Z counts megabases per strand (plan7.pyx:7389-7396)
+            residues = int(1000000 * self.Z) * (2 if self.strand is None else 1)
+        res = longtarget.search(om, sequences, evalue_window=max_length, evalue_residues=residues, F1=self.F1, F2=self.F2, F3=self.F3, bias_filter=self.bias_filter, null2=self.null2,
                                 B1=self.B1, B2=self.B2, B3=self.B3, block_length=self.block_length, strand=self.strand,
                                 seed=self.seed, host_threads=self.host_threads, backend_factory=self._backend_factory)
         return self._long_target_tophits(query, om, sequences, res, cut)

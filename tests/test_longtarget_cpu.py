@@ -234,6 +234,13 @@ def test_long_targets_pipeline_front_end(monkeypatch, tmp_path, strand, E):
         buf = io.BytesIO()
         th.write(buf, format=fmt)
         assert buf.getvalue() == open(str(tmp_path / "ref") + ext, "rb").read(), (fmt, buf.getvalue()[:800])
+    # a user-set Z replaces the residues searched by 1e6 Z per strand in the E-values
+    pz = plan7.LongTargetsPipeline(pair.hmm.alphabet, strand=strand, block_length=20000, E=E, incE=E / 100, Z=3.0)
+    pz._backend_factory = pli._backend_factory
+    tz = pz.search_hmm(pair.hmm, block)
+    shift = math.log(3e6 * (2 if strand is None else 1) / th.searched_residues)
+    byname = {(h.name, h.domains[0].env_from): h for h in th}
+    assert len(tz) == len(th) and all(abs((h.lnP - byname[(h.name, h.domains[0].env_from)].lnP) - shift) < 1e-5 for h in tz)
     with pytest.raises(ValueError):
         plan7.LongTargetsPipeline(plan7.Alphabet.amino())
     with pytest.raises(ValueError):
