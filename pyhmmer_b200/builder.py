@@ -270,33 +270,8 @@ class Builder:
         t[:, 3], t[:, 4], t[:, 5], t[:, 6] = f32(1.0 - self.pextend), f32(self.pextend), f32(1.0 - self.pextend), f32(self.pextend)
         t[M, 0], t[M, 2], t[M, 5], t[M, 6] = f32(1.0 - self.popen), 0.0, 1.0, 0.0
         hmm.nseq, hmm.command_line, hmm.creation_time = 1, "[HMM created from a query sequence]", time.asctime()
-        # p7_hmm_SetComposition (p7_hmm.c): occupancy-weighted mean of the emission distributions
-        mocc, iocc = np.zeros(M + 1, f32), np.zeros(M + 1, f32)
-        mocc[1] = f32(t[0, 1] + t[0, 0])
-        for k in range(2, M + 1):
-            mocc[k] = f32(np.float64(f32(mocc[k - 1] * f32(t[k - 1, 0] + t[k - 1, 1]))) + (1.0 - np.float64(mocc[k - 1])) * np.float64(t[k - 1, 5]))
-        iocc[0] = f32(t[0, 1] / t[0, 3])
-        for k in range(1, M + 1):
-            iocc[k] = f32(f32(mocc[k] * t[k, 1]) / t[k, 3])
-        compo = np.zeros(K, f32)
-        compo += hmm.insert_emissions[0] * iocc[0]
-        for k in range(1, M + 1):
-            compo += hmm.match_emissions[k] * mocc[k]
-            compo += hmm.insert_emissions[k] * iocc[k]
-        s = f32(0.0)
-        c = f32(0.0)
-        for v in compo:                                   # esl_vec_FNorm over a compensated sum
-            y = f32(v - c)
-            tt = f32(s + y)
-            c = f32(f32(tt - s) - y)
-            s = tt
-        hmm._compo[:] = 0.0
-        hmm._compo[:K] = compo / s
-        # p7_hmm_SetConsensus: the query itself, upper case where its own emission probability reaches the threshold
-        thresh = 0.9 if K == 4 else 0.5
-        sym = abc.symbols
-        hmm.consensus = "".join((sym[x].upper() if hmm.match_emissions[k + 1, x] >= thresh else sym[x].lower()) if x < K
-                                else sym[x].lower() for k, x in enumerate(codes))
+        hmm.set_composition()
+        hmm.set_consensus(sequence)
         self.calibrate(hmm, background)
         if K == 4:
             if self.window_length:
@@ -332,14 +307,7 @@ class Builder:
         if self.seed != 0:
             r.reinit()                                    # do_reseeding: the same random sequences for every model
         LOG2 = 0.69314718055994529
-        KL = 0.0
-        for k in range(1, hmm.M + 1):                     # p7_MeanMatchRelativeEntropy: float sums of p log2(p/q) per node
-            kl = np.float32(0.0)
-            for p, q in zip(hmm.match_emissions[k], bgf[:K]):
-                if p > 0:
-                    kl = np.float32(np.float64(kl) + np.float64(p) * math.log2(float(np.float32(p / q))))
-            KL += float(kl)
-        lam = LOG2 + 1.44 / (float(hmm.M) * (KL / float(hmm.M)))
+        lam = LOG2 + 1.44 / (float(hmm.M) * hmm.mean_match_relative_entropy(background))     # p7_Lambda
         om = plan7.Profile(hmm.M, abc).configure(hmm, background, self.EvL).to_optimized()
         scorer = self._scorer or self._gpu_scores
         mus = []

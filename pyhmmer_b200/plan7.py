@@ -170,6 +170,72 @@ class HMM:
         compo /= compo.sum()
         self._compo[:K] = compo.astype(np.float32)
 
+    def to_profile(self, background=None, L=400, multihit=True, local=True):
+        """``HMM.to_profile`` (plan7.pyx:3329): a `Profile` configured for target length ``L``."""
+        return Profile(self.M, self.alphabet).configure(self, background if background is not None else Background(self.alphabet),
+                                                        L, multihit, local)
+
+    def match_occupancy(self, inserts=False):
+        """``HMM.match_occupancy`` = p7_hmm_CalculateOccupancy (p7_hmm.c:1338): the probability that a path visits each
+        match state (index 0 unused), in the reference's float arithmetic; with ``inserts`` also the expected number of
+        residues each insert state emits."""
+        f32, f64 = np.float32, np.float64
+        t, M = self.transition_probabilities, self.M
+        mocc, iocc = np.zeros(M + 1, f32), np.zeros(M + 1, f32)
+        mocc[1] = f32(t[0, 1] + t[0, 0])
+        for k in range(2, M + 1):
+            mocc[k] = f32(f64(f32(mocc[k - 1] * f32(t[k - 1, 0] + t[k - 1, 1]))) + (1.0 - f64(mocc[k - 1])) * f64(t[k - 1, 5]))
+        if not inserts:
+            return mocc
+        iocc[0] = f32(t[0, 1] / t[0, 3])
+        for k in range(1, M + 1):
+            iocc[k] = f32(f32(mocc[k] * t[k, 1]) / t[k, 3])
+        return mocc, iocc
+
+    def set_composition(self):
+        """``HMM.set_composition`` = p7_hmm_SetComposition (p7_hmm.c:1391): the occupancy-weighted mean emission distribution."""
+        f32 = np.float32
+        K = self.alphabet.K
+        mocc, iocc = self.match_occupancy(inserts=True)
+        compo = np.zeros(K, f32)
+        compo += self.insert_emissions[0] * iocc[0]
+        for k in range(1, self.M + 1):
+            compo += self.match_emissions[k] * mocc[k]
+            compo += self.insert_emissions[k] * iocc[k]
+        s = c = f32(0.0)
+        for v in compo:                                   # esl_vec_FNorm over a compensated sum
+            y = f32(v - c)
+            tt = f32(s + y)
+            c = f32(f32(tt - s) - y)
+            s = tt
+        self._compo[:] = 0.0
+        self._compo[:K] = compo / s
+
+    def set_consensus(self, sequence=None):
+        """``HMM.set_consensus`` = p7_hmm_SetConsensus (p7_hmm.c:1449): the most probable residue per node (or the residues of
+        ``sequence``), upper case where its emission probability reaches 0.5 (0.9 for nucleotides)."""
+        K, sym = self.alphabet.K, self.alphabet.symbols
+        thresh = 0.9 if K == 4 else 0.5
+        codes = np.asarray(sequence.sequence) if sequence is not None else self.match_emissions[1:, :K].argmax(axis=1)
+        if len(codes) != self.M:
+            raise ValueError("sequence length differs from the model length")
+        # (a degenerate residue of the query has no emission probability of its own: lower case)
+        self.consensus = "".join(sym[x].upper() if x < K and self.match_emissions[k + 1, x] >= thresh else sym[x].lower()
+                                 for k, x in enumerate(codes))
+
+    def mean_match_relative_entropy(self, background):
+        """``HMM.mean_match_relative_entropy`` = p7_MeanMatchRelativeEntropy (modelstats.c:95), in bits."""
+        K = self.alphabet.K
+        bgf = np.asarray(background.residue_frequencies, np.float32)
+        KL = 0.0
+        for k in range(1, self.M + 1):                    # esl_vec_FRelEntropy: a float sum of p log2(p/q) per node
+            kl = np.float32(0.0)
+            for p, q in zip(self.match_emissions[k], bgf[:K]):
+                if p > 0:
+                    kl = np.float32(np.float64(kl) + np.float64(p) * math.log2(float(np.float32(p / q))))
+            KL += float(kl)
+        return KL / float(self.M)
+
     def compute_max_length(self, beta=1e-7):
         """``p7_Builder_MaxLength`` (p7_builder.c:651): the window length beyond which the model emits less than ``beta``
         of its probability mass -- what hmmbuild stores as MAXL and nhmmer recomputes for ``--w_beta``."""
