@@ -846,3 +846,23 @@ def test_scan_tables_match_the_reference_writers(amino, tmp_path, monkeypatch):
         th.write(buf, format=fmt)
         want = open(prefix + ext, "rb").read()
         assert buf.getvalue() == want, (fmt, buf.getvalue()[:900], want[:900])
+
+
+@pytest.mark.parametrize("name", ["PF02826", "Thioesterase", "LuxC"])
+def test_model_statistics_reproduce_what_hmmbuild_stored(amino, name):
+    """`HMM.set_composition` / `set_consensus` recompute the COMPO line and the consensus annotation hmmbuild wrote into the
+    reference's own model files (p7_hmm_SetComposition, p7_hmm_SetConsensus), to the precision of the file."""
+    with gzip.open(os.path.join(GOLD, "data", name + ".hmm.gz")) as f:
+        hmm = plan7.HMMFile(f).read()
+    stored_compo, stored_cons = hmm._compo.copy(), hmm.consensus
+    hmm.set_composition()
+    hmm.set_consensus()
+    if stored_compo[:20].any():                          # (a model file may come without a COMPO line)
+        assert np.allclose(-np.log(hmm._compo[:20]), -np.log(stored_compo[:20]), atol=2e-5, rtol=0)
+    else:
+        assert abs(float(hmm._compo[:20].sum()) - 1.0) < 1e-5
+    same = sum(a == b for a, b in zip(hmm.consensus, stored_cons))
+    assert len(hmm.consensus) == hmm.M and same >= hmm.M - 2          # (a probability at the 0.5 threshold may round either way in the file)
+    occ = hmm.match_occupancy()
+    assert occ.shape == (hmm.M + 1,) and occ[0] == 0 and np.all((occ[1:] > 0) & (occ[1:] <= 1.0 + 1e-6))
+    assert hmm.to_profile(L=123).L == 123 and 0.1 < hmm.mean_match_relative_entropy(plan7.Background(amino)) < 5.0
