@@ -38,26 +38,20 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 N_PROFILES = 100
 N_SEQS = 50000
 PLANT_FRAC = 0.01
+# one string for both arms (the driver compares the two lines' config.workload)
+WORKLOAD = ("hmmsearch: 100 Pfam-like profiles (M~200) vs 50k synthetic proteins on 1xB200 (BASELINE configs[1]); "
+            "per-rank shard of 50k targets at N>1")
 
 
 def build_inputs(rank, world, n_profiles=N_PROFILES, n_seqs=N_SEQS):
-    """Seeded synthetic inputs.  Profiles are identical on every rank; each rank gets its own target shard."""
-    from pyhmmer_b200 import easel, synth
+    """Seeded synthetic inputs (bench_inputs.c2_inputs) as package objects.  Profiles are identical on every rank; each
+    rank gets its own target shard."""
+    import bench_inputs
+    from pyhmmer_b200 import easel
     abc = easel.Alphabet.amino()
-    prng = np.random.default_rng(20240901)
-    Ms = np.clip(np.rint(np.exp(prng.normal(np.log(180.0), 0.55, n_profiles))), 30, 800).astype(int)
-    hmms = [synth.random_hmm(abc, int(M), prng, name="synPF%05d" % i) for i, M in enumerate(Ms)]
-    srng = np.random.default_rng(777 + rank)
-    seqs = synth.random_sequences(abc, n_seqs, srng, prefix="r%d_" % rank)
-    nplant = int(n_seqs * PLANT_FRAC)
-    where = srng.choice(n_seqs, nplant, replace=False)
-    for j, t in enumerate(where):
-        dom = synth.emit_sequence(hmms[j % n_profiles], srng)
-        s = seqs[int(t)]
-        cut = int(srng.integers(0, len(s) + 1))
-        s.sequence = np.concatenate([s.sequence[:cut], dom, s.sequence[cut:]])[:1500]
-    seqs._cache = {}
-    return abc, hmms, seqs
+    models, seqs, _ = bench_inputs.c2_inputs(rank, n_profiles, n_seqs)
+    hmms = bench_inputs.to_hmms(models, abc)
+    return abc, hmms, bench_inputs.to_block(seqs, abc, prefix="r%d_" % rank)
 
 
 STATS_FILE = os.path.join(ROOT, "tests", "golden", "bench_stats.json")
@@ -125,27 +119,28 @@ def peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def time_reference(hmms, seqs, sample_p, sample_s, warmup, steps):
+def time_reference(models, seqs, sample_p, sample_s, warmup, steps):
     """Time oracle/_ref (HMMER 3.4 built from the reference's sources) on the host cores: every step is the whole
     p7_Pipeline over sample_p profiles x sample_s sequences, work-queue threaded.  Both thread counts (physical
-    cores, logical CPUs) are tried and the faster one is reported, so the reference gets its best configuration."""
+    cores, logical CPUs) are tried and the faster one is reported, so the reference gets its best configuration.
+    <models> / <seqs> are bench_inputs arrays: nothing of pyhmmer_b200 is touched on this path."""
+    import bench_inputs
     from oracle import refshim
     import psutil
     logical = psutil.cpu_count(logical=True) or os.cpu_count() or 1
     physical = psutil.cpu_count(logical=False) or logical
-    sub = seqs[:sample_s]
+    codes = seqs[:sample_s]
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "q.hmm")
-        write_hmm_file(hmms[:sample_p], path)
-        models = [refshim.RefModel(path, i, 400) for i in range(sample_p)]
-        codes = [s.sequence for s in sub]
-        cells = float(sum(h.M for h in hmms[:sample_p])) * float(sum(len(s) for s in sub))
+        bench_inputs.write_hmm_file(models[:sample_p], path)       # the same HMMER3 ASCII text the product arm reads
+        refs = [refshim.RefModel(path, i, 400) for i in range(sample_p)]
+        cells = float(sum(m["M"] for m in models[:sample_p])) * float(sum(len(s) for s in codes))
         best = None
         for ncore in sorted({max(1, min(physical, 256)), max(1, min(logical, 256))}):
             times = []
             for it in range(warmup + steps):
                 t0 = time.perf_counter()
-                nh, ctr = refshim.search_mt(models, codes, ncore)
+                nh, ctr = refshim.search_mt(refs, codes, ncore)
                 dt = time.perf_counter() - t0
                 if it >= warmup:
                     times.append(dt)
@@ -159,13 +154,14 @@ def time_reference(hmms, seqs, sample_p, sample_s, warmup, steps):
 
 def reference_arm(args, rank, world_size):
     """The reference's own CPU implementation of the path (oracle/_ref = HMMER 3.4 compiled from the reference's
-    sources), all host threads, on the same workload (all 100 profiles x 50k sequences per step by default)."""
+    sources), all host threads, on the same workload (all 100 profiles x 50k sequences per step by default).  The inputs
+    come from bench_inputs (numpy only): this arm never imports pyhmmer_b200 and never loads libb2h.so."""
     if rank != 0:
         return
-    abc, hmms, seqs = build_inputs(0, 1)
-    calibrated = apply_stats(hmms)
+    import bench_inputs
+    models, seqs, calibrated = bench_inputs.c2_inputs(0)
     sample_p, sample_s = args.ref_profiles, min(args.ref_seqs, len(seqs))
-    r = time_reference(hmms, seqs, sample_p, sample_s, args.warmup, args.steps)
+    r = time_reference(models, seqs, sample_p, sample_s, args.warmup, args.steps)
     gcups, tot, n = r["gcups"], r["tot"], r["n"]
     sample = "%d profiles x %d of the %d sequences per step (same generator, seed, planted homologs), %.2f s/step on %d threads; %s" % (
         sample_p, sample_s, N_SEQS, tot / n, r["cores"], "committed GPU-fitted statistics" if calibrated else "placeholder statistics")
@@ -174,7 +170,7 @@ def reference_arm(args, rank, world_size):
         "steps": n, "warmup": args.warmup, "ms_per_step": 1e3 * tot / n, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "seqs_per_s": sample_s * sample_p * n / tot,
-        "config": {"workload": "hmmsearch: 100 Pfam-like profiles (M~200) vs 50k synthetic proteins (BASELINE configs[1]); reference CPU pipeline (HMMER 3.4 SSE2, work-queue threads)",
+        "config": {"workload": WORKLOAD, "arm": "reference CPU pipeline (HMMER 3.4 SSE2 from the reference's sources, work-queue threads)",
                    "profiles": sample_p, "sequences": sample_s, "hits": r["hits"], "pipeline_counters": r["counters"]},
         "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": r["cores"], "kind": "reference", "sample": sample},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -371,8 +367,7 @@ def main():
         "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "seqs_per_s": comps_all * K / (tot_ms * 1e-3),
-        "config": {"workload": "hmmsearch: 100 Pfam-like profiles (M~200) vs 50k synthetic proteins on 1xB200 (BASELINE configs[1]); "
-                               "per-rank shard of 50k targets at N>1",
+        "config": {"workload": WORKLOAD, "arm": "pyhmmer_b200 CUDA engine",
                    "profiles": len(hmms), "sequences_per_rank": len(seqs), "sum_M": int(sum(h.M for h in hmms)),
                    "residues_per_rank": int(seqs.total_residues), "planted_homolog_fraction": PLANT_FRAC,
                    "l2": "flushed (256 MiB write) between steps", "sharding": "targets by rank, one all-gather of hit records",
@@ -395,7 +390,8 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         try:
             sp, ss = 100, len(seqs)
-            r = time_reference(hmms, seqs, sp, ss, 1, 3)
+            import bench_inputs
+            r = time_reference(bench_inputs.c2_inputs(rank)[0], [q.sequence for q in seqs], sp, ss, 1, 3)
             line["cpu_baseline"] = {"value": r["gcups"], "unit": "GCUPS", "cores": r["cores"], "kind": "reference",
                                     "sample": "%d profiles x all %d sequences (the whole step), mean of 3 passes after 1 warm-up, %.2f s/pass on %d threads (best of physical/logical core counts); oracle/_ref = HMMER 3.4 SSE2 built from the reference sources" % (sp, ss, r["tot"] / r["n"], r["cores"]),
                                     "pipeline_counters": r["counters"], "hits": r["hits"]}

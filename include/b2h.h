@@ -215,6 +215,9 @@ typedef struct {
   int32_t  do_null2;          /* pli->do_null2                                                       */
   uint32_t seed;              /* RNG seed for stochastic traceback clustering (42)                   */
   int32_t  host_threads;      /* worker threads for the host-side domain definition (0 = all cores) */
+  int32_t  seq_counters;      /* 1: also count the pass counters per SEQUENCE (b2h_results_seq_counters): what every
+                                 scan_seq result of a multi-query hmmscan reports (plan7.pyx:6534-6677)      */
+  int32_t  reserved;
 } b2h_search_params;
 
 typedef struct {              /* mirrors P7_HIT (hmmer.h:711-743) without strings */
@@ -249,6 +252,8 @@ const b2h_domain *b2h_results_domains (const b2h_results *r);
 const char       *b2h_results_text    (const b2h_results *r, size_t *nbytes);
 /* [P][4] = n_past_msv, n_past_bias, n_past_vit, n_past_fwd per profile (P7_PIPELINE counters, hmmer.h:1228-1241) */
 const int64_t    *b2h_results_counters(const b2h_results *r);
+/* [N][4] the same four counters per sequence of the database (summed over the profiles); NULL unless params.seq_counters */
+const int64_t    *b2h_results_seq_counters(const b2h_results *r);
 void              b2h_results_destroy (b2h_results *r);
 
 /* Diagnostic (used by the CPU-only tests of the host-side domain definition): build a profile object

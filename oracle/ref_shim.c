@@ -935,3 +935,255 @@ long ref_search_mt(REFM **models, int nmodels, const uint8_t *const *dsq, const 
   free(th); free(jobs); free(next);
   return nhits;
 }
+
+/* =====================================================================================
+ * Round 2 additions: models from arrays, hmmscan with full results, threaded timing runs
+ * for hmmscan (BASELINE configs[3]) and nhmmer (configs[4]).
+ * ===================================================================================== */
+
+/* A model built from probability arrays instead of a file: what `HMM(alphabet, M, name)` + array assignment gives a pyhmmer
+ * user (plan7.pyx:2130-2200), then configured like refm_read.  t [(M+1)*7] MM MI MD IM II DM DD, mat / ins [(M+1)*K],
+ * compo [K] (NULL: p7_hmm_SetComposition), consensus [M] characters (NULL: p7_hmm_SetConsensus(hmm, NULL)), evparam [6]. */
+REFM *refm_from_arrays(int abc_type, int M, const float *t, const float *mat, const float *ins, const float *compo,
+                       const float *evparam, int max_length, const char *name, const char *consensus, int L)
+{
+  REFM *m = calloc(1, sizeof(REFM));
+  int k, x;
+  ref_init();
+  m->abc = esl_alphabet_Create(abc_type);
+  m->hmm = p7_hmm_Create(M, m->abc);
+  for (k = 0; k <= M; k++) {
+    for (x = 0; x < 7; x++)        m->hmm->t[k][x]   = t[k * 7 + x];
+    for (x = 0; x < m->abc->K; x++) { m->hmm->mat[k][x] = mat[k * m->abc->K + x]; m->hmm->ins[k][x] = ins[k * m->abc->K + x]; }
+  }
+  p7_hmm_SetName(m->hmm, (char *)name);
+  if (compo) { for (x = 0; x < m->abc->K; x++) m->hmm->compo[x] = compo[x]; m->hmm->flags |= p7H_COMPO; }
+  else p7_hmm_SetComposition(m->hmm);
+  if (consensus) {
+    m->hmm->consensus = malloc(M + 2);
+    m->hmm->consensus[0] = ' '; memcpy(m->hmm->consensus + 1, consensus, M); m->hmm->consensus[M + 1] = '\0';
+    m->hmm->flags |= p7H_CONS;
+  } else p7_hmm_SetConsensus(m->hmm, NULL);
+  for (x = 0; x < p7_NEVPARAM; x++) m->hmm->evparam[x] = evparam[x];
+  m->hmm->flags |= p7H_STATS;
+  m->hmm->max_length = max_length;
+  m->hmm->nseq = 1; m->hmm->eff_nseq = 1.0f;
+  m->bg = p7_bg_Create(m->abc);
+  m->gm = p7_profile_Create(M, m->abc);
+  m->om = p7_oprofile_Create(M, m->abc);
+  p7_ProfileConfig(m->hmm, m->bg, m->gm, L, p7_LOCAL);
+  p7_oprofile_Convert(m->gm, m->om);
+  m->ox  = p7_omx_Create(M, 0, 400);
+  m->oxb = p7_omx_Create(M, 0, 400);
+  return m;
+}
+
+/* the same for n models on <nthreads> threads (the conversion costs ~0.5 ms per model): arrays concatenated model after
+ * model, Ms[n]; compo [n][K] or NULL; names = n NUL-terminated strings back to back; max_length [n] or NULL; out[n]
+ * receives the handles */
+typedef struct { int abc_type, n, L; const int *Ms; const long *off; const float *t, *mat, *ins, *compo, *evparam; const char *cons;
+                 const char *const *names; const int *maxl; REFM **out; int *next; } FA_JOB;
+static void *fa_worker(void *arg)
+{
+  FA_JOB *j = (FA_JOB *)arg;
+  int K = (j->abc_type == eslAMINO) ? 20 : 4, i;
+  for (i = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED); i < j->n; i = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED)) {
+    long o = j->off[i];                       /* sum of (M+1) of the models before i */
+    j->out[i] = refm_from_arrays(j->abc_type, j->Ms[i], j->t + o * 7, j->mat + o * K, j->ins + o * K, j->compo ? j->compo + (long)i * K : NULL,
+                                 j->evparam + (long)i * 6, j->maxl ? j->maxl[i] : 0, j->names[i], j->cons ? j->cons + (o - i) : NULL, j->L);
+  }
+  return NULL;
+}
+int refm_from_arrays_many(int abc_type, int n, const int *Ms, const float *t, const float *mat, const float *ins, const float *compo,
+                          const float *evparam, const char *cons, const char *names, const int *max_length, int L, int nthreads, REFM **out)
+{
+  long *off = malloc(sizeof(long) * (n + 1));
+  const char **nm = malloc(sizeof(char *) * (n + 1));
+  pthread_t *th = malloc(sizeof(pthread_t) * nthreads);
+  FA_JOB job; int next = 0, i;
+  ref_init();
+  off[0] = 0; for (i = 0; i < n; i++) off[i + 1] = off[i] + Ms[i] + 1;
+  for (i = 0; i < n; i++) { nm[i] = names; names += strlen(names) + 1; }
+  job.abc_type = abc_type; job.n = n; job.L = L; job.Ms = Ms; job.off = off; job.t = t; job.mat = mat; job.ins = ins; job.compo = compo;
+  job.evparam = evparam; job.cons = cons; job.names = nm; job.maxl = max_length; job.out = out; job.next = &next;
+  for (i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, fa_worker, &job);
+  for (i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+  free(th); free(off); free(nm);
+  return n;
+}
+
+/* hmmscan of ONE sequence against a list of models as pyhmmer runs it (Pipeline._scan_loop, plan7.pyx:6625-6677), reporting
+ * thresholds opened wide so that every comparison p7_Pipeline scores to completion comes back; hit.seq = index of the MODEL. */
+REF_RESULT *ref_scan(REFM **models, int nmodels, const uint8_t *dsq, long len,
+                     double F1, double F2, double F3, int do_bias, int do_null2, unsigned seed)
+{
+  REF_RESULT  *r   = calloc(1, sizeof(REF_RESULT));
+  P7_PIPELINE *pli = p7_pipeline_Create(NULL, 100, (int)len, FALSE, p7_SCAN_MODELS);
+  P7_TOPHITS  *th  = p7_tophits_Create();
+  ESL_SQ *sq = esl_sq_CreateDigitalFrom(models[0]->abc, "query", dsq, len, NULL, NULL, NULL);
+  int *idx = malloc(sizeof(int) * (nmodels + 1));
+  int t;
+  pli->F1 = F1; pli->F2 = F2; pli->F3 = F3;
+  pli->do_biasfilter = do_bias; pli->do_null2 = do_null2;
+  pli->E = 1e300; pli->domE = 1e300; pli->incE = 1e300; pli->incdomE = 1e300;
+  if (seed != 42) { esl_randomness_Init(pli->r, seed); pli->do_reseeding = pli->ddef->do_reseeding = (seed != 0); }
+  p7_pli_NewSeq(pli, sq);
+  for (t = 0; t < nmodels; t++) {
+    REFM *m = models[t];
+    uint64_t before = th->N;
+    p7_oprofile_ReconfigMultihit(m->om, 400);
+    p7_pli_NewModel(pli, m->om, m->bg);
+    p7_bg_SetLength(m->bg, sq->n);
+    p7_oprofile_ReconfigLength(m->om, sq->n);
+    p7_Pipeline(pli, m->om, m->bg, sq, NULL, th);
+    p7_pipeline_Reuse(pli);
+    if (th->N > before) idx[before] = t;
+  }
+  collect(th, idx, r);
+  r->counters[0] = pli->n_past_msv; r->counters[1] = pli->n_past_bias; r->counters[2] = pli->n_past_vit; r->counters[3] = pli->n_past_fwd;
+  free(idx); esl_sq_Destroy(sq); p7_tophits_Destroy(th); p7_pipeline_Destroy(pli);
+  return r;
+}
+
+/* ---- threaded timing run of hmmscan: the threads pull blocks of SC_BLOCK models from a shared counter; every thread owns a
+ * pipeline in scan mode and a copy of the query.  (pyhmmer's own hmmscan gives ONE thread to one query, _hmmscan.py:29-37;
+ * this is the reference's C pipeline given all the host's threads.)  A model is touched by one thread only. */
+#define SC_BLOCK 16
+typedef struct { REFM **models; int nmodels; const uint8_t *dsq; long len; int *next; double F1, F2, F3; int do_bias, do_null2;
+                 long nhits; long counters[4]; } SC_JOB;
+static void *sc_worker(void *arg)
+{
+  SC_JOB *job = (SC_JOB *)arg;
+  P7_PIPELINE *pli = p7_pipeline_Create(NULL, 100, (int)job->len, FALSE, p7_SCAN_MODELS);
+  P7_TOPHITS  *th  = p7_tophits_Create();
+  ESL_SQ *sq = esl_sq_CreateDigitalFrom(job->models[0]->abc, "query", job->dsq, job->len, NULL, NULL, NULL);
+  int t0, t;
+  pli->F1 = job->F1; pli->F2 = job->F2; pli->F3 = job->F3; pli->do_biasfilter = job->do_bias; pli->do_null2 = job->do_null2;
+  p7_pli_NewSeq(pli, sq);
+  for (t0 = __atomic_fetch_add(job->next, SC_BLOCK, __ATOMIC_RELAXED); t0 < job->nmodels; t0 = __atomic_fetch_add(job->next, SC_BLOCK, __ATOMIC_RELAXED)) {
+    int t1 = t0 + SC_BLOCK < job->nmodels ? t0 + SC_BLOCK : job->nmodels;
+    for (t = t0; t < t1; t++) {
+      REFM *m = job->models[t];
+      p7_oprofile_ReconfigMultihit(m->om, 400);
+      p7_pli_NewModel(pli, m->om, m->bg);
+      p7_bg_SetLength(m->bg, sq->n);
+      p7_oprofile_ReconfigLength(m->om, sq->n);
+      p7_Pipeline(pli, m->om, m->bg, sq, NULL, th);
+      p7_pipeline_Reuse(pli);
+    }
+  }
+  job->nhits = th->N;
+  job->counters[0] = pli->n_past_msv; job->counters[1] = pli->n_past_bias; job->counters[2] = pli->n_past_vit; job->counters[3] = pli->n_past_fwd;
+  esl_sq_Destroy(sq); p7_tophits_Destroy(th); p7_pipeline_Destroy(pli);
+  return NULL;
+}
+long ref_scan_mt(REFM **models, int nmodels, const uint8_t *dsq, long len, int nthreads,
+                 double F1, double F2, double F3, int do_bias, int do_null2, long *counters4)
+{
+  pthread_t *th = malloc(sizeof(pthread_t) * nthreads);
+  SC_JOB *jobs = calloc(nthreads, sizeof(SC_JOB));
+  int next = 0, t, c; long nhits = 0;
+  for (t = 0; t < nthreads; t++) {
+    jobs[t].models = models; jobs[t].nmodels = nmodels; jobs[t].dsq = dsq; jobs[t].len = len; jobs[t].next = &next;
+    jobs[t].F1 = F1; jobs[t].F2 = F2; jobs[t].F3 = F3; jobs[t].do_bias = do_bias; jobs[t].do_null2 = do_null2;
+    pthread_create(&th[t], NULL, sc_worker, &jobs[t]);
+  }
+  for (c = 0; c < 4; c++) counters4[c] = 0;
+  for (t = 0; t < nthreads; t++) { pthread_join(th[t], NULL); nhits += jobs[t].nhits; for (c = 0; c < 4; c++) counters4[c] += jobs[t].counters[c]; }
+  free(th); free(jobs);
+  return nhits;
+}
+
+/* ---- threaded timing run of nhmmer: the windows of ref_nhmmer's loop (block_length residues + max_length of context, both
+ * strands) are pulled from a shared counter by threads that each own a pipeline, a profile clone, score data and a hit list;
+ * the hit lists are merged and post-processed as in ref_nhmmer.  (pyhmmer's own nhmmer gives ONE thread to one query.)
+ * Returns the number of hits left after duplicate removal; stats [6] as in ref_nhmmer. */
+typedef struct { REFM *m; int nseq; const uint8_t **dsq; const long *len; long W; int strands; double F1, F2, F3; int do_bias, do_null2;
+                 long nwin; const int *win_seq; const long *win_i; long *next; P7_TOPHITS *th; P7_PIPELINE *pli; } NH_JOB;
+static void *nh_worker(void *arg)
+{
+  NH_JOB *job = (NH_JOB *)arg;
+  REFM *m = job->m;
+  P7_OPROFILE *om = p7_oprofile_Clone(m->om);
+  P7_BG *bg = p7_bg_Clone(m->bg);
+  P7_PIPELINE *pli = p7_pipeline_Create(NULL, om->M, 100, TRUE, p7_SEARCH_SEQS);
+  P7_SCOREDATA *data = p7_hmm_ScoreDataCreate(om, NULL);
+  ESL_SQ *tmpsq = esl_sq_CreateDigital(m->abc);
+  long C = om->max_length, W = job->W, w;
+  pli->F1 = job->F1; pli->F2 = job->F2; pli->F3 = job->F3; pli->do_biasfilter = job->do_bias; pli->do_null2 = job->do_null2;
+  pli->strands = (job->strands == 1) ? p7_STRAND_TOPONLY : (job->strands == 2) ? p7_STRAND_BOTTOMONLY : p7_STRAND_BOTH;
+  pli->block_length = (int)W;
+  pli->nseqs = 0;
+  p7_pli_NewModel(pli, om, bg);
+  job->th = p7_tophits_Create();
+  for (w = __atomic_fetch_add(job->next, 1, __ATOMIC_RELAXED); w < job->nwin; w = __atomic_fetch_add(job->next, 1, __ATOMIC_RELAXED)) {
+    int t = job->win_seq[w]; long i = job->win_i[w];
+    char name[64];
+    snprintf(name, sizeof name, "seq%d", t);
+    tmpsq->idx = t; tmpsq->L = -1;
+    esl_sq_SetAccession(tmpsq, ""); esl_sq_SetName(tmpsq, name); esl_sq_SetDesc(tmpsq, ""); esl_sq_SetSource(tmpsq, name);
+    esl_sq_GrowTo(tmpsq, ESL_MIN(W + C, job->len[t]));
+    tmpsq->C = (i == 0) ? 0 : ESL_MIN(C, job->len[t] - i);
+    tmpsq->W = ESL_MIN(W, job->len[t] - i - tmpsq->C);
+    tmpsq->n = tmpsq->C + tmpsq->W;
+    tmpsq->start = i + 1;
+    tmpsq->end = i + tmpsq->n;
+    memcpy(tmpsq->dsq + 1, job->dsq[t] + i + 1, tmpsq->n);
+    tmpsq->dsq[0] = tmpsq->dsq[tmpsq->n + 1] = eslDSQ_SENTINEL;
+    p7_pli_NewSeq(pli, tmpsq);
+    if (pli->strands != p7_STRAND_BOTTOMONLY) {
+      pli->nres -= tmpsq->C;
+      p7_Pipeline_LongTarget(pli, om, data, bg, job->th, t, tmpsq, p7_NOCOMPLEMENT, NULL, NULL, NULL);
+      p7_pipeline_Reuse(pli);
+    } else pli->nres -= tmpsq->n;
+    if (pli->strands != p7_STRAND_TOPONLY) {
+      esl_sq_ReverseComplement(tmpsq);
+      p7_Pipeline_LongTarget(pli, om, data, bg, job->th, t, tmpsq, p7_COMPLEMENT, NULL, NULL, NULL);
+      p7_pipeline_Reuse(pli);
+      pli->nres += tmpsq->W;
+    }
+    esl_sq_Reuse(tmpsq);
+  }
+  job->pli = pli;
+  esl_sq_Destroy(tmpsq); p7_hmm_ScoreDataDestroy(data); p7_bg_Destroy(bg); p7_oprofile_Destroy(om);
+  return NULL;
+}
+long ref_nhmmer_mt(REFM *m, int nseq, const uint8_t **dsq, const long *len, long block_length, int strands, int nthreads,
+                   double F1, double F2, double F3, int do_bias, int do_null2, long evalue_window, long *stats)
+{
+  long C = m->om->max_length, W = block_length, nwin = 0, i, w = 0, next = 0, nout;
+  int t, c;
+  if (C <= 0 || W <= C) return -1;
+  for (t = 0; t < nseq; t++) for (i = 0; i < len[t]; i += W - C) nwin++;
+  int *win_seq = malloc(sizeof(int) * (nwin + 1)); long *win_i = malloc(sizeof(long) * (nwin + 1));
+  for (t = 0; t < nseq; t++) for (i = 0; i < len[t]; i += W - C) { win_seq[w] = t; win_i[w] = i; w++; }
+  pthread_t *th = malloc(sizeof(pthread_t) * nthreads);
+  NH_JOB *jobs = calloc(nthreads, sizeof(NH_JOB));
+  for (t = 0; t < nthreads; t++) {
+    jobs[t].m = m; jobs[t].nseq = nseq; jobs[t].dsq = dsq; jobs[t].len = len; jobs[t].W = W; jobs[t].strands = strands;
+    jobs[t].F1 = F1; jobs[t].F2 = F2; jobs[t].F3 = F3; jobs[t].do_bias = do_bias; jobs[t].do_null2 = do_null2;
+    jobs[t].nwin = nwin; jobs[t].win_seq = win_seq; jobs[t].win_i = win_i; jobs[t].next = &next;
+    pthread_create(&th[t], NULL, nh_worker, &jobs[t]);
+  }
+  for (t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  for (c = 0; c < 6; c++) stats[c] = 0;
+  for (t = 1; t < nthreads; t++) {
+    p7_tophits_Merge(jobs[0].th, jobs[t].th);
+    p7_pipeline_Merge(jobs[0].pli, jobs[t].pli);
+  }
+  {
+    P7_PIPELINE *pli = jobs[0].pli; P7_TOPHITS *hits = jobs[0].th;
+    pli->nseqs = nseq;
+    p7_tophits_ComputeNhmmerEvalues(hits, (double)pli->nres, evalue_window > 0 ? (int)evalue_window : m->om->max_length);
+    p7_tophits_SortBySeqidxAndAlipos(hits);
+    p7_tophits_RemoveDuplicates(hits, TRUE);
+    p7_tophits_SortBySortkey(hits);
+    p7_tophits_Threshold(hits, pli);
+    stats[0] = pli->nres; stats[1] = nseq; stats[2] = pli->pos_past_msv; stats[3] = pli->pos_past_bias; stats[4] = pli->pos_past_vit; stats[5] = pli->pos_past_fwd;
+    nout = 0;
+    for (i = 0; i < (long)hits->N; i++) if (!(hits->hit[i]->flags & p7_IS_DUPLICATE)) nout++;
+  }
+  for (t = 0; t < nthreads; t++) { p7_tophits_Destroy(jobs[t].th); p7_pipeline_Destroy(jobs[t].pli); }
+  free(th); free(jobs); free(win_seq); free(win_i);
+  return nout;
+}

@@ -94,6 +94,16 @@ def lib():
         L.ref_result_counters.restype = ctypes.POINTER(ctypes.c_long); L.ref_result_counters.argtypes = [vp]
         L.ref_search_mt.restype = ctypes.c_long
         L.ref_search_mt.argtypes = [vp, ci, vp, vp, ci, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, vp]
+        L.refm_from_arrays.restype = vp
+        L.refm_from_arrays.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, ctypes.c_char_p, ctypes.c_char_p, ci]
+        L.refm_from_arrays_many.restype = ci
+        L.refm_from_arrays_many.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, ctypes.c_char_p, ctypes.c_char_p, vp, ci, ci, vp]
+        L.ref_scan.restype = vp
+        L.ref_scan.argtypes = [vp, ci, vp, ctypes.c_long, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ctypes.c_uint]
+        L.ref_scan_mt.restype = ctypes.c_long
+        L.ref_scan_mt.argtypes = [vp, ci, vp, ctypes.c_long, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, vp]
+        L.ref_nhmmer_mt.restype = ctypes.c_long
+        L.ref_nhmmer_mt.argtypes = [vp, ci, vp, vp, ctypes.c_long, ci, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci, ci, ctypes.c_long, vp]
         _lib = L
     return _lib
 
@@ -159,12 +169,24 @@ def mt_stream(seed, n):
 class RefModel:
     """One HMM of a file, configured as Pipeline.search_hmm configures an HMM query."""
 
-    def __init__(self, path, index=0, L=400):
+    def __init__(self, path, index=0, L=400, _handle=None):
         self.L = lib()
-        self.h = self.L.refm_read(os.fsencode(path), index, L)
+        self.h = _handle if _handle is not None else self.L.refm_read(os.fsencode(path), index, L)
         if not self.h:
             raise ValueError("cannot read HMM %d of %s" % (index, path))
         self.M, self.K, self.Kp = self.L.refm_M(self.h), self.L.refm_K(self.h), self.L.refm_Kp(self.h)
+
+    @classmethod
+    def from_arrays(cls, abc_type, t, mat, ins, evparam, name, compo=None, consensus=None, max_length=0, L=400):
+        """A model from probability arrays (refm_from_arrays): t [(M+1), 7], mat / ins [(M+1), K] float32; abc_type 2 = DNA,
+        3 = amino (esl_alphabet.h)."""
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+        t, mat, ins, ev, compo = f32(t), f32(mat), f32(ins), f32(evparam), f32(compo)
+        M = t.shape[0] - 1
+        enc = lambda v: None if v is None else (v if isinstance(v, bytes) else v.encode())
+        h = lib().refm_from_arrays(abc_type, M, t.ctypes.data, mat.ctypes.data, ins.ctypes.data, None if compo is None else compo.ctypes.data,
+                                   ev.ctypes.data, int(max_length), enc(name), enc(consensus), L)
+        return cls(None, _handle=h)
 
     def __del__(self):
         try:
@@ -409,3 +431,72 @@ def search_mt(models, seqs, nthreads, F1=0.02, F2=1e-3, F3=1e-5, bias_filter=Tru
     ctr = (ctypes.c_long * 4)()
     nh = L.ref_search_mt(mp, len(models), ptrs, lens.ctypes.data, n, nthreads, F1, F2, F3, int(bias_filter), int(null2), ctr)
     return nh, list(ctr)
+
+
+def models_from_arrays(abc_type, Ms, t, mat, ins, evparam, names, compo=None, consensus=None, max_length=None, L=400, nthreads=1):
+    """n models from concatenated arrays (refm_from_arrays_many, converted on <nthreads> threads): Ms [n]; t [sum(M+1), 7],
+    mat / ins [sum(M+1), K], evparam [n, 6], compo [n, K] (None: p7_hmm_SetComposition) float32; names [n]; consensus = the
+    concatenated consensus strings (sum(M) characters) or None; max_length [n] or None.  Returns RefModel objects."""
+    Lb = lib()
+    Ms = np.ascontiguousarray(Ms, dtype=np.int32)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    t, mat, ins, ev = f32(t), f32(mat), f32(ins), f32(evparam)
+    compo = None if compo is None else f32(compo)
+    maxl = None if max_length is None else np.ascontiguousarray(max_length, dtype=np.int32)
+    n = len(Ms)
+    out = (ctypes.c_void_p * max(n, 1))()
+    enc = lambda v: v if isinstance(v, bytes) else v.encode()
+    Lb.refm_from_arrays_many(abc_type, n, Ms.ctypes.data, t.ctypes.data, mat.ctypes.data, ins.ctypes.data,
+                             None if compo is None else compo.ctypes.data, ev.ctypes.data,
+                             None if consensus is None else enc(consensus), b"".join(enc(v) + b"\0" for v in names),
+                             None if maxl is None else maxl.ctypes.data, L, max(1, int(nthreads)), out)
+    return [RefModel(None, _handle=out[i]) for i in range(n)]
+
+
+def _result(L, r):
+    try:
+        nh, nd = L.ref_result_nhits(r), L.ref_result_ndoms(r)
+        hp, dp = L.ref_result_hits(r), L.ref_result_doms(r)
+        hits = [RefHit.from_buffer_copy(hp[i]) for i in range(nh)]
+        doms = [RefDom.from_buffer_copy(dp[i]) for i in range(nd)]
+        ntext = sum(4 * (d.N + 1) for d in doms)
+        text = ctypes.string_at(L.ref_result_text(r), ntext) if ntext else b""
+        cp = L.ref_result_counters(r)
+        counters = [cp[i] for i in range(4)]
+    finally:
+        L.ref_result_free(r)
+    return hits, doms, text, counters
+
+
+def scan(models, codes, F1=0.02, F2=1e-3, F3=1e-5, bias_filter=True, null2=True, seed=42):
+    """hmmscan of one sequence against RefModel objects as Pipeline.scan_seq runs it (ref_scan), thresholds wide open:
+    (hits, doms, text, counters); hit.seq = index of the MODEL."""
+    L = lib()
+    d = dsq_of(codes)
+    hs = (ctypes.c_void_p * len(models))(*[m.h for m in models])
+    return _result(L, L.ref_scan(hs, len(models), d.ctypes.data, d.size - 2, F1, F2, F3, int(bias_filter), int(null2), seed))
+
+
+def scan_mt(models, codes, nthreads, F1=0.02, F2=1e-3, F3=1e-5, bias_filter=True, null2=True):
+    """Timing run of hmmscan, the models spread over <nthreads> threads (ref_scan_mt): (number of reported hits, counters)."""
+    L = lib()
+    d = dsq_of(codes)
+    hs = (ctypes.c_void_p * len(models))(*[m.h for m in models])
+    ctr = (ctypes.c_long * 4)()
+    nh = L.ref_scan_mt(hs, len(models), d.ctypes.data, d.size - 2, nthreads, F1, F2, F3, int(bias_filter), int(null2), ctr)
+    return nh, list(ctr)
+
+
+def nhmmer_mt(model, seqs, nthreads, block_length=0x40000, strand=None, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, null2=True,
+              evalue_window=0):
+    """Timing run of nhmmer, the windows spread over <nthreads> threads (ref_nhmmer_mt): (hits after duplicate removal, stats [6])."""
+    L = lib()
+    dsqs = [dsq_of(c) for c in seqs]
+    n = len(dsqs)
+    ptrs = (ctypes.c_void_p * max(n, 1))(*[d.ctypes.data for d in dsqs])
+    lens = (ctypes.c_long * max(n, 1))(*[d.size - 2 for d in dsqs])
+    stats = (ctypes.c_long * 6)()
+    nh = L.ref_nhmmer_mt(model.h, n, ptrs, lens, block_length, {None: 0, "watson": 1, "crick": 2}[strand], nthreads, F1, F2, F3,
+                         int(bias_filter), int(null2), int(evalue_window), stats)
+    assert nh >= 0, nh
+    return nh, list(stats)

@@ -50,7 +50,8 @@ class LenParams(ctypes.Structure):
 class SearchParams(ctypes.Structure):
     """``b2h_search_params`` (include/b2h.h)."""
     _fields_ = [("F1", ctypes.c_double), ("F2", ctypes.c_double), ("F3", ctypes.c_double),
-                ("do_biasfilter", c_i32), ("do_null2", c_i32), ("seed", ctypes.c_uint32), ("host_threads", c_i32)]
+                ("do_biasfilter", c_i32), ("do_null2", c_i32), ("seed", ctypes.c_uint32), ("host_threads", c_i32),
+                ("seq_counters", c_i32), ("reserved", c_i32)]
 
 
 class HitRec(ctypes.Structure):
@@ -147,6 +148,7 @@ def _load():
     sig("b2h_results_domains", P(DomainRec), c_void_p)
     sig("b2h_results_text", c_void_p, c_void_p, P(c_size_t))
     sig("b2h_results_counters", P(c_i64), c_void_p)
+    sig("b2h_results_seq_counters", P(c_i64), c_void_p)
     sig("b2h_results_destroy", None, c_void_p)
     sig("b2h_profile_set_annotation", c_int, c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p)
     sig("b2h_seqdb_h2d_bytes", ctypes.c_size_t, c_void_p)

@@ -12,6 +12,7 @@ struct b2h_results {
   std::vector<b2h_domain> doms;
   std::vector<char>       text;
   std::vector<int64_t>    counters;
+  std::vector<int64_t>    seq_counters;   // [N][4], only when asked for
 };
 
 struct b2h_survivor { int32_t profile, seq; float fwdsc, filtersc; };

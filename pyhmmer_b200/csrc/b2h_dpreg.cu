@@ -806,6 +806,8 @@ int b2h_launch_vit2(b2h_ctx *ctx, int C2, const WorkList &wl, const SeqDev &sd, 
     const size_t smem = (size_t)32 * 32 * (C2 / 2) * 4;
     int occ = 1;
     { const int st = b2h_kernel_occupancy(ctx, (const void *)kernel, 256, smem, &occ); if (st != B2H_OK) return st; }
+    static const int occ_cap = getenv("B2H_VIT_OCC") ? atoi(getenv("B2H_VIT_OCC")) : 0;       // experiments: resident CTAs per SM (co-residency with SSV)
+    if (occ_cap > 0 && occ > occ_cap) occ = occ_cap;
     int grid = ctx->sm_count * occ;
     if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
     if (grid < 1) grid = 1;

@@ -330,7 +330,7 @@ int b2h_launch_bias(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int nent
 
 // A compacted list of comparisons produced by a stage's epilogue (device memory).  Appends are
 // atomic (*n, and cnt[p] for the later grouping by profile); a,b carry the stage's scores.
-struct SurvList { int32_t *p, *s; float *a, *b; int *n; int *cnt; int cap; };
+struct SurvList { int32_t *p, *s; float *a, *b; int *n; int *cnt; int cap; int *cnts = nullptr; };   // cnts: optional per-sequence counts
 
 #define B2H_SSV_CHUNK 128      // sequences per SSV work item
 struct SsvArgs {

@@ -94,7 +94,7 @@ __device__ __forceinline__ double gumbel_surv(double x, double mu, double lambda
 __device__ __forceinline__ void surv_append(const SurvList &l, int p, int s, float a, float b)
 {
   const int slot = atomicAdd(l.n, 1);            // *n may run past cap: the host checks and re-runs with a smaller batch
-  if (slot < l.cap) { l.p[slot] = p; l.s[slot] = s; if (l.a) l.a[slot] = a; if (l.b) l.b[slot] = b; atomicAdd(l.cnt + p, 1); }
+  if (slot < l.cap) { l.p[slot] = p; l.s[slot] = s; if (l.a) l.a[slot] = a; if (l.b) l.b[slot] = b; atomicAdd(l.cnt + p, 1); if (l.cnts) atomicAdd(l.cnts + s, 1); }
 }
 
 // First-level filter decision of p7_Pipeline (p7_pipeline.c:721-725): P-value of the MSV score against F1.
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
         const float f = __half2float(__ushort_as_half((unsigned short)v));
         v = (f > 30000.0f) ? 30000 : (int)f;
       }
-      if (gl == 0 && valid) {
+      if (gl == 0 && valid && (a.mode != 2 || L > 0)) {         // p7_Pipeline returns at once for an empty target (p7_pipeline.c:713): it enters no list
         float sc; int status;
         ssv_finish(v, P, (int)a.sd.tjb[s], sc, status);
         if (a.mode == 0) { a.out_sc[s] = sc; a.out_status[s] = status; }

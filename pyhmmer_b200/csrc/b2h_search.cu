@@ -45,13 +45,13 @@ __device__ __forceinline__ double exp_surv(double x, double mu, double lambda)
 __device__ __forceinline__ void surv_append(const SurvList &l, int p, int s, float a, float b)
 {
   const int slot = atomicAdd(l.n, 1);
-  if (slot < l.cap) { l.p[slot] = p; l.s[slot] = s; if (l.a) l.a[slot] = a; if (l.b) l.b[slot] = b; atomicAdd(l.cnt + p, 1); }
+  if (slot < l.cap) { l.p[slot] = p; l.s[slot] = s; if (l.a) l.a[slot] = a; if (l.b) l.b[slot] = b; atomicAdd(l.cnt + p, 1); if (l.cnts) atomicAdd(l.cnts + s, 1); }
 }
 __device__ __forceinline__ float bits(float sc, float null) { return (float)((double)(sc - null) / 0.69314718055994529); }
 
 // after the bias filter (p7_pipeline.c:728-754): entries of the grouped MSV-survivor list
 __global__ void bias_post_kernel(const ProfDev *profs, const SeqDev sd, const Grouped g, const int32_t *nent,
-                                 const float *filtersc, int do_bias, double F1, double F2, int *cnt_bias, SurvList V, SurvList F)
+                                 const float *filtersc, int do_bias, double F1, double F2, int *cnt_bias, int *cnts_bias, SurvList V, SurvList F)
 {
   const int n = *nent;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
@@ -62,6 +62,7 @@ __global__ void bias_post_kernel(const ProfDev *profs, const SeqDev sd, const Gr
     const double pv = gumbel_surv((double)bits(usc, fsc), (double)P.evparam[0], (double)P.evparam[1]);
     if (do_bias && pv > F1) continue;
     atomicAdd(cnt_bias + p, 1);
+    if (cnts_bias) atomicAdd(cnts_bias + s, 1);
     if (pv > F2) surv_append(V, p, s, fsc, 0.f); else surv_append(F, p, s, fsc, 0.f);
   }
 }
@@ -69,7 +70,7 @@ __global__ void bias_post_kernel(const ProfDev *profs, const SeqDev sd, const Gr
 // Bias filter and ViterbiFilter computed side by side for every MSV survivor; the two tests of p7_pipeline.c:728-762 are
 // then applied in the reference's order: bias P-value > F1 drops the comparison; P <= F2 skips the Viterbi test.
 __global__ void bias_vit_post_kernel(const ProfDev *profs, const SeqDev sd, const Grouped g, const int32_t *nent,
-                                     const float *filtersc, const float *vfsc, int do_bias, double F1, double F2, int *cnt_bias, SurvList F)
+                                     const float *filtersc, const float *vfsc, int do_bias, double F1, double F2, int *cnt_bias, int *cnts_bias, SurvList F)
 {
   const int n = *nent;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
@@ -80,6 +81,7 @@ __global__ void bias_vit_post_kernel(const ProfDev *profs, const SeqDev sd, cons
     const double pv = gumbel_surv((double)bits(usc, fsc), (double)P.evparam[0], (double)P.evparam[1]);
     if (do_bias && pv > F1) continue;
     atomicAdd(cnt_bias + p, 1);
+    if (cnts_bias) atomicAdd(cnts_bias + s, 1);
     if (pv > F2) {
       const double pvv = gumbel_surv((double)bits(vfsc[e], fsc), (double)P.evparam[2], (double)P.evparam[3]);
       if (pvv > F2) continue;
@@ -167,7 +169,7 @@ struct CascadeWave {
 };
 
 static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int p0, int p1, const b2h_seqdb *db,
-                           const b2h_search_params *prm, CascadeWave &cw)
+                           const b2h_search_params *prm, CascadeWave &cw, int *seqcnt /* device [4][N] per-sequence pass counts, or NULL */)
 {
   const int P = p1 - p0, N = (int)db->n;
   const size_t cap = (size_t)P * N;
@@ -209,6 +211,7 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
   TRY(make_list(pool, V, cap, P, d_ctr + 2, cntV, false));
   TRY(make_list(pool, F, cap, P, d_ctr + 3, cntF, false));
   TRY(make_list(pool, D, cap, P, d_ctr + 4, cntD, true));
+  if (seqcnt) { A.cnts = seqcnt; F.cnts = seqcnt + 2 * (size_t)N; D.cnts = seqcnt + 3 * (size_t)N; }
   Grouped G;
   TRY(pool.get(&G.p, cap)); TRY(pool.get(&G.s, cap)); TRY(pool.get(&G.a, cap)); G.b = nullptr;
   TRY(pool.get(&G.poff, (size_t)P + 1)); TRY(pool.get(&G.itemoff, (size_t)P + 1)); G.fill = fill;
@@ -266,7 +269,7 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
   if (serial_bias) {
     { StageTimer tm(ctx, 2);
       if (prm->do_biasfilter) TRY(b2h_launch_bias(ctx, wl, sd, ctx->sm_count * 128 * 8, stage_sc));
-      bias_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, sd, G, nent, stage_sc, prm->do_biasfilter, prm->F1, prm->F2, cntB, V, F);
+      bias_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, sd, G, nent, stage_sc, prm->do_biasfilter, prm->F1, prm->F2, cntB, seqcnt ? seqcnt + N : nullptr, V, F);
       ctx->launches++; }
     if (overlap == 2) TRY(to_post_lane());
     { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, V, P, G)); }
@@ -293,7 +296,7 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
     StageOut so; so.sc = stage_sc; so.status = stage_st; so.fwd_xmx = so.bck_xmx = nullptr; so.xoff = nullptr;
     TRY(b2h_launch_viterbi(ctx, wl, sd, mpads, 0, so));
     if (prm->do_biasfilter) B2H_CUDA(cudaStreamWaitEvent(ctx->stream, cw.bias_join, 0));
-    bias_vit_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, sd, G, nent, bias_sc, stage_sc, prm->do_biasfilter, prm->F1, prm->F2, cntB, F);
+    bias_vit_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, sd, G, nent, bias_sc, stage_sc, prm->do_biasfilter, prm->F1, prm->F2, cntB, seqcnt ? seqcnt + N : nullptr, F);
     ctx->launches++;
   }
   // 5. Forward parser
@@ -655,6 +658,13 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     const bool host_env = getenv("B2H_ENVELOPES_ON_HOST") != nullptr;     // debugging aid: rescore envelopes with the host code
     DdefQueue ddef(ddpool, prm, res, host_env ? nullptr : &envgpu);
     size_t nsurv = 0;
+    int *d_seqcnt = nullptr;                             // per-sequence pass counters (hmmscan of several queries)
+    struct SeqCntGuard { int *&p; ~SeqCntGuard() { if (p) cudaFree(p); } } seqcnt_guard{d_seqcnt};
+    if (prm->seq_counters) {
+      B2H_CUDA(cudaSetDevice(ctx->device));
+      B2H_CUDA(cudaMalloc(&d_seqcnt, 4 * N * sizeof(int)));
+      B2H_CUDA(cudaMemsetAsync(d_seqcnt, 0, 4 * N * sizeof(int), ctx->stream));
+    }
     // Software pipeline over the waves, driven by events.  The cascade of waves w+1, w+2 is queued on the main lane before
     // the host looks at wave w.  When a wave's cascade has finished, its survivor list is fetched and its Forward/Backward
     // passes are queued on one of two high-priority survivor lanes (their kernels slip in between the following wave's SSV
@@ -669,7 +679,7 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     auto top_up = [&](size_t upto) {                     // keep the lanes fed: queue waves [queued, upto]
       for (; queued <= upto && queued < nw && st == B2H_OK; queued++) {
         waves[queued].reset(new CascadeWave());
-        st = cascade_enqueue(ctx, sp.data(), (int)bounds[queued], (int)bounds[queued + 1], db, prm, *waves[queued]);
+        st = cascade_enqueue(ctx, sp.data(), (int)bounds[queued], (int)bounds[queued + 1], db, prm, *waves[queued], d_seqcnt);
       }
     };
     auto fired = [](cudaEvent_t e) { const cudaError_t q = cudaEventQuery(e); if (q != cudaSuccess) (void)cudaGetLastError(); return q != cudaErrorNotReady; };
@@ -709,6 +719,12 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     const double t1 = now_ms();
     st = ddef.finish();
     if (st != B2H_OK) { ctx->err = "domain definition failed"; delete res; return st; }
+    if (d_seqcnt) {                                     // every wave has been collected: the counts are final
+      std::vector<int> h(4 * N);
+      if (cudaMemcpy(h.data(), d_seqcnt, 4 * N * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { ctx->err = "per-sequence counters"; delete res; return B2H_ECUDA; }
+      res->seq_counters.resize(4 * N);
+      for (size_t s = 0; s < N; s++) for (int c = 0; c < 4; c++) res->seq_counters[s * 4 + c] = h[(size_t)c * N + s];
+    }
     for (b2h_hit &h : res->hits) h.profile = order[h.profile];
     for (size_t i = 0; i < P; i++) for (int c = 0; c < 4; c++) res->counters[(size_t)order[i] * 4 + c] = scnt[i * 4 + c];
     std::stable_sort(res->hits.begin(), res->hits.end(), [](const b2h_hit &x, const b2h_hit &y) {
@@ -822,6 +838,7 @@ size_t            b2h_results_ndomains(const b2h_results *r) { return r ? r->dom
 const b2h_domain *b2h_results_domains (const b2h_results *r) { return r ? r->doms.data() : nullptr; }
 const char       *b2h_results_text    (const b2h_results *r, size_t *n) { if (n) *n = r ? r->text.size() : 0; return r ? r->text.data() : nullptr; }
 const int64_t    *b2h_results_counters(const b2h_results *r) { return r ? r->counters.data() : nullptr; }
+const int64_t    *b2h_results_seq_counters(const b2h_results *r) { return (r && !r->seq_counters.empty()) ? r->seq_counters.data() : nullptr; }
 void              b2h_results_destroy (b2h_results *r) { delete r; }
 
 } // extern "C"

@@ -207,12 +207,53 @@ class DigitalSequenceBlock(list):
             self.append(s)
 
     def __setitem__(self, i, v):
+        if isinstance(i, slice):
+            v = list(v)
+            for s in v:
+                self._check(s)
+        else:
+            self._check(v)
         self._cache = {}
         super().__setitem__(i, v)
 
     def __delitem__(self, i):
         self._cache = {}
         super().__delitem__(i)
+
+    # every other mutating method of `list` drops the packed / device copies too (a search after a mutation must never
+    # run against the previous database) and keeps the type / alphabet check
+    def insert(self, i, seq):
+        self._check(seq)
+        self._cache = {}
+        super().insert(i, seq)
+
+    def pop(self, i=-1):
+        self._cache = {}
+        return super().pop(i)
+
+    def remove(self, seq):
+        self._cache = {}
+        super().remove(seq)
+
+    def clear(self):
+        self._cache = {}
+        super().clear()
+
+    def sort(self, *, key=None, reverse=False):
+        self._cache = {}
+        super().sort(key=key, reverse=reverse)
+
+    def reverse(self):
+        self._cache = {}
+        super().reverse()
+
+    def __iadd__(self, seqs):
+        self.extend(seqs)
+        return self
+
+    def __imul__(self, n):
+        self._cache = {}
+        return super().__imul__(n)
 
     def __getitem__(self, i):
         if isinstance(i, slice):

@@ -152,24 +152,6 @@ class HMM:
     def __repr__(self):
         return "<HMM name=%r M=%d alphabet=%r>" % (self.name, self.M, self.alphabet)
 
-    def set_composition(self):
-        """``p7_hmm_SetComposition`` (p7_hmm.c:621): occupancy-weighted mean emission."""
-        t = self.transition_probabilities.astype(np.float64)
-        M, K = self.M, self.alphabet.K
-        mocc = np.zeros(M + 1)
-        mocc[1] = t[0, 1] + t[0, 0]
-        for k in range(2, M + 1):
-            mocc[k] = mocc[k - 1] * (t[k - 1, 0] + t[k - 1, 1]) + (1.0 - mocc[k - 1]) * t[k - 1, 5]
-        iocc = np.zeros(M + 1)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            iocc[0] = t[0, 1] / t[0, 3]
-            iocc[1:] = mocc[1:] * t[1:, 1] / t[1:, 3]
-        iocc = np.nan_to_num(iocc, nan=0.0, posinf=0.0)
-        compo = (self.insert_emissions.astype(np.float64) * iocc[:, None]).sum(0) + \
-                (self.match_emissions.astype(np.float64)[1:] * mocc[1:, None]).sum(0)
-        compo /= compo.sum()
-        self._compo[:K] = compo.astype(np.float32)
-
     def to_profile(self, background=None, L=400, multihit=True, local=True):
         """``HMM.to_profile`` (plan7.pyx:3329): a `Profile` configured for target length ``L``."""
         return Profile(self.M, self.alphabet).configure(self, background if background is not None else Background(self.alphabet),
@@ -1465,11 +1447,15 @@ class Domain:
 
     @property
     def c_evalue(self):
-        return math.exp(self.lnP) * self.hit.hits.domZ
+        """Conditional E-value (plan7.pyx:1557-1565): for long-target hits the search space is already inside lnP."""
+        hits = self.hit.hits
+        return math.exp(self.lnP) if hits.long_targets else math.exp(self.lnP) * hits.domZ
 
     @property
     def i_evalue(self):
-        return math.exp(self.lnP) * self.hit.hits.Z
+        """Independent E-value (plan7.pyx:1566-1574)."""
+        hits = self.hit.hits
+        return math.exp(self.lnP) if hits.long_targets else math.exp(self.lnP) * hits.Z
 
 
 _LN2_INV_F = 1.0 / 0.69314718055994529
@@ -1635,6 +1621,17 @@ class TopHits:
                     for d in h._domains:
                         d.reported = self._domain_reportable(d.score, d.lnP)
                         d.included = h.included and self._domain_includable(d.score, d.lnP)
+        # workaround_bug_h74 (p7_tophits.c:756-778, always applied at the end of p7_tophits_Threshold): when envelopes of
+        # a target overlapped, two domains may carry the same alignment; only the better-scoring one stays reported
+        for h in self._hits:
+            if h._rec.noverlaps:
+                ds = h._domains
+                for d1 in range(len(ds)):
+                    for d2 in range(d1 + 1, len(ds)):
+                        a, b = ds[d1]._rec, ds[d2]._rec
+                        if a.iali == b.iali and a.jali == b.jali:
+                            gone = ds[d2] if a.bitscore >= b.bitscore else ds[d1]
+                            gone.reported = gone.included = False
 
     def sort(self, by="key"):
         """``TopHits.sort`` (plan7.pyx:8932): ``key`` = by sort key (p7_tophits_SortBySortkey), ``seqidx`` = by target index and
@@ -1996,18 +1993,49 @@ class TopHits:
                         dr.hmmfrom, dr.hmmto, desc if desc else "-"))
         fh.write("".join(out).encode())
 
+    def _check_threshold_parameters(self, other):
+        """``TopHits._check_threshold_parameters`` (plan7.pyx:8832-8861)."""
+        p, q = self._params, other._params
+        if self.long_targets and not other.long_targets:
+            raise ValueError("Trying to merge a `TopHits` from a long targets pipeline to a `TopHits` from a regular pipeline.")
+        if (p["Z"] is None) != (q["Z"] is None):
+            raise ValueError("Trying to merge `TopHits` with `Z` values obtained with different methods.")
+        if p["Z"] is not None and self.Z != other.Z:
+            raise ValueError("Trying to merge `TopHits` obtained from pipelines manually configured to different `Z` values.")
+        if (p["domZ"] is None) != (q["domZ"] is None):
+            raise ValueError("Trying to merge `TopHits` with `domZ` values obtained with different methods.")
+        if p["domZ"] is not None and self.domZ != other.domZ:
+            raise ValueError("Trying to merge `TopHits` obtained from pipelines manually configured to different `domZ` values.")
+        for mode, what in (("by_E", "reporting"), ("dom_by_E", "domain reporting"), ("inc_by_E", "inclusion"), ("incdom_by_E", "domain inclusion")):
+            if p[mode] != q[mode]:
+                raise ValueError("Trying to merge `TopHits` obtained from pipelines with different %s threshold modes" % what)
+        for mode, e, t, what in (("by_E", "E", "T", "reporting"), ("inc_by_E", "incE", "incT", "inclusion"),
+                                 ("dom_by_E", "domE", "domT", "domain reporting"), ("incdom_by_E", "incdomE", "incdomT", "domain inclusion")):
+            k = e if p[mode] else t
+            if p[k] != q[k]:
+                raise ValueError("Trying to merge `TopHits` obtained from pipelines with different %s thresholds." % what)
+
     def merge(self, *others):
-        """``TopHits.merge`` (plan7.pyx:9172-9273): combine hits of target-sharded searches of one query."""
-        merged = TopHits(self.query, self.mode)
-        merged._params = dict(self._params)
-        merged.long_targets = self.long_targets
-        parts = (self,) + others
-        for part in parts:
-            for h in part._hits:
+        """``TopHits.merge`` (plan7.pyx:9172-9273): combine hits of target-sharded searches of one query.  The parts are
+        copied (the inputs keep their own flags and E-values), their queries and threshold parameters must agree."""
+        merged = self.copy()
+        parts = [self]
+        for other in others:
+            mq, oq = merged.query, other.query
+            ident = lambda q: (type(q).__name__ if not isinstance(q, (HMM, Profile, OptimizedProfile)) else "model",
+                               getattr(q, "name", None), getattr(q, "M", None) or (len(q) if hasattr(q, "__len__") else None),
+                               getattr(q, "accession", None))
+            mismatch = mq is not oq and ident(mq) != ident(oq)
+            if mismatch:
+                raise ValueError("Trying to merge `TopHits` obtained from different queries")
+            merged._check_threshold_parameters(other)
+            oc = other.copy()
+            for h in oc._hits:
                 h.hits = merged
                 merged._hits.append(h)
-            for a in ("searched_sequences", "searched_residues", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd"):
-                setattr(merged, a, getattr(merged, a) + getattr(part, a))
+            parts.append(other)
+        for a in ("searched_sequences", "searched_residues", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd"):
+            setattr(merged, a, sum(getattr(part, a) for part in parts))
         merged.searched_models, merged.searched_nodes = self.searched_models, self.searched_nodes
         if self.mode == "scan":
             merged.searched_models = sum(p.searched_models for p in parts)
@@ -2072,8 +2100,9 @@ class Pipeline:
         conv = dict(zip(idx, _convert_hmms([queries[i] for i in idx], self.background, L, threads=self.host_threads)))
         return [conv[i] if i in conv else self._optimized(q, L) for i, q in enumerate(queries)]
 
-    def _params_struct(self):
-        return _lib.SearchParams(self.F1, self.F2, self.F3, int(self.bias_filter), int(self.null2), self.seed, int(self.host_threads))
+    def _params_struct(self, seq_counters=False):
+        return _lib.SearchParams(self.F1, self.F2, self.F3, int(self.bias_filter), int(self.null2), self.seed, int(self.host_threads),
+                                 int(bool(seq_counters)), 0)
 
     def _cutoffs(self, om):
         """p7_pli_NewModelThresholds (p7_pipeline.c:535): model-specific bit thresholds."""
@@ -2098,7 +2127,9 @@ class Pipeline:
                      T=cut[0], incT=cut[0], domT=cut[1], incdomT=cut[1])
         return th
 
-    def _run(self, oms, block):
+    def _run(self, oms, block, seq_counters=False):
+        """One ``b2h_search`` of the profiles against the block.  Returns the hit / domain records, the alignment text and
+        the pass counters: per profile [P][4], or per SEQUENCE [N][4] with ``seq_counters`` (scan mode)."""
         ctx = self._ctx
         t0 = time.perf_counter()
         if block._cache.get(("db", ctx)) is None and sum(1 for om in oms if om._dev.get(ctx) is None) > 8:
@@ -2116,7 +2147,7 @@ class Pipeline:
         else:
             db = SequenceDatabase.of(ctx, block)
             handles = (ctypes.c_void_p * len(oms))(*OptimizedProfile._device_many(ctx, oms))
-        prm = self._params_struct()
+        prm = self._params_struct(seq_counters)
         out = ctypes.c_void_p()
         t1 = time.perf_counter()
         st = lib.b2h_search(ctx.handle, handles, len(oms), db.handle, ctypes.byref(prm), ctypes.byref(out))
@@ -2126,8 +2157,12 @@ class Pipeline:
         check(st, "b2h_search", ctx.handle)
         try:
             hits, doms, text = _lib.read_results(out)
-            cp = lib.b2h_results_counters(out)
-            counters = np.ctypeslib.as_array(cp, shape=(len(oms), 4)).copy()
+            if seq_counters:
+                cp = lib.b2h_results_seq_counters(out)
+                counters = np.ctypeslib.as_array(cp, shape=(len(block), 4)).copy()
+            else:
+                cp = lib.b2h_results_counters(out)
+                counters = np.ctypeslib.as_array(cp, shape=(len(oms), 4)).copy()
         finally:
             lib.b2h_results_destroy(out)
         self._last_run_s = (t1 - t0, t2 - t1, time.perf_counter() - t2)    # (uploads / handles, b2h_search, reading the results)
@@ -2234,10 +2269,11 @@ class Pipeline:
         if world is not None and world.size > 1:
             b = parallel.shard_bounds([om.M for om in oms], world.size)
             lo, local = b[world.rank], oms[b[world.rank]:b[world.rank + 1]]
+        # the pass counters are kept per QUERY SEQUENCE: every scan_seq result reports its own (plan7.pyx:6534-6677)
         if local and len(block):
-            hits, doms, text, counters = self._run(local, block)
+            hits, doms, text, counters = self._run(local, block, seq_counters=True)
         else:
-            hits, doms, text, counters = [], [], b"", np.zeros((len(local), 4), np.int64)
+            hits, doms, text, counters = [], [], b"", np.zeros((len(block), 4), np.int64)
         if world is not None and world.size > 1:
             mine = parallel.pack_records(hits, doms, text, counters, 0, profile_offset=lo)
             hits, doms, tbuf, cparts = [], [], bytearray(), []
@@ -2247,7 +2283,7 @@ class Pipeline:
                 for r in d:
                     r.text_offset += len(tbuf)
                 hits.extend(h); doms.extend(d); tbuf.extend(t); cparts.append(c.reshape(-1, 4))
-            text, counters = bytes(tbuf), np.concatenate(cparts) if cparts else np.zeros((0, 4), np.int64)
+            text, counters = bytes(tbuf), np.sum(cparts, axis=0) if cparts else np.zeros((len(block), 4), np.int64)
         results = []
         for si, seq in enumerate(queries):
             th = self._tophits(seq, "scan", None)
@@ -2263,8 +2299,7 @@ class Pipeline:
             th.domZ = float(self.domZ) if self.domZ is not None else 0.0
             th.searched_models, th.searched_nodes = len(oms), sum(om.M for om in oms)
             th.searched_sequences, th.searched_residues = 1, len(seq)
-            if len(counters):
-                th.n_past_msv, th.n_past_bias, th.n_past_vit, th.n_past_fwd = (int(v) for v in counters.sum(0)) if len(queries) == 1 else (0, 0, 0, 0)
+            th.n_past_msv, th.n_past_bias, th.n_past_vit, th.n_past_fwd = (int(v) for v in counters[si])
             th._sort_by_key()
             th._threshold()
             results.append(th)

@@ -230,8 +230,9 @@ for om in oms:
     om._evparam[:] = np.array([-8.0, 0.7, -9.0, 0.7, -4.0, 0.7], np.float32)
 queries = [easel.DigitalSequence(abc, name=b"q%%d" %% i, sequence=rng.integers(0, 20, 50 + i).astype(np.uint8)) for i in range(3)]
 
-def fake_run(self, local, block):
+def fake_run(self, local, block, seq_counters=False):
     """stands in for the device: a deterministic set of hits for (profile, query) pairs, keyed by the MODEL (not its index)"""
+    assert seq_counters                                   # scan mode keeps the pass counters per query sequence
     hits, doms, text = [], [], b""
     for p, om in enumerate(local):
         for s in range(len(block)):
@@ -242,7 +243,7 @@ def fake_run(self, local, block):
                 d.N, d.text_offset, d.bitscore, d.lnP, d.ienv, d.jenv = 2, len(text), 3.0 + s, -3.0, 1, 10
                 text += b"AB\0ab\0AB\0**\0"
                 hits.append(h); doms.append(d)
-    return hits, doms, text, np.array([[om.M, 1, 2, 3] for om in local], np.int64).reshape(len(local), 4)
+    return hits, doms, text, np.array([[sum(om.M + s for om in local), len(local), 2 * len(local), sum(om.M %% 3 for om in local)] for s in range(len(block))], np.int64)
 
 pli = object.__new__(plan7.Pipeline)                     # no device here: the attributes the scan path reads are set by hand
 for k, v in dict(alphabet=abc, background=bg, bias_filter=True, null2=True, seed=42, Z=None, domZ=None, F1=0.02, F2=1e-3, F3=1e-5,
@@ -255,6 +256,9 @@ single = pli._scan_many(queries, oms, world=None)
 sig = lambda ths: [[(h.name, h.score, h.lnP, h.reported, h.included, h.domains[0].alignment.hmm_from, len(h.domains)) for h in th] for th in ths]
 assert sig(sharded) == sig(single) and sum(len(th) for th in single) >= 8
 assert [th.Z for th in sharded] == [11.0] * 3 and [th.searched_models for th in sharded] == [11] * 3
+ctr = lambda ths: [(th.n_past_msv, th.n_past_bias, th.n_past_vit, th.n_past_fwd) for th in ths]
+assert ctr(sharded) == ctr(single)                       # per-query counters: the ranks' shares add up
+assert ctr(single)[1] == (sum(om.M + 1 for om in oms), 11, 22, sum(om.M %% 3 for om in oms))
 dist.barrier(); dist.destroy_process_group()
 print("rank", w.rank, "ok")
 '''
