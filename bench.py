@@ -190,6 +190,15 @@ def main():
     ap.add_argument("--ref-profiles", type=int, default=100)
     ap.add_argument("--ref-seqs", type=int, default=50000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config.extra blocks (BASELINE configs[2..4])")
+    ap.add_argument("--extras", default="c4,c5,c3", help="which extra configurations to run (comma separated: c3, c4, c5)")
+    ap.add_argument("--pfam-n", type=int, default=20000, help="profiles of the Pfam-A-sized set (configs[2], [3])")
+    ap.add_argument("--c4-len", type=int, default=5000)
+    ap.add_argument("--c5-mb", type=float, default=100.0)
+    ap.add_argument("--c5-ref-mb", type=float, default=16.0)
+    ap.add_argument("--c3-seqs", type=int, default=100000)
+    ap.add_argument("--c3-ref-profiles", type=int, default=200)
+    ap.add_argument("--extra-steps", type=int, default=4)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b2h":
         args.warmup = 3
@@ -328,9 +337,21 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_gcups = cells_all * len(e2e_times) / float(te.item()) / 1e9
     h2d = int(_lib.lib.b2h_seqdb_h2d_bytes(plan7.SequenceDatabase.of(ctx, seqs).handle)) + int(sum(_lib.lib.b2h_profile_h2d_bytes(om._device(ctx)) for om in oms))
+    nhits_rank0 = len(hits)
     nh = sum(len(r) for r in res)
     d2h = int(nh * 96 + sum(len(h.domains) * 88 + sum(4 * (len(d.alignment) + 1) for d in h.domains) for r in res for h in r))
 
+    extra = None
+    if not args.no_extras:
+        import bench_extras
+        del res, hits
+        gc.collect()
+        try:
+            extra = bench_extras.run(args, ctx, rank, world, torch, dist, lambda m: print(m, file=sys.stderr, flush=True) if rank == 0 else None)
+        except Exception as exc:                          # the headline stands on its own; say what happened to the rest
+            import traceback
+            traceback.print_exc()
+            extra = {"failed": repr(exc)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -371,7 +392,7 @@ def main():
                    "profiles": len(hmms), "sequences_per_rank": len(seqs), "sum_M": int(sum(h.M for h in hmms)),
                    "residues_per_rank": int(seqs.total_residues), "planted_homolog_fraction": PLANT_FRAC,
                    "l2": "flushed (256 MiB write) between steps", "sharding": "targets by rank, one all-gather of hit records",
-                   "hits_rank0": len(hits), "pipeline_counters_rank0": counters.sum(0).tolist(),
+                   "hits_rank0": nhits_rank0, "pipeline_counters_rank0": counters.sum(0).tolist(),
                    "stage_ms_per_step": {k: v / K for k, v in stage_ms.items()},
                    "ssv_kernel_gcups": (cells_local / (ssv_ms * 1e-3) / 1e9) if ssv_ms > 0 else None,
                    "ssv_kernel_gcups_incl_padding": (padded_cells / (ssv_ms * 1e-3) / 1e9) if ssv_ms > 0 else None},
@@ -397,6 +418,8 @@ def main():
                                     "pipeline_counters": r["counters"], "hits": r["hits"]}
         except Exception as exc:                      # the checker is optional for the measurement itself
             line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (exc,)}
+    if extra:
+        line["config"]["extra"] = extra
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

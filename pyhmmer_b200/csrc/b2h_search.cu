@@ -280,6 +280,7 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
       ctx->launches++; }
   } else {
     float *bias_sc; TRY(pool.get(&bias_sc, cap));
+    if (overlap == 2) TRY(to_post_lane());
     StageTimer tm(ctx, 3);
     if (prm->do_biasfilter) {
       B2H_CUDA(cudaEventCreateWithFlags(&cw.bias_fork, cudaEventDisableTiming));

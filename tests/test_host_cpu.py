@@ -842,7 +842,7 @@ def test_scan_tables_match_the_reference_writers(amino, tmp_path, monkeypatch):
                      host_threads=1).items():
         setattr(pli, k, v)
     pli.clear()
-    monkeypatch.setattr(plan7.Pipeline, "_run", lambda self, oms, block: (hits, doms, text, np.zeros((len(oms), 4), np.int64)))
+    monkeypatch.setattr(plan7.Pipeline, "_run", lambda self, oms, block, seq_counters=False: (hits, doms, text, np.zeros((len(block) if seq_counters else len(oms), 4), np.int64)))
     th = pli._scan_many([query], hmms)[0]
     assert th.mode == "scan" and th.Z == float(len(hmms)) and len(th) == nref
     for fmt, ext in (("targets", ".tbl"), ("domains", ".domtbl"), ("pfam", ".pfam")):

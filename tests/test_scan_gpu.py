@@ -126,7 +126,7 @@ def test_rrefam_scan_table(amino):
     expected = {}
     for q, rows in itertools.groupby(_table("RREFam.scan.tbl"), key=lambda r: r[2]):
         expected[q] = list(rows)
-    assert len(expected) == 8 and sum(len(v) for v in expected.values()) == 10
+    assert len(expected) == 7 and sum(len(v) for v in expected.values()) == 10
     seqs = _proteome(amino)
     hmms = _hmms("RREFam")
     seen = 0

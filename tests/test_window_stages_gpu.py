@@ -95,10 +95,12 @@ def test_long_windows_are_cut_at_80kb(make_pair):
     dna = pair.hmm.alphabet
     block = lt_common.easel.DigitalSequenceBlock(dna, [lt_common.easel.DigitalSequence(dna, name=b"rep", sequence=seq)])
     got = longtarget.stages(pair.om, block, **KW)
-    # 80 kb of back-to-back homologs score ~1e5 nats: float32 resolves 8e-3 there and both implementations add thousands of
-    # rounded log(scale) terms, at different rows -- the Forward scores of THIS test are compared to 1e-4 relative, everything
-    # else (landmarks, windows, gates, counters) exactly as in the tests above
-    tot = lt_common.compare_with_reference(pair, block, got, exact_scores=False, fwd_rel=1e-4, **KW)
+    # 80 kb windows of back-to-back homologs: the Forward scores are far above 512 nats, where float32 is coarser than the
+    # 1e-4 nats bar.  No relative tolerance: at most 1e-4 nats or 6 float32 spacings of the score (3.7e-4 nats at 769 nats),
+    # whichever is larger -- each implementation rounds its running log-scale sum to float32 at every one of the ~10 rescaling
+    # rows per hundred nats (fwdback.c:418-435; ours adds the same terms the same way, b2h_dpreg.cu), so a handful of
+    # spacings is the precision of the REFERENCE's own number.  Landmarks, windows, gates and counters: exact, as above.
+    tot = lt_common.compare_with_reference(pair, block, got, exact_scores=False, fwd_ulps=6.0, **KW)
     assert got["vitwin"]["length"].max() == 80000 and tot["vitwin"] >= 3
 
 
