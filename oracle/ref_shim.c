@@ -1104,7 +1104,7 @@ static void *nh_worker(void *arg)
 {
   NH_JOB *job = (NH_JOB *)arg;
   REFM *m = job->m;
-  P7_OPROFILE *om = p7_oprofile_Clone(m->om);
+  P7_OPROFILE *om = p7_oprofile_Copy(m->om);      /* a deep copy, as nhmmer.c gives its threads: the long-target domain definition rewrites the emission scores */
   P7_BG *bg = p7_bg_Clone(m->bg);
   P7_PIPELINE *pli = p7_pipeline_Create(NULL, om->M, 100, TRUE, p7_SEARCH_SEQS);
   P7_SCOREDATA *data = p7_hmm_ScoreDataCreate(om, NULL);
@@ -1182,6 +1182,7 @@ long ref_nhmmer_mt(REFM *m, int nseq, const uint8_t **dsq, const long *len, long
     stats[0] = pli->nres; stats[1] = nseq; stats[2] = pli->pos_past_msv; stats[3] = pli->pos_past_bias; stats[4] = pli->pos_past_vit; stats[5] = pli->pos_past_fwd;
     nout = 0;
     for (i = 0; i < (long)hits->N; i++) if (!(hits->hit[i]->flags & p7_IS_DUPLICATE)) nout++;
+    if (getenv("REF_DEBUG")) for (i = 0; i < (long)hits->N; i++) fprintf(stderr, "mt hit %ld: seq %ld env %ld..%ld score %.1f flags %d\n", i, (long)hits->hit[i]->seqidx, (long)hits->hit[i]->dcl[0].ienv, (long)hits->hit[i]->dcl[0].jenv, hits->hit[i]->score, hits->hit[i]->flags);
   }
   for (t = 0; t < nthreads; t++) { p7_tophits_Destroy(jobs[t].th); p7_pipeline_Destroy(jobs[t].pli); }
   free(th); free(jobs); free(win_seq); free(win_i);
