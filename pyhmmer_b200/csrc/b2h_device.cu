@@ -244,11 +244,50 @@ int b2h_seqdb_create(b2h_ctx *ctx, const uint8_t *const *dsq, const int64_t *len
 int b2h_seqdb_create_packed(b2h_ctx *ctx, const uint8_t *residues, const int64_t *offsets, size_t n, b2h_seqdb **out)
 { return seqdb_build(ctx, n, nullptr, nullptr, residues, offsets, out); }
 
+} // extern "C"
+
+const b2h_chunkview *b2h_seqdb_chunk_view(const b2h_seqdb *cdb, int O, int S, cudaStream_t strm)
+{
+  b2h_seqdb *db = const_cast<b2h_seqdb *>(cdb);
+  for (const b2h_chunkview &v : db->views) if (v.O == O && v.S == S) return &v;
+  b2h_ctx *ctx = db->ctx;
+  std::vector<int64_t> off; std::vector<int32_t> len, parent;
+  for (size_t s = 0; s < db->n; s++)
+    for (int64_t a = 0; a < db->h_len[s]; a += S) {
+      off.push_back(db->h_off[s] + a);
+      len.push_back((int32_t)std::min<int64_t>(db->h_len[s] - a, (int64_t)S + O));
+      parent.push_back((int32_t)s);
+    }
+  const size_t n = off.size(), n1 = std::max<size_t>(n, 1);
+  std::vector<int32_t> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
+  b2h_chunkview v; v.O = O; v.S = S; v.n = (int)n;
+  const size_t o_off = 0, o_len = (n1 * 8 + 255) & ~(size_t)255, o_ord = o_len + ((n1 * 4 + 255) & ~(size_t)255), o_par = o_ord + ((n1 * 4 + 255) & ~(size_t)255),
+               bytes = o_par + n1 * 4;
+  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&v.d_block, bytes) != cudaSuccess) { ctx->err = "chunk view allocation failed"; return nullptr; }
+  uint8_t *b = (uint8_t *)v.d_block;
+  v.d_off = (int64_t *)(b + o_off); v.d_len = (int32_t *)(b + o_len); v.d_order = (int32_t *)(b + o_ord); v.d_parent = (int32_t *)(b + o_par);
+  if (n) {                                                  // pageable sources: the copies are staged before these calls return
+    cudaMemcpyAsync(v.d_off, off.data(), n * 8, cudaMemcpyHostToDevice, strm);
+    cudaMemcpyAsync(v.d_len, len.data(), n * 4, cudaMemcpyHostToDevice, strm);
+    cudaMemcpyAsync(v.d_order, order.data(), n * 4, cudaMemcpyHostToDevice, strm);
+    cudaMemcpyAsync(v.d_parent, parent.data(), n * 4, cudaMemcpyHostToDevice, strm);
+    cudaStreamSynchronize(strm);
+  }
+  if (db->views.capacity() < 64) db->views.reserve(64);     // (callers copy the view at once; keep the storage stable anyway)
+  db->views.push_back(v);
+  return &db->views.back();
+}
+
+extern "C" {
+
 void b2h_seqdb_destroy(b2h_seqdb *db)
 {
   if (!db) return;
   b2h_ctx *ctx = db->ctx;
   if (ctx) cudaSetDevice(ctx->device);
+  for (b2h_chunkview &v : db->views) if (v.d_block) cudaFree(v.d_block);
   if (db->d_block) { if (ctx) cudaFreeAsync(db->d_block, ctx->stream); else cudaFree(db->d_block); }
   if (db->h_block) {
     if (ctx) {

@@ -15,7 +15,7 @@ struct b2h_results {
   std::vector<int64_t>    seq_counters;   // [N][4], only when asked for
 };
 
-struct b2h_survivor { int32_t profile, seq; float fwdsc, filtersc; };
+struct b2h_survivor { int32_t profile, seq; float fwdsc, filtersc; int64_t fxoff = -1; };   // fxoff: row offset of the Forward specials the cascade stored (-1: none)
 
 struct b2h_ddef_task {
   b2h_survivor       surv;

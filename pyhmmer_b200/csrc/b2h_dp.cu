@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) fwd_kernel(const WorkList wl, const SeqDe
       const int L = sd.len[s];
       const uint8_t *seq = sd.res + sd.off[s];
       const float pmove = sd.pmove[s], ploop = 1.0f - pmove;
-      float *xout = out.fwd_xmx ? out.fwd_xmx + out.xoff[e] * 6 : nullptr;
+      float *xout = (out.fwd_xmx && out.xoff[e] >= 0) ? out.fwd_xmx + out.xoff[e] * 6 : nullptr;
 
       for (int j = lane; j < 6 * S; j += 32) rows[j] = 0.0f;
       __syncwarp();

@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqD
       const int s = wl.ent_s[e];
       const int L = sd.len[s];
       const float pmove = sd.pmove[s], ploop = 1.0f - pmove;
-      float *xout = out.fwd_xmx ? out.fwd_xmx + out.xoff[e] * 6 : nullptr;
+      float *xout = (out.fwd_xmx && out.xoff[e] >= 0) ? out.fwd_xmx + out.xoff[e] * 6 : nullptr;
       SeqWin sw; sw.init(sd.res + sd.off[s], L, lane);
       float M[C], I[C], D[C];
 #pragma unroll

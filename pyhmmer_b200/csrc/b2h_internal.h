@@ -81,6 +81,15 @@ void  b2h_pin_put(b2h_ctx *ctx, void *p);
 // device block shared by the profiles of one batched upload; freed when the last of them is destroyed
 struct b2h_devblock { void *d = nullptr; std::atomic<int> refs{0}; };
 
+// A view of the arena as overlapping chunks (scan orientation: few long sequences): chunk c of sequence s covers residues
+// [c*S, min(L, c*S + S + O)) of s.  An ungapped diagonal of a model of M <= O + 1 nodes spans at most M rows, so it lies
+// wholly inside one chunk and the maximum over the chunks of the chunk-local SSV maxima IS the SSV maximum of the sequence.
+struct b2h_chunkview {
+  int O = 0, S = 0, n = 0;
+  void *d_block = nullptr;
+  int64_t *d_off = nullptr; int32_t *d_len = nullptr, *d_order = nullptr, *d_parent = nullptr;
+};
+
 struct b2h_seqdb {
   b2h_ctx  *ctx = nullptr;
   size_t    n = 0;
@@ -106,7 +115,10 @@ struct b2h_seqdb {
   float    *d_null1 = nullptr;
   float    *d_p1 = nullptr;
   float    *d_flta = nullptr, *d_fltb = nullptr;
+  std::vector<b2h_chunkview> views;   // built on demand by b2h_seqdb_chunk_view (driving thread of b2h_search only)
 };
+// the (O, S) chunk view of a database, built and uploaded (stream-ordered on <strm>) at first use
+const b2h_chunkview *b2h_seqdb_chunk_view(const b2h_seqdb *db, int O, int S, cudaStream_t strm);
 
 struct b2h_profile {
   b2h_ctx *ctx = nullptr;
@@ -343,11 +355,17 @@ struct SsvArgs {
                                // short high-priority kernels of the survivor / envelope lanes are not kept waiting by a long SSV launch
   int           *counter;
   int            mode;         // 0: dense p7_SSVFilter  1: dense, queue eslENORESULT in R  2: cascade (P-value test, A and R)
+                               // 3: scan orientation: <sd> is a chunk view, the chunk maxima are folded into raw[profile][parent]
+  const int32_t *parent = nullptr; int *raw = nullptr; int raw_stride = 0;   // mode 3
+  int            threads = 0;  // CTA size (0 = the full 256): a chunk view of one long query holds a handful of chunks per profile
   float         *out_sc; int32_t *out_status;
   SurvList       A, R;
   double         F1;
 };
 int b2h_launch_ssv(b2h_ctx *ctx, int G, int NR, const SsvArgs &a, cudaStream_t strm);
+// scan orientation, after the mode-3 launches: p7_SSVFilter's post-processing and the F1 test for every (profile, sequence)
+// from raw[P][n] -- appends to A (passed) and R (eslENORESULT: needs the full MSV filter)
+int b2h_launch_ssv_finish(b2h_ctx *ctx, const ProfDev *profs, int P, const SeqDev &sd, const int *raw, SurvList A, SurvList R, double F1);
 // full MSV (with J) over a grouped work list; mode 1: dense outputs indexed by sequence, 2: cascade append to A
 int b2h_launch_msv(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, int mode,
                    float *out_sc, int32_t *out_status, SurvList A, double F1);

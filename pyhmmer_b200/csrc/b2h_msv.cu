@@ -223,6 +223,9 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
         const float f = __half2float(__ushort_as_half((unsigned short)v));
         v = (f > 30000.0f) ? 30000 : (int)f;
       }
+      if (a.mode == 3) {                                      // scan orientation: fold this chunk's maximum into its sequence's
+        if (gl == 0 && valid) atomicMax(a.raw + (size_t)pidx * a.raw_stride + a.parent[s], v);
+      } else
       if (gl == 0 && valid && (a.mode != 2 || L > 0)) {         // p7_Pipeline returns at once for an empty target (p7_pipeline.c:713): it enters no list
         float sc; int status;
         ssv_finish(v, P, (int)a.sd.tjb[s], sc, status);
@@ -465,19 +468,35 @@ __global__ void group_scatter_kernel(const SurvList in, const int32_t *poff, int
   }
 }
 
+// p7_SSVFilter's post-processing + the F1 test of p7_Pipeline for the raw maxima of the scan orientation
+__global__ void ssv_finish_kernel(const ProfDev *profs, int P, const SeqDev sd, const int *raw, const SurvList A, const SurvList R, double F1)
+{
+  const long long total = (long long)P * sd.n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / sd.n), s = (int)(idx - (long long)p * sd.n);
+    if (sd.len[s] <= 0) continue;                          // p7_Pipeline skips empty targets
+    const ProfDev &Pf = profs[p];
+    float sc; int status;
+    ssv_finish(raw[idx], Pf, (int)sd.tjb[s], sc, status);
+    if (status == B2H_ENORESULT) surv_append(R, p, s, 0.f, 0.f);
+    else if (msv_passes(sc, sd.null1[s], Pf, F1)) surv_append(A, p, s, sc, 0.f);
+  }
+}
+
 template <int G, int NR>
 int launch_ssv_tile(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
 {
   const size_t smem = (size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR);
+  const int threads = (a.threads > 0 && a.threads <= SSV_THREADS) ? a.threads : SSV_THREADS;
   int occ = 1;
-  { const int st = b2h_kernel_occupancy(ctx, (const void *)ssv_kernel<G, NR>, SSV_THREADS, smem, &occ); if (st != B2H_OK) return st; }
+  { const int st = b2h_kernel_occupancy(ctx, (const void *)ssv_kernel<G, NR>, threads, smem, &occ); if (st != B2H_OK) return st; }
   static const int occ_cap = getenv("B2H_SSV_OCC") ? atoi(getenv("B2H_SSV_OCC")) : 0;       // experiments: resident CTAs per SM
   if (occ_cap > 0 && occ > occ_cap) occ = occ_cap;
   int grid = ctx->sm_count * occ;
   const long long nitems = (long long)a.ncls * a.chunks;
   if (grid > nitems) grid = (int)(nitems > 0 ? nitems : 1);
   if (a.items_per_cta > 0) grid = (int)std::max<long long>(grid, (nitems + a.items_per_cta - 1) / a.items_per_cta);
-  ssv_kernel<G, NR><<<grid, SSV_THREADS, smem, strm>>>(a);
+  ssv_kernel<G, NR><<<grid, threads, smem, strm>>>(a);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());
   return B2H_OK;
@@ -500,6 +519,17 @@ int b2h_launch_ssv(b2h_ctx *ctx, int G, int NR, const SsvArgs &a, cudaStream_t s
   }
   ctx->err = "no SSV kernel for this register tile";
   return B2H_EINVAL;
+}
+
+int b2h_launch_ssv_finish(b2h_ctx *ctx, const ProfDev *profs, int P, const SeqDev &sd, const int *raw, SurvList A, SurvList R, double F1)
+{
+  const long long total = (long long)P * sd.n;
+  if (total <= 0) return B2H_OK;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+  ssv_finish_kernel<<<grid, 256, 0, ctx->stream>>>(profs, P, sd, raw, A, R, F1);
+  ctx->launches++;
+  B2H_CUDA(cudaGetLastError());
+  return B2H_OK;
 }
 
 int b2h_launch_msv(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int max_Mpad, int nitems_hint, int mode,

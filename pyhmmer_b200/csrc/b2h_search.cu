@@ -103,16 +103,49 @@ __global__ void vit_post_kernel(const ProfDev *profs, const Grouped g, const int
 }
 
 __global__ void fwd_post_kernel(const ProfDev *profs, const Grouped g, const int32_t *nent, const float *fwdsc, const int32_t *fst,
-                                double F3, SurvList D, int *nerr)
+                                double F3, SurvList D, int *nerr, const int64_t *xoff, int64_t *dxoff)
 {
   const int n = *nent;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const int p = g.p[e];
+    const int p = g.p[e], s = g.s[e];
     const ProfDev &P = profs[p];
     if (fst[e] != B2H_OK) { atomicAdd(nerr, 1); continue; }
     const double pv = exp_surv((double)bits(fwdsc[e], g.a[e]), (double)P.evparam[4], (double)P.evparam[5]);
     if (pv > F3) continue;
-    surv_append(D, p, g.s[e], fwdsc[e], g.a[e]);
+    const int slot = atomicAdd(D.n, 1);                  // surv_append, plus where this comparison's Forward specials were stored
+    if (slot < D.cap) {
+      D.p[slot] = p; D.s[slot] = s; D.a[slot] = fwdsc[e]; D.b[slot] = g.a[e]; dxoff[slot] = xoff ? xoff[e] : -1;
+      atomicAdd(D.cnt + p, 1); if (D.cnts) atomicAdd(D.cnts + s, 1);
+    }
+  }
+}
+
+// Row offsets of the Forward special-state rows of a grouped list: exclusive prefix sum of (L + 1) over the entries, -1 for the
+// entries that would not fit in <cap_rows> (their survivors take the Forward pass again on the survivor lane).  One CTA.
+__global__ void __launch_bounds__(1024) xoff_scan_kernel(const int32_t *ent_s, const int32_t *nent, const int32_t *len, int64_t cap_rows, int64_t *xoff)
+{
+  __shared__ long long s_part[1024];
+  const int n = *nent, t = threadIdx.x;
+  const int per = (n + 1023) / 1024, b = min(n, t * per), e = min(n, b + per);
+  long long sum = 0;
+  for (int i = b; i < e; i++) sum += len[ent_s[i]] + 1;
+  s_part[t] = sum;
+  __syncthreads();
+  if (t == 0) { long long a = 0; for (int i = 0; i < 1024; i++) { const long long v = s_part[i]; s_part[i] = a; a += v; } }
+  __syncthreads();
+  long long a = s_part[t];
+  for (int i = b; i < e; i++) { const long long r = len[ent_s[i]] + 1; xoff[i] = (a + r <= cap_rows) ? a : -1; a += r; }
+}
+
+// Copy the special-state rows of the F3 survivors out of the cascade's Forward buffer into the compact layout the Backward
+// pass and the host expect: rows [src[e], src[e] + n[e]) -> [dst[e], ...), 6 floats per row.  One CTA per entry (grid-stride).
+__global__ void gather_rows_kernel(const float *src, float *dst, const int64_t *src_off, const int64_t *dst_off, const int32_t *ent_s,
+                                   const int32_t *len, int n)
+{
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const int64_t words = (int64_t)(len[ent_s[e]] + 1) * 6;
+    const float *a = src + src_off[e] * 6; float *b = dst + dst_off[e] * 6;
+    for (int64_t i = threadIdx.x; i < words; i += blockDim.x) b[i] = a[i];
   }
 }
 
@@ -163,9 +196,10 @@ struct CascadeWave {
   int p0 = 0, P = 0;
   std::vector<int> perm;
   Pinned<int> hctr; Pinned<ProfDev> hprof; Pinned<int32_t> hcls;
-  SurvList D;
+  SurvList D; int64_t *D_xoff = nullptr;
+  float *d_fx = nullptr; cudaStream_t fx_stream = nullptr;     // Forward special-state rows of every entry of list F (kept beyond the wave's pool: the survivor lane reads them)
   cudaEvent_t done = nullptr, ssv_done = nullptr, bias_fork = nullptr, bias_join = nullptr;
-  ~CascadeWave() { for (cudaEvent_t e : {done, ssv_done, bias_fork, bias_join}) if (e) cudaEventDestroy(e); }
+  ~CascadeWave() { for (cudaEvent_t e : {done, ssv_done, bias_fork, bias_join}) if (e) cudaEventDestroy(e); if (d_fx) cudaFreeAsync(d_fx, fx_stream); }
 };
 
 static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int p0, int p1, const b2h_seqdb *db,
@@ -221,6 +255,43 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
   const int pgrid = ctx->sm_count * 8;
 
   // 1. SSV over every comparison
+  // Scan orientation (few, possibly long sequences: hmmscan): one comparison per profile would keep one lane group of a
+  // CTA busy and walk the whole sequence serially.  SSV is exactly decomposable along the sequence -- an ungapped diagonal
+  // spans at most M rows -- so every sequence is taken as overlapping chunks (b2h_chunkview), the kernel folds the chunk
+  // maxima into raw[profile][sequence] and a finish kernel applies p7_SSVFilter's post-processing and the F1 test.
+  static const int scan_max = getenv("B2H_SCAN_MAXSEQ") ? atoi(getenv("B2H_SCAN_MAXSEQ")) : 2048;
+  const bool scan_mode = N <= scan_max;
+  if (scan_mode) {
+    StageTimer tm(ctx, 0);
+    int *raw; TRY(pool.get(&raw, cap));
+    B2H_CUDA(cudaMemsetAsync(raw, 0, cap * sizeof(int), ctx->stream));
+    {
+      ForkJoin fj(ctx);
+      int ssv_cls = 0;
+      for (auto &cr : cls_ranges) {
+        const int Gc = cr.first / 64, NRc = cr.first % 64, NG = 32 / Gc;
+        const int O = ((2 * Gc * NRc + 127) / 128) * 128;
+        auto nchunks = [&](int S) { long long c = 0; for (int s = 0; s < N; s++) c += (db->h_len[s] + S - 1) / S; return c; };
+        int S = 4 * O;                                        // 1.25x the cells; finer cuts (2x, 1x the overlap) when the job is small
+        if ((long long)cr.second.second * nchunks(S) < 16384) S = 2 * O;
+        if ((long long)cr.second.second * nchunks(S) < 16384) S = O;
+        const b2h_chunkview *vp = b2h_seqdb_chunk_view(db, O, S, ctx->stream);
+        if (!vp) return B2H_EMEM;
+        const b2h_chunkview v = *vp;
+        if (v.n == 0) continue;
+        SsvArgs a;
+        a.profs = d_prof; a.cls = d_cls + cr.second.first; a.ncls = cr.second.second;
+        a.sd = sd; a.sd.off = v.d_off; a.sd.len = v.d_len; a.sd.order = v.d_order; a.sd.n = v.n;
+        a.chunks = (v.n + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK; a.counter = ctx->d_counters + 32 + (ssv_cls++ % 24); a.mode = 3;
+        a.items_per_cta = 2;
+        a.out_sc = nullptr; a.out_status = nullptr; a.A = A; a.R = R; a.F1 = prm->F1;
+        a.parent = v.d_parent; a.raw = raw; a.raw_stride = N;
+        a.threads = 32 * std::max(1, std::min(8, (std::min(v.n, B2H_SSV_CHUNK) + NG - 1) / NG));
+        TRY(b2h_launch_ssv(ctx, Gc, NRc, a, fj.next()));
+      }
+    }
+    TRY(b2h_launch_ssv_finish(ctx, d_prof, P, sd, raw, A, R, prm->F1));
+  } else
   { StageTimer tm(ctx, 0);
   ForkJoin fj(ctx);
   int ssv_cls = 0;
@@ -304,10 +375,26 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
   if (overlap == 3) TRY(to_post_lane());
   { StageTimer tg(ctx, 6); TRY(b2h_launch_group(ctx, F, P, G)); }
   { StageTimer tm(ctx, 4);
+    // The Forward stage keeps the special-state rows of every comparison it scores (a prefix sum over the grouped list gives
+    // the row offsets), so that the F3 survivors need only the Backward pass afterwards (p7_pipeline.c:764-773 runs Forward
+    // once, too).  The buffer is sized on the host for the common case; entries beyond it are marked and redone later.
+    static const long long fx_budget = getenv("B2H_FX_ROWS") ? atoll(getenv("B2H_FX_ROWS")) : ((long long)16 << 20);   // rows of 6 floats (384 MB)
+    const long long cap_rows = std::min<long long>(fx_budget, (long long)P * ((long long)db->nres + N));
+    int64_t *d_xoffF = nullptr, *d_Dx = nullptr;
+    TRY(pool.get(&d_xoffF, cap)); TRY(pool.get(&d_Dx, cap));
     StageOut so; so.sc = stage_sc; so.status = stage_st; so.fwd_xmx = so.bck_xmx = nullptr; so.xoff = nullptr;
+    if (cap_rows > 0 && !getenv("B2H_FWD_TWICE")) {
+      if (cudaMallocAsync((void **)&cw.d_fx, (size_t)cap_rows * 6 * sizeof(float), ctx->stream) == cudaSuccess) {
+        cw.fx_stream = ctx->stream;
+        xoff_scan_kernel<<<1, 1024, 0, ctx->stream>>>(G.s, nent, sd.len, (int64_t)cap_rows, d_xoffF);
+        ctx->launches++;
+        so.fwd_xmx = cw.d_fx; so.xoff = d_xoffF;
+      } else { (void)cudaGetLastError(); cw.d_fx = nullptr; }
+    }
     TRY(b2h_launch_forward(ctx, wl, sd, mpads, 0, so));
-    fwd_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, G, nent, stage_sc, stage_st, prm->F3, D, d_ctr + 5);
-    ctx->launches++; }
+    fwd_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, G, nent, stage_sc, stage_st, prm->F3, D, d_ctr + 5, so.xoff, d_Dx);
+    ctx->launches++;
+    cw.D_xoff = d_Dx; }
   B2H_CUDA(cudaGetLastError());
 
   // 6. the counters come home (page-locked: the copy must not block the host, the next wave is queued behind it)
@@ -334,7 +421,9 @@ static int cascade_collect(b2h_ctx *ctx, CascadeWave &cw, cudaStream_t copy_stre
   }
   if (nD) {
     Pinned<int32_t> h; TRY(h.alloc(ctx, (size_t)4 * nD));
+    Pinned<int64_t> hx; TRY(hx.alloc(ctx, (size_t)nD));
     const SurvList &D = cw.D;
+    B2H_CUDA(cudaMemcpyAsync(hx.data(), cw.D_xoff, nD * sizeof(int64_t), cudaMemcpyDeviceToHost, copy_stream));
     B2H_CUDA(cudaMemcpyAsync(h.data(), D.p, nD * sizeof(int32_t), cudaMemcpyDeviceToHost, copy_stream));
     B2H_CUDA(cudaMemcpyAsync(h.data() + nD, D.s, nD * sizeof(int32_t), cudaMemcpyDeviceToHost, copy_stream));
     B2H_CUDA(cudaMemcpyAsync(h.data() + 2 * (size_t)nD, D.a, nD * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
@@ -342,7 +431,7 @@ static int cascade_collect(b2h_ctx *ctx, CascadeWave &cw, cudaStream_t copy_stre
     B2H_CUDA(cudaStreamSynchronize(copy_stream));
     outD.reserve(outD.size() + nD);
     const float *fa = reinterpret_cast<const float *>(h.data() + 2 * (size_t)nD), *fb = reinterpret_cast<const float *>(h.data() + 3 * (size_t)nD);
-    for (int i = 0; i < nD; i++) { b2h_survivor v; v.profile = p0 + cw.perm[h[i]]; v.seq = h[(size_t)nD + i]; v.fwdsc = fa[i]; v.filtersc = fb[i]; outD.push_back(v); }
+    for (int i = 0; i < nD; i++) { b2h_survivor v; v.profile = p0 + cw.perm[h[i]]; v.seq = h[(size_t)nD + i]; v.fwdsc = fa[i]; v.filtersc = fb[i]; v.fxoff = cw.d_fx ? hx[i] : -1; outD.push_back(v); }
   }
   cw.pool.reset();                                    // stream-ordered frees on the wave's lane, after everything queued there so far
   return B2H_OK;
@@ -516,12 +605,13 @@ struct DdefQueue {
 // with its D2H copies behind it; <done> fires when everything has arrived in the page-locked job buffers.
 struct SurvChunk {
   std::unique_ptr<Pool> pool; std::unique_ptr<DdefJob> job;
-  std::vector<ProfDev> hprof; std::vector<int32_t> poff, itemoff, ent_s; std::vector<int64_t> xoff;   // H2D sources: alive until <done>
+  std::vector<ProfDev> hprof; std::vector<int32_t> poff, itemoff, ent_s; std::vector<int64_t> xoff, srcoff;   // H2D sources: alive until <done>
   size_t i0 = 0; int n = 0;
 };
 struct SurvPending {
   std::vector<b2h_survivor> surv; std::vector<std::unique_ptr<SurvChunk>> chunks; cudaEvent_t done = nullptr; size_t wave = 0;
-  ~SurvPending() { if (done) cudaEventDestroy(done); }
+  float *fx_src = nullptr; cudaStream_t fx_stream = nullptr;    // the cascade's Forward special-state rows (list F) of this wave
+  ~SurvPending() { if (done) cudaEventDestroy(done); if (fx_src) cudaFreeAsync(fx_src, fx_stream); }
 };
 
 static int survivors_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, SurvPending &sp)
@@ -543,11 +633,13 @@ static int survivors_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, c
     ck.i0 = i0; ck.n = n;
     // work list of this chunk: profiles present, in order
     std::vector<ProfDev> &hprof = ck.hprof; std::vector<int32_t> &poff = ck.poff, &itemoff = ck.itemoff, &ent_s = ck.ent_s; std::vector<int64_t> &xoff = ck.xoff;
-    ent_s.resize(n); xoff.resize(n);
+    ent_s.resize(n); xoff.resize(n); ck.srcoff.resize(n);
     std::vector<int> mpads;
     int64_t acc = 0; int items = 0;
+    bool have_fwd = sp.fx_src != nullptr;                  // every entry's Forward rows were stored by the cascade?
     for (int e = 0; e < n; e++) {
       const b2h_survivor &v = surv[i0 + e];
+      ck.srcoff[e] = v.fxoff; if (v.fxoff < 0) have_fwd = false;
       if (e == 0 || v.profile != surv[i0 + e - 1].profile) {
         if (e) items += ((e - poff.back()) + B2H_ITEM_ENTRIES - 1) / B2H_ITEM_ENTRIES;
         hprof.push_back(b2h_profdev(profiles[v.profile])); poff.push_back(e); itemoff.push_back(items); mpads.push_back(hprof.back().Mpad);
@@ -571,7 +663,16 @@ static int survivors_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, c
     WorkList wl; wl.profs = d_prof; wl.ent_s = d_ent; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = Pc; wl.counter = ctx->d_counters + 8; wl.plo = 0; wl.phi = Pc;
     StageOut sf; sf.sc = d_fsc; sf.status = d_fst; sf.fwd_xmx = d_fx; sf.bck_xmx = nullptr; sf.xoff = d_xoff;
     StageOut sb; sb.sc = d_bsc; sb.status = d_bst; sb.fwd_xmx = d_fx; sb.bck_xmx = d_bx; sb.xoff = d_xoff;
-    { StageTimer tm(ctx, 5); TRY(b2h_launch_forward_backward(ctx, wl, sd, mpads, items, sf, sb)); }
+    if (have_fwd) {                                        // the rows are there: compact them, then Backward only
+      StageTimer tm(ctx, 5);
+      int64_t *d_srcoff; TRY(pool.get(&d_srcoff, n));
+      B2H_CUDA(cudaMemcpyAsync(d_srcoff, ck.srcoff.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+      gather_rows_kernel<<<std::min(n, ctx->sm_count * 8), 256, 0, ctx->stream>>>(sp.fx_src, d_fx, d_srcoff, d_xoff, d_ent, sd.len, n);
+      ctx->launches++;
+      B2H_CUDA(cudaGetLastError());
+      B2H_CUDA(cudaMemsetAsync(d_bst, 0, n * sizeof(int32_t), ctx->stream));
+      TRY(b2h_launch_backward(ctx, wl, sd, mpads, items, sb));
+    } else { StageTimer tm(ctx, 5); TRY(b2h_launch_forward_backward(ctx, wl, sd, mpads, items, sf, sb)); }
     ck.job.reset(new DdefJob());
     Pinned<float> &fx = ck.job->fx, &bx = ck.job->bx; Pinned<int32_t> &bst = ck.job->bst;
     TRY(fx.alloc(ctx, (size_t)acc * 6)); TRY(bx.alloc(ctx, (size_t)acc * 6)); TRY(bst.alloc(ctx, n));
@@ -580,6 +681,7 @@ static int survivors_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, c
     B2H_CUDA(cudaMemcpyAsync(bst.data(), d_bst, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     i0 = i1;
   }
+  if (sp.fx_src) { cudaFreeAsync(sp.fx_src, ctx->stream); sp.fx_src = nullptr; }   // (stream-ordered: after the gathers queued above)
   B2H_CUDA(cudaEventCreateWithFlags(&sp.done, cudaEventDisableTiming));
   B2H_CUDA(cudaEventRecord(sp.done, ctx->stream));
   return B2H_OK;
@@ -704,6 +806,7 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
         p->wave = w;
         const int lane_id = (w & 1) ? B2H_LANE_SURV2 : B2H_LANE_SURV;
         st = cascade_collect(ctx, *waves[w], ctx->lanes[lane_id].stream, p->surv, scnt.data());
+        p->fx_src = waves[w]->d_fx; p->fx_stream = ctx->lanes[lane_id].stream; waves[w]->d_fx = nullptr;
         waves[w].reset();
         if (trace) fprintf(stderr, "[b2h_search]   wave %zu (%zu profiles): cascade collected at +%.1f ms (queued up to wave %zu)\n", w, bounds[w + 1] - bounds[w], now_ms() - t0, queued - 1);
         if (st == B2H_OK) { b2h_lane_switch lane(ctx, lane_id); st = survivors_enqueue(ctx, sp.data(), db, *p); }

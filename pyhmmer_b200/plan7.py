@@ -1304,20 +1304,93 @@ def long_target_windows(om, chunks, F1=0.02):
 
 
 class OptimizedProfileBlock(list):
-    """An ordered block of `OptimizedProfile` sharing one alphabet (``pyhmmer.plan7.OptimizedProfileBlock``)."""
+    """An ordered block of `OptimizedProfile` sharing one alphabet (``pyhmmer.plan7.OptimizedProfileBlock``).
+
+    What a scan needs of the whole block -- the array of device handles, the node total -- is cached per block and dropped
+    by every mutating method, so that a scan of one query does not walk 20 000 Python objects."""
 
     def __init__(self, alphabet, iterable=()):
         super().__init__()
         self.alphabet = alphabet
+        self._cache = {}
         for om in iterable:
             self.append(om)
 
-    def append(self, om):
+    def _check(self, om):
         if not isinstance(om, OptimizedProfile):
             raise TypeError("expected OptimizedProfile, found %s" % type(om).__name__)
         if om.alphabet != self.alphabet:
             raise AlphabetMismatch(self.alphabet, om.alphabet)
+
+    def append(self, om):
+        self._check(om)
+        self._cache = {}
         super().append(om)
+
+    def extend(self, oms):
+        for om in oms:
+            self.append(om)
+
+    def insert(self, i, om):
+        self._check(om)
+        self._cache = {}
+        super().insert(i, om)
+
+    def __setitem__(self, i, v):
+        for om in (v if isinstance(i, slice) else (v,)):
+            self._check(om)
+        self._cache = {}
+        super().__setitem__(i, v)
+
+    def __delitem__(self, i):
+        self._cache = {}
+        super().__delitem__(i)
+
+    def pop(self, i=-1):
+        self._cache = {}
+        return super().pop(i)
+
+    def remove(self, om):
+        self._cache = {}
+        super().remove(om)
+
+    def clear(self):
+        self._cache = {}
+        super().clear()
+
+    def sort(self, *, key=None, reverse=False):
+        self._cache = {}
+        super().sort(key=key, reverse=reverse)
+
+    def reverse(self):
+        self._cache = {}
+        super().reverse()
+
+    def __iadd__(self, oms):
+        self.extend(oms)
+        return self
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return OptimizedProfileBlock(self.alphabet, list.__getitem__(self, i))
+        return list.__getitem__(self, i)
+
+    def copy(self):
+        return OptimizedProfileBlock(self.alphabet, self)
+
+    @property
+    def total_nodes(self):
+        n = self._cache.get("nodes")
+        if n is None:
+            n = self._cache["nodes"] = sum(om.M for om in self)
+        return n
+
+    def _handles(self, ctx):
+        """ctypes array of the profiles' device handles (uploading what is not resident yet)."""
+        h = self._cache.get(("handles", ctx))
+        if h is None:
+            h = self._cache[("handles", ctx)] = (ctypes.c_void_p * len(self))(*OptimizedProfile._device_many(ctx, self))
+        return h
 
 
 class _DeviceHandle:
@@ -2146,7 +2219,8 @@ class Pipeline:
             db = SequenceDatabase.of(ctx, block)
         else:
             db = SequenceDatabase.of(ctx, block)
-            handles = (ctypes.c_void_p * len(oms))(*OptimizedProfile._device_many(ctx, oms))
+            handles = oms._handles(ctx) if isinstance(oms, OptimizedProfileBlock) else \
+                (ctypes.c_void_p * len(oms))(*OptimizedProfile._device_many(ctx, oms))
         prm = self._params_struct(seq_counters)
         out = ctypes.c_void_p()
         t1 = time.perf_counter()
@@ -2261,14 +2335,22 @@ class Pipeline:
         records gives every rank the same `TopHits` (Z = all models)."""
         if any(q.alphabet != self.alphabet for q in queries):
             raise AlphabetMismatch(self.alphabet, [q.alphabet for q in queries if q.alphabet != self.alphabet][0])
-        oms = self._optimized_many(targets, self.L_HINT)
-        cuts = [self._cutoffs(om) for om in oms]
+        if isinstance(targets, OptimizedProfileBlock):      # the pre-fetched database of hmmscan: nothing to convert
+            if targets.alphabet != self.alphabet:
+                raise AlphabetMismatch(self.alphabet, targets.alphabet)
+            oms = targets
+        else:
+            oms = OptimizedProfileBlock(self.alphabet, self._optimized_many(targets, self.L_HINT))
+        cuts = [self._cutoffs(om) for om in oms] if self.bit_cutoffs is not None else None
         block = DigitalSequenceBlock(self.alphabet, queries)
         from . import parallel
         lo, local = 0, oms
         if world is not None and world.size > 1:
-            b = parallel.shard_bounds([om.M for om in oms], world.size)
-            lo, local = b[world.rank], oms[b[world.rank]:b[world.rank + 1]]
+            key = ("shard", world.size, world.rank)
+            if key not in oms._cache:                           # this rank's run of the block, kept with the block
+                b = parallel.shard_bounds([om.M for om in oms], world.size)
+                oms._cache[key] = (b[world.rank], oms[b[world.rank]:b[world.rank + 1]])
+            lo, local = oms._cache[key]
         # the pass counters are kept per QUERY SEQUENCE: every scan_seq result reports its own (plan7.pyx:6534-6677)
         if local and len(block):
             hits, doms, text, counters = self._run(local, block, seq_counters=True)
@@ -2289,7 +2371,7 @@ class Pipeline:
             th = self._tophits(seq, "scan", None)
             mine = sorted((r for r in hits if r.seq == si), key=lambda r: r.profile)
             for rec in mine:
-                cut = cuts[rec.profile]
+                cut = cuts[rec.profile] if cuts is not None else None
                 if cut is not None:
                     th._params.update(by_E=False, dom_by_E=False, inc_by_E=False, incdom_by_E=False,
                                       T=cut[0], incT=cut[0], domT=cut[1], incdomT=cut[1])
@@ -2297,7 +2379,7 @@ class Pipeline:
                 self._admit(th, rec, oms[rec.profile], doms, text, Z_running, cut)
             th.Z = float(self.Z) if self.Z is not None else float(len(oms))
             th.domZ = float(self.domZ) if self.domZ is not None else 0.0
-            th.searched_models, th.searched_nodes = len(oms), sum(om.M for om in oms)
+            th.searched_models, th.searched_nodes = len(oms), oms.total_nodes
             th.searched_sequences, th.searched_residues = 1, len(seq)
             th.n_past_msv, th.n_past_bias, th.n_past_vit, th.n_past_fwd = (int(v) for v in counters[si])
             th._sort_by_key()

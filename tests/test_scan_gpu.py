@@ -251,3 +251,48 @@ def test_reduced_c3_slice_counters(amino):
     nh, ctr = refshim.search_mt(refs, seqs_arr, psutil.cpu_count(logical=True) or 8)
     assert counters.sum(0).tolist() == ctr
     assert len(hits) == nh and nh >= 150
+
+
+_ORIENT_WORKER = r'''
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from pyhmmer_b200 import easel, plan7, synth
+abc = easel.Alphabet.amino()
+rng = np.random.default_rng(2024)
+Ms = (1, 7, 60, 254, 255, 256, 300, 511, 512, 700, 1023, 1024, 1500, 2300)
+hmms = [synth.random_hmm(abc, M, rng, name="m%%d" %% M) for M in Ms]
+lens = (0, 1, 2, 37, 350, 1027, 5000, 12000, 4096)
+seqs = []
+for i, L in enumerate(lens):
+    s = rng.integers(0, 20, L).astype(np.uint8)
+    for j in range(L // 900):                                # homologs of various models all along the long ones
+        d = synth.emit_sequence(hmms[(i + 3 * j) %% len(hmms)], rng)
+        pos = int(rng.integers(0, max(1, L - len(d))))
+        s[pos:pos + len(d)] = d[:L - pos]
+    seqs.append(easel.DigitalSequence(abc, name="s%%d" %% i, sequence=s))
+block = easel.DigitalSequenceBlock(abc, seqs)
+pli = plan7.Pipeline(abc)
+oms = [pli._optimized(h, 100) for h in hmms]
+hits, doms, text, counters = pli._run(oms, block, seq_counters=True)
+hits2, doms2, text2, pcounters = pli._run(oms, block)
+print(json.dumps({"seq_counters": counters.tolist(), "profile_counters": pcounters.tolist(),
+                  "hits": [(h.profile, h.seq, round(float(h.score), 4), h.ndom) for h in hits]}))
+'''
+
+
+def test_scan_orientation_equals_search_orientation():
+    """The chunked SSV pass of the scan orientation (few, long sequences: every sequence cut into overlapping chunks whose
+    maxima are folded per sequence) decides exactly what the search-orientation kernel decides: same pass counters per
+    sequence and per profile, same hits -- models at every overlap-class boundary, sequences from 0 to 12 000 residues."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({}, {"B2H_SCAN_MAXSEQ": "0"}):
+        r = subprocess.run([sys.executable, "-c", _ORIENT_WORKER % (root,)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1]
+    assert len(outs[0]["hits"]) >= 10 and sum(c[0] for c in outs[0]["seq_counters"]) > len(outs[0]["hits"])
