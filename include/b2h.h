@@ -373,6 +373,15 @@ int  b2h_longtarget_hits(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *wi
                          const int64_t *seq_start, const int32_t *complement, const int32_t *seq,
                          const b2h_search_params *params, b2h_results **out);
 
+/* The windows of a long-target search as one packed residue buffer (what LongTargetsPipeline._search_loop_longtargets hands
+ * to p7_Pipeline_LongTarget window by window, plan7.pyx:7541-7663): window w = residues [offset, offset + len) of target
+ * win_target[w] (0-based offset, no sentinels), reverse-complemented (esl_sq_ReverseComplement, esl_sq.c:1545: the window
+ * reversed, every code mapped through comp_table[Kp]) when win_comp[w] != 0; written at out + out_off[w].  Host only,
+ * <nthreads> threads (0 = all cores). */
+int b2h_pack_windows(const uint8_t *const *targets, size_t nwin, const int32_t *win_target, const int64_t *win_offset,
+                     const int64_t *win_len, const int32_t *win_comp, const uint8_t *comp_table, int Kp,
+                     uint8_t *out, const int64_t *out_off, int nthreads);
+
 /* Register tile the SSV kernel uses for a model of M nodes: G lanes per comparison (32/G comparisons per warp), NR packed
  * registers (2*NR nodes) per lane, and the number of 128-byte shared-memory wavefronts one DP row of one WARP moves
  * (emission loads + shuffles) -- the quantity bench.py's on-chip roofline is computed from.  B2H_EINVAL if M > 3071. */

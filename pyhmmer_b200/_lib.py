@@ -153,6 +153,7 @@ def _load():
     sig("b2h_profile_set_annotation", c_int, c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p)
     sig("b2h_seqdb_h2d_bytes", ctypes.c_size_t, c_void_p)
     sig("b2h_profile_h2d_bytes", ctypes.c_size_t, c_void_p)
+    sig("b2h_pack_windows", c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int)
     sig("b2h_ssv_tile_info", c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double))
     sig("b2h_generic_scores", c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_float,
         c_void_p, c_void_p, c_void_p, c_void_p)

@@ -62,6 +62,7 @@ void b2h_ctx_destroy(b2h_ctx *ctx)
   for (int i = 0; i < 8; i++) { if (ctx->env_side[i]) cudaStreamDestroy(ctx->env_side[i]); if (ctx->env_join[i]) cudaEventDestroy(ctx->env_join[i]); }
   for (auto &pf : ctx->pinned_free) cudaFreeHost(pf.first);
   for (auto &pf : ctx->pin_pool) cudaFreeHost(pf.first);
+  for (auto &b : ctx->bigbufs) { if (b.p) cudaFree(b.p); if (b.free_ev) cudaEventDestroy(b.free_ev); }
   for (auto &l : ctx->lanes) {
     if (l.counters) cudaFree(l.counters);
     if (l.stream) cudaStreamDestroy(l.stream);
@@ -652,6 +653,27 @@ void b2h_pin_put(b2h_ctx *ctx, void *q)
   ctx->pin_pool.emplace_back(p, *(size_t *)p);
 }
 
+
+void *b2h_bigbuf_get(b2h_ctx *ctx, size_t bytes, cudaStream_t strm)
+{
+  b2h_ctx::BigBuf *best = nullptr;
+  for (auto &b : ctx->bigbufs) if (!b.in_use && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+  if (!best) {
+    for (auto &b : ctx->bigbufs) if (!b.in_use && (!best || b.bytes > best->bytes)) best = &b;       // grow the largest idle one
+    if (best) { cudaEventSynchronize(best->free_ev); cudaFree(best->p); best->p = nullptr; best->bytes = 0; }
+    else { ctx->bigbufs.emplace_back(); best = &ctx->bigbufs.back(); cudaEventCreateWithFlags(&best->free_ev, cudaEventDisableTiming); }
+    if (cudaMalloc(&best->p, bytes) != cudaSuccess) { (void)cudaGetLastError(); best->p = nullptr; best->bytes = 0; return nullptr; }
+    best->bytes = bytes;
+    cudaEventRecord(best->free_ev, strm);
+  }
+  best->in_use = true;
+  cudaStreamWaitEvent(strm, best->free_ev, 0);             // its previous user (on whatever lane) is done
+  return best->p;
+}
+void b2h_bigbuf_put(b2h_ctx *ctx, void *p, cudaStream_t strm)
+{
+  for (auto &b : ctx->bigbufs) if (b.p == p) { cudaEventRecord(b.free_ev, strm); b.in_use = false; return; }
+}
 
 int b2h_kernel_occupancy(b2h_ctx *ctx, const void *kernel, int threads, size_t smem, int *occ)
 {

@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <limits>
 #include <vector>
+#include <atomic>
+#include <thread>
 #include "b2h.h"
 
 namespace {
@@ -423,6 +425,33 @@ int b2h_hmm_max_length(int M, const float *t, double emit_thresh, int32_t *max_l
     if (surv < emit_thresh) { *max_length = col; break; }
     cp = 1 - cp;
   }
+  return B2H_OK;
+}
+
+int b2h_pack_windows(const uint8_t *const *targets, size_t nwin, const int32_t *win_target, const int64_t *win_offset,
+                     const int64_t *win_len, const int32_t *win_comp, const uint8_t *comp_table, int Kp,
+                     uint8_t *out, const int64_t *out_off, int nthreads)
+{
+  if ((!targets || !win_target || !win_offset || !win_len || !win_comp || !out || !out_off) && nwin) return B2H_EINVAL;
+  if (comp_table && (Kp < 1 || Kp > 256)) return B2H_EINVAL;
+  uint8_t table[256];
+  for (int x = 0; x < 256; x++) table[x] = (comp_table && x < Kp) ? comp_table[x] : (uint8_t)x;
+  for (size_t w = 0; w < nwin; w++) if (win_comp[w] && !comp_table) return B2H_EINVAL;
+  auto work = [&](size_t w) {
+    const uint8_t *src = targets[win_target[w]] + win_offset[w];
+    uint8_t *dst = out + out_off[w];
+    const int64_t n = win_len[w];
+    if (!win_comp[w]) { memcpy(dst, src, (size_t)n); return; }
+    for (int64_t q = 0; q < n; q++) dst[q] = table[src[n - 1 - q]];
+  };
+  int T = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+  int64_t total = 0; for (size_t w = 0; w < nwin; w++) total += win_len[w];
+  T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(T, 32), std::min<int64_t>((int64_t)nwin, total / (1 << 20) + 1)));
+  if (T <= 1) { for (size_t w = 0; w < nwin; w++) work(w); return B2H_OK; }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; t++) th.emplace_back([&]() { for (size_t w = next.fetch_add(1); w < nwin; w = next.fetch_add(1)) work(w); });
+  for (auto &t : th) t.join();
   return B2H_OK;
 }
 

@@ -59,7 +59,16 @@ struct b2h_ctx {
   cudaStream_t bias_stream = nullptr;  // the bias filter of a wave runs here, next to that wave's Viterbi launches
   // page-locked result buffers (survivor lists, parser special rows) recycled between searches
   std::mutex    pin_mu; std::vector<std::pair<void *, size_t>> pin_pool;
+  // Large device buffers that travel between lanes (the Forward special-state rows a cascade wave leaves for the survivor
+  // lane): kept for the life of the context and handed over with an event, because the stream-ordered allocator cannot
+  // reuse a block freed on one stream for an allocation on another without new physical memory.
+  struct BigBuf { void *p = nullptr; size_t bytes = 0; cudaEvent_t free_ev = nullptr; bool in_use = false; };
+  std::vector<BigBuf> bigbufs;
 };
+// a device buffer of at least <bytes> for work queued on <strm> (nullptr: out of memory); b2h_bigbuf_put: the work queued on
+// <strm> so far is its last user
+void *b2h_bigbuf_get(b2h_ctx *ctx, size_t bytes, cudaStream_t strm);
+void  b2h_bigbuf_put(b2h_ctx *ctx, void *p, cudaStream_t strm);
 
 // RAII: make one of the extra lanes the current one (only the thread that drives b2h_search does this)
 #define B2H_LANE_SURV 0

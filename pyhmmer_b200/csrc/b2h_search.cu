@@ -197,9 +197,10 @@ struct CascadeWave {
   std::vector<int> perm;
   Pinned<int> hctr; Pinned<ProfDev> hprof; Pinned<int32_t> hcls;
   SurvList D; int64_t *D_xoff = nullptr;
-  float *d_fx = nullptr; cudaStream_t fx_stream = nullptr;     // Forward special-state rows of every entry of list F (kept beyond the wave's pool: the survivor lane reads them)
+  b2h_ctx *ctx = nullptr;
+  float *d_fx = nullptr; cudaStream_t fx_stream = nullptr;     // Forward special-state rows of every entry of list F (a context buffer: the survivor lane reads them after this wave is gone)
   cudaEvent_t done = nullptr, ssv_done = nullptr, bias_fork = nullptr, bias_join = nullptr;
-  ~CascadeWave() { for (cudaEvent_t e : {done, ssv_done, bias_fork, bias_join}) if (e) cudaEventDestroy(e); if (d_fx) cudaFreeAsync(d_fx, fx_stream); }
+  ~CascadeWave() { for (cudaEvent_t e : {done, ssv_done, bias_fork, bias_join}) if (e) cudaEventDestroy(e); if (d_fx) b2h_bigbuf_put(ctx, d_fx, fx_stream); }
 };
 
 static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int p0, int p1, const b2h_seqdb *db,
@@ -384,12 +385,14 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
     TRY(pool.get(&d_xoffF, cap)); TRY(pool.get(&d_Dx, cap));
     StageOut so; so.sc = stage_sc; so.status = stage_st; so.fwd_xmx = so.bck_xmx = nullptr; so.xoff = nullptr;
     if (cap_rows > 0 && !getenv("B2H_FWD_TWICE")) {
-      if (cudaMallocAsync((void **)&cw.d_fx, (size_t)cap_rows * 6 * sizeof(float), ctx->stream) == cudaSuccess) {
+      cw.ctx = ctx;
+      cw.d_fx = (float *)b2h_bigbuf_get(ctx, (size_t)cap_rows * 6 * sizeof(float), ctx->stream);
+      if (cw.d_fx) {
         cw.fx_stream = ctx->stream;
         xoff_scan_kernel<<<1, 1024, 0, ctx->stream>>>(G.s, nent, sd.len, (int64_t)cap_rows, d_xoffF);
         ctx->launches++;
         so.fwd_xmx = cw.d_fx; so.xoff = d_xoffF;
-      } else { (void)cudaGetLastError(); cw.d_fx = nullptr; }
+      }
     }
     TRY(b2h_launch_forward(ctx, wl, sd, mpads, 0, so));
     fwd_post_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_prof, G, nent, stage_sc, stage_st, prm->F3, D, d_ctr + 5, so.xoff, d_Dx);
@@ -610,8 +613,9 @@ struct SurvChunk {
 };
 struct SurvPending {
   std::vector<b2h_survivor> surv; std::vector<std::unique_ptr<SurvChunk>> chunks; cudaEvent_t done = nullptr; size_t wave = 0;
+  b2h_ctx *ctx = nullptr;
   float *fx_src = nullptr; cudaStream_t fx_stream = nullptr;    // the cascade's Forward special-state rows (list F) of this wave
-  ~SurvPending() { if (done) cudaEventDestroy(done); if (fx_src) cudaFreeAsync(fx_src, fx_stream); }
+  ~SurvPending() { if (done) cudaEventDestroy(done); if (fx_src) b2h_bigbuf_put(ctx, fx_src, fx_stream); }
 };
 
 static int survivors_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, SurvPending &sp)
@@ -681,7 +685,7 @@ static int survivors_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, c
     B2H_CUDA(cudaMemcpyAsync(bst.data(), d_bst, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     i0 = i1;
   }
-  if (sp.fx_src) { cudaFreeAsync(sp.fx_src, ctx->stream); sp.fx_src = nullptr; }   // (stream-ordered: after the gathers queued above)
+  if (sp.fx_src) { b2h_bigbuf_put(ctx, sp.fx_src, ctx->stream); sp.fx_src = nullptr; }   // (its last users are the gathers queued above)
   B2H_CUDA(cudaEventCreateWithFlags(&sp.done, cudaEventDisableTiming));
   B2H_CUDA(cudaEventRecord(sp.done, ctx->stream));
   return B2H_OK;
@@ -806,7 +810,7 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
         p->wave = w;
         const int lane_id = (w & 1) ? B2H_LANE_SURV2 : B2H_LANE_SURV;
         st = cascade_collect(ctx, *waves[w], ctx->lanes[lane_id].stream, p->surv, scnt.data());
-        p->fx_src = waves[w]->d_fx; p->fx_stream = ctx->lanes[lane_id].stream; waves[w]->d_fx = nullptr;
+        p->ctx = ctx; p->fx_src = waves[w]->d_fx; p->fx_stream = ctx->lanes[lane_id].stream; waves[w]->d_fx = nullptr;
         waves[w].reset();
         if (trace) fprintf(stderr, "[b2h_search]   wave %zu (%zu profiles): cascade collected at +%.1f ms (queued up to wave %zu)\n", w, bounds[w + 1] - bounds[w], now_ms() - t0, queued - 1);
         if (st == B2H_OK) { b2h_lane_switch lane(ctx, lane_id); st = survivors_enqueue(ctx, sp.data(), db, *p); }

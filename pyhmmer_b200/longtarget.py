@@ -260,13 +260,39 @@ def stages(om, chunks, F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=2
 _DNA_COMPLEMENT = "TGCA-YRKMSWDVBHN*~"      # of ACGT-RYMKSWHBVDN*~ (esl_alphabet.c: set_complementarity)
 
 
-def reverse_complement(alphabet, codes):
-    """esl_sq_ReverseComplement on digital residues (nucleotide alphabets only)."""
+def complement_table(alphabet):
+    """The digital complement of every residue code (ESL_ALPHABET.complement, esl_alphabet.c:create_dna / create_rna)."""
     if alphabet.K != 4:
         raise ValueError("reverse complement needs a nucleotide alphabet")
-    table = np.array([alphabet.symbols.index(c if c in alphabet.symbols else {"T": "U"}.get(c, c)) for c in
-                      (_DNA_COMPLEMENT if "T" in alphabet.symbols else _DNA_COMPLEMENT.replace("T", "U"))], np.uint8)
-    return np.ascontiguousarray(table[codes[::-1]])
+    return np.array([alphabet.symbols.index(c if c in alphabet.symbols else {"T": "U"}.get(c, c)) for c in
+                     (_DNA_COMPLEMENT if "T" in alphabet.symbols else _DNA_COMPLEMENT.replace("T", "U"))], np.uint8)
+
+
+def reverse_complement(alphabet, codes):
+    """esl_sq_ReverseComplement on digital residues (nucleotide alphabets only)."""
+    return np.ascontiguousarray(complement_table(alphabet)[codes[::-1]])
+
+
+def pack_windows(alphabet, sequences, wins, host_threads=0):
+    """The windows of `target_windows` as one packed residue buffer + offsets, cut (and reverse-complemented) by the host
+    library's threads (b2h_pack_windows)."""
+    n = len(wins)
+    w = np.array(wins, dtype=np.int64).reshape(n, 6) if n else np.zeros((0, 6), np.int64)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(w[:, 2], out=off[1:])
+    res = np.empty(int(off[-1]), np.uint8)
+    used = sorted(set(int(t) for t in w[:, 0]))
+    codes = {t: np.ascontiguousarray(sequences[t].sequence, dtype=np.uint8) for t in used}
+    ptrs = (ctypes.c_void_p * max(1, len(sequences)))()
+    for t, c in codes.items():
+        ptrs[t] = c.ctypes.data
+    # a reverse-strand window is the same stretch of the target, reversed and complemented
+    target, offset, length, comp = (np.ascontiguousarray(w[:, 0], np.int32), np.ascontiguousarray(w[:, 1], np.int64),
+                                    np.ascontiguousarray(w[:, 2], np.int64), np.ascontiguousarray(w[:, 3], np.int32))
+    table = complement_table(alphabet) if comp.any() else None
+    check(lib.b2h_pack_windows(ptrs, n, ptr(target), ptr(offset), ptr(length), ptr(comp), None if table is None else ptr(table),
+                               0 if table is None else len(table), ptr(res), ptr(off), int(host_threads)), "b2h_pack_windows")
+    return res, off
 
 
 class _Chunk:
@@ -283,6 +309,13 @@ class _ChunkBlock:
 
     def __init__(self, alphabet, pieces):
         self.alphabet, self._pieces, self._cache = alphabet, pieces, {}
+
+    @classmethod
+    def from_packed(cls, alphabet, res, off):
+        """A block over an already packed buffer: the pieces are views into it."""
+        self = cls(alphabet, [res[off[i]:off[i + 1]] for i in range(len(off) - 1)])
+        self._cache["packed"] = (res, off)
+        return self
 
     def __len__(self):
         return len(self._pieces)
@@ -409,17 +442,7 @@ def _search_windows(om, sequences, wins, F1, F2, F3, bias_filter, null2, B1, B2,
     if not wins:
         return none
     clock = _Clock(timings)
-    rc = {}                                                # reverse complement of a whole target, made once
-    pieces = []
-    for (t, i, n, comp, w, c) in wins:
-        codes = sequences[t].sequence
-        if comp:
-            if t not in rc:
-                rc[t] = reverse_complement(abc, codes)
-            pieces.append(rc[t][len(codes) - (i + n):len(codes) - i])
-        else:
-            pieces.append(codes[i:i + n])
-    block = _ChunkBlock(abc, pieces)
+    block = _ChunkBlock.from_packed(abc, *pack_windows(abc, sequences, wins, host_threads))
     clock.lap("cut_windows")
     be = (backend_factory or CudaBackend)(om, block)
     clock.lap("upload")
