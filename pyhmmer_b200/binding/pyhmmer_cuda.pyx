@@ -1,0 +1,315 @@
+# cython: language_level=3
+"""pyhmmer_cuda -- the B200 engine bound INTO pyhmmer: `CudaPipeline(pyhmmer.plan7.Pipeline)`.
+
+A Cython extension compiled against an installed pyhmmer (its .pxd files, headers and shared libraries, as
+PyHMMERConfig.cmake advertises them: src/cmake/PyHMMERConfig.cmake.in) and against include/b2h.h.  `search_hmm` and
+`scan_seq` keep pyhmmer's signatures and semantics and return genuine `pyhmmer.plan7.TopHits` (a real P7_TOPHITS filled
+through p7_tophits_CreateNextHit), but the loops over targets -- `Pipeline._search_loop` / `_scan_loop`
+(src/pyhmmer/plan7.pyx:6394-6453, 6625-6677) -- are one `b2h_search` call each (b2h_pyhmmer_glue.c).
+
+    import pyhmmer, pyhmmer_cuda
+    hits = pyhmmer_cuda.CudaPipeline(alphabet).search_hmm(hmm, sequences)       # pyhmmer objects in, pyhmmer TopHits out
+    pyhmmer_cuda.install()          # pyhmmer.hmmsearch / hmmscan workers build CudaPipeline objects (pipeline_class hook)
+"""
+from libc.stdint cimport uint8_t, int32_t, int64_t, uint32_t, uint64_t
+from libc.stdlib cimport malloc, free
+
+cimport libeasel
+from libeasel.sq cimport ESL_SQ
+from libhmmer.p7_bg cimport P7_BG
+from libhmmer.p7_pipeline cimport P7_PIPELINE, p7_pipemodes_e
+from libhmmer.p7_tophits cimport P7_TOPHITS
+from libhmmer.impl_sse.p7_oprofile cimport P7_OPROFILE, P7_OM_BLOCK
+
+from pyhmmer.easel cimport Alphabet, DigitalSequence, DigitalSequenceBlock
+from pyhmmer.plan7 cimport Pipeline, TopHits, HMM, Profile, OptimizedProfile, OptimizedProfileBlock, Background
+
+from pyhmmer.errors import AlphabetMismatch, UnexpectedError, MissingCutoffs
+
+
+cdef extern from "b2h.h" nogil:
+    ctypedef struct b2h_ctx
+    ctypedef struct b2h_seqdb
+    ctypedef struct b2h_profile
+    int  b2h_ctx_create(int device, b2h_ctx **out)
+    void b2h_ctx_destroy(b2h_ctx *ctx)
+    const char *b2h_ctx_last_error(const b2h_ctx *ctx)
+    unsigned long long b2h_ctx_launch_count(const b2h_ctx *ctx)
+    void b2h_seqdb_destroy(b2h_seqdb *db)
+    void b2h_profile_destroy(b2h_profile *p)
+
+cdef extern from "b2h_pyhmmer_glue.h" nogil:
+    int b2h_glue_upload_oprofile(b2h_ctx *ctx, const P7_OPROFILE *om, const P7_BG *bg, b2h_profile **out)
+    int b2h_glue_seqdb(b2h_ctx *ctx, ESL_SQ *const *sq, size_t n, b2h_seqdb **out)
+    int b2h_glue_search_loop(b2h_ctx *ctx, const b2h_seqdb *db, P7_PIPELINE *pli, P7_OPROFILE *om, P7_BG *bg,
+                             ESL_SQ *const *sq, size_t n_targets, P7_TOPHITS *th, unsigned seed, int host_threads)
+    int b2h_glue_scan_loop(b2h_ctx *ctx, const b2h_profile *const *profs, P7_PIPELINE *pli, const ESL_SQ *sq, P7_BG *bg,
+                           P7_OPROFILE *const *om, size_t n_targets, P7_TOPHITS *th, unsigned seed, int host_threads)
+
+cdef enum:
+    eslOK = 0
+    eslEINVAL = 11
+    eslERANGE = 16
+    B2H_ECUDA = 100
+
+DEF HMMER_TARGET_LIMIT = 100000
+
+
+cdef class _Engine:
+    """One CUDA context per process, the target databases and profile blocks it keeps resident."""
+    cdef b2h_ctx* ctx
+    cdef dict _dbs          # id(block) -> (_SeqDB, length, first ESL_SQ*)
+    cdef dict _blocks       # id(profile block) -> (_ProfBlock, length)
+
+    def __cinit__(self):
+        self.ctx = NULL
+        self._dbs = {}
+        self._blocks = {}
+
+    def __init__(self, int device=0):
+        cdef int status = b2h_ctx_create(device, &self.ctx)
+        if status != eslOK:
+            raise RuntimeError("b2h_ctx_create failed with status %d: no sm_100 CUDA device? (there is no CPU fallback)" % status)
+
+    def __dealloc__(self):
+        self._dbs = None
+        self._blocks = None
+        if self.ctx != NULL:
+            b2h_ctx_destroy(self.ctx)
+            self.ctx = NULL
+
+    cdef str last_error(self):
+        cdef const char* e = b2h_ctx_last_error(self.ctx)
+        return e.decode("utf-8", "replace") if e != NULL else ""
+
+    @property
+    def launch_count(self):
+        return int(b2h_ctx_launch_count(self.ctx))
+
+
+cdef class _SeqDB:
+    cdef b2h_seqdb* db
+    cdef _Engine engine
+    def __cinit__(self):
+        self.db = NULL
+    def __dealloc__(self):
+        if self.db != NULL:
+            b2h_seqdb_destroy(self.db)
+
+
+cdef class _ProfBlock:
+    cdef b2h_profile** profs
+    cdef size_t n
+    cdef _Engine engine
+    def __cinit__(self):
+        self.profs = NULL
+        self.n = 0
+    def __dealloc__(self):
+        cdef size_t i
+        if self.profs != NULL:
+            for i in range(self.n):
+                if self.profs[i] != NULL:
+                    b2h_profile_destroy(self.profs[i])
+            free(self.profs)
+
+
+cdef _Engine _ENGINE = None
+
+def engine(int device=0):
+    """The process-wide engine (created on first use)."""
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = _Engine(device)
+    return _ENGINE
+
+
+cdef void _raise(_Engine eng, int status, str fn) except *:
+    if status == eslERANGE:
+        raise OverflowError("numerical overflow in the optimized vector implementation")
+    if status == B2H_ECUDA:
+        raise RuntimeError("%s: CUDA failure: %s" % (fn, eng.last_error()))
+    raise UnexpectedError(status, fn)
+
+
+cdef class CudaPipeline(Pipeline):
+    """`pyhmmer.plan7.Pipeline` whose comparison loops run on the GPU.  Same constructor, same results."""
+
+    cdef _Engine _engine
+    cdef int     _host_threads
+
+    def __init__(self, Alphabet alphabet, Background background=None, *, int device=0, int host_threads=0, **kwargs):
+        super().__init__(alphabet, background, **kwargs)
+        self._engine = engine(device)
+        self._host_threads = host_threads
+
+    cdef _SeqDB _database(self, DigitalSequenceBlock sequences):
+        """The block, resident on the device: cached per block object, re-uploaded when the block changed."""
+        cdef _SeqDB sdb
+        cdef int status
+        key = id(sequences)
+        hit = self._engine._dbs.get(key)
+        first = <size_t> sequences._refs[0] if sequences._length > 0 else 0
+        if hit is not None and hit[1] == sequences._length and hit[2] == first and hit[3]() is sequences:
+            return hit[0]
+        import weakref
+        sdb = _SeqDB()
+        sdb.engine = self._engine
+        cdef b2h_ctx* ctx = self._engine.ctx
+        cdef ESL_SQ *const * refs = <ESL_SQ *const *> sequences._refs
+        cdef size_t n = sequences._length
+        with nogil:
+            status = b2h_glue_seqdb(ctx, refs, n, &sdb.db)
+        if status != eslOK:
+            _raise(self._engine, status, "b2h_seqdb_create")
+        dbs = self._engine._dbs
+        self._engine._dbs[key] = (sdb, sequences._length, first, weakref.ref(sequences, lambda _r, k=key, d=dbs: d.pop(k, None)))
+        return sdb
+
+    def search_hmm(self, query, sequences):
+        """`Pipeline.search_hmm` (plan7.pyx:6155-6258) for targets in a `DigitalSequenceBlock`."""
+        cdef size_t       L
+        cdef int          status
+        cdef P7_OPROFILE* om
+        cdef TopHits      hits
+        cdef _SeqDB       sdb
+        cdef DigitalSequenceBlock block
+        cdef OptimizedProfile opt
+        cdef Profile      gm
+        cdef b2h_ctx*     ctx = self._engine.ctx
+        cdef unsigned     seed = self._seed
+        cdef int          nthreads = self._host_threads
+        if not isinstance(sequences, DigitalSequenceBlock):
+            return super().search_hmm(query, sequences)                  # SequenceFile targets: the reference's own loop
+        if not isinstance(query, (HMM, Profile, OptimizedProfile)):
+            raise TypeError("Expected HMM, Profile or OptimizedProfile, found %s" % type(query).__name__)
+        block = sequences
+        hits = TopHits(query)
+        if not self.alphabet._eq(query.alphabet):
+            raise AlphabetMismatch(self.alphabet, query.alphabet)
+        if not self.alphabet._eq(block.alphabet):
+            raise AlphabetMismatch(self.alphabet, block.alphabet)
+        L = self.L_HINT if block._length == 0 else block._refs[0].L
+        if block._length > 0 and len(block.largest()) > HMMER_TARGET_LIMIT:
+            raise ValueError(f"sequence length over comparison pipeline limit ({HMMER_TARGET_LIMIT})")
+        # the optimized profile of the query, as Pipeline._get_om_from_query builds it (plan7.pyx:5979-6013):
+        # HMM -> Profile.configure(hmm, background, L) -> OptimizedProfile
+        if isinstance(query, OptimizedProfile):
+            opt = <OptimizedProfile> query
+        elif isinstance(query, Profile):
+            opt = (<Profile> query).to_optimized()
+        else:
+            gm = Profile((<HMM> query).M, self.alphabet)
+            gm.configure(<HMM> query, self.background, L)
+            opt = gm.to_optimized()
+        om = opt._om
+        sdb = self._database(block)
+        cdef b2h_seqdb* db = sdb.db
+        cdef P7_BG* bg = self.background._bg
+        cdef ESL_SQ *const * refs = <ESL_SQ *const *> block._refs
+        cdef size_t n = block._length
+        with nogil:
+            self._pli.mode = p7_pipemodes_e.p7_SEARCH_SEQS
+            self._pli.nseqs = 0
+            status = b2h_glue_search_loop(ctx, db, self._pli, om, bg, refs, n, hits._th, seed, nthreads)
+        if status == eslEINVAL:
+            raise MissingCutoffs(query.name, self.bit_cutoffs)
+        elif status != eslOK:
+            _raise(self._engine, status, "b2h_search")
+        with nogil:
+            hits._sort_by_key()
+            hits._threshold(self)
+        hits._query = query
+        hits._empty = False
+        return hits
+
+    cdef _ProfBlock _profiles(self, OptimizedProfileBlock targets):
+        cdef _ProfBlock pb
+        cdef size_t i
+        cdef int status = eslOK
+        key = id(targets)
+        hit = self._engine._blocks.get(key)
+        if hit is not None and hit[1] == <size_t> targets._block.count and hit[2]() is targets:
+            return hit[0]
+        import weakref
+        pb = _ProfBlock()
+        pb.engine = self._engine
+        cdef size_t n = <size_t> targets._block.count
+        cdef P7_OPROFILE** oms = targets._block.list
+        cdef b2h_ctx* ctx = self._engine.ctx
+        cdef P7_BG* bg = self.background._bg
+        pb.n = n
+        pb.profs = <b2h_profile**> malloc(sizeof(b2h_profile*) * max(1, n))
+        if pb.profs == NULL:
+            raise MemoryError()
+        for i in range(n):
+            pb.profs[i] = NULL
+        with nogil:
+            for i in range(n):
+                status = b2h_glue_upload_oprofile(ctx, oms[i], bg, &pb.profs[i])
+                if status != eslOK:
+                    break
+        if status != eslOK:
+            _raise(self._engine, status, "b2h_profile_upload")
+        blocks = self._engine._blocks
+        self._engine._blocks[key] = (pb, n, weakref.ref(targets, lambda _r, k=key, d=blocks: d.pop(k, None)))
+        return pb
+
+    def scan_seq(self, DigitalSequence query, targets):
+        """`Pipeline.scan_seq` (plan7.pyx:6534-6620) for targets pre-fetched into an `OptimizedProfileBlock`."""
+        cdef int          status
+        cdef TopHits      hits
+        cdef _ProfBlock   pb
+        cdef OptimizedProfileBlock block
+        cdef b2h_ctx*     ctx = self._engine.ctx
+        cdef unsigned     seed = self._seed
+        cdef int          nthreads = self._host_threads
+        if not isinstance(targets, OptimizedProfileBlock):
+            return super().scan_seq(query, targets)                      # HMMPressedFile targets: the reference's own loop
+        block = targets
+        hits = TopHits(query)
+        if not self.alphabet._eq(query.alphabet):
+            raise AlphabetMismatch(self.alphabet, query.alphabet)
+        if not self.alphabet._eq(block.alphabet):
+            raise AlphabetMismatch(self.alphabet, block.alphabet)
+        if len(query) > HMMER_TARGET_LIMIT:
+            raise ValueError(f"sequence length over comparison pipeline limit ({HMMER_TARGET_LIMIT})")
+        pb = self._profiles(block)
+        cdef const b2h_profile *const * profs = <const b2h_profile *const *> pb.profs
+        cdef P7_OPROFILE *const * oms = <P7_OPROFILE *const *> block._block.list
+        cdef size_t n = <size_t> block._block.count
+        cdef const ESL_SQ* sq = query._sq
+        cdef P7_BG* bg = self.background._bg
+        with nogil:
+            self._pli.mode = p7_pipemodes_e.p7_SCAN_MODELS
+            self._pli.nmodels = 0
+            status = b2h_glue_scan_loop(ctx, profs, self._pli, sq, bg, oms, n, hits._th, seed, nthreads)
+        if status == eslEINVAL:
+            raise MissingCutoffs(b"?", self.bit_cutoffs)
+        elif status != eslOK:
+            _raise(self._engine, status, "b2h_search")
+        with nogil:
+            hits._sort_by_key()
+            hits._threshold(self)
+        hits._query = query
+        hits._empty = False
+        return hits
+
+
+def install():
+    """Make `pyhmmer.hmmsearch` / `pyhmmer.hmmscan` build `CudaPipeline` objects in their workers (the `pipeline_class` hook
+    of pyhmmer.hmmer._base._BaseWorker).  Returns a function that undoes it."""
+    import pyhmmer.hmmer._hmmsearch as hs, pyhmmer.hmmer._hmmscan as sc
+    saved = [(cls, cls.__dict__.get("pipeline_class")) for cls in (hs._SEARCHWorker, sc._SCANWorker)]
+    for cls, _ in saved:
+        cls.pipeline_class = CudaPipeline
+
+    def uninstall():
+        for cls, old in saved:
+            if old is None:
+                try:
+                    del cls.pipeline_class
+                except AttributeError:
+                    pass
+            else:
+                cls.pipeline_class = old
+    return uninstall

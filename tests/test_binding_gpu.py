@@ -1,0 +1,126 @@
+"""The engine bound INTO the reference: `pyhmmer_cuda.CudaPipeline(pyhmmer.plan7.Pipeline)` (pyhmmer_b200/binding/), a Cython
+extension compiled against the unmodified reference installed under baseline/_ref.  pyhmmer's own objects go in
+(`HMM`, `DigitalSequenceBlock`, `OptimizedProfileBlock`), pyhmmer's own `TopHits` come out -- so the reference's OWN test
+classes can be run against it, and its results compared object by object with the reference's CPU pipeline."""
+import importlib
+import os
+import sys
+import unittest
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+
+@pytest.fixture(scope="module")
+def bound():
+    if not os.path.isdir(os.path.join(REF, "pyhmmer")):
+        pytest.skip("the reference is not installed under baseline/_ref (pip install --target baseline/_ref, DESIGN.md)")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import pyhmmer
+    from pyhmmer_b200.binding import build as bbuild
+    bbuild.build()                                        # no-op when the module is up to date
+    from pyhmmer_b200.binding import pyhmmer_cuda
+    return pyhmmer, pyhmmer_cuda
+
+
+def _data(pyhmmer, *parts):
+    return os.path.join(os.path.dirname(pyhmmer.__file__), "tests", "data", *parts)
+
+
+def _run_cases(cases):
+    suite = unittest.TestSuite()
+    for c in cases:
+        suite.addTests(unittest.defaultTestLoader.loadTestsFromTestCase(c))
+    res = unittest.TestResult()
+    suite.run(res)
+    return res
+
+
+def test_reference_pipeline_test_classes_run_on_cuda(bound):
+    """The reference's TestSearchPipeline / TestScanPipeline (src/pyhmmer/tests/test_plan7/test_pipeline.py) with `Pipeline`
+    replaced by `CudaPipeline` in the test module: every case passes, and the block-based ones launched GPU kernels."""
+    pyhmmer, pyhmmer_cuda = bound
+    mod = importlib.import_module("pyhmmer.tests.test_plan7.test_pipeline")
+    saved = mod.Pipeline
+    launches0 = pyhmmer_cuda.engine().launch_count
+    mod.Pipeline = pyhmmer_cuda.CudaPipeline
+    try:
+        res = _run_cases([mod.TestSearchPipeline, mod.TestScanPipeline])
+    finally:
+        mod.Pipeline = saved
+    assert res.testsRun >= 20
+    assert not res.failures and not res.errors, [str(f[0]) + "\n" + f[1] for f in res.failures + res.errors]
+    assert pyhmmer_cuda.engine().launch_count > launches0 + 50
+
+
+def test_reference_hmmer_test_classes_run_on_cuda(bound):
+    """The reference's TestHmmsearch* / TestHMMScan (src/pyhmmer/tests/test_hmmer.py: golden tables PF02826.tbl, RREFam.tbl,
+    RREFam.domtbl, RREFam.scan.tbl) with the workers of pyhmmer.hmmsearch / hmmscan building CudaPipeline objects."""
+    pyhmmer, pyhmmer_cuda = bound
+    mod = importlib.import_module("pyhmmer.tests.test_hmmer")
+    undo = pyhmmer_cuda.install()
+    launches0 = pyhmmer_cuda.engine().launch_count
+    try:
+        cases = [getattr(mod, n) for n in ("TestHmmsearch", "TestHmmsearchSingle", "TestHmmsearchReverse", "TestHMMScan") if hasattr(mod, n)]
+        res = _run_cases(cases)
+    finally:
+        undo()
+    assert len(cases) >= 3 and res.testsRun >= 15
+    assert not res.failures and not res.errors, [str(f[0]) + "\n" + f[1] for f in res.failures + res.errors]
+    assert pyhmmer_cuda.engine().launch_count > launches0 + 100
+
+
+def test_cuda_pipeline_equals_reference_pipeline(bound):
+    """Object-level comparison: the same queries and targets through pyhmmer's Pipeline (CPU) and CudaPipeline (GPU) -- hit
+    lists, flags, every score, domain coordinates and alignment rows, the accounting of the TopHits, pickling."""
+    import pickle
+    pyhmmer, pyhmmer_cuda = bound
+    abc = pyhmmer.easel.Alphabet.amino()
+    with pyhmmer.easel.SequenceFile(_data(pyhmmer, "seqs", "938293.PRJEB85.HG003687.faa"), digital=True, alphabet=abc) as f:
+        seqs = f.read_block()
+    hmms = []
+    for name in ("PF02826", "Thioesterase", "RREFam"):
+        with pyhmmer.plan7.HMMFile(_data(pyhmmer, "hmms", "txt", name + ".hmm")) as f:
+            hmms += list(f)
+    nhits = 0
+    for kwargs in ({}, {"Z": 5000.0, "domE": 1e-3}, {"bias_filter": False}, {"null2": False}, {"T": 20.0, "domT": 15.0}):
+        for hmm in hmms[:4] if kwargs else hmms:
+            ref = pyhmmer.plan7.Pipeline(abc, **kwargs).search_hmm(hmm, seqs)
+            got = pyhmmer_cuda.CudaPipeline(abc, **kwargs).search_hmm(hmm, seqs)
+            assert type(got) is pyhmmer.plan7.TopHits
+            assert len(got) == len(ref), (hmm.name, kwargs, len(got), len(ref))
+            assert (got.Z, got.domZ, got.searched_sequences, got.searched_residues, got.searched_models, got.searched_nodes) == \
+                   (ref.Z, ref.domZ, ref.searched_sequences, ref.searched_residues, ref.searched_models, ref.searched_nodes)
+            assert len(got.reported) == len(ref.reported) and len(got.included) == len(ref.included)
+            for a, b in zip(got, ref):
+                assert a.name == b.name and a.accession == b.accession and a.description == b.description
+                assert abs(a.score - b.score) < 2e-3 and abs(a.pre_score - b.pre_score) < 2e-3 and abs(a.bias - b.bias) < 2e-3
+                assert abs(a.evalue - b.evalue) <= 2e-3 * b.evalue + 1e-300
+                assert (a.reported, a.included, len(a.domains)) == (b.reported, b.included, len(b.domains))
+                for d, e in zip(a.domains, b.domains):
+                    assert (d.env_from, d.env_to, d.reported, d.included) == (e.env_from, e.env_to, e.reported, e.included)
+                    assert abs(d.score - e.score) < 2e-3 and abs(d.bias - e.bias) < 2e-3 and abs(d.envelope_score - e.envelope_score) < 2e-3
+                    x, y = d.alignment, e.alignment
+                    assert (x.hmm_from, x.hmm_to, x.target_from, x.target_to, x.hmm_name, x.target_name, x.hmm_length, x.target_length) == \
+                           (y.hmm_from, y.hmm_to, y.target_from, y.target_to, y.hmm_name, y.target_name, y.hmm_length, y.target_length)
+                    assert x.hmm_sequence == y.hmm_sequence and x.target_sequence == y.target_sequence and x.identity_sequence == y.identity_sequence
+                    assert sum(1 for p, q in zip(x.posterior_probabilities, y.posterior_probabilities) if p != q) <= max(1, len(x.hmm_sequence) // 100)
+            nhits += len(got)
+            clone = pickle.loads(pickle.dumps(got))                       # p7_hit_Serialize over the hits we filled
+            assert [h.name for h in clone] == [h.name for h in got] and clone.Z == got.Z
+    assert nhits >= 60
+    # scan orientation: every proteome sequence with a golden hit, against the RREFam block
+    with pyhmmer.plan7.HMMFile(_data(pyhmmer, "hmms", "txt", "RREFam.hmm")) as f:
+        block = pyhmmer.plan7.OptimizedProfileBlock(abc, [h.to_profile(pyhmmer.plan7.Background(abc)).to_optimized() for h in f])
+    picked = [s for s in seqs if s.name in (b"938293.PRJEB85.HG003691_78", b"938293.PRJEB85.HG003686_714", "938293.PRJEB85.HG003691_78", "938293.PRJEB85.HG003686_714")]
+    picked += [seqs[0], seqs[7]]
+    assert len(picked) == 4
+    for q in picked:
+        ref = pyhmmer.plan7.Pipeline(abc).scan_seq(q, block)
+        got = pyhmmer_cuda.CudaPipeline(abc).scan_seq(q, block)
+        assert [(h.name, h.reported, h.included, len(h.domains)) for h in got] == [(h.name, h.reported, h.included, len(h.domains)) for h in ref]
+        assert all(abs(a.score - b.score) < 2e-3 for a, b in zip(got, ref)) and (got.Z, got.searched_models) == (ref.Z, ref.searched_models)
