@@ -143,26 +143,32 @@ cdef class CudaPipeline(Pipeline):
         self._host_threads = host_threads
 
     cdef _SeqDB _database(self, DigitalSequenceBlock sequences):
-        """The block, resident on the device: cached per block object, re-uploaded when the block changed."""
+        """The block, resident on the device.  The engine keeps the two most recent blocks (pyhmmer's blocks cannot be weakly
+        referenced, so they are held strongly); a block is recognised by identity plus a checksum over its ESL_SQ pointers
+        and lengths, i.e. appending, removing or replacing sequences re-uploads it."""
         cdef _SeqDB sdb
         cdef int status
+        cdef size_t i, n = sequences._length
+        cdef uint64_t sig = 1469598103934665603ULL
+        cdef ESL_SQ *const * refs = <ESL_SQ *const *> sequences._refs
+        cdef b2h_ctx* ctx = self._engine.ctx
+        for i in range(n):
+            sig = (sig ^ <uint64_t> <size_t> refs[i]) * 1099511628211ULL
+            sig = (sig ^ <uint64_t> refs[i].n) * 1099511628211ULL
         key = id(sequences)
         hit = self._engine._dbs.get(key)
-        first = <size_t> sequences._refs[0] if sequences._length > 0 else 0
-        if hit is not None and hit[1] == sequences._length and hit[2] == first and hit[3]() is sequences:
+        if hit is not None and hit[1] is sequences and hit[2] == n and hit[3] == sig:
             return hit[0]
-        import weakref
         sdb = _SeqDB()
         sdb.engine = self._engine
-        cdef b2h_ctx* ctx = self._engine.ctx
-        cdef ESL_SQ *const * refs = <ESL_SQ *const *> sequences._refs
-        cdef size_t n = sequences._length
         with nogil:
             status = b2h_glue_seqdb(ctx, refs, n, &sdb.db)
         if status != eslOK:
             _raise(self._engine, status, "b2h_seqdb_create")
-        dbs = self._engine._dbs
-        self._engine._dbs[key] = (sdb, sequences._length, first, weakref.ref(sequences, lambda _r, k=key, d=dbs: d.pop(k, None)))
+        self._engine._dbs.pop(key, None)
+        while len(self._engine._dbs) >= 2:
+            self._engine._dbs.pop(next(iter(self._engine._dbs)))
+        self._engine._dbs[key] = (sdb, sequences, n, sig)
         return sdb
 
     def search_hmm(self, query, sequences):
@@ -223,20 +229,23 @@ cdef class CudaPipeline(Pipeline):
         return hits
 
     cdef _ProfBlock _profiles(self, OptimizedProfileBlock targets):
+        """The profile block, resident on the device (same caching rule as `_database`)."""
         cdef _ProfBlock pb
         cdef size_t i
         cdef int status = eslOK
-        key = id(targets)
-        hit = self._engine._blocks.get(key)
-        if hit is not None and hit[1] == <size_t> targets._block.count and hit[2]() is targets:
-            return hit[0]
-        import weakref
-        pb = _ProfBlock()
-        pb.engine = self._engine
         cdef size_t n = <size_t> targets._block.count
         cdef P7_OPROFILE** oms = targets._block.list
         cdef b2h_ctx* ctx = self._engine.ctx
         cdef P7_BG* bg = self.background._bg
+        cdef uint64_t sig = 1469598103934665603ULL
+        for i in range(n):
+            sig = (sig ^ <uint64_t> <size_t> oms[i]) * 1099511628211ULL
+        key = id(targets)
+        hit = self._engine._blocks.get(key)
+        if hit is not None and hit[1] is targets and hit[2] == n and hit[3] == sig:
+            return hit[0]
+        pb = _ProfBlock()
+        pb.engine = self._engine
         pb.n = n
         pb.profs = <b2h_profile**> malloc(sizeof(b2h_profile*) * max(1, n))
         if pb.profs == NULL:
@@ -250,8 +259,10 @@ cdef class CudaPipeline(Pipeline):
                     break
         if status != eslOK:
             _raise(self._engine, status, "b2h_profile_upload")
-        blocks = self._engine._blocks
-        self._engine._blocks[key] = (pb, n, weakref.ref(targets, lambda _r, k=key, d=blocks: d.pop(k, None)))
+        self._engine._blocks.pop(key, None)
+        while len(self._engine._blocks) >= 2:
+            self._engine._blocks.pop(next(iter(self._engine._blocks)))
+        self._engine._blocks[key] = (pb, targets, n, sig)
         return pb
 
     def scan_seq(self, DigitalSequence query, targets):

@@ -1259,7 +1259,9 @@ b2h_ddef_pool::b2h_ddef_pool(int n)
     n = (int)std::thread::hardware_concurrency();
     int ranks = 1;
     if (const char *ev = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(ev));
-    n = std::max(1, n / ranks - 2);
+    // (the thread that feeds the GPU and the one that drives this pool mostly wait on events: only a single-rank job, which
+    //  has cores to spare, leaves two of them alone)
+    n = std::max(1, ranks > 1 ? n / ranks : n - 2);
   }
   nthreads = std::max(1, std::min(n, 128));
 }

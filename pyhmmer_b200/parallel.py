@@ -104,42 +104,78 @@ def unpack_records(buf):
     return hits, doms, text, counters
 
 
-_AG_CAP = [1 << 16]          # payload bytes per rank of the fixed-size exchange; grows to fit (every rank sees the same sizes)
+class _Exchange:
+    """Persistent buffers of the one exchange of the path: page-locked host staging and device slots that grow to the
+    largest payload seen, so that a step moves exactly what it has to -- no zero-filled pageable slot, no power-of-two
+    padding, no blocking pageable copies."""
+
+    def __init__(self):
+        self.key, self.cap = None, 0
+        self.h_in = self.h_out = self.d_in = self.d_out = self.h_sz = self.d_sz = self.d_szs = self.h_szs = None
+
+    def ensure(self, torch, dev, world, need):
+        key = (str(dev), world.size)
+        if key != self.key or need > self.cap:
+            cap = max(1 << 16, 1 << (int(need) - 1).bit_length())
+            pin = dev.type == "cuda"
+            self.h_in = torch.empty(cap, dtype=torch.uint8, pin_memory=pin)
+            self.h_out = torch.empty(world.size * cap, dtype=torch.uint8, pin_memory=pin)
+            self.d_in = torch.empty(cap, dtype=torch.uint8, device=dev)
+            self.d_out = torch.empty(world.size * cap, dtype=torch.uint8, device=dev)
+            self.h_sz = torch.zeros(1, dtype=torch.int64, pin_memory=pin)
+            self.h_szs = torch.zeros(world.size, dtype=torch.int64, pin_memory=pin)
+            self.d_sz = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.d_szs = torch.zeros(world.size, dtype=torch.int64, device=dev)
+            self.key, self.cap = key, cap
+
+
+_EXCHANGE = _Exchange()
 
 
 def all_gather_bytes(data, world):
     """The one exchange of the path: a variable-length all-gather of byte strings (NCCL over NVLink, or gloo on CPU).
 
-    Common case = ONE collective and ONE device->host copy: every rank contributes an 8-byte length header plus its
-    payload in a fixed-capacity slot.  Only if some rank's payload does not fit (all ranks see that in the headers, so
-    they agree) is the capacity raised and the exchange repeated once."""
+    Two collectives: the 8-byte payload sizes first, then the payloads in slots of exactly the largest size (rounded up to
+    256 bytes), through persistent page-locked / device buffers; one device->host copy of the gathered slots."""
     if world.size == 1:
         return [data]
     import torch
     dist = world.dist
     dev = world.device or torch.device("cpu")
     n = len(data)
-    payload = np.frombuffer(data, dtype=np.uint8) if n else np.zeros(0, np.uint8)
-    while True:
-        cap = _AG_CAP[0]
-        slot = np.zeros(8 + cap, dtype=np.uint8)
-        slot[:8] = np.frombuffer(np.int64(n).tobytes(), dtype=np.uint8)
-        k = min(n, cap)
-        slot[8:8 + k] = payload[:k]
-        mine = torch.from_numpy(slot).to(dev, non_blocking=True)
-        out = torch.empty(world.size * (8 + cap), dtype=torch.uint8, device=dev)
-        try:
-            dist.all_gather_into_tensor(out, mine)
-        except (RuntimeError, AttributeError, NotImplementedError):   # a backend without the flat form: list form
-            outs = [torch.empty(8 + cap, dtype=torch.uint8, device=dev) for _ in range(world.size)]
-            dist.all_gather(outs, mine)
-            out = torch.cat(outs)
-        host = out.cpu().numpy().reshape(world.size, 8 + cap)
-        sizes = [int(np.frombuffer(host[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(world.size)]
-        if max(sizes) <= cap:
-            return [host[r, 8:8 + sizes[r]].tobytes() for r in range(world.size)]
-        while _AG_CAP[0] < max(sizes):
-            _AG_CAP[0] *= 2
+    ex = _EXCHANGE
+    ex.ensure(torch, dev, world, max(n, 1))
+    # 1. sizes
+    ex.h_sz[0] = n
+    ex.d_sz.copy_(ex.h_sz, non_blocking=True)
+    try:
+        dist.all_gather_into_tensor(ex.d_szs, ex.d_sz)
+    except (RuntimeError, AttributeError, NotImplementedError):       # a backend without the flat form: list form
+        outs = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world.size)]
+        dist.all_gather(outs, ex.d_sz)
+        ex.d_szs.copy_(torch.cat(outs))
+    ex.h_szs.copy_(ex.d_szs, non_blocking=True)
+    if dev.type == "cuda":
+        torch.cuda.current_stream().synchronize()
+    sizes = [int(v) for v in ex.h_szs.tolist()]
+    slot = (max(max(sizes), 1) + 255) & ~255
+    ex.ensure(torch, dev, world, slot)                                 # (every rank sees the same sizes: they all grow together)
+    # 2. payloads, in slots of <slot> bytes
+    if n:
+        ex.h_in.numpy()[:n] = np.frombuffer(data, dtype=np.uint8)
+    d_in, d_out, h_out = ex.d_in[:slot], ex.d_out[:world.size * slot], ex.h_out[:world.size * slot]
+    d_in.copy_(ex.h_in[:slot], non_blocking=True)
+    try:
+        dist.all_gather_into_tensor(d_out, d_in)
+    except (RuntimeError, AttributeError, NotImplementedError):
+        outs = [torch.empty(slot, dtype=torch.uint8, device=dev) for _ in range(world.size)]
+        dist.all_gather(outs, d_in)
+        d_out.copy_(torch.cat(outs))
+    h_out.copy_(d_out, non_blocking=True)
+    if dev.type == "cuda":
+        torch.cuda.current_stream().synchronize()
+    host = h_out.numpy().reshape(world.size, slot)
+    return [host[r, :sizes[r]].tobytes() for r in range(world.size)]
 
 
 def merge_rank_records(parts):
