@@ -22,6 +22,16 @@
 #include "hmmer.h"
 #include "impl_sse/impl_sse.h"
 #include "b2h.h"
+#include <pthread.h>
+
+/* pyhmmer's hmmsearch / hmmscan run one Pipeline per worker THREAD with the GIL released; a b2h context drives one GPU with
+ * its own streams and lanes and takes one call at a time, so the workers of a process queue up here (each call fills the
+ * whole device anyway). */
+static pthread_mutex_t g_engine_mu = PTHREAD_MUTEX_INITIALIZER;
+#define ENGINE_LOCK()   pthread_mutex_lock(&g_engine_mu)
+#define ENGINE_UNLOCK() pthread_mutex_unlock(&g_engine_mu)
+void b2h_glue_seqdb_destroy(b2h_seqdb *db)     { ENGINE_LOCK(); b2h_seqdb_destroy(db);  ENGINE_UNLOCK(); }
+void b2h_glue_profile_destroy(b2h_profile *p)  { ENGINE_LOCK(); b2h_profile_destroy(p); ENGINE_UNLOCK(); }
 
 /* ---- P7_OPROFILE -> device profile: de-stripe the SSE tables, copy the scalars (include/b2h.h: b2h_oprofile_desc) ---- */
 int b2h_glue_upload_oprofile(b2h_ctx *ctx, const P7_OPROFILE *om, const P7_BG *bg, b2h_profile **out)
@@ -47,7 +57,9 @@ int b2h_glue_upload_oprofile(b2h_ctx *ctx, const P7_OPROFILE *om, const P7_BG *b
   for (x = 0; x < B2H_MAXABET; x++) d.compo[x] = (x < p7_MAXABET) ? om->compo[x] : 0.f;
   for (x = 0; x < K && x < B2H_MAXABET; x++) d.bgf[x] = bg->f[x];
   d.degen = degen;
+  ENGINE_LOCK();
   status = b2h_profile_upload(ctx, &d, out);
+  ENGINE_UNLOCK();
   if (status == B2H_OK)
     b2h_profile_set_annotation(*out, om->consensus + 1, (om->rf && om->rf[0]) ? om->rf + 1 : NULL, (om->cs && om->cs[0]) ? om->cs + 1 : NULL, abc->sym);
 DONE:
@@ -62,7 +74,9 @@ int b2h_glue_seqdb(b2h_ctx *ctx, ESL_SQ *const *sq, size_t n, b2h_seqdb **out)
   size_t i; int status;
   if (!dsq || !len) { free(dsq); free(len); return B2H_EMEM; }
   for (i = 0; i < n; i++) { dsq[i] = sq[i]->dsq; len[i] = sq[i]->n; }
+  ENGINE_LOCK();
   status = b2h_seqdb_create(ctx, dsq, len, n, out);
+  ENGINE_UNLOCK();
   free(dsq); free(len);
   return status;
 }
@@ -154,8 +168,10 @@ int b2h_glue_search_loop(b2h_ctx *ctx, const b2h_seqdb *db, P7_PIPELINE *pli, P7
   if ((status = b2h_glue_upload_oprofile(ctx, om, bg, &prof)) != B2H_OK) return status;
   params_of(pli, seed, host_threads, 0, &prm);
   plist[0] = prof;
+  ENGINE_LOCK();
   status = b2h_search(ctx, plist, 1, db, &prm, &res);
-  if (status != B2H_OK) { b2h_profile_destroy(prof); return status; }
+  ENGINE_UNLOCK();
+  if (status != B2H_OK) { ENGINE_LOCK(); b2h_profile_destroy(prof); ENGINE_UNLOCK(); return status; }
   nh = b2h_results_nhits(res); hits = b2h_results_hits(res); doms = b2h_results_domains(res); text = b2h_results_text(res, NULL);
   ctr = b2h_results_counters(res);
   /* accounting: what p7_pli_NewSeq does for every target (p7_pipeline.c:576), what p7_Pipeline counts (:725-770) */
@@ -169,7 +185,8 @@ int b2h_glue_search_loop(b2h_ctx *ctx, const b2h_seqdb *db, P7_PIPELINE *pli, P7
   }
   pli->nseqs = nseqs0 + n_targets;
   if (pli->Z_setby == p7_ZSETBY_NTARGETS) pli->Z = (double)pli->nseqs;
-  b2h_results_destroy(res); b2h_profile_destroy(prof);
+  b2h_results_destroy(res);
+  ENGINE_LOCK(); b2h_profile_destroy(prof); ENGINE_UNLOCK();
   return status;
 }
 
@@ -186,8 +203,10 @@ int b2h_glue_scan_loop(b2h_ctx *ctx, const b2h_profile *const *profs, P7_PIPELIN
   one[0] = (ESL_SQ *)sq;
   if ((status = b2h_glue_seqdb(ctx, one, 1, &db)) != B2H_OK) return status;
   params_of(pli, seed, host_threads, 1, &prm);
+  ENGINE_LOCK();
   status = b2h_search(ctx, profs, n_targets, db, &prm, &res);
-  if (status != B2H_OK) { b2h_seqdb_destroy(db); return status; }
+  ENGINE_UNLOCK();
+  if (status != B2H_OK) { ENGINE_LOCK(); b2h_seqdb_destroy(db); ENGINE_UNLOCK(); return status; }
   nh = b2h_results_nhits(res); hits = b2h_results_hits(res); doms = b2h_results_domains(res); text = b2h_results_text(res, NULL);
   ctr = b2h_results_seq_counters(res);
   if (ctr) { pli->n_past_msv += ctr[0]; pli->n_past_bias += ctr[1]; pli->n_past_vit += ctr[2]; pli->n_past_fwd += ctr[3]; }
@@ -198,6 +217,7 @@ int b2h_glue_scan_loop(b2h_ctx *ctx, const b2h_profile *const *profs, P7_PIPELIN
     if (status == eslOK && p7_pli_TargetReportable(pli, h->score, h->lnP)) status = fill_hit(pli, th, h, doms, text, sq, om[h->profile]);
   }
   for (; t < n_targets && status == eslOK; t++) status = p7_pli_NewModel(pli, om[t], bg);
-  b2h_results_destroy(res); b2h_seqdb_destroy(db);
+  b2h_results_destroy(res);
+  ENGINE_LOCK(); b2h_seqdb_destroy(db); ENGINE_UNLOCK();
   return status;
 }

@@ -45,6 +45,8 @@ cdef extern from "b2h_pyhmmer_glue.h" nogil:
                              ESL_SQ *const *sq, size_t n_targets, P7_TOPHITS *th, unsigned seed, int host_threads)
     int b2h_glue_scan_loop(b2h_ctx *ctx, const b2h_profile *const *profs, P7_PIPELINE *pli, const ESL_SQ *sq, P7_BG *bg,
                            P7_OPROFILE *const *om, size_t n_targets, P7_TOPHITS *th, unsigned seed, int host_threads)
+    void b2h_glue_seqdb_destroy(b2h_seqdb *db)
+    void b2h_glue_profile_destroy(b2h_profile *p)
 
 cdef enum:
     eslOK = 0
@@ -94,7 +96,7 @@ cdef class _SeqDB:
         self.db = NULL
     def __dealloc__(self):
         if self.db != NULL:
-            b2h_seqdb_destroy(self.db)
+            b2h_glue_seqdb_destroy(self.db)
 
 
 cdef class _ProfBlock:
@@ -109,7 +111,7 @@ cdef class _ProfBlock:
         if self.profs != NULL:
             for i in range(self.n):
                 if self.profs[i] != NULL:
-                    b2h_profile_destroy(self.profs[i])
+                    b2h_glue_profile_destroy(self.profs[i])
             free(self.profs)
 
 
