@@ -784,6 +784,9 @@ bool render_domain(const Model &m, const b2h_profile *prof, const uint8_t *dsq, 
   if (has_rf) rfline.assign(N, ' ');
   if (has_cs) csline.assign(N, ' ');
   const std::string &sym = prof->symbols;
+  int code_of[256];                                        // residue code of an (upper-case) consensus character, -1: none
+  for (int c = 0; c < 256; c++) code_of[c] = -1;
+  for (size_t c = sym.size(); c-- > 0;) code_of[(unsigned char)sym[c]] = (int)c;
   auto cons = [&](int k) -> char { return (k >= 1 && k <= (int)prof->consensus.size()) ? prof->consensus[k - 1] : 'x'; };
   for (int z = z1; z <= z2; z++) {
     const int k = tr.k[z], ii = tr.i[z], s = tr.st[z], a = z - z1;
@@ -794,8 +797,7 @@ bool render_domain(const Model &m, const b2h_profile *prof, const uint8_t *dsq, 
     if (s == ST_M) {
       model[a] = cons(k);
       const char cu = (char)toupper((unsigned char)cons(k));
-      const size_t cpos = sym.find(cu);
-      if (cpos != std::string::npos && (int)cpos == x) mline[a] = model[a];
+      if (code_of[(unsigned char)cu] == x) mline[a] = model[a];
       else if (m.r(x, k) > 1.0f) mline[a] = '+';
       else mline[a] = ' ';
       aseq[a] = (char)toupper((unsigned char)sym[x]);
@@ -815,8 +817,11 @@ bool render_domain(const Model &m, const b2h_profile *prof, const uint8_t *dsq, 
   if (has_cs) { out.text += csline; out.text.push_back('\0'); }
 
   float domcorrection = 0.0f;
-  if (!e.null2_done)
-    for (int pos = i; pos <= j; pos++) n2sc[pos] = logf(e.null2[dsq[pos - 1] < m.Kp ? dsq[pos - 1] : m.Kp - 1]);
+  if (!e.null2_done) {                                     // (one logf per residue CODE, not per position: same values)
+    float lg[B2H_NCODE];
+    for (int x = 0; x < m.Kp; x++) lg[x] = logf(e.null2[x]);
+    for (int pos = i; pos <= j; pos++) n2sc[pos] = lg[dsq[pos - 1] < m.Kp ? dsq[pos - 1] : m.Kp - 1];
+  }
   for (int pos = i; pos <= j; pos++) domcorrection += n2sc[pos];
   d.domcorrection = domcorrection;
   d.iali = d.sqfrom; d.jali = d.sqto; d.ienv = i; d.jenv = j; d.envsc = e.envsc; d.oasc = e.oasc;

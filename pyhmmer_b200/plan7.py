@@ -1512,7 +1512,18 @@ class Domain:
         self.lnP = float(rec.lnP)
         self.reported = False
         self.included = False
-        self.alignment = Alignment(self, rec, text)
+        self._text, self._alignment = text, None
+
+    @property
+    def alignment(self):
+        a = self._alignment
+        if a is None:
+            a = self._alignment = Alignment(self, self._rec, self._text)
+        return a
+
+    @alignment.setter
+    def alignment(self, value):
+        self._alignment = value
 
     @property
     def pvalue(self):
@@ -1578,9 +1589,17 @@ class Hit:
         self.new = False
         self.duplicate = False
         self._index = rec.seq if hits.mode == "search" else rec.profile
-        self._domains = [Domain(self, doms[rec.dom_offset + d], text) for d in range(rec.ndom)]
+        off = rec.dom_offset
+        self._domains = [Domain(self, doms[off + d], text) for d in range(rec.ndom)]
         self.best_domain = self._domains[rec.best_domain]
-        self.domains = Domains(self)
+
+    @property
+    def domains(self):
+        return Domains(self)
+
+    @domains.setter
+    def domains(self, value):
+        pass
 
     @property
     def pvalue(self):
@@ -1668,7 +1687,7 @@ class TopHits:
             self._hits.sort(key=lambda h: (-h.sortkey, h.name, 0 if h._domains[0]._rec.iali < h._domains[0]._rec.jali else 1,
                                            h._domains[0]._rec.iali))
             return
-        self._hits.sort(key=lambda h: (-h.sortkey, h.name, h._domains[0].alignment.target_from))
+        self._hits.sort(key=lambda h: (-h.sortkey, h.name, h._domains[0]._rec.sqfrom))
 
     def _threshold(self):
         """p7_tophits_Threshold (p7_tophits.c:1057)."""
@@ -1745,11 +1764,9 @@ class TopHits:
             for d in h._domains:
                 dc = _copy.copy(d)
                 dc.hit = c
-                dc.alignment = _copy.copy(d.alignment)
-                dc.alignment.domain = dc
+                dc._alignment = None                         # rebuilt on demand for the copy
                 c._domains.append(dc)
             c.best_domain = c._domains[h._domains.index(h.best_domain)]
-            c.domains = Domains(c)
             new._hits.append(c)
         return new
 
