@@ -133,6 +133,16 @@ struct Mx {
 // nodes it becomes (1) independent local chains per block, which the core overlaps, and (2) one vectorisable pass
 // adding the block's incoming value times the prefix products of t (precomputed per model). ----
 constexpr int CB = 16;
+// The O(M*L) host loops below are unit-stride and written for the compiler's vectoriser.  B2H_SIMD_CLONES compiles each of them
+// twice -- an AVX2 clone and a baseline x86-64 clone -- and the dynamic loader picks one per CPU (GCC function multiversioning),
+// so the library does not require AVX2 of its host.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define B2H_SIMD_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define B2H_SIMD_CLONES
+#endif
+
+B2H_SIMD_CLONES
 void chain_prefix(const float *tDD /* index k-1 */, int M, std::vector<float> &up, std::vector<float> &dn)
 {
   up.assign(M + 2, 0.f); dn.assign(M + 2, 0.f);
@@ -177,6 +187,7 @@ inline void chain_down(float *__restrict__ y, const float *__restrict__ tDD, con
 }
 
 // forward_engine, do_full (fwdback.c:256-463).  dsq[0..L-1].  Returns false on eslERANGE.
+B2H_SIMD_CLONES
 bool forward_full(const Model &m, const uint8_t *dsq, int L, Mx &ox, float *sc)
 {
   const int M = m.M;
@@ -235,6 +246,7 @@ bool forward_full(const Model &m, const uint8_t *dsq, int L, Mx &ox, float *sc)
 //   pp(i,k) = f(i,k) * b(i,k) * rs[i],   rs[i] = scaleproduct(i) * fwd scale(i)
 // with the per-row factor kept apart (it is only known once Backward has reached row 0).  bk receives the Backward
 // specials.  Returns false on eslERANGE from either routine.
+B2H_SIMD_CLONES
 bool backward_decode(const Model &m, const uint8_t *dsq, int L, const Mx &fwd, Mx &bk, Mx &pp, std::vector<float> &brow)
 {
   const int M = m.M;
@@ -352,6 +364,7 @@ bool backward_decode(const Model &m, const uint8_t *dsq, int L, const Mx &fwd, M
 // p7_OptimalAccuracy (optacc.c:58-176).  "impossible transition" contributes 0.0 (the AND-mask trick), not -inf.
 // The D(k) <- D(k-1) dependency is a max/mask chain: exact under any re-association, so it is blocked like the
 // Forward chain (local chains per block, then the incoming value gated by the block's running AND of the masks).
+B2H_SIMD_CLONES
 float optimal_accuracy(const Model &m, const Mx &pp, Mx &ox, std::vector<float> &pmask)
 {
   const int M = m.M, L = pp.L;
@@ -609,6 +622,7 @@ void avg_degenerate(const Model &m, float *null2)      // esl_abc_FAvgScVec + th
 }
 
 // p7_Null2_ByExpectation (null2.c:44-110)
+B2H_SIMD_CLONES
 void null2_by_expectation(const Model &m, const Mx &pp, float *null2)
 {
   const int M = m.M, Ld = pp.L;
@@ -829,6 +843,7 @@ bool render_domain(const Model &m, const b2h_profile *prof, const uint8_t *dsq, 
 }
 
 // p7_Null2_ByExpectation's second half from the column sums of the posterior matrix (the GPU returns those)
+B2H_SIMD_CLONES
 void null2_from_sums(const Model &m, int Ld, const float *em_in, const float *ei_in, float xn, float xc, float xj, float *null2)
 {
   const int M = m.M;

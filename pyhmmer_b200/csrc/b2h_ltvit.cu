@@ -106,9 +106,12 @@ __global__ void __launch_bounds__(256) lt_vit_kernel(const LtVitArgs a)
   constexpr int STRIDE = 32 * C * W;
   constexpr uint32_t TAB_BYTES = 32u * STRIDE * 4u;
   const ProfDev &P = a.P;
+  // W == 8 (models of 1537 .. 3072 nodes): the lane-grouped table would not fit in shared memory (393 KB); the emission scores
+  // are read from the node-major int16 table in global memory instead (L1 / L2 resident: 2 * Mpad bytes per residue row)
+  constexpr bool GLOBAL_TAB = (W == 8);
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
-  if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_rsc, P.vit_rsc32, TAB_BYTES, &s_bar); }
+  if (!GLOBAL_TAB && threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_rsc, P.vit_rsc32, TAB_BYTES, &s_bar); }
   int tBM[C], tMM[C], tIM[C], tDM[C], tMD[C], tMI[C], tII[C], tDD[C];
   int tDDin;
   {
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(256) lt_vit_kernel(const LtVitArgs a)
     tDDin = __shfl_up_sync(FULL, tDD[C - 1], 1);
     if (lane == 0) tDDin = (W > 1 && wi > 0 && gl * C - 1 < Mp) ? (int)ts[7 * Mp + gl * C - 1] : NEG16;
   }
-  mbar_wait(&s_bar, 0);
+  if (!GLOBAL_TAB) mbar_wait(&s_bar, 0);
   const int xwEm = P.xw_E_move, xwEl = P.xw_E_loop, base_w = P.base_w, ddbound = P.ddbound_w, Mnodes = P.M;
   const int *my_rsc = s_rsc + wi * 32 * C;
 
@@ -154,7 +157,11 @@ __global__ void __launch_bounds__(256) lt_vit_kernel(const LtVitArgs a)
       if ((i & 31) == 0) myres = (i + lane < L) ? (int)__ldg(res + i + lane) : 0;
       const int x = __shfl_sync(FULL, myres, i & 31) & 31;
       int r[C];
-      load_emis<C>(my_rsc, STRIDE, x, lane, r);
+      if (GLOBAL_TAB) {
+        const int16_t *row = P.vit_rsc + (size_t)x * P.Mpad + gl * C;
+#pragma unroll
+        for (int c = 0; c < C; c++) r[c] = (gl * C + c < P.Mpad) ? (int)__ldg(row + c) : NEG16;
+      } else load_emis<C>(my_rsc, STRIDE, x, lane, r);
       int mp = __shfl_up_sync(FULL, M[C - 1], 1), ip = __shfl_up_sync(FULL, I[C - 1], 1), dp = __shfl_up_sync(FULL, D[C - 1], 1);
       if (lane == 0) { mp = cM; ip = cI; dp = cD; }
       int xEm = NEG16;
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(256) lt_vit_kernel(const LtVitArgs a)
 template <int C, int W>
 int launch_ltvit(b2h_ctx *ctx, const LtVitArgs &a, cudaStream_t strm)
 {
-  const size_t smem = (size_t)32 * 32 * C * W * 4;
+  const size_t smem = (W == 8) ? 0 : (size_t)32 * 32 * C * W * 4;
   int occ = 1;
   { const int st = b2h_kernel_occupancy(ctx, (const void *)lt_vit_kernel<C, W>, 256, smem, &occ); if (st != B2H_OK) return st; }
   const int groups = 8 / W;
@@ -347,7 +354,8 @@ extern "C" int b2h_longtarget_viterbi_windows(b2h_ctx *ctx, const b2h_profile *p
   if (!ctx || !p || !windows || p->ctx != ctx || windows->ctx != ctx || !filtersc || !marks_out || !nmarks_out || !out || !nout) return B2H_EINVAL;
   *marks_out = *out = nullptr; *nmarks_out = *nout = 0;
   if (p->max_length <= 0) { ctx->err = "long-target search needs the model's max_length (MAXL)"; return B2H_EINVAL; }
-  if (!p->regC) { ctx->err = "long-target Viterbi: models above 1536 nodes are not supported yet"; return B2H_EINVAL; }
+  if (!p->regC && p->M > 3072) { ctx->err = "long-target Viterbi: models above 3072 nodes are not supported"; return B2H_EINVAL; }
+  const int cls = p->regC ? p->regW * 64 + p->regC : 8 * 64 + 12;     // above 1536 nodes: 8 warps x 32 lanes x 12 nodes, table in global memory
   const size_t n = windows->n;
   if (n == 0) return B2H_OK;
   B2H_CUDA(cudaSetDevice(ctx->device));
@@ -392,12 +400,12 @@ extern "C" int b2h_longtarget_viterbi_windows(b2h_ctx *ctx, const b2h_profile *p
       cudaMemsetAsync(d_nm, 0, sizeof(int), st);
       cudaMemsetAsync(a.counter, 0, sizeof(int), st);
       rc = B2H_EINVAL;
-      switch (p->regW * 64 + p->regC) {
+      switch (cls) {
 #define CASE(CC, WW) case (WW) * 64 + (CC): rc = launch_ltvit<CC, WW>(ctx, a, st); break;
         CASE(2, 1) CASE(3, 1) CASE(4, 1) CASE(5, 1) CASE(6, 1) CASE(7, 1) CASE(8, 1)
         CASE(9, 1) CASE(10, 1) CASE(11, 1) CASE(12, 1) CASE(14, 1) CASE(16, 1)
         CASE(9, 2) CASE(10, 2) CASE(11, 2) CASE(12, 2) CASE(14, 2) CASE(16, 2)
-        CASE(10, 4) CASE(12, 4)
+        CASE(10, 4) CASE(12, 4) CASE(12, 8)
 #undef CASE
       }
       int nm = 0;

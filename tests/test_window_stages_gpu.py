@@ -18,8 +18,9 @@ pytestmark = pytest.mark.gpu
 KW = dict(F1=0.02, F2=3e-3, F3=3e-5, bias_filter=True, B1=100, B2=240, B3=1000)
 
 
-# register tiles of the Viterbi scan: C = 2 / 4 / 11 nodes per lane on one warp, two warps, four warps
-@pytest.mark.parametrize("M,mu_shift", [(40, -3.0), (121, -2.0), (333, -2.0), (600, -1.0), (1100, -1.0)])
+# register tiles of the Viterbi scan: C = 2 / 4 / 11 nodes per lane on one warp, two warps, four warps; above 1536 nodes the
+# eight-warp class that reads its emission scores from global memory (LSU-rRNA-sized models)
+@pytest.mark.parametrize("M,mu_shift", [(40, -3.0), (121, -2.0), (333, -2.0), (600, -1.0), (1100, -1.0), (1700, -1.0), (2900, -1.0)])
 def test_window_stages(make_pair, M, mu_shift):
     pair, rng = lt_common.dna_model(make_pair, M, mu_shift=mu_shift)
     block = lt_common.dna_chunks(pair, rng, [60000, 0, 9, 25000, 262144 // 4], nplant=6)
