@@ -1113,6 +1113,47 @@ struct LtWindow {
   int64_t window_start, seq_start; int complement; int seq; bool bck_own_scales;
 };
 
+// p7_pli_postViterbi_LongTarget's arithmetic for one rescored envelope (p7_pipeline.c:1150-1262): the score corrections to the
+// model's max_length window, the coordinates mapped to the target, one hit per domain appended to <outs>.
+void lt_finish_hit(const b2h_profile *prof, const LtWindow &lw, int i, int j, float envsc, float domcorrection, DomOut &dom, std::vector<HitOut> &outs)
+{
+  const int maxL = prof->max_length;
+  const double LOG2 = 0.69314718055994529;
+  const double tau = prof->evparam[4], lam = prof->evparam[5];
+  auto logsurv = [&](double x) { return (x < tau) ? 0.0 : -lam * (x - tau); };
+  if (domcorrection < envsc) envsc = domcorrection;
+  b2h_domain &dd = dom.d;
+  dd.domcorrection = domcorrection - envsc;
+  dd.envsc = envsc; dd.ienv = i; dd.jenv = j;
+  const int env_len = dd.jenv - dd.ienv + 1, ali_len = dd.jali - dd.iali + 1;
+  if (ali_len < 8) return;
+  float bitscore = dd.envsc;
+  bitscore = (float)((double)bitscore - 2 * log(2. / (env_len + 2)));
+  bitscore = (float)((double)bitscore + 2 * log(2. / (maxL + 2)));
+  bitscore = (float)((double)bitscore - (env_len - ali_len) * log((double)((float)env_len / (float)(env_len + 2))));
+  bitscore = (float)((double)bitscore + (std::max(maxL, env_len) - ali_len) * log((double)((float)maxL / (float)(maxL + 2))));
+  const float dom_bias = dd.domcorrection;
+  b2h_len_params lp; b2h_length_params(std::max(maxL, env_len), 1.0f, &lp);
+  const float dom_score = (float)((double)(bitscore - lp.null1) / LOG2);
+  const double dom_lnP = logsurv((double)dom_score);
+  // positions in the target: x + seq_start + window_start - 2 on the top strand, seq_start - (window_start + x) + 2 on the other
+  auto map  = [&](int x) -> int32_t { return (int32_t)((int64_t)x + lw.seq_start + lw.window_start - 2); };
+  auto mapc = [&](int x) -> int32_t { return (int32_t)(lw.seq_start - (lw.window_start + (int64_t)x) + 2); };
+  if (lw.complement) { dd.ienv = mapc(dd.ienv); dd.jenv = mapc(dd.jenv); dd.iali = mapc(dd.iali); dd.jali = mapc(dd.jali); dd.sqfrom = mapc(dd.sqfrom); dd.sqto = mapc(dd.sqto); }
+  else               { dd.ienv = map(dd.ienv);  dd.jenv = map(dd.jenv);  dd.iali = map(dd.iali);  dd.jali = map(dd.jali);  dd.sqfrom = map(dd.sqfrom);  dd.sqto = map(dd.sqto); }
+  dd.dombias = dom_bias; dd.bitscore = dom_score; dd.lnP = dom_lnP;
+  HitOut out;
+  b2h_hit &h = out.hit;
+  memset(&h, 0, sizeof h);
+  h.profile = 0; h.seq = lw.seq;
+  h.pre_score = (float)((double)bitscore / LOG2); h.pre_lnP = logsurv((double)h.pre_score);
+  h.score = h.sum_score = dom_score; h.lnP = h.sum_lnP = dom_lnP;
+  h.ndom = 1; h.best_domain = 0;
+  out.doms.push_back(std::move(dom));
+  out.valid = true;
+  outs.push_back(std::move(out));
+}
+
 // One window: regions and envelopes exactly as for proteins (ddef_regions), then per envelope the long-target rescoring and
 // the hit the reference builds from it.  Hits are appended in the order of ddef->dcl.
 void lt_window(Worker &w, const b2h_profile *prof, const LtWindow &lw, const b2h_search_params *prm, std::vector<HitOut> &outs)
@@ -1123,11 +1164,8 @@ void lt_window(Worker &w, const b2h_profile *prof, const LtWindow &lw, const b2h
   TaskState ts;
   ddef_regions(w, t, prm, ts);
   if (ts.dead || ts.nregions == 0 || ts.envs.empty()) return;
-  const int max_env_extra = 20, maxL = prof->max_length;
+  const int max_env_extra = 20;
   std::vector<float> rsc, n2sc((size_t)lw.L + 1, 0.f);
-  const double LOG2 = 0.69314718055994529;
-  const double tau = prof->evparam[4], lam = prof->evparam[5];
-  auto logsurv = [&](double x) { return (x < tau) ? 0.0 : -lam * (x - tau); };
   for (size_t d = 0; d < ts.envs.size(); d++) {
     EnvRec &e = ts.envs[d];
     int i = e.i, j = e.j;
@@ -1158,46 +1196,12 @@ void lt_window(Worker &w, const b2h_profile *prof, const LtWindow &lw, const b2h
       float sc = domcorrection;
       if (forward_full(mo, lw.dsq + i - 1, Ld, w.fwd, &sc)) domcorrection = sc;
     }
-    if (domcorrection < envsc) envsc = domcorrection;
-    b2h_domain &dd = dom.d;
-    dd.domcorrection = domcorrection - envsc;
-    dd.envsc = envsc; dd.ienv = i; dd.jenv = j;
-
-    // p7_pli_postViterbi_LongTarget (p7_pipeline.c:1150-1262): one hit per domain
-    const int env_len = dd.jenv - dd.ienv + 1, ali_len = dd.jali - dd.iali + 1;
-    if (ali_len < 8) continue;
-    float bitscore = dd.envsc;
-    bitscore = (float)((double)bitscore - 2 * log(2. / (env_len + 2)));
-    bitscore = (float)((double)bitscore + 2 * log(2. / (maxL + 2)));
-    bitscore = (float)((double)bitscore - (env_len - ali_len) * log((double)((float)env_len / (float)(env_len + 2))));
-    bitscore = (float)((double)bitscore + (std::max(maxL, env_len) - ali_len) * log((double)((float)maxL / (float)(maxL + 2))));
-    const float dom_bias = dd.domcorrection;
-    b2h_len_params lp; b2h_length_params(std::max(maxL, env_len), 1.0f, &lp);
-    const float dom_score = (float)((double)(bitscore - lp.null1) / LOG2);
-    const double dom_lnP = logsurv((double)dom_score);
-    // positions in the target: x + seq_start + window_start - 2 on the top strand, seq_start - (window_start + x) + 2 on the other
-    auto map  = [&](int x) -> int32_t { return (int32_t)((int64_t)x + lw.seq_start + lw.window_start - 2); };
-    auto mapc = [&](int x) -> int32_t { return (int32_t)(lw.seq_start - (lw.window_start + (int64_t)x) + 2); };
-    if (lw.complement) { dd.ienv = mapc(dd.ienv); dd.jenv = mapc(dd.jenv); dd.iali = mapc(dd.iali); dd.jali = mapc(dd.jali); dd.sqfrom = mapc(dd.sqfrom); dd.sqto = mapc(dd.sqto); }
-    else               { dd.ienv = map(dd.ienv);  dd.jenv = map(dd.jenv);  dd.iali = map(dd.iali);  dd.jali = map(dd.jali);  dd.sqfrom = map(dd.sqfrom);  dd.sqto = map(dd.sqto); }
-    dd.dombias = dom_bias; dd.bitscore = dom_score; dd.lnP = dom_lnP;
-    HitOut out;
-    b2h_hit &h = out.hit;
-    memset(&h, 0, sizeof h);
-    h.profile = 0; h.seq = lw.seq;
-    h.pre_score = (float)((double)bitscore / LOG2); h.pre_lnP = logsurv((double)h.pre_score);
-    h.score = h.sum_score = dom_score; h.lnP = h.sum_lnP = dom_lnP;
-    h.ndom = 1; h.best_domain = 0;
-    out.doms.push_back(std::move(dom));
-    out.valid = true;
-    outs.push_back(std::move(out));
+    lt_finish_hit(prof, lw, i, j, envsc, domcorrection, dom, outs);
   }
 }
 
 } // namespace
 
-// Odds-space Forward/Backward rows decay into denormals away from the alignment; x86 handles those ~100x slower.
-// HMMER's own programs run with flush-to-zero (impl_Init); pyhmmer cannot set it process-wide, we can per worker.
 struct FtzScope {
 #if defined(__SSE2__)
   unsigned int saved;
@@ -1350,6 +1354,133 @@ int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_param
     }
     res->hits.push_back(h);
   }
+  return B2H_OK;
+}
+
+// The same with the O(M*Ld) rescoring of the envelopes on a backend (the GPU envelope kernels), batched over ALL windows:
+//   A   (host threads) regions and envelopes of every window (ddef_regions);
+//   B0  (backend)      every envelope: Forward, Backward + decoding, optimal accuracy + trace, with the emission odds
+//                      re-estimated from the envelope (lt_reparameterize) and the profile configured for the envelope length;
+//   C0  (host threads) alignments; an envelope reaching more than 20 residues beyond its alignment is trimmed ...
+//   B1  (backend)      ... and rescored the same way; then one Forward-only pass of every final envelope with the model's OWN
+//                      emissions (the bias of the reference = the score without the re-estimation);
+//   C1  (host threads) the hit arithmetic (lt_finish_hit).
+// An envelope the backend cannot do falls back to the host code, one by one.  windows[w] is task w: task.surv.seq must be the
+// index of the window in the backend's database.
+int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wins, const int32_t *db_index, size_t n, const b2h_search_params *prm,
+                                   int nthreads, b2h_env_backend *backend, b2h_results *res)
+{
+  const int max_env_extra = 20;
+  nthreads = std::max(1, nthreads);
+  std::vector<b2h_ddef_task> tasks(n);
+  std::vector<TaskState> states(n);
+  std::vector<LtWindow> lws(n);
+  for (size_t q = 0; q < n; q++) {
+    const b2h_lt_window &x = wins[q];
+    LtWindow &lw = lws[q];
+    lw.dsq = x.dsq; lw.L = x.L; lw.fx = x.fwd_xmx; lw.bx = x.bck_xmx; lw.window_start = x.window_start; lw.seq_start = x.seq_start;
+    lw.complement = x.complement; lw.seq = x.seq; lw.bck_own_scales = x.bck_own_scales != 0;
+    b2h_ddef_task &t = tasks[q];
+    t.surv.profile = 0; t.surv.seq = db_index[q]; t.surv.fwdsc = 0.f; t.surv.filtersc = 0.f;
+    t.prof = p; t.dsq = x.dsq; t.L = x.L; t.fx = x.fwd_xmx; t.bx = x.bck_xmx; t.bck_own_scales = lw.bck_own_scales;
+  }
+  ThreadPool::get().parallel_for(n, nthreads, [&](Worker &w, size_t q) { ddef_regions(w, tasks[q], prm, states[q]); });
+  struct Env { uint32_t win, d; int i, j; std::vector<float> rsc; DomOut dom; bool ok = false, trimmed = false; float envsc = 0.f, domcorrection = 0.f; };
+  std::vector<Env> envs;
+  for (size_t q = 0; q < n; q++) {
+    if (states[q].dead || states[q].nregions == 0) continue;
+    for (size_t d = 0; d < states[q].envs.size(); d++) { Env e; e.win = (uint32_t)q; e.d = (uint32_t)d; e.i = states[q].envs[d].i; e.j = states[q].envs[d].j; envs.push_back(std::move(e)); }
+  }
+  const size_t ne = envs.size();
+  // one rescoring pass over the envelopes listed in <which>: backend first, the host for what it leaves
+  auto rescore = [&](const std::vector<uint32_t> &which) -> int {
+    const size_t m = which.size();
+    if (m == 0) return B2H_OK;
+    ThreadPool::get().parallel_for(m, nthreads, [&](Worker &, size_t z) {
+      Env &e = envs[which[z]];
+      if (prm->do_null2) lt_reparameterize(p, lws[e.win].dsq, lws[e.win].L, e.i, e.j - e.i + 1, e.rsc);
+    });
+    std::vector<b2h_env_job> jobs(m);
+    for (size_t z = 0; z < m; z++) {
+      Env &e = envs[which[z]];
+      jobs[z].task = (int)e.win; jobs[z].i = e.i; jobs[z].j = e.j; jobs[z].cfg_len = e.j - e.i + 1;
+      jobs[z].rsc = prm->do_null2 ? e.rsc.data() : nullptr;
+    }
+    if (backend) { const int st = backend->run(tasks, jobs); if (st != B2H_OK) return st; }
+    ThreadPool::get().parallel_for(m, nthreads, [&](Worker &w, size_t z) {
+      Env &e = envs[which[z]];
+      const LtWindow &lw = lws[e.win];
+      EnvRec &er = states[e.win].envs[e.d];
+      const int Ld = e.j - e.i + 1;
+      Model mm; model_of(w, p, mm);
+      configure(mm, false, Ld);
+      if (prm->do_null2) mm.rsc = e.rsc.data();
+      er.i = e.i; er.j = e.j; er.null2_done = true;
+      bool ok;
+      if (backend && jobs[z].status == 0) { er.envsc = jobs[z].envsc; er.oasc = jobs[z].oasc; ok = er.ok = trace_from_records(jobs[z].trace, Ld, er.tr); }
+      else ok = rescore_numeric(w, mm, lw.dsq, er);
+      std::vector<float> n2sc((size_t)lw.L + 1, 0.f);
+      e.ok = ok && render_domain(mm, p, lw.dsq, er, n2sc, e.dom);
+      e.envsc = er.envsc;
+    });
+    return B2H_OK;
+  };
+  std::vector<uint32_t> all(ne);
+  for (size_t z = 0; z < ne; z++) all[z] = (uint32_t)z;
+  int st = rescore(all);
+  if (st != B2H_OK) return st;
+  std::vector<uint32_t> again;
+  for (size_t z = 0; z < ne; z++) {
+    Env &e = envs[z];
+    if (e.ok && (e.i < e.dom.d.sqfrom - max_env_extra || e.j > e.dom.d.sqto + max_env_extra)) {
+      e.i = std::max(e.i, e.dom.d.sqfrom - max_env_extra);     // trim the envelope around the alignment and do it again
+      e.j = std::min(e.j, e.dom.d.sqto + max_env_extra);
+      e.trimmed = true;
+      again.push_back((uint32_t)z);
+    }
+  }
+  if ((st = rescore(again)) != B2H_OK) return st;
+  // the score without the re-estimated background: a plain Forward of every final envelope
+  for (size_t z = 0; z < ne; z++) envs[z].domcorrection = envs[z].envsc;
+  if (prm->do_null2) {
+    std::vector<uint32_t> live;
+    for (size_t z = 0; z < ne; z++) if (envs[z].ok) live.push_back((uint32_t)z);
+    std::vector<b2h_env_job> jobs(live.size());
+    for (size_t z = 0; z < live.size(); z++) {
+      const Env &e = envs[live[z]];
+      jobs[z].task = (int)e.win; jobs[z].i = e.i; jobs[z].j = e.j; jobs[z].cfg_len = e.j - e.i + 1; jobs[z].rsc = nullptr; jobs[z].fwd_only = true;
+    }
+    if (backend && !jobs.empty()) { if ((st = backend->run(tasks, jobs)) != B2H_OK) return st; }
+    ThreadPool::get().parallel_for(live.size(), nthreads, [&](Worker &w, size_t z) {
+      Env &e = envs[live[z]];
+      if (backend && jobs[z].status == 0) { e.domcorrection = jobs[z].envsc; return; }
+      if (backend && std::isinf(jobs[z].envsc)) return;        // (p7_Forward's range error: the reference keeps envsc)
+      Model mo; model_of(w, p, mo);
+      const int Ld = e.j - e.i + 1;
+      configure(mo, false, Ld);
+      float sc = e.domcorrection;
+      if (forward_full(mo, lws[e.win].dsq + e.i - 1, Ld, w.fwd, &sc)) e.domcorrection = sc;
+    });
+  }
+  std::vector<std::vector<HitOut>> outs(n);
+  for (size_t z = 0; z < ne; z++) {                         // in the order of ddef->dcl
+    Env &e = envs[z];
+    if (!e.ok) continue;
+    lt_finish_hit(p, lws[e.win], e.i, e.j, e.envsc, e.domcorrection, e.dom, outs[e.win]);
+  }
+  for (size_t q = 0; q < n; q++)
+    for (auto &o : outs[q]) {
+      b2h_hit h = o.hit;
+      h.profile = (int32_t)q;                              // the window the hit came from
+      h.dom_offset = (int64_t)res->doms.size();
+      for (auto &dm : o.doms) {
+        b2h_domain d = dm.d;
+        d.text_offset = (int64_t)res->text.size();
+        res->text.insert(res->text.end(), dm.text.begin(), dm.text.end());
+        res->doms.push_back(d);
+      }
+      res->hits.push_back(h);
+    }
   return B2H_OK;
 }
 

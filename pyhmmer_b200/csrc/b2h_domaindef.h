@@ -30,6 +30,9 @@ struct b2h_ddef_task {
 struct b2h_env_job {
   int task = 0;                    // index into the task list
   int i = 0, j = 0;                // envelope in the target, 1-based
+  const float *rsc = nullptr;      // long targets: this envelope's re-estimated emission odds [Kp][M] (nullptr: the profile's)
+  int cfg_len = 0;                 // length the profile is configured for (0: the task's sequence length; long targets: the envelope)
+  bool fwd_only = false;           // only the Forward score is wanted
   // results
   int   status = -1;               // 0 = done; anything else: rescore this envelope on the host
   float envsc = 0.f, oasc = 0.f;
@@ -53,3 +56,7 @@ struct b2h_ddef_pool {
 // Long-target (nhmmer) windows behind the Forward gate -> hits, one per domain (p7_pli_postViterbi_LongTarget); hit.profile
 // carries the index of the window the hit came from.
 int b2h_longtarget_domains_host(const b2h_profile *p, const b2h_lt_window *wins, size_t n, const b2h_search_params *prm, int nthreads, b2h_results *res);
+// The same, the envelope rescoring on <backend> (nullptr: host) batched over all windows; db_index[w] = index of window w in the
+// backend's sequence database.
+int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wins, const int32_t *db_index, size_t n, const b2h_search_params *prm,
+                                   int nthreads, b2h_env_backend *backend, b2h_results *res);

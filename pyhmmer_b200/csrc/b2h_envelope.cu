@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) efwd_kernel(const EnvDev ev, const SeqDev
     const uint8_t *seq = sd.res + sd.off[s] + (i0 - 1);        // residue of envelope row i is seq[i-1]
     const float pmove = ev.pmove[e], ploop = 1.0f - pmove;
     const float tEC = 1.0f, tEJ = 0.0f;
+    const float *rsc = (ev.rsc_off && ev.rsc_off[e] >= 0) ? ev.rsc_pool + ev.rsc_off[e] : P.fwd_rsc;   // this envelope's own emission odds (long targets)
     float *Fm = ev.F + 3 * ev.moff[e];
     float *xout = ev.fx + ev.xoff[e] * 6;
     float M[C], I[C], D[C];
@@ -123,13 +124,13 @@ __global__ void __launch_bounds__(256) efwd_kernel(const EnvDev ev, const SeqDev
     float cM = 0.f, cI = 0.f, cD = 0.f;
     if (gl == 0) { xout[0] = 0.f; xout[1] = 1.f; xout[2] = 0.f; xout[3] = xB; xout[4] = 0.f; xout[5] = 1.f; }
     float rn[C];
-    if (L >= 1) load_nodes<C>(P.fwd_rsc + (size_t)seq[0] * Mpad, k0, Mpad, rn);
+    if (L >= 1) load_nodes<C>(rsc + (size_t)seq[0] * Mpad, k0, Mpad, rn);
 
     for (int i = 1; i <= L; i++) {
       float r[C];
 #pragma unroll
       for (int c = 0; c < C; c++) r[c] = rn[c];
-      if (i < L) load_nodes<C>(P.fwd_rsc + (size_t)seq[i] * Mpad, k0, Mpad, rn);     // prefetch the next row's emissions
+      if (i < L) load_nodes<C>(rsc + (size_t)seq[i] * Mpad, k0, Mpad, rn);     // prefetch the next row's emissions
       float mp = __shfl_up_sync(FULL, M[C - 1], 1), ip = __shfl_up_sync(FULL, I[C - 1], 1), dp = __shfl_up_sync(FULL, D[C - 1], 1);
       if (lane == 0) { mp = cM; ip = cI; dp = cD; }
       float esum = 0.f;
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(256) ebck_kernel(const EnvDev ev, const SeqDev
     const uint8_t *seq = sd.res + sd.off[s] + (i0 - 1);
     const float pmove = ev.pmove[e], ploop = 1.0f - pmove;
     const float tEC = 1.0f, tEJ = 0.0f;
+    const float *rsc = (ev.rsc_off && ev.rsc_off[e] >= 0) ? ev.rsc_pool + ev.rsc_off[e] : P.fwd_rsc;
     const float *Fm = ev.F + 3 * ev.moff[e];
     float *Pm = ev.PP + 2 * ev.moff[e];
     const float *fx = ev.fx + ev.xoff[e] * 6;
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(256) ebck_kernel(const EnvDev ev, const SeqDev
       const int x = seq[i];                               // x_{i+1}
       fetch_f(i);
       float r[C];
-      load_nodes<C>(P.fwd_rsc + (size_t)x * Mpad, k0, Mpad, r);
+      load_nodes<C>(rsc + (size_t)x * Mpad, k0, Mpad, r);
       float me[C];
 #pragma unroll
       for (int c = 0; c < C; c++) me[c] = Mv[c] * r[c];
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(256) ebck_kernel(const EnvDev ev, const SeqDev
       float menext = __shfl_down_sync(FULL, me[0], 1);
       if (lane == 31) {
         menext = 0.f;
-        if (W > 1 && wi < W - 1) { const int kn = (wi + 1) * 32 * C; menext = X[3][wi + 1] * ((kn < Mpad) ? __ldg(P.fwd_rsc + (size_t)x * Mpad + kn) : 0.f); }
+        if (W > 1 && wi < W - 1) { const int kn = (wi + 1) * 32 * C; menext = X[3][wi + 1] * ((kn < Mpad) ? __ldg(rsc + (size_t)x * Mpad + kn) : 0.f); }
       }
 #pragma unroll
       for (int c = 0; c < C; c++) {
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(256) ebck_kernel(const EnvDev ev, const SeqDev
     }
     {
       float r[C];
-      load_nodes<C>(P.fwd_rsc + (size_t)seq[0] * Mpad, k0, Mpad, r);
+      load_nodes<C>(rsc + (size_t)seq[0] * Mpad, k0, Mpad, r);
       float bsum = 0.f;
       if (L >= 1) {
 #pragma unroll

@@ -299,6 +299,7 @@ struct EnvDev {
   float *F, *PP, *OA, *fx, *bx, *ox; uint8_t *BP;
   float *envsc, *oasc, *em, *ei, *xnull; int32_t *status, *tlen; int4 *trace;
   int *counter; int e_lo, e_hi;
+  const float *rsc_pool = nullptr; const int64_t *rsc_off = nullptr;   // per-envelope emission odds [Kp][Mpad] (offset in floats, -1: the profile's)
 };
 int b2h_launch_envelope(b2h_ctx *ctx, int kind, int C, int W, const EnvDev &ev, const SeqDev &sd, cudaStream_t strm);
 struct b2h_envclass { int bound, C, W; };

@@ -467,7 +467,20 @@ struct EnvGpu : b2h_env_backend {
       while (c < B2H_N_ENV_CLASSES && M > B2H_ENV_CLASSES[c].bound) c++;
       cls[q] = c;                                            // == B2H_N_ENV_CLASSES: longer than any class (cannot happen: SSV tiles stop at 3071)
     }
-    const size_t BUDGET = (size_t)6 << 30;                   // bytes of matrix scratch per pass
+    // bytes of matrix scratch per pass: 6 GB, or -- when a pass would not hold the job (long-target envelopes of kilobase
+    // models are ~50 MB each) -- up to a third of what the device has free, so that few, well-filled passes are launched
+    size_t BUDGET = (size_t)6 << 30;
+    {
+      size_t want = 0;
+      for (size_t q = 0; q < n; q++) {
+        const int c = std::min(cls[q], B2H_N_ENV_CLASSES - 1);
+        want += (size_t)(jobs[q].j - jobs[q].i + 2) * (size_t)32 * B2H_ENV_CLASSES[c].C * B2H_ENV_CLASSES[c].W * (8 * sizeof(float) + 1);
+      }
+      size_t free_b = 0, total_b = 0;
+      if (want > BUDGET && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) BUDGET = std::max(BUDGET, std::min(want, free_b / 3));
+    }
+    bool fwd_only = n > 0;
+    for (size_t q = 0; q < n; q++) fwd_only = fwd_only && jobs[q].fwd_only;
     std::vector<char> done(n, 0);
     for (;;) {
       // take envelopes class by class until the scratch budget is full
@@ -492,8 +505,9 @@ struct EnvGpu : b2h_env_backend {
       std::vector<ProfDev> hprof; std::vector<const b2h_profile *> seen;
       std::vector<int32_t> h_prof(m), h_seq(m), h_i0(m), h_Ld(m), h_tcap(m);
       std::vector<float> h_pmove(m);
-      std::vector<int64_t> h_moff(m), h_moffn(m), h_xoff(m), h_toff(m);
-      int64_t moff = 0, moffn = 0, xoff = 0, toff = 0;
+      std::vector<int64_t> h_moff(m), h_moffn(m), h_xoff(m), h_toff(m), h_rscoff(m, -1);
+      int64_t moff = 0, moffn = 0, xoff = 0, toff = 0, rscoff = 0;
+      bool any_rsc = false;
       for (int z = 0; z < m; z++) {
         const b2h_env_job &jb = jobs[perm[z]];
         const b2h_ddef_task &t = tasks[jb.task];
@@ -503,7 +517,8 @@ struct EnvGpu : b2h_env_backend {
         const int64_t Mp = (int64_t)32 * B2H_ENV_CLASSES[c].C * B2H_ENV_CLASSES[c].W;
         const int Ld = jb.j - jb.i + 1;
         h_prof[z] = (int32_t)pi; h_seq[z] = t.surv.seq; h_i0[z] = jb.i; h_Ld[z] = Ld;
-        h_pmove[z] = (2.0f + 0.0f) / ((float)t.L + 2.0f + 0.0f);     // configure(m, false, L)
+        h_pmove[z] = (2.0f + 0.0f) / ((float)(jb.cfg_len > 0 ? jb.cfg_len : t.L) + 2.0f + 0.0f);     // configure(m, false, L)
+        if (jb.rsc) { h_rscoff[z] = rscoff; rscoff += (int64_t)t.prof->Kp * t.prof->Mpad; any_rsc = true; }
         h_tcap[z] = Ld + t.prof->M + 16;
         h_moff[z] = moff; h_moffn[z] = moffn; h_xoff[z] = xoff; h_toff[z] = toff;
         moff += (int64_t)(Ld + 1) * Mp; moffn += Mp; xoff += Ld + 1; toff += h_tcap[z];
@@ -520,11 +535,24 @@ struct EnvGpu : b2h_env_backend {
       A(dalloc(keep, &ev.fx, (size_t)xoff * 6)); A(dalloc(keep, &ev.bx, (size_t)xoff * 6)); A(dalloc(keep, &ev.ox, (size_t)xoff * 6));
       A(dalloc(keep, &ev.envsc, m)); A(dalloc(keep, &ev.oasc, m)); A(dalloc(keep, &ev.em, (size_t)moffn)); A(dalloc(keep, &ev.ei, (size_t)moffn));
       A(dalloc(keep, &ev.xnull, (size_t)m * 4)); A(dalloc(keep, &ev.status, m)); A(dalloc(keep, &ev.tlen, m)); A(dalloc(keep, &ev.trace, (size_t)toff));
+      float *d_rsc = nullptr; int64_t *d_rscoff = nullptr;
+      std::vector<float> h_rsc;
+      if (any_rsc) {                                           // the envelopes' own emission odds, padded to the device row length
+        A(dalloc(keep, &d_rsc, (size_t)rscoff)); A(dalloc(keep, &d_rscoff, m));
+        h_rsc.assign((size_t)rscoff, 0.0f);
+        for (int z = 0; z < m; z++) {
+          const b2h_env_job &jb = jobs[perm[z]];
+          if (!jb.rsc) continue;
+          const b2h_profile *pf = tasks[jb.task].prof;
+          for (int x = 0; x < pf->Kp; x++) memcpy(h_rsc.data() + h_rscoff[z] + (size_t)x * pf->Mpad, jb.rsc + (size_t)x * pf->M, (size_t)pf->M * sizeof(float));
+        }
+      }
       auto release = [&]() { for (void *p : keep) cudaFreeAsync(p, st); };
       if (rc != B2H_OK) { release(); return rc; }
 #define H2D(dst, src) cudaMemcpyAsync(dst, (src).data(), (src).size() * sizeof((src)[0]), cudaMemcpyHostToDevice, st)
       H2D(d_prof, hprof); H2D(d_pi, h_prof); H2D(d_seq, h_seq); H2D(d_i0, h_i0); H2D(d_Ld, h_Ld); H2D(d_tcap, h_tcap); H2D(d_pmove, h_pmove);
       H2D(d_moff, h_moff); H2D(d_moffn, h_moffn); H2D(d_xoff, h_xoff); H2D(d_toff, h_toff);
+      if (any_rsc) { H2D(d_rsc, h_rsc); H2D(d_rscoff, h_rscoff); ev.rsc_pool = d_rsc; ev.rsc_off = d_rscoff; }
 #undef H2D
       cudaMemsetAsync(ev.tlen, 0xff, (size_t)m * sizeof(int32_t), st);
       ev.profs = d_prof; ev.prof = d_pi; ev.seq = d_seq; ev.i0 = d_i0; ev.Ld = d_Ld; ev.pmove = d_pmove;
@@ -537,7 +565,7 @@ struct EnvGpu : b2h_env_backend {
         cudaStream_t sc = ctx->env_side[c];
         cudaStreamWaitEvent(sc, ctx->env_fork, 0);
         ev.e_lo = cls_lo[c]; ev.e_hi = cls_lo[c + 1]; ev.counter = ctx->d_env_counter + c;
-        for (int kind = 0; kind < 3 && rc == B2H_OK; kind++) rc = b2h_launch_envelope(ctx, kind, B2H_ENV_CLASSES[c].C, B2H_ENV_CLASSES[c].W, ev, sd, sc);
+        for (int kind = 0; kind < (fwd_only ? 1 : 3) && rc == B2H_OK; kind++) rc = b2h_launch_envelope(ctx, kind, B2H_ENV_CLASSES[c].C, B2H_ENV_CLASSES[c].W, ev, sd, sc);
         cudaEventRecord(ctx->env_join[c], sc);
         cudaStreamWaitEvent(st, ctx->env_join[c], 0);
       }
@@ -555,6 +583,7 @@ struct EnvGpu : b2h_env_backend {
         b2h_env_job &jb = jobs[perm[z]];
         const int M = tasks[jb.task].prof->M;
         const int base = r_status[z] & 0xff;                                             // a Forward range error only makes envsc = inf
+        if (fwd_only) { jb.status = (base == B2H_OK) ? 0 : 1; jb.envsc = r_envsc[z]; continue; }
         if ((base != B2H_OK && base != B2H_ERANGE) || (r_status[z] & 0x300) || r_tlen[z] < 0) { jb.status = 1; continue; }
         jb.status = 0; jb.envsc = r_envsc[z]; jb.oasc = r_oasc[z];
         jb.xn = r_xnull[(size_t)z * 4 + 0]; jb.xc = r_xnull[(size_t)z * 4 + 1]; jb.xj = r_xnull[(size_t)z * 4 + 2];
@@ -867,7 +896,11 @@ int b2h_longtarget_domains(const b2h_profile *p, const b2h_lt_window *windows, s
   b2h_results *res = new b2h_results();
   res->counters.assign(4, 0);
   b2h_ddef_pool pool(prm->host_threads);
-  const int st = b2h_longtarget_domains_host(p, windows, n, prm, pool.nthreads, res);
+  // the batched driver the GPU path uses, without a backend: every envelope is rescored by the host code
+  std::vector<int32_t> idx(n);
+  for (size_t i = 0; i < n; i++) idx[i] = (int32_t)i;
+  const int st = getenv("B2H_LT_WINDOW_BY_WINDOW") ? b2h_longtarget_domains_host(p, windows, n, prm, pool.nthreads, res)
+                                                   : b2h_longtarget_domains_backend(p, windows, idx.data(), n, prm, pool.nthreads, nullptr, res);
   if (st != B2H_OK) { delete res; return st; }
   *out = res;
   return B2H_OK;
@@ -931,7 +964,9 @@ int b2h_longtarget_hits(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *win
       x.bck_own_scales = (bst[e] & 0x100) != 0; x.reserved = 0;
     }
     const size_t h0 = res->hits.size();
-    TRY(b2h_longtarget_domains_host(p, lw.data(), (size_t)nb, prm, pool.nthreads, res));
+    static const bool lt_host_env = getenv("B2H_ENVELOPES_ON_HOST") != nullptr;     // debugging aid: rescore envelopes with the host code
+    if (lt_host_env) TRY(b2h_longtarget_domains_host(p, lw.data(), (size_t)nb, prm, pool.nthreads, res));
+    else { EnvGpu envgpu(ctx, windows); TRY(b2h_longtarget_domains_backend(p, lw.data(), ent.data(), (size_t)nb, prm, pool.nthreads, &envgpu, res)); }
     for (size_t h = h0; h < res->hits.size(); h++) res->hits[h].profile += (int32_t)i0;      // window index in the whole list
     i0 = i1;
   }
