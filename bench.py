@@ -275,6 +275,13 @@ def main():
         e2e_phases.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3))
         return res
 
+    # The inputs are ~10^5 long-lived Python objects (50 000 sequences, their arrays, the profiles).  A full collection that
+    # walks them costs tens of milliseconds and used to land inside one timed step (round 1: step 12 of 20 took 2x): after
+    # this point they are frozen out of the collector's generations, so the collections a step's own short-lived result
+    # objects trigger stay cheap.
+    import gc
+    gc.collect()
+    gc.freeze()
     sampler = ClockSampler(local)
     times, stage_acc = [], {}
     host_split = []
@@ -315,7 +322,6 @@ def main():
 
     # end-to-end through the public API with host buffers
     e2e_times = []
-    import gc
     for it in range(2 + max(3, K)):
         res = None
         gc.collect()                                              # (untimed) the previous step's result objects: keep collector pauses out of the next step
