@@ -18,6 +18,7 @@
 // Moving the envelope DP to the GPU is SURVEY 8(f) rank 1 (next round).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1301,7 +1302,11 @@ int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_param
   std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
     return (int64_t)tasks[a].prof->M * tasks[a].L > (int64_t)tasks[b].prof->M * tasks[b].L; });
   // phase A: regions and envelopes
+  const bool trace = getenv("B2H_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tA0 = now();
   ThreadPool::get().parallel_for(n, nthreads, [&](Worker &w, size_t i) { const uint32_t e = order[i]; ddef_regions(w, tasks[e], prm, states[e]); });
+  const double tA1 = now();
   // phase B: the O(M*Ld) numeric rescoring of every envelope, largest first
   std::vector<std::pair<uint32_t, uint32_t>> envs;
   for (size_t e = 0; e < n; e++) for (size_t d = 0; d < states[e].envs.size(); d++) envs.emplace_back((uint32_t)e, (uint32_t)d);
@@ -1341,7 +1346,10 @@ int b2h_ddef_pool::run(std::vector<b2h_ddef_task> &tasks, const b2h_search_param
     rescore_numeric(w, m, t.dsq, states[envs[i].first].envs[envs[i].second]);
   });
   // phase C: alignments and scores
+  const double tC0 = now();
   ThreadPool::get().parallel_for(n, nthreads, [&](Worker &, size_t i) { ddef_finish(tasks[i], prm, states[i], outs[i]); });
+  if (trace) fprintf(stderr, "[b2h_ddef]   %zu survivors on %d threads: regions %.2f ms, envelopes (backend + unpack + host leftovers) %.2f ms, alignments + scores %.2f ms\n",
+                     n, nthreads, tA1 - tA0, tC0 - tA1, now() - tC0);
   for (size_t e = 0; e < n; e++) {
     if (!outs[e].valid) continue;
     b2h_hit h = outs[e].hit;
