@@ -67,12 +67,17 @@ __device__ __forceinline__ uint32_t hfma2_relu_add(uint32_t m, uint32_t e)
 }
 __device__ __forceinline__ int half_bits_to_int(uint32_t bits) { return (int)__half2float(__ushort_as_half((unsigned short)bits)); }
 
-struct LtWin { int32_t seq, idx, k, length; long long n; float score; int32_t pad; };
+struct LtWin { int32_t seq, idx, k, length; long long n; float score; int32_t item; };
+
+// A stretch of one chunk for one lane group: rows [scan_from, row_end] are computed from a zero row, diagonals are detected
+// from row detect_from on (the rows before it only warm the DP row up).  Without items a group scans a whole chunk.
+struct LtItem { int32_t seq, scan_from, detect_from, row_end, id; };
 
 struct LtArgs {
   ProfDev P; SeqDev sd;
   int sc_thresh, tjb, Q;
   LtWin *win; int *nwin; int cap; int *counter;
+  const LtItem *items = nullptr; int nitems = 0;
 };
 
 template <int G, int NR>
@@ -106,11 +111,15 @@ __global__ void __launch_bounds__(128) lt_ssv_kernel(const LtArgs a)
     int e0 = 0;
     if (lane == 0) e0 = atomicAdd(a.counter, NG);
     e0 = __shfl_sync(FULL, e0, 0);
-    if (e0 >= a.sd.n) break;
+    const int nwork = a.items ? a.nitems : a.sd.n;
+    if (e0 >= nwork) break;
     const int e = e0 + grp;
-    const bool valid = e < a.sd.n;
-    const int s = valid ? a.sd.order[e] : 0;
-    const int L = valid ? a.sd.len[s] : 0;
+    const bool valid = e < nwork;
+    LtItem it; it.seq = 0; it.scan_from = 1; it.detect_from = 1; it.row_end = 0; it.id = 0;
+    if (valid) { if (a.items) it = a.items[e]; else { it.seq = a.sd.order[e]; it.row_end = a.sd.len[it.seq]; } }
+    const int s = it.seq;
+    const int L = valid ? a.sd.len[s] : 0;                    // the chunk's true length: the diagonal walks may leave the item's rows
+    const int row_end = valid ? it.row_end : 0, detect_from = it.detect_from;
     const uint8_t *seq = a.sd.res + a.sd.off[s];
     const uint32_t *seqw = reinterpret_cast<const uint32_t *>(seq);
     const int nwords = (L + 3) >> 2;
@@ -118,11 +127,11 @@ __global__ void __launch_bounds__(128) lt_ssv_kernel(const LtArgs a)
     uint32_t m[NR];
 #pragma unroll
     for (int j = 0; j < NR; j++) m[j] = 0u;
-    int i = 1, nemit = 0;                                      // next row of this group's scan (1-based), windows emitted so far
+    int i = it.scan_from, nemit = 0;                           // next row of this group's scan (1-based), windows emitted so far
     int w0 = -G; uint32_t myw = 0;
 
-    while (__any_sync(FULL, i <= L)) {
-      const bool active = i <= L;
+    while (__any_sync(FULL, i <= row_end)) {
+      const bool active = i <= row_end;
       uint32_t x = B2H_PAD_CODE;
       {
         const int w = active ? ((i - 1) >> 2) : w0;            // word holding residue i
@@ -142,12 +151,12 @@ __global__ void __launch_bounds__(128) lt_ssv_kernel(const LtArgs a)
 #pragma unroll
       for (int j = 0; j + 1 < NR; j += 2) xe = __vimax3_s16x2(xe, m[j], m[j+1]);
       if (NR & 1) xe = __vimax3_s16x2(xe, m[NR-1], m[NR-1]);
-      const bool lanehit = active && (max((int)(xe & 0xffffu), (int)(xe >> 16)) >= thr_bits);
+      const bool lanehit = active && i >= detect_from && (max((int)(xe & 0xffffu), (int)(xe >> 16)) >= thr_bits);
       if (__any_sync(FULL, lanehit)) {
         // the cell the reference picks: the largest value >= threshold among the model's nodes, first in its striped scan
         // order (q outer, z inner; node k = q + Q*z + 1) -- packed as (value bits << 16) | (0xffff - (q*16 + z))
         int best = 0;
-        if (active) {
+        if (active && i >= detect_from) {                      // (another group of the warp may have triggered this block)
 #pragma unroll
           for (int j = 0; j < NR; j++) {
 #pragma unroll
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(128) lt_ssv_kernel(const LtArgs a)
           ret_sc /= P.scale_b;
           ret_sc -= 3.0f;
           const int slot = atomicAdd(a.nwin, 1);
-          if (slot < a.cap) { LtWin w; w.seq = s; w.idx = nemit; w.k = end; w.length = end - start + 1; w.n = target_start; w.score = ret_sc; w.pad = 0; a.win[slot] = w; }
+          if (slot < a.cap) { LtWin w; w.seq = s; w.idx = nemit; w.k = end; w.length = end - start + 1; w.n = target_start; w.score = ret_sc; w.item = it.id; a.win[slot] = w; }
           new_i = target_end;                                                       // skip forward (msvfilter.c:411)
         }
         best = __shfl_sync(FULL, best, 0, G);
@@ -211,7 +220,8 @@ int launch_lt(b2h_ctx *ctx, const LtArgs &a, cudaStream_t strm)
   int occ = 1;
   { const int st = b2h_kernel_occupancy(ctx, (const void *)lt_ssv_kernel<G, NR>, 128, smem, &occ); if (st != B2H_OK) return st; }
   const int NG = 32 / G;
-  int grid = std::min(ctx->sm_count * occ, std::max(1, (a.sd.n + 4 * NG - 1) / (4 * NG)));
+  const int nwork = a.items ? a.nitems : a.sd.n;
+  int grid = std::min(ctx->sm_count * occ, std::max(1, (nwork + 4 * NG - 1) / (4 * NG)));
   lt_ssv_kernel<G, NR><<<grid, 128, smem, strm>>>(a);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());
@@ -322,34 +332,110 @@ extern "C" int b2h_longtarget_windows(b2h_ctx *ctx, const b2h_profile *p, const 
   if ((e = cudaMallocAsync((void **)&a.win, (size_t)a.cap * sizeof(LtWin), st)) != cudaSuccess ||
       (e = cudaMallocAsync((void **)&d_nwin, sizeof(int), st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); return B2H_EMEM; }
   a.nwin = d_nwin;
-  cudaMemsetAsync(d_nwin, 0, sizeof(int), st);
-  cudaMemsetAsync(a.counter, 0, sizeof(int), st);
-  int rc = B2H_EINVAL;
-  switch (p->G * 64 + p->NR) {
+  struct Release { LtArgs &a; int *nw; cudaStream_t st; ~Release() { cudaFreeAsync(a.win, st); cudaFreeAsync(nw, st); } } release{a, d_nwin, st};
+  // one launch over <items> (nullptr: every chunk whole); its diagonals are appended to <out>
+  auto launch = [&](const std::vector<LtItem> *items, std::vector<LtWin> &out) -> int {
+    LtItem *d_items = nullptr;
+    if (items) {
+      if (items->empty()) return B2H_OK;
+      if ((e = cudaMallocAsync((void **)&d_items, items->size() * sizeof(LtItem), st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); return B2H_EMEM; }
+      cudaMemcpyAsync(d_items, items->data(), items->size() * sizeof(LtItem), cudaMemcpyHostToDevice, st);
+      a.items = d_items; a.nitems = (int)items->size();
+    } else { a.items = nullptr; a.nitems = 0; }
+    cudaMemsetAsync(d_nwin, 0, sizeof(int), st);
+    cudaMemsetAsync(a.counter, 0, sizeof(int), st);
+    int rc = B2H_EINVAL;
+    switch (p->G * 64 + p->NR) {
 #define CASE(g, n_) case (g) * 64 + (n_): rc = launch_lt<g, n_>(ctx, a, st); break;
 #define CASE8(g, n_) CASE(g, n_) CASE(g, n_ + 1) CASE(g, n_ + 2) CASE(g, n_ + 3) CASE(g, n_ + 4) CASE(g, n_ + 5) CASE(g, n_ + 6) CASE(g, n_ + 7)
-    CASE8(8, 1) CASE8(8, 9) CASE8(8, 17) CASE8(8, 25)
-    CASE8(16, 17) CASE8(16, 25)
-    CASE(32, 18) CASE(32, 20) CASE(32, 22) CASE(32, 24) CASE(32, 26) CASE(32, 28) CASE(32, 30) CASE(32, 32) CASE(32, 40) CASE(32, 48)
+      CASE8(8, 1) CASE8(8, 9) CASE8(8, 17) CASE8(8, 25)
+      CASE8(16, 17) CASE8(16, 25)
+      CASE(32, 18) CASE(32, 20) CASE(32, 22) CASE(32, 24) CASE(32, 26) CASE(32, 28) CASE(32, 30) CASE(32, 32) CASE(32, 40) CASE(32, 48)
 #undef CASE8
 #undef CASE
-  }
-  int nwin = 0;
+    }
+    int nwin = 0;
+    if (rc == B2H_OK) {
+      cudaMemcpyAsync(&nwin, d_nwin, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { ctx->err = std::string("long-target SSV kernel: ") + cudaGetErrorString(e); rc = B2H_ECUDA; }
+      else if (nwin > a.cap) { ctx->err = "long-target SSV: window list overflow"; rc = B2H_ERANGE; }
+      else if (nwin > 0) {
+        const size_t at = out.size();
+        out.resize(at + nwin);
+        cudaMemcpyAsync(out.data() + at, a.win, (size_t)nwin * sizeof(LtWin), cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = B2H_ECUDA; }
+      }
+    }
+    if (d_items) cudaFreeAsync(d_items, st);
+    return rc;
+  };
   std::vector<LtWin> hw;
-  if (rc == B2H_OK) {
-    cudaMemcpyAsync(&nwin, d_nwin, sizeof(int), cudaMemcpyDeviceToHost, st);
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { ctx->err = std::string("long-target SSV kernel: ") + cudaGetErrorString(e); rc = B2H_ECUDA; }
-    else if (nwin > a.cap) { ctx->err = "long-target SSV: window list overflow"; rc = B2H_ERANGE; }
-    else if (nwin > 0) {
-      hw.resize(nwin);
-      cudaMemcpyAsync(hw.data(), a.win, (size_t)nwin * sizeof(LtWin), cudaMemcpyDeviceToHost, st);
-      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = B2H_ECUDA; }
+  // A chunk is ONE dependent scan in the reference (the DP row is reset behind every diagonal), which leaves a 100 Mb genome with
+  // ~800 chains of 262 144 rows: latency bound.  Speculative stretches: the chunk is cut into stretches of S rows, each scanned
+  // from a zero row O = M rows early (a cell depends on the < M rows of its diagonal only, so the row is exact when detection
+  // starts) -- provided no diagonal of the chunk ended within those O rows, which is decided from the PREVIOUS stretch's own,
+  // exact, diagonals: if its scan resumed (target end + 1) later than O rows before this stretch, this stretch is scanned again
+  // from that row.  Stretches of a chunk are confirmed in order; a round rescans, in parallel over the chunks, the first
+  // unconfirmed stretch of each; after 6 rounds what is left of a chunk is scanned in one piece.
+  static const int stretch = getenv("B2H_LT_STRETCH") ? atoi(getenv("B2H_LT_STRETCH")) : 8192;
+  const int S = std::max(256, stretch), O = p->M;
+  bool whole = stretch <= 0;
+  if (!whole) { size_t nst = 0; for (size_t s2 = 0; s2 < n; s2++) nst += (db->h_len[s2] + S - 1) / S; whole = nst <= n + n / 2; }   // chunks no longer than a stretch
+  if (whole) { const int rc = launch(nullptr, hw); if (rc != B2H_OK) return rc; }
+  else {
+    std::vector<LtItem> items;
+    for (size_t s2 = 0; s2 < n; s2++)
+      for (int c = 0, L2 = db->h_len[s2]; c * S < L2; c++)
+        items.push_back(LtItem{(int32_t)s2, std::max(1, c * S + 1 - O), c * S + 1, std::min(L2, (c + 1) * S), c});
+    std::vector<LtWin> spec;
+    { const int rc = launch(&items, spec); if (rc != B2H_OK) return rc; }
+    auto by_scan = [](const LtWin &x, const LtWin &y) { return x.seq != y.seq ? x.seq < y.seq : x.item != y.item ? x.item < y.item : x.idx < y.idx; };
+    std::sort(spec.begin(), spec.end(), by_scan);
+    std::vector<size_t> first(n + 1, 0);                      // spec[first[s] .. first[s+1]) = diagonals of chunk s
+    { size_t q = 0; for (size_t s2 = 0; s2 < n; s2++) { first[s2] = q; while (q < spec.size() && (size_t)spec[q].seq == s2) q++; } first[n] = spec.size(); }
+    struct Cursor { int c = 0; long long resume = 0; size_t q = 0; bool waiting = false; };     // resume: row the reference's scan resumed at behind its last diagonal
+    std::vector<Cursor> cur(n);
+    for (size_t s2 = 0; s2 < n; s2++) cur[s2].q = first[s2];
+    auto take = [&](size_t s2, const LtWin *w, size_t cnt) {   // confirmed diagonals of the current stretch of chunk s2
+      for (size_t z = 0; z < cnt; z++) { LtWin x = w[z]; x.idx = (int32_t)hw.size(); hw.push_back(x); cur[s2].resume = x.n + x.length; }   // target_end + 1
+    };
+    for (int round = 0;; round++) {
+      std::vector<LtItem> redo;
+      std::vector<size_t> redo_of;
+      for (size_t s2 = 0; s2 < n; s2++) {
+        Cursor &k = cur[s2];
+        const int L2 = db->h_len[s2];
+        while (!k.waiting && (long long)k.c * S < L2) {
+          const long long a0 = (long long)k.c * S + 1, end = std::min<long long>(L2, (long long)(k.c + 1) * S);
+          size_t q1 = k.q; while (q1 < first[s2 + 1] && spec[q1].item == k.c) q1++;
+          if (k.resume <= a0 - O || k.resume <= 1) { take(s2, spec.data() + k.q, q1 - k.q); k.q = q1; k.c++; continue; }   // the speculation held
+          k.q = q1;                                            // its speculative diagonals are void
+          if (k.resume > end) { k.c++; continue; }             // the scan skipped this stretch altogether
+          const bool rest = round >= 6;                        // a dense chunk: finish it in one sequential piece
+          redo.push_back(LtItem{(int32_t)s2, (int32_t)k.resume, (int32_t)std::max(a0, k.resume), (int32_t)(rest ? L2 : end), k.c});
+          redo_of.push_back(s2);
+          if (rest) { k.c = (L2 + S - 1) / S; k.q = first[s2 + 1]; }
+          k.waiting = true;
+        }
+      }
+      if (redo.empty()) break;
+      std::vector<LtWin> got;
+      { const int rc = launch(&redo, got); if (rc != B2H_OK) return rc; }
+      std::sort(got.begin(), got.end(), by_scan);
+      size_t g = 0;
+      for (size_t z = 0; z < redo_of.size(); z++) {            // redo is in chunk order, so is got
+        const size_t s2 = redo_of[z];
+        size_t g1 = g; while (g1 < got.size() && (size_t)got[g1].seq == s2) g1++;
+        take(s2, got.data() + g, g1 - g);
+        g = g1;
+        Cursor &k = cur[s2];
+        k.waiting = false;
+        if ((long long)k.c * S < db->h_len[s2]) k.c++;       // (a "rest" item has already closed its chunk)
+      }
     }
   }
-  cudaFreeAsync(a.win, st); cudaFreeAsync(d_nwin, st);
-  if (rc != B2H_OK) return rc;
   // every chunk's diagonals in the order its scan produced them
-  std::sort(hw.begin(), hw.end(), [](const LtWin &x, const LtWin &y) { return x.seq != y.seq ? x.seq < y.seq : x.idx < y.idx; });
+  std::stable_sort(hw.begin(), hw.end(), [](const LtWin &x, const LtWin &y) { return x.seq != y.seq ? x.seq < y.seq : x.idx < y.idx; });   // (idx: scan order inside a chunk in both modes)
   b2h_window *raw = (b2h_window *)malloc(std::max<size_t>(1, hw.size()) * sizeof(b2h_window));
   b2h_window *mer = (b2h_window *)malloc(std::max<size_t>(1, hw.size()) * sizeof(b2h_window));
   if (!raw || !mer) { free(raw); free(mer); return B2H_EMEM; }
