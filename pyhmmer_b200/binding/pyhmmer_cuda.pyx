@@ -133,8 +133,8 @@ cdef void _raise(_Engine eng, int status, str fn) except *:
     raise UnexpectedError(status, fn)
 
 
-cdef class CudaPipeline(Pipeline):
-    """`pyhmmer.plan7.Pipeline` whose comparison loops run on the GPU.  Same constructor, same results."""
+cdef class _CudaPipelineBase(Pipeline):
+    """`pyhmmer.plan7.Pipeline` whose comparison loops run on the GPU (the extension type; use `CudaPipeline`)."""
 
     cdef _Engine _engine
     cdef int     _host_threads
@@ -308,11 +308,23 @@ cdef class CudaPipeline(Pipeline):
         return hits
 
 
+class CudaPipeline(_CudaPipelineBase):
+    """`pyhmmer.plan7.Pipeline` whose comparison loops run on the GPU.  Same constructor, same results.
+
+    A Python-level class on purpose: `Pipeline.search_seq`, `search_msa` and `IterativeSearch._search_hmm` call the cpdef
+    `search_hmm` through the C vtable, and Cython only looks for an overriding method there when the object's type is a
+    heap type (the dispatch check of cpdef methods is skipped for static extension types).  With this class phmmer's and
+    jackhmmer's searches -- every iteration -- reach the GPU `search_hmm` above."""
+    __slots__ = ()
+
+
 def install():
-    """Make `pyhmmer.hmmsearch` / `pyhmmer.hmmscan` build `CudaPipeline` objects in their workers (the `pipeline_class` hook
-    of pyhmmer.hmmer._base._BaseWorker).  Returns a function that undoes it."""
-    import pyhmmer.hmmer._hmmsearch as hs, pyhmmer.hmmer._hmmscan as sc
-    saved = [(cls, cls.__dict__.get("pipeline_class")) for cls in (hs._SEARCHWorker, sc._SCANWorker)]
+    """Make `pyhmmer.hmmsearch` / `hmmscan` / `phmmer` / `jackhmmer` build `CudaPipeline` objects in their workers (the
+    `pipeline_class` hook of pyhmmer.hmmer._base._BaseWorker).  phmmer's `search_seq` / `search_msa` and jackhmmer's
+    `IterativeSearch` (plan7.pyx:4273-4389) build their models with pyhmmer's own `Builder` and then call
+    `pipeline.search_hmm`, i.e. every search iteration runs on the GPU.  Returns a function that undoes it."""
+    import pyhmmer.hmmer._hmmsearch as hs, pyhmmer.hmmer._hmmscan as sc, pyhmmer.hmmer._phmmer as ph, pyhmmer.hmmer._jackhmmer as jk
+    saved = [(cls, cls.__dict__.get("pipeline_class")) for cls in (hs._SEARCHWorker, sc._SCANWorker, ph._PHMMERWorker, jk._JACKHMMERWorker)]
     for cls, _ in saved:
         cls.pipeline_class = CudaPipeline
 

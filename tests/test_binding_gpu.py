@@ -74,6 +74,78 @@ def test_reference_hmmer_test_classes_run_on_cuda(bound):
     assert pyhmmer_cuda.engine().launch_count > launches0 + 100
 
 
+def test_reference_phmmer_jackhmmer_test_classes_run_on_cuda(bound):
+    """the reference's TestPhmmer / TestJackhmmer (src/pyhmmer/tests/test_hmmer.py:417-629; golden table
+    A0A089QRB9.domtbl, the jackhmmer CLI's 3 iterations / 5 hits / 17 aligned sequences on PKSI) with the workers of
+    pyhmmer.phmmer / jackhmmer building CudaPipeline objects: models come from pyhmmer's own Builder on the CPU, every search
+    iteration of `IterativeSearch` (plan7.pyx:4332-4389) runs on the GPU."""
+    pyhmmer, pyhmmer_cuda = bound
+    mod = importlib.import_module("pyhmmer.tests.test_hmmer")
+    undo = pyhmmer_cuda.install()
+    launches0 = pyhmmer_cuda.engine().launch_count
+    try:
+        res = _run_cases([mod.TestPhmmer, mod.TestJackhmmer])
+    finally:
+        undo()
+    assert res.testsRun >= 8
+    assert not res.failures and not res.errors, [str(f[0]) + "\n" + f[1] for f in res.failures + res.errors]
+    assert pyhmmer_cuda.engine().launch_count > launches0 + 100
+
+
+def test_iterative_search_on_cuda_equals_reference(bound):
+    """jackhmmer iteration by iteration: `CudaPipeline.iterate_seq` / `iterate_hmm` against `Pipeline.iterate_seq` /
+    `iterate_hmm` -- the same hits, inclusion flags and scores, the same alignment handed to the builder, the same model
+    length and convergence at every iteration; `search_seq` / `search_msa` likewise.  The GPU launch counter proves that the
+    cpdef calls inside the reference (`self.search_hmm[...]`, `IterativeSearch._search_hmm`) reach the override."""
+    pyhmmer, pyhmmer_cuda = bound
+    abc = pyhmmer.easel.Alphabet.amino()
+    with pyhmmer.easel.SequenceFile(_data(pyhmmer, "seqs", "PKSI.faa"), digital=True, alphabet=abc) as f:
+        seqs = f.read_block()
+    eng = pyhmmer_cuda.engine()
+
+    def same(got, ref):
+        assert len(got) == len(ref) and len(got.included) == len(ref.included) and len(got.reported) == len(ref.reported)
+        for a, b in zip(got, ref):
+            assert a.name == b.name and (a.included, a.reported, len(a.domains)) == (b.included, b.reported, len(b.domains))
+            assert abs(a.score - b.score) < 2e-3 and abs(a.bias - b.bias) < 2e-3
+            for d, e in zip(a.domains, b.domains):
+                assert (d.env_from, d.env_to, d.alignment.target_from, d.alignment.target_to, d.included) == \
+                       (e.env_from, e.env_to, e.alignment.target_from, e.alignment.target_to, e.included)
+
+    for query in (seqs[-1], seqs[0]):
+        n0 = eng.launch_count
+        same(pyhmmer_cuda.CudaPipeline(abc).search_seq(query, seqs), pyhmmer.plan7.Pipeline(abc).search_seq(query, seqs))
+        assert eng.launch_count > n0 + 5
+        it_ref = pyhmmer.plan7.Pipeline(abc).iterate_seq(query, seqs)
+        it_got = pyhmmer_cuda.CudaPipeline(abc).iterate_seq(query, seqs)
+        last = None
+        for k in range(5):
+            n0 = eng.launch_count
+            r, g = next(it_ref), next(it_got)
+            assert eng.launch_count > n0 + 5, "iteration %d did not run on the GPU" % (k + 1)
+            same(g.hits, r.hits)
+            assert (g.iteration, g.converged, g.hmm.M, len(g.msa.sequences), g.msa.name) == (r.iteration, r.converged, r.hmm.M, len(r.msa.sequences), r.msa.name)
+            assert [bytes(x) for x in g.msa.alignment] == [bytes(x) for x in r.msa.alignment] if hasattr(g.msa, "alignment") else True
+            last = g
+            if r.converged:
+                break
+        assert last is not None and last.iteration >= 2
+        # alignment query (phmmer / hmmsearch with an MSA): the alignment of the last iteration as the query
+        n0 = eng.launch_count
+        same(pyhmmer_cuda.CudaPipeline(abc).search_msa(last.msa, seqs), pyhmmer.plan7.Pipeline(abc).search_msa(last.msa, seqs))
+        assert eng.launch_count > n0 + 5
+    with pyhmmer.plan7.HMMFile(_data(pyhmmer, "hmms", "txt", "KR.hmm")) as f:
+        hmm = f.read()
+    it_ref = pyhmmer.plan7.Pipeline(abc).iterate_hmm(hmm, seqs)
+    it_got = pyhmmer_cuda.CudaPipeline(abc).iterate_hmm(hmm, seqs)
+    for k in range(3):
+        r, g = next(it_ref), next(it_got)
+        same(g.hits, r.hits)
+        assert (g.converged, g.hmm.M, len(g.msa.sequences)) == (r.converged, r.hmm.M, len(r.msa.sequences))
+        if r.converged:
+            break
+
+
 def test_cuda_pipeline_equals_reference_pipeline(bound):
     """Object-level comparison: the same queries and targets through pyhmmer's Pipeline (CPU) and CudaPipeline (GPU) -- hit
     lists, flags, every score, domain coordinates and alignment rows, the accounting of the TopHits, pickling."""
