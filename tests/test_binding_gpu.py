@@ -107,7 +107,10 @@ def test_iterative_search_on_cuda_equals_reference(bound):
         assert len(got) == len(ref) and len(got.included) == len(ref.included) and len(got.reported) == len(ref.reported)
         for a, b in zip(got, ref):
             assert a.name == b.name and (a.included, a.reported, len(a.domains)) == (b.included, b.reported, len(b.domains))
-            assert abs(a.score - b.score) < 2e-3 and abs(a.bias - b.bias) < 2e-3
+            # 2e-3 bits, or 1e-5 of the score for the kilobit self-hits of these multi-kilobase proteins (a 4 675-bit score
+            # is 3 240 nats: float32 carries it to 2.4e-4 nats, and both implementations sum ~2 000 rescaling logs into it)
+            tol = max(2e-3, 1e-5 * abs(b.score))
+            assert abs(a.score - b.score) < tol and abs(a.bias - b.bias) < tol
             for d, e in zip(a.domains, b.domains):
                 assert (d.env_from, d.env_to, d.alignment.target_from, d.alignment.target_to, d.included) == \
                        (e.env_from, e.env_to, e.alignment.target_from, e.alignment.target_to, e.included)
@@ -132,7 +135,8 @@ def test_iterative_search_on_cuda_equals_reference(bound):
         assert last is not None and last.iteration >= 2
         # alignment query (phmmer / hmmsearch with an MSA): the alignment of the last iteration as the query
         n0 = eng.launch_count
-        same(pyhmmer_cuda.CudaPipeline(abc).search_msa(last.msa, seqs), pyhmmer.plan7.Pipeline(abc).search_msa(last.msa, seqs))
+        # (p7_Builder rewrites the alignment it is given -- weights, fragment marks, RF line: a copy each)
+        same(pyhmmer_cuda.CudaPipeline(abc).search_msa(last.msa.copy(), seqs), pyhmmer.plan7.Pipeline(abc).search_msa(last.msa.copy(), seqs))
         assert eng.launch_count > n0 + 5
     with pyhmmer.plan7.HMMFile(_data(pyhmmer, "hmms", "txt", "KR.hmm")) as f:
         hmm = f.read()
