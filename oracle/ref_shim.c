@@ -613,6 +613,47 @@ int ref_single_builder(int alphabet_type, const uint8_t *dsq, int L, const char 
   return eslOK;
 }
 
+/* Builder.build_msa (plan7.pyx:1018-1119 -> p7_Builder, p7_builder.c:415) on a digital alignment given as <nseq> rows of <alen>
+ * residue codes (no sentinels): default builder (PB weights, entropy-weighted effective sequence number, the alphabet's mixture
+ * Dirichlet priors), architecture 0 = fast (symfrac) / 1 = hand (needs <rf>), effn < 0: entropy weighting, 0: none, > 0: set.
+ * The HMM is written in ASCII to <path>; the weights p7_Builder left in the alignment come back in <wgt_out> (may be NULL). */
+#include "esl_msa.h"
+int ref_msa_builder(int alphabet_type, const uint8_t *rows, int nseq, int alen, const char *const *names, const char *msaname,
+                    const char *rf, int architecture, double symfrac, double fragthresh, double effn, int laplace, unsigned seed,
+                    const char *path, double *wgt_out)
+{
+  ESL_ALPHABET *abc = esl_alphabet_Create(alphabet_type);
+  P7_BG *bg = p7_bg_Create(abc);
+  P7_BUILDER *bld = p7_builder_Create(NULL, abc);
+  ESL_MSA *msa = esl_msa_CreateDigital(abc, nseq, alen);
+  P7_HMM *hmm = NULL;
+  FILE *fp;
+  int i, j, status;
+  ref_init();
+  for (i = 0; i < nseq; i++) {
+    esl_msa_SetSeqName(msa, i, names[i], -1);
+    msa->ax[i][0] = msa->ax[i][alen + 1] = eslDSQ_SENTINEL;
+    for (j = 0; j < alen; j++) msa->ax[i][j + 1] = rows[(size_t)i * alen + j];
+  }
+  esl_msa_SetName(msa, msaname, -1);
+  if (rf) { msa->rf = malloc(alen + 1); memcpy(msa->rf, rf, alen); msa->rf[alen] = 0; }
+  if (seed != 42) { esl_randomness_Destroy(bld->r); bld->r = esl_randomness_CreateFast(seed); }
+  bld->do_reseeding = (seed != 0);
+  bld->w_len = -1; bld->w_beta = p7_DEFAULT_WINDOW_BETA;
+  bld->arch_strategy = architecture ? p7_ARCH_HAND : p7_ARCH_FAST;
+  bld->symfrac = symfrac; bld->fragthresh = fragthresh;
+  if (effn == 0.0) bld->effn_strategy = p7_EFFN_NONE;
+  else if (effn > 0.0) { bld->effn_strategy = p7_EFFN_SET; bld->eset = effn; }
+  if (laplace) { p7_prior_Destroy(bld->prior); bld->prior = p7_prior_CreateLaplace(abc); }
+  if ((status = p7_Builder(bld, msa, bg, &hmm, NULL, NULL, NULL, NULL)) != eslOK) return status;
+  if (wgt_out) for (i = 0; i < nseq; i++) wgt_out[i] = msa->wgt[i];
+  if ((fp = fopen(path, "w")) == NULL) return -1;
+  p7_hmmfile_WriteASCII(fp, -1, hmm);
+  fclose(fp);
+  p7_hmm_Destroy(hmm); esl_msa_Destroy(msa); p7_builder_Destroy(bld); p7_bg_Destroy(bg); esl_alphabet_Destroy(abc);
+  return eslOK;
+}
+
 /* esl_random stream of the Mersenne Twister seeded <seed> (esl_random.c), and iid digital sequences drawn with it */
 void ref_mt_stream(unsigned seed, int n, double *out)
 {

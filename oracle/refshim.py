@@ -157,6 +157,26 @@ def single_builder(alphabet_type, codes, name, path, matrix="BLOSUM62", popen=0.
         raise ValueError("p7_SingleBuilder failed with status %d" % st)
 
 
+def msa_builder(alphabet_type, rows, names, msaname, path, rf=None, architecture="fast", symfrac=0.5, fragthresh=0.5, effn=-1.0,
+                laplace=False, seed=42):
+    """Builder.build_msa of a digital alignment by the reference (p7_Builder), HMM written to <path>; returns the relative
+    weights the builder left in the alignment (ref_msa_builder)."""
+    L = lib()
+    rows = np.ascontiguousarray(rows, np.uint8)
+    nseq, alen = rows.shape
+    L.ref_msa_builder.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p,
+                                  ctypes.c_char_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_uint,
+                                  ctypes.c_char_p, ctypes.c_void_p]
+    enc = lambda v: v if isinstance(v, bytes) else v.encode()
+    arr = (ctypes.c_char_p * nseq)(*[enc(n) for n in names])
+    wgt = np.zeros(nseq, np.float64)
+    st = L.ref_msa_builder(alphabet_type, rows.ctypes.data, nseq, alen, arr, enc(msaname), enc(rf) if rf is not None else None,
+                           1 if architecture == "hand" else 0, symfrac, fragthresh, effn, int(laplace), seed, os.fsencode(path), wgt.ctypes.data)
+    if st != 0:
+        raise ValueError("p7_Builder failed with status %d" % st)
+    return wgt
+
+
 def mt_stream(seed, n):
     """The first n esl_random() values of Easel's Mersenne Twister seeded <seed>."""
     L = lib()

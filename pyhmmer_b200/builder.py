@@ -3,7 +3,8 @@ queries (p7_SingleBuilder, vendor/hmmer/src/p7_builder.c:440) -- a profile HMM f
 matrix (p7_Seqmodel, seqmodel.c:49), its composition and consensus, and the calibration of its E-value parameters
 (p7_Calibrate, evalues.c:58) on random sequences drawn with Easel's Mersenne Twister, scored by the GPU filters.
 
-Building models from multiple alignments (weights, priors, effective sequence number) is not here.
+Models from multiple alignments (`Builder.build_msa`: weights, architecture, priors, effective sequence number) are built
+by `msabuild`; both kinds share the calibration below.
 """
 import math
 
@@ -230,11 +231,28 @@ class Builder:
     calibrated HMM with a substitution score matrix (phmmer / nhmmer sequence queries).  The calibration draws its random
     sequences with Easel's generator and scores them with the GPU filters."""
 
-    def __init__(self, alphabet, *, seed=42, popen=None, pextend=None, score_matrix=None, window_length=None, window_beta=None,
+    def __init__(self, alphabet, *, architecture="fast", weighting="pb", effective_number="entropy", prior_scheme="alphabet",
+                 symfrac=0.5, fragthresh=0.5, esigma=45.0, ere=None,
+                 seed=42, popen=None, pextend=None, score_matrix=None, window_length=None, window_beta=None,
                  EmL=200, EmN=200, EvL=200, EvN=200, EfL=100, EfN=200, Eft=0.04):
+        from .msabuild import Prior, ETARGET
         nucleotide = alphabet.K == 4
         self.alphabet = alphabet
         self.seed = int(seed)
+        # alignment queries (build_msa): plan7.pyx:638-831
+        if architecture not in ("fast", "hand"):
+            raise ValueError("invalid architecture %r (expected 'fast' or 'hand')" % (architecture,))
+        if weighting not in ("pb", "gsc", "blosum", "none", "given"):
+            raise ValueError("invalid weighting %r (expected 'pb', 'gsc', 'blosum', 'none' or 'given')" % (weighting,))
+        if isinstance(effective_number, str):
+            if effective_number not in ("entropy", "exp", "clust", "none"):
+                raise ValueError("invalid effective_number %r (expected 'entropy', 'exp', 'clust', 'none' or a number)" % (effective_number,))
+        elif not isinstance(effective_number, (int, float)):
+            raise TypeError("Expected str, int or float, found %s" % type(effective_number).__name__)
+        self.architecture, self.weighting, self.effective_number, self.prior_scheme = architecture, weighting, effective_number, prior_scheme
+        self.symfrac, self.fragthresh, self.esigma = float(symfrac), float(fragthresh), float(esigma)
+        self.re_target = float(ere) if ere is not None else ETARGET.get(alphabet.type, 1.0)
+        self.prior = Prior.for_alphabet(alphabet, prior_scheme)
         self.popen = (0.03125 if nucleotide else 0.02) if popen is None else float(popen)
         self.pextend = (0.75 if nucleotide else 0.4) if pextend is None else float(pextend)
         self.score_matrix = ("DNA1" if nucleotide else "BLOSUM62") if score_matrix is None else score_matrix
@@ -282,6 +300,17 @@ class Builder:
                 hmm.max_length = hmm.compute_max_length(self.window_beta)
         profile = plan7.Profile(M, abc).configure(hmm, background, self.EvL)
         return hmm, profile, profile.to_optimized()
+
+    def build_msa(self, msa, background):
+        """(HMM, Profile, OptimizedProfile) from a `DigitalMSA` (p7_Builder, p7_builder.c:415; see `msabuild`)."""
+        from .msabuild import build_msa
+        return build_msa(self, msa, background)
+
+    def copy(self):
+        b = Builder.__new__(Builder)
+        b.__dict__.update(self.__dict__)
+        b.randomness = FastRandomness(self.seed)
+        return b
 
     # -- p7_Calibrate (evalues.c:58) ------------------------------------------------------------------------------------
     def _gpu_scores(self, om, seqs, which):

@@ -381,8 +381,20 @@ class TextMSA:
         self.reference = reference
         self.posterior_probabilities = list(posterior_probabilities) if posterior_probabilities is not None else None
         self.consensus_posterior_probabilities = consensus_posterior_probabilities
+        self.description = self.accession = self.author = None
+        self.model_mask = self.secondary_structure = None
         if len({len(r) for r in self.alignment}) > 1:
             raise ValueError("aligned sequences of different lengths")
+
+    def digitize(self, alphabet):
+        """``TextMSA.digitize``: the same alignment in digital mode (esl_msa_Digitize)."""
+        msa = DigitalMSA(alphabet, name=self.name, names=self.names, rows=[alphabet.encode(r) for r in self.alignment],
+                         accessions=self.accessions, descriptions=self.descriptions, reference=self.reference)
+        msa.description, msa.accession, msa.author = self.description, self.accession, self.author
+        msa.model_mask, msa.secondary_structure = self.model_mask, self.secondary_structure
+        msa.posterior_probabilities = self.posterior_probabilities
+        msa.consensus_posterior_probabilities = self.consensus_posterior_probabilities
+        return msa
 
     def __len__(self):
         return len(self.alignment[0]) if self.alignment else 0
@@ -426,3 +438,72 @@ class TextMSA:
         else:
             raise ValueError("invalid format %r (expected 'stockholm', 'pfam' or 'afa')" % (format,))
         fh.write("".join(out).encode())
+
+
+class DigitalMSA:
+    """A multiple alignment in digital mode (``pyhmmer.easel.DigitalMSA``): ``ax[nseq][alen]`` residue codes (gap = K, missing
+    data = Kp - 1), row names, the per-column annotation lines a model builder reads (RF, model mask, consensus structure),
+    sequence weights and cutoffs.  `Builder.build_msa` rewrites its argument the way p7_Builder does (weights, fragment
+    marks, RF line): hand it a `copy()` to keep the original."""
+
+    def __init__(self, alphabet, name=None, description=None, accession=None, sequences=None, author=None, *, names=None, rows=None,
+                 accessions=None, descriptions=None, reference=None):
+        self.alphabet = alphabet
+        self.name, self.description, self.accession, self.author = name, description, accession, author
+        if sequences is not None:                            # aligned DigitalSequence objects, as pyhmmer takes them
+            names = [q.name for q in sequences]
+            rows = [np.asarray(q.sequence, np.uint8) for q in sequences]
+            accessions = [q.accession or None for q in sequences]
+            descriptions = [q.description or None for q in sequences]
+        rows = [np.asarray(r, np.uint8) for r in (rows or [])]
+        if len({len(r) for r in rows}) > 1:
+            raise ValueError("all sequences must have the same length")
+        self.ax = np.array(rows, np.uint8).reshape(len(rows), len(rows[0]) if rows else 0)
+        self.names = list(names or [])
+        if len(self.names) != len(rows):
+            raise ValueError("one name per aligned sequence is needed")
+        if len(set(self.names)) != len(self.names):
+            raise ValueError("duplicate name in alignment")
+        self.accessions = list(accessions) if accessions is not None else [None] * len(rows)
+        self.descriptions = list(descriptions) if descriptions is not None else [None] * len(rows)
+        self.reference = reference
+        self.model_mask = self.secondary_structure = None
+        self.posterior_probabilities = self.consensus_posterior_probabilities = None
+        self.sequence_weights = None
+        self.cutoffs = {}
+
+    def __len__(self):
+        return int(self.ax.shape[1])
+
+    @property
+    def sequences(self):
+        """The rows as `DigitalSequence` (aligned codes)."""
+        return [DigitalSequence(self.alphabet, name=n, description=d or "", accession=a or "", sequence=r)
+                for n, a, d, r in zip(self.names, self.accessions, self.descriptions, self.ax)]
+
+    @property
+    def alignment(self):
+        return [r.copy() for r in self.ax]
+
+    @property
+    def checksum(self):
+        from .msabuild import msa_checksum
+        return msa_checksum(self.ax)
+
+    def copy(self):
+        m = DigitalMSA(self.alphabet, self.name, self.description, self.accession, None, self.author, names=self.names,
+                       rows=list(self.ax), accessions=self.accessions, descriptions=self.descriptions, reference=self.reference)
+        m.model_mask, m.secondary_structure = self.model_mask, self.secondary_structure
+        m.posterior_probabilities, m.consensus_posterior_probabilities = self.posterior_probabilities, self.consensus_posterior_probabilities
+        m.sequence_weights = None if self.sequence_weights is None else np.array(self.sequence_weights, np.float64)
+        m.cutoffs = dict(self.cutoffs)
+        return m
+
+    def textize(self):
+        """``DigitalMSA.textize``: the alignment in text mode (gaps as ``-``)."""
+        m = TextMSA(name=self.name, names=self.names, sequences=[self.alphabet.decode(r) for r in self.ax], accessions=self.accessions,
+                    descriptions=self.descriptions, reference=self.reference, posterior_probabilities=self.posterior_probabilities,
+                    consensus_posterior_probabilities=self.consensus_posterior_probabilities)
+        m.description, m.accession, m.author = self.description, self.accession, self.author
+        m.model_mask, m.secondary_structure = self.model_mask, self.secondary_structure
+        return m

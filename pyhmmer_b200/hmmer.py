@@ -1,5 +1,5 @@
-"""`hmmsearch` / `hmmscan` entry points with the reference's signatures (src/pyhmmer/hmmer/_hmmsearch.py:294,
-_hmmscan.py:91), running on the B200 engine.
+"""`hmmsearch` / `hmmscan` / `nhmmer` / `phmmer` / `jackhmmer` entry points with the reference's signatures
+(src/pyhmmer/hmmer/_hmmsearch.py:294, _hmmscan.py:91, _nhmmer.py, _phmmer.py, _jackhmmer.py), running on the B200 engine.
 
 The reference fans queries (or target slices) out over CPU threads; here one process drives one GPU and
 every query batch is ONE fused cascade launch sequence over (batch x database).  With several GPUs
@@ -14,7 +14,7 @@ from . import plan7
 from .easel import DigitalSequenceBlock, DigitalSequence, SequenceFile
 from .plan7 import Pipeline, LongTargetsPipeline, HMM, Profile, OptimizedProfile, OptimizedProfileBlock
 
-__all__ = ["hmmsearch", "hmmscan", "nhmmer", "phmmer"]
+__all__ = ["hmmsearch", "hmmscan", "nhmmer", "phmmer", "jackhmmer"]
 
 _QUERY_BATCH = 256
 
@@ -112,8 +112,8 @@ def hmmscan(queries, profiles, *, cpus=0, callback=None, backend="threading", ba
 
 def nhmmer(queries, sequences, *, cpus=0, callback=None, backend="threading", builder=None, **options):
     """Search nucleotide HMM / profile queries against long nucleotide targets; yields one `TopHits` per query, in order
-    (``pyhmmer.hmmer.nhmmer``, src/pyhmmer/hmmer/_nhmmer.py).  `DigitalSequence` queries become single-sequence models
-    (`pyhmmer_b200.builder.Builder`); alignment queries are rejected (no alignment builder in this package)."""
+    (``pyhmmer.hmmer.nhmmer``, src/pyhmmer/hmmer/_nhmmer.py).  `DigitalSequence` queries become single-sequence models,
+    `DigitalMSA` queries go through ``Builder.build_msa`` (`pyhmmer_b200.builder.Builder`)."""
     if isinstance(queries, (HMM, Profile, OptimizedProfile)):
         queries = (queries,)
     it = iter(queries)
@@ -144,16 +144,17 @@ def phmmer(queries, sequences, *, cpus=0, callback=None, backend="threading", bu
     """Search protein query SEQUENCES against a sequence database; yields one `TopHits` per query, in order
     (``pyhmmer.hmmer.phmmer``, src/pyhmmer/hmmer/_phmmer.py): every query becomes a single-sequence model
     (`pyhmmer_b200.builder.Builder`: BLOSUM62, gap open 0.02 / extend 0.4, calibrated) and is searched like an HMM.
-    Alignment queries are rejected (no alignment builder in this package)."""
+    `DigitalMSA` queries go through ``Builder.build_msa``."""
     from .builder import Builder
-    if isinstance(queries, DigitalSequence):
+    from .easel import DigitalMSA
+    if isinstance(queries, (DigitalSequence, DigitalMSA)):
         queries = (queries,)
     it = iter(queries)
     first = next(it, None)
     if first is None:
         return
-    if not isinstance(first, DigitalSequence):
-        raise TypeError("phmmer queries must be DigitalSequence, found %s" % type(first).__name__)
+    if not isinstance(first, (DigitalSequence, DigitalMSA)):
+        raise TypeError("phmmer queries must be DigitalSequence or DigitalMSA, found %s" % type(first).__name__)
     alphabet = first.alphabet
     block = _as_block(sequences, alphabet)
     options.setdefault("host_threads", cpus or 0)
@@ -161,7 +162,48 @@ def phmmer(queries, sequences, *, cpus=0, callback=None, backend="threading", bu
     builder = Builder(alphabet, seed=pipeline.seed) if builder is None else builder
     import itertools
     for index, query in enumerate(itertools.chain((first,), it)):
-        hits = pipeline.search_seq(query, block, builder)
+        hits = pipeline.search_msa(query, block, builder) if isinstance(query, DigitalMSA) else pipeline.search_seq(query, block, builder)
         if callback is not None:
             callback(query, index + 1)
         yield hits
+
+
+def jackhmmer(queries, sequences, *, cpus=0, callback=None, backend="threading", builder=None, max_iterations=5, select_hits=None,
+              checkpoints=False, **options):
+    """Iterative search of query sequences or HMMs against a sequence database (``pyhmmer.hmmer.jackhmmer``,
+    src/pyhmmer/hmmer/_jackhmmer.py:37-127): for every query, up to ``max_iterations`` rounds of `IterativeSearch` (build a
+    model on the host, search on the GPU, align the included hits, rebuild); yields the last `IterationResult` per query,
+    or the list of all of them with ``checkpoints``."""
+    from .builder import Builder
+    import itertools
+    if isinstance(queries, (DigitalSequence, HMM)):
+        queries = (queries,)
+    it = iter(queries)
+    first = next(it, None)
+    if first is None:
+        return
+    alphabet = first.alphabet
+    block = _as_block(sequences, alphabet)
+    options.setdefault("host_threads", cpus or 0)
+    options.setdefault("incE", 0.001)                     # jackhmmer's inclusion thresholds (_jackhmmer.py: incE = incdomE = 1e-3)
+    options.setdefault("incdomE", 0.001)
+    pipeline = Pipeline(alphabet, **options)
+    builder = Builder(alphabet, seed=pipeline.seed, architecture="hand") if builder is None else builder
+    for index, query in enumerate(itertools.chain((first,), it)):
+        if isinstance(query, DigitalSequence):
+            steps = pipeline.iterate_seq(query, block, builder, select_hits)
+        elif isinstance(query, HMM):
+            steps = pipeline.iterate_hmm(query, block, builder, select_hits)
+        else:
+            raise TypeError("Unsupported query type for `jackhmmer`: %s" % type(query).__name__)
+        done = []
+        last = None
+        for last in itertools.islice(steps, max_iterations):
+            if checkpoints:
+                done.append(last)
+            if last.converged:
+                break
+        if callback is not None:
+            callback(query, index + 1)
+        pipeline.clear()
+        yield done if checkpoints else last

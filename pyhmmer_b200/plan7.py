@@ -9,6 +9,7 @@ CUDA kernels behind the C ABI of ``include/b2h.h``; nothing here scores on the C
 Reference: src/pyhmmer/plan7.pyx (HMM 2236-3321, HMMFile 3323-3800, Background 427-560,
 Profile 7767-8310, OptimizedProfile 4392-5070, Pipeline 5423-6906, TopHits 8312-9278).
 """
+import collections
 import copy
 import ctypes
 import math
@@ -1613,6 +1614,75 @@ class Hit:
         return "<Hit name=%r score=%.1f evalue=%.2g>" % (self.name, self.score, self.evalue)
 
 
+class Trace:
+    """A state path (``pyhmmer.plan7.Trace``): parallel lists of state letters, node indices and sequence positions.  Only what
+    `TopHits.to_msa` reads -- jackhmmer aligns its query with `Trace.from_sequence` (plan7.pyx:9288: B, M1..ML, E)."""
+
+    def __init__(self, states=(), k=(), i=(), M=0, L=0):
+        self.states, self.k, self.i, self.M, self.L = list(states), list(k), list(i), int(M), int(L)
+
+    @classmethod
+    def from_sequence(cls, sequence):
+        n = len(sequence)
+        return cls(["B"] + ["M"] * n + ["E"], [0] + list(range(1, n + 1)) + [0], [0] + list(range(1, n + 1)) + [0], n, n)
+
+    def __len__(self):
+        return len(self.states)
+
+
+IterationResult = collections.namedtuple("IterationResult", ["hmm", "hits", "msa", "converged", "iteration"])
+
+
+class IterativeSearch:
+    """``pyhmmer.plan7.IterativeSearch`` (plan7.pyx:4273-4389): jackhmmer's loop.  Every step builds a model (from the query
+    on the first step, from the previous step's alignment afterwards), searches the targets on the GPU, ranks the included
+    hits against the previous step's (p7_tophits_CompareRanking) and aligns them -- query first -- into the next
+    alignment; converged when no new sequence was included and the alignment did not grow."""
+
+    def __init__(self, pipeline, builder, query, targets, select_hits=None):
+        self.pipeline, self.builder, self.query, self.targets, self.select_hits = pipeline, builder, query, targets, select_hits
+        self.background = pipeline.background
+        self.converged = False
+        self.ranking = {}
+        self.msa = None
+        self.iteration = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.converged:
+            raise StopIteration
+        is_hmm = isinstance(self.query, HMM)
+        if self.iteration == 0:
+            hmm = self.query if is_hmm else self.builder.build(self.query, self.background)[0]
+            n_prev = 1
+        else:
+            hmm = self.builder.build_msa(self.msa, self.background)[0]
+            n_prev = len(self.msa.names)
+        extra_sequences = None if is_hmm else [self.query]
+        extra_traces = None if is_hmm else [Trace.from_sequence(self.query)]
+        hits = self._search_hmm(hmm)
+        hits.sort(by="key")
+        if self.select_hits is not None:
+            self.select_hits(hits)
+        n_new = hits.compare_ranking(self.ranking)
+        self.msa = hits.to_msa(self.pipeline.alphabet, sequences=extra_sequences, traces=extra_traces, all_consensus_cols=True, digitize=True)
+        txt = lambda v: v.decode() if isinstance(v, (bytes, bytearray)) else v
+        self.msa.name = "%s-i%d" % (txt(self.query.name), self.iteration + 1)
+        self.msa.description = txt(self.query.description) or None
+        self.msa.accession = txt(self.query.accession) or None
+        self.msa.author = "jackhmmer (pyHMMER)"
+        if n_new == 0 and len(self.msa.names) <= n_prev:
+            self.converged = True
+        self.pipeline.clear()
+        self.iteration += 1
+        return IterationResult(hmm, hits, self.msa, self.converged, self.iteration)
+
+    def _search_hmm(self, hmm):
+        return self.pipeline.search_hmm(hmm, self.targets)
+
+
 class TopHits:
     """A sorted, thresholded list of hits (``P7_TOPHITS`` + the P7_PIPELINE snapshot pyhmmer keeps)."""
 
@@ -1826,18 +1896,37 @@ class TopHits:
                 d.reported, d.included = rep, inc
             self._hits.append(h)
 
+    def compare_ranking(self, ranking):
+        """``TopHits.compare_ranking`` = p7_tophits_CompareRanking (p7_tophits.c:925): flag the included hits that were not
+        in ``ranking`` (a name -> rank mapping from the previous iteration) as new, the known ones that are no longer
+        included as dropped; ``ranking`` becomes the list of this round's included hits.  Returns the number of new hits."""
+        nnew = 0
+        for h in self._hits:
+            old = ranking.get(h.name, -1)
+            if h.included:
+                if old == -1:
+                    h.new = True
+                    nnew += 1
+            elif old >= 0:
+                h.dropped = True
+        ranking.clear()
+        for h in self._hits:
+            if h.included and h.name not in ranking:
+                ranking[h.name] = len(ranking)
+        return nnew
+
     def to_msa(self, alphabet, sequences=None, traces=None, trim=False, digitize=False, all_consensus_cols=False):
         """A multiple alignment of all included domains (``TopHits.to_msa``, plan7.pyx:8960-9080 = p7_tophits_Alignment,
         p7_tophits.c:1251): every included domain becomes a row named ``target/from-to``, rebuilt from its alignment display
         as the reference does (p7_alidisplay_Backconvert), and the rows are laid out by p7_tracealign_Seqs (tracealign.c:
         map_new_msa, make_text_msa, annotate_rf, annotate_posterior_probability, rejustify_insertions_text) -- match columns
         in upper case, insertions in lower case split half left / half right, ``x`` in the RF line on consensus columns.
-        Returns an `easel.TextMSA`.  Extra sequences / traces and digital alignments are not supported."""
+        ``sequences`` / ``traces``: extra rows placed first (jackhmmer's query with `Trace.from_sequence`), without posterior
+        probabilities.  Returns an `easel.TextMSA`, or an `easel.DigitalMSA` with ``digitize`` (p7_DIGITIZE)."""
         from .easel import TextMSA
-        if sequences or traces:
-            raise NotImplementedError("additional sequences / traces are not supported")
-        if digitize:
-            raise NotImplementedError("digital alignments are not supported")
+        sequences, traces = list(sequences or ()), list(traces or ())
+        if len(sequences) != len(traces):
+            raise ValueError("`sequences` and `traces` must have the same length")
         txt = lambda v: "" if v is None else (v.decode() if isinstance(v, bytes) else str(v))
         rows = []
         M = 0
@@ -1848,8 +1937,13 @@ class TopHits:
                 if d.included:
                     a = d.alignment
                     rows.append((h, d, a.hmm_sequence, a.target_sequence, a.posterior_probabilities))
-                    M = M or int(getattr(self.query, "M", 0)) or a.hmm_to
-        if not rows:
+                    M = M or int(a.hmm_length or 0) or int(getattr(self.query, "M", 0)) or a.hmm_to
+        if traces:
+            if M == 0:
+                M = traces[0].M
+            elif M != traces[0].M:
+                raise ValueError("top hits and included trace(s) have different profile lengths")
+        if not rows and not traces:
             raise ValueError("No included domains found")
         gap = "-_."
         # states per display column: k advances on every non-gap model character; I = insert after node k
@@ -1857,6 +1951,22 @@ class TopHits:
         inscount = [0] * (M + 1)
         matuse = [bool(all_consensus_cols)] * (M + 1)
         matuse[0] = False
+        for sq, tr in zip(sequences, traces):             # the extra rows: states of the given trace over the given sequence
+            text = sq.sequence if isinstance(sq.sequence, str) else alphabet.decode(sq.sequence)
+            path, insnum = [], {}
+            for st, k, i in zip(tr.states, tr.k, tr.i):
+                if st == "M":
+                    path.append(("M", k, text[i - 1], None))
+                    matuse[k] = True
+                elif st == "D":
+                    path.append(("D", k, None, None))
+                elif st == "I" or (st in "NCJ" and i > 0):
+                    kk = 0 if st == "N" else (M if st == "C" else k)
+                    path.append(("I", kk, text[i - 1], None))
+                    insnum[kk] = insnum.get(kk, 0) + 1
+            for kk, v in insnum.items():
+                inscount[kk] = max(inscount[kk], v)
+            paths.append(path)
         for h, d, model, aseq, pp in rows:
             k = d._rec.hmmfrom - 1
             path, insnum = [], {}
@@ -1900,9 +2010,10 @@ class TopHits:
             for st, k, c, p in path:
                 if st == "M":
                     row[matmap[k] - 1] = c.upper()
-                    ppr[matmap[k] - 1] = encode(decode(p))
-                    totp[matmap[k] - 1] += decode(p)
-                    npp[matmap[k] - 1] += 1
+                    if p is not None:
+                        ppr[matmap[k] - 1] = encode(decode(p))
+                        totp[matmap[k] - 1] += decode(p)
+                        npp[matmap[k] - 1] += 1
                     apos = matmap[k]
                 elif st == "D":
                     if matuse[k]:
@@ -1910,7 +2021,8 @@ class TopHits:
                     apos = matmap[k]
                 elif not trim or (k != 0 and k != M):
                     row[apos] = c.lower()
-                    ppr[apos] = encode(decode(p))
+                    if p is not None:
+                        ppr[apos] = encode(decode(p))
                     apos += 1
             # rejustify_insertions_text: the second half of every insertion longer than one goes to the right edge
             for k in range(0, M):
@@ -1936,11 +2048,17 @@ class TopHits:
             if matuse[k]:
                 rf[matmap[k] - 1] = "x"
         ppcons = "".join(encode(totp[i] / npp[i]) if npp[i] else "." for i in range(alen))
-        names = [("%s/%d-%d" % (txt(h.name), d._rec.sqfrom, d._rec.sqto)).encode() for h, d, _, _, _ in rows]
-        descs = [("[subseq from] %s" % (txt(h.description) if h.description else txt(h.name))).encode() for h, d, _, _, _ in rows]
-        accs = [txt(h.accession).encode() if h.accession else None for h, d, _, _, _ in rows]
-        return TextMSA(names=names, sequences=arows, accessions=accs, descriptions=descs, reference="".join(rf),
-                       posterior_probabilities=prows, consensus_posterior_probabilities=ppcons)
+        nx = len(sequences)
+        names = [txt(q.name).encode() for q in sequences] + \
+                [("%s/%d-%d" % (txt(h.name), d._rec.sqfrom, d._rec.sqto)).encode() for h, d, _, _, _ in rows]
+        descs = [txt(q.description).encode() if q.description else None for q in sequences] + \
+                [("[subseq from] %s" % (txt(h.description) if h.description else txt(h.name))).encode() for h, d, _, _, _ in rows]
+        accs = [txt(q.accession).encode() if q.accession else None for q in sequences] + \
+               [txt(h.accession).encode() if h.accession else None for h, d, _, _, _ in rows]
+        prows = [None] * nx + prows[nx:]
+        msa = TextMSA(names=names, sequences=arows, accessions=accs, descriptions=descs, reference="".join(rf),
+                      posterior_probabilities=prows if rows else None, consensus_posterior_probabilities=ppcons if rows else None)
+        return msa.digitize(alphabet) if digitize else msa
 
     def write(self, fh, format="targets", header=True):
         """Write the hits in tabular form to a file opened in binary mode (``TopHits.write``, plan7.pyx:9096-9168):
@@ -2293,6 +2411,35 @@ class Pipeline:
         hits = self.search_hmm(opt, sequences)
         hits.query = query
         return hits
+
+    def search_msa(self, query, sequences, builder=None):
+        """Search with a query ALIGNMENT (plan7.pyx:6264-6328): a model is built with ``builder.build_msa`` (default:
+        ``Builder(alphabet, seed=seed)``) and searched like any HMM; the hits remember the alignment as their query."""
+        from .builder import Builder
+        if query.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, query.alphabet)
+        builder = Builder(self.alphabet, seed=self.seed) if builder is None else builder
+        hmm, profile, opt = builder.build_msa(query, self.background)
+        hits = self.search_hmm(opt, sequences)
+        hits.query = query
+        return hits
+
+    def iterate_hmm(self, query, sequences, builder=None, select_hits=None):
+        """jackhmmer from an HMM query (plan7.pyx:6739-6804): an iterator of `IterationResult`."""
+        from .builder import Builder
+        if query.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, query.alphabet)
+        if sequences.alphabet != self.alphabet:
+            raise AlphabetMismatch(self.alphabet, sequences.alphabet)
+        if builder is None:
+            builder = Builder(self.alphabet, seed=self.seed, architecture="hand")
+        elif builder.architecture != "hand":
+            raise ValueError("`iterate_seq` only supports a builder with 'hand' architecture")
+        return IterativeSearch(self, builder, query, sequences, select_hits)
+
+    def iterate_seq(self, query, sequences, builder=None, select_hits=None):
+        """jackhmmer from a sequence query (plan7.pyx:6806-6906): an iterator of `IterationResult`."""
+        return self.iterate_hmm(query, sequences, builder, select_hits)
 
     def _search_many(self, queries, sequences):
         if not isinstance(sequences, DigitalSequenceBlock):

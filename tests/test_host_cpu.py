@@ -733,9 +733,15 @@ def test_to_msa_matches_the_reference_alignment(amino, name, all_cols, tmp_path)
     again = tmp_path / "mine.sto"
     again.write_bytes(buf.getvalue())
     assert _read_pfam_stockholm(str(again))[:3] == (names, rows, pp)
-    for bad in (dict(digitize=True), dict(sequences=[1], traces=[1])):
-        with pytest.raises(NotImplementedError):
-            th.to_msa(amino, **bad)
+    # digital mode, and an extra row placed first (what jackhmmer does with its query: plan7.pyx:4369)
+    dig = th.to_msa(amino, all_consensus_cols=all_cols, digitize=True)
+    assert isinstance(dig, easel.DigitalMSA) and [amino.decode(r) for r in dig.ax] == [r.upper().replace(".", "-") for r in msa.alignment]
+    extra = easel.DigitalSequence(amino, name=b"query", sequence=np.arange(hmm.M, dtype=np.uint8) % 20)
+    withq = th.to_msa(amino, sequences=[extra], traces=[plan7.Trace.from_sequence(extra)], all_consensus_cols=True)
+    assert withq.names[0] == b"query" and withq.names[1:] == th.to_msa(amino, all_consensus_cols=True).names
+    assert withq.alignment[0].replace(".", "") == amino.decode(extra.sequence) and withq.posterior_probabilities[0] is None
+    with pytest.raises(ValueError):
+        th.to_msa(amino, sequences=[extra], traces=[])
 
 
 @needs_ref
