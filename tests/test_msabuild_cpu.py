@@ -209,7 +209,10 @@ def check_iteration(got, want, score_tol=None):
     txt = lambda v: v.decode() if isinstance(v, bytes) else v
     assert txt(got.msa.name) == want["msa"]["name"] and [txt(n) for n in m.names] == want["msa"]["names"]
     assert m.reference == want["msa"]["rf"]
-    assert [r.upper().replace(".", "-") for r in m.alignment] == [r.upper().replace(".", "-") for r in want["msa"]["rows"]]
+    # (an alignment that has already been through the builder carries its fragment marks: p7_Builder rewrites its input, and
+    # with checkpoints=True the reference hands out the very objects it rebuilds from)
+    norm = lambda r: r.upper().replace(".", "-").replace("~", "-")
+    assert [norm(r) for r in m.alignment] == [norm(r) for r in want["msa"]["rows"]]
 
 
 @needs_ref
