@@ -280,6 +280,17 @@ __device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t)hi
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return ((int)v) >> 16; }
 
+__device__ __forceinline__ uint32_t dp_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
+}
+
 template <int H>
 __device__ __forceinline__ void load_emis2(const uint32_t *tab, int x, int lane, uint32_t (&r)[H])
 {
@@ -297,7 +308,7 @@ __device__ __forceinline__ void load_emis2(const uint32_t *tab, int x, int lane,
 }
 
 template <int C>
-__global__ void __launch_bounds__(256, (C <= 4) ? 4 : (C <= 8) ? 3 : (C <= 12) ? 2 : 1) rvit2_kernel(const WorkList wl, const SeqDev sd, const StageOut out)
+__global__ void __launch_bounds__(256, (C <= 4) ? 4 : (C <= 12) ? 2 : 1) rvit2_kernel(const WorkList wl, const SeqDev sd, const StageOut out)
 {
   constexpr int H = C / 2;
   extern __shared__ __align__(128) uint32_t s_rsc2[];       // [32][32*H] packed emission scores
@@ -305,10 +316,13 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : (C <= 8) ? 3 : (C <= 12) ?
   __shared__ int s_item;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   constexpr uint32_t TAB_BYTES = 32u * 32u * H * 4u;
+  constexpr uint32_t ROWB2 = 32u * H * 4u;                   // bytes of one residue's row of packed emission scores
+  constexpr int LW = (H % 4 == 0) ? 16 : (H % 2 == 0) ? 8 : 4;   // bytes a lane reads per load (LDS.128 / .64 / .32)
   constexpr uint32_t FLOOR2 = ((uint32_t)(uint16_t)(int16_t)B2H_V2_FLOOR << 16) | (uint32_t)(uint16_t)(int16_t)B2H_V2_FLOOR;
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   uint32_t phase = 0;
   int cur_p = -1;
+  const uint32_t tab_lane = dp_smem_u32(s_rsc2) + lane * LW;
   uint32_t tBM[H], tMM[H], tIM[H], tDM[H], tMD[H], tMI[H], tII[H], tDD[H];
   uint32_t tlink[H], tfull[H];                             // (0, T_hi[j]) and (T[j], T[H+j]): see the D->D closure
   int tDDin0 = B2H_V2_TF;
@@ -326,6 +340,10 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : (C <= 8) ? 3 : (C <= 12) ?
         tBM[j] = pack2(tv(0, ka), tv(0, kb)); tMM[j] = pack2(tv(1, ka), tv(1, kb)); tIM[j] = pack2(tv(2, ka), tv(2, kb));
         tDM[j] = pack2(tv(3, ka), tv(3, kb)); tMD[j] = pack2(tv(4, ka), tv(4, kb)); tMI[j] = pack2(tv(5, ka), tv(5, kb));
         tII[j] = pack2(tv(6, ka), tv(6, kb)); tDD[j] = pack2(tv(7, ka), tv(7, kb));
+      }
+      if (lane == 0) {                                          // nothing enters the model's first node from "node 0" (see row())
+        constexpr uint32_t TF_LO = (uint32_t)(uint16_t)(int16_t)B2H_V2_TF;
+        tMM[0] = (tMM[0] & 0xffff0000u) | TF_LO; tIM[0] = (tIM[0] & 0xffff0000u) | TF_LO; tDM[0] = (tDM[0] & 0xffff0000u) | TF_LO;
       }
       tDDin0 = __shfl_up_sync(FULL, hi16(tDD[H - 1]), 1);      // D_{k-1} -> D_k for this lane's first node
       if (lane == 0) tDDin0 = B2H_V2_TF;
@@ -349,22 +367,40 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : (C <= 8) ? 3 : (C <= 12) ?
       const int L = sd.len[s];
       const int xw_move = sd.xwmove[s];
       bool redo = !P.v2_ok || (base_w + xw_move + P.tbm_min < B2H_V2_LO);
-      SeqWin sw; sw.init(sd.res + sd.off[s], L, lane);
+      const uint32_t *seqw = reinterpret_cast<const uint32_t *>(sd.res + sd.off[s]);
+      const int nwords = (L + 3) >> 2;
       uint32_t M[H], I[H], D[H];
 #pragma unroll
       for (int j = 0; j < H; j++) { M[j] = FLOOR2; I[j] = FLOOR2; D[j] = FLOOR2; }
-      int xN = base_w, xB = (int16_t)(xN + xw_move), xJ = NEG16, xC = NEG16;        // specials in true coordinates
+      // specials in true coordinates.  The reference keeps them in int16 with saturating adds; here they are plain ints:
+      // xE < V2_HI on every row that is kept, the loop / move scores are <= 0 and every maximum below contains a term that
+      // is representable, so no value ever leaves the int16 range and the two arithmetics agree.
+      const int xNm = base_w + xw_move;                       // xN + tNB: N never changes (tNN = 0 in the filter)
+      int xB = xNm, xJ = NEG16, xC = NEG16;
 
-      for (int i = 0; i < L && !redo; i++) {
-        const int x = sw.get(i, lane);
+      // One DP row for residue code x (byte address of its table row = x * ROWB2).  Returns false when the packed
+      // arithmetic cannot decide this comparison (row maximum at or above V2_HI).
+      auto row = [&](uint32_t x) -> bool {
         uint32_t r[H];
-        load_emis2<H>(s_rsc2, x, lane, r);
-        // cells of node k-1 for this lane's first halves: low <- last node of the lane to the left, high <- own node H-1
-        uint32_t mt = __shfl_up_sync(FULL, M[H - 1], 1), itt = __shfl_up_sync(FULL, I[H - 1], 1), dt = __shfl_up_sync(FULL, D[H - 1], 1);
-        if (lane == 0) { mt = FLOOR2; itt = FLOOR2; dt = FLOOR2; }
+        {
+          const uint32_t a = tab_lane + x * ROWB2;
+          if (H % 4 == 0) {
+#pragma unroll
+            for (int g = 0; g < H / 4; g++) { const uint4 v = lds128(a + g * 512); r[4*g] = v.x; r[4*g+1] = v.y; r[4*g+2] = v.z; r[4*g+3] = v.w; }
+          } else if (H % 2 == 0) {
+#pragma unroll
+            for (int g = 0; g < H / 2; g++) { const uint2 v = lds64(a + g * 256); r[2*g] = v.x; r[2*g+1] = v.y; }
+          } else {
+#pragma unroll
+            for (int g = 0; g < H; g++) r[g] = lds32(a + g * 128);
+          }
+        }
+        // cells of node k-1 for this lane's first halves: low <- last node of the lane to the left, high <- own node H-1.
+        // Lane 0 gets its own last node from the shuffle: harmless, the transitions INTO the model's first node are V2_TF
+        // (set with the transition registers above), so those terms stay below V2_LO and never win against the begin term.
+        const uint32_t mt = __shfl_up_sync(FULL, M[H - 1], 1), itt = __shfl_up_sync(FULL, I[H - 1], 1), dt = __shfl_up_sync(FULL, D[H - 1], 1);
         const uint32_t m0 = __byte_perm(mt, M[H - 1], 0x5432u), i0 = __byte_perm(itt, I[H - 1], 0x5432u), d0 = __byte_perm(dt, D[H - 1], 0x5432u);
-        const int xBs = xB + B2H_V2_SIG;
-        const uint32_t xB2 = pack2(xBs, xBs);
+        const uint32_t xB2 = __byte_perm((uint32_t)(xB + B2H_V2_SIG), 0u, 0x1010u);
 #pragma unroll
         for (int j = H - 1; j >= 0; j--) {
           const uint32_t pm = (j == 0) ? m0 : M[j - 1], pi = (j == 0) ? i0 : I[j - 1], pd = (j == 0) ? d0 : D[j - 1];
@@ -380,7 +416,8 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : (C <= 8) ? 3 : (C <= 12) ?
 #pragma unroll
         for (int j = 0; j + 1 < H; j += 2) xe2 = __vimax3_s16x2(xe2, M[j], M[j + 1]);
         if (H & 1) xe2 = __vimax3_s16x2(xe2, M[H - 1], M[H - 1]);
-        const int xE = __reduce_max_sync(FULL, max(lo16(xe2), hi16(xe2))) - B2H_V2_SIG;
+        xe2 = __vmaxs2(xe2, __byte_perm(xe2, 0u, 0x1032u));        // both halves = the lane's maximum
+        const int xE = __reduce_max_sync(FULL, (int)(int16_t)xe2) - B2H_V2_SIG;
         // M->D partials: D of node k is what enters from M of node k-1
         const uint32_t mdl = __viaddmax_s16x2(M[H - 1], tMD[H - 1], FLOOR2);
         uint32_t mdt = __shfl_up_sync(FULL, mdl, 1);
@@ -392,11 +429,12 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : (C <= 8) ? 3 : (C <= 12) ?
 #pragma unroll
         for (int j = 0; j + 1 < H; j += 2) dm2 = __vimax3_s16x2(dm2, D[j], D[j + 1]);
         if (H & 1) dm2 = __vimax3_s16x2(dm2, D[H - 1], D[H - 1]);
-        const int Dmax = __reduce_max_sync(FULL, max(lo16(dm2), hi16(dm2))) - B2H_V2_SIG;
-        if (xE >= B2H_V2_HI) { redo = true; break; }
-        xC = (int16_t)max(xC, xE + xwEm);
-        xJ = (int16_t)max(xJ, xE + xwEl);
-        xB = (int16_t)max(xJ + xw_move, xN + xw_move);
+        dm2 = __vmaxs2(dm2, __byte_perm(dm2, 0u, 0x1032u));
+        const int Dmax = __reduce_max_sync(FULL, (int)(int16_t)dm2) - B2H_V2_SIG;
+        if (xE >= B2H_V2_HI) return false;
+        xC = max(xC, xE + xwEm);
+        xJ = max(xJ, xE + xwEl);
+        xB = max(xJ + xw_move, xNm);
         if (Dmax + ddbound > xB) {
           // Close the D->D chain in packed form.  (1) the two half-chains of the lane side by side; (2) the end of the
           // low half-chain enters the high one; (3) lane-to-lane: the closed D of the left lane's last node enters a lane
@@ -423,6 +461,29 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : (C <= 8) ? 3 : (C <= 12) ?
               for (int j = 0; j < H; j++) D[j] = __viaddmax_s16x2(DIN2, tfull[j], D[j]);
             }
           }
+        }
+        return true;
+      };
+
+      // residues come as 32-bit words of four (the arena pads every sequence to 16 bytes): each lane keeps one word of the
+      // current 128-row window, a word is broadcast once and its four rows are unrolled with constant byte selectors
+      uint32_t myw = 0;
+      const int nfull = L >> 2;
+      int w = 0;
+      if (!redo) {
+        for (; w < nfull; w++) {
+          if ((w & 31) == 0) myw = (w + lane < nwords) ? __ldg(seqw + w + lane) : 0x1f1f1f1fu;
+          const uint32_t wr = __shfl_sync(FULL, myw, w & 31);
+          if (!row(__byte_perm(wr, 0u, 0x4440u))) { redo = true; break; }
+          if (!row(__byte_perm(wr, 0u, 0x4441u))) { redo = true; break; }
+          if (!row(__byte_perm(wr, 0u, 0x4442u))) { redo = true; break; }
+          if (!row(__byte_perm(wr, 0u, 0x4443u))) { redo = true; break; }
+        }
+        if (!redo && (L & 3)) {
+          if ((w & 31) == 0) myw = (w + lane < nwords) ? __ldg(seqw + w + lane) : 0x1f1f1f1fu;
+          const uint32_t wr = __shfl_sync(FULL, myw, w & 31);
+          for (int rr = 0; rr < (L & 3); rr++)
+            if (!row((wr >> (8 * rr)) & 0xffu)) { redo = true; break; }
         }
       }
       if (!redo && xC < B2H_V2_LO) redo = true;             // nothing exact reached E (e.g. a target of impossible residues)
