@@ -246,13 +246,36 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    wave_split = []
+
+    def search_step():
+        """One pass of the path: the search wave by wave (b2h_search_begin / _next / _end); while the GPU searches the
+        following waves, the finished wave's hit records are exchanged (N > 1: one all-gather per wave, the only collective
+        of the path) and its thresholded `TopHits` are built -- one per query, the job's output (the CPU arm's p7_Pipeline
+        builds its P7_TOPHITS inside its timed region, too).  Uploads anything that is not resident."""
+        w = parallel.World.current()
+        res = [None] * len(oms)
+        nlocal, gen = pli._run_waves(oms, seqs)               # (what Pipeline._search_many / parallel.search_sharded do)
+        empty = ([], [], [], b"", np.zeros((len(oms), 4), np.int64))
+        first, nrec = True, 0
+        for _ in range(parallel.agree_max(nlocal, w)):
+            profs, hits, doms, text, counters = next(gen, empty)
+            if world > 1:
+                parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, counters, 0, profiles=profs), w)
+            # (weak scaling: every rank holds its own shard only, so it assembles its own records)
+            for qi, th in zip(profs, pli._assemble(oms, oms, seqs, hits, doms, text, counters, only=profs, count_targets=first)):
+                res[qi] = th
+            first = False
+            nrec += len(hits)
+        for _ in gen:
+            pass
+        wave_split.append(pli._last_run_s)
+        return res, nrec
+
     def one_step_resident():
-        hits, doms, text, counters = pli._run(oms, seqs)
-        if world > 1:                                              # the single exchange of the path: all-gather of the hit records
-            w = parallel.World.current()
-            parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, counters, 0), w)
-        pli._assemble(oms, oms, seqs, hits, doms, text, counters)  # thresholded TopHits, one per query: the job's output (as the CPU arm's p7_Pipeline builds its P7_TOPHITS)
-        return hits, counters
+        res, nrec = search_step()
+        counters = np.array([[th.n_past_msv, th.n_past_bias, th.n_past_vit, th.n_past_fwd] for th in res], np.int64)
+        return nrec, counters
 
     e2e_phases = []
 
@@ -262,17 +285,11 @@ def main():
             om._dev = {}                                           # re-upload the profile tables
         t0 = time.perf_counter()
         # the call a user's hmmsearch makes: packs + uploads the database and builds + uploads every profile's tables (side
-        # by side), then b2h_search and the D2H of the hit records
-        hits, doms, text, counters = pli._run(oms, seqs)
-        t3 = time.perf_counter()
-        t1 = t0 + pli._last_run_s[0]                               # uploads / handles
-        t2 = t1
-        if world > 1:
-            w = parallel.World.current()
-            parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, counters, 0), w)
-        res = pli._assemble(oms, oms, seqs, hits, doms, text, counters)   # thresholded TopHits, one per query
+        # by side), then the search with the D2H of the hit records and the assembly of the TopHits, wave by wave
+        res, _ = search_step()
         t4 = time.perf_counter()
-        e2e_phases.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3))
+        up, waited, read = pli._last_run_s
+        e2e_phases.append((up, waited, read, (t4 - t0) - up - waited - read))
         return res
 
     # The inputs are ~10^5 long-lived Python objects (50 000 sequences, their arrays, the profiles).  A full collection that
@@ -335,17 +352,17 @@ def main():
             e2e_times.append(dt)
     if rank == 0:
         hs = np.array(host_split) * 1e3
-        print("[bench] resident step, host wall ms (whole step, handles, b2h_search, reading results): mean %s; device-event ms %s"
+        print("[bench] resident step, host wall ms (whole step, handles, waiting for waves, reading results; the rest = exchange + TopHits assembly, overlapped with the following waves): mean %s; device-event ms %s"
               % (np.round(hs.mean(0), 2).tolist(), np.round(times, 1).tolist()), file=sys.stderr)
         ph = np.array(e2e_phases[2:]) * 1e3
-        print("[bench] e2e phases ms (database + profile uploads, -, search+D2H, TopHits assembly): mean %s, per step %s"
+        print("[bench] e2e phases ms (database + profile uploads, waiting for waves, reading results, exchange + TopHits assembly): mean %s, per step %s"
               % (np.round(ph.mean(0), 1).tolist(), np.round(ph.sum(1), 1).tolist()), file=sys.stderr)
     te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_gcups = cells_all * len(e2e_times) / float(te.item()) / 1e9
     h2d = int(_lib.lib.b2h_seqdb_h2d_bytes(plan7.SequenceDatabase.of(ctx, seqs).handle)) + int(sum(_lib.lib.b2h_profile_h2d_bytes(om._device(ctx)) for om in oms))
-    nhits_rank0 = len(hits)
+    nhits_rank0 = int(hits)                                   # comparisons scored to completion (hit records) of the last step
     nh = sum(len(r) for r in res)
     d2h = int(nh * 96 + sum(len(h.domains) * 88 + sum(4 * (len(d.alignment) + 1) for d in h.domains) for r in res for h in r))
 

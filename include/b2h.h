@@ -256,6 +256,26 @@ const int64_t    *b2h_results_counters(const b2h_results *r);
 const int64_t    *b2h_results_seq_counters(const b2h_results *r);
 void              b2h_results_destroy (b2h_results *r);
 
+/* The same search with its results handed out wave by wave.  b2h_search processes the profiles in a few waves (longest
+ * models first); every comparison of a wave's profiles is final as soon as the wave is through domain definition, while
+ * the GPU is already busy with the waves behind it.  pyhmmer.hmmsearch is a generator for the same reason -- results of the
+ * first queries are consumed while later ones are still being searched (src/pyhmmer/hmmer/_hmmsearch.py:294-420,
+ * _base.py:_BaseDispatcher.run) -- so the host-side assembly of `TopHits` (and, on several GPUs, the exchange of hit
+ * records) of wave w overlaps the cascade of waves w+1...; only the last, smallest wave's post-processing is exposed.
+ *   b2h_search_begin   starts the search on a driver thread of the library; *nwaves = number of waves that will come.
+ *                      The context must not be used for anything else until b2h_search_end.  params.seq_counters must be 0.
+ *   b2h_search_next    blocks until the next wave is complete: *out = its results (hits carry the caller's profile
+ *                      indices, ordered by (profile, target); counters are [P][4] with the rows of the wave's profiles
+ *                      filled; b2h_results_profiles lists them).  The caller destroys every result.  *out = NULL and the
+ *                      status of the search after the last wave.
+ *   b2h_search_end     joins the driver thread, frees the job; returns the status of the search. */
+typedef struct b2h_search_job b2h_search_job;
+int b2h_search_begin(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const b2h_seqdb *db,
+                     const b2h_search_params *params, b2h_search_job **out, size_t *nwaves);
+int b2h_search_next (b2h_search_job *job, b2h_results **out);
+int b2h_search_end  (b2h_search_job *job);
+const int32_t    *b2h_results_profiles(const b2h_results *r, size_t *n);
+
 /* Diagnostic (used by the CPU-only tests of the host-side domain definition): build a profile object
  * without any device state, and run the post-Backward part of p7_Pipeline for ONE comparison from given
  * Forward/Backward parser specials ((L+1) rows of {E,N,J,B,C,SCALE}).  dsq[0..L-1] are the residues. */

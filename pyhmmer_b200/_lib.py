@@ -150,6 +150,10 @@ def _load():
     sig("b2h_results_counters", P(c_i64), c_void_p)
     sig("b2h_results_seq_counters", P(c_i64), c_void_p)
     sig("b2h_results_destroy", None, c_void_p)
+    sig("b2h_search_begin", c_int, c_void_p, c_void_p, c_size_t, c_void_p, P(SearchParams), P(c_void_p), P(c_size_t))
+    sig("b2h_search_next", c_int, c_void_p, P(c_void_p))
+    sig("b2h_search_end", c_int, c_void_p)
+    sig("b2h_results_profiles", P(c_i32), c_void_p, P(c_size_t))
     sig("b2h_profile_set_annotation", c_int, c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p)
     sig("b2h_seqdb_h2d_bytes", ctypes.c_size_t, c_void_p)
     sig("b2h_profile_h2d_bytes", ctypes.c_size_t, c_void_p)

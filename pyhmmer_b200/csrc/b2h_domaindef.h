@@ -13,6 +13,7 @@ struct b2h_results {
   std::vector<char>       text;
   std::vector<int64_t>    counters;
   std::vector<int64_t>    seq_counters;   // [N][4], only when asked for
+  std::vector<int32_t>    profiles;       // the profiles this object is final for (results of one wave: b2h_search_next)
 };
 
 struct b2h_survivor { int32_t profile, seq; float fwdsc, filtersc; int64_t fxoff = -1; };   // fxoff: row offset of the Forward specials the cascade stored (-1: none)

@@ -52,20 +52,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 struct Item { int p, e_begin, e_end; };
+// SUB > 1: a CTA takes 1/SUB of a work item at a time.  The multi-warp classes keep only 4 (W = 2) or 2 (W = 4) comparisons
+// in flight per CTA and a comparison is one dependent chain of L rows, so whole items (16 entries) serialise 4 to 8 such
+// chains per group while other SMs idle at the end of the stage; with sub-items every group holds one comparison.
+template <int SUB = 1>
 __device__ __forceinline__ bool next_item(const WorkList &wl, int *s_item, Item &it)
 {
   __syncthreads();
   if (threadIdx.x == 0) *s_item = atomicAdd(wl.counter, 1);
   __syncthreads();
-  const int item = *s_item + wl.itemoff[wl.plo];
+  const int raw = *s_item;
+  const int item = raw / SUB + wl.itemoff[wl.plo];
   if (item >= wl.itemoff[wl.phi]) return false;
   int lo = wl.plo, hi = wl.phi;
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (wl.itemoff[mid] <= item) lo = mid; else hi = mid; }
   it.p = lo;
-  it.e_begin = wl.poff[lo] + (item - wl.itemoff[lo]) * B2H_ITEM_ENTRIES;
-  it.e_end   = min(wl.poff[lo + 1], it.e_begin + B2H_ITEM_ENTRIES);
+  constexpr int PER = B2H_ITEM_ENTRIES / SUB;
+  const int e0 = wl.poff[lo] + (item - wl.itemoff[lo]) * B2H_ITEM_ENTRIES;
+  const int e1 = min(wl.poff[lo + 1], e0 + B2H_ITEM_ENTRIES);
+  it.e_begin = e0 + (raw % SUB) * PER;
+  it.e_end   = min(e1, it.e_begin + PER);
   return true;
 }
+template <int W> struct ItemSplit { static constexpr int SUB = (W >= 4) ? 8 : (W == 2) ? 4 : 1; };
 
 // The C emission values of this lane for residue x.  Table layout: [32 residues][W warps][C/G groups][32 lanes][G]
 // with G = 4 (C % 4 == 0), 2 (C even) or 1, so every access is one conflict-free LDS.128 / LDS.64 / LDS.32 per lane; <tab> already
@@ -134,7 +143,7 @@ __global__ void __launch_bounds__(256) rvit_kernel(const WorkList wl, const SeqD
   int tBM[C], tMM[C], tIM[C], tDM[C], tMD[C], tMI[C], tII[C], tDD[C];
   int tDDin = NEG16;                                        // D_{k-1}->D_k for this lane's first node (the left lane's last tDD)
   Item it;
-  while (next_item(wl, &s_item, it)) {
+  while (next_item<ItemSplit<W>::SUB>(wl, &s_item, it)) {
     const ProfDev &P = wl.profs[it.p];
     if (it.p != cur_p) {
       cur_p = it.p;
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(256) rfwd_kernel(const WorkList wl, const SeqD
   float tBM[C], tMM[C], tIM[C], tDM[C], tMD[C], tMI[C], tII[C], tDD[C];
   float tDDin = 0.f;
   Item it;
-  while (next_item(wl, &s_item, it)) {
+  while (next_item<ItemSplit<W>::SUB>(wl, &s_item, it)) {
     const ProfDev &P = wl.profs[it.p];
     if (it.p != cur_p) {
       cur_p = it.p;
@@ -677,7 +686,7 @@ __global__ void __launch_bounds__(256) rbck_kernel(const WorkList wl, const SeqD
   // per node k (own): tBM[k], tMD[k], tMI[k], tII[k], tDD[k]; and towards k+1: tMMn = tMM[k+1], tIMn = tIM[k+1], tDMn = tDM[k+1]
   float tBM[C], tMD[C], tMI[C], tII[C], tDD[C], tMMn[C], tIMn[C], tDMn[C];
   Item it;
-  while (next_item(wl, &s_item, it)) {
+  while (next_item<ItemSplit<W>::SUB>(wl, &s_item, it)) {
     const ProfDev &P = wl.profs[it.p];
     const int M = P.M;
     if (it.p != cur_p) {
@@ -847,7 +856,8 @@ int launch_reg(b2h_ctx *ctx, K kernel, int C, int W, const WorkList &wl, const S
   static const int occ_cap = getenv("B2H_DP_OCC") ? atoi(getenv("B2H_DP_OCC")) : 0;         // experiments: resident CTAs per SM
   if (occ_cap > 0 && occ > occ_cap) occ = occ_cap;
   int grid = ctx->sm_count * occ;
-  if (nitems_hint > 0 && grid > nitems_hint) grid = nitems_hint;
+  const int sub = (W >= 4) ? 8 : (W == 2) ? 4 : 1;            // ItemSplit<W>::SUB: CTAs of the multi-warp classes pull sub-items
+  if (nitems_hint > 0 && grid > nitems_hint * sub) grid = nitems_hint * sub;
   if (grid < 1) grid = 1;
   B2H_CUDA(cudaMemsetAsync(wl.counter, 0, sizeof(int), strm));
   kernel<<<grid, 256, smem, strm>>>(wl, sd, out);

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -603,12 +604,16 @@ struct EnvGpu : b2h_env_backend {
 // the GPU (it never waits for a domain definition before the very end).
 struct DdefJob {
   Pinned<float> fx, bx; Pinned<int32_t> bst; std::vector<b2h_ddef_task> tasks;   // page-locked: the D2H copies run at PCIe speed
+  b2h_results *res = nullptr;          // where this chunk's hits go: the result object of its wave
+  int wave = -1; bool last = false;    // last chunk of its wave (a wave without survivors sends an empty marker job)
 };
 struct DdefQueue {
-  b2h_ddef_pool &pool; const b2h_search_params *prm; b2h_results *res; b2h_env_backend *backend;
+  b2h_ddef_pool &pool; const b2h_search_params *prm; b2h_env_backend *backend;
+  std::function<void(int)> wave_done;  // called on the domain-definition thread when a wave's last chunk is through
   std::thread th; std::mutex mu; std::condition_variable cv; std::deque<std::unique_ptr<DdefJob>> q;
   bool closing = false; int status = B2H_OK; double total_ms = 0.0;
-  DdefQueue(b2h_ddef_pool &p, const b2h_search_params *pr, b2h_results *r, b2h_env_backend *be) : pool(p), prm(pr), res(r), backend(be) {
+  DdefQueue(b2h_ddef_pool &p, const b2h_search_params *pr, b2h_env_backend *be, std::function<void(int)> done)
+    : pool(p), prm(pr), backend(be), wave_done(std::move(done)) {
     th = std::thread([this]() {
       for (;;) {
         std::unique_ptr<DdefJob> job;
@@ -617,10 +622,12 @@ struct DdefQueue {
           if (q.empty()) return;
           job = std::move(q.front()); q.pop_front(); }
         const double t0 = now_ms();
-        const int st = (status == B2H_OK) ? pool.run(job->tasks, prm, res, backend) : status;    // after a failure the rest is dropped
+        int st = status;                                                                        // after a failure the rest is dropped
+        if (st == B2H_OK && !job->tasks.empty()) st = pool.run(job->tasks, prm, job->res, backend);
         const double ms = now_ms() - t0;
         { std::lock_guard<std::mutex> lk(mu); if (status == B2H_OK) status = st; total_ms += ms; }
-        if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search]   chunk of %zu survivors: host domain definition %.1f ms on %d threads\n", job->tasks.size(), ms, pool.nthreads);
+        if (getenv("B2H_TRACE") && !job->tasks.empty()) fprintf(stderr, "[b2h_search]   chunk of %zu survivors: host domain definition %.1f ms on %d threads\n", job->tasks.size(), ms, pool.nthreads);
+        if (job->last && st == B2H_OK && wave_done) wave_done(job->wave);
       }
     });
   }
@@ -721,12 +728,19 @@ static int survivors_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, c
 }
 
 // <done> has fired: hand the chunks to the domain-definition thread, one task per survivor
-static int survivors_complete(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, SurvPending &sp, DdefQueue &ddef)
+static int survivors_complete(b2h_ctx *ctx, const b2h_profile *const *profiles, const b2h_seqdb *db, SurvPending &sp, DdefQueue &ddef, b2h_results *wres)
 {
   b2h_resolve_timers(ctx);
+  if (sp.chunks.empty()) {                                       // nothing survived: the wave is complete as soon as its turn comes
+    std::unique_ptr<DdefJob> marker(new DdefJob());
+    marker->res = wres; marker->wave = (int)sp.wave; marker->last = true;
+    ddef.push(std::move(marker));
+    return B2H_OK;
+  }
   for (auto &ckp : sp.chunks) {
     SurvChunk &ck = *ckp;
     DdefJob &job = *ck.job;
+    job.res = wres; job.wave = (int)sp.wave; job.last = (&ckp == &sp.chunks.back());
     job.tasks.resize(ck.n);
     for (int e = 0; e < ck.n; e++) {
       b2h_ddef_task &t = job.tasks[e];
@@ -742,57 +756,86 @@ static int survivors_complete(b2h_ctx *ctx, const b2h_profile *const *profiles, 
   return B2H_OK;
 }
 
-extern "C" {
+// The plan of one search: profiles longest first, cut into waves (see search_impl).
+struct WavePlan { std::vector<int> order; std::vector<size_t> bounds; };
 
-int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const b2h_seqdb *db,
-               const b2h_search_params *prm, b2h_results **out)
+static WavePlan plan_waves(const b2h_profile *const *profiles, size_t P, const b2h_seqdb *db)
 {
-  if (!ctx || !profiles || !db || !prm || !out || db->ctx != ctx) return B2H_EINVAL;
-  for (size_t i = 0; i < P; i++) if (!profiles[i] || profiles[i]->ctx != ctx) return B2H_EINVAL;
-  *out = nullptr;
-  struct ExitTrace { double t; ~ExitTrace() { if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search] returned after %.1f ms\n", now_ms() - t); } } exit_trace{now_ms()};
-  b2h_results *res = new b2h_results();
-  res->counters.assign(P * 4, 0);
+  // Profiles are processed longest first, in waves of about equal DP volume: while the host threads define the
+  // domains of one wave's survivors the GPU already runs the cascade of the next wave, and the wave whose host
+  // work cannot be hidden (the last) holds the shortest models.
+  WavePlan pl;
   const size_t N = db->n;
-  if (N > 0 && P > 0) {
+  pl.order.resize(P);
+  std::iota(pl.order.begin(), pl.order.end(), 0);
+  pl.bounds.push_back(0);
+  if (N == 0 || P == 0) return pl;
+  std::stable_sort(pl.order.begin(), pl.order.end(), [&](int a, int b) { return profiles[a]->M > profiles[b]->M; });
+  double cells = 0.0;
+  for (size_t i = 0; i < P; i++) cells += profiles[i]->M;
+  const size_t CAP = (size_t)1 << 25;                 // comparisons per batch: every list is sized for the worst case
+  const size_t pb = std::max<size_t>(1, CAP / N);
+  // Waves shrink geometrically: the host work of every wave but the last hides behind the next wave's cascade, so
+  // the last wave -- whose survivor passes, envelope kernels and host domain definition are exposed -- is the smallest.
+  // Waves only pay when a wave's cascade is long enough to hide the previous wave's host work behind it; a small job
+  // (hmmscan of one query: latency-bound launches of a few ms whatever their size) runs as one wave.
+  const double job_cells = cells * (double)db->nres;
+  int nwaves = (P >= 16 && job_cells >= 1.5e11) ? 4 : (P >= 6 && job_cells >= 4e10) ? 2 : 1;   // measured on B200 (100 profiles x 50k sequences, 3.7e11 cells, ms/step): 3 waves 44.1, 4 waves 42.6, 5 waves 45.4
+  double ratio = 0.6;
+  if (const char *ev = getenv("B2H_WAVES")) nwaves = std::max(1, atoi(ev));
+  if (const char *ev = getenv("B2H_WAVE_RATIO")) ratio = std::min(1.0, std::max(0.05, atof(ev)));
+  std::vector<double> cum(nwaves + 1, 0.0);            // cumulative share of the DP cells after each wave
+  { double wsum = 0.0, wgt = 1.0; for (int i = 0; i < nwaves; i++) { wsum += wgt; cum[i + 1] = wsum; wgt *= ratio; }
+    for (int i = 0; i <= nwaves; i++) cum[i] /= wsum; }
+  double acc = 0.0; size_t start = 0; int slot = 1;
+  for (size_t i = 0; i < P; i++) {
+    acc += profiles[pl.order[i]]->M;
+    if (i + 1 == P || i + 1 - start >= pb || acc >= cells * cum[slot]) {
+      pl.bounds.push_back(i + 1); start = i + 1;
+      while (slot < nwaves && acc >= cells * cum[slot]) slot++;
+    }
+  }
+  return pl;
+}
+
+// Receives the result object of every wave, in wave order, as soon as the wave's last survivor is through domain
+// definition (on the domain-definition thread).  Hits carry the caller's profile indices, sorted by (profile, target);
+// counters are [P][4] with the rows of the wave's profiles filled; profiles = the wave's profile indices.
+struct WaveSink { virtual void wave(std::unique_ptr<b2h_results> r) = 0; virtual ~WaveSink() {} };
+
+static int search_impl(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const b2h_seqdb *db,
+                       const b2h_search_params *prm, const WavePlan &plan, WaveSink &sink, std::vector<int64_t> *seq_counters)
+{
+  struct ExitTrace { double t; ~ExitTrace() { if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search] returned after %.1f ms\n", now_ms() - t); } } exit_trace{now_ms()};
+  const size_t N = db->n;
+  if (N == 0 || P == 0) return B2H_OK;
+  {
     const double t0 = now_ms();
-    // Profiles are processed longest first, in waves of about equal DP volume: while the host threads define the
-    // domains of one wave's survivors the GPU already runs the cascade of the next wave, and the wave whose host
-    // work cannot be hidden (the last) holds the shortest models.  Hits are re-sorted by (profile, target) at the end.
-    std::vector<int> order(P);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return profiles[a]->M > profiles[b]->M; });
+    const std::vector<int> &order = plan.order;
+    const std::vector<size_t> &bounds = plan.bounds;
     std::vector<const b2h_profile *> sp(P);
-    double cells = 0.0;
-    for (size_t i = 0; i < P; i++) { sp[i] = profiles[order[i]]; cells += sp[i]->M; }
-    const size_t CAP = (size_t)1 << 25;                 // comparisons per batch: every list is sized for the worst case
-    const size_t pb = std::max<size_t>(1, CAP / N);
-    // Waves shrink geometrically: the host work of every wave but the last hides behind the next wave's cascade, so
-    // the last wave -- whose survivor passes, envelope kernels and host domain definition are exposed -- is the smallest.
-    // Waves only pay when a wave's cascade is long enough to hide the previous wave's host work behind it; a small job
-    // (hmmscan of one query: latency-bound launches of a few ms whatever their size) runs as one wave.
-    const double job_cells = cells * (double)db->nres;
-    int nwaves = (P >= 16 && job_cells >= 1.5e11) ? 4 : (P >= 6 && job_cells >= 4e10) ? 2 : 1;   // measured on B200 (100 profiles x 50k sequences, 3.7e11 cells, ms/step): 3 waves 44.1, 4 waves 42.6, 5 waves 45.4
-    double ratio = 0.6;
-    if (const char *ev = getenv("B2H_WAVES")) nwaves = std::max(1, atoi(ev));
-    if (const char *ev = getenv("B2H_WAVE_RATIO")) ratio = std::min(1.0, std::max(0.05, atof(ev)));
-    std::vector<double> cum(nwaves + 1, 0.0);            // cumulative share of the DP cells after each wave
-    { double wsum = 0.0, wgt = 1.0; for (int i = 0; i < nwaves; i++) { wsum += wgt; cum[i + 1] = wsum; wgt *= ratio; }
-      for (int i = 0; i <= nwaves; i++) cum[i] /= wsum; }
-    std::vector<size_t> bounds{0};                       // wave boundaries in sorted order
-    { double acc = 0.0; size_t start = 0; int slot = 1;
-      for (size_t i = 0; i < P; i++) {
-        acc += sp[i]->M;
-        if (i + 1 == P || i + 1 - start >= pb || acc >= cells * cum[slot]) {
-          bounds.push_back(i + 1); start = i + 1;
-          while (slot < nwaves && acc >= cells * cum[slot]) slot++;
-        }
-      } }
+    for (size_t i = 0; i < P; i++) sp[i] = profiles[order[i]];
     std::vector<int64_t> scnt(P * 4, 0);
     b2h_ddef_pool ddpool(prm->host_threads);
     EnvGpu envgpu(ctx, db);
     const bool host_env = getenv("B2H_ENVELOPES_ON_HOST") != nullptr;     // debugging aid: rescore envelopes with the host code
-    DdefQueue ddef(ddpool, prm, res, host_env ? nullptr : &envgpu);
+    const size_t nw = bounds.size() - 1;
+    std::vector<std::unique_ptr<b2h_results>> wres(nw);
+    for (auto &r : wres) r.reset(new b2h_results());
+    DdefQueue ddef(ddpool, prm, host_env ? nullptr : &envgpu, [&](int w) {
+      // the wave is final: hits in the caller's profile numbering, ordered by (profile, target), with its counters
+      std::unique_ptr<b2h_results> r = std::move(wres[w]);
+      for (b2h_hit &h : r->hits) h.profile = order[h.profile];
+      std::stable_sort(r->hits.begin(), r->hits.end(), [](const b2h_hit &x, const b2h_hit &y) {
+        return x.profile != y.profile ? x.profile < y.profile : x.seq < y.seq; });
+      r->counters.assign(P * 4, 0);
+      r->profiles.reserve(bounds[w + 1] - bounds[w]);
+      for (size_t i = bounds[w]; i < bounds[w + 1]; i++) {
+        r->profiles.push_back(order[i]);
+        for (int c = 0; c < 4; c++) r->counters[(size_t)order[i] * 4 + c] = scnt[i * 4 + c];
+      }
+      sink.wave(std::move(r));
+    });
     size_t nsurv = 0;
     int *d_seqcnt = nullptr;                             // per-sequence pass counters (hmmscan of several queries)
     struct SeqCntGuard { int *&p; ~SeqCntGuard() { if (p) cudaFree(p); } } seqcnt_guard{d_seqcnt};
@@ -806,7 +849,6 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
     // passes are queued on one of two high-priority survivor lanes (their kernels slip in between the following wave's SSV
     // launches, and the passes of two consecutive waves may run side by side); when those have arrived on the host, the
     // chunk goes to the domain-definition thread.  This thread never blocks on either while the other can make progress.
-    const size_t nw = bounds.size() - 1;
     std::vector<std::unique_ptr<CascadeWave>> waves(nw);
     int st = B2H_OK;
     size_t ahead = 2;                                    // waves queued beyond the one being collected
@@ -828,7 +870,7 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
       if (!pend.empty() && fired(pend.front()->done)) {
         SurvPending &p = *pend.front();
         if (trace) fprintf(stderr, "[b2h_search]   wave %zu: %zu survivors through Forward/Backward at +%.1f ms\n", p.wave, p.surv.size(), now_ms() - t0);
-        st = survivors_complete(ctx, sp.data(), db, p, ddef);
+        st = survivors_complete(ctx, sp.data(), db, p, ddef, wres[p.wave].get());
         nsurv += p.surv.size();
         pend.pop_front();
         continue;
@@ -852,26 +894,104 @@ int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const
       else std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
     const double tg = now_ms() - t0;
-    if (st != B2H_OK) { cudaStreamSynchronize(ctx->stream); for (auto &l : ctx->lanes) cudaStreamSynchronize(l.stream); ddef.finish(); pend.clear(); waves.clear(); delete res; return st; }
+    if (st != B2H_OK) { cudaStreamSynchronize(ctx->stream); for (auto &l : ctx->lanes) cudaStreamSynchronize(l.stream); ddef.finish(); pend.clear(); waves.clear(); return st; }
     const double t1 = now_ms();
     st = ddef.finish();
-    if (st != B2H_OK) { ctx->err = "domain definition failed"; delete res; return st; }
-    if (d_seqcnt) {                                     // every wave has been collected: the counts are final
+    if (st != B2H_OK) { ctx->err = "domain definition failed"; return st; }
+    if (d_seqcnt && seq_counters) {                     // every wave has been collected: the counts are final
       std::vector<int> h(4 * N);
-      if (cudaMemcpy(h.data(), d_seqcnt, 4 * N * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { ctx->err = "per-sequence counters"; delete res; return B2H_ECUDA; }
-      res->seq_counters.resize(4 * N);
-      for (size_t s = 0; s < N; s++) for (int c = 0; c < 4; c++) res->seq_counters[s * 4 + c] = h[(size_t)c * N + s];
+      if (cudaMemcpy(h.data(), d_seqcnt, 4 * N * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { ctx->err = "per-sequence counters"; return B2H_ECUDA; }
+      seq_counters->resize(4 * N);
+      for (size_t s = 0; s < N; s++) for (int c = 0; c < 4; c++) (*seq_counters)[s * 4 + c] = h[(size_t)c * N + s];
     }
-    for (b2h_hit &h : res->hits) h.profile = order[h.profile];
-    for (size_t i = 0; i < P; i++) for (int c = 0; c < 4; c++) res->counters[(size_t)order[i] * 4 + c] = scnt[i * 4 + c];
-    std::stable_sort(res->hits.begin(), res->hits.end(), [](const b2h_hit &x, const b2h_hit &y) {
-      return x.profile != y.profile ? x.profile < y.profile : x.seq < y.seq; });
     if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_search] %zu waves: GPU cascade + survivor parsers %.1f ms, %zu survivors, host domain definition %.1f ms in total (%.1f ms not hidden; %zu envelopes on the GPU, %.1f ms), all %.1f ms\n",
                                      bounds.size() - 1, tg, nsurv, ddef.total_ms, now_ms() - t1, envgpu.nenv, envgpu.ms, now_ms() - t0);
   }
-  *out = res;
   return B2H_OK;
 }
+
+// A search whose waves are handed out as they complete (b2h_search_begin / _next / _end): the pipeline above runs on a
+// driver thread of its own, the caller -- a Python thread assembling `TopHits`, an all-gather per wave -- works on wave w
+// while the GPU is busy with the waves behind it.  Only the last (smallest) wave's post-processing stays exposed.
+struct b2h_search_job : WaveSink {
+  b2h_ctx *ctx = nullptr; std::vector<const b2h_profile *> profiles; const b2h_seqdb *db = nullptr; b2h_search_params prm;
+  WavePlan plan; std::thread th; std::mutex mu; std::condition_variable cv;
+  std::deque<std::unique_ptr<b2h_results>> ready; bool finished = false; int status = B2H_OK; size_t handed = 0;
+  void wave(std::unique_ptr<b2h_results> r) override { { std::lock_guard<std::mutex> lk(mu); ready.push_back(std::move(r)); } cv.notify_all(); }
+};
+
+extern "C" {
+
+int b2h_search(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const b2h_seqdb *db,
+               const b2h_search_params *prm, b2h_results **out)
+{
+  if (!ctx || !profiles || !db || !prm || !out || db->ctx != ctx) return B2H_EINVAL;
+  for (size_t i = 0; i < P; i++) if (!profiles[i] || profiles[i]->ctx != ctx) return B2H_EINVAL;
+  *out = nullptr;
+  struct Collect : WaveSink {
+    std::vector<std::unique_ptr<b2h_results>> parts;
+    void wave(std::unique_ptr<b2h_results> r) override { parts.push_back(std::move(r)); }
+  } sink;
+  std::unique_ptr<b2h_results> res(new b2h_results());
+  res->counters.assign(P * 4, 0);
+  const WavePlan plan = plan_waves(profiles, P, db);
+  const int st = search_impl(ctx, profiles, P, db, prm, plan, sink, &res->seq_counters);
+  if (st != B2H_OK) return st;
+  // one result: the waves' records back to back (every profile belongs to one wave), ordered by (profile, target)
+  for (auto &part : sink.parts) {
+    const int64_t dbase = (int64_t)res->doms.size(), tbase = (int64_t)res->text.size();
+    for (b2h_hit &h : part->hits) { h.dom_offset += dbase; res->hits.push_back(h); }
+    for (b2h_domain &d : part->doms) { d.text_offset += tbase; res->doms.push_back(d); }
+    res->text.insert(res->text.end(), part->text.begin(), part->text.end());
+    for (int32_t p : part->profiles) for (int c = 0; c < 4; c++) res->counters[(size_t)p * 4 + c] = part->counters[(size_t)p * 4 + c];
+  }
+  std::stable_sort(res->hits.begin(), res->hits.end(), [](const b2h_hit &x, const b2h_hit &y) {
+    return x.profile != y.profile ? x.profile < y.profile : x.seq < y.seq; });
+  *out = res.release();
+  return B2H_OK;
+}
+
+int b2h_search_begin(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P, const b2h_seqdb *db,
+                     const b2h_search_params *prm, b2h_search_job **out, size_t *nwaves)
+{
+  if (!ctx || !profiles || !db || !prm || !out || db->ctx != ctx || prm->seq_counters) return B2H_EINVAL;
+  for (size_t i = 0; i < P; i++) if (!profiles[i] || profiles[i]->ctx != ctx) return B2H_EINVAL;
+  b2h_search_job *job = new b2h_search_job();
+  job->ctx = ctx; job->profiles.assign(profiles, profiles + P); job->db = db; job->prm = *prm;
+  job->plan = plan_waves(job->profiles.data(), P, db);
+  if (nwaves) *nwaves = job->plan.bounds.size() - 1;
+  job->th = std::thread([job]() {
+    cudaSetDevice(job->ctx->device);
+    const int st = search_impl(job->ctx, job->profiles.data(), job->profiles.size(), job->db, &job->prm, job->plan, *job, nullptr);
+    { std::lock_guard<std::mutex> lk(job->mu); job->status = st; job->finished = true; }
+    job->cv.notify_all();
+  });
+  *out = job;
+  return B2H_OK;
+}
+
+// Blocks until the next wave is complete: *out = its results (the caller destroys them), or NULL after the last wave.
+int b2h_search_next(b2h_search_job *job, b2h_results **out)
+{
+  if (!job || !out) return B2H_EINVAL;
+  *out = nullptr;
+  std::unique_lock<std::mutex> lk(job->mu);
+  job->cv.wait(lk, [&] { return !job->ready.empty() || job->finished; });
+  if (!job->ready.empty()) { *out = job->ready.front().release(); job->ready.pop_front(); job->handed++; return B2H_OK; }
+  return job->status;
+}
+
+// Waits for the driver thread and frees the job (results not fetched are dropped).  Returns the status of the search.
+int b2h_search_end(b2h_search_job *job)
+{
+  if (!job) return B2H_EINVAL;
+  if (job->th.joinable()) job->th.join();
+  const int st = job->status;
+  delete job;
+  return st;
+}
+
+const int32_t *b2h_results_profiles(const b2h_results *r, size_t *n) { if (n) *n = r ? r->profiles.size() : 0; return r ? r->profiles.data() : nullptr; }
 
 int b2h_debug_domaindef(const b2h_profile *p, const uint8_t *dsq, int L, const float *fwd_xmx, const float *bck_xmx,
                         float fwdsc, const b2h_search_params *prm, b2h_results **out)

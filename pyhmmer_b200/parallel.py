@@ -1,4 +1,4 @@
-"""Multi-GPU search: shard the TARGET database across ranks, all-gather the hits once at the end.
+"""Multi-GPU search: shard the TARGET database across ranks, all-gather the hit records (once per wave of profiles).
 
 Every (profile, sequence) comparison is independent, so the path shards with no data-path collective
 (SURVEY 8(e)).  One process per GPU (``torch.distributed``, backend ``nccl``; ``gloo`` for the CPU tests of
@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 from .easel import DigitalSequenceBlock
 
-__all__ = ["World", "shard_block", "search_sharded", "all_gather_bytes", "pack_records", "unpack_records"]
+__all__ = ["World", "shard_block", "search_sharded", "exchanged_waves", "all_gather_bytes", "pack_records", "unpack_records"]
 
 
 class World:
@@ -77,8 +77,8 @@ def _raw_bytes(recs, rectype):
     return bytes((rectype * max(n, 1))(*recs))[: n * ctypes.sizeof(rectype)]
 
 
-def pack_records(hits, doms, text, counters, seq_offset, profile_offset=0):
-    """Serialize one rank's results: header | HitRec[] | DomainRec[] | text | counters (int64)."""
+def pack_records(hits, doms, text, counters, seq_offset, profile_offset=0, profiles=None):
+    """Serialize one rank's results: header | HitRec[] | DomainRec[] | text | counters (int64) [| profile indices (int32)]."""
     nh, nd = len(hits), len(doms)
     hb = bytearray(_raw_bytes(hits, _lib.HitRec))
     if nh and seq_offset:
@@ -86,13 +86,14 @@ def pack_records(hits, doms, text, counters, seq_offset, profile_offset=0):
     if nh and profile_offset:
         np.frombuffer(hb, dtype=np.dtype(_lib.HitRec))["profile"] += profile_offset   # local -> global profile index (scan)
     cnt = np.ascontiguousarray(counters, dtype=np.int64)
-    header = np.array([nh, nd, len(text), cnt.size], dtype=np.int64).tobytes()
-    return b"".join([header, bytes(hb), _raw_bytes(doms, _lib.DomainRec), bytes(text), cnt.tobytes()])
+    prof = np.ascontiguousarray([] if profiles is None else profiles, dtype=np.int32)
+    header = np.array([nh, nd, len(text), cnt.size, prof.size], dtype=np.int64).tobytes()
+    return b"".join([header, bytes(hb), _raw_bytes(doms, _lib.DomainRec), bytes(text), cnt.tobytes(), prof.tobytes()])
 
 
-def unpack_records(buf):
-    nh, nd, nt, nc = (int(v) for v in np.frombuffer(buf[:32], dtype=np.int64))
-    o = 32
+def unpack_records(buf, with_profiles=False):
+    nh, nd, nt, nc, npf = (int(v) for v in np.frombuffer(buf[:40], dtype=np.int64))
+    o = 40
     hs, ds = ctypes.sizeof(_lib.HitRec), ctypes.sizeof(_lib.DomainRec)
     hits = list((_lib.HitRec * nh).from_buffer_copy(buf[o:o + nh * hs])) if nh else []
     o += nh * hs
@@ -101,6 +102,9 @@ def unpack_records(buf):
     text = bytes(buf[o:o + nt])
     o += nt
     counters = np.frombuffer(buf[o:o + 8 * nc], dtype=np.int64).copy()
+    o += 8 * nc
+    if with_profiles:
+        return hits, doms, text, counters, np.frombuffer(buf[o:o + 4 * npf], dtype=np.int32).tolist()
     return hits, doms, text, counters
 
 
@@ -112,6 +116,16 @@ class _Exchange:
     def __init__(self):
         self.key, self.cap = None, 0
         self.h_in = self.h_out = self.d_in = self.d_out = self.h_sz = self.d_sz = self.d_szs = self.h_szs = None
+        self.stream = None
+
+    def side_stream(self, torch, dev):
+        """The exchange has a (high-priority) stream of its own: the engine's lanes hold the queued cascades of the waves
+        still being searched, and a collective issued behind them would wait for all of them."""
+        if dev.type != "cuda":
+            return None
+        if self.stream is None or self.stream.device != dev:
+            self.stream = torch.cuda.Stream(device=dev, priority=-1)
+        return self.stream
 
     def ensure(self, torch, dev, world, need):
         key = (str(dev), world.size)
@@ -140,8 +154,16 @@ def all_gather_bytes(data, world):
     if world.size == 1:
         return [data]
     import torch
-    dist = world.dist
     dev = world.device or torch.device("cpu")
+    side = _EXCHANGE.side_stream(torch, dev)
+    if side is None:
+        return _all_gather_bytes(data, world, torch, dev, None)
+    with torch.cuda.stream(side):
+        return _all_gather_bytes(data, world, torch, dev, side)
+
+
+def _all_gather_bytes(data, world, torch, dev, side):
+    dist = world.dist
     n = len(data)
     ex = _EXCHANGE
     ex.ensure(torch, dev, world, max(n, 1))
@@ -155,8 +177,8 @@ def all_gather_bytes(data, world):
         dist.all_gather(outs, ex.d_sz)
         ex.d_szs.copy_(torch.cat(outs))
     ex.h_szs.copy_(ex.d_szs, non_blocking=True)
-    if dev.type == "cuda":
-        torch.cuda.current_stream().synchronize()
+    if side is not None:
+        side.synchronize()
     sizes = [int(v) for v in ex.h_szs.tolist()]
     slot = (max(max(sizes), 1) + 255) & ~255
     ex.ensure(torch, dev, world, slot)                                 # (every rank sees the same sizes: they all grow together)
@@ -172,8 +194,8 @@ def all_gather_bytes(data, world):
         dist.all_gather(outs, d_in)
         d_out.copy_(torch.cat(outs))
     h_out.copy_(d_out, non_blocking=True)
-    if dev.type == "cuda":
-        torch.cuda.current_stream().synchronize()
+    if side is not None:
+        side.synchronize()
     host = h_out.numpy().reshape(world.size, slot)
     return [host[r, :sizes[r]].tobytes() for r in range(world.size)]
 
@@ -196,16 +218,69 @@ def merge_rank_records(parts):
     return hits, doms, bytes(text), counters
 
 
+def agree_max(value, world):
+    """The largest ``value`` of any rank (one 8-byte all-reduce on the exchange stream)."""
+    if world.size == 1:
+        return int(value)
+    import torch
+    dev = world.device or torch.device("cpu")
+    side = _EXCHANGE.side_stream(torch, dev)
+    t = torch.tensor([int(value)], dtype=torch.int64)
+    if side is None:
+        world.dist.all_reduce(t, op=world.dist.ReduceOp.MAX)
+        return int(t.item())
+    with torch.cuda.stream(side):
+        d = t.to(dev, non_blocking=True)
+        world.dist.all_reduce(d, op=world.dist.ReduceOp.MAX)
+        out = d.cpu()
+    return int(out.item())
+
+
+def exchanged_waves(pipeline, oms, sub, lo, world):
+    """This rank's search of its shard ``sub`` (first target = global index ``lo``), wave by wave, with one all-gather of hit
+    records per wave: a generator of ``(complete, hits, doms, text, counters)`` -- the records of EVERY rank for the profiles
+    in ``complete`` (those every rank has finished), hits ordered by (profile, global target), ``counters`` [P][4] summed over
+    the ranks so far.  While a wave's records are exchanged and assembled, the GPUs search the following waves; the ranks
+    agree on the number of rounds first (their wave plans may differ when their shards do), a rank that runs out of waves
+    contributes empty payloads, and records of profiles some rank has not finished yet wait for the round that completes them."""
+    P = len(oms)
+    if len(sub) and P >= 16:
+        nlocal, gen = pipeline._run_waves(oms, sub)
+    elif len(sub):
+        nlocal, gen = 1, iter([(list(range(P)),) + tuple(pipeline._run(oms, sub))])
+    else:
+        nlocal, gen = 1, iter([(list(range(P)), [], [], b"", np.zeros((P, 4), np.int64))])
+    rounds = agree_max(nlocal, world)
+    done = np.zeros(P, np.int32)
+    total = np.zeros((P, 4), np.int64)
+    carry = None
+    for _ in range(rounds):
+        profs, hits, doms, text, counters = next(gen, ([], [], [], b"", np.zeros((P, 4), np.int64)))
+        mine = pack_records(hits, doms, text, counters, lo, profiles=profs)
+        parts = [unpack_records(b, with_profiles=True) for b in all_gather_bytes(mine, world)]
+        for part in parts:
+            done[part[4]] += 1
+        hits, doms, text, counters = merge_rank_records(([carry] if carry else []) + [p[:4] for p in parts])
+        total += counters.reshape(P, 4)
+        ready = done == world.size
+        complete = np.nonzero(ready)[0].tolist()
+        done[ready] = -(1 << 20)                               # reported once
+        rest = [h for h in hits if not ready[h.profile]] if len(complete) < P else []
+        carry = (rest, doms, text, np.zeros(P * 4, np.int64)) if rest else None
+        yield complete, ([h for h in hits if ready[h.profile]] if rest else hits), doms, text, total
+    for _ in gen:                                              # (drains the engine's job: nothing is left by construction)
+        pass
+
+
 def search_sharded(pipeline, queries, block, local, world):
     """One query batch against the sharded database; every rank returns the same list of `TopHits`."""
     lo, sub = local
     L = len(block[0]) if len(block) else pipeline.L_HINT
     oms = pipeline._optimized_many(queries, L)
-    if len(sub):
-        hits, doms, text, counters = pipeline._run(oms, sub)
-    else:
-        hits, doms, text, counters = [], [], b"", np.zeros((len(oms), 4), np.int64)
-    mine = pack_records(hits, doms, text, counters, lo)
-    parts = [unpack_records(b) for b in all_gather_bytes(mine, world)]
-    hits, doms, text, counters = merge_rank_records(parts)
-    return pipeline._assemble(queries, oms, block, hits, doms, text, counters.reshape(len(oms), 4))
+    results = [None] * len(oms)
+    first = True
+    for complete, hits, doms, text, counters in exchanged_waves(pipeline, oms, sub, lo, world):
+        for qi, th in zip(complete, pipeline._assemble(queries, oms, block, hits, doms, text, counters, only=complete, count_targets=first)):
+            results[qi] = th
+        first = False
+    return results

@@ -2377,6 +2377,67 @@ class Pipeline:
         self._last_run_s = (t1 - t0, t2 - t1, time.perf_counter() - t2)    # (uploads / handles, b2h_search, reading the results)
         return hits, doms, text, counters
 
+    def _run_waves(self, oms, block):
+        """The same search with its results wave by wave (b2h_search_begin / _next / _end, include/b2h.h): returns
+        ``(n_waves, generator)``; the generator yields ``(profile_indices, hits, doms, text, counters[P][4])``, every tuple
+        final for the listed profiles.  The search starts at once and goes on with the following waves on the engine's own
+        driver thread while the caller works on what it was handed (assembling `TopHits`, exchanging hit records)."""
+        ctx = self._ctx
+        t0 = time.perf_counter()
+        if block._cache.get(("db", ctx)) is None and sum(1 for om in oms if om._dev.get(ctx) is None) > 8:
+            import threading
+            box = []
+            th = threading.Thread(target=lambda: box.append(SequenceDatabase.of(ctx, block)))
+            th.start()
+            try:
+                handles = (ctypes.c_void_p * len(oms))(*OptimizedProfile._device_many(ctx, oms))
+            finally:
+                th.join()
+            db = SequenceDatabase.of(ctx, block)
+        else:
+            db = SequenceDatabase.of(ctx, block)
+            handles = oms._handles(ctx) if isinstance(oms, OptimizedProfileBlock) else \
+                (ctypes.c_void_p * len(oms))(*OptimizedProfile._device_many(ctx, oms))
+        prm = self._params_struct(False)
+        job, nw = ctypes.c_void_p(), ctypes.c_size_t()
+        t1 = time.perf_counter()
+        check(lib.b2h_search_begin(ctx.handle, handles, len(oms), db.handle, ctypes.byref(prm), ctypes.byref(job), ctypes.byref(nw)),
+              "b2h_search_begin", ctx.handle)
+        self._last_run_s = (t1 - t0, 0.0, 0.0)
+        return int(nw.value), self._wave_results(job, len(oms), t1 - t0)
+
+    def _wave_results(self, job, P, t_upload):
+        ctx = self._ctx
+        waited = read = 0.0
+        try:
+            while True:
+                out = ctypes.c_void_p()
+                tw = time.perf_counter()
+                st = lib.b2h_search_next(job, ctypes.byref(out))            # (the GIL is released while this waits)
+                waited += time.perf_counter() - tw
+                if st == _lib.B2H_ERANGE:
+                    raise OverflowError("numerical overflow in the optimized vector implementation")
+                check(st, "b2h_search", ctx.handle)
+                if not out.value:
+                    break
+                tr = time.perf_counter()
+                try:
+                    hits, doms, text = _lib.read_results(out)
+                    counters = np.ctypeslib.as_array(lib.b2h_results_counters(out), shape=(P, 4)).copy()
+                    n = ctypes.c_size_t()
+                    pp = lib.b2h_results_profiles(out, ctypes.byref(n))
+                    profs = [pp[i] for i in range(n.value)]
+                finally:
+                    lib.b2h_results_destroy(out)
+                read += time.perf_counter() - tr
+                self._last_run_s = (t_upload, waited, read)
+                yield profs, hits, doms, text, counters
+        finally:
+            st = lib.b2h_search_end(job)
+        if st == _lib.B2H_ERANGE:
+            raise OverflowError("numerical overflow in the optimized vector implementation")
+        check(st, "b2h_search", ctx.handle)
+
     def _admit(self, th, rec, target, doms, text, Z_running, cut):
         """Hit admission as p7_Pipeline does it at the moment the comparison finishes (p7_pipeline.c:838):
         with the *running* Z when the search space is being counted (p7_pipeline.c:580)."""
@@ -2455,22 +2516,32 @@ class Pipeline:
             raise ValueError("sequence length over comparison pipeline limit (100000)")
         L = len(sequences[0]) if len(sequences) else self.L_HINT
         oms = self._optimized_many(queries, L)
-        if len(sequences):
-            hits, doms, text, counters = self._run(oms, sequences)
-        else:
-            hits, doms, text, counters = [], [], b"", np.zeros((len(oms), 4), np.int64)
-        return self._assemble(queries, oms, sequences, hits, doms, text, counters)
+        if not len(sequences):
+            return self._assemble(queries, oms, sequences, [], [], b"", np.zeros((len(oms), 4), np.int64))
+        if len(oms) < 16:                                      # a single wave anyway (plan_waves): one blocking call
+            return self._assemble(queries, oms, sequences, *self._run(oms, sequences))
+        # wave by wave: the `TopHits` of a wave's queries are built while the GPU searches the following waves
+        results = [None] * len(oms)
+        first = True
+        for profs, hits, doms, text, counters in self._run_waves(oms, sequences)[1]:
+            for qi, th in zip(profs, self._assemble(queries, oms, sequences, hits, doms, text, counters, only=profs, count_targets=first)):
+                results[qi] = th
+            first = False
+        return results
 
-    def _assemble(self, queries, oms, sequences, hits, doms, text, counters):
-        """Turn raw hit records (ordered by profile, then target) into thresholded `TopHits`, one per query."""
-        cuts = [self._cutoffs(om) for om in oms]
+    def _assemble(self, queries, oms, sequences, hits, doms, text, counters, only=None, count_targets=True):
+        """Turn raw hit records (ordered by profile, then target) into thresholded `TopHits`, one per query -- or, with
+        ``only``, one per listed query index, in that order (``count_targets``: add the targets to the pipeline's totals)."""
+        which = range(len(oms)) if only is None else only
+        cuts = {qi: self._cutoffs(oms[qi]) for qi in which}
         n = len(sequences)
         nres = sequences.total_residues
         results = []
-        by_query = [[] for _ in oms]
+        by_query = {qi: [] for qi in which}
         for rec in hits:
             by_query[rec.profile].append(rec)
-        for qi, (query, om) in enumerate(zip(queries, oms)):
+        for qi in which:
+            query, om = queries[qi], oms[qi]
             th = self._tophits(query, "search", cuts[qi])
             self._nmodels += 1
             self._nnodes += om.M
@@ -2485,8 +2556,9 @@ class Pipeline:
             th._sort_by_key()
             th._threshold()
             results.append(th)
-        self._nseqs += n
-        self._nres += nres
+        if count_targets:
+            self._nseqs += n
+            self._nres += nres
         return results
 
     def scan_seq(self, query, targets):

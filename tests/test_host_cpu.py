@@ -214,6 +214,87 @@ def test_all_gather_and_merge_world_size_2_gloo():
     assert all("ok" in o for o in outs)
 
 
+_SEARCH_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch.distributed as dist
+from pyhmmer_b200 import parallel, _lib, plan7, easel, synth
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%d" %% int(sys.argv[1]), rank=int(sys.argv[2]), world_size=2)
+w = parallel.World.current()
+abc = easel.Alphabet.amino()
+rng = np.random.default_rng(5)
+bg = plan7.Background(abc)
+hmms = [synth.random_hmm(abc, int(m), rng, name="p%%d" %% i) for i, m in enumerate(rng.integers(20, 300, 20))]
+for h in hmms:
+    h._evparam[:] = np.array([-8.0, 0.7, -9.0, 0.7, -4.0, 0.7], np.float32)
+block = easel.DigitalSequenceBlock(abc, [easel.DigitalSequence(abc, name=b"t%%d" %% i, sequence=rng.integers(0, 20, 30 + 7 * i).astype(np.uint8)) for i in range(9)])
+
+def records(oms, sub, profs):
+    """stands in for the device: deterministic hits for (model, target) pairs, keyed by the objects (not their local indices)"""
+    hits, doms, text = [], [], b""
+    for p in profs:
+        for s in range(len(sub)):
+            key = oms[p].M + len(sub[s])
+            if key %% 3 == 0:
+                h = _lib.HitRec()
+                h.profile, h.seq, h.score, h.pre_score, h.sum_score, h.lnP, h.ndom, h.dom_offset = p, s, key * 0.1, key * 0.1 + 1, key * 0.1, -float(key %% 23), 1, len(doms)
+                d = _lib.DomainRec()
+                d.N, d.text_offset, d.bitscore, d.lnP, d.ienv, d.jenv = 2, len(text), 3.0 + (key %% 5), -3.0, 1, 10
+                text += b"AB\0ab\0AB\0**\0"
+                hits.append(h); doms.append(d)
+    counters = np.zeros((len(oms), 4), np.int64)
+    for p in profs:
+        counters[p] = [len(sub) * oms[p].M, len(sub), 2 * len(sub), sum(len(x) for x in sub)]      # additive over shards
+    return hits, doms, text, counters
+
+def fake_run(self, oms, sub, seq_counters=False):
+    return records(oms, sub, range(len(oms)))
+
+def fake_run_waves(self, oms, sub):
+    # the ranks cut their waves differently (as they may when their shards differ): rank 0 in three, rank 1 in two
+    order = sorted(range(len(oms)), key=lambda i: -oms[i].M)
+    cuts = [0, 5, 12, len(oms)] if w.rank == 0 and w.size > 1 else [0, 9, len(oms)]
+    waves = [order[a:b] for a, b in zip(cuts, cuts[1:])]
+    return len(waves), ((wv,) + records(oms, sub, wv) for wv in waves)
+
+pli = object.__new__(plan7.Pipeline)                     # no device here: the attributes the search path reads are set by hand
+for k, v in dict(alphabet=abc, background=bg, bias_filter=True, null2=True, seed=42, Z=None, domZ=None, F1=0.02, F2=1e-3, F3=1e-5,
+                 E=10.0, T=None, domE=10.0, domT=None, incE=0.01, incT=None, incdomE=0.01, incdomT=None, bit_cutoffs=None, host_threads=1).items():
+    setattr(pli, k, v)
+pli.clear()
+plan7.Pipeline._run = fake_run
+plan7.Pipeline._run_waves = fake_run_waves
+sharded = parallel.search_sharded(pli, hmms, block, parallel.shard_block(block, w), w)
+assert (pli._nseqs, pli._nres) == (len(block), block.total_residues)
+single = pli._search_many(hmms, block)                    # one process, wave by wave
+oms = pli._optimized_many(hmms, len(block[0]))
+whole = pli._assemble(hmms, oms, block, *fake_run(pli, oms, block))      # one process, one blocking call
+sig = lambda ths: [[(h.name, h.score, h.lnP, h.reported, h.included, len(h.domains)) for h in th] +
+                   [(th.Z, th.searched_sequences, th.n_past_msv, th.n_past_bias, th.n_past_vit, th.n_past_fwd)] for th in ths]
+assert sig(sharded) == sig(whole) and sig(single) == sig(whole) and sum(len(th) for th in whole) >= 30
+assert [th.query.name for th in sharded] == [h.name for h in hmms]
+# an empty shard on one rank: it still takes part in every round
+tiny = easel.DigitalSequenceBlock(abc, list(block)[:1])
+a = parallel.search_sharded(pli, hmms, tiny, parallel.shard_block(tiny, w), w)
+assert [len(th) for th in a] == [len(th) for th in pli._assemble(hmms, oms, tiny, *fake_run(pli, oms, tiny))]
+dist.barrier(); dist.destroy_process_group()
+print("rank", w.rank, "ok")
+'''
+
+
+def test_search_wave_exchange_world_size_2_gloo():
+    """hmmsearch over two ranks, wave by wave: every rank searches its shard in waves of profiles, one all-gather of hit
+    records per wave, profiles assembled as soon as every rank has finished them -- with ranks that cut their waves
+    DIFFERENTLY and a rank with an empty shard; results identical to the unsharded search (host logic, stand-in device)."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port_ = s.getsockname()[1]; s.close()
+    code = _SEARCH_WORKER % (ROOT,)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(port_), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
 _SCAN_WORKER = r'''
 import os, sys
 sys.path.insert(0, %r)

@@ -149,6 +149,54 @@ def test_synthetic_with_planted_homologs(amino):
         assert nhit >= 40
 
 
+def test_search_wave_by_wave_equals_one_call(amino, monkeypatch):
+    """b2h_search_begin / _next / _end (results handed out wave by wave while the following waves are searched) against
+    the blocking b2h_search: the same records, every profile final in exactly one wave, waves in order; `Pipeline._search_many`
+    (which assembles `TopHits` per wave) against `_run` + `_assemble`; an early exit leaves the engine usable."""
+    rng = np.random.default_rng(78)
+    Ms = [int(m) for m in rng.integers(25, 420, 24)] + [560, 700]            # two multi-warp (W = 2) models as well
+    hmms = [synth.random_hmm(amino, M, rng, name="wv%d" % i) for i, M in enumerate(Ms)]
+    synth.calibrate(hmms)
+    seqs = synth.random_sequences(amino, 2500, rng)
+    for i in range(120):
+        s = seqs[int(rng.integers(0, len(seqs)))]
+        cut = int(rng.integers(0, len(s)))
+        s.sequence = np.concatenate([s.sequence[:cut], synth.emit_sequence(hmms[i % len(hmms)], rng), s.sequence[cut:]])[:1500]
+    seqs._cache = {}
+    pli = plan7.Pipeline(amino)
+    oms = [pli._optimized(h, len(seqs[0])) for h in hmms]
+    for nwaves in (1, 3, 5):
+        monkeypatch.setenv("B2H_WAVES", str(nwaves))
+        hits, doms, text, counters = pli._run(oms, seqs)
+        n, gen = pli._run_waves(oms, seqs)
+        assert n == nwaves
+        seen, got, waves = [], [], 0
+        for profs, wh, wd, wt, wc in gen:
+            waves += 1
+            assert sorted({h.profile for h in wh}) <= sorted(profs) and not set(profs) & set(seen)
+            assert [(h.profile, h.seq) for h in wh] == sorted((h.profile, h.seq) for h in wh)
+            assert all(oms[a].M >= oms[b].M for a in seen for b in profs)        # longest models first
+            assert np.array_equal(wc[profs], counters[profs]) and not wc[[p for p in range(len(oms)) if p not in profs]].any()
+            seen += profs
+            for h in wh:
+                d0, r0 = wd[h.dom_offset], None
+                got.append((h.profile, h.seq, round(float(h.score), 3), h.ndom, d0.ienv, d0.jenv, wt[d0.text_offset:d0.text_offset + d0.N + 1]))
+        assert waves == nwaves and sorted(seen) == list(range(len(oms)))
+        want = [(h.profile, h.seq, round(float(h.score), 3), h.ndom, doms[h.dom_offset].ienv, doms[h.dom_offset].jenv,
+                 text[doms[h.dom_offset].text_offset:doms[h.dom_offset].text_offset + doms[h.dom_offset].N + 1]) for h in hits]
+        assert sorted(got) == want and len(want) >= 100
+        a = pli._search_many(hmms, seqs)
+        b = pli._assemble(hmms, oms, seqs, hits, doms, text, counters)
+        sig = lambda ths: [[(h.name, round(h.score, 3), h.reported, h.included, len(h.domains)) for h in th] + [(th.Z, th.n_past_msv, th.n_past_fwd)] for th in ths]
+        assert sig(a) == sig(b)
+    # leaving the generator early drains the job; the next search is unaffected
+    n, gen = pli._run_waves(oms, seqs)
+    next(gen)
+    gen.close()
+    again = pli._run(oms, seqs)
+    assert [(h.profile, h.seq) for h in again[0]] == [(h.profile, h.seq) for h in hits]
+
+
 def test_hmmscan_matches_search(amino):
     """hmmscan of one sequence against a profile block == the same comparisons via hmmsearch (Z = #models)."""
     seqs = _proteome(amino)
