@@ -214,6 +214,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # NCCL's version / debug lines: not on the JSON line's stream
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pyhmmer_b200 import _lib, plan7, synth, parallel
 
