@@ -313,10 +313,10 @@ int64_t b2h_seqdb_nres(const b2h_seqdb *db) { return db ? db->nres : 0; }
 // and every row is a multiple of 128 bytes.
 static size_t ssv_word_index(int G, int NR, int x, int j, int lane /* physical lane 0..31 */)
 {
-  const int full = NR / 4, gl = lane % G;
+  const int full = NR / 4, GS = G < 8 ? 8 : G, slot = lane % GS;     // G < 8: slot = lane & 7, i.e. group-local lane + G * (group & (8/G - 1))
   const size_t base = (size_t)x * (b2h_ssv_row_bytes(G, NR) / 4);
-  if (j < full * 4) return base + ((size_t)(j / 4) * G + gl) * 4 + (j % 4);
-  return base + (size_t)full * G * 4 + (size_t)(j - full * 4) * 32 + lane;
+  if (j < full * 4) return base + ((size_t)(j / 4) * GS + slot) * 4 + (j % 4);
+  return base + (size_t)full * GS * 4 + (size_t)(j - full * 4) * 32 + lane;
 }
 
 int b2h_profile_create_host(const b2h_oprofile_desc *d, b2h_profile **out)
@@ -326,10 +326,10 @@ int b2h_profile_create_host(const b2h_oprofile_desc *d, b2h_profile **out)
 // (sections 256-byte aligned; offsets in <offs>).  Pure CPU work, safe to run for many profiles in parallel.
 struct ProfStage { std::vector<uint8_t> bytes; uint8_t *ext = nullptr; size_t size = 0; size_t offs[10] = {0}; };   // image in <bytes>, or written straight to <ext>
 // Size of the staged device image of a profile (sections 256-byte aligned, in the order profile_build adds them).
-static void profile_classes(int M, int *G, int *NR, int *regC, int *regW)
+static void profile_classes(int M, int K, int *G, int *NR, int *regC, int *regW)
 {
   *G = *NR = *regC = *regW = 0;
-  b2h_ssv_tile(M, G, NR);
+  b2h_ssv_tile(M, G, NR, K == 20);
   const b2h_regclass *rcls; const int nrcls = b2h_reg_classes(&rcls);
   for (int rc = 0; rc < nrcls; rc++) if (M <= rcls[rc].bound) { *regC = rcls[rc].C; *regW = rcls[rc].W; break; }
 }
@@ -351,7 +351,7 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
   *out = nullptr;
   const int M = d->M, Kp = d->Kp;
   int G = 0, NR = 0;
-  if (!b2h_ssv_tile(M, &G, &NR)) { if (ctx) ctx->err = "model too long for the register-tiled SSV kernel (M > 3071)"; return B2H_EINVAL; }
+  if (!b2h_ssv_tile(M, &G, &NR, d->K == 20)) { if (ctx) ctx->err = "model too long for the register-tiled SSV kernel (M > 3071)"; return B2H_EINVAL; }
   b2h_profile *p = new b2h_profile();
   p->ctx = ctx; p->M = M; p->K = d->K; p->Kp = Kp; p->max_length = d->max_length; p->multihit = d->mode_multihit;
   p->NR = NR; p->G = G; p->tbm_b = d->tbm_b; p->tec_b = d->tec_b; p->base_b = d->base_b; p->bias_b = d->bias_b; p->scale_b = d->scale_b;
@@ -384,7 +384,7 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
         // has overflowed, so any decrement >= 127 takes it to the floor either way.  One table serves both kernels.
         const int slo = (int)d->bias_b - clo, shi = (int)d->bias_b - chi;
         const uint32_t w = ((uint32_t)half_of[shi + 256] << 16) | (uint32_t)half_of[slo + 256];
-        if (j < (NR / 4) * 4) ssv[ssv_word_index(G, NR, x, j, gl)] = w;
+        if (j < (NR / 4) * 4) for (int lane = gl; lane < (G < 8 ? 8 : G); lane += G) ssv[ssv_word_index(G, NR, x, j, lane)] = w;   // (G < 8: one copy per group of a quarter-warp)
         else for (int lane = gl; lane < 32; lane += G) ssv[ssv_word_index(G, NR, x, j, lane)] = w;     // leftover words: one copy per group of the warp
       }
 
@@ -536,7 +536,7 @@ int b2h_profile_upload_many(b2h_ctx *ctx, const b2h_oprofile_desc *const *descs,
   std::vector<size_t> base(n + 1, 0);
   for (size_t i = 0; i < n; i++) {
     if (!descs[i] || descs[i]->M < 1) return B2H_EINVAL;
-    int G, NR, rC, rW; profile_classes(descs[i]->M, &G, &NR, &rC, &rW);
+    int G, NR, rC, rW; profile_classes(descs[i]->M, descs[i]->K, &G, &NR, &rC, &rW);
     if (!G) { ctx->err = "model too long for the register-tiled SSV kernel (M > 3071)"; return B2H_EINVAL; }
     base[i + 1] = base[i] + ((profile_stage_bytes(descs[i]->M, G, NR, rC, rW) + 255) & ~(size_t)255);
   }
@@ -614,10 +614,10 @@ extern "C" size_t b2h_profile_h2d_bytes(const b2h_profile *p) { return p ? p->h2
 extern "C" int b2h_ssv_tile_info(int M, int *G, int *NR, double *wavefronts_per_row)
 {
   int g = 0, nr = 0;
-  if (M < 1 || !b2h_ssv_tile(M, &g, &nr)) return B2H_EINVAL;
+  if (M < 1 || !b2h_ssv_tile(M, &g, &nr, true)) return B2H_EINVAL;                   // (the tile of a PROTEIN profile)
   if (G) *G = g;
   if (NR) *NR = nr;
-  if (wavefronts_per_row) *wavefronts_per_row = 4.0 * (nr / 4) + (nr % 4) + 1.25;   // LDS.128 x NR/4, LDS.32 x NR%4, diagonal SHFL, residue SHFL / 4 rows
+  if (wavefronts_per_row) *wavefronts_per_row = b2h_ssv_tile_cost(g, nr) * 32.0 / g;  // per WARP and row: LDS.128 x NR/4, LDS.32 x NR%4, diagonal SHFL, residue SHFL / 4 rows
   return B2H_OK;
 }
 

@@ -224,18 +224,46 @@ struct ForkJoin {
 // every lane owns 2*NR consecutive nodes.  Needs 2*G*NR >= M+1 so that the last cell of the group's last lane is always
 // padding (see b2h_msv.cu).  The narrowest group that fits is taken: it wastes the fewest padded cells (granularity
 // 2*G nodes) and spreads the per-row shuffle over the most cells.
-static inline bool b2h_ssv_tile(int M, int *G, int *NR) {
-  const int need = M + 1;
-  if (need <= 16 * 32) { *G = 8;  *NR = (need + 15) / 16; return true; }
-  if (need <= 32 * 32) { *G = 16; *NR = (need + 31) / 32; return true; }
-  int nr = (need + 63) / 64;
-  static const int allowed[] = {18, 20, 22, 24, 26, 28, 30, 32, 40, 48};
-  for (int a : allowed) if (a >= nr) { *G = 32; *NR = a; return true; }
-  return false;
+// Shared-memory wavefronts one DP row of one COMPARISON costs with a (G, NR) tile: a warp holds 32/G comparisons and moves
+// 4 wavefronts per LDS.128, 1 per leftover LDS.32, 1 for the diagonal shuffle (none when a single lane owns the model) and
+// 1/4 for the residue-word shuffle.
+static inline double b2h_ssv_tile_cost(int G, int NR) {
+  return (4.0 * (NR / 4) + (NR % 4) + (G > 1 ? 1.0 : 0.0) + 0.25) * G / 32.0;
 }
-// bytes of one residue row of the lane-striped SSV table of a (G, NR) tile, and shared-memory wavefronts (128 B each)
-// one DP row of one warp moves: 4 per LDS.128, 1 per leftover LDS.32, 1 diagonal shuffle, 1/4 residue-word shuffle
-static inline size_t b2h_ssv_row_bytes(int G, int NR) { return (size_t)(NR / 4) * G * 16 + (size_t)(NR % 4) * 128; }
+// The register tile of a model of M nodes: G lanes per comparison, NR packed registers (2 NR cells) per lane, 2 G NR >= M + 1
+// (one spare cell: the value that wraps around the group must be a padding cell).  The fewer lanes share a model, the
+// fewer shuffles a cell costs and the better the lanes are used, so short models go to groups of 4, 2 or 1 lanes
+// (<small_ok>: protein profiles; the long-target kernels keep the 8 / 16 / 32-lane tiles) -- the cheapest tile by the
+// wavefront count above among the instantiated ones: G = 1, 2, 4: NR 4 .. 32; G = 8: NR 1 .. 32; G = 16: NR 17 .. 32;
+// G = 32: the list below.
+static inline bool b2h_ssv_tile(int M, int *G, int *NR, bool small_ok = false) {
+  const int need = M + 1;
+  int bg = 0, bnr = 0;
+  if (need <= 16 * 32) { bg = 8;  bnr = (need + 15) / 16; }
+  else if (need <= 32 * 32) { bg = 16; bnr = (need + 31) / 32; }
+  else {
+    const int nr = (need + 63) / 64;
+    static const int allowed[] = {18, 20, 22, 24, 26, 28, 30, 32, 40, 48};
+    for (int a : allowed) if (a >= nr) { bg = 32; bnr = a; break; }
+    if (!bg) return false;
+  }
+  if (small_ok) {
+    double best = b2h_ssv_tile_cost(bg, bnr);
+    for (int g = 4; g >= 1; g >>= 1) {                     // (ties keep the wider group: fewer registers per lane)
+      const int nr = std::max(4, (need + 2 * g - 1) / (2 * g));
+      if (nr > 32) continue;
+      const double c = b2h_ssv_tile_cost(g, nr);
+      if (c < best - 1e-9) { best = c; bg = g; bnr = nr; }
+    }
+  }
+  *G = bg; *NR = bnr;
+  return true;
+}
+// bytes of one residue row of the lane-striped SSV table of a (G, NR) tile.  An LDS.128 wavefront serves a quarter-warp
+// (8 lanes): with fewer than 8 lanes per group the 8/G groups of a quarter-warp read different residue rows at the same
+// in-row offset, so every 16-byte chunk is stored 8/G times side by side -- slot (lane & 7) -- and the eight lanes always
+// fall into eight different bank quartets, whatever rows they read.  The row geometry of G < 8 is that of G = 8.
+static inline size_t b2h_ssv_row_bytes(int G, int NR) { return (size_t)(NR / 4) * (G < 8 ? 8 : G) * 16 + (size_t)(NR % 4) * 128; }
 
 
 // ---------------------------------------------------------------------------------------------

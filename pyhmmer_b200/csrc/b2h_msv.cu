@@ -3,7 +3,7 @@
 // Replaces p7_SSVFilter (impl_sse/ssvfilter.c:876-926) and p7_MSVFilter (impl_sse/msvfilter.c:74-208).
 // This is a new design, not a translation of the SSE code:
 //
-//  * one GROUP of G lanes (8, 16 or 32: b2h_ssv_tile picks the narrowest that holds the model) per
+//  * one GROUP of G lanes (1 .. 32: b2h_ssv_tile picks the tile with the fewest shared-memory wavefronts per cell) per
 //    (profile x sequence) comparison, so a warp runs 32/G comparisons side by side; persistent CTAs
 //    pull sequences (longest first) from a global work counter;
 //  * the profile's emission table is staged ONCE per CTA into shared memory with a TMA bulk copy
@@ -73,10 +73,10 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 template <int G, int NR>
 __device__ __forceinline__ void load_row(uint32_t addr, uint32_t addr_rem, uint32_t (&e)[NR])
 {
-  constexpr int FULLQ = NR / 4, REM = NR % 4;
+  constexpr int FULLQ = NR / 4, REM = NR % 4, GS = (G < 8) ? 8 : G;     // 16-byte slots per chunk (b2h_ssv_row_bytes)
 #pragma unroll
   for (int g = 0; g < FULLQ; g++) {
-    uint4 v = lds128(addr + g * (G * 16));
+    uint4 v = lds128(addr + g * (GS * 16));
     e[4*g+0] = v.x; e[4*g+1] = v.y; e[4*g+2] = v.z; e[4*g+3] = v.w;
   }
 #pragma unroll
@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
   __shared__ uint64_t s_bar;
   __shared__ int s_item;
   constexpr int FULLQ = NR / 4, REM = NR % 4, NG = 32 / G;
-  constexpr uint32_t ROWB = (uint32_t)FULLQ * G * 16 + (uint32_t)REM * 128;
+  constexpr int GS = (G < 8) ? 8 : G;                       // 16-byte slots per chunk: groups narrower than a quarter-warp read replicas
+  constexpr uint32_t ROWB = (uint32_t)FULLQ * GS * 16 + (uint32_t)REM * 128;
   constexpr uint32_t TAB_BYTES = (uint32_t)B2H_NCODE * ROWB;
   constexpr uint32_t PADW = 0x01010101u * B2H_PAD_CODE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -155,8 +156,8 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
   int cur_pc = -1;
 
   const int src_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1));   // rotate inside the group: its lane 0 reads the last cell of its last lane, which is always padding (= 0)
-  const uint32_t tab_lane = smem_u32(s_tab) + gl * 16;
-  const uint32_t tab_rem  = smem_u32(s_tab) + FULLQ * G * 16 + lane * 4;
+  const uint32_t tab_lane = smem_u32(s_tab) + (lane & (GS - 1)) * 16;
+  const uint32_t tab_rem  = smem_u32(s_tab) + FULLQ * GS * 16 + lane * 4;
   const int nitems = a.ncls * a.chunks;
   int budget = a.items_per_cta > 0 ? a.items_per_cta : 0x7fffffff;
 
@@ -338,14 +339,15 @@ __global__ void __launch_bounds__(128) rmsv_kernel(const WorkList wl, const SeqD
   __shared__ uint64_t s_bar;
   __shared__ int s_item;
   constexpr int FULLQ = NR / 4, REM = NR % 4, NG = 32 / G;
-  constexpr uint32_t ROWB = (uint32_t)FULLQ * G * 16 + (uint32_t)REM * 128;
+  constexpr int GS = (G < 8) ? 8 : G;                       // 16-byte slots per chunk: groups narrower than a quarter-warp read replicas
+  constexpr uint32_t ROWB = (uint32_t)FULLQ * GS * 16 + (uint32_t)REM * 128;
   constexpr uint32_t TAB_BYTES = (uint32_t)B2H_NCODE * ROWB;
   constexpr uint32_t PADW = 0x01010101u * B2H_PAD_CODE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int gl = lane & (G - 1), grp = lane / G;
   const int src_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1));
-  const uint32_t tab_lane = smem_u32(s_tab) + gl * 16;
-  const uint32_t tab_rem  = smem_u32(s_tab) + FULLQ * G * 16 + lane * 4;
+  const uint32_t tab_lane = smem_u32(s_tab) + (lane & (GS - 1)) * 16;
+  const uint32_t tab_rem  = smem_u32(s_tab) + FULLQ * GS * 16 + lane * 4;
 
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   uint32_t phase = 0;
@@ -487,7 +489,9 @@ template <int G, int NR>
 int launch_ssv_tile(b2h_ctx *ctx, const SsvArgs &a, cudaStream_t strm)
 {
   const size_t smem = (size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR);
-  const int threads = (a.threads > 0 && a.threads <= SSV_THREADS) ? a.threads : SSV_THREADS;
+  constexpr int NG = 32 / G;                                // comparisons per warp: an item of B2H_SSV_CHUNK sequences keeps at most CHUNK / NG warps busy
+  const int fit = 32 * std::max(1, std::min(SSV_THREADS / 32, (B2H_SSV_CHUNK + NG - 1) / NG));
+  const int threads = (a.threads > 0 && a.threads <= SSV_THREADS) ? a.threads : fit;
   int occ = 1;
   { const int st = b2h_kernel_occupancy(ctx, (const void *)ssv_kernel<G, NR>, threads, smem, &occ); if (st != B2H_OK) return st; }
   static const int occ_cap = getenv("B2H_SSV_OCC") ? atoi(getenv("B2H_SSV_OCC")) : 0;       // experiments: resident CTAs per SM
@@ -512,6 +516,9 @@ int b2h_launch_ssv(b2h_ctx *ctx, int G, int NR, const SsvArgs &a, cudaStream_t s
 #define CASE(g, n) case (g) * 64 + (n): return launch_ssv_tile<g, n>(ctx, a, strm);
 #define CASE8(g, n) CASE(g, n) CASE(g, n + 1) CASE(g, n + 2) CASE(g, n + 3) CASE(g, n + 4) CASE(g, n + 5) CASE(g, n + 6) CASE(g, n + 7)
     CASE8(8, 1) CASE8(8, 9) CASE8(8, 17) CASE8(8, 25)
+    CASE(4, 4) CASE(4, 5) CASE(4, 6) CASE(4, 7) CASE(4, 8) CASE8(4, 9) CASE8(4, 17) CASE8(4, 25)
+    CASE(2, 4) CASE(2, 5) CASE(2, 6) CASE(2, 7) CASE(2, 8) CASE8(2, 9) CASE8(2, 17) CASE8(2, 25)
+    CASE(1, 4) CASE(1, 5) CASE(1, 6) CASE(1, 7) CASE(1, 8) CASE8(1, 9) CASE8(1, 17) CASE8(1, 25)
     CASE8(16, 17) CASE8(16, 25)
     CASE(32, 18) CASE(32, 20) CASE(32, 22) CASE(32, 24) CASE(32, 26) CASE(32, 28) CASE(32, 30) CASE(32, 32) CASE(32, 40) CASE(32, 48)
 #undef CASE8
@@ -582,6 +589,9 @@ int b2h_launch_msv_tiled(b2h_ctx *ctx, const WorkList &wl_in, const SeqDev &sd, 
 #define CASE(g, n) case (g) * 64 + (n): st = launch_rmsv_tile<g, n>(ctx, wl, sd, mode, out_sc, out_status, A, F1, strm); break;
 #define CASE8(g, n) CASE(g, n) CASE(g, n + 1) CASE(g, n + 2) CASE(g, n + 3) CASE(g, n + 4) CASE(g, n + 5) CASE(g, n + 6) CASE(g, n + 7)
       CASE8(8, 1) CASE8(8, 9) CASE8(8, 17) CASE8(8, 25)
+      CASE(4, 4) CASE(4, 5) CASE(4, 6) CASE(4, 7) CASE(4, 8) CASE8(4, 9) CASE8(4, 17) CASE8(4, 25)
+      CASE(2, 4) CASE(2, 5) CASE(2, 6) CASE(2, 7) CASE(2, 8) CASE8(2, 9) CASE8(2, 17) CASE8(2, 25)
+      CASE(1, 4) CASE(1, 5) CASE(1, 6) CASE(1, 7) CASE(1, 8) CASE8(1, 9) CASE8(1, 17) CASE8(1, 25)
       CASE8(16, 17) CASE8(16, 25)
       CASE(32, 18) CASE(32, 20) CASE(32, 22) CASE(32, 24) CASE(32, 26) CASE(32, 28) CASE(32, 30) CASE(32, 32) CASE(32, 40) CASE(32, 48)
 #undef CASE8
