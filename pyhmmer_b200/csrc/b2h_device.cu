@@ -324,7 +324,7 @@ int b2h_profile_create_host(const b2h_oprofile_desc *d, b2h_profile **out)
 
 // Host half of an upload: the profile object and, when a context is given, the staged image of its device block
 // (sections 256-byte aligned; offsets in <offs>).  Pure CPU work, safe to run for many profiles in parallel.
-struct ProfStage { std::vector<uint8_t> bytes; uint8_t *ext = nullptr; size_t size = 0; size_t offs[10] = {0}; };   // image in <bytes>, or written straight to <ext>
+struct ProfStage { std::vector<uint8_t> bytes; uint8_t *ext = nullptr; size_t size = 0; size_t offs[11] = {0}; };   // image in <bytes>, or written straight to <ext>
 // Size of the staged device image of a profile (sections 256-byte aligned, in the order profile_build adds them).
 static void profile_classes(int M, int K, int *G, int *NR, int *regC, int *regW)
 {
@@ -338,7 +338,9 @@ static size_t profile_stage_bytes(int M, int G, int NR, int regC, int regW)
   const size_t Mp = (size_t)((M + 31) & ~31);
   size_t used = 0;
   auto add = [&](size_t bytes) { used = ((used + 255) & ~(size_t)255) + bytes; };
+  int Gw = 0, NRw = 0; b2h_ssv_tile(M, &Gw, &NRw, false);
   add((size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR)); add(B2H_NCODE * Mp);
+  if (Gw != G || NRw != NR) add((size_t)B2H_NCODE * b2h_ssv_row_bytes(Gw, NRw));     // the wide tile's table (last section)
   add(B2H_NCODE * Mp * 2); add(8 * Mp * 2); add(B2H_NCODE * Mp * 4); add(8 * Mp * 4); add((size_t)B2H_NCODE * 2 * 4);
   if (regC) { add((size_t)B2H_NCODE * 32 * regC * regW * 4); add((size_t)B2H_NCODE * 32 * regC * regW * 4); }
   if (regC && regW == 1) add((size_t)B2H_NCODE * 32 * ((regC + 1) / 2) * 4);       // packed Viterbi table
@@ -366,13 +368,13 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
   p->symbols = (d->K == 20) ? "ACDEFGHIKLMNPQRSTVWY-BJZOUX*~" : "ACGT-RYMKSWHBVDN*~";
 
   // --- SSV signed scores / MSV costs, lane-striped ---
-  const size_t nwords = (size_t)B2H_NCODE * (b2h_ssv_row_bytes(G, NR) / 4);
-  std::vector<uint32_t> ssv(nwords);
   auto cost_of = [&](int x, int k) -> int {          // k is 1-based; anything off the model is the -inf cost
     return (x < Kp && k <= M) ? (int)d->msv_cost[(size_t)x * M + (k-1)] : 255;
   };
   uint16_t half_of[512];                                 // fp16 bit patterns of the integers -256 .. 255 (exact)
   for (int v = -256; v < 256; v++) half_of[v + 256] = __half_as_ushort(__float2half_rn((float)v));
+  auto ssv_table = [&](int G, int NR, std::vector<uint32_t> &ssv) {
+  ssv.assign((size_t)B2H_NCODE * (b2h_ssv_row_bytes(G, NR) / 4), 0u);
   for (int x = 0; x < B2H_NCODE; x++)
     for (int gl = 0; gl < G; gl++)
       for (int j = 0; j < NR; j++) {
@@ -387,6 +389,12 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
         if (j < (NR / 4) * 4) for (int lane = gl; lane < (G < 8 ? 8 : G); lane += G) ssv[ssv_word_index(G, NR, x, j, lane)] = w;   // (G < 8: one copy per group of a quarter-warp)
         else for (int lane = gl; lane < 32; lane += G) ssv[ssv_word_index(G, NR, x, j, lane)] = w;     // leftover words: one copy per group of the warp
       }
+  };
+  std::vector<uint32_t> ssv, ssv_w;
+  ssv_table(G, NR, ssv);
+  p->Gw = G; p->NRw = NR;
+  b2h_ssv_tile(M, &p->Gw, &p->NRw, false);
+  if (p->Gw != G || p->NRw != NR) ssv_table(p->Gw, p->NRw, ssv_w);
 
   // --- Viterbi / Forward tables, padded ---
   const int Mp = p->Mpad;
@@ -480,6 +488,7 @@ static int profile_build(b2h_ctx *ctx, const b2h_oprofile_desc *d, b2h_profile *
     stg->offs[6] = add(eo.data(), eo.size() * 4);
     if (p->regC) { stg->offs[7] = add(vr32.data(), vr32.size() * 4); stg->offs[8] = add(frr.data(), frr.size() * 4); }
     if (p->v2C) stg->offs[9] = add(vr2.data(), vr2.size() * 4);
+    stg->offs[10] = ssv_w.empty() ? stg->offs[0] : add(ssv_w.data(), ssv_w.size() * 4);
     if (used > profile_stage_bytes(M, G, NR, p->regC, p->regW)) { delete p; return B2H_EINVAL; }   // (cannot happen: same arithmetic)
     stg->size = used;
     p->h2d_bytes = used;
@@ -503,6 +512,7 @@ static int profile_commit(b2h_ctx *ctx, b2h_profile *p, const ProfStage &stg)
   p->d_fwd_rsc = (float *)(b + stg.offs[4]); p->d_fwd_tsc = (float *)(b + stg.offs[5]); p->d_bias_eo = (float *)(b + stg.offs[6]);
   if (p->regC) { p->d_vit_rsc32 = (int32_t *)(b + stg.offs[7]); p->d_fwd_rscr = (float *)(b + stg.offs[8]); }
   if (p->v2C) p->d_vit_rsc2 = (uint32_t *)(b + stg.offs[9]);
+  p->d_ssv_emis_w = (uint32_t *)(b + stg.offs[10]);
   return B2H_OK;
 }
 
@@ -570,6 +580,7 @@ int b2h_profile_upload_many(b2h_ctx *ctx, const b2h_oprofile_desc *const *descs,
       p->d_fwd_rsc = (float *)(b + sg.offs[4]); p->d_fwd_tsc = (float *)(b + sg.offs[5]); p->d_bias_eo = (float *)(b + sg.offs[6]);
       if (p->regC) { p->d_vit_rsc32 = (int32_t *)(b + sg.offs[7]); p->d_fwd_rscr = (float *)(b + sg.offs[8]); }
       if (p->v2C) p->d_vit_rsc2 = (uint32_t *)(b + sg.offs[9]);
+      p->d_ssv_emis_w = (uint32_t *)(b + sg.offs[10]);
     }
   } else {
     for (size_t i = 0; i < n; i++) { b2h_profile_destroy(out[i]); out[i] = nullptr; }

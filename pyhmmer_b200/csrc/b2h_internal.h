@@ -136,6 +136,9 @@ struct b2h_profile {
   int M = 0, K = 0, Kp = 0, max_length = 0, multihit = 1;
   // MSV
   int NR = 0, G = 0;              // SSV register tile: G lanes per comparison, NR packed cell registers (2*NR nodes) per lane
+  int NRw = 0, Gw = 0;            // the 8 / 16 / 32-lane tile of the same model: fewest registers per lane = shortest row.  The scan
+                                  // orientation (one long query: a comparison is a latency chain, not a throughput problem) uses it.
+  uint32_t *d_ssv_emis_w = nullptr;   // its table (== d_ssv_emis when the two tiles coincide)
   uint8_t tbm_b = 0, tec_b = 0, base_b = 0, bias_b = 0;
   float scale_b = 0;
   uint32_t *d_ssv_emis = nullptr; // [32 residues][b2h_ssv_row_bytes(G, NR)] packed fp16x2 signed scores (SSV), lane-striped
@@ -287,6 +290,7 @@ struct ProfDev {
   const int32_t *vit_rsc32; const float *fwd_rscr;
   const uint32_t *vit_rsc2; int v2C, v2_ok, tbm_min;     // packed ViterbiFilter: table, nodes per lane (even), usable, min tBM
   int M, Mpad, NR, G;
+  const uint32_t *ssv_emis_w; int NRw, Gw;               // the wide tile and its table (scan orientation)
   int tbm, tec, base, bias; float scale_b;
   int xw_E_move, xw_E_loop, base_w, ddbound_w; float scale_w;
   float xf_E_move, xf_E_loop;
@@ -297,6 +301,7 @@ static inline ProfDev b2h_profdev(const b2h_profile *p) {
   ProfDev d; d.ssv_emis = p->d_ssv_emis; d.msv_cost8 = p->d_msv_cost8; d.vit_rsc = p->d_vit_rsc; d.vit_tsc = p->d_vit_tsc;
   d.fwd_rsc = p->d_fwd_rsc; d.fwd_tsc = p->d_fwd_tsc; d.bias_eo = p->d_bias_eo; d.vit_rsc32 = p->d_vit_rsc32; d.fwd_rscr = p->d_fwd_rscr;
   d.vit_rsc2 = p->d_vit_rsc2; d.v2C = p->v2C; d.v2_ok = p->v2_ok; d.tbm_min = p->tbm_min;
+  d.ssv_emis_w = p->d_ssv_emis_w; d.NRw = p->NRw; d.Gw = p->Gw;
   d.M = p->M; d.Mpad = p->Mpad; d.NR = p->NR; d.G = p->G; d.tbm = p->tbm_b; d.tec = p->tec_b; d.base = p->base_b; d.bias = p->bias_b; d.scale_b = p->scale_b;
   d.xw_E_move = p->xw[0][0]; d.xw_E_loop = p->xw[0][1]; d.base_w = p->base_w; d.ddbound_w = p->ddbound_w; d.scale_w = p->scale_w;
   d.xf_E_move = p->xf[0][0]; d.xf_E_loop = p->xf[0][1];
@@ -396,6 +401,7 @@ struct SsvArgs {
                                // 3: scan orientation: <sd> is a chunk view, the chunk maxima are folded into raw[profile][parent]
   const int32_t *parent = nullptr; int *raw = nullptr; int raw_stride = 0;   // mode 3
   int            threads = 0;  // CTA size (0 = the full 256): a chunk view of one long query holds a handful of chunks per profile
+  int            wide = 0;     // 1: (G, NR) is the profiles' WIDE tile, read ProfDev::ssv_emis_w (scan orientation)
   float         *out_sc; int32_t *out_status;
   SurvList       A, R;
   double         F1;

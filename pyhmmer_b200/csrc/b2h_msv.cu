@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(SSV_THREADS) ssv_kernel(const SsvArgs a)
     const ProfDev &P = a.profs[pidx];
     if (pc != cur_pc) {
       cur_pc = pc;
-      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_tab, P.ssv_emis, TAB_BYTES, &s_bar); }
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_tab, a.wide ? P.ssv_emis_w : P.ssv_emis, TAB_BYTES, &s_bar); }
       mbar_wait(&s_bar, phase); phase ^= 1;
     }
     const int e_end = min(a.sd.n, (chunk + 1) * B2H_SSV_CHUNK);
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(128) rmsv_kernel(const WorkList wl, const SeqD
     const ProfDev &P = wl.profs[it.p];
     if (it.p != cur_p) {
       cur_p = it.p;
-      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_tab, P.ssv_emis, TAB_BYTES, &s_bar); }
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, TAB_BYTES); tma_load_1d(s_tab, (mode & 8) ? P.ssv_emis_w : P.ssv_emis, TAB_BYTES, &s_bar); }
       mbar_wait(&s_bar, phase); phase ^= 1;
     }
     const float bias = (float)P.bias, base = (float)P.base, tec = (float)P.tec;
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(128) rmsv_kernel(const WorkList wl, const SeqD
         float sc; int status = B2H_OK;
         if (overflow) { sc = INFINITY; status = B2H_ERANGE; }
         else { sc = ((xJ - (float)tjb) - base); sc /= P.scale_b; sc -= 3.0f; }
-        if (mode == 1) { out_sc[s] = sc; out_status[s] = status; }
+        if ((mode & 7) == 1) { out_sc[s] = sc; out_status[s] = status; }
         else if (msv_passes(sc, sd.null1[s], P, F1)) surv_append(A, it.p, s, sc, 0.f);
       }
     }
@@ -572,7 +572,8 @@ int launch_rmsv_tile(b2h_ctx *ctx, const WorkList &wl, const SeqDev &sd, int mod
 } // namespace
 
 // Full MSV over a grouped work list whose profiles are sorted by model length: one launch per SSV register tile
-// (tiles[p] = G*64 + NR of profile p of the list), the launches side by side on the side streams.
+// (tiles[p] = G*64 + NR of profile p of the list), the launches side by side on the side streams.  mode | 8: the tiles are
+// the profiles' WIDE tiles (ProfDev::ssv_emis_w; scan orientation).
 int b2h_launch_msv_tiled(b2h_ctx *ctx, const WorkList &wl_in, const SeqDev &sd, const std::vector<int> &tiles, int mode,
                          float *out_sc, int32_t *out_status, SurvList A, double F1)
 {

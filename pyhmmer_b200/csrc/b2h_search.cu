@@ -223,10 +223,16 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
   std::iota(perm.begin(), perm.end(), 0);
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return profiles[p0 + a]->M < profiles[p0 + b]->M; });   // (Mpad and the SSV tile are monotone in M)
   int max_Mpad = 0;
+  // Scan orientation (few, possibly long sequences: hmmscan): every comparison is a latency chain, so the SSV / MSV kernels
+  // take the profiles' wide tiles (fewest registers per lane = shortest row); the search orientation takes the tiles with
+  // the fewest shared-memory wavefronts per cell.
+  static const int scan_max = getenv("B2H_SCAN_MAXSEQ") ? atoi(getenv("B2H_SCAN_MAXSEQ")) : 2048;
+  const bool scan_mode = (int)db->n <= scan_max;
+  auto tile_of = [&](const ProfDev &pd) { return scan_mode ? pd.Gw * 64 + pd.NRw : pd.G * 64 + pd.NR; };
   for (int i = 0; i < P; i++) {
     hprof[i] = b2h_profdev(profiles[p0 + perm[i]]);
     mpads[i] = hprof[i].Mpad;
-    classes[hprof[i].G * 64 + hprof[i].NR].push_back(i);
+    classes[tile_of(hprof[i])].push_back(i);
     max_Mpad = std::max(max_Mpad, hprof[i].Mpad);
   }
   ProfDev *d_prof; TRY(pool.get(&d_prof, P));
@@ -261,8 +267,6 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
   // CTA busy and walk the whole sequence serially.  SSV is exactly decomposable along the sequence -- an ungapped diagonal
   // spans at most M rows -- so every sequence is taken as overlapping chunks (b2h_chunkview), the kernel folds the chunk
   // maxima into raw[profile][sequence] and a finish kernel applies p7_SSVFilter's post-processing and the F1 test.
-  static const int scan_max = getenv("B2H_SCAN_MAXSEQ") ? atoi(getenv("B2H_SCAN_MAXSEQ")) : 2048;
-  const bool scan_mode = N <= scan_max;
   if (scan_mode) {
     StageTimer tm(ctx, 0);
     int *raw; TRY(pool.get(&raw, cap));
@@ -287,7 +291,7 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
         a.chunks = (v.n + B2H_SSV_CHUNK - 1) / B2H_SSV_CHUNK; a.counter = ctx->d_counters + 32 + (ssv_cls++ % 24); a.mode = 3;
         a.items_per_cta = 2;
         a.out_sc = nullptr; a.out_status = nullptr; a.A = A; a.R = R; a.F1 = prm->F1;
-        a.parent = v.d_parent; a.raw = raw; a.raw_stride = N;
+        a.parent = v.d_parent; a.raw = raw; a.raw_stride = N; a.wide = 1;
         a.threads = 32 * std::max(1, std::min(8, (std::min(v.n, B2H_SSV_CHUNK) + NG - 1) / NG));
         TRY(b2h_launch_ssv(ctx, Gc, NRc, a, fj.next()));
       }
@@ -329,8 +333,8 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
     StageTimer tm(ctx, 1);
     static const bool smem_msv = getenv("B2H_MSV_SMEM") != nullptr;      // debugging aid: the shared-memory MSV kernel
     if (smem_msv) TRY(b2h_launch_msv(ctx, wl, sd, max_Mpad, 0, 2, nullptr, nullptr, A, prm->F1));
-    else { std::vector<int> tiles(P); for (int i = 0; i < P; i++) tiles[i] = hprof[i].G * 64 + hprof[i].NR;
-           TRY(b2h_launch_msv_tiled(ctx, wl, sd, tiles, 2, nullptr, nullptr, A, prm->F1)); }
+    else { std::vector<int> tiles(P); for (int i = 0; i < P; i++) tiles[i] = tile_of(hprof[i]);
+           TRY(b2h_launch_msv_tiled(ctx, wl, sd, tiles, scan_mode ? (2 | 8) : 2, nullptr, nullptr, A, prm->F1)); }
   }
   // 3 + 4. bias filter and ViterbiFilter on the MSV survivors.  The bias filter is a serial chain of divides per
   // residue, one thread per comparison: latency bound, a few hundred microseconds whatever the list size.  Instead of
