@@ -16,7 +16,9 @@ A "step" is one complete hmmsearch of the 100 queries against the database: the 
 `value` is measured with the database and the profiles already resident in HBM (and includes building the thresholded
 `TopHits` of every query); `e2e` repeats the step
 through the public Python API with host buffers (packing, H2D upload of sequences and profile tables, D2H
-of the results all inside the timed region).
+of the results all inside the timed region).  Both consume the search the way `Pipeline.search_hmm` / `hmmer.hmmsearch` do:
+wave by wave (b2h_search_begin / _next / _end) -- the hit records of a finished wave are exchanged between the ranks (N > 1)
+and turned into `TopHits` while the GPU searches the following waves; the step ends when the last `TopHits` exists.
 """
 import argparse
 import json
