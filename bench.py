@@ -259,19 +259,15 @@ def main():
         w = parallel.World.current()
         res = [None] * len(oms)
         nlocal, gen = pli._run_waves(oms, seqs)               # (what Pipeline._search_many / parallel.search_sharded do)
-        empty = ([], [], [], b"", np.zeros((len(oms), 4), np.int64))
         first, nrec = True, 0
-        for _ in range(parallel.agree_max(nlocal, w)):
-            profs, hits, doms, text, counters = next(gen, empty)
-            if world > 1:
-                parallel.all_gather_bytes(parallel.pack_records(hits, doms, text, counters, 0, profiles=profs), w)
+        # parallel.gathered_waves: one all-gather of the packed hit records per wave (N > 1), the number of rounds agreed on the way
+        rounds = parallel.gathered_waves(nlocal, gen, w, 0, len(oms)) if world > 1 else ((wave, None) for wave in gen)
+        for (profs, hits, doms, text, counters), _gathered in rounds:
             # (weak scaling: every rank holds its own shard only, so it assembles its own records)
             for qi, th in zip(profs, pli._assemble(oms, oms, seqs, hits, doms, text, counters, only=profs, count_targets=first)):
                 res[qi] = th
             first = False
             nrec += len(hits)
-        for _ in gen:
-            pass
         wave_split.append(pli._last_run_s)
         return res, nrec
 

@@ -169,7 +169,7 @@ static int seqdb_build(b2h_ctx *ctx, size_t n, const int64_t *len,
         for (int64_t i = L; i < end; i++) dst[i] = (uint8_t)B2H_PAD_CODE;
       }
     };
-    const int T = (total > ((size_t)4 << 20)) ? (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    const int T = (total > ((size_t)4 << 20)) ? b2h_rank_threads(8) : 1;
     if (T <= 1) fill(0, n);
     else {
       std::vector<std::thread> th;
@@ -537,7 +537,7 @@ int b2h_profile_upload_many(b2h_ctx *ctx, const b2h_oprofile_desc *const *descs,
   if (n == 0) return B2H_OK;
   std::vector<ProfStage> stg(n);
   std::vector<int> status(n, B2H_OK);
-  const int T = (int)std::min<size_t>(std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())), n);
+  const int T = (int)std::min<size_t>((size_t)b2h_rank_threads(16), n);
   auto run_parallel = [&](const std::function<void(size_t)> &fn) {
     auto work = [&](int t) { for (size_t i = t; i < n; i += T) fn(i); };
     if (T <= 1) work(0);

@@ -8,6 +8,7 @@
 #include <utility>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 #include "b2h.h"
 
@@ -227,6 +228,15 @@ struct ForkJoin {
 // every lane owns 2*NR consecutive nodes.  Needs 2*G*NR >= M+1 so that the last cell of the group's last lane is always
 // padding (see b2h_msv.cu).  The narrowest group that fits is taken: it wastes the fewest padded cells (granularity
 // 2*G nodes) and spreads the per-row shuffle over the most cells.
+// Host threads a helper loop of this process may use: <want>, but no more than this rank's fair share of the node's hardware
+// threads in a one-process-per-GPU job (torchrun exports LOCAL_WORLD_SIZE) -- eight ranks that each spawn sixteen packing
+// threads on a 32-thread host only slow each other down.
+static inline int b2h_rank_threads(int want) {
+  int hw = (int)std::thread::hardware_concurrency(), ranks = 1;
+  if (const char *ev = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(ev));
+  return std::max(1, std::min(want, std::max(1, hw / ranks)));
+}
+
 // Shared-memory wavefronts one DP row of one COMPARISON costs with a (G, NR) tile: a warp holds 32/G comparisons and moves
 // 4 wavefronts per LDS.128, 1 per leftover LDS.32, 1 for the diagonal shuffle (none when a single lane owns the model) and
 // 1/4 for the residue-word shuffle.

@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 from .easel import DigitalSequenceBlock
 
-__all__ = ["World", "shard_block", "search_sharded", "exchanged_waves", "all_gather_bytes", "pack_records", "unpack_records"]
+__all__ = ["World", "shard_block", "search_sharded", "exchanged_waves", "gathered_waves", "all_gather_bytes", "pack_records", "unpack_records"]
 
 
 class World:
@@ -117,6 +117,7 @@ class _Exchange:
         self.key, self.cap = None, 0
         self.h_in = self.h_out = self.d_in = self.d_out = self.h_sz = self.d_sz = self.d_szs = self.h_szs = None
         self.stream = None
+        self.slot = 1 << 16                                  # slot size every rank uses: grows only from what ALL ranks saw
 
     def side_stream(self, torch, dev):
         """The exchange has a (high-priority) stream of its own: the engine's lanes hold the queued cascades of the waves
@@ -131,6 +132,7 @@ class _Exchange:
         key = (str(dev), world.size)
         if key != self.key or need > self.cap:
             cap = max(1 << 16, 1 << (int(need) - 1).bit_length())
+            self.slot = max(self.slot, 1 << 16) if key == self.key else 1 << 16       # (a new process group starts over)
             pin = dev.type == "cuda"
             self.h_in = torch.empty(cap, dtype=torch.uint8, pin_memory=pin)
             self.h_out = torch.empty(world.size * cap, dtype=torch.uint8, pin_memory=pin)
@@ -147,10 +149,12 @@ _EXCHANGE = _Exchange()
 
 
 def all_gather_bytes(data, world):
-    """The one exchange of the path: a variable-length all-gather of byte strings (NCCL over NVLink, or gloo on CPU).
+    """The exchange of the path: a variable-length all-gather of byte strings (NCCL over NVLink, or gloo on CPU).
 
-    Two collectives: the 8-byte payload sizes first, then the payloads in slots of exactly the largest size (rounded up to
-    256 bytes), through persistent page-locked / device buffers; one device->host copy of the gathered slots."""
+    ONE collective in the common case: every rank contributes a slot of the agreed size -- 8 bytes of payload length, then
+    the payload -- through persistent page-locked / device buffers, and one device->host copy brings the gathered slots
+    back.  When some payload does not fit, every rank sees that in the gathered lengths, the agreed slot size doubles up to
+    the largest payload, and the gather is repeated once (the size then stays for the rest of the process)."""
     if world.size == 1:
         return [data]
     import torch
@@ -166,38 +170,31 @@ def _all_gather_bytes(data, world, torch, dev, side):
     dist = world.dist
     n = len(data)
     ex = _EXCHANGE
-    ex.ensure(torch, dev, world, max(n, 1))
-    # 1. sizes
-    ex.h_sz[0] = n
-    ex.d_sz.copy_(ex.h_sz, non_blocking=True)
-    try:
-        dist.all_gather_into_tensor(ex.d_szs, ex.d_sz)
-    except (RuntimeError, AttributeError, NotImplementedError):       # a backend without the flat form: list form
-        outs = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world.size)]
-        dist.all_gather(outs, ex.d_sz)
-        ex.d_szs.copy_(torch.cat(outs))
-    ex.h_szs.copy_(ex.d_szs, non_blocking=True)
-    if side is not None:
-        side.synchronize()
-    sizes = [int(v) for v in ex.h_szs.tolist()]
-    slot = (max(max(sizes), 1) + 255) & ~255
-    ex.ensure(torch, dev, world, slot)                                 # (every rank sees the same sizes: they all grow together)
-    # 2. payloads, in slots of <slot> bytes
-    if n:
-        ex.h_in.numpy()[:n] = np.frombuffer(data, dtype=np.uint8)
-    d_in, d_out, h_out = ex.d_in[:slot], ex.d_out[:world.size * slot], ex.h_out[:world.size * slot]
-    d_in.copy_(ex.h_in[:slot], non_blocking=True)
-    try:
-        dist.all_gather_into_tensor(d_out, d_in)
-    except (RuntimeError, AttributeError, NotImplementedError):
-        outs = [torch.empty(slot, dtype=torch.uint8, device=dev) for _ in range(world.size)]
-        dist.all_gather(outs, d_in)
-        d_out.copy_(torch.cat(outs))
-    h_out.copy_(d_out, non_blocking=True)
-    if side is not None:
-        side.synchronize()
-    host = h_out.numpy().reshape(world.size, slot)
-    return [host[r, :sizes[r]].tobytes() for r in range(world.size)]
+    while True:
+        slot = ex.slot
+        ex.ensure(torch, dev, world, slot)
+        h = ex.h_in.numpy()
+        h[:8] = np.frombuffer(np.int64(n).tobytes(), dtype=np.uint8)
+        fits = n + 8 <= slot
+        if n and fits:
+            h[8:8 + n] = np.frombuffer(data, dtype=np.uint8)
+        used = ((8 + (n if fits else 0)) + 255) & ~255       # bytes of the slot that carry anything: all that goes up
+        d_in, d_out, h_out = ex.d_in[:slot], ex.d_out[:world.size * slot], ex.h_out[:world.size * slot]
+        d_in[:used].copy_(ex.h_in[:used], non_blocking=True)
+        try:
+            dist.all_gather_into_tensor(d_out, d_in)
+        except (RuntimeError, AttributeError, NotImplementedError):       # a backend without the flat form: list form
+            outs = [torch.empty(slot, dtype=torch.uint8, device=dev) for _ in range(world.size)]
+            dist.all_gather(outs, d_in)
+            d_out.copy_(torch.cat(outs))
+        h_out.copy_(d_out, non_blocking=True)
+        if side is not None:
+            side.synchronize()
+        host = h_out.numpy().reshape(world.size, slot)
+        sizes = [int(np.frombuffer(host[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(world.size)]
+        if max(sizes) + 8 <= slot:
+            return [host[r, 8:8 + sizes[r]].tobytes() for r in range(world.size)]
+        ex.slot = max(1 << 16, 1 << (max(sizes) + 8 - 1).bit_length())     # the same on every rank: they all saw the same lengths
 
 
 def merge_rank_records(parts):
@@ -236,6 +233,25 @@ def agree_max(value, world):
     return int(out.item())
 
 
+def gathered_waves(nlocal, gen, world, lo, P):
+    """The rounds of a wave-by-wave exchange: for every round yields ``(local wave tuple, [every rank's packed records])``.
+    The first payload carries this rank's number of waves, so the ranks know the number of rounds (the largest of them)
+    after the first gather -- no collective of its own; a rank that has run out of waves contributes empty payloads."""
+    empty = ([], [], [], b"", np.zeros((P, 4), np.int64))
+    rounds, r = nlocal, 0
+    while r < rounds:
+        local = next(gen, empty)
+        profs, hits, doms, text, counters = local
+        mine = np.int64(nlocal).tobytes() + pack_records(hits, doms, text, counters, lo, profiles=profs)
+        got = all_gather_bytes(mine, world)
+        if r == 0:
+            rounds = max(int(np.frombuffer(b[:8], dtype=np.int64)[0]) for b in got)
+        yield local, [b[8:] for b in got]
+        r += 1
+    for _ in gen:                                              # (drains the engine's job: nothing is left by construction)
+        pass
+
+
 def exchanged_waves(pipeline, oms, sub, lo, world):
     """This rank's search of its shard ``sub`` (first target = global index ``lo``), wave by wave, with one all-gather of hit
     records per wave: a generator of ``(complete, hits, doms, text, counters)`` -- the records of EVERY rank for the profiles
@@ -250,14 +266,11 @@ def exchanged_waves(pipeline, oms, sub, lo, world):
         nlocal, gen = 1, iter([(list(range(P)),) + tuple(pipeline._run(oms, sub))])
     else:
         nlocal, gen = 1, iter([(list(range(P)), [], [], b"", np.zeros((P, 4), np.int64))])
-    rounds = agree_max(nlocal, world)
     done = np.zeros(P, np.int32)
     total = np.zeros((P, 4), np.int64)
     carry = None
-    for _ in range(rounds):
-        profs, hits, doms, text, counters = next(gen, ([], [], [], b"", np.zeros((P, 4), np.int64)))
-        mine = pack_records(hits, doms, text, counters, lo, profiles=profs)
-        parts = [unpack_records(b, with_profiles=True) for b in all_gather_bytes(mine, world)]
+    for local, gathered in gathered_waves(nlocal, gen, world, lo, P):
+        parts = [unpack_records(b, with_profiles=True) for b in gathered]
         for part in parts:
             done[part[4]] += 1
         hits, doms, text, counters = merge_rank_records(([carry] if carry else []) + [p[:4] for p in parts])
@@ -268,8 +281,6 @@ def exchanged_waves(pipeline, oms, sub, lo, world):
         rest = [h for h in hits if not ready[h.profile]] if len(complete) < P else []
         carry = (rest, doms, text, np.zeros(P * 4, np.int64)) if rest else None
         yield complete, ([h for h in hits if ready[h.profile]] if rest else hits), doms, text, total
-    for _ in gen:                                              # (drains the engine's job: nothing is left by construction)
-        pass
 
 
 def search_sharded(pipeline, queries, block, local, world):
