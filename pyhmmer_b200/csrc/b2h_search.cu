@@ -966,7 +966,10 @@ int b2h_search_begin(b2h_ctx *ctx, const b2h_profile *const *profiles, size_t P,
   if (nwaves) *nwaves = job->plan.bounds.size() - 1;
   job->th = std::thread([job]() {
     cudaSetDevice(job->ctx->device);
-    const int st = search_impl(job->ctx, job->profiles.data(), job->profiles.size(), job->db, &job->prm, job->plan, *job, nullptr);
+    int st;
+    try { st = search_impl(job->ctx, job->profiles.data(), job->profiles.size(), job->db, &job->prm, job->plan, *job, nullptr); }
+    catch (const std::bad_alloc &) { job->ctx->err = "out of host memory"; st = B2H_EMEM; }      // (nothing may leave a thread of the library)
+    catch (const std::exception &e) { job->ctx->err = e.what(); st = B2H_EINVAL; }
     { std::lock_guard<std::mutex> lk(job->mu); job->status = st; job->finished = true; }
     job->cv.notify_all();
   });
