@@ -312,8 +312,11 @@ static int cascade_enqueue(b2h_ctx *ctx, const b2h_profile *const *profiles, int
   } }
   // The tail of the cascade can move to the high-priority POST lane so that the SSV launches of the next wave (queued on
   // the main lane right behind) run next to it.  B2H_OVERLAP = 1: everything after SSV, 2: Viterbi + Forward, 3: Forward
-  // only, 0: nothing.  Measured on B200 (ms/step): 0 -> 44.9, 1 -> 48.0, 2 -> 46.4, 3 -> 43.4: the ALU-bound stages lose
-  // more from sharing the SMs with SSV than the overlap wins; the latency-bound Forward pass hides for free.
+  // only, 0: nothing.  Measured on B200 (ms/step), round 1: 0 -> 44.9, 1 -> 48.0, 2 -> 46.4, 3 -> 43.4: the ALU-bound stages
+  // lose more from sharing the SMs with SSV than the overlap wins; the latency-bound Forward pass hides for free.  Round 2,
+  // with the leaner packed Viterbi row (ALU pipe 61-74 % instead of 90 %): 100 x 50 000: 3 -> 38.8, 2 -> 37.9 (the stages still
+  // trade time, SSV 24.5 -> 31 ms, but the sum comes out a millisecond ahead); 20 000 x 100 000: 3 -> 10.4 s, 2 -> 12.6 s.
+  // 3 stays the default: it never loses.
   static const int overlap = getenv("B2H_OVERLAP") ? atoi(getenv("B2H_OVERLAP")) : 3;
   std::unique_ptr<b2h_lane_switch> post;
   auto to_post_lane = [&]() -> int {
