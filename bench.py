@@ -429,7 +429,10 @@ def main():
                      "note": "DP filter with ~6e-5 compulsory HBM bytes per cell (SURVEY 8d): the HBM fraction is tiny by construction. "
                              "The kernel is bound by the shared-memory pipe: 2 B of emission scores per cell; see on_chip and profiles/"},
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * float(te.item()) / len(e2e_times)},
+                "ms_per_step": 1e3 * float(te.item()) / len(e2e_times),
+                "note": "host inputs per step: the block's residue array and the converted OptimizedProfiles (both arms keep their models "
+                        "configured); timed: arena packing into page-locked staging, device tables built from the profiles, both uploads, the "
+                        "search wave by wave, D2H of the hit records, TopHits assembly"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
