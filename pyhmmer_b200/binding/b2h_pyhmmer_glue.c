@@ -221,3 +221,36 @@ int b2h_glue_scan_loop(b2h_ctx *ctx, const b2h_profile *const *profs, P7_PIPELIN
   ENGINE_LOCK(); b2h_seqdb_destroy(db); ENGINE_UNLOCK();
   return status;
 }
+
+
+/* LongTargetsPipeline.search_hmm (plan7.pyx:7258-7412) behind its window loop: the engine's long-target search has produced
+ * one record per hit -- a single domain in target coordinates (start > end on the reverse strand), its lnP already carrying
+ * the search-space term of p7_tophits_ComputeNhmmerEvalues (p7_tophits.c:796), duplicates of overlapping windows already
+ * marked as p7_tophits_RemoveDuplicates (:823) marks them, hits ordered by target and alignment position -- and this
+ * function turns them into the P7_HITs p7_pli_postDomainDef / postViterbi_LongTarget would have appended
+ * (p7_pipeline.c:1195-1262), with the accounting of the window loop.  The caller sorts by key and thresholds, as the
+ * reference does. */
+int b2h_glue_longtarget_fill(P7_PIPELINE *pli, P7_TOPHITS *th, const void *hits_v, size_t nh, const void *doms_v, const char *text,
+                             const unsigned char *dup, ESL_SQ *const *sq, P7_OPROFILE *om, P7_BG *bg,
+                             int64_t nseqs, int64_t nres, const int64_t *pos_past)
+{
+  const b2h_hit *hits = (const b2h_hit *)hits_v; const b2h_domain *doms = (const b2h_domain *)doms_v;
+  size_t i; int status;
+  if ((status = p7_pli_NewModel(pli, om, bg)) != eslOK) return status;          /* thresholds of this model, nmodels, nnodes */
+  pli->nseqs += (uint64_t)nseqs; pli->nres += (uint64_t)nres;
+  pli->pos_past_msv += pos_past[0]; pli->pos_past_bias += pos_past[1]; pli->pos_past_vit += pos_past[2]; pli->pos_past_fwd += pos_past[3];
+  for (i = 0; i < nh; i++) {
+    const b2h_hit *h = &hits[i];
+    P7_HIT *hit;
+    const size_t before = th->N;
+    if ((status = fill_hit(pli, th, h, doms, text, sq[h->seq], om)) != eslOK) return status;
+    if (th->N != before + 1) return eslEINCONCEIVABLE;
+    hit = &th->unsrt[th->N - 1];
+    hit->sortkey = -h->lnP;                                                      /* p7_tophits_ComputeNhmmerEvalues: always by E-value */
+    hit->window_length = om->max_length;
+    hit->seqidx = h->seq;
+    hit->subseq_start = 1;
+    if (dup && dup[i]) { hit->flags |= p7_IS_DUPLICATE; hit->flags &= ~(p7_IS_REPORTED | p7_IS_INCLUDED); }
+  }
+  return eslOK;
+}

@@ -22,7 +22,7 @@ from libhmmer.p7_tophits cimport P7_TOPHITS
 from libhmmer.impl_sse.p7_oprofile cimport P7_OPROFILE, P7_OM_BLOCK
 
 from pyhmmer.easel cimport Alphabet, DigitalSequence, DigitalSequenceBlock
-from pyhmmer.plan7 cimport Pipeline, TopHits, HMM, Profile, OptimizedProfile, OptimizedProfileBlock, Background
+from pyhmmer.plan7 cimport Pipeline, LongTargetsPipeline, TopHits, HMM, Profile, OptimizedProfile, OptimizedProfileBlock, Background
 
 from pyhmmer.errors import AlphabetMismatch, UnexpectedError, MissingCutoffs
 
@@ -45,6 +45,9 @@ cdef extern from "b2h_pyhmmer_glue.h" nogil:
                              ESL_SQ *const *sq, size_t n_targets, P7_TOPHITS *th, unsigned seed, int host_threads)
     int b2h_glue_scan_loop(b2h_ctx *ctx, const b2h_profile *const *profs, P7_PIPELINE *pli, const ESL_SQ *sq, P7_BG *bg,
                            P7_OPROFILE *const *om, size_t n_targets, P7_TOPHITS *th, unsigned seed, int host_threads)
+    int b2h_glue_longtarget_fill(P7_PIPELINE *pli, P7_TOPHITS *th, const void *hits, size_t nh, const void *doms, const char *text,
+                                 const unsigned char *dup, ESL_SQ *const *sq, P7_OPROFILE *om, P7_BG *bg,
+                                 int64_t nseqs, int64_t nres, const int64_t *pos_past)
     void b2h_glue_seqdb_destroy(b2h_seqdb *db)
     void b2h_glue_profile_destroy(b2h_profile *p)
 
@@ -86,7 +89,14 @@ cdef class _Engine:
 
     @property
     def launch_count(self):
-        return int(b2h_ctx_launch_count(self.ctx))
+        """Kernels launched for this process's searches: the engine's own context plus the host layer's, through which the
+        long-target searches run (CudaLongTargetsPipeline)."""
+        import sys
+        n = int(b2h_ctx_launch_count(self.ctx))
+        m = sys.modules.get("pyhmmer_b200._lib")
+        if m is not None:
+            n += sum(c.launch_count for c in list(m._contexts.values()) if c.handle)
+        return n
 
 
 cdef class _SeqDB:
@@ -318,15 +328,136 @@ class CudaPipeline(_CudaPipelineBase):
     __slots__ = ()
 
 
+# The long-target (nhmmer) pipeline.  Its window loop -- `LongTargetsPipeline._search_loop_longtargets` (plan7.pyx:7541-7663):
+# p7_Pipeline_LongTarget window by window, both strands -- is replaced by the engine's long-target search (stage by stage over
+# ALL windows: pyhmmer_b200/longtarget.py over the C ABI); the records it returns become real P7_HITs (b2h_glue_longtarget_fill)
+# and the reference's own tail -- sort by key, p7_tophits_Threshold, output tallies -- finishes the job.
+_MIRROR_BLOCKS = {}                 # id(pyhmmer block) -> (pyhmmer block, mirror block): the device copy stays with the mirror block
+
+
+def _mirror_block(m_easel, m_abc, DigitalSequenceBlock sequences):
+    hit = _MIRROR_BLOCKS.get(id(sequences))
+    if hit is not None and hit[0] is sequences and len(hit[1]) == len(sequences) and \
+            all(len(a) == len(b) for a, b in zip(hit[1], sequences)):
+        return hit[1]
+    import numpy as np
+    block = m_easel.DigitalSequenceBlock(m_abc, [
+        m_easel.DigitalSequence(m_abc, name=q.name, description=q.description or "", accession=q.accession or "",
+                                sequence=np.frombuffer(q.sequence, dtype=np.uint8).copy()) for q in sequences])
+    while len(_MIRROR_BLOCKS) >= 2:
+        _MIRROR_BLOCKS.pop(next(iter(_MIRROR_BLOCKS)))
+    _MIRROR_BLOCKS[id(sequences)] = (sequences, block)
+    return block
+
+
+class CudaLongTargetsPipeline(LongTargetsPipeline):
+    """`pyhmmer.plan7.LongTargetsPipeline` whose search runs on the GPU.  Same constructor (+ ``host_threads``), same results:
+    `search_hmm` with an `HMM` query and a `DigitalSequenceBlock`; `search_seq` / `search_msa` build their model with pyhmmer's
+    `Builder` and arrive here.  Other argument types go to the reference's own loop."""
+
+    def __init__(self, alphabet, background=None, *, host_threads=0, **kwargs):
+        super().__init__(alphabet, background, **kwargs)
+        self._b2h_host_threads = int(host_threads)
+        engine(0)                                            # fails loudly without a device
+
+    def search_hmm(self, query, sequences):
+        import ctypes, io
+        import numpy as np
+        from pyhmmer_b200 import easel as m_easel, plan7 as m_plan7, _lib as m_lib
+        cdef LongTargetsPipeline me = <LongTargetsPipeline> self
+        cdef DigitalSequenceBlock block
+        cdef TopHits hits
+        cdef HMM hmm
+        cdef Profile gm
+        cdef OptimizedProfile opt
+        cdef int status
+        cdef size_t nh, j
+        cdef size_t a_hits = 0, a_doms = 0, a_dup = 0, a_pos = 0
+        cdef const char* c_text = NULL
+        cdef int64_t nseqs, nres, span
+        if not isinstance(sequences, DigitalSequenceBlock) or not isinstance(query, HMM):
+            return super().search_hmm(query, sequences)      # SequenceFile targets, Profile / OptimizedProfile queries: the reference's loop
+        block, hmm = sequences, query
+        if not me.alphabet._eq(hmm.alphabet):
+            raise AlphabetMismatch(me.alphabet, hmm.alphabet)
+        if not me.alphabet._eq(block.alphabet):
+            raise AlphabetMismatch(me.alphabet, block.alphabet)
+        # the same query and targets as objects of the engine's host layer (binary HMM format: every float32 as it is)
+        m_abc = m_easel.Alphabet.rna() if me.alphabet.is_rna() else m_easel.Alphabet.dna()
+        buf = io.BytesIO()
+        hmm.write(buf, binary=True)
+        buf.seek(0)
+        with m_plan7.HMMFile(buf) as f:
+            m_hmm = f.read()
+        m_block = _mirror_block(m_easel, m_abc, block)
+        # (read from the struct: enum p7_strands_e is TOPONLY=0, BOTTOMONLY=1, BOTH=2, hmmer.h:90 -- the `strand` getter of
+        # plan7.pyx:7077 indexes (None, "watson", "crick") with it and answers "crick" for a search of both strands)
+        strand = {0: "watson", 1: "crick"}.get(<int> me._pli.strands, None)
+        opts = dict(F1=me._pli.F1, F2=me._pli.F2, F3=me._pli.F3, B1=me._pli.B1, B2=me._pli.B2, B3=me._pli.B3,
+                    bias_filter=bool(me._pli.do_biasfilter), null2=bool(me._pli.do_null2), seed=self.seed, Z=self.Z, domZ=self.domZ,
+                    bit_cutoffs=self.bit_cutoffs, strand=strand, block_length=int(me._pli.block_length),
+                    window_length=self.window_length, window_beta=self.window_beta, host_threads=self._b2h_host_threads)
+        m_pli = m_plan7.LongTargetsPipeline(m_abc, **opts)
+        try:
+            m_om, m_cut, (m_hits, m_doms, m_text, m_dup, stats) = m_pli._search_records(m_hmm, m_block)
+        except m_plan7.MissingCutoffs:
+            raise MissingCutoffs(query.name, self.bit_cutoffs)
+        # the reference's optimized profile of the query (thresholds, names and model length of the hits come from it)
+        L = self.L_HINT if len(block) == 0 else block._refs[0].L
+        gm = Profile(hmm.M, me.alphabet)
+        gm.configure(hmm, me.background, L)
+        opt = gm.to_optimized()
+        opt._om.max_length = int(m_om._desc.max_length)
+        hits = TopHits(query)
+        nh = len(m_hits)
+        keep = []                                            # (the ctypes buffers must outlive the call)
+        if nh:
+            harr = (m_lib.HitRec * nh)(*m_hits); keep.append(harr)
+            a_hits = <size_t> ctypes.addressof(harr)
+            darr = m_doms.raw if getattr(m_doms, "raw", None) is not None and len(m_doms.raw) == len(m_doms) else (m_lib.DomainRec * len(m_doms))(*m_doms)
+            keep.append(darr)
+            a_doms = <size_t> ctypes.addressof(darr)
+            dupa = np.ascontiguousarray(np.array(m_dup, dtype=np.uint8)); keep.append(dupa)
+            a_dup = <size_t> dupa.ctypes.data
+            text_b = bytes(m_text); keep.append(text_b)
+            c_text = text_b
+        pos = np.array([stats["pos_past_msv"], stats["pos_past_bias"], stats["pos_past_vit"], stats["pos_past_fwd"]], dtype=np.int64)
+        a_pos = <size_t> pos.ctypes.data
+        nseqs, nres = stats["nseqs"], stats["nres"]
+        with nogil:
+            me._pli.mode = p7_pipemodes_e.p7_SEARCH_SEQS
+            me._pli.nseqs = 0
+            status = b2h_glue_longtarget_fill(me._pli, hits._th, <const void*> a_hits, nh, <const void*> a_doms, c_text,
+                                              <const unsigned char*> a_dup, <ESL_SQ *const *> block._refs, opt._om, me.background._bg,
+                                              nseqs, nres, <const int64_t*> a_pos)
+        if status == eslEINVAL:
+            raise MissingCutoffs(query.name, self.bit_cutoffs)
+        elif status != eslOK:
+            raise UnexpectedError(status, "b2h_glue_longtarget_fill")
+        with nogil:
+            hits._sort_by_key()
+            hits._threshold(me)
+            hits._pli.n_output = hits._pli.pos_output = 0
+            for j in range(hits._th.N):
+                if (hits._th.hit[j].flags & 1) or (hits._th.hit[j].flags & 2):          # p7_IS_INCLUDED | p7_IS_REPORTED
+                    hits._pli.n_output += 1
+                    span = hits._th.hit[j].dcl[0].jali - hits._th.hit[j].dcl[0].iali
+                    hits._pli.pos_output += 1 + (span if span >= 0 else -span)
+        hits._query = query
+        hits._empty = False
+        return hits
+
+
 def install():
-    """Make `pyhmmer.hmmsearch` / `hmmscan` / `phmmer` / `jackhmmer` build `CudaPipeline` objects in their workers (the
+    """Make `pyhmmer.hmmsearch` / `hmmscan` / `phmmer` / `jackhmmer` / `nhmmer` build `CudaPipeline` (`CudaLongTargetsPipeline`) objects in their workers (the
     `pipeline_class` hook of pyhmmer.hmmer._base._BaseWorker).  phmmer's `search_seq` / `search_msa` and jackhmmer's
     `IterativeSearch` (plan7.pyx:4273-4389) build their models with pyhmmer's own `Builder` and then call
     `pipeline.search_hmm`, i.e. every search iteration runs on the GPU.  Returns a function that undoes it."""
     import pyhmmer.hmmer._hmmsearch as hs, pyhmmer.hmmer._hmmscan as sc, pyhmmer.hmmer._phmmer as ph, pyhmmer.hmmer._jackhmmer as jk
-    saved = [(cls, cls.__dict__.get("pipeline_class")) for cls in (hs._SEARCHWorker, sc._SCANWorker, ph._PHMMERWorker, jk._JACKHMMERWorker)]
+    import pyhmmer.hmmer._nhmmer as nh
+    saved = [(cls, cls.__dict__.get("pipeline_class")) for cls in (hs._SEARCHWorker, sc._SCANWorker, ph._PHMMERWorker, jk._JACKHMMERWorker, nh._NHMMERWorker)]
     for cls, _ in saved:
-        cls.pipeline_class = CudaPipeline
+        cls.pipeline_class = CudaLongTargetsPipeline if cls is nh._NHMMERWorker else CudaPipeline
 
     def uninstall():
         for cls, old in saved:

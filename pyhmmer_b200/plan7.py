@@ -2664,6 +2664,13 @@ class LongTargetsPipeline(Pipeline):
 
     def search_hmm(self, query, sequences):
         """nhmmer: one query against a `DigitalSequenceBlock` of long targets; returns `TopHits` (plan7.pyx:7258-7412)."""
+        om, cut, res = self._search_records(query, sequences)
+        return self._long_target_tophits(query, om, sequences, res, cut)
+
+    def _search_records(self, query, sequences):
+        """The search itself: ``(optimized profile, bit cutoffs or None, (hits, doms, text, duplicate flags, stats))`` -- the
+        records of every hit with its final (search-space corrected) lnP, before any `TopHits` is built.  The Cython binding
+        fills a real ``P7_TOPHITS`` from them (pyhmmer_cuda.CudaLongTargetsPipeline)."""
         from . import longtarget
         if not isinstance(sequences, DigitalSequenceBlock):
             raise TypeError("expected DigitalSequenceBlock, found %s" % type(sequences).__name__)
@@ -2701,7 +2708,7 @@ class LongTargetsPipeline(Pipeline):
         res = longtarget.search(om, sequences, evalue_window=max_length, evalue_residues=residues, F1=self.F1, F2=self.F2, F3=self.F3, bias_filter=self.bias_filter, null2=self.null2,
                                 B1=self.B1, B2=self.B2, B3=self.B3, block_length=self.block_length, strand=self.strand,
                                 seed=self.seed, host_threads=self.host_threads, backend_factory=self._backend_factory)
-        return self._long_target_tophits(query, om, sequences, res, cut)
+        return om, cut, res
 
     def search_seq(self, query, sequences, builder=None):
         """nhmmer with a query SEQUENCE (plan7.pyx:7420-7540): the model comes from a `Builder` that shares this pipeline's

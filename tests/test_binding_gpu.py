@@ -150,6 +150,85 @@ def test_iterative_search_on_cuda_equals_reference(bound):
             break
 
 
+def test_reference_nhmmer_test_classes_run_on_cuda(bound):
+    """The long-target pipeline through the binding: the reference's TestNhmmer (src/pyhmmer/tests/test_hmmer.py:631-797;
+    goldens bmyD1/2/3.tbl from the nhmmer CLI, RF00001 on the reverse strand, window_length) with pyhmmer.nhmmer's workers
+    building `CudaLongTargetsPipeline`, and TestLongTargetsPipeline / TestIteratePipeline (tests/test_plan7/test_pipeline.py:
+    257-400; the jackhmmer CLI's alignments of P12748 and KR, iteration by iteration) with the pipeline classes swapped."""
+    pyhmmer, pyhmmer_cuda = bound
+    mod = importlib.import_module("pyhmmer.tests.test_hmmer")
+    undo = pyhmmer_cuda.install()
+    launches0 = pyhmmer_cuda.engine().launch_count
+    try:
+        res = _run_cases([mod.TestNhmmer])
+    finally:
+        undo()
+    assert res.testsRun >= 9
+    assert not res.failures and not res.errors, [str(f[0]) + "\n" + f[1] for f in res.failures + res.errors]
+    assert pyhmmer_cuda.engine().launch_count > launches0 + 50
+    mod = importlib.import_module("pyhmmer.tests.test_plan7.test_pipeline")
+    saved = mod.Pipeline, mod.LongTargetsPipeline
+    mod.Pipeline, mod.LongTargetsPipeline = pyhmmer_cuda.CudaPipeline, pyhmmer_cuda.CudaLongTargetsPipeline
+    try:
+        res = _run_cases([mod.TestLongTargetsPipeline, mod.TestIteratePipeline])
+    finally:
+        mod.Pipeline, mod.LongTargetsPipeline = saved
+    assert res.testsRun >= 5
+    assert not res.failures and not res.errors, [str(f[0]) + "\n" + f[1] for f in res.failures + res.errors]
+
+
+def test_cuda_long_targets_pipeline_equals_reference(bound):
+    """Object-level comparison of `CudaLongTargetsPipeline` with `LongTargetsPipeline`: hit lists in order, flags, strands,
+    coordinates, scores, E-values, the residue counters of the pipeline; sequence queries; a user-set Z; one strand only."""
+    pyhmmer, pyhmmer_cuda = bound
+    dna = pyhmmer.easel.Alphabet.dna()
+    with pyhmmer.plan7.HMMFile(_data(pyhmmer, "hmms", "txt", "bmyD.hmm")) as f:
+        bmyd = f.read()
+    with pyhmmer.plan7.HMMFile(_data(pyhmmer, "hmms", "txt", "RF00001.hmm")) as f:
+        rf = f.read()
+    blocks = {}
+    for name, abc in (("1390.SAMEA104415756.OFHT01000022", bmyd.alphabet), ("1390.SAMEA104415756.OFHT01000024", rf.alphabet)):
+        with pyhmmer.easel.SequenceFile(_data(pyhmmer, "seqs", name + ".fna"), "fasta", digital=True, alphabet=abc) as f:
+            blocks[name] = f.read_block()
+    with pyhmmer.easel.SequenceFile(_data(pyhmmer, "seqs", "bmyD.fna"), "fasta", digital=True, alphabet=dna) as f:
+        bmyd_seq = next(f)
+    eng = pyhmmer_cuda.engine()
+
+    def same(got, ref):
+        assert type(got) is pyhmmer.plan7.TopHits and len(got) == len(ref)
+        assert len(got.reported) == len(ref.reported) and len(got.included) == len(ref.included)
+        assert (got.searched_sequences, got.searched_residues, got.searched_nodes) == (ref.searched_sequences, ref.searched_residues, ref.searched_nodes)
+        for a, b in zip(got, ref):
+            assert a.name == b.name and (a.reported, a.included, a.duplicate) == (b.reported, b.included, b.duplicate)
+            assert abs(a.score - b.score) < 2e-3 and abs(a.evalue - b.evalue) <= 2e-3 * b.evalue + 1e-300
+            d, e = a.best_domain, b.best_domain
+            assert (d.strand, d.env_from, d.env_to, d.alignment.target_from, d.alignment.target_to, d.alignment.hmm_from, d.alignment.hmm_to) == \
+                   (e.strand, e.env_from, e.env_to, e.alignment.target_from, e.alignment.target_to, e.alignment.hmm_from, e.alignment.hmm_to)
+            assert d.alignment.target_sequence == e.alignment.target_sequence and d.alignment.hmm_sequence == e.alignment.hmm_sequence
+            assert abs(d.bias - e.bias) < 2e-3 and d.alignment.target_length == e.alignment.target_length
+
+    n = 0
+    cases = [(bmyd, "1390.SAMEA104415756.OFHT01000022", {}), (rf, "1390.SAMEA104415756.OFHT01000024", {}),
+             (rf, "1390.SAMEA104415756.OFHT01000024", {"window_length": 3878}), (bmyd, "1390.SAMEA104415756.OFHT01000022", {"Z": 50.0}),
+             (bmyd, "1390.SAMEA104415756.OFHT01000022", {"strand": "watson"}), (rf, "1390.SAMEA104415756.OFHT01000024", {"strand": "crick", "E": 1e-3})]
+    for hmm, key, kw in cases:
+        n0 = eng.launch_count
+        got = pyhmmer_cuda.CudaLongTargetsPipeline(hmm.alphabet, **kw).search_hmm(hmm, blocks[key])
+        assert eng.launch_count > n0 + 5
+        ref = pyhmmer.plan7.LongTargetsPipeline(hmm.alphabet, **kw).search_hmm(hmm, blocks[key])
+        same(got, ref)
+        n += len(got)
+    assert n >= 8
+    # a sequence query: pyhmmer's Builder on the host, then the search above
+    with pyhmmer.easel.SequenceFile(_data(pyhmmer, "seqs", "BGC0001090.gbk"), digital=True, alphabet=dna) as f:
+        bgc = f.read_block()
+    n0 = eng.launch_count
+    got = pyhmmer_cuda.CudaLongTargetsPipeline(dna).search_seq(bmyd_seq, bgc)
+    assert eng.launch_count > n0 + 5
+    same(got, pyhmmer.plan7.LongTargetsPipeline(dna).search_seq(bmyd_seq, bgc))
+    assert len(got) == 1
+
+
 def test_cuda_pipeline_equals_reference_pipeline(bound):
     """Object-level comparison: the same queries and targets through pyhmmer's Pipeline (CPU) and CudaPipeline (GPU) -- hit
     lists, flags, every score, domain coordinates and alignment rows, the accounting of the TopHits, pickling."""
