@@ -342,6 +342,10 @@ int  b2h_hmm_max_length(int M, const float *t, double emit_thresh, int32_t *max_
 typedef struct { int32_t seq; int32_t k; int64_t n; int32_t length; float score; } b2h_window;
 int  b2h_longtarget_windows(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, double F1,
                             b2h_window **raw, size_t *nraw, b2h_window **merged, size_t *nmerged);
+/* What that scan uses for a profile and F1 (host only): the threshold on the byte scale (msvfilter.c:289-327) and whether the
+ * two-instruction cell applies (begin floor < threshold <= 256 - bias: the saturation of adds_epu8 cannot bind on a kept cell;
+ * otherwise the byte arithmetic is written out in full).  Either way the diagonals are the reference's. */
+int  b2h_longtarget_scan_info(const b2h_profile *p, double F1, int *sc_thresh, int *fast_cells);
 void b2h_free(void *p);
 /* The prefix / suffix length tables [M+1] of p7_hmm_ScoreDataComputeRest for a profile (host only; works on a profile made by
  * b2h_profile_create_host). */

@@ -164,6 +164,7 @@ def _load():
     sig("b2h_generic_decoding", c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
         c_void_p, c_void_p, P(c_float), P(c_float), c_void_p, c_void_p, c_void_p)
     sig("b2h_longtarget_windows", c_int, c_void_p, c_void_p, c_void_p, ctypes.c_double, P(c_void_p), P(c_size_t), P(c_void_p), P(c_size_t))
+    sig("b2h_longtarget_scan_info", c_int, c_void_p, ctypes.c_double, P(c_int), P(c_int))
     sig("b2h_free", None, c_void_p)
     sig("b2h_window_lengths", c_int, c_void_p, c_void_p, c_void_p)
     sig("b2h_extend_merge_windows", c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_float, P(c_size_t))

@@ -9,6 +9,7 @@
 #include <tuple>
 #include <numeric>
 #include <thread>
+#include <chrono>
 #include "b2h_internal.h"
 
 extern "C" {
@@ -551,9 +552,13 @@ int b2h_profile_upload_many(b2h_ctx *ctx, const b2h_oprofile_desc *const *descs,
     base[i + 1] = base[i] + ((profile_stage_bytes(descs[i]->M, G, NR, rC, rW) + 255) & ~(size_t)255);
   }
   cudaSetDevice(ctx->device);
+  static const bool trace = getenv("B2H_TRACE") != nullptr;
+  const auto tr0 = std::chrono::steady_clock::now();
   uint8_t *h = (uint8_t *)b2h_pin_get(ctx, base[n]);
   if (!h) { ctx->err = "cudaHostAlloc failed"; return B2H_EMEM; }
+  const auto tr1 = std::chrono::steady_clock::now();
   run_parallel([&](size_t i) { stg[i].ext = h + base[i]; status[i] = profile_build(ctx, descs[i], &out[i], &stg[i]); });
+  const auto tr2 = std::chrono::steady_clock::now();
   int st = B2H_OK;
   for (size_t i = 0; i < n && st == B2H_OK; i++) st = status[i];
   b2h_devblock *blk = nullptr;
@@ -569,6 +574,12 @@ int b2h_profile_upload_many(b2h_ctx *ctx, const b2h_oprofile_desc *const *descs,
     }
   }
   if (h) b2h_pin_put(ctx, h);
+  if (trace) {
+    const auto tr3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[b2h_profile_upload_many] %zu profiles, %.1f MB on %d threads: staging %.2f ms, tables %.2f ms, alloc + copy %.2f ms\n",
+            n, base[n] / 1e6, T, ms(tr0, tr1), ms(tr1, tr2), ms(tr2, tr3));
+  }
   if (st == B2H_OK) {
     blk->refs = (int)n;
     for (size_t i = 0; i < n; i++) {

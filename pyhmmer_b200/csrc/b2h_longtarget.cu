@@ -11,6 +11,7 @@
 // over chunks (a 100 Mb genome on both strands is ~800 chunks of 262 144) and over the model (the SSV register tiles):
 // every group of G lanes scans one chunk with the cell arithmetic of rmsv_kernel (fp16x2, exact for byte values), keeps
 // its own row pointer, and the rare hit handling runs on the group's first lane.
+#include <chrono>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <algorithm>
@@ -80,8 +81,18 @@ struct LtArgs {
   const LtItem *items = nullptr; int nitems = 0;
 };
 
-template <int G, int NR>
-__global__ void __launch_bounds__(128) lt_ssv_kernel(const LtArgs a)
+// FAST: the begin floor kept inside the row (m' = max(m, xB), two instructions per cell pair instead of three) and the
+// saturation of adds_epu8(.., bias) left out.  Exact when xB < threshold <= 256 - bias: every cell a scan keeps is below the
+// threshold (a row that reaches it is recorded and zeroed; the warm-up rows of a stretch hold lower bounds of rows in which
+// the reference found nothing), hence <= 255 - bias, so the min() never binds; max(relu(x), xB) = max(x, xB) for xB >= 0, and a
+// cell >= threshold > xB has m' = m.  The host picks the path per search (launch_lt).
+template <int G, int NR> struct LtShape {
+  static constexpr uint32_t TAB_BYTES = (uint32_t)B2H_NCODE * ((uint32_t)(NR / 4) * G * 16 + (uint32_t)(NR % 4) * 128);
+  static constexpr int THREADS = TAB_BYTES > 76 * 1024 ? 512 : 256;          // warps share the CTA's copy of the table
+  static constexpr int MINB = TAB_BYTES > 76 * 1024 ? 1 : 3;                  // 24 warps per SM: 80 registers
+};
+template <int G, int NR, bool FAST>
+__global__ void __launch_bounds__(LtShape<G, NR>::THREADS, LtShape<G, NR>::MINB) lt_ssv_kernel(const LtArgs a)
 {
   extern __shared__ __align__(128) uint32_t s_tab[];
   __shared__ uint64_t s_bar;
@@ -124,9 +135,10 @@ __global__ void __launch_bounds__(128) lt_ssv_kernel(const LtArgs a)
     const uint32_t *seqw = reinterpret_cast<const uint32_t *>(seq);
     const int nwords = (L + 3) >> 2;
 
+    const uint32_t zero_row = FAST ? xBh : 0u;
     uint32_t m[NR];
 #pragma unroll
-    for (int j = 0; j < NR; j++) m[j] = 0u;
+    for (int j = 0; j < NR; j++) m[j] = zero_row;
     int i = it.scan_from, nemit = 0;                           // next row of this group's scan (1-based), windows emitted so far
     int w0 = -G; uint32_t myw = 0;
 
@@ -144,13 +156,20 @@ __global__ void __launch_bounds__(128) lt_ssv_kernel(const LtArgs a)
       const uint32_t t  = __shfl_sync(FULL, m[NR-1], src_lane);
       const uint32_t s0 = __byte_perm(t, m[NR-1], 0x5432u);
       // sv = subs_epu8(adds_epu8(max(mpv, xB), bias), cost) == relu(min(max(mpv, xB), 255 - bias) + (bias - cost))
+      if (FAST) {
 #pragma unroll
-      for (int j = NR - 1; j >= 1; j--) m[j] = hfma2_relu_add(__vimin3_s16x2(__vimax3_s16x2(m[j-1], xBh, xBh), caph, caph), ev[j]);
-      m[0] = hfma2_relu_add(__vimin3_s16x2(__vimax3_s16x2(s0, xBh, xBh), caph, caph), ev[0]);
-      uint32_t xe = 0u;
+        for (int j = NR - 1; j >= 1; j--) m[j] = __vmaxs2(hfma2_relu_add(m[j-1], ev[j]), xBh);
+        m[0] = __vmaxs2(hfma2_relu_add(s0, ev[0]), xBh);
+      } else {
 #pragma unroll
-      for (int j = 0; j + 1 < NR; j += 2) xe = __vimax3_s16x2(xe, m[j], m[j+1]);
-      if (NR & 1) xe = __vimax3_s16x2(xe, m[NR-1], m[NR-1]);
+        for (int j = NR - 1; j >= 1; j--) m[j] = hfma2_relu_add(__vimin3_s16x2(__vimax3_s16x2(m[j-1], xBh, xBh), caph, caph), ev[j]);
+        m[0] = hfma2_relu_add(__vimin3_s16x2(__vimax3_s16x2(s0, xBh, xBh), caph, caph), ev[0]);
+      }
+      uint32_t xq[4] = {0u, 0u, 0u, 0u};                       // four independent chains, then one join
+#pragma unroll
+      for (int j = 0; j + 1 < NR; j += 2) xq[(j >> 1) & 3] = __vimax3_s16x2(xq[(j >> 1) & 3], m[j], m[j+1]);
+      if (NR & 1) xq[3] = __vimax3_s16x2(xq[3], m[NR-1], m[NR-1]);
+      const uint32_t xe = __vimax3_s16x2(__vimax3_s16x2(xq[0], xq[1], xq[2]), xq[3], xq[3]);
       const bool lanehit = active && i >= detect_from && (max((int)(xe & 0xffffu), (int)(xe >> 16)) >= thr_bits);
       if (__any_sync(FULL, lanehit)) {
         // the cell the reference picks: the largest value >= threshold among the model's nodes, first in its striped scan
@@ -204,7 +223,7 @@ __global__ void __launch_bounds__(128) lt_ssv_kernel(const LtArgs a)
         new_i = __shfl_sync(FULL, new_i, 0, G);
         if (best > 0) {                                                             // this group recorded a window: reset its row
 #pragma unroll
-          for (int j = 0; j < NR; j++) m[j] = 0u;
+          for (int j = 0; j < NR; j++) m[j] = zero_row;
           i = new_i; nemit++;
         }
       }
@@ -213,19 +232,35 @@ __global__ void __launch_bounds__(128) lt_ssv_kernel(const LtArgs a)
   }
 }
 
-template <int G, int NR>
-int launch_lt(b2h_ctx *ctx, const LtArgs &a, cudaStream_t strm)
+static bool lt_fast_cells(int base, int tbm, int bias, int tjb, int sc_thresh)
 {
+  const int xB = std::max(base - ((tjb + tbm) & 0xff), 0);
+  return xB < sc_thresh && sc_thresh <= 256 - bias && !getenv("B2H_LT_FULL_CELLS");       // (the variable: tests of the general path)
+}
+
+template <int G, int NR, bool FAST>
+int launch_lt_path(b2h_ctx *ctx, const LtArgs &a, cudaStream_t strm)
+{
+  // One scan is a chain of dependent rows, ~100-135 instructions each: what an SM delivers is set by the warps it holds.  The
+  // CTA shares one copy of the table, so the warps per CTA follow the table size (LtShape): 8 (three 64 KB tables per SM = 24
+  // warps), 16 when only one or two tables fit.
   const size_t smem = (size_t)B2H_NCODE * b2h_ssv_row_bytes(G, NR);
+  const int threads = LtShape<G, NR>::THREADS, wpc = threads / 32;
   int occ = 1;
-  { const int st = b2h_kernel_occupancy(ctx, (const void *)lt_ssv_kernel<G, NR>, 128, smem, &occ); if (st != B2H_OK) return st; }
+  { const int st = b2h_kernel_occupancy(ctx, (const void *)lt_ssv_kernel<G, NR, FAST>, threads, smem, &occ); if (st != B2H_OK) return st; }
   const int NG = 32 / G;
   const int nwork = a.items ? a.nitems : a.sd.n;
-  int grid = std::min(ctx->sm_count * occ, std::max(1, (nwork + 4 * NG - 1) / (4 * NG)));
-  lt_ssv_kernel<G, NR><<<grid, 128, smem, strm>>>(a);
+  int grid = std::min(ctx->sm_count * occ, std::max(1, (nwork + wpc * NG - 1) / (wpc * NG)));
+  lt_ssv_kernel<G, NR, FAST><<<grid, threads, smem, strm>>>(a);
   ctx->launches++;
   B2H_CUDA(cudaGetLastError());
   return B2H_OK;
+}
+template <int G, int NR>
+int launch_lt(b2h_ctx *ctx, const LtArgs &a, cudaStream_t strm)
+{
+  const bool fast = lt_fast_cells(a.P.base, a.P.tbm, a.P.bias, a.tjb, a.sc_thresh);
+  return fast ? launch_lt_path<G, NR, true>(ctx, a, strm) : launch_lt_path<G, NR, false>(ctx, a, strm);
 }
 
 // esl_gumbel_invsurv (vendor/easel/esl_gumbel.c:185)
@@ -306,6 +341,26 @@ extern "C" int b2h_window_lengths(const b2h_profile *p, float *prefix, float *su
   return B2H_OK;
 }
 
+// threshold on the byte scale for P-value F1 with the length model of max_length (msvfilter.c:289-327)
+static int lt_threshold(const b2h_profile *p, double F1, b2h_len_params *lp)
+{
+  b2h_length_params(p->max_length, 1.0f, lp);
+  const float invP = (float)gumbel_invsurv(F1, (double)p->evparam[0], (double)p->evparam[1]);
+  return (int)(uint8_t)(int)ceil((((double)lp->null1 + ((double)invP * 0.69314718055994529) + 3.0) * (double)p->scale_b)
+                                 + (double)p->base_b + (double)p->tec_b + (double)lp->tjb_b);
+}
+
+// What a scan with this profile and F1 would use: the byte threshold and whether the two-instruction cell applies (tests).
+extern "C" int b2h_longtarget_scan_info(const b2h_profile *p, double F1, int *sc_thresh, int *fast_cells)
+{
+  if (!p || p->max_length <= 0) return B2H_EINVAL;
+  b2h_len_params lp;
+  const int thr = lt_threshold(p, F1, &lp);
+  if (sc_thresh) *sc_thresh = thr;
+  if (fast_cells) *fast_cells = lt_fast_cells(p->base_b, p->tbm_b, p->bias_b, lp.tjb_b, thr) ? 1 : 0;
+  return B2H_OK;
+}
+
 extern "C" int b2h_longtarget_windows(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *db, double F1,
                                       b2h_window **raw_out, size_t *nraw_out, b2h_window **merged_out, size_t *nmerged_out)
 {
@@ -316,12 +371,8 @@ extern "C" int b2h_longtarget_windows(b2h_ctx *ctx, const b2h_profile *p, const 
   if (n == 0) return B2H_OK;
   B2H_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  // threshold on the byte scale for P-value F1 with the length model of max_length (msvfilter.c:289-327)
   b2h_len_params lp;
-  b2h_length_params(p->max_length, 1.0f, &lp);
-  const float invP = (float)gumbel_invsurv(F1, (double)p->evparam[0], (double)p->evparam[1]);
-  const int sc_thresh = (int)(uint8_t)(int)ceil((((double)lp.null1 + ((double)invP * 0.69314718055994529) + 3.0) * (double)p->scale_b)
-                                                + (double)p->base_b + (double)p->tec_b + (double)lp.tjb_b);
+  const int sc_thresh = lt_threshold(p, F1, &lp);
   LtArgs a;
   a.P = b2h_profdev(p); a.sd = b2h_seqdev(db); a.sc_thresh = sc_thresh; a.tjb = lp.tjb_b;
   a.Q = std::max(2, (p->M - 1) / 16 + 1);                     // p7O_NQB(M): the striping the reference's tie-break follows
@@ -344,6 +395,8 @@ extern "C" int b2h_longtarget_windows(b2h_ctx *ctx, const b2h_profile *p, const 
     } else { a.items = nullptr; a.nitems = 0; }
     cudaMemsetAsync(d_nwin, 0, sizeof(int), st);
     cudaMemsetAsync(a.counter, 0, sizeof(int), st);
+    static const bool trace = getenv("B2H_TRACE") != nullptr;
+    const auto t_launch = std::chrono::steady_clock::now();
     int rc = B2H_EINVAL;
     switch (p->G * 64 + p->NR) {
 #define CASE(g, n_) case (g) * 64 + (n_): rc = launch_lt<g, n_>(ctx, a, st); break;
@@ -367,6 +420,8 @@ extern "C" int b2h_longtarget_windows(b2h_ctx *ctx, const b2h_profile *p, const 
       }
     }
     if (d_items) cudaFreeAsync(d_items, st);
+    if (trace) fprintf(stderr, "[b2h_longtarget_windows] scan of %zu %s: %d diagonals, %.2f ms\n", items ? items->size() : n, items ? "stretches" : "chunks",
+                       nwin, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_launch).count());
     return rc;
   };
   std::vector<LtWin> hw;

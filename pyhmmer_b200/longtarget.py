@@ -57,14 +57,22 @@ def null1(L):
 
 
 def window_residues(block, seq, start, length):
-    """Concatenated residues and offsets of the windows (seq[i], 1-based start[i], length[i]) of a sequence block."""
+    """Concatenated residues and offsets of the windows (seq[i], 1-based start[i], length[i]) of a sequence block: one memcpy
+    per window on the host library's threads (b2h_pack_windows over the block's packed residues)."""
     res, off = block._packed()
-    length = np.asarray(length, np.int64)
-    woff = np.zeros(len(length) + 1, np.int64)
+    res = np.ascontiguousarray(res, np.uint8)
+    length = np.ascontiguousarray(length, np.int64)
+    n = len(length)
+    woff = np.zeros(n + 1, np.int64)
     np.cumsum(length, out=woff[1:])
-    src0 = off[np.asarray(seq, np.int64)] + np.asarray(start, np.int64) - 1
-    idx = np.repeat(src0 - woff[:-1], length) + np.arange(woff[-1], dtype=np.int64)
-    return np.ascontiguousarray(res[idx]), woff
+    src0 = np.ascontiguousarray(np.asarray(off, np.int64)[np.asarray(seq, np.int64)] + np.asarray(start, np.int64) - 1)
+    if n and (src0.min() < 0 or (src0 + length).max() > len(res) or length.min() < 0):
+        raise IndexError("window outside its sequence block")
+    out = np.empty(int(woff[-1]), np.uint8)
+    zero32 = np.zeros(n, np.int32)
+    ptrs = (ctypes.c_void_p * 1)(res.ctypes.data)
+    check(lib.b2h_pack_windows(ptrs, n, ptr(zero32), ptr(src0), ptr(length), ptr(zero32), None, 0, ptr(out), ptr(woff), 0), "b2h_pack_windows")
+    return out, woff
 
 
 class CudaBackend:

@@ -2,7 +2,10 @@
 homologs on both strands, through `plan7.LongTargetsPipeline` -- wall time per stage (`longtarget` timings), hits found, and
 the reference's own loop (oracle/_ref, single thread) on a bounded sample of the genome for comparison.
 
-    python tools/nhmmer_probe.py <M> <megabases> [reference sample in megabases, default 2]
+    python tools/nhmmer_probe.py <M> <megabases> [reference sample in megabases, default 2] [bench]
+
+With `bench` as the fourth argument the inputs are bench.py's configs[4] block (bench_inputs.c5_inputs: 1 planted homolog per Mb,
+calibrated statistics) instead of the hit-dense genome above.
 """
 import os, sys, time
 import numpy as np
@@ -25,6 +28,12 @@ for j in range(nplant):
         dom = longtarget.reverse_complement(dna, dom)
     pos = int(rng.integers(0, len(genome) - len(dom)))
     genome[pos:pos + len(dom)] = dom
+if len(sys.argv) > 4 and sys.argv[4] == "bench":
+    import bench_inputs
+    model, genome, nplant, cal = bench_inputs.c5_inputs(M, MB)
+    h = synth.hmm_from_arrays(dna, model)
+    if h.max_length is None or h.max_length <= 0:
+        h.max_length = h.compute_max_length()
 block = easel.DigitalSequenceBlock(dna, [easel.DigitalSequence(dna, name=b"genome", sequence=genome)])
 pli = plan7.LongTargetsPipeline(dna)
 print("M=%d max_length=%d, %.1f Mb x 2 strands, %d planted" % (M, h.max_length, MB, nplant), flush=True)
