@@ -1380,6 +1380,10 @@ int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wi
 {
   const int max_env_extra = 20;
   nthreads = std::max(1, nthreads);
+  const bool trace = getenv("B2H_TRACE") != nullptr;
+  auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_prev = tnow();
+  auto lap = [&](const char *what, size_t count) { if (trace) { const double t = tnow(); fprintf(stderr, "[b2h_longtarget_hits]   %s (%zu): %.2f ms\n", what, count, t - t_prev); t_prev = t; } };
   std::vector<b2h_ddef_task> tasks(n);
   std::vector<TaskState> states(n);
   std::vector<LtWindow> lws(n);
@@ -1393,6 +1397,7 @@ int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wi
     t.prof = p; t.dsq = x.dsq; t.L = x.L; t.fx = x.fwd_xmx; t.bx = x.bck_xmx; t.bck_own_scales = lw.bck_own_scales;
   }
   ThreadPool::get().parallel_for(n, nthreads, [&](Worker &w, size_t q) { ddef_regions(w, tasks[q], prm, states[q]); });
+  lap("regions of the windows, host", n);
   struct Env { uint32_t win, d; int i, j; std::vector<float> rsc; DomOut dom; bool ok = false, trimmed = false; float envsc = 0.f, domcorrection = 0.f; };
   std::vector<Env> envs;
   for (size_t q = 0; q < n; q++) {
@@ -1408,6 +1413,7 @@ int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wi
       Env &e = envs[which[z]];
       if (prm->do_null2) lt_reparameterize(p, lws[e.win].dsq, lws[e.win].L, e.i, e.j - e.i + 1, e.rsc);
     });
+    lap("re-estimated emission tables, host", m);
     std::vector<b2h_env_job> jobs(m);
     for (size_t z = 0; z < m; z++) {
       Env &e = envs[which[z]];
@@ -1415,6 +1421,7 @@ int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wi
       jobs[z].rsc = prm->do_null2 ? e.rsc.data() : nullptr;
     }
     if (backend) { const int st = backend->run(tasks, jobs); if (st != B2H_OK) return st; }
+    lap("envelope Forward / Backward / OA on the device", m);
     ThreadPool::get().parallel_for(m, nthreads, [&](Worker &w, size_t z) {
       Env &e = envs[which[z]];
       const LtWindow &lw = lws[e.win];
@@ -1431,6 +1438,7 @@ int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wi
       e.ok = ok && render_domain(mm, p, lw.dsq, er, n2sc, e.dom);
       e.envsc = er.envsc;
     });
+    lap("traces, null2, alignment rendering, host", m);
     return B2H_OK;
   };
   std::vector<uint32_t> all(ne);
@@ -1459,6 +1467,7 @@ int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wi
       jobs[z].task = (int)e.win; jobs[z].i = e.i; jobs[z].j = e.j; jobs[z].cfg_len = e.j - e.i + 1; jobs[z].rsc = nullptr; jobs[z].fwd_only = true;
     }
     if (backend && !jobs.empty()) { if ((st = backend->run(tasks, jobs)) != B2H_OK) return st; }
+    lap("plain Forward of the final envelopes on the device", jobs.size());
     ThreadPool::get().parallel_for(live.size(), nthreads, [&](Worker &w, size_t z) {
       Env &e = envs[live[z]];
       if (backend && jobs[z].status == 0) { e.domcorrection = jobs[z].envsc; return; }

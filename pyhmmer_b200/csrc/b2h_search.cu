@@ -1078,11 +1078,13 @@ int b2h_longtarget_hits(b2h_ctx *ctx, const b2h_profile *p, const b2h_seqdb *win
       WorkList wl; wl.profs = d_prof; wl.ent_s = d_ent; wl.poff = d_poff; wl.itemoff = d_itemoff; wl.P = 1; wl.counter = ctx->d_counters + 8; wl.plo = 0; wl.phi = 1;
       StageOut sf; sf.sc = d_fsc; sf.status = d_fst; sf.fwd_xmx = d_fx; sf.bck_xmx = nullptr; sf.xoff = d_xoff;
       StageOut sb; sb.sc = d_bsc; sb.status = d_bst; sb.fwd_xmx = d_fx; sb.bck_xmx = d_bx; sb.xoff = d_xoff;
+      const double t_fb = now_ms();
       TRY(b2h_launch_forward_backward(ctx, wl, sd, mpads, items, sf, sb));
       B2H_CUDA(cudaMemcpyAsync(fx.data(), d_fx, (size_t)acc * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
       B2H_CUDA(cudaMemcpyAsync(bx.data(), d_bx, (size_t)acc * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
       B2H_CUDA(cudaMemcpyAsync(bst.data(), d_bst, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (getenv("B2H_TRACE")) fprintf(stderr, "[b2h_longtarget_hits] %d windows, %lld rows: Forward / Backward parsers + specials to the host %.2f ms\n", nb, (long long)acc, now_ms() - t_fb);
     }
     std::vector<b2h_lt_window> lw(nb);
     for (int e = 0; e < nb; e++) {
