@@ -1398,9 +1398,7 @@ int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wi
   }
   ThreadPool::get().parallel_for(n, nthreads, [&](Worker &w, size_t q) { ddef_regions(w, tasks[q], prm, states[q]); });
   lap("regions of the windows, host", n);
-  // (plain_*: the Forward score of the envelope under the model's own emissions, asked for in the same device pass as the rescoring)
-  struct Env { uint32_t win, d; int i, j; std::vector<float> rsc; DomOut dom; bool ok = false, trimmed = false; float envsc = 0.f, domcorrection = 0.f;
-               int plain_status = 1; float plain_sc = 0.f; };
+  struct Env { uint32_t win, d; int i, j; std::vector<float> rsc; DomOut dom; bool ok = false, trimmed = false; float envsc = 0.f, domcorrection = 0.f; };
   std::vector<Env> envs;
   for (size_t q = 0; q < n; q++) {
     if (states[q].dead || states[q].nregions == 0) continue;
@@ -1416,22 +1414,13 @@ int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wi
       if (prm->do_null2) lt_reparameterize(p, lws[e.win].dsq, lws[e.win].L, e.i, e.j - e.i + 1, e.rsc);
     });
     lap("re-estimated emission tables, host", m);
-    // with a re-estimated background every envelope is scored twice -- rescored under its own emission table, and a plain Forward
-    // under the model's (the bias term): both jobs go into ONE device pass (a pass costs the latency of its longest envelope)
-    const bool with_plain = prm->do_null2 && backend != nullptr;
-    std::vector<b2h_env_job> jobs(with_plain ? 2 * m : m);
+    std::vector<b2h_env_job> jobs(m);
     for (size_t z = 0; z < m; z++) {
       Env &e = envs[which[z]];
       jobs[z].task = (int)e.win; jobs[z].i = e.i; jobs[z].j = e.j; jobs[z].cfg_len = e.j - e.i + 1;
       jobs[z].rsc = prm->do_null2 ? e.rsc.data() : nullptr;
-      if (with_plain) { b2h_env_job &pj = jobs[m + z]; pj.task = (int)e.win; pj.i = e.i; pj.j = e.j; pj.cfg_len = e.j - e.i + 1; pj.rsc = nullptr; pj.fwd_only = true; }
     }
     if (backend) { const int st = backend->run(tasks, jobs); if (st != B2H_OK) return st; }
-    for (size_t z = 0; z < m; z++) {
-      Env &e = envs[which[z]];
-      e.plain_status = with_plain ? (jobs[m + z].status == 0 ? 0 : std::isinf(jobs[m + z].envsc) ? 2 : 1) : 1;
-      e.plain_sc = with_plain ? jobs[m + z].envsc : 0.f;
-    }
     lap("envelope Forward / Backward / OA on the device", m);
     ThreadPool::get().parallel_for(m, nthreads, [&](Worker &w, size_t z) {
       Env &e = envs[which[z]];
@@ -1472,17 +1461,23 @@ int b2h_longtarget_domains_backend(const b2h_profile *p, const b2h_lt_window *wi
   if (prm->do_null2) {
     std::vector<uint32_t> live;
     for (size_t z = 0; z < ne; z++) if (envs[z].ok) live.push_back((uint32_t)z);
+    std::vector<b2h_env_job> jobs(live.size());
+    for (size_t z = 0; z < live.size(); z++) {
+      const Env &e = envs[live[z]];
+      jobs[z].task = (int)e.win; jobs[z].i = e.i; jobs[z].j = e.j; jobs[z].cfg_len = e.j - e.i + 1; jobs[z].rsc = nullptr; jobs[z].fwd_only = true;
+    }
+    if (backend && !jobs.empty()) { if ((st = backend->run(tasks, jobs)) != B2H_OK) return st; }
+    lap("plain Forward of the final envelopes on the device", jobs.size());
     ThreadPool::get().parallel_for(live.size(), nthreads, [&](Worker &w, size_t z) {
       Env &e = envs[live[z]];
-      if (e.plain_status == 0) { e.domcorrection = e.plain_sc; return; }
-      if (e.plain_status == 2) return;                          // (p7_Forward's range error: the reference keeps envsc)
+      if (backend && jobs[z].status == 0) { e.domcorrection = jobs[z].envsc; return; }
+      if (backend && std::isinf(jobs[z].envsc)) return;        // (p7_Forward's range error: the reference keeps envsc)
       Model mo; model_of(w, p, mo);
       const int Ld = e.j - e.i + 1;
       configure(mo, false, Ld);
       float sc = e.domcorrection;
       if (forward_full(mo, lws[e.win].dsq + e.i - 1, Ld, w.fwd, &sc)) e.domcorrection = sc;
     });
-    lap("plain Forward scores taken (host for what the device left)", live.size());
   }
   std::vector<std::vector<HitOut>> outs(n);
   for (size_t z = 0; z < ne; z++) {                         // in the order of ddef->dcl

@@ -591,7 +591,7 @@ struct EnvGpu : b2h_env_backend {
         b2h_env_job &jb = jobs[perm[z]];
         const int M = tasks[jb.task].prof->M;
         const int base = r_status[z] & 0xff;                                             // a Forward range error only makes envsc = inf
-        if (jb.fwd_only) { jb.status = (base == B2H_OK) ? 0 : 1; jb.envsc = r_envsc[z]; continue; }   // (in a mixed pass its Backward / OA results are not looked at)
+        if (fwd_only) { jb.status = (base == B2H_OK) ? 0 : 1; jb.envsc = r_envsc[z]; continue; }
         if ((base != B2H_OK && base != B2H_ERANGE) || (r_status[z] & 0x300) || r_tlen[z] < 0) { jb.status = 1; continue; }
         jb.status = 0; jb.envsc = r_envsc[z]; jb.oasc = r_oasc[z];
         jb.xn = r_xnull[(size_t)z * 4 + 0]; jb.xc = r_xnull[(size_t)z * 4 + 1]; jb.xj = r_xnull[(size_t)z * 4 + 2];
