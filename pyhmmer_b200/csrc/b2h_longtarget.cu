@@ -81,11 +81,12 @@ struct LtArgs {
   const LtItem *items = nullptr; int nitems = 0;
 };
 
-// FAST: the begin floor kept inside the row (m' = max(m, xB), two instructions per cell pair instead of three) and the
-// saturation of adds_epu8(.., bias) left out.  Exact when xB < threshold <= 256 - bias: every cell a scan keeps is below the
-// threshold (a row that reaches it is recorded and zeroed; the warm-up rows of a stretch hold lower bounds of rows in which
-// the reference found nothing), hence <= 255 - bias, so the min() never binds; max(relu(x), xB) = max(x, xB) for xB >= 0, and a
-// cell >= threshold > xB has m' = m.  The host picks the path per search (launch_lt).
+// FAST: cells kept RELATIVE to the begin floor, c = max(m, xB) - xB, which turns the recurrence into the plain SSV one,
+// c' = relu(c + (bias - cost)): ONE instruction per cell pair (HFMA2.RELU) instead of three, and the saturation of
+// adds_epu8(.., bias) left out.  Exact when xB < threshold <= 256 - bias: every cell a scan keeps is below the threshold (a row
+// that reaches it is recorded and zeroed; the warm-up rows of a stretch hold lower bounds of rows in which the reference found
+// nothing), hence <= 255 - bias, so the min() never binds; max(relu(x), xB) = max(x, xB) for xB >= 0; a cell >= threshold > xB
+// has max(m, xB) = m; all values are integers below 2048, exact in fp16.  The host picks the path per search (launch_lt).
 template <int G, int NR> struct LtShape {
   static constexpr uint32_t TAB_BYTES = (uint32_t)B2H_NCODE * ((uint32_t)(NR / 4) * G * 16 + (uint32_t)(NR % 4) * 128);
   static constexpr int THREADS = TAB_BYTES > 76 * 1024 ? 512 : 256;          // warps share the CTA's copy of the table
@@ -116,7 +117,8 @@ __global__ void __launch_bounds__(LtShape<G, NR>::THREADS, LtShape<G, NR>::MINB)
   const int floor_sc = base - a.tjb - P.tbm;                   // the level a diagonal left the begin state at (msvfilter.c:384)
   const __half2 xb2 = __float2half2_rn((float)xB), cap2 = __float2half2_rn((float)(255 - bias)), th2 = __float2half2_rn((float)a.sc_thresh);
   const uint32_t xBh = *reinterpret_cast<const uint32_t *>(&xb2), caph = *reinterpret_cast<const uint32_t *>(&cap2);
-  const int thr_bits = (int)(*reinterpret_cast<const uint32_t *>(&th2) & 0xffffu);
+  const __half2 thf2 = __float2half2_rn((float)(a.sc_thresh - xB));
+  const int thr_bits = (int)(*reinterpret_cast<const uint32_t *>(FAST ? &thf2 : &th2) & 0xffffu);     // FAST: on the scale of c
 
   for (;;) {
     int e0 = 0;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(LtShape<G, NR>::THREADS, LtShape<G, NR>::MINB)
     const uint32_t *seqw = reinterpret_cast<const uint32_t *>(seq);
     const int nwords = (L + 3) >> 2;
 
-    const uint32_t zero_row = FAST ? xBh : 0u;
+    const uint32_t zero_row = 0u;
     uint32_t m[NR];
 #pragma unroll
     for (int j = 0; j < NR; j++) m[j] = zero_row;
@@ -158,8 +160,8 @@ __global__ void __launch_bounds__(LtShape<G, NR>::THREADS, LtShape<G, NR>::MINB)
       // sv = subs_epu8(adds_epu8(max(mpv, xB), bias), cost) == relu(min(max(mpv, xB), 255 - bias) + (bias - cost))
       if (FAST) {
 #pragma unroll
-        for (int j = NR - 1; j >= 1; j--) m[j] = __vmaxs2(hfma2_relu_add(m[j-1], ev[j]), xBh);
-        m[0] = __vmaxs2(hfma2_relu_add(s0, ev[0]), xBh);
+        for (int j = NR - 1; j >= 1; j--) m[j] = hfma2_relu_add(m[j-1], ev[j]);
+        m[0] = hfma2_relu_add(s0, ev[0]);
       } else {
 #pragma unroll
         for (int j = NR - 1; j >= 1; j--) m[j] = hfma2_relu_add(__vimin3_s16x2(__vimax3_s16x2(m[j-1], xBh, xBh), caph, caph), ev[j]);
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(LtShape<G, NR>::THREADS, LtShape<G, NR>::MINB)
         if (best > 0 && gl == 0) {
           const int key = 0xffff - (best & 0xffff);
           int end = (key >> 4) + a.Q * (key & 15) + 1;
-          int rem_sc = half_bits_to_int((uint32_t)best >> 16);
+          int rem_sc = half_bits_to_int((uint32_t)best >> 16) + (FAST ? xB : 0);
           int sc = rem_sc;
           int start = end, target_start = i, target_end = i;
           while (rem_sc > floor_sc && start >= 1 && target_start >= 1) {          // walk the diagonal back to the begin level

@@ -37,7 +37,7 @@ if len(sys.argv) > 4 and sys.argv[4] == "bench":
 block = easel.DigitalSequenceBlock(dna, [easel.DigitalSequence(dna, name=b"genome", sequence=genome)])
 pli = plan7.LongTargetsPipeline(dna)
 print("M=%d max_length=%d, %.1f Mb x 2 strands, %d planted" % (M, h.max_length, MB, nplant), flush=True)
-for rep in range(3):
+for rep in range(int(os.environ.get("PROBE_REPS", "3"))):
     om = pli._optimized(h, 100)
     tm = {}
     t0 = time.perf_counter()
