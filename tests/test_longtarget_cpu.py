@@ -363,3 +363,30 @@ def test_randomised_searches_against_the_reference_loop():
         nh, _ = lt_common.compare_nhmmer(pair, [s.sequence for s in seqs], got, **kw)
         total += nh
     assert total >= 30
+
+
+def test_window_residues_gather():
+    """`longtarget.window_residues` (the C packer behind every window database of the long-target stages) against a plain
+    numpy gather: ragged windows of a multi-sequence block, windows that touch both ends of their sequence, zero-length
+    windows, an empty list, and a window outside the packed residues."""
+    from pyhmmer_b200 import easel, longtarget
+    dna = easel.Alphabet.dna()
+    rng = np.random.default_rng(5)
+    lens = [70000, 1, 12, 3000000, 257]
+    seqs = [easel.DigitalSequence(dna, name=b"s%d" % i, sequence=rng.integers(0, 4, n).astype(np.uint8)) for i, n in enumerate(lens)]
+    block = easel.DigitalSequenceBlock(dna, seqs)
+    n = 4000
+    seq = rng.integers(0, len(lens), n)
+    L = np.array([lens[s] for s in seq])
+    length = np.minimum(rng.integers(0, 4000, n), L)
+    start = np.array([int(rng.integers(1, l - ln + 2)) for l, ln in zip(L, length)])
+    start[:50] = 1                                                  # from the first residue ...
+    length[50:100] = L[50:100] - start[50:100] + 1                  # ... and to the last
+    res, off = longtarget.window_residues(block, seq, start, length)
+    assert res.dtype == np.uint8 and len(res) == int(length.sum()) and np.array_equal(off, np.concatenate(([0], np.cumsum(length))))
+    for i in range(n):
+        assert np.array_equal(res[off[i]:off[i + 1]], seqs[seq[i]].sequence[start[i] - 1:start[i] - 1 + length[i]]), i
+    res, off = longtarget.window_residues(block, np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64))
+    assert len(res) == 0 and list(off) == [0]
+    with pytest.raises(IndexError):
+        longtarget.window_residues(block, [len(lens) - 1], [200], [100])
