@@ -279,3 +279,39 @@ def test_cuda_pipeline_equals_reference_pipeline(bound):
         got = pyhmmer_cuda.CudaPipeline(abc).scan_seq(q, block)
         assert [(h.name, h.reported, h.included, len(h.domains)) for h in got] == [(h.name, h.reported, h.included, len(h.domains)) for h in ref]
         assert all(abs(a.score - b.score) < 2e-3 for a, b in zip(got, ref)) and (got.Z, got.searched_models) == (ref.Z, ref.searched_models)
+
+
+def test_one_call_wrappers(bound):
+    """`pyhmmer_b200.binding.hmmsearch / hmmscan / nhmmer`: pyhmmer's functions with the CUDA pipelines installed for the duration of
+    the call -- same hits as pyhmmer's own, kernels launched, and the workers' `pipeline_class` restored afterwards."""
+    pyhmmer, pyhmmer_cuda = bound
+    from pyhmmer_b200 import binding
+    import pyhmmer.hmmer._hmmsearch as hs, pyhmmer.hmmer._nhmmer as nh
+    abc = pyhmmer.easel.Alphabet.amino()
+    with pyhmmer.easel.SequenceFile(_data(pyhmmer, "seqs", "938293.PRJEB85.HG003687.faa"), digital=True, alphabet=abc) as f:
+        seqs = f.read_block()
+    with pyhmmer.plan7.HMMFile(_data(pyhmmer, "hmms", "txt", "PF02826.hmm")) as f:
+        hmm = f.read()
+    eng = pyhmmer_cuda.engine()
+    before = (hs._SEARCHWorker.__dict__.get("pipeline_class"), nh._NHMMERWorker.__dict__.get("pipeline_class"))
+    n0 = eng.launch_count
+    got = list(binding.hmmsearch(hmm, seqs, cpus=1))
+    assert eng.launch_count > n0 + 5
+    assert (hs._SEARCHWorker.__dict__.get("pipeline_class"), nh._NHMMERWorker.__dict__.get("pipeline_class")) == before
+    ref = list(pyhmmer.hmmsearch(hmm, seqs, cpus=1))
+    assert len(got) == len(ref) == 1 and len(got[0]) == len(ref[0]) > 0
+    for a, b in zip(got[0], ref[0]):
+        assert a.name == b.name and abs(a.score - b.score) < 2e-3 and (a.reported, a.included) == (b.reported, b.included)
+    n0 = eng.launch_count
+    scan = list(binding.hmmscan(seqs[:3], [hmm], cpus=1))
+    assert eng.launch_count > n0 and len(scan) == 3
+    ref = list(pyhmmer.hmmscan(seqs[:3], [hmm], cpus=1))
+    assert [len(t) for t in scan] == [len(t) for t in ref]
+    with pyhmmer.plan7.HMMFile(_data(pyhmmer, "hmms", "txt", "bmyD.hmm")) as f:
+        bmyd = f.read()
+    with pyhmmer.easel.SequenceFile(_data(pyhmmer, "seqs", "BGC0001090.gbk"), digital=True, alphabet=bmyd.alphabet) as f:
+        bgc = f.read_block()
+    n0 = eng.launch_count
+    hits = next(binding.nhmmer(bmyd, bgc, cpus=1))
+    assert eng.launch_count > n0 + 5 and len(hits.reported) == 2
+    assert (hs._SEARCHWorker.__dict__.get("pipeline_class"), nh._NHMMERWorker.__dict__.get("pipeline_class")) == before
